@@ -1,0 +1,201 @@
+/*
+ * vgan_gpu.h -- C ABI of the B200-native read x path likelihood engine for vgan.
+ *
+ * The reference (grenaud/vgan) has no plugin / FFI interface; the drop-in boundary is the set of
+ * C++ call sites listed in SURVEY.md 8(b).  Every entry point below names the reference interface
+ * it replaces (file:line relative to the reference root).  Plain pointers and sizes only; no C++,
+ * STL or torch types cross this boundary; nothing throws (the reference's call sites are
+ * `noexcept`, src/update_likelihood.cpp:10) -- every call returns a status and
+ * vgl_last_error() describes the last failure on the calling thread.
+ *
+ * Threading / process model: one caller thread per context; the CUDA context is
+ * created lazily inside vgl_create(), never in a static initialiser, so a host that fork()s its
+ * mapping children first (src/HaploCart.cpp:313-378) is safe as long as it calls vgl_create()
+ * afterwards.
+ */
+#ifndef VGAN_GPU_H
+#define VGAN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGL_ABI_VERSION 1
+
+/* status codes */
+enum {
+    VGL_OK = 0,
+    VGL_ERR_INVALID = 1,    /* bad argument                                                            */
+    VGL_ERR_CUDA = 2,       /* CUDA runtime failure (message in vgl_last_error)                        */
+    VGL_ERR_STATE = 3,      /* call order violated (e.g. accumulate before set_tables)                 */
+    VGL_ERR_BAD_NODE = 4,   /* a mapping names a node with no pangenome_map entry / outside the table:
+                               the reference would throw from map::at inside a noexcept function
+                               (src/process_mapping.cpp:33) and terminate                              */
+    VGL_ERR_BAD_READ = 5,   /* malformed alignment (see vgh_* packer)                                  */
+    VGL_ERR_NO_DEVICE = 6   /* no CUDA device: there is NO CPU fallback                                */
+};
+
+typedef struct vgl_ctx vgl_ctx;
+
+/* ------------------------------------------------------------------------------------------- */
+/* context                                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device_id` (first CUDA call of the library happens here).   */
+int vgl_create(int device_id, vgl_ctx** out);
+void vgl_destroy(vgl_ctx* ctx);
+const char* vgl_last_error(void);
+int vgl_abi_version(void);
+
+/* Run all work of this context on an externally owned CUDA stream (cudaStream_t passed as a
+ * pointer).  NULL restores the context's own stream.  Lets a host that already owns device
+ * memory and streams (e.g. torch.distributed glue) order its collectives against our kernels. */
+int vgl_set_stream(vgl_ctx* ctx, void* cuda_stream);
+int vgl_synchronize(vgl_ctx* ctx);
+
+/* Pinned host memory for batches (optional; pageable pointers are accepted everywhere).        */
+int vgl_host_alloc(void** out, size_t bytes);
+int vgl_host_free(void* p);
+/* Raw device memory, for callers that keep batches resident in HBM.                            */
+int vgl_device_alloc(vgl_ctx* ctx, void** out, size_t bytes);
+int vgl_device_free(vgl_ctx* ctx, void* p);
+int vgl_memcpy_h2d(vgl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int vgl_memcpy_d2h(vgl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------- */
+/* HaploCart tables                                                                            */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Immutable per-process tables (reference: built once at src/HaploCart.cpp:279-286).
+ *   support_bits : the node x path membership matrix NodeInfo::pathsgo (src/NodeInfo.h:28-42,
+ *                  filled at src/readPathHandleGraph.cpp:24-34 from path_supports,
+ *                  src/load.cpp:283-300), bit-packed: bit (p & 31) of word
+ *                  support_bits[row * row_words + (p >> 5)] is pathsgo[p] of node id `row`.
+ *                  Row index == node id, exactly as the reference indexes path_supports[i].
+ *   node_mappability[row] : mappabilities[pangenome_map.at(id)]      (src/process_mapping.cpp:33-35)
+ *   node_match_prob[row]  : pow(1 - 30*mu(pangenome_base), 8)        (src/get_p_obs_base.cpp:43-64)
+ *   node_valid[row]       : 1 iff pangenome_map holds the node id    (src/load.cpp:27-41)
+ *   qscore[Q]             : get_qscore_vec()                          (src/miscfunc.h:198-212)
+ *   p_incorrect_map[Q]    : precompute_incorrect_mapping_probs()      (src/haplocart_functions.cpp:100-107)
+ *   bg_freq[0..3]         : get_background_freq('A','C','G','T')      (src/haplocart_functions.cpp:81-97)
+ *   background_error_prob : -e                                        (src/HaploCart.cpp:87-209)
+ *   is_consensus_fasta    : consensus-FASTA mode (also forces the background error mode,
+ *                           src/HaploCart.cpp:395-401)
+ */
+typedef struct vgl_hc_tables {
+    int32_t n_rows;
+    int32_t n_paths;
+    int32_t row_words; /* >= (n_paths + 31) / 32 */
+    int32_t reserved0;
+    const uint32_t* support_bits;
+    const double* node_mappability;
+    const double* node_match_prob;
+    const uint8_t* node_valid;
+    double qscore[100];
+    double p_incorrect_map[100];
+    double bg_freq[4];
+    double background_error_prob;
+    int32_t is_consensus_fasta;
+    int32_t reserved1;
+} vgl_hc_tables;
+
+int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* tables);
+
+/* Haplogroup tree for the posterior (reference: parents.txt / children.txt, src/load.cpp:303-345,
+ * consumed by get_posterior, src/get_posterior.cpp:87-127).
+ *   clade_bits[c * row_words + w] : bit-set over paths of the STRICT descendants of clade c that are
+ *                                   path names (what get_posterior_of_clade collects, :51-76)
+ *   anc_off[p] .. anc_off[p+1]    : for path p, indices into anc_clade listing the clades reported
+ *                                   for a call of p, in parents[p] order with consecutive duplicates
+ *                                   removed (:110-118)                                           */
+int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, const int32_t* anc_off,
+                    const int32_t* anc_clade);
+
+/* ------------------------------------------------------------------------------------------- */
+/* HaploCart read batch (SoA, layout v1: host-reconstructed aligned columns)                   */
+/* ------------------------------------------------------------------------------------------- */
+
+/* One batch = the reads of one call to the hot loop (src/HaploCart.cpp:408-421) after
+ * reconstruct_graph_sequence (src/vgan_utils.h:6-79) has produced, per read, the aligned graph
+ * string, the aligned read string and the per-edit sizes.  For read r:
+ *   columns   col_off[r] .. col_off[r+1]   (n = |aligned read string| == |aligned graph string|)
+ *     gcol[]  aligned graph string  (ASCII: A C G T N '-' 'S')
+ *     rcol[]  aligned read string   (ASCII: A C G T N '-')
+ *     qual[]  quality byte at the SAME column index (raw PHRED, as vg.Alignment.quality holds
+ *             it); 0 for column indices >= n_qual[r]  (the reference indexes the quality string by
+ *             aligned column, src/update_likelihood.cpp:40-44)
+ *   mappings  map_off[r] .. map_off[r+1]   (one per vg Mapping of the path)
+ *     map_node[]  Mapping.position.node_id
+ *     map_len[]   mppg_sizes[i] -- the size of the i-th EDIT of the read, indexed by mapping
+ *                 number exactly as src/update_likelihood.cpp:35-37 does
+ *   n_qual[r]   length of the quality string (<= number of columns)
+ *   mapq[r]     Alignment.mapping_quality (0..99)
+ * All arrays are host pointers for vgl_hc_accumulate and device pointers for
+ * vgl_hc_accumulate_device.                                                                    */
+typedef struct vgl_hc_batch {
+    uint32_t n_reads;
+    uint32_t reserved;
+    uint64_t n_cols;
+    uint64_t n_maps;
+    const uint32_t* col_off; /* [n_reads + 1] */
+    const uint32_t* map_off; /* [n_reads + 1] */
+    const uint8_t* gcol;     /* [n_cols] */
+    const uint8_t* rcol;     /* [n_cols] */
+    const uint8_t* qual;     /* [n_cols] */
+    const int32_t* map_node; /* [n_maps] */
+    const uint16_t* map_len; /* [n_maps] */
+    const uint16_t* n_qual;  /* [n_reads] */
+    const uint8_t* mapq;     /* [n_reads] */
+} vgl_hc_batch;
+
+/* Bytes the batch occupies (what crosses PCIe / is read from HBM once per pass).               */
+uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b);
+
+/* ------------------------------------------------------------------------------------------- */
+/* HaploCart hot path                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Start a new sample: zero the accumulators (reference: fill(final_vec, 0), HaploCart.cpp:481). */
+int vgl_hc_reset(vgl_ctx* ctx);
+
+/* Replaces the `#pragma omp parallel for` body + critical-section sum of src/HaploCart.cpp:408-421
+ * (Haplocart::update -> update_likelihood -> process_mapping -> get_p_obs_base, SURVEY.md 8a rows
+ * a3-a9) for every read of the batch.  May be called repeatedly; contributions add up.
+ * Asynchronous with respect to the host (stream ordered); errors surface at finalize/synchronize. */
+int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* host_batch);
+int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* device_batch);
+
+/* Collapse the accumulators into the per-path log-likelihood vector final_vec[P]
+ * (src/HaploCart.cpp:297-299,419-420) on the device.  ll_dev (device pointer, P doubles) receives
+ * this context's (this GPU's) vector; pass NULL to keep it internal.                            */
+int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev);
+
+/* Multi-GPU: replace the internal vector by the fixed-order sum of `n_parts` device vectors of P
+ * doubles each (parts[k * P + p], e.g. the result of an all-gather over ranks).  Summing in rank
+ * order keeps paths with identical support bit-identical, so std::max_element ties resolve as in
+ * the single-GPU run.                                                                           */
+int vgl_hc_set_paths_from_parts(vgl_ctx* ctx, const double* parts_dev, int32_t n_parts);
+
+/* Replaces std::max_element (src/HaploCart.cpp:423-424) and Haplocart::get_posterior
+ * (src/get_posterior.cpp:87-127): argmax with first-max-wins, log-sum-exp over all paths, posterior
+ * of the call and of every clade on its ancestor list.  Host outputs:
+ *   ll_out[P] (may be NULL), *argmax_out, *total_out (log-sum-exp),
+ *   post_out[0] = posterior of the call, post_out[1 + k] = posterior of its k-th listed clade,
+ *   *n_post_out = 1 + number of listed clades (post_cap bounds the array).
+ * If no tree was set only post_out[0] is produced.                                             */
+int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
+                    int32_t post_cap, int32_t* n_post_out);
+
+/* Number of kernels this context has launched since creation (bench.py reports it).            */
+uint64_t vgl_launch_count(const vgl_ctx* ctx);
+/* Device time in milliseconds spent in the read kernel since the last vgl_hc_reset (CUDA events
+ * on the launching stream); valid after vgl_synchronize / vgl_hc_finalize.                      */
+int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGAN_GPU_H */

@@ -1,0 +1,146 @@
+/*
+ * vgan_host.h -- C ABI of libvgan_host.so: the HOST side of the drop-in boundary.
+ *
+ * These are the pieces of the reference that sit directly on either side of the likelihood hot
+ * path and that a C++ host (vgan itself) or a test harness needs in order to feed
+ * include/vgan_gpu.h:
+ *   - a GAM reader                     (reference: readGAM, src/readGAM.h:20-68)
+ *   - alignment reconstruction         (reference: reconstruct_graph_sequence, src/vgan_utils.h:6-79)
+ *   - the SoA batch packer             (new: AlignmentInfo -> vgl_hc_batch)
+ *   - HaploCart table construction     (reference: src/load.cpp:6-58,283-345,
+ *                                       src/readPathHandleGraph.cpp:14-37, src/miscfunc.h:180-216,
+ *                                       src/haplocart_functions.cpp:81-107, src/get_p_obs_base.cpp:43-64)
+ *   - the haplogroup tree for the posterior (reference: src/load.cpp:303-345, src/get_posterior.cpp:36-76)
+ * It is plain C++17 with no CUDA dependency except optional pinned allocation through
+ * vgl_host_alloc.  No likelihood arithmetic happens here; that is all on the device.
+ */
+#ifndef VGAN_HOST_H
+#define VGAN_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vgan_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    VGH_OK = 0,
+    VGH_ERR_INVALID = 101,
+    VGH_ERR_IO = 102,
+    VGH_ERR_FORMAT = 103,   /* malformed GAM / table text                                          */
+    VGH_ERR_BAD_READ = 104, /* an alignment the reference could not process either (it would throw
+                               from std::string::substr / vector::at inside a noexcept function)    */
+    VGH_ERR_BAD_NODE = 105
+};
+
+const char* vgh_last_error(void);
+
+/* ---- graph node sequences (stands in for bdsg::ODGI::get_sequence) ------------------------- */
+typedef struct vgh_graph vgh_graph;
+/* node ids min_id .. min_id + n_nodes - 1; seq_off[n_nodes + 1] into forward-strand `seq`.      */
+int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out);
+void vgh_graph_destroy(vgh_graph* g);
+
+/* ---- alignments (flat view of vector<AlignmentInfo*>, reference src/AlignmentInfo.h:16-46) --- */
+typedef struct vgh_alignments {
+    int64_t n_reads;
+    const int64_t* seq_off;  /* [n_reads + 1] into seq                                    */
+    const char* seq;         /* Alignment.sequence                                        */
+    const int64_t* qual_off; /* [n_reads + 1] into qual                                   */
+    const char* qual;        /* Alignment.quality, raw PHRED bytes                        */
+    const int32_t* mapq;     /* Alignment.mapping_quality                                 */
+    const double* identity;  /* Alignment.identity                                        */
+    const uint8_t* paired;   /* Alignment.read_paired (may be NULL)                       */
+    const int64_t* map_off;  /* [n_reads + 1] into the mapping arrays                     */
+    const int64_t* map_node; /* Mapping.position.node_id                                  */
+    const int64_t* map_offset;
+    const uint8_t* map_rev;
+    const int64_t* edit_off; /* [n_maps + 1] into the edit arrays                         */
+    const int32_t* edit_from;
+    const int32_t* edit_to;
+    const int64_t* edit_seq_off; /* [n_edits + 1] into edit_seq                           */
+    const char* edit_seq;
+} vgh_alignments;
+
+/* GAM reader: gzip/BGZF or plain stream of framed vg.Alignment messages.  Like the reference's
+ * readGAM it drops alignments whose identity is exactly 0 when drop_unmapped != 0
+ * (src/readGAM.h:47).                                                                         */
+typedef struct vgh_gam vgh_gam;
+int vgh_gam_read_file(const char* path, int drop_unmapped, vgh_gam** out);
+int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out);
+const vgh_alignments* vgh_gam_view(const vgh_gam* g);
+void vgh_gam_destroy(vgh_gam* g);
+
+/* reconstruct_graph_sequence for read r: aligned graph string, aligned read string, one size per
+ * EDIT.  Buffers hold `cap` entries.                                                           */
+int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char* graph_seq, char* read_seq,
+                    int32_t* sizes, int32_t cap, int32_t* n_graph, int32_t* n_read, int32_t* n_sizes);
+
+/* ---- batch packer --------------------------------------------------------------------------- */
+typedef struct vgh_hc_packed vgh_hc_packed;
+/* Pack reads [r0, r1) into one vgl_hc_batch.  Reads with identity < 1e-10 are skipped exactly as
+ * the hot loop skips them (src/HaploCart.cpp:411).  `pinned` != 0 allocates the arrays with
+ * vgl_host_alloc (needs a CUDA device).  n_threads <= 0: all cores.                            */
+int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                vgh_hc_packed** out);
+const vgl_hc_batch* vgh_hc_packed_batch(const vgh_hc_packed* p);
+int64_t vgh_hc_packed_skipped(const vgh_hc_packed* p);
+void vgh_hc_packed_destroy(vgh_hc_packed* p);
+
+/* ---- HaploCart tables ----------------------------------------------------------------------- */
+typedef struct vgh_hc_tables vgh_hc_tables;
+/* Inputs as the reference holds them in memory:
+ *   supports[n_rows][n_paths] bytes (NodeInfo::pathsgo; row index == node id),
+ *   pangenome_map as (node id, stored value = file coordinate + 1) pairs (src/load.cpp:27-41),
+ *   mappabilities expanded per base (src/load.cpp:6-24).                                        */
+int vgh_hc_tables_build(int32_t n_rows, int32_t n_paths, const uint8_t* supports, int64_t n_pmap,
+                        const int64_t* pmap_node, const int32_t* pmap_val, int64_t n_mappab, const double* mappab,
+                        double background_error_prob, int is_consensus_fasta, vgh_hc_tables** out);
+const vgl_hc_tables* vgh_hc_tables_view(const vgh_hc_tables* t);
+void vgh_hc_tables_destroy(vgh_hc_tables* t);
+/* pow(1 - 30*mu(pangenome_base), 8): the only surviving term of get_p_obs_base
+ * (src/get_p_obs_base.cpp:43-67).                                                              */
+double vgh_hc_region_match_prob(int32_t pangenome_base);
+
+/* ---- haplogroup tree ------------------------------------------------------------------------ */
+typedef struct vgh_hc_tree vgh_hc_tree;
+/* path_names_txt: one name per line in path_supports column order (src/load.cpp:44-58);
+ * parents_txt / children_txt: the reference's file formats (src/load.cpp:303-345).             */
+int vgh_hc_tree_build(int32_t n_paths, const char* path_names_txt, const char* parents_txt, const char* children_txt,
+                      vgh_hc_tree** out);
+int32_t vgh_hc_tree_n_clades(const vgh_hc_tree* t);
+int32_t vgh_hc_tree_row_words(const vgh_hc_tree* t);
+const uint32_t* vgh_hc_tree_clade_bits(const vgh_hc_tree* t);
+const int32_t* vgh_hc_tree_anc_off(const vgh_hc_tree* t);
+const int32_t* vgh_hc_tree_anc_clade(const vgh_hc_tree* t);
+const char* vgh_hc_tree_clade_name(const vgh_hc_tree* t, int32_t clade);
+void vgh_hc_tree_destroy(vgh_hc_tree* t);
+
+/* ---- synthetic HaploCart-shaped workloads (benchmark / test inputs) --- */
+/* The real tables (share/vgan/hcfiles) are FTP downloads; tests and bench.py generate inputs of the
+ * same shapes instead.  Pure functions of their seeds.                                            */
+typedef struct vgh_synth_hc vgh_synth_hc;
+int vgh_synth_hc_create(uint64_t seed, int32_t n_paths, int32_t n_rows, int32_t n_nodes, vgh_synth_hc** out);
+void vgh_synth_hc_destroy(vgh_synth_hc* s);
+const vgh_graph* vgh_synth_hc_graph(const vgh_synth_hc* s);
+int64_t vgh_synth_hc_graph_seq(const vgh_synth_hc* s, const int64_t** seq_off, const char** seq);
+const uint8_t* vgh_synth_hc_supports(const vgh_synth_hc* s);
+int64_t vgh_synth_hc_n_pmap(const vgh_synth_hc* s);
+const int64_t* vgh_synth_hc_pmap_node(const vgh_synth_hc* s);
+const int32_t* vgh_synth_hc_pmap_val(const vgh_synth_hc* s);
+int64_t vgh_synth_hc_n_mappab(const vgh_synth_hc* s);
+const double* vgh_synth_hc_mappab(const vgh_synth_hc* s);
+const char* vgh_synth_hc_names(const vgh_synth_hc* s);
+const char* vgh_synth_hc_parents(const vgh_synth_hc* s);
+const char* vgh_synth_hc_children(const vgh_synth_hc* s);
+int32_t vgh_synth_hc_total_len(const vgh_synth_hc* s);
+int vgh_synth_hc_reads(const vgh_synth_hc* s, uint64_t seed, int64_t n_reads, int32_t fixed_len, double sub_rate,
+                       double indel_rate, int damage, int32_t origin_path, vgh_gam** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGAN_HOST_H */

@@ -1,0 +1,670 @@
+// =====================================================================================
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the vgan read x path likelihood hot path.
+//
+// This file is the checker, not the product.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may build, load or call it.  Nothing
+// under vgan_b200/ links against it and the product path never falls back to it.
+//
+// It is a plain C++17 / `long double` restatement of the reference's algorithm, written
+// from a reading of the reference sources (cited per function as file:line relative to
+// /root/reference).  The reference itself cannot be compiled here (it needs libvg, libgab,
+// bdsg, protobuf -- none vendored), so there is no oracle/_ref.
+//
+// PARITY PINNING
+//   * alignment reconstruction is pinned by the reference's own 10 `reconstruction`
+//     known-answer strings (src/test.cpp:855-994) -- tests/test_oracle_reconstruct.py.
+//   * the likelihood / posterior ARITHMETIC is "parity unpinned": the reference holds no
+//     numeric golden vector for any log-likelihood or posterior.  The
+//     oracle is instead cross-checked in two independently written modes that must agree
+//     bit for bit (MODE_LITERAL follows the reference's per-path loops, MODE_HOISTED
+//     evaluates each mapping's two path-independent scalars once).
+//
+// Third-party semantics restated from their published behaviour (absent from the tree):
+//   vg::algorithms::path_string, vg::io::edit_is_{match,sub,insertion,deletion},
+//   bdsg::ODGI::get_sequence (orientation aware), libgab isValidDNA / oplusnatl /
+//   oplusInitnatl.  vg and libgab are unpinned in the reference (src/Makefile:121-126).
+//
+// DEFINED BEHAVIOUR WHERE THE REFERENCE HAS NONE (SURVEY.md 8a quirk list)
+//   Q4  quality bytes read past the end of the quality string count as byte 0 and never
+//       latch the background-error mode; the COUNT of such bytes matches the reference.
+//   Q4b a quality byte that is negative as `signed char` indexes qscore_vec out of range
+//       in the reference; here it yields 0.25 (the value get_p_seq_error gives for Q<=2).
+//   Q8  parent_vec[-1] compares "different".
+//   children.find(p) of an absent name is treated as "no children".
+// Everything else (Q1,Q2,Q3,Q5,Q6,Q7,Q9,Q10) is reproduced as written in the reference.
+// =====================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+extern "C" {
+
+typedef struct {
+    int64_t n_nodes;         // node ids min_id .. min_id + n_nodes - 1
+    int64_t min_id;
+    const int64_t* seq_off;  // [n_nodes + 1]
+    const char* seq;         // forward-strand node sequences
+} orc_graph;
+
+typedef struct {
+    int64_t n_reads;
+    const int64_t* seq_off;   // [n_reads + 1]
+    const char* seq;
+    const int64_t* qual_off;  // [n_reads + 1]
+    const char* qual;         // raw PHRED bytes (vg.Alignment.quality)
+    const int32_t* mapq;      // [n_reads]
+    const double* identity;   // [n_reads]
+    const int64_t* map_off;   // [n_reads + 1] into the mapping arrays
+    const int64_t* map_node;
+    const int64_t* map_offset;
+    const uint8_t* map_rev;
+    const int64_t* edit_off;  // [n_maps + 1] into the edit arrays
+    const int32_t* edit_from;
+    const int32_t* edit_to;
+    const int64_t* edit_seq_off;  // [n_edits + 1]
+    const char* edit_seq;
+} orc_reads;
+
+typedef struct {
+    int32_t n_rows;           // rows of path_supports; row index == node id (load.cpp:283-300)
+    int32_t n_paths;
+    const uint8_t* supports;  // [n_rows][n_paths], 0/1  (NodeInfo::pathsgo, readPathHandleGraph.cpp:31)
+    int64_t n_pmap;           // parsed_pangenome_mapping entries (load.cpp:27-41)
+    const int64_t* pmap_node;
+    const int32_t* pmap_val;  // value as stored by the reference: file coordinate + 1
+    int64_t n_mappab;         // mappability.tsv expanded per base (load.cpp:6-24)
+    const double* mappab;
+    double background_error_prob;  // -e, default 0.0001 (HaploCart.cpp)
+    int32_t is_consensus_fasta;    // sets use_background_error_prob too (HaploCart.cpp:397-401)
+    int32_t min_id;                // graph.min_node_id()
+} orc_hc_tables;
+
+enum { ORC_MODE_LITERAL = 0, ORC_MODE_HOISTED = 1 };
+enum { ORC_OK = 0, ORC_ERR_NODE = -1, ORC_ERR_SUBSTR = -2, ORC_ERR_SIZES = -3, ORC_ERR_PMAP = -4,
+       ORC_ERR_CAP = -5, ORC_ERR_RANGE = -6 };
+
+}  // extern "C"
+
+namespace {
+
+using std::string;
+using std::vector;
+typedef long double ld;
+
+// ---- vg edit classification (vg io: edit_is_*) ---------------------------------------------
+struct Edit { int32_t from_length, to_length; string sequence; };
+inline bool edit_is_match(const Edit& e) { return e.from_length == e.to_length && e.sequence.empty(); }
+inline bool edit_is_sub(const Edit& e) { return e.from_length == e.to_length && !e.sequence.empty(); }
+inline bool edit_is_insertion(const Edit& e) { return e.from_length == 0 && e.to_length > 0 && !e.sequence.empty(); }
+inline bool edit_is_deletion(const Edit& e) { return e.from_length > 0 && e.to_length == 0; }
+
+struct Mapping { int64_t node_id, offset; bool is_reverse; vector<Edit> edit; };
+
+struct ReadView {
+    string seq, quality;
+    int32_t mapping_quality;
+    double identity;
+    vector<Mapping> mapping;
+};
+
+ReadView load_read(const orc_reads& R, int64_t r) {
+    ReadView v;
+    v.seq.assign(R.seq + R.seq_off[r], R.seq + R.seq_off[r + 1]);
+    v.quality.assign(R.qual + R.qual_off[r], R.qual + R.qual_off[r + 1]);
+    v.mapping_quality = R.mapq[r];
+    v.identity = R.identity[r];
+    for (int64_t m = R.map_off[r]; m < R.map_off[r + 1]; ++m) {
+        Mapping mp;
+        mp.node_id = R.map_node[m];
+        mp.offset = R.map_offset[m];
+        mp.is_reverse = R.map_rev[m] != 0;
+        for (int64_t e = R.edit_off[m]; e < R.edit_off[m + 1]; ++e) {
+            Edit ed;
+            ed.from_length = R.edit_from[e];
+            ed.to_length = R.edit_to[e];
+            ed.sequence.assign(R.edit_seq + R.edit_seq_off[e], R.edit_seq + R.edit_seq_off[e + 1]);
+            mp.edit.push_back(ed);
+        }
+        v.mapping.push_back(mp);
+    }
+    return v;
+}
+
+// ---- bdsg::ODGI::get_sequence(get_handle(id, is_reverse)) ----------------------------------
+inline char complement(char c) {
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return c;  // N stays N
+    }
+}
+int node_sequence(const orc_graph& g, int64_t id, bool rev, string& out) {
+    const int64_t k = id - g.min_id;
+    if (k < 0 || k >= g.n_nodes) return ORC_ERR_NODE;
+    out.assign(g.seq + g.seq_off[k], g.seq + g.seq_off[k + 1]);
+    if (rev) {
+        std::reverse(out.begin(), out.end());
+        for (char& c : out) c = complement(c);
+    }
+    return ORC_OK;
+}
+
+// std::string::substr semantics: throws when pos > size (the call sites are noexcept, so the
+// reference would terminate); we surface that as an error code.
+inline int substr_checked(const string& s, size_t pos, size_t n, string& out) {
+    if (pos > s.size()) return ORC_ERR_SUBSTR;
+    out = s.substr(pos, n);
+    return ORC_OK;
+}
+
+// ---- vg::algorithms::path_string (third party; rebuilds the READ from the path) ------------
+int path_string(const orc_graph& g, const vector<Mapping>& path, string& out) {
+    out.clear();
+    for (const Mapping& m : path) {
+        string node_seq;
+        int rc = node_sequence(g, m.node_id, m.is_reverse, node_seq);
+        if (rc) return rc;
+        size_t f = (size_t)m.offset;
+        for (const Edit& e : m.edit) {
+            if (edit_is_match(e)) {
+                string piece;
+                rc = substr_checked(node_seq, f, (size_t)e.from_length, piece);
+                if (rc) return rc;
+                out += piece;
+            } else if (edit_is_sub(e) || edit_is_insertion(e)) {
+                out += e.sequence;
+            }
+            f += (size_t)e.from_length;
+        }
+    }
+    return ORC_OK;
+}
+
+// ---- reconstruct_graph_sequence, reference src/vgan_utils.h:6-79 ---------------------------
+// Returns the aligned graph string G ('-' for insertions, 'S' for "softclips"), the aligned read
+// string (path_string with '-' inserted for deletions at the running from_length coordinate) and
+// ONE SIZE PER EDIT (vgan_utils.h:72).  Quirk Q3: mppg_counter / edit_counter never advance
+// (vgan_utils.h:12-13,28), so the soft-clip test reduces to "insertion met while the running
+// node offset is 0".
+int reconstruct_graph_sequence(const orc_graph& g, const vector<Mapping>& path,
+                               string& graph_seq, string& ps, vector<int>& mppg_sizes) {
+    graph_seq.clear();
+    mppg_sizes.clear();
+    const int mppg_counter = 0;
+    int edit_counter = 0;
+    int rc = path_string(g, path, ps);
+    if (rc) return rc;
+    int f = 0;
+    for (const Mapping& mppg : path) {
+        string node_seq;
+        rc = node_sequence(g, mppg.node_id, mppg.is_reverse, node_seq);
+        if (rc) return rc;
+        int aligned_length = 0;
+        edit_counter = 0;
+        int offset = (int)mppg.offset;
+        for (const Edit& edit : mppg.edit) {
+            const int32_t to_length = edit.to_length;
+            const int32_t from_length = edit.from_length;
+            const bool ins = edit_is_insertion(edit);
+            const bool softclip =
+                (mppg_counter == 0 && offset == 0 && edit_counter == 0 && from_length == 0 && to_length > 0 && ins) ||
+                ((size_t)mppg_counter == path.size() - 1 && offset == 0 && (size_t)edit_counter == mppg.edit.size() &&
+                 from_length == 0 && to_length > 0 && ins);
+            if (edit_is_match(edit) || edit_is_sub(edit)) {
+                string piece;
+                rc = substr_checked(node_seq, (size_t)offset, (size_t)from_length, piece);
+                if (rc) return rc;
+                graph_seq += piece;
+                aligned_length = (int)piece.size();
+            } else if (ins) {
+                graph_seq += string((size_t)to_length, softclip ? 'S' : '-');
+                aligned_length = to_length;
+            } else if (edit_is_deletion(edit)) {
+                string piece;
+                rc = substr_checked(node_seq, (size_t)offset, (size_t)from_length, piece);
+                if (rc) return rc;
+                graph_seq += piece;
+                aligned_length = (int)piece.size();
+                if ((size_t)f > ps.size()) return ORC_ERR_SUBSTR;  // string::insert would throw
+                ps.insert((size_t)f, string((size_t)from_length, '-'));
+            }
+            offset += from_length;
+            f += from_length;
+            mppg_sizes.push_back(aligned_length);
+        }
+    }
+    return ORC_OK;
+}
+
+// ---- PHRED tables, reference src/miscfunc.h:180-216, haplocart_functions.cpp:81-107 ----------
+inline double get_p_seq_error(int Q) {
+    if (Q > 2) return std::pow(10, ((-1 * Q) * 0.1));
+    return 0.25;
+}
+vector<double> get_qscore_vec() {  // HaploCart's table: qs[2] == 0.25 (quirk Q7)
+    vector<double> v;
+    for (int Q = 0; Q < 100; ++Q) v.push_back(Q >= 2 ? get_p_seq_error(Q) : 0.25);
+    return v;
+}
+vector<double> precompute_incorrect_mapping_probs() {
+    vector<double> v;
+    for (int Q = 0; Q != 100; ++Q) v.push_back(std::pow(10, ((-1 * Q) * 0.1)));
+    return v;
+}
+inline double get_background_freq(char base) {
+    switch (base) {
+        case 'A': return 0.27532; case 'C': return 0.30044; case 'G': return 0.16644; case 'T': return 0.25780;
+    }
+    return 0.25;
+}
+inline bool isValidDNA(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }  // libgab
+
+// ---- get_p_obs_base, reference src/get_p_obs_base.cpp:38-69 ----------------------------------
+// Quirk Q6: the integer divisions (2/3), (1/3), (22/23), (1/46) are 0, so the coding-region rate
+// is 0 and the transition / transversion terms vanish.
+inline bool inRange(unsigned low, unsigned high, unsigned x) { return low <= x && x <= high; }
+double region_mu(int pangenome_base) {
+    const unsigned pb = (unsigned)pangenome_base;
+    double mu;
+    if (inRange(57, 372, pb)) mu = 1.64273e-7;
+    else if (inRange(1, 56, pb) || inRange(373, 576, pb)) mu = 2.29640e-8;
+    else if (inRange(16384, 16569, pb)) mu = 1.54555e-8;
+    else if (inRange(3307, 4262, pb) || inRange(4470, 5511, pb) || inRange(5904, 7445, pb) || inRange(7586, 8269, pb) ||
+             inRange(8366, 9990, pb) || inRange(10059, 10403, pb) || inRange(10470, 12137, pb) ||
+             inRange(12337, 14673, pb) || inRange(14747, 15886, pb))
+        mu = 8.87640e-9 * (2 / 3) * 1.92596e-8 * (1 / 3);
+    else if (inRange(577, 647, pb) || inRange(1602, 1670, pb) || inRange(3230, 3304, pb) || inRange(4263, 4400, pb) ||
+             inRange(4402, 4469, pb) || inRange(5512, 5579, pb) || inRange(5587, 5654, pb) || inRange(5657, 5728, pb) ||
+             inRange(5761, 5891, pb) || inRange(7446, 7514, pb) || inRange(7518, 7585, pb) || inRange(8295, 8364, pb) ||
+             inRange(15888, 15953, pb) || inRange(15956, 16023, pb))
+        mu = 6.91285e-9;
+    else if (inRange(648, 1601, pb) || inRange(1671, 3229, pb)) mu = 6.91285e-9;
+    else mu = 2.48537e-8;
+    return mu * 30;
+}
+inline ld get_p_obs_base(int pangenome_base, double epsilon, int generations) {
+    const double mu = region_mu(pangenome_base);
+    const double match = std::pow((1 - mu), generations);
+    const double tv = (1 - std::pow((1 - mu), generations)) * (22 / 23);
+    const double ts = (1 - std::pow((1 - mu), generations)) * (1 / 46);
+    ld ret = match * (1 - epsilon) + (epsilon * (2 * tv + ts));
+    return ret;
+}
+
+// ---- get_p_no_seq_error_mapping, reference src/get_p_obs_base.cpp:3-27 -----------------------
+inline double qscore_lookup(const vector<double>& qs, int q) {
+    if (q < 0 || q >= (int)qs.size()) return 0.25;  // Q4b (reference: out-of-range read)
+    return qs[(size_t)q];
+}
+vector<ld> get_p_no_seq_error_mapping(const string& mapping_seq, const vector<int>& quality_scores,
+                                      const string& graph_seq, const vector<double>& qscore_vec,
+                                      bool use_bep, double bep) {
+    vector<ld> ret;
+    for (size_t i = 0; i < graph_seq.size(); ++i) {
+        const char graph_base = graph_seq[i];
+        const char read_base = i < mapping_seq.size() ? mapping_seq[i] : '\0';
+        const int q = i < quality_scores.size() ? quality_scores[i] : 0;
+        if (use_bep) ret.push_back(graph_base == read_base ? bep : 1 - bep);
+        else ret.push_back(graph_base == read_base ? qscore_lookup(qscore_vec, q) : 1 - qscore_lookup(qscore_vec, q));
+    }
+    return ret;
+}
+
+// ---- get_log_lik_if_unsupported, reference src/process_mapping.cpp:4-24 ----------------------
+// Quirk Q5: `counter % 4 == 4` never holds, so every quality counts as a mismatch.
+double get_log_lik_if_unsupported(const vector<int>& quality_scores) {
+    bool mismatch = true;
+    int counter = 0;
+    double ret = 0;
+    for (const int& Q : quality_scores) {
+        if (mismatch) ret += std::log(get_p_seq_error(Q));
+        else ret += std::log(1 - get_p_seq_error(Q));
+        counter += 1;
+        mismatch = !(counter % 4 == 4);
+    }
+    return ret;
+}
+
+struct HcContext {
+    const orc_hc_tables* T;
+    std::map<string, int> pangenome_map;       // literal mode: keyed by decimal string (load.cpp:27-41)
+    std::map<int64_t, int> pangenome_map_int;  // hoisted mode
+    vector<double> qscore_vec, incorrect_mapping_vec;
+};
+
+void build_context(const orc_hc_tables& T, HcContext& C) {
+    C.T = &T;
+    for (int64_t i = 0; i < T.n_pmap; ++i) {
+        C.pangenome_map.insert(std::make_pair(std::to_string(T.pmap_node[i]), T.pmap_val[i]));
+        C.pangenome_map_int.insert(std::make_pair(T.pmap_node[i], T.pmap_val[i]));
+    }
+    C.qscore_vec = get_qscore_vec();
+    C.incorrect_mapping_vec = precompute_incorrect_mapping_probs();
+}
+
+// Per-mapping scalar for a SUPPORTED path, reference src/process_mapping.cpp:57-77.
+inline ld log_lik_if_mapped(const HcContext& C, int pangenome_base, const string& mapping_seq, const string& graph_seq,
+                            const vector<ld>& p_no_seq_error, const vector<double>& background_freqs,
+                            ld p_correctly_mapped) {
+    const bool is_fasta = C.T->is_consensus_fasta != 0;
+    const double bep = C.T->background_error_prob;
+    ld acc = 0;
+    for (size_t j = 0; j != graph_seq.size(); ++j) {
+        const char mb = j < mapping_seq.size() ? mapping_seq[j] : '\0';
+        if (graph_seq[j] == 'N' || mb == 'N') continue;
+        if (!isValidDNA(graph_seq[j]) || !isValidDNA(mb)) continue;
+        const ld p_obs_base = get_p_obs_base(pangenome_base, (double)p_no_seq_error[j], 8);
+        ld log_prod;
+        if (!is_fasta) log_prod = logl(((1 - p_correctly_mapped) * background_freqs[j]) + (p_correctly_mapped * p_obs_base));
+        else log_prod = logl((1 - bep) * p_obs_base);
+        acc += log_prod;
+    }
+    return acc;
+}
+
+// process_mapping, reference src/process_mapping.cpp:26-91.  `ll` is taken and returned BY VALUE in
+// literal mode exactly as the reference does (that copy is part of what the CPU baseline times).
+int process_mapping_literal(const HcContext& C, int32_t mapping_quality, vector<ld>& out, vector<ld> ll,
+                            const Mapping& mppg, const string& mapping_seq, const vector<int>& quality_scores,
+                            const string& graph_seq, bool use_bep) {
+    const orc_hc_tables& T = *C.T;
+    auto it = C.pangenome_map.find(std::to_string(mppg.node_id));
+    if (it == C.pangenome_map.end()) return ORC_ERR_PMAP;  // map::at would throw
+    const int pangenome_base = it->second;
+    if (pangenome_base < 0 || pangenome_base >= T.n_mappab) return ORC_ERR_RANGE;
+    if (mapping_quality < 0 || mapping_quality >= 100) return ORC_ERR_RANGE;
+    const double mappability = T.mappab[pangenome_base];
+    vector<double> background_freqs;
+    ld p_correctly_mapped = 0;  // Q10: unused for FASTA input
+    if (!T.is_consensus_fasta) p_correctly_mapped = (1 - C.incorrect_mapping_vec[(size_t)mapping_quality]) * mappability;
+    for (size_t i = 0; i != mapping_seq.size(); ++i) background_freqs.push_back(get_background_freq(mapping_seq[i]));
+    const vector<ld> p_no_seq_error =
+        get_p_no_seq_error_mapping(mapping_seq, quality_scores, graph_seq, C.qscore_vec, use_bep, T.background_error_prob);
+    const int64_t row = mppg.node_id;  // nodevector.at(id - minid)->pathsgo == path_supports[id]
+    if (row < T.min_id || row >= T.n_rows) return ORC_ERR_NODE;
+    const uint8_t* pathsgo = T.supports + (size_t)row * (size_t)T.n_paths;
+    for (int i = 0; i != T.n_paths; ++i) {
+        if (pathsgo[i]) {
+            ll[(size_t)i] += log_lik_if_mapped(C, pangenome_base, mapping_seq, graph_seq, p_no_seq_error, background_freqs,
+                                               p_correctly_mapped);
+        } else {
+            const double log_lik_if_unsupported = get_log_lik_if_unsupported(quality_scores);
+            ll[(size_t)i] += log_lik_if_unsupported;
+        }
+    }
+    out = ll;
+    return ORC_OK;
+}
+
+int process_mapping_hoisted(const HcContext& C, int32_t mapping_quality, vector<ld>& ll, const Mapping& mppg,
+                            const string& mapping_seq, const vector<int>& quality_scores, const string& graph_seq,
+                            bool use_bep, ld* A_out, double* B_out) {
+    const orc_hc_tables& T = *C.T;
+    auto it = C.pangenome_map_int.find(mppg.node_id);
+    if (it == C.pangenome_map_int.end()) return ORC_ERR_PMAP;
+    const int pangenome_base = it->second;
+    if (pangenome_base < 0 || pangenome_base >= T.n_mappab) return ORC_ERR_RANGE;
+    if (mapping_quality < 0 || mapping_quality >= 100) return ORC_ERR_RANGE;
+    const double mappability = T.mappab[pangenome_base];
+    ld p_correctly_mapped = 0;
+    if (!T.is_consensus_fasta) p_correctly_mapped = (1 - C.incorrect_mapping_vec[(size_t)mapping_quality]) * mappability;
+    vector<double> background_freqs;
+    for (size_t i = 0; i != mapping_seq.size(); ++i) background_freqs.push_back(get_background_freq(mapping_seq[i]));
+    const vector<ld> p_no_seq_error =
+        get_p_no_seq_error_mapping(mapping_seq, quality_scores, graph_seq, C.qscore_vec, use_bep, T.background_error_prob);
+    const int64_t row = mppg.node_id;
+    if (row < T.min_id || row >= T.n_rows) return ORC_ERR_NODE;
+    const uint8_t* pathsgo = T.supports + (size_t)row * (size_t)T.n_paths;
+    const ld A = log_lik_if_mapped(C, pangenome_base, mapping_seq, graph_seq, p_no_seq_error, background_freqs, p_correctly_mapped);
+    const double B = get_log_lik_if_unsupported(quality_scores);
+    for (int i = 0; i != T.n_paths; ++i) {
+        if (pathsgo[i]) ll[(size_t)i] += A;
+        else ll[(size_t)i] += B;
+    }
+    if (A_out) *A_out = A;
+    if (B_out) *B_out = B;
+    return ORC_OK;
+}
+
+// update_likelihood, reference src/update_likelihood.cpp:19-53.  Quirks Q1 (sizes are per EDIT
+// but indexed by mapping), Q2 (the WHOLE aligned read string is handed to process_mapping) and
+// Q4 (the quality window runs |algnseq| bytes from position_in_read).
+int update_likelihood(const HcContext& C, const orc_graph& g, const ReadView& rd, int mode, vector<ld>& ll,
+                      vector<ld>* A_list, vector<double>* B_list) {
+    string G, algnseq;
+    vector<int> mppg_sizes;
+    int rc = reconstruct_graph_sequence(g, rd.mapping, G, algnseq, mppg_sizes);
+    if (rc) return rc;
+    bool use_bep = C.T->is_consensus_fasta != 0;
+    size_t position_in_read = 0;
+    for (size_t i = 0; i < rd.mapping.size(); ++i) {
+        if (i >= mppg_sizes.size()) return ORC_ERR_SIZES;  // reference: vector[] out of range
+        vector<int> quality_scores;
+        string graph_seq, read_seq;
+        rc = substr_checked(G, position_in_read, (size_t)mppg_sizes[i], graph_seq);
+        if (rc) return rc;
+        rc = substr_checked(algnseq, position_in_read, (size_t)mppg_sizes[i], read_seq);
+        if (rc) return rc;
+        for (size_t j = position_in_read; j < position_in_read + algnseq.size(); ++j) {
+            int qscore = 0;                                          // Q4: past-the-end bytes read as 0 ...
+            if (j < rd.quality.size()) {
+                qscore = int((signed char)rd.quality[j]);
+                if (qscore >= 90) use_bep = true;                    // ... and only real bytes can latch
+            }
+            quality_scores.push_back(qscore);
+        }
+        position_in_read += read_seq.size();
+        if (mode == ORC_MODE_LITERAL) {
+            vector<ld> next;
+            rc = process_mapping_literal(C, rd.mapping_quality, next, ll, rd.mapping[i], algnseq, quality_scores, graph_seq, use_bep);
+            if (rc) return rc;
+            ll = next;
+        } else {
+            ld A; double B;
+            rc = process_mapping_hoisted(C, rd.mapping_quality, ll, rd.mapping[i], algnseq, quality_scores, graph_seq, use_bep, &A, &B);
+            if (rc) return rc;
+            if (A_list) A_list->push_back(A);
+            if (B_list) B_list->push_back(B);
+        }
+    }
+    return ORC_OK;
+}
+
+// ---- libgab log-space adders ------------------------------------------------------------------
+inline ld oplusnatl(ld x, ld y) { return x > y ? x + log1pl(expl(y - x)) : y + log1pl(expl(x - y)); }
+inline ld oplusInitnatl(ld x, ld y) { return x == 0 ? y : oplusnatl(x, y); }  // Q9
+
+ld sum_log_likelihoods(const vector<ld>& v) {  // reference src/get_posterior.cpp:78-85
+    ld ret = v[0];
+    for (size_t i = 1; i < v.size(); ++i) ret = oplusInitnatl(ret, v[i]);
+    return ret;
+}
+
+typedef std::map<string, vector<string>> Rel;
+
+Rel parse_relations(const char* text) {  // load_parents / load_children, reference src/load.cpp:303-345
+    Rel rel;
+    std::istringstream in(text);
+    string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        vector<string> tokens;
+        string t;
+        while (ls >> t) tokens.push_back(t);
+        if (tokens.empty()) continue;
+        vector<string> v;
+        for (size_t j = 1; j < tokens.size(); ++j)
+            if (tokens[j].find('[') == string::npos) v.push_back(tokens[j]);
+        rel.insert(std::make_pair(tokens[0], v));
+    }
+    return rel;
+}
+
+std::set<string> get_children(const std::set<string>& preds, const Rel& children) {  // get_posterior.cpp:36-49
+    std::set<string> all;
+    for (const string& p : preds) {
+        auto it = children.find(p);
+        if (it == children.end()) continue;
+        for (const string& c : it->second) all.insert(c);
+    }
+    return all;
+}
+
+void get_posterior_of_clade(vector<ld>& all_top, const vector<ld>& final_vec, const std::set<string>& preds,
+                            const Rel& children, const vector<string>& path_names) {  // get_posterior.cpp:51-76
+    std::set<string> child_set = get_children(preds, children);
+    size_t idx = 0;
+    for (const string& path : path_names) {
+        if (child_set.find(path) != child_set.end()) all_top.push_back(final_vec[idx]);
+        idx += 1;
+    }
+    if (!child_set.empty()) get_posterior_of_clade(all_top, final_vec, child_set, children, path_names);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Alignment reconstruction for read r.  Buffers must hold `cap` bytes / ints.
+int orc_reconstruct(const orc_graph* g, const orc_reads* R, int64_t r, char* graph_seq, char* read_seq, int32_t* sizes,
+                    int32_t cap, int32_t* n_graph, int32_t* n_read, int32_t* n_sizes) {
+    ReadView rd = load_read(*R, r);
+    string G, ps;
+    vector<int> sz;
+    int rc = reconstruct_graph_sequence(*g, rd.mapping, G, ps, sz);
+    if (rc) return rc;
+    if ((int64_t)G.size() > cap || (int64_t)ps.size() > cap || (int64_t)sz.size() > cap) return ORC_ERR_CAP;
+    std::memcpy(graph_seq, G.data(), G.size());
+    std::memcpy(read_seq, ps.data(), ps.size());
+    for (size_t i = 0; i < sz.size(); ++i) sizes[i] = sz[i];
+    *n_graph = (int32_t)G.size();
+    *n_read = (int32_t)ps.size();
+    *n_sizes = (int32_t)sz.size();
+    return ORC_OK;
+}
+
+// Per-read log-likelihood vector (Haplocart::update, reference src/update_likelihood.cpp:5-16).
+// ll_out[P] long double.  Optional A/B lists (hoisted mode) sized >= number of mappings.
+int orc_hc_read(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, int64_t r, int mode, long double* ll_out,
+                long double* A_out, double* B_out) {
+    HcContext C;
+    build_context(*T, C);
+    ReadView rd = load_read(*R, r);
+    vector<ld> ll((size_t)T->n_paths, 0);
+    vector<ld> A;
+    vector<double> B;
+    int rc = update_likelihood(C, *g, rd, mode, ll, &A, &B);
+    if (rc) return rc;
+    for (int i = 0; i < T->n_paths; ++i) ll_out[i] = ll[(size_t)i];
+    if (A_out) for (size_t i = 0; i < A.size(); ++i) A_out[i] = A[i];
+    if (B_out) for (size_t i = 0; i < B.size(); ++i) B_out[i] = B[i];
+    return ORC_OK;
+}
+
+// The driver loop, reference src/HaploCart.cpp:407-424: skip identity < 1e-10, sum the per-read
+// vectors into final_vec, argmax with first-max-wins.  Reads [r0, r1).  With n_threads > 1 the
+// per-read vectors are computed under OpenMP and added under a critical section exactly like the
+// reference (so the floating-point order is then scheduling dependent, as it is there);
+// n_threads == 1 gives the deterministic read-order sum the parity tests use.
+int orc_hc_run(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, int64_t r0, int64_t r1, int mode,
+               int n_threads, long double* final_out, int32_t* argmax_out, int64_t* n_used) {
+    HcContext C;
+    build_context(*T, C);
+    const size_t P = (size_t)T->n_paths;
+    vector<ld> final_vec(P, 0);
+    const vector<ld> empty_vec(P, 0);
+    int err = ORC_OK;
+    int64_t used = 0;
+#ifdef _OPENMP
+    if (n_threads < 1) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 1) reduction(+ : used)
+    for (int64_t r = r0; r < r1; ++r) {
+        if (R->identity[r] < 1e-10) continue;
+        ReadView rd = load_read(*R, r);
+        vector<ld> ll = empty_vec;
+        int rc = update_likelihood(C, *g, rd, mode, ll, nullptr, nullptr);
+        if (rc) {
+#pragma omp critical(orc_err)
+            err = rc;
+            continue;
+        }
+        used += 1;
+#pragma omp critical(orc_sum)
+        for (size_t j = 0; j < P; ++j) final_vec[j] += ll[j];
+    }
+    if (err) return err;
+    for (size_t j = 0; j < P; ++j) final_out[j] = final_vec[j];
+    if (argmax_out) *argmax_out = (int32_t)(std::max_element(final_vec.begin(), final_vec.end()) - final_vec.begin());
+    if (n_used) *n_used = used;
+    return ORC_OK;
+}
+
+// Haplocart::get_posterior, reference src/get_posterior.cpp:87-127.  `path_names` is one name per
+// line (column order of path_supports); parents_txt / children_txt are the reference's file formats.
+// clade_idx_out[k] = index into the predicted haplotype's parent list (-1 for the call itself);
+// conf_out[k] the posterior.  Returns the number of (clade, confidence) pairs, or < 0 on error.
+int orc_hc_posterior(const long double* final_vec, int32_t n_paths, const char* path_names_txt, const char* parents_txt,
+                     const char* children_txt, int32_t predicted_idx, int32_t cap, int32_t* clade_idx_out,
+                     double* conf_out, long double* total_out) {
+    vector<string> path_names;
+    {
+        std::istringstream in(path_names_txt);
+        string line;
+        while (std::getline(in, line)) path_names.push_back(line);
+    }
+    if ((int32_t)path_names.size() != n_paths || predicted_idx < 0 || predicted_idx >= n_paths) return ORC_ERR_RANGE;
+    const Rel parents = parse_relations(parents_txt);
+    const Rel children = parse_relations(children_txt);
+    vector<ld> fv(final_vec, final_vec + n_paths);
+    const string predicted = path_names[(size_t)predicted_idx];
+    const ld total_ll = sum_log_likelihoods(fv);
+    if (total_out) *total_out = total_ll;
+    vector<string> parent_vec;
+    auto pit = parents.find(predicted);
+    if (pit != parents.end()) parent_vec = pit->second;
+    vector<int32_t> clade_vec{-1};
+    vector<double> confidence_vec;
+    const size_t pidx = (size_t)(std::find(path_names.begin(), path_names.end(), predicted) - path_names.begin());
+    vector<ld> all_top{fv[pidx]};
+    ld considered = sum_log_likelihoods(all_top);
+    confidence_vec.push_back((double)expl(considered - total_ll));
+    for (size_t j = 0; j < parent_vec.size(); ++j) {
+        const bool differs = (j == 0) || parent_vec[j] != parent_vec[j - 1];  // Q8
+        if (differs) clade_vec.push_back((int32_t)j);
+        std::set<string> pred{parent_vec[j]};
+        all_top.clear();
+        get_posterior_of_clade(all_top, fv, pred, children, path_names);
+        if (all_top.empty()) return ORC_ERR_RANGE;  // reference: log_lik_vec[0] of an empty vector
+        considered = sum_log_likelihoods(all_top);
+        if (differs) confidence_vec.push_back((double)expl(considered - total_ll));
+    }
+    const int32_t n = (int32_t)clade_vec.size();
+    if (n > cap) return ORC_ERR_CAP;
+    for (int32_t k = 0; k < n; ++k) {
+        clade_idx_out[k] = clade_vec[(size_t)k];
+        conf_out[k] = confidence_vec[(size_t)k];
+    }
+    return n;
+}
+
+// Tables the product also needs, exported so tests can compare them entry by entry.
+void orc_hc_qscore_vec(double* out100) { vector<double> v = get_qscore_vec(); for (int i = 0; i < 100; ++i) out100[i] = v[(size_t)i]; }
+void orc_hc_incorrect_mapping_vec(double* out100) { vector<double> v = precompute_incorrect_mapping_probs(); for (int i = 0; i < 100; ++i) out100[i] = v[(size_t)i]; }
+double orc_hc_region_match_prob(int pangenome_base) { return std::pow((1 - region_mu(pangenome_base)), 8); }
+double orc_hc_background_freq(char b) { return get_background_freq(b); }
+double orc_hc_p_seq_error(int Q) { return get_p_seq_error(Q); }
+int orc_sizeof_long_double(void) { return (int)sizeof(long double); }
+
+}  // extern "C"

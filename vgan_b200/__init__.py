@@ -1,0 +1,8 @@
+"""vgan_b200 -- B200-native read x path likelihood engine for vgan (HaploCart hot path).
+
+Layout: csrc/ (CUDA kernels + C ABI + C++ host side), lib/ (built .so files, in-tree),
+_lib.py (ctypes), host.py (handles over the host library), haplocart.py (the reference-shaped
+interface over the device library).  No CPU fallback exists."""
+from . import _lib  # noqa: F401  (raises if the libraries are not built)
+from .haplocart import DeviceBatch, Haplocart  # noqa: F401
+from .host import Alignments, Graph, HcTables, HcTree, PackedBatch, SynthHaplocart, reconstruct  # noqa: F401

@@ -1,0 +1,141 @@
+"""ctypes bindings of the two in-tree C-ABI libraries (include/vgan_gpu.h, include/vgan_host.h).
+
+There is no CPU fallback: if the libraries are missing, importing this module raises, and on a box
+without a CUDA device `vgl_create` fails with VGL_ERR_NO_DEVICE.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+GPU_LIB_PATH = os.path.join(LIB_DIR, "libvgan_gpu.so")
+HOST_LIB_PATH = os.path.join(LIB_DIR, "libvgan_host.so")
+
+
+class VglError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vgan_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class vgl_hc_tables(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_paths", C.c_int32), ("row_words", C.c_int32), ("reserved0", C.c_int32),
+                ("support_bits", C.c_void_p), ("node_mappability", C.c_void_p), ("node_match_prob", C.c_void_p),
+                ("node_valid", C.c_void_p), ("qscore", C.c_double * 100), ("p_incorrect_map", C.c_double * 100),
+                ("bg_freq", C.c_double * 4), ("background_error_prob", C.c_double), ("is_consensus_fasta", C.c_int32),
+                ("reserved1", C.c_int32)]
+
+
+class vgl_hc_batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_cols", C.c_uint64), ("n_maps", C.c_uint64),
+                ("col_off", C.c_void_p), ("map_off", C.c_void_p), ("gcol", C.c_void_p), ("rcol", C.c_void_p),
+                ("qual", C.c_void_p), ("map_node", C.c_void_p), ("map_len", C.c_void_p), ("n_qual", C.c_void_p),
+                ("mapq", C.c_void_p)]
+
+
+class vgh_alignments(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual_off", C.c_void_p),
+                ("qual", C.c_void_p), ("mapq", C.c_void_p), ("identity", C.c_void_p), ("paired", C.c_void_p),
+                ("map_off", C.c_void_p), ("map_node", C.c_void_p), ("map_offset", C.c_void_p), ("map_rev", C.c_void_p),
+                ("edit_off", C.c_void_p), ("edit_from", C.c_void_p), ("edit_to", C.c_void_p),
+                ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p)]
+
+
+# every symbol include/vgan_gpu.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+GPU_SYMBOLS = {
+    "vgl_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "vgl_destroy": (None, [_P]),
+    "vgl_last_error": (C.c_char_p, []),
+    "vgl_abi_version": (C.c_int, []),
+    "vgl_set_stream": (C.c_int, [_P, _P]),
+    "vgl_synchronize": (C.c_int, [_P]),
+    "vgl_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "vgl_host_free": (C.c_int, [_P]),
+    "vgl_device_alloc": (C.c_int, [_P, C.POINTER(_P), C.c_size_t]),
+    "vgl_device_free": (C.c_int, [_P, _P]),
+    "vgl_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "vgl_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "vgl_hc_set_tables": (C.c_int, [_P, C.POINTER(vgl_hc_tables)]),
+    "vgl_hc_set_tree": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "vgl_hc_batch_bytes": (C.c_uint64, [C.POINTER(vgl_hc_batch)]),
+    "vgl_hc_reset": (C.c_int, [_P]),
+    "vgl_hc_accumulate": (C.c_int, [_P, C.POINTER(vgl_hc_batch)]),
+    "vgl_hc_accumulate_device": (C.c_int, [_P, C.POINTER(vgl_hc_batch)]),
+    "vgl_hc_paths": (C.c_int, [_P, _P]),
+    "vgl_hc_set_paths_from_parts": (C.c_int, [_P, _P, C.c_int32]),
+    "vgl_hc_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, C.c_int32,
+                                  C.POINTER(C.c_int32)]),
+    "vgl_launch_count": (C.c_uint64, [_P]),
+    "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+}
+
+HOST_SYMBOLS = {
+    "vgh_last_error": (C.c_char_p, []),
+    "vgh_graph_create": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(_P)]),
+    "vgh_graph_destroy": (None, [_P]),
+    "vgh_gam_read_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "vgh_gam_parse": (C.c_int, [_P, C.c_size_t, C.c_int, C.POINTER(_P)]),
+    "vgh_gam_view": (C.POINTER(vgh_alignments), [_P]),
+    "vgh_gam_destroy": (None, [_P]),
+    "vgh_reconstruct": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, _P, _P, _P, C.c_int32,
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vgh_hc_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vgh_hc_packed_batch": (C.POINTER(vgl_hc_batch), [_P]),
+    "vgh_hc_packed_skipped": (C.c_int64, [_P]),
+    "vgh_hc_packed_destroy": (None, [_P]),
+    "vgh_hc_tables_build": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, C.c_int64, _P, C.c_double, C.c_int,
+                                      C.POINTER(_P)]),
+    "vgh_hc_tables_view": (C.POINTER(vgl_hc_tables), [_P]),
+    "vgh_hc_tables_destroy": (None, [_P]),
+    "vgh_hc_region_match_prob": (C.c_double, [C.c_int32]),
+    "vgh_hc_tree_build": (C.c_int, [C.c_int32, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_P)]),
+    "vgh_hc_tree_n_clades": (C.c_int32, [_P]),
+    "vgh_hc_tree_row_words": (C.c_int32, [_P]),
+    "vgh_hc_tree_clade_bits": (_P, [_P]),
+    "vgh_hc_tree_anc_off": (_P, [_P]),
+    "vgh_hc_tree_anc_clade": (_P, [_P]),
+    "vgh_hc_tree_clade_name": (C.c_char_p, [_P, C.c_int32]),
+    "vgh_hc_tree_destroy": (None, [_P]),
+    "vgh_synth_hc_create": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "vgh_synth_hc_destroy": (None, [_P]),
+    "vgh_synth_hc_graph": (_P, [_P]),
+    "vgh_synth_hc_graph_seq": (C.c_int64, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "vgh_synth_hc_supports": (_P, [_P]),
+    "vgh_synth_hc_n_pmap": (C.c_int64, [_P]),
+    "vgh_synth_hc_pmap_node": (_P, [_P]),
+    "vgh_synth_hc_pmap_val": (_P, [_P]),
+    "vgh_synth_hc_n_mappab": (C.c_int64, [_P]),
+    "vgh_synth_hc_mappab": (_P, [_P]),
+    "vgh_synth_hc_names": (C.c_char_p, [_P]),
+    "vgh_synth_hc_parents": (C.c_char_p, [_P]),
+    "vgh_synth_hc_children": (C.c_char_p, [_P]),
+    "vgh_synth_hc_total_len": (C.c_int32, [_P]),
+    "vgh_synth_hc_reads": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int, C.c_int32,
+                                     C.POINTER(_P)]),
+}
+
+
+def _load(path, symbols):
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `make -C vgan_b200/csrc` (or __graft_entry__.build()); "
+                          "there is no CPU fallback" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in symbols.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+gpu = _load(GPU_LIB_PATH, GPU_SYMBOLS)
+host = _load(HOST_LIB_PATH, HOST_SYMBOLS)
+
+
+def check(rc):
+    """Raise on a non-zero status from either library."""
+    if rc == 0:
+        return
+    if rc >= 100:
+        raise VglError(rc, host.vgh_last_error().decode(errors="replace"))
+    raise VglError(rc, gpu.vgl_last_error().decode(errors="replace"))

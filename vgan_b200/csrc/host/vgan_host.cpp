@@ -1,0 +1,728 @@
+// libvgan_host.so -- host side of the drop-in boundary (include/vgan_host.h).
+// GAM reading, alignment reconstruction, SoA packing and table construction.  No likelihood
+// arithmetic is done here and nothing in this file touches the oracle.
+#include "host_internal.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+thread_local char g_err[512] = "";
+}  // namespace
+
+int vgh_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+const char* vgh_error_text() { return g_err; }
+#define fail vgh_fail
+
+namespace {
+
+struct Cursor {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+    uint64_t varint() {
+        uint64_t v = 0;
+        int shift = 0;
+        while (p < end && shift < 64) {
+            const uint8_t b = *p++;
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) return v;
+            shift += 7;
+        }
+        ok = false;
+        return 0;
+    }
+    // reads a length-delimited field body
+    Cursor sub() {
+        const uint64_t n = varint();
+        if (!ok || n > (uint64_t)(end - p)) { ok = false; return Cursor{p, p, false}; }
+        Cursor c{p, p + n, true};
+        p += n;
+        return c;
+    }
+    void skip(int wt) {
+        switch (wt) {
+            case 0: varint(); break;
+            case 1: if (end - p < 8) ok = false; else p += 8; break;
+            case 2: sub(); break;
+            case 5: if (end - p < 4) ok = false; else p += 4; break;
+            default: ok = false;
+        }
+    }
+};
+
+// One serialized vg.Alignment (field numbers as on the wire).
+bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
+    std::string seq, qual;
+    int32_t mapq = 0;
+    double identity = 0.0;
+    uint8_t paired = 0;
+    const size_t map_mark = out.map_node.size(), edit_mark = out.edit_from.size(), es_mark = out.edit_seq.size();
+    while (c.ok && c.p < c.end) {
+        const uint64_t key = c.varint();
+        const int fno = (int)(key >> 3), wt = (int)(key & 7);
+        if (fno == 1 && wt == 2) { Cursor s = c.sub(); seq.assign((const char*)s.p, (const char*)s.end); }
+        else if (fno == 4 && wt == 2) { Cursor s = c.sub(); qual.assign((const char*)s.p, (const char*)s.end); }
+        else if (fno == 5 && wt == 0) mapq = (int32_t)c.varint();
+        else if (fno == 16 && wt == 1) { if (c.end - c.p < 8) { c.ok = false; break; } memcpy(&identity, c.p, 8); c.p += 8; }
+        else if (fno == 20 && wt == 0) paired = c.varint() ? 1 : 0;
+        else if (fno == 2 && wt == 2) {  // Path
+            Cursor path = c.sub();
+            while (path.ok && path.p < path.end) {
+                const uint64_t k2 = path.varint();
+                if ((k2 >> 3) == 2 && (k2 & 7) == 2) {  // Mapping
+                    Cursor m = path.sub();
+                    int64_t node = 0, offset = 0;
+                    uint8_t rev = 0;
+                    while (m.ok && m.p < m.end) {
+                        const uint64_t k3 = m.varint();
+                        if ((k3 >> 3) == 1 && (k3 & 7) == 2) {  // Position
+                            Cursor pos = m.sub();
+                            while (pos.ok && pos.p < pos.end) {
+                                const uint64_t k4 = pos.varint();
+                                if ((k4 >> 3) == 1 && (k4 & 7) == 0) node = (int64_t)pos.varint();
+                                else if ((k4 >> 3) == 2 && (k4 & 7) == 0) offset = (int64_t)pos.varint();
+                                else if ((k4 >> 3) == 4 && (k4 & 7) == 0) rev = pos.varint() ? 1 : 0;
+                                else pos.skip((int)(k4 & 7));
+                            }
+                            if (!pos.ok) m.ok = false;
+                        } else if ((k3 >> 3) == 2 && (k3 & 7) == 2) {  // Edit
+                            Cursor e = m.sub();
+                            int32_t from = 0, to = 0;
+                            while (e.ok && e.p < e.end) {
+                                const uint64_t k4 = e.varint();
+                                if ((k4 >> 3) == 1 && (k4 & 7) == 0) from = (int32_t)e.varint();
+                                else if ((k4 >> 3) == 2 && (k4 & 7) == 0) to = (int32_t)e.varint();
+                                else if ((k4 >> 3) == 3 && (k4 & 7) == 2) { Cursor s = e.sub(); out.edit_seq.append((const char*)s.p, (const char*)s.end); }
+                                else e.skip((int)(k4 & 7));
+                            }
+                            if (!e.ok) m.ok = false;
+                            out.edit_from.push_back(from);
+                            out.edit_to.push_back(to);
+                            out.edit_seq_off.push_back((int64_t)out.edit_seq.size());
+                        } else {
+                            m.skip((int)(k3 & 7));
+                        }
+                    }
+                    if (!m.ok) path.ok = false;
+                    out.map_node.push_back(node);
+                    out.map_offset.push_back(offset);
+                    out.map_rev.push_back(rev);
+                    out.edit_off.push_back((int64_t)out.edit_from.size());
+                } else {
+                    path.skip((int)(k2 & 7));
+                }
+            }
+            if (!path.ok) c.ok = false;
+        } else {
+            c.skip(wt);
+        }
+    }
+    if (!c.ok) return false;
+    if (drop_unmapped && identity == 0) {  // readGAM keeps only identity != 0 (src/readGAM.h:47)
+        out.map_node.resize(map_mark); out.map_offset.resize(map_mark); out.map_rev.resize(map_mark);
+        out.edit_off.resize(map_mark + 1);
+        out.edit_from.resize(edit_mark); out.edit_to.resize(edit_mark);
+        out.edit_seq_off.resize(edit_mark + 1);
+        out.edit_seq.resize(es_mark);
+        return true;
+    }
+    out.seq += seq; out.seq_off.push_back((int64_t)out.seq.size());
+    out.qual += qual; out.qual_off.push_back((int64_t)out.qual.size());
+    out.mapq.push_back(mapq);
+    out.identity.push_back(identity);
+    out.paired.push_back(paired);
+    out.map_off.push_back((int64_t)out.map_node.size());
+    return true;
+}
+
+int inflate_all(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+    if (n < 2 || in[0] != 0x1f || in[1] != 0x8b) {  // not gzip: plain stream
+        out.assign(in, in + n);
+        return VGH_OK;
+    }
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) return fail(VGH_ERR_IO, "inflateInit2 failed");
+    zs.next_in = const_cast<Bytef*>(in);
+    zs.avail_in = (uInt)n;
+    std::vector<uint8_t> buf(1 << 16);
+    while (true) {
+        zs.next_out = buf.data();
+        zs.avail_out = (uInt)buf.size();
+        const int rc = inflate(&zs, Z_NO_FLUSH);
+        out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
+        if (rc == Z_STREAM_END) {
+            if (zs.avail_in == 0) break;
+            if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); return fail(VGH_ERR_IO, "inflateReset failed"); }  // next BGZF member
+        } else if (rc != Z_OK) {
+            inflateEnd(&zs);
+            return fail(VGH_ERR_FORMAT, "gzip stream corrupt (zlib %d)", rc);
+        } else if (zs.avail_in == 0 && zs.avail_out != 0) {
+            break;  // truncated stream: keep what was decoded
+        }
+    }
+    inflateEnd(&zs);
+    return VGH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vgh_last_error(void) { return g_err; }
+
+int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out) {
+    if (!out || n_nodes < 0 || !seq_off || (!seq && seq_off[n_nodes] > 0)) return fail(VGH_ERR_INVALID, "bad graph arguments");
+    vgh_graph* g = new vgh_graph();
+    g->min_id = min_id;
+    g->n_nodes = n_nodes;
+    g->off.assign(seq_off, seq_off + n_nodes + 1);
+    g->seq.assign(seq, seq + seq_off[n_nodes]);
+    *out = g;
+    return VGH_OK;
+}
+void vgh_graph_destroy(vgh_graph* g) { delete g; }
+
+int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
+    if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
+    std::vector<uint8_t> raw;
+    if (int rc = inflate_all((const uint8_t*)bytes, n, raw)) return rc;
+    vgh_gam* g = new vgh_gam();
+    Cursor c{raw.data(), raw.data() + raw.size(), true};
+    while (c.ok && c.p < c.end) {
+        const uint64_t count = c.varint();  // group: count, then the "GAM" tag, then count-1 messages
+        for (uint64_t k = 0; c.ok && k < count; ++k) {
+            Cursor item = c.sub();
+            if (!c.ok) break;
+            if (k == 0) {
+                if (item.end - item.p != 3 || memcmp(item.p, "GAM", 3) != 0) {
+                    delete g;
+                    return fail(VGH_ERR_FORMAT, "unexpected type tag in GAM stream");
+                }
+                continue;
+            }
+            if (!parse_alignment(item, drop_unmapped, *g)) {
+                delete g;
+                return fail(VGH_ERR_FORMAT, "malformed vg.Alignment message");
+            }
+        }
+    }
+    if (!c.ok) {
+        delete g;
+        return fail(VGH_ERR_FORMAT, "truncated GAM stream");
+    }
+    g->finish();
+    *out = g;
+    return VGH_OK;
+}
+
+int vgh_gam_read_file(const char* path, int drop_unmapped, vgh_gam** out) {
+    if (!path || !out) return fail(VGH_ERR_INVALID, "bad arguments");
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return fail(VGH_ERR_IO, "cannot open %s", path);
+    std::vector<uint8_t> raw;
+    uint8_t buf[1 << 16];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof(buf), fh)) > 0) raw.insert(raw.end(), buf, buf + k);
+    fclose(fh);
+    return vgh_gam_parse(raw.data(), raw.size(), drop_unmapped, out);
+}
+const vgh_alignments* vgh_gam_view(const vgh_gam* g) { return g ? &g->view : nullptr; }
+void vgh_gam_destroy(vgh_gam* g) { delete g; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// alignment reconstruction
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+enum EditKind { kMatch, kSub, kIns, kDel, kOther };
+inline EditKind classify(int32_t from, int32_t to, bool has_seq) {  // vg io edit_is_*
+    if (from == to && !has_seq) return kMatch;
+    if (from == to && has_seq) return kSub;
+    if (from == 0 && to > 0 && has_seq) return kIns;
+    if (from > 0 && to == 0) return kDel;
+    return kOther;
+}
+
+struct Recon {
+    std::string graph_seq, read_seq;
+    std::vector<int32_t> sizes;
+};
+
+// reconstruct_graph_sequence (reference src/vgan_utils.h:6-79), including the behaviours the
+// reference's counters produce: an insertion is an 'S' run whenever the running node
+// offset is 0, a '-' run otherwise; one size per edit; the '-' run of a deletion is spliced into the
+// read string at the running from_length coordinate.
+int reconstruct(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& out) {
+    out.graph_seq.clear();
+    out.read_seq.clear();
+    out.sizes.clear();
+    struct Splice { size_t at; int32_t n; };
+    std::vector<Splice> splices;
+    int64_t from_total = 0;
+    for (int64_t m = a.map_off[r]; m < a.map_off[r + 1]; ++m) {
+        const int64_t node = a.map_node[m];
+        const bool rev = a.map_rev[m] != 0;
+        if (!G.has(node)) return fail(VGH_ERR_BAD_NODE, "read %lld: node %lld is not in the graph", (long long)r, (long long)node);
+        const int64_t nlen = G.length(node);
+        int64_t offset = a.map_offset[m];
+        int32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size (vgan_utils.h:26,72)
+        for (int64_t e = a.edit_off[m]; e < a.edit_off[m + 1]; ++e) {
+            const int32_t from = a.edit_from[e], to = a.edit_to[e];
+            const int64_t s0 = a.edit_seq_off[e], s1 = a.edit_seq_off[e + 1];
+            const EditKind kind = classify(from, to, s1 > s0);
+            if (kind == kMatch || kind == kSub || kind == kDel) {
+                if (offset > nlen || offset < 0)
+                    return fail(VGH_ERR_BAD_READ, "read %lld: offset %lld beyond node %lld (length %lld)", (long long)r,
+                                (long long)offset, (long long)node, (long long)nlen);
+                const int64_t take = std::min<int64_t>(from, nlen - offset);  // std::string::substr clips
+                for (int64_t k = 0; k < take; ++k) out.graph_seq.push_back(G.base(node, rev, offset + k));
+                aligned = (int32_t)take;
+                if (kind == kMatch) out.read_seq.append(out.graph_seq, out.graph_seq.size() - (size_t)take, (size_t)take);
+                else if (kind == kSub) out.read_seq.append(a.edit_seq + s0, (size_t)(s1 - s0));
+                else splices.push_back(Splice{(size_t)from_total, from});
+            } else if (kind == kIns) {
+                out.graph_seq.append((size_t)to, offset == 0 ? 'S' : '-');
+                out.read_seq.append(a.edit_seq + s0, (size_t)(s1 - s0));
+                aligned = to;
+            }
+            offset += from;
+            from_total += from;
+            out.sizes.push_back(aligned);
+        }
+    }
+    for (const Splice& s : splices) {  // applied in order, each against the string as it stands
+        if (s.at > out.read_seq.size()) return fail(VGH_ERR_BAD_READ, "read %lld: deletion beyond the read string", (long long)r);
+        out.read_seq.insert(s.at, (size_t)s.n, '-');
+    }
+    return VGH_OK;
+}
+
+}  // namespace
+
+extern "C" int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char* graph_seq, char* read_seq,
+                               int32_t* sizes, int32_t cap, int32_t* n_graph, int32_t* n_read, int32_t* n_sizes) {
+    if (!g || !a || r < 0 || r >= a->n_reads) return fail(VGH_ERR_INVALID, "bad arguments");
+    Recon rc;
+    if (int e = reconstruct(*g, *a, r, rc)) return e;
+    if ((int64_t)rc.graph_seq.size() > cap || (int64_t)rc.read_seq.size() > cap || (int64_t)rc.sizes.size() > cap)
+        return fail(VGH_ERR_INVALID, "buffers too small");
+    memcpy(graph_seq, rc.graph_seq.data(), rc.graph_seq.size());
+    memcpy(read_seq, rc.read_seq.data(), rc.read_seq.size());
+    for (size_t i = 0; i < rc.sizes.size(); ++i) sizes[i] = rc.sizes[i];
+    *n_graph = (int32_t)rc.graph_seq.size();
+    *n_read = (int32_t)rc.read_seq.size();
+    *n_sizes = (int32_t)rc.sizes.size();
+    return VGH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch packer
+// ------------------------------------------------------------------------------------------------
+struct vgh_hc_packed {
+    vgl_hc_batch batch{};
+    bool pinned = false;
+    int64_t skipped = 0;
+    void* block = nullptr;  // one allocation holds every array
+    size_t block_bytes = 0;
+};
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                vgh_hc_packed** out) {
+    if (!g || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    // The reads the hot loop processes: identity >= 1e-10 (src/HaploCart.cpp:411).
+    std::vector<int64_t> keep;
+    keep.reserve((size_t)(r1 - r0));
+    for (int64_t r = r0; r < r1; ++r)
+        if (!(a->identity[r] < 1e-10)) keep.push_back(r);
+    const size_t R = keep.size();
+    if (R >= 0xffffffffull) return fail(VGH_ERR_INVALID, "too many reads for one batch");
+
+    // pass 1: reconstruct every kept read once to learn its column / mapping counts
+    std::vector<uint32_t> ncols(R), nmaps(R);
+    int err = VGH_OK;
+    std::string err_msg;
+#pragma omp parallel num_threads(n_threads)
+    {
+        Recon rc;
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < (int64_t)R; ++k) {
+            const int64_t r = keep[(size_t)k];
+            int e = reconstruct(*g, *a, r, rc);
+            const int64_t M = a->map_off[r + 1] - a->map_off[r];
+            const int64_t Lq = a->qual_off[r + 1] - a->qual_off[r];
+            if (!e) {
+                if (rc.graph_seq.size() != rc.read_seq.size())
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: aligned graph / read strings differ in length (%zu vs %zu)", (long long)r,
+                             rc.graph_seq.size(), rc.read_seq.size());
+                else if ((int64_t)rc.sizes.size() < M)
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: a mapping has no edits (the reference indexes mppg_sizes out of range)", (long long)r);
+                else if (Lq > (int64_t)rc.read_seq.size())
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: quality string longer than the alignment", (long long)r);
+                else if (rc.read_seq.size() > 65535 || M > 65535)
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: alignment too long for the v1 batch layout", (long long)r);
+                else if (a->mapq[r] < 0 || a->mapq[r] >= 100)
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: mapping quality %d outside [0,100)", (long long)r, a->mapq[r]);
+            }
+            if (e) {
+#pragma omp critical(vgh_pack_err)
+                if (!err) { err = e; err_msg = g_err; }
+                continue;
+            }
+            ncols[(size_t)k] = (uint32_t)rc.read_seq.size();
+            nmaps[(size_t)k] = (uint32_t)M;
+        }
+    }
+    if (err) return fail(err, "%s", err_msg.c_str());
+
+    uint64_t tot_cols = 0, tot_maps = 0;
+    for (size_t k = 0; k < R; ++k) { tot_cols += ncols[k]; tot_maps += nmaps[k]; }
+    if (tot_cols > 0xfffffff0ull || tot_maps > 0xfffffff0ull) return fail(VGH_ERR_INVALID, "batch too large for 32-bit offsets; split it");
+
+    // one block, 256-byte aligned sub-arrays (+16 bytes of slack so device tiles may over-read)
+    size_t o = 0;
+    const size_t o_col_off = o; o = align_up(o + (R + 1) * 4, 256);
+    const size_t o_map_off = o; o = align_up(o + (R + 1) * 4, 256);
+    const size_t o_gcol = o; o = align_up(o + tot_cols + 16, 256);
+    const size_t o_rcol = o; o = align_up(o + tot_cols + 16, 256);
+    const size_t o_qual = o; o = align_up(o + tot_cols + 16, 256);
+    const size_t o_node = o; o = align_up(o + tot_maps * 4 + 16, 256);
+    const size_t o_len = o; o = align_up(o + tot_maps * 2 + 16, 256);
+    const size_t o_nq = o; o = align_up(o + R * 2 + 16, 256);
+    const size_t o_mq = o; o = align_up(o + R + 16, 256);
+    vgh_hc_packed* P = new vgh_hc_packed();
+    P->block_bytes = o;
+    P->pinned = pinned != 0;
+    if (pinned) {
+        if (vgl_host_alloc(&P->block, o) != VGL_OK) {
+            delete P;
+            return fail(VGH_ERR_INVALID, "pinned allocation failed: %s", vgl_last_error());
+        }
+    } else {
+        P->block = aligned_alloc(256, o);
+        if (!P->block) { delete P; return fail(VGH_ERR_INVALID, "out of host memory"); }
+    }
+    uint8_t* base = (uint8_t*)P->block;
+    uint32_t* col_off = (uint32_t*)(base + o_col_off);
+    uint32_t* map_off = (uint32_t*)(base + o_map_off);
+    uint8_t* gcol = base + o_gcol;
+    uint8_t* rcol = base + o_rcol;
+    uint8_t* qual = base + o_qual;
+    int32_t* map_node = (int32_t*)(base + o_node);
+    uint16_t* map_len = (uint16_t*)(base + o_len);
+    uint16_t* n_qual = (uint16_t*)(base + o_nq);
+    uint8_t* mapq = base + o_mq;
+    col_off[0] = 0;
+    map_off[0] = 0;
+    for (size_t k = 0; k < R; ++k) { col_off[k + 1] = col_off[k] + ncols[k]; map_off[k + 1] = map_off[k] + nmaps[k]; }
+    memset(gcol + tot_cols, 0, 16); memset(rcol + tot_cols, 0, 16); memset(qual + tot_cols, 0, 16);
+    memset((uint8_t*)(map_node + tot_maps), 0, 16); memset((uint8_t*)(map_len + tot_maps), 0, 16);
+
+    // pass 2: fill
+#pragma omp parallel num_threads(n_threads)
+    {
+        Recon rc;
+#pragma omp for schedule(static)
+        for (int64_t k = 0; k < (int64_t)R; ++k) {
+            const int64_t r = keep[(size_t)k];
+            if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
+            const uint32_t c0 = col_off[k], m0 = map_off[k];
+            const size_t L = rc.read_seq.size();
+            memcpy(gcol + c0, rc.graph_seq.data(), L);
+            memcpy(rcol + c0, rc.read_seq.data(), L);
+            const int64_t q0 = a->qual_off[r], Lq = a->qual_off[r + 1] - q0;
+            memcpy(qual + c0, a->qual + q0, (size_t)Lq);
+            memset(qual + c0 + Lq, 0, L - (size_t)Lq);
+            const int64_t mm = a->map_off[r];
+            for (uint32_t i = 0; i < nmaps[(size_t)k]; ++i) {
+                const int64_t node = a->map_node[mm + i];
+                map_node[m0 + i] = (node >= 0 && node <= 0x7fffffff) ? (int32_t)node : -1;
+                map_len[m0 + i] = (uint16_t)std::min<int32_t>(rc.sizes[i], 65535);  // sizes[i] <= L <= 65535
+            }
+            n_qual[k] = (uint16_t)Lq;
+            mapq[k] = (uint8_t)a->mapq[r];
+        }
+    }
+    P->skipped = (r1 - r0) - (int64_t)R;
+    P->batch.n_reads = (uint32_t)R;
+    P->batch.n_cols = tot_cols;
+    P->batch.n_maps = tot_maps;
+    P->batch.col_off = col_off; P->batch.map_off = map_off;
+    P->batch.gcol = gcol; P->batch.rcol = rcol; P->batch.qual = qual;
+    P->batch.map_node = map_node; P->batch.map_len = map_len;
+    P->batch.n_qual = n_qual; P->batch.mapq = mapq;
+    *out = P;
+    return VGH_OK;
+}
+
+const vgl_hc_batch* vgh_hc_packed_batch(const vgh_hc_packed* p) { return p ? &p->batch : nullptr; }
+int64_t vgh_hc_packed_skipped(const vgh_hc_packed* p) { return p ? p->skipped : 0; }
+void vgh_hc_packed_destroy(vgh_hc_packed* p) {
+    if (!p) return;
+    if (p->block) {
+        if (p->pinned) vgl_host_free(p->block);
+        else free(p->block);
+    }
+    delete p;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// HaploCart tables
+// ------------------------------------------------------------------------------------------------
+struct vgh_hc_tables {
+    vgl_hc_tables view{};
+    std::vector<uint32_t> bits;
+    std::vector<double> node_mappability, node_match_prob;
+    std::vector<uint8_t> node_valid;
+};
+
+namespace {
+
+// Per-year substitution rates by rCRS region, in the precedence order of get_p_obs_base
+// (reference src/get_p_obs_base.cpp:43-61).  The protein-coding entry is exactly 0 because the
+// reference multiplies by the integer quotients (2/3) and (1/3).
+struct Region { int lo, hi; double mu; };
+const Region kRegions[] = {
+    {57, 372, 1.64273e-7},                                                                   // HVS I
+    {1, 56, 2.29640e-8}, {373, 576, 2.29640e-8},                                             // HVS II
+    {16384, 16569, 1.54555e-8},                                                              // rest of the control region
+    {3307, 4262, 0.0}, {4470, 5511, 0.0}, {5904, 7445, 0.0}, {7586, 8269, 0.0}, {8366, 9990, 0.0},
+    {10059, 10403, 0.0}, {10470, 12137, 0.0}, {12337, 14673, 0.0}, {14747, 15886, 0.0},      // protein coding
+    {577, 647, 6.91285e-9}, {1602, 1670, 6.91285e-9}, {3230, 3304, 6.91285e-9}, {4263, 4400, 6.91285e-9},
+    {4402, 4469, 6.91285e-9}, {5512, 5579, 6.91285e-9}, {5587, 5654, 6.91285e-9}, {5657, 5728, 6.91285e-9},
+    {5761, 5891, 6.91285e-9}, {7446, 7514, 6.91285e-9}, {7518, 7585, 6.91285e-9}, {8295, 8364, 6.91285e-9},
+    {15888, 15953, 6.91285e-9}, {15956, 16023, 6.91285e-9},                                  // tRNA
+    {648, 1601, 6.91285e-9}, {1671, 3229, 6.91285e-9},                                       // rRNA
+};
+const double kMuElsewhere = 2.48537e-8;
+
+double region_rate_per_generation(int32_t pangenome_base) {
+    double mu = kMuElsewhere;
+    const unsigned x = (unsigned)pangenome_base;  // the reference compares as unsigned
+    for (const Region& r : kRegions)
+        if ((unsigned)r.lo <= x && x <= (unsigned)r.hi) { mu = r.mu; break; }
+    return mu * 30;  // years -> generations
+}
+
+}  // namespace
+
+extern "C" {
+
+double vgh_hc_region_match_prob(int32_t pangenome_base) {
+    return std::pow((1 - region_rate_per_generation(pangenome_base)), 8);
+}
+
+int vgh_hc_tables_build(int32_t n_rows, int32_t n_paths, const uint8_t* supports, int64_t n_pmap,
+                        const int64_t* pmap_node, const int32_t* pmap_val, int64_t n_mappab, const double* mappab,
+                        double background_error_prob, int is_consensus_fasta, vgh_hc_tables** out) {
+    if (!out || n_rows <= 0 || n_paths <= 0 || !supports || (n_pmap && (!pmap_node || !pmap_val)) || (n_mappab && !mappab))
+        return fail(VGH_ERR_INVALID, "bad table arguments");
+    vgh_hc_tables* T = new vgh_hc_tables();
+    const int W = (n_paths + 31) / 32;
+    T->bits.assign((size_t)n_rows * (size_t)W, 0u);
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < n_rows; ++n) {
+        const uint8_t* row = supports + (size_t)n * (size_t)n_paths;
+        uint32_t* dst = T->bits.data() + (size_t)n * (size_t)W;
+        for (int p = 0; p < n_paths; ++p)
+            if (row[p]) dst[p >> 5] |= 1u << (p & 31);
+    }
+    T->node_mappability.assign((size_t)n_rows, 0.0);
+    T->node_match_prob.assign((size_t)n_rows, 0.0);
+    T->node_valid.assign((size_t)n_rows, 0);
+    for (int64_t k = 0; k < n_pmap; ++k) {
+        const int64_t node = pmap_node[k];
+        const int32_t pb = pmap_val[k];
+        if (node < 0 || node >= n_rows) continue;  // entry for a node outside the support matrix: unreachable from the hot loop
+        if (T->node_valid[(size_t)node]) continue;  // std::map::insert keeps the first entry (src/load.cpp:39)
+        if (pb < 0 || pb >= n_mappab) {
+            delete T;
+            return fail(VGH_ERR_INVALID, "pangenome coordinate %d of node %lld is outside the mappability vector (%lld entries)", pb,
+                        (long long)node, (long long)n_mappab);
+        }
+        T->node_valid[(size_t)node] = 1;
+        T->node_mappability[(size_t)node] = mappab[pb];
+        T->node_match_prob[(size_t)node] = vgh_hc_region_match_prob(pb);
+    }
+    vgl_hc_tables& v = T->view;
+    v.n_rows = n_rows;
+    v.n_paths = n_paths;
+    v.row_words = W;
+    v.support_bits = T->bits.data();
+    v.node_mappability = T->node_mappability.data();
+    v.node_match_prob = T->node_match_prob.data();
+    v.node_valid = T->node_valid.data();
+    for (int Q = 0; Q < 100; ++Q) {
+        // get_qscore_vec (src/miscfunc.h:198-212): Q >= 2 goes through get_p_seq_error, which itself
+        // returns 0.25 up to Q == 2 (:180-187)
+        v.qscore[Q] = (Q > 2) ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;
+        v.p_incorrect_map[Q] = std::pow(10, ((-1 * Q) * 0.1));  // src/haplocart_functions.cpp:100-107
+    }
+    v.bg_freq[0] = 0.27532; v.bg_freq[1] = 0.30044; v.bg_freq[2] = 0.16644; v.bg_freq[3] = 0.25780;  // :81-97
+    v.background_error_prob = background_error_prob;
+    v.is_consensus_fasta = is_consensus_fasta ? 1 : 0;
+    *out = T;
+    return VGH_OK;
+}
+const vgl_hc_tables* vgh_hc_tables_view(const vgh_hc_tables* t) { return t ? &t->view : nullptr; }
+void vgh_hc_tables_destroy(vgh_hc_tables* t) { delete t; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// haplogroup tree
+// ------------------------------------------------------------------------------------------------
+struct vgh_hc_tree {
+    int32_t n_paths = 0, row_words = 0;
+    std::vector<std::string> clade_names;
+    std::vector<uint32_t> clade_bits;
+    std::vector<int32_t> anc_off, anc_clade;
+};
+
+namespace {
+
+typedef std::map<std::string, std::vector<std::string>> Relations;
+
+// "name rel1 rel2 ..." per line, tokens containing '[' dropped, blank lines skipped, first entry of a
+// repeated name wins (std::map::insert) -- reference src/load.cpp:303-345.
+Relations parse_relations(const char* text) {
+    Relations rel;
+    std::istringstream in(text ? text : "");
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string tok, name;
+        std::vector<std::string> v;
+        bool first = true;
+        while (ls >> tok) {
+            if (first) { name = tok; first = false; }
+            else if (tok.find('[') == std::string::npos) v.push_back(tok);
+        }
+        if (first) continue;
+        rel.insert(std::make_pair(name, v));
+    }
+    return rel;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vgh_hc_tree_build(int32_t n_paths, const char* path_names_txt, const char* parents_txt, const char* children_txt,
+                      vgh_hc_tree** out) {
+    if (!out || n_paths <= 0 || !path_names_txt) return fail(VGH_ERR_INVALID, "bad tree arguments");
+    std::vector<std::string> names;
+    {
+        std::istringstream in(path_names_txt);
+        std::string line;
+        while (std::getline(in, line)) names.push_back(line);
+    }
+    if ((int32_t)names.size() != n_paths) return fail(VGH_ERR_FORMAT, "%zu path names for %d paths", names.size(), n_paths);
+    const Relations parents = parse_relations(parents_txt);
+    const Relations children = parse_relations(children_txt);
+    // A name may label several columns; the reference collects final_vec[idx] for every matching column.
+    std::unordered_map<std::string, std::vector<int32_t>> cols_of;
+    for (int32_t p = 0; p < n_paths; ++p) cols_of[names[(size_t)p]].push_back(p);
+
+    vgh_hc_tree* T = new vgh_hc_tree();
+    T->n_paths = n_paths;
+    T->row_words = (n_paths + 31) / 32;
+    std::unordered_map<std::string, int32_t> clade_id;
+    T->anc_off.assign((size_t)n_paths + 1, 0);
+    for (int32_t p = 0; p < n_paths; ++p) {
+        auto it = parents.find(names[(size_t)p]);
+        if (it != parents.end()) {
+            const std::vector<std::string>& pv = it->second;
+            for (size_t j = 0; j < pv.size(); ++j) {
+                if (j > 0 && pv[j] == pv[j - 1]) continue;  // consecutive duplicates are reported once (get_posterior.cpp:110,117)
+                auto cit = clade_id.find(pv[j]);
+                int32_t id;
+                if (cit == clade_id.end()) {
+                    id = (int32_t)T->clade_names.size();
+                    clade_id.insert(std::make_pair(pv[j], id));
+                    T->clade_names.push_back(pv[j]);
+                } else {
+                    id = cit->second;
+                }
+                T->anc_clade.push_back(id);
+            }
+        }
+        T->anc_off[(size_t)p + 1] = (int32_t)T->anc_clade.size();
+    }
+    // strict descendants of every listed clade, generation by generation (get_posterior_of_clade, :51-76)
+    const size_t W = (size_t)T->row_words;
+    T->clade_bits.assign(std::max<size_t>(T->clade_names.size(), 1) * W, 0u);
+    for (size_t c = 0; c < T->clade_names.size(); ++c) {
+        uint32_t* bits = T->clade_bits.data() + c * W;
+        std::set<std::string> level{T->clade_names[c]}, seen;
+        while (!level.empty()) {
+            std::set<std::string> next;
+            for (const std::string& name : level) {
+                auto it = children.find(name);
+                if (it == children.end()) continue;
+                for (const std::string& ch : it->second) next.insert(ch);
+            }
+            std::set<std::string> fresh;
+            for (const std::string& ch : next) {
+                auto pit = cols_of.find(ch);
+                if (pit != cols_of.end())
+                    for (int32_t p : pit->second) bits[(size_t)p >> 5] |= 1u << (p & 31);
+                if (seen.insert(ch).second) fresh.insert(ch);  // guards against cycles in malformed files
+            }
+            level.swap(fresh);
+        }
+    }
+    *out = T;
+    return VGH_OK;
+}
+int32_t vgh_hc_tree_n_clades(const vgh_hc_tree* t) { return t ? (int32_t)t->clade_names.size() : 0; }
+int32_t vgh_hc_tree_row_words(const vgh_hc_tree* t) { return t ? t->row_words : 0; }
+const uint32_t* vgh_hc_tree_clade_bits(const vgh_hc_tree* t) { return t ? t->clade_bits.data() : nullptr; }
+const int32_t* vgh_hc_tree_anc_off(const vgh_hc_tree* t) { return t ? t->anc_off.data() : nullptr; }
+const int32_t* vgh_hc_tree_anc_clade(const vgh_hc_tree* t) { return t ? t->anc_clade.data() : nullptr; }
+const char* vgh_hc_tree_clade_name(const vgh_hc_tree* t, int32_t clade) {
+    if (!t || clade < 0 || clade >= (int32_t)t->clade_names.size()) return "";
+    return t->clade_names[(size_t)clade].c_str();
+}
+void vgh_hc_tree_destroy(vgh_hc_tree* t) { delete t; }
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// C-ABI layer of libvgan_gpu.so (include/vgan_gpu.h).  Owns device memory, streams and the table
+// preprocessing; the kernels live in hc_kernels.cu.  No CPU fallback exists anywhere in this
+// library: without a CUDA device vgl_create() fails with VGL_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "vgl_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define VGL_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(VGL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n) {
+        if (n <= cap) return VGL_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e != cudaSuccess) return fail(VGL_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return VGL_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct vgl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    // HaploCart tables
+    bool have_tables = false;
+    bool have_tree = false;
+    vgl::HcTablesDev tab{};
+    int row_words = 0;
+    int n_rows_pad = 0;
+    DevBuf<uint16_t> d_node_class;
+    DevBuf<double2> d_class_tab;
+    DevBuf<vgl::HcSmallTables> d_small;
+    DevBuf<uint32_t> d_node_bits;
+    vgl::HcReadLaunch read_cfg{};
+
+    // accumulators
+    DevBuf<double> d_cta_node_acc, d_cta_a_total, d_node_acc, d_a_total, d_chunk_ll, d_ll;
+    DevBuf<int> d_err;
+    int n_chunks = 0;
+    bool ll_valid = false;
+
+    // tree
+    int n_clades = 0;
+    int max_anc = 0;
+    DevBuf<uint32_t> d_clade_bits;
+    DevBuf<int32_t> d_anc_off, d_anc_clade;
+
+    // posterior outputs
+    DevBuf<double> d_post, d_scalars;
+    DevBuf<int32_t> d_idx;
+
+    // staging for host batches
+    DevBuf<uint32_t> s_col_off, s_map_off;
+    DevBuf<uint8_t> s_gcol, s_rcol, s_qual, s_mapq;
+    DevBuf<int32_t> s_map_node;
+    DevBuf<uint16_t> s_map_len, s_n_qual;
+
+    // read-kernel timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+int use_device(vgl_ctx* ctx) {
+    if (!ctx) return fail(VGL_ERR_INVALID, "null context");
+    VGL_CUDA(cudaSetDevice(ctx->device));
+    return VGL_OK;
+}
+
+int upload_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return VGL_OK;
+    VGL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return VGL_OK;
+}
+
+int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
+    if (b.n_reads == 0) return VGL_OK;
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t a, c;
+        VGL_CUDA(cudaEventCreate(&a));
+        VGL_CUDA(cudaEventCreate(&c));
+        ctx->ev_pool.push_back(std::make_pair(a, c));
+    }
+    auto& ev = ctx->ev_pool[ctx->ev_used++];
+    VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
+    VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_cta_a_total.p,
+                                        ctx->d_err.p, ctx->stream));
+    VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
+    ctx->launches += 1;
+    ctx->ll_valid = false;
+    return VGL_OK;
+}
+
+int check_batch(const vgl_hc_batch* b) {
+    if (!b) return fail(VGL_ERR_INVALID, "null batch");
+    if (b->n_reads == 0) return VGL_OK;
+    if (!b->col_off || !b->map_off || !b->n_qual || !b->mapq) return fail(VGL_ERR_INVALID, "batch header arrays missing");
+    if (b->n_cols && (!b->gcol || !b->rcol || !b->qual)) return fail(VGL_ERR_INVALID, "batch column arrays missing");
+    if (b->n_maps && (!b->map_node || !b->map_len)) return fail(VGL_ERR_INVALID, "batch mapping arrays missing");
+    if (b->n_cols > 0xffffffffull || b->n_maps > 0xffffffffull) return fail(VGL_ERR_INVALID, "batch too large for 32-bit offsets; split it");
+    return VGL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vgl_abi_version(void) { return VGL_ABI_VERSION; }
+const char* vgl_last_error(void) { return g_err; }
+
+int vgl_create(int device_id, vgl_ctx** out) {
+    if (!out) return fail(VGL_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(VGL_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_id < 0 || device_id >= n) return fail(VGL_ERR_INVALID, "device %d out of range (have %d)", device_id, n);
+    vgl_ctx* ctx = new (std::nothrow) vgl_ctx();
+    if (!ctx) return fail(VGL_ERR_INVALID, "out of host memory");
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+        delete ctx;
+        return fail(VGL_ERR_CUDA, "cannot select device %d", device_id);
+    }
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(VGL_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device_id, prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(VGL_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return VGL_OK;
+}
+
+void vgl_destroy(vgl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_node_class.release(); ctx->d_class_tab.release(); ctx->d_small.release(); ctx->d_node_bits.release();
+    ctx->d_cta_node_acc.release(); ctx->d_cta_a_total.release(); ctx->d_node_acc.release(); ctx->d_a_total.release();
+    ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_err.release();
+    ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
+    ctx->d_post.release(); ctx->d_scalars.release(); ctx->d_idx.release();
+    ctx->s_col_off.release(); ctx->s_map_off.release(); ctx->s_gcol.release(); ctx->s_rcol.release();
+    ctx->s_qual.release(); ctx->s_mapq.release(); ctx->s_map_node.release(); ctx->s_map_len.release(); ctx->s_n_qual.release();
+    for (auto& ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int vgl_set_stream(vgl_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(VGL_ERR_INVALID, "null context");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VGL_OK;
+}
+
+int vgl_synchronize(vgl_ctx* ctx) {
+    if (int rc = use_device(ctx)) return rc;
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VGL_OK;
+}
+
+int vgl_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(VGL_ERR_INVALID, "null out pointer");
+    VGL_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return VGL_OK;
+}
+int vgl_host_free(void* p) {
+    if (p) VGL_CUDA(cudaFreeHost(p));
+    return VGL_OK;
+}
+int vgl_device_alloc(vgl_ctx* ctx, void** out, size_t bytes) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!out) return fail(VGL_ERR_INVALID, "null out pointer");
+    VGL_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return VGL_OK;
+}
+int vgl_device_free(vgl_ctx* ctx, void* p) {
+    if (int rc = use_device(ctx)) return rc;
+    if (p) VGL_CUDA(cudaFree(p));
+    return VGL_OK;
+}
+int vgl_memcpy_h2d(vgl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (int rc = use_device(ctx)) return rc;
+    VGL_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VGL_OK;
+}
+int vgl_memcpy_d2h(vgl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (int rc = use_device(ctx)) return rc;
+    VGL_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VGL_OK;
+}
+
+uint64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b) {
+    if (!b) return 0;
+    return (uint64_t)(b->n_reads + 1) * 8 + b->n_cols * 3 + b->n_maps * 6 + (uint64_t)b->n_reads * 3;
+}
+
+// -------------------------------------------------------------------------------------------
+// tables
+// -------------------------------------------------------------------------------------------
+int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!T) return fail(VGL_ERR_INVALID, "null tables");
+    if (T->n_rows <= 0 || T->n_paths <= 0) return fail(VGL_ERR_INVALID, "empty tables (%d rows, %d paths)", T->n_rows, T->n_paths);
+    if (T->row_words < (T->n_paths + 31) / 32) return fail(VGL_ERR_INVALID, "row_words %d too small for %d paths", T->row_words, T->n_paths);
+    if (!T->support_bits || !T->node_mappability || !T->node_match_prob || !T->node_valid)
+        return fail(VGL_ERR_INVALID, "table arrays missing");
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    const int N = T->n_rows, P = T->n_paths;
+    const int n_words = (N + 31) / 32;
+
+    // (mappability, match_prob) dictionary: one class per distinct pair, so the read kernel can keep a
+    // 2-byte class id per node in shared memory instead of 16 bytes per node.
+    std::vector<uint16_t> node_class((size_t)N, 0xFFFFu);
+    std::vector<double2> class_tab;
+    {
+        std::map<std::pair<double, double>, int> dict;
+        for (int n = 0; n < N; ++n) {
+            if (!T->node_valid[n]) continue;
+            const std::pair<double, double> key(T->node_mappability[n], T->node_match_prob[n]);
+            auto it = dict.find(key);
+            int id;
+            if (it == dict.end()) {
+                id = (int)class_tab.size();
+                if (id >= 0xFFFF) return fail(VGL_ERR_INVALID, "more than 65534 distinct (mappability, match_prob) pairs");
+                dict.insert(std::make_pair(key, id));
+                class_tab.push_back(make_double2(key.first, key.second));
+            } else {
+                id = it->second;
+            }
+            node_class[(size_t)n] = (uint16_t)id;
+        }
+        if (class_tab.empty()) class_tab.push_back(make_double2(0.0, 0.0));
+    }
+
+    // Small tables, with the reference's exact double-precision expressions.
+    vgl::HcSmallTables small;
+    memset(&small, 0, sizeof(small));
+    const double bep = T->background_error_prob;
+    for (int b = 0; b < 256; ++b) {
+        const int Q = (int)(int8_t)(uint8_t)b;  // the reference reads quality bytes as (signed) char
+        // get_p_no_seq_error_mapping (src/get_p_obs_base.cpp:3-27); a negative byte would index qscore_vec
+        // out of range in the reference -- defined here as 0.25.  Bytes >= 90
+        // never reach the table because they latch the background-error mode first.
+        const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
+        const double eps_match = qs;
+        const double eps_mis = 1 - qs;
+        small.f_match[b] = 1 - eps_match;  // get_p_obs_base: match * (1 - epsilon), src/get_p_obs_base.cpp:67
+        small.f_mis[b] = 1 - eps_mis;
+        const double perr = (Q > 2) ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;  // get_p_seq_error, src/miscfunc.h:180-187
+        small.log_err[b] = std::log(perr);
+        small.base_code[b] = 4;
+    }
+    small.base_code[(int)'A'] = 0; small.base_code[(int)'C'] = 1; small.base_code[(int)'G'] = 2; small.base_code[(int)'T'] = 3;
+    for (int q = 0; q < 100; ++q) small.p_correct[q] = 1 - T->p_incorrect_map[q];
+    for (int k = 0; k < 4; ++k) small.bg[k] = T->bg_freq[k];
+    small.f_match_bep = 1 - bep;
+    small.f_mis_bep = 1 - (1 - bep);
+    small.one_minus_bep = 1 - bep;
+    small.is_fasta = T->is_consensus_fasta ? 1 : 0;
+
+    // Membership matrix re-laid as node-words x paths: word (w, p) holds pathsgo[p] of nodes 32w..32w+31.
+    // Bits of nodes >= n_rows are set ("supported": contributes nothing).
+    std::vector<uint32_t> node_bits((size_t)n_words * (size_t)P, 0u);
+    for (int n = 0; n < n_words * 32; ++n) {
+        uint32_t* dst = node_bits.data() + (size_t)(n >> 5) * (size_t)P;
+        const uint32_t bit = 1u << (n & 31);
+        if (n >= N) {
+            for (int p = 0; p < P; ++p) dst[p] |= bit;
+            continue;
+        }
+        const uint32_t* row = T->support_bits + (size_t)n * (size_t)T->row_words;
+        for (int w = 0; w < (P + 31) / 32; ++w) {
+            uint32_t word = row[w];
+            const int pbase = w * 32;
+            while (word) {
+                const int k = __builtin_ctz(word);
+                word &= word - 1;
+                if (pbase + k < P) dst[pbase + k] |= bit;
+            }
+        }
+    }
+
+    ctx->read_cfg = vgl::hc_read_launch_config(N, ctx->sm_count, ctx->max_smem_optin);
+    if (ctx->read_cfg.grid == 0)
+        return fail(VGL_ERR_INVALID, "node table of %d rows needs %zu bytes of shared memory per CTA (limit %d)", N,
+                    ctx->read_cfg.smem, ctx->max_smem_optin);
+    VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg.smem));
+
+    if (int rc = ctx->d_node_class.reserve((size_t)N)) return rc;
+    if (int rc = ctx->d_class_tab.reserve(class_tab.size())) return rc;
+    if (int rc = ctx->d_small.reserve(1)) return rc;
+    if (int rc = ctx->d_node_bits.reserve(node_bits.size())) return rc;
+    VGL_CUDA(cudaMemcpy(ctx->d_node_class.p, node_class.data(), (size_t)N * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->d_class_tab.p, class_tab.data(), class_tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->d_small.p, &small, sizeof(small), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->d_node_bits.p, node_bits.data(), node_bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+    ctx->tab.n_rows = N;
+    ctx->tab.n_paths = P;
+    ctx->tab.n_words = n_words;
+    ctx->tab.n_class = (int)class_tab.size();
+    ctx->tab.node_class = ctx->d_node_class.p;
+    ctx->tab.class_tab = ctx->d_class_tab.p;
+    ctx->tab.small = ctx->d_small.p;
+    ctx->tab.node_bits = ctx->d_node_bits.p;
+    ctx->row_words = (P + 31) / 32;
+    ctx->n_rows_pad = n_words * 32;
+    ctx->n_chunks = vgl::hc_path_chunks(n_words);
+
+    if (int rc = ctx->d_cta_node_acc.reserve((size_t)ctx->read_cfg.grid * (size_t)N)) return rc;
+    if (int rc = ctx->d_cta_a_total.reserve((size_t)ctx->read_cfg.grid)) return rc;
+    if (int rc = ctx->d_node_acc.reserve((size_t)ctx->n_rows_pad)) return rc;
+    if (int rc = ctx->d_a_total.reserve(1)) return rc;
+    if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
+    if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
+    if (int rc = ctx->d_err.reserve(1)) return rc;
+    if (int rc = ctx->d_scalars.reserve(2)) return rc;
+    if (int rc = ctx->d_idx.reserve(2)) return rc;
+    if (int rc = ctx->d_post.reserve(64)) return rc;
+    ctx->have_tables = true;
+    ctx->have_tree = false;
+    return vgl_hc_reset(ctx);
+}
+
+int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, const int32_t* anc_off,
+                    const int32_t* anc_clade) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (n_clades < 0 || !anc_off || (n_clades > 0 && (!clade_bits || !anc_clade))) return fail(VGL_ERR_INVALID, "tree arrays missing");
+    const int P = ctx->tab.n_paths;
+    int max_anc = 0;
+    if (anc_off[0] != 0) return fail(VGL_ERR_INVALID, "anc_off[0] must be 0");
+    for (int p = 0; p < P; ++p) {
+        const int k = anc_off[p + 1] - anc_off[p];
+        if (k < 0) return fail(VGL_ERR_INVALID, "anc_off not monotone at path %d", p);
+        max_anc = std::max(max_anc, k);
+    }
+    const int n_anc = anc_off[P];
+    for (int k = 0; k < n_anc; ++k)
+        if (anc_clade[k] < 0 || anc_clade[k] >= n_clades) return fail(VGL_ERR_INVALID, "anc_clade[%d] = %d out of range", k, anc_clade[k]);
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (int rc = ctx->d_clade_bits.reserve((size_t)std::max(n_clades, 1) * (size_t)ctx->row_words)) return rc;
+    if (int rc = ctx->d_anc_off.reserve((size_t)P + 1)) return rc;
+    if (int rc = ctx->d_anc_clade.reserve((size_t)std::max(n_anc, 1))) return rc;
+    if (int rc = ctx->d_post.reserve((size_t)max_anc + 1)) return rc;
+    if (n_clades)
+        VGL_CUDA(cudaMemcpy(ctx->d_clade_bits.p, clade_bits, (size_t)n_clades * ctx->row_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->d_anc_off.p, anc_off, ((size_t)P + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (n_anc) VGL_CUDA(cudaMemcpy(ctx->d_anc_clade.p, anc_clade, (size_t)n_anc * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->n_clades = n_clades;
+    ctx->max_anc = max_anc;
+    ctx->have_tree = true;
+    return VGL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// hot path
+// -------------------------------------------------------------------------------------------
+int vgl_hc_reset(vgl_ctx* ctx) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(cudaMemsetAsync(ctx->d_cta_node_acc.p, 0, (size_t)ctx->read_cfg.grid * ctx->tab.n_rows * sizeof(double), s));
+    VGL_CUDA(cudaMemsetAsync(ctx->d_cta_a_total.p, 0, (size_t)ctx->read_cfg.grid * sizeof(double), s));
+    VGL_CUDA(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), s));
+    ctx->ev_used = 0;
+    ctx->ll_valid = false;
+    return VGL_OK;
+}
+
+int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* b) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (int rc = check_batch(b)) return rc;
+    vgl::HcBatchDev d{b->n_reads, b->col_off, b->map_off, b->gcol, b->rcol, b->qual, b->map_node, b->map_len, b->n_qual, b->mapq};
+    return launch_read(ctx, d);
+}
+
+int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (int rc = check_batch(b)) return rc;
+    if (b->n_reads == 0) return VGL_OK;
+    const size_t R = b->n_reads;
+    // The staging buffers are reused: wait for the previous pass over them before growing them.
+    if (R + 1 > ctx->s_col_off.cap || b->n_cols > ctx->s_gcol.cap || b->n_maps > ctx->s_map_node.cap)
+        VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (int rc = ctx->s_col_off.reserve(R + 1)) return rc;
+    if (int rc = ctx->s_map_off.reserve(R + 1)) return rc;
+    if (int rc = ctx->s_n_qual.reserve(R)) return rc;
+    if (int rc = ctx->s_mapq.reserve(R)) return rc;
+    if (int rc = ctx->s_gcol.reserve((size_t)b->n_cols + 16)) return rc;
+    if (int rc = ctx->s_rcol.reserve((size_t)b->n_cols + 16)) return rc;
+    if (int rc = ctx->s_qual.reserve((size_t)b->n_cols + 16)) return rc;
+    if (int rc = ctx->s_map_node.reserve((size_t)b->n_maps + 16)) return rc;
+    if (int rc = ctx->s_map_len.reserve((size_t)b->n_maps + 16)) return rc;
+    cudaStream_t s = ctx->stream;
+    if (int rc = upload_async(ctx->s_col_off.p, b->col_off, (R + 1) * 4, s)) return rc;
+    if (int rc = upload_async(ctx->s_map_off.p, b->map_off, (R + 1) * 4, s)) return rc;
+    if (int rc = upload_async(ctx->s_n_qual.p, b->n_qual, R * 2, s)) return rc;
+    if (int rc = upload_async(ctx->s_mapq.p, b->mapq, R, s)) return rc;
+    if (int rc = upload_async(ctx->s_gcol.p, b->gcol, (size_t)b->n_cols, s)) return rc;
+    if (int rc = upload_async(ctx->s_rcol.p, b->rcol, (size_t)b->n_cols, s)) return rc;
+    if (int rc = upload_async(ctx->s_qual.p, b->qual, (size_t)b->n_cols, s)) return rc;
+    if (int rc = upload_async(ctx->s_map_node.p, b->map_node, (size_t)b->n_maps * 4, s)) return rc;
+    if (int rc = upload_async(ctx->s_map_len.p, b->map_len, (size_t)b->n_maps * 2, s)) return rc;
+    vgl::HcBatchDev d{b->n_reads, ctx->s_col_off.p, ctx->s_map_off.p, ctx->s_gcol.p, ctx->s_rcol.p, ctx->s_qual.p,
+                      ctx->s_map_node.p, ctx->s_map_len.p, ctx->s_n_qual.p, ctx->s_mapq.p};
+    return launch_read(ctx, d);
+}
+
+int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(vgl::hc_launch_reduce_ctas(ctx->d_cta_node_acc.p, ctx->d_cta_a_total.p, ctx->read_cfg.grid, ctx->tab.n_rows,
+                                        ctx->n_rows_pad, ctx->d_node_acc.p, ctx->d_a_total.p, s));
+    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_node_acc.p, ctx->d_chunk_ll.p, s));
+    VGL_CUDA(vgl::hc_launch_path_sum(ctx->d_chunk_ll.p, ctx->n_chunks, ctx->tab.n_paths, ctx->d_a_total.p, ctx->d_ll.p, s));
+    ctx->launches += 3;
+    ctx->ll_valid = true;
+    if (ll_dev) VGL_CUDA(cudaMemcpyAsync(ll_dev, ctx->d_ll.p, (size_t)ctx->tab.n_paths * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return VGL_OK;
+}
+
+int vgl_hc_set_paths_from_parts(vgl_ctx* ctx, const double* parts_dev, int32_t n_parts) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!parts_dev || n_parts <= 0) return fail(VGL_ERR_INVALID, "no parts");
+    VGL_CUDA(vgl::hc_launch_sum_parts(parts_dev, n_parts, ctx->tab.n_paths, ctx->d_ll.p, ctx->stream));
+    ctx->launches += 1;
+    ctx->ll_valid = true;
+    return VGL_OK;
+}
+
+int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
+                    int32_t post_cap, int32_t* n_post_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!ctx->ll_valid)
+        if (int rc = vgl_hc_paths(ctx, nullptr)) return rc;
+    cudaStream_t s = ctx->stream;
+    const int P = ctx->tab.n_paths;
+    const int cap = (int)std::min<size_t>(ctx->d_post.cap, (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1));
+    VGL_CUDA(vgl::hc_launch_posterior(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
+                                      ctx->have_tree ? ctx->d_anc_off.p : nullptr,
+                                      ctx->have_tree ? ctx->d_anc_clade.p : nullptr, ctx->d_post.p, cap, ctx->d_scalars.p,
+                                      ctx->d_idx.p, s));
+    ctx->launches += 1;
+    double scalars[2];
+    int32_t idx[2];
+    int err = 0;
+    std::vector<double> post((size_t)cap);
+    VGL_CUDA(cudaMemcpyAsync(scalars, ctx->d_scalars.p, sizeof(scalars), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, sizeof(idx), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(&err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(post.data(), ctx->d_post.p, (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->d_ll.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    if (err & VGL_ERR_BAD_NODE)
+        return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
+    if (argmax_out) *argmax_out = idx[0];
+    if (total_out) *total_out = scalars[0];
+    const int n_post = idx[1];
+    if (n_post_out) *n_post_out = n_post;
+    if (post_out) {
+        if (post_cap < n_post) return fail(VGL_ERR_INVALID, "post_cap %d < %d posteriors", post_cap, n_post);
+        for (int k = 0; k < n_post; ++k) post_out[k] = post[(size_t)k];
+    }
+    return VGL_OK;
+}
+
+int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out) {
+    if (int rc = use_device(ctx)) return rc;
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    float tot = 0.f;
+    for (size_t k = 0; k < ctx->ev_used; ++k) {
+        float ms = 0.f;
+        VGL_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[k].first, ctx->ev_pool[k].second));
+        tot += ms;
+    }
+    if (ms_out) *ms_out = tot;
+    if (launches_out) *launches_out = (int32_t)ctx->ev_used;
+    return VGL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Internal declarations shared by the C-ABI layer (vgl_api.cu) and the kernels (hc_kernels.cu).
+// Not installed; the public surface is include/vgan_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vgan_gpu.h"
+
+namespace vgl {
+
+// Small per-process lookup tables, copied into shared memory by every CTA of the read kernel.
+// Indexed by the RAW quality byte (0..255); bytes >= 128 are negative as `signed char`, which is
+// how the reference sees them (src/update_likelihood.cpp:41).
+struct HcSmallTables {
+    double f_match[256];   // 1 - eps,  eps = qscore[Q]         graph base == read base
+    double f_mis[256];     // 1 - eps,  eps = 1 - qscore[Q]     graph base != read base
+    double log_err[256];   // log(get_p_seq_error(Q))           src/process_mapping.cpp:11
+    double p_correct[100]; // 1 - p_incorrect_map[mapq]         src/process_mapping.cpp:41
+    double bg[4];          // background frequency of A,C,G,T   src/haplocart_functions.cpp:81-97
+    double f_match_bep;    // 1 - bep
+    double f_mis_bep;      // 1 - (1 - bep)
+    double one_minus_bep;  // FASTA mode multiplier              src/process_mapping.cpp:73
+    int32_t is_fasta;
+    int32_t pad;
+    uint8_t base_code[256]; // 'A','C','G','T' -> 0..3, everything else 4 (libgab isValidDNA)
+};
+
+struct HcTablesDev {
+    int32_t n_rows;
+    int32_t n_paths;
+    int32_t n_words;           // number of 32-node words = ceil(n_rows / 32)
+    int32_t n_class;
+    const uint16_t* node_class; // [n_rows]   0xFFFF = node has no pangenome_map entry
+    const double2* class_tab;   // [n_class]  {mappability, match_prob}
+    const HcSmallTables* small;
+    const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
+};
+
+struct HcBatchDev {
+    uint32_t n_reads;
+    const uint32_t* col_off;
+    const uint32_t* map_off;
+    const uint8_t* gcol;
+    const uint8_t* rcol;
+    const uint8_t* qual;
+    const int32_t* map_node;
+    const uint16_t* map_len;
+    const uint16_t* n_qual;
+    const uint8_t* mapq;
+};
+
+// Read kernel launch geometry (one persistent CTA per SM).
+struct HcReadLaunch {
+    int grid;
+    int block;
+    size_t smem;
+};
+
+HcReadLaunch hc_read_launch_config(int n_rows, int sm_count, int max_smem_optin);
+cudaError_t hc_read_configure(size_t smem);
+
+// K1: per-read, per-mapping scalars scattered into per-CTA node accumulators.
+//   cta_node_acc[cta][n_rows]  += sum over this CTA's mappings at node n of (B_i - A_i)
+//   cta_a_total[cta]           += sum over this CTA's mappings of A_i
+cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
+                                  double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
+
+// K2a: fixed-order reduction of the per-CTA accumulators -> node_acc[n_rows_pad], a_total[1].
+cudaError_t hc_launch_reduce_ctas(const double* cta_node_acc, const double* cta_a_total, int n_ctas, int n_rows,
+                                  int n_rows_pad, double* node_acc, double* a_total, cudaStream_t s);
+
+// K2b: bit-GEMV over the node x path membership: chunk_ll[chunk][P].
+int hc_path_chunks(int n_words);
+cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, cudaStream_t s);
+
+// K2c: ll[p] = a_total + sum_chunks chunk_ll[chunk][p]   (fixed order, identical for every p)
+cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths, const double* a_total, double* ll,
+                               cudaStream_t s);
+
+// Multi-GPU: ll[p] = sum_k parts[k][p] in k order.
+cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s);
+
+// K3: argmax (first max wins), log-sum-exp, posterior of the call and of its listed clades.
+//   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post
+cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
+                                const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
+                                double* out_scalars, int32_t* out_idx, cudaStream_t s);
+
+}  // namespace vgl

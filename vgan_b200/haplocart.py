@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference's HaploCart hot-path interface over the C ABI.
+
+The reference's call sites are
+    Haplocart::update(...) per read + `final_vec[j] +=`          src/HaploCart.cpp:408-421
+    std::max_element -> predicted haplotype                       src/HaploCart.cpp:423-424
+    Haplocart::get_posterior(final_vec, path_names, parents, ...) src/get_posterior.cpp:87-127
+`Haplocart` below keeps those names; every method forwards to libvgan_gpu.so (include/vgan_gpu.h).
+There is no CPU path here: construction fails without a CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, gpu
+
+
+class Haplocart:
+    def __init__(self, device=0):
+        self.ctx = C.c_void_p()
+        check(gpu.vgl_create(int(device), C.byref(self.ctx)))
+        self.device = int(device)
+        self.n_paths = 0
+        self.tree = None
+        self.path_names = None
+        self._max_post = 1
+
+    def close(self):
+        if self.ctx:
+            gpu.vgl_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables (reference: loaded once, src/HaploCart.cpp:279-286) -------------------------------
+    def load(self, tables, tree=None, path_names=None):
+        check(gpu.vgl_hc_set_tables(self.ctx, C.byref(tables.view)))
+        self.n_paths = int(tables.n_paths)
+        self.path_names = list(path_names) if path_names is not None else (tree.path_names if tree else None)
+        self.tree = tree
+        if tree is not None:
+            bits = np.ascontiguousarray(tree.clade_bits())
+            check(gpu.vgl_hc_set_tree(self.ctx, tree.n_clades, bits.ctypes.data_as(C.c_void_p),
+                                      tree.anc_off.ctypes.data_as(C.c_void_p),
+                                      tree.anc_clade.ctypes.data_as(C.c_void_p) if tree.anc_clade.size else
+                                      np.zeros(1, np.int32).ctypes.data_as(C.c_void_p)))
+            self._max_post = 1 + int(np.max(np.diff(tree.anc_off))) if tree.anc_off.size > 1 else 1
+
+    def set_stream(self, cuda_stream_ptr):
+        check(gpu.vgl_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    # ---- per-sample hot loop ------------------------------------------------------------------------
+    def reset(self):
+        """fill(final_vec, 0) -- start of a sample (src/HaploCart.cpp:481)."""
+        check(gpu.vgl_hc_reset(self.ctx))
+
+    def update(self, packed):
+        """Haplocart::update for every read of a packed host batch, summed into final_vec."""
+        check(gpu.vgl_hc_accumulate(self.ctx, C.byref(packed.batch)))
+
+    def update_device(self, batch_struct):
+        """Same, for a batch whose arrays already live in HBM (a `_lib.vgl_hc_batch` of device pointers)."""
+        check(gpu.vgl_hc_accumulate_device(self.ctx, C.byref(batch_struct)))
+
+    def paths(self, ll_dev_ptr=None):
+        """Collapse into this GPU's final_vec[P] on the device (optionally copied to `ll_dev_ptr`)."""
+        check(gpu.vgl_hc_paths(self.ctx, C.c_void_p(ll_dev_ptr) if ll_dev_ptr else None))
+
+    def set_paths_from_parts(self, parts_dev_ptr, n_parts):
+        check(gpu.vgl_hc_set_paths_from_parts(self.ctx, C.c_void_p(parts_dev_ptr), int(n_parts)))
+
+    def get_posterior(self, want_ll=True):
+        """argmax + Haplocart::get_posterior.  Returns a dict with final_vec, the call and its clade posteriors."""
+        ll = np.zeros(self.n_paths, dtype=np.float64) if want_ll else None
+        arg, npost, total = C.c_int32(), C.c_int32(), C.c_double()
+        post = np.zeros(max(self._max_post, 1), dtype=np.float64)
+        check(gpu.vgl_hc_finalize(self.ctx, ll.ctypes.data_as(C.c_void_p) if want_ll else None, C.byref(arg),
+                                  C.byref(total), post.ctypes.data_as(C.c_void_p), post.size, C.byref(npost)))
+        res = {"final_vec": ll, "maxh_index": arg.value, "total_ll": total.value,
+               "confidence_vec": post[:npost.value].copy()}
+        if self.path_names is not None:
+            res["predicted_haplotype"] = self.path_names[arg.value]
+            if self.tree is not None:
+                res["clade_vec"] = [res["predicted_haplotype"]] + self.tree.clades_of(arg.value)
+        return res
+
+    def run_sample(self, batches, want_ll=True):
+        """One sample end to end: reset, update over the packed host batches, posterior."""
+        self.reset()
+        for b in batches:
+            self.update(b)
+        return self.get_posterior(want_ll=want_ll)
+
+    # ---- instrumentation ----------------------------------------------------------------------------
+    def synchronize(self):
+        check(gpu.vgl_synchronize(self.ctx))
+
+    def launch_count(self):
+        return int(gpu.vgl_launch_count(self.ctx))
+
+    def read_kernel_ms(self):
+        ms, n = C.c_float(), C.c_int32()
+        check(gpu.vgl_hc_read_kernel_ms(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ---- device-resident batches --------------------------------------------------------------------
+    def upload(self, packed):
+        """Copy a packed host batch into HBM once; returns a DeviceBatch usable with update_device."""
+        return DeviceBatch(self, packed)
+
+
+class DeviceBatch:
+    _FIELDS = [("col_off", 4, "r1"), ("map_off", 4, "r1"), ("gcol", 1, "c"), ("rcol", 1, "c"), ("qual", 1, "c"),
+               ("map_node", 4, "m"), ("map_len", 2, "m"), ("n_qual", 2, "r"), ("mapq", 1, "r")]
+
+    def __init__(self, hc, packed):
+        self.hc = hc
+        b = packed.batch
+        counts = {"r": int(b.n_reads), "r1": int(b.n_reads) + 1, "c": int(b.n_cols), "m": int(b.n_maps)}
+        self.batch = _lib.vgl_hc_batch()
+        self.batch.n_reads, self.batch.n_cols, self.batch.n_maps = b.n_reads, b.n_cols, b.n_maps
+        self.ptrs = []
+        self.nbytes = 0
+        for name, size, kind in self._FIELDS:
+            n = counts[kind] * size
+            p = C.c_void_p()
+            check(gpu.vgl_device_alloc(hc.ctx, C.byref(p), n + 16))
+            self.ptrs.append(p)
+            if n:
+                check(gpu.vgl_memcpy_h2d(hc.ctx, p, C.c_void_p(getattr(b, name)), n))
+            setattr(self.batch, name, p.value)
+            self.nbytes += n
+
+    def free(self):
+        for p in self.ptrs:
+            gpu.vgl_device_free(self.hc.ctx, p)
+        self.ptrs = []
+
+    def __del__(self):
+        try:
+            if self.hc.ctx:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,251 @@
+"""Python handles over libvgan_host.so (include/vgan_host.h): graph sequences, GAM alignments,
+alignment reconstruction, the SoA batch packer, HaploCart tables, the haplogroup tree and the
+synthetic workload generator.  All work happens in the C++ library; this file only owns handles."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, host
+
+
+def _as_array(ptr, n, dtype):
+    """Copy n items of dtype from a raw pointer into a numpy array."""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr if isinstance(ptr, int) else ptr.value)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class Graph:
+    """Node sequences with contiguous ids (what the hot path asks of bdsg::ODGI::get_sequence)."""
+
+    def __init__(self, handle, owner=None):
+        self.handle = handle
+        self._owner = owner  # keeps a synth object alive when the graph belongs to it
+
+    @classmethod
+    def from_sequences(cls, node_seqs, min_id=None):
+        if isinstance(node_seqs, dict):
+            ids = sorted(node_seqs)
+            min_id = ids[0] if min_id is None else min_id
+            seqs = [node_seqs.get(i, "") for i in range(min_id, ids[-1] + 1)]
+        else:
+            seqs = list(node_seqs)
+            min_id = 1 if min_id is None else min_id
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+        blob = "".join(seqs).encode()
+        h = C.c_void_p()
+        check(host.vgh_graph_create(int(min_id), len(seqs), off.ctypes.data_as(C.c_void_p), blob, C.byref(h)))
+        g = cls(h)
+        g._owned = True
+        return g
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self.handle:
+            host.vgh_graph_destroy(self.handle)
+            self.handle = None
+
+
+class Alignments:
+    """A set of alignments held by the C++ library (from a GAM stream or the synthetic generator)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+        self.view = host.vgh_gam_view(handle).contents
+
+    @classmethod
+    def from_gam_file(cls, path, drop_unmapped=True):
+        h = C.c_void_p()
+        check(host.vgh_gam_read_file(str(path).encode(), int(drop_unmapped), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_gam_bytes(cls, data, drop_unmapped=True):
+        h = C.c_void_p()
+        check(host.vgh_gam_parse(data, len(data), int(drop_unmapped), C.byref(h)))
+        return cls(h)
+
+    def __len__(self):
+        return int(self.view.n_reads)
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_gam_destroy(self.handle)
+            self.handle = None
+
+    def arrays(self):
+        """The flat arrays as numpy copies (used by tests to hand the same reads to the oracle)."""
+        v = self.view
+        n = int(v.n_reads)
+        seq_off = _as_array(v.seq_off, n + 1, np.int64)
+        qual_off = _as_array(v.qual_off, n + 1, np.int64)
+        map_off = _as_array(v.map_off, n + 1, np.int64)
+        nm = int(map_off[-1]) if n else 0
+        edit_off = _as_array(v.edit_off, nm + 1, np.int64)
+        ne = int(edit_off[-1]) if nm else 0
+        edit_seq_off = _as_array(v.edit_seq_off, ne + 1, np.int64)
+        return {
+            "n_reads": n,
+            "seq_off": seq_off, "seq": _as_array(v.seq, int(seq_off[-1]), np.uint8),
+            "qual_off": qual_off, "qual": _as_array(v.qual, int(qual_off[-1]), np.uint8),
+            "mapq": _as_array(v.mapq, n, np.int32), "identity": _as_array(v.identity, n, np.float64),
+            "paired": _as_array(v.paired, n, np.uint8),
+            "map_off": map_off, "map_node": _as_array(v.map_node, nm, np.int64),
+            "map_offset": _as_array(v.map_offset, nm, np.int64), "map_rev": _as_array(v.map_rev, nm, np.uint8),
+            "edit_off": edit_off, "edit_from": _as_array(v.edit_from, ne, np.int32),
+            "edit_to": _as_array(v.edit_to, ne, np.int32), "edit_seq_off": edit_seq_off,
+            "edit_seq": _as_array(v.edit_seq, int(edit_seq_off[-1]) if ne else 0, np.uint8),
+        }
+
+
+def reconstruct(graph, alns, r, cap=8192):
+    """reconstruct_graph_sequence of read r -> (graph_seq, read_seq, sizes) (reference src/vgan_utils.h:6-79)."""
+    g = np.zeros(cap, dtype=np.uint8)
+    p = np.zeros(cap, dtype=np.uint8)
+    s = np.zeros(cap, dtype=np.int32)
+    ng, npp, ns = C.c_int32(), C.c_int32(), C.c_int32()
+    check(host.vgh_reconstruct(graph.handle, C.byref(alns.view), int(r), g.ctypes.data_as(C.c_void_p),
+                               p.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), cap, C.byref(ng),
+                               C.byref(npp), C.byref(ns)))
+    return g[:ng.value].tobytes().decode(), p[:npp.value].tobytes().decode(), s[:ns.value].tolist()
+
+
+class PackedBatch:
+    """One vgl_hc_batch in host memory (pinned when asked)."""
+
+    def __init__(self, graph, alns, r0=0, r1=None, n_threads=0, pinned=False):
+        r1 = len(alns) if r1 is None else r1
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_pack(graph.handle, C.byref(alns.view), int(r0), int(r1), int(n_threads), int(pinned),
+                               C.byref(self.handle)))
+        self.batch = host.vgh_hc_packed_batch(self.handle).contents
+        self.skipped = int(host.vgh_hc_packed_skipped(self.handle))
+
+    @property
+    def n_reads(self):
+        return int(self.batch.n_reads)
+
+    @property
+    def nbytes(self):
+        return int(_lib.gpu.vgl_hc_batch_bytes(C.byref(self.batch)))
+
+    def arrays(self):
+        b = self.batch
+        R, nc, nm = int(b.n_reads), int(b.n_cols), int(b.n_maps)
+        return {
+            "col_off": _as_array(b.col_off, R + 1, np.uint32), "map_off": _as_array(b.map_off, R + 1, np.uint32),
+            "gcol": _as_array(b.gcol, nc, np.uint8), "rcol": _as_array(b.rcol, nc, np.uint8),
+            "qual": _as_array(b.qual, nc, np.uint8), "map_node": _as_array(b.map_node, nm, np.int32),
+            "map_len": _as_array(b.map_len, nm, np.uint16), "n_qual": _as_array(b.n_qual, R, np.uint16),
+            "mapq": _as_array(b.mapq, R, np.uint8),
+        }
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_hc_packed_destroy(self.handle)
+            self.handle = None
+
+
+class HcTables:
+    """HaploCart tables in the form vgl_hc_set_tables wants, built from the reference's in-memory inputs."""
+
+    def __init__(self, supports, pmap_node, pmap_val, mappab, bep=1e-4, is_fasta=False):
+        supports = np.ascontiguousarray(supports, dtype=np.uint8)
+        pmap_node = np.ascontiguousarray(pmap_node, dtype=np.int64)
+        pmap_val = np.ascontiguousarray(pmap_val, dtype=np.int32)
+        mappab = np.ascontiguousarray(mappab, dtype=np.float64)
+        self.n_rows, self.n_paths = supports.shape
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_tables_build(self.n_rows, self.n_paths, supports.ctypes.data_as(C.c_void_p), pmap_node.size,
+                                       pmap_node.ctypes.data_as(C.c_void_p), pmap_val.ctypes.data_as(C.c_void_p),
+                                       mappab.size, mappab.ctypes.data_as(C.c_void_p), float(bep), int(bool(is_fasta)),
+                                       C.byref(self.handle)))
+        self.view = host.vgh_hc_tables_view(self.handle).contents
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_hc_tables_destroy(self.handle)
+            self.handle = None
+
+
+class HcTree:
+    def __init__(self, path_names, parents_txt, children_txt):
+        self.path_names = list(path_names)
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_tree_build(len(self.path_names), ("\n".join(self.path_names)).encode(), parents_txt.encode(),
+                                     children_txt.encode(), C.byref(self.handle)))
+        self.n_clades = int(host.vgh_hc_tree_n_clades(self.handle))
+        self.row_words = int(host.vgh_hc_tree_row_words(self.handle))
+        self.anc_off = _as_array(host.vgh_hc_tree_anc_off(self.handle), len(self.path_names) + 1, np.int32)
+        self.anc_clade = _as_array(host.vgh_hc_tree_anc_clade(self.handle), int(self.anc_off[-1]), np.int32)
+
+    def clade_bits(self):
+        return _as_array(host.vgh_hc_tree_clade_bits(self.handle), max(self.n_clades, 1) * self.row_words,
+                         np.uint32).reshape(max(self.n_clades, 1), self.row_words)
+
+    def clade_name(self, c):
+        return host.vgh_hc_tree_clade_name(self.handle, int(c)).decode()
+
+    def clades_of(self, path_idx):
+        """Names of the clades reported for a call of `path_idx` (reference clade_vec[1:], get_posterior.cpp:109-112)."""
+        a, b = int(self.anc_off[path_idx]), int(self.anc_off[path_idx + 1])
+        return [self.clade_name(c) for c in self.anc_clade[a:b]]
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_hc_tree_destroy(self.handle)
+            self.handle = None
+
+
+class SynthHaplocart:
+    """Synthetic HaploCart-shaped tables + graph (11825 rows x 5179 paths, 11821 nodes)."""
+
+    def __init__(self, seed=20260, n_paths=5179, n_rows=11825, n_nodes=11821):
+        self.n_paths, self.n_rows, self.n_nodes = n_paths, n_rows, n_nodes
+        self.handle = C.c_void_p()
+        check(host.vgh_synth_hc_create(int(seed), n_paths, n_rows, n_nodes, C.byref(self.handle)))
+        self.graph = Graph(C.c_void_p(host.vgh_synth_hc_graph(self.handle)), owner=self)
+        self.total_len = int(host.vgh_synth_hc_total_len(self.handle))
+        self.path_names = host.vgh_synth_hc_names(self.handle).decode().split("\n")[:-1]
+        self.parents_txt = host.vgh_synth_hc_parents(self.handle).decode()
+        self.children_txt = host.vgh_synth_hc_children(self.handle).decode()
+
+    # the reference's in-memory inputs, as numpy copies
+    def supports(self):
+        return _as_array(host.vgh_synth_hc_supports(self.handle), self.n_rows * self.n_paths,
+                         np.uint8).reshape(self.n_rows, self.n_paths)
+
+    def pmap(self):
+        n = int(host.vgh_synth_hc_n_pmap(self.handle))
+        return (_as_array(host.vgh_synth_hc_pmap_node(self.handle), n, np.int64),
+                _as_array(host.vgh_synth_hc_pmap_val(self.handle), n, np.int32))
+
+    def mappab(self):
+        return _as_array(host.vgh_synth_hc_mappab(self.handle), int(host.vgh_synth_hc_n_mappab(self.handle)), np.float64)
+
+    def node_sequences(self):
+        off, seq = C.c_void_p(), C.c_void_p()
+        n = int(host.vgh_synth_hc_graph_seq(self.handle, C.byref(off), C.byref(seq)))
+        offs = _as_array(off, n + 1, np.int64)
+        blob = _as_array(seq, int(offs[-1]), np.uint8).tobytes().decode()
+        return [blob[offs[i]:offs[i + 1]] for i in range(n)]
+
+    def tables(self, bep=1e-4, is_fasta=False):
+        node, val = self.pmap()
+        return HcTables(self.supports(), node, val, self.mappab(), bep=bep, is_fasta=is_fasta)
+
+    def tree(self):
+        return HcTree(self.path_names, self.parents_txt, self.children_txt)
+
+    def reads(self, n_reads, seed=20261, fixed_len=100, sub_rate=0.005, indel_rate=0.0005, damage=False, origin_path=-1):
+        h = C.c_void_p()
+        check(host.vgh_synth_hc_reads(self.handle, int(seed), int(n_reads), int(fixed_len), float(sub_rate),
+                                      float(indel_rate), int(bool(damage)), int(origin_path), C.byref(h)))
+        return Alignments(h)
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_synth_hc_destroy(self.handle)
+            self.handle = None
