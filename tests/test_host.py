@@ -1,0 +1,249 @@
+"""CPU tests of the C++ host side (libvgan_host.so) and of the C-ABI surface.  No GPU compute here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import vgan_b200 as vb
+from vgan_b200 import _lib
+from oracle import oracle as orc
+
+import helpers as H
+
+FIXTURES = ["test_reads.gam", "J2a1a1a1.gam", "all_the_same.gam", "all_the_same_reverse.gam", "two_unique.gam"]
+
+
+def _flat_equal(arrays, alns):
+    """Compare the product's flat arrays with a list of alignment dicts."""
+    ref = orc.Reads(alns)
+    n = len(alns)
+    assert arrays["n_reads"] == n
+    for k in ("seq_off", "qual_off", "map_off", "edit_off", "edit_seq_off"):
+        assert np.array_equal(arrays[k], getattr(ref, k)), k
+    nm, ne = int(ref.map_off[-1]), int(ref.edit_off[-1])
+    assert np.array_equal(arrays["seq"], ref.seq[:-1]) and np.array_equal(arrays["qual"], ref.qual[:-1])
+    assert np.array_equal(arrays["mapq"], ref.mapq) and np.array_equal(arrays["identity"], ref.identity)
+    assert np.array_equal(arrays["map_node"], ref.map_node[:nm]) and np.array_equal(arrays["map_offset"], ref.map_offset[:nm])
+    assert np.array_equal(arrays["map_rev"], ref.map_rev[:nm])
+    assert np.array_equal(arrays["edit_from"], ref.edit_from[:ne]) and np.array_equal(arrays["edit_to"], ref.edit_to[:ne])
+    assert np.array_equal(arrays["edit_seq"], ref.edit_seq[:-1])
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_gam_reader_on_reference_fixtures(name):
+    a = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, name))
+    _flat_equal(a.arrays(), H.decoded_fixture(name))
+
+
+def test_gam_reader_drops_identity_zero_and_skips_empty_groups():
+    alns = [H.aln("ACGT", [(5, 0, False, [(4, 4, "")])], identity=0.0),
+            H.aln("AATA", [(5, 0, False, [(4, 4, "")])], identity=0.5)]
+    raw = H.encode_gam(alns[:1]) + bytes([1, 3]) + b"GAM" + H.encode_gam(alns[1:])
+    a = vb.Alignments.from_gam_bytes(raw)
+    assert len(a) == 1 and a.arrays()["seq"].tobytes() == b"AATA"   # readGAM keeps identity != 0 only
+    assert len(vb.Alignments.from_gam_bytes(raw, drop_unmapped=False)) == 2
+    with pytest.raises(_lib.VglError):
+        vb.Alignments.from_gam_bytes(raw[:-3])
+
+
+def test_reconstruct_known_answers():
+    kat = json.load(open(os.path.join(H.GOLDEN, "reconstruct_kat.json")))["cases"]
+    nodes, _ = H.toy_graph()
+    g = vb.Graph.from_sequences(nodes)
+    a = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "test_reads.gam"))
+    for case in kat:
+        gs, rs, sizes = vb.reconstruct(g, a, case["read_index"])
+        assert (gs, rs) == (case["graph_seq"], case["read_seq"]), case["case"]
+
+
+def test_reconstruct_matches_oracle_on_synthetic_reads_with_indels():
+    S = vb.SynthHaplocart(seed=11, n_paths=40, n_rows=310, n_nodes=301)
+    A = S.reads(400, seed=12, sub_rate=0.03, indel_rate=0.02, damage=True, fixed_len=0)
+    R = orc.FlatReads(A.arrays())
+    og = orc.Graph(S.node_sequences(), min_id=1)
+    kinds = set()
+    for r in range(len(A)):
+        want = orc.reconstruct(og, R, r)
+        assert vb.reconstruct(S.graph, A, r) == want
+        kinds |= set(want[0]) | set(want[1])
+    assert {"-", "S"} <= kinds  # deletions, insertions and the offset-0 "softclip" quirk all occurred
+
+
+def test_reconstruct_unrecognised_edit_repeats_previous_size():
+    # an edit with from != to (both > 0) matches no branch of the reference: nothing is appended and the
+    # previous aligned_length of the same mapping is pushed again (src/vgan_utils.h:26,72)
+    nodes, _ = H.toy_graph()
+    alns = [H.aln("GCTACGA", [(9, 0, False, [(4, 4, ""), (2, 3, "CGA")])])]
+    a = vb.Alignments.from_gam_bytes(H.encode_gam(alns))
+    got = vb.reconstruct(vb.Graph.from_sequences(nodes), a, 0)
+    assert got == orc.reconstruct(orc.Graph(nodes), orc.Reads(alns), 0)
+    assert got[2] == [4, 4]
+
+
+def _repack_with_oracle(og, R, arrays):
+    """What the packed batch must contain, derived from the oracle's reconstruction."""
+    keep = [r for r in range(arrays["n_reads"]) if not arrays["identity"][r] < 1e-10]
+    g, p, q, ln, nodes, nq, mq = [], [], [], [], [], [], []
+    for r in keep:
+        gs, rs, sizes = orc.reconstruct(og, R, r)
+        M = int(arrays["map_off"][r + 1] - arrays["map_off"][r])
+        qual = arrays["qual"][arrays["qual_off"][r]:arrays["qual_off"][r + 1]]
+        g.append(gs); p.append(rs)
+        q.append(bytes(qual) + bytes(len(rs) - len(qual)))
+        ln += sizes[:M]
+        nodes += arrays["map_node"][arrays["map_off"][r]:arrays["map_off"][r + 1]].tolist()
+        nq.append(len(qual)); mq.append(int(arrays["mapq"][r]))
+    return "".join(g), "".join(p), b"".join(q), ln, nodes, nq, mq, keep
+
+
+def test_packer_against_oracle_reconstruction():
+    S = vb.SynthHaplocart(seed=21, n_paths=33, n_rows=310, n_nodes=301)
+    A = S.reads(300, seed=22, sub_rate=0.02, indel_rate=0.01)
+    arrays = A.arrays()
+    R = orc.FlatReads(arrays)
+    og = orc.Graph(S.node_sequences(), min_id=1)
+    pb = vb.PackedBatch(S.graph, A, n_threads=3)
+    b = pb.arrays()
+    g, p, q, ln, nodes, nq, mq, keep = _repack_with_oracle(og, orc.FlatReads(A.arrays()), A.arrays())
+    assert pb.n_reads == len(keep) and pb.skipped == len(A) - len(keep)
+    assert b["gcol"].tobytes().decode() == g and b["rcol"].tobytes().decode() == p and b["qual"].tobytes() == q
+    assert b["map_len"].tolist() == ln and b["map_node"].tolist() == nodes
+    assert b["n_qual"].tolist() == nq and b["mapq"].tolist() == mq
+    assert np.array_equal(np.diff(b["col_off"].astype(np.int64)), [len(orc.reconstruct(og, R, r)[1]) for r in keep])
+    # a sub-range packs the same bytes
+    pb2 = vb.PackedBatch(S.graph, A, r0=100, r1=200)
+    c0, c1 = b["col_off"][np.searchsorted(keep, 100)], b["col_off"][np.searchsorted(keep, 200)]
+    assert pb2.arrays()["gcol"].tobytes() == b["gcol"][c0:c1].tobytes()
+    assert pb.nbytes == (pb.n_reads + 1) * 8 + 3 * len(g) + 6 * len(ln) + 3 * pb.n_reads
+
+
+def test_packer_rejects_what_the_reference_cannot_process():
+    nodes, _ = H.toy_graph()
+    g = vb.Graph.from_sequences(nodes)
+    cases = {
+        "mapping without edits": H.aln("ACGT", [(9, 0, False, [(4, 4, "")]), (10, 0, False, [])]),
+        "node outside the graph": H.aln("ACGT", [(999, 0, False, [(4, 4, "")])]),
+        "offset beyond the node": H.aln("ACGT", [(10, 5, False, [(1, 1, "")])]),
+        "mapping quality out of range": H.aln("GCTA", [(9, 0, False, [(4, 4, "")])], mapq=100),
+        "quality longer than the alignment": H.aln("GCTA", [(9, 0, False, [(4, 4, "")])], quality=bytes([30] * 9)),
+        "substitution shorter than its span": H.aln("GCTA", [(9, 0, False, [(4, 4, "GC")])]),
+    }
+    for why, bad in cases.items():
+        a = vb.Alignments.from_gam_bytes(H.encode_gam([bad]))
+        with pytest.raises(_lib.VglError):
+            vb.PackedBatch(g, a)
+    ok = vb.PackedBatch(g, vb.Alignments.from_gam_bytes(H.encode_gam([H.aln("GCTA", [(9, 0, False, [(4, 4, "")])])])))
+    assert ok.n_reads == 1
+    empty = vb.PackedBatch(g, vb.Alignments.from_gam_bytes(b""))
+    assert empty.n_reads == 0
+
+
+def test_tables_match_oracle_tables():
+    S = vb.SynthHaplocart(seed=31, n_paths=70, n_rows=310, n_nodes=301)
+    T = S.tables(bep=2e-4)
+    v = T.view
+    assert np.array_equal(np.array(v.qscore[:]), orc.qscore_vec())
+    assert np.array_equal(np.array(v.p_incorrect_map[:]), orc.incorrect_mapping_vec())
+    assert [orc.lib().orc_hc_background_freq(C.c_char(b)) for b in b"ACGT"] == list(v.bg_freq[:])
+    for pb in list(range(0, 17000, 7)) + [56, 57, 372, 373, 576, 577, 16383, 16384, 16569, 16570]:
+        assert _lib.host.vgh_hc_region_match_prob(pb) == orc.region_match_prob(pb), pb
+    sup = S.supports()
+    bits = vb.host._as_array(v.support_bits, v.n_rows * v.row_words, np.uint32).reshape(v.n_rows, v.row_words)
+    unpacked = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(v.n_rows, -1)[:, :v.n_paths]
+    assert np.array_equal(unpacked, sup)
+    node, val = S.pmap()
+    mapp = S.mappab()
+    nm = vb.host._as_array(v.node_mappability, v.n_rows, np.float64)
+    nk = vb.host._as_array(v.node_match_prob, v.n_rows, np.float64)
+    valid = vb.host._as_array(v.node_valid, v.n_rows, np.uint8)
+    assert valid.sum() == len(set(node.tolist()))
+    for n, pb in zip(node, val):
+        assert nm[n] == mapp[pb] and nk[n] == orc.region_match_prob(int(pb))
+
+
+def test_tree_builder_against_plain_python():
+    S = vb.SynthHaplocart(seed=41, n_paths=150, n_rows=310, n_nodes=301)
+    tr = S.tree()
+
+    def rel(txt):
+        out = {}
+        for line in txt.split("\n"):
+            t = line.split()
+            if t and t[0] not in out:
+                out[t[0]] = [x for x in t[1:] if "[" not in x]
+        return out
+    parents, children = rel(S.parents_txt), rel(S.children_txt)
+    col = {n: i for i, n in enumerate(S.path_names)}
+    bits = tr.clade_bits()
+    for p, name in enumerate(S.path_names):
+        pv = parents.get(name, [])
+        want = [x for j, x in enumerate(pv) if j == 0 or x != pv[j - 1]]
+        assert tr.clades_of(p) == want
+    for c in range(tr.n_clades):
+        desc, level = set(), {tr.clade_name(c)}
+        while level:
+            nxt = {k for x in level for k in children.get(x, [])}
+            desc |= nxt
+            level = nxt
+        want = np.zeros(len(S.path_names), dtype=bool)
+        for d in desc:
+            if d in col:
+                want[col[d]] = True
+        got = ((bits[c][:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:len(S.path_names)].astype(bool)
+        assert np.array_equal(got, want), tr.clade_name(c)
+    assert "mt-MRCA" in [tr.clade_name(c) for c in range(tr.n_clades)]
+
+
+def test_synthetic_generator_shapes_and_determinism():
+    S = vb.SynthHaplocart()  # config 2 shapes
+    assert (S.n_rows, S.n_paths, S.n_nodes) == (11825, 5179, 11821)      # reference src/test.cpp:605-655
+    seqs = S.node_sequences()
+    assert len(seqs) == 11821 and max(map(len, seqs)) <= 8 and 15000 < S.total_len < 18500
+    sup = S.supports()
+    assert sup.shape == (11825, 5179) and sup[0].sum() == 0 and sup[11822:].sum() == 0
+    a1 = S.reads(2000, seed=5).arrays()
+    a2 = vb.SynthHaplocart().reads(2000, seed=5).arrays()
+    assert all(np.array_equal(a1[k], a2[k]) for k in a1 if k != "n_reads")
+    nm = np.diff(a1["map_off"])
+    assert 40 < nm.mean() < 56 and set(np.unique(a1["mapq"])) <= {0, 1, 3, 60}
+    # every read walks a real path: its nodes are all supported by at least one common path
+    r = 17
+    nodes = a1["map_node"][a1["map_off"][r]:a1["map_off"][r + 1]]
+    assert sup[nodes].all(axis=0).any()
+
+
+def _declared(header):
+    txt = open(os.path.join(os.path.dirname(H.GOLDEN), "..", "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vg[lh]_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_libraries_export_every_declared_symbol():
+    for header, lib, table in (("vgan_gpu.h", _lib.gpu, _lib.GPU_SYMBOLS), ("vgan_host.h", _lib.host, _lib.HOST_SYMBOLS)):
+        names = _declared(header)
+        assert len(names) > 10
+        for n in names:
+            assert hasattr(lib, n), "%s declared in %s but not exported" % (n, header)
+            assert n in table, "%s has no ctypes signature" % n
+    assert _lib.gpu.vgl_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.VglError) as ei:
+        vb.Haplocart(device=0)
+    assert ei.value.code == 6  # VGL_ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(H.GOLDEN), "..", "vgan_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "vgan_oracle" not in txt, f

@@ -14,6 +14,9 @@
 #include <vector>
 
 #include "host_internal.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -255,15 +258,31 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
     if (!S || !out || n_reads < 0) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
     static const double k5p[5] = {0.329405, 0.221745, 0.187678, 0.161196, 0.144011};  // C>T column of dhigh5p.prof
     static const double k3p[5] = {0.32891, 0.223405, 0.188599, 0.164419, 0.146352};   // G>A column of dhigh3p.prof
-    Rng rng(seed);
-    vgh_gam* G = new vgh_gam();
     const int n_sites = (int)S->site_ref.size();
     struct Piece { int32_t node; bool rev; int32_t off, len; };
+#ifdef _OPENMP
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(omp_get_max_threads(), n_reads / 2048 + 1));
+#else
+    const int n_threads = 1;
+#endif
+    std::vector<vgh_gam*> parts((size_t)n_threads, nullptr);
+#pragma omp parallel num_threads(n_threads)
+    {
+#ifdef _OPENMP
+    const int tid = omp_get_thread_num();
+#else
+    const int tid = 0;
+#endif
+    const int64_t r_begin = n_reads * tid / n_threads, r_end = n_reads * (tid + 1) / n_threads;
+    vgh_gam* G = new vgh_gam();
+    parts[(size_t)tid] = G;
     std::vector<Piece> walk;
     std::string gseq, rseq, qual;
     std::vector<uint8_t> op;  // per graph base: 0 match, 1 substitution, 2 deleted
-    std::vector<std::string> ins_before;
-    for (int64_t r = 0; r < n_reads; ++r) {
+    std::vector<uint8_t> ins_len;     // inserted read bases in front of graph base j (0..3)
+    std::vector<char> ins_bases;      // [n][3]
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        Rng rng(seed * 0x9e3779b97f4a7c15ull + (uint64_t)r * 0xd1342543de82ef95ull + 1);  // one stream per read: thread-count independent
         const int p = origin_path >= 0 ? origin_path % S->n_paths : (int)rng.below((uint64_t)S->n_paths);
         int L = fixed_len;
         if (L <= 0) {
@@ -291,14 +310,16 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
             for (int j = 0; j < w.len; ++j) gseq.push_back(S->graph.base(w.node, w.rev, w.off + j));
         const int n = (int)gseq.size();
         op.assign((size_t)n, 0);
-        ins_before.assign((size_t)n, std::string());
+        ins_len.assign((size_t)n, 0);
+        ins_bases.resize((size_t)n * 3);
         std::string bases = gseq;
         for (int j = 0; j < n; ++j) {
             if (rng.uniform() < sub_rate) bases[(size_t)j] = other_base(rng, gseq[(size_t)j]);
             if (j > 0 && j < n - 1 && rng.uniform() < indel_rate) {
                 if (rng.uniform() < 0.5) {
                     const int k = 1 + (int)rng.below(3);
-                    for (int t = 0; t < k; ++t) ins_before[(size_t)j].push_back(kBases[rng.below(4)]);
+                    ins_len[(size_t)j] = (uint8_t)k;
+                    for (int t = 0; t < k; ++t) ins_bases[(size_t)j * 3 + t] = kBases[rng.below(4)];
                 } else {
                     op[(size_t)j] = 2;
                 }
@@ -329,19 +350,19 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
             G->map_rev.push_back(w.rev ? 1 : 0);
             const int end = j + w.len;
             while (j < end) {
-                if (!ins_before[(size_t)j].empty()) {
-                    const std::string& ins = ins_before[(size_t)j];
+                if (ins_len[(size_t)j]) {
+                    const int k = ins_len[(size_t)j];
                     G->edit_from.push_back(0);
-                    G->edit_to.push_back((int32_t)ins.size());
-                    G->edit_seq += ins;
+                    G->edit_to.push_back(k);
+                    G->edit_seq.append(&ins_bases[(size_t)j * 3], (size_t)k);
                     G->edit_seq_off.push_back((int64_t)G->edit_seq.size());
-                    rseq += ins;
-                    ins_before[(size_t)j].clear();
+                    rseq.append(&ins_bases[(size_t)j * 3], (size_t)k);
+                    ins_len[(size_t)j] = 0;
                     continue;
                 }
                 const uint8_t kind = op[(size_t)j];
                 int e = j + 1;
-                while (e < end && op[(size_t)e] == kind && ins_before[(size_t)e].empty()) ++e;
+                while (e < end && op[(size_t)e] == kind && !ins_len[(size_t)e]) ++e;
                 const int len = e - j;
                 if (kind == 2) {
                     G->edit_from.push_back(len);
@@ -365,6 +386,29 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
         G->identity.push_back(rng.uniform() < 0.001 ? 0.0 : 1.0);  // a few "unmapped" reads the hot loop must skip
         G->paired.push_back(0);
         G->map_off.push_back((int64_t)G->map_node.size());
+    }
+    }  // omp parallel
+    // concatenate the per-thread pieces in read order
+    vgh_gam* G = parts[0];
+    for (int t = 1; t < n_threads; ++t) {
+        vgh_gam* Q = parts[(size_t)t];
+        const int64_t s0 = (int64_t)G->seq.size(), q0 = (int64_t)G->qual.size(), m0 = (int64_t)G->map_node.size();
+        const int64_t e0 = (int64_t)G->edit_from.size(), es0 = (int64_t)G->edit_seq.size();
+        G->seq += Q->seq; G->qual += Q->qual; G->edit_seq += Q->edit_seq;
+        for (size_t k = 1; k < Q->seq_off.size(); ++k) G->seq_off.push_back(Q->seq_off[k] + s0);
+        for (size_t k = 1; k < Q->qual_off.size(); ++k) G->qual_off.push_back(Q->qual_off[k] + q0);
+        for (size_t k = 1; k < Q->map_off.size(); ++k) G->map_off.push_back(Q->map_off[k] + m0);
+        for (size_t k = 1; k < Q->edit_off.size(); ++k) G->edit_off.push_back(Q->edit_off[k] + e0);
+        for (size_t k = 1; k < Q->edit_seq_off.size(); ++k) G->edit_seq_off.push_back(Q->edit_seq_off[k] + es0);
+        G->mapq.insert(G->mapq.end(), Q->mapq.begin(), Q->mapq.end());
+        G->identity.insert(G->identity.end(), Q->identity.begin(), Q->identity.end());
+        G->paired.insert(G->paired.end(), Q->paired.begin(), Q->paired.end());
+        G->map_node.insert(G->map_node.end(), Q->map_node.begin(), Q->map_node.end());
+        G->map_offset.insert(G->map_offset.end(), Q->map_offset.begin(), Q->map_offset.end());
+        G->map_rev.insert(G->map_rev.end(), Q->map_rev.begin(), Q->map_rev.end());
+        G->edit_from.insert(G->edit_from.end(), Q->edit_from.begin(), Q->edit_from.end());
+        G->edit_to.insert(G->edit_to.end(), Q->edit_to.begin(), Q->edit_to.end());
+        delete Q;
     }
     G->finish();
     *out = G;
