@@ -115,26 +115,47 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
                     const int32_t* anc_clade);
 
 /* ------------------------------------------------------------------------------------------- */
-/* HaploCart read batch (SoA, layout v1: host-reconstructed aligned columns)                   */
+/* HaploCart read batch (SoA)                                                                  */
 /* ------------------------------------------------------------------------------------------- */
 
 /* One batch = the reads of one call to the hot loop (src/HaploCart.cpp:408-421) after
  * reconstruct_graph_sequence (src/vgan_utils.h:6-79) has produced, per read, the aligned graph
- * string, the aligned read string and the per-edit sizes.  For read r:
- *   columns   col_off[r] .. col_off[r+1]   (n = |aligned read string| == |aligned graph string|)
- *     gcol[]  aligned graph string  (ASCII: A C G T N '-' 'S')
- *     rcol[]  aligned read string   (ASCII: A C G T N '-')
- *     qual[]  quality byte at the SAME column index (raw PHRED, as vg.Alignment.quality holds
- *             it); 0 for column indices >= n_qual[r]  (the reference indexes the quality string by
- *             aligned column, src/update_likelihood.cpp:40-44)
- *   mappings  map_off[r] .. map_off[r+1]   (one per vg Mapping of the path)
- *     map_node[]  Mapping.position.node_id
- *     map_len[]   mppg_sizes[i] -- the size of the i-th EDIT of the read, indexed by mapping
- *                 number exactly as src/update_likelihood.cpp:35-37 does
- *   n_qual[r]   length of the quality string (<= number of columns)
- *   mapq[r]     Alignment.mapping_quality (0..99)
+ * string G, the aligned read string `algnseq` and the per-edit sizes, marshalled the way
+ * update_likelihood hands them to process_mapping (src/update_likelihood.cpp:33-49):
+ *
+ *   mapping i of the read (i < number of vg Mappings):
+ *       size_i = mppg_sizes[i]            -- the size of the i-th EDIT, indexed by mapping number
+ *       pos_i  = min(sum_{k<i} size_k, n) -- position_in_read, n = |algnseq| = number of columns
+ *       it compares graph_seq = G[pos_i .. pos_i+size_i) with mapping_seq = algnseq[0 ..) (the WHOLE
+ *       aligned read string, indexed from 0) and quality_scores[j] = quality[pos_i + j].
+ *
+ *   column c of the read (0 <= c < n) therefore carries
+ *       bits 0-7   quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c >= n_qual:
+ *                  the reference indexes the quality string by aligned column)
+ *       bits 8-9   the read base process_mapping pairs with G[c]: algnseq[c - pos_i] of the mapping i
+ *                  that owns column c (A=0 C=1 G=2 T=3)
+ *       bit 10     VALID: a mapping owns the column and both G[c] and that read base are A/C/G/T
+ *                  (the isValidDNA / 'N' filter of src/process_mapping.cpp:62-63)
+ *       bit 11     MATCH: G[c] == that read base (src/get_p_obs_base.cpp:15,20)
+ *   The graph base itself is not shipped: get_p_obs_base ignores its base arguments
+ *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.
+ *
+ *   mapping record: bits 0-19 Mapping.position.node_id (row of the membership matrix, < 2^20),
+ *                   bits 20-31 size_i (< 4096)
+ *   n_qual[r]  length of the quality string (<= n);  mapq[r]  Alignment.mapping_quality (0..99)
+ *
  * All arrays are host pointers for vgl_hc_accumulate and device pointers for
- * vgl_hc_accumulate_device.                                                                    */
+ * vgl_hc_accumulate_device; every array must be readable 16 bytes past its last element.
+ * Algorithmic bytes per read: 2 n + 4 M + 11.                                                 */
+#define VGL_HC_COL_QUAL(rec) ((rec) & 0xffu)
+#define VGL_HC_COL_BASE(rec) (((rec) >> 8) & 3u)
+#define VGL_HC_COL_VALID 0x0400u
+#define VGL_HC_COL_MATCH 0x0800u
+#define VGL_HC_MAP_NODE_BITS 20
+#define VGL_HC_MAP_MAX_NODE ((1u << VGL_HC_MAP_NODE_BITS) - 1u)
+#define VGL_HC_MAP_MAX_SIZE 4095u
+#define VGL_HC_MAP_REC(node, size) ((uint32_t)(node) | ((uint32_t)(size) << VGL_HC_MAP_NODE_BITS))
+
 typedef struct vgl_hc_batch {
     uint32_t n_reads;
     uint32_t reserved;
@@ -142,11 +163,8 @@ typedef struct vgl_hc_batch {
     uint64_t n_maps;
     const uint32_t* col_off; /* [n_reads + 1] */
     const uint32_t* map_off; /* [n_reads + 1] */
-    const uint8_t* gcol;     /* [n_cols] */
-    const uint8_t* rcol;     /* [n_cols] */
-    const uint8_t* qual;     /* [n_cols] */
-    const int32_t* map_node; /* [n_maps] */
-    const uint16_t* map_len; /* [n_maps] */
+    const uint16_t* col;     /* [n_cols] column records */
+    const uint32_t* map;     /* [n_maps] mapping records */
     const uint16_t* n_qual;  /* [n_reads] */
     const uint8_t* mapq;     /* [n_reads] */
 } vgl_hc_batch;

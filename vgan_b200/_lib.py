@@ -28,9 +28,12 @@ class vgl_hc_tables(C.Structure):
 
 class vgl_hc_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_cols", C.c_uint64), ("n_maps", C.c_uint64),
-                ("col_off", C.c_void_p), ("map_off", C.c_void_p), ("gcol", C.c_void_p), ("rcol", C.c_void_p),
-                ("qual", C.c_void_p), ("map_node", C.c_void_p), ("map_len", C.c_void_p), ("n_qual", C.c_void_p),
-                ("mapq", C.c_void_p)]
+                ("col_off", C.c_void_p), ("map_off", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
+                ("n_qual", C.c_void_p), ("mapq", C.c_void_p)]
+
+# column / mapping record fields (include/vgan_gpu.h)
+COL_VALID, COL_MATCH = 0x0400, 0x0800
+MAP_NODE_BITS = 20
 
 
 class vgh_alignments(C.Structure):

@@ -400,6 +400,15 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                     e = fail(VGH_ERR_BAD_READ, "read %lld: alignment too long for the v1 batch layout", (long long)r);
                 else if (a->mapq[r] < 0 || a->mapq[r] >= 100)
                     e = fail(VGH_ERR_BAD_READ, "read %lld: mapping quality %d outside [0,100)", (long long)r, a->mapq[r]);
+                else {
+                    for (int64_t i = 0; i < M && !e; ++i) {
+                        const int64_t node = a->map_node[a->map_off[r] + i];
+                        if (node < 0 || node > (int64_t)VGL_HC_MAP_MAX_NODE)
+                            e = fail(VGH_ERR_BAD_NODE, "read %lld: node id %lld does not fit the mapping record", (long long)r, (long long)node);
+                        else if (rc.sizes[(size_t)i] > (int32_t)VGL_HC_MAP_MAX_SIZE)
+                            e = fail(VGH_ERR_BAD_READ, "read %lld: edit of %d columns does not fit the mapping record", (long long)r, rc.sizes[(size_t)i]);
+                    }
+                }
             }
             if (e) {
 #pragma omp critical(vgh_pack_err)
@@ -416,15 +425,12 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     for (size_t k = 0; k < R; ++k) { tot_cols += ncols[k]; tot_maps += nmaps[k]; }
     if (tot_cols > 0xfffffff0ull || tot_maps > 0xfffffff0ull) return fail(VGH_ERR_INVALID, "batch too large for 32-bit offsets; split it");
 
-    // one block, 256-byte aligned sub-arrays (+16 bytes of slack so device tiles may over-read)
+    // one block, 256-byte aligned sub-arrays (+16 bytes of slack: the device stages tiles with 16-byte bulk copies)
     size_t o = 0;
-    const size_t o_col_off = o; o = align_up(o + (R + 1) * 4, 256);
-    const size_t o_map_off = o; o = align_up(o + (R + 1) * 4, 256);
-    const size_t o_gcol = o; o = align_up(o + tot_cols + 16, 256);
-    const size_t o_rcol = o; o = align_up(o + tot_cols + 16, 256);
-    const size_t o_qual = o; o = align_up(o + tot_cols + 16, 256);
-    const size_t o_node = o; o = align_up(o + tot_maps * 4 + 16, 256);
-    const size_t o_len = o; o = align_up(o + tot_maps * 2 + 16, 256);
+    const size_t o_col_off = o; o = align_up(o + (R + 1) * 4 + 16, 256);
+    const size_t o_map_off = o; o = align_up(o + (R + 1) * 4 + 16, 256);
+    const size_t o_col = o; o = align_up(o + tot_cols * 2 + 16, 256);
+    const size_t o_map = o; o = align_up(o + tot_maps * 4 + 16, 256);
     const size_t o_nq = o; o = align_up(o + R * 2 + 16, 256);
     const size_t o_mq = o; o = align_up(o + R + 16, 256);
     vgh_hc_packed* P = new vgh_hc_packed();
@@ -442,20 +448,21 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     uint8_t* base = (uint8_t*)P->block;
     uint32_t* col_off = (uint32_t*)(base + o_col_off);
     uint32_t* map_off = (uint32_t*)(base + o_map_off);
-    uint8_t* gcol = base + o_gcol;
-    uint8_t* rcol = base + o_rcol;
-    uint8_t* qual = base + o_qual;
-    int32_t* map_node = (int32_t*)(base + o_node);
-    uint16_t* map_len = (uint16_t*)(base + o_len);
+    uint16_t* col = (uint16_t*)(base + o_col);
+    uint32_t* map = (uint32_t*)(base + o_map);
     uint16_t* n_qual = (uint16_t*)(base + o_nq);
     uint8_t* mapq = base + o_mq;
     col_off[0] = 0;
     map_off[0] = 0;
     for (size_t k = 0; k < R; ++k) { col_off[k + 1] = col_off[k] + ncols[k]; map_off[k + 1] = map_off[k] + nmaps[k]; }
-    memset(gcol + tot_cols, 0, 16); memset(rcol + tot_cols, 0, 16); memset(qual + tot_cols, 0, 16);
-    memset((uint8_t*)(map_node + tot_maps), 0, 16); memset((uint8_t*)(map_len + tot_maps), 0, 16);
+    memset((uint8_t*)(col_off + R + 1), 0, 16); memset((uint8_t*)(map_off + R + 1), 0, 16);
+    memset((uint8_t*)(col + tot_cols), 0, 16); memset((uint8_t*)(map + tot_maps), 0, 16);
+    memset((uint8_t*)(n_qual + R), 0, 16); memset(mapq + R, 0, 16);
 
-    // pass 2: fill
+    // pass 2: fill.  Column records pair G[c] with the read base process_mapping compares it with
+    // (src/update_likelihood.cpp:33-49, src/process_mapping.cpp:47,59-66): for mapping i the graph slice
+    // G[pos_i, pos_i + size_i) faces algnseq[0, size_i) -- the whole aligned read string from its start.
+    auto base_code = [](char ch) -> int { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; };
 #pragma omp parallel num_threads(n_threads)
     {
         Recon rc;
@@ -465,16 +472,22 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
             if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
             const uint32_t c0 = col_off[k], m0 = map_off[k];
             const size_t L = rc.read_seq.size();
-            memcpy(gcol + c0, rc.graph_seq.data(), L);
-            memcpy(rcol + c0, rc.read_seq.data(), L);
             const int64_t q0 = a->qual_off[r], Lq = a->qual_off[r + 1] - q0;
-            memcpy(qual + c0, a->qual + q0, (size_t)Lq);
-            memset(qual + c0 + Lq, 0, L - (size_t)Lq);
+            for (size_t c = 0; c < L; ++c) col[c0 + c] = (uint16_t)((int64_t)c < Lq ? (uint8_t)a->qual[q0 + (int64_t)c] : 0);
             const int64_t mm = a->map_off[r];
+            size_t pos = 0;
             for (uint32_t i = 0; i < nmaps[(size_t)k]; ++i) {
-                const int64_t node = a->map_node[mm + i];
-                map_node[m0 + i] = (node >= 0 && node <= 0x7fffffff) ? (int32_t)node : -1;
-                map_len[m0 + i] = (uint16_t)std::min<int32_t>(rc.sizes[i], 65535);  // sizes[i] <= L <= 65535
+                const size_t size = (size_t)rc.sizes[i];
+                const size_t lg = std::min(size, L - pos);
+                for (size_t j = 0; j < lg; ++j) {
+                    const char gb = rc.graph_seq[pos + j], rb = rc.read_seq[j];
+                    const int cg = base_code(gb), cb = base_code(rb);
+                    uint16_t rec = col[c0 + pos + j];
+                    if (cg < 4 && cb < 4) rec |= (uint16_t)(VGL_HC_COL_VALID | (cb << 8) | (gb == rb ? VGL_HC_COL_MATCH : 0));
+                    col[c0 + pos + j] = rec;
+                }
+                map[m0 + i] = VGL_HC_MAP_REC((uint32_t)a->map_node[mm + i], (uint32_t)size);
+                pos += lg;
             }
             n_qual[k] = (uint16_t)Lq;
             mapq[k] = (uint8_t)a->mapq[r];
@@ -485,8 +498,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     P->batch.n_cols = tot_cols;
     P->batch.n_maps = tot_maps;
     P->batch.col_off = col_off; P->batch.map_off = map_off;
-    P->batch.gcol = gcol; P->batch.rcol = rcol; P->batch.qual = qual;
-    P->batch.map_node = map_node; P->batch.map_len = map_len;
+    P->batch.col = col; P->batch.map = map;
     P->batch.n_qual = n_qual; P->batch.mapq = mapq;
     *out = P;
     return VGH_OK;

@@ -93,11 +93,17 @@ struct vgl_ctx {
     DevBuf<double> d_post, d_scalars;
     DevBuf<int32_t> d_idx;
 
-    // staging for host batches
-    DevBuf<uint32_t> s_col_off, s_map_off;
-    DevBuf<uint8_t> s_gcol, s_rcol, s_qual, s_mapq;
-    DevBuf<int32_t> s_map_node;
-    DevBuf<uint16_t> s_map_len, s_n_qual;
+    // staging for host batches: two slots so that the H2D copy of chunk k+1 overlaps the read kernel on chunk k
+    struct Slot {
+        DevBuf<uint32_t> col_off, map_off, map;
+        DevBuf<uint16_t> col, n_qual;
+        DevBuf<uint8_t> mapq;
+        cudaEvent_t copied = nullptr, consumed = nullptr;
+        bool used = false;
+    } slot[2];
+    cudaStream_t copy_stream = nullptr;
+    uint32_t chunk_reads = 131072;
+    DevBuf<unsigned long long> d_stats;
 
     // read-kernel timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -129,7 +135,7 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
     auto& ev = ctx->ev_pool[ctx->ev_used++];
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
     VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_cta_a_total.p,
-                                        ctx->d_err.p, ctx->stream));
+                                        ctx->d_err.p, ctx->d_stats.p, ctx->stream));
     VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches += 1;
     ctx->ll_valid = false;
@@ -140,8 +146,8 @@ int check_batch(const vgl_hc_batch* b) {
     if (!b) return fail(VGL_ERR_INVALID, "null batch");
     if (b->n_reads == 0) return VGL_OK;
     if (!b->col_off || !b->map_off || !b->n_qual || !b->mapq) return fail(VGL_ERR_INVALID, "batch header arrays missing");
-    if (b->n_cols && (!b->gcol || !b->rcol || !b->qual)) return fail(VGL_ERR_INVALID, "batch column arrays missing");
-    if (b->n_maps && (!b->map_node || !b->map_len)) return fail(VGL_ERR_INVALID, "batch mapping arrays missing");
+    if (b->n_cols && !b->col) return fail(VGL_ERR_INVALID, "batch column records missing");
+    if (b->n_maps && !b->map) return fail(VGL_ERR_INVALID, "batch mapping records missing");
     if (b->n_cols > 0xffffffffull || b->n_maps > 0xffffffffull) return fail(VGL_ERR_INVALID, "batch too large for 32-bit offsets; split it");
     return VGL_OK;
 }
@@ -181,6 +187,14 @@ int vgl_create(int device_id, vgl_ctx** out) {
         return fail(VGL_ERR_CUDA, "cudaStreamCreate failed");
     }
     ctx->stream = ctx->own_stream;
+    bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& sl : ctx->slot)
+        ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        vgl_destroy(ctx);
+        return fail(VGL_ERR_CUDA, "cannot create the copy stream / events");
+    }
     *out = ctx;
     return VGL_OK;
 }
@@ -194,8 +208,13 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_err.release();
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_post.release(); ctx->d_scalars.release(); ctx->d_idx.release();
-    ctx->s_col_off.release(); ctx->s_map_off.release(); ctx->s_gcol.release(); ctx->s_rcol.release();
-    ctx->s_qual.release(); ctx->s_mapq.release(); ctx->s_map_node.release(); ctx->s_map_len.release(); ctx->s_n_qual.release();
+    for (auto& sl : ctx->slot) {
+        sl.col_off.release(); sl.map_off.release(); sl.map.release(); sl.col.release(); sl.n_qual.release(); sl.mapq.release();
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.consumed) cudaEventDestroy(sl.consumed);
+    }
+    ctx->d_stats.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -250,7 +269,7 @@ uint64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b) {
     if (!b) return 0;
-    return (uint64_t)(b->n_reads + 1) * 8 + b->n_cols * 3 + b->n_maps * 6 + (uint64_t)b->n_reads * 3;
+    return (uint64_t)(b->n_reads + 1) * 8 + b->n_cols * 2 + b->n_maps * 4 + (uint64_t)b->n_reads * 3;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -296,6 +315,11 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     vgl::HcSmallTables small;
     memset(&small, 0, sizeof(small));
     const double bep = T->background_error_prob;
+    small.f_match_bep = 1 - bep;
+    small.f_mis_bep = 1 - (1 - bep);
+    small.one_minus_bep = 1 - bep;
+    small.is_fasta = T->is_consensus_fasta ? 1 : 0;
+    small.log_err_scale = -std::log(10.0) / 10.0;
     for (int b = 0; b < 256; ++b) {
         const int Q = (int)(int8_t)(uint8_t)b;  // the reference reads quality bytes as (signed) char
         // get_p_no_seq_error_mapping (src/get_p_obs_base.cpp:3-27); a negative byte would index qscore_vec
@@ -304,19 +328,18 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
         const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
         const double eps_match = qs;
         const double eps_mis = 1 - qs;
-        small.f_match[b] = 1 - eps_match;  // get_p_obs_base: match * (1 - epsilon), src/get_p_obs_base.cpp:67
-        small.f_mis[b] = 1 - eps_mis;
+        // get_p_obs_base: match * (1 - epsilon), src/get_p_obs_base.cpp:67.  In consensus-FASTA mode the
+        // background error probability replaces the quality for every base (src/HaploCart.cpp:397-401).
+        small.f_pair[b] = small.is_fasta ? small.f_match_bep : 1 - eps_match;
+        small.f_pair[256 + b] = small.is_fasta ? small.f_mis_bep : 1 - eps_mis;
         const double perr = (Q > 2) ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;  // get_p_seq_error, src/miscfunc.h:180-187
         small.log_err[b] = std::log(perr);
-        small.base_code[b] = 4;
+        // fast_log table: rc ~ 1 / c_k and -log(rc) for the bucket centre c_k = 1 + (k + 0.5) / 256
+        const double rc = 1.0 / (1.0 + (b + 0.5) / 256.0);
+        small.log_tab[b] = make_double2(rc, (double)(-logl((long double)rc)));
     }
-    small.base_code[(int)'A'] = 0; small.base_code[(int)'C'] = 1; small.base_code[(int)'G'] = 2; small.base_code[(int)'T'] = 3;
     for (int q = 0; q < 100; ++q) small.p_correct[q] = 1 - T->p_incorrect_map[q];
     for (int k = 0; k < 4; ++k) small.bg[k] = T->bg_freq[k];
-    small.f_match_bep = 1 - bep;
-    small.f_mis_bep = 1 - (1 - bep);
-    small.one_minus_bep = 1 - bep;
-    small.is_fasta = T->is_consensus_fasta ? 1 : 0;
 
     // Membership matrix re-laid as node-words x paths: word (w, p) holds pathsgo[p] of nodes 32w..32w+31.
     // Bits of nodes >= n_rows are set ("supported": contributes nothing).
@@ -347,6 +370,7 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg.smem));
 
     if (int rc = ctx->d_node_class.reserve((size_t)N)) return rc;
+    class_tab.resize(std::max<size_t>(class_tab.size(), (size_t)vgl::kClassCache), make_double2(0.0, 0.0));
     if (int rc = ctx->d_class_tab.reserve(class_tab.size())) return rc;
     if (int rc = ctx->d_small.reserve(1)) return rc;
     if (int rc = ctx->d_node_bits.reserve(node_bits.size())) return rc;
@@ -377,6 +401,9 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     if (int rc = ctx->d_scalars.reserve(2)) return rc;
     if (int rc = ctx->d_idx.reserve(2)) return rc;
     if (int rc = ctx->d_post.reserve(64)) return rc;
+    if (int rc = ctx->d_stats.reserve(4)) return rc;
+    VGL_CUDA(cudaMemset(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long)));
+    if (vgl::hc_posterior_smem(P) > 48 * 1024) VGL_CUDA(vgl::hc_posterior_configure(vgl::hc_posterior_smem(P)));
     ctx->have_tables = true;
     ctx->have_tree = false;
     return vgl_hc_reset(ctx);
@@ -432,7 +459,7 @@ int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
-    vgl::HcBatchDev d{b->n_reads, b->col_off, b->map_off, b->gcol, b->rcol, b->qual, b->map_node, b->map_len, b->n_qual, b->mapq};
+    vgl::HcBatchDev d{b->n_reads, b->col_off, b->map_off, b->col, b->map, b->n_qual, b->mapq};
     return launch_read(ctx, d);
 }
 
@@ -441,32 +468,52 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
     if (b->n_reads == 0) return VGL_OK;
-    const size_t R = b->n_reads;
-    // The staging buffers are reused: wait for the previous pass over them before growing them.
-    if (R + 1 > ctx->s_col_off.cap || b->n_cols > ctx->s_gcol.cap || b->n_maps > ctx->s_map_node.cap)
-        VGL_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (int rc = ctx->s_col_off.reserve(R + 1)) return rc;
-    if (int rc = ctx->s_map_off.reserve(R + 1)) return rc;
-    if (int rc = ctx->s_n_qual.reserve(R)) return rc;
-    if (int rc = ctx->s_mapq.reserve(R)) return rc;
-    if (int rc = ctx->s_gcol.reserve((size_t)b->n_cols + 16)) return rc;
-    if (int rc = ctx->s_rcol.reserve((size_t)b->n_cols + 16)) return rc;
-    if (int rc = ctx->s_qual.reserve((size_t)b->n_cols + 16)) return rc;
-    if (int rc = ctx->s_map_node.reserve((size_t)b->n_maps + 16)) return rc;
-    if (int rc = ctx->s_map_len.reserve((size_t)b->n_maps + 16)) return rc;
-    cudaStream_t s = ctx->stream;
-    if (int rc = upload_async(ctx->s_col_off.p, b->col_off, (R + 1) * 4, s)) return rc;
-    if (int rc = upload_async(ctx->s_map_off.p, b->map_off, (R + 1) * 4, s)) return rc;
-    if (int rc = upload_async(ctx->s_n_qual.p, b->n_qual, R * 2, s)) return rc;
-    if (int rc = upload_async(ctx->s_mapq.p, b->mapq, R, s)) return rc;
-    if (int rc = upload_async(ctx->s_gcol.p, b->gcol, (size_t)b->n_cols, s)) return rc;
-    if (int rc = upload_async(ctx->s_rcol.p, b->rcol, (size_t)b->n_cols, s)) return rc;
-    if (int rc = upload_async(ctx->s_qual.p, b->qual, (size_t)b->n_cols, s)) return rc;
-    if (int rc = upload_async(ctx->s_map_node.p, b->map_node, (size_t)b->n_maps * 4, s)) return rc;
-    if (int rc = upload_async(ctx->s_map_len.p, b->map_len, (size_t)b->n_maps * 2, s)) return rc;
-    vgl::HcBatchDev d{b->n_reads, ctx->s_col_off.p, ctx->s_map_off.p, ctx->s_gcol.p, ctx->s_rcol.p, ctx->s_qual.p,
-                      ctx->s_map_node.p, ctx->s_map_len.p, ctx->s_n_qual.p, ctx->s_mapq.p};
-    return launch_read(ctx, d);
+    // The batch is cut into chunks of reads; the H2D copy of a chunk runs on the copy stream into one of two
+    // staging slots while the read kernel works on the other.  Offsets stay absolute: the kernel is given array
+    // bases shifted back by the chunk's first element.
+    const uint32_t R = b->n_reads;
+    uint32_t n_chunk = 0;
+    for (uint32_t r0 = 0; r0 < R; r0 += ctx->chunk_reads, ++n_chunk) {
+        const uint32_t r1 = std::min(R, r0 + ctx->chunk_reads);
+        const uint32_t nr = r1 - r0;
+        const uint32_t c0 = b->col_off[r0], c1 = b->col_off[r1];
+        const uint32_t m0 = b->map_off[r0], m1 = b->map_off[r1];
+        if (c1 < c0 || m1 < m0 || c1 > b->n_cols || m1 > b->n_maps) return fail(VGL_ERR_INVALID, "batch offsets are not monotone");
+        vgl_ctx::Slot& sl = ctx->slot[n_chunk & 1];
+        if (sl.used) VGL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, sl.consumed, 0));  // the kernel that last read this slot
+        const bool grow = nr + 1 > sl.col_off.cap || c1 - c0 > sl.col.cap || m1 - m0 > sl.map.cap;
+        if (grow) VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (int rc = sl.col_off.reserve((size_t)nr + 1 + 8)) return rc;
+        if (int rc = sl.map_off.reserve((size_t)nr + 1 + 8)) return rc;
+        if (int rc = sl.n_qual.reserve((size_t)nr + 16)) return rc;
+        if (int rc = sl.mapq.reserve((size_t)nr + 32)) return rc;
+        if (int rc = sl.col.reserve((size_t)(c1 - c0) + 16)) return rc;
+        if (int rc = sl.map.reserve((size_t)(m1 - m0) + 16)) return rc;
+        cudaStream_t cs = ctx->copy_stream;
+        if (int rc = upload_async(sl.col_off.p, b->col_off + r0, ((size_t)nr + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.map_off.p, b->map_off + r0, ((size_t)nr + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.n_qual.p, b->n_qual + r0, (size_t)nr * 2, cs)) return rc;
+        if (int rc = upload_async(sl.mapq.p, b->mapq + r0, (size_t)nr, cs)) return rc;
+        if (int rc = upload_async(sl.col.p, b->col + c0, (size_t)(c1 - c0) * 2, cs)) return rc;
+        if (int rc = upload_async(sl.map.p, b->map + m0, (size_t)(m1 - m0) * 4, cs)) return rc;
+        VGL_CUDA(cudaEventRecord(sl.copied, cs));
+        VGL_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
+        // absolute offsets index the shifted bases; (uintptr_t arithmetic: the shifted pointers are never dereferenced below the slot)
+        vgl::HcBatchDev d;
+        d.n_reads = nr;
+        d.col_off = sl.col_off.p;
+        d.map_off = sl.map_off.p;
+        d.col = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col.p) - (uintptr_t)c0 * 2);
+        d.map = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.map.p) - (uintptr_t)m0 * 4);
+        d.n_qual = sl.n_qual.p;
+        d.mapq = sl.mapq.p;
+        if (int rc = launch_read(ctx, d)) return rc;
+        VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
+        sl.used = true;
+    }
+    // The caller may reuse its host buffers as soon as this returns.
+    VGL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return VGL_OK;
 }
 
 int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {

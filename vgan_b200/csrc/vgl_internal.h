@@ -12,18 +12,20 @@ namespace vgl {
 // Indexed by the RAW quality byte (0..255); bytes >= 128 are negative as `signed char`, which is
 // how the reference sees them (src/update_likelihood.cpp:41).
 struct HcSmallTables {
-    double f_match[256];   // 1 - eps,  eps = qscore[Q]         graph base == read base
-    double f_mis[256];     // 1 - eps,  eps = 1 - qscore[Q]     graph base != read base
+    double f_pair[512];    // 1 - eps: [q] graph base == read base (eps = qscore[Q]); [256 + q] mismatch (eps = 1 - qscore[Q])
     double log_err[256];   // log(get_p_seq_error(Q))           src/process_mapping.cpp:11
+    double2 log_tab[256];  // fast_log table: {rc_k ~ 1/c_k, -log(rc_k)}, c_k = 1 + (k + 0.5)/256
     double p_correct[100]; // 1 - p_incorrect_map[mapq]         src/process_mapping.cpp:41
     double bg[4];          // background frequency of A,C,G,T   src/haplocart_functions.cpp:81-97
     double f_match_bep;    // 1 - bep
     double f_mis_bep;      // 1 - (1 - bep)
     double one_minus_bep;  // FASTA mode multiplier              src/process_mapping.cpp:73
+    double log_err_scale;  // -ln(10)/10: log(get_p_seq_error(Q)) for Q > 2 is Q * this
     int32_t is_fasta;
     int32_t pad;
-    uint8_t base_code[256]; // 'A','C','G','T' -> 0..3, everything else 4 (libgab isValidDNA)
 };
+
+constexpr int kClassCache = 64;  // (mappability, match_prob) classes mirrored in shared memory
 
 struct HcTablesDev {
     int32_t n_rows;
@@ -31,7 +33,7 @@ struct HcTablesDev {
     int32_t n_words;           // number of 32-node words = ceil(n_rows / 32)
     int32_t n_class;
     const uint16_t* node_class; // [n_rows]   0xFFFF = node has no pangenome_map entry
-    const double2* class_tab;   // [n_class]  {mappability, match_prob}
+    const double2* class_tab;   // [max(n_class, kClassCache)]  {mappability, match_prob}
     const HcSmallTables* small;
     const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
 };
@@ -40,11 +42,8 @@ struct HcBatchDev {
     uint32_t n_reads;
     const uint32_t* col_off;
     const uint32_t* map_off;
-    const uint8_t* gcol;
-    const uint8_t* rcol;
-    const uint8_t* qual;
-    const int32_t* map_node;
-    const uint16_t* map_len;
+    const uint16_t* col;
+    const uint32_t* map;
     const uint16_t* n_qual;
     const uint8_t* mapq;
 };
@@ -62,8 +61,10 @@ cudaError_t hc_read_configure(size_t smem);
 // K1: per-read, per-mapping scalars scattered into per-CTA node accumulators.
 //   cta_node_acc[cta][n_rows]  += sum over this CTA's mappings at node n of (B_i - A_i)
 //   cta_a_total[cta]           += sum over this CTA's mappings of A_i
+//   stats[0] += reads that took the generic (slow) path
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
-                                  double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
+                                  double* cta_node_acc, double* cta_a_total, int* err_flag,
+                                  unsigned long long* stats, cudaStream_t s);
 
 // K2a: fixed-order reduction of the per-CTA accumulators -> node_acc[n_rows_pad], a_total[1].
 cudaError_t hc_launch_reduce_ctas(const double* cta_node_acc, const double* cta_a_total, int n_ctas, int n_rows,
@@ -82,6 +83,8 @@ cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, d
 
 // K3: argmax (first max wins), log-sum-exp, posterior of the call and of its listed clades.
 //   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post
+size_t hc_posterior_smem(int n_paths);
+cudaError_t hc_posterior_configure(size_t smem);
 cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
                                 double* out_scalars, int32_t* out_idx, cudaStream_t s);

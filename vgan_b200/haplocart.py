@@ -114,8 +114,8 @@ class Haplocart:
 
 
 class DeviceBatch:
-    _FIELDS = [("col_off", 4, "r1"), ("map_off", 4, "r1"), ("gcol", 1, "c"), ("rcol", 1, "c"), ("qual", 1, "c"),
-               ("map_node", 4, "m"), ("map_len", 2, "m"), ("n_qual", 2, "r"), ("mapq", 1, "r")]
+    _FIELDS = [("col_off", 4, "r1"), ("map_off", 4, "r1"), ("col", 2, "c"), ("map", 4, "m"), ("n_qual", 2, "r"),
+               ("mapq", 1, "r")]
 
     def __init__(self, hc, packed):
         self.hc = hc

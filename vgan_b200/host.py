@@ -136,10 +136,8 @@ class PackedBatch:
         R, nc, nm = int(b.n_reads), int(b.n_cols), int(b.n_maps)
         return {
             "col_off": _as_array(b.col_off, R + 1, np.uint32), "map_off": _as_array(b.map_off, R + 1, np.uint32),
-            "gcol": _as_array(b.gcol, nc, np.uint8), "rcol": _as_array(b.rcol, nc, np.uint8),
-            "qual": _as_array(b.qual, nc, np.uint8), "map_node": _as_array(b.map_node, nm, np.int32),
-            "map_len": _as_array(b.map_len, nm, np.uint16), "n_qual": _as_array(b.n_qual, R, np.uint16),
-            "mapq": _as_array(b.mapq, R, np.uint8),
+            "col": _as_array(b.col, nc, np.uint16), "map": _as_array(b.map, nm, np.uint32),
+            "n_qual": _as_array(b.n_qual, R, np.uint16), "mapq": _as_array(b.mapq, R, np.uint8),
         }
 
     def __del__(self):
