@@ -115,7 +115,7 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
                     const int32_t* anc_clade);
 
 /* ------------------------------------------------------------------------------------------- */
-/* HaploCart read batch (SoA)                                                                  */
+/* HaploCart read batch (warp-striped SoA)                                                     */
 /* ------------------------------------------------------------------------------------------- */
 
 /* One batch = the reads of one call to the hot loop (src/HaploCart.cpp:408-421) after
@@ -129,44 +129,60 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
  *       it compares graph_seq = G[pos_i .. pos_i+size_i) with mapping_seq = algnseq[0 ..) (the WHOLE
  *       aligned read string, indexed from 0) and quality_scores[j] = quality[pos_i + j].
  *
- *   column c of the read (0 <= c < n) therefore carries
- *       bits 0-7   quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c >= n_qual:
- *                  the reference indexes the quality string by aligned column)
- *       bits 8-9   the read base process_mapping pairs with G[c]: algnseq[c - pos_i] of the mapping i
- *                  that owns column c (A=0 C=1 G=2 T=3)
- *       bit 10     VALID: a mapping owns the column and both G[c] and that read base are A/C/G/T
- *                  (the isValidDNA / 'N' filter of src/process_mapping.cpp:62-63)
- *       bit 11     MATCH: G[c] == that read base (src/get_p_obs_base.cpp:15,20)
+ *   column record c of a read (0 <= c < n), 16 bits:
+ *       bits 0-7   quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c is past the
+ *                  end of the quality string: the reference indexes the quality string by aligned column)
+ *       bit 8      MISMATCH: G[c] != the read base process_mapping pairs with it, algnseq[c - pos_i] of the
+ *                  mapping i that owns column c (src/get_p_obs_base.cpp:15,20)
+ *       bits 9-10  that read base (A=0 C=1 G=2 T=3)
+ *       bit 11     VALID: a mapping owns the column and both bases are A/C/G/T (the isValidDNA / 'N'
+ *                  filter of src/process_mapping.cpp:62-63)
  *   The graph base itself is not shipped: get_p_obs_base ignores its base arguments
  *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.
  *
- *   mapping record: bits 0-19 Mapping.position.node_id (row of the membership matrix, < 2^20),
- *                   bits 20-31 size_i (< 4096)
- *   n_qual[r]  length of the quality string (<= n);  mapq[r]  Alignment.mapping_quality (0..99)
+ *   mapping record i of a read, 32 bits: bits 0-19 Mapping.position.node_id (row of the membership
+ *   matrix, < 2^20), bits 20-31 pos_i (< 4096).
  *
- * All arrays are host pointers for vgl_hc_accumulate and device pointers for
- * vgl_hc_accumulate_device; every array must be readable 16 bytes past its last element.
- * Algorithmic bytes per read: 2 n + 4 M + 11.                                                 */
+ *   per read lane: n_cols (n), n_maps, cov_end = pos_{M-1} + min(size_{M-1}, n - pos_{M-1}) (where the
+ *   columns of the last mapping end), first_q90 = index of the first REAL quality byte >= 90 (0xFFFF if
+ *   none; that byte latches the background-error mode, src/update_likelihood.cpp:42), mapq (0..99).
+ *
+ * Reads are stored in groups of 32 "lanes" (one per thread of a warp); the sum over reads is order
+ * independent, so the packer is free to group reads of similar shape.  Records are blocked so that every
+ * lane fetches 16 bytes at a time and a warp fetches 512 contiguous bytes:
+ *   column block  = 32 lanes x 8 consecutive column records  (col[(blk * 32 + lane) * 8 + (c & 7)], c >> 3 = block)
+ *   mapping block = 32 lanes x 4 consecutive mapping records (map[(blk * 32 + lane) * 4 + (i & 3)], i >> 2 = block)
+ * Group g owns column blocks grp_col_blk[g] .. grp_col_blk[g+1] and mapping blocks grp_map_blk[g] ..
+ * grp_map_blk[g+1] (as many as its longest read needs); records past a lane's own length, and every
+ * record of the unused lanes of the last group, are zero (n_cols = n_maps = 0 for unused lanes).
+ * All arrays are host pointers for vgl_hc_accumulate and device pointers for vgl_hc_accumulate_device.
+ * Algorithmic bytes per read: 2 n + 4 M + 9 plus padding (a few percent when lanes are grouped by shape). */
 #define VGL_HC_COL_QUAL(rec) ((rec) & 0xffu)
-#define VGL_HC_COL_BASE(rec) (((rec) >> 8) & 3u)
-#define VGL_HC_COL_VALID 0x0400u
-#define VGL_HC_COL_MATCH 0x0800u
+#define VGL_HC_COL_MISMATCH 0x0100u
+#define VGL_HC_COL_BASE(rec) (((rec) >> 9) & 3u)
+#define VGL_HC_COL_VALID 0x0800u
 #define VGL_HC_MAP_NODE_BITS 20
 #define VGL_HC_MAP_MAX_NODE ((1u << VGL_HC_MAP_NODE_BITS) - 1u)
-#define VGL_HC_MAP_MAX_SIZE 4095u
-#define VGL_HC_MAP_REC(node, size) ((uint32_t)(node) | ((uint32_t)(size) << VGL_HC_MAP_NODE_BITS))
+#define VGL_HC_MAP_MAX_POS 4095u
+#define VGL_HC_MAP_REC(node, pos) ((uint32_t)(node) | ((uint32_t)(pos) << VGL_HC_MAP_NODE_BITS))
+#define VGL_HC_LANES 32
+#define VGL_HC_COL_BLK 8
+#define VGL_HC_MAP_BLK 4
 
 typedef struct vgl_hc_batch {
-    uint32_t n_reads;
-    uint32_t reserved;
-    uint64_t n_cols;
-    uint64_t n_maps;
-    const uint32_t* col_off; /* [n_reads + 1] */
-    const uint32_t* map_off; /* [n_reads + 1] */
-    const uint16_t* col;     /* [n_cols] column records */
-    const uint32_t* map;     /* [n_maps] mapping records */
-    const uint16_t* n_qual;  /* [n_reads] */
-    const uint8_t* mapq;     /* [n_reads] */
+    uint32_t n_reads;            /* real reads (unused lanes of the last group excluded) */
+    uint32_t n_groups;           /* groups of 32 lanes */
+    uint64_t n_col_blks;         /* = grp_col_blk[n_groups] */
+    uint64_t n_map_blks;         /* = grp_map_blk[n_groups] */
+    const uint32_t* grp_col_blk; /* [n_groups + 1] */
+    const uint32_t* grp_map_blk; /* [n_groups + 1] */
+    const uint16_t* col;         /* [n_col_blks][32][8] column records (16-byte aligned) */
+    const uint32_t* map;         /* [n_map_blks][32][4] mapping records (16-byte aligned) */
+    const uint16_t* n_cols;      /* [n_groups * 32] */
+    const uint16_t* n_maps;      /* [n_groups * 32] */
+    const uint16_t* cov_end;     /* [n_groups * 32] */
+    const uint16_t* first_q90;   /* [n_groups * 32] */
+    const uint8_t* mapq;         /* [n_groups * 32] */
 } vgl_hc_batch;
 
 /* Bytes the batch occupies (what crosses PCIe / is read from HBM once per pass).               */

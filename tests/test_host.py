@@ -84,29 +84,35 @@ def test_reconstruct_unrecognised_edit_repeats_previous_size():
 
 
 def _repack_with_oracle(og, R, arrays):
-    """What the packed batch must contain, derived independently from the oracle's reconstruction and the
+    """What each packed read lane must contain, derived independently from the oracle's reconstruction and the
     marshalling rule of update_likelihood / process_mapping (src/update_likelihood.cpp:33-49)."""
     keep = [r for r in range(arrays["n_reads"]) if not arrays["identity"][r] < 1e-10]
     code = {"A": 0, "C": 1, "G": 2, "T": 3}
-    cols, maps, ncol, nq, mq = [], [], [], [], []
+    lanes = []
     for r in keep:
         gs, rs, sizes = orc.reconstruct(og, R, r)
         M = int(arrays["map_off"][r + 1] - arrays["map_off"][r])
         qual = arrays["qual"][arrays["qual_off"][r]:arrays["qual_off"][r + 1]]
         rec = [int(qual[c]) if c < len(qual) else 0 for c in range(len(rs))]
+        q90 = [c for c in range(len(qual)) if 90 <= int(qual[c]) < 128]
         pos = 0
         nodes = arrays["map_node"][arrays["map_off"][r]:arrays["map_off"][r + 1]].tolist()
+        maps = []
         for i in range(M):
             lg = min(sizes[i], len(rs) - pos)
             for j in range(lg):
                 g, b = gs[pos + j], rs[j]            # the read string is indexed from 0 for every mapping (quirk Q2)
                 if g in code and b in code:
-                    rec[pos + j] |= 0x0400 | (code[b] << 8) | (0x0800 if g == b else 0)
-            maps.append(nodes[i] | (sizes[i] << 20))
+                    rec[pos + j] |= 0x0800 | (code[b] << 9) | (0 if g == b else 0x0100)
+            maps.append(nodes[i] | (pos << 20))
             pos += lg
-        cols += rec
-        ncol.append(len(rs)); nq.append(len(qual)); mq.append(int(arrays["mapq"][r]))
-    return cols, maps, ncol, nq, mq, keep
+        lanes.append({"col": rec, "map": maps, "n_cols": len(rs), "cov_end": pos, "first_q90": q90[0] if q90 else 0xFFFF,
+                      "mapq": int(arrays["mapq"][r])})
+    return lanes, keep
+
+
+def _lane_key(d):
+    return (len(d["map"]), d["n_cols"], tuple(d["col"]), tuple(d["map"]), d["mapq"])
 
 
 def test_packer_against_oracle_reconstruction():
@@ -116,19 +122,31 @@ def test_packer_against_oracle_reconstruction():
     R = orc.FlatReads(arrays)
     og = orc.Graph(S.node_sequences(), min_id=1)
     pb = vb.PackedBatch(S.graph, A, n_threads=3)
-    b = pb.arrays()
-    cols, maps, ncol, nq, mq, keep = _repack_with_oracle(og, R, arrays)
-    assert pb.n_reads == len(keep) and pb.skipped == len(A) - len(keep)
-    assert b["col"].tolist() == cols and b["map"].tolist() == maps
-    assert b["n_qual"].tolist() == nq and b["mapq"].tolist() == mq
-    assert np.diff(b["col_off"].astype(np.int64)).tolist() == ncol
+    want, keep = _repack_with_oracle(og, R, arrays)
+    got = pb.lanes()
+    assert pb.n_reads == len(keep) == len(got) and pb.skipped == len(A) - len(keep)
+    # the packer groups reads by shape, so compare as multisets of lanes
+    assert sorted(map(_lane_key, got)) == sorted(map(_lane_key, want))
+    assert sorted((d["cov_end"], d["first_q90"]) for d in got) == sorted((d["cov_end"], d["first_q90"]) for d in want)
+    shapes = [(len(d["map"]), d["n_cols"]) for d in got]
+    assert shapes == sorted(shapes)
     # mis-slicing (quirk Q1) happened: some read has more edits than mappings, so some columns have no owner
-    assert any(not (c & 0x0400) for c in cols)
-    # a sub-range packs the same records
-    pb2 = vb.PackedBatch(S.graph, A, r0=100, r1=200)
-    c0, c1 = b["col_off"][np.searchsorted(keep, 100)], b["col_off"][np.searchsorted(keep, 200)]
-    assert pb2.arrays()["col"].tolist() == b["col"][c0:c1].tolist()
-    assert pb.nbytes == (pb.n_reads + 1) * 8 + 2 * len(cols) + 4 * len(maps) + 3 * pb.n_reads
+    assert any(d["cov_end"] < d["n_cols"] for d in got)
+    # padding: rows of a group are as long as its longest lane, unused records are zero
+    a = pb.arrays()
+    G = int(pb.batch.n_groups)
+    assert G == (pb.n_reads + 31) // 32
+    for g in range(G):
+        lanes_g = got[g * 32:(g + 1) * 32]
+        assert a["grp_col_blk"][g + 1] - a["grp_col_blk"][g] == (max(d["n_cols"] for d in lanes_g) + 7) // 8
+        assert a["grp_map_blk"][g + 1] - a["grp_map_blk"][g] == (max(len(d["map"]) for d in lanes_g) + 3) // 4
+    assert a["n_cols"][pb.n_reads:].sum() == 0 and a["n_maps"][pb.n_reads:].sum() == 0
+    assert pb.nbytes == (G + 1) * 8 + 512 * (int(a["grp_col_blk"][-1]) + int(a["grp_map_blk"][-1])) + 9 * 32 * G
+    # a quality byte >= 90 is reported with its index
+    alns = [H.aln("GCTACGATGG", [(9, 0, False, [(10, 10, "")])], quality=bytes([30, 30, 30, 95, 30, 200, 30, 30, 99, 30]))]
+    nodes, _ = H.toy_graph()
+    one = vb.PackedBatch(vb.Graph.from_sequences(nodes), vb.Alignments.from_gam_bytes(H.encode_gam(alns))).lanes()[0]
+    assert one["first_q90"] == 3
 
 
 def test_packer_rejects_what_the_reference_cannot_process():
@@ -141,7 +159,7 @@ def test_packer_rejects_what_the_reference_cannot_process():
         "mapping quality out of range": H.aln("GCTA", [(9, 0, False, [(4, 4, "")])], mapq=100),
         "quality longer than the alignment": H.aln("GCTA", [(9, 0, False, [(4, 4, "")])], quality=bytes([30] * 9)),
         "substitution shorter than its span": H.aln("GCTA", [(9, 0, False, [(4, 4, "GC")])]),
-        "edit too long for the mapping record": H.aln("A" * 5000, [(9, 0, False, [(0, 5000, "A" * 5000)])]),
+        "alignment too long for the mapping record": H.aln("A" * 5000, [(9, 0, False, [(0, 5000, "A" * 5000)])]),
     }
     for why, bad in cases.items():
         a = vb.Alignments.from_gam_bytes(H.encode_gam([bad]))

@@ -27,13 +27,16 @@ class vgl_hc_tables(C.Structure):
 
 
 class vgl_hc_batch(C.Structure):
-    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_cols", C.c_uint64), ("n_maps", C.c_uint64),
-                ("col_off", C.c_void_p), ("map_off", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
-                ("n_qual", C.c_void_p), ("mapq", C.c_void_p)]
+    _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_map_blks", C.c_uint64),
+                ("grp_col_blk", C.c_void_p), ("grp_map_blk", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
+                ("n_cols", C.c_void_p), ("n_maps", C.c_void_p), ("cov_end", C.c_void_p), ("first_q90", C.c_void_p),
+                ("mapq", C.c_void_p)]
+
 
 # column / mapping record fields (include/vgan_gpu.h)
-COL_VALID, COL_MATCH = 0x0400, 0x0800
+COL_MISMATCH, COL_VALID = 0x0100, 0x0800
 MAP_NODE_BITS = 20
+LANES, COL_BLK, MAP_BLK = 32, 8, 4
 
 
 class vgh_alignments(C.Structure):

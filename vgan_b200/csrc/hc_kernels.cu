@@ -28,42 +28,8 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- read kernel geometry ------------------------------------------------------------------
-constexpr int kConsumerWarps = 16;
-constexpr int kReadBlock = (kConsumerWarps + 1) * 32;  // + one producer warp
-constexpr int kTileReads = 32;                         // reads per staged tile
-constexpr int kStages = 3;
-constexpr int kTileColCap = 4096;                      // column records per staged tile
-constexpr int kTileMapCap = 2048;                      // mapping records per staged tile
-constexpr int kFastCols = 128;                         // fast path: the read is one 128-column chunk ...
-constexpr int kFastMaps = 64;                          // ... and at most two rounds of 32 mappings
-
-// byte layout of one stage (every sub-buffer 16-byte aligned; +slack for the 16-byte alignment of bulk copies)
-constexpr int kStHdr = 0;                                       // StageHeader
-constexpr int kStColOff = 64;                                   // (32 + 1) u32, up to 3 before / 3 after
-constexpr int kStMapOff = kStColOff + 176;
-constexpr int kStNq = kStMapOff + 176;                          // 32 u16
-constexpr int kStMq = kStNq + 96;                               // 32 u8
-constexpr int kStCol = kStMq + 64;                              // kTileColCap u16
-constexpr int kStMap = kStCol + kTileColCap * 2 + 32;           // kTileMapCap u32
-constexpr int kStageBytes = kStMap + kTileMapCap * 4 + 32;
-static_assert(kStageBytes % 16 == 0, "stage size must keep 16-byte alignment");
-
-struct StageHeader {
-    uint32_t r0, n_reads, direct;  // direct != 0: column / mapping records were too many to stage; read them from global
-    uint32_t sh_col_off, sh_map_off, sh_nq, sh_mq, sh_col, sh_map;  // element shift of each staged array
-    uint32_t c0, m0;               // first column / mapping record of the tile
-};
-
-// per consumer warp scratch
-struct WarpBuf {
-    double xs[kFastCols];       // per-column mixture value x (1.0 where the column does not count)
-    uint32_t pq[kFastCols];     // inclusive prefix over columns of (sum of q for q > 2) | (count of q <= 2) << 16
-    double2 ac[kFastMaps];      // per mapping {1 - pcm, pcm * K}
-    uint16_t pad16[kFastMaps];  // (spare)
-    uint32_t mask[4];           // bit c set: a mapping with at least one column starts at column c
-    uint32_t pad[4];
-};
-static_assert(sizeof(WarpBuf) % 16 == 0, "WarpBuf must keep 16-byte alignment");
+constexpr int kReadBlock = 768;     // 24 warps: one read per thread, one 32-lane group per warp at a time
+constexpr int kMapChunk = 96;       // mappings finalised per pass (per-thread product / quality lists live in local memory)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,22 +38,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// the producer lane waits for a stage to drain with a sleep between probes so it does not compete for issue slots
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -105,65 +55,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// 16-byte aligned window around [base + first, base + first + nbytes): returns its size, sets the source and the shift
-__device__ __forceinline__ uint32_t aligned_window(const void* base, size_t first, size_t nbytes, const void*& src,
-                                                   uint32_t& shift) {
-    const uintptr_t a = (uintptr_t)base + first;
-    const uintptr_t a0 = a & ~(uintptr_t)15;
-    shift = (uint32_t)(a - a0);
-    src = (const void*)a0;
-    return (uint32_t)(((a + nbytes + 15) & ~(uintptr_t)15) - a0);
-}
 
-__device__ __forceinline__ int warp_incl_scan_i32(int v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(kFull, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-__device__ __forceinline__ double warp_incl_scan_f64(double v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        double t = __shfl_up_sync(kFull, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
     return v;
 }
 
-// ---- explicit shared-space accessors (32-bit shared addresses; keeps ptxas on LDS/STS/ATOMS instead of generic LD/ST) ----
-// `_c` variants read tables that are constant for the kernel's lifetime (non-volatile: may be scheduled freely);
-// the others touch staged tiles / warp scratch that are rewritten, so they stay ordered.
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint4 lds_v4u32(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
-__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-__device__ __forceinline__ double2 lds_v2f64(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+// ---- explicit shared-space accessors (32-bit shared addresses keep ptxas on LDS / ATOMS instead of generic LD) ----
+// Tables are constant for the kernel's lifetime, so the loads are non-volatile and may be scheduled freely.
 __device__ __forceinline__ uint32_t lds_u16_c(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds_f64_c(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double2 lds_v2f64_c(uint32_t a) { double2 v; asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_v4u32(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
-__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
-__device__ __forceinline__ void atoms_or_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void atoms_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+// streaming global loads of the batch: every byte is used exactly once, keep it out of L1
+__device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) { uint16_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) { uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 
-// byte offsets inside HcSmallTables
 constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_pair);
 constexpr uint32_t kOffLogErr = offsetof(HcSmallTables, log_err);
 constexpr uint32_t kOffLogTab = offsetof(HcSmallTables, log_tab);
 constexpr uint32_t kOffPCorrect = offsetof(HcSmallTables, p_correct);
 constexpr uint32_t kOffBg = offsetof(HcSmallTables, bg);
 
-// log(x) for x > 0 (x == 0 gives -inf) with the table in shared memory at byte address `tab`.
+// log(x) for x > 0 (x == 0 gives -inf) to ~1e-16: 8-bit table on the mantissa + degree-5 log1p, straight log1p
+// within 2^-9 of 1 (exactly 0 at x == 1).  Table at shared byte address `tab`.
 __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
@@ -171,7 +88,7 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 t = lds_v2f64_c(tab + (uint32_t)((hi >> 12) & 0xff) * 16u);
     const double d = x - 1.0;
-    const bool near = fabs(d) < 0.001953125;  // 2^-9: straight log1p keeps the relative accuracy near 1
+    const bool near = fabs(d) < 0.001953125;
     const double r = near ? d : fma(m, t.x, -1.0);
     const double base = near ? 0.0 : fma((double)e, 0.6931471805599453094, t.y);
     double p = fma(r, 0.2, -0.25);
@@ -179,289 +96,26 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
     p = fma(r, p, -0.5);
     p = fma(r, p, 1.0);
     const double v = fma(r, p, base);
-    return hi < 0x00100000 ? -CUDART_INF : v;  // zero (a denormal product cannot occur: factors are renormalised every 16)
-}
-
-// log(x) for x > 0 to ~1e-16 absolute + 1e-16 relative: 8-bit table on the mantissa, degree-5 log1p.
-// Exactly 0 at x == 1.  Denormals / zero go through the library log.
-__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
-    const int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
-    if (hi < 0x00100000) return log(x);
-    const int e = (hi >> 20) - 1023;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 t = tab[(hi >> 12) & 0xff];
-    double r = fma(m, t.x, -1.0);
-    double base = fma((double)e, 0.6931471805599453094, t.y);
-    const double d = x - 1.0;
-    if (fabs(d) < 0.001953125) {  // 2^-9: straight log1p keeps the relative accuracy near 1
-        r = d;
-        base = 0.0;
-    }
-    double p = fma(r, 0.2, -0.25);
-    p = fma(r, p, 0.33333333333333333333);
-    p = fma(r, p, -0.5);
-    p = fma(r, p, 1.0);
-    return fma(r, p, base);
-}
-
-struct ReadSmem {
-    double* acc;            // [n_rows]
-    const HcSmallTables* tab;
-    const double2* cls_cache;  // [kClassCache]
-    const uint16_t* node_class;
-};
-
-// {1 - pcm, pcm * K} of a mapping at `node` (src/process_mapping.cpp:33-42); false if the node has no table entry
-__device__ __forceinline__ bool mapping_scalars(const ReadSmem& S, const HcTablesDev& t, int node, double pc, double& aa,
-                                                double& cc) {
-    if (node >= t.n_rows) return false;
-    const uint32_t cls = S.node_class[node];
-    if (cls == 0xFFFFu) return false;
-    const double2 mk = cls < (uint32_t)kClassCache ? S.cls_cache[cls] : t.class_tab[cls];  // {mappability, match_prob}
-    if (S.tab->is_fasta) {
-        aa = 0.0;
-        cc = S.tab->one_minus_bep * mk.y;
-    } else {
-        const double pcm = pc * mk.x;
-        aa = 1.0 - pcm;
-        cc = pcm * mk.y;
-    }
-    return true;
+    return hi < 0x00100000 ? -CUDART_INF : v;  // zero; products are rescaled long before they go denormal
 }
 
 // ------------------------------------------------------------------------------------------
-// Generic per-read path: any length, any number of mappings, zero-length mappings anywhere, the
-// background-error latch.  Lane per mapping with an inline column loop, records read from `col` /
-// `map` wherever they live (shared or global).  Warp-collective.
+// K1: one read per thread, one 32-lane group per warp at a time.
+//
+// The batch is stored lane-interleaved (include/vgan_gpu.h), so the 32 threads of a warp read 64 (column
+// records) or 128 (mapping records) contiguous bytes per step: perfectly coalesced streaming loads, each byte
+// used once, no staging needed.  Per read the thread walks its columns from the LAST to the first:
+//   * the running sum of log(err) over the columns seen so far is exactly the quality sum the reference takes
+//     for the mapping that starts at the current column (src/update_likelihood.cpp:40-44 reads |algnseq|
+//     qualities from position_in_read; the `pos` bytes past the end count as quality 0);
+//   * the running product of the per-base mixtures (src/process_mapping.cpp:59-77) is the mapping's
+//     exp(A_i); one log per mapping instead of one per base.
+// When the walk reaches the first column of mapping i both are parked in per-thread lists (local memory,
+// lane-interleaved by the hardware); a second, branch-free pass over the mappings takes the log, forms B_i
+// and scatters B_i - A_i into the CTA's node vector with a shared-memory fp64 atomic.
+//
+// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | class cache | node_class u16[n_rows] ]
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void hc_generic_read(const uint16_t* __restrict__ col, const uint32_t* __restrict__ map, int Lp,
-                                             int M, int Lq, int mq, const ReadSmem& S, const HcTablesDev& t,
-                                             double& a_sum, int* err_flag, int lane) {
-    const HcSmallTables* T = S.tab;
-    const double le0 = T->log_err[0];
-    double qtot = 0.0;
-    int f90 = 0x7fffffff;  // first real quality byte >= 90: latches the background error mode (src/update_likelihood.cpp:42)
-    for (int c = lane; c < Lp; c += 32) {
-        const uint32_t qb = col[c] & 0xffu;
-        qtot += T->log_err[qb];
-        if (c < Lq && (int)(int8_t)qb >= 90) f90 = min(f90, c);
-    }
-    qtot = warp_sum_f64(qtot);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) f90 = min(f90, __shfl_xor_sync(kFull, f90, d));
-    const double pc = T->p_correct[mq];
-    int carry_len = 0;
-    double carry_seg = 0.0;
-    for (int base = 0; base < M; base += 32) {
-        const int i = base + lane;
-        const bool active = i < M;
-        const uint32_t rec = active ? map[i] : 0u;
-        const int node = (int)(rec & VGL_HC_MAP_MAX_NODE);
-        const int len = (int)(rec >> VGL_HC_MAP_NODE_BITS);
-        const int incl = warp_incl_scan_i32(len, lane);
-        const int pos = min(carry_len + incl - len, Lp);  // position_in_read (src/update_likelihood.cpp:37,45)
-        const int lg = min(len, Lp - pos);
-        carry_len += __shfl_sync(kFull, incl, 31);
-        double aa = 0.0, cc = 0.0;
-        bool ok = false;
-        if (active) {
-            ok = mapping_scalars(S, t, node, pc, aa, cc);
-            if (!ok) atomicOr(err_flag, VGL_ERR_BAD_NODE);
-        }
-        const bool latched = T->is_fasta || (f90 < pos + Lp);
-        double A = 0.0, seg = 0.0, prod = 1.0;
-        for (int j = 0; j < lg; ++j) {
-            const uint32_t cr = col[pos + j];
-            const uint32_t qb = cr & 0xffu;
-            seg += T->log_err[qb];
-            if (cr & VGL_HC_COL_VALID) {
-                const bool match = (cr & VGL_HC_COL_MATCH) != 0;
-                double f;
-                if (latched) f = match ? T->f_match_bep : T->f_mis_bep;
-                else f = T->f_pair[(match ? 0u : 256u) + qb];
-                prod *= fma(cc, f, aa * T->bg[VGL_HC_COL_BASE(cr)]);
-                if ((j & 15) == 15) {
-                    A += fast_log(prod, T->log_tab);
-                    prod = 1.0;
-                }
-            }
-        }
-        A += fast_log(prod, T->log_tab);
-        // log(err) over [pos, pos + Lp): stored columns from pos on, plus `pos` bytes past the end that count
-        // as quality 0 (src/update_likelihood.cpp:40-44)
-        const double seg_incl = warp_incl_scan_f64(seg, lane);
-        const double before = carry_seg + seg_incl - seg;
-        carry_seg += __shfl_sync(kFull, seg_incl, 31);
-        if (ok) {
-            const double B = (qtot - before) + (double)pos * le0;
-            atomicAdd(&S.acc[node], B - A);
-            a_sum += A;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Fast per-read path: Lp <= 128 columns, M <= 64 mappings, no quality byte >= 90, zero-length
-// mappings only at the end, at most kClassCache table classes.  Returns false (before any side effect)
-// when the read needs the generic path.  Warp-collective.  Everything it touches is addressed as shared
-// memory: `col` / `map` are byte addresses of the read's records inside the staged tile.
-// ------------------------------------------------------------------------------------------
-struct FastCtx {
-    uint32_t acc;        // node accumulators (f64)
-    uint32_t tab;        // HcSmallTables
-    uint32_t cls;        // class cache (double2)
-    uint32_t node_class; // u16 per node
-    uint32_t wb;         // this warp's WarpBuf
-    int n_rows;
-    bool fasta;
-    double one_minus_bep;
-};
-constexpr uint32_t kWbXs = offsetof(WarpBuf, xs);
-constexpr uint32_t kWbPq = offsetof(WarpBuf, pq);
-constexpr uint32_t kWbAc = offsetof(WarpBuf, ac);
-constexpr uint32_t kWbMask = offsetof(WarpBuf, mask);
-
-__device__ __forceinline__ bool hc_fast_read(uint32_t col, uint32_t map, int Lp, int M, int Lq, int mq, const FastCtx& F,
-                                             double& a_sum, bool& bad_node, int lane) {
-    // (1) quality pre-pass, blocked layout: this lane owns columns 4*lane .. 4*lane + 3
-    uint32_t qpack = 0;
-    {
-        const int cb = 4 * lane;
-        const uint32_t a = col + 2u * (uint32_t)cb;
-        const uint32_t r0 = cb + 0 < Lp ? lds_u16(a + 0) : 0u;
-        const uint32_t r1 = cb + 1 < Lp ? lds_u16(a + 2) : 0u;
-        const uint32_t r2 = cb + 2 < Lp ? lds_u16(a + 4) : 0u;
-        const uint32_t r3 = cb + 3 < Lp ? lds_u16(a + 6) : 0u;
-        qpack = (r0 & 0xffu) | ((r1 & 0xffu) << 8) | ((r2 & 0xffu) << 16) | (r3 << 24);
-    }
-    const int nin = max(0, min(4, Lp - 4 * lane));
-    const int nq = max(0, min(4, Lq - 4 * lane));
-    const uint32_t inb = nin >= 4 ? 0xffffffffu : ((1u << (8 * nin)) - 1u);
-    const uint32_t qin = nq >= 4 ? 0xffffffffu : ((1u << (8 * nq)) - 1u);
-    if (__any_sync(kFull, (__vcmpges4(qpack, 0x5a5a5a5au) & qin) != 0u)) return false;  // a real byte >= 90
-    const uint32_t gt = __vcmpgts4(qpack, 0x02020202u) & inb;  // 0xff where (signed) quality > 2
-    // per column: quality if > 2, else 1 << 16 (a stored column whose log(err) is log(0.25))
-    const uint32_t low = ~gt & inb;
-    const uint32_t qg = qpack & gt;
-    const uint32_t t0 = (qg & 0xffu) + ((low & 1u) << 16);
-    const uint32_t t1 = t0 + ((qg >> 8) & 0xffu) + ((low & 0x100u) << 8);
-    const uint32_t t2 = t1 + ((qg >> 16) & 0xffu) + (low & 0x10000u);
-    const uint32_t t3 = t2 + (qg >> 24) + ((low & 0x1000000u) >> 8);
-    const uint32_t incl = (uint32_t)warp_incl_scan_i32((int)t3, lane);
-    const uint32_t excl = incl - t3;
-    const uint32_t qtot = __shfl_sync(kFull, incl, 31);
-    sts_v4u32(F.wb + kWbPq + 16u * (uint32_t)lane, make_uint4(excl + t0, excl + t1, excl + t2, excl + t3));
-    if (lane < 4) sts_u32(F.wb + kWbMask + 4u * (uint32_t)lane, 0u);
-    __syncwarp();
-
-    // (2) per-mapping scalars, two rounds of 32 lanes
-    const double pc = lds_f64_c(F.tab + kOffPCorrect + 8u * (uint32_t)mq);
-    int node_[2], pos_[2], lg_[2];
-    bool ok_[2];
-    int carry = 0;
-    bool irregular = false;
-    uint32_t nz0 = 0;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int i = 32 * s + lane;
-        const bool active = i < M;
-        const uint32_t rec = active ? lds_u32(map + 4u * (uint32_t)i) : 0u;
-        const int node = (int)(rec & VGL_HC_MAP_MAX_NODE);
-        const int len = (int)(rec >> VGL_HC_MAP_NODE_BITS);
-        const int inc = warp_incl_scan_i32(len, lane);
-        const int pos = min(carry + inc - len, Lp);
-        const int lg = min(len, Lp - pos);
-        carry += __shfl_sync(kFull, inc, 31);
-        const uint32_t nz = __ballot_sync(kFull, lg > 0);
-        irregular |= (nz & (nz + 1u)) != 0u;  // columns must belong to a prefix of the mappings
-        if (s == 0) nz0 = nz;
-        else irregular |= (nz0 != kFull && nz != 0u);
-        bool ok = !active;
-        if (active) {
-            const uint32_t cls = node < F.n_rows ? lds_u16_c(F.node_class + 2u * (uint32_t)node) : 0xFFFFu;
-            ok = cls != 0xFFFFu;
-            const double2 mk = lds_v2f64_c(F.cls + 16u * (ok ? cls : 0u));  // {mappability, match_prob}
-            const double pcm = pc * mk.x;                                   // p_correctly_mapped, src/process_mapping.cpp:41
-            const double aa = F.fasta ? 0.0 : 1.0 - pcm;
-            const double cc = (F.fasta ? F.one_minus_bep : pcm) * mk.y;
-            sts_v2f64(F.wb + kWbAc + 16u * (uint32_t)i, aa, cc);
-            if (lg > 0) atoms_or_u32(F.wb + kWbMask + 4u * (uint32_t)(pos >> 5), 1u << (pos & 31));
-        }
-        node_[s] = node; pos_[s] = pos; lg_[s] = lg; ok_[s] = ok;
-    }
-    if (irregular) return false;
-    bad_node |= !ok_[0] | !ok_[1];
-    __syncwarp();
-
-    // (3) columns, strided layout: lane handles columns lane, lane + 32, ...
-    {
-        const uint4 m4 = lds_v4u32(F.wb + kWbMask);
-        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-        int before = -1;
-        const uint32_t lemask = 0xffffffffu >> (31 - lane);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            if (32 * it < Lp) {
-                const int c = 32 * it + lane;
-                const uint32_t rec = c < Lp ? lds_u16(col + 2u * (uint32_t)c) : 0u;
-                const int rank = max(before + __popc(mw[it] & lemask), 0);
-                const double2 ac = lds_v2f64(F.wb + kWbAc + 16u * (uint32_t)rank);
-                const double f = lds_f64_c(F.tab + kOffFPair + 8u * (((rec & VGL_HC_COL_MATCH) ? 0u : 256u) + (rec & 0xffu)));
-                const double bgv = lds_f64_c(F.tab + kOffBg + 8u * VGL_HC_COL_BASE(rec));
-                const double x = fma(ac.y, f, ac.x * bgv);
-                sts_f64(F.wb + kWbXs + 8u * (uint32_t)c, (rec & VGL_HC_COL_VALID) ? x : 1.0);
-            }
-            before += __popc(mw[it]);
-        }
-    }
-    __syncwarp();
-
-    // (4) per-mapping product -> A_i, quality prefix -> B_i, scatter
-    const double le0 = lds_f64_c(F.tab + kOffLogErr);
-    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
-    const bool any_long = __any_sync(kFull, lg_[0] > 8 || lg_[1] > 8);
-    double a_read = 0.0;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int i = 32 * s + lane;
-        if (i < M) {
-            const int pos = pos_[s], lg = lg_[s];
-            const uint32_t xa = F.wb + kWbXs + 8u * (uint32_t)pos;
-            double prod = 1.0, A = 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < lg) prod *= lds_f64(xa + 8u * j);
-            if (any_long) {
-                for (int j = 8; j < lg; ++j) {
-                    prod *= lds_f64(xa + 8u * (uint32_t)j);
-                    if ((j & 15) == 15) {
-                        A += fast_log_s(prod, F.tab + kOffLogTab);
-                        prod = 1.0;
-                    }
-                }
-            }
-            A += fast_log_s(prod, F.tab + kOffLogTab);
-            const uint32_t pre = pos > 0 ? lds_u32(F.wb + kWbPq + 4u * (uint32_t)(pos - 1)) : 0u;
-            const int sq = (int)(qtot & 0xffffu) - (int)(pre & 0xffffu);
-            const int nl = (int)(qtot >> 16) - (int)(pre >> 16) + pos;  // + `pos` bytes past the end (quality 0)
-            const double B = fma((double)sq, scale, (double)nl * le0);
-            if (ok_[s]) {
-                atoms_add_f64(F.acc + 8u * (uint32_t)node_[s], B - A);
-                a_read += A;
-            }
-        }
-    }
-    a_sum += a_read;
-    __syncwarp();
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------
-// K1
-// ------------------------------------------------------------------------------------------
-// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | class cache | node_class u16[n_rows] | WarpBuf x 16 |
-//                  stages x 3 | mbarriers ]
 __global__ void __launch_bounds__(kReadBlock, 1)
 hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
                int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
@@ -474,14 +128,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     double2* s_cls = reinterpret_cast<double2*>(smem_raw + off);
     off += kClassCache * sizeof(double2);
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
-    off += ((size_t)t.n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
-    WarpBuf* s_wb = reinterpret_cast<WarpBuf*>(smem_raw + off);
-    off += kConsumerWarps * sizeof(WarpBuf);
-    unsigned char* s_stage = smem_raw + off;
-    off += (size_t)kStages * kStageBytes;
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + off);  // full[kStages], empty[kStages]
-    __shared__ double s_warp_a[kConsumerWarps];
-    __shared__ unsigned int s_generic;
+    __shared__ double s_warp_a[kReadBlock / 32];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -497,124 +144,174 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         for (int k = tid; k < (int)(sizeof(HcSmallTables) / 4); k += kReadBlock) dst[k] = src[k];
         if (tid < kClassCache) s_cls[tid] = t.class_tab[tid];
     }
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(smem_u32(&s_bar[s]), 1);                         // full: the producer's expect_tx arrival
-            mbar_init(smem_u32(&s_bar[kStages + s]), kConsumerWarps);  // empty: one arrival per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_generic = 0;
-    }
     __syncthreads();
 
-    const uint32_t n_tiles = (b.n_reads + kTileReads - 1) / kTileReads;
+    const uint32_t A_acc = smem_u32(s_acc), A_tab = smem_u32(s_tab), A_cls = smem_u32(s_cls), A_class = smem_u32(s_class);
+    const uint32_t A_f = A_tab + kOffFPair, A_bg = A_tab + kOffBg, A_log = A_tab + kOffLogTab;
+    const bool fasta = s_tab->is_fasta != 0;
+    const double one_minus_bep = s_tab->one_minus_bep;
+    const double le0 = s_tab->log_err[0];
+    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
+    const bool classes_cached = t.n_class <= kClassCache;
+    const int n_rows = t.n_rows;
 
-    if (warp == kConsumerWarps) {
-        // ===== producer warp: one elected lane stages tiles with TMA bulk copies =====
-        if (lane == 0) {
-            uint32_t k = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-                const uint32_t st = k % kStages;
-                const uint32_t phase = (k / kStages) & 1u;
-                unsigned char* sb = s_stage + (size_t)st * kStageBytes;
-                const uint32_t full = smem_u32(&s_bar[st]);
-                mbar_wait_backoff(smem_u32(&s_bar[kStages + st]), phase ^ 1u);
-                const uint32_t r0 = tile * kTileReads;
-                const uint32_t nr = min((uint32_t)kTileReads, b.n_reads - r0);
-                const uint32_t c0 = __ldg(b.col_off + r0), c1 = __ldg(b.col_off + r0 + nr);
-                const uint32_t m0 = __ldg(b.map_off + r0), m1 = __ldg(b.map_off + r0 + nr);
-                StageHeader h;
-                h.r0 = r0; h.n_reads = nr; h.c0 = c0; h.m0 = m0;
-                h.direct = (c1 - c0 > (uint32_t)kTileColCap || m1 - m0 > (uint32_t)kTileMapCap) ? 1u : 0u;
-                const void *p_co, *p_mo, *p_nq, *p_mq, *p_col = nullptr, *p_map = nullptr;
-                uint32_t sh;
-                const uint32_t n_co = aligned_window(b.col_off, (size_t)r0 * 4, (size_t)(nr + 1) * 4, p_co, sh);
-                h.sh_col_off = sh / 4;
-                const uint32_t n_mo = aligned_window(b.map_off, (size_t)r0 * 4, (size_t)(nr + 1) * 4, p_mo, sh);
-                h.sh_map_off = sh / 4;
-                const uint32_t n_nq = aligned_window(b.n_qual, (size_t)r0 * 2, (size_t)nr * 2, p_nq, sh);
-                h.sh_nq = sh / 2;
-                const uint32_t n_mq = aligned_window(b.mapq, (size_t)r0, (size_t)nr, p_mq, sh);
-                h.sh_mq = sh;
-                uint32_t n_col = 0, n_map = 0;
-                h.sh_col = h.sh_map = 0;
-                if (!h.direct) {
-                    if (c1 > c0) { n_col = aligned_window(b.col, (size_t)c0 * 2, (size_t)(c1 - c0) * 2, p_col, sh); h.sh_col = sh / 2; }
-                    if (m1 > m0) { n_map = aligned_window(b.map, (size_t)m0 * 4, (size_t)(m1 - m0) * 4, p_map, sh); h.sh_map = sh / 4; }
+    double a_sum = 0.0;
+    bool bad_node = false;
+    double plist[kMapChunk];    // exp(A_i) of the mappings of the current pass
+    uint32_t slist[kMapChunk];  // quality sums from the mapping's first column on: (sum of q for q > 2) | (count of q <= 2) << 20
+
+    // {1 - pcm, pcm * K} of a mapping whose node is in table class `cls` (src/process_mapping.cpp:33-42)
+    auto scalars = [&](uint32_t cls, double pc, double& aa, double& cc) {
+        const bool ok = cls != 0xFFFFu;  // 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it
+        bad_node |= !ok;
+        const double2 mk = classes_cached ? lds_v2f64_c(A_cls + 16u * (ok ? cls : 0u)) : t.class_tab[ok ? cls : 0u];  // {mappability, match_prob}
+        const double pcm = pc * mk.x;
+        aa = fasta ? 0.0 : 1.0 - pcm;
+        cc = (fasta ? one_minus_bep : pcm) * mk.y;
+    };
+
+    const uint32_t warps_total = gridDim.x * (kReadBlock / 32);
+    for (uint32_t g = blockIdx.x * (kReadBlock / 32) + warp; g < b.n_groups; g += warps_total) {
+        const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
+        const int ncb = (int)(__ldg(b.grp_col_blk + g + 1) - cb0);  // 8-column blocks of this group
+        const int nmb = (int)(__ldg(b.grp_map_blk + g + 1) - mb0);  // 4-mapping blocks
+        if (nmb == 0) continue;  // no read of this group has a mapping
+        const uint4* gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
+        const uint4* gm = reinterpret_cast<const uint4*>(b.map) + (size_t)mb0 * 32 + lane;
+        const uint32_t r = g * 32 + lane;
+        const int Lp = (int)__ldg(b.n_cols + r);
+        const int M = (int)__ldg(b.n_maps + r);
+        const int f90 = (int)__ldg(b.first_q90 + r);  // 0xFFFF: no real quality byte >= 90
+        const double pc = lds_f64_c(A_tab + kOffPCorrect + 8u * (uint32_t)__ldg(b.mapq + r));
+        const int maxm = nmb * VGL_HC_MAP_BLK;
+
+        uint32_t suf = 0;   // quality sums over the columns walked so far (from the end of the read)
+        int c_done = Lp;    // columns >= c_done have been walked
+        // passes of up to kMapChunk mappings, from the last mappings to the first (one pass unless a read of the
+        // group has more than kMapChunk mappings)
+        for (int hi_u = maxm; hi_u > 0; hi_u -= kMapChunk) {
+            const int lo_u = max(hi_u - kMapChunk, 0);
+            const int hi = min(M, hi_u), lo = min(M, lo_u);
+            // ---- pass 1: columns, descending ----
+            int i = hi - 1;                 // current mapping
+            int pos = -1;                   // its first column
+            uint32_t and_m = 0x1ffu, or_m = 0u;  // f-table index = (record & and_m) | or_m
+            double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
+            // mapping records come in blocks of 4; the block below the current one is fetched ahead of need
+            int mb_idx = i >= 0 ? (i >> 2) : 0;
+            uint4 mb_cur = ldg_stream_v4(gm + (size_t)mb_idx * 32);
+            uint4 mb_prev = mb_idx > 0 ? ldg_stream_v4(gm + (size_t)(mb_idx - 1) * 32) : make_uint4(0, 0, 0, 0);
+            auto map_rec = [&](int idx) -> uint32_t {
+                if ((idx >> 2) != mb_idx) {
+                    mb_cur = mb_prev;
+                    --mb_idx;
+                    mb_prev = mb_idx > 0 ? ldg_stream_v4(gm + (size_t)(mb_idx - 1) * 32) : make_uint4(0, 0, 0, 0);
                 }
-                *reinterpret_cast<StageHeader*>(sb + kStHdr) = h;
-                mbar_expect_tx(full, n_co + n_mo + n_nq + n_mq + n_col + n_map);
-                bulk_g2s(smem_u32(sb + kStColOff), p_co, n_co, full);
-                bulk_g2s(smem_u32(sb + kStMapOff), p_mo, n_mo, full);
-                bulk_g2s(smem_u32(sb + kStNq), p_nq, n_nq, full);
-                bulk_g2s(smem_u32(sb + kStMq), p_mq, n_mq, full);
-                if (n_col) bulk_g2s(smem_u32(sb + kStCol), p_col, n_col, full);
-                if (n_map) bulk_g2s(smem_u32(sb + kStMap), p_map, n_map, full);
+                const int e = idx & 3;
+                return e == 0 ? mb_cur.x : e == 1 ? mb_cur.y : e == 2 ? mb_cur.z : mb_cur.w;
+            };
+            auto open_mapping = [&]() {
+                if (i < lo) { pos = -1; return; }
+                const uint32_t rec = map_rec(i);
+                pos = (int)(rec >> VGL_HC_MAP_NODE_BITS);
+                const uint32_t node = rec & VGL_HC_MAP_MAX_NODE;
+                const uint32_t cls = node < (uint32_t)n_rows ? lds_u16_c(A_class + 2u * node) : 0xFFFFu;
+                scalars(cls, pc, aa, cc);  // unconditional: a "class changed" branch would run for a lane or two on most steps
+                // the background error mode is on for this mapping once a real quality byte >= 90 lies before the
+                // end of its quality window [pos, pos + Lp)  (src/update_likelihood.cpp:40-44)
+                const bool latched = f90 < pos + Lp;
+                and_m = latched ? 0x100u : 0x1ffu;
+                or_m = latched ? 0x200u : 0u;
+            };
+            auto close_mapping = [&]() {
+                plist[i - lo] = prod;
+                slist[i - lo] = suf;
+                if (a_ext != 0.0) {  // the product was rescaled (more than ~30 very unlikely bases in one mapping)
+                    const uint32_t node = map_rec(i) & VGL_HC_MAP_MAX_NODE;
+                    if (node < (uint32_t)n_rows) atoms_add_f64(A_acc + 8u * node, -a_ext);
+                    a_sum += a_ext;
+                    a_ext = 0.0;
+                }
+                prod = 1.0;
+                --i;
+            };
+            open_mapping();
+            while (i >= lo && pos >= c_done) {  // mappings that own no column (they start at or past the end)
+                close_mapping();
+                open_mapping();
             }
-        }
-        __syncwarp();
-    } else {
-        // ===== consumer warps: one read at a time =====
-        ReadSmem S{s_acc, s_tab, s_cls, s_class};
-        FastCtx F;
-        F.acc = smem_u32(s_acc); F.tab = smem_u32(s_tab); F.cls = smem_u32(s_cls); F.node_class = smem_u32(s_class);
-        F.wb = smem_u32(&s_wb[warp]);
-        F.n_rows = t.n_rows; F.fasta = s_tab->is_fasta != 0; F.one_minus_bep = s_tab->one_minus_bep;
-        const bool classes_cached = t.n_class <= kClassCache;
-        const uint32_t stage_base = smem_u32(s_stage), bar_base = smem_u32(s_bar);
-        bool bad_node = false;
-        double a_sum = 0.0;
-        unsigned int n_generic = 0;
-        uint32_t k = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            const uint32_t st = k % kStages;
-            const uint32_t phase = (k / kStages) & 1u;
-            const unsigned char* sb = s_stage + (size_t)st * kStageBytes;
-            const uint32_t sa = stage_base + st * (uint32_t)kStageBytes;
-            mbar_wait(bar_base + 8u * st, phase);
-            // StageHeader fields (explicit shared loads)
-            const uint32_t h_n_reads = lds_u32(sa + kStHdr + offsetof(StageHeader, n_reads));
-            const uint32_t h_direct = lds_u32(sa + kStHdr + offsetof(StageHeader, direct));
-            const uint32_t a_co = sa + kStColOff + 4u * lds_u32(sa + kStHdr + offsetof(StageHeader, sh_col_off));
-            const uint32_t a_mo = sa + kStMapOff + 4u * lds_u32(sa + kStHdr + offsetof(StageHeader, sh_map_off));
-            const uint32_t a_nq = sa + kStNq + 2u * lds_u32(sa + kStHdr + offsetof(StageHeader, sh_nq));
-            const uint32_t a_mq = sa + kStMq + lds_u32(sa + kStHdr + offsetof(StageHeader, sh_mq));
-            const uint32_t h_sh_col = lds_u32(sa + kStHdr + offsetof(StageHeader, sh_col));
-            const uint32_t h_sh_map = lds_u32(sa + kStHdr + offsetof(StageHeader, sh_map));
-            const uint32_t h_c0 = lds_u32(sa + kStHdr + offsetof(StageHeader, c0));
-            const uint32_t h_m0 = lds_u32(sa + kStHdr + offsetof(StageHeader, m0));
-            const uint32_t a_col = sa + kStCol + 2u * h_sh_col;  // record c of the tile is at a_col + 2 * (c - c0)
-            const uint32_t a_map = sa + kStMap + 4u * h_sh_map;
-            for (uint32_t ri = warp; ri < h_n_reads; ri += kConsumerWarps) {
-                const uint32_t c_lo = lds_u32(a_co + 4u * ri), m_lo = lds_u32(a_mo + 4u * ri);
-                const int Lp = (int)(lds_u32(a_co + 4u * ri + 4u) - c_lo);
-                const int M = (int)(lds_u32(a_mo + 4u * ri + 4u) - m_lo);
-                const int Lq = (int)lds_u16(a_nq + 2u * ri);
-                const int mq = (int)lds_u8(a_mq + ri);
-                bool done = false;
-                if (!h_direct && classes_cached && Lp <= kFastCols && M <= kFastMaps && M > 0)
-                    done = hc_fast_read(a_col + 2u * (c_lo - h_c0), a_map + 4u * (m_lo - h_m0), Lp, M, Lq, mq, F, a_sum, bad_node, lane);
-                if (!done && M > 0) {
-                    if (h_direct) {
-                        hc_generic_read(b.col + c_lo, b.map + m_lo, Lp, M, Lq, mq, S, t, a_sum, err_flag, lane);
-                    } else {
-                        const uint16_t* t_col = reinterpret_cast<const uint16_t*>(sb + kStCol) + h_sh_col;
-                        const uint32_t* t_map = reinterpret_cast<const uint32_t*>(sb + kStMap) + h_sh_map;
-                        hc_generic_read(t_col + (c_lo - h_c0), t_map + (m_lo - h_m0), Lp, M, Lq, mq, S, t, a_sum, err_flag, lane);
+            int c_stop = 0;
+            if (lo > 0 && lo < M) {
+                const uint4 q = ldg_stream_v4(gm + (size_t)(lo >> 2) * 32);
+                const int e = lo & 3;
+                c_stop = (int)((e == 0 ? q.x : e == 1 ? q.y : e == 2 ? q.z : q.w) >> VGL_HC_MAP_NODE_BITS);
+            }
+            const bool walking = hi > lo;
+            auto column = [&](int c, uint32_t rec) {
+                if (c < c_done && c >= c_stop && walking) {
+                    const uint32_t q = rec & 0xffu;
+                    suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
+                    if (rec & VGL_HC_COL_VALID) {
+                        const double f = lds_f64_c(A_f + 8u * ((rec & and_m) | or_m));
+                        const double bgv = lds_f64_c(A_bg + 8u * VGL_HC_COL_BASE(rec));
+                        prod *= fma(cc, f, aa * bgv);
+                        if (prod < 1e-280) {  // keep the product normal: fold the tiny part into a correction term
+                            a_ext += fast_log_s(prod, A_log);
+                            prod = 1.0;
+                        }
                     }
-                    n_generic += 1;
+                    while (c == pos) {
+                        close_mapping();
+                        open_mapping();
+                    }
+                }
+            };
+            // column records come in blocks of 8, fetched two blocks ahead of the walk
+            uint4 cb_cur = ncb > 0 ? ldg_stream_v4(gc + (size_t)(ncb - 1) * 32) : make_uint4(0, 0, 0, 0);
+            uint4 cb_nxt = ncb > 1 ? ldg_stream_v4(gc + (size_t)(ncb - 2) * 32) : make_uint4(0, 0, 0, 0);
+            for (int cb = ncb - 1; cb >= 0; --cb) {
+                const uint4 cb_nxt2 = cb > 1 ? ldg_stream_v4(gc + (size_t)(cb - 2) * 32) : make_uint4(0, 0, 0, 0);
+                const int c8 = cb * VGL_HC_COL_BLK;
+                if (c8 < c_done) {  // (uniformly true in the single-pass case except for padding blocks)
+                    column(c8 + 7, cb_cur.w >> 16);
+                    column(c8 + 6, cb_cur.w & 0xffffu);
+                    column(c8 + 5, cb_cur.z >> 16);
+                    column(c8 + 4, cb_cur.z & 0xffffu);
+                    column(c8 + 3, cb_cur.y >> 16);
+                    column(c8 + 2, cb_cur.y & 0xffffu);
+                    column(c8 + 1, cb_cur.x >> 16);
+                    column(c8 + 0, cb_cur.x & 0xffffu);
+                }
+                cb_cur = cb_nxt;
+                cb_nxt = cb_nxt2;
+            }
+            if (walking) c_done = c_stop;
+            // ---- pass 2: mappings ----
+            for (int mbk = lo_u >> 2; mbk < (hi_u >> 2); ++mbk) {
+                const uint4 rb = ldg_stream_v4(gm + (size_t)mbk * 32);
+                const uint32_t recs[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int idx = mbk * 4 + e;
+                    if (idx < hi) {
+                        const uint32_t rm = recs[e];
+                        const uint32_t node = rm & VGL_HC_MAP_MAX_NODE;
+                        const double A = fast_log_s(plist[idx - lo_u], A_log);
+                        const uint32_t s = slist[idx - lo_u];
+                        // log(err) over [pos, pos + Lp): the stored columns from pos on plus `pos` bytes past the end
+                        // that count as quality 0  
+                        const double B = fma((double)(s & 0xfffffu), scale, (double)((s >> 20) + (rm >> VGL_HC_MAP_NODE_BITS)) * le0);
+                        if (node < (uint32_t)n_rows) atoms_add_f64(A_acc + 8u * node, B - A);
+                        a_sum += A;
+                    }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8u * (kStages + st));
-        }
-        if (__any_sync(kFull, bad_node) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
-        a_sum = warp_sum_f64(a_sum);
-        if (lane == 0) {
-            s_warp_a[warp] = a_sum;
-            if (n_generic) atomicAdd(&s_generic, n_generic);
         }
     }
+
+    if (__any_sync(kFull, bad_node) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
+    a_sum = warp_sum_f64(a_sum);
+    if (lane == 0) s_warp_a[warp] = a_sum;
     __syncthreads();
     double* my_acc = cta_node_acc + (size_t)blockIdx.x * (size_t)t.n_rows;
     for (int n = tid; n < t.n_rows; n += kReadBlock) {
@@ -623,9 +320,8 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     }
     if (tid == 0) {
         double tot = 0.0;
-        for (int w = 0; w < kConsumerWarps; ++w) tot += s_warp_a[w];
+        for (int w = 0; w < kReadBlock / 32; ++w) tot += s_warp_a[w];
         cta_a_total[blockIdx.x] += tot;
-        if (s_generic) atomicAdd(stats, (unsigned long long)s_generic);
     }
 }
 
@@ -840,9 +536,6 @@ static size_t read_smem_bytes(int n_rows) {
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     s += kClassCache * sizeof(double2);
     s += ((size_t)n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
-    s += kConsumerWarps * sizeof(WarpBuf);
-    s += (size_t)kStages * kStageBytes;
-    s += 2 * kStages * sizeof(unsigned long long);
     return (s + 127) & ~(size_t)127;
 }
 

@@ -396,8 +396,9 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                     e = fail(VGH_ERR_BAD_READ, "read %lld: a mapping has no edits (the reference indexes mppg_sizes out of range)", (long long)r);
                 else if (Lq > (int64_t)rc.read_seq.size())
                     e = fail(VGH_ERR_BAD_READ, "read %lld: quality string longer than the alignment", (long long)r);
-                else if (rc.read_seq.size() > 65535 || M > 65535)
-                    e = fail(VGH_ERR_BAD_READ, "read %lld: alignment too long for the v1 batch layout", (long long)r);
+                else if (rc.read_seq.size() > VGL_HC_MAP_MAX_POS || M > 65535)
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: alignment of %zu columns does not fit the mapping record (max %u)", (long long)r,
+                             rc.read_seq.size(), VGL_HC_MAP_MAX_POS);
                 else if (a->mapq[r] < 0 || a->mapq[r] >= 100)
                     e = fail(VGH_ERR_BAD_READ, "read %lld: mapping quality %d outside [0,100)", (long long)r, a->mapq[r]);
                 else {
@@ -405,8 +406,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                         const int64_t node = a->map_node[a->map_off[r] + i];
                         if (node < 0 || node > (int64_t)VGL_HC_MAP_MAX_NODE)
                             e = fail(VGH_ERR_BAD_NODE, "read %lld: node id %lld does not fit the mapping record", (long long)r, (long long)node);
-                        else if (rc.sizes[(size_t)i] > (int32_t)VGL_HC_MAP_MAX_SIZE)
-                            e = fail(VGH_ERR_BAD_READ, "read %lld: edit of %d columns does not fit the mapping record", (long long)r, rc.sizes[(size_t)i]);
+
                     }
                 }
             }
@@ -421,85 +421,128 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     }
     if (err) return fail(err, "%s", err_msg.c_str());
 
-    uint64_t tot_cols = 0, tot_maps = 0;
-    for (size_t k = 0; k < R; ++k) { tot_cols += ncols[k]; tot_maps += nmaps[k]; }
-    if (tot_cols > 0xfffffff0ull || tot_maps > 0xfffffff0ull) return fail(VGH_ERR_INVALID, "batch too large for 32-bit offsets; split it");
+    // Group reads of similar shape into warps of 32 lanes (the sum over reads is order independent): sort by
+    // (mappings, columns) so that the zero padding up to each group's longest read stays small.
+    std::vector<uint32_t> order(R);
+    for (size_t k = 0; k < R; ++k) order[k] = (uint32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return ((uint64_t)nmaps[x] << 32 | ncols[x]) < ((uint64_t)nmaps[y] << 32 | ncols[y]);
+    });
+    const size_t n_groups = (R + VGL_HC_LANES - 1) / VGL_HC_LANES;
+    std::vector<uint32_t> g_col(n_groups + 1, 0), g_map(n_groups + 1, 0);
+    for (size_t gI = 0; gI < n_groups; ++gI) {
+        uint32_t mc = 0, mm = 0;
+        for (size_t l = 0; l < VGL_HC_LANES && gI * VGL_HC_LANES + l < R; ++l) {
+            const uint32_t k = order[gI * VGL_HC_LANES + l];
+            mc = std::max(mc, ncols[k]);
+            mm = std::max(mm, nmaps[k]);
+        }
+        const uint64_t nc = (uint64_t)g_col[gI] + (mc + VGL_HC_COL_BLK - 1) / VGL_HC_COL_BLK;
+        const uint64_t nm = (uint64_t)g_map[gI] + (mm + VGL_HC_MAP_BLK - 1) / VGL_HC_MAP_BLK;
+        if (nc > 0x007fffffull || nm > 0x007fffffull) return fail(VGH_ERR_INVALID, "batch too large for 32-bit block offsets; split it");
+        g_col[gI + 1] = (uint32_t)nc;
+        g_map[gI + 1] = (uint32_t)nm;
+    }
+    const size_t col_blks = g_col[n_groups], map_blks = g_map[n_groups], lanes = n_groups * VGL_HC_LANES;
+    const size_t kColBlk = (size_t)VGL_HC_LANES * VGL_HC_COL_BLK, kMapBlk = (size_t)VGL_HC_LANES * VGL_HC_MAP_BLK;  // records per block
 
-    // one block, 256-byte aligned sub-arrays (+16 bytes of slack: the device stages tiles with 16-byte bulk copies)
+    // one block, 256-byte aligned sub-arrays
     size_t o = 0;
-    const size_t o_col_off = o; o = align_up(o + (R + 1) * 4 + 16, 256);
-    const size_t o_map_off = o; o = align_up(o + (R + 1) * 4 + 16, 256);
-    const size_t o_col = o; o = align_up(o + tot_cols * 2 + 16, 256);
-    const size_t o_map = o; o = align_up(o + tot_maps * 4 + 16, 256);
-    const size_t o_nq = o; o = align_up(o + R * 2 + 16, 256);
-    const size_t o_mq = o; o = align_up(o + R + 16, 256);
+    const size_t o_gc = o; o = align_up(o + (n_groups + 1) * 4, 256);
+    const size_t o_gm = o; o = align_up(o + (n_groups + 1) * 4, 256);
+    const size_t o_col = o; o = align_up(o + col_blks * kColBlk * 2, 256);
+    const size_t o_map = o; o = align_up(o + map_blks * kMapBlk * 4, 256);
+    const size_t o_nc = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_nm = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_ce = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_q9 = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_mq = o; o = align_up(o + lanes, 256);
     vgh_hc_packed* P = new vgh_hc_packed();
-    P->block_bytes = o;
+    P->block_bytes = std::max<size_t>(o, 256);
     P->pinned = pinned != 0;
     if (pinned) {
-        if (vgl_host_alloc(&P->block, o) != VGL_OK) {
+        if (vgl_host_alloc(&P->block, P->block_bytes) != VGL_OK) {
             delete P;
             return fail(VGH_ERR_INVALID, "pinned allocation failed: %s", vgl_last_error());
         }
     } else {
-        P->block = aligned_alloc(256, o);
+        P->block = aligned_alloc(256, P->block_bytes);
         if (!P->block) { delete P; return fail(VGH_ERR_INVALID, "out of host memory"); }
     }
     uint8_t* base = (uint8_t*)P->block;
-    uint32_t* col_off = (uint32_t*)(base + o_col_off);
-    uint32_t* map_off = (uint32_t*)(base + o_map_off);
+    uint32_t* grp_col_blk = (uint32_t*)(base + o_gc);
+    uint32_t* grp_map_blk = (uint32_t*)(base + o_gm);
     uint16_t* col = (uint16_t*)(base + o_col);
     uint32_t* map = (uint32_t*)(base + o_map);
-    uint16_t* n_qual = (uint16_t*)(base + o_nq);
+    uint16_t* n_cols = (uint16_t*)(base + o_nc);
+    uint16_t* n_maps = (uint16_t*)(base + o_nm);
+    uint16_t* cov_end = (uint16_t*)(base + o_ce);
+    uint16_t* first_q90 = (uint16_t*)(base + o_q9);
     uint8_t* mapq = base + o_mq;
-    col_off[0] = 0;
-    map_off[0] = 0;
-    for (size_t k = 0; k < R; ++k) { col_off[k + 1] = col_off[k] + ncols[k]; map_off[k + 1] = map_off[k] + nmaps[k]; }
-    memset((uint8_t*)(col_off + R + 1), 0, 16); memset((uint8_t*)(map_off + R + 1), 0, 16);
-    memset((uint8_t*)(col + tot_cols), 0, 16); memset((uint8_t*)(map + tot_maps), 0, 16);
-    memset((uint8_t*)(n_qual + R), 0, 16); memset(mapq + R, 0, 16);
+    memcpy(grp_col_blk, g_col.data(), (n_groups + 1) * 4);
+    memcpy(grp_map_blk, g_map.data(), (n_groups + 1) * 4);
 
-    // pass 2: fill.  Column records pair G[c] with the read base process_mapping compares it with
-    // (src/update_likelihood.cpp:33-49, src/process_mapping.cpp:47,59-66): for mapping i the graph slice
+    // pass 2: fill, one group per task.  Column records pair G[c] with the read base process_mapping compares it
+    // with (src/update_likelihood.cpp:33-49, src/process_mapping.cpp:47,59-66): for mapping i the graph slice
     // G[pos_i, pos_i + size_i) faces algnseq[0, size_i) -- the whole aligned read string from its start.
     auto base_code = [](char ch) -> int { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; };
 #pragma omp parallel num_threads(n_threads)
     {
         Recon rc;
-#pragma omp for schedule(static)
-        for (int64_t k = 0; k < (int64_t)R; ++k) {
-            const int64_t r = keep[(size_t)k];
-            if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
-            const uint32_t c0 = col_off[k], m0 = map_off[k];
-            const size_t L = rc.read_seq.size();
-            const int64_t q0 = a->qual_off[r], Lq = a->qual_off[r + 1] - q0;
-            for (size_t c = 0; c < L; ++c) col[c0 + c] = (uint16_t)((int64_t)c < Lq ? (uint8_t)a->qual[q0 + (int64_t)c] : 0);
-            const int64_t mm = a->map_off[r];
-            size_t pos = 0;
-            for (uint32_t i = 0; i < nmaps[(size_t)k]; ++i) {
-                const size_t size = (size_t)rc.sizes[i];
-                const size_t lg = std::min(size, L - pos);
-                for (size_t j = 0; j < lg; ++j) {
-                    const char gb = rc.graph_seq[pos + j], rb = rc.read_seq[j];
-                    const int cg = base_code(gb), cb = base_code(rb);
-                    uint16_t rec = col[c0 + pos + j];
-                    if (cg < 4 && cb < 4) rec |= (uint16_t)(VGL_HC_COL_VALID | (cb << 8) | (gb == rb ? VGL_HC_COL_MATCH : 0));
-                    col[c0 + pos + j] = rec;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t gI = 0; gI < (int64_t)n_groups; ++gI) {
+            uint16_t* gcol = col + (size_t)g_col[(size_t)gI] * kColBlk;
+            uint32_t* gmap = map + (size_t)g_map[(size_t)gI] * kMapBlk;
+            memset(gcol, 0, (size_t)(g_col[(size_t)gI + 1] - g_col[(size_t)gI]) * kColBlk * 2);
+            memset(gmap, 0, (size_t)(g_map[(size_t)gI + 1] - g_map[(size_t)gI]) * kMapBlk * 4);
+            // record c of lane l: block c / 8, then lane, then c % 8 (mapping records: blocks of 4)
+            auto col_at = [&](size_t c, size_t l) -> uint16_t& { return gcol[((c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK]; };
+            auto map_at = [&](size_t i, size_t l) -> uint32_t& { return gmap[((i / VGL_HC_MAP_BLK) * VGL_HC_LANES + l) * VGL_HC_MAP_BLK + i % VGL_HC_MAP_BLK]; };
+            for (size_t l = 0; l < VGL_HC_LANES; ++l) {
+                const size_t lane_id = (size_t)gI * VGL_HC_LANES + l;
+                n_cols[lane_id] = n_maps[lane_id] = cov_end[lane_id] = 0;
+                first_q90[lane_id] = 0xFFFF;
+                mapq[lane_id] = 0;
+                if (lane_id >= R) continue;
+                const uint32_t k = order[lane_id];
+                const int64_t r = keep[k];
+                if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
+                const size_t L = rc.read_seq.size();
+                const int64_t q0 = a->qual_off[r], Lq = a->qual_off[r + 1] - q0;
+                for (size_t c = 0; c < L; ++c) {
+                    const uint8_t qb = (int64_t)c < Lq ? (uint8_t)a->qual[q0 + (int64_t)c] : 0;
+                    col_at(c, l) = qb;
+                    if ((int64_t)c < Lq && (int)(int8_t)qb >= 90 && first_q90[lane_id] == 0xFFFF) first_q90[lane_id] = (uint16_t)c;
                 }
-                map[m0 + i] = VGL_HC_MAP_REC((uint32_t)a->map_node[mm + i], (uint32_t)size);
-                pos += lg;
+                const int64_t mm = a->map_off[r];
+                size_t pos = 0;
+                for (uint32_t i = 0; i < nmaps[k]; ++i) {
+                    const size_t lg = std::min((size_t)rc.sizes[i], L - pos);
+                    for (size_t j = 0; j < lg; ++j) {
+                        const char gb = rc.graph_seq[pos + j], rb = rc.read_seq[j];
+                        const int cg = base_code(gb), cb = base_code(rb);
+                        if (cg < 4 && cb < 4)
+                            col_at(pos + j, l) |= (uint16_t)(VGL_HC_COL_VALID | (cb << 9) | (gb == rb ? 0 : VGL_HC_COL_MISMATCH));
+                    }
+                    map_at(i, l) = VGL_HC_MAP_REC((uint32_t)a->map_node[mm + i], (uint32_t)pos);
+                    pos += lg;
+                }
+                n_cols[lane_id] = (uint16_t)L;
+                n_maps[lane_id] = (uint16_t)nmaps[k];
+                cov_end[lane_id] = (uint16_t)pos;
+                mapq[lane_id] = (uint8_t)a->mapq[r];
             }
-            n_qual[k] = (uint16_t)Lq;
-            mapq[k] = (uint8_t)a->mapq[r];
         }
     }
     P->skipped = (r1 - r0) - (int64_t)R;
     P->batch.n_reads = (uint32_t)R;
-    P->batch.n_cols = tot_cols;
-    P->batch.n_maps = tot_maps;
-    P->batch.col_off = col_off; P->batch.map_off = map_off;
+    P->batch.n_groups = (uint32_t)n_groups;
+    P->batch.n_col_blks = col_blks;
+    P->batch.n_map_blks = map_blks;
+    P->batch.grp_col_blk = grp_col_blk; P->batch.grp_map_blk = grp_map_blk;
     P->batch.col = col; P->batch.map = map;
-    P->batch.n_qual = n_qual; P->batch.mapq = mapq;
+    P->batch.n_cols = n_cols; P->batch.n_maps = n_maps; P->batch.cov_end = cov_end;
+    P->batch.first_q90 = first_q90; P->batch.mapq = mapq;
     *out = P;
     return VGH_OK;
 }

@@ -95,14 +95,14 @@ struct vgl_ctx {
 
     // staging for host batches: two slots so that the H2D copy of chunk k+1 overlaps the read kernel on chunk k
     struct Slot {
-        DevBuf<uint32_t> col_off, map_off, map;
-        DevBuf<uint16_t> col, n_qual;
+        DevBuf<uint32_t> grp_col_blk, grp_map_blk, map;
+        DevBuf<uint16_t> col, n_cols, n_maps, first_q90;
         DevBuf<uint8_t> mapq;
         cudaEvent_t copied = nullptr, consumed = nullptr;
         bool used = false;
     } slot[2];
     cudaStream_t copy_stream = nullptr;
-    uint32_t chunk_reads = 131072;
+    uint32_t chunk_groups = 4096;  // 131072 reads per H2D chunk
     DevBuf<unsigned long long> d_stats;
 
     // read-kernel timing
@@ -125,7 +125,7 @@ int upload_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 }
 
 int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
-    if (b.n_reads == 0) return VGL_OK;
+    if (b.n_groups == 0) return VGL_OK;
     if (ctx->ev_used == ctx->ev_pool.size()) {
         cudaEvent_t a, c;
         VGL_CUDA(cudaEventCreate(&a));
@@ -144,11 +144,12 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
 
 int check_batch(const vgl_hc_batch* b) {
     if (!b) return fail(VGL_ERR_INVALID, "null batch");
-    if (b->n_reads == 0) return VGL_OK;
-    if (!b->col_off || !b->map_off || !b->n_qual || !b->mapq) return fail(VGL_ERR_INVALID, "batch header arrays missing");
-    if (b->n_cols && !b->col) return fail(VGL_ERR_INVALID, "batch column records missing");
-    if (b->n_maps && !b->map) return fail(VGL_ERR_INVALID, "batch mapping records missing");
-    if (b->n_cols > 0xffffffffull || b->n_maps > 0xffffffffull) return fail(VGL_ERR_INVALID, "batch too large for 32-bit offsets; split it");
+    if (b->n_groups == 0) return VGL_OK;
+    if ((uint64_t)b->n_groups * VGL_HC_LANES < b->n_reads) return fail(VGL_ERR_INVALID, "n_groups too small for n_reads");
+    if (!b->grp_col_blk || !b->grp_map_blk || !b->n_cols || !b->n_maps || !b->cov_end || !b->first_q90 || !b->mapq)
+        return fail(VGL_ERR_INVALID, "batch header arrays missing");
+    if (b->n_col_blks && !b->col) return fail(VGL_ERR_INVALID, "batch column records missing");
+    if (b->n_map_blks && !b->map) return fail(VGL_ERR_INVALID, "batch mapping records missing");
     return VGL_OK;
 }
 
@@ -209,7 +210,8 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_post.release(); ctx->d_scalars.release(); ctx->d_idx.release();
     for (auto& sl : ctx->slot) {
-        sl.col_off.release(); sl.map_off.release(); sl.map.release(); sl.col.release(); sl.n_qual.release(); sl.mapq.release();
+        sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
+        sl.n_maps.release(); sl.first_q90.release(); sl.mapq.release();
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.consumed) cudaEventDestroy(sl.consumed);
     }
@@ -269,7 +271,8 @@ uint64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b) {
     if (!b) return 0;
-    return (uint64_t)(b->n_reads + 1) * 8 + b->n_cols * 2 + b->n_maps * 4 + (uint64_t)b->n_reads * 3;
+    return (uint64_t)(b->n_groups + 1) * 8 + (b->n_col_blks + b->n_map_blks) * 512 +
+           (uint64_t)b->n_groups * VGL_HC_LANES * 9;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -332,6 +335,8 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
         // background error probability replaces the quality for every base (src/HaploCart.cpp:397-401).
         small.f_pair[b] = small.is_fasta ? small.f_match_bep : 1 - eps_match;
         small.f_pair[256 + b] = small.is_fasta ? small.f_mis_bep : 1 - eps_mis;
+        small.f_pair[512 + b] = small.f_match_bep;  // latched reads: index (record & 0x100) | 0x200
+        small.f_pair[768 + b] = small.f_mis_bep;
         const double perr = (Q > 2) ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;  // get_p_seq_error, src/miscfunc.h:180-187
         small.log_err[b] = std::log(perr);
         // fast_log table: rc ~ 1 / c_k and -log(rc) for the bucket centre c_k = 1 + (k + 0.5) / 256
@@ -459,7 +464,7 @@ int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
-    vgl::HcBatchDev d{b->n_reads, b->col_off, b->map_off, b->col, b->map, b->n_qual, b->mapq};
+    vgl::HcBatchDev d{b->n_groups, b->grp_col_blk, b->grp_map_blk, b->col, b->map, b->n_cols, b->n_maps, b->first_q90, b->mapq};
     return launch_read(ctx, d);
 }
 
@@ -467,45 +472,52 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
-    if (b->n_reads == 0) return VGL_OK;
-    // The batch is cut into chunks of reads; the H2D copy of a chunk runs on the copy stream into one of two
-    // staging slots while the read kernel works on the other.  Offsets stay absolute: the kernel is given array
-    // bases shifted back by the chunk's first element.
-    const uint32_t R = b->n_reads;
+    if (b->n_groups == 0) return VGL_OK;
+    // The batch is cut into chunks of groups; the H2D copy of a chunk runs on the copy stream into one of two
+    // staging slots while the read kernel works on the other.  Row offsets stay absolute: the kernel is given
+    // record bases shifted back by the chunk's first row.
+    const uint32_t G = b->n_groups;
     uint32_t n_chunk = 0;
-    for (uint32_t r0 = 0; r0 < R; r0 += ctx->chunk_reads, ++n_chunk) {
-        const uint32_t r1 = std::min(R, r0 + ctx->chunk_reads);
-        const uint32_t nr = r1 - r0;
-        const uint32_t c0 = b->col_off[r0], c1 = b->col_off[r1];
-        const uint32_t m0 = b->map_off[r0], m1 = b->map_off[r1];
-        if (c1 < c0 || m1 < m0 || c1 > b->n_cols || m1 > b->n_maps) return fail(VGL_ERR_INVALID, "batch offsets are not monotone");
+    for (uint32_t g0 = 0; g0 < G; g0 += ctx->chunk_groups, ++n_chunk) {
+        const uint32_t g1 = std::min(G, g0 + ctx->chunk_groups);
+        const uint32_t ng = g1 - g0;
+        const size_t nl = (size_t)ng * VGL_HC_LANES;
+        const uint64_t c0 = b->grp_col_blk[g0], c1 = b->grp_col_blk[g1];
+        const uint64_t m0 = b->grp_map_blk[g0], m1 = b->grp_map_blk[g1];
+        if (c1 < c0 || m1 < m0 || c1 > b->n_col_blks || m1 > b->n_map_blks) return fail(VGL_ERR_INVALID, "batch block offsets are not monotone");
+        const size_t ncol = (size_t)(c1 - c0) * VGL_HC_LANES * VGL_HC_COL_BLK, nmap = (size_t)(m1 - m0) * VGL_HC_LANES * VGL_HC_MAP_BLK;
         vgl_ctx::Slot& sl = ctx->slot[n_chunk & 1];
         if (sl.used) VGL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, sl.consumed, 0));  // the kernel that last read this slot
-        const bool grow = nr + 1 > sl.col_off.cap || c1 - c0 > sl.col.cap || m1 - m0 > sl.map.cap;
-        if (grow) VGL_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (int rc = sl.col_off.reserve((size_t)nr + 1 + 8)) return rc;
-        if (int rc = sl.map_off.reserve((size_t)nr + 1 + 8)) return rc;
-        if (int rc = sl.n_qual.reserve((size_t)nr + 16)) return rc;
-        if (int rc = sl.mapq.reserve((size_t)nr + 32)) return rc;
-        if (int rc = sl.col.reserve((size_t)(c1 - c0) + 16)) return rc;
-        if (int rc = sl.map.reserve((size_t)(m1 - m0) + 16)) return rc;
+        if (ng + 1 > sl.grp_col_blk.cap || ncol > sl.col.cap || nmap > sl.map.cap) VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (int rc = sl.grp_col_blk.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.grp_map_blk.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.n_cols.reserve(nl)) return rc;
+        if (int rc = sl.n_maps.reserve(nl)) return rc;
+        if (int rc = sl.first_q90.reserve(nl)) return rc;
+        if (int rc = sl.mapq.reserve(nl)) return rc;
+        if (int rc = sl.col.reserve(ncol)) return rc;
+        if (int rc = sl.map.reserve(nmap)) return rc;
         cudaStream_t cs = ctx->copy_stream;
-        if (int rc = upload_async(sl.col_off.p, b->col_off + r0, ((size_t)nr + 1) * 4, cs)) return rc;
-        if (int rc = upload_async(sl.map_off.p, b->map_off + r0, ((size_t)nr + 1) * 4, cs)) return rc;
-        if (int rc = upload_async(sl.n_qual.p, b->n_qual + r0, (size_t)nr * 2, cs)) return rc;
-        if (int rc = upload_async(sl.mapq.p, b->mapq + r0, (size_t)nr, cs)) return rc;
-        if (int rc = upload_async(sl.col.p, b->col + c0, (size_t)(c1 - c0) * 2, cs)) return rc;
-        if (int rc = upload_async(sl.map.p, b->map + m0, (size_t)(m1 - m0) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.grp_col_blk.p, b->grp_col_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.grp_map_blk.p, b->grp_map_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.n_cols.p, b->n_cols + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.n_maps.p, b->n_maps + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.first_q90.p, b->first_q90 + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.mapq.p, b->mapq + (size_t)g0 * VGL_HC_LANES, nl, cs)) return rc;
+        if (int rc = upload_async(sl.col.p, b->col + (size_t)c0 * VGL_HC_LANES * VGL_HC_COL_BLK, ncol * 2, cs)) return rc;
+        if (int rc = upload_async(sl.map.p, b->map + (size_t)m0 * VGL_HC_LANES * VGL_HC_MAP_BLK, nmap * 4, cs)) return rc;
         VGL_CUDA(cudaEventRecord(sl.copied, cs));
         VGL_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
-        // absolute offsets index the shifted bases; (uintptr_t arithmetic: the shifted pointers are never dereferenced below the slot)
         vgl::HcBatchDev d;
-        d.n_reads = nr;
-        d.col_off = sl.col_off.p;
-        d.map_off = sl.map_off.p;
-        d.col = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col.p) - (uintptr_t)c0 * 2);
-        d.map = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.map.p) - (uintptr_t)m0 * 4);
-        d.n_qual = sl.n_qual.p;
+        d.n_groups = ng;
+        d.grp_col_blk = sl.grp_col_blk.p;
+        d.grp_map_blk = sl.grp_map_blk.p;
+        // (uintptr_t arithmetic: the shifted bases are only ever dereferenced at rows >= c0 / m0, i.e. inside the slot)
+        d.col = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col.p) - (uintptr_t)c0 * 512);
+        d.map = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.map.p) - (uintptr_t)m0 * 512);
+        d.n_cols = sl.n_cols.p;
+        d.n_maps = sl.n_maps.p;
+        d.first_q90 = sl.first_q90.p;
         d.mapq = sl.mapq.p;
         if (int rc = launch_read(ctx, d)) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));

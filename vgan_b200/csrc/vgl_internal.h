@@ -12,7 +12,8 @@ namespace vgl {
 // Indexed by the RAW quality byte (0..255); bytes >= 128 are negative as `signed char`, which is
 // how the reference sees them (src/update_likelihood.cpp:41).
 struct HcSmallTables {
-    double f_pair[512];    // 1 - eps: [q] graph base == read base (eps = qscore[Q]); [256 + q] mismatch (eps = 1 - qscore[Q])
+    double f_pair[1024];   // 1 - eps: [q] graph base == read base (eps = qscore[Q]); [256 + q] mismatch (eps = 1 - qscore[Q]);
+                           // [512] / [768]: the same with the background error probability (latched reads)
     double log_err[256];   // log(get_p_seq_error(Q))           src/process_mapping.cpp:11
     double2 log_tab[256];  // fast_log table: {rc_k ~ 1/c_k, -log(rc_k)}, c_k = 1 + (k + 0.5)/256
     double p_correct[100]; // 1 - p_incorrect_map[mapq]         src/process_mapping.cpp:41
@@ -39,12 +40,14 @@ struct HcTablesDev {
 };
 
 struct HcBatchDev {
-    uint32_t n_reads;
-    const uint32_t* col_off;
-    const uint32_t* map_off;
+    uint32_t n_groups;
+    const uint32_t* grp_col_blk;
+    const uint32_t* grp_map_blk;
     const uint16_t* col;
     const uint32_t* map;
-    const uint16_t* n_qual;
+    const uint16_t* n_cols;
+    const uint16_t* n_maps;
+    const uint16_t* first_q90;
     const uint8_t* mapq;
 };
 

@@ -114,19 +114,19 @@ class Haplocart:
 
 
 class DeviceBatch:
-    _FIELDS = [("col_off", 4, "r1"), ("map_off", 4, "r1"), ("col", 2, "c"), ("map", 4, "m"), ("n_qual", 2, "r"),
-               ("mapq", 1, "r")]
-
     def __init__(self, hc, packed):
         self.hc = hc
         b = packed.batch
-        counts = {"r": int(b.n_reads), "r1": int(b.n_reads) + 1, "c": int(b.n_cols), "m": int(b.n_maps)}
+        G, L = int(b.n_groups), _lib.LANES
+        sizes = {"grp_col_blk": (G + 1) * 4, "grp_map_blk": (G + 1) * 4, "col": int(b.n_col_blks) * 512,
+                 "map": int(b.n_map_blks) * 512, "n_cols": G * L * 2, "n_maps": G * L * 2, "cov_end": G * L * 2,
+                 "first_q90": G * L * 2, "mapq": G * L}
         self.batch = _lib.vgl_hc_batch()
-        self.batch.n_reads, self.batch.n_cols, self.batch.n_maps = b.n_reads, b.n_cols, b.n_maps
+        self.batch.n_reads, self.batch.n_groups = b.n_reads, b.n_groups
+        self.batch.n_col_blks, self.batch.n_map_blks = b.n_col_blks, b.n_map_blks
         self.ptrs = []
         self.nbytes = 0
-        for name, size, kind in self._FIELDS:
-            n = counts[kind] * size
+        for name, n in sizes.items():
             p = C.c_void_p()
             check(gpu.vgl_device_alloc(hc.ctx, C.byref(p), n + 16))
             self.ptrs.append(p)

@@ -133,12 +133,36 @@ class PackedBatch:
 
     def arrays(self):
         b = self.batch
-        R, nc, nm = int(b.n_reads), int(b.n_cols), int(b.n_maps)
+        G, ncb, nmb = int(b.n_groups), int(b.n_col_blks), int(b.n_map_blks)
+        L, CB, MB = _lib.LANES, _lib.COL_BLK, _lib.MAP_BLK
         return {
-            "col_off": _as_array(b.col_off, R + 1, np.uint32), "map_off": _as_array(b.map_off, R + 1, np.uint32),
-            "col": _as_array(b.col, nc, np.uint16), "map": _as_array(b.map, nm, np.uint32),
-            "n_qual": _as_array(b.n_qual, R, np.uint16), "mapq": _as_array(b.mapq, R, np.uint8),
+            "grp_col_blk": _as_array(b.grp_col_blk, G + 1, np.uint32), "grp_map_blk": _as_array(b.grp_map_blk, G + 1, np.uint32),
+            "col": _as_array(b.col, ncb * L * CB, np.uint16).reshape(ncb, L, CB),
+            "map": _as_array(b.map, nmb * L * MB, np.uint32).reshape(nmb, L, MB),
+            "n_cols": _as_array(b.n_cols, G * L, np.uint16), "n_maps": _as_array(b.n_maps, G * L, np.uint16),
+            "cov_end": _as_array(b.cov_end, G * L, np.uint16), "first_q90": _as_array(b.first_q90, G * L, np.uint16),
+            "mapq": _as_array(b.mapq, G * L, np.uint8),
         }
+
+    def lanes(self):
+        """Per-read records, un-blocked: a list of dicts (col records, map records, n_cols, cov_end, first_q90, mapq),
+        one per non-empty lane, in the packer's (shape-sorted) order."""
+        a = self.arrays()
+        out = []
+        for g in range(int(self.batch.n_groups)):
+            c0, c1 = int(a["grp_col_blk"][g]), int(a["grp_col_blk"][g + 1])
+            m0, m1 = int(a["grp_map_blk"][g]), int(a["grp_map_blk"][g + 1])
+            for l in range(_lib.LANES):
+                k = g * _lib.LANES + l
+                if k >= self.n_reads:
+                    break
+                nc, nm = int(a["n_cols"][k]), int(a["n_maps"][k])
+                cols = a["col"][c0:c1, l, :].reshape(-1)
+                maps = a["map"][m0:m1, l, :].reshape(-1)
+                assert not cols[nc:].any() and not maps[nm:].any()  # padding records are zero
+                out.append({"col": cols[:nc].tolist(), "map": maps[:nm].tolist(), "n_cols": nc,
+                            "cov_end": int(a["cov_end"][k]), "first_q90": int(a["first_q90"][k]), "mapq": int(a["mapq"][k])})
+        return out
 
     def __del__(self):
         if self.handle:
