@@ -211,19 +211,19 @@ def main():
     reads_local = packed.n_reads
     batch_bytes = packed.nbytes
 
-    ll_local = torch.zeros(N_PATHS, dtype=torch.float64, device="cuda")
-    parts = torch.zeros(world * N_PATHS, dtype=torch.float64, device="cuda") if world > 1 else None
+    sharded = None
+    if world > 1:
+        from vgan_b200.dist import ShardedSample
+        sharded = ShardedSample(hc)  # all-gather of the per-rank final_vec + fixed-order sum (vgan_b200/dist.py)
 
     def step(host_buffers):
+        if sharded is not None:
+            return sharded.run([packed] if host_buffers else [dev], device_resident=not host_buffers)
         hc.reset()
         if host_buffers:
             hc.update(packed)
         else:
             hc.update_device(dev.batch)
-        if world > 1:
-            hc.paths(ll_local.data_ptr())
-            dist.all_gather_into_tensor(parts, ll_local)      # the one exchange step of the path (41 KB per rank)
-            hc.set_paths_from_parts(parts.data_ptr(), world)  # fixed rank order: ties stay bit-identical
         return hc.get_posterior(want_ll=False)
 
     def barrier():

@@ -1,0 +1,76 @@
+"""N > 1 host logic on CPU: two `gloo` ranks shard the reads, each computes its share of final_vec (here with the
+CPU oracle standing in for the device, since no GPU exists in this container), the vectors are all-gathered and
+summed in rank order exactly as vgan_b200.dist does for NCCL, and the call must equal the single-process call."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_reads, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vgan_b200 as vb
+    from vgan_b200 import dist as vd
+    from oracle import oracle as orc
+    import helpers as H
+    S = vb.SynthHaplocart(seed=51, n_paths=120, n_rows=610, n_nodes=601)
+    alns = S.reads(n_reads, seed=52)
+    T, G, R = H.oracle_side(S, alns.arrays())
+    lo, hi = vd.shard_range(n_reads, rank, world)
+    final, _, used = orc.hc_run(T, G, R, r0=lo, r1=hi)
+    local = torch.from_numpy(final.astype(np.float64))
+    parts = vd.gather_paths(local)
+    total = vd.sum_in_rank_order(parts.numpy())
+    used_t = torch.tensor([used], dtype=torch.int64)
+    dist.all_reduce(used_t)
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.concatenate([total, [float(used_t.item()), lo, hi]]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vgan_b200 as vb
+    from oracle import oracle as orc
+    import helpers as H
+    n_reads, world = 41, 2
+    mp.spawn(_worker, args=(world, _free_port(), n_reads, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "rank0.npy")
+    r1 = np.load(tmp_path / "rank1.npy")
+    assert np.array_equal(r0[:-3], r1[:-3])                    # every rank holds the identical, fixed-order sum
+    assert (r0[-2], r0[-1], r1[-2], r1[-1]) == (0, 21, 21, 41)  # block partition covers the reads once
+    S = vb.SynthHaplocart(seed=51, n_paths=120, n_rows=610, n_nodes=601)
+    alns = S.reads(n_reads, seed=52)
+    T, G, R = H.oracle_side(S, alns.arrays())
+    final, argmax, used = orc.hc_run(T, G, R)
+    assert r0[-3] == used
+    assert int(np.argmax(r0[:-3])) == argmax
+    assert H.rel_err(r0[:-3], final.astype(np.float64)) < 1e-13
+
+
+def test_shard_range_partitions():
+    from vgan_b200 import dist as vd
+    for n in (0, 1, 7, 64, 1000003):
+        for w in (1, 2, 3, 8):
+            cuts = [vd.shard_range(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[k][1] == cuts[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1

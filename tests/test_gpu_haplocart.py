@@ -318,3 +318,28 @@ def test_config2_shape_properties():
     final, argmax, _ = orc.hc_run(T, G, R, r0=0, r1=sub, n_threads=0)
     assert r["maxh_index"] == argmax and H.rel_err(r["final_vec"], final.astype(np.float64)) < LL_RTOL
     hc.close()
+
+
+def test_parts_summed_in_rank_order_equal_the_whole(small):
+    """The multi-GPU exchange on one device: two 'ranks' each reduce their half of the reads to a final_vec in
+    device memory; vgl_hc_set_paths_from_parts adds them in order and the posterior kernel runs on the sum."""
+    from vgan_b200._lib import gpu, check
+    alns = small.reads(500, seed=208)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    whole = hc.run_sample([vb.PackedBatch(small.graph, alns)])
+    P = small.n_paths
+    parts = C.c_void_p()
+    check(gpu.vgl_device_alloc(hc.ctx, C.byref(parts), 2 * P * 8))
+    for k, (a, b) in enumerate(((0, 250), (250, 500))):
+        hc.reset()
+        hc.update(vb.PackedBatch(small.graph, alns, r0=a, r1=b))
+        hc.paths(parts.value + k * P * 8)
+    hc.reset()
+    hc.set_paths_from_parts(parts.value, 2)
+    both = hc.get_posterior()
+    assert both["maxh_index"] == whole["maxh_index"]
+    assert H.rel_err(both["final_vec"], whole["final_vec"]) < 1e-13
+    assert np.allclose(both["confidence_vec"], whole["confidence_vec"], rtol=1e-9)
+    check(gpu.vgl_device_free(hc.ctx, parts))
+    hc.close()

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing for the HaploCart path: one process per GPU, `torch.distributed` for the single
+exchange step.
+
+The path shards by reads: every rank runs the read kernel and the node x path pass on its own share of the
+sample with replicated tables and ends up with its own final_vec[P].  The ranks all-gather those vectors
+(41 KB each for the HaploCart graph -- pure latency on NVLink) and every rank adds them IN RANK ORDER before
+the posterior kernel.  A ring all-reduce would add different chunks of the vector in different rank orders,
+which could break exact ties between identically supported paths; the fixed order keeps the call
+bit-identical on every rank and independent of the collective algorithm.
+
+`torch` is used only here and in bench.py: for the process group and for device memory that NCCL can see.
+"""
+import numpy as np
+
+
+def shard_range(n_reads, rank, world):
+    """Contiguous block of reads for `rank` (block partition)."""
+    base, extra = divmod(int(n_reads), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sum_in_rank_order(parts):
+    """Fixed-order sum of per-rank vectors (host mirror of vgl_hc_set_paths_from_parts)."""
+    parts = np.asarray(parts, dtype=np.float64)
+    total = np.zeros(parts.shape[1], dtype=np.float64)
+    for k in range(parts.shape[0]):
+        total += parts[k]
+    return total
+
+
+def gather_paths(local_vec, group=None):
+    """All-gather this rank's final_vec (a 1-D float64 torch tensor on the backend's device) into [world, P]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = torch.empty((world, local_vec.numel()), dtype=local_vec.dtype, device=local_vec.device)
+    dist.all_gather_into_tensor(parts.view(-1), local_vec.contiguous(), group=group)
+    return parts
+
+
+class ShardedSample:
+    """One sample spread over the ranks of a process group.  Each rank owns a `Haplocart` on its own GPU."""
+
+    def __init__(self, hc, group=None):
+        import torch
+        import torch.distributed as dist
+        self.hc, self.group = hc, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.local = torch.zeros(hc.n_paths, dtype=torch.float64, device="cuda")
+        self.parts = torch.zeros(self.world * hc.n_paths, dtype=torch.float64, device="cuda")
+        hc.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def run(self, local_batches, device_resident=False, want_ll=False):
+        import torch.distributed as dist
+        hc = self.hc
+        hc.reset()
+        for b in local_batches:
+            if device_resident:
+                hc.update_device(b.batch)
+            else:
+                hc.update(b)
+        hc.paths(self.local.data_ptr())
+        dist.all_gather_into_tensor(self.parts, self.local, group=self.group)
+        hc.set_paths_from_parts(self.parts.data_ptr(), self.world)
+        return hc.get_posterior(want_ll=want_ll)
