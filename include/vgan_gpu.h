@@ -229,6 +229,88 @@ uint64_t vgl_launch_count(const vgl_ctx* ctx);
  * on the launching stream); valid after vgl_synchronize / vgl_hc_finalize.                      */
 int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out);
 
+/* ------------------------------------------------------------------------------------------- */
+/* euka: per-read "in clade" vs "random alignment" likelihoods with ancient-DNA damage         */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Replaces the body of the per-alignment lambda of readGAM3 (src/readGAM_Euka.h:103-549, caller
+ * src/Euka.cpp:534-537): clade of the read from its first node, per aligned column the damage-aware
+ * in-clade likelihood and the random-alignment likelihood, the per-read clade_like value, the pass
+ * filter, the per-clade count and the per-bin coverage.  euka scores every read against exactly ONE
+ * clade, so a "read x clade evaluation" is one read.  The baseshift counters
+ * (src/readGAM_Euka.h:160-173) are an integer histogram outside the likelihood path and stay on the host.
+ *
+ *   clade_dist[c]        clade_vec->at(c*6+1)->dist                       (src/load.cpp:108-157)
+ *   bin_off/bin_lo/hi    chunks.at(c): node-id ranges of the clade's bins (src/load.cpp:71-95)
+ *   deam[i5][i3][a][b]   subDeamDiNuc[L][l].p[a][b] with i5 = min(l, k5-1), i3 = min(L-l-1, k3-1):
+ *                        Damage::initDeamProbabilities repeats the last profile row to the end of the
+ *                        fragment, so the matrix depends on (L, l) only through those two indices
+ *                        (src/damage.cpp:41-258); k5/k3 = rows of the --deam5p/--deam3p profiles (1 if none)
+ *   qscore[Q]            Euka::get_qscore_vec: qs[2] = 10^-0.2, unlike HaploCart's (src/Euka.cpp:38-51)
+ *   base_freq_log[5]     base_freq['A','C','G','T','N'] (already logs)    (src/Euka.cpp:446-450)
+ *   tt_ratio[a][b]       t_T_ratio over A,C,G,T                           (src/Euka.cpp:453-468)
+ *   minimum_mq           --minMQ (default 29)                             (src/Euka.cpp:184,282-284)     */
+typedef struct vgl_euka_tables {
+    int32_t n_clades;
+    int32_t n_bins;
+    int32_t max_node;     /* largest node id of the graph (the node -> clade table covers 0..max_node) */
+    int32_t k5, k3;
+    uint32_t minimum_mq;
+    const double* clade_dist; /* [n_clades] */
+    const int32_t* bin_off;   /* [n_clades + 1] */
+    const int32_t* bin_lo;    /* [n_bins] */
+    const int32_t* bin_hi;    /* [n_bins] */
+    const double* deam;       /* [k5 * k3 * 16] */
+    double qscore[100];
+    double base_freq_log[5];
+    double tt_ratio[4][4];
+} vgl_euka_tables;
+
+int vgl_euka_set_tables(vgl_ctx* ctx, const vgl_euka_tables* tables);
+
+/* euka read batch, warp-striped like vgl_hc_batch (groups of 32 lanes, column blocks of 8 records,
+ * mapping blocks of 4).  Column record m of a read (m < n_cols = |aligned graph string|), 16 bits:
+ *   bits 0-7   quality byte at ALIGNED COLUMN m (src/readGAM_Euka.h:264,286; 0 past the end)
+ *   bits 8-11  symbol of the aligned graph string, bits 12-15 symbol of the aligned read string:
+ *              0-3 = A C G T, 4 = N, 5 = '-', 6 = an IUPAC code flagged in rare_bases (W M K R Y B D H V),
+ *              7 = 'S' (soft clip marker), 8 = anything else
+ * Mapping record: the node id.  Per lane: n_cols, n_maps, seq_len = |Alignment.sequence|, mapq,
+ * flags bit 0 = first mapping on the reverse strand, read_index = position of the read in the caller's
+ * order (per-read results are written there).                                                  */
+#define VGL_EUKA_SYM_N 4
+#define VGL_EUKA_SYM_GAP 5
+#define VGL_EUKA_SYM_RARE 6
+#define VGL_EUKA_SYM_SOFTCLIP 7
+#define VGL_EUKA_SYM_OTHER 8
+typedef struct vgl_euka_batch {
+    uint32_t n_reads;
+    uint32_t n_groups;
+    uint64_t n_col_blks;
+    uint64_t n_map_blks;
+    const uint32_t* grp_col_blk; /* [n_groups + 1] */
+    const uint32_t* grp_map_blk; /* [n_groups + 1] */
+    const uint16_t* col;         /* [n_col_blks][32][8] */
+    const uint32_t* map;         /* [n_map_blks][32][4] */
+    const uint16_t* n_cols;      /* [n_groups * 32] */
+    const uint16_t* n_maps;      /* [n_groups * 32] */
+    const uint16_t* seq_len;     /* [n_groups * 32] */
+    const uint8_t* mapq;         /* [n_groups * 32] */
+    const uint8_t* flags;        /* [n_groups * 32] */
+    const uint32_t* read_index;  /* [n_groups * 32] */
+} vgl_euka_batch;
+
+/* Zero the per-clade counts and bin coverage (start of a sample). */
+int vgl_euka_reset(vgl_ctx* ctx);
+/* Score a host batch.  Per-read outputs (host arrays indexed by read_index, each may be NULL):
+ *   clade[r]   clade id c_n;  in_lik[r] / not_lik[r] the two log-likelihoods;
+ *   like[r]    map_q * exp(in - logsumexp(in, not))  (clade_like; clade_not_like is 1 - like);
+ *   pass[r]    1 if in - not > 1 and mapq > minimum_mq (the read is counted and adds bin coverage).   */
+int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* host_batch, uint32_t n_out, int32_t* clade, double* in_lik,
+                 double* not_lik, double* like, uint8_t* pass);
+/* Per-clade count (Clade::count) and per-bin coverage (get<3>(chunks[c][j])) accumulated since the reset. */
+int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov);
+uint64_t vgl_euka_batch_bytes(const vgl_euka_batch* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,25 @@ const int32_t* vgh_hc_tree_anc_clade(const vgh_hc_tree* t);
 const char* vgh_hc_tree_clade_name(const vgh_hc_tree* t, int32_t clade);
 void vgh_hc_tree_destroy(vgh_hc_tree* t);
 
+/* ---- euka: tables and batch packer -------------------------------------------------------------- */
+typedef struct vgh_euka_tables vgh_euka_tables;
+/* deam5p_prof / deam3p_prof: CONTENTS of the --deam5p / --deam3p profile files (src/miscfunc.h:84-136),
+ * NULL or "" for none.  Builds the combined substitution matrices of Damage::initDeamProbabilities
+ * (src/damage.cpp:41-258) for every distinct (5' row, 3' row) pair.                                 */
+int vgh_euka_tables_build(int32_t n_clades, const double* clade_dist, const int32_t* bin_off, const int32_t* bin_lo,
+                          const int32_t* bin_hi, int32_t max_node, const char* deam5p_prof, const char* deam3p_prof,
+                          uint32_t minimum_mq, vgh_euka_tables** out);
+const vgl_euka_tables* vgh_euka_tables_view(const vgh_euka_tables* t);
+void vgh_euka_tables_destroy(vgh_euka_tables* t);
+
+typedef struct vgh_euka_packed vgh_euka_packed;
+/* Pack reads [r0, r1) (identity != 0, as readGAM3 keeps them, src/readGAM_Euka.h:73); read_index is relative
+ * to r0.  Fragments outside [15, 1000] bp are rejected: the reference indexes subDeamDiNuc out of range. */
+int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                  vgh_euka_packed** out);
+const vgl_euka_batch* vgh_euka_packed_batch(const vgh_euka_packed* p);
+void vgh_euka_packed_destroy(vgh_euka_packed* p);
+
 /* ---- synthetic HaploCart-shaped workloads (benchmark / test inputs) --- */
 /* The real tables (share/vgan/hcfiles) are FTP downloads; tests and bench.py generate inputs of the
  * same shapes instead.  Pure functions of their seeds.                                            */
@@ -139,6 +158,20 @@ const char* vgh_synth_hc_children(const vgh_synth_hc* s);
 int32_t vgh_synth_hc_total_len(const vgh_synth_hc* s);
 int vgh_synth_hc_reads(const vgh_synth_hc* s, uint64_t seed, int64_t n_reads, int32_t fixed_len, double sub_rate,
                        double indel_rate, int damage, int32_t origin_path, vgh_gam** out);
+
+/* euka-shaped workload: clades own consecutive node ranges, 10-15 overlapping bins each. */
+typedef struct vgh_synth_euka vgh_synth_euka;
+int vgh_synth_euka_create(uint64_t seed, int32_t n_clades, int32_t genome_len, vgh_synth_euka** out);
+void vgh_synth_euka_destroy(vgh_synth_euka* s);
+const vgh_graph* vgh_synth_euka_graph(const vgh_synth_euka* s);
+int64_t vgh_synth_euka_graph_seq(const vgh_synth_euka* s, const int64_t** seq_off, const char** seq);
+int32_t vgh_synth_euka_n_clades(const vgh_synth_euka* s);
+const double* vgh_synth_euka_dist(const vgh_synth_euka* s);
+const int32_t* vgh_synth_euka_bin_off(const vgh_synth_euka* s);
+const int32_t* vgh_synth_euka_bin_lo(const vgh_synth_euka* s);
+const int32_t* vgh_synth_euka_bin_hi(const vgh_synth_euka* s);
+int vgh_synth_euka_reads(const vgh_synth_euka* s, uint64_t seed, int64_t n_reads, int32_t fixed_len, double indel_rate,
+                         int damage, double n_rate, double softclip_rate, vgh_gam** out);
 
 #ifdef __cplusplus
 }

@@ -230,3 +230,40 @@ def incorrect_mapping_vec():
 
 def region_match_prob(pb):
     return lib().orc_hc_region_match_prob(int(pb))
+
+
+# ---- euka ------------------------------------------------------------------------------------------------------
+class _EukaTables(C.Structure):
+    _fields_ = [("n_clades", C.c_int32), ("clade_dist", C.c_void_p), ("bin_off", C.c_void_p), ("bin_lo", C.c_void_p),
+                ("bin_hi", C.c_void_p), ("deam5p_prof", C.c_char_p), ("deam3p_prof", C.c_char_p), ("minimum_mq", C.c_uint32)]
+
+
+def euka_run(clade_dist, bin_off, bin_lo, bin_hi, graph, reads, deam5p_prof="", deam3p_prof="", minimum_mq=29):
+    """The readGAM3 lambda over every read.  Returns a dict of per-read arrays plus clade_count / bin_cov."""
+    dist = np.ascontiguousarray(clade_dist, dtype=np.float64)
+    boff = np.ascontiguousarray(bin_off, dtype=np.int64)
+    blo = np.ascontiguousarray(bin_lo, dtype=np.int32)
+    bhi = np.ascontiguousarray(bin_hi, dtype=np.int32)
+    T = _EukaTables(dist.size, _ptr(dist), _ptr(boff), _ptr(blo), _ptr(bhi), (deam5p_prof or "").encode(),
+                    (deam3p_prof or "").encode(), int(minimum_mq))
+    n = reads.n
+    out = {"clade": np.zeros(n, dtype=np.int32), "in_lik": np.zeros(n), "not_lik": np.zeros(n), "like": np.zeros(n),
+           "not_like": np.zeros(n), "pass": np.zeros(n, dtype=np.uint8)}
+    count = np.zeros(dist.size, dtype=np.int64)
+    cov = np.zeros(max(int(boff[-1]), 1), dtype=np.float64)
+    rc = lib().orc_euka_run(C.byref(T), C.byref(graph.c), C.byref(reads.c), _ptr(out["clade"]), _ptr(out["in_lik"]),
+                            _ptr(out["not_lik"]), _ptr(out["like"]), _ptr(out["not_like"]), _ptr(out["pass"]), _ptr(count),
+                            _ptr(cov))
+    if rc:
+        raise RuntimeError("orc_euka_run failed: %d" % rc)
+    out["clade_count"] = count
+    out["bin_cov"] = cov[:int(boff[-1])]
+    return out
+
+
+def euka_deam_matrix(deam5p_prof, deam3p_prof, L, l):
+    m = np.zeros(16)
+    rc = lib().orc_euka_deam_matrix((deam5p_prof or "").encode(), (deam3p_prof or "").encode(), int(L), int(l), _ptr(m))
+    if rc:
+        raise RuntimeError("orc_euka_deam_matrix failed: %d" % rc)
+    return m.reshape(4, 4)

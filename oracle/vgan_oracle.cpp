@@ -34,6 +34,7 @@
 // Everything else (Q1,Q2,Q3,Q5,Q6,Q7,Q9,Q10) is reproduced as written in the reference.
 // =====================================================================================
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -658,6 +659,282 @@ int orc_hc_posterior(const long double* final_vec, int32_t n_paths, const char* 
     }
     return n;
 }
+
+}  // extern "C"
+
+// =====================================================================================
+// euka: per-read "in clade" vs "random alignment" likelihoods with ancient-DNA damage.
+// Restates the per-alignment lambda of readGAM3 (reference src/readGAM_Euka.h:67-577) and
+// Damage::initDeamProbabilities (src/damage.cpp:18-36,41-258, profile reader src/miscfunc.h:84-136).
+// The baseshift substitution counters (src/readGAM_Euka.h:160-173) are an integer histogram outside
+// the likelihood path and are not restated.
+//
+// Defined behaviour where the reference has none:
+//   * the quality string is indexed by ALIGNED COLUMN (src/readGAM_Euka.h:264,286); a column index at
+//     or past its end reads as byte 0 (std::string::operator[] guarantees that only AT the end);
+//   * base_freq / t_T_ratio / rare_bases are class-member arrays indexed by char and written for a
+//     handful of letters only (src/Euka.cpp:446-486, src/Euka.h:50-52); every other entry reads as
+//     0.0 / false here (rare_bases is declared one entry too short for 'Y' in the reference);
+//   * fragments shorter than MINLENGTHFRAGMENT (15) or longer than MAXLENGTHFRAGMENT (1000) index
+//     subDeamDiNuc out of range in the reference; orc_euka_run reports ORC_ERR_RANGE for them.
+// =====================================================================================
+namespace {
+
+const unsigned MINLENGTHFRAGMENT = 15, MAXLENGTHFRAGMENT = 1000;  // src/damage.h:42-43
+
+struct DiNuc { long double p[4][4]; };
+
+// dimer2indexInt (libgab): position of the substitution nuc1>nuc2 in the .prof column order
+// A>C A>G A>T C>A C>G C>T G>A G>C G>T T>A T>C T>G (src/baseshift.cpp:152)
+inline int dimer2indexInt(int nuc1, int nuc2) { return nuc1 * 3 + (nuc2 > nuc1 ? nuc2 - 1 : nuc2); }
+
+// readNucSubstitionRatesFreq (src/miscfunc.h:84-136): header line, then rows of 12 tab-separated rates
+// (an optional 13th field is dropped).
+int read_profile(const char* text, vector<std::array<long double, 12>>& rows) {
+    rows.clear();
+    std::istringstream in(text);
+    string line;
+    if (!std::getline(in, line)) return ORC_ERR_RANGE;
+    while (std::getline(in, line)) {
+        vector<string> f;
+        std::istringstream ls(line);
+        string tok;
+        while (std::getline(ls, tok, '\t')) f.push_back(tok);
+        if (f.size() == 13) f.pop_back();
+        if (f.size() != 12) return ORC_ERR_RANGE;
+        std::array<long double, 12> r;
+        for (int k = 0; k < 12; ++k) r[(size_t)k] = strtold(f[(size_t)k].c_str(), nullptr);
+        rows.push_back(r);
+    }
+    return ORC_OK;
+}
+
+struct Damage {
+    vector<DiNuc> sub5pDiNuc, sub3pDiNuc;  // per position from the 5' / 3' end, MAXLENGTHFRAGMENT entries each
+
+    static int side(const char* text, vector<DiNuc>& out) {
+        vector<std::array<long double, 12>> rates;
+        if (text && text[0]) {
+            int rc = read_profile(text, rates);
+            if (rc) return rc;
+            if (rates.empty()) return ORC_ERR_RANGE;
+        } else {
+            std::array<long double, 12> z;
+            z.fill(0.0L);
+            rates.assign(MAXLENGTHFRAGMENT, z);
+        }
+        vector<std::array<long double, 16>> sub;
+        for (size_t i = 0; i < rates.size(); ++i) {
+            std::array<long double, 16> toadd;
+            toadd.fill(0.0L);
+            for (int nuc1 = 0; nuc1 < 4; ++nuc1) {
+                double probIdentical = 1.0;
+                for (int nuc2 = 0; nuc2 < 4; ++nuc2) {
+                    if (nuc1 == nuc2) continue;
+                    const int ind2 = dimer2indexInt(nuc1, nuc2);
+                    probIdentical = probIdentical - rates[i][(size_t)ind2];
+                    toadd[(size_t)(nuc1 * 4 + nuc2)] = rates[i][(size_t)ind2];
+                }
+                if (probIdentical < 0) return ORC_ERR_RANGE;
+                toadd[(size_t)(nuc1 * 4 + nuc1)] = probIdentical;
+            }
+            sub.push_back(toadd);
+        }
+        for (size_t i = sub.size() - 1; i < MAXLENGTHFRAGMENT; ++i) sub.push_back(sub[sub.size() - 1]);  // repeat the last row
+        out.clear();
+        for (unsigned i = 0; i < MAXLENGTHFRAGMENT; ++i) {
+            DiNuc d;
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) d.p[a][b] = sub[i][(size_t)(a * 4 + b)];
+            out.push_back(d);
+        }
+        return ORC_OK;
+    }
+    int init(const char* deam5p, const char* deam3p) {
+        int rc = side(deam5p, sub5pDiNuc);
+        if (rc) return rc;
+        return side(deam3p, sub3pDiNuc);
+    }
+    // subDeamDiNuc[L][l]: per original base the 5' or the 3' row with the SMALLER diagonal (combineDeamRates)
+    DiNuc at(unsigned L, unsigned l) const {
+        DiNuc d;
+        for (int b1 = 0; b1 < 4; ++b1) {
+            const long double* f1 = sub5pDiNuc[l].p[b1];
+            const long double* f2 = sub3pDiNuc[L - l - 1].p[b1];
+            const long double m = f1[b1] < f2[b1] ? f1[b1] : f2[b1];
+            const long double* f = (f1[b1] == m) ? f1 : f2;
+            for (int b2 = 0; b2 < 4; ++b2) d.p[b1][b2] = f[b2];
+        }
+        return d;
+    }
+};
+
+vector<double> euka_qscore_vec() {  // Euka::get_qscore_vec, src/Euka.cpp:38-51 (qs[2] = 10^-0.2, quirk Q7)
+    vector<double> v;
+    for (int Q = 0; Q < 100; ++Q) v.push_back(Q >= 2 ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25);
+    return v;
+}
+
+struct EukaTables {
+    double base_freq[256];
+    double t_T_ratio[256][256];
+    bool rare_bases[256];
+    EukaTables() {
+        for (int i = 0; i < 256; ++i) {
+            base_freq[i] = 0.0;
+            rare_bases[i] = false;
+            for (int j = 0; j < 256; ++j) t_T_ratio[i][j] = 0.0;
+        }
+        base_freq['A'] = std::log(0.362815); base_freq['C'] = std::log(0.207743); base_freq['G'] = std::log(0.116809);
+        base_freq['N'] = std::log(0.25); base_freq['T'] = std::log(0.312435);
+        const char* B = "ACGT";
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) t_T_ratio[(int)B[i]][(int)B[j]] = (i == j) ? 1.0 : 0.02381;
+        t_T_ratio['A']['G'] = t_T_ratio['G']['A'] = t_T_ratio['C']['T'] = t_T_ratio['T']['C'] = 0.95238;
+        for (const char* c = "WMKRYBDHV"; *c; ++c) rare_bases[(int)*c] = true;
+    }
+};
+
+inline ld oplusnatl_ld(ld x, ld y) { return x > y ? x + log1pl(expl(y - x)) : y + log1pl(expl(x - y)); }
+inline ld oplusInitnatl_ld(ld x, ld y) { return x == 0 ? y : oplusnatl_ld(x, y); }
+inline int quality_at(const string& q, size_t m) { return m < q.size() ? (int)(signed char)q[m] : 0; }
+inline double euka_qs(const vector<double>& qs, int q) { return (q >= 0 && q < (int)qs.size()) ? qs[(size_t)q] : 0.25; }
+
+}  // namespace
+
+extern "C" {
+
+typedef struct {
+    int32_t n_clades;
+    const double* clade_dist;   // clade_vec->at(c * 6 + 1)->dist (src/load.cpp:108-157)
+    const int64_t* bin_off;     // [n_clades + 1] into bin_lo / bin_hi: chunks.at(c) (src/load.cpp:71-95)
+    const int32_t* bin_lo;
+    const int32_t* bin_hi;
+    const char* deam5p_prof;    // contents of the --deam5p / --deam3p profile files ("" = none)
+    const char* deam3p_prof;
+    uint32_t minimum_mq;        // --minMQ (default 29)
+} orc_euka_tables;
+
+// Runs the lambda over reads [0, n) with identity != 0.  Per-read outputs are indexed by read; reads that are
+// skipped (identity == 0) keep clade = -1.  clade_count / bin_cov are the per-clade count and per-bin coverage.
+int orc_euka_run(const orc_euka_tables* T, const orc_graph* g, const orc_reads* R, int32_t* clade_out, double* in_out,
+                 double* not_out, double* like_out, double* not_like_out, uint8_t* pass_out, int64_t* clade_count,
+                 double* bin_cov) {
+    Damage dmg;
+    int rc = dmg.init(T->deam5p_prof, T->deam3p_prof);
+    if (rc) return rc;
+    const EukaTables E;
+    const vector<double> qscore_vec = euka_qscore_vec();
+    const char* ACGT = "ACGT";
+    for (int c = 0; c < T->n_clades; ++c) clade_count[c] = 0;
+    for (int64_t b = 0; b < T->bin_off[T->n_clades]; ++b) bin_cov[b] = 0.0;
+    for (int64_t r = 0; r < R->n_reads; ++r) {
+        clade_out[r] = -1;
+        in_out[r] = not_out[r] = like_out[r] = not_like_out[r] = 0.0;
+        pass_out[r] = 0;
+        if (R->identity[r] == 0) continue;  // unmapped (src/readGAM_Euka.h:73)
+        ReadView a = load_read(*R, r);
+        if (a.mapping.empty()) return ORC_ERR_RANGE;
+        const int n_index = (int)a.mapping[0].node_id;
+        // clade of the read: the LAST bin (over all clades, in file order) containing the first node id (:115-140)
+        int c_n = 0;
+        for (int i = 0; i < T->n_clades; ++i)
+            for (int64_t j = T->bin_off[i]; j < T->bin_off[i + 1]; ++j)
+                if (n_index == std::clamp(n_index, T->bin_lo[j], T->bin_hi[j])) c_n = i;
+        const double pair_dist = T->clade_dist[c_n];
+        string graph_seq, read_seq;
+        vector<int> mppg_sizes;
+        rc = reconstruct_graph_sequence(*g, a.mapping, graph_seq, read_seq, mppg_sizes);
+        if (rc) return rc;
+        double in_clade_lik = 0.0, not_in_clade_lik = 0.0;
+        double log_lik = 0.0, log_lik_2 = 0.0;
+        int softclip_count = 0;
+        unsigned int n = 0;
+        const unsigned int Lseq = (unsigned)a.seq.size();
+        if (Lseq < MINLENGTHFRAGMENT || Lseq > MAXLENGTHFRAGMENT) return ORC_ERR_RANGE;
+        const bool isrev = a.mapping[0].is_reverse;
+        if (isrev) n = Lseq - 1;
+        for (unsigned int m = 0; m < graph_seq.size(); m++) {
+            const unsigned char G = (unsigned char)graph_seq[m];
+            const unsigned char Rb = m < read_seq.size() ? (unsigned char)read_seq[m] : 0;
+            if (G == 'N' || Rb == 'N') {
+                log_lik = E.base_freq[Rb];
+                log_lik_2 = E.base_freq[Rb];
+            } else if (G == '-' || Rb == '-') {
+                log_lik = std::log(0.002);
+                log_lik_2 = std::log(0.2);
+            } else if (E.rare_bases[G] || E.rare_bases[Rb]) {
+                log_lik = std::log((1 - pair_dist) * 0.001);
+                log_lik_2 = std::log(0.001);
+            } else if (G == 'S' || Rb == 'S') {
+                const int base_quality = quality_at(a.quality, m);
+                ++softclip_count;
+                if (softclip_count % 3 == 0) log_lik = std::log(1 - euka_qs(qscore_vec, base_quality));
+                else log_lik = std::log(euka_qs(qscore_vec, base_quality) / 3);
+                log_lik_2 = std::log(0.25);
+            } else {
+                const int base_quality = quality_at(a.quality, m);
+                const double e = euka_qs(qscore_vec, base_quality);
+                if (n >= Lseq) return ORC_ERR_RANGE;  // subDeamDiNuc[Lseq][n] out of range in the reference
+                const DiNuc D = dmg.at(Lseq, n);
+                double probBasePreDamage[4];
+                for (int bpo = 0; bpo < 4; bpo++) {
+                    if (ACGT[bpo] == (char)G) probBasePreDamage[bpo] = (1 - pair_dist);
+                    else probBasePreDamage[bpo] = pair_dist * E.t_T_ratio[G][(unsigned char)ACGT[bpo]];
+                }
+                double probBasePostDamage[4] = {0, 0, 0, 0};
+                for (int bpd = 0; bpd < 4; bpd++)
+                    for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
+                double log_lik_marg = 0.0;
+                for (int bpd = 0; bpd < 4; bpd++) {
+                    if (ACGT[bpd] == (char)Rb) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd] * (1 - e)));
+                    else log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd] * (e / 3)));
+                }
+                log_lik = log_lik_marg;
+                if (G == Rb) log_lik_2 = std::log(1 - 0.25536);
+                else log_lik_2 = std::log(0.25536);
+            }
+            in_clade_lik += log_lik;
+            not_in_clade_lik += log_lik_2;
+            if (Rb != '-' && !isrev) n++;
+            else if (Rb != '-' && isrev) n--;
+        }
+        const int mq = a.mapping_quality;
+        const double map_q = (1 - std::pow(10, ((-1 * mq) * 0.1)));  // 1 - get_p_incorrectly_mapped (src/miscfunc.h:215-216)
+        const double like = map_q * std::exp((double)((in_clade_lik) - oplusInitnatl_ld(in_clade_lik, not_in_clade_lik)));
+        clade_out[r] = c_n;
+        in_out[r] = in_clade_lik;
+        not_out[r] = not_in_clade_lik;
+        like_out[r] = like;
+        not_like_out[r] = 1 - like;
+        if (((in_clade_lik) - (not_in_clade_lik) > 1) && ((unsigned)mq > T->minimum_mq)) {
+            pass_out[r] = 1;
+            clade_count[c_n]++;
+            for (size_t i = 0; i < a.mapping.size(); ++i) {
+                const int n_id = (int)a.mapping[i].node_id;
+                for (int64_t j = T->bin_off[c_n]; j < T->bin_off[c_n + 1]; ++j)
+                    if (n_id == std::clamp(n_id, T->bin_lo[j], T->bin_hi[j])) bin_cov[j] += 1.0 / (double)a.mapping.size();
+            }
+        }
+    }
+    return ORC_OK;
+}
+
+// subDeamDiNuc[L][l].p as 16 doubles (rounded from long double), for table tests.
+int orc_euka_deam_matrix(const char* deam5p, const char* deam3p, uint32_t L, uint32_t l, double* out16) {
+    Damage dmg;
+    int rc = dmg.init(deam5p, deam3p);
+    if (rc) return rc;
+    if (L < MINLENGTHFRAGMENT || L > MAXLENGTHFRAGMENT || l >= L) return ORC_ERR_RANGE;
+    const DiNuc d = dmg.at(L, l);
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) out16[a * 4 + b] = (double)d.p[a][b];
+    return ORC_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // Tables the product also needs, exported so tests can compare them entry by entry.
 void orc_hc_qscore_vec(double* out100) { vector<double> v = get_qscore_vec(); for (int i = 0; i < 100; ++i) out100[i] = v[(size_t)i]; }

@@ -39,6 +39,20 @@ MAP_NODE_BITS = 20
 LANES, COL_BLK, MAP_BLK = 32, 8, 4
 
 
+class vgl_euka_tables(C.Structure):
+    _fields_ = [("n_clades", C.c_int32), ("n_bins", C.c_int32), ("max_node", C.c_int32), ("k5", C.c_int32), ("k3", C.c_int32),
+                ("minimum_mq", C.c_uint32), ("clade_dist", C.c_void_p), ("bin_off", C.c_void_p), ("bin_lo", C.c_void_p),
+                ("bin_hi", C.c_void_p), ("deam", C.c_void_p), ("qscore", C.c_double * 100), ("base_freq_log", C.c_double * 5),
+                ("tt_ratio", (C.c_double * 4) * 4)]
+
+
+class vgl_euka_batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_map_blks", C.c_uint64),
+                ("grp_col_blk", C.c_void_p), ("grp_map_blk", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
+                ("n_cols", C.c_void_p), ("n_maps", C.c_void_p), ("seq_len", C.c_void_p), ("mapq", C.c_void_p),
+                ("flags", C.c_void_p), ("read_index", C.c_void_p)]
+
+
 class vgh_alignments(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual_off", C.c_void_p),
                 ("qual", C.c_void_p), ("mapq", C.c_void_p), ("identity", C.c_void_p), ("paired", C.c_void_p),
@@ -72,6 +86,11 @@ GPU_SYMBOLS = {
     "vgl_hc_set_paths_from_parts": (C.c_int, [_P, _P, C.c_int32]),
     "vgl_hc_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, C.c_int32,
                                   C.POINTER(C.c_int32)]),
+    "vgl_euka_set_tables": (C.c_int, [_P, C.POINTER(vgl_euka_tables)]),
+    "vgl_euka_reset": (C.c_int, [_P]),
+    "vgl_euka_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P, _P, _P, _P]),
+    "vgl_euka_results": (C.c_int, [_P, _P, _P]),
+    "vgl_euka_batch_bytes": (C.c_uint64, [C.POINTER(vgl_euka_batch)]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
@@ -103,6 +122,23 @@ HOST_SYMBOLS = {
     "vgh_hc_tree_anc_clade": (_P, [_P]),
     "vgh_hc_tree_clade_name": (C.c_char_p, [_P, C.c_int32]),
     "vgh_hc_tree_destroy": (None, [_P]),
+    "vgh_euka_tables_build": (C.c_int, [C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(_P)]),
+    "vgh_euka_tables_view": (C.POINTER(vgl_euka_tables), [_P]),
+    "vgh_euka_tables_destroy": (None, [_P]),
+    "vgh_euka_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vgh_euka_packed_batch": (C.POINTER(vgl_euka_batch), [_P]),
+    "vgh_euka_packed_destroy": (None, [_P]),
+    "vgh_synth_euka_create": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "vgh_synth_euka_destroy": (None, [_P]),
+    "vgh_synth_euka_graph": (_P, [_P]),
+    "vgh_synth_euka_graph_seq": (C.c_int64, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "vgh_synth_euka_n_clades": (C.c_int32, [_P]),
+    "vgh_synth_euka_dist": (_P, [_P]),
+    "vgh_synth_euka_bin_off": (_P, [_P]),
+    "vgh_synth_euka_bin_lo": (_P, [_P]),
+    "vgh_synth_euka_bin_hi": (_P, [_P]),
+    "vgh_synth_euka_reads": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int32, C.c_double, C.c_int, C.c_double, C.c_double,
+                                       C.POINTER(_P)]),
     "vgh_synth_hc_create": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "vgh_synth_hc_destroy": (None, [_P]),
     "vgh_synth_hc_graph": (_P, [_P]),

@@ -1,0 +1,152 @@
+// euka per-read kernel for sm_100a: the body of the per-alignment lambda of readGAM3
+// (reference src/readGAM_Euka.h:103-549) with one read per thread over the warp-striped batch.
+//
+// Per aligned column the reference takes log() of a 4-term marginal over the post-damage base and adds it to the
+// in-clade log-likelihood (:312-394); here the marginal is multiplied into a running product and one log is taken
+// per read (rescaled long before it can underflow); the constant-per-column cases (N, gap, rare IUPAC code, soft
+// clip, model 2) are table look-ups.  euka scores each read against exactly one clade.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "vgl_internal.h"
+
+namespace vgl {
+
+namespace {
+
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+constexpr int kEukaBlock = 128;
+
+__global__ void __launch_bounds__(kEukaBlock)
+euka_read_kernel(EukaBatchDev b, EukaTablesDev t, EukaOutDev o) {
+    __shared__ EukaSmallTables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int k = threadIdx.x; k < (int)(sizeof(EukaSmallTables) / 4); k += kEukaBlock) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (kEukaBlock / 32) + (threadIdx.x >> 5);
+    if (g >= b.n_groups) return;
+    const uint32_t r = g * 32 + lane;
+    const int nc = (int)__ldg(b.n_cols + r);
+    const int nm = (int)__ldg(b.n_maps + r);
+    if (nm == 0) return;  // unused lane
+    const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
+    const uint4* gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;
+    const uint4* gm = reinterpret_cast<const uint4*>(b.map) + (size_t)mb0 * 32 + lane;
+    const int Lseq = (int)__ldg(b.seq_len + r);
+    const int mq = (int)__ldg(b.mapq + r);
+    const bool isrev = (__ldg(b.flags + r) & 1) != 0;
+    const uint32_t ridx = __ldg(b.read_index + r);
+
+    // clade of the read: the last bin (all clades, file order) that contains its first node (:115-140),
+    // looked up in the node -> clade table the library built from the bins
+    const uint32_t first_node = ldg_stream_v4(gm).x;
+    const int c_n = first_node <= (uint32_t)t.max_node ? (int)__ldg(t.node_clade + first_node) : 0;
+    const double d = __ldg(t.clade_dist + c_n);  // pair_dist
+    const double one_minus_d = 1.0 - d;
+    const double log_rare_in = log(one_minus_d * 0.001);
+
+    double in_acc = 0.0, not_acc = 0.0, prod = 1.0;
+    int n = isrev ? Lseq - 1 : 0;  // coordinate on the fragment, from its 5' end
+    int softclips = 0;
+    const int ncb = (nc + 7) >> 3;
+    for (int cb = 0; cb < ncb; ++cb) {
+        const uint4 blk = ldg_stream_v4(gc + (size_t)cb * 32);
+        const uint32_t w[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int m = cb * 8 + k;
+            if (m < nc) {
+                const uint32_t rec = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+                const uint32_t q = rec & 0xffu;
+                const int G = (int)((rec >> 8) & 15u), R = (int)(rec >> 12);
+                if (G == VGL_EUKA_SYM_N || R == VGL_EUKA_SYM_N) {
+                    const double v = s_tab.base_freq_log[R];
+                    in_acc += v;
+                    not_acc += v;
+                } else if (G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP) {
+                    in_acc += s_tab.log_gap_in;
+                    not_acc += s_tab.log_gap_not;
+                } else if (G == VGL_EUKA_SYM_RARE || R == VGL_EUKA_SYM_RARE) {
+                    in_acc += log_rare_in;
+                    not_acc += s_tab.log_rare_not;
+                } else if (G == VGL_EUKA_SYM_SOFTCLIP || R == VGL_EUKA_SYM_SOFTCLIP) {
+                    ++softclips;
+                    in_acc += (softclips % 3 == 0) ? s_tab.log_one_minus_e[q] : s_tab.log_e_third[q];
+                    not_acc += s_tab.log_quarter;
+                } else {
+                    // model 1: mutation since the clade's sequences (pair_dist, ts/tv), damage, sequencing error (:312-394)
+                    const int i5 = min(n, t.k5 - 1), i3 = min(Lseq - 1 - n, t.k3 - 1);
+                    const double* __restrict__ D = t.deam + ((size_t)i5 * t.k3 + i3) * 16;
+                    double pre[4];
+#pragma unroll
+                    for (int bpo = 0; bpo < 4; ++bpo)
+                        pre[bpo] = (bpo == G) ? one_minus_d : (G < 4 ? d * s_tab.tt[G][bpo] : 0.0);
+                    const double e1 = s_tab.one_minus_e[q], e3 = s_tab.e_third[q];
+                    double s = 0.0;
+#pragma unroll
+                    for (int bpd = 0; bpd < 4; ++bpd) {
+                        double post = 0.0;
+#pragma unroll
+                        for (int bpo = 0; bpo < 4; ++bpo) post = fma(pre[bpo], __ldg(D + bpo * 4 + bpd), post);
+                        s = fma(post, (bpd == R) ? e1 : e3, s);
+                    }
+                    prod *= s;
+                    if (prod < 1e-280) {
+                        in_acc += log(prod);
+                        prod = 1.0;
+                    }
+                    not_acc += (G == R) ? s_tab.log_match2 : s_tab.log_mis2;  // model 2 (:420-443)
+                }
+                if (R != VGL_EUKA_SYM_GAP) n += isrev ? -1 : 1;
+            }
+        }
+    }
+    const double in_lik = in_acc + log(prod);
+    const double not_lik = not_acc;
+    // clade_like = map_q * exp(in - oplusInitnatl(in, not))  (:485-492; oplusInitnatl(0, y) = y)
+    const double hi = fmax(in_lik, not_lik), lo = fmin(in_lik, not_lik);
+    const double lse = (in_lik == 0.0) ? not_lik : hi + log1p(exp(lo - hi));
+    const double map_q = 1.0 - pow(10.0, ((-1 * mq) * 0.1));
+    const double like = map_q * exp(in_lik - lse);
+    const bool pass = (in_lik - not_lik > 1.0) && ((uint32_t)mq > t.minimum_mq);
+    if (ridx < o.n_out) {
+        if (o.clade) o.clade[ridx] = c_n;
+        if (o.in_lik) o.in_lik[ridx] = in_lik;
+        if (o.not_lik) o.not_lik[ridx] = not_lik;
+        if (o.like) o.like[ridx] = like;
+        if (o.pass) o.pass[ridx] = pass ? 1 : 0;
+    }
+    if (pass) {  // count the read and spread 1/M over the bins its nodes fall into (:504-549)
+        atomicAdd(o.clade_count + c_n, 1ull);
+        const double share = 1.0 / (double)nm;
+        const int b0 = __ldg(t.bin_off + c_n), b1 = __ldg(t.bin_off + c_n + 1);
+        for (int i = 0; i < nm; ++i) {
+            const uint4 mb = ldg_stream_v4(gm + (size_t)(i >> 2) * 32);
+            const int e = i & 3;
+            const int node = (int)(e == 0 ? mb.x : e == 1 ? mb.y : e == 2 ? mb.z : mb.w);
+            for (int j = b0; j < b1; ++j)
+                if (node >= __ldg(t.bin_lo + j) && node <= __ldg(t.bin_hi + j)) atomicAdd(o.bin_cov + j, share);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& t, const EukaOutDev& o, cudaStream_t s) {
+    if (b.n_groups == 0) return cudaSuccess;
+    const int warps = kEukaBlock / 32;
+    euka_read_kernel<<<(b.n_groups + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, o);
+    return cudaGetLastError();
+}
+
+}  // namespace vgl

@@ -59,3 +59,11 @@ struct vgh_gam {
     }
 };
 
+
+// reconstruct_graph_sequence (reference src/vgan_utils.h:6-79) for read r: aligned graph string, aligned read string,
+// one size per edit.  Defined in vgan_host.cpp.
+struct Recon {
+    std::string graph_seq, read_seq;
+    std::vector<int32_t> sizes;
+};
+int vgh_recon(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& out);

@@ -247,19 +247,37 @@ int64_t vgh_synth_hc_graph_seq(const vgh_synth_hc* s, const int64_t** seq_off, c
     return s->graph.n_nodes;
 }
 
-// Reads: `fixed_len` > 0 gives reads spanning exactly that many graph bases (config 2: 100); 0 gives the
-// ancient-DNA fragment-length distribution of config 3 (log-normal, mean 60, clipped to [30,150]).
-// `damage` != 0 applies C->T at the 5' end and G->A at the 3' end with the per-position rates of the
-// reference's share/vgan/damageProfiles/dhigh{5p,3p}.prof (first five positions; the rate halves with
-// every further position).  `origin_path` >= 0 samples every read from that path (a "sample" of one
-// haplogroup); -1 picks a random path per read.
-int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, int32_t fixed_len, double sub_rate,
-                       double indel_rate, int damage, int32_t origin_path, vgh_gam** out) {
-    if (!S || !out || n_reads < 0) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
+}  // extern "C"
+
+namespace {
+
+struct Piece { int32_t node; bool rev; int32_t off, len; };
+
+struct ReadParams {
+    int32_t fixed_len;    // > 0: graph bases spanned; 0: ancient-DNA fragment lengths (log-normal, mean 60, [30,150])
+    double sub_rate, indel_rate;
+    int damage;           // C->T at the 5' end / G->A at the 3' end with the reference's dhigh profiles
+    double n_rate;        // read bases replaced by 'N'
+    double softclip_rate; // reads that start with 1..5 unaligned bases (an insertion edit in front of the first match)
+};
+
+inline int draw_length(Rng& rng, const ReadParams& P, int total_len) {
+    int L = P.fixed_len;
+    if (L <= 0) {
+        const double sigma = 0.4, mu = std::log(60.0) - 0.5 * sigma * sigma;
+        L = (int)std::lround(std::exp(mu + sigma * rng.normal()));
+        L = std::min(150, std::max(30, L));
+    }
+    return std::min(L, total_len);
+}
+
+// Shared read simulator: `walk_fn(rng, r, walk)` lays out the oriented node pieces the read aligns to; the rest
+// (substitutions, indels, deamination, edits, qualities) is common.  One RNG stream per read, so the output does
+// not depend on the number of threads.
+template <typename WalkFn>
+vgh_gam* simulate_reads(const vgh_graph& graph, uint64_t seed, int64_t n_reads, const ReadParams& P, WalkFn walk_fn) {
     static const double k5p[5] = {0.329405, 0.221745, 0.187678, 0.161196, 0.144011};  // C>T column of dhigh5p.prof
     static const double k3p[5] = {0.32891, 0.223405, 0.188599, 0.164419, 0.146352};   // G>A column of dhigh3p.prof
-    const int n_sites = (int)S->site_ref.size();
-    struct Piece { int32_t node; bool rev; int32_t off, len; };
 #ifdef _OPENMP
     const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(omp_get_max_threads(), n_reads / 2048 + 1));
 #else
@@ -278,54 +296,39 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
     parts[(size_t)tid] = G;
     std::vector<Piece> walk;
     std::string gseq, rseq, qual;
-    std::vector<uint8_t> op;  // per graph base: 0 match, 1 substitution, 2 deleted
-    std::vector<uint8_t> ins_len;     // inserted read bases in front of graph base j (0..3)
-    std::vector<char> ins_bases;      // [n][3]
+    std::vector<uint8_t> op;       // per graph base: 0 match, 1 substitution, 2 deleted
+    std::vector<uint8_t> ins_len;  // inserted read bases in front of graph base j (0..5)
+    std::vector<char> ins_bases;   // [n][5]
     for (int64_t r = r_begin; r < r_end; ++r) {
-        Rng rng(seed * 0x9e3779b97f4a7c15ull + (uint64_t)r * 0xd1342543de82ef95ull + 1);  // one stream per read: thread-count independent
-        const int p = origin_path >= 0 ? origin_path % S->n_paths : (int)rng.below((uint64_t)S->n_paths);
-        int L = fixed_len;
-        if (L <= 0) {
-            const double sigma = 0.4, mu = std::log(60.0) - 0.5 * sigma * sigma;
-            L = (int)std::lround(std::exp(mu + sigma * rng.normal()));
-            L = std::min(150, std::max(30, L));
-        }
-        L = std::min(L, S->total_len);
-        const int s = (int)rng.below((uint64_t)(S->total_len - L + 1));
-        const bool rev = rng.uniform() < 0.5;
-        int k0 = (int)(std::upper_bound(S->site_off.begin(), S->site_off.end(), s) - S->site_off.begin()) - 1;
+        Rng rng(seed * 0x9e3779b97f4a7c15ull + (uint64_t)r * 0xd1342543de82ef95ull + 1);
         walk.clear();
-        for (int k = k0; k < n_sites && S->site_off[(size_t)k] < s + L; ++k) {
-            const int a = std::max(s, S->site_off[(size_t)k]), b = std::min(s + L, S->site_off[(size_t)k + 1]);
-            const bool alt = S->site_alt[(size_t)k] >= 0 && p >= S->site_lo[(size_t)k] && p < S->site_hi[(size_t)k];
-            const int node = alt ? S->site_alt[(size_t)k] : S->site_ref[(size_t)k];
-            const int nlen = S->site_off[(size_t)k + 1] - S->site_off[(size_t)k];
-            const int fo = a - S->site_off[(size_t)k];
-            walk.push_back(Piece{node, rev, rev ? nlen - (fo + (b - a)) : fo, b - a});
-        }
-        if (rev) std::reverse(walk.begin(), walk.end());
-        // oriented graph bases
+        walk_fn(rng, r, walk);
         gseq.clear();
         for (const Piece& w : walk)
-            for (int j = 0; j < w.len; ++j) gseq.push_back(S->graph.base(w.node, w.rev, w.off + j));
+            for (int j = 0; j < w.len; ++j) gseq.push_back(graph.base(w.node, w.rev, w.off + j));
         const int n = (int)gseq.size();
         op.assign((size_t)n, 0);
         ins_len.assign((size_t)n, 0);
-        ins_bases.resize((size_t)n * 3);
+        ins_bases.resize((size_t)n * 5 + 5);
         std::string bases = gseq;
         for (int j = 0; j < n; ++j) {
-            if (rng.uniform() < sub_rate) bases[(size_t)j] = other_base(rng, gseq[(size_t)j]);
-            if (j > 0 && j < n - 1 && rng.uniform() < indel_rate) {
+            if (rng.uniform() < P.sub_rate) bases[(size_t)j] = other_base(rng, gseq[(size_t)j]);
+            if (j > 0 && j < n - 1 && rng.uniform() < P.indel_rate) {
                 if (rng.uniform() < 0.5) {
                     const int k = 1 + (int)rng.below(3);
                     ins_len[(size_t)j] = (uint8_t)k;
-                    for (int t = 0; t < k; ++t) ins_bases[(size_t)j * 3 + t] = kBases[rng.below(4)];
+                    for (int t = 0; t < k; ++t) ins_bases[(size_t)j * 5 + t] = kBases[rng.below(4)];
                 } else {
                     op[(size_t)j] = 2;
                 }
             }
         }
-        if (damage) {
+        if (n > 0 && P.softclip_rate > 0 && rng.uniform() < P.softclip_rate) {
+            const int k = 1 + (int)rng.below(5);
+            ins_len[0] = (uint8_t)k;
+            for (int t = 0; t < k; ++t) ins_bases[(size_t)t] = kBases[rng.below(4)];
+        }
+        if (P.damage) {
             int rp = 0;  // read position from the 5' end, counting surviving bases only
             int surviving = 0;
             for (int j = 0; j < n; ++j) surviving += op[(size_t)j] != 2;
@@ -339,6 +342,9 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
                 ++rp;
             }
         }
+        if (P.n_rate > 0)
+            for (int j = 0; j < n; ++j)
+                if (op[(size_t)j] != 2 && rng.uniform() < P.n_rate) bases[(size_t)j] = 'N';
         for (int j = 0; j < n; ++j)
             if (op[(size_t)j] != 2 && bases[(size_t)j] != gseq[(size_t)j]) op[(size_t)j] = 1;
         // emit mappings / edits
@@ -354,9 +360,9 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
                     const int k = ins_len[(size_t)j];
                     G->edit_from.push_back(0);
                     G->edit_to.push_back(k);
-                    G->edit_seq.append(&ins_bases[(size_t)j * 3], (size_t)k);
+                    G->edit_seq.append(&ins_bases[(size_t)j * 5], (size_t)k);
                     G->edit_seq_off.push_back((int64_t)G->edit_seq.size());
-                    rseq.append(&ins_bases[(size_t)j * 3], (size_t)k);
+                    rseq.append(&ins_bases[(size_t)j * 5], (size_t)k);
                     ins_len[(size_t)j] = 0;
                     continue;
                 }
@@ -383,7 +389,7 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
         G->seq += rseq; G->seq_off.push_back((int64_t)G->seq.size());
         G->qual += qual; G->qual_off.push_back((int64_t)G->qual.size());
         G->mapq.push_back(draw_hist(rng, kMapqVal, kMapqCnt));
-        G->identity.push_back(rng.uniform() < 0.001 ? 0.0 : 1.0);  // a few "unmapped" reads the hot loop must skip
+        G->identity.push_back(rng.uniform() < 0.001 ? 0.0 : 1.0);  // a few "unmapped" reads the hot loops must skip
         G->paired.push_back(0);
         G->map_off.push_back((int64_t)G->map_node.size());
     }
@@ -411,7 +417,135 @@ int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, in
         delete Q;
     }
     G->finish();
-    *out = G;
+    return G;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// euka-shaped workload: clades own consecutive node ranges (one linear mitogenome chopped
+// into nodes of up to 32 bp), 10-15 overlapping bins per clade, a pairwise distance per clade.
+// ------------------------------------------------------------------------------------------------
+struct vgh_synth_euka {
+    int32_t n_clades = 0;
+    vgh_graph graph;
+    std::vector<double> dist;
+    std::vector<int32_t> snode, enode;      // node range of each clade
+    std::vector<int32_t> bin_off, bin_lo, bin_hi;
+    std::vector<int32_t> node_off;          // coordinate of each node inside its clade's genome
+    std::vector<int32_t> clade_len;         // genome length of each clade
+};
+
+extern "C" {
+
+// Reads: `fixed_len` > 0 gives reads spanning exactly that many graph bases (config 2: 100); 0 gives the
+// ancient-DNA fragment-length distribution of config 3 (log-normal, mean 60, clipped to [30,150]).
+// `damage` != 0 applies C->T at the 5' end and G->A at the 3' end with the per-position rates of the
+// reference's share/vgan/damageProfiles/dhigh{5p,3p}.prof (first five positions; the rate halves with
+// every further position).  `origin_path` >= 0 samples every read from that path (a "sample" of one
+// haplogroup); -1 picks a random path per read.
+int vgh_synth_hc_reads(const vgh_synth_hc* S, uint64_t seed, int64_t n_reads, int32_t fixed_len, double sub_rate,
+                       double indel_rate, int damage, int32_t origin_path, vgh_gam** out) {
+    if (!S || !out || n_reads < 0) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
+    const ReadParams P{fixed_len, sub_rate, indel_rate, damage, 0.0, 0.0};
+    const int n_sites = (int)S->site_ref.size();
+    *out = simulate_reads(S->graph, seed, n_reads, P, [&](Rng& rng, int64_t, std::vector<Piece>& walk) {
+        const int p = origin_path >= 0 ? origin_path % S->n_paths : (int)rng.below((uint64_t)S->n_paths);
+        const int L = draw_length(rng, P, S->total_len);
+        const int s = (int)rng.below((uint64_t)(S->total_len - L + 1));
+        const bool rev = rng.uniform() < 0.5;
+        const int k0 = (int)(std::upper_bound(S->site_off.begin(), S->site_off.end(), s) - S->site_off.begin()) - 1;
+        for (int k = k0; k < n_sites && S->site_off[(size_t)k] < s + L; ++k) {
+            const int a = std::max(s, S->site_off[(size_t)k]), b = std::min(s + L, S->site_off[(size_t)k + 1]);
+            const bool alt = S->site_alt[(size_t)k] >= 0 && p >= S->site_lo[(size_t)k] && p < S->site_hi[(size_t)k];
+            const int node = alt ? S->site_alt[(size_t)k] : S->site_ref[(size_t)k];
+            const int nlen = S->site_off[(size_t)k + 1] - S->site_off[(size_t)k];
+            const int fo = a - S->site_off[(size_t)k];
+            walk.push_back(Piece{node, rev, rev ? nlen - (fo + (b - a)) : fo, b - a});
+        }
+        if (rev) std::reverse(walk.begin(), walk.end());
+    });
+    return VGH_OK;
+}
+
+int vgh_synth_euka_create(uint64_t seed, int32_t n_clades, int32_t genome_len, vgh_synth_euka** out) {
+    if (!out || n_clades < 1 || genome_len < 400) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
+    Rng rng(seed);
+    vgh_synth_euka* S = new vgh_synth_euka();
+    S->n_clades = n_clades;
+    S->graph.min_id = 1;
+    S->graph.off.push_back(0);
+    S->bin_off.push_back(0);
+    S->node_off.push_back(0);  // node id 0 does not exist; keeps node_off indexable by id
+    int next_id = 1;
+    for (int c = 0; c < n_clades; ++c) {
+        S->dist.push_back(0.05 + 0.15 * rng.uniform());
+        const int glen = genome_len + (int)rng.below((uint64_t)(genome_len / 8 + 1));
+        S->snode.push_back(next_id);
+        int pos = 0;
+        while (pos < glen) {
+            const int len = std::min(glen - pos, 1 + (int)rng.below(32));
+            for (int j = 0; j < len; ++j) S->graph.seq.push_back(kBases[rng.below(4)]);
+            S->graph.off.push_back((int64_t)S->graph.seq.size());
+            S->node_off.push_back(pos);
+            pos += len;
+            ++next_id;
+        }
+        S->enode.push_back(next_id - 1);
+        S->clade_len.push_back(glen);
+        // 10..15 bins that overlap their neighbours by ~10 % of a bin (as in share/vgan/euka_dir/euka_db.bins)
+        const int nb = 10 + (int)rng.below(6);
+        const int first = S->snode[(size_t)c], last = S->enode[(size_t)c], span = last - first + 1;
+        for (int j = 0; j < nb; ++j) {
+            const int lo = first + (int)((int64_t)span * j / nb);
+            const int hi = std::min(last, first + (int)((int64_t)span * (j + 1) / nb) + span / (10 * nb));
+            S->bin_lo.push_back(std::max(first, lo - (j ? span / (10 * nb) : 0)));
+            S->bin_hi.push_back(hi);
+        }
+        S->bin_off.push_back((int32_t)S->bin_lo.size());
+    }
+    S->graph.n_nodes = next_id - 1;
+    *out = S;
+    return VGH_OK;
+}
+void vgh_synth_euka_destroy(vgh_synth_euka* s) { delete s; }
+const vgh_graph* vgh_synth_euka_graph(const vgh_synth_euka* s) { return &s->graph; }
+int64_t vgh_synth_euka_graph_seq(const vgh_synth_euka* s, const int64_t** seq_off, const char** seq) {
+    *seq_off = s->graph.off.data();
+    *seq = s->graph.seq.data();
+    return s->graph.n_nodes;
+}
+int32_t vgh_synth_euka_n_clades(const vgh_synth_euka* s) { return s->n_clades; }
+const double* vgh_synth_euka_dist(const vgh_synth_euka* s) { return s->dist.data(); }
+const int32_t* vgh_synth_euka_bin_off(const vgh_synth_euka* s) { return s->bin_off.data(); }
+const int32_t* vgh_synth_euka_bin_lo(const vgh_synth_euka* s) { return s->bin_lo.data(); }
+const int32_t* vgh_synth_euka_bin_hi(const vgh_synth_euka* s) { return s->bin_hi.data(); }
+
+// Reads of a random clade; substitutions at a quarter of the clade's pairwise distance, plus the knobs above.
+int vgh_synth_euka_reads(const vgh_synth_euka* S, uint64_t seed, int64_t n_reads, int32_t fixed_len, double indel_rate,
+                         int damage, double n_rate, double softclip_rate, vgh_gam** out) {
+    if (!S || !out || n_reads < 0) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
+    ReadParams P{fixed_len, 0.03, indel_rate, damage, n_rate, softclip_rate};
+    *out = simulate_reads(S->graph, seed, n_reads, P, [&](Rng& rng, int64_t, std::vector<Piece>& walk) {
+        const int c = (int)rng.below((uint64_t)S->n_clades);
+        const int glen = S->clade_len[(size_t)c];
+        const int L = draw_length(rng, P, glen);
+        const int s = (int)rng.below((uint64_t)(glen - L + 1));
+        const bool rev = rng.uniform() < 0.5;
+        // first node of the clade whose coordinate range reaches s
+        int lo = S->snode[(size_t)c], hi = S->enode[(size_t)c];
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) / 2;
+            if (S->node_off[(size_t)mid] <= s) lo = mid; else hi = mid - 1;
+        }
+        for (int id = lo; id <= S->enode[(size_t)c] && S->node_off[(size_t)id] < s + L; ++id) {
+            const int nlen = (int)S->graph.length(id);
+            const int a = std::max(s, S->node_off[(size_t)id]), b = std::min(s + L, S->node_off[(size_t)id] + nlen);
+            const int fo = a - S->node_off[(size_t)id];
+            walk.push_back(Piece{id, rev, rev ? nlen - (fo + (b - a)) : fo, b - a});
+        }
+        if (rev) std::reverse(walk.begin(), walk.end());
+    });
     return VGH_OK;
 }
 

@@ -268,16 +268,14 @@ inline EditKind classify(int32_t from, int32_t to, bool has_seq) {  // vg io edi
     return kOther;
 }
 
-struct Recon {
-    std::string graph_seq, read_seq;
-    std::vector<int32_t> sizes;
-};
 
 // reconstruct_graph_sequence (reference src/vgan_utils.h:6-79), including the behaviours the
 // reference's counters produce: an insertion is an 'S' run whenever the running node
 // offset is 0, a '-' run otherwise; one size per edit; the '-' run of a deletion is spliced into the
 // read string at the running from_length coordinate.
-int reconstruct(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& out) {
+}  // namespace
+
+int vgh_recon(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& out) {
     out.graph_seq.clear();
     out.read_seq.clear();
     out.sizes.clear();
@@ -322,7 +320,7 @@ int reconstruct(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& o
     return VGH_OK;
 }
 
-}  // namespace
+static inline int reconstruct(const vgh_graph& G, const vgh_alignments& a, int64_t r, Recon& out) { return vgh_recon(G, a, r, out); }
 
 extern "C" int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char* graph_seq, char* read_seq,
                                int32_t* sizes, int32_t cap, int32_t* n_graph, int32_t* n_read, int32_t* n_sizes) {

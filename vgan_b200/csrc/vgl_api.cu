@@ -108,6 +108,21 @@ struct vgl_ctx {
     // read-kernel timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
+
+    // euka
+    bool have_euka = false;
+    vgl::EukaTablesDev etab{};
+    DevBuf<uint16_t> e_node_clade;
+    DevBuf<double> e_dist, e_deam, e_bin_cov, e_in, e_not, e_like;
+    DevBuf<int32_t> e_bin_off, e_bin_lo, e_bin_hi, e_clade;
+    DevBuf<vgl::EukaSmallTables> e_small;
+    DevBuf<unsigned long long> e_count;
+    DevBuf<uint8_t> e_pass;
+    struct EukaStage {
+        DevBuf<uint32_t> grp_col_blk, grp_map_blk, map, read_index;
+        DevBuf<uint16_t> col, n_cols, n_maps, seq_len;
+        DevBuf<uint8_t> mapq, flags;
+    } estage;
 };
 
 namespace {
@@ -216,6 +231,12 @@ void vgl_destroy(vgl_ctx* ctx) {
         if (sl.consumed) cudaEventDestroy(sl.consumed);
     }
     ctx->d_stats.release();
+    ctx->e_node_clade.release(); ctx->e_dist.release(); ctx->e_deam.release(); ctx->e_bin_cov.release(); ctx->e_in.release();
+    ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
+    ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
+    ctx->estage.grp_col_blk.release(); ctx->estage.grp_map_blk.release(); ctx->estage.map.release(); ctx->estage.read_index.release();
+    ctx->estage.col.release(); ctx->estage.n_cols.release(); ctx->estage.n_maps.release(); ctx->estage.seq_len.release();
+    ctx->estage.mapq.release(); ctx->estage.flags.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -600,6 +621,152 @@ int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out) {
     }
     if (ms_out) *ms_out = tot;
     if (launches_out) *launches_out = (int32_t)ctx->ev_used;
+    return VGL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// euka
+// -------------------------------------------------------------------------------------------
+int vgl_euka_set_tables(vgl_ctx* ctx, const vgl_euka_tables* T) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!T || T->n_clades < 1 || T->n_clades > 65535 || !T->clade_dist || !T->bin_off || !T->deam || T->k5 < 1 || T->k3 < 1 || T->max_node < 0)
+        return fail(VGL_ERR_INVALID, "bad euka tables");
+    if (T->n_bins != T->bin_off[T->n_clades] || (T->n_bins && (!T->bin_lo || !T->bin_hi))) return fail(VGL_ERR_INVALID, "bad euka bins");
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    // node -> clade: the LAST bin over all clades (file order) that contains the node wins; nodes in no bin go to
+    // clade 0, the reference's initial value of c_n (src/readGAM_Euka.h:115-140)
+    std::vector<uint16_t> node_clade((size_t)T->max_node + 1, 0);
+    for (int c = 0; c < T->n_clades; ++c)
+        for (int j = T->bin_off[c]; j < T->bin_off[c + 1]; ++j) {
+            const int64_t lo = std::max<int64_t>(T->bin_lo[j], 0), hi = std::min<int64_t>(T->bin_hi[j], T->max_node);
+            for (int64_t n = lo; n <= hi; ++n) node_clade[(size_t)n] = (uint16_t)c;
+        }
+    vgl::EukaSmallTables small;
+    memset(&small, 0, sizeof(small));
+    for (int b = 0; b < 256; ++b) {
+        const int Q = (int)(int8_t)(uint8_t)b;
+        const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
+        small.one_minus_e[b] = 1 - qs;
+        small.e_third[b] = qs / 3;
+        small.log_one_minus_e[b] = std::log(1 - qs);
+        small.log_e_third[b] = std::log(qs / 3);
+    }
+    for (int k = 0; k < 5; ++k) small.base_freq_log[k] = T->base_freq_log[k];  // symbol codes 0..4 = A C G T N
+    for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y) small.tt[x][y] = T->tt_ratio[x][y];
+    small.log_gap_in = std::log(0.002);   // src/readGAM_Euka.h:244-249
+    small.log_gap_not = std::log(0.2);
+    small.log_rare_not = std::log(0.001); // :252-257
+    small.log_quarter = std::log(0.25);   // :278
+    small.log_match2 = std::log(1 - 0.25536);  // :423
+    small.log_mis2 = std::log(0.25536);        // :440
+    const size_t nb = (size_t)std::max(T->n_bins, 1);
+    if (int rc = ctx->e_node_clade.reserve(node_clade.size())) return rc;
+    if (int rc = ctx->e_dist.reserve((size_t)T->n_clades)) return rc;
+    if (int rc = ctx->e_bin_off.reserve((size_t)T->n_clades + 1)) return rc;
+    if (int rc = ctx->e_bin_lo.reserve(nb)) return rc;
+    if (int rc = ctx->e_bin_hi.reserve(nb)) return rc;
+    if (int rc = ctx->e_deam.reserve((size_t)T->k5 * T->k3 * 16)) return rc;
+    if (int rc = ctx->e_small.reserve(1)) return rc;
+    if (int rc = ctx->e_count.reserve((size_t)T->n_clades)) return rc;
+    if (int rc = ctx->e_bin_cov.reserve(nb)) return rc;
+    VGL_CUDA(cudaMemcpy(ctx->e_node_clade.p, node_clade.data(), node_clade.size() * 2, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->e_dist.p, T->clade_dist, (size_t)T->n_clades * 8, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->e_bin_off.p, T->bin_off, ((size_t)T->n_clades + 1) * 4, cudaMemcpyHostToDevice));
+    if (T->n_bins) {
+        VGL_CUDA(cudaMemcpy(ctx->e_bin_lo.p, T->bin_lo, (size_t)T->n_bins * 4, cudaMemcpyHostToDevice));
+        VGL_CUDA(cudaMemcpy(ctx->e_bin_hi.p, T->bin_hi, (size_t)T->n_bins * 4, cudaMemcpyHostToDevice));
+    }
+    VGL_CUDA(cudaMemcpy(ctx->e_deam.p, T->deam, (size_t)T->k5 * T->k3 * 16 * 8, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->e_small.p, &small, sizeof(small), cudaMemcpyHostToDevice));
+    vgl::EukaTablesDev& d = ctx->etab;
+    d.n_clades = T->n_clades; d.n_bins = T->n_bins; d.max_node = T->max_node; d.k5 = T->k5; d.k3 = T->k3;
+    d.minimum_mq = T->minimum_mq;
+    d.node_clade = ctx->e_node_clade.p; d.clade_dist = ctx->e_dist.p; d.bin_off = ctx->e_bin_off.p;
+    d.bin_lo = ctx->e_bin_lo.p; d.bin_hi = ctx->e_bin_hi.p; d.deam = ctx->e_deam.p; d.small = ctx->e_small.p;
+    ctx->have_euka = true;
+    return vgl_euka_reset(ctx);
+}
+
+int vgl_euka_reset(vgl_ctx* ctx) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
+    VGL_CUDA(cudaMemsetAsync(ctx->e_count.p, 0, (size_t)ctx->etab.n_clades * sizeof(unsigned long long), ctx->stream));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_bin_cov.p, 0, (size_t)std::max(ctx->etab.n_bins, 1) * sizeof(double), ctx->stream));
+    return VGL_OK;
+}
+
+uint64_t vgl_euka_batch_bytes(const vgl_euka_batch* b) {
+    if (!b) return 0;
+    return (uint64_t)(b->n_groups + 1) * 8 + (b->n_col_blks + b->n_map_blks) * 512 + (uint64_t)b->n_groups * VGL_HC_LANES * 12;
+}
+
+int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* b, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
+                 double* like, uint8_t* pass) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
+    if (!b) return fail(VGL_ERR_INVALID, "null batch");
+    if (b->n_groups == 0) return VGL_OK;
+    if (!b->grp_col_blk || !b->grp_map_blk || !b->col || !b->map || !b->n_cols || !b->n_maps || !b->seq_len || !b->mapq || !b->flags ||
+        !b->read_index)
+        return fail(VGL_ERR_INVALID, "euka batch arrays missing");
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
+    const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
+    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_HC_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    vgl_ctx::EukaStage& st = ctx->estage;
+    if (int rc = st.grp_col_blk.reserve(G + 1)) return rc;
+    if (int rc = st.grp_map_blk.reserve(G + 1)) return rc;
+    if (int rc = st.col.reserve(ncol)) return rc;
+    if (int rc = st.map.reserve(nmap)) return rc;
+    if (int rc = st.n_cols.reserve(nl)) return rc;
+    if (int rc = st.n_maps.reserve(nl)) return rc;
+    if (int rc = st.seq_len.reserve(nl)) return rc;
+    if (int rc = st.mapq.reserve(nl)) return rc;
+    if (int rc = st.flags.reserve(nl)) return rc;
+    if (int rc = st.read_index.reserve(nl)) return rc;
+    if (int rc = upload_async(st.grp_col_blk.p, b->grp_col_blk, (G + 1) * 4, s)) return rc;
+    if (int rc = upload_async(st.grp_map_blk.p, b->grp_map_blk, (G + 1) * 4, s)) return rc;
+    if (int rc = upload_async(st.col.p, b->col, ncol * 2, s)) return rc;
+    if (int rc = upload_async(st.map.p, b->map, nmap * 4, s)) return rc;
+    if (int rc = upload_async(st.n_cols.p, b->n_cols, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.n_maps.p, b->n_maps, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.seq_len.p, b->seq_len, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.mapq.p, b->mapq, nl, s)) return rc;
+    if (int rc = upload_async(st.flags.p, b->flags, nl, s)) return rc;
+    if (int rc = upload_async(st.read_index.p, b->read_index, nl * 4, s)) return rc;
+    const size_t no = std::max<size_t>(n_out, 1);
+    if (int rc = ctx->e_clade.reserve(no)) return rc;
+    if (int rc = ctx->e_in.reserve(no)) return rc;
+    if (int rc = ctx->e_not.reserve(no)) return rc;
+    if (int rc = ctx->e_like.reserve(no)) return rc;
+    if (int rc = ctx->e_pass.reserve(no)) return rc;
+    VGL_CUDA(cudaMemsetAsync(ctx->e_clade.p, 0xff, no * 4, s));  // reads that were not in the batch keep clade -1
+    VGL_CUDA(cudaMemsetAsync(ctx->e_in.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_not.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_like.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_pass.p, 0, no, s));
+    vgl::EukaBatchDev d{b->n_groups, st.grp_col_blk.p, st.grp_map_blk.p, st.col.p, st.map.p, st.n_cols.p, st.n_maps.p,
+                        st.seq_len.p, st.mapq.p, st.flags.p, st.read_index.p};
+    vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p};
+    VGL_CUDA(vgl::euka_launch_read_kernel(d, ctx->etab, o, s));
+    ctx->launches += 1;
+    if (clade) VGL_CUDA(cudaMemcpyAsync(clade, ctx->e_clade.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
+    if (in_lik) VGL_CUDA(cudaMemcpyAsync(in_lik, ctx->e_in.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (not_lik) VGL_CUDA(cudaMemcpyAsync(not_lik, ctx->e_not.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (like) VGL_CUDA(cudaMemcpyAsync(like, ctx->e_like.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (pass) VGL_CUDA(cudaMemcpyAsync(pass, ctx->e_pass.p, (size_t)n_out, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    return VGL_OK;
+}
+
+int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
+    cudaStream_t s = ctx->stream;
+    if (clade_count) VGL_CUDA(cudaMemcpyAsync(clade_count, ctx->e_count.p, (size_t)ctx->etab.n_clades * 8, cudaMemcpyDeviceToHost, s));
+    if (bin_cov && ctx->etab.n_bins) VGL_CUDA(cudaMemcpyAsync(bin_cov, ctx->e_bin_cov.p, (size_t)ctx->etab.n_bins * 8, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
     return VGL_OK;
 }
 

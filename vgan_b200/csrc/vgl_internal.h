@@ -92,4 +92,56 @@ cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, co
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
                                 double* out_scalars, int32_t* out_idx, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------------------
+// euka
+// ---------------------------------------------------------------------------------------------------------
+struct EukaSmallTables {
+    double one_minus_e[256];      // 1 - qscore[Q] by raw quality byte (negative as signed char -> 0.25, as get_p_seq_error)
+    double e_third[256];          // qscore[Q] / 3
+    double log_one_minus_e[256];  // soft-clip column counted as a match    (src/readGAM_Euka.h:272)
+    double log_e_third[256];      // soft-clip column counted as a mismatch (src/readGAM_Euka.h:276)
+    double base_freq_log[16];     // by read symbol code: A C G T N, everything else 0
+    double tt[4][4];              // t_T_ratio
+    double log_gap_in, log_gap_not, log_rare_not, log_quarter, log_match2, log_mis2;
+};
+
+struct EukaTablesDev {
+    int32_t n_clades, n_bins, max_node, k5, k3;
+    uint32_t minimum_mq;
+    const uint16_t* node_clade;  // [max_node + 1]
+    const double* clade_dist;
+    const int32_t* bin_off;
+    const int32_t* bin_lo;
+    const int32_t* bin_hi;
+    const double* deam;          // [k5 * k3 * 16]
+    const EukaSmallTables* small;
+};
+
+struct EukaBatchDev {
+    uint32_t n_groups;
+    const uint32_t* grp_col_blk;
+    const uint32_t* grp_map_blk;
+    const uint16_t* col;
+    const uint32_t* map;
+    const uint16_t* n_cols;
+    const uint16_t* n_maps;
+    const uint16_t* seq_len;
+    const uint8_t* mapq;
+    const uint8_t* flags;
+    const uint32_t* read_index;
+};
+
+struct EukaOutDev {
+    uint32_t n_out;
+    int32_t* clade;
+    double* in_lik;
+    double* not_lik;
+    double* like;
+    uint8_t* pass;
+    unsigned long long* clade_count;  // [n_clades]
+    double* bin_cov;                  // [n_bins]
+};
+
+cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& t, const EukaOutDev& o, cudaStream_t s);
+
 }  // namespace vgl
