@@ -311,6 +311,43 @@ int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* host_batch, uint32_t n_out,
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov);
 uint64_t vgl_euka_batch_bytes(const vgl_euka_batch* b);
 
+/* ------------------------------------------------------------------------------------------- */
+/* soibean: per-read x per-path log-likelihoods                                                */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Replaces the per-alignment body of analyse_GAM (src/getLCAfromGAM.h:102-604, caller src/soibean.cpp:558-561):
+ * AlignmentInfo::pathMap of every read, i.e. the R x P matrix that convertMapsToVector (src/soibean.cpp:131-155)
+ * hands to the MCMC.  For edit i of the read the reference computes, for every path separately, either the
+ * "supported" sum or the "unsupported" sum over the slice of aligned columns -- neither depends on the path --
+ * so the device computes the two scalars once per edit and selects per path from the membership bits.
+ *   member_bits[(node - min_id) * row_words + (p >> 5)] bit (p & 31): path p goes through the node
+ *       (the reference keeps the path NAMES per node, src/soibean.cpp:476-491)
+ *   deam / k5 / k3 as in vgl_euka_tables;  qscore = Euka::get_qscore_vec (src/soibean.cpp:471);
+ *   penalty = PENALTY (default 7).                                                                  */
+typedef struct vgl_soibean_tables {
+    int32_t n_rows;
+    int32_t min_id;
+    int32_t n_paths;
+    int32_t row_words;
+    int32_t k5, k3;
+    int32_t penalty;
+    int32_t reserved;
+    const uint32_t* member_bits;
+    const double* deam;
+    double qscore[100];
+} vgl_soibean_tables;
+
+/* The batch has the layout of vgl_euka_batch with one difference: the "mapping" records are EDIT records, one per
+ * entry of mppg_sizes (analyse_GAM loops over edits, src/getLCAfromGAM.h:144): bits 20-31 the size of the edit,
+ * bits 0-19 the node id of the MAPPING with the same index, or 0xFFFFF when there is none ("No_support",
+ * :156-160); n_maps counts edits.  Column records, seq_len, flags and read_index are as for euka.        */
+typedef vgl_euka_batch vgl_soibean_batch;
+#define VGL_SOIBEAN_NO_NODE 0xFFFFFu
+
+int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* tables);
+/* path_ll[r * n_paths + p] = pathMap[pathNames[p]] of read r (r = read_index); used[r] = 1 for reads of the batch. */
+int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* host_batch, uint32_t n_out, double* path_ll, uint8_t* used);
+
 #ifdef __cplusplus
 }
 #endif

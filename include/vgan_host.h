@@ -138,6 +138,17 @@ int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64
 const vgl_euka_batch* vgh_euka_packed_batch(const vgh_euka_packed* p);
 void vgh_euka_packed_destroy(vgh_euka_packed* p);
 
+/* ---- soibean: tables and batch packer ----------------------------------------------------------- */
+typedef struct vgh_soibean_tables vgh_soibean_tables;
+/* member[(node - min_id) * n_paths + p] != 0: path p goes through the node (soibean's nodepaths, src/soibean.cpp:476-491) */
+int vgh_soibean_tables_build(int32_t n_rows, int32_t min_id, int32_t n_paths, const uint8_t* member, const char* deam5p_prof,
+                             const char* deam3p_prof, int32_t penalty, vgh_soibean_tables** out);
+const vgl_soibean_tables* vgh_soibean_tables_view(const vgh_soibean_tables* t);
+void vgh_soibean_tables_destroy(vgh_soibean_tables* t);
+/* Same packer as vgh_euka_pack, with edit records instead of mapping records (see vgl_soibean_batch). */
+int vgh_soibean_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                     vgh_euka_packed** out);
+
 /* ---- synthetic HaploCart-shaped workloads (benchmark / test inputs) --- */
 /* The real tables (share/vgan/hcfiles) are FTP downloads; tests and bench.py generate inputs of the
  * same shapes instead.  Pure functions of their seeds.                                            */

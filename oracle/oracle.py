@@ -267,3 +267,17 @@ def euka_deam_matrix(deam5p_prof, deam3p_prof, L, l):
     if rc:
         raise RuntimeError("orc_euka_deam_matrix failed: %d" % rc)
     return m.reshape(4, 4)
+
+
+# ---- soibean ---------------------------------------------------------------------------------------------------
+def soibean_run(graph, reads, member, min_id=0, penalty=7, deam5p_prof="", deam3p_prof=""):
+    """analyse_GAM's pathMap for every read: (matrix [R, P] in pathNames order, used [R])."""
+    member = np.ascontiguousarray(member, dtype=np.uint8)
+    n_rows, P = member.shape
+    out = np.zeros((reads.n, P), dtype=np.float64)
+    used = np.zeros(reads.n, dtype=np.uint8)
+    rc = lib().orc_soibean_run(C.byref(graph.c), C.byref(reads.c), _ptr(member), C.c_int64(n_rows), int(min_id), int(P), int(penalty),
+                               (deam5p_prof or "").encode(), (deam3p_prof or "").encode(), _ptr(out), _ptr(used))
+    if rc:
+        raise RuntimeError("orc_soibean_run failed: %d" % rc)
+    return out, used

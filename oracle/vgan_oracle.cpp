@@ -38,6 +38,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <set>
 #include <sstream>
@@ -915,6 +916,119 @@ int orc_euka_run(const orc_euka_tables* T, const orc_graph* g, const orc_reads* 
                 for (int64_t j = T->bin_off[c_n]; j < T->bin_off[c_n + 1]; ++j)
                     if (n_id == std::clamp(n_id, T->bin_lo[j], T->bin_hi[j])) bin_cov[j] += 1.0 / (double)a.mapping.size();
             }
+        }
+    }
+    return ORC_OK;
+}
+
+// =====================================================================================
+// soibean: per-read x per-path log-likelihoods.  Restates the per-alignment body of analyse_GAM
+// (reference src/getLCAfromGAM.h:102-604).  `member[(node - min_id) * n_paths + p]` says whether path p goes
+// through the node (the reference keeps path NAMES per node, src/soibean.cpp:476-491, and searches them,
+// src/getLCAfromGAM.h:194); out[r * n_paths + p] is pathMap[pathNames[p]] of read r.
+//
+// Behaviours reproduced as written: the loop runs over mppg_sizes (one entry per EDIT) while nodes are taken
+// from the mapping with the same index, surplus entries get no support (:144-167); the quality is indexed by
+// the position INSIDE the slice (:227,410); the damage matrix is taken at [|graph_seq|][baseIX] for the whole
+// slice (:327); both branches of the marginal add the same term, so it is the log of the row sum, clamped to
+// log(0.9999999) (:338-353); an unsupported base costs log(1-e) when |baseOnRead| % PENALTY == 0 and log(e/3)
+// otherwise (:473-497); on the reverse strand slices start at max(baseIX - size - 1, 0) (:173-176).
+// Defined here where the reference has none: quality index past the end reads byte 0; negative quality bytes
+// give 0.25; std::string::substr / vector::at failures and damage-table indices out of range return an error.
+// =====================================================================================
+int orc_soibean_run(const orc_graph* g, const orc_reads* R, const uint8_t* member, int64_t member_rows, int32_t member_min_id,
+                    int32_t n_paths, int32_t penalty, const char* deam5p, const char* deam3p, double* out, uint8_t* used) {
+    Damage dmg;
+    int rc = dmg.init(deam5p, deam3p);
+    if (rc) return rc;
+    const vector<double> qscore_vec = euka_qscore_vec();  // soibean uses Euka's table (src/soibean.cpp:471)
+    const char* ACGT = "ACGT";
+    for (int64_t r = 0; r < R->n_reads; ++r) {
+        double* pathMap = out + (size_t)r * (size_t)n_paths;
+        for (int p = 0; p < n_paths; ++p) pathMap[p] = 0.0;
+        used[r] = 0;
+        if (R->identity[r] == 0) continue;
+        used[r] = 1;
+        ReadView a = load_read(*R, r);
+        if (a.mapping.empty()) return ORC_ERR_RANGE;
+        string graph_seq, read_seq;
+        vector<int> mppg_sizes;
+        rc = reconstruct_graph_sequence(*g, a.mapping, graph_seq, read_seq, mppg_sizes);
+        if (rc) return rc;
+        const bool rev = a.mapping[0].is_reverse;
+        int baseIX = rev ? (int)a.seq.size() - 1 : 0;
+        int baseOnRead = baseIX;
+        const int Lseq = (int)graph_seq.size();
+        const size_t E = mppg_sizes.size(), M = a.mapping.size();
+        for (size_t i = 0; i < E; ++i) {
+            bool no_support = false;
+            int64_t nID = 0;
+            if (E != M && i >= E - (E - M)) no_support = true;
+            else {
+                if (i >= M) return ORC_ERR_SIZES;
+                nID = a.mapping[i].node_id;
+                if (nID - member_min_id < 0 || nID - member_min_id >= member_rows) return ORC_ERR_NODE;  // nodepaths.at()
+            }
+            string nodeSeq, partReadSeq;
+            int startIndex = 0;
+            if (rev) {
+                startIndex = (baseIX - mppg_sizes[i] - 1 >= 0) ? (baseIX - mppg_sizes[i] - 1) : 0;
+                rc = substr_checked(graph_seq, (size_t)startIndex, (size_t)mppg_sizes[i], nodeSeq);
+                if (rc) return rc;
+                rc = substr_checked(read_seq, (size_t)startIndex, (size_t)mppg_sizes[i], partReadSeq);
+                if (rc) return rc;
+            } else {
+                if (baseIX < 0) return ORC_ERR_SUBSTR;
+                rc = substr_checked(graph_seq, (size_t)baseIX, (size_t)mppg_sizes[i], nodeSeq);
+                if (rc) return rc;
+                rc = substr_checked(read_seq, (size_t)baseIX, (size_t)mppg_sizes[i], partReadSeq);
+                if (rc) return rc;
+            }
+            for (int m = 0; m < n_paths; ++m) {
+                const bool supported = !no_support && member[(size_t)(nID - member_min_id) * (size_t)n_paths + (size_t)m] != 0;
+                if (supported) {
+                    for (size_t s = 0; s < nodeSeq.size(); ++s) {
+                        const int base_quality = quality_at(a.quality, s);
+                        const double e = euka_qs(qscore_vec, base_quality);
+                        const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
+                        if (gb == 'N' || rb == 'N') pathMap[m] += std::log(0.25);
+                        else if (gb == 'S' || rb == 'S') pathMap[m] += std::log(e / 3);
+                        else if (gb == '-' || rb == '-') pathMap[m] += std::log(0.02);
+                        else {
+                            if (Lseq < (int)MINLENGTHFRAGMENT || Lseq > (int)MAXLENGTHFRAGMENT || baseIX < 0 || baseIX >= Lseq) return ORC_ERR_RANGE;
+                            const DiNuc D = dmg.at((unsigned)Lseq, (unsigned)baseIX);
+                            double probBasePreDamage[4];
+                            for (int bpo = 0; bpo < 4; bpo++) probBasePreDamage[bpo] = (ACGT[bpo] == gb) ? 1 - e : (e / 3);
+                            double probBasePostDamage[4] = {0.0, 0.0, 0.0, 0.0};
+                            for (int bpd = 0; bpd < 4; bpd++)
+                                for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
+                            double log_lik_marg = -std::numeric_limits<double>::infinity();
+                            for (int bpd = 0; bpd < 4; bpd++) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd]));
+                            if (log_lik_marg > std::log(0.9999999)) log_lik_marg = std::log(0.9999999);
+                            pathMap[m] += log_lik_marg;
+                            if (rev && rb != '-') baseOnRead--;
+                            else if (!rev && rb != '-') baseOnRead++;
+                        }
+                    }
+                } else {
+                    for (size_t s = 0; s < nodeSeq.size(); ++s) {
+                        const int base_quality = quality_at(a.quality, s);
+                        const double e = euka_qs(qscore_vec, base_quality);
+                        const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
+                        if (gb == 'N' || rb == 'N') pathMap[m] += std::log(0.25);
+                        else if (gb == 'S' || rb == 'S') pathMap[m] += std::log(e / 3);
+                        else if (gb == '-' || rb == '-') pathMap[m] += std::log(0.02);
+                        else if (std::abs(baseOnRead) % penalty == 0) pathMap[m] += std::log(1 - e);
+                        else pathMap[m] += std::log(e / 3);
+                        if (rev && rb != '-') baseOnRead--;
+                        else if (!rev && rb != '-') baseOnRead++;
+                    }
+                }
+                baseOnRead = baseIX;
+            }
+            if (rev) baseIX = startIndex;
+            else baseIX += mppg_sizes[i];
+            baseOnRead = baseIX;
         }
     }
     return ORC_OK;

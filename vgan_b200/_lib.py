@@ -53,6 +53,12 @@ class vgl_euka_batch(C.Structure):
                 ("flags", C.c_void_p), ("read_index", C.c_void_p)]
 
 
+class vgl_soibean_tables(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("min_id", C.c_int32), ("n_paths", C.c_int32), ("row_words", C.c_int32), ("k5", C.c_int32),
+                ("k3", C.c_int32), ("penalty", C.c_int32), ("reserved", C.c_int32), ("member_bits", C.c_void_p), ("deam", C.c_void_p),
+                ("qscore", C.c_double * 100)]
+
+
 class vgh_alignments(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual_off", C.c_void_p),
                 ("qual", C.c_void_p), ("mapq", C.c_void_p), ("identity", C.c_void_p), ("paired", C.c_void_p),
@@ -91,6 +97,8 @@ GPU_SYMBOLS = {
     "vgl_euka_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_euka_results": (C.c_int, [_P, _P, _P]),
     "vgl_euka_batch_bytes": (C.c_uint64, [C.POINTER(vgl_euka_batch)]),
+    "vgl_soibean_set_tables": (C.c_int, [_P, C.POINTER(vgl_soibean_tables)]),
+    "vgl_soibean_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
@@ -128,6 +136,10 @@ HOST_SYMBOLS = {
     "vgh_euka_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "vgh_euka_packed_batch": (C.POINTER(vgl_euka_batch), [_P]),
     "vgh_euka_packed_destroy": (None, [_P]),
+    "vgh_soibean_tables_build": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(_P)]),
+    "vgh_soibean_tables_view": (C.POINTER(vgl_soibean_tables), [_P]),
+    "vgh_soibean_tables_destroy": (None, [_P]),
+    "vgh_soibean_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "vgh_synth_euka_create": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "vgh_synth_euka_destroy": (None, [_P]),
     "vgh_synth_euka_graph": (_P, [_P]),

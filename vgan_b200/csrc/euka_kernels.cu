@@ -149,4 +149,132 @@ cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// soibean: per-read x per-path log-likelihoods (reference src/getLCAfromGAM.h:102-604)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// K5a: one read per thread.  For edit i the reference evaluates, for every path, either the "supported" or the
+// "unsupported" sum over the slice of aligned columns; both are path independent, so they are computed once here.
+__global__ void __launch_bounds__(kEukaBlock)
+soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup, double* __restrict__ uns, int* __restrict__ err_flag) {
+    __shared__ EukaSmallTables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int k = threadIdx.x; k < (int)(sizeof(EukaSmallTables) / 4); k += kEukaBlock) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (kEukaBlock / 32) + (threadIdx.x >> 5);
+    if (g >= b.n_groups) return;
+    const uint32_t r = g * 32 + lane;
+    const int nc = (int)__ldg(b.n_cols + r);
+    const int ne = (int)__ldg(b.n_maps + r);  // edits
+    if (ne == 0) return;
+    const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
+    const uint16_t* colbase = b.col + ((size_t)cb0 * 32 + lane) * 8;
+    const size_t mapbase = ((size_t)mb0 * 32 + lane) * 4;
+    const bool rev = (__ldg(b.flags + r) & 1) != 0;
+    auto col_at = [&](int c) -> uint32_t { return (uint32_t)__ldg(colbase + (size_t)(c >> 3) * 256 + (c & 7)); };
+    const double log_quarter = s_tab.log_quarter, log_gap = log(0.02), log_cap = log(0.9999999);
+    int baseIX = rev ? (int)__ldg(b.seq_len + r) - 1 : 0;
+    for (int i = 0; i < ne; ++i) {
+        const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
+        const uint32_t rec = __ldg(b.map + mi);
+        const int size = (int)(rec >> 20);
+        int start = baseIX;
+        if (rev) start = (baseIX - size - 1 >= 0) ? (baseIX - size - 1) : 0;
+        if (start < 0 || start > nc) {  // std::string::substr would throw inside the reference
+            atomicOr(err_flag, 1);
+            return;
+        }
+        const int len = min(size, nc - start);
+        double s_sup = 0.0, s_uns = 0.0;
+        int bor = baseIX;  // baseOnRead
+        bool need_damage = false;
+        for (int s = 0; s < len; ++s) {
+            const uint32_t cr = col_at(start + s);
+            const uint32_t q = col_at(s) & 0xffu;  // a.quality()[s]: indexed by the position INSIDE the slice
+            const int G = (int)((cr >> 8) & 15u), R = (int)(cr >> 12);
+            if (G == VGL_EUKA_SYM_N || R == VGL_EUKA_SYM_N) { s_sup += log_quarter; s_uns += log_quarter; }
+            else if (G == VGL_EUKA_SYM_SOFTCLIP || R == VGL_EUKA_SYM_SOFTCLIP) { s_sup += s_tab.log_e_third[q]; s_uns += s_tab.log_e_third[q]; }
+            else if (G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP) { s_sup += log_gap; s_uns += log_gap; }
+            else {
+                need_damage = true;
+                if (baseIX >= 0 && baseIX < nc) {
+                    const int i5 = min(baseIX, t.k5 - 1), i3 = min(nc - baseIX - 1, t.k3 - 1);
+                    const double* __restrict__ D = t.deam + ((size_t)i5 * t.k3 + i3) * 16;
+                    const double e1 = s_tab.one_minus_e[q], e3 = s_tab.e_third[q];
+                    double tot = 0.0;
+#pragma unroll
+                    for (int bpd = 0; bpd < 4; ++bpd) {
+                        double post = 0.0;
+#pragma unroll
+                        for (int bpo = 0; bpo < 4; ++bpo) post = fma((bpo == G) ? e1 : e3, __ldg(D + bpo * 4 + bpd), post);
+                        tot += post;
+                    }
+                    s_sup += fmin(log(tot), log_cap);
+                }
+                s_uns += ((bor < 0 ? -bor : bor) % t.penalty == 0) ? s_tab.log_one_minus_e[q] : s_tab.log_e_third[q];
+            }
+            if (R != VGL_EUKA_SYM_GAP) bor += rev ? -1 : 1;
+        }
+        // the damage table is indexed [|graph_seq|][baseIX]: outside it the reference reads out of range
+        if (need_damage && (rec & 0xFFFFFu) != VGL_SOIBEAN_NO_NODE && (baseIX < 0 || baseIX >= nc)) atomicOr(err_flag, 1);
+        sup[mi] = s_sup;
+        uns[mi] = s_uns;
+        baseIX = rev ? start : baseIX + size;
+    }
+}
+
+// K5b: one warp per read, lanes over paths.
+__global__ void __launch_bounds__(kEukaBlock)
+soibean_path_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict__ sup, const double* __restrict__ uns, uint32_t n_out,
+                    double* __restrict__ out, uint8_t* __restrict__ used, int* __restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * (kEukaBlock / 32) + (threadIdx.x >> 5);  // read lane index
+    if (r >= b.n_groups * 32u) return;
+    const int ne = (int)__ldg(b.n_maps + r);
+    if (ne == 0) return;
+    const uint32_t ridx = __ldg(b.read_index + r);
+    if (ridx >= n_out) return;
+    const uint32_t g = r >> 5, l = r & 31;
+    const size_t mapbase = ((size_t)__ldg(b.grp_map_blk + g) * 32 + l) * 4;
+    for (int p0 = 0; p0 < t.n_paths; p0 += 32) {
+        const int p = p0 + lane;
+        double acc = 0.0;
+        for (int i = 0; i < ne; ++i) {
+            const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
+            const uint32_t node = __ldg(b.map + mi) & 0xFFFFFu;
+            bool member = false;
+            if (node != VGL_SOIBEAN_NO_NODE) {
+                const int row = (int)node - t.min_id;
+                if (row < 0 || row >= t.n_rows) {
+                    if (lane == 0 && p0 == 0) atomicOr(err_flag, 2);  // nodepaths.at() would throw
+                } else if (p < t.n_paths) {
+                    member = (__ldg(t.member_bits + (size_t)row * t.row_words + (p >> 5)) >> (p & 31)) & 1u;
+                }
+            }
+            acc += member ? __ldg(sup + mi) : __ldg(uns + mi);
+        }
+        if (p < t.n_paths) out[(size_t)ridx * t.n_paths + p] = acc;
+    }
+    if (lane == 0 && used) used[ridx] = 1;
+}
+
+}  // namespace
+
+cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
+                           double* out, uint8_t* used, int* err_flag, cudaStream_t s) {
+    if (b.n_groups == 0) return cudaSuccess;
+    const int warps = kEukaBlock / 32;
+    soibean_edit_kernel<<<(b.n_groups + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, sup, uns, err_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t lanes = b.n_groups * 32u;
+    soibean_path_kernel<<<(lanes + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
+    return cudaGetLastError();
+}
+
 }  // namespace vgl

@@ -89,6 +89,12 @@ struct vgh_euka_tables {
     std::vector<int32_t> bin_off, bin_lo, bin_hi;
 };
 
+struct vgh_soibean_tables {
+    vgl_soibean_tables view{};
+    std::vector<uint32_t> bits;
+    std::vector<double> deam;
+};
+
 struct vgh_euka_packed {
     vgl_euka_batch batch{};
     bool pinned = false;
@@ -145,10 +151,49 @@ int vgh_euka_tables_build(int32_t n_clades, const double* clade_dist, const int3
     return VGH_OK;
 }
 const vgl_euka_tables* vgh_euka_tables_view(const vgh_euka_tables* t) { return t ? &t->view : nullptr; }
+
+int vgh_soibean_tables_build(int32_t n_rows, int32_t min_id, int32_t n_paths, const uint8_t* member, const char* deam5p_prof,
+                             const char* deam3p_prof, int32_t penalty, vgh_soibean_tables** out) {
+    if (!out || n_rows < 1 || n_paths < 1 || !member || penalty < 1) return vgh_fail(VGH_ERR_INVALID, "bad soibean table arguments");
+    std::vector<std::array<long double, 16>> p5, p3;
+    if (int rc = profile_rows(deam5p_prof, p5)) return rc;
+    if (int rc = profile_rows(deam3p_prof, p3)) return rc;
+    vgh_soibean_tables* T = new vgh_soibean_tables();
+    const int W = (n_paths + 31) / 32;
+    T->bits.assign((size_t)n_rows * W, 0u);
+    for (int n = 0; n < n_rows; ++n)
+        for (int p = 0; p < n_paths; ++p)
+            if (member[(size_t)n * n_paths + p]) T->bits[(size_t)n * W + (p >> 5)] |= 1u << (p & 31);
+    const int k5 = (int)p5.size(), k3 = (int)p3.size();
+    T->deam.assign((size_t)k5 * k3 * 16, 0.0);
+    for (int i5 = 0; i5 < k5; ++i5)
+        for (int i3 = 0; i3 < k3; ++i3)
+            for (int a = 0; a < 4; ++a) {
+                const long double* f1 = &p5[(size_t)i5][(size_t)(a * 4)];
+                const long double* f2 = &p3[(size_t)i3][(size_t)(a * 4)];
+                const long double mn = f1[a] < f2[a] ? f1[a] : f2[a];
+                const long double* f = (f1[a] == mn) ? f1 : f2;
+                for (int b = 0; b < 4; ++b) T->deam[((size_t)i5 * k3 + i3) * 16 + a * 4 + b] = (double)f[b];
+            }
+    vgl_soibean_tables& v = T->view;
+    v.n_rows = n_rows; v.min_id = min_id; v.n_paths = n_paths; v.row_words = W; v.k5 = k5; v.k3 = k3; v.penalty = penalty;
+    v.member_bits = T->bits.data();
+    v.deam = T->deam.data();
+    for (int Q = 0; Q < 100; ++Q) v.qscore[Q] = Q >= 2 ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;  // Euka::get_qscore_vec (src/soibean.cpp:471)
+    *out = T;
+    return VGH_OK;
+}
+const vgl_soibean_tables* vgh_soibean_tables_view(const vgh_soibean_tables* t) { return t ? &t->view : nullptr; }
+void vgh_soibean_tables_destroy(vgh_soibean_tables* t) { delete t; }
 void vgh_euka_tables_destroy(vgh_euka_tables* t) { delete t; }
 
-int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
-                  vgh_euka_packed** out) {
+}  // extern "C"
+
+// One packer for both tools.  soibean != 0: "mapping" records are edit records (size << 20 | node of the mapping with the
+// same index, 0xFFFFF when that mapping does not exist), the fragment-length check applies to the aligned graph string
+// (analyse_GAM indexes the damage table with |graph_seq|, reference src/getLCAfromGAM.h:109,327).
+static int pack_symbols(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned, int soibean,
+                        vgh_euka_packed** out) {
     if (!g || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return vgh_fail(VGH_ERR_INVALID, "bad arguments");
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -170,7 +215,7 @@ int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64
             const int64_t r = keep[(size_t)k];
             int e = vgh_recon(*g, *a, r, rc);
             const int64_t M = a->map_off[r + 1] - a->map_off[r];
-            const int64_t Lseq = a->seq_off[r + 1] - a->seq_off[r];
+            const int64_t Lseq = soibean ? (int64_t)rc.graph_seq.size() : a->seq_off[r + 1] - a->seq_off[r];
             if (!e) {
                 if (M < 1) e = vgh_fail(VGH_ERR_BAD_READ, "read %lld: no mapping", (long long)r);
                 else if (rc.graph_seq.size() != rc.read_seq.size())
@@ -194,8 +239,20 @@ int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64
                 if (!err) { err = e; err_msg = vgh_error_text(); }
                 continue;
             }
+            if (soibean) {
+                for (int64_t i = 0; i < std::min<int64_t>(M, (int64_t)rc.sizes.size()); ++i) {
+                    const int64_t node = a->map_node[a->map_off[r] + i];
+                    if (node < 0 || node >= (int64_t)VGL_SOIBEAN_NO_NODE) e = vgh_fail(VGH_ERR_BAD_NODE, "read %lld: node id %lld does not fit the edit record", (long long)r, (long long)node);
+                }
+                if (a->seq_off[r + 1] - a->seq_off[r] < 1) e = vgh_fail(VGH_ERR_BAD_READ, "read %lld: empty sequence", (long long)r);
+                if (e) {
+#pragma omp critical(vgh_euka_pack_err)
+                    if (!err) { err = e; err_msg = vgh_error_text(); }
+                    continue;
+                }
+            }
             ncols[(size_t)k] = (uint32_t)rc.graph_seq.size();
-            nmaps[(size_t)k] = (uint32_t)M;
+            nmaps[(size_t)k] = soibean ? (uint32_t)rc.sizes.size() : (uint32_t)M;
         }
     }
     if (err) return vgh_fail(err, "%s", err_msg.c_str());
@@ -271,8 +328,18 @@ int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64
                     gcol[((m / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + m % VGL_HC_COL_BLK] = rec;
                 }
                 const int64_t mm = a->map_off[r];
-                for (uint32_t i = 0; i < nmaps[k]; ++i)
-                    gmap[((size_t)(i / VGL_HC_MAP_BLK) * VGL_HC_LANES + l) * VGL_HC_MAP_BLK + i % VGL_HC_MAP_BLK] = (uint32_t)a->map_node[mm + i];
+                const int64_t M = a->map_off[r + 1] - mm;
+                for (uint32_t i = 0; i < nmaps[k]; ++i) {
+                    uint32_t rec;
+                    if (soibean) {
+                        // entries past the number of mappings get no support when the two counts differ (getLCAfromGAM.h:156-160)
+                        const bool none = (int64_t)rc.sizes.size() != M && (int64_t)i >= M;
+                        rec = ((uint32_t)rc.sizes[i] << 20) | (none ? VGL_SOIBEAN_NO_NODE : (uint32_t)a->map_node[mm + i]);
+                    } else {
+                        rec = (uint32_t)a->map_node[mm + i];
+                    }
+                    gmap[((size_t)(i / VGL_HC_MAP_BLK) * VGL_HC_LANES + l) * VGL_HC_MAP_BLK + i % VGL_HC_MAP_BLK] = rec;
+                }
                 n_cols[lane_id] = (uint16_t)L;
                 n_maps[lane_id] = (uint16_t)nmaps[k];
                 seq_len[lane_id] = (uint16_t)(a->seq_off[r + 1] - a->seq_off[r]);
@@ -294,6 +361,17 @@ int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64
     *out = P;
     return VGH_OK;
 }
+extern "C" {
+
+int vgh_euka_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                  vgh_euka_packed** out) {
+    return pack_symbols(g, a, r0, r1, n_threads, pinned, 0, out);
+}
+int vgh_soibean_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+                     vgh_euka_packed** out) {
+    return pack_symbols(g, a, r0, r1, n_threads, pinned, 1, out);
+}
+
 const vgl_euka_batch* vgh_euka_packed_batch(const vgh_euka_packed* p) { return p ? &p->batch : nullptr; }
 void vgh_euka_packed_destroy(vgh_euka_packed* p) {
     if (!p) return;

@@ -118,6 +118,14 @@ struct vgl_ctx {
     DevBuf<vgl::EukaSmallTables> e_small;
     DevBuf<unsigned long long> e_count;
     DevBuf<uint8_t> e_pass;
+    // soibean
+    bool have_soibean = false;
+    vgl::SoibeanTablesDev stab{};
+    DevBuf<uint32_t> s_member;
+    DevBuf<double> s_deam, s_sup, s_uns, s_out;
+    DevBuf<vgl::EukaSmallTables> s_small;
+    DevBuf<uint8_t> s_used;
+    DevBuf<int> s_err;
     struct EukaStage {
         DevBuf<uint32_t> grp_col_blk, grp_map_blk, map, read_index;
         DevBuf<uint16_t> col, n_cols, n_maps, seq_len;
@@ -234,6 +242,8 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->e_node_clade.release(); ctx->e_dist.release(); ctx->e_deam.release(); ctx->e_bin_cov.release(); ctx->e_in.release();
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
+    ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release();
+    ctx->s_small.release(); ctx->s_used.release(); ctx->s_err.release();
     ctx->estage.grp_col_blk.release(); ctx->estage.grp_map_blk.release(); ctx->estage.map.release(); ctx->estage.read_index.release();
     ctx->estage.col.release(); ctx->estage.n_cols.release(); ctx->estage.n_maps.release(); ctx->estage.seq_len.release();
     ctx->estage.mapq.release(); ctx->estage.flags.release();
@@ -767,6 +777,110 @@ int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov) {
     if (clade_count) VGL_CUDA(cudaMemcpyAsync(clade_count, ctx->e_count.p, (size_t)ctx->etab.n_clades * 8, cudaMemcpyDeviceToHost, s));
     if (bin_cov && ctx->etab.n_bins) VGL_CUDA(cudaMemcpyAsync(bin_cov, ctx->e_bin_cov.p, (size_t)ctx->etab.n_bins * 8, cudaMemcpyDeviceToHost, s));
     VGL_CUDA(cudaStreamSynchronize(s));
+    return VGL_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------
+// soibean
+// -------------------------------------------------------------------------------------------
+namespace {
+int stage_symbol_batch(vgl_ctx* ctx, const vgl_euka_batch* b, vgl::EukaBatchDev& d) {
+    cudaStream_t s = ctx->stream;
+    const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
+    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_HC_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    vgl_ctx::EukaStage& st = ctx->estage;
+    if (int rc = st.grp_col_blk.reserve(G + 1)) return rc;
+    if (int rc = st.grp_map_blk.reserve(G + 1)) return rc;
+    if (int rc = st.col.reserve(ncol)) return rc;
+    if (int rc = st.map.reserve(nmap)) return rc;
+    if (int rc = st.n_cols.reserve(nl)) return rc;
+    if (int rc = st.n_maps.reserve(nl)) return rc;
+    if (int rc = st.seq_len.reserve(nl)) return rc;
+    if (int rc = st.mapq.reserve(nl)) return rc;
+    if (int rc = st.flags.reserve(nl)) return rc;
+    if (int rc = st.read_index.reserve(nl)) return rc;
+    if (int rc = upload_async(st.grp_col_blk.p, b->grp_col_blk, (G + 1) * 4, s)) return rc;
+    if (int rc = upload_async(st.grp_map_blk.p, b->grp_map_blk, (G + 1) * 4, s)) return rc;
+    if (int rc = upload_async(st.col.p, b->col, ncol * 2, s)) return rc;
+    if (int rc = upload_async(st.map.p, b->map, nmap * 4, s)) return rc;
+    if (int rc = upload_async(st.n_cols.p, b->n_cols, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.n_maps.p, b->n_maps, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.seq_len.p, b->seq_len, nl * 2, s)) return rc;
+    if (int rc = upload_async(st.mapq.p, b->mapq, nl, s)) return rc;
+    if (int rc = upload_async(st.flags.p, b->flags, nl, s)) return rc;
+    if (int rc = upload_async(st.read_index.p, b->read_index, nl * 4, s)) return rc;
+    d = vgl::EukaBatchDev{b->n_groups, st.grp_col_blk.p, st.grp_map_blk.p, st.col.p, st.map.p, st.n_cols.p, st.n_maps.p,
+                          st.seq_len.p, st.mapq.p, st.flags.p, st.read_index.p};
+    return VGL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* T) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!T || T->n_rows < 1 || T->n_paths < 1 || T->row_words < (T->n_paths + 31) / 32 || !T->member_bits || !T->deam || T->k5 < 1 ||
+        T->k3 < 1 || T->penalty < 1)
+        return fail(VGL_ERR_INVALID, "bad soibean tables");
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    vgl::EukaSmallTables small;
+    memset(&small, 0, sizeof(small));
+    for (int b = 0; b < 256; ++b) {
+        const int Q = (int)(int8_t)(uint8_t)b;
+        const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
+        small.one_minus_e[b] = 1 - qs;
+        small.e_third[b] = qs / 3;
+        small.log_one_minus_e[b] = std::log(1 - qs);
+        small.log_e_third[b] = std::log(qs / 3);
+    }
+    small.log_quarter = std::log(0.25);
+    if (int rc = ctx->s_member.reserve((size_t)T->n_rows * T->row_words)) return rc;
+    if (int rc = ctx->s_deam.reserve((size_t)T->k5 * T->k3 * 16)) return rc;
+    if (int rc = ctx->s_small.reserve(1)) return rc;
+    if (int rc = ctx->s_err.reserve(1)) return rc;
+    VGL_CUDA(cudaMemcpy(ctx->s_member.p, T->member_bits, (size_t)T->n_rows * T->row_words * 4, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->s_deam.p, T->deam, (size_t)T->k5 * T->k3 * 16 * 8, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->s_small.p, &small, sizeof(small), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemset(ctx->s_err.p, 0, sizeof(int)));
+    vgl::SoibeanTablesDev& d = ctx->stab;
+    d.n_rows = T->n_rows; d.min_id = T->min_id; d.n_paths = T->n_paths; d.row_words = T->row_words; d.k5 = T->k5; d.k3 = T->k3;
+    d.penalty = T->penalty; d.member_bits = ctx->s_member.p; d.deam = ctx->s_deam.p; d.small = ctx->s_small.p;
+    ctx->have_soibean = true;
+    return VGL_OK;
+}
+
+int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* b, uint32_t n_out, double* path_ll, uint8_t* used) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_soibean) return fail(VGL_ERR_STATE, "vgl_soibean_set_tables must come first");
+    if (!b) return fail(VGL_ERR_INVALID, "null batch");
+    if (b->n_groups == 0) return VGL_OK;
+    if (!b->grp_col_blk || !b->grp_map_blk || !b->col || !b->map || !b->n_cols || !b->n_maps || !b->seq_len || !b->mapq || !b->flags ||
+        !b->read_index)
+        return fail(VGL_ERR_INVALID, "soibean batch arrays missing");
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
+    vgl::EukaBatchDev d;
+    if (int rc = stage_symbol_batch(ctx, b, d)) return rc;
+    const size_t nmap = std::max<size_t>((size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK, 1);
+    const size_t P = (size_t)ctx->stab.n_paths, no = std::max<size_t>(n_out, 1);
+    if (int rc = ctx->s_sup.reserve(nmap)) return rc;
+    if (int rc = ctx->s_uns.reserve(nmap)) return rc;
+    if (int rc = ctx->s_out.reserve(no * P)) return rc;
+    if (int rc = ctx->s_used.reserve(no)) return rc;
+    VGL_CUDA(cudaMemsetAsync(ctx->s_out.p, 0, no * P * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->s_used.p, 0, no, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
+    VGL_CUDA(vgl::soibean_launch(d, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, n_out, ctx->s_out.p, ctx->s_used.p, ctx->s_err.p, s));
+    ctx->launches += 2;
+    int err = 0;
+    VGL_CUDA(cudaMemcpyAsync(&err, ctx->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (path_ll) VGL_CUDA(cudaMemcpyAsync(path_ll, ctx->s_out.p, (size_t)n_out * P * 8, cudaMemcpyDeviceToHost, s));
+    if (used) VGL_CUDA(cudaMemcpyAsync(used, ctx->s_used.p, (size_t)n_out, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    if (err & 2) return fail(VGL_ERR_BAD_NODE, "an edit names a node outside the membership table (the reference would throw from vector::at)");
+    if (err & 1) return fail(VGL_ERR_BAD_READ, "an alignment slices past its aligned strings or the damage table (the reference would throw / read out of range)");
     return VGL_OK;
 }
 

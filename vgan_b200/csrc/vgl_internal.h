@@ -144,4 +144,19 @@ struct EukaOutDev {
 
 cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& t, const EukaOutDev& o, cudaStream_t s);
 
+// ---------------------------------------------------------------------------------------------------------
+// soibean (same batch layout as euka; "mapping" records are edit records)
+// ---------------------------------------------------------------------------------------------------------
+struct SoibeanTablesDev {
+    int32_t n_rows, min_id, n_paths, row_words, k5, k3, penalty;
+    const uint32_t* member_bits;
+    const double* deam;
+    const EukaSmallTables* small;  // one_minus_e / e_third / their logs by quality byte
+};
+
+// K5a: per read and edit, the "supported" and "unsupported" sums over the edit's slice -> sup / uns (indexed like the
+//      edit records); K5b: out[read][p] = sum over edits of (path p goes through the edit's node ? sup : uns).
+cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
+                           double* out, uint8_t* used, int* err_flag, cudaStream_t s);
+
 }  // namespace vgl

@@ -1,0 +1,73 @@
+"""soibean per-read x per-path likelihood path over the C ABI (reference: analyse_GAM, src/getLCAfromGAM.h:102-604).
+
+`Soibean.analyse` returns the R x P matrix of AlignmentInfo::pathMap values (what convertMapsToVector,
+src/soibean.cpp:131-155, hands to the MCMC), columns in pathNames order.  No CPU path."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, gpu, host
+
+
+class SoibeanTables:
+    def __init__(self, member, min_id=0, deam5p_prof="", deam3p_prof="", penalty=7):
+        member = np.ascontiguousarray(member, dtype=np.uint8)
+        self.n_rows, self.n_paths = member.shape
+        self.handle = C.c_void_p()
+        check(host.vgh_soibean_tables_build(self.n_rows, int(min_id), self.n_paths, member.ctypes.data_as(C.c_void_p),
+                                            (deam5p_prof or "").encode(), (deam3p_prof or "").encode(), int(penalty),
+                                            C.byref(self.handle)))
+        self.view = host.vgh_soibean_tables_view(self.handle).contents
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_soibean_tables_destroy(self.handle)
+            self.handle = None
+
+
+class SoibeanPackedBatch:
+    def __init__(self, graph, alns, r0=0, r1=None, n_threads=0, pinned=False):
+        r1 = len(alns) if r1 is None else r1
+        self.n_span = int(r1 - r0)
+        self.handle = C.c_void_p()
+        check(host.vgh_soibean_pack(graph.handle, C.byref(alns.view), int(r0), int(r1), int(n_threads), int(pinned), C.byref(self.handle)))
+        self.batch = host.vgh_euka_packed_batch(self.handle).contents
+
+    @property
+    def n_reads(self):
+        return int(self.batch.n_reads)
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_euka_packed_destroy(self.handle)
+            self.handle = None
+
+
+class Soibean:
+    def __init__(self, device=0):
+        self.ctx = C.c_void_p()
+        check(gpu.vgl_create(int(device), C.byref(self.ctx)))
+        self.tables = None
+
+    def close(self):
+        if self.ctx:
+            gpu.vgl_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, tables):
+        check(gpu.vgl_soibean_set_tables(self.ctx, C.byref(tables.view)))
+        self.tables = tables
+
+    def analyse(self, packed):
+        """pathMap of every read of the packed range: (matrix [n, P], used [n])."""
+        n, P = packed.n_span, self.tables.n_paths
+        out = np.zeros((n, P), dtype=np.float64)
+        used = np.zeros(n, dtype=np.uint8)
+        check(gpu.vgl_soibean_run(self.ctx, C.byref(packed.batch), n, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
+        return out, used
