@@ -79,6 +79,15 @@ void vgh_gam_destroy(vgh_gam* g);
 int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char* graph_seq, char* read_seq,
                     int32_t* sizes, int32_t cap, int32_t* n_graph, int32_t* n_read, int32_t* n_sizes);
 
+/* ---- duplicate removal (reference: Dup_Remover::remove_duplicates_internal, src/rmdup.cpp:20-110) ---------- */
+/* The reference marks read j a duplicate when an EARLIER read i that is not paired starts at the same
+ * (node id, offset) of its first mapping, strand ignored (update_for_single, src/rmdup.cpp:20-39) -- an O(n^2)
+ * scan directly in front of the hot loop (src/HaploCart.cpp:390).  This is the same predicate in one hash pass.
+ * Paired reads: update_for_paired indexes mapping()[n_mappings], one past the end (src/rmdup.cpp:48-49,55-59), so
+ * its result is undefined in the reference; here a paired read i marks nothing.
+ * is_dup[r] (n_reads bytes) receives 1 for duplicates; returns the number of reads kept via *n_kept.        */
+int vgh_dedup(const vgh_alignments* a, uint8_t* is_dup, int64_t* n_kept);
+
 /* ---- batch packer --------------------------------------------------------------------------- */
 typedef struct vgh_hc_packed vgh_hc_packed;
 /* Pack reads [r0, r1) into one vgl_hc_batch.  Reads with identity < 1e-10 are skipped exactly as

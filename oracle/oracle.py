@@ -281,3 +281,13 @@ def soibean_run(graph, reads, member, min_id=0, penalty=7, deam5p_prof="", deam3
     if rc:
         raise RuntimeError("orc_soibean_run failed: %d" % rc)
     return out, used
+
+
+def dedup(reads, paired=None):
+    """The reference's O(n^2) duplicate marking (src/rmdup.cpp:20-110)."""
+    mask = np.zeros(reads.n, dtype=np.uint8)
+    pz = None if paired is None else np.ascontiguousarray(paired, dtype=np.uint8)
+    rc = lib().orc_dedup(C.byref(reads.c), None if pz is None else _ptr(pz), _ptr(mask))
+    if rc:
+        raise RuntimeError("orc_dedup failed: %d" % rc)
+    return mask.astype(bool)

@@ -1050,6 +1050,22 @@ int orc_euka_deam_matrix(const char* deam5p, const char* deam3p, uint32_t L, uin
 
 extern "C" {
 
+// Dup_Remover::remove_duplicates_internal for unpaired reads, as written (src/rmdup.cpp:20-39,68-110): for every read i,
+// every later read j with the same (node id, offset) of its first mapping is marked.  O(n^2) on purpose.
+int orc_dedup(const orc_reads* R, const uint8_t* paired, uint8_t* is_dup) {
+    for (int64_t r = 0; r < R->n_reads; ++r) is_dup[r] = 0;
+    for (int64_t i = 0; i < R->n_reads; ++i) {
+        if (paired && paired[i]) continue;  // update_for_paired reads mapping()[n_mappings]: undefined in the reference
+        if (R->map_off[i + 1] == R->map_off[i]) return ORC_ERR_RANGE;
+        const int64_t node = R->map_node[R->map_off[i]], off = R->map_offset[R->map_off[i]];
+        for (int64_t j = i + 1; j != R->n_reads; ++j) {
+            if (R->map_off[j + 1] == R->map_off[j]) return ORC_ERR_RANGE;
+            if (i < j && R->map_node[R->map_off[j]] == node && R->map_offset[R->map_off[j]] == off) is_dup[j] = 1;
+        }
+    }
+    return ORC_OK;
+}
+
 // Tables the product also needs, exported so tests can compare them entry by entry.
 void orc_hc_qscore_vec(double* out100) { vector<double> v = get_qscore_vec(); for (int i = 0; i < 100; ++i) out100[i] = v[(size_t)i]; }
 void orc_hc_incorrect_mapping_vec(double* out100) { vector<double> v = precompute_incorrect_mapping_probs(); for (int i = 0; i < 100; ++i) out100[i] = v[(size_t)i]; }

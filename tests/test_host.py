@@ -277,3 +277,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "vgan_oracle" not in txt, f
+
+
+def test_dedup_matches_the_reference_quadratic_scan():
+    S = vb.SynthHaplocart(seed=61, n_paths=20, n_rows=130, n_nodes=121)   # tiny graph: many shared start coordinates
+    A = S.reads(3000, seed=62)
+    arr = A.arrays()
+    want = orc.dedup(orc.FlatReads(arr), arr["paired"])
+    got, kept = vb.host.dedup(A)
+    assert np.array_equal(got, want) and kept == int((~want).sum())
+    assert 0 < kept < 600                                               # ~2 x 220 distinct (node, offset) starts at most
+    # strand is ignored, the offset is not
+    a = [H.aln("GCTA", [(9, 0, False, [(4, 4, "")])]), H.aln("TAGC", [(9, 0, True, [(4, 4, "")])]),
+         H.aln("CTAC", [(9, 1, False, [(4, 4, "")])]), H.aln("GCTA", [(9, 0, False, [(4, 4, "")])])]
+    X = vb.Alignments.from_gam_bytes(H.encode_gam(a))
+    assert vb.host.dedup(X)[0].tolist() == [False, True, False, True]
+    assert np.array_equal(orc.dedup(orc.Reads(a)), [False, True, False, True])
+    # a real fixture: all_the_same.gam is 128 copies of one alignment
+    import os
+    F = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "all_the_same.gam"))
+    m, kept = vb.host.dedup(F)
+    assert kept == 1 and m[1:].all() and np.array_equal(m, orc.dedup(orc.FlatReads(F.arrays())))

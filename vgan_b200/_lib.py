@@ -113,6 +113,7 @@ HOST_SYMBOLS = {
     "vgh_gam_destroy": (None, [_P]),
     "vgh_reconstruct": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, _P, _P, _P, C.c_int32,
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vgh_dedup": (C.c_int, [C.POINTER(vgh_alignments), _P, C.POINTER(C.c_int64)]),
     "vgh_hc_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "vgh_hc_packed_batch": (C.POINTER(vgl_hc_batch), [_P]),
     "vgh_hc_packed_skipped": (C.c_int64, [_P]),

@@ -71,6 +71,9 @@ __device__ __forceinline__ void atoms_add_f64(uint32_t a, double v) { asm volati
 // streaming global loads of the batch: every byte is used exactly once, keep it out of L1
 __device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) { uint16_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_l1_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) { uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 
 constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_pair);
@@ -102,9 +105,9 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // ------------------------------------------------------------------------------------------
 // K1: one read per thread, one 32-lane group per warp at a time.
 //
-// The batch is stored lane-interleaved (include/vgan_gpu.h), so the 32 threads of a warp read 64 (column
-// records) or 128 (mapping records) contiguous bytes per step: perfectly coalesced streaming loads, each byte
-// used once, no staging needed.  Per read the thread walks its columns from the LAST to the first:
+// The batch is stored lane-interleaved in 16-byte blocks (include/vgan_gpu.h), so the 32 threads of a warp read
+// 512 contiguous bytes per step: perfectly coalesced streaming loads, each byte used once, no staging needed.
+// Per read the thread walks its columns from the LAST to the first:
 //   * the running sum of log(err) over the columns seen so far is exactly the quality sum the reference takes
 //     for the mapping that starts at the current column (src/update_likelihood.cpp:40-44 reads |algnseq|
 //     qualities from position_in_read; the `pos` bytes past the end count as quality 0);
@@ -114,8 +117,164 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // lane-interleaved by the hardware); a second, branch-free pass over the mappings takes the log, forms B_i
 // and scatters B_i - A_i into the CTA's node vector with a shared-memory fp64 atomic.
 //
-// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | class cache | node_class u16[n_rows] ]
+// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | node_class u16[n_rows] | ac table double2[100][n_class] ]
+// The ac table holds {1 - pcm, pcm * K} (src/process_mapping.cpp:33-42) for every (mapping quality, table class)
+// pair, so opening a mapping costs two shared loads and no arithmetic.
 // ------------------------------------------------------------------------------------------
+struct ReadKernelShared {
+    uint32_t acc, f, bg, logtab, node_class, ac;  // shared byte addresses
+    int n_rows, n_class;
+    double le0;
+};
+
+// kLatch: some read of the group holds a real quality byte >= 90 (it switches mappings to the background error
+// probability, src/update_likelihood.cpp:42); the common case compiles the test away.
+// kSingle: no read of the group has more than kMapChunk mappings, so one pass covers it and the per-column range
+// checks of the multi-pass walk disappear.
+template <bool kLatch, bool kSingle>
+__device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const ReadKernelShared& S, uint32_t g, int lane, double& a_sum,
+                                                 bool& bad_node) {
+    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
+    const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
+    const int ncb = (int)(__ldg(b.grp_col_blk + g + 1) - cb0);  // 8-column blocks of this group
+    const int nmb = (int)(__ldg(b.grp_map_blk + g + 1) - mb0);  // 4-mapping blocks
+    const uint4* gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
+    const uint4* gm = reinterpret_cast<const uint4*>(b.map) + (size_t)mb0 * 32 + lane;
+    const uint32_t* gm32 = reinterpret_cast<const uint32_t*>(gm);  // record i of this lane: gm32[(i >> 2) * 128 + (i & 3)]
+    const uint32_t r = g * 32 + lane;
+    const int Lp = (int)__ldg(b.n_cols + r);
+    const int M = (int)__ldg(b.n_maps + r);
+    const int f90 = kLatch ? (int)__ldg(b.first_q90 + r) : 0xFFFF;
+    const uint32_t ac_row = S.ac + 16u * (uint32_t)(S.n_class + 1) * (uint32_t)__ldg(b.mapq + r);
+    const int maxm = nmb * VGL_HC_MAP_BLK;
+
+    double plist[kMapChunk];    // exp(A_i) of the mappings of the current pass
+    uint32_t slist[kMapChunk];  // quality sums from the mapping's first column on: (sum of q for q > 2) | (count of q <= 2) << 20
+    // Quality sums over the columns walked so far (from the end of the read).  The single-pass walk visits every record of
+    // the group's blocks; records past a read's own columns are zero and would count as quality-0 columns, so the sum
+    // starts that much lower (mod 2^32) instead of testing every column against the read's length.
+    uint32_t suf = kSingle ? 0u - ((uint32_t)(ncb * VGL_HC_COL_BLK - Lp) << 20) : 0u;
+    int c_done = Lp;  // columns >= c_done have been walked
+    for (int hi_u = maxm; hi_u > 0; hi_u -= kMapChunk) {  // one iteration when kSingle
+        const int lo_u = kSingle ? 0 : max(hi_u - kMapChunk, 0);
+        const int hi = min(M, hi_u), lo = kSingle ? 0 : min(M, lo_u);
+        // ---- pass 1: columns, descending ----
+        int i = hi - 1;  // current mapping
+        int pos = -1;    // its first column
+        uint32_t and_m = 0x1ffu, or_m = 0u;  // f-table index = (record & and_m) | or_m
+        double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
+        // mapping records are read one mapping ahead of need
+        const uint32_t* prec = gm32 + (size_t)(max(i, 0) >> 2) * 128 + (max(i, 0) & 3);
+        uint32_t rec_next = i >= lo ? ldg_stream_u32(prec) : 0u;
+        auto open_mapping = [&]() {
+            if (i < lo) { pos = -1; return; }
+            const uint32_t rec = rec_next;
+            if (i > lo) {
+                prec -= (i & 3) ? 1 : 125;  // previous record of this lane: same block, or the last one of the block below
+                rec_next = ldg_stream_u32(prec);
+            }
+            pos = (int)(rec >> VGL_HC_MAP_NODE_BITS);
+            const uint32_t node = rec & VGL_HC_MAP_MAX_NODE;
+            // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
+            const uint32_t cls = node < (uint32_t)S.n_rows ? lds_u16_c(S.node_class + 2u * node) : 0xFFFFu;
+            bad_node |= cls == 0xFFFFu;
+            const double2 ac = lds_v2f64_c(ac_row + 16u * min(cls, (uint32_t)S.n_class));
+            aa = ac.x;
+            cc = ac.y;
+            if (kLatch) {
+                // the background error mode is on for this mapping once a real quality byte >= 90 lies before the end of
+                // its quality window [pos, pos + Lp)  (src/update_likelihood.cpp:40-44)
+                const bool latched = f90 < pos + Lp;
+                and_m = latched ? 0x100u : 0x1ffu;
+                or_m = latched ? 0x200u : 0u;
+            }
+        };
+        open_mapping();
+        while (i >= lo && pos >= c_done) {  // mappings that own no column (they start at or past the end)
+            plist[i - lo] = 1.0;
+            slist[i - lo] = kSingle ? 0u : suf;
+            --i;
+            open_mapping();
+        }
+        int c_stop = 0;
+        if (!kSingle && lo > 0 && lo < M) c_stop = (int)(ldg_stream_u32(gm32 + (size_t)(lo >> 2) * 128 + (lo & 3)) >> VGL_HC_MAP_NODE_BITS);
+        const bool walking = hi > lo;
+        auto column = [&](int c, uint32_t rec) {
+            if (!kSingle && !(c < c_done && c >= c_stop && walking)) return;
+            const uint32_t q = rec & 0xffu;
+            suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
+            if (rec & VGL_HC_COL_VALID) {
+                const double f = lds_f64_c(S.f + 8u * (kLatch ? ((rec & and_m) | or_m) : (rec & 0x1ffu)));
+                const double bgv = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec));
+                prod *= fma(cc, f, aa * bgv);
+            }
+            while (c == pos) {
+                if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
+                    const uint32_t node = ldg_stream_u32(gm32 + (size_t)(i >> 2) * 128 + (i & 3)) & VGL_HC_MAP_MAX_NODE;
+                    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, -a_ext);
+                    a_sum += a_ext;
+                    a_ext = 0.0;
+                }
+                plist[i - lo] = prod;
+                slist[i - lo] = suf;
+                prod = 1.0;
+                --i;
+                open_mapping();
+            }
+        };
+        // column records come in blocks of 8, fetched two blocks ahead of the walk
+        uint4 cb_cur = ncb > 0 ? ldg_stream_v4(gc + (size_t)(ncb - 1) * 32) : make_uint4(0, 0, 0, 0);
+        uint4 cb_nxt = ncb > 1 ? ldg_stream_v4(gc + (size_t)(ncb - 2) * 32) : make_uint4(0, 0, 0, 0);
+        for (int cb = ncb - 1; cb >= 0; --cb) {
+            const uint4 cb_nxt2 = cb > 1 ? ldg_stream_v4(gc + (size_t)(cb - 2) * 32) : make_uint4(0, 0, 0, 0);
+            const int c8 = cb * VGL_HC_COL_BLK;
+            column(c8 + 7, cb_cur.w >> 16);
+            column(c8 + 6, cb_cur.w & 0xffffu);
+            column(c8 + 5, cb_cur.z >> 16);
+            column(c8 + 4, cb_cur.z & 0xffffu);
+            column(c8 + 3, cb_cur.y >> 16);
+            column(c8 + 2, cb_cur.y & 0xffffu);
+            column(c8 + 1, cb_cur.x >> 16);
+            column(c8 + 0, cb_cur.x & 0xffffu);
+            if (prod < 1e-100) {  // keep the product normal (eight more factors cannot take it below 1e-200)
+                a_ext += fast_log_s(prod, S.logtab);
+                prod = 1.0;
+            }
+            cb_cur = cb_nxt;
+            cb_nxt = cb_nxt2;
+        }
+        if (!kSingle && walking) c_done = c_stop;
+        // ---- pass 2: mappings, four at a time so that the list loads of a block are in flight together ----
+        for (int mbk = lo_u >> 2; mbk < (hi_u >> 2); ++mbk) {
+            const uint4 rb = ldg_stream_v4(gm + (size_t)mbk * 32);
+            const uint32_t recs[4] = {rb.x, rb.y, rb.z, rb.w};
+            const int k0 = mbk * 4 - lo_u;
+            double pr[4];
+            uint32_t sv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool on = mbk * 4 + e < hi;
+                pr[e] = on ? plist[k0 + e] : 1.0;
+                sv[e] = on ? slist[k0 + e] : 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (mbk * 4 + e < hi) {
+                    const uint32_t rm = recs[e];
+                    const uint32_t node = rm & VGL_HC_MAP_MAX_NODE;
+                    const double A = fast_log_s(pr[e], S.logtab);
+                    // log(err) over [pos, pos + Lp): the stored columns from pos on plus `pos` bytes past the end that
+                    // count as quality 0  
+                    const double B = fma((double)(sv[e] & 0xfffffu), scale, (double)((sv[e] >> 20) + (rm >> VGL_HC_MAP_NODE_BITS)) * S.le0);
+                    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, B - A);
+                    a_sum += A;
+                }
+            }
+        }
+        if (kSingle) break;
+    }
+}
+
 __global__ void __launch_bounds__(kReadBlock, 1)
 hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
                int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
@@ -125,9 +284,9 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     off += ((size_t)t.n_rows * sizeof(double) + 15) & ~(size_t)15;
     HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + off);
     off += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
-    double2* s_cls = reinterpret_cast<double2*>(smem_raw + off);
-    off += kClassCache * sizeof(double2);
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
+    off += ((size_t)t.n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
+    double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // [100][n_class + 1]
     __shared__ double s_warp_a[kReadBlock / 32];
 
     const int tid = threadIdx.x;
@@ -142,171 +301,45 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_tab);
         for (int k = tid; k < (int)(sizeof(HcSmallTables) / 4); k += kReadBlock) dst[k] = src[k];
-        if (tid < kClassCache) s_cls[tid] = t.class_tab[tid];
+    }
+    __syncthreads();
+    {
+        // {1 - pcm, pcm * K} for every (mapping quality, class): p_correctly_mapped = (1 - p_incorrect[mq]) * mappability
+        // (src/process_mapping.cpp:41); consensus-FASTA mode uses (1 - bep) * K alone (:73)
+        const bool fasta = s_tab->is_fasta != 0;
+        const int row = t.n_class + 1;  // entry n_class of every row is the neutral {1, 0} used for unknown nodes
+        for (int k = tid; k < 100 * row; k += kReadBlock) {
+            const int mq = k / row, cls = k - mq * row;
+            if (cls == t.n_class) { s_ac[k] = make_double2(1.0, 0.0); continue; }
+            const double2 mk = t.class_tab[cls];  // {mappability, match_prob}
+            const double pcm = s_tab->p_correct[mq] * mk.x;
+            s_ac[k] = make_double2(fasta ? 0.0 : 1.0 - pcm, (fasta ? s_tab->one_minus_bep : pcm) * mk.y);
+        }
     }
     __syncthreads();
 
-    const uint32_t A_acc = smem_u32(s_acc), A_tab = smem_u32(s_tab), A_cls = smem_u32(s_cls), A_class = smem_u32(s_class);
-    const uint32_t A_f = A_tab + kOffFPair, A_bg = A_tab + kOffBg, A_log = A_tab + kOffLogTab;
-    const bool fasta = s_tab->is_fasta != 0;
-    const double one_minus_bep = s_tab->one_minus_bep;
-    const double le0 = s_tab->log_err[0];
-    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
-    const bool classes_cached = t.n_class <= kClassCache;
-    const int n_rows = t.n_rows;
+    ReadKernelShared S;
+    S.acc = smem_u32(s_acc);
+    S.f = smem_u32(s_tab) + kOffFPair;
+    S.bg = smem_u32(s_tab) + kOffBg;
+    S.logtab = smem_u32(s_tab) + kOffLogTab;
+    S.node_class = smem_u32(s_class);
+    S.ac = smem_u32(s_ac);
+    S.n_rows = t.n_rows;
+    S.n_class = t.n_class;
+    S.le0 = s_tab->log_err[0];
 
     double a_sum = 0.0;
     bool bad_node = false;
-    double plist[kMapChunk];    // exp(A_i) of the mappings of the current pass
-    uint32_t slist[kMapChunk];  // quality sums from the mapping's first column on: (sum of q for q > 2) | (count of q <= 2) << 20
-
-    // {1 - pcm, pcm * K} of a mapping whose node is in table class `cls` (src/process_mapping.cpp:33-42)
-    auto scalars = [&](uint32_t cls, double pc, double& aa, double& cc) {
-        const bool ok = cls != 0xFFFFu;  // 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it
-        bad_node |= !ok;
-        const double2 mk = classes_cached ? lds_v2f64_c(A_cls + 16u * (ok ? cls : 0u)) : t.class_tab[ok ? cls : 0u];  // {mappability, match_prob}
-        const double pcm = pc * mk.x;
-        aa = fasta ? 0.0 : 1.0 - pcm;
-        cc = (fasta ? one_minus_bep : pcm) * mk.y;
-    };
-
     const uint32_t warps_total = gridDim.x * (kReadBlock / 32);
     for (uint32_t g = blockIdx.x * (kReadBlock / 32) + warp; g < b.n_groups; g += warps_total) {
-        const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
-        const int ncb = (int)(__ldg(b.grp_col_blk + g + 1) - cb0);  // 8-column blocks of this group
-        const int nmb = (int)(__ldg(b.grp_map_blk + g + 1) - mb0);  // 4-mapping blocks
-        if (nmb == 0) continue;  // no read of this group has a mapping
-        const uint4* gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
-        const uint4* gm = reinterpret_cast<const uint4*>(b.map) + (size_t)mb0 * 32 + lane;
-        const uint32_t r = g * 32 + lane;
-        const int Lp = (int)__ldg(b.n_cols + r);
-        const int M = (int)__ldg(b.n_maps + r);
-        const int f90 = (int)__ldg(b.first_q90 + r);  // 0xFFFF: no real quality byte >= 90
-        const double pc = lds_f64_c(A_tab + kOffPCorrect + 8u * (uint32_t)__ldg(b.mapq + r));
-        const int maxm = nmb * VGL_HC_MAP_BLK;
-
-        uint32_t suf = 0;   // quality sums over the columns walked so far (from the end of the read)
-        int c_done = Lp;    // columns >= c_done have been walked
-        // passes of up to kMapChunk mappings, from the last mappings to the first (one pass unless a read of the
-        // group has more than kMapChunk mappings)
-        for (int hi_u = maxm; hi_u > 0; hi_u -= kMapChunk) {
-            const int lo_u = max(hi_u - kMapChunk, 0);
-            const int hi = min(M, hi_u), lo = min(M, lo_u);
-            // ---- pass 1: columns, descending ----
-            int i = hi - 1;                 // current mapping
-            int pos = -1;                   // its first column
-            uint32_t and_m = 0x1ffu, or_m = 0u;  // f-table index = (record & and_m) | or_m
-            double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
-            // mapping records come in blocks of 4; the block below the current one is fetched ahead of need
-            int mb_idx = i >= 0 ? (i >> 2) : 0;
-            uint4 mb_cur = ldg_stream_v4(gm + (size_t)mb_idx * 32);
-            uint4 mb_prev = mb_idx > 0 ? ldg_stream_v4(gm + (size_t)(mb_idx - 1) * 32) : make_uint4(0, 0, 0, 0);
-            auto map_rec = [&](int idx) -> uint32_t {
-                if ((idx >> 2) != mb_idx) {
-                    mb_cur = mb_prev;
-                    --mb_idx;
-                    mb_prev = mb_idx > 0 ? ldg_stream_v4(gm + (size_t)(mb_idx - 1) * 32) : make_uint4(0, 0, 0, 0);
-                }
-                const int e = idx & 3;
-                return e == 0 ? mb_cur.x : e == 1 ? mb_cur.y : e == 2 ? mb_cur.z : mb_cur.w;
-            };
-            auto open_mapping = [&]() {
-                if (i < lo) { pos = -1; return; }
-                const uint32_t rec = map_rec(i);
-                pos = (int)(rec >> VGL_HC_MAP_NODE_BITS);
-                const uint32_t node = rec & VGL_HC_MAP_MAX_NODE;
-                const uint32_t cls = node < (uint32_t)n_rows ? lds_u16_c(A_class + 2u * node) : 0xFFFFu;
-                scalars(cls, pc, aa, cc);  // unconditional: a "class changed" branch would run for a lane or two on most steps
-                // the background error mode is on for this mapping once a real quality byte >= 90 lies before the
-                // end of its quality window [pos, pos + Lp)  (src/update_likelihood.cpp:40-44)
-                const bool latched = f90 < pos + Lp;
-                and_m = latched ? 0x100u : 0x1ffu;
-                or_m = latched ? 0x200u : 0u;
-            };
-            auto close_mapping = [&]() {
-                plist[i - lo] = prod;
-                slist[i - lo] = suf;
-                if (a_ext != 0.0) {  // the product was rescaled (more than ~30 very unlikely bases in one mapping)
-                    const uint32_t node = map_rec(i) & VGL_HC_MAP_MAX_NODE;
-                    if (node < (uint32_t)n_rows) atoms_add_f64(A_acc + 8u * node, -a_ext);
-                    a_sum += a_ext;
-                    a_ext = 0.0;
-                }
-                prod = 1.0;
-                --i;
-            };
-            open_mapping();
-            while (i >= lo && pos >= c_done) {  // mappings that own no column (they start at or past the end)
-                close_mapping();
-                open_mapping();
-            }
-            int c_stop = 0;
-            if (lo > 0 && lo < M) {
-                const uint4 q = ldg_stream_v4(gm + (size_t)(lo >> 2) * 32);
-                const int e = lo & 3;
-                c_stop = (int)((e == 0 ? q.x : e == 1 ? q.y : e == 2 ? q.z : q.w) >> VGL_HC_MAP_NODE_BITS);
-            }
-            const bool walking = hi > lo;
-            auto column = [&](int c, uint32_t rec) {
-                if (c < c_done && c >= c_stop && walking) {
-                    const uint32_t q = rec & 0xffu;
-                    suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
-                    if (rec & VGL_HC_COL_VALID) {
-                        const double f = lds_f64_c(A_f + 8u * ((rec & and_m) | or_m));
-                        const double bgv = lds_f64_c(A_bg + 8u * VGL_HC_COL_BASE(rec));
-                        prod *= fma(cc, f, aa * bgv);
-                        if (prod < 1e-280) {  // keep the product normal: fold the tiny part into a correction term
-                            a_ext += fast_log_s(prod, A_log);
-                            prod = 1.0;
-                        }
-                    }
-                    while (c == pos) {
-                        close_mapping();
-                        open_mapping();
-                    }
-                }
-            };
-            // column records come in blocks of 8, fetched two blocks ahead of the walk
-            uint4 cb_cur = ncb > 0 ? ldg_stream_v4(gc + (size_t)(ncb - 1) * 32) : make_uint4(0, 0, 0, 0);
-            uint4 cb_nxt = ncb > 1 ? ldg_stream_v4(gc + (size_t)(ncb - 2) * 32) : make_uint4(0, 0, 0, 0);
-            for (int cb = ncb - 1; cb >= 0; --cb) {
-                const uint4 cb_nxt2 = cb > 1 ? ldg_stream_v4(gc + (size_t)(cb - 2) * 32) : make_uint4(0, 0, 0, 0);
-                const int c8 = cb * VGL_HC_COL_BLK;
-                if (c8 < c_done) {  // (uniformly true in the single-pass case except for padding blocks)
-                    column(c8 + 7, cb_cur.w >> 16);
-                    column(c8 + 6, cb_cur.w & 0xffffu);
-                    column(c8 + 5, cb_cur.z >> 16);
-                    column(c8 + 4, cb_cur.z & 0xffffu);
-                    column(c8 + 3, cb_cur.y >> 16);
-                    column(c8 + 2, cb_cur.y & 0xffffu);
-                    column(c8 + 1, cb_cur.x >> 16);
-                    column(c8 + 0, cb_cur.x & 0xffffu);
-                }
-                cb_cur = cb_nxt;
-                cb_nxt = cb_nxt2;
-            }
-            if (walking) c_done = c_stop;
-            // ---- pass 2: mappings ----
-            for (int mbk = lo_u >> 2; mbk < (hi_u >> 2); ++mbk) {
-                const uint4 rb = ldg_stream_v4(gm + (size_t)mbk * 32);
-                const uint32_t recs[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int idx = mbk * 4 + e;
-                    if (idx < hi) {
-                        const uint32_t rm = recs[e];
-                        const uint32_t node = rm & VGL_HC_MAP_MAX_NODE;
-                        const double A = fast_log_s(plist[idx - lo_u], A_log);
-                        const uint32_t s = slist[idx - lo_u];
-                        // log(err) over [pos, pos + Lp): the stored columns from pos on plus `pos` bytes past the end
-                        // that count as quality 0  
-                        const double B = fma((double)(s & 0xfffffu), scale, (double)((s >> 20) + (rm >> VGL_HC_MAP_NODE_BITS)) * le0);
-                        if (node < (uint32_t)n_rows) atoms_add_f64(A_acc + 8u * node, B - A);
-                        a_sum += A;
-                    }
-                }
-            }
-        }
+        const bool latch = __any_sync(kFull, __ldg(b.first_q90 + g * 32 + lane) != 0xFFFFu);
+        const uint32_t n_map_blk = __ldg(b.grp_map_blk + g + 1) - __ldg(b.grp_map_blk + g);
+        if (n_map_blk == 0) continue;  // no read of this group has a mapping
+        const bool single = n_map_blk * VGL_HC_MAP_BLK <= (uint32_t)kMapChunk;
+        if (single && !latch) hc_process_group<false, true>(b, S, g, lane, a_sum, bad_node);
+        else if (single) hc_process_group<true, true>(b, S, g, lane, a_sum, bad_node);
+        else hc_process_group<true, false>(b, S, g, lane, a_sum, bad_node);
     }
 
     if (__any_sync(kFull, bad_node) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
@@ -530,21 +563,21 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // ------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------
-static size_t read_smem_bytes(int n_rows) {
+static size_t read_smem_bytes(int n_rows, int n_class) {
     size_t s = 0;
     s += ((size_t)n_rows * sizeof(double) + 15) & ~(size_t)15;
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
-    s += kClassCache * sizeof(double2);
     s += ((size_t)n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
+    s += (size_t)100 * (n_class + 1) * sizeof(double2);
     return (s + 127) & ~(size_t)127;
 }
 
-HcReadLaunch hc_read_launch_config(int n_rows, int sm_count, int max_smem_optin) {
+HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin) {
     HcReadLaunch c;
     c.grid = sm_count;
     c.block = kReadBlock;
-    c.smem = read_smem_bytes(n_rows);
-    if (c.smem + 256 > (size_t)max_smem_optin) c.grid = 0;  // caller reports VGL_ERR_INVALID (table too large for this layout)
+    c.smem = read_smem_bytes(n_rows, n_class);
+    if (c.smem + 256 > (size_t)max_smem_optin) c.grid = 0;  // caller reports VGL_ERR_INVALID (tables too large for this layout)
     return c;
 }
 

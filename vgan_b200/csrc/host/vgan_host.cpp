@@ -339,6 +339,28 @@ extern "C" int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// duplicate removal
+// ------------------------------------------------------------------------------------------------
+extern "C" int vgh_dedup(const vgh_alignments* a, uint8_t* is_dup, int64_t* n_kept) {
+    if (!a || !is_dup) return fail(VGH_ERR_INVALID, "bad arguments");
+    struct Key { int64_t node, offset; bool operator==(const Key& o) const { return node == o.node && offset == o.offset; } };
+    struct KeyHash { size_t operator()(const Key& k) const { return std::hash<int64_t>()(k.node * 1000003 + k.offset); } };
+    std::unordered_map<Key, char, KeyHash> seen;  // start coordinates of the unpaired reads met so far
+    seen.reserve((size_t)a->n_reads * 2 + 16);
+    int64_t kept = 0;
+    for (int64_t r = 0; r < a->n_reads; ++r) {
+        if (a->map_off[r + 1] == a->map_off[r]) return fail(VGH_ERR_BAD_READ, "read %lld has no mapping (the reference dereferences mapping()[0])", (long long)r);
+        const Key k{a->map_node[a->map_off[r]], a->map_offset[a->map_off[r]]};
+        is_dup[r] = seen.count(k) ? 1 : 0;
+        kept += !is_dup[r];
+        const bool paired = a->paired && a->paired[r];
+        if (!paired) seen.emplace(k, 1);
+    }
+    if (n_kept) *n_kept = kept;
+    return VGH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // batch packer
 // ------------------------------------------------------------------------------------------------
 struct vgh_hc_packed {

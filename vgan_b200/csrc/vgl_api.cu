@@ -399,14 +399,13 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
         }
     }
 
-    ctx->read_cfg = vgl::hc_read_launch_config(N, ctx->sm_count, ctx->max_smem_optin);
+    ctx->read_cfg = vgl::hc_read_launch_config(N, (int)class_tab.size(), ctx->sm_count, ctx->max_smem_optin);
     if (ctx->read_cfg.grid == 0)
-        return fail(VGL_ERR_INVALID, "node table of %d rows needs %zu bytes of shared memory per CTA (limit %d)", N,
-                    ctx->read_cfg.smem, ctx->max_smem_optin);
+        return fail(VGL_ERR_INVALID, "%d node rows and %zu (mappability, match probability) classes need %zu bytes of shared memory per CTA (limit %d)", N,
+                    class_tab.size(), ctx->read_cfg.smem, ctx->max_smem_optin);
     VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg.smem));
 
     if (int rc = ctx->d_node_class.reserve((size_t)N)) return rc;
-    class_tab.resize(std::max<size_t>(class_tab.size(), (size_t)vgl::kClassCache), make_double2(0.0, 0.0));
     if (int rc = ctx->d_class_tab.reserve(class_tab.size())) return rc;
     if (int rc = ctx->d_small.reserve(1)) return rc;
     if (int rc = ctx->d_node_bits.reserve(node_bits.size())) return rc;

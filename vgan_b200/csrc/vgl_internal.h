@@ -26,15 +26,13 @@ struct HcSmallTables {
     int32_t pad;
 };
 
-constexpr int kClassCache = 64;  // (mappability, match_prob) classes mirrored in shared memory
-
 struct HcTablesDev {
     int32_t n_rows;
     int32_t n_paths;
     int32_t n_words;           // number of 32-node words = ceil(n_rows / 32)
     int32_t n_class;
     const uint16_t* node_class; // [n_rows]   0xFFFF = node has no pangenome_map entry
-    const double2* class_tab;   // [max(n_class, kClassCache)]  {mappability, match_prob}
+    const double2* class_tab;   // [n_class]  {mappability, match_prob}
     const HcSmallTables* small;
     const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
 };
@@ -58,7 +56,7 @@ struct HcReadLaunch {
     size_t smem;
 };
 
-HcReadLaunch hc_read_launch_config(int n_rows, int sm_count, int max_smem_optin);
+HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin);
 cudaError_t hc_read_configure(size_t smem);
 
 // K1: per-read, per-mapping scalars scattered into per-CTA node accumulators.

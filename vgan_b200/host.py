@@ -112,6 +112,14 @@ def reconstruct(graph, alns, r, cap=8192):
     return g[:ng.value].tobytes().decode(), p[:npp.value].tobytes().decode(), s[:ns.value].tolist()
 
 
+def dedup(alns):
+    """Duplicate mask of Dup_Remover::remove_duplicates_internal (reference src/rmdup.cpp:20-110) in one hash pass."""
+    mask = np.zeros(len(alns), dtype=np.uint8)
+    kept = C.c_int64()
+    check(host.vgh_dedup(C.byref(alns.view), mask.ctypes.data_as(C.c_void_p), C.byref(kept)))
+    return mask.astype(bool), int(kept.value)
+
+
 class PackedBatch:
     """One vgl_hc_batch in host memory (pinned when asked)."""
 
