@@ -129,44 +129,64 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
  *       it compares graph_seq = G[pos_i .. pos_i+size_i) with mapping_seq = algnseq[0 ..) (the WHOLE
  *       aligned read string, indexed from 0) and quality_scores[j] = quality[pos_i + j].
  *
- *   column record c of a read (0 <= c < n), 16 bits:
+ *   Mapping i therefore owns the columns [pos_i, pos_{i+1}) (pos_M := min(pos_{M-1} + size_{M-1}, n)); the
+ *   columns from pos_M on belong to no mapping and only their quality bytes count.
+ *
+ *   column record c of a read (0 <= c < n), 32 bits:
  *       bits 0-7   quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c is past the
  *                  end of the quality string: the reference indexes the quality string by aligned column)
  *       bit 8      MISMATCH: G[c] != the read base process_mapping pairs with it, algnseq[c - pos_i] of the
  *                  mapping i that owns column c (src/get_p_obs_base.cpp:15,20)
- *       bits 9-10  that read base (A=0 C=1 G=2 T=3)
- *       bit 11     VALID: a mapping owns the column and both bases are A/C/G/T (the isValidDNA / 'N'
+ *       bit 9      LATCHED: the owning mapping runs in background-error mode: a real quality byte >= 90 lies
+ *                  before the end of its quality window [pos_i, pos_i + n) (src/update_likelihood.cpp:40-44)
+ *       bits 10-11 that read base (A=0 C=1 G=2 T=3)
+ *       bit 12     VALID: a mapping owns the column and both bases are A/C/G/T (the isValidDNA / 'N'
  *                  filter of src/process_mapping.cpp:62-63)
+ *       bit 13     OPEN: last column of its mapping (the kernel walks a read from its last column to its first
+ *                  and picks up the node's constants here)
+ *       bit 14     CLOSE: some mapping has pos_i == c: the product over the columns walked since the previous
+ *                  CLOSE and the quality sums from c on are what that mapping needs.  Set also where only
+ *                  EMPTY mappings (size 0) start, including c = pos_M when the trailing mappings are empty.
+ *       bits 15-31 Mapping.position.node_id of the owning mapping (row of the membership matrix, <=
+ *                  VGL_HC_MAX_NODE), VGL_HC_NO_NODE for columns no mapping owns.
  *   The graph base itself is not shipped: get_p_obs_base ignores its base arguments
- *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.
+ *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.  Bits 0-9 index the kernel's table of
+ *   per-column factors directly.
  *
- *   mapping record i of a read, 32 bits: bits 0-19 Mapping.position.node_id (row of the membership
- *   matrix, < 2^20), bits 20-31 pos_i (< 4096).
+ *   "extra" record, 32 bits, one per EMPTY mapping (size_i == 0 or pos_i == n; it owns no column but still
+ *   contributes log(err) over its quality window): bits 0-19 node id, bits 20-31 pos_i (< 4096), in mapping
+ *   order.  Real alignments hardly ever have one.
  *
- *   per read lane: n_cols (n), n_maps, cov_end = pos_{M-1} + min(size_{M-1}, n - pos_{M-1}) (where the
- *   columns of the last mapping end), first_q90 = index of the first REAL quality byte >= 90 (0xFFFF if
- *   none; that byte latches the background-error mode, src/update_likelihood.cpp:42), mapq (0..99).
+ *   per read lane: n_cols (n), n_close (number of CLOSE bits), n_extra, mapq (0..99).
  *
  * Reads are stored in groups of 32 "lanes" (one per thread of a warp); the sum over reads is order
  * independent, so the packer is free to group reads of similar shape.  Records are blocked so that every
  * lane fetches 16 bytes at a time and a warp fetches 512 contiguous bytes:
- *   column block  = 32 lanes x 8 consecutive column records  (col[(blk * 32 + lane) * 8 + (c & 7)], c >> 3 = block)
- *   mapping block = 32 lanes x 4 consecutive mapping records (map[(blk * 32 + lane) * 4 + (i & 3)], i >> 2 = block)
- * Group g owns column blocks grp_col_blk[g] .. grp_col_blk[g+1] and mapping blocks grp_map_blk[g] ..
+ *   column block = 32 lanes x 4 consecutive column records (col[(blk * 32 + lane) * 4 + (c & 3)], c >> 2 = block)
+ *   extra block  = 32 lanes x 4 consecutive extra records  (map[(blk * 32 + lane) * 4 + (i & 3)], i >> 2 = block)
+ * Group g owns column blocks grp_col_blk[g] .. grp_col_blk[g+1] and extra blocks grp_map_blk[g] ..
  * grp_map_blk[g+1] (as many as its longest read needs); records past a lane's own length, and every
- * record of the unused lanes of the last group, are zero (n_cols = n_maps = 0 for unused lanes).
+ * record of the unused lanes of the last group, are zero (n_cols = n_close = n_extra = 0 for unused lanes).
  * All arrays are host pointers for vgl_hc_accumulate and device pointers for vgl_hc_accumulate_device.
- * Algorithmic bytes per read: 2 n + 4 M + 9 plus padding (a few percent when lanes are grouped by shape). */
+ * Algorithmic bytes per read: 4 n + 7 (+ 4 per empty mapping) plus padding (a few percent when lanes are
+ * grouped by shape). */
 #define VGL_HC_COL_QUAL(rec) ((rec) & 0xffu)
 #define VGL_HC_COL_MISMATCH 0x0100u
-#define VGL_HC_COL_BASE(rec) (((rec) >> 9) & 3u)
-#define VGL_HC_COL_VALID 0x0800u
+#define VGL_HC_COL_LATCHED 0x0200u
+#define VGL_HC_COL_BASE(rec) (((rec) >> 10) & 3u)
+#define VGL_HC_COL_VALID 0x1000u
+#define VGL_HC_COL_OPEN 0x2000u
+#define VGL_HC_COL_CLOSE 0x4000u
+#define VGL_HC_COL_NODE_SHIFT 15
+#define VGL_HC_COL_NODE(rec) ((rec) >> VGL_HC_COL_NODE_SHIFT)
+#define VGL_HC_NO_NODE 0x1FFFFu
+#define VGL_HC_MAX_NODE 0x1FFFEu
 #define VGL_HC_MAP_NODE_BITS 20
 #define VGL_HC_MAP_MAX_NODE ((1u << VGL_HC_MAP_NODE_BITS) - 1u)
 #define VGL_HC_MAP_MAX_POS 4095u
 #define VGL_HC_MAP_REC(node, pos) ((uint32_t)(node) | ((uint32_t)(pos) << VGL_HC_MAP_NODE_BITS))
 #define VGL_HC_LANES 32
-#define VGL_HC_COL_BLK 8
+#define VGL_HC_COL_BLK 4
 #define VGL_HC_MAP_BLK 4
 
 typedef struct vgl_hc_batch {
@@ -176,12 +196,11 @@ typedef struct vgl_hc_batch {
     uint64_t n_map_blks;         /* = grp_map_blk[n_groups] */
     const uint32_t* grp_col_blk; /* [n_groups + 1] */
     const uint32_t* grp_map_blk; /* [n_groups + 1] */
-    const uint16_t* col;         /* [n_col_blks][32][8] column records (16-byte aligned) */
-    const uint32_t* map;         /* [n_map_blks][32][4] mapping records (16-byte aligned) */
+    const uint32_t* col;         /* [n_col_blks][32][4] column records (16-byte aligned) */
+    const uint32_t* map;         /* [n_map_blks][32][4] extra records (16-byte aligned) */
     const uint16_t* n_cols;      /* [n_groups * 32] */
-    const uint16_t* n_maps;      /* [n_groups * 32] */
-    const uint16_t* cov_end;     /* [n_groups * 32] */
-    const uint16_t* first_q90;   /* [n_groups * 32] */
+    const uint16_t* n_close;     /* [n_groups * 32] */
+    const uint16_t* n_extra;     /* [n_groups * 32] */
     const uint8_t* mapq;         /* [n_groups * 32] */
 } vgl_hc_batch;
 
@@ -268,8 +287,8 @@ typedef struct vgl_euka_tables {
 
 int vgl_euka_set_tables(vgl_ctx* ctx, const vgl_euka_tables* tables);
 
-/* euka read batch, warp-striped like vgl_hc_batch (groups of 32 lanes, column blocks of 8 records,
- * mapping blocks of 4).  Column record m of a read (m < n_cols = |aligned graph string|), 16 bits:
+/* euka read batch, warp-striped like vgl_hc_batch (groups of 32 lanes, column blocks of VGL_EUKA_COL_BLK = 8
+ * 16-bit records, mapping blocks of 4).  Column record m of a read (m < n_cols = |aligned graph string|), 16 bits:
  *   bits 0-7   quality byte at ALIGNED COLUMN m (src/readGAM_Euka.h:264,286; 0 past the end)
  *   bits 8-11  symbol of the aligned graph string, bits 12-15 symbol of the aligned read string:
  *              0-3 = A C G T, 4 = N, 5 = '-', 6 = an IUPAC code flagged in rare_bases (W M K R Y B D H V),
@@ -277,6 +296,7 @@ int vgl_euka_set_tables(vgl_ctx* ctx, const vgl_euka_tables* tables);
  * Mapping record: the node id.  Per lane: n_cols, n_maps, seq_len = |Alignment.sequence|, mapq,
  * flags bit 0 = first mapping on the reverse strand, read_index = position of the read in the caller's
  * order (per-read results are written there).                                                  */
+#define VGL_EUKA_COL_BLK 8
 #define VGL_EUKA_SYM_N 4
 #define VGL_EUKA_SYM_GAP 5
 #define VGL_EUKA_SYM_RARE 6

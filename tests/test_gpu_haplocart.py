@@ -138,6 +138,14 @@ def _edge_reads(S):
     reads.append(H.aln(sa + sa, [(a, 0, False, [(len(sa), len(sa), "")]), (a, 0, False, [(len(sa), len(sa), "")])]))
     # a single-column read
     reads.append(H.aln(sa[:1], [(a, 0, False, [(1, 1, "")])]))
+    # mappings that own no column (their edit-size slot is 0, quirk Q1): in the middle, sharing the start of the next ...
+    full = lambda n_, s_: (n_, 0, False, [(len(s_), len(s_), "")])
+    reads.append(H.aln(sa + sb + sc, [full(a, sa), (b, 0, False, [(0, 0, ""), (len(sb), len(sb), "")]), full(c, sc)]))
+    # ... trailing, where the columns no mapping owns begin ...
+    reads.append(H.aln(sa + sb + sc, [full(a, sa), (b, 0, False, [(len(sb), len(sb), ""), (0, 0, "")]), full(c, sc)], mapq=20))
+    # ... first of the read, and past the last column
+    reads.append(H.aln(sa + sb, [(a, 0, False, [(0, 0, ""), (len(sa), len(sa), "")]), full(b, sb)], mapq=41))
+    reads.append(H.aln(sa + sb, [full(a, sa), full(b, sb), (c, 0, False, [(0, 0, "")])], mapq=17))
     return reads
 
 

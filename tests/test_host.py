@@ -88,31 +88,43 @@ def _repack_with_oracle(og, R, arrays):
     marshalling rule of update_likelihood / process_mapping (src/update_likelihood.cpp:33-49)."""
     keep = [r for r in range(arrays["n_reads"]) if not arrays["identity"][r] < 1e-10]
     code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    NO_NODE = 0x1FFFF
     lanes = []
     for r in keep:
         gs, rs, sizes = orc.reconstruct(og, R, r)
+        n = len(rs)
         M = int(arrays["map_off"][r + 1] - arrays["map_off"][r])
         qual = arrays["qual"][arrays["qual_off"][r]:arrays["qual_off"][r + 1]]
-        rec = [int(qual[c]) if c < len(qual) else 0 for c in range(len(rs))]
         q90 = [c for c in range(len(qual)) if 90 <= int(qual[c]) < 128]
-        pos = 0
         nodes = arrays["map_node"][arrays["map_off"][r]:arrays["map_off"][r + 1]].tolist()
-        maps = []
+        # per column: quality byte, owner node, flags
+        qb = [int(qual[c]) if c < len(qual) else 0 for c in range(n)]
+        owner, flags = [NO_NODE] * n, [0] * n
+        pos, extras, starts = 0, [], set()
         for i in range(M):
-            lg = min(sizes[i], len(rs) - pos)
+            lg = min(sizes[i], n - pos)
+            latched = 0x0200 if q90 and q90[0] < pos + n else 0   # a byte >= 90 inside the window [pos, pos + n)
             for j in range(lg):
                 g, b = gs[pos + j], rs[j]            # the read string is indexed from 0 for every mapping (quirk Q2)
+                owner[pos + j] = nodes[i]
+                flags[pos + j] = latched
                 if g in code and b in code:
-                    rec[pos + j] |= 0x0800 | (code[b] << 9) | (0 if g == b else 0x0100)
-            maps.append(nodes[i] | (pos << 20))
+                    flags[pos + j] |= 0x1000 | (code[b] << 10) | (0 if g == b else 0x0100)
+            if lg:
+                flags[pos + lg - 1] |= 0x2000        # OPEN on the mapping's last column
+            else:
+                extras.append(nodes[i] | (pos << 20))
+            if pos < n:
+                starts.add(pos)
             pos += lg
-        lanes.append({"col": rec, "map": maps, "n_cols": len(rs), "cov_end": pos, "first_q90": q90[0] if q90 else 0xFFFF,
+        rec = [qb[c] | flags[c] | (0x4000 if c in starts else 0) | (owner[c] << 15) for c in range(n)]
+        lanes.append({"col": rec, "extra": extras, "n_cols": n, "n_close": len(starts), "cov_end": pos,
                       "mapq": int(arrays["mapq"][r])})
     return lanes, keep
 
 
 def _lane_key(d):
-    return (len(d["map"]), d["n_cols"], tuple(d["col"]), tuple(d["map"]), d["mapq"])
+    return (d["n_close"], d["n_cols"], tuple(d["col"]), tuple(d["extra"]), d["mapq"])
 
 
 def test_packer_against_oracle_reconstruction():
@@ -127,26 +139,30 @@ def test_packer_against_oracle_reconstruction():
     assert pb.n_reads == len(keep) == len(got) and pb.skipped == len(A) - len(keep)
     # the packer groups reads by shape, so compare as multisets of lanes
     assert sorted(map(_lane_key, got)) == sorted(map(_lane_key, want))
-    assert sorted((d["cov_end"], d["first_q90"]) for d in got) == sorted((d["cov_end"], d["first_q90"]) for d in want)
-    shapes = [(len(d["map"]), d["n_cols"]) for d in got]
+    shapes = [(d["n_close"], d["n_cols"]) for d in got]
     assert shapes == sorted(shapes)
     # mis-slicing (quirk Q1) happened: some read has more edits than mappings, so some columns have no owner
-    assert any(d["cov_end"] < d["n_cols"] for d in got)
+    assert any(d["cov_end"] < d["n_cols"] for d in want)
+    assert any((c >> 15) == 0x1FFFF for d in got for c in d["col"])
     # padding: rows of a group are as long as its longest lane, unused records are zero
     a = pb.arrays()
     G = int(pb.batch.n_groups)
     assert G == (pb.n_reads + 31) // 32
     for g in range(G):
         lanes_g = got[g * 32:(g + 1) * 32]
-        assert a["grp_col_blk"][g + 1] - a["grp_col_blk"][g] == (max(d["n_cols"] for d in lanes_g) + 7) // 8
-        assert a["grp_map_blk"][g + 1] - a["grp_map_blk"][g] == (max(len(d["map"]) for d in lanes_g) + 3) // 4
-    assert a["n_cols"][pb.n_reads:].sum() == 0 and a["n_maps"][pb.n_reads:].sum() == 0
-    assert pb.nbytes == (G + 1) * 8 + 512 * (int(a["grp_col_blk"][-1]) + int(a["grp_map_blk"][-1])) + 9 * 32 * G
-    # a quality byte >= 90 is reported with its index
+        assert a["grp_col_blk"][g + 1] - a["grp_col_blk"][g] == (max(d["n_cols"] for d in lanes_g) + 3) // 4
+        assert a["grp_map_blk"][g + 1] - a["grp_map_blk"][g] == (max(len(d["extra"]) for d in lanes_g) + 3) // 4
+    assert a["n_cols"][pb.n_reads:].sum() == 0 and a["n_close"][pb.n_reads:].sum() == 0 and a["n_extra"][pb.n_reads:].sum() == 0
+    assert pb.nbytes == (G + 1) * 8 + 512 * (int(a["grp_col_blk"][-1]) + int(a["grp_map_blk"][-1])) + 7 * 32 * G
+    # a quality byte >= 90 latches the background-error mode of every mapping whose window holds it
     alns = [H.aln("GCTACGATGG", [(9, 0, False, [(10, 10, "")])], quality=bytes([30, 30, 30, 95, 30, 200, 30, 30, 99, 30]))]
     nodes, _ = H.toy_graph()
     one = vb.PackedBatch(vb.Graph.from_sequences(nodes), vb.Alignments.from_gam_bytes(H.encode_gam(alns))).lanes()[0]
-    assert one["first_q90"] == 3
+    assert all(c & 0x0200 for c in one["col"]) and one["col"][0] & 0x4000 and one["col"][-1] & 0x2000
+    # mappings that own no column travel as extra records
+    alns = [H.aln("GCTAC", [(9, 0, False, [(0, 0, ""), (5, 5, "")]), (9, 5, False, [(3, 3, "")])])]
+    two = vb.PackedBatch(vb.Graph.from_sequences(nodes), vb.Alignments.from_gam_bytes(H.encode_gam(alns))).lanes()[0]
+    assert two["extra"] == [9] and two["n_close"] == 1
 
 
 def test_packer_rejects_what_the_reference_cannot_process():

@@ -29,14 +29,15 @@ class vgl_hc_tables(C.Structure):
 class vgl_hc_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_map_blks", C.c_uint64),
                 ("grp_col_blk", C.c_void_p), ("grp_map_blk", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
-                ("n_cols", C.c_void_p), ("n_maps", C.c_void_p), ("cov_end", C.c_void_p), ("first_q90", C.c_void_p),
-                ("mapq", C.c_void_p)]
+                ("n_cols", C.c_void_p), ("n_close", C.c_void_p), ("n_extra", C.c_void_p), ("mapq", C.c_void_p)]
 
 
 # column / mapping record fields (include/vgan_gpu.h)
-COL_MISMATCH, COL_VALID = 0x0100, 0x0800
+COL_MISMATCH, COL_LATCHED, COL_VALID, COL_OPEN, COL_CLOSE = 0x0100, 0x0200, 0x1000, 0x2000, 0x4000
+COL_BASE_SHIFT, COL_NODE_SHIFT, NO_NODE = 10, 15, 0x1FFFF
 MAP_NODE_BITS = 20
-LANES, COL_BLK, MAP_BLK = 32, 8, 4
+LANES, COL_BLK, MAP_BLK = 32, 4, 4
+EUKA_COL_BLK = 8
 
 
 class vgl_euka_tables(C.Structure):

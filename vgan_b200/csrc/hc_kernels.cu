@@ -29,7 +29,6 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // ---- read kernel geometry ------------------------------------------------------------------
 constexpr int kReadBlock = 768;     // 24 warps: one read per thread, one 32-lane group per warp at a time
-constexpr int kMapChunk = 96;       // mappings finalised per pass (per-thread product / quality lists live in local memory)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -107,171 +106,195 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 //
 // The batch is stored lane-interleaved in 16-byte blocks (include/vgan_gpu.h), so the 32 threads of a warp read
 // 512 contiguous bytes per step: perfectly coalesced streaming loads, each byte used once, no staging needed.
+// Every global load of the walk is issued by the whole warp at a fixed point of the loop, well ahead of its use:
+// a load issued from divergent code would make every lane wait for the most recent one of its neighbours
+// (scoreboards are per warp), i.e. a full HBM round trip per mapping.  That is why the column record carries
+// everything the walk needs (node id, OPEN / CLOSE marks) and no per-mapping array is read here.
 // Per read the thread walks its columns from the LAST to the first:
 //   * the running sum of log(err) over the columns seen so far is exactly the quality sum the reference takes
 //     for the mapping that starts at the current column (src/update_likelihood.cpp:40-44 reads |algnseq|
 //     qualities from position_in_read; the `pos` bytes past the end count as quality 0);
 //   * the running product of the per-base mixtures (src/process_mapping.cpp:59-77) is the mapping's
 //     exp(A_i); one log per mapping instead of one per base.
-// When the walk reaches the first column of mapping i both are parked in per-thread lists (local memory,
-// lane-interleaved by the hardware); a second, branch-free pass over the mappings takes the log, forms B_i
-// and scatters B_i - A_i into the CTA's node vector with a shared-memory fp64 atomic.
+// At a CLOSE mark (first column of a mapping) the pair is pushed onto the warp's queue in shared memory
+// (ballot + popc give every closing lane its slot, one 16-byte store each).  Whenever the queue holds 32
+// entries the warp drains them, one entry per lane: log of the product, B_i from the quality sums, and
+// B_i - A_i scattered into the CTA's node vector with a shared-memory fp64 atomic.  Entries are self-contained,
+// so the queue simply carries over from one group to the next and the finalisation always runs on full warps.
+// (Per-thread lists in local memory, the obvious alternative, cost ~9 KB of L2 traffic per read.)
 //
-// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | node_class u16[n_rows] | ac table double2[100][n_class] ]
+// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | node_class u16[n_rows + 1] | ac table double2[100][n_class + 1]
+//                  | close queues uint4[warps][64] ]
 // The ac table holds {1 - pcm, pcm * K} (src/process_mapping.cpp:33-42) for every (mapping quality, table class)
-// pair, so opening a mapping costs two shared loads and no arithmetic.
+// pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
+constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
+
 struct ReadKernelShared {
-    uint32_t acc, f, bg, logtab, node_class, ac;  // shared byte addresses
+    uint32_t acc, f, bg, logtab, node_class, ac, queue;  // shared byte addresses (queue: this warp's ring)
     int n_rows, n_class;
     double le0;
 };
 
-// kLatch: some read of the group holds a real quality byte >= 90 (it switches mappings to the background error
-// probability, src/update_likelihood.cpp:42); the common case compiles the test away.
-// kSingle: no read of the group has more than kMapChunk mappings, so one pass covers it and the per-column range
-// checks of the multi-pass walk disappear.
-template <bool kLatch, bool kSingle>
-__device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const ReadKernelShared& S, uint32_t g, int lane, double& a_sum,
-                                                 bool& bad_node) {
-    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
-    const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
-    const int ncb = (int)(__ldg(b.grp_col_blk + g + 1) - cb0);  // 8-column blocks of this group
-    const int nmb = (int)(__ldg(b.grp_map_blk + g + 1) - mb0);  // 4-mapping blocks
-    const uint4* gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
-    const uint4* gm = reinterpret_cast<const uint4*>(b.map) + (size_t)mb0 * 32 + lane;
-    const uint32_t* gm32 = reinterpret_cast<const uint32_t*>(gm);  // record i of this lane: gm32[(i >> 2) * 128 + (i & 3)]
-    const uint32_t r = g * 32 + lane;
-    const int Lp = (int)__ldg(b.n_cols + r);
-    const int M = (int)__ldg(b.n_maps + r);
-    const int f90 = kLatch ? (int)__ldg(b.first_q90 + r) : 0xFFFF;
-    const uint32_t ac_row = S.ac + 16u * (uint32_t)(S.n_class + 1) * (uint32_t)__ldg(b.mapq + r);
-    const int maxm = nmb * VGL_HC_MAP_BLK;
+// What a lane needs to know about its read of a group; loaded one group ahead of use.
+struct GroupHdr {
+    const uint4* gc;  // column block k of this lane: gc[k * 32]
+    int ncb;          // 4-column blocks of the group
+    int n_cols;       // this read's own columns
+    uint32_t mapq;
+    int n_extra;      // this read's empty mappings
+};
+__device__ __forceinline__ GroupHdr hc_load_hdr(const HcBatchDev& b, uint32_t g, int lane) {
+    GroupHdr h;
+    h.gc = nullptr;
+    h.ncb = h.n_cols = h.n_extra = 0;
+    h.mapq = 0;
+    if (g < b.n_groups) {
+        const uint32_t cb0 = __ldg(b.grp_col_blk + g);
+        h.ncb = (int)(__ldg(b.grp_col_blk + g + 1) - cb0);
+        h.gc = reinterpret_cast<const uint4*>(b.col) + (size_t)cb0 * 32 + lane;
+        const uint32_t r = g * 32 + lane;
+        h.n_cols = (int)__ldg(b.n_cols + r);
+        h.mapq = __ldg(b.mapq + r);
+        h.n_extra = (int)__ldg(b.n_extra + r);
+    }
+    return h;
+}
+__device__ __forceinline__ uint4 hc_fetch(const GroupHdr& h, int cb) {
+    return cb >= 0 ? ldg_stream_v4(h.gc + (size_t)cb * 32) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
 
-    double plist[kMapChunk];    // exp(A_i) of the mappings of the current pass
-    uint32_t slist[kMapChunk];  // quality sums from the mapping's first column on: (sum of q for q > 2) | (count of q <= 2) << 20
-    // Quality sums over the columns walked so far (from the end of the read).  The single-pass walk visits every record of
-    // the group's blocks; records past a read's own columns are zero and would count as quality-0 columns, so the sum
-    // starts that much lower (mod 2^32) instead of testing every column against the read's length.
-    uint32_t suf = kSingle ? 0u - ((uint32_t)(ncb * VGL_HC_COL_BLK - Lp) << 20) : 0u;
-    int c_done = Lp;  // columns >= c_done have been walked
-    for (int hi_u = maxm; hi_u > 0; hi_u -= kMapChunk) {  // one iteration when kSingle
-        const int lo_u = kSingle ? 0 : max(hi_u - kMapChunk, 0);
-        const int hi = min(M, hi_u), lo = kSingle ? 0 : min(M, lo_u);
-        // ---- pass 1: columns, descending ----
-        int i = hi - 1;  // current mapping
-        int pos = -1;    // its first column
-        uint32_t and_m = 0x1ffu, or_m = 0u;  // f-table index = (record & and_m) | or_m
-        double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
-        // mapping records are read one mapping ahead of need
-        const uint32_t* prec = gm32 + (size_t)(max(i, 0) >> 2) * 128 + (max(i, 0) & 3);
-        uint32_t rec_next = i >= lo ? ldg_stream_u32(prec) : 0u;
-        auto open_mapping = [&]() {
-            if (i < lo) { pos = -1; return; }
-            const uint32_t rec = rec_next;
-            if (i > lo) {
-                prec -= (i & 3) ? 1 : 125;  // previous record of this lane: same block, or the last one of the block below
-                rec_next = ldg_stream_u32(prec);
-            }
-            pos = (int)(rec >> VGL_HC_MAP_NODE_BITS);
-            const uint32_t node = rec & VGL_HC_MAP_MAX_NODE;
+// Finalise one queued mapping: entry = {exp(A) lo, hi, quality sums, node | first column << 17}.
+__device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uint4& e, double& a_sum) {
+    const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
+    const uint32_t node = e.w & VGL_HC_NO_NODE, pos = e.w >> 17;
+    const double A = fast_log_s(__hiloint2double((int)e.y, (int)e.x), S.logtab);
+    // log(err) over [pos, pos + n): the stored columns from pos on plus `pos` bytes past the end that count as
+    // quality 0  
+    const double B = fma((double)(e.z & 0xfffffu), scale, (double)((e.z >> 20) + pos) * S.le0);
+    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, B - A);
+    a_sum += A;
+}
+
+// One group.  On entry v0, v1 hold its last two column blocks (the walk is descending); on exit they hold those of
+// the warp's next group `gn`, whose header is loaded here as well: neither the header nor the first blocks of a
+// group are ever waited for.  q_head / q_tail: the warp's close queue (uniform across the warp).
+__device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const ReadKernelShared& S, uint32_t g, uint32_t gn, const GroupHdr& H,
+                                                 GroupHdr& Hn, uint4& v0, uint4& v1, uint32_t& q_head, uint32_t& q_tail, int lane,
+                                                 double& a_sum, bool& bad_node) {
+    const double scale = -0.23025850929940456840;
+    Hn = hc_load_hdr(b, gn, lane);
+    const int ncb = H.ncb;
+    const uint32_t ac_row = S.ac + 16u * (uint32_t)(S.n_class + 1) * H.mapq;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int x = H.n_extra - 1;  // empty mappings (no column of their own): rare, handled on the side
+    // Quality sums over the columns walked so far (from the end of the read): (sum of q for q > 2) | (count of q <= 2) << 20.
+    // The walk visits every record of the group's blocks; records past a read's own columns are zero and would count as
+    // quality-0 columns, so the sum starts that much lower (mod 2^32) instead of testing every column against the
+    // read's length.
+    uint32_t suf = 0u - ((uint32_t)(ncb * VGL_HC_COL_BLK - H.n_cols) << 20);
+    double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
+
+    auto extra_rec = [&](int i) -> uint32_t {
+        const uint32_t* gx = b.map + ((size_t)__ldg(b.grp_map_blk + g) * 32 + lane) * VGL_HC_MAP_BLK;
+        return __ldg(gx + (size_t)(i >> 2) * 128 + (i & 3));
+    };
+    auto add_extra = [&](uint32_t xn, double Bx) {
+        if (xn < (uint32_t)S.n_rows && lds_u16_c(S.node_class + 2u * xn) != 0xFFFFu) atoms_add_f64(S.acc + 8u * xn, Bx);
+        else bad_node = true;
+    };
+
+    auto column = [&](int c, uint32_t rec, double f, double bgv, uint32_t cls) {
+        const uint32_t q = rec & 0xffu;
+        suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
+        if (rec & VGL_HC_COL_OPEN) {
             // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
-            const uint32_t cls = node < (uint32_t)S.n_rows ? lds_u16_c(S.node_class + 2u * node) : 0xFFFFu;
             bad_node |= cls == 0xFFFFu;
             const double2 ac = lds_v2f64_c(ac_row + 16u * min(cls, (uint32_t)S.n_class));
             aa = ac.x;
             cc = ac.y;
-            if (kLatch) {
-                // the background error mode is on for this mapping once a real quality byte >= 90 lies before the end of
-                // its quality window [pos, pos + Lp)  (src/update_likelihood.cpp:40-44)
-                const bool latched = f90 < pos + Lp;
-                and_m = latched ? 0x100u : 0x1ffu;
-                or_m = latched ? 0x200u : 0u;
-            }
-        };
-        open_mapping();
-        while (i >= lo && pos >= c_done) {  // mappings that own no column (they start at or past the end)
-            plist[i - lo] = 1.0;
-            slist[i - lo] = kSingle ? 0u : suf;
-            --i;
-            open_mapping();
         }
-        int c_stop = 0;
-        if (!kSingle && lo > 0 && lo < M) c_stop = (int)(ldg_stream_u32(gm32 + (size_t)(lo >> 2) * 128 + (lo & 3)) >> VGL_HC_MAP_NODE_BITS);
-        const bool walking = hi > lo;
-        auto column = [&](int c, uint32_t rec) {
-            if (!kSingle && !(c < c_done && c >= c_stop && walking)) return;
-            const uint32_t q = rec & 0xffu;
-            suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
-            if (rec & VGL_HC_COL_VALID) {
-                const double f = lds_f64_c(S.f + 8u * (kLatch ? ((rec & and_m) | or_m) : (rec & 0x1ffu)));
-                const double bgv = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec));
-                prod *= fma(cc, f, aa * bgv);
+        const double px = prod * fma(cc, f, aa * bgv);
+        prod = (rec & VGL_HC_COL_VALID) ? px : prod;
+        const bool close = (rec & VGL_HC_COL_CLOSE) != 0;
+        if (close && (a_ext != 0.0 || x >= 0)) {  // rare
+            const uint32_t node = VGL_HC_COL_NODE(rec);
+            if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
+                if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, -a_ext);
+                a_sum += a_ext;
+                a_ext = 0.0;
             }
-            while (c == pos) {
-                if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
-                    const uint32_t node = ldg_stream_u32(gm32 + (size_t)(i >> 2) * 128 + (i & 3)) & VGL_HC_MAP_MAX_NODE;
-                    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, -a_ext);
-                    a_sum += a_ext;
-                    a_ext = 0.0;
-                }
-                plist[i - lo] = prod;
-                slist[i - lo] = suf;
-                prod = 1.0;
-                --i;
-                open_mapping();
+            // empty mappings at or past this column: A = 0, B as for a mapping that starts here (past the last column:
+            // no stored quality at all)
+            const double B = fma((double)(suf & 0xfffffu), scale, (double)((suf >> 20) + (uint32_t)c) * S.le0);
+            while (x >= 0) {
+                const uint32_t xr = extra_rec(x);
+                const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
+                if (xp < (uint32_t)c) break;
+                add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
+                --x;
             }
-        };
-        // column records come in blocks of 8, fetched two blocks ahead of the walk
-        uint4 cb_cur = ncb > 0 ? ldg_stream_v4(gc + (size_t)(ncb - 1) * 32) : make_uint4(0, 0, 0, 0);
-        uint4 cb_nxt = ncb > 1 ? ldg_stream_v4(gc + (size_t)(ncb - 2) * 32) : make_uint4(0, 0, 0, 0);
-        for (int cb = ncb - 1; cb >= 0; --cb) {
-            const uint4 cb_nxt2 = cb > 1 ? ldg_stream_v4(gc + (size_t)(cb - 2) * 32) : make_uint4(0, 0, 0, 0);
-            const int c8 = cb * VGL_HC_COL_BLK;
-            column(c8 + 7, cb_cur.w >> 16);
-            column(c8 + 6, cb_cur.w & 0xffffu);
-            column(c8 + 5, cb_cur.z >> 16);
-            column(c8 + 4, cb_cur.z & 0xffffu);
-            column(c8 + 3, cb_cur.y >> 16);
-            column(c8 + 2, cb_cur.y & 0xffffu);
-            column(c8 + 1, cb_cur.x >> 16);
-            column(c8 + 0, cb_cur.x & 0xffffu);
-            if (prod < 1e-100) {  // keep the product normal (eight more factors cannot take it below 1e-200)
-                a_ext += fast_log_s(prod, S.logtab);
-                prod = 1.0;
-            }
-            cb_cur = cb_nxt;
-            cb_nxt = cb_nxt2;
         }
-        if (!kSingle && walking) c_done = c_stop;
-        // ---- pass 2: mappings, four at a time so that the list loads of a block are in flight together ----
-        for (int mbk = lo_u >> 2; mbk < (hi_u >> 2); ++mbk) {
-            const uint4 rb = ldg_stream_v4(gm + (size_t)mbk * 32);
-            const uint32_t recs[4] = {rb.x, rb.y, rb.z, rb.w};
-            const int k0 = mbk * 4 - lo_u;
-            double pr[4];
-            uint32_t sv[4];
+        // push {exp(A), quality sums, node | column}; a CLOSE on a column nobody owns only served the empty mappings
+        const bool push = close && VGL_HC_COL_NODE(rec) != VGL_HC_NO_NODE;
+        const uint32_t m = __ballot_sync(kFull, push);
+        if (push) {
+            const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (kQueueSlots - 1);
+            sts_v4(S.queue + 16u * slot, (uint32_t)__double2loint(prod), (uint32_t)__double2hiint(prod), suf,
+                   VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17));
+        }
+        prod = close ? 1.0 : prod;
+        q_tail += __popc(m);
+        if (q_tail - q_head >= 32u) {
+            __syncwarp();
+            const uint4 e = lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1)));
+            __syncwarp();
+            q_head += 32u;
+            hc_finalise(S, e, a_sum);
+        }
+    };
+    auto block = [&](int cb, const uint4& v) {
+        const uint32_t rec[4] = {v.x, v.y, v.z, v.w};
+        // the table lookups of the four columns do not depend on the walk's state: issue them together
+        double f[4], bgv[4];
+        uint32_t cls[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool on = mbk * 4 + e < hi;
-                pr[e] = on ? plist[k0 + e] : 1.0;
-                sv[e] = on ? slist[k0 + e] : 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (mbk * 4 + e < hi) {
-                    const uint32_t rm = recs[e];
-                    const uint32_t node = rm & VGL_HC_MAP_MAX_NODE;
-                    const double A = fast_log_s(pr[e], S.logtab);
-                    // log(err) over [pos, pos + Lp): the stored columns from pos on plus `pos` bytes past the end that
-                    // count as quality 0  
-                    const double B = fma((double)(sv[e] & 0xfffffu), scale, (double)((sv[e] >> 20) + (rm >> VGL_HC_MAP_NODE_BITS)) * S.le0);
-                    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, B - A);
-                    a_sum += A;
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            f[j] = lds_f64_c(S.f + 8u * (rec[j] & 0x3ffu));
+            bgv[j] = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec[j]));
+            cls[j] = lds_u16_c(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows));  // entry n_rows: 0xFFFF
         }
-        if (kSingle) break;
+        const int c4 = cb * VGL_HC_COL_BLK;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) column(c4 + j, rec[j], f[j], bgv[j], cls[j]);
+        if (prod < 1e-100) {  // keep the product normal (four more factors cannot take it out of range)
+            a_ext += fast_log_s(prod, S.logtab);
+            prod = 1.0;
+        }
+    };
+    // two blocks in flight from ONE load site: a block is waited for a whole block (hundreds of issue slots) after its
+    // load, and no other outstanding load shares its scoreboard
+    for (int cb = ncb - 1; cb >= 0; --cb) {
+        const uint4 v = v0;
+        v0 = v1;
+        v1 = hc_fetch(H, cb - 2);
+        block(cb, v);
+    }
+    // the next group's last blocks are requested now; they arrive while it is being set up
+    v0 = hc_fetch(Hn, Hn.ncb - 1);
+    v1 = hc_fetch(Hn, Hn.ncb - 2);
+    while (x >= 0) {  // empty mappings that start past the last column
+        const uint32_t xr = extra_rec(x);
+        add_extra(xr & VGL_HC_MAP_MAX_NODE, (double)(xr >> VGL_HC_MAP_NODE_BITS) * S.le0);
+        --x;
     }
 }
 
@@ -285,8 +308,10 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + off);
     off += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
-    off += ((size_t)t.n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
+    off += ((size_t)(t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // entry n_rows: "no such node"
     double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // [100][n_class + 1]
+    off += (size_t)100 * (t.n_class + 1) * sizeof(double2);
+    uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + off);  // [warps][kQueueSlots]
     __shared__ double s_warp_a[kReadBlock / 32];
 
     const int tid = threadIdx.x;
@@ -297,6 +322,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         s_acc[n] = 0.0;
         s_class[n] = t.node_class[n];
     }
+    if (tid == 0) s_class[t.n_rows] = 0xFFFFu;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_tab);
@@ -325,22 +351,26 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     S.logtab = smem_u32(s_tab) + kOffLogTab;
     S.node_class = smem_u32(s_class);
     S.ac = smem_u32(s_ac);
+    S.queue = smem_u32(s_queue + (size_t)warp * kQueueSlots);
     S.n_rows = t.n_rows;
     S.n_class = t.n_class;
     S.le0 = s_tab->log_err[0];
 
     double a_sum = 0.0;
     bool bad_node = false;
+    uint32_t q_head = 0, q_tail = 0;
     const uint32_t warps_total = gridDim.x * (kReadBlock / 32);
-    for (uint32_t g = blockIdx.x * (kReadBlock / 32) + warp; g < b.n_groups; g += warps_total) {
-        const bool latch = __any_sync(kFull, __ldg(b.first_q90 + g * 32 + lane) != 0xFFFFu);
-        const uint32_t n_map_blk = __ldg(b.grp_map_blk + g + 1) - __ldg(b.grp_map_blk + g);
-        if (n_map_blk == 0) continue;  // no read of this group has a mapping
-        const bool single = n_map_blk * VGL_HC_MAP_BLK <= (uint32_t)kMapChunk;
-        if (single && !latch) hc_process_group<false, true>(b, S, g, lane, a_sum, bad_node);
-        else if (single) hc_process_group<true, true>(b, S, g, lane, a_sum, bad_node);
-        else hc_process_group<true, false>(b, S, g, lane, a_sum, bad_node);
+    uint32_t g = blockIdx.x * (kReadBlock / 32) + warp;
+    GroupHdr H = hc_load_hdr(b, g, lane), Hn;
+    uint4 v0 = hc_fetch(H, H.ncb - 1), v1 = hc_fetch(H, H.ncb - 2);
+    while (g < b.n_groups) {
+        const uint32_t gn = g + warps_total;
+        hc_process_group(b, S, g, gn, H, Hn, v0, v1, q_head, q_tail, lane, a_sum, bad_node);
+        H = Hn;
+        g = gn;
     }
+    __syncwarp();
+    if ((uint32_t)lane < q_tail - q_head) hc_finalise(S, lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1))), a_sum);
 
     if (__any_sync(kFull, bad_node) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
     a_sum = warp_sum_f64(a_sum);
@@ -567,8 +597,9 @@ static size_t read_smem_bytes(int n_rows, int n_class) {
     size_t s = 0;
     s += ((size_t)n_rows * sizeof(double) + 15) & ~(size_t)15;
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
-    s += ((size_t)n_rows * sizeof(uint16_t) + 15) & ~(size_t)15;
+    s += ((size_t)(n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
     s += (size_t)100 * (n_class + 1) * sizeof(double2);
+    s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }
 

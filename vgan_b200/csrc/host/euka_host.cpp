@@ -270,10 +270,10 @@ static int pack_symbols(const vgh_graph* g, const vgh_alignments* a, int64_t r0,
             mc = std::max(mc, ncols[order[gI * VGL_HC_LANES + l]]);
             mm = std::max(mm, nmaps[order[gI * VGL_HC_LANES + l]]);
         }
-        g_col[gI + 1] = g_col[gI] + (mc + VGL_HC_COL_BLK - 1) / VGL_HC_COL_BLK;
+        g_col[gI + 1] = g_col[gI] + (mc + VGL_EUKA_COL_BLK - 1) / VGL_EUKA_COL_BLK;
         g_map[gI + 1] = g_map[gI] + (mm + VGL_HC_MAP_BLK - 1) / VGL_HC_MAP_BLK;
     }
-    const size_t kColBlk = (size_t)VGL_HC_LANES * VGL_HC_COL_BLK, kMapBlk = (size_t)VGL_HC_LANES * VGL_HC_MAP_BLK;
+    const size_t kColBlk = (size_t)VGL_HC_LANES * VGL_EUKA_COL_BLK, kMapBlk = (size_t)VGL_HC_LANES * VGL_HC_MAP_BLK;
     size_t o = 0;
     const size_t o_gc = o; o = align_up(o + (n_groups + 1) * 4, 256);
     const size_t o_gm = o; o = align_up(o + (n_groups + 1) * 4, 256);
@@ -325,7 +325,7 @@ static int pack_symbols(const vgh_graph* g, const vgh_alignments* a, int64_t r0,
                     const uint16_t qb = (int64_t)m < Lq ? (uint8_t)a->qual[q0 + (int64_t)m] : 0;  // quality by ALIGNED COLUMN
                     const uint16_t rec = (uint16_t)(qb | (symbol_code((unsigned char)rc.graph_seq[m]) << 8) |
                                                     (symbol_code((unsigned char)rc.read_seq[m]) << 12));
-                    gcol[((m / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + m % VGL_HC_COL_BLK] = rec;
+                    gcol[((m / VGL_EUKA_COL_BLK) * VGL_HC_LANES + l) * VGL_EUKA_COL_BLK + m % VGL_EUKA_COL_BLK] = rec;
                 }
                 const int64_t mm = a->map_off[r];
                 const int64_t M = a->map_off[r + 1] - mm;

@@ -396,7 +396,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     if (R >= 0xffffffffull) return fail(VGH_ERR_INVALID, "too many reads for one batch");
 
     // pass 1: reconstruct every kept read once to learn its column / mapping counts
-    std::vector<uint32_t> ncols(R), nmaps(R);
+    std::vector<uint32_t> ncols(R), nmaps(R), ncloses(R), nextras(R);
     int err = VGH_OK;
     std::string err_msg;
 #pragma omp parallel num_threads(n_threads)
@@ -417,16 +417,15 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                 else if (Lq > (int64_t)rc.read_seq.size())
                     e = fail(VGH_ERR_BAD_READ, "read %lld: quality string longer than the alignment", (long long)r);
                 else if (rc.read_seq.size() > VGL_HC_MAP_MAX_POS || M > 65535)
-                    e = fail(VGH_ERR_BAD_READ, "read %lld: alignment of %zu columns does not fit the mapping record (max %u)", (long long)r,
+                    e = fail(VGH_ERR_BAD_READ, "read %lld: alignment of %zu columns does not fit the batch records (max %u)", (long long)r,
                              rc.read_seq.size(), VGL_HC_MAP_MAX_POS);
                 else if (a->mapq[r] < 0 || a->mapq[r] >= 100)
                     e = fail(VGH_ERR_BAD_READ, "read %lld: mapping quality %d outside [0,100)", (long long)r, a->mapq[r]);
                 else {
                     for (int64_t i = 0; i < M && !e; ++i) {
                         const int64_t node = a->map_node[a->map_off[r] + i];
-                        if (node < 0 || node > (int64_t)VGL_HC_MAP_MAX_NODE)
-                            e = fail(VGH_ERR_BAD_NODE, "read %lld: node id %lld does not fit the mapping record", (long long)r, (long long)node);
-
+                        if (node < 0 || node > (int64_t)VGL_HC_MAX_NODE)
+                            e = fail(VGH_ERR_BAD_NODE, "read %lld: node id %lld does not fit the column record", (long long)r, (long long)node);
                     }
                 }
             }
@@ -435,8 +434,20 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                 if (!err) { err = e; err_msg = g_err; }
                 continue;
             }
-            ncols[(size_t)k] = (uint32_t)rc.read_seq.size();
+            // mapping i starts at pos_i = min(sum of the earlier sizes, n); CLOSE bits sit at the distinct pos_i < n
+            const size_t L = rc.read_seq.size();
+            size_t pos = 0, last_close = (size_t)-1;
+            uint32_t n_close = 0, n_extra = 0;
+            for (int64_t i = 0; i < M; ++i) {
+                const size_t lg = std::min((size_t)rc.sizes[(size_t)i], L - pos);
+                if (lg == 0) ++n_extra;
+                if (pos < L && pos != last_close) { ++n_close; last_close = pos; }
+                pos += lg;
+            }
+            ncols[(size_t)k] = (uint32_t)L;
             nmaps[(size_t)k] = (uint32_t)M;
+            ncloses[(size_t)k] = n_close;
+            nextras[(size_t)k] = n_extra;
         }
     }
     if (err) return fail(err, "%s", err_msg.c_str());
@@ -446,7 +457,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     std::vector<uint32_t> order(R);
     for (size_t k = 0; k < R; ++k) order[k] = (uint32_t)k;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        return ((uint64_t)nmaps[x] << 32 | ncols[x]) < ((uint64_t)nmaps[y] << 32 | ncols[y]);
+        return ((uint64_t)ncloses[x] << 32 | ncols[x]) < ((uint64_t)ncloses[y] << 32 | ncols[y]);
     });
     const size_t n_groups = (R + VGL_HC_LANES - 1) / VGL_HC_LANES;
     std::vector<uint32_t> g_col(n_groups + 1, 0), g_map(n_groups + 1, 0);
@@ -455,7 +466,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
         for (size_t l = 0; l < VGL_HC_LANES && gI * VGL_HC_LANES + l < R; ++l) {
             const uint32_t k = order[gI * VGL_HC_LANES + l];
             mc = std::max(mc, ncols[k]);
-            mm = std::max(mm, nmaps[k]);
+            mm = std::max(mm, nextras[k]);
         }
         const uint64_t nc = (uint64_t)g_col[gI] + (mc + VGL_HC_COL_BLK - 1) / VGL_HC_COL_BLK;
         const uint64_t nm = (uint64_t)g_map[gI] + (mm + VGL_HC_MAP_BLK - 1) / VGL_HC_MAP_BLK;
@@ -470,12 +481,11 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     size_t o = 0;
     const size_t o_gc = o; o = align_up(o + (n_groups + 1) * 4, 256);
     const size_t o_gm = o; o = align_up(o + (n_groups + 1) * 4, 256);
-    const size_t o_col = o; o = align_up(o + col_blks * kColBlk * 2, 256);
+    const size_t o_col = o; o = align_up(o + col_blks * kColBlk * 4, 256);
     const size_t o_map = o; o = align_up(o + map_blks * kMapBlk * 4, 256);
     const size_t o_nc = o; o = align_up(o + lanes * 2, 256);
-    const size_t o_nm = o; o = align_up(o + lanes * 2, 256);
-    const size_t o_ce = o; o = align_up(o + lanes * 2, 256);
-    const size_t o_q9 = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_ncl = o; o = align_up(o + lanes * 2, 256);
+    const size_t o_nx = o; o = align_up(o + lanes * 2, 256);
     const size_t o_mq = o; o = align_up(o + lanes, 256);
     vgh_hc_packed* P = new vgh_hc_packed();
     P->block_bytes = std::max<size_t>(o, 256);
@@ -492,12 +502,11 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     uint8_t* base = (uint8_t*)P->block;
     uint32_t* grp_col_blk = (uint32_t*)(base + o_gc);
     uint32_t* grp_map_blk = (uint32_t*)(base + o_gm);
-    uint16_t* col = (uint16_t*)(base + o_col);
+    uint32_t* col = (uint32_t*)(base + o_col);
     uint32_t* map = (uint32_t*)(base + o_map);
     uint16_t* n_cols = (uint16_t*)(base + o_nc);
-    uint16_t* n_maps = (uint16_t*)(base + o_nm);
-    uint16_t* cov_end = (uint16_t*)(base + o_ce);
-    uint16_t* first_q90 = (uint16_t*)(base + o_q9);
+    uint16_t* n_close = (uint16_t*)(base + o_ncl);
+    uint16_t* n_extra = (uint16_t*)(base + o_nx);
     uint8_t* mapq = base + o_mq;
     memcpy(grp_col_blk, g_col.data(), (n_groups + 1) * 4);
     memcpy(grp_map_blk, g_map.data(), (n_groups + 1) * 4);
@@ -511,17 +520,16 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
         Recon rc;
 #pragma omp for schedule(dynamic, 16)
         for (int64_t gI = 0; gI < (int64_t)n_groups; ++gI) {
-            uint16_t* gcol = col + (size_t)g_col[(size_t)gI] * kColBlk;
+            uint32_t* gcol = col + (size_t)g_col[(size_t)gI] * kColBlk;
             uint32_t* gmap = map + (size_t)g_map[(size_t)gI] * kMapBlk;
-            memset(gcol, 0, (size_t)(g_col[(size_t)gI + 1] - g_col[(size_t)gI]) * kColBlk * 2);
+            memset(gcol, 0, (size_t)(g_col[(size_t)gI + 1] - g_col[(size_t)gI]) * kColBlk * 4);
             memset(gmap, 0, (size_t)(g_map[(size_t)gI + 1] - g_map[(size_t)gI]) * kMapBlk * 4);
-            // record c of lane l: block c / 8, then lane, then c % 8 (mapping records: blocks of 4)
-            auto col_at = [&](size_t c, size_t l) -> uint16_t& { return gcol[((c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK]; };
+            // record c of lane l: block c / 4, then lane, then c % 4 (extra records likewise)
+            auto col_at = [&](size_t c, size_t l) -> uint32_t& { return gcol[((c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK]; };
             auto map_at = [&](size_t i, size_t l) -> uint32_t& { return gmap[((i / VGL_HC_MAP_BLK) * VGL_HC_LANES + l) * VGL_HC_MAP_BLK + i % VGL_HC_MAP_BLK]; };
             for (size_t l = 0; l < VGL_HC_LANES; ++l) {
                 const size_t lane_id = (size_t)gI * VGL_HC_LANES + l;
-                n_cols[lane_id] = n_maps[lane_id] = cov_end[lane_id] = 0;
-                first_q90[lane_id] = 0xFFFF;
+                n_cols[lane_id] = n_close[lane_id] = n_extra[lane_id] = 0;
                 mapq[lane_id] = 0;
                 if (lane_id >= R) continue;
                 const uint32_t k = order[lane_id];
@@ -529,27 +537,34 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
                 if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
                 const size_t L = rc.read_seq.size();
                 const int64_t q0 = a->qual_off[r], Lq = a->qual_off[r + 1] - q0;
+                size_t first_q90 = (size_t)-1;  // the first REAL quality byte >= 90 latches the background-error mode
                 for (size_t c = 0; c < L; ++c) {
                     const uint8_t qb = (int64_t)c < Lq ? (uint8_t)a->qual[q0 + (int64_t)c] : 0;
-                    col_at(c, l) = qb;
-                    if ((int64_t)c < Lq && (int)(int8_t)qb >= 90 && first_q90[lane_id] == 0xFFFF) first_q90[lane_id] = (uint16_t)c;
+                    col_at(c, l) = (uint32_t)qb | (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT);
+                    if ((int64_t)c < Lq && (int)(int8_t)qb >= 90 && first_q90 == (size_t)-1) first_q90 = c;
                 }
                 const int64_t mm = a->map_off[r];
-                size_t pos = 0;
+                size_t pos = 0, n_x = 0;
                 for (uint32_t i = 0; i < nmaps[k]; ++i) {
                     const size_t lg = std::min((size_t)rc.sizes[i], L - pos);
+                    const uint32_t node = (uint32_t)a->map_node[mm + i];
+                    // its quality window is [pos, pos + L)  (src/update_likelihood.cpp:40-44)
+                    const uint32_t latched = (first_q90 != (size_t)-1 && first_q90 < pos + L) ? VGL_HC_COL_LATCHED : 0u;
                     for (size_t j = 0; j < lg; ++j) {
                         const char gb = rc.graph_seq[pos + j], rb = rc.read_seq[j];
                         const int cg = base_code(gb), cb = base_code(rb);
-                        if (cg < 4 && cb < 4)
-                            col_at(pos + j, l) |= (uint16_t)(VGL_HC_COL_VALID | (cb << 9) | (gb == rb ? 0 : VGL_HC_COL_MISMATCH));
+                        uint32_t& rec = col_at(pos + j, l);
+                        rec = (rec & 0xffu) | (node << VGL_HC_COL_NODE_SHIFT) | latched;
+                        if (cg < 4 && cb < 4) rec |= VGL_HC_COL_VALID | ((uint32_t)cb << 10) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
                     }
-                    map_at(i, l) = VGL_HC_MAP_REC((uint32_t)a->map_node[mm + i], (uint32_t)pos);
+                    if (lg) col_at(pos + lg - 1, l) |= VGL_HC_COL_OPEN;
+                    else map_at(n_x++, l) = VGL_HC_MAP_REC(node, (uint32_t)pos);
+                    if (pos < L) col_at(pos, l) |= VGL_HC_COL_CLOSE;
                     pos += lg;
                 }
                 n_cols[lane_id] = (uint16_t)L;
-                n_maps[lane_id] = (uint16_t)nmaps[k];
-                cov_end[lane_id] = (uint16_t)pos;
+                n_close[lane_id] = (uint16_t)ncloses[k];
+                n_extra[lane_id] = (uint16_t)n_x;
                 mapq[lane_id] = (uint8_t)a->mapq[r];
             }
         }
@@ -561,8 +576,7 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
     P->batch.n_map_blks = map_blks;
     P->batch.grp_col_blk = grp_col_blk; P->batch.grp_map_blk = grp_map_blk;
     P->batch.col = col; P->batch.map = map;
-    P->batch.n_cols = n_cols; P->batch.n_maps = n_maps; P->batch.cov_end = cov_end;
-    P->batch.first_q90 = first_q90; P->batch.mapq = mapq;
+    P->batch.n_cols = n_cols; P->batch.n_close = n_close; P->batch.n_extra = n_extra; P->batch.mapq = mapq;
     *out = P;
     return VGH_OK;
 }

@@ -95,8 +95,8 @@ struct vgl_ctx {
 
     // staging for host batches: two slots so that the H2D copy of chunk k+1 overlaps the read kernel on chunk k
     struct Slot {
-        DevBuf<uint32_t> grp_col_blk, grp_map_blk, map;
-        DevBuf<uint16_t> col, n_cols, n_maps, first_q90;
+        DevBuf<uint32_t> grp_col_blk, grp_map_blk, col, map;
+        DevBuf<uint16_t> n_cols, n_close, n_extra;
         DevBuf<uint8_t> mapq;
         cudaEvent_t copied = nullptr, consumed = nullptr;
         bool used = false;
@@ -169,10 +169,10 @@ int check_batch(const vgl_hc_batch* b) {
     if (!b) return fail(VGL_ERR_INVALID, "null batch");
     if (b->n_groups == 0) return VGL_OK;
     if ((uint64_t)b->n_groups * VGL_HC_LANES < b->n_reads) return fail(VGL_ERR_INVALID, "n_groups too small for n_reads");
-    if (!b->grp_col_blk || !b->grp_map_blk || !b->n_cols || !b->n_maps || !b->cov_end || !b->first_q90 || !b->mapq)
+    if (!b->grp_col_blk || !b->grp_map_blk || !b->n_cols || !b->n_close || !b->n_extra || !b->mapq)
         return fail(VGL_ERR_INVALID, "batch header arrays missing");
     if (b->n_col_blks && !b->col) return fail(VGL_ERR_INVALID, "batch column records missing");
-    if (b->n_map_blks && !b->map) return fail(VGL_ERR_INVALID, "batch mapping records missing");
+    if (b->n_map_blks && !b->map) return fail(VGL_ERR_INVALID, "batch extra records missing");
     return VGL_OK;
 }
 
@@ -234,7 +234,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_post.release(); ctx->d_scalars.release(); ctx->d_idx.release();
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
-        sl.n_maps.release(); sl.first_q90.release(); sl.mapq.release();
+        sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.consumed) cudaEventDestroy(sl.consumed);
     }
@@ -303,7 +303,7 @@ uint64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; 
 uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b) {
     if (!b) return 0;
     return (uint64_t)(b->n_groups + 1) * 8 + (b->n_col_blks + b->n_map_blks) * 512 +
-           (uint64_t)b->n_groups * VGL_HC_LANES * 9;
+           (uint64_t)b->n_groups * VGL_HC_LANES * 7;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -494,7 +494,7 @@ int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
-    vgl::HcBatchDev d{b->n_groups, b->grp_col_blk, b->grp_map_blk, b->col, b->map, b->n_cols, b->n_maps, b->first_q90, b->mapq};
+    vgl::HcBatchDev d{b->n_groups, b->grp_col_blk, b->grp_map_blk, b->col, b->map, b->n_cols, b->n_close, b->n_extra, b->mapq};
     return launch_read(ctx, d);
 }
 
@@ -522,8 +522,8 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
         if (int rc = sl.grp_col_blk.reserve((size_t)ng + 1)) return rc;
         if (int rc = sl.grp_map_blk.reserve((size_t)ng + 1)) return rc;
         if (int rc = sl.n_cols.reserve(nl)) return rc;
-        if (int rc = sl.n_maps.reserve(nl)) return rc;
-        if (int rc = sl.first_q90.reserve(nl)) return rc;
+        if (int rc = sl.n_close.reserve(nl)) return rc;
+        if (int rc = sl.n_extra.reserve(nl)) return rc;
         if (int rc = sl.mapq.reserve(nl)) return rc;
         if (int rc = sl.col.reserve(ncol)) return rc;
         if (int rc = sl.map.reserve(nmap)) return rc;
@@ -531,10 +531,10 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
         if (int rc = upload_async(sl.grp_col_blk.p, b->grp_col_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
         if (int rc = upload_async(sl.grp_map_blk.p, b->grp_map_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
         if (int rc = upload_async(sl.n_cols.p, b->n_cols + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
-        if (int rc = upload_async(sl.n_maps.p, b->n_maps + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
-        if (int rc = upload_async(sl.first_q90.p, b->first_q90 + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.n_close.p, b->n_close + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.n_extra.p, b->n_extra + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
         if (int rc = upload_async(sl.mapq.p, b->mapq + (size_t)g0 * VGL_HC_LANES, nl, cs)) return rc;
-        if (int rc = upload_async(sl.col.p, b->col + (size_t)c0 * VGL_HC_LANES * VGL_HC_COL_BLK, ncol * 2, cs)) return rc;
+        if (int rc = upload_async(sl.col.p, b->col + (size_t)c0 * VGL_HC_LANES * VGL_HC_COL_BLK, ncol * 4, cs)) return rc;
         if (int rc = upload_async(sl.map.p, b->map + (size_t)m0 * VGL_HC_LANES * VGL_HC_MAP_BLK, nmap * 4, cs)) return rc;
         VGL_CUDA(cudaEventRecord(sl.copied, cs));
         VGL_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
@@ -543,11 +543,11 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
         d.grp_col_blk = sl.grp_col_blk.p;
         d.grp_map_blk = sl.grp_map_blk.p;
         // (uintptr_t arithmetic: the shifted bases are only ever dereferenced at rows >= c0 / m0, i.e. inside the slot)
-        d.col = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col.p) - (uintptr_t)c0 * 512);
+        d.col = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.col.p) - (uintptr_t)c0 * 512);
         d.map = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.map.p) - (uintptr_t)m0 * 512);
         d.n_cols = sl.n_cols.p;
-        d.n_maps = sl.n_maps.p;
-        d.first_q90 = sl.first_q90.p;
+        d.n_close = sl.n_close.p;
+        d.n_extra = sl.n_extra.p;
         d.mapq = sl.mapq.p;
         if (int rc = launch_read(ctx, d)) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
@@ -722,7 +722,7 @@ int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* b, uint32_t n_out, int32_t*
     cudaStream_t s = ctx->stream;
     VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
     const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
-    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_HC_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_EUKA_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
     vgl_ctx::EukaStage& st = ctx->estage;
     if (int rc = st.grp_col_blk.reserve(G + 1)) return rc;
     if (int rc = st.grp_map_blk.reserve(G + 1)) return rc;
@@ -788,7 +788,7 @@ namespace {
 int stage_symbol_batch(vgl_ctx* ctx, const vgl_euka_batch* b, vgl::EukaBatchDev& d) {
     cudaStream_t s = ctx->stream;
     const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
-    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_HC_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_EUKA_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
     vgl_ctx::EukaStage& st = ctx->estage;
     if (int rc = st.grp_col_blk.reserve(G + 1)) return rc;
     if (int rc = st.grp_map_blk.reserve(G + 1)) return rc;

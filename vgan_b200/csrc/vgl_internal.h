@@ -41,11 +41,11 @@ struct HcBatchDev {
     uint32_t n_groups;
     const uint32_t* grp_col_blk;
     const uint32_t* grp_map_blk;
-    const uint16_t* col;
+    const uint32_t* col;
     const uint32_t* map;
     const uint16_t* n_cols;
-    const uint16_t* n_maps;
-    const uint16_t* first_q90;
+    const uint16_t* n_close;
+    const uint16_t* n_extra;
     const uint8_t* mapq;
 };
 

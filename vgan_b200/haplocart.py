@@ -119,8 +119,8 @@ class DeviceBatch:
         b = packed.batch
         G, L = int(b.n_groups), _lib.LANES
         sizes = {"grp_col_blk": (G + 1) * 4, "grp_map_blk": (G + 1) * 4, "col": int(b.n_col_blks) * 512,
-                 "map": int(b.n_map_blks) * 512, "n_cols": G * L * 2, "n_maps": G * L * 2, "cov_end": G * L * 2,
-                 "first_q90": G * L * 2, "mapq": G * L}
+                 "map": int(b.n_map_blks) * 512, "n_cols": G * L * 2, "n_close": G * L * 2, "n_extra": G * L * 2,
+                 "mapq": G * L}
         self.batch = _lib.vgl_hc_batch()
         self.batch.n_reads, self.batch.n_groups = b.n_reads, b.n_groups
         self.batch.n_col_blks, self.batch.n_map_blks = b.n_col_blks, b.n_map_blks

@@ -145,16 +145,15 @@ class PackedBatch:
         L, CB, MB = _lib.LANES, _lib.COL_BLK, _lib.MAP_BLK
         return {
             "grp_col_blk": _as_array(b.grp_col_blk, G + 1, np.uint32), "grp_map_blk": _as_array(b.grp_map_blk, G + 1, np.uint32),
-            "col": _as_array(b.col, ncb * L * CB, np.uint16).reshape(ncb, L, CB),
+            "col": _as_array(b.col, ncb * L * CB, np.uint32).reshape(ncb, L, CB),
             "map": _as_array(b.map, nmb * L * MB, np.uint32).reshape(nmb, L, MB),
-            "n_cols": _as_array(b.n_cols, G * L, np.uint16), "n_maps": _as_array(b.n_maps, G * L, np.uint16),
-            "cov_end": _as_array(b.cov_end, G * L, np.uint16), "first_q90": _as_array(b.first_q90, G * L, np.uint16),
-            "mapq": _as_array(b.mapq, G * L, np.uint8),
+            "n_cols": _as_array(b.n_cols, G * L, np.uint16), "n_close": _as_array(b.n_close, G * L, np.uint16),
+            "n_extra": _as_array(b.n_extra, G * L, np.uint16), "mapq": _as_array(b.mapq, G * L, np.uint8),
         }
 
     def lanes(self):
-        """Per-read records, un-blocked: a list of dicts (col records, map records, n_cols, cov_end, first_q90, mapq),
-        one per non-empty lane, in the packer's (shape-sorted) order."""
+        """Per-read records, un-blocked: a list of dicts (col records, extra records, n_cols, n_close, mapq), one per
+        non-empty lane, in the packer's (shape-sorted) order."""
         a = self.arrays()
         out = []
         for g in range(int(self.batch.n_groups)):
@@ -164,12 +163,12 @@ class PackedBatch:
                 k = g * _lib.LANES + l
                 if k >= self.n_reads:
                     break
-                nc, nm = int(a["n_cols"][k]), int(a["n_maps"][k])
+                nc, nm = int(a["n_cols"][k]), int(a["n_extra"][k])
                 cols = a["col"][c0:c1, l, :].reshape(-1)
                 maps = a["map"][m0:m1, l, :].reshape(-1)
                 assert not cols[nc:].any() and not maps[nm:].any()  # padding records are zero
-                out.append({"col": cols[:nc].tolist(), "map": maps[:nm].tolist(), "n_cols": nc,
-                            "cov_end": int(a["cov_end"][k]), "first_q90": int(a["first_q90"][k]), "mapq": int(a["mapq"][k])})
+                out.append({"col": cols[:nc].tolist(), "extra": maps[:nm].tolist(), "n_cols": nc,
+                            "n_close": int(a["n_close"][k]), "mapq": int(a["mapq"][k])})
         return out
 
     def __del__(self):
