@@ -19,6 +19,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "vgl_internal.h"
 
 namespace vgl {
@@ -66,7 +68,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 __device__ __forceinline__ uint32_t lds_u16_c(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds_f64_c(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double2 lds_v2f64_c(uint32_t a) { double2 v; asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ void atoms_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+// fire-and-forget fp64 add performed by the L2 atomic unit (SASS: RED.E.ADD.F64).  Shared memory has no native fp64 add:
+// red.shared.add.f64 is a compare-and-swap loop that costs ~37 shared wavefronts per warp instruction.
+__device__ __forceinline__ void red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 // streaming global loads of the batch: every byte is used exactly once, keep it out of L1
 __device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) { uint16_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
 __device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
@@ -81,18 +85,17 @@ constexpr uint32_t kOffLogTab = offsetof(HcSmallTables, log_tab);
 constexpr uint32_t kOffPCorrect = offsetof(HcSmallTables, p_correct);
 constexpr uint32_t kOffBg = offsetof(HcSmallTables, bg);
 
-// log(x) for x > 0 (x == 0 gives -inf) to ~1e-16: 8-bit table on the mantissa + degree-5 log1p, straight log1p
-// within 2^-9 of 1 (exactly 0 at x == 1).  Table at shared byte address `tab`.
+// log(x) for x > 0 (x == 0 gives -inf): 8-bit table on the mantissa + degree-5 log1p of the remainder (|r| < 2^-9).
+// Absolute error ~1e-16 (one ulp of ln 2 when the exponent is non-zero), which is what a SUM of logs needs; the result
+// for x within 2^-9 of 1 is not relatively accurate and does not have to be.  Table at shared byte address `tab`.
 __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 t = lds_v2f64_c(tab + (uint32_t)((hi >> 12) & 0xff) * 16u);
-    const double d = x - 1.0;
-    const bool near = fabs(d) < 0.001953125;
-    const double r = near ? d : fma(m, t.x, -1.0);
-    const double base = near ? 0.0 : fma((double)e, 0.6931471805599453094, t.y);
+    const double r = fma(m, t.x, -1.0);
+    const double base = fma((double)e, 0.6931471805599453094, t.y);
     double p = fma(r, 0.2, -0.25);
     p = fma(r, p, 0.33333333333333333333);
     p = fma(r, p, -0.5);
@@ -119,11 +122,11 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // At a CLOSE mark (first column of a mapping) the pair is pushed onto the warp's queue in shared memory
 // (ballot + popc give every closing lane its slot, one 16-byte store each).  Whenever the queue holds 32
 // entries the warp drains them, one entry per lane: log of the product, B_i from the quality sums, and
-// B_i - A_i scattered into the CTA's node vector with a shared-memory fp64 atomic.  Entries are self-contained,
+// B_i - A_i added to the CTA's node vector (global memory, L2 resident) with a fire-and-forget fp64 reduction.  Entries are self-contained,
 // so the queue simply carries over from one group to the next and the finalisation always runs on full warps.
 // (Per-thread lists in local memory, the obvious alternative, cost ~9 KB of L2 traffic per read.)
 //
-// Shared memory: [ node_acc f64[n_rows] | HcSmallTables | node_class u16[n_rows + 1] | ac table double2[100][n_class + 1]
+// Shared memory: [ HcSmallTables | node_class u16[n_rows + 1] | ac table double2[100][n_class + 1]
 //                  | close queues uint4[warps][64] ]
 // The ac table holds {1 - pcm, pcm * K} (src/process_mapping.cpp:33-42) for every (mapping quality, table class)
 // pair, so opening a mapping costs one shared load and no arithmetic.
@@ -131,7 +134,8 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
-    uint32_t acc, f, bg, logtab, node_class, ac, queue;  // shared byte addresses (queue: this warp's ring)
+    uint32_t f, bg, logtab, node_class, ac, queue;  // shared byte addresses (queue: this warp's ring)
+    double* acc;                                     // this CTA's node vector (global, lives in L2)
     int n_rows, n_class;
     double le0;
 };
@@ -180,7 +184,7 @@ __device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uin
     // log(err) over [pos, pos + n): the stored columns from pos on plus `pos` bytes past the end that count as
     // quality 0  
     const double B = fma((double)(e.z & 0xfffffu), scale, (double)((e.z >> 20) + pos) * S.le0);
-    if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, B - A);
+    if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, B - A);
     a_sum += A;
 }
 
@@ -189,13 +193,14 @@ __device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uin
 // group are ever waited for.  q_head / q_tail: the warp's close queue (uniform across the warp).
 __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const ReadKernelShared& S, uint32_t g, uint32_t gn, const GroupHdr& H,
                                                  GroupHdr& Hn, uint4& v0, uint4& v1, uint32_t& q_head, uint32_t& q_tail, int lane,
-                                                 double& a_sum, bool& bad_node) {
+                                                 double& a_sum, uint32_t& bad_cls, bool& bad_node) {
     const double scale = -0.23025850929940456840;
     Hn = hc_load_hdr(b, gn, lane);
     const int ncb = H.ncb;
     const uint32_t ac_row = S.ac + 16u * (uint32_t)(S.n_class + 1) * H.mapq;
     const uint32_t lt_mask = (1u << lane) - 1u;
     int x = H.n_extra - 1;  // empty mappings (no column of their own): rare, handled on the side
+    bool rare = x >= 0;     // ... as is a rescaled product
     // Quality sums over the columns walked so far (from the end of the read): (sum of q for q > 2) | (count of q <= 2) << 20.
     // The walk visits every record of the group's blocks; records past a read's own columns are zero and would count as
     // quality-0 columns, so the sum starts that much lower (mod 2^32) instead of testing every column against the
@@ -208,49 +213,55 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         return __ldg(gx + (size_t)(i >> 2) * 128 + (i & 3));
     };
     auto add_extra = [&](uint32_t xn, double Bx) {
-        if (xn < (uint32_t)S.n_rows && lds_u16_c(S.node_class + 2u * xn) != 0xFFFFu) atoms_add_f64(S.acc + 8u * xn, Bx);
+        if (xn < (uint32_t)S.n_rows && lds_u16_c(S.node_class + 2u * xn) != 0xFFFFu) red_add_f64(S.acc + xn, Bx);
         else bad_node = true;
     };
 
-    auto column = [&](int c, uint32_t rec, double f, double bgv, uint32_t cls) {
+    // kRare: some lane of the warp has a rescaled product or empty mappings pending; the common instantiation carries
+    // neither test.  Predicated loads / stores (inline PTX) instead of branches: at every column SOME lane opens or
+    // closes a mapping, so a branch would be taken by the warp anyway and only add reconvergence overhead.
+    auto column = [&](auto rare_tag, int c, uint32_t rec, double f, double bgv, uint32_t cls) {
+        constexpr bool kRare = decltype(rare_tag)::value;
         const uint32_t q = rec & 0xffu;
         suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
-        if (rec & VGL_HC_COL_OPEN) {
-            // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
-            bad_node |= cls == 0xFFFFu;
-            const double2 ac = lds_v2f64_c(ac_row + 16u * min(cls, (uint32_t)S.n_class));
-            aa = ac.x;
-            cc = ac.y;
-        }
+        const uint32_t open = rec & VGL_HC_COL_OPEN;
+        // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
+        bad_cls = max(bad_cls, open ? cls : 0u);
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
+            : "+d"(aa), "+d"(cc)
+            : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
         const double px = prod * fma(cc, f, aa * bgv);
         prod = (rec & VGL_HC_COL_VALID) ? px : prod;
-        const bool close = (rec & VGL_HC_COL_CLOSE) != 0;
-        if (close && (a_ext != 0.0 || x >= 0)) {  // rare
-            const uint32_t node = VGL_HC_COL_NODE(rec);
-            if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
-                if (node < (uint32_t)S.n_rows) atoms_add_f64(S.acc + 8u * node, -a_ext);
-                a_sum += a_ext;
-                a_ext = 0.0;
-            }
-            // empty mappings at or past this column: A = 0, B as for a mapping that starts here (past the last column:
-            // no stored quality at all)
-            const double B = fma((double)(suf & 0xfffffu), scale, (double)((suf >> 20) + (uint32_t)c) * S.le0);
-            while (x >= 0) {
-                const uint32_t xr = extra_rec(x);
-                const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
-                if (xp < (uint32_t)c) break;
-                add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
-                --x;
+        const uint32_t close = rec & VGL_HC_COL_CLOSE;
+        if (kRare) {
+            if (close && rare) {
+                const uint32_t node = VGL_HC_COL_NODE(rec);
+                if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
+                    if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, -a_ext);
+                    a_sum += a_ext;
+                    a_ext = 0.0;
+                }
+                // empty mappings at or past this column: A = 0, B as for a mapping that starts here (past the last
+                // column: no stored quality at all)
+                const double B = fma((double)(suf & 0xfffffu), scale, (double)((suf >> 20) + (uint32_t)c) * S.le0);
+                while (x >= 0) {
+                    const uint32_t xr = extra_rec(x);
+                    const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
+                    if (xp < (uint32_t)c) break;
+                    add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
+                    --x;
+                }
+                rare = x >= 0;
             }
         }
         // push {exp(A), quality sums, node | column}; a CLOSE on a column nobody owns only served the empty mappings
-        const bool push = close && VGL_HC_COL_NODE(rec) != VGL_HC_NO_NODE;
+        const uint32_t push = (close && VGL_HC_COL_NODE(rec) != VGL_HC_NO_NODE) ? 1u : 0u;
         const uint32_t m = __ballot_sync(kFull, push);
-        if (push) {
-            const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (kQueueSlots - 1);
-            sts_v4(S.queue + 16u * slot, (uint32_t)__double2loint(prod), (uint32_t)__double2hiint(prod), suf,
-                   VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17));
-        }
+        const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (kQueueSlots - 1);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(S.queue + 16u * slot),
+                     "r"((uint32_t)__double2loint(prod)), "r"((uint32_t)__double2hiint(prod)), "r"(suf),
+                     "r"(VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17)), "r"(push)
+                     : "memory");
         prod = close ? 1.0 : prod;
         q_tail += __popc(m);
         if (q_tail - q_head >= 32u) {
@@ -273,11 +284,17 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
             cls[j] = lds_u16_c(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows));  // entry n_rows: 0xFFFF
         }
         const int c4 = cb * VGL_HC_COL_BLK;
+        if (__any_sync(kFull, rare)) {
 #pragma unroll
-        for (int j = 3; j >= 0; --j) column(c4 + j, rec[j], f[j], bgv[j], cls[j]);
+            for (int j = 3; j >= 0; --j) column(std::true_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+        } else {
+#pragma unroll
+            for (int j = 3; j >= 0; --j) column(std::false_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+        }
         if (prod < 1e-100) {  // keep the product normal (four more factors cannot take it out of range)
             a_ext += fast_log_s(prod, S.logtab);
             prod = 1.0;
+            rare = true;
         }
     };
     // two blocks in flight from ONE load site: a block is waited for a whole block (hundreds of issue slots) after its
@@ -303,8 +320,6 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
                int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     size_t off = 0;
-    double* s_acc = reinterpret_cast<double*>(smem_raw);
-    off += ((size_t)t.n_rows * sizeof(double) + 15) & ~(size_t)15;
     HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + off);
     off += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
@@ -318,10 +333,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
-    for (int n = tid; n < t.n_rows; n += kReadBlock) {
-        s_acc[n] = 0.0;
-        s_class[n] = t.node_class[n];
-    }
+    for (int n = tid; n < t.n_rows; n += kReadBlock) s_class[n] = t.node_class[n];
     if (tid == 0) s_class[t.n_rows] = 0xFFFFu;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
@@ -345,7 +357,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     __syncthreads();
 
     ReadKernelShared S;
-    S.acc = smem_u32(s_acc);
+    S.acc = cta_node_acc + (size_t)blockIdx.x * (size_t)t.n_rows;
     S.f = smem_u32(s_tab) + kOffFPair;
     S.bg = smem_u32(s_tab) + kOffBg;
     S.logtab = smem_u32(s_tab) + kOffLogTab;
@@ -358,6 +370,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
 
     double a_sum = 0.0;
     bool bad_node = false;
+    uint32_t bad_cls = 0;  // largest class seen at an OPEN mark (0xFFFF: a node without pangenome_map entry)
     uint32_t q_head = 0, q_tail = 0;
     const uint32_t warps_total = gridDim.x * (kReadBlock / 32);
     uint32_t g = blockIdx.x * (kReadBlock / 32) + warp;
@@ -365,22 +378,17 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     uint4 v0 = hc_fetch(H, H.ncb - 1), v1 = hc_fetch(H, H.ncb - 2);
     while (g < b.n_groups) {
         const uint32_t gn = g + warps_total;
-        hc_process_group(b, S, g, gn, H, Hn, v0, v1, q_head, q_tail, lane, a_sum, bad_node);
+        hc_process_group(b, S, g, gn, H, Hn, v0, v1, q_head, q_tail, lane, a_sum, bad_cls, bad_node);
         H = Hn;
         g = gn;
     }
     __syncwarp();
     if ((uint32_t)lane < q_tail - q_head) hc_finalise(S, lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1))), a_sum);
 
-    if (__any_sync(kFull, bad_node) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
+    if (__any_sync(kFull, bad_node || bad_cls == 0xFFFFu) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
     a_sum = warp_sum_f64(a_sum);
     if (lane == 0) s_warp_a[warp] = a_sum;
     __syncthreads();
-    double* my_acc = cta_node_acc + (size_t)blockIdx.x * (size_t)t.n_rows;
-    for (int n = tid; n < t.n_rows; n += kReadBlock) {
-        const double v = s_acc[n];
-        if (v != 0.0) my_acc[n] += v;
-    }
     if (tid == 0) {
         double tot = 0.0;
         for (int w = 0; w < kReadBlock / 32; ++w) tot += s_warp_a[w];
@@ -595,7 +603,6 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // ------------------------------------------------------------------------------------------
 static size_t read_smem_bytes(int n_rows, int n_class) {
     size_t s = 0;
-    s += ((size_t)n_rows * sizeof(double) + 15) & ~(size_t)15;
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     s += ((size_t)(n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
     s += (size_t)100 * (n_class + 1) * sizeof(double2);
