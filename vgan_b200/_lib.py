@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("VGAN_B200_LIB_DIR") or os.path.join(_HERE, "lib")  # (override: kernel A/B builds)
 GPU_LIB_PATH = os.path.join(LIB_DIR, "libvgan_gpu.so")
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libvgan_host.so")
 

@@ -30,7 +30,10 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- read kernel geometry ------------------------------------------------------------------
-constexpr int kReadBlock = 768;     // 24 warps: one read per thread, one 32-lane group per warp at a time
+#ifndef VGL_HC_READ_BLOCK
+#define VGL_HC_READ_BLOCK 768
+#endif
+constexpr int kReadBlock = VGL_HC_READ_BLOCK;  // 24 warps: one read per thread, one 32-lane group per warp at a time
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,17 +75,10 @@ __device__ __forceinline__ double2 lds_v2f64_c(uint32_t a) { double2 v; asm("ld.
 // red.shared.add.f64 is a compare-and-swap loop that costs ~37 shared wavefronts per warp instruction.
 __device__ __forceinline__ void red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 // streaming global loads of the batch: every byte is used exactly once, keep it out of L1
-__device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) { uint16_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t ldg_l1_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) { uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 
 constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_pair);
-constexpr uint32_t kOffLogErr = offsetof(HcSmallTables, log_err);
 constexpr uint32_t kOffLogTab = offsetof(HcSmallTables, log_tab);
-constexpr uint32_t kOffPCorrect = offsetof(HcSmallTables, p_correct);
 constexpr uint32_t kOffBg = offsetof(HcSmallTables, bg);
 
 // log(x) for x > 0 (x == 0 gives -inf): 8-bit table on the mantissa + degree-5 log1p of the remainder (|r| < 2^-9).
@@ -131,6 +127,7 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // The ac table holds {1 - pcm, pcm * K} (src/process_mapping.cpp:33-42) for every (mapping quality, table class)
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
+constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
@@ -166,9 +163,6 @@ __device__ __forceinline__ GroupHdr hc_load_hdr(const HcBatchDev& b, uint32_t g,
 }
 __device__ __forceinline__ uint4 hc_fetch(const GroupHdr& h, int cb) {
     return cb >= 0 ? ldg_stream_v4(h.gc + (size_t)cb * 32) : make_uint4(0, 0, 0, 0);
-}
-__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
@@ -357,7 +351,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     __syncthreads();
 
     ReadKernelShared S;
-    S.acc = cta_node_acc + (size_t)blockIdx.x * (size_t)t.n_rows;
+    S.acc = cta_node_acc + (size_t)(blockIdx.x % kAccCopies) * (size_t)(t.n_words * 32);
     S.f = smem_u32(s_tab) + kOffFPair;
     S.bg = smem_u32(s_tab) + kOffBg;
     S.logtab = smem_u32(s_tab) + kOffLogTab;
@@ -392,59 +386,20 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     if (tid == 0) {
         double tot = 0.0;
         for (int w = 0; w < kReadBlock / 32; ++w) tot += s_warp_a[w];
-        cta_a_total[blockIdx.x] += tot;
+        red_add_f64(cta_a_total + blockIdx.x % kAccCopies, tot);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// K2a: node_acc[n] = sum over CTAs (fixed order, Neumaier-compensated within each of 8 slices, then the slices)
-// ------------------------------------------------------------------------------------------
-constexpr int kRedNodes = 32;   // nodes per CTA (one per lane)
-constexpr int kRedSlices = 8;   // warps per CTA, each sums every 8th per-CTA vector
-
-__device__ __forceinline__ void neumaier_add(double& s, double& comp, double v) {
-    const double tsum = s + v;
-    comp += (fabs(s) >= fabs(v)) ? ((s - tsum) + v) : ((v - tsum) + s);
-    s = tsum;
-}
-
-__global__ void __launch_bounds__(kRedNodes * kRedSlices)
-hc_reduce_ctas_kernel(const double* __restrict__ cta_node_acc, const double* __restrict__ cta_a_total, int n_ctas,
-                      int n_rows, int n_rows_pad, double* __restrict__ node_acc, double* __restrict__ a_total) {
-    __shared__ double s_part[kRedSlices][kRedNodes];
-    __shared__ double s_comp[kRedSlices][kRedNodes];
-    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int n = blockIdx.x * kRedNodes + lane;
-    double s = 0.0, comp = 0.0;
-    if (n < n_rows)
-        for (int c = slice; c < n_ctas; c += kRedSlices) neumaier_add(s, comp, __ldg(cta_node_acc + (size_t)c * n_rows + n));
-    s_part[slice][lane] = s;
-    s_comp[slice][lane] = comp;
-    __syncthreads();
-    if (slice == 0 && n < n_rows_pad) {
-        double ts = 0.0, tc = 0.0;
-#pragma unroll
-        for (int k = 0; k < kRedSlices; ++k) {
-            neumaier_add(ts, tc, s_part[k][lane]);
-            tc += s_comp[k][lane];
-        }
-        node_acc[n] = ts + tc;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double ts = 0.0, tc = 0.0;
-        for (int c = 0; c < n_ctas; ++c) neumaier_add(ts, tc, cta_a_total[c]);
-        a_total[0] = ts + tc;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2b: chunk_ll[chunk][p] = sum over the chunk's nodes n with pathsgo[n][p] == 0 of node_acc[n]
+// K2b: chunk_ll[chunk][p] = sum over the chunk's nodes n with pathsgo[n][p] == 0 of D[n],
+//      D[n] = sum of the kAccCopies node vectors (fixed order)
 // ------------------------------------------------------------------------------------------
 constexpr int kPathTile = 128;       // paths per CTA (one per thread)
 constexpr int kWordsPerChunk = 10;   // 320 nodes per CTA
 
 __global__ void __launch_bounds__(kPathTile)
 hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __restrict__ chunk_ll) {
+    __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
     __shared__ __align__(8) unsigned long long s_bar;
     const int chunk = blockIdx.y;
@@ -452,7 +407,7 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     const int nw = min(kWordsPerChunk, t.n_words - w0);
     const int p = blockIdx.x * kPathTile + threadIdx.x;
 
-    // Stage this chunk of the node vector with one TMA bulk copy (cp.async.bulk -> UBLKCP).
+    // Stage this chunk of every copy of the node vector with TMA bulk copies (cp.async.bulk -> UBLKCP).
     const uint32_t bar = smem_u32(&s_bar);
     const uint32_t bytes = (uint32_t)nw * 32u * 8u;
     if (threadIdx.x == 0) {
@@ -461,15 +416,23 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(s_d), node_acc + (size_t)w0 * 32, bytes, bar);
+        mbar_expect_tx(bar, bytes * kAccCopies);
+        for (int c = 0; c < kAccCopies; ++c)
+            bulk_g2s(smem_u32(&s_c[c][0]), node_acc + (size_t)c * t.n_words * 32 + (size_t)w0 * 32, bytes, bar);
     }
-    // Issue the membership loads while the bulk copy is in flight.
+    // Issue the membership loads while the bulk copies are in flight.
     uint32_t words[kWordsPerChunk];
 #pragma unroll
     for (int k = 0; k < kWordsPerChunk; ++k)
         words[k] = (k < nw && p < t.n_paths) ? __ldg(t.node_bits + (size_t)(w0 + k) * t.n_paths + p) : 0xffffffffu;
     mbar_wait(bar, 0);
+    for (int i = threadIdx.x; i < nw * 32; i += kPathTile) {
+        double d = 0.0;
+#pragma unroll
+        for (int c = 0; c < kAccCopies; ++c) d += s_c[c][i];
+        s_d[i] = d;
+    }
+    __syncthreads();
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < kWordsPerChunk; ++k) {
@@ -485,13 +448,17 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     if (p < t.n_paths) chunk_ll[(size_t)chunk * t.n_paths + p] = acc;
 }
 
+// K2c: ll[p] = sum of the A totals + sum over chunks (fixed order, identical for every p)
 __global__ void hc_path_sum_kernel(const double* __restrict__ chunk_ll, int n_chunks, int n_paths,
                                    const double* __restrict__ a_total, double* __restrict__ ll) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
+    double a = 0.0;
+#pragma unroll
+    for (int c = 0; c < kAccCopies; ++c) a += a_total[c];
     double s = 0.0;
     for (int c = 0; c < n_chunks; ++c) s += chunk_ll[(size_t)c * n_paths + p];
-    ll[p] = a_total[0] + s;
+    ll[p] = a + s;
 }
 
 __global__ void hc_sum_parts_kernel(const double* __restrict__ parts, int n_parts, int n_paths, double* __restrict__ ll) {
@@ -511,7 +478,7 @@ constexpr int kPostBlock = 1024;
 __global__ void __launch_bounds__(kPostBlock)
 hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, const uint32_t* __restrict__ clade_bits,
                     const int32_t* __restrict__ anc_off, const int32_t* __restrict__ anc_clade, double* __restrict__ post,
-                    int post_cap, double* __restrict__ out_scalars, int32_t* __restrict__ out_idx) {
+                    int post_cap, double* __restrict__ out_scalars, int32_t* __restrict__ out_idx, const int* __restrict__ err_flag) {
     extern __shared__ __align__(16) double s_e[];  // [n_paths] exp(ll - max)
     __shared__ double s_val[kPostBlock / 32];
     __shared__ int s_idx[kPostBlock / 32];
@@ -593,7 +560,10 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
         s = warp_sum_f64(s);
         if (lane == 0) post[1 + k] = s / tot;
     }
-    if (tid == 0) out_idx[1] = 1 + n_anc;
+    if (tid == 0) {
+        out_idx[1] = 1 + n_anc;
+        out_idx[2] = *err_flag;  // travels with the results: one device-to-host copy per sample
+    }
 }
 
 }  // namespace
@@ -630,13 +600,6 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
     return cudaGetLastError();
 }
 
-cudaError_t hc_launch_reduce_ctas(const double* cta_node_acc, const double* cta_a_total, int n_ctas, int n_rows,
-                                  int n_rows_pad, double* node_acc, double* a_total, cudaStream_t s) {
-    hc_reduce_ctas_kernel<<<(n_rows_pad + kRedNodes - 1) / kRedNodes, kRedNodes * kRedSlices, 0, s>>>(
-        cta_node_acc, cta_a_total, n_ctas, n_rows, n_rows_pad, node_acc, a_total);
-    return cudaGetLastError();
-}
-
 int hc_path_chunks(int n_words) { return (n_words + kWordsPerChunk - 1) / kWordsPerChunk; }
 
 cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, cudaStream_t s) {
@@ -666,9 +629,9 @@ cudaError_t hc_posterior_configure(size_t smem) {
 
 cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
-                                double* out_scalars, int32_t* out_idx, cudaStream_t s) {
+                                double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s) {
     hc_posterior_kernel<<<1, kPostBlock, hc_posterior_smem(n_paths), s>>>(ll, n_paths, row_words, clade_bits, anc_off,
-                                                                          anc_clade, post, post_cap, out_scalars, out_idx);
+                                                                          anc_clade, post, post_cap, out_scalars, out_idx, err_flag);
     return cudaGetLastError();
 }
 

@@ -78,8 +78,10 @@ struct vgl_ctx {
     vgl::HcReadLaunch read_cfg{};
 
     // accumulators
-    DevBuf<double> d_cta_node_acc, d_cta_a_total, d_node_acc, d_a_total, d_chunk_ll, d_ll;
-    DevBuf<int> d_err;
+    // one allocation, one memset per sample: node vectors [copies][n_rows_pad] | A totals [copies] | error flag
+    DevBuf<double> d_cta_node_acc, d_chunk_ll, d_ll;
+    double* d_a_total = nullptr;
+    int* d_err = nullptr;
     int n_chunks = 0;
     bool ll_valid = false;
 
@@ -90,8 +92,10 @@ struct vgl_ctx {
     DevBuf<int32_t> d_anc_off, d_anc_clade;
 
     // posterior outputs
-    DevBuf<double> d_post, d_scalars;
-    DevBuf<int32_t> d_idx;
+    // one block {double total, max; int32 argmax, n_post, err, pad; double post[]} and its pinned host mirror
+    DevBuf<double> d_result;
+    double* h_result = nullptr;
+    size_t h_result_cap = 0;
 
     // staging for host batches: two slots so that the H2D copy of chunk k+1 overlaps the read kernel on chunk k
     struct Slot {
@@ -157,11 +161,22 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
     }
     auto& ev = ctx->ev_pool[ctx->ev_used++];
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
-    VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_cta_a_total.p,
-                                        ctx->d_err.p, ctx->d_stats.p, ctx->stream));
+    VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total,
+                                        ctx->d_err, ctx->d_stats.p, ctx->stream));
     VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches += 1;
     ctx->ll_valid = false;
+    return VGL_OK;
+}
+
+int reserve_result(vgl_ctx* ctx, size_t n_post) {
+    if (n_post <= ctx->h_result_cap) return VGL_OK;
+    if (int rc = ctx->d_result.reserve(4 + n_post)) return rc;
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    ctx->h_result = nullptr;
+    ctx->h_result_cap = 0;
+    VGL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_result), (4 + n_post) * sizeof(double)));
+    ctx->h_result_cap = n_post;
     return VGL_OK;
 }
 
@@ -228,10 +243,11 @@ void vgl_destroy(vgl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->d_node_class.release(); ctx->d_class_tab.release(); ctx->d_small.release(); ctx->d_node_bits.release();
-    ctx->d_cta_node_acc.release(); ctx->d_cta_a_total.release(); ctx->d_node_acc.release(); ctx->d_a_total.release();
-    ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_err.release();
+    ctx->d_cta_node_acc.release();
+    ctx->d_chunk_ll.release(); ctx->d_ll.release();
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
-    ctx->d_post.release(); ctx->d_scalars.release(); ctx->d_idx.release();
+    ctx->d_result.release();
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
         sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
@@ -426,16 +442,12 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     ctx->n_rows_pad = n_words * 32;
     ctx->n_chunks = vgl::hc_path_chunks(n_words);
 
-    if (int rc = ctx->d_cta_node_acc.reserve((size_t)ctx->read_cfg.grid * (size_t)N)) return rc;
-    if (int rc = ctx->d_cta_a_total.reserve((size_t)ctx->read_cfg.grid)) return rc;
-    if (int rc = ctx->d_node_acc.reserve((size_t)ctx->n_rows_pad)) return rc;
-    if (int rc = ctx->d_a_total.reserve(1)) return rc;
+    if (int rc = ctx->d_cta_node_acc.reserve((size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad + VGL_HC_ACC_COPIES + 1)) return rc;
+    ctx->d_a_total = ctx->d_cta_node_acc.p + (size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad;
+    ctx->d_err = reinterpret_cast<int*>(ctx->d_a_total + VGL_HC_ACC_COPIES);
     if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
     if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
-    if (int rc = ctx->d_err.reserve(1)) return rc;
-    if (int rc = ctx->d_scalars.reserve(2)) return rc;
-    if (int rc = ctx->d_idx.reserve(2)) return rc;
-    if (int rc = ctx->d_post.reserve(64)) return rc;
+    if (int rc = reserve_result(ctx, 64)) return rc;
     if (int rc = ctx->d_stats.reserve(4)) return rc;
     VGL_CUDA(cudaMemset(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long)));
     if (vgl::hc_posterior_smem(P) > 48 * 1024) VGL_CUDA(vgl::hc_posterior_configure(vgl::hc_posterior_smem(P)));
@@ -464,7 +476,7 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
     if (int rc = ctx->d_clade_bits.reserve((size_t)std::max(n_clades, 1) * (size_t)ctx->row_words)) return rc;
     if (int rc = ctx->d_anc_off.reserve((size_t)P + 1)) return rc;
     if (int rc = ctx->d_anc_clade.reserve((size_t)std::max(n_anc, 1))) return rc;
-    if (int rc = ctx->d_post.reserve((size_t)max_anc + 1)) return rc;
+    if (int rc = reserve_result(ctx, (size_t)max_anc + 1)) return rc;
     if (n_clades)
         VGL_CUDA(cudaMemcpy(ctx->d_clade_bits.p, clade_bits, (size_t)n_clades * ctx->row_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     VGL_CUDA(cudaMemcpy(ctx->d_anc_off.p, anc_off, ((size_t)P + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -482,9 +494,7 @@ int vgl_hc_reset(vgl_ctx* ctx) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     cudaStream_t s = ctx->stream;
-    VGL_CUDA(cudaMemsetAsync(ctx->d_cta_node_acc.p, 0, (size_t)ctx->read_cfg.grid * ctx->tab.n_rows * sizeof(double), s));
-    VGL_CUDA(cudaMemsetAsync(ctx->d_cta_a_total.p, 0, (size_t)ctx->read_cfg.grid * sizeof(double), s));
-    VGL_CUDA(cudaMemsetAsync(ctx->d_err.p, 0, sizeof(int), s));
+    VGL_CUDA(cudaMemsetAsync(ctx->d_cta_node_acc.p, 0, ((size_t)VGL_HC_ACC_COPIES * ctx->n_rows_pad + VGL_HC_ACC_COPIES + 1) * sizeof(double), s));
     ctx->ev_used = 0;
     ctx->ll_valid = false;
     return VGL_OK;
@@ -562,11 +572,9 @@ int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     cudaStream_t s = ctx->stream;
-    VGL_CUDA(vgl::hc_launch_reduce_ctas(ctx->d_cta_node_acc.p, ctx->d_cta_a_total.p, ctx->read_cfg.grid, ctx->tab.n_rows,
-                                        ctx->n_rows_pad, ctx->d_node_acc.p, ctx->d_a_total.p, s));
-    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_node_acc.p, ctx->d_chunk_ll.p, s));
-    VGL_CUDA(vgl::hc_launch_path_sum(ctx->d_chunk_ll.p, ctx->n_chunks, ctx->tab.n_paths, ctx->d_a_total.p, ctx->d_ll.p, s));
-    ctx->launches += 3;
+    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, s));
+    VGL_CUDA(vgl::hc_launch_path_sum(ctx->d_chunk_ll.p, ctx->n_chunks, ctx->tab.n_paths, ctx->d_a_total, ctx->d_ll.p, s));
+    ctx->launches += 2;
     ctx->ll_valid = true;
     if (ll_dev) VGL_CUDA(cudaMemcpyAsync(ll_dev, ctx->d_ll.p, (size_t)ctx->tab.n_paths * sizeof(double), cudaMemcpyDeviceToDevice, s));
     return VGL_OK;
@@ -590,22 +598,22 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
         if (int rc = vgl_hc_paths(ctx, nullptr)) return rc;
     cudaStream_t s = ctx->stream;
     const int P = ctx->tab.n_paths;
-    const int cap = (int)std::min<size_t>(ctx->d_post.cap, (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1));
+    const int cap = (int)std::min<size_t>(ctx->h_result_cap, (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1));
+    double* d_scalars = ctx->d_result.p;
+    int32_t* d_idx = reinterpret_cast<int32_t*>(ctx->d_result.p + 2);
+    double* d_post = ctx->d_result.p + 4;
     VGL_CUDA(vgl::hc_launch_posterior(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
                                       ctx->have_tree ? ctx->d_anc_off.p : nullptr,
-                                      ctx->have_tree ? ctx->d_anc_clade.p : nullptr, ctx->d_post.p, cap, ctx->d_scalars.p,
-                                      ctx->d_idx.p, s));
+                                      ctx->have_tree ? ctx->d_anc_clade.p : nullptr, d_post, cap, d_scalars, d_idx,
+                                      ctx->d_err, s));
     ctx->launches += 1;
-    double scalars[2];
-    int32_t idx[2];
-    int err = 0;
-    std::vector<double> post((size_t)cap);
-    VGL_CUDA(cudaMemcpyAsync(scalars, ctx->d_scalars.p, sizeof(scalars), cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaMemcpyAsync(idx, ctx->d_idx.p, sizeof(idx), cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaMemcpyAsync(&err, ctx->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaMemcpyAsync(post.data(), ctx->d_post.p, (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, (4 + (size_t)cap) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->d_ll.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
     VGL_CUDA(cudaStreamSynchronize(s));
+    const double* scalars = ctx->h_result;
+    const int32_t* idx = reinterpret_cast<const int32_t*>(ctx->h_result + 2);
+    const double* post = ctx->h_result + 4;
+    const int err = idx[2];
     if (err & VGL_ERR_BAD_NODE)
         return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
     if (argmax_out) *argmax_out = idx[0];
@@ -614,7 +622,7 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
     if (n_post_out) *n_post_out = n_post;
     if (post_out) {
         if (post_cap < n_post) return fail(VGL_ERR_INVALID, "post_cap %d < %d posteriors", post_cap, n_post);
-        for (int k = 0; k < n_post; ++k) post_out[k] = post[(size_t)k];
+        for (int k = 0; k < n_post; ++k) post_out[k] = post[k];
     }
     return VGL_OK;
 }

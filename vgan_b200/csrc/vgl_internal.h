@@ -6,6 +6,10 @@
 
 #include "../../include/vgan_gpu.h"
 
+#ifndef VGL_HC_ACC_COPIES
+#define VGL_HC_ACC_COPIES 16
+#endif
+
 namespace vgl {
 
 // Small per-process lookup tables, copied into shared memory by every CTA of the read kernel.
@@ -59,23 +63,18 @@ struct HcReadLaunch {
 HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin);
 cudaError_t hc_read_configure(size_t smem);
 
-// K1: per-read, per-mapping scalars scattered into per-CTA node accumulators.
-//   cta_node_acc[cta][n_rows]  += sum over this CTA's mappings at node n of (B_i - A_i)
-//   cta_a_total[cta]           += sum over this CTA's mappings of A_i
-//   stats[0] += reads that took the generic (slow) path
+// K1: per-read, per-mapping scalars added into VGL_HC_ACC_COPIES node vectors (CTA b adds into copy b % copies).
+//   node_acc[copy][n_words * 32]  += sum over the copy's mappings at node n of (B_i - A_i)
+//   a_total[copy]                 += sum over the copy's mappings of A_i
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
                                   double* cta_node_acc, double* cta_a_total, int* err_flag,
                                   unsigned long long* stats, cudaStream_t s);
 
-// K2a: fixed-order reduction of the per-CTA accumulators -> node_acc[n_rows_pad], a_total[1].
-cudaError_t hc_launch_reduce_ctas(const double* cta_node_acc, const double* cta_a_total, int n_ctas, int n_rows,
-                                  int n_rows_pad, double* node_acc, double* a_total, cudaStream_t s);
-
-// K2b: bit-GEMV over the node x path membership: chunk_ll[chunk][P].
+// K2b: sums the copies and runs the bit-GEMV over the node x path membership: chunk_ll[chunk][P].
 int hc_path_chunks(int n_words);
 cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, cudaStream_t s);
 
-// K2c: ll[p] = a_total + sum_chunks chunk_ll[chunk][p]   (fixed order, identical for every p)
+// K2c: ll[p] = sum_copies a_total[copy] + sum_chunks chunk_ll[chunk][p]   (fixed order, identical for every p)
 cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths, const double* a_total, double* ll,
                                cudaStream_t s);
 
@@ -83,12 +82,13 @@ cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s);
 
 // K3: argmax (first max wins), log-sum-exp, posterior of the call and of its listed clades.
-//   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post
+//   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post,
+//   out_idx[2] = *err_flag
 size_t hc_posterior_smem(int n_paths);
 cudaError_t hc_posterior_configure(size_t smem);
 cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
-                                double* out_scalars, int32_t* out_idx, cudaStream_t s);
+                                double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------------------
 // euka

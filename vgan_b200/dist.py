@@ -50,18 +50,25 @@ class ShardedSample:
         self.rank = dist.get_rank(group)
         self.local = torch.zeros(hc.n_paths, dtype=torch.float64, device="cuda")
         self.parts = torch.zeros(self.world * hc.n_paths, dtype=torch.float64, device="cuda")
-        hc.set_stream(torch.cuda.current_stream().cuda_stream)
+        # One stream orders the kernels, the all-gather and the final sum.  The legacy default stream has handle 0, which
+        # vgl_set_stream reads as "use the context's own stream": take a real stream unless the caller already runs on one.
+        self.stream = torch.cuda.current_stream()
+        if self.stream.cuda_stream == 0:
+            self.stream = torch.cuda.Stream()
+        hc.set_stream(self.stream.cuda_stream)
 
     def run(self, local_batches, device_resident=False, want_ll=False):
+        import torch
         import torch.distributed as dist
         hc = self.hc
-        hc.reset()
-        for b in local_batches:
-            if device_resident:
-                hc.update_device(b.batch)
-            else:
-                hc.update(b)
-        hc.paths(self.local.data_ptr())
-        dist.all_gather_into_tensor(self.parts, self.local, group=self.group)
-        hc.set_paths_from_parts(self.parts.data_ptr(), self.world)
-        return hc.get_posterior(want_ll=want_ll)
+        with torch.cuda.stream(self.stream):
+            hc.reset()
+            for b in local_batches:
+                if device_resident:
+                    hc.update_device(b.batch)
+                else:
+                    hc.update(b)
+            hc.paths(self.local.data_ptr())
+            dist.all_gather_into_tensor(self.parts, self.local, group=self.group)
+            hc.set_paths_from_parts(self.parts.data_ptr(), self.world)
+            return hc.get_posterior(want_ll=want_ll)
