@@ -71,6 +71,33 @@ def test_synthetic_samples_match_oracle(small, kw):
     hc.close()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("fasta", [False, True])
+def test_large_class_tables_take_the_other_kernel_layouts(small, monkeypatch, mode, fasta):
+    """With more (mappability, match probability) classes than shared memory holds per mapping quality, the read kernel
+    keeps the class table itself in shared (mode 1) or global (mode 2) memory; both must agree with the oracle."""
+    monkeypatch.setenv("VGL_HC_TABLE_MODE", mode)
+    alns = small.reads(300, seed=212, sub_rate=0.02, indel_rate=0.005)
+    reads = alns
+    if not fasta:  # add the hand-made corner cases as well
+        extra = vb.Alignments.from_gam_bytes(H.encode_gam(_edge_reads(small)))
+        hc = vb.Haplocart()
+        hc.load(small.tables(bep=2e-3), small.tree())
+        res = hc.run_sample([vb.PackedBatch(small.graph, extra), vb.PackedBatch(small.graph, alns)])
+        f1, _, _ = _oracle(small, extra, bep=2e-3)
+        f2, _, _ = _oracle(small, alns, bep=2e-3)
+        final = np.asarray(f1, dtype=np.longdouble) + np.asarray(f2, dtype=np.longdouble)
+        _check(res, final, int(np.argmax(final)), small)
+        hc.close()
+        return
+    hc = vb.Haplocart()
+    hc.load(small.tables(bep=1e-3, is_fasta=True), small.tree())
+    res = hc.run_sample([vb.PackedBatch(small.graph, reads)])
+    final, argmax, _ = _oracle(small, reads, bep=1e-3, is_fasta=True)
+    _check(res, final, argmax, small)
+    hc.close()
+
+
 def test_literal_reference_shaped_oracle_agrees_too(small):
     alns = small.reads(40, seed=203)
     hc = vb.Haplocart()

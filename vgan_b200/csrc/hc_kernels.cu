@@ -80,6 +80,7 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) { uint4 v; asm vo
 constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_pair);
 constexpr uint32_t kOffLogTab = offsetof(HcSmallTables, log_tab);
 constexpr uint32_t kOffBg = offsetof(HcSmallTables, bg);
+constexpr uint32_t kOffPCorrect = offsetof(HcSmallTables, p_correct);
 
 // log(x) for x > 0 (x == 0 gives -inf): 8-bit table on the mantissa + degree-5 log1p of the remainder (|r| < 2^-9).
 // Absolute error ~1e-16 (one ulp of ln 2 when the exponent is non-zero), which is what a SUM of logs needs; the result
@@ -131,10 +132,12 @@ constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
-    uint32_t f, bg, logtab, node_class, ac, queue;  // shared byte addresses (queue: this warp's ring)
-    double* acc;                                     // this CTA's node vector (global, lives in L2)
+    uint32_t f, bg, logtab, node_class, ac, queue, p_correct;  // shared byte addresses (queue: this warp's ring)
+    double* acc;                                                // this CTA's node vector (global, lives in L2)
+    const double2* class_tab;                                   // [n_class + 1] {mappability, K}; last entry neutral
     int n_rows, n_class;
-    double le0;
+    bool fasta;
+    double le0, one_minus_bep;
 };
 
 // What a lane needs to know about its read of a group; loaded one group ahead of use.
@@ -185,13 +188,19 @@ __device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uin
 // One group.  On entry v0, v1 hold its last two column blocks (the walk is descending); on exit they hold those of
 // the warp's next group `gn`, whose header is loaded here as well: neither the header nor the first blocks of a
 // group are ever waited for.  q_head / q_tail: the warp's close queue (uniform across the warp).
+template <int kAcMode>
 __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const ReadKernelShared& S, uint32_t g, uint32_t gn, const GroupHdr& H,
                                                  GroupHdr& Hn, uint4& v0, uint4& v1, uint32_t& q_head, uint32_t& q_tail, int lane,
                                                  double& a_sum, uint32_t& bad_cls, bool& bad_node) {
     const double scale = -0.23025850929940456840;
     Hn = hc_load_hdr(b, gn, lane);
     const int ncb = H.ncb;
-    const uint32_t ac_row = S.ac + 16u * (uint32_t)(S.n_class + 1) * H.mapq;
+    // kAcMode 0: S.ac is the {1 - pcm, pcm * K} table [100][n_class + 1] in shared memory -> row of this read's mapping quality
+    // kAcMode 1: S.ac is the class table {mappability, K} [n_class + 1] in shared memory (too many classes for mode 0)
+    // kAcMode 2: the class table stays in global memory (S.class_tab)
+    const uint32_t ac_row = kAcMode == 0 ? S.ac + 16u * (uint32_t)(S.n_class + 1) * H.mapq : S.ac;
+    const double pc = kAcMode == 0 ? 0.0 : lds_f64_c(S.p_correct + 8u * H.mapq);  // 1 - p_incorrect_map[mapq]
+    double mk_m = 0.0, mk_k = 0.0;                                                 // modes 1, 2: {mappability, K} of the open mapping
     const uint32_t lt_mask = (1u << lane) - 1u;
     int x = H.n_extra - 1;  // empty mappings (no column of their own): rare, handled on the side
     bool rare = x >= 0;     // ... as is a rescaled product
@@ -221,9 +230,25 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         const uint32_t open = rec & VGL_HC_COL_OPEN;
         // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
         bad_cls = max(bad_cls, open ? cls : 0u);
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
-            : "+d"(aa), "+d"(cc)
-            : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
+        if (kAcMode == 0) {
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
+                : "+d"(aa), "+d"(cc)
+                : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
+        } else {
+            if (kAcMode == 1)
+                asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
+                    : "+d"(mk_m), "+d"(mk_k)
+                    : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
+            else
+                asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.f64 {%0,%1}, [%2];\n\t}"
+                    : "+d"(mk_m), "+d"(mk_k)
+                    : "l"(S.class_tab + min(cls, (uint32_t)S.n_class)), "r"(open));
+            // p_correctly_mapped = (1 - p_incorrect[mq]) * mappability (src/process_mapping.cpp:41); consensus-FASTA mode
+            // uses (1 - bep) * K alone (:73)
+            const double pcm = pc * mk_m;
+            aa = S.fasta ? 0.0 : 1.0 - pcm;
+            cc = (S.fasta ? S.one_minus_bep : pcm) * mk_k;
+        }
         const double px = prod * fma(cc, f, aa * bgv);
         prod = (rec & VGL_HC_COL_VALID) ? px : prod;
         const uint32_t close = rec & VGL_HC_COL_CLOSE;
@@ -309,6 +334,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     }
 }
 
+template <int kAcMode>
 __global__ void __launch_bounds__(kReadBlock, 1)
 hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
                int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
@@ -318,8 +344,8 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     off += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
     off += ((size_t)(t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // entry n_rows: "no such node"
-    double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // [100][n_class + 1]
-    off += (size_t)100 * (t.n_class + 1) * sizeof(double2);
+    double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // mode 0: [100][n_class + 1]; mode 1: [n_class + 1]
+    off += (kAcMode == 0 ? (size_t)100 : kAcMode == 1 ? (size_t)1 : (size_t)0) * (t.n_class + 1) * sizeof(double2);
     uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + off);  // [warps][kQueueSlots]
     __shared__ double s_warp_a[kReadBlock / 32];
 
@@ -335,7 +361,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         for (int k = tid; k < (int)(sizeof(HcSmallTables) / 4); k += kReadBlock) dst[k] = src[k];
     }
     __syncthreads();
-    {
+    if (kAcMode == 0) {
         // {1 - pcm, pcm * K} for every (mapping quality, class): p_correctly_mapped = (1 - p_incorrect[mq]) * mappability
         // (src/process_mapping.cpp:41); consensus-FASTA mode uses (1 - bep) * K alone (:73)
         const bool fasta = s_tab->is_fasta != 0;
@@ -347,6 +373,8 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
             const double pcm = s_tab->p_correct[mq] * mk.x;
             s_ac[k] = make_double2(fasta ? 0.0 : 1.0 - pcm, (fasta ? s_tab->one_minus_bep : pcm) * mk.y);
         }
+    } else if (kAcMode == 1) {
+        for (int k = tid; k <= t.n_class; k += kReadBlock) s_ac[k] = t.class_tab[k];  // entry n_class: {0, 0}
     }
     __syncthreads();
 
@@ -357,6 +385,10 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     S.logtab = smem_u32(s_tab) + kOffLogTab;
     S.node_class = smem_u32(s_class);
     S.ac = smem_u32(s_ac);
+    S.p_correct = smem_u32(s_tab) + kOffPCorrect;
+    S.class_tab = t.class_tab;
+    S.fasta = s_tab->is_fasta != 0;
+    S.one_minus_bep = s_tab->one_minus_bep;
     S.queue = smem_u32(s_queue + (size_t)warp * kQueueSlots);
     S.n_rows = t.n_rows;
     S.n_class = t.n_class;
@@ -372,7 +404,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     uint4 v0 = hc_fetch(H, H.ncb - 1), v1 = hc_fetch(H, H.ncb - 2);
     while (g < b.n_groups) {
         const uint32_t gn = g + warps_total;
-        hc_process_group(b, S, g, gn, H, Hn, v0, v1, q_head, q_tail, lane, a_sum, bad_cls, bad_node);
+        hc_process_group<kAcMode>(b, S, g, gn, H, Hn, v0, v1, q_head, q_tail, lane, a_sum, bad_cls, bad_node);
         H = Hn;
         g = gn;
     }
@@ -547,15 +579,15 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
     for (int k = warp; k < n_anc; k += kPostBlock / 32) {
         const int clade = anc_clade[anc_off[call] + k];
         const uint32_t* bits = clade_bits + (size_t)clade * row_words;
+        // lane l looks at bit l of every word (one uniform load per word, independent iterations): a clade near the
+        // root holds thousands of paths, walking its set bits one by one would serialise the whole kernel
         double s = 0.0;
-        for (int w = lane; w < row_words; w += 32) {
-            uint32_t word = bits[w];
-            const int pbase = w * 32;
-            while (word) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                if (pbase + bit < n_paths) s += s_e[pbase + bit];
-            }
+#pragma unroll 8
+        for (int w = 0; w < row_words; ++w) {
+            const uint32_t word = __ldg(bits + w);
+            const int p = w * 32 + lane;
+            const double e = p < n_paths ? s_e[p] : 0.0;
+            s += ((word >> lane) & 1u) ? e : 0.0;
         }
         s = warp_sum_f64(s);
         if (lane == 0) post[1 + k] = s / tot;
@@ -571,32 +603,40 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // ------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------
-static size_t read_smem_bytes(int n_rows, int n_class) {
+static size_t read_smem_bytes(int n_rows, int n_class, int ac_mode) {
     size_t s = 0;
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     s += ((size_t)(n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    s += (size_t)100 * (n_class + 1) * sizeof(double2);
+    s += (ac_mode == 0 ? (size_t)100 : ac_mode == 1 ? (size_t)1 : (size_t)0) * (n_class + 1) * sizeof(double2);
     s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }
 
-HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin) {
+HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin, int force_mode) {
     HcReadLaunch c;
     c.grid = sm_count;
     c.block = kReadBlock;
-    c.smem = read_smem_bytes(n_rows, n_class);
-    if (c.smem + 256 > (size_t)max_smem_optin) c.grid = 0;  // caller reports VGL_ERR_INVALID (tables too large for this layout)
+    // the fastest table layout that fits: per-(mapq, class) constants, else the class table, else the class table in global memory
+    for (c.ac_mode = force_mode >= 0 ? force_mode : 0; c.ac_mode < 3; ++c.ac_mode) {
+        c.smem = read_smem_bytes(n_rows, n_class, c.ac_mode);
+        if (c.smem + 256 <= (size_t)max_smem_optin) return c;
+        if (force_mode >= 0) break;
+    }
+    c.grid = 0;  // caller reports VGL_ERR_INVALID (node table too large for this layout)
     return c;
 }
 
-cudaError_t hc_read_configure(size_t smem) {
-    return cudaFuncSetAttribute(hc_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t hc_read_configure(const HcReadLaunch& cfg) {
+    const void* fn = cfg.ac_mode == 0 ? (const void*)hc_read_kernel<0> : cfg.ac_mode == 1 ? (const void*)hc_read_kernel<1> : (const void*)hc_read_kernel<2>;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
 }
 
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
                                   double* cta_node_acc, double* cta_a_total, int* err_flag,
                                   unsigned long long* stats, cudaStream_t s) {
-    hc_read_kernel<<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
+    if (cfg.ac_mode == 0) hc_read_kernel<0><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
+    else if (cfg.ac_mode == 1) hc_read_kernel<1><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
+    else hc_read_kernel<2><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
     return cudaGetLastError();
 }
 

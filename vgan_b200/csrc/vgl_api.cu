@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -415,11 +416,15 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
         }
     }
 
-    ctx->read_cfg = vgl::hc_read_launch_config(N, (int)class_tab.size(), ctx->sm_count, ctx->max_smem_optin);
+    const int n_class = (int)class_tab.size();
+    class_tab.push_back(make_double2(0.0, 0.0));  // neutral entry for nodes without a class
+    int force_mode = -1;  // VGL_HC_TABLE_MODE=0|1|2 pins the table layout of the read kernel (tests)
+    if (const char* e = getenv("VGL_HC_TABLE_MODE")) force_mode = atoi(e);
+    ctx->read_cfg = vgl::hc_read_launch_config(N, n_class, ctx->sm_count, ctx->max_smem_optin, force_mode);
     if (ctx->read_cfg.grid == 0)
-        return fail(VGL_ERR_INVALID, "%d node rows and %zu (mappability, match probability) classes need %zu bytes of shared memory per CTA (limit %d)", N,
-                    class_tab.size(), ctx->read_cfg.smem, ctx->max_smem_optin);
-    VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg.smem));
+        return fail(VGL_ERR_INVALID, "%d node rows need %zu bytes of shared memory per CTA (limit %d)", N, ctx->read_cfg.smem,
+                    ctx->max_smem_optin);
+    VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg));
 
     if (int rc = ctx->d_node_class.reserve((size_t)N)) return rc;
     if (int rc = ctx->d_class_tab.reserve(class_tab.size())) return rc;
@@ -433,7 +438,7 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     ctx->tab.n_rows = N;
     ctx->tab.n_paths = P;
     ctx->tab.n_words = n_words;
-    ctx->tab.n_class = (int)class_tab.size();
+    ctx->tab.n_class = n_class;
     ctx->tab.node_class = ctx->d_node_class.p;
     ctx->tab.class_tab = ctx->d_class_tab.p;
     ctx->tab.small = ctx->d_small.p;

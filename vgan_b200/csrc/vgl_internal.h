@@ -36,7 +36,7 @@ struct HcTablesDev {
     int32_t n_words;           // number of 32-node words = ceil(n_rows / 32)
     int32_t n_class;
     const uint16_t* node_class; // [n_rows]   0xFFFF = node has no pangenome_map entry
-    const double2* class_tab;   // [n_class]  {mappability, match_prob}
+    const double2* class_tab;   // [n_class + 1]  {mappability, match_prob}; entry n_class = {0, 0}
     const HcSmallTables* small;
     const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
 };
@@ -58,10 +58,12 @@ struct HcReadLaunch {
     int grid;
     int block;
     size_t smem;
+    int ac_mode;  // 0: {1 - pcm, pcm * K} per (mapq, class) in shared memory; 1: class table in shared memory; 2: in global memory
 };
 
-HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin);
-cudaError_t hc_read_configure(size_t smem);
+// force_mode < 0: the fastest mode that fits the shared-memory limit.
+HcReadLaunch hc_read_launch_config(int n_rows, int n_class, int sm_count, int max_smem_optin, int force_mode);
+cudaError_t hc_read_configure(const HcReadLaunch& cfg);
 
 // K1: per-read, per-mapping scalars added into VGL_HC_ACC_COPIES node vectors (CTA b adds into copy b % copies).
 //   node_acc[copy][n_words * 32]  += sum over the copy's mappings at node n of (B_i - A_i)
