@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_rate(S, alns, seconds_target, threads=0):
+def cpu_reference_rate(S, alns, seconds_target, threads=0, hoisted=False):
     """Time the literal (reference-shaped) CPU restatement on a bounded sample; returns a dict."""
     from oracle import oracle as orc
     node, val = S.pmap()
@@ -119,10 +119,19 @@ def cpu_reference_rate(S, alns, seconds_target, threads=0):
     t = time.perf_counter()
     _, argmax, used = orc.hc_run(T, G, R, r0=0, r1=n, mode=orc.MODE_LITERAL, n_threads=cores)
     dt = time.perf_counter() - t
-    return {"value": used * N_PATHS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d reads of the same synthetic set, literal per-path loops (oracle MODE_LITERAL, long double, "
-                      "-O3 -fopenmp), %.1f s wall" % (n, dt),
-            "reads": used, "seconds": dt}
+    out = {"value": used * N_PATHS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "first %d reads of the same synthetic set, literal per-path loops (oracle MODE_LITERAL, long double, "
+                     "-O3 -fopenmp), %.1f s wall" % (n, dt),
+           "reads": used, "seconds": dt}
+    if hoisted:
+        # the fair optimised-CPU comparator: A_i / B_i once per mapping, then the per-path select-add
+        nh = int(min(len(alns), 20 * n))
+        t = time.perf_counter()
+        _, _, uh = orc.hc_run(T, G, R, r0=0, r1=nh, mode=orc.MODE_HOISTED, n_threads=cores)
+        dth = time.perf_counter() - t
+        out["hoisted"] = {"value": uh * N_PATHS / dth, "reads": uh, "seconds": dth,
+                          "what": "same oracle with A_i / B_i computed once per mapping (MODE_HOISTED)"}
+    return out
 
 
 def run_reference(args):
@@ -208,7 +217,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     hc.set_stream(stream.cuda_stream)
+    t_pack = time.perf_counter()
     packed = vb.PackedBatch(S.graph, alns, pinned=True)
+    t_pack = time.perf_counter() - t_pack
     dev = hc.upload(packed)
     reads_local = packed.n_reads
     batch_bytes = packed.nbytes
@@ -270,6 +281,20 @@ def main():
     ms_e2e, _, _, _, res_e2e = timed(True, e2e_steps)
     clocks = sampler.finish()
 
+    # per-sample latency at the size one real sample can reach after duplicate removal (SURVEY 8d scale caveat):
+    # host batch -> H2D -> kernels -> posterior on the host, one sample at a time
+    latency = None
+    if world == 1:
+        n_lat = min(20000, len(alns))
+        small = vb.PackedBatch(S.graph, alns, r0=0, r1=n_lat, pinned=True)
+        for _ in range(3):
+            hc.run_sample([small], want_ll=False)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            hc.run_sample([small], want_ll=False)
+        latency = {"reads": small.n_reads, "ms_per_sample": (time.perf_counter() - t0) / 20 * 1e3,
+                   "what": "reset + accumulate (host batch) + finalize, host wall clock, mean of 20"}
+
     total_reads = reads_local
     if world > 1:
         t = torch.tensor([reads_local], dtype=torch.float64, device="cuda")
@@ -302,14 +327,18 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 28 + 8 * hc._max_post,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "latency": latency,
+            "host_pack": {"seconds": t_pack, "reads_per_s": reads_local / t_pack, "threads": os.cpu_count(),
+                          "what": "vgh_hc_pack (reconstruction + packing, OpenMP) of the step's batch; outside the timed regions"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "hc_read_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "batch_bytes_with_padding": batch_bytes,
-                         "kernel_ms": kernel_ms, "bytes_per_read": alg_bytes / max(reads_local, 1)},
+                         "kernel_ms": kernel_ms, "bytes_per_read": alg_bytes / max(reads_local, 1),
+                         "frac_at_survey_562B_per_read": 562.0 * reads_local / (kernel_ms * 1e-3) / 1e9 / peak},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(S, alns, args.cpu_seconds)
+            line["cpu_baseline"] = cpu_reference_rate(S, alns, args.cpu_seconds, hoisted=True)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Throughput of the euka and soibean sibling kernels (reduced read counts), end to end
+through the C ABI with host batches (H2D and the per-read results' D2H inside the timed region).
+Usage: python profiles/bench_siblings.py [euka_reads] [soibean_reads]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import vgan_b200 as vb
+
+n_euka = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+n_soi = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+out = {}
+
+S = vb.SynthEuka(seed=20264, n_clades=335)
+alns = S.reads(n_euka, seed=20265)
+t = time.perf_counter()
+pb = vb.EukaPackedBatch(S.graph, alns, pinned=True)
+pack_s = time.perf_counter() - t
+ek = vb.Euka()
+ek.load(S.tables(vb.DHIGH5P_PROF, vb.DHIGH3P_PROF))
+cols = int(np.diff(alns.arrays()["seq_off"]).sum())
+for _ in range(2):
+    ek.reset(); ek.run(pb)
+t = time.perf_counter()
+for _ in range(5):
+    ek.reset(); res = ek.run(pb)
+dt = (time.perf_counter() - t) / 5
+out["euka"] = {"reads": pb.n_reads, "clades": 335, "reads_per_s": pb.n_reads / dt, "read_bases_per_s": cols / dt, "ms": dt * 1e3,
+               "batch_bytes": pb.nbytes, "host_pack_s": pack_s,
+               "what": "config 4 shape: vgl_euka_run on a host batch incl. H2D and per-read D2H; evaluations = reads"}
+ek.close()
+
+for P in (31, 127, 399):
+    Sh = vb.SynthHaplocart(seed=20266, n_paths=P, n_rows=11825, n_nodes=11821)
+    al = Sh.reads(n_soi, seed=20267, fixed_len=0, sub_rate=0.01, indel_rate=0.001, damage=True)
+    sb = vb.Soibean()
+    sb.load(vb.SoibeanTables(Sh.supports(), 0, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 7))
+    pk = vb.SoibeanPackedBatch(Sh.graph, al, pinned=True)
+    sb.analyse(pk)
+    t = time.perf_counter()
+    for _ in range(3):
+        got, used = sb.analyse(pk)
+    dt = (time.perf_counter() - t) / 3
+    out["soibean_P%d" % P] = {"reads": pk.n_reads, "paths": P, "evals_per_s": pk.n_reads * P / dt, "reads_per_s": pk.n_reads / dt,
+                              "ms": dt * 1e3, "out_bytes": int(got.nbytes),
+                              "what": "config 5 shape: vgl_soibean_run incl. H2D and the R x P matrix D2H into pageable numpy"}
+    sb.close()
+print("SIBLINGS", json.dumps(out))

@@ -129,13 +129,16 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
+// bytes per mapping-quality row of the {1 - pcm, pcm * K} table: an odd number of 16-byte entries, so that the same class
+// in rows of different mapping qualities falls into different banks
+__host__ __device__ constexpr int ac_row_bytes(int n_class) { return 16 * ((n_class + 1) | 1); }
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
     uint32_t f, bg, logtab, node_class, ac, queue, p_correct;  // shared byte addresses (queue: this warp's ring)
     double* acc;                                                // this CTA's node vector (global, lives in L2)
     const double2* class_tab;                                   // [n_class + 1] {mappability, K}; last entry neutral
-    int n_rows, n_class;
+    int n_rows, n_class, ac_stride;  // ac_stride: bytes per mapping-quality row of the mode-0 table
     bool fasta;
     double le0, one_minus_bep;
 };
@@ -198,7 +201,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // kAcMode 0: S.ac is the {1 - pcm, pcm * K} table [100][n_class + 1] in shared memory -> row of this read's mapping quality
     // kAcMode 1: S.ac is the class table {mappability, K} [n_class + 1] in shared memory (too many classes for mode 0)
     // kAcMode 2: the class table stays in global memory (S.class_tab)
-    const uint32_t ac_row = kAcMode == 0 ? S.ac + 16u * (uint32_t)(S.n_class + 1) * H.mapq : S.ac;
+    const uint32_t ac_row = kAcMode == 0 ? S.ac + (uint32_t)S.ac_stride * H.mapq : S.ac;
     const double pc = kAcMode == 0 ? 0.0 : lds_f64_c(S.p_correct + 8u * H.mapq);  // 1 - p_incorrect_map[mapq]
     double mk_m = 0.0, mk_k = 0.0;                                                 // modes 1, 2: {mappability, K} of the open mapping
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -300,7 +303,12 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         for (int j = 0; j < 4; ++j) {
             f[j] = lds_f64_c(S.f + 8u * (rec[j] & 0x3ffu));
             bgv[j] = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec[j]));
-            cls[j] = lds_u16_c(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows));  // entry n_rows: 0xFFFF
+            // the class is needed where a mapping opens only: predicated, so that the other lanes cost no bank conflicts
+            uint16_t c16 = 0;
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
+                : "+h"(c16)
+                : "r"(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: 0xFFFF
+            cls[j] = c16;
         }
         const int c4 = cb * VGL_HC_COL_BLK;
         if (__any_sync(kFull, rare)) {
@@ -345,7 +353,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
     off += ((size_t)(t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // entry n_rows: "no such node"
     double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // mode 0: [100][n_class + 1]; mode 1: [n_class + 1]
-    off += (kAcMode == 0 ? (size_t)100 : kAcMode == 1 ? (size_t)1 : (size_t)0) * (t.n_class + 1) * sizeof(double2);
+    off += kAcMode == 0 ? (size_t)100 * ac_row_bytes(t.n_class) : kAcMode == 1 ? (size_t)(t.n_class + 1) * sizeof(double2) : (size_t)0;
     uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + off);  // [warps][kQueueSlots]
     __shared__ double s_warp_a[kReadBlock / 32];
 
@@ -366,12 +374,14 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         // (src/process_mapping.cpp:41); consensus-FASTA mode uses (1 - bep) * K alone (:73)
         const bool fasta = s_tab->is_fasta != 0;
         const int row = t.n_class + 1;  // entry n_class of every row is the neutral {1, 0} used for unknown nodes
+        const int stride = ac_row_bytes(t.n_class) / 16;
         for (int k = tid; k < 100 * row; k += kReadBlock) {
             const int mq = k / row, cls = k - mq * row;
-            if (cls == t.n_class) { s_ac[k] = make_double2(1.0, 0.0); continue; }
+            double2& dst = s_ac[mq * stride + cls];
+            if (cls == t.n_class) { dst = make_double2(1.0, 0.0); continue; }
             const double2 mk = t.class_tab[cls];  // {mappability, match_prob}
             const double pcm = s_tab->p_correct[mq] * mk.x;
-            s_ac[k] = make_double2(fasta ? 0.0 : 1.0 - pcm, (fasta ? s_tab->one_minus_bep : pcm) * mk.y);
+            dst = make_double2(fasta ? 0.0 : 1.0 - pcm, (fasta ? s_tab->one_minus_bep : pcm) * mk.y);
         }
     } else if (kAcMode == 1) {
         for (int k = tid; k <= t.n_class; k += kReadBlock) s_ac[k] = t.class_tab[k];  // entry n_class: {0, 0}
@@ -392,6 +402,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     S.queue = smem_u32(s_queue + (size_t)warp * kQueueSlots);
     S.n_rows = t.n_rows;
     S.n_class = t.n_class;
+    S.ac_stride = ac_row_bytes(t.n_class);
     S.le0 = s_tab->log_err[0];
 
     double a_sum = 0.0;
@@ -607,7 +618,7 @@ static size_t read_smem_bytes(int n_rows, int n_class, int ac_mode) {
     size_t s = 0;
     s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
     s += ((size_t)(n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    s += (ac_mode == 0 ? (size_t)100 : ac_mode == 1 ? (size_t)1 : (size_t)0) * (n_class + 1) * sizeof(double2);
+    s += ac_mode == 0 ? (size_t)100 * ac_row_bytes(n_class) : ac_mode == 1 ? (size_t)(n_class + 1) * sizeof(double2) : (size_t)0;
     s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }
