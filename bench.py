@@ -42,9 +42,11 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def workload(n_gpus, reads):
-    if n_gpus == 1:
-        return dict(name="HaploCart config 2: synthetic %d x 100bp reads x %d paths" % (reads, N_PATHS), seed=20261,
+def workload(n_gpus, reads, config=2):
+    """Config 2 (BASELINE.json configs[1]) is the bench workload at every N: the same reads-per-GPU, so the per-N values
+    are one weak-scaling series.  --workload 3 selects the config-3 shape (ancient-damaged reads, log-normal lengths)."""
+    if config == 2:
+        return dict(name="HaploCart config 2: synthetic %d x 100bp reads per GPU x %d paths" % (reads, N_PATHS), seed=20261,
                     kw=dict(fixed_len=100, sub_rate=0.005, indel_rate=0.0005, damage=False))
     return dict(name="HaploCart config 3 shape: synthetic ancient-damaged reads (log-normal 30-150bp), %d per GPU x %d "
                      "paths" % (reads, N_PATHS), seed=20263,
@@ -141,7 +143,7 @@ def run_reference(args):
         return 0
     import vgan_b200 as vb
     from oracle import oracle as orc
-    wl = workload(args.gpus, args.reads)
+    wl = workload(args.gpus, args.reads, args.workload)
     S = vb.SynthHaplocart(seed=TABLE_SEED, n_paths=N_PATHS, n_rows=N_ROWS, n_nodes=N_NODES)
     cores = os.cpu_count() or 1
     # bounded sample: sized so that warmup + steps end within a few minutes
@@ -185,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="vgan_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--workload", type=int, default=2, choices=[2, 3], help="SURVEY 8d config whose read shape is generated")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,7 +211,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
-    wl = workload(n_gpus, args.reads)
+    wl = workload(n_gpus, args.reads, args.workload)
     S = vb.SynthHaplocart(seed=TABLE_SEED, n_paths=N_PATHS, n_rows=N_ROWS, n_nodes=N_NODES)
     alns = S.reads(args.reads, seed=wl["seed"] + 1000 * rank, **wl["kw"])
     hc = vb.Haplocart(device=local)

@@ -8,7 +8,7 @@ import vgan_b200 as vb
 import bench
 
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-wl = bench.workload(1, reads)
+wl = bench.workload(1, reads, 2)
 S = vb.SynthHaplocart(seed=bench.TABLE_SEED, n_paths=bench.N_PATHS, n_rows=bench.N_ROWS, n_nodes=bench.N_NODES)
 alns = S.reads(reads, seed=wl["seed"], **wl["kw"])
 hc = vb.Haplocart(0)

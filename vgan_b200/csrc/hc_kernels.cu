@@ -129,9 +129,6 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
-// bytes per mapping-quality row of the {1 - pcm, pcm * K} table: an odd number of 16-byte entries, so that the same class
-// in rows of different mapping qualities falls into different banks
-__host__ __device__ constexpr int ac_row_bytes(int n_class) { return 16 * ((n_class + 1) | 1); }
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
@@ -347,46 +344,30 @@ __global__ void __launch_bounds__(kReadBlock, 1)
 hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
                int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    size_t off = 0;
-    HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + off);
-    off += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
-    uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + off);
-    off += ((size_t)(t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // entry n_rows: "no such node"
-    double2* s_ac = reinterpret_cast<double2*>(smem_raw + off);  // mode 0: [100][n_class + 1]; mode 1: [n_class + 1]
-    off += kAcMode == 0 ? (size_t)100 * ac_row_bytes(t.n_class) : kAcMode == 1 ? (size_t)(t.n_class + 1) * sizeof(double2) : (size_t)0;
-    uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + off);  // [warps][kQueueSlots]
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_warp_a[kReadBlock / 32];
+    const HcImageLayout L = t.layout;
+    HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + L.off_small);
+    uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + L.off_class);
+    double2* s_ac = reinterpret_cast<double2*>(smem_raw + L.off_ac);  // mode 0: [100][row]; mode 1: [n_class + 1]
+    uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + ((L.bytes + 127u) & ~127u));  // [warps][kQueueSlots]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
-    for (int n = tid; n < t.n_rows; n += kReadBlock) s_class[n] = t.node_class[n];
-    if (tid == 0) s_class[t.n_rows] = 0xFFFFu;
+    // the tables arrive as one TMA bulk copy of the prepared image (cp.async.bulk -> UBLKCP)
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_tab);
-        for (int k = tid; k < (int)(sizeof(HcSmallTables) / 4); k += kReadBlock) dst[k] = src[k];
-    }
-    __syncthreads();
-    if (kAcMode == 0) {
-        // {1 - pcm, pcm * K} for every (mapping quality, class): p_correctly_mapped = (1 - p_incorrect[mq]) * mappability
-        // (src/process_mapping.cpp:41); consensus-FASTA mode uses (1 - bep) * K alone (:73)
-        const bool fasta = s_tab->is_fasta != 0;
-        const int row = t.n_class + 1;  // entry n_class of every row is the neutral {1, 0} used for unknown nodes
-        const int stride = ac_row_bytes(t.n_class) / 16;
-        for (int k = tid; k < 100 * row; k += kReadBlock) {
-            const int mq = k / row, cls = k - mq * row;
-            double2& dst = s_ac[mq * stride + cls];
-            if (cls == t.n_class) { dst = make_double2(1.0, 0.0); continue; }
-            const double2 mk = t.class_tab[cls];  // {mappability, match_prob}
-            const double pcm = s_tab->p_correct[mq] * mk.x;
-            dst = make_double2(fasta ? 0.0 : 1.0 - pcm, (fasta ? s_tab->one_minus_bep : pcm) * mk.y);
+        const uint32_t bar = smem_u32(&s_bar);
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, L.bytes);
+            bulk_g2s(smem_u32(smem_raw), t.image, L.bytes, bar);
         }
-    } else if (kAcMode == 1) {
-        for (int k = tid; k <= t.n_class; k += kReadBlock) s_ac[k] = t.class_tab[k];  // entry n_class: {0, 0}
+        __syncthreads();
+        mbar_wait(bar, 0);
     }
-    __syncthreads();
 
     ReadKernelShared S;
     S.acc = cta_node_acc + (size_t)(blockIdx.x % kAccCopies) * (size_t)(t.n_words * 32);
@@ -402,7 +383,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     S.queue = smem_u32(s_queue + (size_t)warp * kQueueSlots);
     S.n_rows = t.n_rows;
     S.n_class = t.n_class;
-    S.ac_stride = ac_row_bytes(t.n_class);
+    S.ac_stride = (int)L.ac_row_bytes;
     S.le0 = s_tab->log_err[0];
 
     double a_sum = 0.0;
@@ -615,10 +596,7 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // launch wrappers
 // ------------------------------------------------------------------------------------------
 static size_t read_smem_bytes(int n_rows, int n_class, int ac_mode) {
-    size_t s = 0;
-    s += (sizeof(HcSmallTables) + 15) & ~(size_t)15;
-    s += ((size_t)(n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    s += ac_mode == 0 ? (size_t)100 * ac_row_bytes(n_class) : ac_mode == 1 ? (size_t)(n_class + 1) * sizeof(double2) : (size_t)0;
+    size_t s = ((size_t)hc_image_layout(n_rows, n_class, ac_mode).bytes + 127) & ~(size_t)127;
     s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }

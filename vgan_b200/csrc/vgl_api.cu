@@ -72,9 +72,8 @@ struct vgl_ctx {
     vgl::HcTablesDev tab{};
     int row_words = 0;
     int n_rows_pad = 0;
-    DevBuf<uint16_t> d_node_class;
     DevBuf<double2> d_class_tab;
-    DevBuf<vgl::HcSmallTables> d_small;
+    DevBuf<unsigned char> d_image;  // the read kernel's shared-memory image (vgl::HcImageLayout)
     DevBuf<uint32_t> d_node_bits;
     vgl::HcReadLaunch read_cfg{};
 
@@ -243,7 +242,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_node_class.release(); ctx->d_class_tab.release(); ctx->d_small.release(); ctx->d_node_bits.release();
+    ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release();
     ctx->d_cta_node_acc.release();
     ctx->d_chunk_ll.release(); ctx->d_ll.release();
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
@@ -426,22 +425,45 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
                     ctx->max_smem_optin);
     VGL_CUDA(vgl::hc_read_configure(ctx->read_cfg));
 
-    if (int rc = ctx->d_node_class.reserve((size_t)N)) return rc;
+    // the read kernel's shared-memory image
+    const vgl::HcImageLayout L = vgl::hc_image_layout(N, n_class, ctx->read_cfg.ac_mode);
+    std::vector<unsigned char> image((size_t)L.bytes, 0);
+    memcpy(image.data() + L.off_small, &small, sizeof(small));
+    {
+        uint16_t* cls = reinterpret_cast<uint16_t*>(image.data() + L.off_class);
+        memcpy(cls, node_class.data(), (size_t)N * sizeof(uint16_t));
+        cls[N] = 0xFFFFu;  // "no such node"
+        double2* ac = reinterpret_cast<double2*>(image.data() + L.off_ac);
+        if (ctx->read_cfg.ac_mode == 0) {
+            // {1 - pcm, pcm * K} for every (mapping quality, class): p_correctly_mapped = (1 - p_incorrect[mq]) * mappability
+            // (src/process_mapping.cpp:41); consensus-FASTA mode uses (1 - bep) * K alone (:73)
+            const size_t stride = L.ac_row_bytes / 16;
+            for (int mq = 0; mq < 100; ++mq) {
+                for (int c = 0; c < n_class; ++c) {
+                    const double pcm = small.p_correct[mq] * class_tab[(size_t)c].x;
+                    ac[(size_t)mq * stride + c] = make_double2(small.is_fasta ? 0.0 : 1.0 - pcm,
+                                                               (small.is_fasta ? small.one_minus_bep : pcm) * class_tab[(size_t)c].y);
+                }
+                ac[(size_t)mq * stride + n_class] = make_double2(1.0, 0.0);  // neutral entry for unknown nodes
+            }
+        } else if (ctx->read_cfg.ac_mode == 1) {
+            memcpy(ac, class_tab.data(), class_tab.size() * sizeof(double2));
+        }
+    }
     if (int rc = ctx->d_class_tab.reserve(class_tab.size())) return rc;
-    if (int rc = ctx->d_small.reserve(1)) return rc;
+    if (int rc = ctx->d_image.reserve(image.size())) return rc;
     if (int rc = ctx->d_node_bits.reserve(node_bits.size())) return rc;
-    VGL_CUDA(cudaMemcpy(ctx->d_node_class.p, node_class.data(), (size_t)N * sizeof(uint16_t), cudaMemcpyHostToDevice));
     VGL_CUDA(cudaMemcpy(ctx->d_class_tab.p, class_tab.data(), class_tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    VGL_CUDA(cudaMemcpy(ctx->d_small.p, &small, sizeof(small), cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->d_image.p, image.data(), image.size(), cudaMemcpyHostToDevice));
     VGL_CUDA(cudaMemcpy(ctx->d_node_bits.p, node_bits.data(), node_bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
     ctx->tab.n_rows = N;
     ctx->tab.n_paths = P;
     ctx->tab.n_words = n_words;
     ctx->tab.n_class = n_class;
-    ctx->tab.node_class = ctx->d_node_class.p;
     ctx->tab.class_tab = ctx->d_class_tab.p;
-    ctx->tab.small = ctx->d_small.p;
+    ctx->tab.image = ctx->d_image.p;
+    ctx->tab.layout = L;
     ctx->tab.node_bits = ctx->d_node_bits.p;
     ctx->row_words = (P + 31) / 32;
     ctx->n_rows_pad = n_words * 32;

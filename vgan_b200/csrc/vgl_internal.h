@@ -30,14 +30,33 @@ struct HcSmallTables {
     int32_t pad;
 };
 
+// The read kernel's constant tables live in global memory as one image with exactly the layout they have in shared
+// memory; every CTA fetches it with a single TMA bulk copy.
+//   [ HcSmallTables | node_class u16[n_rows + 1] (entry n_rows = 0xFFFF) | mode 0: {1 - pcm, pcm * K} double2[100][row]
+//                                                                          mode 1: class table double2[n_class + 1] ]
+// row = an odd number of 16-byte entries >= n_class + 1, so that one class in rows of different mapping qualities falls
+// into different banks; entry n_class of every row is the neutral {1, 0} (class table: {0, 0}).
+struct HcImageLayout {
+    uint32_t off_small, off_class, off_ac, ac_row_bytes, bytes;
+};
+inline HcImageLayout hc_image_layout(int n_rows, int n_class, int ac_mode) {
+    HcImageLayout L;
+    L.off_small = 0;
+    L.off_class = (uint32_t)((sizeof(HcSmallTables) + 15) & ~(size_t)15);
+    L.off_ac = L.off_class + (uint32_t)((((size_t)n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
+    L.ac_row_bytes = 16u * (uint32_t)((n_class + 1) | 1);
+    L.bytes = L.off_ac + (ac_mode == 0 ? 100u * L.ac_row_bytes : ac_mode == 1 ? 16u * (uint32_t)(n_class + 1) : 0u);
+    return L;
+}
+
 struct HcTablesDev {
     int32_t n_rows;
     int32_t n_paths;
     int32_t n_words;           // number of 32-node words = ceil(n_rows / 32)
     int32_t n_class;
-    const uint16_t* node_class; // [n_rows]   0xFFFF = node has no pangenome_map entry
     const double2* class_tab;   // [n_class + 1]  {mappability, match_prob}; entry n_class = {0, 0}
-    const HcSmallTables* small;
+    const unsigned char* image;  // see HcImageLayout
+    HcImageLayout layout;
     const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
 };
 
