@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="vgan_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU exchange of the P-vector")
     ap.add_argument("--workload", type=int, default=2, choices=[2, 3], help="SURVEY 8d config whose read shape is generated")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -235,7 +236,8 @@ def main():
     sharded = None
     if world > 1:
         from vgan_b200.dist import ShardedSample
-        sharded = ShardedSample(hc)  # all-gather of the per-rank final_vec + fixed-order sum (vgan_b200/dist.py)
+        # exchange of the per-rank final_vec + fixed-order sum (vgan_b200/dist.py): peer-memory kernels, NCCL as fallback
+        sharded = ShardedSample(hc, exchange=args.exchange)
 
     def step(host_buffers):
         if sharded is not None:
@@ -325,7 +327,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "reads_per_gpu": reads_local, "paths": N_PATHS, "rows": N_ROWS,
                        "l2": "batch of %.0f MB per step exceeds the 126 MB L2 (no flush needed)" % (batch_bytes / 1e6),
-                       "parallelism": "reads sharded over %d GPU(s); one all-gather of P doubles per sample" % n_gpus,
+                       "parallelism": "reads sharded over %d GPU(s); one exchange of P doubles per sample (%s)" % (
+                           n_gpus, "none" if sharded is None else sharded.exchange),
                        "called_haplogroup": res.get("predicted_haplotype")},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 28 + 8 * hc._max_post,

@@ -35,7 +35,8 @@ enum {
                                the reference would throw from map::at inside a noexcept function
                                (src/process_mapping.cpp:33) and terminate                              */
     VGL_ERR_BAD_READ = 5,   /* malformed alignment (see vgh_* packer)                                  */
-    VGL_ERR_NO_DEVICE = 6   /* no CUDA device: there is NO CPU fallback                                */
+    VGL_ERR_NO_DEVICE = 6,  /* no CUDA device: there is NO CPU fallback                                */
+    VGL_ERR_PEER = 7        /* multi-GPU exchange: a peer did not deliver its vector in time            */
 };
 
 typedef struct vgl_ctx vgl_ctx;
@@ -231,6 +232,20 @@ int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev);
  * order keeps paths with identical support bit-identical, so std::max_element ties resolve as in
  * the single-GPU run.                                                                           */
 int vgl_hc_set_paths_from_parts(vgl_ctx* ctx, const double* parts_dev, int32_t n_parts);
+
+/* Multi-GPU without a library collective: the ranks of one node exchange their vectors through NVLink peer memory.
+ * Every rank owns an exchange buffer (two generations of `world` slots of P doubles plus arrival flags) that its
+ * peers map through CUDA IPC.  vgl_hc_exchange_paths launches two kernels on the context's stream: the first writes
+ * this rank's final_vec[P] into slot `rank` of EVERY rank's buffer (peer stores over NVLink) and raises the flags; the
+ * second waits for the `world` flags of its own buffer and sums the slots in rank order -- the same fixed-order sum
+ * as vgl_hc_set_paths_from_parts, so calls stay bit-identical to a single-GPU run.  All ranks must call it once
+ * per sample, in the same order.  A peer that does not deliver within ~10 s raises VGL_ERR_PEER at finalize.
+ *   vgl_hc_peer_export : allocate the buffer for `world` ranks, return its IPC handle (VGL_PEER_HANDLE_BYTES bytes)
+ *   vgl_hc_peer_attach : handles[k * VGL_PEER_HANDLE_BYTES ...] = the handle exported by rank k (own slot ignored)  */
+#define VGL_PEER_HANDLE_BYTES 64
+int vgl_hc_peer_export(vgl_ctx* ctx, int32_t world, unsigned char* handle_out);
+int vgl_hc_peer_attach(vgl_ctx* ctx, int32_t rank, int32_t world, const unsigned char* handles);
+int vgl_hc_exchange_paths(vgl_ctx* ctx);
 
 /* Replaces std::max_element (src/HaploCart.cpp:423-424) and Haplocart::get_posterior
  * (src/get_posterior.cpp:87-127): argmax with first-max-wins, log-sum-exp over all paths, posterior

@@ -37,6 +37,7 @@ COL_MISMATCH, COL_LATCHED, COL_VALID, COL_OPEN, COL_CLOSE = 0x0100, 0x0200, 0x10
 COL_BASE_SHIFT, COL_NODE_SHIFT, NO_NODE = 10, 15, 0x1FFFF
 MAP_NODE_BITS = 20
 LANES, COL_BLK, MAP_BLK = 32, 4, 4
+PEER_HANDLE_BYTES = 64
 EUKA_COL_BLK = 8
 
 
@@ -91,6 +92,9 @@ GPU_SYMBOLS = {
     "vgl_hc_accumulate_device": (C.c_int, [_P, C.POINTER(vgl_hc_batch)]),
     "vgl_hc_paths": (C.c_int, [_P, _P]),
     "vgl_hc_set_paths_from_parts": (C.c_int, [_P, _P, C.c_int32]),
+    "vgl_hc_peer_export": (C.c_int, [_P, C.c_int32, _P]),
+    "vgl_hc_peer_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "vgl_hc_exchange_paths": (C.c_int, [_P]),
     "vgl_hc_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, C.c_int32,
                                   C.POINTER(C.c_int32)]),
     "vgl_euka_set_tables": (C.c_int, [_P, C.POINTER(vgl_euka_tables)]),

@@ -494,6 +494,61 @@ __global__ void hc_sum_parts_kernel(const double* __restrict__ parts, int n_part
 }
 
 // ------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory (no library collective).
+// Buffer of every rank: parts[2][world][n_pad] doubles, then flags[2][world] u64; generation = epoch & 1.
+//   push: CTA q copies this rank's ll[P] into slot `rank` of rank q's buffer (peer stores), then publishes `epoch`
+//         in q's flag with a system-scope release;
+//   sum : every CTA waits (system-scope acquire) until the `world` flags of the local buffer hold `epoch`, then adds
+//         the slots in rank order.
+// ------------------------------------------------------------------------------------------
+struct PeerBufs {
+    double* base[VGL_HC_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+hc_peer_push_kernel(PeerBufs peers, int rank, int world, int n_paths, int n_pad, unsigned long long epoch,
+                    const double* __restrict__ ll) {
+    const int q = blockIdx.x;
+    const int gen = (int)(epoch & 1ull);
+    double* slot = peers.base[q] + ((size_t)gen * world + rank) * (size_t)n_pad;
+    for (int p = threadIdx.x; p < n_paths; p += blockDim.x) slot[p] = ll[p];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[q] + (size_t)2 * world * n_pad) + (size_t)gen * world + rank;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hc_peer_sum_kernel(const double* __restrict__ local, int world, int n_paths, int n_pad, unsigned long long epoch,
+                   double* __restrict__ ll, int* __restrict__ err_flag) {
+    const int gen = (int)(epoch & 1ull);
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(local + (size_t)2 * world * n_pad) + (size_t)gen * world;
+    if ((int)threadIdx.x < world) {
+        unsigned long long t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) {  // 10 s: a peer is gone; report instead of hanging the GPU
+                atomicOr(err_flag, 0x40000000);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const double* parts = local + (size_t)gen * world * (size_t)n_pad;
+    double s = 0.0;
+    for (int k = 0; k < world; ++k) s += __ldcg(parts + (size_t)k * n_pad + p);  // written by peers: bypass L1
+    ll[p] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: argmax + log-softmax posterior + clade support, one CTA.  exp(ll[p] - max) is evaluated once
 // per path into shared memory; every clade is then a masked sum over its descendant bitmap.
 // ------------------------------------------------------------------------------------------
@@ -661,6 +716,17 @@ cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, co
                                 double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s) {
     hc_posterior_kernel<<<1, kPostBlock, hc_posterior_smem(n_paths), s>>>(ll, n_paths, row_words, clade_bits, anc_off,
                                                                           anc_clade, post, post_cap, out_scalars, out_idx, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_peer_exchange(double* const* peer_bufs, int rank, int world, int n_paths, int n_pad,
+                                    unsigned long long epoch, double* ll, int* err_flag, cudaStream_t s) {
+    PeerBufs pb;
+    for (int k = 0; k < VGL_HC_MAX_PEERS; ++k) pb.base[k] = k < world ? peer_bufs[k] : nullptr;
+    hc_peer_push_kernel<<<world, 256, 0, s>>>(pb, rank, world, n_paths, n_pad, epoch, ll);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    hc_peer_sum_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(peer_bufs[rank], world, n_paths, n_pad, epoch, ll, err_flag);
     return cudaGetLastError();
 }
 

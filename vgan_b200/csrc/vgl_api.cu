@@ -92,6 +92,12 @@ struct vgl_ctx {
     DevBuf<int32_t> d_anc_off, d_anc_clade;
 
     // posterior outputs
+    // multi-GPU exchange through peer memory
+    double* peer_local = nullptr;             // this rank's buffer (cudaMalloc)
+    double* peer_bufs[VGL_HC_MAX_PEERS] = {};  // every rank's buffer as mapped here
+    int peer_rank = -1, peer_world = 0, peer_pad = 0;
+    unsigned long long peer_epoch = 0;
+
     // one block {double total, max; int32 argmax, n_post, err, pad; double post[]} and its pinned host mirror
     DevBuf<double> d_result;
     double* h_result = nullptr;
@@ -167,6 +173,17 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
     ctx->launches += 1;
     ctx->ll_valid = false;
     return VGL_OK;
+}
+
+void peer_detach(vgl_ctx* ctx) {
+    for (int k = 0; k < VGL_HC_MAX_PEERS; ++k) {
+        if (ctx->peer_bufs[k] && ctx->peer_bufs[k] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_bufs[k]);
+        ctx->peer_bufs[k] = nullptr;
+    }
+    if (ctx->peer_local) cudaFree(ctx->peer_local);
+    ctx->peer_local = nullptr;
+    ctx->peer_rank = -1;
+    ctx->peer_world = 0;
 }
 
 int reserve_result(vgl_ctx* ctx, size_t n_post) {
@@ -248,6 +265,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    peer_detach(ctx);
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
         sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
@@ -617,6 +635,53 @@ int vgl_hc_set_paths_from_parts(vgl_ctx* ctx, const double* parts_dev, int32_t n
     return VGL_OK;
 }
 
+int vgl_hc_peer_export(vgl_ctx* ctx, int32_t world, unsigned char* handle_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (world < 1 || world > VGL_HC_MAX_PEERS || !handle_out) return fail(VGL_ERR_INVALID, "world size %d outside [1, %d]", world, VGL_HC_MAX_PEERS);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= VGL_PEER_HANDLE_BYTES, "IPC handle does not fit");
+    peer_detach(ctx);
+    ctx->peer_pad = (ctx->tab.n_paths + 31) & ~31;
+    const size_t bytes = (size_t)2 * world * ctx->peer_pad * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+    VGL_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->peer_local), bytes));
+    VGL_CUDA(cudaMemset(ctx->peer_local, 0, bytes));
+    cudaIpcMemHandle_t h;
+    VGL_CUDA(cudaIpcGetMemHandle(&h, ctx->peer_local));
+    memset(handle_out, 0, VGL_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    ctx->peer_world = world;
+    ctx->peer_epoch = 0;
+    return VGL_OK;
+}
+
+int vgl_hc_peer_attach(vgl_ctx* ctx, int32_t rank, int32_t world, const unsigned char* handles) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->peer_local || world != ctx->peer_world) return fail(VGL_ERR_STATE, "vgl_hc_peer_export(world = %d) must come first", world);
+    if (rank < 0 || rank >= world || !handles) return fail(VGL_ERR_INVALID, "bad rank %d of %d", rank, world);
+    for (int k = 0; k < world; ++k) {
+        if (k == rank) { ctx->peer_bufs[k] = ctx->peer_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)k * VGL_PEER_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        VGL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_bufs[k] = static_cast<double*>(p);
+    }
+    ctx->peer_rank = rank;
+    return VGL_OK;
+}
+
+int vgl_hc_exchange_paths(vgl_ctx* ctx) {
+    if (int rc = use_device(ctx)) return rc;
+    if (ctx->peer_rank < 0) return fail(VGL_ERR_STATE, "vgl_hc_peer_attach must come first");
+    if (!ctx->ll_valid)
+        if (int rc = vgl_hc_paths(ctx, nullptr)) return rc;
+    ctx->peer_epoch += 1;
+    VGL_CUDA(vgl::hc_launch_peer_exchange(ctx->peer_bufs, ctx->peer_rank, ctx->peer_world, ctx->tab.n_paths, ctx->peer_pad,
+                                          ctx->peer_epoch, ctx->d_ll.p, ctx->d_err, ctx->stream));
+    ctx->launches += 2;
+    return VGL_OK;
+}
+
 int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
                     int32_t post_cap, int32_t* n_post_out) {
     if (int rc = use_device(ctx)) return rc;
@@ -641,6 +706,8 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
     const int32_t* idx = reinterpret_cast<const int32_t*>(ctx->h_result + 2);
     const double* post = ctx->h_result + 4;
     const int err = idx[2];
+    if (err & 0x40000000)
+        return fail(VGL_ERR_PEER, "multi-GPU exchange: a peer rank did not deliver its vector within 10 s");
     if (err & VGL_ERR_BAD_NODE)
         return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
     if (argmax_out) *argmax_out = idx[0];

@@ -10,6 +10,8 @@
 #define VGL_HC_ACC_COPIES 16
 #endif
 
+#define VGL_HC_MAX_PEERS 16
+
 namespace vgl {
 
 // Small per-process lookup tables, copied into shared memory by every CTA of the read kernel.
@@ -101,6 +103,12 @@ cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths
 
 // Multi-GPU: ll[p] = sum_k parts[k][p] in k order.
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s);
+
+// Multi-GPU exchange through peer memory: peer_bufs[k] = rank k's exchange buffer as mapped into this process
+// (layout: parts[2][world][n_pad] doubles, flags[2][world] u64).  Writes this rank's ll into every buffer, waits for
+// all ranks' vectors in the local buffer, leaves their rank-ordered sum in ll.
+cudaError_t hc_launch_peer_exchange(double* const* peer_bufs, int rank, int world, int n_paths, int n_pad,
+                                    unsigned long long epoch, double* ll, int* err_flag, cudaStream_t s);
 
 // K3: argmax (first max wins), log-sum-exp, posterior of the call and of its listed clades.
 //   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post,

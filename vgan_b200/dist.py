@@ -42,7 +42,7 @@ def gather_paths(local_vec, group=None):
 class ShardedSample:
     """One sample spread over the ranks of a process group.  Each rank owns a `Haplocart` on its own GPU."""
 
-    def __init__(self, hc, group=None):
+    def __init__(self, hc, group=None, exchange="peer"):
         import torch
         import torch.distributed as dist
         self.hc, self.group = hc, group
@@ -56,6 +56,23 @@ class ShardedSample:
         if self.stream.cuda_stream == 0:
             self.stream = torch.cuda.Stream()
         hc.set_stream(self.stream.cuda_stream)
+        # The exchange step: "peer" = the library's own kernels over NVLink peer memory (CUDA IPC between the ranks of one
+        # node); "nccl" = all-gather + vgl_hc_set_paths_from_parts.  Both add the vectors in rank order.
+        self.exchange = exchange
+        if exchange == "peer":
+            try:
+                mine = hc.peer_export(self.world)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, mine, group=group)
+                hc.peer_attach(self.rank, self.world, handles)
+                ok = 1
+            except Exception as e:  # no peer access between these devices: use the collective
+                self.exchange_error = repr(e)
+                ok = 0
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            if int(t.item()) == 0:
+                self.exchange = "nccl"
 
     def run(self, local_batches, device_resident=False, want_ll=False):
         import torch
@@ -68,7 +85,10 @@ class ShardedSample:
                     hc.update_device(b.batch)
                 else:
                     hc.update(b)
-            hc.paths(self.local.data_ptr())
-            dist.all_gather_into_tensor(self.parts, self.local, group=self.group)
-            hc.set_paths_from_parts(self.parts.data_ptr(), self.world)
+            if self.exchange == "peer":
+                hc.exchange_paths()
+            else:
+                hc.paths(self.local.data_ptr())
+                dist.all_gather_into_tensor(self.parts, self.local, group=self.group)
+                hc.set_paths_from_parts(self.parts.data_ptr(), self.world)
             return hc.get_posterior(want_ll=want_ll)

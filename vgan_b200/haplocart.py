@@ -73,6 +73,23 @@ class Haplocart:
     def set_paths_from_parts(self, parts_dev_ptr, n_parts):
         check(gpu.vgl_hc_set_paths_from_parts(self.ctx, C.c_void_p(parts_dev_ptr), int(n_parts)))
 
+    # ---- multi-GPU exchange through NVLink peer memory (include/vgan_gpu.h) ---------------------------
+    def peer_export(self, world):
+        """Allocate this rank's exchange buffer; returns its IPC handle (bytes) for the other ranks."""
+        buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+        check(gpu.vgl_hc_peer_export(self.ctx, int(world), buf))
+        return bytes(buf)
+
+    def peer_attach(self, rank, world, handles):
+        """handles: the `world` exported handles in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == world * _lib.PEER_HANDLE_BYTES
+        check(gpu.vgl_hc_peer_attach(self.ctx, int(rank), int(world), C.c_char_p(blob)))
+
+    def exchange_paths(self):
+        """Every rank's final_vec summed in rank order, on every rank (all ranks call it once per sample)."""
+        check(gpu.vgl_hc_exchange_paths(self.ctx))
+
     def get_posterior(self, want_ll=True):
         """argmax + Haplocart::get_posterior.  Returns a dict with final_vec, the call and its clade posteriors."""
         ll = np.zeros(self.n_paths, dtype=np.float64) if want_ll else None
