@@ -129,6 +129,7 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
+constexpr uint32_t kEntryAllPaths = 1u << 29;  // queue entry: the mapping's node is on every path
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
@@ -173,15 +174,19 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     return v;
 }
 
-// Finalise one queued mapping: entry = {exp(A) lo, hi, quality sums, node | first column << 17}.
+// Finalise one queued mapping: entry = {exp(A) lo, hi, quality sums, node | first column << 17 | ALLPATHS << 29}.
+// A node every path goes through (ALLPATHS) never shows up in the sum over unsupported nodes, so its D[n] is never read:
+// such a mapping contributes its A only and the scatter is skipped.
 __device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uint4& e, double& a_sum) {
     const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
-    const uint32_t node = e.w & VGL_HC_NO_NODE, pos = e.w >> 17;
+    const uint32_t node = e.w & VGL_HC_NO_NODE, pos = (e.w >> 17) & 0xfffu;
     const double A = fast_log_s(__hiloint2double((int)e.y, (int)e.x), S.logtab);
-    // log(err) over [pos, pos + n): the stored columns from pos on plus `pos` bytes past the end that count as
-    // quality 0  
-    const double B = fma((double)(e.z & 0xfffffu), scale, (double)((e.z >> 20) + pos) * S.le0);
-    if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, B - A);
+    if (!(e.w & kEntryAllPaths) && node < (uint32_t)S.n_rows) {
+        // log(err) over [pos, pos + n): the stored columns from pos on plus `pos` bytes past the end that count as
+        // quality 0  
+        const double B = fma((double)(e.z & 0xfffffu), scale, (double)((e.z >> 20) + pos) * S.le0);
+        red_add_f64(S.acc + node, B - A);
+    }
     a_sum += A;
 }
 
@@ -210,25 +215,29 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // read's length.
     uint32_t suf = 0u - ((uint32_t)(ncb * VGL_HC_COL_BLK - H.n_cols) << 20);
     double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
+    uint32_t open_cls = 0;  // node-table entry of the mapping being walked
 
     auto extra_rec = [&](int i) -> uint32_t {
         const uint32_t* gx = b.map + ((size_t)__ldg(b.grp_map_blk + g) * 32 + lane) * VGL_HC_MAP_BLK;
         return __ldg(gx + (size_t)(i >> 2) * 128 + (i & 3));
     };
     auto add_extra = [&](uint32_t xn, double Bx) {
-        if (xn < (uint32_t)S.n_rows && lds_u16_c(S.node_class + 2u * xn) != 0xFFFFu) red_add_f64(S.acc + xn, Bx);
+        if (xn < (uint32_t)S.n_rows && (lds_u16_c(S.node_class + 2u * xn) & VGL_HC_CLASS_MASK) != VGL_HC_CLASS_NONE) red_add_f64(S.acc + xn, Bx);
         else bad_node = true;
     };
 
     // kRare: some lane of the warp has a rescaled product or empty mappings pending; the common instantiation carries
     // neither test.  Predicated loads / stores (inline PTX) instead of branches: at every column SOME lane opens or
     // closes a mapping, so a branch would be taken by the warp anyway and only add reconvergence overhead.
-    auto column = [&](auto rare_tag, int c, uint32_t rec, double f, double bgv, uint32_t cls) {
+    auto column = [&](auto rare_tag, int c, uint32_t rec, double f, double bgv, uint32_t cls_raw) {
         constexpr bool kRare = decltype(rare_tag)::value;
         const uint32_t q = rec & 0xffu;
         suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
         const uint32_t open = rec & VGL_HC_COL_OPEN;
-        // class 0xFFFF: no pangenome_map entry -- the reference would terminate; flag it and use the neutral entry
+        // table entry: class id | ALLPATHS bit.  Class VGL_HC_CLASS_NONE: no pangenome_map entry -- the reference would
+        // terminate; flag it and use the neutral entry
+        open_cls = open ? cls_raw : open_cls;
+        const uint32_t cls = cls_raw & VGL_HC_CLASS_MASK;
         bad_cls = max(bad_cls, open ? cls : 0u);
         if (kAcMode == 0) {
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
@@ -279,7 +288,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (kQueueSlots - 1);
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(S.queue + 16u * slot),
                      "r"((uint32_t)__double2loint(prod)), "r"((uint32_t)__double2hiint(prod)), "r"(suf),
-                     "r"(VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17)), "r"(push)
+                     "r"(VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17) | ((open_cls & VGL_HC_CLASS_ALLPATHS) << 14)), "r"(push)
                      : "memory");
         prod = close ? 1.0 : prod;
         q_tail += __popc(m);
@@ -304,7 +313,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
             uint16_t c16 = 0;
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
                 : "+h"(c16)
-                : "r"(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: 0xFFFF
+                : "r"(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: CLASS_NONE
             cls[j] = c16;
         }
         const int c4 = cb * VGL_HC_COL_BLK;
@@ -388,7 +397,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
 
     double a_sum = 0.0;
     bool bad_node = false;
-    uint32_t bad_cls = 0;  // largest class seen at an OPEN mark (0xFFFF: a node without pangenome_map entry)
+    uint32_t bad_cls = 0;  // largest class seen at an OPEN mark (CLASS_NONE: a node without pangenome_map entry)
     uint32_t q_head = 0, q_tail = 0;
     const uint32_t warps_total = gridDim.x * (kReadBlock / 32);
     uint32_t g = blockIdx.x * (kReadBlock / 32) + warp;
@@ -403,7 +412,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     __syncwarp();
     if ((uint32_t)lane < q_tail - q_head) hc_finalise(S, lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1))), a_sum);
 
-    if (__any_sync(kFull, bad_node || bad_cls == 0xFFFFu) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
+    if (__any_sync(kFull, bad_node || bad_cls == VGL_HC_CLASS_NONE) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
     a_sum = warp_sum_f64(a_sum);
     if (lane == 0) s_warp_a[warp] = a_sum;
     __syncthreads();

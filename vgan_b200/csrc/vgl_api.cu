@@ -357,7 +357,7 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
 
     // (mappability, match_prob) dictionary: one class per distinct pair, so the read kernel can keep a
     // 2-byte class id per node in shared memory instead of 16 bytes per node.
-    std::vector<uint16_t> node_class((size_t)N, 0xFFFFu);
+    std::vector<uint16_t> node_class((size_t)N, (uint16_t)VGL_HC_CLASS_NONE);
     std::vector<double2> class_tab;
     {
         std::map<std::pair<double, double>, int> dict;
@@ -368,13 +368,22 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
             int id;
             if (it == dict.end()) {
                 id = (int)class_tab.size();
-                if (id >= 0xFFFF) return fail(VGL_ERR_INVALID, "more than 65534 distinct (mappability, match_prob) pairs");
+                if (id >= (int)VGL_HC_CLASS_NONE) return fail(VGL_ERR_INVALID, "more than 32767 distinct (mappability, match_prob) pairs");
                 dict.insert(std::make_pair(key, id));
                 class_tab.push_back(make_double2(key.first, key.second));
             } else {
                 id = it->second;
             }
             node_class[(size_t)n] = (uint16_t)id;
+            // a node every path goes through never appears in any path's sum over unsupported nodes: mark it, the read
+            // kernel then skips the scatter for its mappings
+            const uint32_t* row = T->support_bits + (size_t)n * (size_t)T->row_words;
+            bool all = true;
+            for (int p = 0; p < P && all; p += 32) {
+                const uint32_t want = P - p >= 32 ? 0xffffffffu : (1u << (P - p)) - 1u;
+                all = (row[p >> 5] & want) == want;
+            }
+            if (all) node_class[(size_t)n] |= (uint16_t)VGL_HC_CLASS_ALLPATHS;
         }
         if (class_tab.empty()) class_tab.push_back(make_double2(0.0, 0.0));
     }
@@ -450,7 +459,7 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     {
         uint16_t* cls = reinterpret_cast<uint16_t*>(image.data() + L.off_class);
         memcpy(cls, node_class.data(), (size_t)N * sizeof(uint16_t));
-        cls[N] = 0xFFFFu;  // "no such node"
+        cls[N] = (uint16_t)VGL_HC_CLASS_NONE;  // "no such node"
         double2* ac = reinterpret_cast<double2*>(image.data() + L.off_ac);
         if (ctx->read_cfg.ac_mode == 0) {
             // {1 - pcm, pcm * K} for every (mapping quality, class): p_correctly_mapped = (1 - p_incorrect[mq]) * mappability

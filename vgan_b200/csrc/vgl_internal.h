@@ -11,6 +11,11 @@
 #endif
 
 #define VGL_HC_MAX_PEERS 16
+// node table entry (u16): class id in bits 0-14 (VGL_HC_CLASS_NONE: no pangenome_map entry), bit 15: every path goes
+// through the node
+#define VGL_HC_CLASS_MASK 0x7FFFu
+#define VGL_HC_CLASS_NONE 0x7FFFu
+#define VGL_HC_CLASS_ALLPATHS 0x8000u
 
 namespace vgl {
 
@@ -34,7 +39,7 @@ struct HcSmallTables {
 
 // The read kernel's constant tables live in global memory as one image with exactly the layout they have in shared
 // memory; every CTA fetches it with a single TMA bulk copy.
-//   [ HcSmallTables | node_class u16[n_rows + 1] (entry n_rows = 0xFFFF) | mode 0: {1 - pcm, pcm * K} double2[100][row]
+//   [ HcSmallTables | node_class u16[n_rows + 1] (entry n_rows = VGL_HC_CLASS_NONE) | mode 0: {1 - pcm, pcm * K} double2[100][row]
 //                                                                          mode 1: class table double2[n_class + 1] ]
 // row = an odd number of 16-byte entries >= n_class + 1, so that one class in rows of different mapping qualities falls
 // into different banks; entry n_class of every row is the neutral {1, 0} (class table: {0, 0}).
