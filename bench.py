@@ -286,6 +286,38 @@ def main():
     ms_e2e, _, _, _, res_e2e = timed(True, e2e_steps)
     clocks = sampler.finish()
 
+    # the same sample from RAW alignments: H2D of the compact alignment arrays, reconstruction + packing on the device
+    # (SURVEY 8f rank 1), kernels, result -- against the host packer's rate reported in `host_pack`
+    raw_path = None
+    if world == 1:
+        t0 = time.perf_counter()
+        raw = vb.RawBatch(alns, pinned=True)
+        t_raw = time.perf_counter() - t0
+        hc.load_graph(S.graph)
+
+        def raw_step():
+            hc.reset()
+            hc.update_raw(raw)
+            return hc.get_posterior(want_ll=False)
+
+        for _ in range(3):
+            res_raw = raw_step()
+        raw_steps = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(raw_steps):
+            res_raw = raw_step()
+        e1.record(stream)
+        barrier()
+        ms_raw = e0.elapsed_time(e1) / raw_steps
+        raw_path = {"value": raw.n_reads * N_PATHS / (ms_raw * 1e-3), "unit": UNIT, "ms_per_step": ms_raw, "steps": raw_steps,
+                    "h2d_bytes_per_step": raw.nbytes, "host_build_seconds": t_raw,
+                    "same_call_as_packed_route": res_raw.get("maxh_index") == res.get("maxh_index"),
+                    "what": "vgl_hc_accumulate_raw: pinned raw alignments -> H2D -> device reconstruction + packing -> read kernel "
+                            "-> posterior; host_build_seconds is the one-pass copy into the compact raw arrays (no reconstruction)"}
+        del raw
+
     # per-sample latency at the size one real sample can reach after duplicate removal (SURVEY 8d scale caveat):
     # host batch -> H2D -> kernels -> posterior on the host, one sample at a time
     latency = None
@@ -333,6 +365,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 28 + 8 * hc._max_post,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "raw_path": raw_path,
             "latency": latency,
             "host_pack": {"seconds": t_pack, "reads_per_s": reads_local / t_pack, "threads": os.cpu_count(),
                           "what": "vgh_hc_pack (reconstruction + packing, OpenMP) of the step's batch; outside the timed regions"},

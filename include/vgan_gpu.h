@@ -222,6 +222,49 @@ int vgl_hc_reset(vgl_ctx* ctx);
 int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* host_batch);
 int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* device_batch);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Device-side reconstruction and packing                                */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Instead of a packed vgl_hc_batch the host may hand over the RAW alignments: the library then runs
+ * reconstruct_graph_sequence (src/vgan_utils.h:6-79) and the marshalling of update_likelihood
+ * (src/update_likelihood.cpp:33-49) on the device and feeds the resulting batch to the read kernel.
+ * vgl_hc_raw is a compact copy of the fields of vector<AlignmentInfo*> the path reads (built by
+ * vgh_hc_raw_build, one linear pass):
+ *   qual_off[r] .. qual_off[r+1]   quality bytes of read r (raw PHRED)
+ *   str_off[r+1] - str_off[r]      capacity reserved for read r's aligned strings: sum over its edits of
+ *                                  from_length + to_length + |sequence|
+ *   map_node[m]                    Mapping.position.node_id | is_reverse << 31;  map_offset[m] = position.offset
+ *   edit_from / edit_to [e]        Edit.from_length / to_length (<= 65535); edit_seq_off[e] .. [e+1] its sequence
+ * Only reads with identity >= 1e-10 are listed (src/HaploCart.cpp:411).  All pointers are HOST pointers.      */
+typedef struct vgl_hc_raw {
+    uint32_t n_reads, n_maps, n_edits, reserved;
+    const uint32_t* qual_off;     /* [n_reads + 1] */
+    const uint8_t* qual;
+    const uint8_t* mapq;          /* [n_reads]     */
+    const uint32_t* str_off;      /* [n_reads + 1] */
+    const uint32_t* map_off;      /* [n_reads + 1] */
+    const uint32_t* map_node;     /* [n_maps]      */
+    const uint32_t* map_offset;   /* [n_maps]      */
+    const uint32_t* edit_off;     /* [n_maps + 1]  */
+    const uint16_t* edit_from;    /* [n_edits]     */
+    const uint16_t* edit_to;      /* [n_edits]     */
+    const uint32_t* edit_seq_off; /* [n_edits + 1] */
+    const uint8_t* edit_seq;
+} vgl_hc_raw;
+uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
+
+/* Node sequences of the graph (what reconstruct_graph_sequence asks of bdsg::ODGI::get_sequence): node
+ * min_id + k has the forward sequence seq[seq_off[k] .. seq_off[k+1]).  Once per process.        */
+int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq);
+
+/* Reconstruct and pack `raw` on the device; *device_batch receives device pointers that stay valid until
+ * the next vgl_hc_pack_raw / vgl_hc_accumulate_raw on this context (for inspection and tests).    */
+int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* device_batch);
+/* vgl_hc_accumulate for raw alignments: H2D of `raw`, reconstruction, packing, read kernel -- no host sync.
+ * Malformed reads surface as VGL_ERR_BAD_READ / VGL_ERR_BAD_NODE at vgl_hc_finalize.              */
+int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw);
+
 /* Collapse the accumulators into the per-path log-likelihood vector final_vec[P]
  * (src/HaploCart.cpp:297-299,419-420) on the device.  ll_dev (device pointer, P doubles) receives
  * this context's (this GPU's) vector; pass NULL to keep it internal.                            */

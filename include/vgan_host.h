@@ -43,6 +43,8 @@ typedef struct vgh_graph vgh_graph;
 /* node ids min_id .. min_id + n_nodes - 1; seq_off[n_nodes + 1] into forward-strand `seq`.      */
 int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out);
 void vgh_graph_destroy(vgh_graph* g);
+/* The node table as stored (for vgl_hc_set_graph): ids min_id .. min_id + n_nodes - 1, node k = seq[seq_off[k] .. seq_off[k+1]). */
+int vgh_graph_view(const vgh_graph* g, int64_t* min_id, int64_t* n_nodes, const int64_t** seq_off, const char** seq);
 
 /* ---- alignments (flat view of vector<AlignmentInfo*>, reference src/AlignmentInfo.h:16-46) --- */
 typedef struct vgh_alignments {
@@ -98,6 +100,15 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
 const vgl_hc_batch* vgh_hc_packed_batch(const vgh_hc_packed* p);
 int64_t vgh_hc_packed_skipped(const vgh_hc_packed* p);
 void vgh_hc_packed_destroy(vgh_hc_packed* p);
+
+/* ---- raw alignments for the device-side reconstruction (vgl_hc_raw, include/vgan_gpu.h) ------ */
+typedef struct vgh_hc_raw vgh_hc_raw;
+/* One linear pass over reads [r0, r1): keeps those with identity >= 1e-10 (src/HaploCart.cpp:411) and copies the
+ * fields the path reads into one (optionally pinned) block.  No reconstruction happens here.              */
+int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out);
+const vgl_hc_raw* vgh_hc_raw_view(const vgh_hc_raw* p);
+int64_t vgh_hc_raw_skipped(const vgh_hc_raw* p);
+void vgh_hc_raw_destroy(vgh_hc_raw* p);
 
 /* ---- HaploCart tables ----------------------------------------------------------------------- */
 typedef struct vgh_hc_tables vgh_hc_tables;

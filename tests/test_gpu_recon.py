@@ -1,0 +1,167 @@
+"""Device-side reconstruction and packing (vgan_b200/csrc/recon_kernels.cu): the batch the GPU
+builds from raw alignments must hold, lane for lane, the records the host packer builds (which tests/test_host.py pins
+against the oracle's reconstruction and the reference's reconstruction known answers), and the likelihoods computed
+from it must match the oracle."""
+import numpy as np
+import pytest
+
+import vgan_b200 as vb
+from vgan_b200 import _lib
+from oracle import oracle as orc
+
+import helpers as H
+from test_gpu_haplocart import _check, _edge_reads, _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_lanes(hc, b):
+    """Un-block a device batch (as PackedBatch.lanes does for a host batch)."""
+    G, n = int(b.n_groups), int(b.n_reads)
+    gcb = hc.download(b.grp_col_blk, G + 1, np.uint32)
+    gmb = hc.download(b.grp_map_blk, G + 1, np.uint32)
+    assert gcb[-1] == b.n_col_blks and gmb[-1] == b.n_map_blks
+    col = hc.download(b.col, int(b.n_col_blks) * 128, np.uint32).reshape(-1, 32, 4)
+    xmap = hc.download(b.map, int(b.n_map_blks) * 128, np.uint32).reshape(-1, 32, 4)
+    n_cols = hc.download(b.n_cols, G * 32, np.uint16)
+    n_close = hc.download(b.n_close, G * 32, np.uint16)
+    n_extra = hc.download(b.n_extra, G * 32, np.uint16)
+    mapq = hc.download(b.mapq, G * 32, np.uint8)
+    lanes = []
+    for g in range(G):
+        for l in range(32):
+            k = g * 32 + l
+            cols = col[gcb[g]:gcb[g + 1], l, :].reshape(-1)
+            ex = xmap[gmb[g]:gmb[g + 1], l, :].reshape(-1)
+            if k >= n:
+                assert not cols.any() and not ex.any() and n_cols[k] == 0
+                continue
+            nc, nx = int(n_cols[k]), int(n_extra[k])
+            assert not cols[nc:].any() and not ex[nx:].any()
+            lanes.append((int(n_close[k]), nc, tuple(cols[:nc].tolist()), tuple(ex[:nx].tolist()), int(mapq[k])))
+    return lanes, n_cols[:n]
+
+
+def _host_lanes(graph, alns):
+    pb = vb.PackedBatch(graph, alns)
+    return [(d["n_close"], d["n_cols"], tuple(d["col"]), tuple(d["extra"]), d["mapq"]) for d in pb.lanes()], pb
+
+
+@pytest.fixture(scope="module")
+def small():
+    return vb.SynthHaplocart(seed=101, n_paths=300, n_rows=1210, n_nodes=1201)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=700, sub_rate=0.01, indel_rate=0.002),
+    dict(n=500, sub_rate=0.03, indel_rate=0.02, fixed_len=0, damage=True),
+    dict(n=33, sub_rate=0.0, indel_rate=0.0),
+])
+def test_device_batch_equals_host_batch(small, kw):
+    kw = dict(kw)
+    alns = small.reads(kw.pop("n"), seed=303, **kw)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    raw = vb.RawBatch(alns)
+    got, n_cols = _device_lanes(hc, hc.pack_raw(raw))
+    want, pb = _host_lanes(small.graph, alns)
+    assert raw.n_reads == pb.n_reads and raw.skipped == pb.skipped
+    assert sorted(got) == sorted(want)
+    assert np.all(np.diff(n_cols.astype(np.int64)) >= 0)      # lanes sorted by column count: groups are evenly long
+    hc.close()
+
+
+def test_corner_case_alignments_and_reference_fixtures(small):
+    hc = vb.Haplocart()
+    hc.load(small.tables(bep=2e-3), small.tree())
+    hc.load_graph(small.graph)
+    alns = vb.Alignments.from_gam_bytes(H.encode_gam(_edge_reads(small)))
+    got, _ = _device_lanes(hc, hc.pack_raw(vb.RawBatch(alns)))
+    want, _ = _host_lanes(small.graph, alns)
+    assert sorted(got) == sorted(want)
+    hc.reset()
+    hc.update_raw(vb.RawBatch(alns))
+    final, argmax, _ = _oracle(small, alns, bep=2e-3)
+    _check(hc.get_posterior(), final, argmax, small)
+    hc.close()
+
+
+def test_reference_fixtures_on_the_device():
+    """The reads of the reference's `reconstruction` known-answer suite (src/test.cpp:855-994, toy graph) and its
+    real-graph GAM fixtures, reconstructed and packed on the GPU: same records as the host packer, same likelihoods."""
+    import os
+    nodes, paths = H.toy_graph()
+    n_rows = max(nodes) + 1
+    sup = np.zeros((n_rows, len(paths)), dtype=np.uint8)
+    for p, (_, steps) in enumerate(paths):
+        for nid, _ in steps:
+            sup[nid, p] = 1
+    ids = sorted(nodes)
+    coord = (np.cumsum([0] + [len(nodes[i]) for i in ids])[:-1] + 1).astype(np.int32)
+    mapp = np.linspace(0.3, 1.0, int(coord[-1]) + 40)
+    names = [n for n, _ in paths]
+    graph = vb.Graph.from_sequences(nodes)
+    hc = vb.Haplocart()
+    hc.load(vb.HcTables(sup, np.array(ids), coord, mapp), vb.HcTree(names, "".join("%s root\n" % n for n in names), "root " + " ".join(names) + "\n"))
+    hc.load_graph(graph)
+    for fixture in ("test_reads.gam", "all_the_same_reverse.gam"):
+        alns = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, fixture))
+        got, _ = _device_lanes(hc, hc.pack_raw(vb.RawBatch(alns)))
+        want, _ = _host_lanes(graph, alns)
+        assert sorted(got) == sorted(want)
+    hc.close()
+    S = vb.SynthHaplocart()  # 11825 x 5179
+    for name in ("J2a1a1a1.gam", "two_unique.gam"):
+        node_seqs = H.graph_from_alignments(H.decoded_fixture(name), S.n_nodes)
+        g = vb.Graph.from_sequences(node_seqs, min_id=1)
+        alns = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, name))
+        hc = vb.Haplocart()
+        hc.load(S.tables(), S.tree())
+        hc.load_graph(g)
+        got, _ = _device_lanes(hc, hc.pack_raw(vb.RawBatch(alns)))
+        want, _ = _host_lanes(g, alns)
+        assert sorted(got) == sorted(want)
+        hc.reset()
+        hc.update_raw(vb.RawBatch(alns))
+        final, argmax, _ = _oracle(S, alns, node_seqs=node_seqs)
+        _check(hc.get_posterior(), final, argmax, S)
+        hc.close()
+
+
+def test_likelihoods_from_raw_alignments_match_oracle(small):
+    alns = small.reads(3000, seed=304, sub_rate=0.01, indel_rate=0.003)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    raw = vb.RawBatch(alns, pinned=True)
+    hc.reset()
+    hc.update_raw(raw)
+    hc.update_raw(raw)                                           # contributions add up; buffers are reused
+    res = hc.get_posterior()
+    final, argmax, _ = _oracle(small, alns)
+    _check(res, 2 * np.asarray(final, dtype=np.longdouble), argmax, None)
+    # same call and posteriors as the host-packed route
+    hc.reset()
+    hc.update(vb.PackedBatch(small.graph, alns))
+    hc.update(vb.PackedBatch(small.graph, alns))
+    res2 = hc.get_posterior()
+    assert res2["maxh_index"] == res["maxh_index"]
+    assert np.allclose(res2["final_vec"], res["final_vec"], rtol=1e-13)
+    hc.close()
+
+
+def test_malformed_reads_are_reported_not_guessed(small):
+    seqs = small.node_sequences()
+    node, _ = small.pmap()
+    a = sorted(set(node.tolist()))[5]
+    sa = seqs[a - 1]
+    bad = [H.aln(sa, [(a, len(sa) + 3, False, [(len(sa), len(sa), "")])])]       # offset beyond the node
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    hc.reset()
+    hc.update_raw(vb.RawBatch(vb.Alignments.from_gam_bytes(H.encode_gam(bad))))
+    with pytest.raises(RuntimeError):
+        hc.get_posterior()
+    hc.close()

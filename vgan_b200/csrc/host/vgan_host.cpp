@@ -204,6 +204,14 @@ int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, co
     return VGH_OK;
 }
 void vgh_graph_destroy(vgh_graph* g) { delete g; }
+int vgh_graph_view(const vgh_graph* g, int64_t* min_id, int64_t* n_nodes, const int64_t** seq_off, const char** seq) {
+    if (!g || !min_id || !n_nodes || !seq_off || !seq) return fail(VGH_ERR_INVALID, "bad arguments");
+    *min_id = g->min_id;
+    *n_nodes = g->n_nodes;
+    *seq_off = g->off.data();
+    *seq = g->seq.data();
+    return VGH_OK;
+}
 
 int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
     if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
@@ -584,6 +592,127 @@ int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t
 const vgl_hc_batch* vgh_hc_packed_batch(const vgh_hc_packed* p) { return p ? &p->batch : nullptr; }
 int64_t vgh_hc_packed_skipped(const vgh_hc_packed* p) { return p ? p->skipped : 0; }
 void vgh_hc_packed_destroy(vgh_hc_packed* p) {
+    if (!p) return;
+    if (p->block) {
+        if (p->pinned) vgl_host_free(p->block);
+        else free(p->block);
+    }
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw alignments for the device-side reconstruction
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct vgh_hc_raw {
+    vgl_hc_raw view{};
+    bool pinned = false;
+    int64_t skipped = 0;
+    void* block = nullptr;
+};
+
+extern "C" {
+
+int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+    if (!a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+    std::vector<int64_t> keep;
+    keep.reserve((size_t)(r1 - r0));
+    for (int64_t r = r0; r < r1; ++r)
+        if (!(a->identity[r] < 1e-10)) keep.push_back(r);
+    const size_t R = keep.size();
+    // per-read extents, then exclusive prefix sums: every read's slice of every array is known before the (parallel) fill
+    std::vector<uint64_t> pm(R + 1, 0), pe(R + 1, 0), pq(R + 1, 0), ps(R + 1, 0), pc(R + 1, 0);
+    int err = VGH_OK;
+    std::string err_msg;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)R; ++k) {
+        const int64_t r = keep[(size_t)k];
+        const int64_t e0 = a->edit_off[a->map_off[r]], e1 = a->edit_off[a->map_off[r + 1]];
+        pm[(size_t)k + 1] = (uint64_t)(a->map_off[r + 1] - a->map_off[r]);
+        pe[(size_t)k + 1] = (uint64_t)(e1 - e0);
+        pq[(size_t)k + 1] = (uint64_t)(a->qual_off[r + 1] - a->qual_off[r]);
+        ps[(size_t)k + 1] = (uint64_t)(a->edit_seq_off[e1] - a->edit_seq_off[e0]);
+        uint64_t cap = ps[(size_t)k + 1];
+        int e = VGH_OK;
+        for (int64_t x = e0; x < e1; ++x) {
+            const int64_t f = a->edit_from[x], t = a->edit_to[x];
+            if (f < 0 || f > 65535 || t < 0 || t > 65535) { e = VGH_ERR_BAD_READ; break; }
+            cap += (uint64_t)(f + t);
+        }
+        if (!e && (a->mapq[r] < 0 || a->mapq[r] > 255)) e = VGH_ERR_BAD_READ;
+        for (int64_t m = a->map_off[r]; !e && m < a->map_off[r + 1]; ++m)
+            if (a->map_node[m] < 0 || a->map_node[m] > 0x7fffffffll || a->map_offset[m] < 0 || a->map_offset[m] > 0xffffffffll) e = VGH_ERR_BAD_READ;
+        pc[(size_t)k + 1] = cap;
+        if (e) {
+#pragma omp critical(vgh_raw_err)
+            if (!err) { err = e; err_msg = "read " + std::to_string(r) + ": mapping quality, node id, offset or edit length out of range"; }
+        }
+    }
+    if (err) return fail(err, "%s", err_msg.c_str());
+    for (size_t k = 0; k < R; ++k) { pm[k + 1] += pm[k]; pe[k + 1] += pe[k]; pq[k + 1] += pq[k]; ps[k + 1] += ps[k]; pc[k + 1] += pc[k]; }
+    const uint64_t nm = pm[R], ne = pe[R], nq = pq[R], ns = ps[R];
+    if (R >= 0x7fffffffull || nm >= 0xffffffffull || ne >= 0xffffffffull || nq >= 0xffffffffull || ns >= 0xffffffffull || pc[R] >= 0xffffffffull)
+        return fail(VGH_ERR_INVALID, "batch too large for 32-bit offsets; split it");
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
+    const size_t o_node = take(nm * 4), o_offs = take(nm * 4), o_eoff = take((nm + 1) * 4), o_from = take(ne * 2), o_to = take(ne * 2);
+    const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns);
+    vgh_hc_raw* P = new vgh_hc_raw();
+    P->pinned = pinned != 0;
+    const size_t bytes = std::max<size_t>(o, 256);
+    if (pinned) {
+        if (vgl_host_alloc(&P->block, bytes) != VGL_OK) {
+            delete P;
+            return fail(VGH_ERR_INVALID, "pinned allocation failed: %s", vgl_last_error());
+        }
+    } else {
+        P->block = aligned_alloc(256, bytes);
+        if (!P->block) { delete P; return fail(VGH_ERR_INVALID, "out of host memory"); }
+    }
+    uint8_t* base = (uint8_t*)P->block;
+    uint32_t* qoff = (uint32_t*)(base + o_qoff); uint32_t* soff = (uint32_t*)(base + o_soff); uint32_t* moff = (uint32_t*)(base + o_moff);
+    uint8_t* mq = base + o_mq; uint8_t* q = base + o_q;
+    uint32_t* node = (uint32_t*)(base + o_node); uint32_t* offs = (uint32_t*)(base + o_offs); uint32_t* eoff = (uint32_t*)(base + o_eoff);
+    uint16_t* from = (uint16_t*)(base + o_from); uint16_t* to = (uint16_t*)(base + o_to);
+    uint32_t* esoff = (uint32_t*)(base + o_esoff); uint8_t* eseq = base + o_eseq;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)R; ++k) {
+        const int64_t r = keep[(size_t)k];
+        uint64_t cm = pm[(size_t)k], ce = pe[(size_t)k], cs = ps[(size_t)k];
+        qoff[k] = (uint32_t)pq[(size_t)k]; soff[k] = (uint32_t)pc[(size_t)k]; moff[k] = (uint32_t)cm;
+        mq[k] = (uint8_t)a->mapq[r];
+        memcpy(q + pq[(size_t)k], a->qual + a->qual_off[r], (size_t)(pq[(size_t)k + 1] - pq[(size_t)k]));
+        for (int64_t m = a->map_off[r]; m < a->map_off[r + 1]; ++m) {
+            node[cm] = (uint32_t)a->map_node[m] | (a->map_rev[m] ? 0x80000000u : 0u);
+            offs[cm] = (uint32_t)a->map_offset[m];
+            eoff[cm] = (uint32_t)ce;
+            ++cm;
+            for (int64_t e = a->edit_off[m]; e < a->edit_off[m + 1]; ++e) {
+                const int64_t sl = a->edit_seq_off[e + 1] - a->edit_seq_off[e];
+                from[ce] = (uint16_t)a->edit_from[e];
+                to[ce] = (uint16_t)a->edit_to[e];
+                esoff[ce] = (uint32_t)cs;
+                memcpy(eseq + cs, a->edit_seq + a->edit_seq_off[e], (size_t)sl);
+                cs += (uint64_t)sl;
+                ++ce;
+            }
+        }
+    }
+    const uint64_t cq = nq, ccap = pc[R], cm = nm, ce = ne, cs = ns;
+    qoff[R] = (uint32_t)cq; soff[R] = (uint32_t)ccap; moff[R] = (uint32_t)cm; eoff[cm] = (uint32_t)ce; esoff[ce] = (uint32_t)cs;
+    P->skipped = (r1 - r0) - (int64_t)R;
+    vgl_hc_raw& v = P->view;
+    v.n_reads = (uint32_t)R; v.n_maps = (uint32_t)cm; v.n_edits = (uint32_t)ce;
+    v.qual_off = qoff; v.qual = q; v.mapq = mq; v.str_off = soff; v.map_off = moff; v.map_node = node; v.map_offset = offs;
+    v.edit_off = eoff; v.edit_from = from; v.edit_to = to; v.edit_seq_off = esoff; v.edit_seq = eseq;
+    *out = P;
+    return VGH_OK;
+}
+const vgl_hc_raw* vgh_hc_raw_view(const vgh_hc_raw* p) { return p ? &p->view : nullptr; }
+int64_t vgh_hc_raw_skipped(const vgh_hc_raw* p) { return p ? p->skipped : 0; }
+void vgh_hc_raw_destroy(vgh_hc_raw* p) {
     if (!p) return;
     if (p->block) {
         if (p->pinned) vgl_host_free(p->block);

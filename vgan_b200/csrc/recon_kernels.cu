@@ -1,0 +1,347 @@
+// Device-side alignment reconstruction and batch packing.
+//
+// The host packer (vgh_hc_pack) rebuilds every read's aligned graph / read strings with
+// reconstruct_graph_sequence (reference src/vgan_utils.h:6-79) and marshals them the way update_likelihood hands
+// them to process_mapping (src/update_likelihood.cpp:33-49); at ~2e6 reads/s on 16 threads it is 60x slower than the
+// read kernel.  These kernels do the same work on the device from the raw alignments (vgl_hc_raw: quality bytes,
+// mappings, edits) and a copy of the node sequences, and leave a vgl_hc_batch in HBM for hc_read_kernel:
+//   R1 hc_recon_kernel   one thread per read: graph string, read string (with the deletion splices), the size slot of
+//                        every mapping (quirk Q1), column / CLOSE / empty-mapping counts, histogram of column counts
+//   R2 hc_scan4096       exclusive scan of the histogram                      (counting sort of the reads by columns,
+//   R3 hc_order_kernel   scatter of the read ids into their buckets            so that a group's 32 lanes are equally long)
+//   R4 hc_groups_kernel  per group of 32 lanes: column blocks, extra blocks;  R5 hc_scan_groups: their prefix sums
+//   R6 hc_pack_kernel    one thread per lane: the 32-bit column records of include/vgan_gpu.h, 16 bytes per store
+// Every quirk of the host implementation is kept (Q1 sizes per edit, Q2 read string from 0, Q3 'S' at node offset 0,
+// stale size for an edit of no recognised kind); tests/test_gpu_recon.py compares the device batch with the host
+// packer's record for record.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vgl_internal.h"
+
+namespace vgl {
+
+namespace {
+
+constexpr int kErrBadRead = 0x20000000;   // bits of the context's error word
+constexpr int kErrBadNodeRaw = 0x10000000;
+
+enum EditKind { kMatch, kSub, kIns, kDel, kOther };
+__device__ __forceinline__ EditKind classify(uint32_t from, uint32_t to, bool has_seq) {  // vg io edit_is_*
+    if (from == to && !has_seq) return kMatch;
+    if (from == to && has_seq) return kSub;
+    if (from == 0 && to > 0 && has_seq) return kIns;
+    if (from > 0 && to == 0) return kDel;
+    return kOther;
+}
+
+// base at oriented offset k of a node (what get_sequence(get_handle(id, rev))[k] returns)
+__device__ __forceinline__ uint8_t node_base(const ReconGraphDev& G, uint32_t row, bool rev, uint32_t k) {
+    const uint32_t a = G.seq_off[row], n = G.seq_off[row + 1] - a;
+    if (!rev) return G.seq[a + k];
+    const uint8_t c = G.seq[a + n - 1 - k];
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return c;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restrict__ err_flag) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= raw.n_reads) return;
+    const uint32_t m0 = raw.map_off[r], m1 = raw.map_off[r + 1], M = m1 - m0;
+    const uint32_t s0 = raw.str_off[r], cap = raw.str_off[r + 1] - s0;
+    uint8_t* gs = W.gstr + s0;
+    uint8_t* rs = W.rstr + s0;
+    uint32_t glen = 0, rlen = 0, e_idx = 0;
+    int err = 0;
+    for (uint32_t m = m0; m < m1 && !err; ++m) {
+        const uint32_t node = raw.map_node[m] & 0x7fffffffu;
+        const bool rev = (raw.map_node[m] >> 31) != 0;
+        if (node < G.min_id || node >= G.min_id + G.n_nodes || node > VGL_HC_MAX_NODE) { err = kErrBadNodeRaw; break; }
+        const uint32_t row = node - G.min_id;
+        const uint32_t nlen = G.seq_off[row + 1] - G.seq_off[row];
+        uint32_t offset = raw.map_offset[m];
+        uint32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size
+        for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
+            const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
+            const uint32_t q0 = raw.edit_seq_off[e], q1 = raw.edit_seq_off[e + 1];
+            const EditKind kind = classify(from, to, q1 > q0);
+            if (kind == kMatch || kind == kSub || kind == kDel) {
+                if (offset > nlen) { err = kErrBadRead; break; }
+                const uint32_t take = min(from, nlen - offset);  // std::string::substr clips
+                if (glen + take > cap) { err = kErrBadRead; break; }
+                for (uint32_t k = 0; k < take; ++k) gs[glen + k] = node_base(G, row, rev, offset + k);
+                aligned = take;
+                if (kind == kMatch) {
+                    if (rlen + take > cap) { err = kErrBadRead; break; }
+                    for (uint32_t k = 0; k < take; ++k) rs[rlen + k] = gs[glen + k];
+                    rlen += take;
+                } else if (kind == kSub) {
+                    if (rlen + (q1 - q0) > cap) { err = kErrBadRead; break; }
+                    for (uint32_t k = 0; k < q1 - q0; ++k) rs[rlen + k] = raw.edit_seq[q0 + k];
+                    rlen += q1 - q0;
+                }
+                glen += take;
+            } else if (kind == kIns) {
+                if (glen + to > cap || rlen + (q1 - q0) > cap) { err = kErrBadRead; break; }
+                const uint8_t fill = offset == 0 ? 'S' : '-';
+                for (uint32_t k = 0; k < to; ++k) gs[glen + k] = fill;
+                glen += to;
+                for (uint32_t k = 0; k < q1 - q0; ++k) rs[rlen + k] = raw.edit_seq[q0 + k];
+                rlen += q1 - q0;
+                aligned = to;
+            }
+            offset += from;
+            if (e_idx < M) W.sizes[m0 + e_idx] = (uint16_t)min(aligned, 0xffffu);
+            ++e_idx;
+        }
+    }
+    // deletions: a '-' run spliced into the read string at the running from_length coordinate, in order, each against the
+    // string as it stands (src/vgan_utils.h:67)
+    if (!err) {
+        uint32_t from_total = 0;
+        for (uint32_t m = m0; m < m1 && !err; ++m) {
+            for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
+                const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
+                const bool has_seq = raw.edit_seq_off[e + 1] > raw.edit_seq_off[e];
+                if (classify(from, to, has_seq) == kDel) {
+                    if (from_total > rlen || rlen + from > cap) { err = kErrBadRead; break; }
+                    for (uint32_t k = rlen; k > from_total; --k) rs[k - 1 + from] = rs[k - 1];
+                    for (uint32_t k = 0; k < from; ++k) rs[from_total + k] = '-';
+                    rlen += from;
+                }
+                from_total += from;
+            }
+        }
+    }
+    const uint32_t Lq = raw.qual_off[r + 1] - raw.qual_off[r];
+    if (!err && (glen != rlen || e_idx < M || Lq > rlen || rlen > VGL_HC_MAP_MAX_POS || M > 65535u || raw.mapq[r] >= 100)) err = kErrBadRead;
+    uint32_t n_close = 0, n_extra = 0;
+    if (!err) {
+        // mapping i starts at pos_i = min(sum of the earlier size slots, n); CLOSE bits sit at the distinct pos_i < n
+        uint32_t pos = 0, last_close = 0xffffffffu;
+        for (uint32_t i = 0; i < M; ++i) {
+            const uint32_t lg = min((uint32_t)W.sizes[m0 + i], rlen - pos);
+            if (lg == 0) ++n_extra;
+            if (pos < rlen && pos != last_close) { ++n_close; last_close = pos; }
+            pos += lg;
+        }
+    } else {
+        atomicOr(err_flag, err);
+        rlen = 0;
+        n_close = 0xffffu;  // marks the read as dead for the packer
+    }
+    W.n_cols[r] = (uint16_t)rlen;
+    W.n_close[r] = (uint16_t)n_close;
+    W.n_extra[r] = (uint16_t)n_extra;
+    atomicAdd(W.hist + rlen, 1u);
+}
+
+// exclusive scan of 4096 counters, one block of 1024 threads (4 per thread)
+__global__ void __launch_bounds__(1024) hc_scan4096(const uint32_t* __restrict__ hist, uint32_t* __restrict__ start) {
+    __shared__ uint32_t s_warp[32];
+    const int t = threadIdx.x;
+    const uint32_t a = hist[4 * t], b = hist[4 * t + 1], c = hist[4 * t + 2], d = hist[4 * t + 3];
+    const uint32_t mine = a + b + c + d;
+    uint32_t v = mine;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, k);
+        if ((t & 31) >= k) v += o;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = v;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t w = s_warp[t];
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, k);
+            if (t >= k) w += o;
+        }
+        s_warp[t] = w;
+    }
+    __syncthreads();
+    const uint32_t base = v - mine + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    start[4 * t] = base;
+    start[4 * t + 1] = base + a;
+    start[4 * t + 2] = base + a + b;
+    start[4 * t + 3] = base + a + b + c;
+}
+
+__global__ void __launch_bounds__(256)
+hc_order_kernel(uint32_t n_reads, const uint16_t* __restrict__ n_cols, const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                uint32_t* __restrict__ order) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t key = n_cols[r];
+    order[start[key] + atomicAdd(cursor + key, 1u)] = r;
+}
+
+__global__ void __launch_bounds__(256)
+hc_groups_kernel(uint32_t n_reads, uint32_t n_groups, const uint32_t* __restrict__ order, const uint16_t* __restrict__ n_cols,
+                 const uint16_t* __restrict__ n_extra, uint32_t* __restrict__ grp_cb, uint32_t* __restrict__ grp_mb) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    uint32_t mc = 0, mx = 0;
+    for (uint32_t l = 0; l < 32 && g * 32 + l < n_reads; ++l) {
+        const uint32_t r = order[g * 32 + l];
+        mc = max(mc, (uint32_t)n_cols[r]);
+        mx = max(mx, (uint32_t)n_extra[r]);
+    }
+    grp_cb[g] = (mc + VGL_HC_COL_BLK - 1) / VGL_HC_COL_BLK;
+    grp_mb[g] = (mx + VGL_HC_MAP_BLK - 1) / VGL_HC_MAP_BLK;
+}
+
+// in-place exclusive scan of two arrays of n + 1 entries (entry n receives the total), one block
+__global__ void __launch_bounds__(1024) hc_scan_groups(uint32_t n, uint32_t* __restrict__ a, uint32_t* __restrict__ b) {
+    __shared__ uint32_t s_wa[32], s_wb[32];
+    __shared__ uint32_t s_ca, s_cb;
+    const int t = threadIdx.x;
+    if (t == 0) { s_ca = 0; s_cb = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + t;
+        const uint32_t va = i < n ? a[i] : 0u, vb = i < n ? b[i] : 0u;
+        uint32_t xa = va, xb = vb;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t oa = __shfl_up_sync(0xffffffffu, xa, k), ob = __shfl_up_sync(0xffffffffu, xb, k);
+            if ((t & 31) >= k) { xa += oa; xb += ob; }
+        }
+        if ((t & 31) == 31) { s_wa[t >> 5] = xa; s_wb[t >> 5] = xb; }
+        __syncthreads();
+        if (t < 32) {
+            uint32_t wa = s_wa[t], wb = s_wb[t];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t oa = __shfl_up_sync(0xffffffffu, wa, k), ob = __shfl_up_sync(0xffffffffu, wb, k);
+                if (t >= k) { wa += oa; wb += ob; }
+            }
+            s_wa[t] = wa;
+            s_wb[t] = wb;
+        }
+        __syncthreads();
+        const uint32_t pa = s_ca + ((t >> 5) ? s_wa[(t >> 5) - 1] : 0u) + xa - va;
+        const uint32_t pb = s_cb + ((t >> 5) ? s_wb[(t >> 5) - 1] : 0u) + xb - vb;
+        if (i < n) { a[i] = pa; b[i] = pb; }
+        __syncthreads();
+        if (t == 0) { s_ca += s_wa[31]; s_cb += s_wb[31]; }
+        __syncthreads();
+    }
+    if (t == 0) { a[n] = s_ca; b[n] = s_cb; }
+}
+
+__device__ __forceinline__ int base_code(uint8_t ch) { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4; }
+
+// One thread per lane of the batch: column records pair G[c] with the read base process_mapping compares it with
+// (src/update_likelihood.cpp:33-49, src/process_mapping.cpp:47,59-66): for mapping i the graph slice
+// G[pos_i, pos_i + size_i) faces algnseq[0, size_i) -- the whole aligned read string from its start.
+__global__ void __launch_bounds__(128)
+hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_cap_blks, uint32_t map_cap_blks,
+               uint32_t* __restrict__ col, uint32_t* __restrict__ xmap, uint16_t* __restrict__ o_n_cols,
+               uint16_t* __restrict__ o_n_close, uint16_t* __restrict__ o_n_extra, uint8_t* __restrict__ o_mapq,
+               int* __restrict__ err_flag) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = slot >> 5, lane = slot & 31;
+    if (g >= n_groups) return;
+    if (W.grp_cb[n_groups] > col_cap_blks || W.grp_mb[n_groups] > map_cap_blks) {  // cannot happen for sorted groups; never write past the buffers
+        if (slot == 0) atomicOr(err_flag, kErrBadRead);
+        return;
+    }
+    const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0;
+    uint4* gc = reinterpret_cast<uint4*>(col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
+    if (slot >= raw.n_reads) {  // unused lane of the last group
+        for (uint32_t cb = 0; cb < ncb; ++cb) gc[(size_t)cb * 32] = make_uint4(0, 0, 0, 0);
+        o_n_cols[slot] = o_n_close[slot] = o_n_extra[slot] = 0;
+        o_mapq[slot] = 0;
+        return;
+    }
+    const uint32_t r = W.order[slot];
+    const uint32_t L = W.n_cols[r];
+    const bool dead = W.n_close[r] == 0xffffu;  // rejected by the reconstruction: an empty lane
+    const uint32_t m0 = raw.map_off[r], M = dead ? 0u : raw.map_off[r + 1] - m0;
+    const uint32_t q0 = raw.qual_off[r], Lq = raw.qual_off[r + 1] - q0;
+    const uint8_t* gs = W.gstr + raw.str_off[r];
+    const uint8_t* rs = W.rstr + raw.str_off[r];
+    uint32_t* gx = xmap + ((size_t)W.grp_mb[g] * 32 + lane) * VGL_HC_MAP_BLK;  // extra record i: gx[(i >> 2) * 128 + (i & 3)]
+    // the first REAL quality byte >= 90 latches the background-error mode (src/update_likelihood.cpp:42)
+    uint32_t f90 = 0xffffffffu;
+    for (uint32_t c = 0; c < Lq; ++c)
+        if ((int)(int8_t)raw.qual[q0 + c] >= 90) { f90 = c; break; }
+    uint32_t nxt = 0, npos = 0;  // next mapping to start and its first column
+    uint32_t own_node = VGL_HC_NO_NODE, own_pos = 0, own_end = 0, latched = 0, n_x = 0;
+    for (uint32_t cb = 0; cb < ncb; ++cb) {
+        uint32_t rec[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = cb * 4 + j;
+            if (c >= L) { rec[j] = 0; continue; }
+            uint32_t v = c < Lq ? raw.qual[q0 + c] : 0u;
+            while (nxt < M && npos == c) {  // mappings that start at this column (quirk Q1: size slot = the nxt-th edit's size)
+                const uint32_t lg = min((uint32_t)W.sizes[m0 + nxt], L - npos);
+                const uint32_t node = raw.map_node[m0 + nxt] & 0x7fffffffu;
+                v |= VGL_HC_COL_CLOSE;
+                if (lg) {
+                    own_node = node;
+                    own_pos = c;
+                    own_end = c + lg;
+                    latched = (f90 != 0xffffffffu && f90 < c + L) ? VGL_HC_COL_LATCHED : 0u;  // its quality window is [pos, pos + L)
+                    npos = own_end;
+                } else {
+                    gx[(size_t)(n_x >> 2) * 128 + (n_x & 3)] = VGL_HC_MAP_REC(node, c);
+                    ++n_x;
+                }
+                ++nxt;
+            }
+            if (c < own_end) {
+                const uint8_t gb = gs[c], rb = rs[c - own_pos];
+                const int cg = base_code(gb), cr = base_code(rb);
+                v |= (own_node << VGL_HC_COL_NODE_SHIFT) | latched;
+                if (cg < 4 && cr < 4) v |= VGL_HC_COL_VALID | ((uint32_t)cr << 10) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
+                if (c + 1 == own_end) v |= VGL_HC_COL_OPEN;
+            } else {
+                v |= VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT;
+            }
+            rec[j] = v;
+        }
+        gc[(size_t)cb * 32] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+    }
+    for (; nxt < M; ++nxt) {  // mappings that start past the last column
+        gx[(size_t)(n_x >> 2) * 128 + (n_x & 3)] = VGL_HC_MAP_REC(raw.map_node[m0 + nxt] & 0x7fffffffu, L);
+        ++n_x;
+    }
+    o_n_cols[slot] = (uint16_t)L;
+    o_n_close[slot] = dead ? (uint16_t)0 : W.n_close[r];
+    o_n_extra[slot] = (uint16_t)n_x;
+    o_mapq[slot] = raw.mapq[r];
+}
+
+}  // namespace
+
+cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int* err_flag, cudaStream_t s) {
+    if (raw.n_reads == 0) return cudaSuccess;
+    hc_recon_kernel<<<(raw.n_reads + 127) / 128, 128, 0, s>>>(raw, G, W, err_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    hc_scan4096<<<1, 1024, 0, s>>>(W.hist, W.start);
+    hc_order_kernel<<<(raw.n_reads + 255) / 256, 256, 0, s>>>(raw.n_reads, W.n_cols, W.start, W.cursor, W.order);
+    const uint32_t n_groups = (raw.n_reads + 31) / 32;
+    hc_groups_kernel<<<(n_groups + 255) / 256, 256, 0, s>>>(raw.n_reads, n_groups, W.order, W.n_cols, W.n_extra, W.grp_cb, W.grp_mb);
+    hc_scan_groups<<<1, 1024, 0, s>>>(n_groups, W.grp_cb, W.grp_mb);
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32_t col_cap_blks, uint32_t map_cap_blks, uint32_t* col,
+                           uint32_t* xmap, uint16_t* n_cols, uint16_t* n_close, uint16_t* n_extra, uint8_t* mapq, int* err_flag,
+                           cudaStream_t s) {
+    if (raw.n_reads == 0) return cudaSuccess;
+    const uint32_t n_groups = (raw.n_reads + 31) / 32;
+    hc_pack_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(raw, W, n_groups, col_cap_blks, map_cap_blks, col, xmap, n_cols, n_close,
+                                                               n_extra, mapq, err_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace vgl

@@ -92,6 +92,24 @@ struct vgl_ctx {
     DevBuf<int32_t> d_anc_off, d_anc_clade;
 
     // posterior outputs
+    // device-side reconstruction (recon_kernels.cu): node sequences, staged raw alignments, scratch, the packed batch
+    bool have_graph = false;
+    uint32_t g_min_id = 0, g_n_nodes = 0;
+    DevBuf<uint32_t> g_seq_off;
+    DevBuf<uint8_t> g_seq;
+    struct RawDev {
+        DevBuf<uint32_t> qual_off, str_off, map_off, map_node, map_offset, edit_off, edit_seq_off;
+        DevBuf<uint16_t> edit_from, edit_to;
+        DevBuf<uint8_t> qual, mapq, edit_seq;
+        DevBuf<uint8_t> gstr, rstr;
+        DevBuf<uint16_t> sizes, n_cols, n_close, n_extra;
+        DevBuf<uint32_t> hist3, order, grp_cb, grp_mb;   // hist3: hist | start | cursor
+        DevBuf<uint32_t> col, xmap;
+        DevBuf<uint16_t> o_n_cols, o_n_close, o_n_extra;
+        DevBuf<uint8_t> o_mapq;
+        uint32_t col_cap_blks = 0, map_cap_blks = 0;
+    } rawdev;
+
     // multi-GPU exchange through peer memory
     double* peer_local = nullptr;             // this rank's buffer (cudaMalloc)
     double* peer_bufs[VGL_HC_MAX_PEERS] = {};  // every rank's buffer as mapped here
@@ -266,6 +284,15 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     peer_detach(ctx);
+    {
+        vgl_ctx::RawDev& R = ctx->rawdev;
+        ctx->g_seq_off.release(); ctx->g_seq.release();
+        R.qual_off.release(); R.str_off.release(); R.map_off.release(); R.map_node.release(); R.map_offset.release(); R.edit_off.release();
+        R.edit_seq_off.release(); R.edit_from.release(); R.edit_to.release(); R.qual.release(); R.mapq.release(); R.edit_seq.release();
+        R.gstr.release(); R.rstr.release(); R.sizes.release(); R.n_cols.release(); R.n_close.release(); R.n_extra.release();
+        R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
+        R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
+    }
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
         sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
@@ -622,6 +649,109 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
     return VGL_OK;
 }
 
+uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* r) {
+    if (!r) return 0;
+    return (uint64_t)(r->n_reads + 1) * 12 + r->n_reads + r->qual_off[r->n_reads] + (uint64_t)r->n_maps * 8 + (uint64_t)(r->n_maps + 1) * 4 +
+           (uint64_t)r->n_edits * 4 + (uint64_t)(r->n_edits + 1) * 4 + r->edit_seq_off[r->n_edits];
+}
+
+int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq) {
+    if (int rc = use_device(ctx)) return rc;
+    if (min_id < 0 || n_nodes <= 0 || !seq_off || !seq || min_id + n_nodes > (int64_t)VGL_HC_MAX_NODE + 1 || seq_off[n_nodes] > 0xffffffffll)
+        return fail(VGL_ERR_INVALID, "bad node table (node ids must fit the column record, <= %u)", VGL_HC_MAX_NODE);
+    std::vector<uint32_t> off((size_t)n_nodes + 1);
+    for (int64_t k = 0; k <= n_nodes; ++k) off[(size_t)k] = (uint32_t)seq_off[k];
+    if (int rc = ctx->g_seq_off.reserve(off.size())) return rc;
+    if (int rc = ctx->g_seq.reserve((size_t)seq_off[n_nodes] + 1)) return rc;
+    VGL_CUDA(cudaMemcpy(ctx->g_seq_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    VGL_CUDA(cudaMemcpy(ctx->g_seq.p, seq, (size_t)seq_off[n_nodes], cudaMemcpyHostToDevice));
+    ctx->g_min_id = (uint32_t)min_id;
+    ctx->g_n_nodes = (uint32_t)n_nodes;
+    ctx->have_graph = true;
+    return VGL_OK;
+}
+
+// H2D of the raw alignments, reconstruction and packing on ctx->stream; fills the read kernel's batch descriptor.
+static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchDev& d) {
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
+    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq)
+        return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
+    vgl_ctx::RawDev& R = ctx->rawdev;
+    cudaStream_t s = ctx->stream;
+    const size_t n = raw->n_reads, nm = raw->n_maps, ne = raw->n_edits;
+    const size_t nq = raw->qual_off[n], nseq = raw->edit_seq_off[ne], ncap = raw->str_off[n];
+    const size_t G = (n + 31) / 32;
+    // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read
+    const size_t col_cap = ncap / 128 + 1024 + G + 1, map_cap = G + 4096;
+    if (col_cap > 0x7fffffffull) return fail(VGL_ERR_INVALID, "batch too large; split it");
+    // the previous batch's kernels read these buffers: growing one needs the stream to be idle
+    if (n + 1 > R.qual_off.cap || nq > R.qual.cap || nm > R.map_node.cap || ne > R.edit_from.cap || nseq > R.edit_seq.cap ||
+        ncap > R.gstr.cap || col_cap * 128 > R.col.cap)
+        VGL_CUDA(cudaStreamSynchronize(s));
+#define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
+    RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
+    RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
+    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
+    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, nm); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
+    RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
+    RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
+    RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
+#undef RSV
+    R.col_cap_blks = (uint32_t)col_cap;
+    R.map_cap_blks = (uint32_t)map_cap;
+    d = vgl::HcBatchDev{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p};
+    if (n == 0) return VGL_OK;
+#define H2D(dst, src, bytes) if ((size_t)(bytes) != 0 && (src) != nullptr) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, s))
+    H2D(R.qual_off.p, raw->qual_off, (n + 1) * 4); H2D(R.str_off.p, raw->str_off, (n + 1) * 4); H2D(R.map_off.p, raw->map_off, (n + 1) * 4);
+    H2D(R.mapq.p, raw->mapq, n); H2D(R.qual.p, raw->qual, nq);
+    H2D(R.map_node.p, raw->map_node, nm * 4); H2D(R.map_offset.p, raw->map_offset, nm * 4); H2D(R.edit_off.p, raw->edit_off, (nm + 1) * 4);
+    H2D(R.edit_from.p, raw->edit_from, ne * 2); H2D(R.edit_to.p, raw->edit_to, ne * 2); H2D(R.edit_seq_off.p, raw->edit_seq_off, (ne + 1) * 4);
+    H2D(R.edit_seq.p, raw->edit_seq, nseq);
+#undef H2D
+    VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
+    VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
+    const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
+    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p,
+                              R.edit_off.p, R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p};
+    const vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
+                               R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, ctx->d_err, s));
+    VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
+                                 R.o_mapq.p, ctx->d_err, s));
+    ctx->launches += 6;
+    return VGL_OK;
+}
+
+int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!out) return fail(VGL_ERR_INVALID, "null output");
+    vgl::HcBatchDev d;
+    if (int rc = pack_raw_on_device(ctx, raw, d)) return rc;
+    memset(out, 0, sizeof(*out));
+    out->n_reads = raw->n_reads;
+    out->n_groups = d.n_groups;
+    out->grp_col_blk = d.grp_col_blk; out->grp_map_blk = d.grp_map_blk; out->col = d.col; out->map = d.map;
+    out->n_cols = d.n_cols; out->n_close = d.n_close; out->n_extra = d.n_extra; out->mapq = d.mapq;
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (d.n_groups) {
+        uint32_t tot[2] = {0, 0};
+        VGL_CUDA(cudaMemcpy(&tot[0], d.grp_col_blk + d.n_groups, 4, cudaMemcpyDeviceToHost));
+        VGL_CUDA(cudaMemcpy(&tot[1], d.grp_map_blk + d.n_groups, 4, cudaMemcpyDeviceToHost));
+        out->n_col_blks = tot[0];
+        out->n_map_blks = tot[1];
+    }
+    return VGL_OK;
+}
+
+int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
+    if (int rc = use_device(ctx)) return rc;
+    vgl::HcBatchDev d;
+    if (int rc = pack_raw_on_device(ctx, raw, d)) return rc;
+    if (d.n_groups == 0) return VGL_OK;
+    return launch_read(ctx, d);
+}
+
 int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
@@ -717,6 +847,10 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
     const int err = idx[2];
     if (err & 0x40000000)
         return fail(VGL_ERR_PEER, "multi-GPU exchange: a peer rank did not deliver its vector within 10 s");
+    if (err & 0x20000000)
+        return fail(VGL_ERR_BAD_READ, "device-side reconstruction rejected a read (malformed alignment: lengths, offsets, mapping quality or edit sizes out of range)");
+    if (err & 0x10000000)
+        return fail(VGL_ERR_BAD_NODE, "device-side reconstruction: a mapping names a node outside the graph");
     if (err & VGL_ERR_BAD_NODE)
         return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
     if (argmax_out) *argmax_out = idx[0];

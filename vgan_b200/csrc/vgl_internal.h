@@ -125,6 +125,50 @@ cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, co
                                 double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------------------
+// device-side reconstruction and packing (recon_kernels.cu)
+// ---------------------------------------------------------------------------------------------------------
+struct ReconGraphDev {
+    uint32_t min_id, n_nodes;
+    const uint32_t* seq_off;  // [n_nodes + 1]
+    const uint8_t* seq;
+};
+struct ReconRawDev {  // device copy of a vgl_hc_raw
+    uint32_t n_reads;
+    const uint32_t* qual_off;
+    const uint8_t* qual;
+    const uint8_t* mapq;
+    const uint32_t* str_off;
+    const uint32_t* map_off;
+    const uint32_t* map_node;
+    const uint32_t* map_offset;
+    const uint32_t* edit_off;
+    const uint16_t* edit_from;
+    const uint16_t* edit_to;
+    const uint32_t* edit_seq_off;
+    const uint8_t* edit_seq;
+};
+struct ReconWorkDev {  // scratch
+    uint8_t* gstr;      // aligned graph strings, read r at str_off[r]
+    uint8_t* rstr;      // aligned read strings
+    uint16_t* sizes;    // [n_maps] size slot of every mapping (the size of the read's i-th EDIT, quirk Q1)
+    uint16_t* n_cols;   // [n_reads] in caller order
+    uint16_t* n_close;
+    uint16_t* n_extra;
+    uint32_t* hist;     // [4096] reads per column count
+    uint32_t* start;    // [4096]
+    uint32_t* cursor;   // [4096]
+    uint32_t* order;    // [n_reads] read ids sorted by column count
+    uint32_t* grp_cb;   // [n_groups + 1] -> the batch's grp_col_blk
+    uint32_t* grp_mb;   // [n_groups + 1] -> the batch's grp_map_blk
+};
+// hist and cursor must be zero on entry.
+cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int* err_flag, cudaStream_t s);
+// xmap (the extra records) must be zero on entry.
+cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32_t col_cap_blks, uint32_t map_cap_blks, uint32_t* col,
+                           uint32_t* xmap, uint16_t* n_cols, uint16_t* n_close, uint16_t* n_extra, uint8_t* mapq, int* err_flag,
+                           cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------------
 // euka
 // ---------------------------------------------------------------------------------------------------------
 struct EukaSmallTables {

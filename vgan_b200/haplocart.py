@@ -50,6 +50,13 @@ class Haplocart:
                                       np.zeros(1, np.int32).ctypes.data_as(C.c_void_p)))
             self._max_post = 1 + int(np.max(np.diff(tree.anc_off))) if tree.anc_off.size > 1 else 1
 
+    def load_graph(self, graph):
+        """Node sequences for the device-side reconstruction (update_raw)."""
+        mid, n = C.c_int64(), C.c_int64()
+        off, seq = C.c_void_p(), C.c_void_p()
+        check(_lib.host.vgh_graph_view(graph.handle, C.byref(mid), C.byref(n), C.byref(off), C.byref(seq)))
+        check(gpu.vgl_hc_set_graph(self.ctx, mid.value, n.value, off, seq))
+
     def set_stream(self, cuda_stream_ptr):
         check(gpu.vgl_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
@@ -61,6 +68,24 @@ class Haplocart:
     def update(self, packed):
         """Haplocart::update for every read of a packed host batch, summed into final_vec."""
         check(gpu.vgl_hc_accumulate(self.ctx, C.byref(packed.batch)))
+
+    def update_raw(self, raw):
+        """Haplocart::update for the raw alignments of a RawBatch: reconstruction and packing happen on the device."""
+        check(gpu.vgl_hc_accumulate_raw(self.ctx, C.byref(raw.raw)))
+
+    def pack_raw(self, raw):
+        """Reconstruct and pack on the device only; returns the device batch (a `_lib.vgl_hc_batch` of device pointers,
+        valid until the next raw call on this object) for inspection."""
+        b = _lib.vgl_hc_batch()
+        check(gpu.vgl_hc_pack_raw(self.ctx, C.byref(raw.raw), C.byref(b)))
+        return b
+
+    def download(self, dev_ptr, n, dtype):
+        """Copy n items of dtype from device memory (tests)."""
+        out = np.zeros(n, dtype=dtype)
+        if n:
+            check(gpu.vgl_memcpy_d2h(self.ctx, out.ctypes.data_as(C.c_void_p), C.c_void_p(dev_ptr), out.nbytes))
+        return out
 
     def update_device(self, batch_struct):
         """Same, for a batch whose arrays already live in HBM (a `_lib.vgl_hc_batch` of device pointers)."""

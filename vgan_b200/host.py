@@ -177,6 +177,30 @@ class PackedBatch:
             self.handle = None
 
 
+class RawBatch:
+    """The raw alignments of reads [r0, r1) in the compact form the device-side reconstruction reads (vgl_hc_raw)."""
+
+    def __init__(self, alns, r0=0, r1=None, pinned=False):
+        r1 = len(alns) if r1 is None else r1
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_raw_build(C.byref(alns.view), int(r0), int(r1), int(pinned), C.byref(self.handle)))
+        self.raw = host.vgh_hc_raw_view(self.handle).contents
+        self.skipped = int(host.vgh_hc_raw_skipped(self.handle))
+
+    @property
+    def n_reads(self):
+        return int(self.raw.n_reads)
+
+    @property
+    def nbytes(self):
+        return int(_lib.gpu.vgl_hc_raw_bytes(C.byref(self.raw)))
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_hc_raw_destroy(self.handle)
+            self.handle = None
+
+
 class HcTables:
     """HaploCart tables in the form vgl_hc_set_tables wants, built from the reference's in-memory inputs."""
 
