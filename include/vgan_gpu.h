@@ -233,7 +233,7 @@ int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* device_batch);
  * vgh_hc_raw_build, one linear pass):
  *   qual_off[r] .. qual_off[r+1]   quality bytes of read r (raw PHRED)
  *   str_off[r+1] - str_off[r]      capacity reserved for read r's aligned strings: sum over its edits of
- *                                  from_length + to_length + |sequence|
+ *                                  from_length + to_length + |sequence|, rounded up to a multiple of 4
  *   map_node[m]                    Mapping.position.node_id | is_reverse << 31;  map_offset[m] = position.offset
  *   edit_from / edit_to [e]        Edit.from_length / to_length (<= 65535); edit_seq_off[e] .. [e+1] its sequence
  * Only reads with identity >= 1e-10 are listed (src/HaploCart.cpp:411).  All pointers are HOST pointers.      */

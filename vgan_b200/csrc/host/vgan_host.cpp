@@ -643,7 +643,7 @@ int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
         if (!e && (a->mapq[r] < 0 || a->mapq[r] > 255)) e = VGH_ERR_BAD_READ;
         for (int64_t m = a->map_off[r]; !e && m < a->map_off[r + 1]; ++m)
             if (a->map_node[m] < 0 || a->map_node[m] > 0x7fffffffll || a->map_offset[m] < 0 || a->map_offset[m] > 0xffffffffll) e = VGH_ERR_BAD_READ;
-        pc[(size_t)k + 1] = cap;
+        pc[(size_t)k + 1] = (cap + 3) & ~(uint64_t)3;  // every read's strings start 4-byte aligned on the device
         if (e) {
 #pragma omp critical(vgh_raw_err)
             if (!err) { err = e; err_msg = "read " + std::to_string(r) + ": mapping quality, node id, offset or edit length out of range"; }

@@ -35,11 +35,26 @@ __device__ __forceinline__ EditKind classify(uint32_t from, uint32_t to, bool ha
     return kOther;
 }
 
-// base at oriented offset k of a node (what get_sequence(get_handle(id, rev))[k] returns)
-__device__ __forceinline__ uint8_t node_base(const ReconGraphDev& G, uint32_t row, bool rev, uint32_t k) {
-    const uint32_t a = G.seq_off[row], n = G.seq_off[row + 1] - a;
-    if (!rev) return G.seq[a + k];
-    const uint8_t c = G.seq[a + n - 1 - k];
+// Appends bytes to a string in global memory four at a time (the strings start 4-byte aligned): one 32-bit store per four
+// bytes instead of four scattered byte stores.
+struct ByteWriter {
+    uint8_t* base;
+    uint32_t len = 0, word = 0;
+    __device__ __forceinline__ explicit ByteWriter(uint8_t* b) : base(b) {}
+    __device__ __forceinline__ void put(uint8_t c) {
+        word |= (uint32_t)c << (8 * (len & 3));
+        ++len;
+        if ((len & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(base + len - 4) = word;
+            word = 0;
+        }
+    }
+    __device__ __forceinline__ void flush() {  // the tail of a partially filled word
+        for (uint32_t k = len & ~3u; k < len; ++k) base[k] = (uint8_t)(word >> (8 * (k & 3)));
+    }
+};
+
+__device__ __forceinline__ uint8_t complement(uint8_t c) {
     switch (c) {
         case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
         case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
@@ -53,45 +68,41 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restric
     if (r >= raw.n_reads) return;
     const uint32_t m0 = raw.map_off[r], m1 = raw.map_off[r + 1], M = m1 - m0;
     const uint32_t s0 = raw.str_off[r], cap = raw.str_off[r + 1] - s0;
-    uint8_t* gs = W.gstr + s0;
-    uint8_t* rs = W.rstr + s0;
-    uint32_t glen = 0, rlen = 0, e_idx = 0;
+    ByteWriter gw(W.gstr + s0), rw(W.rstr + s0);
+    uint32_t e_idx = 0, n_del = 0;
     int err = 0;
     for (uint32_t m = m0; m < m1 && !err; ++m) {
-        const uint32_t node = raw.map_node[m] & 0x7fffffffu;
-        const bool rev = (raw.map_node[m] >> 31) != 0;
+        const uint32_t mn = raw.map_node[m];
+        const uint32_t node = mn & 0x7fffffffu;
+        const bool rev = (mn >> 31) != 0;
         if (node < G.min_id || node >= G.min_id + G.n_nodes || node > VGL_HC_MAX_NODE) { err = kErrBadNodeRaw; break; }
-        const uint32_t row = node - G.min_id;
-        const uint32_t nlen = G.seq_off[row + 1] - G.seq_off[row];
+        const uint32_t na = G.seq_off[node - G.min_id], nlen = G.seq_off[node - G.min_id + 1] - na;
         uint32_t offset = raw.map_offset[m];
         uint32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size
-        for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
+        const uint32_t e1 = raw.edit_off[m + 1];
+        for (uint32_t e = raw.edit_off[m]; e < e1; ++e) {
             const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
             const uint32_t q0 = raw.edit_seq_off[e], q1 = raw.edit_seq_off[e + 1];
             const EditKind kind = classify(from, to, q1 > q0);
             if (kind == kMatch || kind == kSub || kind == kDel) {
                 if (offset > nlen) { err = kErrBadRead; break; }
                 const uint32_t take = min(from, nlen - offset);  // std::string::substr clips
-                if (glen + take > cap) { err = kErrBadRead; break; }
-                for (uint32_t k = 0; k < take; ++k) gs[glen + k] = node_base(G, row, rev, offset + k);
-                aligned = take;
-                if (kind == kMatch) {
-                    if (rlen + take > cap) { err = kErrBadRead; break; }
-                    for (uint32_t k = 0; k < take; ++k) rs[rlen + k] = gs[glen + k];
-                    rlen += take;
-                } else if (kind == kSub) {
-                    if (rlen + (q1 - q0) > cap) { err = kErrBadRead; break; }
-                    for (uint32_t k = 0; k < q1 - q0; ++k) rs[rlen + k] = raw.edit_seq[q0 + k];
-                    rlen += q1 - q0;
+                if (gw.len + take > cap || rw.len + max(take, q1 - q0) > cap) { err = kErrBadRead; break; }
+                for (uint32_t k = 0; k < take; ++k) {
+                    // base at oriented offset of the node (what get_sequence(get_handle(id, rev))[k] returns)
+                    const uint8_t c = rev ? complement(G.seq[na + nlen - 1 - (offset + k)]) : G.seq[na + offset + k];
+                    gw.put(c);
+                    if (kind == kMatch) rw.put(c);
                 }
-                glen += take;
+                aligned = take;
+                if (kind == kSub)
+                    for (uint32_t k = q0; k < q1; ++k) rw.put(raw.edit_seq[k]);
+                n_del += kind == kDel;
             } else if (kind == kIns) {
-                if (glen + to > cap || rlen + (q1 - q0) > cap) { err = kErrBadRead; break; }
+                if (gw.len + to > cap || rw.len + (q1 - q0) > cap) { err = kErrBadRead; break; }
                 const uint8_t fill = offset == 0 ? 'S' : '-';
-                for (uint32_t k = 0; k < to; ++k) gs[glen + k] = fill;
-                glen += to;
-                for (uint32_t k = 0; k < q1 - q0; ++k) rs[rlen + k] = raw.edit_seq[q0 + k];
-                rlen += q1 - q0;
+                for (uint32_t k = 0; k < to; ++k) gw.put(fill);
+                for (uint32_t k = q0; k < q1; ++k) rw.put(raw.edit_seq[k]);
                 aligned = to;
             }
             offset += from;
@@ -99,9 +110,14 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restric
             ++e_idx;
         }
     }
+    gw.flush();
+    rw.flush();
+    const uint32_t glen = gw.len;
+    uint32_t rlen = rw.len;
     // deletions: a '-' run spliced into the read string at the running from_length coordinate, in order, each against the
     // string as it stands (src/vgan_utils.h:67)
-    if (!err) {
+    if (!err && n_del) {
+        uint8_t* rs = W.rstr + s0;
         uint32_t from_total = 0;
         for (uint32_t m = m0; m < m1 && !err; ++m) {
             for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
@@ -137,7 +153,9 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restric
     W.n_cols[r] = (uint16_t)rlen;
     W.n_close[r] = (uint16_t)n_close;
     W.n_extra[r] = (uint16_t)n_extra;
-    atomicAdd(W.hist + rlen, 1u);
+    // histogram of column counts: one atomic per distinct value in the warp
+    const uint32_t peers = __match_any_sync(__activemask(), rlen);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + rlen, (uint32_t)__popc(peers));
 }
 
 // exclusive scan of 4096 counters, one block of 1024 threads (4 per thread)
@@ -177,7 +195,13 @@ hc_order_kernel(uint32_t n_reads, const uint16_t* __restrict__ n_cols, const uin
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const uint32_t key = n_cols[r];
-    order[start[key] + atomicAdd(cursor + key, 1u)] = r;
+    // one atomic per distinct key in the warp (reads of one batch are mostly equally long: a single hot counter otherwise)
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[start[key] + base + __popc(peers & ((1u << lane) - 1u))] = r;
 }
 
 __global__ void __launch_bounds__(256)
