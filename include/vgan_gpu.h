@@ -261,8 +261,8 @@ int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_
 /* Reconstruct and pack `raw` on the device; *device_batch receives device pointers that stay valid until
  * the next vgl_hc_pack_raw / vgl_hc_accumulate_raw on this context (for inspection and tests).    */
 int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* device_batch);
-/* vgl_hc_accumulate for raw alignments: H2D of `raw`, reconstruction, packing, read kernel -- no host sync.
- * Malformed reads surface as VGL_ERR_BAD_READ / VGL_ERR_BAD_NODE at vgl_hc_finalize.              */
+/* vgl_hc_accumulate for raw alignments: H2D of `raw`, reconstruction, packing, read kernel.  Returns when the host
+ * arrays have been copied (the caller may reuse them); the kernels run asynchronously.  Malformed reads surface as VGL_ERR_BAD_READ / VGL_ERR_BAD_NODE at vgl_hc_finalize.              */
 int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw);
 
 /* Collapse the accumulators into the per-path log-likelihood vector final_vec[P]

@@ -18,6 +18,7 @@ struct AlignmentInfo { std::string seq, quality_scores; Path path; int32_t mappi
 int main(int argc, char** argv) {
     const int n_reads = argc > 1 ? atoi(argv[1]) : 200;
     const bool compile_only = argc > 2 && std::string(argv[2]) == "--no-gpu";
+    const bool on_device = argc > 2 && std::string(argv[2]) == "--device-reconstruction";  // raw alignments, packed on the GPU
     vgh_synth_hc* S = nullptr;
     if (vgh_synth_hc_create(101, 300, 1210, 1201, &S)) return 2;
     vgh_gam* gam = nullptr;
@@ -60,7 +61,8 @@ int main(int argc, char** argv) {
         { std::string all = vgh_synth_hc_names(S); size_t a = 0; for (size_t k = 0; k < all.size(); ++k) if (all[k] == '\n') { names.push_back(all.substr(a, k - a)); a = k + 1; } }
         hc.load_tree(names, vgh_synth_hc_parents(S), vgh_synth_hc_children(S));
         hc.reset();
-        hc.update(algnvector, 4);
+        if (on_device) hc.update_on_device(algnvector);
+        else hc.update(algnvector, 4);
         const vgan_b200::Posterior post = hc.get_posterior(true);
         printf("call %d %s total %.17g\n", post.maxh_index, names[post.maxh_index].c_str(), post.total_ll);
         for (size_t k = 0; k < post.confidence_vec.size(); ++k)

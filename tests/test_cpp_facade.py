@@ -31,8 +31,9 @@ def test_facade_compiles_and_flattens_alignment_objects():
 
 
 @pytest.mark.gpu
-def test_facade_end_to_end_matches_oracle():
-    out = subprocess.check_output([_build(), "200"]).decode().splitlines()
+@pytest.mark.parametrize("route", [[], ["--device-reconstruction"]])
+def test_facade_end_to_end_matches_oracle(route):
+    out = subprocess.check_output([_build(), "200"] + route).decode().splitlines()
     S = vb.SynthHaplocart(seed=101, n_paths=300, n_rows=1210, n_nodes=1201)
     alns = S.reads(200, seed=202)
     T, G, R = H.oracle_side(S, alns.arrays())

@@ -119,6 +119,7 @@ public:
         if (graph_) vgh_graph_destroy(graph_);
         graph_ = nullptr;
         check(vgh_graph_create(min_id, (int64_t)node_seqs.size(), off.data(), blob.data(), &graph_), "cannot build the node table");
+        check(vgl_hc_set_graph(ctx_, min_id, (int64_t)node_seqs.size(), off.data(), blob.data()), "cannot upload the node table");
     }
 
     // The tables exactly as the reference holds them: NodeInfo::pathsgo rows (row index == node id),
@@ -165,6 +166,19 @@ public:
         check(vgh_hc_pack(graph_, &v, 0, v.n_reads, n_threads, /*pinned=*/1, &packed), "cannot pack the alignments");
         const int rc = vgl_hc_accumulate(ctx_, vgh_hc_packed_batch(packed));
         vgh_hc_packed_destroy(packed);
+        check(rc, "likelihood kernel");
+    }
+
+    // Same, with reconstruct_graph_sequence and the packing done on the GPU: the host only copies the alignments' fields
+    // into the compact raw arrays (one linear pass, no per-read string building).
+    template <typename AlignmentInfoPtrVector>
+    void update_on_device(const AlignmentInfoPtrVector& algnvector) {
+        flat_.assign(algnvector);
+        const vgh_alignments v = flat_.view();
+        vgh_hc_raw* raw = nullptr;
+        check(vgh_hc_raw_build(&v, 0, v.n_reads, /*pinned=*/1, &raw), "cannot marshal the alignments");
+        const int rc = vgl_hc_accumulate_raw(ctx_, vgh_hc_raw_view(raw));  // returns once the host arrays have been copied
+        vgh_hc_raw_destroy(raw);
         check(rc, "likelihood kernel");
     }
 

@@ -108,6 +108,7 @@ struct vgl_ctx {
         DevBuf<uint16_t> o_n_cols, o_n_close, o_n_extra;
         DevBuf<uint8_t> o_mapq;
         uint32_t col_cap_blks = 0, map_cap_blks = 0;
+        cudaEvent_t copied = nullptr;  // the H2D copies of the last raw batch
     } rawdev;
 
     // multi-GPU exchange through peer memory
@@ -292,6 +293,7 @@ void vgl_destroy(vgl_ctx* ctx) {
         R.gstr.release(); R.rstr.release(); R.sizes.release(); R.n_cols.release(); R.n_close.release(); R.n_extra.release();
         R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
         R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
+        if (R.copied) cudaEventDestroy(R.copied);
     }
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
@@ -709,6 +711,8 @@ static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchD
     H2D(R.edit_from.p, raw->edit_from, ne * 2); H2D(R.edit_to.p, raw->edit_to, ne * 2); H2D(R.edit_seq_off.p, raw->edit_seq_off, (ne + 1) * 4);
     H2D(R.edit_seq.p, raw->edit_seq, nseq);
 #undef H2D
+    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
+    VGL_CUDA(cudaEventRecord(R.copied, s));
     VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
     const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
@@ -720,6 +724,12 @@ static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchD
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
                                  R.o_mapq.p, ctx->d_err, s));
     ctx->launches += 6;
+    return VGL_OK;
+}
+
+// The caller may reuse its host buffers as soon as an entry point returns: wait for the H2D copies (not for the kernels).
+static int wait_raw_copied(vgl_ctx* ctx) {
+    if (ctx->rawdev.copied) VGL_CUDA(cudaEventSynchronize(ctx->rawdev.copied));
     return VGL_OK;
 }
 
@@ -749,7 +759,8 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     vgl::HcBatchDev d;
     if (int rc = pack_raw_on_device(ctx, raw, d)) return rc;
     if (d.n_groups == 0) return VGL_OK;
-    return launch_read(ctx, d);
+    if (int rc = launch_read(ctx, d)) return rc;
+    return wait_raw_copied(ctx);
 }
 
 int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
