@@ -204,17 +204,13 @@ soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup
                 need_damage = true;
                 if (baseIX >= 0 && baseIX < nc) {
                     const int i5 = min(baseIX, t.k5 - 1), i3 = min(nc - baseIX - 1, t.k3 - 1);
-                    const double* __restrict__ D = t.deam + ((size_t)i5 * t.k3 + i3) * 16;
+                    const double* __restrict__ D = t.deam + ((size_t)i5 * t.k3 + i3) * 4;  // row sums of the damage matrix
                     const double e1 = s_tab.one_minus_e[q], e3 = s_tab.e_third[q];
                     double tot = 0.0;
 #pragma unroll
-                    for (int bpd = 0; bpd < 4; ++bpd) {
-                        double post = 0.0;
-#pragma unroll
-                        for (int bpo = 0; bpo < 4; ++bpo) post = fma((bpo == G) ? e1 : e3, __ldg(D + bpo * 4 + bpd), post);
-                        tot += post;
-                    }
-                    s_sup += fmin(log(tot), log_cap);
+                    for (int bpo = 0; bpo < 4; ++bpo) tot = fma((bpo == G) ? e1 : e3, __ldg(D + bpo), tot);
+                    // min(log(tot), log(0.9999999)) (src/getLCAfromGAM.h:351-353): the log is only needed below the cap
+                    s_sup += tot >= 0.9999999 ? log_cap : fmin(log(tot), log_cap);
                 }
                 s_uns += ((bor < 0 ? -bor : bor) % t.penalty == 0) ? s_tab.log_one_minus_e[q] : s_tab.log_e_third[q];
             }
@@ -228,7 +224,13 @@ soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup
     }
 }
 
-// K5b: one warp per read, lanes over paths.
+// K5b: one warp per read.  pathMap[p] = sum over edits of (path p goes through the edit's node ? sup : uns)
+//                              = sum of sup  +  sum over edits of !member(edit, p) * (uns - sup)
+// ("supported" is the baseline: a well supported path is a sum of small terms and carries no cancellation),
+// so a lane keeps the running sums of "its" paths (p = 32 k + lane, bit `lane` of membership word k) in registers and
+// every edit costs one uniform load per membership word instead of a pass over the edit list per 32 paths.
+// kSoibeanWordsPerPass membership words (32 paths each) are covered per pass over the edit list.
+template <int kSoibeanWordsPerPass>
 __global__ void __launch_bounds__(kEukaBlock)
 soibean_path_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict__ sup, const double* __restrict__ uns, uint32_t n_out,
                     double* __restrict__ out, uint8_t* __restrict__ used, int* __restrict__ err_flag) {
@@ -241,24 +243,36 @@ soibean_path_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict
     if (ridx >= n_out) return;
     const uint32_t g = r >> 5, l = r & 31;
     const size_t mapbase = ((size_t)__ldg(b.grp_map_blk + g) * 32 + l) * 4;
-    for (int p0 = 0; p0 < t.n_paths; p0 += 32) {
-        const int p = p0 + lane;
-        double acc = 0.0;
+    const int n_words = (t.n_paths + 31) >> 5;
+    for (int w0 = 0; w0 < n_words; w0 += kSoibeanWordsPerPass) {
+        double acc[kSoibeanWordsPerPass];
+#pragma unroll
+        for (int k = 0; k < kSoibeanWordsPerPass; ++k) acc[k] = 0.0;
+        double base = 0.0;
         for (int i = 0; i < ne; ++i) {
             const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
             const uint32_t node = __ldg(b.map + mi) & 0xFFFFFu;
-            bool member = false;
-            if (node != VGL_SOIBEAN_NO_NODE) {
-                const int row = (int)node - t.min_id;
-                if (row < 0 || row >= t.n_rows) {
-                    if (lane == 0 && p0 == 0) atomicOr(err_flag, 2);  // nodepaths.at() would throw
-                } else if (p < t.n_paths) {
-                    member = (__ldg(t.member_bits + (size_t)row * t.row_words + (p >> 5)) >> (p & 31)) & 1u;
-                }
+            const double u = __ldg(uns + mi);
+            const int row = (int)node - t.min_id;
+            if (node == VGL_SOIBEAN_NO_NODE || row < 0 || row >= t.n_rows) {
+                // surplus entries get no support on any path (src/getLCAfromGAM.h:156-160); a node outside the table: nodepaths.at() would throw
+                if (node != VGL_SOIBEAN_NO_NODE && lane == 0 && w0 == 0) atomicOr(err_flag, 2);
+                base += u;
+                continue;
             }
-            acc += member ? __ldg(sup + mi) : __ldg(uns + mi);
+            const double sp = __ldg(sup + mi);
+            base += sp;
+            const double delta = u - sp;
+            const uint32_t* bits = t.member_bits + (size_t)row * t.row_words + w0;
+#pragma unroll
+            for (int k = 0; k < kSoibeanWordsPerPass; ++k)
+                if (w0 + k < n_words && !((__ldg(bits + k) >> lane) & 1u)) acc[k] += delta;
         }
-        if (p < t.n_paths) out[(size_t)ridx * t.n_paths + p] = acc;
+#pragma unroll
+        for (int k = 0; k < kSoibeanWordsPerPass; ++k) {
+            const int p = (w0 + k) * 32 + lane;
+            if (w0 + k < n_words && p < t.n_paths) out[(size_t)ridx * t.n_paths + p] = base + acc[k];
+        }
     }
     if (lane == 0 && used) used[ridx] = 1;
 }
@@ -273,7 +287,12 @@ cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, dou
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const uint32_t lanes = b.n_groups * 32u;
-    soibean_path_kernel<<<(lanes + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
+    const int n_words = (t.n_paths + 31) / 32;
+    const unsigned grid = (lanes + warps - 1) / warps;
+    if (n_words <= 1) soibean_path_kernel<1><<<grid, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
+    else if (n_words <= 4) soibean_path_kernel<4><<<grid, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
+    else if (n_words <= 8) soibean_path_kernel<8><<<grid, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
+    else soibean_path_kernel<16><<<grid, kEukaBlock, 0, s>>>(b, t, sup, uns, n_out, out, used, err_flag);
     return cudaGetLastError();
 }
 

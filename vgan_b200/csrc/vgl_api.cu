@@ -1092,11 +1092,22 @@ int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* T) {
     }
     small.log_quarter = std::log(0.25);
     if (int rc = ctx->s_member.reserve((size_t)T->n_rows * T->row_words)) return rc;
-    if (int rc = ctx->s_deam.reserve((size_t)T->k5 * T->k3 * 16)) return rc;
+    if (int rc = ctx->s_deam.reserve((size_t)T->k5 * T->k3 * 4)) return rc;
     if (int rc = ctx->s_small.reserve(1)) return rc;
     if (int rc = ctx->s_err.reserve(1)) return rc;
     VGL_CUDA(cudaMemcpy(ctx->s_member.p, T->member_bits, (size_t)T->n_rows * T->row_words * 4, cudaMemcpyHostToDevice));
-    VGL_CUDA(cudaMemcpy(ctx->s_deam.p, T->deam, (size_t)T->k5 * T->k3 * 16 * 8, cudaMemcpyHostToDevice));
+    {
+        // soibean marginalises over ALL four post-damage bases (src/getLCAfromGAM.h:340-349): per original base only the
+        // row sum of the damage matrix matters
+        std::vector<double> rowsum((size_t)T->k5 * T->k3 * 4);
+        for (size_t m = 0; m < (size_t)T->k5 * T->k3; ++m)
+            for (int bpo = 0; bpo < 4; ++bpo) {
+                double s = 0.0;
+                for (int bpd = 0; bpd < 4; ++bpd) s += T->deam[m * 16 + (size_t)bpo * 4 + bpd];
+                rowsum[m * 4 + bpo] = s;
+            }
+        VGL_CUDA(cudaMemcpy(ctx->s_deam.p, rowsum.data(), rowsum.size() * 8, cudaMemcpyHostToDevice));
+    }
     VGL_CUDA(cudaMemcpy(ctx->s_small.p, &small, sizeof(small), cudaMemcpyHostToDevice));
     VGL_CUDA(cudaMemset(ctx->s_err.p, 0, sizeof(int)));
     vgl::SoibeanTablesDev& d = ctx->stab;

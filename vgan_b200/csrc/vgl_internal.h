@@ -226,7 +226,7 @@ cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& 
 struct SoibeanTablesDev {
     int32_t n_rows, min_id, n_paths, row_words, k5, k3, penalty;
     const uint32_t* member_bits;
-    const double* deam;
+    const double* deam;  // [k5 * k3][4] row sums of the damage matrices
     const EukaSmallTables* small;  // one_minus_e / e_third / their logs by quality byte
 };
 

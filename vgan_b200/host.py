@@ -17,6 +17,36 @@ def _as_array(ptr, n, dtype):
     return np.frombuffer(buf, dtype=dtype, count=n).copy()
 
 
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(_lib.gpu.vgl_host_alloc(C.byref(self.ptr), max(int(nbytes), 1)))
+
+    def __del__(self):
+        if self.ptr:
+            _lib.gpu.vgl_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array in page-locked host memory (vgl_host_alloc): device-to-host results land in it at PCIe speed."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    blk = _PinnedBlock(n * dt.itemsize)
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(blk.ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    arr = arr.view(_PinnedArray)
+    arr._block = blk
+    return arr
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray view that keeps its pinned block alive."""
+
+    def __array_finalize__(self, obj):
+        self._block = getattr(obj, "_block", None)
+
+
 class Graph:
     """Node sequences with contiguous ids (what the hot path asks of bdsg::ODGI::get_sequence)."""
 

@@ -64,10 +64,17 @@ class Soibean:
         check(gpu.vgl_soibean_set_tables(self.ctx, C.byref(tables.view)))
         self.tables = tables
 
-    def analyse(self, packed):
-        """pathMap of every read of the packed range: (matrix [n, P], used [n])."""
+    def analyse(self, packed, pinned=False):
+        """pathMap of every read of the packed range: (matrix [n, P], used [n]).  pinned=True returns arrays in page-locked
+        memory (the R x P matrix then comes back at PCIe speed)."""
         n, P = packed.n_span, self.tables.n_paths
-        out = np.zeros((n, P), dtype=np.float64)
-        used = np.zeros(n, dtype=np.uint8)
+        if pinned:
+            from .host import pinned_empty
+            out, used = pinned_empty((n, P), np.float64), pinned_empty((n,), np.uint8)
+            out[...] = 0.0
+            used[...] = 0
+        else:
+            out = np.zeros((n, P), dtype=np.float64)
+            used = np.zeros(n, dtype=np.uint8)
         check(gpu.vgl_soibean_run(self.ctx, C.byref(packed.batch), n, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
         return out, used
