@@ -225,6 +225,13 @@ def main():
     packed = vb.PackedBatch(S.graph, alns, pinned=True)
     t_pack = time.perf_counter() - t_pack
     dev = hc.upload(packed)
+    # the e2e route ships the batch in its wire form (16-bit column records + one node id per mapping) and expands it on
+    # the device; graphs with node ids above 65535 would ship the 32-bit batch itself
+    try:
+        wire = vb.WireBatch(packed, pinned=True)
+    except RuntimeError:
+        wire = None
+    host_batch = wire if wire is not None else packed
     reads_local = packed.n_reads
     batch_bytes = packed.nbytes
     # algorithmic bytes of the read kernel: 4 per column + 4 per empty mapping + 7 per read + 8 per group
@@ -241,10 +248,13 @@ def main():
 
     def step(host_buffers):
         if sharded is not None:
-            return sharded.run([packed] if host_buffers else [dev], device_resident=not host_buffers)
+            return sharded.run([host_batch] if host_buffers else [dev], device_resident=not host_buffers)
         hc.reset()
         if host_buffers:
-            hc.update(packed)
+            if wire is not None:
+                hc.update_wire(wire)
+            else:
+                hc.update(packed)
         else:
             hc.update_device(dev.batch)
         return hc.get_posterior(want_ll=False)
@@ -370,7 +380,8 @@ def main():
                            n_gpus, "none" if sharded is None else sharded.exchange),
                        "called_haplogroup": res.get("predicted_haplotype")},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 28 + 8 * hc._max_post,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_batch.nbytes,
+                    "route": "vgl_hc_accumulate_wire (wire form, expanded on the device)" if wire is not None else "vgl_hc_accumulate", "d2h_bytes_per_step": 28 + 8 * hc._max_post,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "raw_path": raw_path,
             "latency": latency,

@@ -208,6 +208,38 @@ typedef struct vgl_hc_batch {
 /* Bytes the batch occupies (what crosses PCIe / is read from HBM once per pass).               */
 uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b);
 
+/* The same batch in its WIRE form, for host -> device transfers (PCIe is the bound of vgl_hc_accumulate): the node
+ * id, which the 32-bit column record repeats on every column of a mapping, travels once per mapping.
+ *   col  : 16-bit column records, blocks of 8 per lane (32 lanes x 16 bytes): bits 0-14 as in the 32-bit record,
+ *          bit 15 OWNED (a mapping owns the column)
+ *   node : 16-bit node ids (graphs with node ids <= 65535, e.g. HaploCart's 11825 rows) of the read's non-empty
+ *          mappings, LAST mapping first (the order in which a walk from the read's last column meets their OPEN marks),
+ *          blocks of 8 per lane
+ *   extras (map), per-lane arrays: as in vgl_hc_batch.
+ * vgl_hc_accumulate_wire copies it chunk by chunk, expands each chunk into 32-bit records on the device
+ * (hc_expand_kernel) and runs the read kernel on it; results are identical to vgl_hc_accumulate of the 32-bit batch.
+ * Bytes per read: 2 n + 2 M' + 7 (M' non-empty mappings) -- 295 instead of 407 at config 2.                         */
+#define VGL_HC_WIRE_OWNED 0x8000u
+#define VGL_HC_WIRE_BLK 8
+typedef struct vgl_hc_wire {
+    uint32_t n_reads;
+    uint32_t n_groups;
+    uint64_t n_col_blks;          /* = grp_col_blk[n_groups]  */
+    uint64_t n_node_blks;         /* = grp_node_blk[n_groups] */
+    uint64_t n_map_blks;          /* = grp_map_blk[n_groups]  */
+    const uint32_t* grp_col_blk;  /* [n_groups + 1] */
+    const uint32_t* grp_node_blk; /* [n_groups + 1] */
+    const uint32_t* grp_map_blk;  /* [n_groups + 1] */
+    const uint16_t* col;          /* [n_col_blks][32][8]  */
+    const uint16_t* node;         /* [n_node_blks][32][8] */
+    const uint32_t* map;          /* [n_map_blks][32][4] extra records */
+    const uint16_t* n_cols;       /* [n_groups * 32] */
+    const uint16_t* n_close;      /* [n_groups * 32] */
+    const uint16_t* n_extra;      /* [n_groups * 32] */
+    const uint8_t* mapq;          /* [n_groups * 32] */
+} vgl_hc_wire;
+uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w);
+
 /* ------------------------------------------------------------------------------------------- */
 /* HaploCart hot path                                                                          */
 /* ------------------------------------------------------------------------------------------- */
@@ -221,6 +253,7 @@ int vgl_hc_reset(vgl_ctx* ctx);
  * Asynchronous with respect to the host (stream ordered); errors surface at finalize/synchronize. */
 int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* host_batch);
 int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* device_batch);
+int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* host_wire);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Device-side reconstruction and packing                                */

@@ -101,6 +101,14 @@ const vgl_hc_batch* vgh_hc_packed_batch(const vgh_hc_packed* p);
 int64_t vgh_hc_packed_skipped(const vgh_hc_packed* p);
 void vgh_hc_packed_destroy(vgh_hc_packed* p);
 
+/* ---- wire form of a packed batch (vgl_hc_wire, include/vgan_gpu.h) ---------------------------- */
+typedef struct vgh_hc_wire vgh_hc_wire;
+/* Re-encodes a packed batch for the host -> device transfer: 16-bit column records plus one 16-bit node id per
+ * non-empty mapping.  Fails with VGH_ERR_INVALID when a node id exceeds 65535 (use the 32-bit batch then).  */
+int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, vgh_hc_wire** out);
+const vgl_hc_wire* vgh_hc_wire_view(const vgh_hc_wire* w);
+void vgh_hc_wire_destroy(vgh_hc_wire* w);
+
 /* ---- raw alignments for the device-side reconstruction (vgl_hc_raw, include/vgan_gpu.h) ------ */
 typedef struct vgh_hc_raw vgh_hc_raw;
 /* One linear pass over reads [r0, r1): keeps those with identity >= 1e-10 (src/HaploCart.cpp:411) and copies the

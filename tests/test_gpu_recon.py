@@ -165,3 +165,26 @@ def test_malformed_reads_are_reported_not_guessed(small):
     with pytest.raises(RuntimeError):
         hc.get_posterior()
     hc.close()
+
+
+def test_wire_form_gives_the_same_results(small):
+    """vgl_hc_wire: 16-bit column records + one node id per mapping, expanded on the device (hc_expand_kernel)."""
+    hc = vb.Haplocart()
+    hc.load(small.tables(bep=2e-3), small.tree())
+    edge = vb.Alignments.from_gam_bytes(H.encode_gam(_edge_reads(small)))
+    for alns, bep in ((small.reads(5000, seed=305, sub_rate=0.01, indel_rate=0.003), 2e-3),
+                      (small.reads(700, seed=306, fixed_len=0, damage=True, sub_rate=0.03, indel_rate=0.02), 2e-3), (edge, 2e-3)):
+        packed = vb.PackedBatch(small.graph, alns, pinned=True)
+        wire = vb.WireBatch(packed, pinned=True)
+        assert wire.n_reads == packed.n_reads and (packed.n_reads < 500 or wire.nbytes < 0.8 * packed.nbytes)
+        hc.reset()
+        hc.update(packed)
+        want = hc.get_posterior()
+        hc.reset()
+        hc.update_wire(wire)
+        got = hc.get_posterior()
+        assert got["maxh_index"] == want["maxh_index"]
+        assert np.allclose(got["final_vec"], want["final_vec"], rtol=1e-13, atol=0)
+        final, argmax, _ = _oracle(small, alns, bep=bep)
+        _check(got, final, argmax, small)
+    hc.close()

@@ -314,3 +314,29 @@ def test_dedup_matches_the_reference_quadratic_scan():
     F = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "all_the_same.gam"))
     m, kept = vb.host.dedup(F)
     assert kept == 1 and m[1:].all() and np.array_equal(m, orc.dedup(orc.FlatReads(F.arrays())))
+
+
+def test_wire_form_of_a_packed_batch():
+    """The wire form holds the 32-bit records minus the node field, and the nodes once per mapping, last mapping first."""
+    S = vb.SynthHaplocart(seed=21, n_paths=33, n_rows=310, n_nodes=301)
+    A = S.reads(200, seed=23, sub_rate=0.02, indel_rate=0.01)
+    pb = vb.PackedBatch(S.graph, A)
+    wb = vb.WireBatch(pb)
+    w = wb.wire
+    G = int(w.n_groups)
+    gc = vb.host._as_array(w.grp_col_blk, G + 1, np.uint32)
+    gn = vb.host._as_array(w.grp_node_blk, G + 1, np.uint32)
+    col = vb.host._as_array(w.col, int(w.n_col_blks) * 256, np.uint16).reshape(-1, 32, 8)
+    node = vb.host._as_array(w.node, int(w.n_node_blks) * 256, np.uint16).reshape(-1, 32, 8)
+    assert gc[-1] == w.n_col_blks and gn[-1] == w.n_node_blks
+    lanes = pb.lanes()
+    for k, d in enumerate(lanes):
+        g, l = divmod(k, 32)
+        c16 = col[gc[g]:gc[g + 1], l, :].reshape(-1)
+        n16 = node[gn[g]:gn[g + 1], l, :].reshape(-1)
+        recs = d["col"]
+        assert [int(x) & 0x7fff for x in c16[:len(recs)]] == [r & 0x7fff for r in recs] and not c16[len(recs):].any()
+        assert [bool(x & 0x8000) for x in c16[:len(recs)]] == [(r >> 15) != 0x1FFFF for r in recs]
+        opens = [r >> 15 for r in reversed(recs) if r & 0x2000]
+        assert n16[:len(opens)].tolist() == opens and not n16[len(opens):].any()
+    assert wb.nbytes < 0.8 * pb.nbytes

@@ -26,6 +26,13 @@ class vgl_hc_tables(C.Structure):
                 ("reserved1", C.c_int32)]
 
 
+class vgl_hc_wire(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_node_blks", C.c_uint64),
+                ("n_map_blks", C.c_uint64), ("grp_col_blk", C.c_void_p), ("grp_node_blk", C.c_void_p), ("grp_map_blk", C.c_void_p),
+                ("col", C.c_void_p), ("node", C.c_void_p), ("map", C.c_void_p), ("n_cols", C.c_void_p), ("n_close", C.c_void_p),
+                ("n_extra", C.c_void_p), ("mapq", C.c_void_p)]
+
+
 class vgl_hc_raw(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_maps", C.c_uint32), ("n_edits", C.c_uint32), ("reserved", C.c_uint32),
                 ("qual_off", C.c_void_p), ("qual", C.c_void_p), ("mapq", C.c_void_p), ("str_off", C.c_void_p),
@@ -99,6 +106,8 @@ GPU_SYMBOLS = {
     "vgl_hc_accumulate_device": (C.c_int, [_P, C.POINTER(vgl_hc_batch)]),
     "vgl_hc_paths": (C.c_int, [_P, _P]),
     "vgl_hc_set_paths_from_parts": (C.c_int, [_P, _P, C.c_int32]),
+    "vgl_hc_wire_bytes": (C.c_uint64, [_P]),
+    "vgl_hc_accumulate_wire": (C.c_int, [_P, _P]),
     "vgl_hc_raw_bytes": (C.c_uint64, [_P]),
     "vgl_hc_set_graph": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "vgl_hc_pack_raw": (C.c_int, [_P, _P, _P]),
@@ -124,6 +133,9 @@ HOST_SYMBOLS = {
     "vgh_graph_create": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.POINTER(_P)]),
     "vgh_graph_destroy": (None, [_P]),
     "vgh_graph_view": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vgh_hc_wire_from_packed": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vgh_hc_wire_view": (C.POINTER(vgl_hc_wire), [_P]),
+    "vgh_hc_wire_destroy": (None, [_P]),
     "vgh_hc_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vgh_hc_raw_view": (C.POINTER(vgl_hc_raw), [_P]),
     "vgh_hc_raw_skipped": (C.c_int64, [_P]),

@@ -6,12 +6,13 @@
 // probabilities, :4-24) do not depend on p.  Regrouping the same sum by node,
 //     final_vec[p] = sum_i A_i + sum_n [pathsgo[n][p] == 0] * Dn,   Dn = sum_{i at node n} (B_i - A_i)
 // is exact algebra (no approximation) and turns the work into
-//   K1  hc_read_kernel   : stream the read batch once from HBM (TMA bulk copies into a 3-stage
-//                          shared-memory ring), one warp per read, compute every mapping's (A_i, B_i)
-//                          and scatter B_i - A_i into a per-CTA fp64 node vector in shared memory;
+//   K1  hc_read_kernel   : stream the read batch once from HBM, one read per thread, compute every
+//                          mapping's (A_i, B_i) and add B_i - A_i into one of VGL_HC_ACC_COPIES fp64 node
+//                          vectors (global memory, L2 resident) with fire-and-forget reductions;
 //   K2  hc_path_kernel   : one pass over the bit-packed node x path membership (7.7 MB for the
-//                          HaploCart graph) with the node vector staged by TMA bulk copy;
-//   K3  hc_posterior_kernel : argmax, log-sum-exp, posterior of the call and its clades.
+//                          HaploCart graph) with the node vectors staged by TMA bulk copies;
+//   K3  hc_posterior_kernel : argmax, log-sum-exp, posterior of the call and its clades;
+//   hc_peer_push / hc_peer_sum : the multi-GPU exchange of the per-path vector over NVLink peer memory.
 // "Supported" is the baseline so that the few best paths (the only ones that matter for the
 // posterior) are sums of few terms and carry no cancellation.
 #include <cuda_runtime.h>
@@ -351,7 +352,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
 template <int kAcMode>
 __global__ void __launch_bounds__(kReadBlock, 1)
 hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
-               int* __restrict__ err_flag, unsigned long long* __restrict__ stats) {
+               int* __restrict__ err_flag) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_warp_a[kReadBlock / 32];
@@ -686,10 +687,10 @@ cudaError_t hc_read_configure(const HcReadLaunch& cfg) {
 
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
                                   double* cta_node_acc, double* cta_a_total, int* err_flag,
-                                  unsigned long long* stats, cudaStream_t s) {
-    if (cfg.ac_mode == 0) hc_read_kernel<0><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
-    else if (cfg.ac_mode == 1) hc_read_kernel<1><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
-    else hc_read_kernel<2><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag, stats);
+                                  cudaStream_t s) {
+    if (cfg.ac_mode == 0) hc_read_kernel<0><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
+    else if (cfg.ac_mode == 1) hc_read_kernel<1><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
+    else hc_read_kernel<2><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
     return cudaGetLastError();
 }
 

@@ -601,6 +601,125 @@ void vgh_hc_packed_destroy(vgh_hc_packed* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// wire form of a packed batch
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct vgh_hc_wire {
+    vgl_hc_wire view{};
+    bool pinned = false;
+    void* block = nullptr;
+};
+
+extern "C" {
+
+int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, vgh_hc_wire** out) {
+    if (!p || !out) return fail(VGH_ERR_INVALID, "bad arguments");
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    const vgl_hc_batch& b = p->batch;
+    const size_t G = b.n_groups;
+    // per group: 16-bit column blocks (8 columns) and node blocks (8 nodes) as its longest lane needs
+    std::vector<uint32_t> g_c16(G + 1, 0), g_n16(G + 1, 0);
+    int err = VGH_OK;
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (int64_t g = 0; g < (int64_t)G; ++g) {
+        const uint32_t cb0 = b.grp_col_blk[g], ncb = b.grp_col_blk[g + 1] - cb0;
+        uint32_t max_cols = 0, max_nodes = 0;
+        for (uint32_t l = 0; l < VGL_HC_LANES; ++l) {
+            const uint32_t L = b.n_cols[(size_t)g * VGL_HC_LANES + l];
+            uint32_t n_open = 0;
+            for (uint32_t c = 0; c < L; ++c) {
+                const uint32_t rec = b.col[(((size_t)cb0 + c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK];
+                if (rec & VGL_HC_COL_OPEN) {
+                    ++n_open;
+                    if (VGL_HC_COL_NODE(rec) > 0xffffu) err = VGH_ERR_INVALID;
+                }
+            }
+            max_cols = std::max(max_cols, L);
+            max_nodes = std::max(max_nodes, n_open);
+        }
+        (void)ncb;
+        g_c16[(size_t)g + 1] = (max_cols + VGL_HC_WIRE_BLK - 1) / VGL_HC_WIRE_BLK;
+        g_n16[(size_t)g + 1] = (max_nodes + VGL_HC_WIRE_BLK - 1) / VGL_HC_WIRE_BLK;
+    }
+    if (err) return fail(VGH_ERR_INVALID, "a node id exceeds 65535: this graph needs the 32-bit batch");
+    for (size_t g = 0; g < G; ++g) { g_c16[g + 1] += g_c16[g]; g_n16[g + 1] += g_n16[g]; }
+    const size_t lanes = G * VGL_HC_LANES, n_map_rec = (size_t)b.n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t o_gc = take((G + 1) * 4), o_gn = take((G + 1) * 4), o_gm = take((G + 1) * 4);
+    const size_t o_col = take((size_t)g_c16[G] * 512), o_node = take((size_t)g_n16[G] * 512), o_map = take(n_map_rec * 4);
+    const size_t o_nc = take(lanes * 2), o_ncl = take(lanes * 2), o_nx = take(lanes * 2), o_mq = take(lanes);
+    vgh_hc_wire* W = new vgh_hc_wire();
+    W->pinned = pinned != 0;
+    const size_t bytes = std::max<size_t>(o, 256);
+    if (pinned) {
+        if (vgl_host_alloc(&W->block, bytes) != VGL_OK) {
+            delete W;
+            return fail(VGH_ERR_INVALID, "pinned allocation failed: %s", vgl_last_error());
+        }
+    } else {
+        W->block = aligned_alloc(256, bytes);
+        if (!W->block) { delete W; return fail(VGH_ERR_INVALID, "out of host memory"); }
+    }
+    uint8_t* base = (uint8_t*)W->block;
+    uint32_t* gc = (uint32_t*)(base + o_gc); uint32_t* gn = (uint32_t*)(base + o_gn); uint32_t* gm = (uint32_t*)(base + o_gm);
+    uint16_t* col = (uint16_t*)(base + o_col); uint16_t* node = (uint16_t*)(base + o_node); uint32_t* map = (uint32_t*)(base + o_map);
+    memcpy(gc, g_c16.data(), (G + 1) * 4);
+    memcpy(gn, g_n16.data(), (G + 1) * 4);
+    memcpy(gm, b.grp_map_blk, (G + 1) * 4);
+    if (n_map_rec) memcpy(map, b.map, n_map_rec * 4);
+    memcpy(base + o_nc, b.n_cols, lanes * 2);
+    memcpy(base + o_ncl, b.n_close, lanes * 2);
+    memcpy(base + o_nx, b.n_extra, lanes * 2);
+    memcpy(base + o_mq, b.mapq, lanes);
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (int64_t g = 0; g < (int64_t)G; ++g) {
+        const uint32_t cb0 = b.grp_col_blk[g];
+        uint16_t* gcol = col + (size_t)g_c16[(size_t)g] * 256;
+        uint16_t* gnode = node + (size_t)g_n16[(size_t)g] * 256;
+        memset(gcol, 0, (size_t)(g_c16[(size_t)g + 1] - g_c16[(size_t)g]) * 512);
+        memset(gnode, 0, (size_t)(g_n16[(size_t)g + 1] - g_n16[(size_t)g]) * 512);
+        for (uint32_t l = 0; l < VGL_HC_LANES; ++l) {
+            const uint32_t L = b.n_cols[(size_t)g * VGL_HC_LANES + l];
+            uint32_t k = 0;  // nodes are listed in the order a walk from the last column meets the OPEN marks
+            for (uint32_t cc = L; cc > 0; --cc) {
+                const uint32_t c = cc - 1;
+                const uint32_t rec = b.col[(((size_t)cb0 + c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK];
+                const uint32_t nd = VGL_HC_COL_NODE(rec);
+                gcol[((size_t)(c / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l) * VGL_HC_WIRE_BLK + c % VGL_HC_WIRE_BLK] =
+                    (uint16_t)((rec & 0x7fffu) | (nd != VGL_HC_NO_NODE ? VGL_HC_WIRE_OWNED : 0u));
+                if (rec & VGL_HC_COL_OPEN) {
+                    gnode[((size_t)(k / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l) * VGL_HC_WIRE_BLK + k % VGL_HC_WIRE_BLK] = (uint16_t)nd;
+                    ++k;
+                }
+            }
+        }
+    }
+    vgl_hc_wire& v = W->view;
+    v.n_reads = b.n_reads; v.n_groups = b.n_groups;
+    v.n_col_blks = g_c16[G]; v.n_node_blks = g_n16[G]; v.n_map_blks = b.n_map_blks;
+    v.grp_col_blk = gc; v.grp_node_blk = gn; v.grp_map_blk = gm; v.col = col; v.node = node; v.map = map;
+    v.n_cols = (const uint16_t*)(base + o_nc); v.n_close = (const uint16_t*)(base + o_ncl); v.n_extra = (const uint16_t*)(base + o_nx);
+    v.mapq = base + o_mq;
+    *out = W;
+    return VGH_OK;
+}
+const vgl_hc_wire* vgh_hc_wire_view(const vgh_hc_wire* w) { return w ? &w->view : nullptr; }
+void vgh_hc_wire_destroy(vgh_hc_wire* w) {
+    if (!w) return;
+    if (w->block) {
+        if (w->pinned) vgl_host_free(w->block);
+        else free(w->block);
+    }
+    delete w;
+}
+
+// ------------------------------------------------------------------------------------------------
 // raw alignments for the device-side reconstruction
 // ------------------------------------------------------------------------------------------------
 }  // extern "C"

@@ -343,7 +343,58 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     o_mapq[slot] = raw.mapq[r];
 }
 
+// Wire form -> 32-bit column records (include/vgan_gpu.h, vgl_hc_wire).  One thread per lane, walking from the read's last
+// column: an OPEN mark takes the next node id of the lane's node stream, every owned column down to the mapping's first
+// gets it.  Group g of the chunk owns 32-bit blocks [2 (c16[g] - c16[0]), 2 (c16[g+1] - c16[0])): twice its 16-bit blocks.
+__global__ void __launch_bounds__(128)
+hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const uint32_t* __restrict__ grp_n16,
+                 const uint16_t* __restrict__ col16, const uint16_t* __restrict__ node16, const uint16_t* __restrict__ n_cols,
+                 uint32_t* __restrict__ col32, uint32_t* __restrict__ grp_c32) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = slot >> 5, lane = slot & 31;
+    if (g >= n_groups) return;
+    const uint32_t c0 = grp_c16[0], cb0 = grp_c16[g], ncb = grp_c16[g + 1] - cb0;
+    if (lane == 0) {
+        grp_c32[g] = 2u * (cb0 - c0);
+        if (g + 1 == n_groups) grp_c32[n_groups] = 2u * (grp_c16[n_groups] - c0);
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(col16) + (size_t)cb0 * 32 + lane;          // block k: src[k * 32]
+    const uint4* nsrc = reinterpret_cast<const uint4*>(node16) + (size_t)grp_n16[g] * 32 + lane;  // node block k: nsrc[k * 32]
+    uint4* dst = reinterpret_cast<uint4*>(col32) + (size_t)2 * (cb0 - c0) * 32 + lane;            // 32-bit block k: dst[k * 32]
+    const uint32_t L = n_cols[slot];
+    uint32_t n_used = 0, cur = VGL_HC_NO_NODE;
+    uint4 nodes = make_uint4(0, 0, 0, 0);
+    for (int cb = (int)ncb - 1; cb >= 0; --cb) {
+        const uint4 v = src[(size_t)cb * 32];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out[8];
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            const uint32_t rec = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            const uint32_t c = (uint32_t)cb * 8 + j;
+            if (c >= L) { out[j] = 0; continue; }
+            if (rec & VGL_HC_COL_OPEN) {
+                if ((n_used & 7u) == 0) nodes = nsrc[(size_t)(n_used >> 3) * 32];
+                const uint32_t k = n_used & 7u;
+                const uint32_t word = k < 2 ? nodes.x : k < 4 ? nodes.y : k < 6 ? nodes.z : nodes.w;
+                cur = (word >> (16 * (k & 1))) & 0xffffu;
+                ++n_used;
+            }
+            out[j] = (rec & 0x7fffu) | (((rec & VGL_HC_WIRE_OWNED) ? cur : VGL_HC_NO_NODE) << VGL_HC_COL_NODE_SHIFT);
+        }
+        dst[(size_t)(2 * cb + 1) * 32] = make_uint4(out[4], out[5], out[6], out[7]);
+        dst[(size_t)(2 * cb) * 32] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
+
 }  // namespace
+
+cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const uint32_t* grp_n16, const uint16_t* col16,
+                             const uint16_t* node16, const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s) {
+    if (n_groups == 0) return cudaSuccess;
+    hc_expand_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(n_groups, grp_c16, grp_n16, col16, node16, n_cols, col32, grp_c32);
+    return cudaGetLastError();
+}
 
 cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int* err_flag, cudaStream_t s) {
     if (raw.n_reads == 0) return cudaSuccess;

@@ -127,12 +127,13 @@ struct vgl_ctx {
         DevBuf<uint32_t> grp_col_blk, grp_map_blk, col, map;
         DevBuf<uint16_t> n_cols, n_close, n_extra;
         DevBuf<uint8_t> mapq;
+        DevBuf<uint32_t> grp_c16, grp_n16;  // wire form of the chunk (vgl_hc_wire)
+        DevBuf<uint16_t> col16, node16;
         cudaEvent_t copied = nullptr, consumed = nullptr;
         bool used = false;
     } slot[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t chunk_groups = 4096;  // 131072 reads per H2D chunk
-    DevBuf<unsigned long long> d_stats;
 
     // read-kernel timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -187,7 +188,7 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
     auto& ev = ctx->ev_pool[ctx->ev_used++];
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
     VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total,
-                                        ctx->d_err, ctx->d_stats.p, ctx->stream));
+                                        ctx->d_err, ctx->stream));
     VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches += 1;
     ctx->ll_valid = false;
@@ -298,10 +299,10 @@ void vgl_destroy(vgl_ctx* ctx) {
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
         sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
+        sl.grp_c16.release(); sl.grp_n16.release(); sl.col16.release(); sl.node16.release();
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.consumed) cudaEventDestroy(sl.consumed);
     }
-    ctx->d_stats.release();
     ctx->e_node_clade.release(); ctx->e_dist.release(); ctx->e_deam.release(); ctx->e_bin_cov.release(); ctx->e_in.release();
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
@@ -531,8 +532,6 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
     if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
     if (int rc = reserve_result(ctx, 64)) return rc;
-    if (int rc = ctx->d_stats.reserve(4)) return rc;
-    VGL_CUDA(cudaMemset(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long)));
     if (vgl::hc_posterior_smem(P) > 48 * 1024) VGL_CUDA(vgl::hc_posterior_configure(vgl::hc_posterior_smem(P)));
     ctx->have_tables = true;
     ctx->have_tree = false;
@@ -761,6 +760,90 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     if (d.n_groups == 0) return VGL_OK;
     if (int rc = launch_read(ctx, d)) return rc;
     return wait_raw_copied(ctx);
+}
+
+uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w) {
+    if (!w) return 0;
+    return (uint64_t)(w->n_groups + 1) * 12 + (w->n_col_blks + w->n_node_blks + w->n_map_blks) * 512 + (uint64_t)w->n_groups * VGL_HC_LANES * 7;
+}
+
+int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!w) return fail(VGL_ERR_INVALID, "null batch");
+    if (w->n_groups == 0) return VGL_OK;
+    if ((uint64_t)w->n_groups * VGL_HC_LANES < w->n_reads) return fail(VGL_ERR_INVALID, "n_groups too small for n_reads");
+    if (!w->grp_col_blk || !w->grp_node_blk || !w->grp_map_blk || !w->n_cols || !w->n_close || !w->n_extra || !w->mapq ||
+        (w->n_col_blks && !w->col) || (w->n_node_blks && !w->node) || (w->n_map_blks && !w->map))
+        return fail(VGL_ERR_INVALID, "wire batch arrays missing");
+    // As vgl_hc_accumulate: chunks of groups, two staging slots, the H2D copy of a chunk overlaps the kernels of the one
+    // before.  Each chunk is expanded into 32-bit records on the device before the read kernel runs on it.
+    const uint32_t G = w->n_groups;
+    uint32_t n_chunk = 0;
+    for (uint32_t g0 = 0; g0 < G; g0 += ctx->chunk_groups, ++n_chunk) {
+        const uint32_t g1 = std::min(G, g0 + ctx->chunk_groups);
+        const uint32_t ng = g1 - g0;
+        const size_t nl = (size_t)ng * VGL_HC_LANES;
+        const uint64_t c0 = w->grp_col_blk[g0], c1 = w->grp_col_blk[g1];
+        const uint64_t n0 = w->grp_node_blk[g0], n1 = w->grp_node_blk[g1];
+        const uint64_t m0 = w->grp_map_blk[g0], m1 = w->grp_map_blk[g1];
+        if (c1 < c0 || n1 < n0 || m1 < m0 || c1 > w->n_col_blks || n1 > w->n_node_blks || m1 > w->n_map_blks)
+            return fail(VGL_ERR_INVALID, "batch block offsets are not monotone");
+        const size_t ncol16 = (size_t)(c1 - c0) * 256, nnode16 = (size_t)(n1 - n0) * 256, nmap = (size_t)(m1 - m0) * 128;
+        const size_t ncol32 = (size_t)(c1 - c0) * 2 * 128;
+        vgl_ctx::Slot& sl = ctx->slot[n_chunk & 1];
+        if (sl.used) VGL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, sl.consumed, 0));  // the kernels that last read this slot
+        if (ng + 1 > sl.grp_c16.cap || ncol16 > sl.col16.cap || nnode16 > sl.node16.cap || ncol32 > sl.col.cap || nmap > sl.map.cap ||
+            ng + 1 > sl.grp_col_blk.cap)
+            VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (int rc = sl.grp_c16.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.grp_n16.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.grp_col_blk.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.grp_map_blk.reserve((size_t)ng + 1)) return rc;
+        if (int rc = sl.n_cols.reserve(nl)) return rc;
+        if (int rc = sl.n_close.reserve(nl)) return rc;
+        if (int rc = sl.n_extra.reserve(nl)) return rc;
+        if (int rc = sl.mapq.reserve(nl)) return rc;
+        if (int rc = sl.col16.reserve(std::max<size_t>(ncol16, 1))) return rc;
+        if (int rc = sl.node16.reserve(std::max<size_t>(nnode16, 1))) return rc;
+        if (int rc = sl.col.reserve(std::max<size_t>(ncol32, 1))) return rc;
+        if (int rc = sl.map.reserve(std::max<size_t>(nmap, 1))) return rc;
+        cudaStream_t cs = ctx->copy_stream;
+        if (int rc = upload_async(sl.grp_c16.p, w->grp_col_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.grp_n16.p, w->grp_node_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.grp_map_blk.p, w->grp_map_blk + g0, ((size_t)ng + 1) * 4, cs)) return rc;
+        if (int rc = upload_async(sl.n_cols.p, w->n_cols + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.n_close.p, w->n_close + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.n_extra.p, w->n_extra + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        if (int rc = upload_async(sl.mapq.p, w->mapq + (size_t)g0 * VGL_HC_LANES, nl, cs)) return rc;
+        if (int rc = upload_async(sl.col16.p, w->col + (size_t)c0 * 256, ncol16 * 2, cs)) return rc;
+        if (int rc = upload_async(sl.node16.p, w->node + (size_t)n0 * 256, nnode16 * 2, cs)) return rc;
+        if (int rc = upload_async(sl.map.p, w->map + (size_t)m0 * 128, nmap * 4, cs)) return rc;
+        VGL_CUDA(cudaEventRecord(sl.copied, cs));
+        VGL_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
+        // the 16-bit arrays keep their absolute block indices: bases shifted back by the chunk's first block (only ever
+        // dereferenced at blocks >= c0 / n0 / m0, i.e. inside the slot)
+        const uint16_t* col16 = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col16.p) - (uintptr_t)c0 * 512);
+        const uint16_t* node16 = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.node16.p) - (uintptr_t)n0 * 512);
+        VGL_CUDA(vgl::hc_launch_expand(ng, sl.grp_c16.p, sl.grp_n16.p, col16, node16, sl.n_cols.p, sl.col.p, sl.grp_col_blk.p, ctx->stream));
+        ctx->launches += 1;
+        vgl::HcBatchDev d;
+        d.n_groups = ng;
+        d.grp_col_blk = sl.grp_col_blk.p;  // chunk relative (written by the expansion)
+        d.grp_map_blk = sl.grp_map_blk.p;
+        d.col = sl.col.p;
+        d.map = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.map.p) - (uintptr_t)m0 * 512);
+        d.n_cols = sl.n_cols.p;
+        d.n_close = sl.n_close.p;
+        d.n_extra = sl.n_extra.p;
+        d.mapq = sl.mapq.p;
+        if (int rc = launch_read(ctx, d)) return rc;
+        VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
+        sl.used = true;
+    }
+    // The caller may reuse its host buffers as soon as this returns.
+    VGL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return VGL_OK;
 }
 
 int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {

@@ -95,8 +95,7 @@ cudaError_t hc_read_configure(const HcReadLaunch& cfg);
 //   node_acc[copy][n_words * 32]  += sum over the copy's mappings at node n of (B_i - A_i)
 //   a_total[copy]                 += sum over the copy's mappings of A_i
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
-                                  double* cta_node_acc, double* cta_a_total, int* err_flag,
-                                  unsigned long long* stats, cudaStream_t s);
+                                  double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
 
 // K2b: sums the copies and runs the bit-GEMV over the node x path membership: chunk_ll[chunk][P].
 int hc_path_chunks(int n_words);
@@ -167,6 +166,11 @@ cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, cons
 cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32_t col_cap_blks, uint32_t map_cap_blks, uint32_t* col,
                            uint32_t* xmap, uint16_t* n_cols, uint16_t* n_close, uint16_t* n_extra, uint8_t* mapq, int* err_flag,
                            cudaStream_t s);
+
+// Wire form of a chunk (vgl_hc_wire) -> 32-bit column records + the chunk-relative grp_col_blk of the 32-bit layout.
+// The 16-bit arrays are addressed with ABSOLUTE block indices (grp_c16 / grp_n16 as shipped); col32 is chunk relative.
+cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const uint32_t* grp_n16, const uint16_t* col16,
+                             const uint16_t* node16, const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------------------
 // euka

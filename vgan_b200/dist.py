@@ -83,6 +83,8 @@ class ShardedSample:
             for b in local_batches:
                 if device_resident:
                     hc.update_device(b.batch)
+                elif hasattr(b, "wire"):
+                    hc.update_wire(b)
                 else:
                     hc.update(b)
             if self.exchange == "peer":

@@ -69,6 +69,10 @@ class Haplocart:
         """Haplocart::update for every read of a packed host batch, summed into final_vec."""
         check(gpu.vgl_hc_accumulate(self.ctx, C.byref(packed.batch)))
 
+    def update_wire(self, wire):
+        """Haplocart::update for a batch in its wire form (WireBatch): fewer bytes over PCIe, expanded on the device."""
+        check(gpu.vgl_hc_accumulate_wire(self.ctx, C.byref(wire.wire)))
+
     def update_raw(self, raw):
         """Haplocart::update for the raw alignments of a RawBatch: reconstruction and packing happen on the device."""
         check(gpu.vgl_hc_accumulate_raw(self.ctx, C.byref(raw.raw)))

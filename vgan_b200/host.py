@@ -207,6 +207,29 @@ class PackedBatch:
             self.handle = None
 
 
+class WireBatch:
+    """A packed batch re-encoded for the host -> device transfer (vgl_hc_wire): 16-bit column records plus one 16-bit node id
+    per non-empty mapping instead of 32-bit records."""
+
+    def __init__(self, packed, n_threads=0, pinned=False):
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_wire_from_packed(packed.handle, int(n_threads), int(pinned), C.byref(self.handle)))
+        self.wire = host.vgh_hc_wire_view(self.handle).contents
+
+    @property
+    def n_reads(self):
+        return int(self.wire.n_reads)
+
+    @property
+    def nbytes(self):
+        return int(_lib.gpu.vgl_hc_wire_bytes(C.byref(self.wire)))
+
+    def __del__(self):
+        if self.handle:
+            host.vgh_hc_wire_destroy(self.handle)
+            self.handle = None
+
+
 class RawBatch:
     """The raw alignments of reads [r0, r1) in the compact form the device-side reconstruction reads (vgl_hc_raw)."""
 
