@@ -217,29 +217,100 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
     if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
     std::vector<uint8_t> raw;
     if (int rc = inflate_all((const uint8_t*)bytes, n, raw)) return rc;
-    vgh_gam* g = new vgh_gam();
-    Cursor c{raw.data(), raw.data() + raw.size(), true};
-    while (c.ok && c.p < c.end) {
-        const uint64_t count = c.varint();  // group: count, then the "GAM" tag, then count-1 messages
-        for (uint64_t k = 0; c.ok && k < count; ++k) {
-            Cursor item = c.sub();
-            if (!c.ok) break;
-            if (k == 0) {
-                if (item.end - item.p != 3 || memcmp(item.p, "GAM", 3) != 0) {
-                    delete g;
-                    return fail(VGH_ERR_FORMAT, "unexpected type tag in GAM stream");
+    // Pass 1 (serial, a few GB/s): walk the framing -- groups of "count, type tag, count-1 length-prefixed messages" -- and
+    // note where every vg.Alignment starts and ends.  Pass 2 (parallel): threads parse contiguous ranges of messages into
+    // pieces of their own; the pieces are then appended in order.  readGAM itself (vg::io::for_each, src/readGAM.h:20-68) is
+    // single-threaded protobuf parsing.
+    std::vector<std::pair<const uint8_t*, const uint8_t*>> msgs;
+    {
+        Cursor c{raw.data(), raw.data() + raw.size(), true};
+        while (c.ok && c.p < c.end) {
+            const uint64_t count = c.varint();  // group: count, then the "GAM" tag, then count-1 messages
+            for (uint64_t k = 0; c.ok && k < count; ++k) {
+                Cursor item = c.sub();
+                if (!c.ok) break;
+                if (k == 0) {
+                    if (item.end - item.p != 3 || memcmp(item.p, "GAM", 3) != 0) return fail(VGH_ERR_FORMAT, "unexpected type tag in GAM stream");
+                    continue;
                 }
-                continue;
+                msgs.emplace_back(item.p, item.end);
             }
-            if (!parse_alignment(item, drop_unmapped, *g)) {
-                delete g;
-                return fail(VGH_ERR_FORMAT, "malformed vg.Alignment message");
+        }
+        if (!c.ok) return fail(VGH_ERR_FORMAT, "truncated GAM stream");
+    }
+    int n_threads = 1;
+#ifdef _OPENMP
+    n_threads = omp_get_max_threads();
+#endif
+    const size_t n_msgs = msgs.size();
+    const int n_parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_msgs / 256 + 1));
+    std::vector<vgh_gam> parts((size_t)n_parts);
+    bool bad = false;
+#pragma omp parallel for schedule(static, 1) num_threads(n_parts)
+    for (int t = 0; t < n_parts; ++t) {
+        const size_t lo = n_msgs * (size_t)t / (size_t)n_parts, hi = n_msgs * ((size_t)t + 1) / (size_t)n_parts;
+        for (size_t k = lo; k < hi; ++k) {
+            Cursor item{msgs[k].first, msgs[k].second, true};
+            if (!parse_alignment(item, drop_unmapped, parts[(size_t)t])) {
+#pragma omp atomic write
+                bad = true;
+                break;
             }
         }
     }
-    if (!c.ok) {
-        delete g;
-        return fail(VGH_ERR_FORMAT, "truncated GAM stream");
+    if (bad) return fail(VGH_ERR_FORMAT, "malformed vg.Alignment message");
+    vgh_gam* g = new vgh_gam();
+    if (n_parts == 1) {
+        *g = std::move(parts[0]);
+    } else {
+        // lay the pieces out one after the other: sizes first, then every piece copies itself (offset arrays rebased)
+        const size_t NP = parts.size();
+        std::vector<size_t> r0(NP + 1, 0), m0(NP + 1, 0), e0(NP + 1, 0), s0(NP + 1, 0), q0(NP + 1, 0), x0(NP + 1, 0);
+        for (size_t t = 0; t < NP; ++t) {
+            const vgh_gam& p = parts[t];
+            r0[t + 1] = r0[t] + p.mapq.size();
+            m0[t + 1] = m0[t] + p.map_node.size();
+            e0[t + 1] = e0[t] + p.edit_from.size();
+            s0[t + 1] = s0[t] + p.seq.size();
+            q0[t + 1] = q0[t] + p.qual.size();
+            x0[t + 1] = x0[t] + p.edit_seq.size();
+        }
+        const size_t nr = r0[NP], nm = m0[NP], ne = e0[NP];
+        g->seq_off.resize(nr + 1); g->qual_off.resize(nr + 1); g->map_off.resize(nr + 1);
+        g->mapq.resize(nr); g->identity.resize(nr); g->paired.resize(nr);
+        g->map_node.resize(nm); g->map_offset.resize(nm); g->map_rev.resize(nm); g->edit_off.resize(nm + 1);
+        g->edit_from.resize(ne); g->edit_to.resize(ne); g->edit_seq_off.resize(ne + 1);
+        g->seq.resize(s0[NP]); g->qual.resize(q0[NP]); g->edit_seq.resize(x0[NP]);
+#pragma omp parallel for schedule(static, 1) num_threads(n_parts)
+        for (int t = 0; t < n_parts; ++t) {
+            vgh_gam& p = parts[(size_t)t];
+            const size_t R = p.mapq.size(), M = p.map_node.size(), E = p.edit_from.size();
+            for (size_t k = 1; k <= R; ++k) {
+                g->seq_off[r0[t] + k] = (int64_t)s0[t] + p.seq_off[k];
+                g->qual_off[r0[t] + k] = (int64_t)q0[t] + p.qual_off[k];
+                g->map_off[r0[t] + k] = (int64_t)m0[t] + p.map_off[k];
+            }
+            for (size_t k = 1; k <= M; ++k) g->edit_off[m0[t] + k] = (int64_t)e0[t] + p.edit_off[k];
+            for (size_t k = 1; k <= E; ++k) g->edit_seq_off[e0[t] + k] = (int64_t)x0[t] + p.edit_seq_off[k];
+            if (R) {
+                memcpy(&g->mapq[r0[t]], p.mapq.data(), R * sizeof(int32_t));
+                memcpy(&g->identity[r0[t]], p.identity.data(), R * sizeof(double));
+                memcpy(&g->paired[r0[t]], p.paired.data(), R);
+            }
+            if (M) {
+                memcpy(&g->map_node[m0[t]], p.map_node.data(), M * sizeof(int64_t));
+                memcpy(&g->map_offset[m0[t]], p.map_offset.data(), M * sizeof(int64_t));
+                memcpy(&g->map_rev[m0[t]], p.map_rev.data(), M);
+            }
+            if (E) {
+                memcpy(&g->edit_from[e0[t]], p.edit_from.data(), E * sizeof(int32_t));
+                memcpy(&g->edit_to[e0[t]], p.edit_to.data(), E * sizeof(int32_t));
+            }
+            if (!p.seq.empty()) memcpy(&g->seq[s0[t]], p.seq.data(), p.seq.size());
+            if (!p.qual.empty()) memcpy(&g->qual[q0[t]], p.qual.data(), p.qual.size());
+            if (!p.edit_seq.empty()) memcpy(&g->edit_seq[x0[t]], p.edit_seq.data(), p.edit_seq.size());
+            p = vgh_gam();  // release the piece
+        }
     }
     g->finish();
     *out = g;
