@@ -108,8 +108,9 @@ struct vgl_ctx {
         DevBuf<uint16_t> o_n_cols, o_n_close, o_n_extra;
         DevBuf<uint8_t> o_mapq;
         uint32_t col_cap_blks = 0, map_cap_blks = 0;
-        cudaEvent_t copied = nullptr;  // the H2D copies of the last raw batch
-    } rawdev;
+        cudaEvent_t copied = nullptr, consumed = nullptr;  // H2D of the chunk done / its kernels done
+        bool used = false;
+    } rawdev[2];
 
     // multi-GPU exchange through peer memory
     double* peer_local = nullptr;             // this rank's buffer (cudaMalloc)
@@ -286,15 +287,15 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     peer_detach(ctx);
-    {
-        vgl_ctx::RawDev& R = ctx->rawdev;
-        ctx->g_seq_off.release(); ctx->g_seq.release();
+    ctx->g_seq_off.release(); ctx->g_seq.release();
+    for (vgl_ctx::RawDev& R : ctx->rawdev) {
         R.qual_off.release(); R.str_off.release(); R.map_off.release(); R.map_node.release(); R.map_offset.release(); R.edit_off.release();
         R.edit_seq_off.release(); R.edit_from.release(); R.edit_to.release(); R.qual.release(); R.mapq.release(); R.edit_seq.release();
         R.gstr.release(); R.rstr.release(); R.sizes.release(); R.n_cols.release(); R.n_close.release(); R.n_extra.release();
         R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
         R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
         if (R.copied) cudaEventDestroy(R.copied);
+        if (R.consumed) cudaEventDestroy(R.consumed);
     }
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
@@ -672,23 +673,28 @@ int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_
     return VGL_OK;
 }
 
-// H2D of the raw alignments, reconstruction and packing on ctx->stream; fills the read kernel's batch descriptor.
-static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchDev& d) {
-    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
-    if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
-    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq)
-        return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
-    vgl_ctx::RawDev& R = ctx->rawdev;
+// Reads [ra, rb) of `raw`: H2D of their slices on `copy_stream` into staging set `R`, then reconstruction and packing on
+// ctx->stream; fills the read kernel's batch descriptor.  The slices keep their absolute indices (offsets into the
+// whole batch): the device pointers are shifted back by each slice's first element and only ever dereferenced inside.
+static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t rb, vgl_ctx::RawDev& R, cudaStream_t copy_stream,
+                          vgl::HcBatchDev& d) {
     cudaStream_t s = ctx->stream;
-    const size_t n = raw->n_reads, nm = raw->n_maps, ne = raw->n_edits;
-    const size_t nq = raw->qual_off[n], nseq = raw->edit_seq_off[ne], ncap = raw->str_off[n];
+    const size_t n = rb - ra;
+    const size_t ma = raw->map_off[ra], mb = raw->map_off[rb], nm = mb - ma;
+    const size_t ea = raw->edit_off[ma], eb = raw->edit_off[mb], ne = eb - ea;
+    const size_t qa = raw->qual_off[ra], nq = raw->qual_off[rb] - qa;
+    const size_t sa = raw->edit_seq_off[ea], nseq = raw->edit_seq_off[eb] - sa;
+    const size_t ca = raw->str_off[ra], ncap = raw->str_off[rb] - ca;
     const size_t G = (n + 31) / 32;
     // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read
     const size_t col_cap = ncap / 128 + 1024 + G + 1, map_cap = G + 4096;
     if (col_cap > 0x7fffffffull) return fail(VGL_ERR_INVALID, "batch too large; split it");
-    // the previous batch's kernels read these buffers: growing one needs the stream to be idle
+    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
+    if (!R.consumed) VGL_CUDA(cudaEventCreateWithFlags(&R.consumed, cudaEventDisableTiming));
+    if (R.used) VGL_CUDA(cudaStreamWaitEvent(copy_stream, R.consumed, 0));  // the kernels that last read this staging set
+    // growing a buffer frees it: the kernels still reading it must have finished
     if (n + 1 > R.qual_off.cap || nq > R.qual.cap || nm > R.map_node.cap || ne > R.edit_from.cap || nseq > R.edit_seq.cap ||
-        ncap > R.gstr.cap || col_cap * 128 > R.col.cap)
+        ncap > R.gstr.cap || col_cap * 128 > R.col.cap || map_cap * 128 > R.xmap.cap)
         VGL_CUDA(cudaStreamSynchronize(s));
 #define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
     RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
@@ -703,22 +709,25 @@ static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchD
     R.map_cap_blks = (uint32_t)map_cap;
     d = vgl::HcBatchDev{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p};
     if (n == 0) return VGL_OK;
-#define H2D(dst, src, bytes) if ((size_t)(bytes) != 0 && (src) != nullptr) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, s))
-    H2D(R.qual_off.p, raw->qual_off, (n + 1) * 4); H2D(R.str_off.p, raw->str_off, (n + 1) * 4); H2D(R.map_off.p, raw->map_off, (n + 1) * 4);
-    H2D(R.mapq.p, raw->mapq, n); H2D(R.qual.p, raw->qual, nq);
-    H2D(R.map_node.p, raw->map_node, nm * 4); H2D(R.map_offset.p, raw->map_offset, nm * 4); H2D(R.edit_off.p, raw->edit_off, (nm + 1) * 4);
-    H2D(R.edit_from.p, raw->edit_from, ne * 2); H2D(R.edit_to.p, raw->edit_to, ne * 2); H2D(R.edit_seq_off.p, raw->edit_seq_off, (ne + 1) * 4);
-    H2D(R.edit_seq.p, raw->edit_seq, nseq);
+#define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, copy_stream))
+    H2D(R.qual_off.p, raw->qual_off + ra, (n + 1) * 4); H2D(R.str_off.p, raw->str_off + ra, (n + 1) * 4);
+    H2D(R.map_off.p, raw->map_off + ra, (n + 1) * 4); H2D(R.mapq.p, raw->mapq + ra, n); H2D(R.qual.p, raw->qual + qa, nq);
+    H2D(R.map_node.p, raw->map_node + ma, nm * 4); H2D(R.map_offset.p, raw->map_offset + ma, nm * 4);
+    H2D(R.edit_off.p, raw->edit_off + ma, (nm + 1) * 4);
+    H2D(R.edit_from.p, raw->edit_from + ea, ne * 2); H2D(R.edit_to.p, raw->edit_to + ea, ne * 2);
+    H2D(R.edit_seq_off.p, raw->edit_seq_off + ea, (ne + 1) * 4); H2D(R.edit_seq.p, raw->edit_seq + sa, nseq);
 #undef H2D
-    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
-    VGL_CUDA(cudaEventRecord(R.copied, s));
+    VGL_CUDA(cudaEventRecord(R.copied, copy_stream));
+    if (copy_stream != s) VGL_CUDA(cudaStreamWaitEvent(s, R.copied, 0));
     VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
     const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
-    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p,
-                              R.edit_off.p, R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p};
-    const vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
-                               R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    // per-read arrays are indexed by the read's position in the chunk; everything they point INTO by absolute index
+    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p - qa, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p - ma,
+                              R.map_offset.p - ma, R.edit_off.p - ma, R.edit_from.p - ea, R.edit_to.p - ea, R.edit_seq_off.p - ea,
+                              R.edit_seq.p - sa};
+    const vgl::ReconWorkDev Wd{R.gstr.p - ca, R.rstr.p - ca, R.sizes.p - ma, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
+                               R.hist3.p + 4096, R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
     VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, ctx->d_err, s));
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
                                  R.o_mapq.p, ctx->d_err, s));
@@ -726,17 +735,21 @@ static int pack_raw_on_device(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl::HcBatchD
     return VGL_OK;
 }
 
-// The caller may reuse its host buffers as soon as an entry point returns: wait for the H2D copies (not for the kernels).
-static int wait_raw_copied(vgl_ctx* ctx) {
-    if (ctx->rawdev.copied) VGL_CUDA(cudaEventSynchronize(ctx->rawdev.copied));
+static int check_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
+    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq ||
+        (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))
+        return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
     return VGL_OK;
 }
 
 int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* out) {
     if (int rc = use_device(ctx)) return rc;
     if (!out) return fail(VGL_ERR_INVALID, "null output");
+    if (int rc = check_raw(ctx, raw)) return rc;
     vgl::HcBatchDev d;
-    if (int rc = pack_raw_on_device(ctx, raw, d)) return rc;
+    if (int rc = pack_raw_chunk(ctx, raw, 0, raw->n_reads, ctx->rawdev[0], ctx->stream, d)) return rc;
     memset(out, 0, sizeof(*out));
     out->n_reads = raw->n_reads;
     out->n_groups = d.n_groups;
@@ -755,11 +768,24 @@ int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* out) {
 
 int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     if (int rc = use_device(ctx)) return rc;
-    vgl::HcBatchDev d;
-    if (int rc = pack_raw_on_device(ctx, raw, d)) return rc;
-    if (d.n_groups == 0) return VGL_OK;
-    if (int rc = launch_read(ctx, d)) return rc;
-    return wait_raw_copied(ctx);
+    if (int rc = check_raw(ctx, raw)) return rc;
+    // Chunks of reads through two staging sets: the H2D copy of a chunk (copy stream) overlaps the reconstruction, packing
+    // and read kernel of the chunk before it.
+    const size_t n = raw->n_reads, step = (size_t)ctx->chunk_groups * VGL_HC_LANES;
+    size_t k = 0;
+    for (size_t ra = 0; ra < n; ra += step, ++k) {
+        const size_t rb = std::min(n, ra + step);
+        vgl_ctx::RawDev& R = ctx->rawdev[k & 1];
+        vgl::HcBatchDev d;
+        if (int rc = pack_raw_chunk(ctx, raw, ra, rb, R, ctx->copy_stream, d)) return rc;
+        if (d.n_groups)
+            if (int rc = launch_read(ctx, d)) return rc;
+        VGL_CUDA(cudaEventRecord(R.consumed, ctx->stream));
+        R.used = true;
+    }
+    // The caller may reuse its host buffers as soon as this returns (the kernels run on).
+    VGL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return VGL_OK;
 }
 
 uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w) {
