@@ -188,3 +188,26 @@ def test_wire_form_gives_the_same_results(small):
         final, argmax, _ = _oracle(small, alns, bep=bep)
         _check(got, final, argmax, small)
     hc.close()
+
+
+def test_routes_agree_across_chunk_boundaries(small):
+    """More reads than one H2D chunk (131072): the packed, wire and raw routes cut the batch at different places and must
+    still give the same vector."""
+    alns = small.reads(140000, seed=307, fixed_len=60, sub_rate=0.01, indel_rate=0.002)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    packed = vb.PackedBatch(small.graph, alns, pinned=True)
+    res = {}
+    for name, fn in (("packed", lambda: hc.update(packed)), ("wire", lambda: hc.update_wire(vb.WireBatch(packed, pinned=True))),
+                     ("raw", lambda: hc.update_raw(vb.RawBatch(alns, pinned=True))), ("device", lambda: hc.update_device(dev.batch))):
+        if name == "device":
+            dev = hc.upload(packed)
+        hc.reset()
+        fn()
+        res[name] = hc.get_posterior()
+    for name in ("wire", "raw", "device"):
+        assert res[name]["maxh_index"] == res["packed"]["maxh_index"]
+        assert np.allclose(res[name]["final_vec"], res["packed"]["final_vec"], rtol=1e-12, atol=0)
+        assert np.allclose(res[name]["confidence_vec"], res["packed"]["confidence_vec"], rtol=1e-9)
+    hc.close()
