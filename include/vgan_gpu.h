@@ -284,6 +284,8 @@ typedef struct vgl_hc_raw {
     const uint16_t* edit_to;      /* [n_edits]     */
     const uint32_t* edit_seq_off; /* [n_edits + 1] */
     const uint8_t* edit_seq;
+    const uint16_t* seq_len;      /* [n_reads] |Alignment.sequence|            (euka / soibean; may be NULL for HaploCart) */
+    const uint32_t* read_index;   /* [n_reads] position in the caller's order  (euka / soibean; may be NULL for HaploCart) */
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 
@@ -418,6 +420,10 @@ int vgl_euka_reset(vgl_ctx* ctx);
  *   pass[r]    1 if in - not > 1 and mapq > minimum_mq (the read is counted and adds bin coverage).   */
 int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* host_batch, uint32_t n_out, int32_t* clade, double* in_lik,
                  double* not_lik, double* like, uint8_t* pass);
+/* The same from RAW alignments (vgl_hc_raw built with vgh_euka_raw_build: reads with identity != 0, seq_len and read_index
+ * filled): reconstruct_graph_sequence and the packing run on the device (vgl_hc_set_graph first).               */
+int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
+                     double* like, uint8_t* pass);
 /* Per-clade count (Clade::count) and per-bin coverage (get<3>(chunks[c][j])) accumulated since the reset. */
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov);
 uint64_t vgl_euka_batch_bytes(const vgl_euka_batch* b);
@@ -458,6 +464,7 @@ typedef vgl_euka_batch vgl_soibean_batch;
 int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* tables);
 /* path_ll[r * n_paths + p] = pathMap[pathNames[p]] of read r (r = read_index); used[r] = 1 for reads of the batch. */
 int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* host_batch, uint32_t n_out, double* path_ll, uint8_t* used);
+int vgl_soibean_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, double* path_ll, uint8_t* used);
 
 #ifdef __cplusplus
 }

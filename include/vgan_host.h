@@ -114,6 +114,8 @@ typedef struct vgh_hc_raw vgh_hc_raw;
 /* One linear pass over reads [r0, r1): keeps those with identity >= 1e-10 (src/HaploCart.cpp:411) and copies the
  * fields the path reads into one (optionally pinned) block.  No reconstruction happens here.              */
 int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out);
+/* The same for euka / soibean: keeps the reads readGAM3 keeps (identity != 0, src/readGAM_Euka.h:73). */
+int vgh_euka_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out);
 const vgl_hc_raw* vgh_hc_raw_view(const vgh_hc_raw* p);
 int64_t vgh_hc_raw_skipped(const vgh_hc_raw* p);
 void vgh_hc_raw_destroy(vgh_hc_raw* p);

@@ -211,3 +211,36 @@ def test_routes_agree_across_chunk_boundaries(small):
         assert np.allclose(res[name]["final_vec"], res["packed"]["final_vec"], rtol=1e-12, atol=0)
         assert np.allclose(res[name]["confidence_vec"], res["packed"]["confidence_vec"], rtol=1e-9)
     hc.close()
+
+
+def test_euka_and_soibean_from_raw_alignments():
+    """The sibling kernels fed by the device-side reconstruction (vgl_euka_run_raw / vgl_soibean_run_raw) give what they
+    give on batches packed by the host (which tests/test_euka.py and tests/test_soibean.py check against the oracle)."""
+    S = vb.SynthEuka(seed=11, n_clades=40, genome_len=3000)
+    alns = S.reads(3000, seed=12, n_rate=0.01, softclip_rate=0.2, indel_rate=0.01)
+    ek = vb.Euka()
+    ek.load(S.tables(vb.DHIGH5P_PROF, vb.DHIGH3P_PROF))
+    ek.load_graph(S.graph)
+    ek.reset()
+    want = ek.run(vb.EukaPackedBatch(S.graph, alns))
+    wc, wcov = ek.results()
+    ek.reset()
+    got = ek.run_raw(vb.RawBatch(alns, euka_rule=True))
+    gc, gcov = ek.results()
+    for k in ("clade", "pass"):
+        assert np.array_equal(got[k], want[k])
+    for k in ("in_lik", "not_lik", "like"):
+        assert np.array_equal(got[k], want[k])          # same records, same kernel: bit-identical per read
+    assert np.array_equal(gc, wc) and np.allclose(gcov, wcov, rtol=1e-12)
+    ek.close()
+
+    Sh = vb.SynthHaplocart(seed=212, n_paths=127, n_rows=610, n_nodes=601)
+    al = Sh.reads(1500, seed=213, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    sb = vb.Soibean()
+    sb.load(vb.SoibeanTables(Sh.supports(), 0, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 7))
+    sb.load_graph(Sh.graph)
+    want, used_w = sb.analyse(vb.SoibeanPackedBatch(Sh.graph, al))
+    got, used = sb.analyse_raw(vb.RawBatch(al, euka_rule=True))
+    assert np.array_equal(used, used_w) and used.sum() >= 1490
+    assert np.array_equal(got, want)
+    sb.close()

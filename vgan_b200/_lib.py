@@ -37,7 +37,8 @@ class vgl_hc_raw(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_maps", C.c_uint32), ("n_edits", C.c_uint32), ("reserved", C.c_uint32),
                 ("qual_off", C.c_void_p), ("qual", C.c_void_p), ("mapq", C.c_void_p), ("str_off", C.c_void_p),
                 ("map_off", C.c_void_p), ("map_node", C.c_void_p), ("map_offset", C.c_void_p), ("edit_off", C.c_void_p),
-                ("edit_from", C.c_void_p), ("edit_to", C.c_void_p), ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p)]
+                ("edit_from", C.c_void_p), ("edit_to", C.c_void_p), ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p),
+                ("seq_len", C.c_void_p), ("read_index", C.c_void_p)]
 
 
 class vgl_hc_batch(C.Structure):
@@ -124,6 +125,8 @@ GPU_SYMBOLS = {
     "vgl_euka_batch_bytes": (C.c_uint64, [C.POINTER(vgl_euka_batch)]),
     "vgl_soibean_set_tables": (C.c_int, [_P, C.POINTER(vgl_soibean_tables)]),
     "vgl_soibean_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P]),
+    "vgl_soibean_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
@@ -136,6 +139,7 @@ HOST_SYMBOLS = {
     "vgh_hc_wire_from_packed": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "vgh_hc_wire_view": (C.POINTER(vgl_hc_wire), [_P]),
     "vgh_hc_wire_destroy": (None, [_P]),
+    "vgh_euka_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vgh_hc_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vgh_hc_raw_view": (C.POINTER(vgl_hc_raw), [_P]),
     "vgh_hc_raw_skipped": (C.c_int64, [_P]),

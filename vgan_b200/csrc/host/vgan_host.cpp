@@ -804,12 +804,19 @@ struct vgh_hc_raw {
 
 extern "C" {
 
+static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, bool euka_rule, vgh_hc_raw** out);
 int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+    return raw_build(a, r0, r1, pinned, false, out);
+}
+int vgh_euka_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+    return raw_build(a, r0, r1, pinned, true, out);
+}
+static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, bool euka_rule, vgh_hc_raw** out) {
     if (!a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
     std::vector<int64_t> keep;
     keep.reserve((size_t)(r1 - r0));
     for (int64_t r = r0; r < r1; ++r)
-        if (!(a->identity[r] < 1e-10)) keep.push_back(r);
+        if (euka_rule ? a->identity[r] != 0 : !(a->identity[r] < 1e-10)) keep.push_back(r);
     const size_t R = keep.size();
     // per-read extents, then exclusive prefix sums: every read's slice of every array is known before the (parallel) fill
     std::vector<uint64_t> pm(R + 1, 0), pe(R + 1, 0), pq(R + 1, 0), ps(R + 1, 0), pc(R + 1, 0);
@@ -848,7 +855,7 @@ int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
     const size_t o_node = take(nm * 4), o_offs = take(nm * 4), o_eoff = take((nm + 1) * 4), o_from = take(ne * 2), o_to = take(ne * 2);
-    const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns);
+    const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns), o_slen = take(R * 2), o_ridx = take(R * 4);
     vgh_hc_raw* P = new vgh_hc_raw();
     P->pinned = pinned != 0;
     const size_t bytes = std::max<size_t>(o, 256);
@@ -867,12 +874,15 @@ int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     uint32_t* node = (uint32_t*)(base + o_node); uint32_t* offs = (uint32_t*)(base + o_offs); uint32_t* eoff = (uint32_t*)(base + o_eoff);
     uint16_t* from = (uint16_t*)(base + o_from); uint16_t* to = (uint16_t*)(base + o_to);
     uint32_t* esoff = (uint32_t*)(base + o_esoff); uint8_t* eseq = base + o_eseq;
+    uint16_t* slen = (uint16_t*)(base + o_slen); uint32_t* ridx = (uint32_t*)(base + o_ridx);
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < (int64_t)R; ++k) {
         const int64_t r = keep[(size_t)k];
         uint64_t cm = pm[(size_t)k], ce = pe[(size_t)k], cs = ps[(size_t)k];
         qoff[k] = (uint32_t)pq[(size_t)k]; soff[k] = (uint32_t)pc[(size_t)k]; moff[k] = (uint32_t)cm;
         mq[k] = (uint8_t)a->mapq[r];
+        slen[k] = (uint16_t)std::min<int64_t>(a->seq_off[r + 1] - a->seq_off[r], 65535);
+        ridx[k] = (uint32_t)(r - r0);
         memcpy(q + pq[(size_t)k], a->qual + a->qual_off[r], (size_t)(pq[(size_t)k + 1] - pq[(size_t)k]));
         for (int64_t m = a->map_off[r]; m < a->map_off[r + 1]; ++m) {
             node[cm] = (uint32_t)a->map_node[m] | (a->map_rev[m] ? 0x80000000u : 0u);
@@ -897,6 +907,7 @@ int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     v.n_reads = (uint32_t)R; v.n_maps = (uint32_t)cm; v.n_edits = (uint32_t)ce;
     v.qual_off = qoff; v.qual = q; v.mapq = mq; v.str_off = soff; v.map_off = moff; v.map_node = node; v.map_offset = offs;
     v.edit_off = eoff; v.edit_from = from; v.edit_to = to; v.edit_seq_off = esoff; v.edit_seq = eseq;
+    v.seq_len = slen; v.read_index = ridx;
     *out = P;
     return VGH_OK;
 }

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kErrBadRead = 0x20000000;   // bits of the context's error word
 constexpr int kErrBadNodeRaw = 0x10000000;
+constexpr int kReconHaplocart = 0, kReconSoibean = 2;  // (1 = euka)
 
 enum EditKind { kMatch, kSub, kIns, kDel, kOther };
 __device__ __forceinline__ EditKind classify(uint32_t from, uint32_t to, bool has_seq) {  // vg io edit_is_*
@@ -63,7 +64,7 @@ __device__ __forceinline__ uint8_t complement(uint8_t c) {
 }
 
 __global__ void __launch_bounds__(128)
-hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restrict__ err_flag) {
+hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int mode, int* __restrict__ err_flag) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= raw.n_reads) return;
     const uint32_t m0 = raw.map_off[r], m1 = raw.map_off[r + 1], M = m1 - m0;
@@ -106,7 +107,7 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restric
                 aligned = to;
             }
             offset += from;
-            if (e_idx < M) W.sizes[m0 + e_idx] = (uint16_t)min(aligned, 0xffffu);
+            W.sizes[e] = (uint16_t)min(aligned, 0xffffu);  // one size per EDIT (src/vgan_utils.h:72)
             ++e_idx;
         }
     }
@@ -134,21 +135,41 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int* __restric
         }
     }
     const uint32_t Lq = raw.qual_off[r + 1] - raw.qual_off[r];
-    if (!err && (glen != rlen || e_idx < M || Lq > rlen || rlen > VGL_HC_MAP_MAX_POS || M > 65535u || raw.mapq[r] >= 100)) err = kErrBadRead;
+    const uint32_t e_first = M ? raw.edit_off[m0] : 0u;  // the read's edits are e_first .. e_first + e_idx - 1
     uint32_t n_close = 0, n_extra = 0;
-    if (!err) {
-        // mapping i starts at pos_i = min(sum of the earlier size slots, n); CLOSE bits sit at the distinct pos_i < n
-        uint32_t pos = 0, last_close = 0xffffffffu;
-        for (uint32_t i = 0; i < M; ++i) {
-            const uint32_t lg = min((uint32_t)W.sizes[m0 + i], rlen - pos);
-            if (lg == 0) ++n_extra;
-            if (pos < rlen && pos != last_close) { ++n_close; last_close = pos; }
-            pos += lg;
+    if (mode == kReconHaplocart) {
+        if (!err && (glen != rlen || e_idx < M || Lq > rlen || rlen > VGL_HC_MAP_MAX_POS || M > 65535u || raw.mapq[r] >= 100)) err = kErrBadRead;
+        if (!err) {
+            // mapping i starts at pos_i = min(sum of the earlier size slots, n) -- the size slot of mapping i is the size of the
+            // read's i-th EDIT (quirk Q1); CLOSE bits sit at the distinct pos_i < n
+            uint32_t pos = 0, last_close = 0xffffffffu;
+            for (uint32_t i = 0; i < M; ++i) {
+                const uint32_t lg = min((uint32_t)W.sizes[e_first + i], rlen - pos);
+                if (lg == 0) ++n_extra;
+                if (pos < rlen && pos != last_close) { ++n_close; last_close = pos; }
+                pos += lg;
+            }
         }
     } else {
+        // euka / soibean (vgh_euka_pack / vgh_soibean_pack): fragment length inside the damage table, the damage position
+        // stays inside the read; the "extra" count is the number of mapping (euka) or edit (soibean) records
+        const uint32_t Lseq = mode == kReconSoibean ? glen : (uint32_t)raw.seq_len[r];
+        uint32_t nongap = 0;
+        for (uint32_t k = 0; k < rlen && !err; ++k) nongap += (W.rstr + s0)[k] != '-';
+        const uint32_t n_rec = mode == kReconSoibean ? e_idx : M;
+        if (!err && (M < 1 || glen != rlen || Lseq < 15u || Lseq > 1000u || glen > 4095u || M > 65535u || n_rec > 65535u || nongap > Lseq)) err = kErrBadRead;
+        if (!err && mode == kReconSoibean) {
+            if (raw.seq_len[r] < 1) err = kErrBadRead;
+            for (uint32_t i = 0; i < min(M, e_idx); ++i)
+                if ((raw.map_node[m0 + i] & 0x7fffffffu) >= VGL_SOIBEAN_NO_NODE) err = kErrBadNodeRaw;
+        }
+        n_extra = n_rec;
+    }
+    if (err) {
         atomicOr(err_flag, err);
         rlen = 0;
         n_close = 0xffffu;  // marks the read as dead for the packer
+        n_extra = 0;
     }
     W.n_cols[r] = (uint16_t)rlen;
     W.n_close[r] = (uint16_t)n_close;
@@ -206,7 +227,7 @@ hc_order_kernel(uint32_t n_reads, const uint16_t* __restrict__ n_cols, const uin
 
 __global__ void __launch_bounds__(256)
 hc_groups_kernel(uint32_t n_reads, uint32_t n_groups, const uint32_t* __restrict__ order, const uint16_t* __restrict__ n_cols,
-                 const uint16_t* __restrict__ n_extra, uint32_t* __restrict__ grp_cb, uint32_t* __restrict__ grp_mb) {
+                 const uint16_t* __restrict__ n_extra, uint32_t col_blk, uint32_t* __restrict__ grp_cb, uint32_t* __restrict__ grp_mb) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     uint32_t mc = 0, mx = 0;
@@ -215,7 +236,7 @@ hc_groups_kernel(uint32_t n_reads, uint32_t n_groups, const uint32_t* __restrict
         mc = max(mc, (uint32_t)n_cols[r]);
         mx = max(mx, (uint32_t)n_extra[r]);
     }
-    grp_cb[g] = (mc + VGL_HC_COL_BLK - 1) / VGL_HC_COL_BLK;
+    grp_cb[g] = (mc + col_blk - 1) / col_blk;
     grp_mb[g] = (mx + VGL_HC_MAP_BLK - 1) / VGL_HC_MAP_BLK;
 }
 
@@ -287,6 +308,7 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     const uint32_t L = W.n_cols[r];
     const bool dead = W.n_close[r] == 0xffffu;  // rejected by the reconstruction: an empty lane
     const uint32_t m0 = raw.map_off[r], M = dead ? 0u : raw.map_off[r + 1] - m0;
+    const uint32_t e_first = M ? raw.edit_off[m0] : 0u;
     const uint32_t q0 = raw.qual_off[r], Lq = raw.qual_off[r + 1] - q0;
     const uint8_t* gs = W.gstr + raw.str_off[r];
     const uint8_t* rs = W.rstr + raw.str_off[r];
@@ -305,7 +327,7 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
             if (c >= L) { rec[j] = 0; continue; }
             uint32_t v = c < Lq ? raw.qual[q0 + c] : 0u;
             while (nxt < M && npos == c) {  // mappings that start at this column (quirk Q1: size slot = the nxt-th edit's size)
-                const uint32_t lg = min((uint32_t)W.sizes[m0 + nxt], L - npos);
+                const uint32_t lg = min((uint32_t)W.sizes[e_first + nxt], L - npos);
                 const uint32_t node = raw.map_node[m0 + nxt] & 0x7fffffffu;
                 v |= VGL_HC_COL_CLOSE;
                 if (lg) {
@@ -341,6 +363,74 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     o_n_close[slot] = dead ? (uint16_t)0 : W.n_close[r];
     o_n_extra[slot] = (uint16_t)n_x;
     o_mapq[slot] = raw.mapq[r];
+}
+
+__device__ __forceinline__ uint32_t symbol_code(uint8_t c) {
+    switch (c) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+        case 'N': return VGL_EUKA_SYM_N;
+        case '-': return VGL_EUKA_SYM_GAP;
+        case 'W': case 'M': case 'K': case 'R': case 'Y': case 'B': case 'D': case 'H': case 'V': return VGL_EUKA_SYM_RARE;
+        case 'S': return VGL_EUKA_SYM_SOFTCLIP;
+        default: return VGL_EUKA_SYM_OTHER;
+    }
+}
+
+// euka / soibean batches (vgl_euka_batch) from the reconstructed strings: one thread per lane.  Column record m =
+// quality byte at ALIGNED COLUMN m | graph symbol << 8 | read symbol << 12; mapping records = node ids (euka) or, for
+// soibean, one record per EDIT: size << 20 | node of the mapping with the same index (NO_NODE for the surplus entries
+// when the two counts differ, src/getLCAfromGAM.h:156-160).
+__global__ void __launch_bounds__(128)
+sym_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, int soibean, uint16_t* __restrict__ col, uint32_t* __restrict__ map,
+                uint16_t* __restrict__ o_n_cols, uint16_t* __restrict__ o_n_maps, uint16_t* __restrict__ o_seq_len,
+                uint8_t* __restrict__ o_mapq, uint8_t* __restrict__ o_flags, uint32_t* __restrict__ o_read_index) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = slot >> 5, lane = slot & 31;
+    if (g >= n_groups) return;
+    const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0, mb0 = W.grp_mb[g], nmb = W.grp_mb[g + 1] - mb0;
+    uint4* gc = reinterpret_cast<uint4*>(col) + (size_t)cb0 * 32 + lane;  // column block k (8 records): gc[k * 32]
+    uint4* gm = reinterpret_cast<uint4*>(map) + (size_t)mb0 * 32 + lane;  // mapping block k (4 records): gm[k * 32]
+    const bool live = slot < raw.n_reads && W.n_close[W.order[slot < raw.n_reads ? slot : 0]] != 0xffffu;
+    const uint32_t r = live ? W.order[slot] : 0u;
+    const uint32_t L = live ? W.n_cols[r] : 0u, n_rec = live ? W.n_extra[r] : 0u;
+    const uint32_t m0 = raw.map_off[r], M = raw.map_off[r + 1] - m0;
+    const uint32_t q0 = raw.qual_off[r], Lq = raw.qual_off[r + 1] - q0;
+    const uint8_t* gs = W.gstr + raw.str_off[r];
+    const uint8_t* rs = W.rstr + raw.str_off[r];
+    for (uint32_t cb = 0; cb < ncb; ++cb) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t m = cb * 8 + j;
+            if (m >= L) continue;
+            const uint32_t qb = m < Lq ? raw.qual[q0 + m] : 0u;  // quality by ALIGNED COLUMN (src/readGAM_Euka.h:264,286)
+            const uint32_t rec = qb | (symbol_code(gs[m]) << 8) | (symbol_code(rs[m]) << 12);
+            w[j >> 1] |= rec << (16 * (j & 1));
+        }
+        gc[(size_t)cb * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    const uint32_t e_first = (live && M) ? raw.edit_off[m0] : 0u;
+    for (uint32_t mb = 0; mb < nmb; ++mb) {
+        uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i = mb * 4 + j;
+            if (i >= n_rec) continue;
+            if (soibean) {
+                const bool none = n_rec != M && i >= M;
+                v[j] = ((uint32_t)W.sizes[e_first + i] << 20) | (none ? VGL_SOIBEAN_NO_NODE : (raw.map_node[m0 + i] & 0x7fffffffu));
+            } else {
+                v[j] = raw.map_node[m0 + i] & 0x7fffffffu;
+            }
+        }
+        gm[(size_t)mb * 32] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+    o_n_cols[slot] = (uint16_t)L;
+    o_n_maps[slot] = (uint16_t)n_rec;
+    o_seq_len[slot] = live ? raw.seq_len[r] : (uint16_t)0;
+    o_mapq[slot] = live ? raw.mapq[r] : (uint8_t)0;
+    o_flags[slot] = (live && M) ? (uint8_t)(raw.map_node[m0] >> 31) : (uint8_t)0;
+    o_read_index[slot] = live ? raw.read_index[r] : 0u;
 }
 
 // Wire form -> 32-bit column records (include/vgan_gpu.h, vgl_hc_wire).  One thread per lane, walking from the read's last
@@ -396,15 +486,16 @@ cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const u
     return cudaGetLastError();
 }
 
-cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int* err_flag, cudaStream_t s) {
+cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, int* err_flag, cudaStream_t s) {
     if (raw.n_reads == 0) return cudaSuccess;
-    hc_recon_kernel<<<(raw.n_reads + 127) / 128, 128, 0, s>>>(raw, G, W, err_flag);
+    hc_recon_kernel<<<(raw.n_reads + 127) / 128, 128, 0, s>>>(raw, G, W, mode, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     hc_scan4096<<<1, 1024, 0, s>>>(W.hist, W.start);
     hc_order_kernel<<<(raw.n_reads + 255) / 256, 256, 0, s>>>(raw.n_reads, W.n_cols, W.start, W.cursor, W.order);
     const uint32_t n_groups = (raw.n_reads + 31) / 32;
-    hc_groups_kernel<<<(n_groups + 255) / 256, 256, 0, s>>>(raw.n_reads, n_groups, W.order, W.n_cols, W.n_extra, W.grp_cb, W.grp_mb);
+    hc_groups_kernel<<<(n_groups + 255) / 256, 256, 0, s>>>(raw.n_reads, n_groups, W.order, W.n_cols, W.n_extra,
+                                                            mode == kReconHaplocart ? (uint32_t)VGL_HC_COL_BLK : (uint32_t)VGL_EUKA_COL_BLK, W.grp_cb, W.grp_mb);
     hc_scan_groups<<<1, 1024, 0, s>>>(n_groups, W.grp_cb, W.grp_mb);
     return cudaGetLastError();
 }
@@ -416,6 +507,15 @@ cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32
     const uint32_t n_groups = (raw.n_reads + 31) / 32;
     hc_pack_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(raw, W, n_groups, col_cap_blks, map_cap_blks, col, xmap, n_cols, n_close,
                                                                n_extra, mapq, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t sym_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, int soibean, uint16_t* col, uint32_t* map, uint16_t* n_cols,
+                            uint16_t* n_maps, uint16_t* seq_len, uint8_t* mapq, uint8_t* flags, uint32_t* read_index, cudaStream_t s) {
+    if (raw.n_reads == 0) return cudaSuccess;
+    const uint32_t n_groups = (raw.n_reads + 31) / 32;
+    sym_pack_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(raw, W, n_groups, soibean, col, map, n_cols, n_maps, seq_len, mapq, flags,
+                                                               read_index);
     return cudaGetLastError();
 }
 

@@ -108,6 +108,11 @@ struct vgl_ctx {
         DevBuf<uint16_t> o_n_cols, o_n_close, o_n_extra;
         DevBuf<uint8_t> o_mapq;
         uint32_t col_cap_blks = 0, map_cap_blks = 0;
+        // euka / soibean batches built on the device
+        DevBuf<uint16_t> seq_len, s_col, s_n_cols, s_n_maps, s_seq_len;
+        DevBuf<uint32_t> read_index, s_map, s_read_index;
+        DevBuf<uint8_t> s_mapq, s_flags;
+        DevBuf<int> s_err;
         cudaEvent_t copied = nullptr, consumed = nullptr;  // H2D of the chunk done / its kernels done
         bool used = false;
     } rawdev[2];
@@ -218,6 +223,12 @@ int reserve_result(vgl_ctx* ctx, size_t n_post) {
     return VGL_OK;
 }
 
+int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
+                       double* like, uint8_t* pass);
+int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map_rec, uint32_t n_out, double* path_ll, uint8_t* used);
+int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::EukaBatchDev& d, size_t& n_map_rec);
+int stage_symbol_batch(vgl_ctx* ctx, const vgl_euka_batch* b, vgl::EukaBatchDev& d);
+
 int check_batch(const vgl_hc_batch* b) {
     if (!b) return fail(VGL_ERR_INVALID, "null batch");
     if (b->n_groups == 0) return VGL_OK;
@@ -294,6 +305,8 @@ void vgl_destroy(vgl_ctx* ctx) {
         R.gstr.release(); R.rstr.release(); R.sizes.release(); R.n_cols.release(); R.n_close.release(); R.n_extra.release();
         R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
         R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
+        R.seq_len.release(); R.s_col.release(); R.s_n_cols.release(); R.s_n_maps.release(); R.s_seq_len.release();
+        R.read_index.release(); R.s_map.release(); R.s_read_index.release(); R.s_mapq.release(); R.s_flags.release(); R.s_err.release();
         if (R.copied) cudaEventDestroy(R.copied);
         if (R.consumed) cudaEventDestroy(R.consumed);
     }
@@ -700,7 +713,7 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
     RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
     RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
-    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, nm); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
+    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
     RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
     RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
     RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
@@ -725,10 +738,10 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     // per-read arrays are indexed by the read's position in the chunk; everything they point INTO by absolute index
     const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p - qa, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p - ma,
                               R.map_offset.p - ma, R.edit_off.p - ma, R.edit_from.p - ea, R.edit_to.p - ea, R.edit_seq_off.p - ea,
-                              R.edit_seq.p - sa};
-    const vgl::ReconWorkDev Wd{R.gstr.p - ca, R.rstr.p - ca, R.sizes.p - ma, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
+                              R.edit_seq.p - sa, nullptr, nullptr};
+    const vgl::ReconWorkDev Wd{R.gstr.p - ca, R.rstr.p - ca, R.sizes.p - ea, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
                                R.hist3.p + 4096, R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
-    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, ctx->d_err, s));
+    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->d_err, s));
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
                                  R.o_mapq.p, ctx->d_err, s));
     ctx->launches += 6;
@@ -1086,52 +1099,20 @@ int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* b, uint32_t n_out, int32_t*
         return fail(VGL_ERR_INVALID, "euka batch arrays missing");
     cudaStream_t s = ctx->stream;
     VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
-    const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
-    const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_EUKA_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
-    vgl_ctx::EukaStage& st = ctx->estage;
-    if (int rc = st.grp_col_blk.reserve(G + 1)) return rc;
-    if (int rc = st.grp_map_blk.reserve(G + 1)) return rc;
-    if (int rc = st.col.reserve(ncol)) return rc;
-    if (int rc = st.map.reserve(nmap)) return rc;
-    if (int rc = st.n_cols.reserve(nl)) return rc;
-    if (int rc = st.n_maps.reserve(nl)) return rc;
-    if (int rc = st.seq_len.reserve(nl)) return rc;
-    if (int rc = st.mapq.reserve(nl)) return rc;
-    if (int rc = st.flags.reserve(nl)) return rc;
-    if (int rc = st.read_index.reserve(nl)) return rc;
-    if (int rc = upload_async(st.grp_col_blk.p, b->grp_col_blk, (G + 1) * 4, s)) return rc;
-    if (int rc = upload_async(st.grp_map_blk.p, b->grp_map_blk, (G + 1) * 4, s)) return rc;
-    if (int rc = upload_async(st.col.p, b->col, ncol * 2, s)) return rc;
-    if (int rc = upload_async(st.map.p, b->map, nmap * 4, s)) return rc;
-    if (int rc = upload_async(st.n_cols.p, b->n_cols, nl * 2, s)) return rc;
-    if (int rc = upload_async(st.n_maps.p, b->n_maps, nl * 2, s)) return rc;
-    if (int rc = upload_async(st.seq_len.p, b->seq_len, nl * 2, s)) return rc;
-    if (int rc = upload_async(st.mapq.p, b->mapq, nl, s)) return rc;
-    if (int rc = upload_async(st.flags.p, b->flags, nl, s)) return rc;
-    if (int rc = upload_async(st.read_index.p, b->read_index, nl * 4, s)) return rc;
-    const size_t no = std::max<size_t>(n_out, 1);
-    if (int rc = ctx->e_clade.reserve(no)) return rc;
-    if (int rc = ctx->e_in.reserve(no)) return rc;
-    if (int rc = ctx->e_not.reserve(no)) return rc;
-    if (int rc = ctx->e_like.reserve(no)) return rc;
-    if (int rc = ctx->e_pass.reserve(no)) return rc;
-    VGL_CUDA(cudaMemsetAsync(ctx->e_clade.p, 0xff, no * 4, s));  // reads that were not in the batch keep clade -1
-    VGL_CUDA(cudaMemsetAsync(ctx->e_in.p, 0, no * 8, s));
-    VGL_CUDA(cudaMemsetAsync(ctx->e_not.p, 0, no * 8, s));
-    VGL_CUDA(cudaMemsetAsync(ctx->e_like.p, 0, no * 8, s));
-    VGL_CUDA(cudaMemsetAsync(ctx->e_pass.p, 0, no, s));
-    vgl::EukaBatchDev d{b->n_groups, st.grp_col_blk.p, st.grp_map_blk.p, st.col.p, st.map.p, st.n_cols.p, st.n_maps.p,
-                        st.seq_len.p, st.mapq.p, st.flags.p, st.read_index.p};
-    vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p};
-    VGL_CUDA(vgl::euka_launch_read_kernel(d, ctx->etab, o, s));
-    ctx->launches += 1;
-    if (clade) VGL_CUDA(cudaMemcpyAsync(clade, ctx->e_clade.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
-    if (in_lik) VGL_CUDA(cudaMemcpyAsync(in_lik, ctx->e_in.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
-    if (not_lik) VGL_CUDA(cudaMemcpyAsync(not_lik, ctx->e_not.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
-    if (like) VGL_CUDA(cudaMemcpyAsync(like, ctx->e_like.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
-    if (pass) VGL_CUDA(cudaMemcpyAsync(pass, ctx->e_pass.p, (size_t)n_out, cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaStreamSynchronize(s));
-    return VGL_OK;
+    vgl::EukaBatchDev d;
+    if (int rc = stage_symbol_batch(ctx, b, d)) return rc;
+    return euka_run_on_device(ctx, d, n_out, clade, in_lik, not_lik, like, pass);
+}
+
+int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
+                     double* like, uint8_t* pass) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
+    vgl::EukaBatchDev d;
+    size_t n_map_rec = 0;
+    if (int rc = pack_raw_symbols(ctx, raw, /*soibean=*/0, d, n_map_rec)) return rc;
+    if (d.n_groups == 0) return VGL_OK;
+    return euka_run_on_device(ctx, d, n_out, clade, in_lik, not_lik, like, pass);
 }
 
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov) {
@@ -1238,7 +1219,25 @@ int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* b, uint32_t n_out, do
     VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
     vgl::EukaBatchDev d;
     if (int rc = stage_symbol_batch(ctx, b, d)) return rc;
-    const size_t nmap = std::max<size_t>((size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK, 1);
+    return soibean_run_on_device(ctx, d, (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK, n_out, path_ll, used);
+}
+
+int vgl_soibean_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, double* path_ll, uint8_t* used) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_soibean) return fail(VGL_ERR_STATE, "vgl_soibean_set_tables must come first");
+    vgl::EukaBatchDev d;
+    size_t n_map_rec = 0;
+    if (int rc = pack_raw_symbols(ctx, raw, /*soibean=*/1, d, n_map_rec)) return rc;
+    if (d.n_groups == 0) return VGL_OK;
+    return soibean_run_on_device(ctx, d, n_map_rec, n_out, path_ll, used);
+}
+
+}  // extern "C"
+
+namespace {
+int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map_rec, uint32_t n_out, double* path_ll, uint8_t* used) {
+    cudaStream_t s = ctx->stream;
+    const size_t nmap = std::max<size_t>(n_map_rec, 1);
     const size_t P = (size_t)ctx->stab.n_paths, no = std::max<size_t>(n_out, 1);
     if (int rc = ctx->s_sup.reserve(nmap)) return rc;
     if (int rc = ctx->s_uns.reserve(nmap)) return rc;
@@ -1259,4 +1258,92 @@ int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* b, uint32_t n_out, do
     return VGL_OK;
 }
 
-}  // extern "C"
+}  // namespace
+
+namespace {
+
+int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
+                       double* like, uint8_t* pass) {
+    cudaStream_t s = ctx->stream;
+    const size_t no = std::max<size_t>(n_out, 1);
+    if (int rc = ctx->e_clade.reserve(no)) return rc;
+    if (int rc = ctx->e_in.reserve(no)) return rc;
+    if (int rc = ctx->e_not.reserve(no)) return rc;
+    if (int rc = ctx->e_like.reserve(no)) return rc;
+    if (int rc = ctx->e_pass.reserve(no)) return rc;
+    VGL_CUDA(cudaMemsetAsync(ctx->e_clade.p, 0xff, no * 4, s));  // reads that were not in the batch keep clade -1
+    VGL_CUDA(cudaMemsetAsync(ctx->e_in.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_not.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_like.p, 0, no * 8, s));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_pass.p, 0, no, s));
+    vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p};
+    VGL_CUDA(vgl::euka_launch_read_kernel(d, ctx->etab, o, s));
+    ctx->launches += 1;
+    if (clade) VGL_CUDA(cudaMemcpyAsync(clade, ctx->e_clade.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
+    if (in_lik) VGL_CUDA(cudaMemcpyAsync(in_lik, ctx->e_in.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (not_lik) VGL_CUDA(cudaMemcpyAsync(not_lik, ctx->e_not.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (like) VGL_CUDA(cudaMemcpyAsync(like, ctx->e_like.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+    if (pass) VGL_CUDA(cudaMemcpyAsync(pass, ctx->e_pass.p, (size_t)n_out, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    return VGL_OK;
+}
+
+// euka / soibean: the whole raw batch in one piece -- H2D, reconstruction (mode 1 / 2), group sizes read back, packing.
+int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::EukaBatchDev& d, size_t& n_map_rec) {
+    if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
+    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq || !raw->seq_len ||
+        !raw->read_index || (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))
+        return fail(VGL_ERR_INVALID, "raw alignment arrays missing (euka / soibean need seq_len and read_index: vgh_euka_raw_build)");
+    vgl_ctx::RawDev& R = ctx->rawdev[0];
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
+    const size_t n = raw->n_reads, nm = raw->n_maps, ne = raw->n_edits;
+    const size_t nq = raw->qual_off[n], nseq = raw->edit_seq_off[ne], ncap = raw->str_off[n], G = (n + 31) / 32;
+    d = vgl::EukaBatchDev{};
+    n_map_rec = 0;
+    if (n == 0) return VGL_OK;
+#define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
+    RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq); RSV(R.seq_len, n);
+    RSV(R.read_index, n); RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
+    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
+    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
+    RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1); RSV(R.s_err, 1);
+    RSV(R.s_n_cols, G * 32); RSV(R.s_n_maps, G * 32); RSV(R.s_seq_len, G * 32); RSV(R.s_mapq, G * 32); RSV(R.s_flags, G * 32);
+    RSV(R.s_read_index, G * 32);
+#define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, s))
+    H2D(R.qual_off.p, raw->qual_off, (n + 1) * 4); H2D(R.str_off.p, raw->str_off, (n + 1) * 4); H2D(R.map_off.p, raw->map_off, (n + 1) * 4);
+    H2D(R.mapq.p, raw->mapq, n); H2D(R.qual.p, raw->qual, nq); H2D(R.seq_len.p, raw->seq_len, n * 2); H2D(R.read_index.p, raw->read_index, n * 4);
+    H2D(R.map_node.p, raw->map_node, nm * 4); H2D(R.map_offset.p, raw->map_offset, nm * 4); H2D(R.edit_off.p, raw->edit_off, (nm + 1) * 4);
+    H2D(R.edit_from.p, raw->edit_from, ne * 2); H2D(R.edit_to.p, raw->edit_to, ne * 2); H2D(R.edit_seq_off.p, raw->edit_seq_off, (ne + 1) * 4);
+    H2D(R.edit_seq.p, raw->edit_seq, nseq);
+#undef H2D
+    VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
+    VGL_CUDA(cudaMemsetAsync(R.s_err.p, 0, sizeof(int), s));
+    const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
+    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p,
+                              R.edit_off.p, R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p, R.seq_len.p, R.read_index.p};
+    const vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
+                               R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, soibean ? 2 : 1, R.s_err.p, s));
+    // the group tables are final: size the record arrays from them
+    uint32_t tot[2] = {0, 0};
+    int err = 0;
+    VGL_CUDA(cudaMemcpyAsync(&tot[0], R.grp_cb.p + G, 4, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(&tot[1], R.grp_mb.p + G, 4, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(&err, R.s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    if (err & 0x10000000) return fail(VGL_ERR_BAD_NODE, "device-side reconstruction: a mapping names a node outside the graph (or beyond the edit record's node field)");
+    if (err) return fail(VGL_ERR_BAD_READ, "device-side reconstruction rejected a read (lengths, offsets, fragment size outside [15, 1000], or the path spells more bases than the read has)");
+    RSV(R.s_col, (size_t)tot[0] * VGL_HC_LANES * VGL_EUKA_COL_BLK);
+    RSV(R.s_map, (size_t)tot[1] * VGL_HC_LANES * VGL_HC_MAP_BLK);
+#undef RSV
+    VGL_CUDA(vgl::sym_launch_pack(Rd, Wd, soibean, R.s_col.p, R.s_map.p, R.s_n_cols.p, R.s_n_maps.p, R.s_seq_len.p, R.s_mapq.p, R.s_flags.p,
+                                  R.s_read_index.p, s));
+    ctx->launches += 6;
+    n_map_rec = (size_t)tot[1] * VGL_HC_LANES * VGL_HC_MAP_BLK;
+    d = vgl::EukaBatchDev{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.s_col.p, R.s_map.p, R.s_n_cols.p, R.s_n_maps.p, R.s_seq_len.p, R.s_mapq.p,
+                          R.s_flags.p, R.s_read_index.p};
+    return VGL_OK;
+}
+
+}  // namespace

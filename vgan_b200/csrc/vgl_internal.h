@@ -145,14 +145,16 @@ struct ReconRawDev {  // device copy of a vgl_hc_raw
     const uint16_t* edit_to;
     const uint32_t* edit_seq_off;
     const uint8_t* edit_seq;
+    const uint16_t* seq_len;      // [n_reads] |Alignment.sequence| (euka / soibean only)
+    const uint32_t* read_index;   // [n_reads] position of the read in the caller's order (euka / soibean only)
 };
 struct ReconWorkDev {  // scratch
     uint8_t* gstr;      // aligned graph strings, read r at str_off[r]
     uint8_t* rstr;      // aligned read strings
-    uint16_t* sizes;    // [n_maps] size slot of every mapping (the size of the read's i-th EDIT, quirk Q1)
+    uint16_t* sizes;    // [n_edits] one size per edit (src/vgan_utils.h:72), by absolute edit index
     uint16_t* n_cols;   // [n_reads] in caller order
     uint16_t* n_close;
-    uint16_t* n_extra;
+    uint16_t* n_extra;  // HaploCart: empty mappings; euka / soibean: mapping / edit records of the read
     uint32_t* hist;     // [4096] reads per column count
     uint32_t* start;    // [4096]
     uint32_t* cursor;   // [4096]
@@ -161,7 +163,11 @@ struct ReconWorkDev {  // scratch
     uint32_t* grp_mb;   // [n_groups + 1] -> the batch's grp_map_blk
 };
 // hist and cursor must be zero on entry.
-cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int* err_flag, cudaStream_t s);
+// mode: 0 HaploCart, 1 euka, 2 soibean (which checks apply, what the record count means, 4- or 8-column blocks)
+cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, int* err_flag, cudaStream_t s);
+// euka / soibean batch from the reconstructed strings (after hc_launch_recon with mode 1 / 2)
+cudaError_t sym_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, int soibean, uint16_t* col, uint32_t* map, uint16_t* n_cols,
+                            uint16_t* n_maps, uint16_t* seq_len, uint8_t* mapq, uint8_t* flags, uint32_t* read_index, cudaStream_t s);
 // xmap (the extra records) must be zero on entry.
 cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32_t col_cap_blks, uint32_t map_cap_blks, uint32_t* col,
                            uint32_t* xmap, uint16_t* n_cols, uint16_t* n_close, uint16_t* n_extra, uint8_t* mapq, int* err_flag,

@@ -96,6 +96,24 @@ class Euka:
         out["not_like"] = 1 - out["like"]  # clade_not_like (src/readGAM_Euka.h:492)
         return out
 
+    def load_graph(self, graph):
+        """Node sequences for run_raw (reconstruction on the device)."""
+        mid, n = C.c_int64(), C.c_int64()
+        off, seq = C.c_void_p(), C.c_void_p()
+        check(_lib.host.vgh_graph_view(graph.handle, C.byref(mid), C.byref(n), C.byref(off), C.byref(seq)))
+        check(gpu.vgl_hc_set_graph(self.ctx, mid.value, n.value, off, seq))
+
+    def run_raw(self, raw):
+        """As run(), from a RawBatch(euka_rule=True): reconstruction and packing happen on the device."""
+        n = raw.n_span
+        out = {"clade": np.full(n, -1, dtype=np.int32), "in_lik": np.zeros(n), "not_lik": np.zeros(n), "like": np.zeros(n),
+               "pass": np.zeros(n, dtype=np.uint8)}
+        check(gpu.vgl_euka_run_raw(self.ctx, C.byref(raw.raw), n, out["clade"].ctypes.data_as(C.c_void_p),
+                                   out["in_lik"].ctypes.data_as(C.c_void_p), out["not_lik"].ctypes.data_as(C.c_void_p),
+                                   out["like"].ctypes.data_as(C.c_void_p), out["pass"].ctypes.data_as(C.c_void_p)))
+        out["not_like"] = 1 - out["like"]
+        return out
+
     def results(self):
         count = np.zeros(self.tables.n_clades, dtype=np.int64)
         cov = np.zeros(max(self.tables.n_bins, 1), dtype=np.float64)

@@ -233,10 +233,13 @@ class WireBatch:
 class RawBatch:
     """The raw alignments of reads [r0, r1) in the compact form the device-side reconstruction reads (vgl_hc_raw)."""
 
-    def __init__(self, alns, r0=0, r1=None, pinned=False):
+    def __init__(self, alns, r0=0, r1=None, pinned=False, euka_rule=False):
+        """euka_rule: keep the reads readGAM3 keeps (identity != 0) instead of HaploCart's identity >= 1e-10."""
         r1 = len(alns) if r1 is None else r1
         self.handle = C.c_void_p()
-        check(host.vgh_hc_raw_build(C.byref(alns.view), int(r0), int(r1), int(pinned), C.byref(self.handle)))
+        self.n_span = int(r1 - r0)
+        build = host.vgh_euka_raw_build if euka_rule else host.vgh_hc_raw_build
+        check(build(C.byref(alns.view), int(r0), int(r1), int(pinned), C.byref(self.handle)))
         self.raw = host.vgh_hc_raw_view(self.handle).contents
         self.skipped = int(host.vgh_hc_raw_skipped(self.handle))
 

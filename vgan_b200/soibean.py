@@ -6,6 +6,7 @@ import ctypes as C
 
 import numpy as np
 
+from . import _lib
 from ._lib import check, gpu, host
 
 
@@ -63,6 +64,21 @@ class Soibean:
     def load(self, tables):
         check(gpu.vgl_soibean_set_tables(self.ctx, C.byref(tables.view)))
         self.tables = tables
+
+    def load_graph(self, graph):
+        """Node sequences for analyse_raw (reconstruction on the device)."""
+        mid, n = C.c_int64(), C.c_int64()
+        off, seq = C.c_void_p(), C.c_void_p()
+        check(_lib.host.vgh_graph_view(graph.handle, C.byref(mid), C.byref(n), C.byref(off), C.byref(seq)))
+        check(gpu.vgl_hc_set_graph(self.ctx, mid.value, n.value, off, seq))
+
+    def analyse_raw(self, raw):
+        """As analyse(), from a RawBatch(euka_rule=True): reconstruction and packing happen on the device."""
+        n, P = raw.n_span, self.tables.n_paths
+        out = np.zeros((n, P), dtype=np.float64)
+        used = np.zeros(n, dtype=np.uint8)
+        check(gpu.vgl_soibean_run_raw(self.ctx, C.byref(raw.raw), n, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
+        return out, used
 
     def analyse(self, packed, pinned=False):
         """pathMap of every read of the packed range: (matrix [n, P], used [n]).  pinned=True returns arrays in page-locked
