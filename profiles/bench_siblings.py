@@ -25,6 +25,21 @@ t = time.perf_counter()
 for _ in range(5):
     ek.reset(); res = ek.run(pb)
 dt = (time.perf_counter() - t) / 5
+# the same from raw alignments: reconstruction + packing on the device
+t = time.perf_counter()
+raw = vb.RawBatch(alns, pinned=True, euka_rule=True)
+raw_build_s = time.perf_counter() - t
+ek.load_graph(S.graph)
+for _ in range(2):
+    ek.reset(); ek.run_raw(raw)
+t = time.perf_counter()
+for _ in range(5):
+    ek.reset(); res_raw = ek.run_raw(raw)
+dt_raw = (time.perf_counter() - t) / 5
+assert np.array_equal(res_raw["in_lik"], res["in_lik"])
+out["euka_raw"] = {"reads": raw.n_reads, "reads_per_s": raw.n_reads / dt_raw, "ms": dt_raw * 1e3, "raw_bytes": raw.nbytes,
+                   "host_build_s": raw_build_s,
+                   "what": "vgl_euka_run_raw: raw alignments -> H2D -> device reconstruction + packing -> euka kernel -> per-read D2H"}
 out["euka"] = {"reads": pb.n_reads, "clades": 335, "reads_per_s": pb.n_reads / dt, "read_bases_per_s": cols / dt, "ms": dt * 1e3,
                "batch_bytes": pb.nbytes, "host_pack_s": pack_s,
                "what": "config 4 shape: vgl_euka_run on a host batch incl. H2D and per-read D2H; evaluations = reads"}

@@ -76,7 +76,7 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int mode, int*
         const uint32_t mn = raw.map_node[m];
         const uint32_t node = mn & 0x7fffffffu;
         const bool rev = (mn >> 31) != 0;
-        if (node < G.min_id || node >= G.min_id + G.n_nodes || node > VGL_HC_MAX_NODE) { err = kErrBadNodeRaw; break; }
+        if (node < G.min_id || node >= G.min_id + G.n_nodes || (mode == kReconHaplocart && node > VGL_HC_MAX_NODE)) { err = kErrBadNodeRaw; break; }
         const uint32_t na = G.seq_off[node - G.min_id], nlen = G.seq_off[node - G.min_id + 1] - na;
         uint32_t offset = raw.map_offset[m];
         uint32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size

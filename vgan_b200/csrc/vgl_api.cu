@@ -672,8 +672,9 @@ uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* r) {
 
 int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq) {
     if (int rc = use_device(ctx)) return rc;
-    if (min_id < 0 || n_nodes <= 0 || !seq_off || !seq || min_id + n_nodes > (int64_t)VGL_HC_MAX_NODE + 1 || seq_off[n_nodes] > 0xffffffffll)
-        return fail(VGL_ERR_INVALID, "bad node table (node ids must fit the column record, <= %u)", VGL_HC_MAX_NODE);
+    // (HaploCart's column record holds node ids <= VGL_HC_MAX_NODE: checked per mapping by the reconstruction kernel)
+    if (min_id < 0 || n_nodes <= 0 || !seq_off || !seq || min_id + n_nodes > 0x7fffffffll || seq_off[n_nodes] > 0xffffffffll)
+        return fail(VGL_ERR_INVALID, "bad node table");
     std::vector<uint32_t> off((size_t)n_nodes + 1);
     for (int64_t k = 0; k <= n_nodes; ++k) off[(size_t)k] = (uint32_t)seq_off[k];
     if (int rc = ctx->g_seq_off.reserve(off.size())) return rc;
