@@ -286,6 +286,12 @@ typedef struct vgl_hc_raw {
     const uint8_t* edit_seq;
     const uint16_t* seq_len;      /* [n_reads] |Alignment.sequence|            (euka / soibean; may be NULL for HaploCart) */
     const uint32_t* read_index;   /* [n_reads] position in the caller's order  (euka / soibean; may be NULL for HaploCart) */
+    /* Narrow twins (NULL, or all three present): what vgl_hc_accumulate_raw ships INSTEAD of map_offset / edit_off /
+     * edit_seq_off when every value fits -- the offsets are rebuilt on the device with prefix sums.  The wide arrays stay
+     * valid on the host (the library reads a few entries to cut the batch into chunks).                               */
+    const uint16_t* map_offset16; /* [n_maps]  Mapping.position.offset                        */
+    const uint8_t* map_n_edits8;  /* [n_maps]  edits of the mapping (edit_off differences)    */
+    const uint8_t* edit_slen8;    /* [n_edits] length of the edit's sequence                  */
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 

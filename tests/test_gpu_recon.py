@@ -141,6 +141,17 @@ def test_likelihoods_from_raw_alignments_match_oracle(small):
     res = hc.get_posterior()
     final, argmax, _ = _oracle(small, alns)
     _check(res, 2 * np.asarray(final, dtype=np.longdouble), argmax, None)
+    # the narrow arrays (16-bit offsets, edit counts, sequence lengths) are what was shipped; without them the 32-bit
+    # offsets travel instead and nothing else changes
+    assert raw.raw.map_offset16 and raw.raw.map_n_edits8 and raw.raw.edit_slen8
+    narrow_bytes = raw.nbytes
+    raw.raw.map_offset16 = raw.raw.map_n_edits8 = raw.raw.edit_slen8 = None
+    assert raw.nbytes > 1.3 * narrow_bytes
+    hc.reset()
+    hc.update_raw(raw)
+    hc.update_raw(raw)
+    res_wide = hc.get_posterior()
+    assert res_wide["maxh_index"] == res["maxh_index"] and np.allclose(res_wide["final_vec"], res["final_vec"], rtol=1e-13)
     # same call and posteriors as the host-packed route
     hc.reset()
     hc.update(vb.PackedBatch(small.graph, alns))

@@ -856,6 +856,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
     const size_t o_node = take(nm * 4), o_offs = take(nm * 4), o_eoff = take((nm + 1) * 4), o_from = take(ne * 2), o_to = take(ne * 2);
     const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns), o_slen = take(R * 2), o_ridx = take(R * 4);
+    const size_t o_off16 = take(nm * 2), o_ne8 = take(nm), o_sl8 = take(ne);
     vgh_hc_raw* P = new vgh_hc_raw();
     P->pinned = pinned != 0;
     const size_t bytes = std::max<size_t>(o, 256);
@@ -875,7 +876,9 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     uint16_t* from = (uint16_t*)(base + o_from); uint16_t* to = (uint16_t*)(base + o_to);
     uint32_t* esoff = (uint32_t*)(base + o_esoff); uint8_t* eseq = base + o_eseq;
     uint16_t* slen = (uint16_t*)(base + o_slen); uint32_t* ridx = (uint32_t*)(base + o_ridx);
-#pragma omp parallel for schedule(static)
+    uint16_t* off16 = (uint16_t*)(base + o_off16); uint8_t* ne8 = base + o_ne8; uint8_t* sl8 = base + o_sl8;
+    bool narrow = true;  // every offset <= 65535, <= 255 edits per mapping, edit sequences <= 255 bytes
+#pragma omp parallel for schedule(static) reduction(&& : narrow)
     for (int64_t k = 0; k < (int64_t)R; ++k) {
         const int64_t r = keep[(size_t)k];
         uint64_t cm = pm[(size_t)k], ce = pe[(size_t)k], cs = ps[(size_t)k];
@@ -888,12 +891,18 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
             node[cm] = (uint32_t)a->map_node[m] | (a->map_rev[m] ? 0x80000000u : 0u);
             offs[cm] = (uint32_t)a->map_offset[m];
             eoff[cm] = (uint32_t)ce;
+            const int64_t n_ed = a->edit_off[m + 1] - a->edit_off[m];
+            off16[cm] = (uint16_t)a->map_offset[m];
+            ne8[cm] = (uint8_t)n_ed;
+            narrow = narrow && a->map_offset[m] <= 65535 && n_ed <= 255;
             ++cm;
             for (int64_t e = a->edit_off[m]; e < a->edit_off[m + 1]; ++e) {
                 const int64_t sl = a->edit_seq_off[e + 1] - a->edit_seq_off[e];
                 from[ce] = (uint16_t)a->edit_from[e];
                 to[ce] = (uint16_t)a->edit_to[e];
                 esoff[ce] = (uint32_t)cs;
+                sl8[ce] = (uint8_t)sl;
+                narrow = narrow && sl <= 255;
                 memcpy(eseq + cs, a->edit_seq + a->edit_seq_off[e], (size_t)sl);
                 cs += (uint64_t)sl;
                 ++ce;
@@ -908,6 +917,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     v.qual_off = qoff; v.qual = q; v.mapq = mq; v.str_off = soff; v.map_off = moff; v.map_node = node; v.map_offset = offs;
     v.edit_off = eoff; v.edit_from = from; v.edit_to = to; v.edit_seq_off = esoff; v.edit_seq = eseq;
     v.seq_len = slen; v.read_index = ridx;
+    if (narrow) { v.map_offset16 = off16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; }
     *out = P;
     return VGH_OK;
 }

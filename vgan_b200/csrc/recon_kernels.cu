@@ -365,6 +365,85 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     o_mapq[slot] = raw.mapq[r];
 }
 
+// Counts (one byte each) -> offsets: out[i] = base + in[0] + ... + in[i-1] for i in [0, n], three small kernels.
+// (The raw alignments ship edit counts per mapping and sequence lengths per edit instead of 32-bit offsets.)
+constexpr int kScanTile = 4096;  // 256 threads x 16 elements
+__global__ void __launch_bounds__(256) scan_u8_tile_sums(const uint8_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t t0 = blockIdx.x * kScanTile + threadIdx.x * 16;
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 16; ++k) v += t0 + k < n ? in[t0 + k] : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_w[w];
+        tile_sum[blockIdx.x] = tot;
+    }
+}
+__global__ void __launch_bounds__(1024) scan_tiles(uint32_t n_tiles, uint32_t base, uint32_t* __restrict__ tile_sum) {  // in place, exclusive, + base
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int t = threadIdx.x;
+    if (t == 0) s_carry = base;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_tiles; b0 += 1024) {
+        const uint32_t i = b0 + t;
+        const uint32_t v = i < n_tiles ? tile_sum[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, x, k);
+            if ((t & 31) >= k) x += o;
+        }
+        if ((t & 31) == 31) s_w[t >> 5] = x;
+        __syncthreads();
+        if (t < 32) {
+            uint32_t w = s_w[t];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, w, k);
+                if (t >= k) w += o;
+            }
+            s_w[t] = w;
+        }
+        __syncthreads();
+        if (i < n_tiles) tile_sum[i] = s_carry + ((t >> 5) ? s_w[(t >> 5) - 1] : 0u) + x - v;
+        __syncthreads();
+        if (t == 0) s_carry += s_w[31];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) scan_u8_final(const uint8_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_off,
+                                                     uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t t0 = blockIdx.x * kScanTile + threadIdx.x * 16;
+    uint32_t e[16], mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; ++k) { e[k] = t0 + k < n ? in[t0 + k] : 0u; mine += e[k]; }
+    uint32_t x = mine;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, x, k);
+        if ((threadIdx.x & 31) >= (unsigned)k) x += o;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t run = tile_off[blockIdx.x] + x - mine;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) run += s_w[w];
+#pragma unroll
+    for (uint32_t k = 0; k < 16; ++k) {
+        if (t0 + k <= n) out[t0 + k] = run;  // entry n receives the total
+        run += e[k];
+    }
+}
+__global__ void __launch_bounds__(256) widen_u16(const uint16_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
 __device__ __forceinline__ uint32_t symbol_code(uint8_t c) {
     switch (c) {
         case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
@@ -507,6 +586,21 @@ cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32
     const uint32_t n_groups = (raw.n_reads + 31) / 32;
     hc_pack_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(raw, W, n_groups, col_cap_blks, map_cap_blks, col, xmap, n_cols, n_close,
                                                                n_extra, mapq, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, uint32_t base, uint32_t* tile_scratch, uint32_t* out,
+                                           cudaStream_t s) {
+    const uint32_t n_tiles = n / kScanTile + 1;  // entry n (the total) lives in tile n / kScanTile
+    scan_u8_tile_sums<<<n_tiles, 256, 0, s>>>(counts, n, tile_scratch);
+    scan_tiles<<<1, 1024, 0, s>>>(n_tiles, base, tile_scratch);
+    scan_u8_final<<<n_tiles, 256, 0, s>>>(counts, n, tile_scratch, out);
+    return cudaGetLastError();
+}
+
+cudaError_t raw_launch_widen_u16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    widen_u16<<<(n + 255) / 256, 256, 0, s>>>(in, n, out);
     return cudaGetLastError();
 }
 

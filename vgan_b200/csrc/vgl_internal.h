@@ -163,6 +163,11 @@ struct ReconWorkDev {  // scratch
     uint32_t* grp_mb;   // [n_groups + 1] -> the batch's grp_map_blk
 };
 // hist and cursor must be zero on entry.
+// The narrow arrays of a vgl_hc_raw, widened on the device: out[i] = base + counts[0] + ... + counts[i-1] for i in [0, n]
+// (tile_scratch: n / 4096 + 1 words); 16-bit offsets to 32 bits.
+cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, uint32_t base, uint32_t* tile_scratch, uint32_t* out,
+                                           cudaStream_t s);
+cudaError_t raw_launch_widen_u16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s);
 // mode: 0 HaploCart, 1 euka, 2 soibean (which checks apply, what the record count means, 4- or 8-column blocks)
 cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, int* err_flag, cudaStream_t s);
 // euka / soibean batch from the reconstructed strings (after hc_launch_recon with mode 1 / 2)
