@@ -221,6 +221,14 @@ def test_routes_agree_across_chunk_boundaries(small):
         assert res[name]["maxh_index"] == res["packed"]["maxh_index"]
         assert np.allclose(res[name]["final_vec"], res["packed"]["final_vec"], rtol=1e-12, atol=0)
         assert np.allclose(res[name]["confidence_vec"], res["packed"]["confidence_vec"], rtol=1e-9)
+    # the routes may be mixed within one sample: contributions add up
+    hc.reset()
+    hc.update(packed)
+    hc.update_wire(vb.WireBatch(packed, pinned=True))
+    hc.update_raw(vb.RawBatch(alns, pinned=True))
+    hc.update_device(dev.batch)
+    four = hc.get_posterior()
+    assert np.allclose(four["final_vec"], 4 * res["packed"]["final_vec"], rtol=1e-12, atol=0)
     hc.close()
 
 

@@ -120,8 +120,9 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // At a CLOSE mark (first column of a mapping) the pair is pushed onto the warp's queue in shared memory
 // (ballot + popc give every closing lane its slot, one 16-byte store each).  Whenever the queue holds 32
 // entries the warp drains them, one entry per lane: log of the product, B_i from the quality sums, and
-// B_i - A_i added to the CTA's node vector (global memory, L2 resident) with a fire-and-forget fp64 reduction.  Entries are self-contained,
-// so the queue simply carries over from one group to the next and the finalisation always runs on full warps.
+// B_i - A_i added to the CTA's node vector (global memory, L2 resident) with a fire-and-forget fp64 reduction.
+// Entries are self-contained, so the queue simply carries over from one group to the next and the finalisation
+// always runs on full warps.
 // (Per-thread lists in local memory, the obvious alternative, cost ~9 KB of L2 traffic per read.)
 //
 // Shared memory: [ HcSmallTables | node_class u16[n_rows + 1] | ac table double2[100][n_class + 1]
