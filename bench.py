@@ -348,6 +348,21 @@ def main():
             hc.run_sample([small], want_ll=False)
         latency = {"reads": small.n_reads, "ms_per_sample": (time.perf_counter() - t0) / 20 * 1e3,
                    "what": "reset + accumulate (host batch) + finalize, host wall clock, mean of 20"}
+        # ... and from the alignments themselves, host marshalling included: the host packer route against the raw route
+        def from_alignments(raw_route):
+            hc.reset()
+            if raw_route:
+                hc.update_raw(vb.RawBatch(alns, r0=0, r1=n_lat))
+            else:
+                hc.update(vb.PackedBatch(S.graph, alns, r0=0, r1=n_lat))
+            return hc.get_posterior(want_ll=False)
+        for key, flag in (("ms_per_sample_from_alignments_host_packer", False), ("ms_per_sample_from_alignments_raw_route", True)):
+            for _ in range(3):
+                from_alignments(flag)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                from_alignments(flag)
+            latency[key] = (time.perf_counter() - t0) / 10 * 1e3
 
     total_reads = reads_local
     if world > 1:
