@@ -433,7 +433,8 @@ constexpr int kPathTile = 128;       // paths per CTA (one per thread)
 constexpr int kWordsPerChunk = 10;   // 320 nodes per CTA
 
 __global__ void __launch_bounds__(kPathTile)
-hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __restrict__ chunk_ll) {
+hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __restrict__ chunk_ll, const double* __restrict__ a_total,
+               double* __restrict__ ll, unsigned int* __restrict__ tile_done) {
     __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -481,19 +482,25 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
         }
     }
     if (p < t.n_paths) chunk_ll[(size_t)chunk * t.n_paths + p] = acc;
-}
-
-// K2c: ll[p] = sum of the A totals + sum over chunks (fixed order, identical for every p)
-__global__ void hc_path_sum_kernel(const double* __restrict__ chunk_ll, int n_chunks, int n_paths,
-                                   const double* __restrict__ a_total, double* __restrict__ ll) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_paths) return;
-    double a = 0.0;
+    // K2c, run by whichever CTA of this path tile finishes last: ll[p] = sum of the A totals + sum over chunks, both in a
+    // fixed order that is the same for every p (who does the sum changes from run to run, the sum does not)
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(tile_done + blockIdx.x, 1u) == gridDim.y - 1;
+        if (s_last) tile_done[blockIdx.x] = 0;  // re-armed for the next sample
+    }
+    __syncthreads();
+    if (s_last && p < t.n_paths) {
+        __threadfence();
+        double a = 0.0;
 #pragma unroll
-    for (int c = 0; c < kAccCopies; ++c) a += a_total[c];
-    double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c) s += chunk_ll[(size_t)c * n_paths + p];
-    ll[p] = a + s;
+        for (int c = 0; c < kAccCopies; ++c) a += a_total[c];
+        double sum = 0.0;
+        for (unsigned c = 0; c < gridDim.y; ++c) sum += __ldcg(chunk_ll + (size_t)c * t.n_paths + p);
+        ll[p] = a + sum;
+    }
 }
 
 __global__ void hc_sum_parts_kernel(const double* __restrict__ parts, int n_parts, int n_paths, double* __restrict__ ll) {
@@ -697,18 +704,13 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
 
 int hc_path_chunks(int n_words) { return (n_words + kWordsPerChunk - 1) / kWordsPerChunk; }
 
-cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, cudaStream_t s) {
+cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+                                  unsigned int* tile_done, cudaStream_t s) {
     dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words));
-    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll);
+    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done);
     return cudaGetLastError();
 }
-
-cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths, const double* a_total, double* ll,
-                               cudaStream_t s) {
-    const int block = 128;
-    hc_path_sum_kernel<<<(n_paths + block - 1) / block, block, 0, s>>>(chunk_ll, n_chunks, n_paths, a_total, ll);
-    return cudaGetLastError();
-}
+int hc_path_tiles(int n_paths) { return (n_paths + kPathTile - 1) / kPathTile; }
 
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s) {
     const int block = 128;

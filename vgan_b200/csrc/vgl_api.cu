@@ -80,6 +80,7 @@ struct vgl_ctx {
     // accumulators
     // one allocation, one memset per sample: node vectors [copies][n_rows_pad] | A totals [copies] | error flag
     DevBuf<double> d_cta_node_acc, d_chunk_ll, d_ll;
+    DevBuf<unsigned int> d_tile_done;  // per path tile: CTAs of the path kernel that have finished
     double* d_a_total = nullptr;
     int* d_err = nullptr;
     int n_chunks = 0;
@@ -297,7 +298,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release();
     ctx->d_cta_node_acc.release();
-    ctx->d_chunk_ll.release(); ctx->d_ll.release();
+    ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_tile_done.release();
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -550,6 +551,8 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     ctx->d_err = reinterpret_cast<int*>(ctx->d_a_total + VGL_HC_ACC_COPIES);
     if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
     if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
+    if (int rc = ctx->d_tile_done.reserve((size_t)vgl::hc_path_tiles(P))) return rc;
+    VGL_CUDA(cudaMemset(ctx->d_tile_done.p, 0, (size_t)vgl::hc_path_tiles(P) * sizeof(unsigned int)));
     if (int rc = reserve_result(ctx, 64)) return rc;
     if (vgl::hc_posterior_smem(P) > 48 * 1024) VGL_CUDA(vgl::hc_posterior_configure(vgl::hc_posterior_smem(P)));
     ctx->have_tables = true;
@@ -910,9 +913,8 @@ int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     cudaStream_t s = ctx->stream;
-    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, s));
-    VGL_CUDA(vgl::hc_launch_path_sum(ctx->d_chunk_ll.p, ctx->n_chunks, ctx->tab.n_paths, ctx->d_a_total, ctx->d_ll.p, s));
-    ctx->launches += 2;
+    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, ctx->d_a_total, ctx->d_ll.p, ctx->d_tile_done.p, s));
+    ctx->launches += 1;
     ctx->ll_valid = true;
     if (ll_dev) VGL_CUDA(cudaMemcpyAsync(ll_dev, ctx->d_ll.p, (size_t)ctx->tab.n_paths * sizeof(double), cudaMemcpyDeviceToDevice, s));
     return VGL_OK;

@@ -99,11 +99,12 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
 
 // K2b: sums the copies and runs the bit-GEMV over the node x path membership: chunk_ll[chunk][P].
 int hc_path_chunks(int n_words);
-cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, cudaStream_t s);
-
-// K2c: ll[p] = sum_copies a_total[copy] + sum_chunks chunk_ll[chunk][p]   (fixed order, identical for every p)
-cudaError_t hc_launch_path_sum(const double* chunk_ll, int n_chunks, int n_paths, const double* a_total, double* ll,
-                               cudaStream_t s);
+int hc_path_tiles(int n_paths);
+// K2b + K2c: chunk_ll[chunk][P], then (by the last CTA of every path tile) ll[p] = sum_copies a_total[copy] + sum_chunks
+// chunk_ll[chunk][p] in a fixed order that is the same for every p.  tile_done: hc_path_tiles(P) counters, zero on entry
+// (the kernel leaves them zero).
+cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+                                  unsigned int* tile_done, cudaStream_t s);
 
 // Multi-GPU: ll[p] = sum_k parts[k][p] in k order.
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s);
