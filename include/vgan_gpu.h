@@ -292,6 +292,8 @@ typedef struct vgl_hc_raw {
     const uint16_t* map_offset16; /* [n_maps]  Mapping.position.offset                        */
     const uint8_t* map_n_edits8;  /* [n_maps]  edits of the mapping (edit_off differences)    */
     const uint8_t* edit_slen8;    /* [n_edits] length of the edit's sequence                  */
+    const uint8_t* edit_from8;    /* [n_edits] from_length, to_length: NULL, or both present (every length <= 255) */
+    const uint8_t* edit_to8;
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 
