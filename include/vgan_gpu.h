@@ -294,6 +294,7 @@ typedef struct vgl_hc_raw {
     const uint8_t* edit_slen8;    /* [n_edits] length of the edit's sequence                  */
     const uint8_t* edit_from8;    /* [n_edits] from_length, to_length: NULL, or both present (every length <= 255) */
     const uint8_t* edit_to8;
+    const uint16_t* map_node16;   /* [n_maps] node_id | is_reverse << 15: NULL, or present (every node id <= 32767) */
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 

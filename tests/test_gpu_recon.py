@@ -146,7 +146,7 @@ def test_likelihoods_from_raw_alignments_match_oracle(small):
     assert raw.raw.map_offset16 and raw.raw.map_n_edits8 and raw.raw.edit_slen8
     narrow_bytes = raw.nbytes
     raw.raw.map_offset16 = raw.raw.map_n_edits8 = raw.raw.edit_slen8 = None
-    raw.raw.edit_from8 = raw.raw.edit_to8 = None
+    raw.raw.edit_from8 = raw.raw.edit_to8 = raw.raw.map_node16 = None
     assert raw.nbytes > 1.3 * narrow_bytes
     hc.reset()
     hc.update_raw(raw)

@@ -131,7 +131,6 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
-constexpr uint32_t kEntryAllPaths = 1u << 29;  // queue entry: the mapping's node is on every path
 constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
 
 struct ReadKernelShared {
@@ -176,20 +175,19 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     return v;
 }
 
-// Finalise one queued mapping: entry = {exp(A) lo, hi, quality sums, node | first column << 17 | ALLPATHS << 29}.
-// A node every path goes through (ALLPATHS) never shows up in the sum over unsupported nodes, so its D[n] is never read:
-// such a mapping contributes its A only and the scatter is skipped.
-__device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uint4& e, double& a_sum) {
+// Finalise one queued mapping: entry = {exp(A) lo, hi, quality sums, node | first column << 17}.
+// Only mappings whose D[n] is read are queued: a node every path goes through (ALLPATHS) never shows up in the sum
+// over unsupported nodes, and the sum of all A_i comes from the read-level product (see `pall` below).
+__device__ __forceinline__ void hc_finalise(const ReadKernelShared& S, const uint4& e) {
     const double scale = -0.23025850929940456840;  // -ln(10)/10: log(get_p_seq_error(Q)) = Q * scale for Q > 2
     const uint32_t node = e.w & VGL_HC_NO_NODE, pos = (e.w >> 17) & 0xfffu;
     const double A = fast_log_s(__hiloint2double((int)e.y, (int)e.x), S.logtab);
-    if (!(e.w & kEntryAllPaths) && node < (uint32_t)S.n_rows) {
+    if (node < (uint32_t)S.n_rows) {
         // log(err) over [pos, pos + n): the stored columns from pos on plus `pos` bytes past the end that count as
         // quality 0  
         const double B = fma((double)(e.z & 0xfffffu), scale, (double)((e.z >> 20) + pos) * S.le0);
         red_add_f64(S.acc + node, B - A);
     }
-    a_sum += A;
 }
 
 // One group.  On entry v0, v1 hold its last two column blocks (the walk is descending); on exit they hold those of
@@ -217,6 +215,9 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // read's length.
     uint32_t suf = 0u - ((uint32_t)(ncb * VGL_HC_COL_BLK - H.n_cols) << 20);
     double aa = 1.0, cc = 0.0, prod = 1.0, a_ext = 0.0;
+    // product of EVERY valid column's mixture of this read: sum_i A_i = log(pall), one log per read instead of one per
+    // mapping; only the mappings whose node some path avoids need their own A_i (for D[n])
+    double pall = 1.0;
     uint32_t open_cls = 0;  // node-table entry of the mapping being walked
 
     auto extra_rec = [&](int i) -> uint32_t {
@@ -240,7 +241,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         // terminate; flag it and use the neutral entry
         open_cls = open ? cls_raw : open_cls;
         const uint32_t cls = cls_raw & VGL_HC_CLASS_MASK;
-        bad_cls = max(bad_cls, open ? cls : 0u);
+        bad_cls = max(bad_cls, cls);  // cls_raw is 0 where no mapping opens (predicated load)
         if (kAcMode == 0) {
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
                 : "+d"(aa), "+d"(cc)
@@ -260,15 +261,16 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
             aa = S.fasta ? 0.0 : 1.0 - pcm;
             cc = (S.fasta ? S.one_minus_bep : pcm) * mk_k;
         }
-        const double px = prod * fma(cc, f, aa * bgv);
-        prod = (rec & VGL_HC_COL_VALID) ? px : prod;
+        const double fac0 = fma(cc, f, aa * bgv);
+        const double fac = (rec & VGL_HC_COL_VALID) ? fac0 : 1.0;
+        prod *= fac;
+        pall *= fac;
         const uint32_t close = rec & VGL_HC_COL_CLOSE;
         if (kRare) {
             if (close && rare) {
                 const uint32_t node = VGL_HC_COL_NODE(rec);
                 if (a_ext != 0.0) {  // the product was rescaled (dozens of very unlikely bases in one mapping)
                     if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, -a_ext);
-                    a_sum += a_ext;
                     a_ext = 0.0;
                 }
                 // empty mappings at or past this column: A = 0, B as for a mapping that starts here (past the last
@@ -284,22 +286,24 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
                 rare = x >= 0;
             }
         }
-        // push {exp(A), quality sums, node | column}; a CLOSE on a column nobody owns only served the empty mappings
-        const uint32_t push = (close && VGL_HC_COL_NODE(rec) != VGL_HC_NO_NODE) ? 1u : 0u;
+        // push {exp(A), quality sums, node | column} unless every path goes through the node; a CLOSE on a column nobody
+        // owns only served the empty mappings
+        static_assert(VGL_HC_CLASS_ALLPATHS == 2 * VGL_HC_COL_CLOSE, "ALLPATHS >> 1 lines up with CLOSE");
+        const uint32_t push = ((rec & ~(open_cls >> 1) & VGL_HC_COL_CLOSE) != 0u && rec < (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT)) ? 1u : 0u;
         const uint32_t m = __ballot_sync(kFull, push);
-        const uint32_t slot = (q_tail + __popc(m & lt_mask)) & (kQueueSlots - 1);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(S.queue + 16u * slot),
+        const uint32_t slot = q_tail + __popc(m & lt_mask);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(S.queue | ((16u * slot) & (16u * (kQueueSlots - 1)))),
                      "r"((uint32_t)__double2loint(prod)), "r"((uint32_t)__double2hiint(prod)), "r"(suf),
-                     "r"(VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17) | ((open_cls & VGL_HC_CLASS_ALLPATHS) << 14)), "r"(push)
+                     "r"(VGL_HC_COL_NODE(rec) | ((uint32_t)c << 17)), "r"(push)
                      : "memory");
         prod = close ? 1.0 : prod;
         q_tail += __popc(m);
         if (q_tail - q_head >= 32u) {
             __syncwarp();
-            const uint4 e = lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1)));
+            const uint4 e = lds_v4(S.queue | ((16u * (q_head + lane)) & (16u * (kQueueSlots - 1))));
             __syncwarp();
             q_head += 32u;
-            hc_finalise(S, e, a_sum);
+            hc_finalise(S, e);
         }
     };
     auto block = [&](int cb, const uint4& v) {
@@ -326,10 +330,16 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
 #pragma unroll
             for (int j = 3; j >= 0; --j) column(std::false_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
         }
-        if (prod < 1e-100) {  // keep the product normal (four more factors cannot take it out of range)
-            a_ext += fast_log_s(prod, S.logtab);
-            prod = 1.0;
-            rare = true;
+        if (fmin(prod, pall) < 1e-100) {  // keep the products normal (four more factors cannot take them out of range)
+            if (prod < 1e-100) {
+                a_ext += fast_log_s(prod, S.logtab);
+                prod = 1.0;
+                rare = true;
+            }
+            if (pall < 1e-100) {
+                a_sum += fast_log_s(pall, S.logtab);
+                pall = 1.0;
+            }
         }
     };
     // two blocks in flight from ONE load site: a block is waited for a whole block (hundreds of issue slots) after its
@@ -343,6 +353,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // the next group's last blocks are requested now; they arrive while it is being set up
     v0 = hc_fetch(Hn, Hn.ncb - 1);
     v1 = hc_fetch(Hn, Hn.ncb - 2);
+    a_sum += fast_log_s(pall, S.logtab);
     while (x >= 0) {  // empty mappings that start past the last column
         const uint32_t xr = extra_rec(x);
         add_extra(xr & VGL_HC_MAP_MAX_NODE, (double)(xr >> VGL_HC_MAP_NODE_BITS) * S.le0);
@@ -361,7 +372,9 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     HcSmallTables* s_tab = reinterpret_cast<HcSmallTables*>(smem_raw + L.off_small);
     uint16_t* s_class = reinterpret_cast<uint16_t*>(smem_raw + L.off_class);
     double2* s_ac = reinterpret_cast<double2*>(smem_raw + L.off_ac);  // mode 0: [100][row]; mode 1: [n_class + 1]
-    uint4* s_queue = reinterpret_cast<uint4*>(smem_raw + ((L.bytes + 127u) & ~127u));  // [warps][kQueueSlots]
+    // [warps][kQueueSlots], every warp's ring on its own 1 KB boundary of the shared window (slot address = base | offset)
+    constexpr uint32_t kRing = kQueueSlots * 16u;
+    const uint32_t q_base = (smem_u32(smem_raw) + L.bytes + kRing - 1u) & ~(kRing - 1u);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -391,7 +404,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     S.class_tab = t.class_tab;
     S.fasta = s_tab->is_fasta != 0;
     S.one_minus_bep = s_tab->one_minus_bep;
-    S.queue = smem_u32(s_queue + (size_t)warp * kQueueSlots);
+    S.queue = q_base + (uint32_t)warp * kRing;
     S.n_rows = t.n_rows;
     S.n_class = t.n_class;
     S.ac_stride = (int)L.ac_row_bytes;
@@ -412,7 +425,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
         g = gn;
     }
     __syncwarp();
-    if ((uint32_t)lane < q_tail - q_head) hc_finalise(S, lds_v4(S.queue + 16u * ((q_head + lane) & (kQueueSlots - 1))), a_sum);
+    if ((uint32_t)lane < q_tail - q_head) hc_finalise(S, lds_v4(S.queue | ((16u * (q_head + lane)) & (16u * (kQueueSlots - 1)))));
 
     if (__any_sync(kFull, bad_node || bad_cls == VGL_HC_CLASS_NONE) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
     a_sum = warp_sum_f64(a_sum);
@@ -669,7 +682,7 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // launch wrappers
 // ------------------------------------------------------------------------------------------
 static size_t read_smem_bytes(int n_rows, int n_class, int ac_mode) {
-    size_t s = ((size_t)hc_image_layout(n_rows, n_class, ac_mode).bytes + 127) & ~(size_t)127;
+    size_t s = (size_t)hc_image_layout(n_rows, n_class, ac_mode).bytes + 1024;  // + alignment slack of the rings (plus the static shared)
     s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }

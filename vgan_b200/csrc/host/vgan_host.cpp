@@ -856,7 +856,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
     const size_t o_node = take(nm * 4), o_offs = take(nm * 4), o_eoff = take((nm + 1) * 4), o_from = take(ne * 2), o_to = take(ne * 2);
     const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns), o_slen = take(R * 2), o_ridx = take(R * 4);
-    const size_t o_off16 = take(nm * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne);
+    const size_t o_off16 = take(nm * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne), o_n16 = take(nm * 2);
     vgh_hc_raw* P = new vgh_hc_raw();
     P->pinned = pinned != 0;
     const size_t bytes = std::max<size_t>(o, 256);
@@ -877,10 +877,11 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     uint32_t* esoff = (uint32_t*)(base + o_esoff); uint8_t* eseq = base + o_eseq;
     uint16_t* slen = (uint16_t*)(base + o_slen); uint32_t* ridx = (uint32_t*)(base + o_ridx);
     uint16_t* off16 = (uint16_t*)(base + o_off16); uint8_t* ne8 = base + o_ne8; uint8_t* sl8 = base + o_sl8;
-    uint8_t* f8 = base + o_f8; uint8_t* t8 = base + o_t8;
+    uint8_t* f8 = base + o_f8; uint8_t* t8 = base + o_t8; uint16_t* n16 = (uint16_t*)(base + o_n16);
+    bool narrow_node = true;  // every node id <= 32767
     bool narrow_len = true;  // every from_length / to_length <= 255
     bool narrow = true;  // every offset <= 65535, <= 255 edits per mapping, edit sequences <= 255 bytes
-#pragma omp parallel for schedule(static) reduction(&& : narrow, narrow_len)
+#pragma omp parallel for schedule(static) reduction(&& : narrow, narrow_len, narrow_node)
     for (int64_t k = 0; k < (int64_t)R; ++k) {
         const int64_t r = keep[(size_t)k];
         uint64_t cm = pm[(size_t)k], ce = pe[(size_t)k], cs = ps[(size_t)k];
@@ -895,6 +896,8 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
             eoff[cm] = (uint32_t)ce;
             const int64_t n_ed = a->edit_off[m + 1] - a->edit_off[m];
             off16[cm] = (uint16_t)a->map_offset[m];
+            n16[cm] = (uint16_t)((a->map_node[m] & 0x7fff) | (a->map_rev[m] ? 0x8000 : 0));
+            narrow_node = narrow_node && a->map_node[m] <= 32767;
             ne8[cm] = (uint8_t)n_ed;
             narrow = narrow && a->map_offset[m] <= 65535 && n_ed <= 255;
             ++cm;
@@ -924,6 +927,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     v.seq_len = slen; v.read_index = ridx;
     if (narrow) { v.map_offset16 = off16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; }
     if (narrow_len) { v.edit_from8 = f8; v.edit_to8 = t8; }
+    if (narrow_node) v.map_node16 = n16;
     *out = P;
     return VGH_OK;
 }

@@ -439,6 +439,10 @@ __global__ void __launch_bounds__(256) scan_u8_final(const uint8_t* __restrict__
         run += e[k];
     }
 }
+__global__ void __launch_bounds__(256) widen_node16(const uint16_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)(in[i] & 0x7fffu) | ((uint32_t)(in[i] >> 15) << 31);  // node | is_reverse << 31
+}
 __global__ void __launch_bounds__(256) widen_u8(const uint8_t* __restrict__ in, uint32_t n, uint16_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -599,6 +603,12 @@ cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, ui
     scan_u8_tile_sums<<<n_tiles, 256, 0, s>>>(counts, n, tile_scratch);
     scan_tiles<<<1, 1024, 0, s>>>(n_tiles, base, tile_scratch);
     scan_u8_final<<<n_tiles, 256, 0, s>>>(counts, n, tile_scratch, out);
+    return cudaGetLastError();
+}
+
+cudaError_t raw_launch_widen_node16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    widen_node16<<<(n + 255) / 256, 256, 0, s>>>(in, n, out);
     return cudaGetLastError();
 }
 

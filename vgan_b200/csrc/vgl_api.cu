@@ -115,7 +115,7 @@ struct vgl_ctx {
         DevBuf<uint8_t> s_mapq, s_flags;
         DevBuf<int> s_err;
         // narrow arrays as shipped + scratch for the prefix sums
-        DevBuf<uint16_t> off16;
+        DevBuf<uint16_t> off16, n16;
         DevBuf<uint8_t> ne8, sl8, f8, t8;
         DevBuf<uint32_t> tiles;
         cudaEvent_t copied = nullptr, consumed = nullptr;  // H2D of the chunk done / its kernels done
@@ -311,7 +311,7 @@ void vgl_destroy(vgl_ctx* ctx) {
         R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
         R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
         R.seq_len.release(); R.s_col.release(); R.s_n_cols.release(); R.s_n_maps.release(); R.s_seq_len.release();
-        R.off16.release(); R.ne8.release(); R.sl8.release(); R.f8.release(); R.t8.release(); R.tiles.release();
+        R.off16.release(); R.n16.release(); R.ne8.release(); R.sl8.release(); R.f8.release(); R.t8.release(); R.tiles.release();
         R.read_index.release(); R.s_map.release(); R.s_read_index.release(); R.s_mapq.release(); R.s_flags.release(); R.s_err.release();
         if (R.copied) cudaEventDestroy(R.copied);
         if (R.consumed) cudaEventDestroy(R.consumed);
@@ -676,9 +676,10 @@ uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* r) {
     if (!r) return 0;
     const uint64_t per_read = (uint64_t)(r->n_reads + 1) * 12 + r->n_reads + r->qual_off[r->n_reads] + r->edit_seq_off[r->n_edits];
     const uint64_t lens = (uint64_t)r->n_edits * (r->edit_from8 ? 2 : 4);  // from_length + to_length per edit
-    if (r->map_offset16)  // narrow: node 4 + offset 2 + edit count 1 per mapping; sequence length 1 per edit
-        return per_read + (uint64_t)r->n_maps * 7 + (uint64_t)r->n_edits + lens;
-    return per_read + (uint64_t)r->n_maps * 8 + (uint64_t)(r->n_maps + 1) * 4 + (uint64_t)(r->n_edits + 1) * 4 + lens;
+    const uint64_t nodes = (uint64_t)r->n_maps * (r->map_node16 ? 2 : 4);
+    if (r->map_offset16)  // narrow: offset 2 + edit count 1 per mapping; sequence length 1 per edit
+        return per_read + nodes + (uint64_t)r->n_maps * 3 + (uint64_t)r->n_edits + lens;
+    return per_read + nodes + (uint64_t)r->n_maps * 4 + (uint64_t)(r->n_maps + 1) * 4 + (uint64_t)(r->n_edits + 1) * 4 + lens;
 }
 
 int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq) {
@@ -725,7 +726,7 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
     RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
     RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
-    RSV(R.off16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
+    RSV(R.off16, nm); RSV(R.n16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
     RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
     RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
     RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
@@ -740,7 +741,11 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     H2D(R.map_off.p, raw->map_off + ra, (n + 1) * 4); H2D(R.mapq.p, raw->mapq + ra, n); H2D(R.qual.p, raw->qual + qa, nq);
     const bool narrow = raw->map_offset16 && raw->map_n_edits8 && raw->edit_slen8;
     const bool narrow_len = raw->edit_from8 && raw->edit_to8;
-    H2D(R.map_node.p, raw->map_node + ma, nm * 4);
+    if (raw->map_node16) {
+        H2D(R.n16.p, raw->map_node16 + ma, nm * 2);
+    } else {
+        H2D(R.map_node.p, raw->map_node + ma, nm * 4);
+    }
     if (narrow_len) {
         H2D(R.f8.p, raw->edit_from8 + ea, ne); H2D(R.t8.p, raw->edit_to8 + ea, ne);
     } else {
@@ -756,6 +761,10 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
 #undef H2D
     VGL_CUDA(cudaEventRecord(R.copied, copy_stream));
     if (copy_stream != s) VGL_CUDA(cudaStreamWaitEvent(s, R.copied, 0));
+    if (raw->map_node16) {
+        VGL_CUDA(vgl::raw_launch_widen_node16(R.n16.p, (uint32_t)nm, R.map_node.p, s));
+        ctx->launches += 1;
+    }
     if (narrow_len) {
         VGL_CUDA(vgl::raw_launch_widen_u8(R.f8.p, (uint32_t)ne, R.edit_from.p, s));
         VGL_CUDA(vgl::raw_launch_widen_u8(R.t8.p, (uint32_t)ne, R.edit_to.p, s));
