@@ -475,6 +475,33 @@ int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* tables);
 int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* host_batch, uint32_t n_out, double* path_ll, uint8_t* used);
 int vgl_soibean_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, double* path_ll, uint8_t* used);
 
+/* ------------------------------------------------------------------------------------------- */
+/* soibean MCMC: log-likelihood of proposals                                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Replaces the read loop of MCMC::run_tree_proportion (src/MCMC.cpp:738-993) with computeBaseLogLike
+ * (src/MCMC.h:111-296) and calculateLogWeightedAverage (src/MCMC.h:299-316): the log-likelihood of a proposal, summed
+ * over the reads of the batch the LAST vgl_soibean_run / vgl_soibean_run_raw call scored -- that batch and its per-edit
+ * sums stay resident in HBM until the next euka / soibean call on the context, so an MCMC iteration moves nothing but
+ * the proposal in and one double out (sum over batches / GPUs on the caller's side when the sample spans several).
+ * A proposal is n_sources sources (state_t_1.positions_tree[y], src/MCMC.cpp:697-709):
+ *   child      index of pos->longname in pathNames        parent   index of pos->parent->longname (child's own at the root)
+ *   pos_branch position on the branch                      dist     pos->dist (0 becomes 1e-5 as in :757-759)
+ *   proportion state_t_1.proportions[y] (unused when n_sources == 1, as in the reference)
+ * freqs7 = params.freqs['A','C','G','T','R','Y','M'] (src/soibean.cpp:618-640); con = the reference's `con`
+ * (src/soibean.cpp:596-598).  Reproduced as written: kappa = 1/22 is an integer division, i.e. 0 (src/MCMC.h:66).
+ * Stated limit: a read or graph base outside ACGT in a supported regular column has base frequency 0 (the reference
+ * indexes freqs by the character, so the IUPAC letters R, Y, M would pick up the purine / pyrimidine / mu entries).
+ * sources[q * n_sources + y]; loglike[q] for q < n_proposals; per_read: NULL or [n_proposals][n_out] by read_index.
+ * VGL_ERR_BAD_READ where the reference would throw (a read's log-likelihood positive, nan or infinite). */
+#define VGL_SOIBEAN_MAX_SOURCES 16
+typedef struct vgl_soibean_source {
+    int32_t child, parent;
+    double pos_branch, dist, proportion;
+} vgl_soibean_source;
+int vgl_soibean_mcmc_loglike(vgl_ctx* ctx, int32_t n_proposals, int32_t n_sources, const vgl_soibean_source* sources,
+                             const double* freqs7, double con, uint32_t n_out, double* per_read, double* loglike);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,47 @@ def soibean_run(graph, reads, member, min_id=0, penalty=7, deam5p_prof="", deam3
     return out, used
 
 
+def soibean_mcmc_loglike(graph, reads, member, sources, freqs7, con, min_id=0, penalty=7, deam5p_prof="", deam3p_prof=""):
+    """Log-likelihood of one MCMC proposal (read loop of MCMC::run_tree_proportion, src/MCMC.cpp:738-993).
+    sources: list of (child path, parent path, pos_branch, dist, proportion).  Returns (logLike, per-read contributions)."""
+    member = np.ascontiguousarray(member, dtype=np.uint8)
+    n_rows, P = member.shape
+    K = len(sources)
+    child = np.array([s[0] for s in sources], dtype=np.int32)
+    parent = np.array([s[1] for s in sources], dtype=np.int32)
+    posb = np.array([s[2] for s in sources], dtype=np.float64)
+    dist = np.array([s[3] for s in sources], dtype=np.float64)
+    prop = np.array([s[4] for s in sources], dtype=np.float64)
+    f7 = np.ascontiguousarray(freqs7, dtype=np.float64)
+    assert f7.shape == (7,)
+    out = C.c_double(0.0)
+    per_read = np.zeros(reads.n, dtype=np.float64)
+    rc = lib().orc_soibean_mcmc_loglike(C.byref(graph.c), C.byref(reads.c), _ptr(member), C.c_int64(n_rows), int(min_id), int(P), int(penalty),
+                                        (deam5p_prof or "").encode(), (deam3p_prof or "").encode(), int(K), _ptr(child), _ptr(parent),
+                                        _ptr(posb), _ptr(dist), _ptr(prop), _ptr(f7), C.c_double(con), C.byref(out), _ptr(per_read))
+    if rc:
+        raise RuntimeError("orc_soibean_mcmc_loglike failed: %d" % rc)
+    return out.value, per_read
+
+
+def soibean_base_loglike(read_base, graph_base, ll, freqs7, t, branch_len):
+    """computeBaseLogLike (src/MCMC.h:111-296) for one supported column."""
+    f7 = np.ascontiguousarray(freqs7, dtype=np.float64)
+    out = C.c_double(0.0)
+    rc = lib().orc_soibean_base_loglike(C.c_char(read_base.encode()), C.c_char(graph_base.encode()), C.c_double(ll), _ptr(f7), C.c_double(t),
+                                        C.c_double(branch_len), C.byref(out))
+    if rc:
+        raise RuntimeError("orc_soibean_base_loglike failed: %d" % rc)
+    return out.value
+
+
+def soibean_freqs7(a, c, g, t):
+    """params.freqs['A','C','G','T','R','Y','M'] as src/soibean.cpp:629-640 derives them from the base frequencies."""
+    R, Y = a + g, c + t
+    M = 1 / (2 * (((22) * (a * g)) + ((22) * (c * t)) + (a * c + (a * t) + (g * c + (g * t)))))
+    return np.array([a, c, g, t, R, Y, M], dtype=np.float64)
+
+
 def dedup(reads, paired=None):
     """The reference's O(n^2) duplicate marking (src/rmdup.cpp:20-110)."""
     mask = np.zeros(reads.n, dtype=np.uint8)

@@ -936,101 +936,264 @@ int orc_euka_run(const orc_euka_tables* T, const orc_graph* g, const orc_reads* 
 // Defined here where the reference has none: quality index past the end reads byte 0; negative quality bytes
 // give 0.25; std::string::substr / vector::at failures and damage-table indices out of range return an error.
 // =====================================================================================
+// AlignmentInfo::BaseInfo (src/AlignmentInfo.h:21-26): what analyse_GAM keeps per (path, edit, base) for the MCMC.
+struct BaseInfo { char readBase, referenceBase; bool pathSupport; double logLikelihood; };
+
+// The per-alignment body of analyse_GAM for read r.  pathMap[m] is filled for the paths with want[m] != 0 (NULL: all);
+// detail, when not NULL, receives detailMap[pathNames[m]] = [edit][base] for those paths (src/getLCAfromGAM.h:192-530).
+static int soibean_read(const orc_graph* g, const orc_reads* R, int64_t r, const uint8_t* member, int64_t member_rows, int32_t member_min_id,
+                        int32_t n_paths, int32_t penalty, Damage& dmg, const vector<double>& qscore_vec, double* pathMap,
+                        const uint8_t* want, vector<vector<vector<BaseInfo>>>* detail) {
+    const char* ACGT = "ACGT";
+    ReadView a = load_read(*R, r);
+    if (a.mapping.empty()) return ORC_ERR_RANGE;
+    string graph_seq, read_seq;
+    vector<int> mppg_sizes;
+    int rc = reconstruct_graph_sequence(*g, a.mapping, graph_seq, read_seq, mppg_sizes);
+    if (rc) return rc;
+    const bool rev = a.mapping[0].is_reverse;
+    int baseIX = rev ? (int)a.seq.size() - 1 : 0;
+    int baseOnRead = baseIX;
+    const int Lseq = (int)graph_seq.size();
+    const size_t E = mppg_sizes.size(), M = a.mapping.size();
+    for (size_t i = 0; i < E; ++i) {
+        bool no_support = false;
+        int64_t nID = 0;
+        if (E != M && i >= E - (E - M)) no_support = true;
+        else {
+            if (i >= M) return ORC_ERR_SIZES;
+            nID = a.mapping[i].node_id;
+            if (nID - member_min_id < 0 || nID - member_min_id >= member_rows) return ORC_ERR_NODE;  // nodepaths.at()
+        }
+        string nodeSeq, partReadSeq;
+        int startIndex = 0;
+        if (rev) {
+            startIndex = (baseIX - mppg_sizes[i] - 1 >= 0) ? (baseIX - mppg_sizes[i] - 1) : 0;
+            rc = substr_checked(graph_seq, (size_t)startIndex, (size_t)mppg_sizes[i], nodeSeq);
+            if (rc) return rc;
+            rc = substr_checked(read_seq, (size_t)startIndex, (size_t)mppg_sizes[i], partReadSeq);
+            if (rc) return rc;
+        } else {
+            if (baseIX < 0) return ORC_ERR_SUBSTR;
+            rc = substr_checked(graph_seq, (size_t)baseIX, (size_t)mppg_sizes[i], nodeSeq);
+            if (rc) return rc;
+            rc = substr_checked(read_seq, (size_t)baseIX, (size_t)mppg_sizes[i], partReadSeq);
+            if (rc) return rc;
+        }
+        for (int m = 0; m < n_paths; ++m) {
+            if (want && !want[m]) continue;  // every path starts from baseOnRead = baseIX: skipping one changes no other
+            vector<BaseInfo> readInfo;
+            auto push = [&](char rb, char gb, bool support, double ll) {
+                pathMap[m] += ll;
+                if (detail) readInfo.push_back(BaseInfo{rb, gb, support, ll});
+            };
+            const bool supported = !no_support && member[(size_t)(nID - member_min_id) * (size_t)n_paths + (size_t)m] != 0;
+            if (supported) {
+                for (size_t s = 0; s < nodeSeq.size(); ++s) {
+                    const int base_quality = quality_at(a.quality, s);
+                    const double e = euka_qs(qscore_vec, base_quality);
+                    const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
+                    if (gb == 'N' || rb == 'N') push(rb, gb, false, std::log(0.25));
+                    else if (gb == 'S' || rb == 'S') push(rb, gb, false, std::log(e / 3));
+                    else if (gb == '-' || rb == '-') push(rb, gb, false, std::log(0.02));
+                    else {
+                        if (Lseq < (int)MINLENGTHFRAGMENT || Lseq > (int)MAXLENGTHFRAGMENT || baseIX < 0 || baseIX >= Lseq) return ORC_ERR_RANGE;
+                        const DiNuc D = dmg.at((unsigned)Lseq, (unsigned)baseIX);
+                        double probBasePreDamage[4];
+                        for (int bpo = 0; bpo < 4; bpo++) probBasePreDamage[bpo] = (ACGT[bpo] == gb) ? 1 - e : (e / 3);
+                        double probBasePostDamage[4] = {0.0, 0.0, 0.0, 0.0};
+                        for (int bpd = 0; bpd < 4; bpd++)
+                            for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
+                        double log_lik_marg = -std::numeric_limits<double>::infinity();
+                        for (int bpd = 0; bpd < 4; bpd++) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd]));
+                        if (log_lik_marg > std::log(0.9999999)) log_lik_marg = std::log(0.9999999);
+                        push(rb, gb, true, log_lik_marg);  // the only entries with pathSupport = true (:374-379)
+                        if (rev && rb != '-') baseOnRead--;
+                        else if (!rev && rb != '-') baseOnRead++;
+                    }
+                }
+            } else {
+                for (size_t s = 0; s < nodeSeq.size(); ++s) {
+                    const int base_quality = quality_at(a.quality, s);
+                    const double e = euka_qs(qscore_vec, base_quality);
+                    const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
+                    if (gb == 'N' || rb == 'N') push(rb, gb, false, std::log(0.25));
+                    else if (gb == 'S' || rb == 'S') push(rb, gb, false, std::log(e / 3));
+                    else if (gb == '-' || rb == '-') push(rb, gb, false, std::log(0.02));
+                    else if (std::abs(baseOnRead) % penalty == 0) push(rb, gb, false, std::log(1 - e));
+                    else push(rb, gb, false, std::log(e / 3));
+                    if (rev && rb != '-') baseOnRead--;
+                    else if (!rev && rb != '-') baseOnRead++;
+                }
+            }
+            if (detail) (*detail)[(size_t)m].push_back(std::move(readInfo));  // :530
+            baseOnRead = baseIX;
+        }
+        if (rev) baseIX = startIndex;
+        else baseIX += mppg_sizes[i];
+        baseOnRead = baseIX;
+    }
+    return ORC_OK;
+}
+
 int orc_soibean_run(const orc_graph* g, const orc_reads* R, const uint8_t* member, int64_t member_rows, int32_t member_min_id,
                     int32_t n_paths, int32_t penalty, const char* deam5p, const char* deam3p, double* out, uint8_t* used) {
     Damage dmg;
     int rc = dmg.init(deam5p, deam3p);
     if (rc) return rc;
     const vector<double> qscore_vec = euka_qscore_vec();  // soibean uses Euka's table (src/soibean.cpp:471)
-    const char* ACGT = "ACGT";
     for (int64_t r = 0; r < R->n_reads; ++r) {
         double* pathMap = out + (size_t)r * (size_t)n_paths;
         for (int p = 0; p < n_paths; ++p) pathMap[p] = 0.0;
         used[r] = 0;
         if (R->identity[r] == 0) continue;
         used[r] = 1;
-        ReadView a = load_read(*R, r);
-        if (a.mapping.empty()) return ORC_ERR_RANGE;
-        string graph_seq, read_seq;
-        vector<int> mppg_sizes;
-        rc = reconstruct_graph_sequence(*g, a.mapping, graph_seq, read_seq, mppg_sizes);
+        rc = soibean_read(g, R, r, member, member_rows, member_min_id, n_paths, penalty, dmg, qscore_vec, pathMap, nullptr, nullptr);
         if (rc) return rc;
-        const bool rev = a.mapping[0].is_reverse;
-        int baseIX = rev ? (int)a.seq.size() - 1 : 0;
-        int baseOnRead = baseIX;
-        const int Lseq = (int)graph_seq.size();
-        const size_t E = mppg_sizes.size(), M = a.mapping.size();
-        for (size_t i = 0; i < E; ++i) {
-            bool no_support = false;
-            int64_t nID = 0;
-            if (E != M && i >= E - (E - M)) no_support = true;
-            else {
-                if (i >= M) return ORC_ERR_SIZES;
-                nID = a.mapping[i].node_id;
-                if (nID - member_min_id < 0 || nID - member_min_id >= member_rows) return ORC_ERR_NODE;  // nodepaths.at()
-            }
-            string nodeSeq, partReadSeq;
-            int startIndex = 0;
-            if (rev) {
-                startIndex = (baseIX - mppg_sizes[i] - 1 >= 0) ? (baseIX - mppg_sizes[i] - 1) : 0;
-                rc = substr_checked(graph_seq, (size_t)startIndex, (size_t)mppg_sizes[i], nodeSeq);
-                if (rc) return rc;
-                rc = substr_checked(read_seq, (size_t)startIndex, (size_t)mppg_sizes[i], partReadSeq);
-                if (rc) return rc;
-            } else {
-                if (baseIX < 0) return ORC_ERR_SUBSTR;
-                rc = substr_checked(graph_seq, (size_t)baseIX, (size_t)mppg_sizes[i], nodeSeq);
-                if (rc) return rc;
-                rc = substr_checked(read_seq, (size_t)baseIX, (size_t)mppg_sizes[i], partReadSeq);
-                if (rc) return rc;
-            }
-            for (int m = 0; m < n_paths; ++m) {
-                const bool supported = !no_support && member[(size_t)(nID - member_min_id) * (size_t)n_paths + (size_t)m] != 0;
-                if (supported) {
-                    for (size_t s = 0; s < nodeSeq.size(); ++s) {
-                        const int base_quality = quality_at(a.quality, s);
-                        const double e = euka_qs(qscore_vec, base_quality);
-                        const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
-                        if (gb == 'N' || rb == 'N') pathMap[m] += std::log(0.25);
-                        else if (gb == 'S' || rb == 'S') pathMap[m] += std::log(e / 3);
-                        else if (gb == '-' || rb == '-') pathMap[m] += std::log(0.02);
-                        else {
-                            if (Lseq < (int)MINLENGTHFRAGMENT || Lseq > (int)MAXLENGTHFRAGMENT || baseIX < 0 || baseIX >= Lseq) return ORC_ERR_RANGE;
-                            const DiNuc D = dmg.at((unsigned)Lseq, (unsigned)baseIX);
-                            double probBasePreDamage[4];
-                            for (int bpo = 0; bpo < 4; bpo++) probBasePreDamage[bpo] = (ACGT[bpo] == gb) ? 1 - e : (e / 3);
-                            double probBasePostDamage[4] = {0.0, 0.0, 0.0, 0.0};
-                            for (int bpd = 0; bpd < 4; bpd++)
-                                for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
-                            double log_lik_marg = -std::numeric_limits<double>::infinity();
-                            for (int bpd = 0; bpd < 4; bpd++) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd]));
-                            if (log_lik_marg > std::log(0.9999999)) log_lik_marg = std::log(0.9999999);
-                            pathMap[m] += log_lik_marg;
-                            if (rev && rb != '-') baseOnRead--;
-                            else if (!rev && rb != '-') baseOnRead++;
-                        }
-                    }
-                } else {
-                    for (size_t s = 0; s < nodeSeq.size(); ++s) {
-                        const int base_quality = quality_at(a.quality, s);
-                        const double e = euka_qs(qscore_vec, base_quality);
-                        const char gb = nodeSeq[s], rb = s < partReadSeq.size() ? partReadSeq[s] : '\0';
-                        if (gb == 'N' || rb == 'N') pathMap[m] += std::log(0.25);
-                        else if (gb == 'S' || rb == 'S') pathMap[m] += std::log(e / 3);
-                        else if (gb == '-' || rb == '-') pathMap[m] += std::log(0.02);
-                        else if (std::abs(baseOnRead) % penalty == 0) pathMap[m] += std::log(1 - e);
-                        else pathMap[m] += std::log(e / 3);
-                        if (rev && rb != '-') baseOnRead--;
-                        else if (!rev && rb != '-') baseOnRead++;
-                    }
-                }
-                baseOnRead = baseIX;
-            }
-            if (rev) baseIX = startIndex;
-            else baseIX += mppg_sizes[i];
-            baseOnRead = baseIX;
-        }
     }
+    return ORC_OK;
+}
+
+// =====================================================================================
+// soibean MCMC: the log-likelihood of one proposal, i.e. the read loop of MCMC::run_tree_proportion
+// (reference src/MCMC.cpp:738-993) with computeBaseLogLike (src/MCMC.h:111-296) and calculateLogWeightedAverage
+// (src/MCMC.h:299-316), literally: per read, per source y, per edit, per base, for the source's path ("child") and the
+// path of its parent node.  A proposal is n_sources x {child path, parent path, pos_branch, pos->dist} + proportions;
+// freqs7 = params.freqs['A','C','G','T','R','Y','M'] (src/soibean.cpp:618-640), con = the shortest branch / 0.01
+// (src/soibean.cpp:596-598).  Behaviours reproduced as written: kappa = 1/22 is an INTEGER division, i.e. 0
+// (src/MCMC.h:66); `pos_branch == 0.9999999999;` is a comparison, not an assignment (src/MCMC.cpp:751-753): nothing
+// changes; t == 0 becomes 1e-5 (:757-759); the child is evaluated at t2 = t - t1, the parent at t1 = pos_branch * t.
+// The reference indexes freqs by the read base's character, so an IUPAC read base 'R', 'Y' or 'M' would pick up the
+// purine / pyrimidine / mu entry; here every base outside ACGT has frequency 0 (stated limit of the restatement).
+// Where the reference throws (a term or running sum that is nan, inf or positive) the function returns ORC_ERR_RANGE.
+// =====================================================================================
+static double mcmc_freq(const double* f7, char b) { return b == 'A' ? f7[0] : b == 'C' ? f7[1] : b == 'G' ? f7[2] : b == 'T' ? f7[3] : 0.0; }
+
+static int computeBaseLogLike(const BaseInfo& detail, const double* f7, const double t, const double branch_len, double& out) {
+    const double kappa = 1 / 22;  // src/MCMC.h:66, integer division
+    const double purinfreq = f7[4], pyrinfreq = f7[5], mu = f7[6];
+    const char refb = detail.referenceBase, readb = detail.readBase;
+    double probBaseHKY[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int bpo = 0; bpo < 4; bpo++) {
+        const char rb = "ACGT"[bpo];
+        const double frb = mcmc_freq(f7, rb);
+        if (rb == refb) {
+            if (rb == 'A' || rb == 'G') {
+                const double A = 1 + purinfreq * (kappa - 1);
+                const double jut1 = frb + frb * ((1 / purinfreq) - 1) * exp(-(mu * t));
+                const double jut11 = ((purinfreq - frb) / purinfreq) * exp(-(mu * t * A));
+                probBaseHKY[bpo] = jut1 + jut11;
+            } else {
+                const double A = 1 + pyrinfreq * (kappa - 1);
+                const double jut1 = frb + frb * ((1 / pyrinfreq) - 1) * exp(-(mu * t));
+                const double jut11 = ((pyrinfreq - frb) / pyrinfreq) * exp(-(mu * t * A));
+                probBaseHKY[bpo] = jut1 + jut11;
+            }
+        } else if ((rb == 'A' && refb == 'G') || (rb == 'G' && refb == 'A')) {
+            const double A = 1 + purinfreq * (kappa - 1);
+            const double jut1 = frb + frb * ((1 / purinfreq) - 1) * exp(-(mu * t));
+            const double jut11 = (frb / purinfreq) * exp(-(mu * t * A));
+            probBaseHKY[bpo] = jut1 > jut11 ? jut1 - jut11 : jut11 - jut1;
+        } else if ((rb == 'C' && refb == 'T') || (rb == 'T' && refb == 'C')) {
+            const double A = 1 + pyrinfreq * (kappa - 1);
+            const double jut1 = frb + frb * ((1 / pyrinfreq) - 1) * exp(-(mu * t));
+            const double jut11 = (frb / pyrinfreq) * exp(-(mu * t * A));
+            probBaseHKY[bpo] = jut1 > jut11 ? jut1 - jut11 : jut11 - jut1;
+        } else {
+            probBaseHKY[bpo] = frb * (1 - exp(-(mu * t)));
+        }
+        if (probBaseHKY[bpo] < 1e-8) probBaseHKY[bpo] = 1e-8;
+        if (std::isnan(probBaseHKY[bpo]) || std::isinf(probBaseHKY[bpo])) return ORC_ERR_RANGE;
+    }
+    double log_lik_marg = -std::numeric_limits<double>::infinity();
+    for (int bpd = 0; bpd < 4; bpd++) {
+        if ("ACGT"[bpd] == readb) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((1 - branch_len))));
+        else log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((branch_len / 3))));
+    }
+    if (log_lik_marg > 1e-8) log_lik_marg = std::log(0.999999999);
+    if (std::isnan(log_lik_marg) || std::isinf(log_lik_marg)) return ORC_ERR_RANGE;
+    log_lik_marg = log_lik_marg + detail.logLikelihood;
+    if (std::isnan(log_lik_marg) || std::isinf(log_lik_marg) || log_lik_marg > 1e-8) return ORC_ERR_RANGE;
+    out = log_lik_marg;
+    return ORC_OK;
+}
+
+static double calculateLogWeightedAverage(double logValueChild, double weightChild, double logValueParent, double weightParent) {
+    const double maxLogValue = std::max(logValueChild + std::log(weightChild), logValueParent + std::log(weightParent));
+    const double logSumExp = maxLogValue + std::log(std::exp(logValueChild + std::log(weightChild) - maxLogValue) + std::exp(logValueParent + std::log(weightParent) - maxLogValue));
+    const double logWeightSum = std::log(weightChild + weightParent);
+    if (std::isinf(logWeightSum)) return -std::numeric_limits<double>::infinity();
+    return logSumExp - logWeightSum;
+}
+
+// computeBaseLogLike for one supported column whose pre-computed logLikelihood is `ll`, exported for the table tests.
+int orc_soibean_base_loglike(char read_base, char graph_base, double ll, const double* freqs7, double t, double branch_len, double* out) {
+    return computeBaseLogLike(BaseInfo{read_base, graph_base, true, ll}, freqs7, t, branch_len, *out);
+}
+
+// per_read (may be NULL) receives each read's contribution (0 for reads with identity == 0, which never reach the MCMC).
+int orc_soibean_mcmc_loglike(const orc_graph* g, const orc_reads* R, const uint8_t* member, int64_t member_rows, int32_t member_min_id,
+                             int32_t n_paths, int32_t penalty, const char* deam5p, const char* deam3p, int32_t n_sources,
+                             const int32_t* child, const int32_t* parent, const double* pos_branch, const double* dist,
+                             const double* proportions, const double* freqs7, double con, double* loglike_out, double* per_read) {
+    Damage dmg;
+    int rc = dmg.init(deam5p, deam3p);
+    if (rc) return rc;
+    if (n_sources < 1) return ORC_ERR_RANGE;
+    const vector<double> qscore_vec = euka_qscore_vec();
+    vector<uint8_t> want((size_t)n_paths, 0);
+    for (int y = 0; y < n_sources; ++y) {
+        if (child[y] < 0 || child[y] >= n_paths || parent[y] < 0 || parent[y] >= n_paths) return ORC_ERR_RANGE;
+        want[(size_t)child[y]] = want[(size_t)parent[y]] = 1;
+    }
+    double logLike = 0.0;
+    vector<double> pathMap((size_t)n_paths);
+    for (int64_t r = 0; r < R->n_reads; ++r) {
+        if (per_read) per_read[r] = 0.0;
+        if (R->identity[r] == 0) continue;
+        vector<vector<vector<BaseInfo>>> detailMap((size_t)n_paths);
+        rc = soibean_read(g, R, r, member, member_rows, member_min_id, n_paths, penalty, dmg, qscore_vec, pathMap.data(), want.data(), &detailMap);
+        if (rc) return rc;
+        double contribution;
+        double inter = -std::numeric_limits<double>::infinity();
+        for (int y = 0; y < n_sources; ++y) {
+            double readLogLike = 0.0, readLogLikeP = 0.0;
+            double t = dist[y];
+            if (t == 0.0) t = 0.00001;
+            const double t1 = pos_branch[y] * t;
+            const double t2 = t - t1;
+            const auto& dc = detailMap[(size_t)child[y]];
+            const auto& dp = detailMap[(size_t)parent[y]];
+            for (size_t basevec = 0; basevec < dc.size(); ++basevec) {
+                for (size_t base = 0; base < dc[basevec].size(); ++base) {
+                    if (dc[basevec][base].pathSupport) {
+                        double v;
+                        if ((rc = computeBaseLogLike(dc[basevec][base], freqs7, t2, con, v))) return rc;
+                        readLogLike += v;
+                    } else readLogLike += dc[basevec][base].logLikelihood;
+                    if (dp.at(basevec).at(base).pathSupport) {
+                        double v;
+                        if ((rc = computeBaseLogLike(dp[basevec][base], freqs7, t1, con, v))) return rc;
+                        readLogLikeP += v;
+                    } else readLogLikeP += dp[basevec][base].logLikelihood;
+                    if (readLogLike > 0 || std::isnan(readLogLike) || std::isinf(readLogLike) || readLogLikeP > 0 || std::isnan(readLogLikeP) || std::isinf(readLogLikeP))
+                        return ORC_ERR_RANGE;
+                }
+            }
+            if (n_sources == 1) {  // src/MCMC.cpp:869
+                contribution = calculateLogWeightedAverage(readLogLike, pos_branch[0], readLogLikeP, (1 - pos_branch[0]));
+            } else {  // :964-970
+                const double interc2 = std::log(pos_branch[y]) + readLogLike;
+                const double interp2 = std::log((1 - pos_branch[y])) + readLogLikeP;
+                const double inter2 = (double)oplusnatl_ld(interc2, interp2);
+                inter = (double)oplusInitnatl_ld(inter, (inter2 + std::log(proportions[y])));
+            }
+        }
+        if (n_sources != 1) contribution = inter;
+        logLike += contribution;
+        if (per_read) per_read[r] = contribution;
+    }
+    *loglike_out = logLike;
     return ORC_OK;
 }
 

@@ -73,5 +73,28 @@ for P in (31, 127, 399):
                               "evals_per_s_pinned_output": pk.n_reads * P / dtp,
                               "what": "config 5 shape: vgl_soibean_run incl. H2D and the R x P matrix D2H into pageable numpy "
                                       "(ms) or into page-locked memory (ms_pinned_output)"}
+    if P == 127:
+        # MCMC proposals scored on the resident batch: one call per proposal (what a single chain
+        # does) and 256 proposals per call (chains / proposals batched); 2 sources per proposal
+        f7 = vb.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
+        rng = np.random.default_rng(5)
+        def proposal():
+            return [(int(rng.integers(P)), int(rng.integers(P)), float(rng.uniform(0.05, 0.95)), float(rng.uniform(0.001, 0.05)), w) for w in (0.6, 0.4)]
+        one = [proposal()]
+        sb.mcmc_loglike(one, f7, 0.01)
+        t = time.perf_counter()
+        for _ in range(20):
+            sb.mcmc_loglike(one, f7, 0.01)
+        dt1 = (time.perf_counter() - t) / 20
+        many = [proposal() for _ in range(256)]
+        sb.mcmc_loglike(many, f7, 0.01)
+        t = time.perf_counter()
+        for _ in range(3):
+            sb.mcmc_loglike(many, f7, 0.01)
+        dtm = (time.perf_counter() - t) / 3
+        out["soibean_mcmc_P127"] = {"reads": pk.n_reads, "sources": 2, "ms_per_proposal_single": dt1 * 1e3,
+                                    "ms_per_proposal_batched_256": dtm * 1e3 / 256, "read_proposals_per_s_batched": pk.n_reads * 256 / dtm,
+                                    "what": "vgl_soibean_mcmc_loglike on the batch left resident by vgl_soibean_run, host wall clock incl. "
+                                            "the proposal H2D and the log-likelihood D2H"}
     sb.close()
 print("SIBLINGS", json.dumps(out))

@@ -80,3 +80,102 @@ def test_reverse_strand_and_symbol_cases_on_the_toy_graph():
     got, used = sb.analyse(vb.SoibeanPackedBatch(vb.Graph.from_sequences(nodes), alns))
     assert used.all() and H.rel_err(got, want) < 1e-12
     sb.close()
+
+
+# ---- MCMC proposal likelihood (src/MCMC.cpp:738-993, src/MCMC.h:111-316) -----------------------------
+F7 = orc.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
+
+
+def test_oracle_base_loglike_against_the_closed_form():
+    """computeBaseLogLike restated independently: HKY with kappa = 1/22 == 0 (integer division, src/MCMC.h:66)."""
+    import math
+    a, c, g, t, R, Y, mu = F7
+    assert abs(mu - 1 / (2 * (22 * a * g + 22 * c * t + a * c + a * t + g * c + g * t))) < 1e-18
+    tt, con = 0.013, 0.01
+    f = dict(A=a, C=c, G=g, T=t)
+
+    def hky(rb, ref):
+        fam = R if rb in "AG" else Y
+        A = 1 - fam                                           # 1 + fam * (kappa - 1) with kappa = 0
+        jut1 = f[rb] + f[rb] * (1 / fam - 1) * math.exp(-mu * tt)
+        if rb == ref:
+            p = jut1 + (fam - f[rb]) / fam * math.exp(-mu * tt * A)
+        elif {rb, ref} in ({"A", "G"}, {"C", "T"}):
+            p = abs(jut1 - f[rb] / fam * math.exp(-mu * tt * A))
+        else:
+            p = f[rb] * (1 - math.exp(-mu * tt))
+        return max(p, 1e-8)
+
+    for read_b in "ACGT":
+        for ref in "ACGT":
+            want = math.log(sum(hky(rb, ref) * ((1 - con) if rb == read_b else con / 3) for rb in "ACGT")) - 0.125
+            got = orc.soibean_base_loglike(read_b, ref, -0.125, F7, tt, con)
+            assert abs(got - want) < 1e-13, (read_b, ref)
+    # a match is worth about log(1 - con), a mismatch costs several nats
+    assert abs(orc.soibean_base_loglike("A", "A", 0.0, F7, 0.01, 0.01) - (-0.0109016)) < 1e-6
+    assert orc.soibean_base_loglike("G", "A", 0.0, F7, 0.01, 0.01) < -5
+
+
+def _mcmc_inputs(P=31, n=400, seed=91):
+    S, alns = _inputs(P, seed, n, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    return S, alns, S.supports(), orc.Graph(S.node_sequences(), min_id=1), orc.FlatReads(alns.arrays())
+
+
+def test_oracle_mcmc_properties():
+    S, alns, member, og, R = _mcmc_inputs()
+    p5, p3 = vb.DHIGH5P_PROF, vb.DHIGH3P_PROF
+    want, used = orc.soibean_run(og, R, member, 0, 7, p5, p3)
+    # child == parent in the middle of the branch: both sides are the same number, the weighted average returns it
+    ll, per = orc.soibean_mcmc_loglike(og, R, member, [(5, 5, 0.5, 0.02, 1.0)], F7, 0.01, 0, 7, p5, p3)
+    assert np.all(per[used == 1] < 0) and np.all(per[used == 0] == 0) and abs(ll - per.sum()) < 1e-9 * abs(ll)
+    # every supported regular column adds an HKY term <= 0, nothing else changes: never above pathMap
+    assert np.all(per <= want[:, 5] + 1e-9)
+    # a path that goes through none of the read's nodes: no column is supported, the proposal's value is pathMap itself
+    member0 = member.copy()
+    member0[:, 5] = 0
+    want0, _ = orc.soibean_run(og, R, member0, 0, 7, p5, p3)
+    _, per0 = orc.soibean_mcmc_loglike(og, R, member0, [(5, 5, 0.5, 0.02, 1.0)], F7, 0.01, 0, 7, p5, p3)
+    assert np.allclose(per0, want0[:, 5], rtol=1e-12, atol=0) and np.all(per0[used == 1] < per[used == 1])
+    # two sources, proportions (1, 0): log(0) removes the second one
+    ll1, per1 = orc.soibean_mcmc_loglike(og, R, member, [(5, 9, 0.3, 0.02, 1.0)], F7, 0.01, 0, 7, p5, p3)
+    ll2, per2 = orc.soibean_mcmc_loglike(og, R, member, [(5, 9, 0.3, 0.02, 1.0), (11, 2, 0.6, 0.01, 0.0)], F7, 0.01, 0, 7, p5, p3)
+    assert np.allclose(per1, per2, rtol=1e-12, atol=0)
+
+
+PROPOSALS = [
+    [(5, 9, 0.3, 0.02, 1.0)],
+    [(5, 5, 0.5, 0.0, 1.0)],          # root: no branch, t becomes 1e-5
+    [(12, 3, 1.0, 0.05, 1.0)],        # at the end of the branch: log(1 - pos_branch) = -inf on the parent's side
+    [(12, 3, 0.0, 0.05, 1.0)],
+]
+PROPOSALS2 = [
+    [(5, 9, 0.3, 0.02, 0.6), (11, 2, 0.9, 0.0, 0.4)],
+    [(0, 1, 0.5, 0.01, 0.01), (30, 29, 0.25, 0.2, 0.99)],
+]
+PROPOSALS3 = [[(5, 9, 0.3, 0.02, 0.2), (11, 2, 0.9, 0.0, 0.3), (20, 21, 0.45, 0.03, 0.5)]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("route", ["packed", "raw"])
+@pytest.mark.parametrize("p5,p3,penalty", [("", "", 7), (vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 3)])
+def test_mcmc_proposal_likelihood_matches_oracle(route, p5, p3, penalty):
+    S, alns, member, og, R = _mcmc_inputs(P=31, n=1200, seed=93)
+    sb = vb.Soibean()
+    sb.load(vb.SoibeanTables(member, 0, p5, p3, penalty))
+    with pytest.raises(RuntimeError):                         # nothing resident yet
+        sb.mcmc_loglike(PROPOSALS, F7, 0.01)
+    if route == "packed":
+        sb.analyse(vb.SoibeanPackedBatch(S.graph, alns))
+    else:
+        sb.load_graph(S.graph)
+        sb.analyse_raw(vb.RawBatch(alns, euka_rule=True))
+    n = len(alns)
+    for props in (PROPOSALS, PROPOSALS2, PROPOSALS3):
+        got, got_per = sb.mcmc_loglike(props, F7, 0.01, n_out=n, per_read=True)
+        for q, prop in enumerate(props):
+            want, want_per = orc.soibean_mcmc_loglike(og, R, member, prop, F7, 0.01, 0, penalty, p5, p3)
+            assert H.rel_err(got_per[q], want_per) < 1e-11
+            assert abs(got[q] - want) < 1e-11 * abs(want)
+        again = sb.mcmc_loglike(props, F7, 0.01)              # fixed-order reduction: bit-identical from run to run
+        assert np.array_equal(again, got)
+    sb.close()

@@ -7,4 +7,4 @@ from . import _lib  # noqa: F401  (raises if the libraries are not built)
 from .haplocart import DeviceBatch, Haplocart  # noqa: F401
 from .host import Alignments, Graph, HcTables, HcTree, PackedBatch, RawBatch, WireBatch, SynthHaplocart, reconstruct  # noqa: F401
 from .euka import Euka, EukaPackedBatch, EukaTables, SynthEuka, DHIGH5P_PROF, DHIGH3P_PROF  # noqa: F401
-from .soibean import Soibean, SoibeanPackedBatch, SoibeanTables  # noqa: F401
+from .soibean import Soibean, SoibeanPackedBatch, SoibeanTables, soibean_freqs7  # noqa: F401

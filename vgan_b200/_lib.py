@@ -72,6 +72,10 @@ class vgl_euka_batch(C.Structure):
                 ("flags", C.c_void_p), ("read_index", C.c_void_p)]
 
 
+class vgl_soibean_source(C.Structure):
+    _fields_ = [("child", C.c_int32), ("parent", C.c_int32), ("pos_branch", C.c_double), ("dist", C.c_double), ("proportion", C.c_double)]
+
+
 class vgl_soibean_tables(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("min_id", C.c_int32), ("n_paths", C.c_int32), ("row_words", C.c_int32), ("k5", C.c_int32),
                 ("k3", C.c_int32), ("penalty", C.c_int32), ("reserved", C.c_int32), ("member_bits", C.c_void_p), ("deam", C.c_void_p),
@@ -128,6 +132,7 @@ GPU_SYMBOLS = {
     "vgl_soibean_set_tables": (C.c_int, [_P, C.POINTER(vgl_soibean_tables)]),
     "vgl_soibean_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P]),
     "vgl_soibean_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    "vgl_soibean_mcmc_loglike": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_uint32, _P, _P]),
     "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

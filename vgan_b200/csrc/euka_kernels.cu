@@ -277,7 +277,197 @@ soibean_path_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict
     if (lane == 0 && used) used[ridx] = 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// soibean MCMC: log-likelihood of proposals (reference: read loop of MCMC::run_tree_proportion, src/MCMC.cpp:738-993,
+// computeBaseLogLike, src/MCMC.h:111-296, calculateLogWeightedAverage, src/MCMC.h:299-316).
+//
+// The reference keeps, per read, path, edit and base, a BaseInfo {read base, graph base, pathSupport, logLikelihood}
+// (detailMap, src/getLCAfromGAM.h:192-530) and re-walks it for every proposal.  Everything in it is a function of the
+// batch that is already resident in HBM: pathSupport is true exactly for the "regular" columns (neither base N, 'S' or
+// '-') of an edit whose node the path goes through, there logLikelihood is the column's share of the edit's "supported"
+// sum; every other entry's logLikelihood is its share of the "supported" (N / S / gap: the same on both sides) or
+// "unsupported" sum.  computeBaseLogLike adds to a supported regular column a term that depends only on (read base,
+// graph base, t, con): 25 values per (source, child | parent), tabulated in shared memory when the CTA starts.  So
+//   ll(path) = sum over edits of  member(edit, path) ? sup[edit] + sum over its regular columns of H[read][graph] : uns[edit]
+// with sup / uns as K5a left them.  One read per thread, one proposal per blockIdx.y; the per-read contributions are
+// reduced in a fixed order (CTA partials, then soibean_mcmc_sum_kernel).
+// ------------------------------------------------------------------------------------------
+constexpr int kMcmcMaxSources = VGL_SOIBEAN_MAX_SOURCES;
+
+struct McmcFreqs { double f[7]; };  // params.freqs['A','C','G','T','R','Y','M']
+
+__device__ __forceinline__ double mcmc_oplus(double x, double y) { return x > y ? x + log1p(exp(y - x)) : y + log1p(exp(x - y)); }
+__device__ __forceinline__ double mcmc_oplus_init(double x, double y) { return x == 0.0 ? y : mcmc_oplus(x, y); }  // libgab oplusInitnatl
+
+// The HKY part of computeBaseLogLike for read base class rb and graph base class gb (0-3 = ACGT, 4 = anything else).
+__device__ double mcmc_hky_log_marg(int rb, int gb, const McmcFreqs& F, double t, double con) {
+    const double kappa = 0.0;  // `double kappa = 1/22;` is an integer division (src/MCMC.h:66)
+    const double mu = F.f[6];
+    double lm = -CUDART_INF;
+    for (int bpo = 0; bpo < 4; ++bpo) {
+        const double frb = F.f[bpo];
+        const bool purine = (bpo == 0 || bpo == 2);
+        const double fam = purine ? F.f[4] : F.f[5];
+        const double A = 1 + fam * (kappa - 1);
+        const double jut1 = frb + frb * ((1 / fam) - 1) * exp(-(mu * t));
+        double p;
+        if (bpo == gb) {
+            p = jut1 + ((fam - frb) / fam) * exp(-(mu * t * A));
+        } else if (gb < 4 && (bpo ^ gb) == 2) {  // A <-> G, C <-> T
+            const double jut11 = (frb / fam) * exp(-(mu * t * A));
+            p = jut1 > jut11 ? jut1 - jut11 : jut11 - jut1;
+        } else {
+            p = frb * (1 - exp(-(mu * t)));
+        }
+        if (p < 1e-8) p = 1e-8;
+        lm = mcmc_oplus_init(lm, log(p) + (bpo == rb ? log(1 - con) : log(con / 3)));
+    }
+    if (lm > 1e-8) lm = log(0.999999999);
+    return lm;
+}
+
+__global__ void __launch_bounds__(kEukaBlock)
+soibean_mcmc_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict__ sup, const double* __restrict__ uns,
+                    const vgl_soibean_source* __restrict__ sources, int n_sources, McmcFreqs F, double con, uint32_t n_out,
+                    double* __restrict__ per_read, double* __restrict__ partials, int* __restrict__ err_flag) {
+    __shared__ double s_H[kMcmcMaxSources][2][25];  // [source][child at t2 | parent at t1][read class * 5 + graph class]
+    __shared__ vgl_soibean_source s_src[kMcmcMaxSources];
+    __shared__ double s_red[kEukaBlock / 32];
+    const vgl_soibean_source* mine = sources + (size_t)blockIdx.y * n_sources;
+    for (int k = threadIdx.x; k < n_sources; k += kEukaBlock) s_src[k] = mine[k];
+    for (int k = threadIdx.x; k < n_sources * 50; k += kEukaBlock) {
+        const int y = k / 50, w = (k / 25) & 1, pair = k % 25;
+        double tt = mine[y].dist;
+        if (tt == 0.0) tt = 0.00001;  // only at the root, which has no branch (src/MCMC.cpp:757-759)
+        const double t1 = mine[y].pos_branch * tt;
+        s_H[y][w][pair] = mcmc_hky_log_marg(pair / 5, pair % 5, F, w ? t1 : tt - t1, con);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (kEukaBlock / 32) + (threadIdx.x >> 5);
+    double contribution = 0.0;
+    bool bad = false;
+    uint32_t r = 0;
+    int ne = 0;
+    if (g < b.n_groups) {
+        r = g * 32 + lane;
+        ne = (int)__ldg(b.n_maps + r);
+    }
+    if (ne > 0) {
+        const int nc = (int)__ldg(b.n_cols + r);
+        const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
+        const uint16_t* colbase = b.col + ((size_t)cb0 * 32 + lane) * 8;
+        const size_t mapbase = ((size_t)mb0 * 32 + lane) * 4;
+        const bool rev = (__ldg(b.flags + r) & 1) != 0;
+        auto col_at = [&](int c) -> uint32_t { return (uint32_t)__ldg(colbase + (size_t)(c >> 3) * 256 + (c & 7)); };
+        double inter = -CUDART_INF;
+        for (int y = 0; y < n_sources; ++y) {
+            const int pc = s_src[y].child, pp = s_src[y].parent;
+            const double* __restrict__ Hc = s_H[y][0];
+            const double* __restrict__ Hp = s_H[y][1];
+            double llc = 0.0, llp = 0.0;
+            int baseIX = rev ? (int)__ldg(b.seq_len + r) - 1 : 0;
+            for (int i = 0; i < ne; ++i) {
+                const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
+                const uint32_t rec = __ldg(b.map + mi);
+                const int size = (int)(rec >> 20);
+                int start = baseIX;
+                if (rev) start = (baseIX - size - 1 >= 0) ? (baseIX - size - 1) : 0;
+                if (start < 0 || start > nc) { bad = true; break; }  // K5a has reported it already
+                const int len = min(size, nc - start);
+                const uint32_t node = rec & 0xFFFFFu;
+                const int row = (int)node - t.min_id;
+                bool in_c = false, in_p = false;
+                if (node != VGL_SOIBEAN_NO_NODE && row >= 0 && row < t.n_rows) {
+                    const uint32_t* bits = t.member_bits + (size_t)row * t.row_words;
+                    in_c = (__ldg(bits + (pc >> 5)) >> (pc & 31)) & 1u;
+                    in_p = (__ldg(bits + (pp >> 5)) >> (pp & 31)) & 1u;
+                }
+                const double sp = __ldg(sup + mi), u = __ldg(uns + mi);
+                double hc = 0.0, hp = 0.0;
+                if (in_c || in_p) {
+                    for (int s = 0; s < len; ++s) {
+                        const uint32_t cr = col_at(start + s);
+                        const int G = (int)((cr >> 8) & 15u), R = (int)(cr >> 12);
+                        const bool special = G == VGL_EUKA_SYM_N || R == VGL_EUKA_SYM_N || G == VGL_EUKA_SYM_SOFTCLIP || R == VGL_EUKA_SYM_SOFTCLIP ||
+                                             G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP;
+                        if (!special) {
+                            const int pair = min(R, 4) * 5 + min(G, 4);
+                            hc += Hc[pair];
+                            hp += Hp[pair];
+                        }
+                    }
+                }
+                llc += in_c ? sp + hc : u;
+                llp += in_p ? sp + hp : u;
+                baseIX = rev ? start : baseIX + size;
+            }
+            // the reference throws when a running sum is positive, nan or infinite (src/MCMC.cpp:841-856,936-953)
+            if (llc > 0.0 || isnan(llc) || isinf(llc) || llp > 0.0 || isnan(llp) || isinf(llp)) bad = true;
+            const double pb = s_src[y].pos_branch;
+            if (n_sources == 1) {  // calculateLogWeightedAverage(readLogLike, pos_branch, readLogLikeP, 1 - pos_branch)
+                const double a = llc + log(pb), c = llp + log(1 - pb);
+                const double mx = fmax(a, c);
+                const double lse = mx + log(exp(a - mx) + exp(c - mx));
+                const double lws = log(pb + (1 - pb));
+                contribution = isinf(lws) ? -CUDART_INF : lse - lws;
+            } else {
+                const double inter2 = mcmc_oplus(log(pb) + llc, log(1 - pb) + llp);
+                inter = mcmc_oplus_init(inter, inter2 + log(s_src[y].proportion));
+            }
+        }
+        if (n_sources != 1) contribution = inter;
+        if (per_read) {
+            const uint32_t ridx = __ldg(b.read_index + r);
+            if (ridx < n_out) per_read[(size_t)blockIdx.y * n_out + ridx] = contribution;
+        }
+    }
+    if (bad) atomicOr(err_flag, 4);
+    // fixed-order reduction: lanes, then warps
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) contribution += __shfl_xor_sync(0xffffffffu, contribution, d);
+    if (lane == 0) s_red[threadIdx.x >> 5] = contribution;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kEukaBlock / 32; ++w) tot += s_red[w];
+        partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+// one warp per proposal: the CTA partials in a fixed order
+__global__ void __launch_bounds__(32) soibean_mcmc_sum_kernel(const double* __restrict__ partials, int n_blocks, double* __restrict__ out) {
+    const double* p = partials + (size_t)blockIdx.x * n_blocks;
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n_blocks; k += 32) s += p[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 }  // namespace
+
+int soibean_mcmc_blocks(const EukaBatchDev& b) { return (int)((b.n_groups + kEukaBlock / 32 - 1) / (kEukaBlock / 32)); }
+
+cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns,
+                                const vgl_soibean_source* sources, int n_proposals, int n_sources, const double* freqs7, double con,
+                                uint32_t n_out, double* per_read, double* partials, double* loglike, int* err_flag, cudaStream_t s) {
+    const int nb = soibean_mcmc_blocks(b);
+    if (nb == 0 || n_proposals == 0) return cudaSuccess;
+    McmcFreqs F;
+    for (int k = 0; k < 7; ++k) F.f[k] = freqs7[k];
+    // grid.y is limited to 65535: proposals go in slices
+    for (int p0 = 0; p0 < n_proposals; p0 += 32768) {
+        const int np = min(32768, n_proposals - p0);
+        soibean_mcmc_kernel<<<dim3((unsigned)nb, (unsigned)np), kEukaBlock, 0, s>>>(
+            b, t, sup, uns, sources + (size_t)p0 * n_sources, n_sources, F, con, n_out, per_read ? per_read + (size_t)p0 * n_out : nullptr,
+            partials + (size_t)p0 * nb, err_flag);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    soibean_mcmc_sum_kernel<<<(unsigned)n_proposals, 32, 0, s>>>(partials, nb, loglike);
+    return cudaGetLastError();
+}
 
 cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
                            double* out, uint8_t* used, int* err_flag, cudaStream_t s) {

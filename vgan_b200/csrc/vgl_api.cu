@@ -167,6 +167,11 @@ struct vgl_ctx {
     DevBuf<vgl::EukaSmallTables> s_small;
     DevBuf<uint8_t> s_used;
     DevBuf<int> s_err;
+    // soibean MCMC: the batch of the last soibean run stays resident (staging area + s_sup / s_uns)
+    bool s_last_valid = false;
+    vgl::EukaBatchDev s_last{};
+    DevBuf<vgl_soibean_source> m_src;
+    DevBuf<double> m_partials, m_loglike, m_per_read;
     struct EukaStage {
         DevBuf<uint32_t> grp_col_blk, grp_map_blk, map, read_index;
         DevBuf<uint16_t> col, n_cols, n_maps, seq_len;
@@ -327,6 +332,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
     ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release();
+    ctx->m_src.release(); ctx->m_partials.release(); ctx->m_loglike.release(); ctx->m_per_read.release();
     ctx->s_small.release(); ctx->s_used.release(); ctx->s_err.release();
     ctx->estage.grp_col_blk.release(); ctx->estage.grp_map_blk.release(); ctx->estage.map.release(); ctx->estage.read_index.release();
     ctx->estage.col.release(); ctx->estage.n_cols.release(); ctx->estage.n_maps.release(); ctx->estage.seq_len.release();
@@ -1176,6 +1182,7 @@ int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov) {
 namespace {
 int stage_symbol_batch(vgl_ctx* ctx, const vgl_euka_batch* b, vgl::EukaBatchDev& d) {
     cudaStream_t s = ctx->stream;
+    ctx->s_last_valid = false;  // the staging area is about to be overwritten
     const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
     const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_EUKA_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
     vgl_ctx::EukaStage& st = ctx->estage;
@@ -1265,6 +1272,41 @@ int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* b, uint32_t n_out, do
     return soibean_run_on_device(ctx, d, (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK, n_out, path_ll, used);
 }
 
+int vgl_soibean_mcmc_loglike(vgl_ctx* ctx, int32_t n_proposals, int32_t n_sources, const vgl_soibean_source* sources,
+                             const double* freqs7, double con, uint32_t n_out, double* per_read, double* loglike) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_soibean || !ctx->s_last_valid) return fail(VGL_ERR_STATE, "vgl_soibean_run / vgl_soibean_run_raw must come first (its batch is what the proposals are scored on)");
+    if (n_proposals < 0 || n_sources < 1 || n_sources > VGL_SOIBEAN_MAX_SOURCES || !sources || !freqs7 || !loglike)
+        return fail(VGL_ERR_INVALID, "bad proposal arguments (1 <= n_sources <= %d)", VGL_SOIBEAN_MAX_SOURCES);
+    if (n_proposals == 0) return VGL_OK;
+    const size_t ns = (size_t)n_proposals * (size_t)n_sources;
+    for (size_t k = 0; k < ns; ++k)
+        if (sources[k].child < 0 || sources[k].child >= ctx->stab.n_paths || sources[k].parent < 0 || sources[k].parent >= ctx->stab.n_paths)
+            return fail(VGL_ERR_INVALID, "proposal %zu names a path outside [0, %d)", k / (size_t)n_sources, ctx->stab.n_paths);
+    cudaStream_t s = ctx->stream;
+    VGL_CUDA(cudaStreamSynchronize(s));  // m_src is reused
+    const int nb = vgl::soibean_mcmc_blocks(ctx->s_last);
+    if (int rc = ctx->m_src.reserve(ns)) return rc;
+    if (int rc = ctx->m_partials.reserve((size_t)n_proposals * std::max(nb, 1))) return rc;
+    if (int rc = ctx->m_loglike.reserve((size_t)n_proposals)) return rc;
+    if (per_read)
+        if (int rc = ctx->m_per_read.reserve((size_t)n_proposals * std::max<size_t>(n_out, 1))) return rc;
+    if (int rc = upload_async(ctx->m_src.p, sources, ns * sizeof(vgl_soibean_source), s)) return rc;
+    VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
+    VGL_CUDA(cudaMemsetAsync(ctx->m_loglike.p, 0, (size_t)n_proposals * 8, s));
+    if (per_read) VGL_CUDA(cudaMemsetAsync(ctx->m_per_read.p, 0, (size_t)n_proposals * n_out * 8, s));
+    VGL_CUDA(vgl::soibean_mcmc_launch(ctx->s_last, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->m_src.p, n_proposals, n_sources, freqs7, con,
+                                      n_out, per_read ? ctx->m_per_read.p : nullptr, ctx->m_partials.p, ctx->m_loglike.p, ctx->s_err.p, s));
+    ctx->launches += 1 + (n_proposals + 32767) / 32768;
+    int err = 0;
+    VGL_CUDA(cudaMemcpyAsync(&err, ctx->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaMemcpyAsync(loglike, ctx->m_loglike.p, (size_t)n_proposals * 8, cudaMemcpyDeviceToHost, s));
+    if (per_read) VGL_CUDA(cudaMemcpyAsync(per_read, ctx->m_per_read.p, (size_t)n_proposals * n_out * 8, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    if (err & 4) return fail(VGL_ERR_BAD_READ, "a read's log-likelihood under a proposal is positive, nan or infinite (the reference throws)");
+    return VGL_OK;
+}
+
 int vgl_soibean_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, double* path_ll, uint8_t* used) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_soibean) return fail(VGL_ERR_STATE, "vgl_soibean_set_tables must come first");
@@ -1298,6 +1340,8 @@ int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map
     VGL_CUDA(cudaStreamSynchronize(s));
     if (err & 2) return fail(VGL_ERR_BAD_NODE, "an edit names a node outside the membership table (the reference would throw from vector::at)");
     if (err & 1) return fail(VGL_ERR_BAD_READ, "an alignment slices past its aligned strings or the damage table (the reference would throw / read out of range)");
+    ctx->s_last = d;  // resident for vgl_soibean_mcmc_loglike
+    ctx->s_last_valid = true;
     return VGL_OK;
 }
 
@@ -1333,6 +1377,7 @@ int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out,
 
 // euka / soibean: the whole raw batch in one piece -- H2D, reconstruction (mode 1 / 2), group sizes read back, packing.
 int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::EukaBatchDev& d, size_t& n_map_rec) {
+    ctx->s_last_valid = false;  // the device-built batch is about to be overwritten
     if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
     if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq || !raw->seq_len ||
         !raw->read_index || (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))

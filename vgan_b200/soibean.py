@@ -1,7 +1,9 @@
 """soibean per-read x per-path likelihood path over the C ABI (reference: analyse_GAM, src/getLCAfromGAM.h:102-604).
 
 `Soibean.analyse` returns the R x P matrix of AlignmentInfo::pathMap values (what convertMapsToVector,
-src/soibean.cpp:131-155, hands to the MCMC), columns in pathNames order.  No CPU path."""
+src/soibean.cpp:131-155, hands to the MCMC), columns in pathNames order.  `Soibean.mcmc_loglike` scores MCMC proposals on the batch the last
+analyse() / analyse_raw() left in HBM (reference: read loop of MCMC::run_tree_proportion, src/MCMC.cpp:738-993).
+No CPU path."""
 import ctypes as C
 
 import numpy as np
@@ -94,3 +96,33 @@ class Soibean:
             used = np.zeros(n, dtype=np.uint8)
         check(gpu.vgl_soibean_run(self.ctx, C.byref(packed.batch), n, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
         return out, used
+
+    def mcmc_loglike(self, proposals, freqs7, con, n_out=0, per_read=False):
+        """Log-likelihood of every proposal over the reads of the last analyse() / analyse_raw() batch.
+        proposals: [n_proposals][n_sources] of (child path, parent path, pos_branch, dist, proportion);
+        freqs7 = params.freqs['A','C','G','T','R','Y','M'] (`soibean_freqs7`); con as src/soibean.cpp:596-598.
+        Returns loglike[n_proposals] (and the per-read contributions [n_proposals, n_out] with per_read=True)."""
+        nq = len(proposals)
+        K = len(proposals[0]) if nq else 1
+        arr = (_lib.vgl_soibean_source * max(nq * K, 1))()
+        for q, prop in enumerate(proposals):
+            if len(prop) != K:
+                raise ValueError("every proposal needs the same number of sources")
+            for y, (c, p, b, d, w) in enumerate(prop):
+                arr[q * K + y] = _lib.vgl_soibean_source(int(c), int(p), float(b), float(d), float(w))
+        f7 = np.ascontiguousarray(freqs7, dtype=np.float64)
+        if f7.shape != (7,):
+            raise ValueError("freqs7 is A, C, G, T, R, Y, M")
+        out = np.zeros(nq, dtype=np.float64)
+        pr = np.zeros((nq, n_out), dtype=np.float64) if per_read else None
+        check(gpu.vgl_soibean_mcmc_loglike(self.ctx, nq, K, C.cast(arr, C.c_void_p), f7.ctypes.data_as(C.c_void_p), float(con), int(n_out),
+                                           pr.ctypes.data_as(C.c_void_p) if per_read else None, out.ctypes.data_as(C.c_void_p)))
+        return (out, pr) if per_read else out
+
+
+def soibean_freqs7(a, c, g, t):
+    """params.freqs['A','C','G','T','R','Y','M'] from the four base frequencies, as src/soibean.cpp:629-640 derives them
+    (the 22 in mu is the transition / transversion ratio the reference hard-codes)."""
+    R, Y = a + g, c + t
+    M = 1 / (2 * (((22) * (a * g)) + ((22) * (c * t)) + (a * c + (a * t) + (g * c + (g * t)))))
+    return np.array([a, c, g, t, R, Y, M], dtype=np.float64)
