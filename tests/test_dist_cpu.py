@@ -66,6 +66,40 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert H.rel_err(r0[:-3], final.astype(np.float64)) < 1e-13
 
 
+def _mcmc_worker(rank, world, port, n_reads, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vgan_b200 import dist as vd
+    import test_soibean as ts
+    from oracle import oracle as orc
+    S, alns, member, og, R = ts._mcmc_inputs(P=31, n=n_reads, seed=95)
+    lo, hi = vd.shard_range(n_reads, rank, world)
+    local = []
+    for prop in ts.PROPOSALS2:  # the oracle stands in for the device: this rank's reads only
+        _, per = orc.soibean_mcmc_loglike(og, R, member, prop, ts.F7, 0.01, 0, 7)
+        local.append(per[lo:hi].sum())
+    total = vd.sum_proposal_loglikes(np.array(local))
+    np.save(os.path.join(out_dir, "mcmc%d.npy" % rank), total)
+    dist.destroy_process_group()
+
+
+def test_two_rank_mcmc_proposal_sum(tmp_path):
+    """soibean MCMC over sharded reads: one double per proposal and rank, added in rank order on every rank."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_soibean as ts
+    from oracle import oracle as orc
+    n_reads, world = 90, 2
+    mp.spawn(_mcmc_worker, args=(world, _free_port(), n_reads, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "mcmc0.npy"), np.load(tmp_path / "mcmc1.npy")
+    assert np.array_equal(r0, r1)
+    S, alns, member, og, R = ts._mcmc_inputs(P=31, n=n_reads, seed=95)
+    want = [orc.soibean_mcmc_loglike(og, R, member, prop, ts.F7, 0.01, 0, 7)[0] for prop in ts.PROPOSALS2]
+    assert np.allclose(r0, want, rtol=1e-13, atol=0)
+
+
 def test_shard_range_partitions():
     from vgan_b200 import dist as vd
     for n in (0, 1, 7, 64, 1000003):

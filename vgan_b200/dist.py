@@ -39,6 +39,18 @@ def gather_paths(local_vec, group=None):
     return parts
 
 
+def sum_proposal_loglikes(local_loglike, group=None, device=None):
+    """soibean MCMC on sharded reads: every rank scores the proposals on its own reads
+    (`Soibean.mcmc_loglike`), the [n_proposals] vectors are all-gathered -- one double per proposal and rank -- and added
+    in rank order, so every rank accepts / rejects on the bit-identical number.  Returns a numpy vector."""
+    import torch
+    local = torch.as_tensor(np.ascontiguousarray(local_loglike, dtype=np.float64))
+    if device is not None:
+        local = local.to(device)
+    parts = gather_paths(local, group)
+    return sum_in_rank_order(parts.cpu().numpy())
+
+
 class ShardedSample:
     """One sample spread over the ranks of a process group.  Each rank owns a `Haplocart` on its own GPU."""
 
