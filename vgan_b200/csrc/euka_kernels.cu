@@ -6,6 +6,8 @@
 // per read (rescaled long before it can underflow); the constant-per-column cases (N, gap, rare IUPAC code, soft
 // clip, model 2) are table look-ups.  euka scores each read against exactly one clade.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math_constants.h>
 #include <stdint.h>
 
@@ -292,7 +294,6 @@ soibean_path_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict
 // with sup / uns as K5a left them.  One read per thread, one proposal per blockIdx.y; the per-read contributions are
 // reduced in a fixed order (CTA partials, then soibean_mcmc_sum_kernel).
 // ------------------------------------------------------------------------------------------
-constexpr int kMcmcMaxSources = VGL_SOIBEAN_MAX_SOURCES;
 
 struct McmcFreqs { double f[7]; };  // params.freqs['A','C','G','T','R','Y','M']
 
@@ -326,123 +327,147 @@ __device__ double mcmc_hky_log_marg(int rb, int gb, const McmcFreqs& F, double t
     return lm;
 }
 
+// H[q][y][child at t2 | parent at t1][read class * 5 + graph class] for every proposal q and source y: 50 values per source
+__global__ void __launch_bounds__(128)
+soibean_mcmc_tables_kernel(const vgl_soibean_source* __restrict__ sources, int n_entries, McmcFreqs F, double con, double* __restrict__ H) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_entries) return;
+    const vgl_soibean_source src = sources[k / 50];
+    const int w = (k / 25) & 1, pair = k % 25;
+    double tt = src.dist;
+    if (tt == 0.0) tt = 0.00001;  // only at the root, which has no branch (src/MCMC.cpp:757-759)
+    const double t1 = src.pos_branch * tt;
+    H[k] = mcmc_hky_log_marg(pair / 5, pair % 5, F, w ? t1 : tt - t1, con);
+}
+
+// One read per thread, a tile of `tile` proposals per blockIdx.y: the read's records are fetched from HBM / L2 once per
+// tile and come from L1 for the other proposals.  Dynamic shared memory: H tables [tile][n_sources][50] doubles, the tile's
+// sources, [tile][warps] partial sums.  out[n_proposals] doubles followed by one double that is set non-zero on error
+// is NOT written here: partials[q][blockIdx.x] go to soibean_mcmc_sum_kernel.
 __global__ void __launch_bounds__(kEukaBlock)
 soibean_mcmc_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict__ sup, const double* __restrict__ uns,
-                    const vgl_soibean_source* __restrict__ sources, int n_sources, McmcFreqs F, double con, uint32_t n_out,
-                    double* __restrict__ per_read, double* __restrict__ partials, int* __restrict__ err_flag) {
-    __shared__ double s_H[kMcmcMaxSources][2][25];  // [source][child at t2 | parent at t1][read class * 5 + graph class]
-    __shared__ vgl_soibean_source s_src[kMcmcMaxSources];
-    __shared__ double s_red[kEukaBlock / 32];
-    const vgl_soibean_source* mine = sources + (size_t)blockIdx.y * n_sources;
-    for (int k = threadIdx.x; k < n_sources; k += kEukaBlock) s_src[k] = mine[k];
-    for (int k = threadIdx.x; k < n_sources * 50; k += kEukaBlock) {
-        const int y = k / 50, w = (k / 25) & 1, pair = k % 25;
-        double tt = mine[y].dist;
-        if (tt == 0.0) tt = 0.00001;  // only at the root, which has no branch (src/MCMC.cpp:757-759)
-        const double t1 = mine[y].pos_branch * tt;
-        s_H[y][w][pair] = mcmc_hky_log_marg(pair / 5, pair % 5, F, w ? t1 : tt - t1, con);
-    }
+                    const vgl_soibean_source* __restrict__ sources, const double* __restrict__ H, int n_proposals, int n_sources,
+                    int tile, uint32_t n_out, double* __restrict__ per_read, double* __restrict__ partials, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char mcmc_smem[];
+    const int q0 = blockIdx.y * tile;
+    const int nq = min(tile, n_proposals - q0);
+    double* s_H = reinterpret_cast<double*>(mcmc_smem);                                         // [tile][n_sources][50]
+    vgl_soibean_source* s_src = reinterpret_cast<vgl_soibean_source*>(s_H + (size_t)tile * n_sources * 50);  // [tile][n_sources]
+    double* s_red = reinterpret_cast<double*>(s_src + (size_t)tile * n_sources);               // [tile][warps]
+    for (int k = threadIdx.x; k < nq * n_sources * 50; k += kEukaBlock) s_H[k] = H[(size_t)q0 * n_sources * 50 + k];
+    for (int k = threadIdx.x; k < nq * n_sources; k += kEukaBlock) s_src[k] = sources[(size_t)q0 * n_sources + k];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * (kEukaBlock / 32) + (threadIdx.x >> 5);
-    double contribution = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * (kEukaBlock / 32) + warp;
     bool bad = false;
-    uint32_t r = 0;
-    int ne = 0;
+    uint32_t r = 0, ridx = 0xffffffffu;
+    int ne = 0, nc = 0, seq_len = 0;
+    bool rev = false;
+    const uint16_t* colbase = nullptr;
+    size_t mapbase = 0;
     if (g < b.n_groups) {
         r = g * 32 + lane;
         ne = (int)__ldg(b.n_maps + r);
+        if (ne > 0) {
+            nc = (int)__ldg(b.n_cols + r);
+            colbase = b.col + ((size_t)__ldg(b.grp_col_blk + g) * 32 + lane) * 8;
+            mapbase = ((size_t)__ldg(b.grp_map_blk + g) * 32 + lane) * 4;
+            rev = (__ldg(b.flags + r) & 1) != 0;
+            seq_len = (int)__ldg(b.seq_len + r);
+            if (per_read) ridx = __ldg(b.read_index + r);
+        }
     }
-    if (ne > 0) {
-        const int nc = (int)__ldg(b.n_cols + r);
-        const uint32_t cb0 = __ldg(b.grp_col_blk + g), mb0 = __ldg(b.grp_map_blk + g);
-        const uint16_t* colbase = b.col + ((size_t)cb0 * 32 + lane) * 8;
-        const size_t mapbase = ((size_t)mb0 * 32 + lane) * 4;
-        const bool rev = (__ldg(b.flags + r) & 1) != 0;
-        auto col_at = [&](int c) -> uint32_t { return (uint32_t)__ldg(colbase + (size_t)(c >> 3) * 256 + (c & 7)); };
-        double inter = -CUDART_INF;
-        for (int y = 0; y < n_sources; ++y) {
-            const int pc = s_src[y].child, pp = s_src[y].parent;
-            const double* __restrict__ Hc = s_H[y][0];
-            const double* __restrict__ Hp = s_H[y][1];
-            double llc = 0.0, llp = 0.0;
-            int baseIX = rev ? (int)__ldg(b.seq_len + r) - 1 : 0;
-            for (int i = 0; i < ne; ++i) {
-                const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
-                const uint32_t rec = __ldg(b.map + mi);
-                const int size = (int)(rec >> 20);
-                int start = baseIX;
-                if (rev) start = (baseIX - size - 1 >= 0) ? (baseIX - size - 1) : 0;
-                if (start < 0 || start > nc) { bad = true; break; }  // K5a has reported it already
-                const int len = min(size, nc - start);
-                const uint32_t node = rec & 0xFFFFFu;
-                const int row = (int)node - t.min_id;
-                bool in_c = false, in_p = false;
-                if (node != VGL_SOIBEAN_NO_NODE && row >= 0 && row < t.n_rows) {
-                    const uint32_t* bits = t.member_bits + (size_t)row * t.row_words;
-                    in_c = (__ldg(bits + (pc >> 5)) >> (pc & 31)) & 1u;
-                    in_p = (__ldg(bits + (pp >> 5)) >> (pp & 31)) & 1u;
-                }
-                const double sp = __ldg(sup + mi), u = __ldg(uns + mi);
-                double hc = 0.0, hp = 0.0;
-                if (in_c || in_p) {
-                    for (int s = 0; s < len; ++s) {
-                        const uint32_t cr = col_at(start + s);
-                        const int G = (int)((cr >> 8) & 15u), R = (int)(cr >> 12);
-                        const bool special = G == VGL_EUKA_SYM_N || R == VGL_EUKA_SYM_N || G == VGL_EUKA_SYM_SOFTCLIP || R == VGL_EUKA_SYM_SOFTCLIP ||
-                                             G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP;
-                        if (!special) {
-                            const int pair = min(R, 4) * 5 + min(G, 4);
-                            hc += Hc[pair];
-                            hp += Hp[pair];
+    auto col_at = [&](int c) -> uint32_t { return (uint32_t)__ldg(colbase + (size_t)(c >> 3) * 256 + (c & 7)); };
+    for (int q = 0; q < nq; ++q) {
+        double contribution = 0.0;
+        if (ne > 0) {
+            double inter = -CUDART_INF;
+            for (int y = 0; y < n_sources; ++y) {
+                const vgl_soibean_source& S = s_src[q * n_sources + y];
+                const int pc = S.child, pp = S.parent;
+                const double* __restrict__ Hc = s_H + ((size_t)q * n_sources + y) * 50;
+                const double* __restrict__ Hp = Hc + 25;
+                double llc = 0.0, llp = 0.0;
+                int baseIX = rev ? seq_len - 1 : 0;
+                for (int i = 0; i < ne; ++i) {
+                    const size_t mi = mapbase + (size_t)(i >> 2) * 128 + (i & 3);
+                    const uint32_t rec = __ldg(b.map + mi);
+                    const int size = (int)(rec >> 20);
+                    int start = baseIX;
+                    if (rev) start = (baseIX - size - 1 >= 0) ? (baseIX - size - 1) : 0;
+                    if (start < 0 || start > nc) { bad = true; break; }  // K5a has reported it already
+                    const int len = min(size, nc - start);
+                    const uint32_t node = rec & 0xFFFFFu;
+                    const int row = (int)node - t.min_id;
+                    bool in_c = false, in_p = false;
+                    if (node != VGL_SOIBEAN_NO_NODE && row >= 0 && row < t.n_rows) {
+                        const uint32_t* bits = t.member_bits + (size_t)row * t.row_words;
+                        in_c = (__ldg(bits + (pc >> 5)) >> (pc & 31)) & 1u;
+                        in_p = (__ldg(bits + (pp >> 5)) >> (pp & 31)) & 1u;
+                    }
+                    const double sp = __ldg(sup + mi), u = __ldg(uns + mi);
+                    double hc = 0.0, hp = 0.0;
+                    if (in_c || in_p) {
+                        for (int s = 0; s < len; ++s) {
+                            const uint32_t cr = col_at(start + s);
+                            const int G = (int)((cr >> 8) & 15u), R = (int)(cr >> 12);
+                            const bool special = G == VGL_EUKA_SYM_N || R == VGL_EUKA_SYM_N || G == VGL_EUKA_SYM_SOFTCLIP ||
+                                                 R == VGL_EUKA_SYM_SOFTCLIP || G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP;
+                            if (!special) {
+                                const int pair = min(R, 4) * 5 + min(G, 4);
+                                hc += Hc[pair];
+                                hp += Hp[pair];
+                            }
                         }
                     }
+                    llc += in_c ? sp + hc : u;
+                    llp += in_p ? sp + hp : u;
+                    baseIX = rev ? start : baseIX + size;
                 }
-                llc += in_c ? sp + hc : u;
-                llp += in_p ? sp + hp : u;
-                baseIX = rev ? start : baseIX + size;
+                // the reference throws when a running sum is positive, nan or infinite (src/MCMC.cpp:841-856,936-953)
+                if (llc > 0.0 || isnan(llc) || isinf(llc) || llp > 0.0 || isnan(llp) || isinf(llp)) bad = true;
+                const double pb = S.pos_branch;
+                if (n_sources == 1) {  // calculateLogWeightedAverage(readLogLike, pos_branch, readLogLikeP, 1 - pos_branch)
+                    const double a = llc + log(pb), c = llp + log(1 - pb);
+                    const double mx = fmax(a, c);
+                    const double lse = mx + log(exp(a - mx) + exp(c - mx));
+                    const double lws = log(pb + (1 - pb));
+                    contribution = isinf(lws) ? -CUDART_INF : lse - lws;
+                } else {
+                    const double inter2 = mcmc_oplus(log(pb) + llc, log(1 - pb) + llp);
+                    inter = mcmc_oplus_init(inter, inter2 + log(S.proportion));
+                }
             }
-            // the reference throws when a running sum is positive, nan or infinite (src/MCMC.cpp:841-856,936-953)
-            if (llc > 0.0 || isnan(llc) || isinf(llc) || llp > 0.0 || isnan(llp) || isinf(llp)) bad = true;
-            const double pb = s_src[y].pos_branch;
-            if (n_sources == 1) {  // calculateLogWeightedAverage(readLogLike, pos_branch, readLogLikeP, 1 - pos_branch)
-                const double a = llc + log(pb), c = llp + log(1 - pb);
-                const double mx = fmax(a, c);
-                const double lse = mx + log(exp(a - mx) + exp(c - mx));
-                const double lws = log(pb + (1 - pb));
-                contribution = isinf(lws) ? -CUDART_INF : lse - lws;
-            } else {
-                const double inter2 = mcmc_oplus(log(pb) + llc, log(1 - pb) + llp);
-                inter = mcmc_oplus_init(inter, inter2 + log(s_src[y].proportion));
-            }
+            if (n_sources != 1) contribution = inter;
+            if (ridx < n_out) per_read[(size_t)(q0 + q) * n_out + ridx] = contribution;
         }
-        if (n_sources != 1) contribution = inter;
-        if (per_read) {
-            const uint32_t ridx = __ldg(b.read_index + r);
-            if (ridx < n_out) per_read[(size_t)blockIdx.y * n_out + ridx] = contribution;
-        }
+        // fixed-order reduction: lanes, then (below) warps
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contribution += __shfl_xor_sync(0xffffffffu, contribution, d);
+        if (lane == 0) s_red[q * (kEukaBlock / 32) + warp] = contribution;
     }
     if (bad) atomicOr(err_flag, 4);
-    // fixed-order reduction: lanes, then warps
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) contribution += __shfl_xor_sync(0xffffffffu, contribution, d);
-    if (lane == 0) s_red[threadIdx.x >> 5] = contribution;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    for (int q = threadIdx.x; q < nq; q += kEukaBlock) {
         double tot = 0.0;
-        for (int w = 0; w < kEukaBlock / 32; ++w) tot += s_red[w];
-        partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+        for (int w = 0; w < kEukaBlock / 32; ++w) tot += s_red[q * (kEukaBlock / 32) + w];
+        partials[(size_t)(q0 + q) * gridDim.x + blockIdx.x] = tot;
     }
 }
 
-// one warp per proposal: the CTA partials in a fixed order
-__global__ void __launch_bounds__(32) soibean_mcmc_sum_kernel(const double* __restrict__ partials, int n_blocks, double* __restrict__ out) {
+// one warp per proposal: the CTA partials in a fixed order.  out[n_proposals] is followed by one double that carries the
+// error flag, so that results and status come back in one copy.
+__global__ void __launch_bounds__(32) soibean_mcmc_sum_kernel(const double* __restrict__ partials, int n_blocks, int n_proposals,
+                                                              double* __restrict__ out, const int* __restrict__ err_flag) {
     const double* p = partials + (size_t)blockIdx.x * n_blocks;
     double s = 0.0;
     for (int k = threadIdx.x; k < n_blocks; k += 32) s += p[k];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (threadIdx.x == 0) out[blockIdx.x] = s;
+    if (threadIdx.x == 0) {
+        out[blockIdx.x] = s;
+        if (blockIdx.x == 0) out[n_proposals] = (double)*err_flag;  // set by the read kernels, which have all finished
+    }
 }
 
 }  // namespace
@@ -451,21 +476,32 @@ int soibean_mcmc_blocks(const EukaBatchDev& b) { return (int)((b.n_groups + kEuk
 
 cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns,
                                 const vgl_soibean_source* sources, int n_proposals, int n_sources, const double* freqs7, double con,
-                                uint32_t n_out, double* per_read, double* partials, double* loglike, int* err_flag, cudaStream_t s) {
+                                uint32_t n_out, double* per_read, double* H, double* partials, double* loglike, int* err_flag,
+                                cudaStream_t s) {
     const int nb = soibean_mcmc_blocks(b);
     if (nb == 0 || n_proposals == 0) return cudaSuccess;
     McmcFreqs F;
     for (int k = 0; k < 7; ++k) F.f[k] = freqs7[k];
-    // grid.y is limited to 65535: proposals go in slices
-    for (int p0 = 0; p0 < n_proposals; p0 += 32768) {
-        const int np = min(32768, n_proposals - p0);
-        soibean_mcmc_kernel<<<dim3((unsigned)nb, (unsigned)np), kEukaBlock, 0, s>>>(
-            b, t, sup, uns, sources + (size_t)p0 * n_sources, n_sources, F, con, n_out, per_read ? per_read + (size_t)p0 * n_out : nullptr,
-            partials + (size_t)p0 * nb, err_flag);
-        cudaError_t e = cudaGetLastError();
+    const int n_entries = n_proposals * n_sources * 50;
+    soibean_mcmc_tables_kernel<<<(n_entries + 127) / 128, 128, 0, s>>>(sources, n_entries, F, con, H);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // proposals per CTA: as many as fit 40 KB of tables (16 at most); with few reads, fewer so that the grid still fills the GPU
+    const size_t per_q = (size_t)n_sources * (50 * sizeof(double) + sizeof(vgl_soibean_source)) + (kEukaBlock / 32) * sizeof(double);
+    int tile = (int)std::min<size_t>(16, std::max<size_t>(1, (40 * 1024) / per_q));
+    tile = std::min(tile, n_proposals);
+    while (tile > 1 && (long long)nb * ((n_proposals + tile - 1) / tile) < 4 * 148) tile = (tile + 1) / 2;
+    const int tiles = (n_proposals + tile - 1) / tile;
+    for (int t0 = 0; t0 < tiles; t0 += 32768) {  // grid.y is limited to 65535
+        const int nt = std::min(32768, tiles - t0);
+        const int q0 = t0 * tile, nq = std::min(n_proposals - q0, nt * tile);
+        soibean_mcmc_kernel<<<dim3((unsigned)nb, (unsigned)nt), kEukaBlock, per_q * tile, s>>>(
+            b, t, sup, uns, sources + (size_t)q0 * n_sources, H + (size_t)q0 * n_sources * 50, nq, n_sources, tile, n_out,
+            per_read ? per_read + (size_t)q0 * n_out : nullptr, partials + (size_t)q0 * nb, err_flag);
+        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    soibean_mcmc_sum_kernel<<<(unsigned)n_proposals, 32, 0, s>>>(partials, nb, loglike);
+    soibean_mcmc_sum_kernel<<<(unsigned)n_proposals, 32, 0, s>>>(partials, nb, n_proposals, loglike, err_flag);
     return cudaGetLastError();
 }
 

@@ -171,7 +171,9 @@ struct vgl_ctx {
     bool s_last_valid = false;
     vgl::EukaBatchDev s_last{};
     DevBuf<vgl_soibean_source> m_src;
-    DevBuf<double> m_partials, m_loglike, m_per_read;
+    DevBuf<double> m_partials, m_loglike, m_per_read, m_H;
+    unsigned char* m_pinned = nullptr;  // proposal in, log-likelihoods + error flag out
+    size_t m_pinned_cap = 0;
     struct EukaStage {
         DevBuf<uint32_t> grp_col_blk, grp_map_blk, map, read_index;
         DevBuf<uint16_t> col, n_cols, n_maps, seq_len;
@@ -332,7 +334,8 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
     ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release();
-    ctx->m_src.release(); ctx->m_partials.release(); ctx->m_loglike.release(); ctx->m_per_read.release();
+    ctx->m_src.release(); ctx->m_partials.release(); ctx->m_loglike.release(); ctx->m_per_read.release(); ctx->m_H.release();
+    if (ctx->m_pinned) cudaFreeHost(ctx->m_pinned);
     ctx->s_small.release(); ctx->s_used.release(); ctx->s_err.release();
     ctx->estage.grp_col_blk.release(); ctx->estage.grp_map_blk.release(); ctx->estage.map.release(); ctx->estage.read_index.release();
     ctx->estage.col.release(); ctx->estage.n_cols.release(); ctx->estage.n_maps.release(); ctx->estage.seq_len.release();
@@ -1284,26 +1287,38 @@ int vgl_soibean_mcmc_loglike(vgl_ctx* ctx, int32_t n_proposals, int32_t n_source
         if (sources[k].child < 0 || sources[k].child >= ctx->stab.n_paths || sources[k].parent < 0 || sources[k].parent >= ctx->stab.n_paths)
             return fail(VGL_ERR_INVALID, "proposal %zu names a path outside [0, %d)", k / (size_t)n_sources, ctx->stab.n_paths);
     cudaStream_t s = ctx->stream;
-    VGL_CUDA(cudaStreamSynchronize(s));  // m_src is reused
+    VGL_CUDA(cudaStreamSynchronize(s));  // the staging blocks are reused
     const int nb = vgl::soibean_mcmc_blocks(ctx->s_last);
     if (int rc = ctx->m_src.reserve(ns)) return rc;
+    if (int rc = ctx->m_H.reserve(ns * 50)) return rc;
     if (int rc = ctx->m_partials.reserve((size_t)n_proposals * std::max(nb, 1))) return rc;
-    if (int rc = ctx->m_loglike.reserve((size_t)n_proposals)) return rc;
+    if (int rc = ctx->m_loglike.reserve((size_t)n_proposals + 1)) return rc;
     if (per_read)
         if (int rc = ctx->m_per_read.reserve((size_t)n_proposals * std::max<size_t>(n_out, 1))) return rc;
-    if (int rc = upload_async(ctx->m_src.p, sources, ns * sizeof(vgl_soibean_source), s)) return rc;
+    // one page-locked block carries the proposal in and the log-likelihoods + error flag out: two async copies, one sync
+    const size_t in_bytes = ns * sizeof(vgl_soibean_source), out_bytes = ((size_t)n_proposals + 1) * sizeof(double);
+    if (in_bytes + out_bytes > ctx->m_pinned_cap) {
+        if (ctx->m_pinned) cudaFreeHost(ctx->m_pinned);
+        ctx->m_pinned = nullptr;
+        ctx->m_pinned_cap = 0;
+        const size_t want = 2 * (in_bytes + out_bytes) + 256;
+        VGL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->m_pinned), want));
+        ctx->m_pinned_cap = want;
+    }
+    double* h_out = reinterpret_cast<double*>(ctx->m_pinned);
+    memcpy(ctx->m_pinned + out_bytes, sources, in_bytes);
+    VGL_CUDA(cudaMemcpyAsync(ctx->m_src.p, ctx->m_pinned + out_bytes, in_bytes, cudaMemcpyHostToDevice, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
-    VGL_CUDA(cudaMemsetAsync(ctx->m_loglike.p, 0, (size_t)n_proposals * 8, s));
     if (per_read) VGL_CUDA(cudaMemsetAsync(ctx->m_per_read.p, 0, (size_t)n_proposals * n_out * 8, s));
     VGL_CUDA(vgl::soibean_mcmc_launch(ctx->s_last, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->m_src.p, n_proposals, n_sources, freqs7, con,
-                                      n_out, per_read ? ctx->m_per_read.p : nullptr, ctx->m_partials.p, ctx->m_loglike.p, ctx->s_err.p, s));
-    ctx->launches += 1 + (n_proposals + 32767) / 32768;
-    int err = 0;
-    VGL_CUDA(cudaMemcpyAsync(&err, ctx->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaMemcpyAsync(loglike, ctx->m_loglike.p, (size_t)n_proposals * 8, cudaMemcpyDeviceToHost, s));
+                                      n_out, per_read ? ctx->m_per_read.p : nullptr, ctx->m_H.p, ctx->m_partials.p, ctx->m_loglike.p,
+                                      ctx->s_err.p, s));
+    ctx->launches += 3;
+    VGL_CUDA(cudaMemcpyAsync(h_out, ctx->m_loglike.p, out_bytes, cudaMemcpyDeviceToHost, s));
     if (per_read) VGL_CUDA(cudaMemcpyAsync(per_read, ctx->m_per_read.p, (size_t)n_proposals * n_out * 8, cudaMemcpyDeviceToHost, s));
     VGL_CUDA(cudaStreamSynchronize(s));
-    if (err & 4) return fail(VGL_ERR_BAD_READ, "a read's log-likelihood under a proposal is positive, nan or infinite (the reference throws)");
+    memcpy(loglike, h_out, (size_t)n_proposals * sizeof(double));
+    if (h_out[n_proposals] != 0.0) return fail(VGL_ERR_BAD_READ, "a read's log-likelihood under a proposal is positive, nan or infinite (the reference throws)");
     return VGL_OK;
 }
 

@@ -253,11 +253,13 @@ struct SoibeanTablesDev {
 cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
                            double* out, uint8_t* used, int* err_flag, cudaStream_t s);
 
-// soibean MCMC: loglike[q] = sum over the batch's reads of the per-read log-likelihood under proposal q (sources[q][n_sources]);
-// per_read (optional) [n_proposals][n_out]; partials: scratch [n_proposals][soibean_mcmc_blocks(b)].  sup / uns as K5a left them.
+// soibean MCMC: loglike[q] = sum over the batch's reads of the per-read log-likelihood under proposal q (sources[q][n_sources]),
+// loglike[n_proposals] = the error flag; per_read (optional) [n_proposals][n_out]; scratch: H [n_proposals][n_sources][50],
+// partials [n_proposals][soibean_mcmc_blocks(b)].  sup / uns as K5a left them.  Launches 2 + number of 32768-tile slices kernels.
 int soibean_mcmc_blocks(const EukaBatchDev& b);
 cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns,
                                 const vgl_soibean_source* sources, int n_proposals, int n_sources, const double* freqs7, double con,
-                                uint32_t n_out, double* per_read, double* partials, double* loglike, int* err_flag, cudaStream_t s);
+                                uint32_t n_out, double* per_read, double* H, double* partials, double* loglike, int* err_flag,
+                                cudaStream_t s);
 
 }  // namespace vgl
