@@ -131,7 +131,15 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kAccCopies = VGL_HC_ACC_COPIES;  // node vectors the CTAs add into (CTA b uses copy b % kAccCopies)
-constexpr int kQueueSlots = 64;  // per warp; a drain leaves < 32 entries and one column adds <= 32
+// Columns walked between two looks at the queue.  A drain leaves < 32 entries and every column adds <= 32, so the ring needs
+// 32 * (1 + kDrainEvery) slots; with more than one column per look the columns in between form one basic block and their
+// independent work overlaps.
+#ifndef VGL_HC_DRAIN_EVERY
+#define VGL_HC_DRAIN_EVERY 4
+#endif
+constexpr int kDrainEvery = VGL_HC_DRAIN_EVERY;
+static_assert(kDrainEvery == 1 || kDrainEvery == 2 || kDrainEvery == 4, "a look at the queue every 1, 2 or 4 columns");
+constexpr int kQueueSlots = kDrainEvery == 1 ? 64 : kDrainEvery == 2 ? 128 : 256;  // per warp, a power of two
 
 struct ReadKernelShared {
     uint32_t f, bg, logtab, node_class, ac, queue, p_correct;  // shared byte addresses (queue: this warp's ring)
@@ -298,7 +306,10 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
                      : "memory");
         prod = close ? 1.0 : prod;
         q_tail += __popc(m);
-        if (q_tail - q_head >= 32u) {
+    };
+    auto drain = [&]() {
+#pragma unroll 1
+        while (q_tail - q_head >= 32u) {
             __syncwarp();
             const uint4 e = lds_v4(S.queue | ((16u * (q_head + lane)) & (16u * (kQueueSlots - 1))));
             __syncwarp();
@@ -316,19 +327,25 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
             f[j] = lds_f64_c(S.f + 8u * (rec[j] & 0x3ffu));
             bgv[j] = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec[j]));
             // the class is needed where a mapping opens only: predicated, so that the other lanes cost no bank conflicts
-            uint16_t c16 = 0;
+            uint32_t c32 = 0;  // (a 16-bit load may target a 32-bit register: zero-extended, no pack / unpack around it)
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
-                : "+h"(c16)
+                : "+r"(c32)
                 : "r"(S.node_class + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: CLASS_NONE
-            cls[j] = c16;
+            cls[j] = c32;
         }
         const int c4 = cb * VGL_HC_COL_BLK;
         if (__any_sync(kFull, rare)) {
 #pragma unroll
-            for (int j = 3; j >= 0; --j) column(std::true_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+            for (int j = 3; j >= 0; --j) {
+                column(std::true_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+                if (j % kDrainEvery == 0) drain();
+            }
         } else {
 #pragma unroll
-            for (int j = 3; j >= 0; --j) column(std::false_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+            for (int j = 3; j >= 0; --j) {
+                column(std::false_type{}, c4 + j, rec[j], f[j], bgv[j], cls[j]);
+                if (j % kDrainEvery == 0) drain();
+            }
         }
         if (fmin(prod, pall) < 1e-100) {  // keep the products normal (four more factors cannot take them out of range)
             if (prod < 1e-100) {
@@ -682,7 +699,7 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
 // launch wrappers
 // ------------------------------------------------------------------------------------------
 static size_t read_smem_bytes(int n_rows, int n_class, int ac_mode) {
-    size_t s = (size_t)hc_image_layout(n_rows, n_class, ac_mode).bytes + 1024;  // + alignment slack of the rings (plus the static shared)
+    size_t s = (size_t)hc_image_layout(n_rows, n_class, ac_mode).bytes + kQueueSlots * sizeof(uint4);  // + alignment slack of the rings
     s += (size_t)(kReadBlock / 32) * kQueueSlots * sizeof(uint4);
     return (s + 127) & ~(size_t)127;
 }
