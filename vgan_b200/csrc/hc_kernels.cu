@@ -226,6 +226,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // product of EVERY valid column's mixture of this read: sum_i A_i = log(pall), one log per read instead of one per
     // mapping; only the mappings whose node some path avoids need their own A_i (for D[n])
     double pall = 1.0;
+    int n_scale = 0;  // times pall was multiplied by 2^400
     uint32_t open_cls = 0;  // node-table entry of the mapping being walked
 
     auto extra_rec = [&](int i) -> uint32_t {
@@ -347,16 +348,17 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
                 if (j % kDrainEvery == 0) drain();
             }
         }
-        if (fmin(prod, pall) < 1e-100) {  // keep the products normal (four more factors cannot take them out of range)
-            if (prod < 1e-100) {
-                a_ext += fast_log_s(prod, S.logtab);
-                prod = 1.0;
-                rare = true;
-            }
-            if (pall < 1e-100) {
-                a_sum += fast_log_s(pall, S.logtab);
-                pall = 1.0;
-            }
+        // keep the products normal (four more factors cannot take them out of range).  The read-level product falls below
+        // any threshold several times per read (the mismatch columns of Q2 cost ~1e-4 each): it is rescaled by 2^400 without
+        // a branch and the count is undone in the log at the end of the group
+        const bool low = pall < 0x1p-400;
+        const double up = pall * 0x1p400;
+        pall = low ? up : pall;
+        n_scale += low ? 1 : 0;
+        if (prod < 1e-100) {  // one mapping's own product: dozens of very unlikely bases in one mapping, rare
+            a_ext += fast_log_s(prod, S.logtab);
+            prod = 1.0;
+            rare = true;
         }
     };
     // two blocks in flight from ONE load site: a block is waited for a whole block (hundreds of issue slots) after its
@@ -370,7 +372,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // the next group's last blocks are requested now; they arrive while it is being set up
     v0 = hc_fetch(Hn, Hn.ncb - 1);
     v1 = hc_fetch(Hn, Hn.ncb - 2);
-    a_sum += fast_log_s(pall, S.logtab);
+    a_sum += fma((double)n_scale, -400.0 * 0.6931471805599453094, fast_log_s(pall, S.logtab));
     while (x >= 0) {  // empty mappings that start past the last column
         const uint32_t xr = extra_rec(x);
         add_extra(xr & VGL_HC_MAP_MAX_NODE, (double)(xr >> VGL_HC_MAP_NODE_BITS) * S.le0);
