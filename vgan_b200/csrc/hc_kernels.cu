@@ -116,17 +116,19 @@ __device__ __forceinline__ double fast_log_s(double x, uint32_t tab) {
 //     for the mapping that starts at the current column (src/update_likelihood.cpp:40-44 reads |algnseq|
 //     qualities from position_in_read; the `pos` bytes past the end count as quality 0);
 //   * the running product of the per-base mixtures (src/process_mapping.cpp:59-77) is the mapping's
-//     exp(A_i); one log per mapping instead of one per base.
-// At a CLOSE mark (first column of a mapping) the pair is pushed onto the warp's queue in shared memory
-// (ballot + popc give every closing lane its slot, one 16-byte store each).  Whenever the queue holds 32
-// entries the warp drains them, one entry per lane: log of the product, B_i from the quality sums, and
+//     exp(A_i); one log per mapping instead of one per base;
+//   * a second running product over ALL valid columns of the read gives sum_i A_i with one log per read, so a mapping's
+//     own A_i is needed only where it feeds D[n]: not at all for a node every path goes through.
+// At a CLOSE mark (first column of a mapping) whose node some path avoids, the pair is pushed onto the warp's queue in
+// shared memory (ballot + popc give every closing lane its slot, one 16-byte store each).  After every block of four
+// columns, while the queue holds 32 entries or more, the warp drains them, one entry per lane: log of the product, B_i from the quality sums, and
 // B_i - A_i added to the CTA's node vector (global memory, L2 resident) with a fire-and-forget fp64 reduction.
 // Entries are self-contained, so the queue simply carries over from one group to the next and the finalisation
 // always runs on full warps.
 // (Per-thread lists in local memory, the obvious alternative, cost ~9 KB of L2 traffic per read.)
 //
 // Shared memory: [ HcSmallTables | node_class u16[n_rows + 1] | ac table double2[100][n_class + 1]
-//                  | close queues uint4[warps][64] ]
+//                  | close queues uint4[warps][kQueueSlots], every ring on its own boundary ]
 // The ac table holds {1 - pcm, pcm * K} (src/process_mapping.cpp:33-42) for every (mapping quality, table class)
 // pair, so opening a mapping costs one shared load and no arithmetic.
 // ------------------------------------------------------------------------------------------
