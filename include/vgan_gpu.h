@@ -435,6 +435,15 @@ int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_
                      double* like, uint8_t* pass);
 /* Per-clade count (Clade::count) and per-bin coverage (get<3>(chunks[c][j])) accumulated since the reset. */
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov);
+/* euka's abundance MCMC (MCMC::run / get_proposal_likelihood, src/MCMC.cpp:1175-1366) re-reads every clade's clade_like vector
+ * for each proposal: sum over the listed clades j of sum_{k >= 1} log(frac_j * clade_like[k] + clade_not_like[k] * (1/334)).
+ * `1/334` is an integer division, i.e. 0, and index 0 is the 0.0 the vector is created with (src/load.cpp:128), so the sum is
+ * like_n[c] * log(frac_j) + like_logsum[c] with, per clade, like_n = the number of reads scored for it and like_logsum = the
+ * sum of log(clade_like) over them -- accumulated by the read kernel since vgl_euka_reset.  vgl_euka_like_sums returns the two
+ * [n_clades] vectors (sum them over batches / GPUs), vgl_euka_proposal_loglike evaluates one proposal on the host (O(n_listed)). */
+int vgl_euka_like_sums(vgl_ctx* ctx, int64_t* like_n, double* like_logsum);
+double vgl_euka_proposal_loglike(int32_t n_listed, const int32_t* clade_ids, const double* frac, const int64_t* like_n,
+                                 const double* like_logsum);
 uint64_t vgl_euka_batch_bytes(const vgl_euka_batch* b);
 
 /* ------------------------------------------------------------------------------------------- */

@@ -261,6 +261,18 @@ def euka_run(clade_dist, bin_off, bin_lo, bin_hi, graph, reads, deam5p_prof="", 
     return out
 
 
+def euka_proposal_loglike(clade, like, not_like, n_clades, clade_ids, frac):
+    """MCMC::get_proposal_likelihood (src/MCMC.cpp:1175-1213) over the per-read outputs of euka_run."""
+    clade = np.ascontiguousarray(clade, dtype=np.int32)
+    like = np.ascontiguousarray(like, dtype=np.float64)
+    nl = np.ascontiguousarray(not_like, dtype=np.float64)
+    ids = np.ascontiguousarray(clade_ids, dtype=np.int32)
+    fr = np.ascontiguousarray(frac, dtype=np.float64)
+    f = lib().orc_euka_proposal_loglike
+    f.restype = C.c_longdouble
+    return float(f(C.c_int64(clade.size), C.c_int32(n_clades), _ptr(clade), _ptr(like), _ptr(nl), C.c_int32(ids.size), _ptr(ids), _ptr(fr)))
+
+
 def euka_deam_matrix(deam5p_prof, deam3p_prof, L, l):
     m = np.zeros(16)
     rc = lib().orc_euka_deam_matrix((deam5p_prof or "").encode(), (deam3p_prof or "").encode(), int(L), int(l), _ptr(m))

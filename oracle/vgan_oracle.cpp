@@ -1197,6 +1197,35 @@ int orc_soibean_mcmc_loglike(const orc_graph* g, const orc_reads* R, const uint8
     return ORC_OK;
 }
 
+// MCMC::get_proposal_likelihood (reference src/MCMC.cpp:1175-1213) for euka's abundance MCMC, literally: the per-clade
+// clade_like / clade_not_like vectors are rebuilt from the per-read values in read order -- each vector starts with the
+// 0.0 it is created with (src/load.cpp:128) and gets one entry per scored read (src/readGAM_Euka.h:491-492); reads with
+// clade < 0 were skipped -- and the loop starts at k = 1.  `1/334` is written as an integer division (:1191).
+long double orc_euka_proposal_loglike(int64_t n_reads, int32_t n_clades, const int32_t* clade, const double* like, const double* not_like,
+                                      int32_t n_listed, const int32_t* clade_list_id, const double* proposal_vec) {
+    vector<vector<double>> clade_like((size_t)n_clades, vector<double>{0.0}), clade_not_like((size_t)n_clades, vector<double>{0.0});
+    for (int64_t r = 0; r < n_reads; ++r) {
+        if (clade[r] < 0 || clade[r] >= n_clades) continue;
+        clade_like[(size_t)clade[r]].emplace_back(like[r]);
+        clade_not_like[(size_t)clade[r]].emplace_back(not_like[r]);
+    }
+    long double proposal_log_likelihood = 0.0;
+    vector<double> total_f_list;
+    for (int i = 0; i < n_listed; i++) {
+        total_f_list.emplace_back(clade_list_id[i]);
+        total_f_list.emplace_back(proposal_vec[i]);
+    }
+    for (size_t j = 0; j < total_f_list.size(); j += 2) {
+        const double frac = total_f_list.at(j + 1);
+        double total_frac = 0.0;
+        const size_t c = (size_t)total_f_list.at(j);
+        for (size_t k = 1; k < clade_like.at(c).size(); k++)
+            total_frac += log(((frac * clade_like.at(c).at(k)) + (clade_not_like.at(c).at(k) * (1 / 334))));
+        proposal_log_likelihood += total_frac;
+    }
+    return proposal_log_likelihood;
+}
+
 // subDeamDiNuc[L][l].p as 16 doubles (rounded from long double), for table tests.
 int orc_euka_deam_matrix(const char* deam5p, const char* deam3p, uint32_t L, uint32_t l, double* out16) {
     Damage dmg;

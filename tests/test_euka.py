@@ -97,6 +97,26 @@ def test_synthetic_reads_match_oracle(p5, p3):
         assert np.array_equal(count, want["clade_count"])
         assert np.allclose(cov, want["bin_cov"], rtol=1e-12) and np.array_equal(cov == 0, want["bin_cov"] == 0)
     assert want["pass"].sum() > 100 and set(np.unique(want["clade"])) >= set(range(40))
+    # abundance MCMC (MCMC::get_proposal_likelihood, src/MCMC.cpp:1175-1213): the per-clade sums the read kernel keeps are the
+    # reference's clade_like vectors reduced the way the proposal likelihood reads them (a mapping quality of 0 gives
+    # clade_like = 0 and log 0 = -inf, on both sides)
+    like_n, like_logsum = ek.like_sums()
+    assert np.array_equal(like_n, np.bincount(want["clade"][mapped], minlength=40))
+    with np.errstate(divide="ignore"):
+        logs = np.log(want["like"])
+    finite = 0
+    for c in range(40):
+        sel = mapped & (want["clade"] == c)
+        ref = logs[sel].sum()
+        if np.isfinite(ref):
+            finite += 1
+            assert abs(like_logsum[c] - ref) < 1e-9 * abs(ref)
+        else:
+            assert like_logsum[c] == -np.inf
+    listed, frac = [3, 17, 29], [0.2, 0.5, 0.3]
+    ll_want = orc.euka_proposal_loglike(np.where(mapped, want["clade"], -1), want["like"], want["not_like"], 40, listed, frac)
+    ll_got = vb.Euka.proposal_loglike(listed, frac, like_n, like_logsum)
+    assert (ll_got == ll_want == -np.inf) or abs(ll_got - ll_want) < 1e-9 * abs(ll_want)
     ek.close()
 
 
@@ -127,3 +147,23 @@ def test_symbol_cases_and_strands():
     count, cov = ek.results()
     assert np.array_equal(count, want["clade_count"]) and np.allclose(cov, want["bin_cov"], rtol=1e-14)
     ek.close()
+
+
+def test_oracle_proposal_likelihood_is_counts_and_log_sums():
+    """get_proposal_likelihood as written: index 0 of every clade_like vector is the 0.0 it was created with and is skipped,
+    `1/334` is an integer division, so a proposal's value is sum_j n_j log(frac_j) + sum log(clade_like)."""
+    rng = np.random.default_rng(3)
+    n, C_ = 500, 6
+    clade = rng.integers(-1, C_, size=n).astype(np.int32)
+    like = rng.uniform(0.01, 1.0, size=n)
+    not_like = 1 - like
+    ids, frac = [4, 0, 2], [0.5, 0.2, 0.3]
+    got = orc.euka_proposal_loglike(clade, like, not_like, C_, ids, frac)
+    want = sum((clade == c).sum() * np.log(f) + np.log(like[clade == c]).sum() for c, f in zip(ids, frac))
+    assert abs(got - want) < 1e-12 * abs(want)
+    # the clade_not_like term really is gone
+    assert orc.euka_proposal_loglike(clade, like, not_like * 7, C_, ids, frac) == got
+    # the product's host-side evaluation from the per-clade sums (no device needed for this one)
+    like_n = np.bincount(clade[clade >= 0], minlength=C_)
+    like_logsum = np.array([np.log(like[clade == c]).sum() for c in range(C_)])
+    assert abs(vb.Euka.proposal_loglike(ids, frac, like_n, like_logsum) - got) < 1e-12 * abs(got)

@@ -128,6 +128,8 @@ GPU_SYMBOLS = {
     "vgl_euka_reset": (C.c_int, [_P]),
     "vgl_euka_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_euka_results": (C.c_int, [_P, _P, _P]),
+    "vgl_euka_like_sums": (C.c_int, [_P, _P, _P]),
+    "vgl_euka_proposal_loglike": (C.c_double, [C.c_int32, _P, _P, _P, _P]),
     "vgl_euka_batch_bytes": (C.c_uint64, [C.POINTER(vgl_euka_batch)]),
     "vgl_soibean_set_tables": (C.c_int, [_P, C.POINTER(vgl_soibean_tables)]),
     "vgl_soibean_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P]),

@@ -128,6 +128,10 @@ euka_read_kernel(EukaBatchDev b, EukaTablesDev t, EukaOutDev o) {
         if (o.like) o.like[ridx] = like;
         if (o.pass) o.pass[ridx] = pass ? 1 : 0;
     }
+    // Clade::clade_like gets one entry per scored read (:491); the abundance MCMC only ever uses sum_k log(frac * clade_like[k])
+    // per clade (src/MCMC.cpp:1190-1193, where `1/334` is an integer division that removes the clade_not_like term)
+    atomicAdd(o.like_n + c_n, 1ull);
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(o.like_logsum + c_n), "d"(log(like)) : "memory");
     if (pass) {  // count the read and spread 1/M over the bins its nodes fall into (:504-549)
         atomicAdd(o.clade_count + c_n, 1ull);
         const double share = 1.0 / (double)nm;

@@ -157,7 +157,8 @@ struct vgl_ctx {
     DevBuf<double> e_dist, e_deam, e_bin_cov, e_in, e_not, e_like;
     DevBuf<int32_t> e_bin_off, e_bin_lo, e_bin_hi, e_clade;
     DevBuf<vgl::EukaSmallTables> e_small;
-    DevBuf<unsigned long long> e_count;
+    DevBuf<unsigned long long> e_count, e_like_n;
+    DevBuf<double> e_like_logsum;
     DevBuf<uint8_t> e_pass;
     // soibean
     bool have_soibean = false;
@@ -333,6 +334,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->e_node_clade.release(); ctx->e_dist.release(); ctx->e_deam.release(); ctx->e_bin_cov.release(); ctx->e_in.release();
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
+    ctx->e_like_n.release(); ctx->e_like_logsum.release();
     ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release();
     ctx->m_src.release(); ctx->m_partials.release(); ctx->m_loglike.release(); ctx->m_per_read.release(); ctx->m_H.release();
     if (ctx->m_pinned) cudaFreeHost(ctx->m_pinned);
@@ -1108,6 +1110,8 @@ int vgl_euka_set_tables(vgl_ctx* ctx, const vgl_euka_tables* T) {
     if (int rc = ctx->e_deam.reserve((size_t)T->k5 * T->k3 * 16)) return rc;
     if (int rc = ctx->e_small.reserve(1)) return rc;
     if (int rc = ctx->e_count.reserve((size_t)T->n_clades)) return rc;
+    if (int rc = ctx->e_like_n.reserve((size_t)T->n_clades)) return rc;
+    if (int rc = ctx->e_like_logsum.reserve((size_t)T->n_clades)) return rc;
     if (int rc = ctx->e_bin_cov.reserve(nb)) return rc;
     VGL_CUDA(cudaMemcpy(ctx->e_node_clade.p, node_clade.data(), node_clade.size() * 2, cudaMemcpyHostToDevice));
     VGL_CUDA(cudaMemcpy(ctx->e_dist.p, T->clade_dist, (size_t)T->n_clades * 8, cudaMemcpyHostToDevice));
@@ -1132,6 +1136,8 @@ int vgl_euka_reset(vgl_ctx* ctx) {
     if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
     VGL_CUDA(cudaMemsetAsync(ctx->e_count.p, 0, (size_t)ctx->etab.n_clades * sizeof(unsigned long long), ctx->stream));
     VGL_CUDA(cudaMemsetAsync(ctx->e_bin_cov.p, 0, (size_t)std::max(ctx->etab.n_bins, 1) * sizeof(double), ctx->stream));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_like_n.p, 0, (size_t)ctx->etab.n_clades * sizeof(unsigned long long), ctx->stream));
+    VGL_CUDA(cudaMemsetAsync(ctx->e_like_logsum.p, 0, (size_t)ctx->etab.n_clades * sizeof(double), ctx->stream));
     return VGL_OK;
 }
 
@@ -1165,6 +1171,25 @@ int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_
     if (int rc = pack_raw_symbols(ctx, raw, /*soibean=*/0, d, n_map_rec)) return rc;
     if (d.n_groups == 0) return VGL_OK;
     return euka_run_on_device(ctx, d, n_out, clade, in_lik, not_lik, like, pass);
+}
+
+int vgl_euka_like_sums(vgl_ctx* ctx, int64_t* like_n, double* like_logsum) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
+    cudaStream_t s = ctx->stream;
+    if (like_n) VGL_CUDA(cudaMemcpyAsync(like_n, ctx->e_like_n.p, (size_t)ctx->etab.n_clades * 8, cudaMemcpyDeviceToHost, s));
+    if (like_logsum) VGL_CUDA(cudaMemcpyAsync(like_logsum, ctx->e_like_logsum.p, (size_t)ctx->etab.n_clades * 8, cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    return VGL_OK;
+}
+
+double vgl_euka_proposal_loglike(int32_t n_listed, const int32_t* clade_ids, const double* frac, const int64_t* like_n, const double* like_logsum) {
+    double ll = 0.0;
+    for (int32_t j = 0; j < n_listed; ++j) {
+        const int32_t c = clade_ids[j];
+        if (like_n[c] > 0) ll += (double)like_n[c] * std::log(frac[j]) + like_logsum[c];
+    }
+    return ll;
 }
 
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov) {
@@ -1378,7 +1403,8 @@ int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out,
     VGL_CUDA(cudaMemsetAsync(ctx->e_not.p, 0, no * 8, s));
     VGL_CUDA(cudaMemsetAsync(ctx->e_like.p, 0, no * 8, s));
     VGL_CUDA(cudaMemsetAsync(ctx->e_pass.p, 0, no, s));
-    vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p};
+    vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p,
+                      ctx->e_like_n.p, ctx->e_like_logsum.p};
     VGL_CUDA(vgl::euka_launch_read_kernel(d, ctx->etab, o, s));
     ctx->launches += 1;
     if (clade) VGL_CUDA(cudaMemcpyAsync(clade, ctx->e_clade.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));

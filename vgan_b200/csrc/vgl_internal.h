@@ -234,6 +234,8 @@ struct EukaOutDev {
     uint8_t* pass;
     unsigned long long* clade_count;  // [n_clades]
     double* bin_cov;                  // [n_bins]
+    unsigned long long* like_n;       // [n_clades] entries appended to Clade::clade_like (every scored read, src/readGAM_Euka.h:491)
+    double* like_logsum;              // [n_clades] sum of log(clade_like) over them: all the abundance MCMC needs (src/MCMC.cpp:1175-1213)
 };
 
 cudaError_t euka_launch_read_kernel(const EukaBatchDev& b, const EukaTablesDev& t, const EukaOutDev& o, cudaStream_t s);

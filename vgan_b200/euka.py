@@ -120,6 +120,24 @@ class Euka:
         check(gpu.vgl_euka_results(self.ctx, count.ctypes.data_as(C.c_void_p), cov.ctypes.data_as(C.c_void_p)))
         return count, cov[:self.tables.n_bins]
 
+    def like_sums(self):
+        """Per clade, since reset(): the number of reads scored for it and the sum of log(clade_like) over them -- all that
+        euka's abundance MCMC reads (MCMC::get_proposal_likelihood, src/MCMC.cpp:1175-1213)."""
+        n = np.zeros(self.tables.n_clades, dtype=np.int64)
+        s = np.zeros(self.tables.n_clades, dtype=np.float64)
+        check(gpu.vgl_euka_like_sums(self.ctx, n.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)))
+        return n, s
+
+    @staticmethod
+    def proposal_loglike(clade_ids, frac, like_n, like_logsum):
+        """get_proposal_likelihood of one proposal: clade_ids = clade_list_id, frac = proposal_vec."""
+        ids = np.ascontiguousarray(clade_ids, dtype=np.int32)
+        fr = np.ascontiguousarray(frac, dtype=np.float64)
+        n = np.ascontiguousarray(like_n, dtype=np.int64)
+        s = np.ascontiguousarray(like_logsum, dtype=np.float64)
+        return float(gpu.vgl_euka_proposal_loglike(int(ids.size), ids.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p),
+                                                   n.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)))
+
     def launch_count(self):
         return int(gpu.vgl_launch_count(self.ctx))
 
