@@ -163,7 +163,8 @@ namespace {
 // K5a: one read per thread.  For edit i the reference evaluates, for every path, either the "supported" or the
 // "unsupported" sum over the slice of aligned columns; both are path independent, so they are computed once here.
 __global__ void __launch_bounds__(kEukaBlock)
-soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup, double* __restrict__ uns, int* __restrict__ err_flag) {
+soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup, double* __restrict__ uns, uint32_t* __restrict__ mcode,
+                    int* __restrict__ err_flag) {
     __shared__ EukaSmallTables s_tab;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(t.small);
@@ -199,6 +200,9 @@ soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup
         double s_sup = 0.0, s_uns = 0.0;
         int bor = baseIX;  // baseOnRead
         bool need_damage = false;
+        // for the MCMC kernel: how many regular columns of the edit pair A/A, C/C, G/G, T/T (7 bits each); bit 31: some regular
+        // column is not such a match (or a count overflowed) and the MCMC kernel has to walk the columns itself
+        uint32_t pairs = 0;
         for (int s = 0; s < len; ++s) {
             const uint32_t cr = col_at(start + s);
             const uint32_t q = col_at(s) & 0xffu;  // a.quality()[s]: indexed by the position INSIDE the slice
@@ -208,6 +212,8 @@ soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup
             else if (G == VGL_EUKA_SYM_GAP || R == VGL_EUKA_SYM_GAP) { s_sup += log_gap; s_uns += log_gap; }
             else {
                 need_damage = true;
+                if (G == R && G < 4 && ((pairs >> (7 * G)) & 127u) != 127u) pairs += 1u << (7 * G);
+                else pairs |= 0x80000000u;
                 if (baseIX >= 0 && baseIX < nc) {
                     const int i5 = min(baseIX, t.k5 - 1), i3 = min(nc - baseIX - 1, t.k3 - 1);
                     const double* __restrict__ D = t.deam + ((size_t)i5 * t.k3 + i3) * 4;  // row sums of the damage matrix
@@ -226,6 +232,7 @@ soibean_edit_kernel(EukaBatchDev b, SoibeanTablesDev t, double* __restrict__ sup
         if (need_damage && (rec & 0xFFFFFu) != VGL_SOIBEAN_NO_NODE && (baseIX < 0 || baseIX >= nc)) atomicOr(err_flag, 1);
         sup[mi] = s_sup;
         uns[mi] = s_uns;
+        mcode[mi] = pairs;
         baseIX = rev ? start : baseIX + size;
     }
 }
@@ -350,7 +357,7 @@ soibean_mcmc_tables_kernel(const vgl_soibean_source* __restrict__ sources, int n
 // is NOT written here: partials[q][blockIdx.x] go to soibean_mcmc_sum_kernel.
 __global__ void __launch_bounds__(kEukaBlock)
 soibean_mcmc_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict__ sup, const double* __restrict__ uns,
-                    const vgl_soibean_source* __restrict__ sources, const double* __restrict__ H, int n_proposals, int n_sources,
+                    const uint32_t* __restrict__ mcode, const vgl_soibean_source* __restrict__ sources, const double* __restrict__ H, int n_proposals, int n_sources,
                     int tile, uint32_t n_out, double* __restrict__ per_read, double* __restrict__ partials, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char mcmc_smem[];
     const int q0 = blockIdx.y * tile;
@@ -411,7 +418,15 @@ soibean_mcmc_kernel(EukaBatchDev b, SoibeanTablesDev t, const double* __restrict
                     }
                     const double sp = __ldg(sup + mi), u = __ldg(uns + mi);
                     double hc = 0.0, hp = 0.0;
-                    if (in_c || in_p) {
+                    const uint32_t pairs = (in_c || in_p) ? __ldg(mcode + mi) : 0u;
+                    if (!(pairs >> 31)) {  // every regular column pairs a base with itself: four counts, no column walk
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double n = (double)((pairs >> (7 * k)) & 127u);
+                            hc = fma(n, Hc[6 * k], hc);
+                            hp = fma(n, Hp[6 * k], hp);
+                        }
+                    } else {
                         for (int s = 0; s < len; ++s) {
                             const uint32_t cr = col_at(start + s);
                             const int G = (int)((cr >> 8) & 15u), R = (int)(cr >> 12);
@@ -478,7 +493,7 @@ __global__ void __launch_bounds__(32) soibean_mcmc_sum_kernel(const double* __re
 
 int soibean_mcmc_blocks(const EukaBatchDev& b) { return (int)((b.n_groups + kEukaBlock / 32 - 1) / (kEukaBlock / 32)); }
 
-cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns,
+cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns, const uint32_t* mcode,
                                 const vgl_soibean_source* sources, int n_proposals, int n_sources, const double* freqs7, double con,
                                 uint32_t n_out, double* per_read, double* H, double* partials, double* loglike, int* err_flag,
                                 cudaStream_t s) {
@@ -500,7 +515,7 @@ cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t
         const int nt = std::min(32768, tiles - t0);
         const int q0 = t0 * tile, nq = std::min(n_proposals - q0, nt * tile);
         soibean_mcmc_kernel<<<dim3((unsigned)nb, (unsigned)nt), kEukaBlock, per_q * tile, s>>>(
-            b, t, sup, uns, sources + (size_t)q0 * n_sources, H + (size_t)q0 * n_sources * 50, nq, n_sources, tile, n_out,
+            b, t, sup, uns, mcode, sources + (size_t)q0 * n_sources, H + (size_t)q0 * n_sources * 50, nq, n_sources, tile, n_out,
             per_read ? per_read + (size_t)q0 * n_out : nullptr, partials + (size_t)q0 * nb, err_flag);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -509,11 +524,11 @@ cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t
     return cudaGetLastError();
 }
 
-cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
+cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t* mcode, uint32_t n_out,
                            double* out, uint8_t* used, int* err_flag, cudaStream_t s) {
     if (b.n_groups == 0) return cudaSuccess;
     const int warps = kEukaBlock / 32;
-    soibean_edit_kernel<<<(b.n_groups + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, sup, uns, err_flag);
+    soibean_edit_kernel<<<(b.n_groups + warps - 1) / warps, kEukaBlock, 0, s>>>(b, t, sup, uns, mcode, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const uint32_t lanes = b.n_groups * 32u;

@@ -250,22 +250,23 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         const uint32_t open = rec & VGL_HC_COL_OPEN;
         // table entry: class id | ALLPATHS bit.  Class VGL_HC_CLASS_NONE: no pangenome_map entry -- the reference would
         // terminate; flag it and use the neutral entry
-        open_cls = open ? cls_raw : open_cls;
         const uint32_t cls = cls_raw & VGL_HC_CLASS_MASK;
+        const uint32_t fetch = open;  // (fetching only when the class differs from the previous mapping's saves L1 wavefronts but costs as many issue slots)
+        open_cls = open ? cls_raw : open_cls;
         bad_cls = max(bad_cls, cls);  // cls_raw is 0 where no mapping opens (predicated load)
         if (kAcMode == 0) {
             asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
                 : "+d"(aa), "+d"(cc)
-                : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
+                : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(fetch));
         } else {
             if (kAcMode == 1)
                 asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0,%1}, [%2];\n\t}"
                     : "+d"(mk_m), "+d"(mk_k)
-                    : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(open));
+                    : "r"(ac_row + 16u * min(cls, (uint32_t)S.n_class)), "r"(fetch));
             else
                 asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.f64 {%0,%1}, [%2];\n\t}"
                     : "+d"(mk_m), "+d"(mk_k)
-                    : "l"(S.class_tab + min(cls, (uint32_t)S.n_class)), "r"(open));
+                    : "l"(S.class_tab + min(cls, (uint32_t)S.n_class)), "r"(fetch));
             // p_correctly_mapped = (1 - p_incorrect[mq]) * mappability (src/process_mapping.cpp:41); consensus-FASTA mode
             // uses (1 - bep) * K alone (:73)
             const double pcm = pc * mk_m;

@@ -165,6 +165,7 @@ struct vgl_ctx {
     vgl::SoibeanTablesDev stab{};
     DevBuf<uint32_t> s_member;
     DevBuf<double> s_deam, s_sup, s_uns, s_out;
+    DevBuf<uint32_t> s_mcode;
     DevBuf<vgl::EukaSmallTables> s_small;
     DevBuf<uint8_t> s_used;
     DevBuf<int> s_err;
@@ -335,7 +336,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->e_not.release(); ctx->e_like.release(); ctx->e_bin_off.release(); ctx->e_bin_lo.release(); ctx->e_bin_hi.release();
     ctx->e_clade.release(); ctx->e_small.release(); ctx->e_count.release(); ctx->e_pass.release();
     ctx->e_like_n.release(); ctx->e_like_logsum.release();
-    ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release();
+    ctx->s_member.release(); ctx->s_deam.release(); ctx->s_sup.release(); ctx->s_uns.release(); ctx->s_out.release(); ctx->s_mcode.release();
     ctx->m_src.release(); ctx->m_partials.release(); ctx->m_loglike.release(); ctx->m_per_read.release(); ctx->m_H.release();
     if (ctx->m_pinned) cudaFreeHost(ctx->m_pinned);
     ctx->s_small.release(); ctx->s_used.release(); ctx->s_err.release();
@@ -1335,7 +1336,7 @@ int vgl_soibean_mcmc_loglike(vgl_ctx* ctx, int32_t n_proposals, int32_t n_source
     VGL_CUDA(cudaMemcpyAsync(ctx->m_src.p, ctx->m_pinned + out_bytes, in_bytes, cudaMemcpyHostToDevice, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
     if (per_read) VGL_CUDA(cudaMemsetAsync(ctx->m_per_read.p, 0, (size_t)n_proposals * n_out * 8, s));
-    VGL_CUDA(vgl::soibean_mcmc_launch(ctx->s_last, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->m_src.p, n_proposals, n_sources, freqs7, con,
+    VGL_CUDA(vgl::soibean_mcmc_launch(ctx->s_last, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->s_mcode.p, ctx->m_src.p, n_proposals, n_sources, freqs7, con,
                                       n_out, per_read ? ctx->m_per_read.p : nullptr, ctx->m_H.p, ctx->m_partials.p, ctx->m_loglike.p,
                                       ctx->s_err.p, s));
     ctx->launches += 3;
@@ -1366,12 +1367,13 @@ int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map
     const size_t P = (size_t)ctx->stab.n_paths, no = std::max<size_t>(n_out, 1);
     if (int rc = ctx->s_sup.reserve(nmap)) return rc;
     if (int rc = ctx->s_uns.reserve(nmap)) return rc;
+    if (int rc = ctx->s_mcode.reserve(nmap)) return rc;
     if (int rc = ctx->s_out.reserve(no * P)) return rc;
     if (int rc = ctx->s_used.reserve(no)) return rc;
     VGL_CUDA(cudaMemsetAsync(ctx->s_out.p, 0, no * P * 8, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_used.p, 0, no, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
-    VGL_CUDA(vgl::soibean_launch(d, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, n_out, ctx->s_out.p, ctx->s_used.p, ctx->s_err.p, s));
+    VGL_CUDA(vgl::soibean_launch(d, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->s_mcode.p, n_out, ctx->s_out.p, ctx->s_used.p, ctx->s_err.p, s));
     ctx->launches += 2;
     int err = 0;
     VGL_CUDA(cudaMemcpyAsync(&err, ctx->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -251,15 +251,15 @@ struct SoibeanTablesDev {
 };
 
 // K5a: per read and edit, the "supported" and "unsupported" sums over the edit's slice -> sup / uns (indexed like the
-//      edit records); K5b: out[read][p] = sum over edits of (path p goes through the edit's node ? sup : uns).
-cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t n_out,
+//      edit records), mcode = the edit's match-pair counts for the MCMC kernel; K5b: out[read][p] = sum over edits of (path p goes through the edit's node ? sup : uns).
+cudaError_t soibean_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, double* sup, double* uns, uint32_t* mcode, uint32_t n_out,
                            double* out, uint8_t* used, int* err_flag, cudaStream_t s);
 
 // soibean MCMC: loglike[q] = sum over the batch's reads of the per-read log-likelihood under proposal q (sources[q][n_sources]),
 // loglike[n_proposals] = the error flag; per_read (optional) [n_proposals][n_out]; scratch: H [n_proposals][n_sources][50],
 // partials [n_proposals][soibean_mcmc_blocks(b)].  sup / uns as K5a left them.  Launches 2 + number of 32768-tile slices kernels.
 int soibean_mcmc_blocks(const EukaBatchDev& b);
-cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns,
+cudaError_t soibean_mcmc_launch(const EukaBatchDev& b, const SoibeanTablesDev& t, const double* sup, const double* uns, const uint32_t* mcode,
                                 const vgl_soibean_source* sources, int n_proposals, int n_sources, const double* freqs7, double con,
                                 uint32_t n_out, double* per_read, double* H, double* partials, double* loglike, int* err_flag,
                                 cudaStream_t s);
