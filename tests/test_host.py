@@ -340,3 +340,38 @@ def test_wire_form_of_a_packed_batch():
         opens = [r >> 15 for r in reversed(recs) if r & 0x2000]
         assert n16[:len(opens)].tolist() == opens and not n16[len(opens):].any()
     assert wb.nbytes < 0.8 * pb.nbytes
+
+
+def _bgzf(data, block=1500):
+    """BGZF as htslib / vg write it: gzip members with a 'BC' extra subfield carrying the member size, then the empty EOF member."""
+    import struct, zlib
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = c.compress(chunk) + c.flush()
+        bsize = 12 + 6 + len(payload) + 8
+        out += b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += payload + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk))
+    return bytes(out)
+
+
+def test_gam_reader_inflates_bgzf_members_in_parallel_and_plain_gzip_serially():
+    import gzip
+    alns = [H.aln("ACGT" * (3 + k % 5), [(1 + k % 7, k % 3, bool(k & 1), [(4, 4, ""), (1, 1, "T"), (7 + k % 5, 7 + k % 5, "")])], mapq=k % 61)
+            for k in range(700)]
+    raw = H.encode_gam(alns, group=64)
+    want = vb.Alignments.from_gam_bytes(raw).arrays()
+    forms = {"bgzf": _bgzf(raw), "bgzf big blocks": _bgzf(raw, block=60000), "one gzip member": gzip.compress(raw),
+             "two gzip members": gzip.compress(raw[:5000]) + gzip.compress(raw[5000:])}
+    assert len(forms["bgzf"]) > 20 * 18                        # many members
+    for name, blob in forms.items():
+        got = vb.Alignments.from_gam_bytes(blob).arrays()
+        assert set(got) == set(want), name
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (name, k)
+    # a flipped payload byte fails the member's CRC / size check instead of yielding other reads
+    broken = bytearray(forms["bgzf"])
+    broken[40] ^= 0x55
+    with pytest.raises(Exception):
+        vb.Alignments.from_gam_bytes(bytes(broken))

@@ -157,10 +157,80 @@ bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
     return true;
 }
 
+// BGZF (what vg writes): a series of gzip members of at most 64 KB, each carrying its own compressed size in a "BC" extra
+// subfield and its uncompressed size in the trailer.  The members are found by hopping from header to header, their
+// output offsets are a prefix sum, and they inflate independently -- in parallel.  Returns false (out untouched) when the
+// stream is not made of such members from start to end; the caller then inflates serially.
+struct BgzfMember { size_t payload, payload_len, out_off; uint32_t isize, crc; };
+bool bgzf_members(const uint8_t* in, size_t n, std::vector<BgzfMember>& ms, size_t& total) {
+    size_t p = 0;
+    total = 0;
+    while (p < n) {
+        if (n - p < 18 || in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) return false;
+        if (in[p + 3] & ~4) return false;  // FNAME / FCOMMENT / FHCRC: not BGZF
+        const size_t xlen = (size_t)in[p + 10] | ((size_t)in[p + 11] << 8);
+        if (n - p < 12 + xlen + 8) return false;
+        size_t bsize = 0;
+        for (size_t q = p + 12; q + 4 <= p + 12 + xlen;) {
+            const size_t slen = (size_t)in[q + 2] | ((size_t)in[q + 3] << 8);
+            if (in[q] == 'B' && in[q + 1] == 'C' && slen == 2 && q + 6 <= p + 12 + xlen) bsize = ((size_t)in[q + 4] | ((size_t)in[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || bsize > n - p) return false;
+        const uint8_t* tail = in + p + bsize - 8;
+        BgzfMember m;
+        m.payload = p + 12 + xlen;
+        m.payload_len = bsize - (12 + xlen) - 8;
+        m.crc = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
+        m.isize = (uint32_t)tail[4] | ((uint32_t)tail[5] << 8) | ((uint32_t)tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        m.out_off = total;
+        total += m.isize;
+        ms.push_back(m);
+        p += bsize;
+    }
+    return !ms.empty();
+}
+
+int inflate_bgzf(const uint8_t* in, const std::vector<BgzfMember>& ms, size_t total, std::vector<uint8_t>& out) {
+    out.resize(total);
+    int bad = 0;
+#pragma omp parallel
+    {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        const bool ready = inflateInit2(&zs, -MAX_WBITS) == Z_OK;  // raw deflate: header and trailer are handled here
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t k = 0; k < (int64_t)ms.size(); ++k) {
+            const BgzfMember& m = ms[(size_t)k];
+            if (!ready) { bad = 1; continue; }
+            if (m.isize == 0) continue;  // the empty end-of-file member
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef*>(in + m.payload);
+            zs.avail_in = (uInt)m.payload_len;
+            zs.next_out = out.data() + m.out_off;
+            zs.avail_out = m.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + m.out_off, m.isize) != m.crc) {
+#pragma omp atomic write
+                bad = 1;
+            }
+        }
+        if (ready) inflateEnd(&zs);
+    }
+    if (bad) return fail(VGH_ERR_FORMAT, "BGZF member corrupt (size or CRC mismatch)");
+    return VGH_OK;
+}
+
 int inflate_all(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
     if (n < 2 || in[0] != 0x1f || in[1] != 0x8b) {  // not gzip: plain stream
         out.assign(in, in + n);
         return VGH_OK;
+    }
+    {
+        std::vector<BgzfMember> ms;
+        size_t total = 0;
+        if (bgzf_members(in, n, ms, total)) return inflate_bgzf(in, ms, total, out);
     }
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
@@ -215,15 +285,21 @@ int vgh_graph_view(const vgh_graph* g, int64_t* min_id, int64_t* n_nodes, const 
 
 int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
     if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
-    std::vector<uint8_t> raw;
-    if (int rc = inflate_all((const uint8_t*)bytes, n, raw)) return rc;
+    std::vector<uint8_t> inflated;
+    const uint8_t* raw_p = (const uint8_t*)bytes;
+    size_t raw_n = n;
+    if (n >= 2 && raw_p[0] == 0x1f && raw_p[1] == 0x8b) {  // gzip / BGZF; a plain stream is parsed where it lies
+        if (int rc = inflate_all(raw_p, n, inflated)) return rc;
+        raw_p = inflated.data();
+        raw_n = inflated.size();
+    }
     // Pass 1 (serial, a few GB/s): walk the framing -- groups of "count, type tag, count-1 length-prefixed messages" -- and
     // note where every vg.Alignment starts and ends.  Pass 2 (parallel): threads parse contiguous ranges of messages into
     // pieces of their own; the pieces are then appended in order.  readGAM itself (vg::io::for_each, src/readGAM.h:20-68) is
     // single-threaded protobuf parsing.
     std::vector<std::pair<const uint8_t*, const uint8_t*>> msgs;
     {
-        Cursor c{raw.data(), raw.data() + raw.size(), true};
+        Cursor c{raw_p, raw_p + raw_n, true};
         while (c.ok && c.p < c.end) {
             const uint64_t count = c.varint();  // group: count, then the "GAM" tag, then count-1 messages
             for (uint64_t k = 0; c.ok && k < count; ++k) {
