@@ -225,7 +225,7 @@ def main():
     packed = vb.PackedBatch(S.graph, alns, pinned=True)
     t_pack = time.perf_counter() - t_pack
     dev = hc.upload(packed)
-    # the e2e route ships the batch in its wire form (16-bit column records + one node id per mapping) and expands it on
+    # the e2e route ships the batch in its wire form (12- or 16-bit column records + one node id per mapping) and expands it on
     # the device; graphs with node ids above 65535 would ship the 32-bit batch itself
     try:
         wire = vb.WireBatch(packed, pinned=True)
@@ -396,7 +396,7 @@ def main():
                        "called_haplogroup": res.get("predicted_haplotype")},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_batch.nbytes,
-                    "route": "vgl_hc_accumulate_wire (wire form, expanded on the device)" if wire is not None else "vgl_hc_accumulate", "d2h_bytes_per_step": 28 + 8 * hc._max_post,
+                    "route": ("vgl_hc_accumulate_wire (wire form, %s columns, expanded on the device)" % ("12-bit" if wire.wire.col8 else "16-bit")) if wire is not None else "vgl_hc_accumulate", "d2h_bytes_per_step": 28 + 8 * hc._max_post,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "raw_path": raw_path,
             "latency": latency,

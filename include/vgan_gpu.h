@@ -237,6 +237,17 @@ typedef struct vgl_hc_wire {
     const uint16_t* n_close;      /* [n_groups * 32] */
     const uint16_t* n_extra;      /* [n_groups * 32] */
     const uint8_t* mapq;          /* [n_groups * 32] */
+    /* NARROW column records (optional: all three NULL, or all three present and then `col` is not read).  When every
+     * quality byte of the batch is <= 63 -- which also means that no mapping is LATCHED -- a column is 12 bits instead of 16:
+     *   col8  [n_col_blks][32][8]  one byte per column: bits 0-5 quality, bits 6-7 read base
+     *   flag4 [n_col_blks][32]     one 32-bit word per lane and block, 4 bits per column (column j in bits 4j .. 4j+3):
+     *                              bit 0 MISMATCH, bit 1 OPEN, bit 2 CLOSE, bit 3 VALID
+     *   n_owned [n_groups * 32]    columns a mapping owns: the first n_owned of the read (the columns past the last
+     *                              mapping's end are the only ones nobody owns)
+     * Bytes per read: 1.5 n + 2 M' + 9 -- 269 instead of 319 at config 2.                                            */
+    const uint8_t* col8;
+    const uint32_t* flag4;
+    const uint16_t* n_owned;
 } vgl_hc_wire;
 uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w);
 

@@ -184,6 +184,7 @@ def test_wire_form_gives_the_same_results(small):
     hc = vb.Haplocart()
     hc.load(small.tables(bep=2e-3), small.tree())
     edge = vb.Alignments.from_gam_bytes(H.encode_gam(_edge_reads(small)))
+    narrow = 0
     for alns, bep in ((small.reads(5000, seed=305, sub_rate=0.01, indel_rate=0.003), 2e-3),
                       (small.reads(700, seed=306, fixed_len=0, damage=True, sub_rate=0.03, indel_rate=0.02), 2e-3), (edge, 2e-3)):
         packed = vb.PackedBatch(small.graph, alns, pinned=True)
@@ -199,6 +200,14 @@ def test_wire_form_gives_the_same_results(small):
         assert np.allclose(got["final_vec"], want["final_vec"], rtol=1e-13, atol=0)
         final, argmax, _ = _oracle(small, alns, bep=bep)
         _check(got, final, argmax, small)
+        if wire.wire.col8:                                      # narrow (12-bit) columns were used: the 16-bit ones give the same
+            narrow += 1
+            wire.wire.col8 = wire.wire.flag4 = wire.wire.n_owned = None
+            hc.reset()
+            hc.update_wire(wire)
+            wide = hc.get_posterior()
+            assert wide["maxh_index"] == want["maxh_index"] and np.allclose(wide["final_vec"], want["final_vec"], rtol=1e-13, atol=0)
+    assert narrow >= 2
     hc.close()
 
 

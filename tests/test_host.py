@@ -340,6 +340,28 @@ def test_wire_form_of_a_packed_batch():
         opens = [r >> 15 for r in reversed(recs) if r & 0x2000]
         assert n16[:len(opens)].tolist() == opens and not n16[len(opens):].any()
     assert wb.nbytes < 0.8 * pb.nbytes
+    # narrow columns (12 bits): present because every quality is <= 63, and they decode to the same 16-bit records
+    assert w.col8 and w.flag4 and w.n_owned
+    c8 = vb.host._as_array(w.col8, int(w.n_col_blks) * 256, np.uint8).reshape(-1, 32, 8)
+    f4 = vb.host._as_array(w.flag4, int(w.n_col_blks) * 32, np.uint32).reshape(-1, 32)
+    own = vb.host._as_array(w.n_owned, G * 32, np.uint16)
+    for k, d in enumerate(lanes):
+        g, l = divmod(k, 32)
+        byte = c8[gc[g]:gc[g + 1], l, :].reshape(-1).astype(np.uint32)
+        word = f4[gc[g]:gc[g + 1], l]
+        nib = np.array([(int(word[c // 8]) >> (4 * (c % 8))) & 0xF for c in range(byte.size)], dtype=np.uint32)
+        c = np.arange(byte.size)
+        rec = (byte & 0x3F) | ((nib & 1) << 8) | ((byte >> 6) << 10) | ((nib & 8) << 9) | ((nib & 2) << 12) | ((nib & 4) << 12) | \
+              np.where(c < own[k], 0x8000, 0).astype(np.uint32)
+        assert np.array_equal(rec.astype(np.uint16), col[gc[g]:gc[g + 1], l, :].reshape(-1)), k
+    narrow_bytes = wb.nbytes
+    w.col8 = None
+    assert wb.nbytes > narrow_bytes * 1.12                     # the 16-bit columns are what is counted now
+    # a quality byte above 63 (here: a latching one) keeps the whole batch on 16-bit columns
+    hi = [H.aln("ACGTACGT", [(1, 0, False, [(8, 8, "")])], quality=bytes([30, 30, 95, 30, 30, 30, 30, 30]))]
+    g1 = vb.Graph.from_sequences({1: "ACGTACGTAC"})
+    wb2 = vb.WireBatch(vb.PackedBatch(g1, vb.Alignments.from_gam_bytes(H.encode_gam(hi))))
+    assert not wb2.wire.col8 and not wb2.wire.flag4 and not wb2.wire.n_owned
 
 
 def _bgzf(data, block=1500):

@@ -30,7 +30,7 @@ class vgl_hc_wire(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_node_blks", C.c_uint64),
                 ("n_map_blks", C.c_uint64), ("grp_col_blk", C.c_void_p), ("grp_node_blk", C.c_void_p), ("grp_map_blk", C.c_void_p),
                 ("col", C.c_void_p), ("node", C.c_void_p), ("map", C.c_void_p), ("n_cols", C.c_void_p), ("n_close", C.c_void_p),
-                ("n_extra", C.c_void_p), ("mapq", C.c_void_p)]
+                ("n_extra", C.c_void_p), ("mapq", C.c_void_p), ("col8", C.c_void_p), ("flag4", C.c_void_p), ("n_owned", C.c_void_p)]
 
 
 class vgl_hc_raw(C.Structure):

@@ -801,6 +801,8 @@ int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, v
     const size_t o_gc = take((G + 1) * 4), o_gn = take((G + 1) * 4), o_gm = take((G + 1) * 4);
     const size_t o_col = take((size_t)g_c16[G] * 512), o_node = take((size_t)g_n16[G] * 512), o_map = take(n_map_rec * 4);
     const size_t o_nc = take(lanes * 2), o_ncl = take(lanes * 2), o_nx = take(lanes * 2), o_mq = take(lanes);
+    // narrow column records (12 bits per column), used when every column of the batch qualifies
+    const size_t o_c8 = take((size_t)g_c16[G] * 256), o_f4 = take((size_t)g_c16[G] * 128), o_own = take(lanes * 2);
     vgh_hc_wire* W = new vgh_hc_wire();
     W->pinned = pinned != 0;
     const size_t bytes = std::max<size_t>(o, 256);
@@ -824,27 +826,46 @@ int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, v
     memcpy(base + o_ncl, b.n_close, lanes * 2);
     memcpy(base + o_nx, b.n_extra, lanes * 2);
     memcpy(base + o_mq, b.mapq, lanes);
-#pragma omp parallel for schedule(static) num_threads(n_threads)
+    uint8_t* col8 = base + o_c8;
+    uint32_t* flag4 = (uint32_t*)(base + o_f4);
+    uint16_t* n_owned = (uint16_t*)(base + o_own);
+    bool narrow = true;  // every quality <= 63, no LATCHED column, VALID only on owned columns, the owned columns a prefix
+#pragma omp parallel for schedule(static) num_threads(n_threads) reduction(&& : narrow)
     for (int64_t g = 0; g < (int64_t)G; ++g) {
         const uint32_t cb0 = b.grp_col_blk[g];
         uint16_t* gcol = col + (size_t)g_c16[(size_t)g] * 256;
         uint16_t* gnode = node + (size_t)g_n16[(size_t)g] * 256;
+        uint8_t* gc8 = col8 + (size_t)g_c16[(size_t)g] * 256;
+        uint32_t* gf4 = flag4 + (size_t)g_c16[(size_t)g] * 32;
         memset(gcol, 0, (size_t)(g_c16[(size_t)g + 1] - g_c16[(size_t)g]) * 512);
         memset(gnode, 0, (size_t)(g_n16[(size_t)g + 1] - g_n16[(size_t)g]) * 512);
+        memset(gc8, 0, (size_t)(g_c16[(size_t)g + 1] - g_c16[(size_t)g]) * 256);
+        memset(gf4, 0, (size_t)(g_c16[(size_t)g + 1] - g_c16[(size_t)g]) * 128);
         for (uint32_t l = 0; l < VGL_HC_LANES; ++l) {
             const uint32_t L = b.n_cols[(size_t)g * VGL_HC_LANES + l];
             uint32_t k = 0;  // nodes are listed in the order a walk from the last column meets the OPEN marks
+            uint32_t owned = 0;      // owned columns seen so far; they must be columns 0 .. owned - 1
+            bool seen_owned = false; // walking down from the last column: once a column is owned, all below it must be
             for (uint32_t cc = L; cc > 0; --cc) {
                 const uint32_t c = cc - 1;
                 const uint32_t rec = b.col[(((size_t)cb0 + c / VGL_HC_COL_BLK) * VGL_HC_LANES + l) * VGL_HC_COL_BLK + c % VGL_HC_COL_BLK];
                 const uint32_t nd = VGL_HC_COL_NODE(rec);
-                gcol[((size_t)(c / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l) * VGL_HC_WIRE_BLK + c % VGL_HC_WIRE_BLK] =
-                    (uint16_t)((rec & 0x7fffu) | (nd != VGL_HC_NO_NODE ? VGL_HC_WIRE_OWNED : 0u));
+                const bool own = nd != VGL_HC_NO_NODE;
+                const size_t at = ((size_t)(c / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l) * VGL_HC_WIRE_BLK + c % VGL_HC_WIRE_BLK;
+                gcol[at] = (uint16_t)((rec & 0x7fffu) | (own ? VGL_HC_WIRE_OWNED : 0u));
                 if (rec & VGL_HC_COL_OPEN) {
                     gnode[((size_t)(k / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l) * VGL_HC_WIRE_BLK + k % VGL_HC_WIRE_BLK] = (uint16_t)nd;
                     ++k;
                 }
+                // narrow form of the same record
+                if ((rec & 0xffu) > 63u || (rec & VGL_HC_COL_LATCHED) || ((rec & VGL_HC_COL_VALID) && !own) || (seen_owned && !own)) narrow = false;
+                if (own) { seen_owned = true; ++owned; }
+                gc8[at] = (uint8_t)((rec & 0x3fu) | (VGL_HC_COL_BASE(rec) << 6));
+                const uint32_t nib = ((rec & VGL_HC_COL_MISMATCH) ? 1u : 0u) | ((rec & VGL_HC_COL_OPEN) ? 2u : 0u) |
+                                     ((rec & VGL_HC_COL_CLOSE) ? 4u : 0u) | ((rec & VGL_HC_COL_VALID) ? 8u : 0u);
+                gf4[(size_t)(c / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l] |= nib << (4 * (c % VGL_HC_WIRE_BLK));
             }
+            n_owned[(size_t)g * VGL_HC_LANES + l] = (uint16_t)owned;
         }
     }
     vgl_hc_wire& v = W->view;
@@ -853,6 +874,7 @@ int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, v
     v.grp_col_blk = gc; v.grp_node_blk = gn; v.grp_map_blk = gm; v.col = col; v.node = node; v.map = map;
     v.n_cols = (const uint16_t*)(base + o_nc); v.n_close = (const uint16_t*)(base + o_ncl); v.n_extra = (const uint16_t*)(base + o_nx);
     v.mapq = base + o_mq;
+    if (narrow) { v.col8 = col8; v.flag4 = flag4; v.n_owned = n_owned; }
     *out = W;
     return VGH_OK;
 }

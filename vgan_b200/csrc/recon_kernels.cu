@@ -523,9 +523,13 @@ sym_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, int soibean,
 // Wire form -> 32-bit column records (include/vgan_gpu.h, vgl_hc_wire).  One thread per lane, walking from the read's last
 // column: an OPEN mark takes the next node id of the lane's node stream, every owned column down to the mapping's first
 // gets it.  Group g of the chunk owns 32-bit blocks [2 (c16[g] - c16[0]), 2 (c16[g+1] - c16[0])): twice its 16-bit blocks.
+// kNarrow: the columns arrive as one byte (quality | base << 6) plus four flag bits each (col8 / flag4 / n_owned of vgl_hc_wire)
+// instead of 16-bit records; the 16-bit record is put together here and the rest of the walk is the same.
+template <bool kNarrow>
 __global__ void __launch_bounds__(128)
 hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const uint32_t* __restrict__ grp_n16,
-                 const uint16_t* __restrict__ col16, const uint16_t* __restrict__ node16, const uint16_t* __restrict__ n_cols,
+                 const uint16_t* __restrict__ col16, const uint8_t* __restrict__ col8, const uint32_t* __restrict__ flag4,
+                 const uint16_t* __restrict__ n_owned, const uint16_t* __restrict__ node16, const uint16_t* __restrict__ n_cols,
                  uint32_t* __restrict__ col32, uint32_t* __restrict__ grp_c32) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t g = slot >> 5, lane = slot & 31;
@@ -539,16 +543,36 @@ hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const 
     const uint4* nsrc = reinterpret_cast<const uint4*>(node16) + (size_t)grp_n16[g] * 32 + lane;  // node block k: nsrc[k * 32]
     uint4* dst = reinterpret_cast<uint4*>(col32) + (size_t)2 * (cb0 - c0) * 32 + lane;            // 32-bit block k: dst[k * 32]
     const uint32_t L = n_cols[slot];
+    uint32_t n_own = 0;
+    if constexpr (kNarrow) n_own = n_owned[slot];
+    const uint2* src8 = reinterpret_cast<const uint2*>(col8) + (size_t)cb0 * 32 + lane;  // narrow block k: src8[k * 32], flag4 likewise
+    const uint32_t* srcf = flag4 + (size_t)cb0 * 32 + lane;
     uint32_t n_used = 0, cur = VGL_HC_NO_NODE;
     uint4 nodes = make_uint4(0, 0, 0, 0);
     for (int cb = (int)ncb - 1; cb >= 0; --cb) {
-        const uint4 v = src[(size_t)cb * 32];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint2 a = make_uint2(0, 0);
+        uint32_t fl = 0;
+        if constexpr (kNarrow) {
+            a = src8[(size_t)cb * 32];
+            fl = srcf[(size_t)cb * 32];
+        } else {
+            const uint4 v = src[(size_t)cb * 32];
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
         uint32_t out[8];
 #pragma unroll
         for (int j = 7; j >= 0; --j) {
-            const uint32_t rec = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
             const uint32_t c = (uint32_t)cb * 8 + j;
+            uint32_t rec;
+            if constexpr (kNarrow) {
+                const uint32_t byte = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+                const uint32_t nib = (fl >> (4 * j)) & 0xfu;
+                rec = (byte & 0x3fu) | ((nib & 1u) << 8) | ((byte >> 6) << 10) | ((nib & 8u) << 9) | ((nib & 2u) << 12) | ((nib & 4u) << 12) |
+                      (c < n_own ? VGL_HC_WIRE_OWNED : 0u);
+            } else {
+                rec = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            }
             if (c >= L) { out[j] = 0; continue; }
             if (rec & VGL_HC_COL_OPEN) {
                 if ((n_used & 7u) == 0) nodes = nsrc[(size_t)(n_used >> 3) * 32];
@@ -567,9 +591,12 @@ hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const 
 }  // namespace
 
 cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const uint32_t* grp_n16, const uint16_t* col16,
-                             const uint16_t* node16, const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s) {
+                             const uint8_t* col8, const uint32_t* flag4, const uint16_t* n_owned, const uint16_t* node16,
+                             const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s) {
     if (n_groups == 0) return cudaSuccess;
-    hc_expand_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(n_groups, grp_c16, grp_n16, col16, node16, n_cols, col32, grp_c32);
+    const unsigned grid = (n_groups * 32 + 127) / 128;
+    if (col8) hc_expand_kernel<true><<<grid, 128, 0, s>>>(n_groups, grp_c16, grp_n16, col16, col8, flag4, n_owned, node16, n_cols, col32, grp_c32);
+    else hc_expand_kernel<false><<<grid, 128, 0, s>>>(n_groups, grp_c16, grp_n16, col16, col8, flag4, n_owned, node16, n_cols, col32, grp_c32);
     return cudaGetLastError();
 }
 

@@ -139,7 +139,9 @@ struct vgl_ctx {
         DevBuf<uint16_t> n_cols, n_close, n_extra;
         DevBuf<uint8_t> mapq;
         DevBuf<uint32_t> grp_c16, grp_n16;  // wire form of the chunk (vgl_hc_wire)
-        DevBuf<uint16_t> col16, node16;
+        DevBuf<uint16_t> col16, node16, n_owned;
+        DevBuf<uint8_t> col8;  // narrow columns of the wire form
+        DevBuf<uint32_t> flag4;
         cudaEvent_t copied = nullptr, consumed = nullptr;
         bool used = false;
     } slot[2];
@@ -328,7 +330,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     for (auto& sl : ctx->slot) {
         sl.grp_col_blk.release(); sl.grp_map_blk.release(); sl.map.release(); sl.col.release(); sl.n_cols.release();
         sl.n_close.release(); sl.n_extra.release(); sl.mapq.release();
-        sl.grp_c16.release(); sl.grp_n16.release(); sl.col16.release(); sl.node16.release();
+        sl.grp_c16.release(); sl.grp_n16.release(); sl.col16.release(); sl.node16.release(); sl.col8.release(); sl.flag4.release(); sl.n_owned.release();
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.consumed) cudaEventDestroy(sl.consumed);
     }
@@ -859,7 +861,9 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
 
 uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w) {
     if (!w) return 0;
-    return (uint64_t)(w->n_groups + 1) * 12 + (w->n_col_blks + w->n_node_blks + w->n_map_blks) * 512 + (uint64_t)w->n_groups * VGL_HC_LANES * 7;
+    const bool narrow = w->col8 && w->flag4 && w->n_owned;
+    const uint64_t cols = narrow ? w->n_col_blks * (256 + 128) + (uint64_t)w->n_groups * VGL_HC_LANES * 2 : w->n_col_blks * 512;
+    return (uint64_t)(w->n_groups + 1) * 12 + cols + (w->n_node_blks + w->n_map_blks) * 512 + (uint64_t)w->n_groups * VGL_HC_LANES * 7;
 }
 
 int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
@@ -869,8 +873,11 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
     if (w->n_groups == 0) return VGL_OK;
     if ((uint64_t)w->n_groups * VGL_HC_LANES < w->n_reads) return fail(VGL_ERR_INVALID, "n_groups too small for n_reads");
     if (!w->grp_col_blk || !w->grp_node_blk || !w->grp_map_blk || !w->n_cols || !w->n_close || !w->n_extra || !w->mapq ||
-        (w->n_col_blks && !w->col) || (w->n_node_blks && !w->node) || (w->n_map_blks && !w->map))
+        (w->n_node_blks && !w->node) || (w->n_map_blks && !w->map))
         return fail(VGL_ERR_INVALID, "wire batch arrays missing");
+    const bool narrow = w->col8 && w->flag4 && w->n_owned;  // 12-bit columns; otherwise the 16-bit records
+    if (!narrow && (w->col8 || w->flag4 || w->n_owned)) return fail(VGL_ERR_INVALID, "col8, flag4 and n_owned come together");
+    if (!narrow && w->n_col_blks && !w->col) return fail(VGL_ERR_INVALID, "wire batch arrays missing");
     // As vgl_hc_accumulate: chunks of groups, two staging slots, the H2D copy of a chunk overlaps the kernels of the one
     // before.  Each chunk is expanded into 32-bit records on the device before the read kernel runs on it.
     const uint32_t G = w->n_groups;
@@ -888,8 +895,8 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
         const size_t ncol32 = (size_t)(c1 - c0) * 2 * 128;
         vgl_ctx::Slot& sl = ctx->slot[n_chunk & 1];
         if (sl.used) VGL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, sl.consumed, 0));  // the kernels that last read this slot
-        if (ng + 1 > sl.grp_c16.cap || ncol16 > sl.col16.cap || nnode16 > sl.node16.cap || ncol32 > sl.col.cap || nmap > sl.map.cap ||
-            ng + 1 > sl.grp_col_blk.cap)
+        if (ng + 1 > sl.grp_c16.cap || (!narrow && ncol16 > sl.col16.cap) || (narrow && (ncol16 > sl.col8.cap || ncol16 / 8 > sl.flag4.cap || nl > sl.n_owned.cap)) ||
+            nnode16 > sl.node16.cap || ncol32 > sl.col.cap || nmap > sl.map.cap || ng + 1 > sl.grp_col_blk.cap)
             VGL_CUDA(cudaStreamSynchronize(ctx->stream));
         if (int rc = sl.grp_c16.reserve((size_t)ng + 1)) return rc;
         if (int rc = sl.grp_n16.reserve((size_t)ng + 1)) return rc;
@@ -899,7 +906,13 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
         if (int rc = sl.n_close.reserve(nl)) return rc;
         if (int rc = sl.n_extra.reserve(nl)) return rc;
         if (int rc = sl.mapq.reserve(nl)) return rc;
-        if (int rc = sl.col16.reserve(std::max<size_t>(ncol16, 1))) return rc;
+        if (narrow) {
+            if (int rc = sl.col8.reserve(std::max<size_t>(ncol16, 1))) return rc;
+            if (int rc = sl.flag4.reserve(std::max<size_t>(ncol16 / 8, 1))) return rc;
+            if (int rc = sl.n_owned.reserve(nl)) return rc;
+        } else {
+            if (int rc = sl.col16.reserve(std::max<size_t>(ncol16, 1))) return rc;
+        }
         if (int rc = sl.node16.reserve(std::max<size_t>(nnode16, 1))) return rc;
         if (int rc = sl.col.reserve(std::max<size_t>(ncol32, 1))) return rc;
         if (int rc = sl.map.reserve(std::max<size_t>(nmap, 1))) return rc;
@@ -911,16 +924,25 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
         if (int rc = upload_async(sl.n_close.p, w->n_close + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
         if (int rc = upload_async(sl.n_extra.p, w->n_extra + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
         if (int rc = upload_async(sl.mapq.p, w->mapq + (size_t)g0 * VGL_HC_LANES, nl, cs)) return rc;
-        if (int rc = upload_async(sl.col16.p, w->col + (size_t)c0 * 256, ncol16 * 2, cs)) return rc;
+        if (narrow) {
+            if (int rc = upload_async(sl.col8.p, w->col8 + (size_t)c0 * 256, ncol16, cs)) return rc;
+            if (int rc = upload_async(sl.flag4.p, w->flag4 + (size_t)c0 * 32, ncol16 / 8 * 4, cs)) return rc;
+            if (int rc = upload_async(sl.n_owned.p, w->n_owned + (size_t)g0 * VGL_HC_LANES, nl * 2, cs)) return rc;
+        } else {
+            if (int rc = upload_async(sl.col16.p, w->col + (size_t)c0 * 256, ncol16 * 2, cs)) return rc;
+        }
         if (int rc = upload_async(sl.node16.p, w->node + (size_t)n0 * 256, nnode16 * 2, cs)) return rc;
         if (int rc = upload_async(sl.map.p, w->map + (size_t)m0 * 128, nmap * 4, cs)) return rc;
         VGL_CUDA(cudaEventRecord(sl.copied, cs));
         VGL_CUDA(cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
         // the 16-bit arrays keep their absolute block indices: bases shifted back by the chunk's first block (only ever
         // dereferenced at blocks >= c0 / n0 / m0, i.e. inside the slot)
-        const uint16_t* col16 = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col16.p) - (uintptr_t)c0 * 512);
+        const uint16_t* col16 = narrow ? nullptr : reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.col16.p) - (uintptr_t)c0 * 512);
+        const uint8_t* col8 = narrow ? reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(sl.col8.p) - (uintptr_t)c0 * 256) : nullptr;
+        const uint32_t* flag4 = narrow ? reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sl.flag4.p) - (uintptr_t)c0 * 128) : nullptr;
         const uint16_t* node16 = reinterpret_cast<const uint16_t*>(reinterpret_cast<uintptr_t>(sl.node16.p) - (uintptr_t)n0 * 512);
-        VGL_CUDA(vgl::hc_launch_expand(ng, sl.grp_c16.p, sl.grp_n16.p, col16, node16, sl.n_cols.p, sl.col.p, sl.grp_col_blk.p, ctx->stream));
+        VGL_CUDA(vgl::hc_launch_expand(ng, sl.grp_c16.p, sl.grp_n16.p, col16, col8, flag4, narrow ? sl.n_owned.p : nullptr, node16, sl.n_cols.p,
+                                       sl.col.p, sl.grp_col_blk.p, ctx->stream));
         ctx->launches += 1;
         vgl::HcBatchDev d;
         d.n_groups = ng;

@@ -184,7 +184,8 @@ cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32
 // Wire form of a chunk (vgl_hc_wire) -> 32-bit column records + the chunk-relative grp_col_blk of the 32-bit layout.
 // The 16-bit arrays are addressed with ABSOLUTE block indices (grp_c16 / grp_n16 as shipped); col32 is chunk relative.
 cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const uint32_t* grp_n16, const uint16_t* col16,
-                             const uint16_t* node16, const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s);
+                             const uint8_t* col8, const uint32_t* flag4, const uint16_t* n_owned, const uint16_t* node16,
+                             const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s);  // col8 != NULL: narrow columns
 
 // ---------------------------------------------------------------------------------------------------------
 // euka

@@ -208,7 +208,8 @@ class PackedBatch:
 
 
 class WireBatch:
-    """A packed batch re-encoded for the host -> device transfer (vgl_hc_wire): 16-bit column records plus one 16-bit node id
+    """A packed batch re-encoded for the host -> device transfer (vgl_hc_wire): 16-bit column records (12-bit ones -- col8 / flag4 /
+    n_owned -- when every quality byte is <= 63) plus one 16-bit node id
     per non-empty mapping instead of 32-bit records."""
 
     def __init__(self, packed, n_threads=0, pinned=False):
