@@ -306,6 +306,8 @@ typedef struct vgl_hc_raw {
     const uint8_t* edit_from8;    /* [n_edits] from_length, to_length: NULL, or both present (every length <= 255) */
     const uint8_t* edit_to8;
     const uint16_t* map_node16;   /* [n_maps] node_id | is_reverse << 15: NULL, or present (every node id <= 32767) */
+    const uint16_t* first_offset16; /* [n_reads] offset of the read's FIRST mapping: NULL, or present when every other mapping starts
+                                     * at offset 0 of its node (what a graph aligner emits); shipped instead of map_offset16 then */
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 

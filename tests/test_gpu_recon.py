@@ -143,8 +143,15 @@ def test_likelihoods_from_raw_alignments_match_oracle(small):
     _check(res, 2 * np.asarray(final, dtype=np.longdouble), argmax, None)
     # the narrow arrays (16-bit offsets, edit counts, sequence lengths) are what was shipped; without them the 32-bit
     # offsets travel instead and nothing else changes
-    assert raw.raw.map_offset16 and raw.raw.map_n_edits8 and raw.raw.edit_slen8
+    assert raw.raw.map_offset16 and raw.raw.map_n_edits8 and raw.raw.edit_slen8 and raw.raw.first_offset16
     narrow_bytes = raw.nbytes
+    raw.raw.first_offset16 = None                                # one 16-bit offset per mapping instead of one per read
+    assert raw.nbytes > narrow_bytes
+    hc.reset()
+    hc.update_raw(raw)
+    hc.update_raw(raw)
+    res_off16 = hc.get_posterior()
+    assert res_off16["maxh_index"] == res["maxh_index"] and np.allclose(res_off16["final_vec"], res["final_vec"], rtol=1e-13)
     raw.raw.map_offset16 = raw.raw.map_n_edits8 = raw.raw.edit_slen8 = None
     raw.raw.edit_from8 = raw.raw.edit_to8 = raw.raw.map_node16 = None
     assert raw.nbytes > 1.3 * narrow_bytes

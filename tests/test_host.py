@@ -397,3 +397,25 @@ def test_gam_reader_inflates_bgzf_members_in_parallel_and_plain_gzip_serially():
     broken[40] ^= 0x55
     with pytest.raises(Exception):
         vb.Alignments.from_gam_bytes(bytes(broken))
+
+
+def test_raw_arrays_ship_one_offset_per_read_when_only_first_mappings_start_inside_a_node():
+    S = vb.SynthHaplocart(seed=21, n_paths=33, n_rows=310, n_nodes=301)
+    A = S.reads(300, seed=29, sub_rate=0.02, indel_rate=0.01)
+    raw = vb.RawBatch(A)
+    r = raw.raw
+    assert r.first_offset16 and r.map_offset16 and r.map_n_edits8 and r.edit_slen8
+    n, nm = int(r.n_reads), int(r.n_maps)
+    moff = vb.host._as_array(r.map_off, n + 1, np.uint32)
+    off = vb.host._as_array(r.map_offset, nm, np.uint32)
+    first = vb.host._as_array(r.first_offset16, n, np.uint16)
+    rebuilt = np.zeros(nm, dtype=np.uint32)                    # what the device does: zero, then one store per read
+    rebuilt[moff[:-1][moff[1:] > moff[:-1]]] = first[moff[1:] > moff[:-1]]
+    assert np.array_equal(rebuilt, off) and off[moff[:-1]].any()
+    with_first = raw.nbytes
+    r.first_offset16 = None
+    assert raw.nbytes - with_first == 2 * nm - 2 * n
+    # a mapping that starts inside its node further down the read: one offset per mapping again
+    odd = [H.aln("ACGTAC", [(1, 2, False, [(3, 3, "")]), (2, 1, False, [(3, 3, "")])])]
+    r2 = vb.RawBatch(vb.Alignments.from_gam_bytes(H.encode_gam(odd))).raw
+    assert not r2.first_offset16 and r2.map_offset16

@@ -40,7 +40,7 @@ class vgl_hc_raw(C.Structure):
                 ("edit_from", C.c_void_p), ("edit_to", C.c_void_p), ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p),
                 ("seq_len", C.c_void_p), ("read_index", C.c_void_p),
                 ("map_offset16", C.c_void_p), ("map_n_edits8", C.c_void_p), ("edit_slen8", C.c_void_p),
-                ("edit_from8", C.c_void_p), ("edit_to8", C.c_void_p), ("map_node16", C.c_void_p)]
+                ("edit_from8", C.c_void_p), ("edit_to8", C.c_void_p), ("map_node16", C.c_void_p), ("first_offset16", C.c_void_p)]
 
 
 class vgl_hc_batch(C.Structure):

@@ -955,6 +955,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     const size_t o_node = take(nm * 4), o_offs = take(nm * 4), o_eoff = take((nm + 1) * 4), o_from = take(ne * 2), o_to = take(ne * 2);
     const size_t o_esoff = take((ne + 1) * 4), o_eseq = take(ns), o_slen = take(R * 2), o_ridx = take(R * 4);
     const size_t o_off16 = take(nm * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne), o_n16 = take(nm * 2);
+    const size_t o_fo16 = take(R * 2);
     vgh_hc_raw* P = new vgh_hc_raw();
     P->pinned = pinned != 0;
     const size_t bytes = std::max<size_t>(o, 256);
@@ -976,10 +977,12 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     uint16_t* slen = (uint16_t*)(base + o_slen); uint32_t* ridx = (uint32_t*)(base + o_ridx);
     uint16_t* off16 = (uint16_t*)(base + o_off16); uint8_t* ne8 = base + o_ne8; uint8_t* sl8 = base + o_sl8;
     uint8_t* f8 = base + o_f8; uint8_t* t8 = base + o_t8; uint16_t* n16 = (uint16_t*)(base + o_n16);
+    uint16_t* fo16 = (uint16_t*)(base + o_fo16);
+    bool first_only = true;   // only a read's first mapping starts inside its node (offset != 0)
     bool narrow_node = true;  // every node id <= 32767
     bool narrow_len = true;  // every from_length / to_length <= 255
     bool narrow = true;  // every offset <= 65535, <= 255 edits per mapping, edit sequences <= 255 bytes
-#pragma omp parallel for schedule(static) reduction(&& : narrow, narrow_len, narrow_node)
+#pragma omp parallel for schedule(static) reduction(&& : narrow, narrow_len, narrow_node, first_only)
     for (int64_t k = 0; k < (int64_t)R; ++k) {
         const int64_t r = keep[(size_t)k];
         uint64_t cm = pm[(size_t)k], ce = pe[(size_t)k], cs = ps[(size_t)k];
@@ -988,7 +991,9 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
         slen[k] = (uint16_t)std::min<int64_t>(a->seq_off[r + 1] - a->seq_off[r], 65535);
         ridx[k] = (uint32_t)(r - r0);
         memcpy(q + pq[(size_t)k], a->qual + a->qual_off[r], (size_t)(pq[(size_t)k + 1] - pq[(size_t)k]));
+        fo16[k] = a->map_off[r + 1] > a->map_off[r] ? (uint16_t)a->map_offset[a->map_off[r]] : (uint16_t)0;
         for (int64_t m = a->map_off[r]; m < a->map_off[r + 1]; ++m) {
+            first_only = first_only && (m == a->map_off[r] || a->map_offset[m] == 0);
             node[cm] = (uint32_t)a->map_node[m] | (a->map_rev[m] ? 0x80000000u : 0u);
             offs[cm] = (uint32_t)a->map_offset[m];
             eoff[cm] = (uint32_t)ce;
@@ -1024,6 +1029,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     v.edit_off = eoff; v.edit_from = from; v.edit_to = to; v.edit_seq_off = esoff; v.edit_seq = eseq;
     v.seq_len = slen; v.read_index = ridx;
     if (narrow) { v.map_offset16 = off16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; }
+    if (narrow && first_only) v.first_offset16 = fo16;  // (narrow: the first offsets fit 16 bits too)
     if (narrow_len) { v.edit_from8 = f8; v.edit_to8 = t8; }
     if (narrow_node) v.map_node16 = n16;
     *out = P;

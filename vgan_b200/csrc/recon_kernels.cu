@@ -443,6 +443,14 @@ __global__ void __launch_bounds__(256) widen_node16(const uint16_t* __restrict__
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)(in[i] & 0x7fffu) | ((uint32_t)(in[i] >> 15) << 31);  // node | is_reverse << 31
 }
+// map_offset[first mapping of read r] = first16[r]; every other entry was zeroed before (vgl_hc_raw::first_offset16)
+__global__ void __launch_bounds__(256) set_first_offsets(const uint32_t* __restrict__ map_off, const uint16_t* __restrict__ first16, uint32_t n,
+                                                         uint32_t* __restrict__ map_offset_abs) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t m0 = map_off[r];
+    if (map_off[r + 1] > m0) map_offset_abs[m0] = first16[r];
+}
 __global__ void __launch_bounds__(256) widen_u8(const uint8_t* __restrict__ in, uint32_t n, uint16_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -636,6 +644,12 @@ cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, ui
 cudaError_t raw_launch_widen_node16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     widen_node16<<<(n + 255) / 256, 256, 0, s>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t raw_launch_first_offsets(const uint32_t* map_off, const uint16_t* first16, uint32_t n, uint32_t* map_offset_abs, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    set_first_offsets<<<(n + 255) / 256, 256, 0, s>>>(map_off, first16, n, map_offset_abs);
     return cudaGetLastError();
 }
 

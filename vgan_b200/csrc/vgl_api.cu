@@ -115,7 +115,7 @@ struct vgl_ctx {
         DevBuf<uint8_t> s_mapq, s_flags;
         DevBuf<int> s_err;
         // narrow arrays as shipped + scratch for the prefix sums
-        DevBuf<uint16_t> off16, n16;
+        DevBuf<uint16_t> off16, n16, fo16;
         DevBuf<uint8_t> ne8, sl8, f8, t8;
         DevBuf<uint32_t> tiles;
         cudaEvent_t copied = nullptr, consumed = nullptr;  // H2D of the chunk done / its kernels done
@@ -322,7 +322,7 @@ void vgl_destroy(vgl_ctx* ctx) {
         R.hist3.release(); R.order.release(); R.grp_cb.release(); R.grp_mb.release(); R.col.release(); R.xmap.release();
         R.o_n_cols.release(); R.o_n_close.release(); R.o_n_extra.release(); R.o_mapq.release();
         R.seq_len.release(); R.s_col.release(); R.s_n_cols.release(); R.s_n_maps.release(); R.s_seq_len.release();
-        R.off16.release(); R.n16.release(); R.ne8.release(); R.sl8.release(); R.f8.release(); R.t8.release(); R.tiles.release();
+        R.off16.release(); R.n16.release(); R.fo16.release(); R.ne8.release(); R.sl8.release(); R.f8.release(); R.t8.release(); R.tiles.release();
         R.read_index.release(); R.s_map.release(); R.s_read_index.release(); R.s_mapq.release(); R.s_flags.release(); R.s_err.release();
         if (R.copied) cudaEventDestroy(R.copied);
         if (R.consumed) cudaEventDestroy(R.consumed);
@@ -691,6 +691,8 @@ uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* r) {
     const uint64_t per_read = (uint64_t)(r->n_reads + 1) * 12 + r->n_reads + r->qual_off[r->n_reads] + r->edit_seq_off[r->n_edits];
     const uint64_t lens = (uint64_t)r->n_edits * (r->edit_from8 ? 2 : 4);  // from_length + to_length per edit
     const uint64_t nodes = (uint64_t)r->n_maps * (r->map_node16 ? 2 : 4);
+    if (r->first_offset16 && r->map_n_edits8 && r->edit_slen8)  // one offset per read, edit count 1 per mapping, sequence length 1 per edit
+        return per_read + nodes + (uint64_t)r->n_reads * 2 + (uint64_t)r->n_maps + (uint64_t)r->n_edits + lens;
     if (r->map_offset16)  // narrow: offset 2 + edit count 1 per mapping; sequence length 1 per edit
         return per_read + nodes + (uint64_t)r->n_maps * 3 + (uint64_t)r->n_edits + lens;
     return per_read + nodes + (uint64_t)r->n_maps * 4 + (uint64_t)(r->n_maps + 1) * 4 + (uint64_t)(r->n_edits + 1) * 4 + lens;
@@ -740,7 +742,7 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
     RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
     RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
-    RSV(R.off16, nm); RSV(R.n16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
+    RSV(R.off16, nm); RSV(R.fo16, n); RSV(R.n16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
     RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
     RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
     RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
@@ -753,7 +755,8 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
 #define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, copy_stream))
     H2D(R.qual_off.p, raw->qual_off + ra, (n + 1) * 4); H2D(R.str_off.p, raw->str_off + ra, (n + 1) * 4);
     H2D(R.map_off.p, raw->map_off + ra, (n + 1) * 4); H2D(R.mapq.p, raw->mapq + ra, n); H2D(R.qual.p, raw->qual + qa, nq);
-    const bool narrow = raw->map_offset16 && raw->map_n_edits8 && raw->edit_slen8;
+    const bool first_only = raw->first_offset16 != nullptr;  // one offset per read instead of one per mapping
+    const bool narrow = (raw->map_offset16 || first_only) && raw->map_n_edits8 && raw->edit_slen8;
     const bool narrow_len = raw->edit_from8 && raw->edit_to8;
     if (raw->map_node16) {
         H2D(R.n16.p, raw->map_node16 + ma, nm * 2);
@@ -767,7 +770,12 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     }
     H2D(R.edit_seq.p, raw->edit_seq + sa, nseq);
     if (narrow) {
-        H2D(R.off16.p, raw->map_offset16 + ma, nm * 2); H2D(R.ne8.p, raw->map_n_edits8 + ma, nm); H2D(R.sl8.p, raw->edit_slen8 + ea, ne);
+        if (first_only) {
+            H2D(R.fo16.p, raw->first_offset16 + ra, n * 2);
+        } else {
+            H2D(R.off16.p, raw->map_offset16 + ma, nm * 2);
+        }
+        H2D(R.ne8.p, raw->map_n_edits8 + ma, nm); H2D(R.sl8.p, raw->edit_slen8 + ea, ne);
     } else {
         H2D(R.map_offset.p, raw->map_offset + ma, nm * 4); H2D(R.edit_off.p, raw->edit_off + ma, (nm + 1) * 4);
         H2D(R.edit_seq_off.p, raw->edit_seq_off + ea, (ne + 1) * 4);
@@ -785,7 +793,12 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
         ctx->launches += 2;
     }
     if (narrow) {  // rebuild the 32-bit offsets (absolute indices: the prefix sums start at the chunk's first edit / byte)
-        VGL_CUDA(vgl::raw_launch_widen_u16(R.off16.p, (uint32_t)nm, R.map_offset.p, s));
+        if (first_only) {
+            VGL_CUDA(cudaMemsetAsync(R.map_offset.p, 0, nm * sizeof(uint32_t), s));
+            VGL_CUDA(vgl::raw_launch_first_offsets(R.map_off.p, R.fo16.p, (uint32_t)n, R.map_offset.p - ma, s));
+        } else {
+            VGL_CUDA(vgl::raw_launch_widen_u16(R.off16.p, (uint32_t)nm, R.map_offset.p, s));
+        }
         VGL_CUDA(vgl::raw_launch_offsets_from_counts(R.ne8.p, (uint32_t)nm, (uint32_t)ea, R.tiles.p, R.edit_off.p, s));
         VGL_CUDA(vgl::raw_launch_offsets_from_counts(R.sl8.p, (uint32_t)ne, (uint32_t)sa, R.tiles.p, R.edit_seq_off.p, s));
         ctx->launches += 7;

@@ -170,6 +170,8 @@ cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, ui
                                            cudaStream_t s);
 cudaError_t raw_launch_widen_u16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s);
 cudaError_t raw_launch_widen_u8(const uint8_t* in, uint32_t n, uint16_t* out, cudaStream_t s);
+// map_offset_abs[map_off[r]] = first16[r] for the n reads of the chunk (map_off holds absolute mapping indices; the rest of map_offset is zero)
+cudaError_t raw_launch_first_offsets(const uint32_t* map_off, const uint16_t* first16, uint32_t n, uint32_t* map_offset_abs, cudaStream_t s);
 cudaError_t raw_launch_widen_node16(const uint16_t* in, uint32_t n, uint32_t* out, cudaStream_t s);  // node | rev << 15 -> node | rev << 31
 // mode: 0 HaploCart, 1 euka, 2 soibean (which checks apply, what the record count means, 4- or 8-column blocks)
 cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, int* err_flag, cudaStream_t s);
