@@ -352,11 +352,26 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
             x0[t + 1] = x0[t] + p.edit_seq.size();
         }
         const size_t nr = r0[NP], nm = m0[NP], ne = e0[NP];
-        g->seq_off.resize(nr + 1); g->qual_off.resize(nr + 1); g->map_off.resize(nr + 1);
-        g->mapq.resize(nr); g->identity.resize(nr); g->paired.resize(nr);
-        g->map_node.resize(nm); g->map_offset.resize(nm); g->map_rev.resize(nm); g->edit_off.resize(nm + 1);
-        g->edit_from.resize(ne); g->edit_to.resize(ne); g->edit_seq_off.resize(ne + 1);
-        g->seq.resize(s0[NP]); g->qual.resize(q0[NP]); g->edit_seq.resize(x0[NP]);
+        // sixteen arrays: allocating and zero-filling them one after the other was the longest part of the whole parse
+#pragma omp parallel sections num_threads(n_parts)
+        {
+#pragma omp section
+            { g->seq_off.resize(nr + 1); g->qual_off.resize(nr + 1); g->map_off.resize(nr + 1); g->mapq.resize(nr); g->paired.resize(nr); }
+#pragma omp section
+            { g->identity.resize(nr); g->map_rev.resize(nm); }
+#pragma omp section
+            g->map_node.resize(nm);
+#pragma omp section
+            g->map_offset.resize(nm);
+#pragma omp section
+            { g->edit_off.resize(nm + 1); g->edit_seq.resize(x0[NP]); }
+#pragma omp section
+            { g->edit_from.resize(ne); g->edit_to.resize(ne); }
+#pragma omp section
+            g->edit_seq_off.resize(ne + 1);
+#pragma omp section
+            { g->seq.resize(s0[NP]); g->qual.resize(q0[NP]); }
+        }
 #pragma omp parallel for schedule(static, 1) num_threads(n_parts)
         for (int t = 0; t < n_parts; ++t) {
             vgh_gam& p = parts[(size_t)t];
