@@ -325,6 +325,21 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
 #pragma omp parallel for schedule(static, 1) num_threads(n_parts)
     for (int t = 0; t < n_parts; ++t) {
         const size_t lo = n_msgs * (size_t)t / (size_t)n_parts, hi = n_msgs * ((size_t)t + 1) / (size_t)n_parts;
+        if (hi > lo) {
+            // room for a typical range up front (an aligned read spends about a seventh of its bytes on each of sequence and
+            // quality, >= 10 bytes per mapping and >= 6 per edit): the vectors hardly ever reallocate while the messages are
+            // parsed.  Only a hint: anything larger still grows, and a failed reservation is ignored.
+            vgh_gam& P = parts[(size_t)t];
+            const size_t bytes = (size_t)(msgs[hi - 1].second - msgs[lo].first), nr = hi - lo;
+            try {
+                P.seq.reserve(bytes / 4); P.qual.reserve(bytes / 4); P.edit_seq.reserve(bytes / 16);
+                P.seq_off.reserve(nr + 1); P.qual_off.reserve(nr + 1); P.map_off.reserve(nr + 1);
+                P.mapq.reserve(nr); P.identity.reserve(nr); P.paired.reserve(nr);
+                P.map_node.reserve(bytes / 10); P.map_offset.reserve(bytes / 10); P.map_rev.reserve(bytes / 10); P.edit_off.reserve(bytes / 10 + 1);
+                P.edit_from.reserve(bytes / 6); P.edit_to.reserve(bytes / 6); P.edit_seq_off.reserve(bytes / 6 + 1);
+            } catch (const std::bad_alloc&) {
+            }
+        }
         for (size_t k = lo; k < hi; ++k) {
             Cursor item{msgs[k].first, msgs[k].second, true};
             if (!parse_alignment(item, drop_unmapped, parts[(size_t)t])) {
