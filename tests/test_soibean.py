@@ -179,3 +179,28 @@ def test_mcmc_proposal_likelihood_matches_oracle(route, p5, p3, penalty):
         again = sb.mcmc_loglike(props, F7, 0.01)              # fixed-order reduction: bit-identical from run to run
         assert np.array_equal(again, got)
     sb.close()
+
+
+def test_oracle_mcmc_on_the_toy_graph_fixture():
+    """The reference's reconstruction fixture (match / mismatch / indel / softclip on both strands) through the MCMC
+    likelihood: finite, never above the pre-computed pathMap value, and the mixture of a source with itself is that source."""
+    import os
+    nodes, paths = H.toy_graph()
+    n_rows = max(nodes) + 1
+    member = np.zeros((n_rows, len(paths)), dtype=np.uint8)
+    for p, (_, steps) in enumerate(paths):
+        for nid, _ in steps:
+            member[nid, p] = 1
+    alns = vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "test_reads.gam"))
+    og, R = orc.Graph(nodes), orc.FlatReads(alns.arrays())
+    want, used = orc.soibean_run(og, R, member, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    P = len(paths)
+    for c in range(P):
+        ll, per = orc.soibean_mcmc_loglike(og, R, member, [(c, (c + 1) % P, 0.35, 0.04, 1.0)], F7, 0.01, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+        assert np.all(np.isfinite(per)) and np.all(per[used == 1] < 0)
+        # log(0.35 e^a + 0.65 e^b) <= max(a, b) <= max of the two pathMap values
+        assert np.all(per <= np.maximum(want[:, c], want[:, (c + 1) % P]) + 1e-9)
+        # two sources that are the same source, proportions adding up to one: the single-source value of the mixture form
+        _, one = orc.soibean_mcmc_loglike(og, R, member, [(c, c, 0.5, 0.04, 1.0)], F7, 0.01, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+        _, two = orc.soibean_mcmc_loglike(og, R, member, [(c, c, 0.5, 0.04, 0.3), (c, c, 0.5, 0.04, 0.7)], F7, 0.01, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+        assert np.allclose(one, two, rtol=1e-12, atol=0)
