@@ -74,7 +74,7 @@ struct Cursor {
 
 // One serialized vg.Alignment (field numbers as on the wire).
 bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
-    std::string seq, qual;
+    const uint8_t *seq_p = nullptr, *seq_e = nullptr, *qual_p = nullptr, *qual_e = nullptr;  // the last occurrence wins, as in protobuf
     int32_t mapq = 0;
     double identity = 0.0;
     uint8_t paired = 0;
@@ -82,8 +82,8 @@ bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
     while (c.ok && c.p < c.end) {
         const uint64_t key = c.varint();
         const int fno = (int)(key >> 3), wt = (int)(key & 7);
-        if (fno == 1 && wt == 2) { Cursor s = c.sub(); seq.assign((const char*)s.p, (const char*)s.end); }
-        else if (fno == 4 && wt == 2) { Cursor s = c.sub(); qual.assign((const char*)s.p, (const char*)s.end); }
+        if (fno == 1 && wt == 2) { Cursor s = c.sub(); seq_p = s.p; seq_e = s.end; }
+        else if (fno == 4 && wt == 2) { Cursor s = c.sub(); qual_p = s.p; qual_e = s.end; }
         else if (fno == 5 && wt == 0) mapq = (int32_t)c.varint();
         else if (fno == 16 && wt == 1) { if (c.end - c.p < 8) { c.ok = false; break; } memcpy(&identity, c.p, 8); c.p += 8; }
         else if (fno == 20 && wt == 0) paired = c.varint() ? 1 : 0;
@@ -148,8 +148,10 @@ bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
         out.edit_seq.resize(es_mark);
         return true;
     }
-    out.seq += seq; out.seq_off.push_back((int64_t)out.seq.size());
-    out.qual += qual; out.qual_off.push_back((int64_t)out.qual.size());
+    if (seq_p) out.seq.append((const char*)seq_p, (const char*)seq_e);
+    out.seq_off.push_back((int64_t)out.seq.size());
+    if (qual_p) out.qual.append((const char*)qual_p, (const char*)qual_e);
+    out.qual_off.push_back((int64_t)out.qual.size());
     out.mapq.push_back(mapq);
     out.identity.push_back(identity);
     out.paired.push_back(paired);
