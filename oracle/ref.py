@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of oracle/_ref/libvgan_ref.so: the REFERENCE'S OWN hot-path
+sources (update_likelihood.cpp, process_mapping.cpp, get_p_obs_base.cpp, get_posterior.cpp, vgan_utils.h,
+miscfunc.h, haplocart_functions.cpp, rmdup.cpp, damage.cpp, ...) compiled unchanged from /root/reference/src against
+the header shim in oracle/ref_shim/ (recipe: oracle/ref_shim/Makefile).  It pins the oracle's arithmetic.
+
+Only tests/, tests/golden/make_ref_golden.py and bench.py's --impl reference / cpu_baseline legs may import this module.
+The library is built in the authoring container (where /root/reference exists) and travels to the GPU box as a built
+file; `available()` is False when neither the built library nor the reference sources are present.
+"""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from . import oracle as orc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libvgan_ref.so")
+_SHIM = os.path.join(_HERE, "ref_shim")
+REF_ROOT = os.environ.get("VGAN_REFERENCE", "/root/reference")
+
+_lib = None
+
+
+def build(force=False):
+    """Compile the reference's sources where they lie (needs REF_ROOT); a no-op when they are absent."""
+    if not os.path.isdir(os.path.join(REF_ROOT, "src")):
+        return _LIB_PATH if os.path.exists(_LIB_PATH) else None
+    cmd = ["make", "-s", "-C", _SHIM, "REF=" + REF_ROOT] + (["-B"] if force else [])
+    subprocess.check_call(cmd)
+    return _LIB_PATH
+
+
+def available():
+    return os.path.exists(_LIB_PATH) or os.path.isdir(os.path.join(REF_ROOT, "src"))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError("oracle/_ref/libvgan_ref.so is not built and %s is absent" % REF_ROOT)
+        _lib = C.CDLL(_LIB_PATH)
+        for f in ("ref_hc_p_seq_error", "ref_hc_background_freq", "ref_hc_region_match_prob"):
+            getattr(_lib, f).restype = C.c_double
+        _lib.ref_damage_create.restype = C.c_void_p
+        assert _lib.ref_sizeof_long_double() == np.dtype(np.longdouble).itemsize
+    return _lib
+
+
+_ptr = orc._ptr
+
+
+def reconstruct(graph, reads, r, cap=8192):
+    """reconstruct_graph_sequence (src/vgan_utils.h:6-79) -> (graph_seq, read_seq, sizes)."""
+    g = np.zeros(cap, dtype=np.uint8)
+    p = np.zeros(cap, dtype=np.uint8)
+    s = np.zeros(cap, dtype=np.int32)
+    ng, npp, ns = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib().ref_reconstruct(C.byref(graph.c), C.byref(reads.c), C.c_int64(r), _ptr(g), _ptr(p), _ptr(s), cap,
+                               C.byref(ng), C.byref(npp), C.byref(ns))
+    if rc:
+        raise RuntimeError("ref_reconstruct failed: %d" % rc)
+    return g[:ng.value].tobytes().decode(), p[:npp.value].tobytes().decode(), s[:ns.value].tolist()
+
+
+def quality_pad(reads, r=None):
+    """Zero bytes to append to a quality string so that the reference's out-of-range quality reads
+    (src/update_likelihood.cpp:40-44, quirk Q4) are defined: the window of the last mapping ends below
+    2 * |aligned read| <= 2 * (|sequence| + deleted bases)."""
+    lo, hi = (0, reads.n) if r is None else (r, r + 1)
+    if hi <= lo:
+        return 1
+    seq_len = int(np.max(reads.seq_off[lo + 1:hi + 1] - reads.seq_off[lo:hi]))
+    m0, m1 = int(reads.map_off[lo]), int(reads.map_off[hi])
+    e0, e1 = int(reads.edit_off[m0]), int(reads.edit_off[m1])
+    dels = int(np.sum(reads.edit_from[e0:e1])) if e1 > e0 else 0
+    return 2 * (seq_len + dels) + 8
+
+
+def hc_read(tables, graph, reads, r, pad_quality=None):
+    """Haplocart::update (src/update_likelihood.cpp:5-53) for one read from the zero vector -> long double[P]."""
+    ll = np.zeros(tables.n_paths, dtype=np.longdouble)
+    pad = quality_pad(reads, r) if pad_quality is None else int(pad_quality)
+    rc = lib().ref_hc_read(C.byref(tables.c), C.byref(graph.c), C.byref(reads.c), C.c_int64(r), pad, _ptr(ll))
+    if rc:
+        raise RuntimeError("ref_hc_read failed: %d" % rc)
+    return ll
+
+
+def hc_run(tables, graph, reads, r0=0, r1=None, n_threads=1, pad_quality=None):
+    """The read loop of Haplocart::run (src/HaploCart.cpp:408-424) over the reference's update()."""
+    r1 = reads.n if r1 is None else r1
+    final = np.zeros(tables.n_paths, dtype=np.longdouble)
+    am = C.c_int32()
+    used = C.c_int64()
+    pad = quality_pad(reads) if pad_quality is None else int(pad_quality)
+    rc = lib().ref_hc_run(C.byref(tables.c), C.byref(graph.c), C.byref(reads.c), C.c_int64(r0), C.c_int64(r1), pad,
+                          int(n_threads), _ptr(final), C.byref(am), C.byref(used))
+    if rc:
+        raise RuntimeError("ref_hc_run failed: %d" % rc)
+    return final, am.value, used.value
+
+
+def hc_posterior(final_vec, path_names, parents_txt, children_txt, predicted_idx, cap=4096):
+    """Haplocart::get_posterior (src/get_posterior.cpp:87-127).  Returns (clade names as the function wrote them,
+    confidences as written (6 significant digits), full-precision confidences from the same member functions, total).
+    The first two are None when the function itself crashed on its undefined parent_vec[-1] read (quirk Q8)."""
+    fv = np.ascontiguousarray(final_vec, dtype=np.longdouble)
+    names = C.create_string_buffer(1 << 20)
+    conf_text = np.zeros(cap)
+    conf_full = np.zeros(cap)
+    total = np.zeros(1, dtype=np.longdouble)
+    fd, tmp = tempfile.mkstemp(prefix="vgan_ref_post_")
+    os.close(fd)
+    try:
+        n_text = C.c_int32(0)
+        n = lib().ref_hc_posterior(_ptr(fv), fv.size, ("\n".join(path_names)).encode(), parents_txt.encode(),
+                                   children_txt.encode(), int(predicted_idx), tmp.encode(), cap, names, len(names),
+                                   _ptr(conf_text), C.byref(n_text), _ptr(conf_full), _ptr(total))
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+    if n < 0:
+        raise RuntimeError("ref_hc_posterior failed: %d" % n)
+    if n_text.value < 0:
+        # get_posterior itself crashed (in a forked child) on its parent_vec[-1] read, quirk Q8: no text capture
+        return None, None, conf_full[:n].copy(), total[0]
+    clades = names.value.decode().split("\n")[:-1]
+    return clades, conf_text[:n_text.value].copy(), conf_full[:n].copy(), total[0]
+
+
+def qscore_vec():
+    v = np.zeros(100)
+    lib().ref_hc_qscore_vec(_ptr(v))
+    return v
+
+
+def incorrect_mapping_vec():
+    v = np.zeros(100)
+    lib().ref_hc_incorrect_mapping_vec(_ptr(v))
+    return v
+
+
+def region_match_prob(pb):
+    return lib().ref_hc_region_match_prob(int(pb))
+
+
+def p_seq_error(q):
+    return lib().ref_hc_p_seq_error(int(q))
+
+
+def background_freq(b):
+    return lib().ref_hc_background_freq(C.c_char(b.encode() if isinstance(b, str) else b))
+
+
+def dedup(reads, paired=None):
+    """Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:68-110) -> is_dup[R]."""
+    out = np.zeros(max(reads.n, 1), dtype=np.uint8)
+    pr = None if paired is None else np.ascontiguousarray(paired, dtype=np.uint8)
+    rc = lib().ref_dedup(C.byref(reads.c), None if pr is None else _ptr(pr), _ptr(out))
+    if rc:
+        raise RuntimeError("ref_dedup failed: %d" % rc)
+    return out[:reads.n].astype(bool)
+
+
+class Damage:
+    """Damage::initDeamProbabilities (src/damage.cpp:41-323) on two .prof files ('' = no damage)."""
+
+    def __init__(self, deam5p="", deam3p=""):
+        self.h = lib().ref_damage_create((deam5p or "").encode(), (deam3p or "").encode())
+        if not self.h:
+            raise RuntimeError("ref_damage_create failed")
+
+    def matrix(self, L, l):
+        out = np.zeros(16)
+        rc = lib().ref_damage_matrix(C.c_void_p(self.h), int(L), int(l), _ptr(out))
+        if rc:
+            raise RuntimeError("ref_damage_matrix failed: %d" % rc)
+        return out.reshape(4, 4)
+
+    def rows(self, L):
+        return lib().ref_damage_rows(C.c_void_p(self.h), int(L))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_damage_destroy(C.c_void_p(self.h))
+            self.h = None

@@ -7,17 +7,24 @@
 //
 // It is a plain C++17 / `long double` restatement of the reference's algorithm, written
 // from a reading of the reference sources (cited per function as file:line relative to
-// /root/reference).  The reference itself cannot be compiled here (it needs libvg, libgab,
-// bdsg, protobuf -- none vendored), so there is no oracle/_ref.
+// /root/reference).
 //
-// PARITY PINNING
+// PARITY PINNING -- the oracle is pinned on the reference's own code and golden vectors:
+//   * oracle/_ref/libvgan_ref.so is the reference's hot-path sources (update_likelihood.cpp +
+//     process_mapping.cpp, get_p_obs_base.cpp, get_posterior.cpp, vgan_utils.h, miscfunc.h,
+//     haplocart_functions.cpp, rmdup.cpp, damage.cpp, ...) compiled UNCHANGED from
+//     /root/reference/src over a header shim (oracle/ref_shim/).  tests/test_ref_pin.py holds
+//     this file to it BIT FOR BIT in long double: per-read vectors, sums, calls, posteriors,
+//     tables, duplicate masks, damage matrices (toy graph, synthetic, corner-case and the
+//     reference's real-graph GAM fixtures; both error modes).
+//   * tests/golden/ref_hc_golden.json holds vectors that build produced
+//     (tests/golden/make_ref_golden.py), so the pin also holds where _ref is absent.
 //   * alignment reconstruction is pinned by the reference's own 10 `reconstruction`
-//     known-answer strings (src/test.cpp:855-994) -- tests/test_oracle_reconstruct.py.
-//   * the likelihood / posterior ARITHMETIC is "parity unpinned": the reference holds no
-//     numeric golden vector for any log-likelihood or posterior.  The
-//     oracle is instead cross-checked in two independently written modes that must agree
-//     bit for bit (MODE_LITERAL follows the reference's per-path loops, MODE_HOISTED
-//     evaluates each mapping's two path-independent scalars once).
+//     known-answer strings (src/test.cpp:855-994), which the reference's own
+//     reconstruct_graph_sequence reproduces through the shim -- tests/test_oracle.py,
+//     tests/test_ref_pin.py.
+//   * the two oracle modes must also agree bit for bit (MODE_LITERAL follows the reference's
+//     per-path loops, MODE_HOISTED evaluates each mapping's two path-independent scalars once).
 //
 // Third-party semantics restated from their published behaviour (absent from the tree):
 //   vg::algorithms::path_string, vg::io::edit_is_{match,sub,insertion,deletion},

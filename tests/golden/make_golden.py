@@ -28,12 +28,25 @@ FIXTURES = [
     "test/input_files/alignments/all_the_same_reverse.gam",
     "test/input_files/alignments/two_unique.gam",
 ]
+# data tables the synthetic configs are specified on: damage profiles and the euka clade / bin lists
+DATA = [
+    ("share/vgan/damageProfiles/dhigh5p.prof", "damageProfiles/dhigh5p.prof"),
+    ("share/vgan/damageProfiles/dhigh3p.prof", "damageProfiles/dhigh3p.prof"),
+    ("share/vgan/damageProfiles/none.prof", "damageProfiles/none.prof"),
+    ("share/vgan/euka_dir/euka_db.clade", "euka_db.clade"),
+    ("share/vgan/euka_dir/euka_db.bins", "euka_db.bins"),
+]
 
 
 def main():
     for rel in FIXTURES:
         shutil.copyfile(os.path.join(REF, rel), os.path.join(HERE, os.path.basename(rel)))
         os.chmod(os.path.join(HERE, os.path.basename(rel)), 0o644)
+
+    for rel, dst in DATA:
+        os.makedirs(os.path.dirname(os.path.join(HERE, dst)), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, rel), os.path.join(HERE, dst))
+        os.chmod(os.path.join(HERE, dst), 0o644)
 
     src = open(os.path.join(REF, "src/test.cpp")).read()
     suite = src[src.index("BOOST_AUTO_TEST_SUITE(reconstruction)"):]

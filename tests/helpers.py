@@ -151,3 +151,64 @@ def rel_err(got, want):
     got = np.asarray(got, dtype=np.float64)
     denom = np.where(want == 0, 1.0, np.abs(want))
     return float(np.max(np.abs(got - want) / denom)) if want.size else 0.0
+
+
+# ---- golden vectors produced by the reference's own code (tests/golden/make_ref_golden.py) ----
+def ld_pairs(x):
+    """long double array -> [[hi, lo], ...] of doubles, exact for the x87 64-bit mantissa."""
+    x = np.asarray(x, dtype=np.longdouble)
+    hi = x.astype(np.float64)
+    lo = (x - hi.astype(np.longdouble)).astype(np.float64)
+    return [[float(a), float(b)] for a, b in zip(hi, lo)]
+
+
+def ld_from_pairs(pairs):
+    p = np.asarray(pairs, dtype=np.float64).reshape(-1, 2)
+    return p[:, 0].astype(np.longdouble) + p[:, 1].astype(np.longdouble)
+
+
+def toy_tables(bep=1e-4, is_fasta=False):
+    """HaploCart tables for the reference's toy graph: membership from the GFA P lines, coordinates cumulative."""
+    nodes, paths = toy_graph()
+    n_rows = max(nodes) + 1
+    sup = np.zeros((n_rows, len(paths)), dtype=np.uint8)
+    for p, (_, steps) in enumerate(paths):
+        for nid, _ in steps:
+            sup[nid, p] = 1
+    ids = sorted(nodes)
+    coord = np.cumsum([0] + [len(nodes[i]) for i in ids])[:-1]
+    mp = np.linspace(0.3, 1.0, int(coord[-1]) + 40)
+    T = orc.HcTables(sup, np.array(ids), (coord + 1).astype(np.int32), mp, bep=bep, is_fasta=is_fasta, min_id=min(ids))
+    names = [n for n, _ in paths]
+    parents = "".join("%s root\n" % n for n in names)
+    children = "root " + " ".join(names) + "\n" + "".join("%s\n" % n for n in names)
+    return T, orc.Graph(nodes), (names, parents, children)
+
+
+def ref_golden_inputs(case):
+    """Rebuild the inputs of one case of tests/golden/ref_hc_golden.json from its descriptor (seeds / fixture names)."""
+    import vgan_b200 as vb
+    from oracle.gam_py import read_gam
+    kind = case["kind"]
+    bep, fasta = case["bep"], case["fasta"]
+    if kind == "toy":
+        T, G, tree = toy_tables(bep=bep, is_fasta=fasta)
+        return T, G, orc.Reads(read_gam(os.path.join(GOLDEN, case["fixture"]))), tree
+    S = vb.SynthHaplocart(**case["synth"])
+    tree = (S.path_names, S.parents_txt, S.children_txt)
+    if kind == "synth":
+        alns = S.reads(case["n"], seed=case["read_seed"], **case["read_kw"])
+        T, G, R = oracle_side(S, alns.arrays(), bep=bep, is_fasta=fasta)
+    elif kind == "edge":
+        from test_ref_pin import _defined_edge_reads
+        alns = vb.Alignments.from_gam_bytes(encode_gam(_defined_edge_reads(S)))
+        T, G, R = oracle_side(S, alns.arrays(), bep=bep, is_fasta=fasta)
+    elif kind == "gamfix":
+        alns_d = decoded_fixture(case["fixture"])[:case["n"]]
+        node_seqs = graph_from_alignments(alns_d, S.n_nodes)
+        alns = vb.Alignments.from_gam_bytes(encode_gam(alns_d))
+        T, G, R = oracle_side(S, alns.arrays(), node_seqs=node_seqs, bep=bep, is_fasta=fasta)
+    else:
+        raise ValueError(kind)
+    R._keep = alns
+    return T, G, R, tree
