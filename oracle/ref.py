@@ -189,3 +189,83 @@ class Damage:
         if getattr(self, "h", None):
             lib().ref_damage_destroy(C.c_void_p(self.h))
             self.h = None
+
+
+# ---- euka: the readGAM3 lambda (src/readGAM_Euka.h:67-577), the reference's own ----------------------------------
+def _write_tmp(text, suffix):
+    fd, path = tempfile.mkstemp(prefix="vgan_ref_", suffix=suffix)
+    with os.fdopen(fd, "w") as fh:
+        fh.write(text)
+    return path
+
+
+def euka_run(clade_dist, bin_off, bin_lo, bin_hi, graph, reads, deam5p_prof="", deam3p_prof="", minimum_mq=29,
+             bin_entropy=None):
+    """Same arguments as oracle.euka_run (profiles as TEXT); the tables reach the reference through its own loaders
+    (Euka::load_clade_info / load_clade_chunks, Damage::initDeamProbabilities) from temporary files.
+    Returns per-read clade / like / not_like and per-clade count / per-bin coverage."""
+    dist = np.ascontiguousarray(clade_dist, dtype=np.float64)
+    boff = np.ascontiguousarray(bin_off, dtype=np.int64)
+    blo = np.ascontiguousarray(bin_lo, dtype=np.int32)
+    bhi = np.ascontiguousarray(bin_hi, dtype=np.int32)
+    nc = dist.size
+    ent = np.full(blo.size, 1.5) if bin_entropy is None else np.asarray(bin_entropy, dtype=np.float64)
+    clade_txt = "".join("%d clade%d %s 1 %d %d\n" % (c, c, repr(float(dist[c])), int(blo[boff[c]]) if boff[c + 1] > boff[c] else 0,
+                                                     int(bhi[boff[c + 1] - 1]) if boff[c + 1] > boff[c] else 0) for c in range(nc))
+    bins_txt = "".join("clade%d " % c + " ".join("%d %d %s" % (int(blo[j]), int(bhi[j]), repr(float(ent[j])))
+                                                  for j in range(int(boff[c]), int(boff[c + 1]))) + "\n" for c in range(nc))
+    files = [_write_tmp(clade_txt, ".clade"), _write_tmp(bins_txt, ".bins")]
+    p5 = _write_tmp(deam5p_prof, ".prof") if deam5p_prof else ""
+    p3 = _write_tmp(deam3p_prof, ".prof") if deam3p_prof else ""
+    files += [f for f in (p5, p3) if f]
+    n = reads.n
+    out = {"clade": np.zeros(max(n, 1), dtype=np.int32), "like": np.zeros(max(n, 1)), "not_like": np.zeros(max(n, 1)),
+           "pass": np.zeros(max(n, 1), dtype=np.uint8)}
+    count = np.zeros(nc, dtype=np.int64)
+    cov = np.zeros(max(int(boff[-1]), 1), dtype=np.float64)
+    try:
+        rc = lib().ref_euka_run(files[0].encode(), files[1].encode(), p5.encode(), p3.encode(), C.byref(graph.c), C.byref(reads.c),
+                                quality_pad(reads), C.c_uint32(int(minimum_mq)), C.c_int32(nc), _ptr(out["clade"]), _ptr(out["like"]), _ptr(out["not_like"]),
+                                _ptr(out["pass"]), _ptr(count), _ptr(cov), C.c_int64(cov.size))
+    finally:
+        for f in files:
+            os.remove(f)
+    if rc:
+        raise RuntimeError("ref_euka_run failed: %d" % rc)
+    for k in ("clade", "like", "not_like", "pass"):
+        out[k] = out[k][:n]
+    out["clade_count"] = count
+    out["bin_cov"] = cov[:int(boff[-1])]
+    return out
+
+
+# ---- soibean: analyse_GAM (src/getLCAfromGAM.h:31-700), the reference's own ------------------------------------------
+def soibean_run(graph, reads, member, min_id=0, penalty=7, deam5p_prof="", deam3p_prof=""):
+    """Same arguments as oracle.soibean_run (profiles as TEXT) -> (matrix [R, P], used [R])."""
+    member = np.ascontiguousarray(member, dtype=np.uint8)
+    n_rows, P = member.shape
+    out = np.zeros((max(reads.n, 1), P), dtype=np.float64)
+    used = np.zeros(max(reads.n, 1), dtype=np.uint8)
+    p5 = _write_tmp(deam5p_prof, ".prof") if deam5p_prof else ""
+    p3 = _write_tmp(deam3p_prof, ".prof") if deam3p_prof else ""
+    try:
+        rc = lib().ref_soibean_run(C.byref(graph.c), C.byref(reads.c), _ptr(member), C.c_int64(n_rows), int(min_id), int(P), int(penalty),
+                                   p5.encode(), p3.encode(), quality_pad(reads), _ptr(out), _ptr(used))
+    finally:
+        for f in (p5, p3):
+            if f:
+                os.remove(f)
+    if rc:
+        raise RuntimeError("ref_soibean_run failed: %d" % rc)
+    return out[:reads.n], used[:reads.n]
+
+
+def soibean_base_loglike(read_base, graph_base, ll, freqs7, t, branch_len):
+    """MCMC::computeBaseLogLike (src/MCMC.h:111-296) for one supported column."""
+    f7 = np.ascontiguousarray(freqs7, dtype=np.float64)
+    out = C.c_double(0.0)
+    rc = lib().ref_soibean_base_loglike(C.c_char(read_base.encode()), C.c_char(graph_base.encode()), C.c_double(ll), _ptr(f7),
+                                        C.c_double(t), C.c_double(branch_len), C.byref(out))
+    if rc:
+        raise RuntimeError("ref_soibean_base_loglike failed: %d" % rc)
+    return out.value

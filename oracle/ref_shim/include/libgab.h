@@ -106,3 +106,10 @@ inline string reverseComplement(const string& s) { string r(s.rbegin(), s.rend()
 inline void printprogressBarCerr(float) {}
 inline string getCWD(const char*) { return "."; }
 inline string getFullPath(const string& s) { return s; }
+
+// libgab prints containers with operator<< (used by debug output in src/MCMC.cpp:850,951)
+template <typename T>
+inline ostream& operator<<(ostream& os, const vector<T>& v) {
+    for (size_t i = 0; i < v.size(); ++i) { if (i) os << " "; os << v[i]; }
+    return os;
+}

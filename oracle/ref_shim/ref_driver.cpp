@@ -21,6 +21,8 @@
 #include "vgan_utils.h"
 #include "Dup_Remover.h"
 #include "damage.h"
+#include "Euka.h"          // pulls in readGAM_Euka.h (the readGAM3 lambda) and MCMC.h (computeBaseLogLike)
+#include "soibean.h"       // pulls in getLCAfromGAM.h (analyse_GAM)
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -33,6 +35,19 @@ Haplocart::~Haplocart() {}
 int main_filter(int, char**) { std::abort(); }
 int main_gamsort(int, char**) { std::abort(); }
 int main_giraffe(int, char**) { std::abort(); }
+// Euka.cpp / soibean.cpp hold the CLI and the graph loaders (gbwt, vg subcommands) and cannot be compiled here; the
+// three small members of theirs that the path needs are restated: the empty constructors (src/Euka.cpp:19-25) and
+// Euka::get_qscore_vec (src/Euka.cpp:38-51: 10^(-Q/10) for Q >= 2, else 0.25 -- quirk Q7, qs[2] = 0.631).
+Euka::Euka() {}
+Euka::~Euka() {}
+vector<double> Euka::get_qscore_vec() {
+    vector<double> qscore_vec;
+    for (int Q = 0; Q < 100; ++Q) {
+        if (Q >= 2) qscore_vec.emplace_back(pow(10, ((-1 * Q) * 0.1)));
+        else qscore_vec.emplace_back(0.25);
+    }
+    return qscore_vec;
+}
 
 extern "C" {
 
@@ -65,10 +80,12 @@ bdsg::ODGI make_graph(const orc_graph* g) {
     return og;
 }
 
-vg::Alignment make_alignment(const orc_reads* R, int64_t r) {
+vg::Alignment make_alignment(const orc_reads* R, int64_t r, int pad_quality = 0) {
     vg::Alignment a;
     a.set_sequence(std::string(R->seq + R->seq_off[r], R->seq + R->seq_off[r + 1]));
-    a.set_quality(std::string(R->qual + R->qual_off[r], R->qual + R->qual_off[r + 1]));
+    // pad_quality zero bytes make reads past the end of the quality string defined (euka and soibean index the
+    // quality by ALIGNED column, which runs past the string for reads with deletions: src/readGAM_Euka.h:264,286)
+    a.set_quality(std::string(R->qual + R->qual_off[r], R->qual + R->qual_off[r + 1]) + std::string((size_t)pad_quality, '\0'));
     a.set_mapping_quality(R->mapq[r]);
     a.set_identity(R->identity[r]);
     vg::Path* p = a.mutable_path();
@@ -371,5 +388,165 @@ int ref_damage_matrix(void* h, uint32_t L, uint32_t l, double* out16) {
     return 0;
 }
 int ref_damage_rows(void* h, uint32_t L) { RefDamage* r = (RefDamage*)h; return L < r->d.subDeamDiNuc.size() ? (int)r->d.subDeamDiNuc[L].size() : -1; }
+
+}  // extern "C"
+
+// =====================================================================================
+// euka: the per-read lambda of readGAM3 (src/readGAM_Euka.h:67-577), the reference's own, run over injected
+// alignments (the shim's vg::io::for_each replays ref_shim::injected()).  Clade / bin tables come through the
+// reference's own loaders (Euka::load_clade_info / load_clade_chunks, src/load.cpp:71-157) from the files named;
+// the damage tables through Damage::initDeamProbabilities.  The model tables base_freq / t_T_ratio / rare_bases are
+// filled with the assignments of Euka::run (src/Euka.cpp:444-486) into zero-initialised arrays (the reference leaves
+// the other entries uninitialised and declares rare_bases one entry too short for 'Y'; 256 entries here).
+// Per-read results are recovered from the per-clade vectors in arrival order.
+// =====================================================================================
+extern "C" {
+
+int ref_euka_run(const char* clade_file, const char* bins_file, const char* deam5p_file, const char* deam3p_file,
+                 const orc_graph* g, const orc_reads* R, int pad_quality, uint32_t minimum_mq, int32_t n_clades,
+                 int32_t* clade_out, double* like_out, double* not_like_out, uint8_t* pass_out, int64_t* clade_count,
+                 double* bin_cov, int64_t bin_cov_cap) {
+    try {
+        Euka ek;
+        const int lengthToProf = 5;
+        vector<Clade*>* clade_vec = ek.load_clade_info(clade_file, lengthToProf);
+        if ((int)clade_vec->size() != n_clades * 6) return -2;
+        vector<vector<tuple<int, int, double, double>>> chunks = ek.load_clade_chunks(bins_file);
+        Damage dmg;
+        dmg.initDeamProbabilities(deam5p_file ? deam5p_file : "", deam3p_file ? deam3p_file : "");
+        const vector<double> qscore_vec = ek.get_qscore_vec();
+        static double base_freq[256];
+        static double t_T_ratio['T' + 1]['T' + 1];
+        static bool rare_bases[256];
+        memset(base_freq, 0, sizeof(base_freq)); memset(t_T_ratio, 0, sizeof(t_T_ratio)); memset(rare_bases, 0, sizeof(rare_bases));
+        base_freq['A'] = log(0.362815); base_freq['C'] = log(0.207743); base_freq['G'] = log(0.116809);
+        base_freq['N'] = log(0.25); base_freq['T'] = log(0.312435);
+        t_T_ratio['A']['A'] = 1.0; t_T_ratio['C']['C'] = 1.0; t_T_ratio['G']['G'] = 1.0; t_T_ratio['T']['T'] = 1.0;
+        t_T_ratio['A']['C'] = 0.02381; t_T_ratio['A']['G'] = 0.95238; t_T_ratio['A']['T'] = 0.02381;
+        t_T_ratio['C']['A'] = 0.02381; t_T_ratio['C']['G'] = 0.02381; t_T_ratio['C']['T'] = 0.95238;
+        t_T_ratio['G']['A'] = 0.95238; t_T_ratio['G']['C'] = 0.02381; t_T_ratio['G']['T'] = 0.02381;
+        t_T_ratio['T']['A'] = 0.02381; t_T_ratio['T']['C'] = 0.95238; t_T_ratio['T']['G'] = 0.02381;
+        for (const char c : std::string("WMKRYBDHV")) rare_bases[(int)c] = true;
+
+        const bdsg::ODGI graph = make_graph(g);
+        std::vector<NodeInfo*> nodevector;  // passed through, never read by the lambda
+        auto& inj = ref_shim::injected();
+        inj.clear();
+        for (int64_t r = 0; r < R->n_reads; ++r) inj.emplace_back(make_alignment(R, r, pad_quality));
+        const unsigned int MINIMUMMQ = minimum_mq, MINNUMOFREADS = 10, MINNUMOFBINS = 6;
+        const double ENTROPY = 1.17;
+        const int MAXBINS = 0;
+        // per read: which clade's vectors grew, by how much count grew
+        // (run once over everything; then walk the reads again to attribute the per-clade entries in order)
+        auto res = readGAM3(graph, clade_file, false, clade_vec, nodevector, qscore_vec, base_freq, t_T_ratio, rare_bases, chunks,
+                            dmg.subDeamDiNuc, lengthToProf, "", MINIMUMMQ, MINNUMOFREADS, MINNUMOFBINS, ENTROPY, MAXBINS);
+        inj.clear();
+        // attribution: the clade of a read is the LAST bin over all clades containing its first node id (:115-140);
+        // recomputed here only to know WHICH clade vector holds the read's entry -- the values are the reference's
+        std::vector<size_t> next((size_t)n_clades, 1);  // index 0 is the dummy 0.0 each vector is created with (load.cpp:128)
+        for (int64_t r = 0; r < R->n_reads; ++r) {
+            clade_out[r] = -1; like_out[r] = not_like_out[r] = 0; pass_out[r] = 0;
+            if (R->identity[r] == 0) continue;
+            const int n_index = (int)R->map_node[R->map_off[r]];
+            int c_n = 0;
+            for (size_t i = 0; i < chunks.size(); ++i)
+                for (size_t j = 0; j < chunks[i].size(); ++j)
+                    if (n_index == std::clamp(n_index, get<0>(chunks[i][j]), get<1>(chunks[i][j]))) c_n = (int)i;
+            Clade* c = clade_vec->at((size_t)c_n * 6 + 1);
+            const size_t k = next[(size_t)c_n]++;
+            if (k >= c->clade_like.size() || k >= c->clade_not_like.size()) return -3;
+            clade_out[r] = c_n;
+            like_out[r] = c->clade_like[k];
+            not_like_out[r] = c->clade_not_like[k];
+        }
+        for (int c = 0; c < n_clades; ++c) {
+            if (next[(size_t)c] != clade_vec->at((size_t)c * 6 + 1)->clade_like.size()) return -4;
+            clade_count[c] = clade_vec->at((size_t)c * 6 + 1)->count;
+        }
+        int64_t b = 0;
+        for (size_t i = 0; i < chunks.size(); ++i)
+            for (size_t j = 0; j < chunks[i].size(); ++j) { if (b >= bin_cov_cap) return -5; bin_cov[b++] = get<3>(chunks[i][j]); }
+        for (auto* c : *clade_vec) delete c;
+        delete clade_vec;
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_euka_run: %s\n", e.what()); return -1; }
+}
+
+// MCMC::get_proposal_likelihood (src/MCMC.cpp:1175-1213) is private to a chain set-up; not exported here.
+
+// =====================================================================================
+// soibean: analyse_GAM (src/getLCAfromGAM.h:31-700), the reference's own, over injected alignments.
+// `nodepaths` is built as soibean::run builds it (src/soibean.cpp:476-491): for node minid + k the names of the paths
+// through it -- here from the membership matrix instead of ODGI steps.  The R x P matrix is read back from each read's
+// pathMap by path name (the reference's convertMapsToVector walks the unordered_map in its iteration order,
+// src/soibean.cpp:131-155; by-name lookup gives the same values in pathNames order).
+// =====================================================================================
+int ref_soibean_run(const orc_graph* g, const orc_reads* R, const uint8_t* member, int64_t member_rows, int32_t member_min_id,
+                    int32_t n_paths, int32_t penalty, const char* deam5p_file, const char* deam3p_file, int pad_quality, double* out,
+                    uint8_t* used) {
+    try {
+        Euka ek;
+        Damage dmg;
+        dmg.initDeamProbabilities(deam5p_file ? deam5p_file : "", deam3p_file ? deam3p_file : "");
+        const vector<double> qscore_vec = ek.get_qscore_vec();   // soibean uses Euka's table (src/soibean.cpp:471)
+        const bdsg::ODGI graph = make_graph(g);
+        std::vector<std::string> pathNames;
+        for (int p = 0; p < n_paths; ++p) { char b[32]; snprintf(b, sizeof(b), "path%06d", p); pathNames.emplace_back(b); }
+        const int minid = member_min_id;
+        std::vector<NodeInfo*> nodevector;
+        std::vector<std::vector<std::string>> nodepaths;
+        for (int64_t k = 0; k < member_rows; ++k) {
+            nodevector.emplace_back(new NodeInfo(minid + k, 0, 0));
+            std::vector<std::string> paths;
+            for (int p = 0; p < n_paths; ++p) if (member[(size_t)k * (size_t)n_paths + (size_t)p]) paths.emplace_back(pathNames[(size_t)p]);
+            nodepaths.push_back(paths);
+        }
+        std::vector<Clade*> clade_vec;
+        auto& inj = ref_shim::injected();
+        inj.clear();
+        for (int64_t r = 0; r < R->n_reads; ++r) inj.emplace_back(make_alignment(R, r, pad_quality));
+        std::streambuf* old = std::cerr.rdbuf();
+        std::ostringstream sink;
+        std::cerr.rdbuf(sink.rdbuf());   // the function prints the GAM file name
+        vector<AlignmentInfo*>* gam = nullptr;
+        try {
+            gam = analyse_GAM(graph, "/dev/null", &clade_vec, nodevector, nodepaths, pathNames, qscore_vec, false, minid, n_paths, penalty,
+                              false, "", false, dmg.subDeamDiNuc);
+        } catch (...) { std::cerr.rdbuf(old); inj.clear(); throw; }
+        std::cerr.rdbuf(old);
+        inj.clear();
+        size_t k = 0;
+        for (int64_t r = 0; r < R->n_reads; ++r) {
+            used[r] = 0;
+            for (int p = 0; p < n_paths; ++p) out[(size_t)r * (size_t)n_paths + (size_t)p] = 0;
+            if (R->identity[r] == 0) continue;
+            if (k >= gam->size()) return -3;
+            AlignmentInfo* ai = gam->at(k++);
+            used[r] = 1;
+            for (int p = 0; p < n_paths; ++p) out[(size_t)r * (size_t)n_paths + (size_t)p] = ai->pathMap.at(pathNames[(size_t)p]);
+        }
+        if (k != gam->size()) return -4;
+        for (auto* ai : *gam) delete ai;
+        delete gam;
+        for (auto* n : nodevector) delete n;
+        return 0;
+    } catch (const std::exception& e) { fprintf(stderr, "ref_soibean_run: %s\n", e.what()); return -1; }
+}
+
+// MCMC::computeBaseLogLike (src/MCMC.h:111-296), the reference's own, for one supported column.
+int ref_soibean_base_loglike(char read_base, char graph_base, double ll, const double* freqs7, double t, double branch_len, double* out) {
+    try {
+        MCMC mc;
+        AlignmentInfo::BaseInfo bi;
+        bi.readBase = read_base; bi.referenceBase = graph_base; bi.pathSupport = true; bi.logLikelihood = ll;
+        RunTreeProportionParams params(nullptr);
+        params.freqs['A'] = freqs7[0]; params.freqs['C'] = freqs7[1]; params.freqs['G'] = freqs7[2]; params.freqs['T'] = freqs7[3];
+        params.freqs['R'] = freqs7[4]; params.freqs['Y'] = freqs7[5]; params.freqs['M'] = freqs7[6];
+        AlignmentInfo read;
+        read.detailMap["p"] = std::vector<std::vector<AlignmentInfo::BaseInfo>>{{bi}};
+        *out = mc.computeBaseLogLike(&read, params, 0, 0, "p", t, branch_len);
+        return 0;
+    } catch (...) { return -1; }
+}
 
 }  // extern "C"

@@ -803,8 +803,13 @@ struct EukaTables {
     }
 };
 
-inline ld oplusnatl_ld(ld x, ld y) { return x > y ? x + log1pl(expl(y - x)) : y + log1pl(expl(x - y)); }
-inline ld oplusInitnatl_ld(ld x, ld y) { return x == 0 ? y : oplusnatl_ld(x, y); }
+// libgab's oplusnatl / oplusInitnatl are function templates over the argument type: euka and soibean call them with
+// doubles, so the sum is formed in double (get_posterior calls them with long doubles).  Held bit for bit against the
+// reference's own euka / soibean code compiled over the shim (tests/test_ref_pin.py), which uses the same template.
+template <typename T>
+inline T oplusnatl_t(const T x, const T y) { return x > y ? x + std::log1p(std::exp(y - x)) : y + std::log1p(std::exp(x - y)); }
+template <typename T>
+inline T oplusInitnatl_t(const T x, const T y) { return x == 0 ? y : oplusnatl_t(x, y); }
 inline int quality_at(const string& q, size_t m) { return m < q.size() ? (int)(signed char)q[m] : 0; }
 inline double euka_qs(const vector<double>& qs, int q) { return (q >= 0 && q < (int)qs.size()) ? qs[(size_t)q] : 0.25; }
 
@@ -895,8 +900,8 @@ int orc_euka_run(const orc_euka_tables* T, const orc_graph* g, const orc_reads* 
                     for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
                 double log_lik_marg = 0.0;
                 for (int bpd = 0; bpd < 4; bpd++) {
-                    if (ACGT[bpd] == (char)Rb) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd] * (1 - e)));
-                    else log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd] * (e / 3)));
+                    if (ACGT[bpd] == (char)Rb) log_lik_marg = oplusInitnatl_t<double>(log_lik_marg, std::log(probBasePostDamage[bpd] * (1 - e)));
+                    else log_lik_marg = oplusInitnatl_t<double>(log_lik_marg, std::log(probBasePostDamage[bpd] * (e / 3)));
                 }
                 log_lik = log_lik_marg;
                 if (G == Rb) log_lik_2 = std::log(1 - 0.25536);
@@ -909,7 +914,7 @@ int orc_euka_run(const orc_euka_tables* T, const orc_graph* g, const orc_reads* 
         }
         const int mq = a.mapping_quality;
         const double map_q = (1 - std::pow(10, ((-1 * mq) * 0.1)));  // 1 - get_p_incorrectly_mapped (src/miscfunc.h:215-216)
-        const double like = map_q * std::exp((double)((in_clade_lik) - oplusInitnatl_ld(in_clade_lik, not_in_clade_lik)));
+        const double like = map_q * std::exp((in_clade_lik) - oplusInitnatl_t<double>(in_clade_lik, not_in_clade_lik));
         clade_out[r] = c_n;
         in_out[r] = in_clade_lik;
         not_out[r] = not_in_clade_lik;
@@ -1012,7 +1017,7 @@ static int soibean_read(const orc_graph* g, const orc_reads* R, int64_t r, const
                         for (int bpd = 0; bpd < 4; bpd++)
                             for (int bpo = 0; bpo < 4; bpo++) probBasePostDamage[bpd] += probBasePreDamage[bpo] * D.p[bpo][bpd];
                         double log_lik_marg = -std::numeric_limits<double>::infinity();
-                        for (int bpd = 0; bpd < 4; bpd++) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, std::log(probBasePostDamage[bpd]));
+                        for (int bpd = 0; bpd < 4; bpd++) log_lik_marg = oplusInitnatl_t<double>(log_lik_marg, std::log(probBasePostDamage[bpd]));
                         if (log_lik_marg > std::log(0.9999999)) log_lik_marg = std::log(0.9999999);
                         push(rb, gb, true, log_lik_marg);  // the only entries with pathSupport = true (:374-379)
                         if (rev && rb != '-') baseOnRead--;
@@ -1114,8 +1119,8 @@ static int computeBaseLogLike(const BaseInfo& detail, const double* f7, const do
     }
     double log_lik_marg = -std::numeric_limits<double>::infinity();
     for (int bpd = 0; bpd < 4; bpd++) {
-        if ("ACGT"[bpd] == readb) log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((1 - branch_len))));
-        else log_lik_marg = (double)oplusInitnatl_ld(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((branch_len / 3))));
+        if ("ACGT"[bpd] == readb) log_lik_marg = oplusInitnatl_t<double>(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((1 - branch_len))));
+        else log_lik_marg = oplusInitnatl_t<double>(log_lik_marg, (std::log(probBaseHKY[bpd]) + std::log((branch_len / 3))));
     }
     if (log_lik_marg > 1e-8) log_lik_marg = std::log(0.999999999);
     if (std::isnan(log_lik_marg) || std::isinf(log_lik_marg)) return ORC_ERR_RANGE;
@@ -1192,8 +1197,8 @@ int orc_soibean_mcmc_loglike(const orc_graph* g, const orc_reads* R, const uint8
             } else {  // :964-970
                 const double interc2 = std::log(pos_branch[y]) + readLogLike;
                 const double interp2 = std::log((1 - pos_branch[y])) + readLogLikeP;
-                const double inter2 = (double)oplusnatl_ld(interc2, interp2);
-                inter = (double)oplusInitnatl_ld(inter, (inter2 + std::log(proportions[y])));
+                const double inter2 = oplusnatl_t<double>(interc2, interp2);
+                inter = oplusInitnatl_t<double>(inter, (inter2 + std::log(proportions[y])));
             }
         }
         if (n_sources != 1) contribution = inter;

@@ -66,3 +66,28 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def siblings():
+    """euka per-read outputs and one soibean R x P matrix from the reference's own readGAM3 lambda / analyse_GAM."""
+    import vgan_b200 as vb
+    from oracle import oracle as orc
+    from test_ref_pin import _euka_inputs
+    S, og, R, _keep = _euka_inputs()
+    e = ref.euka_run(S.dist, S.bin_off, S.bin_lo, S.bin_hi, og, R, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    euka = {"clade": e["clade"].tolist(), "like": e["like"].tolist(), "not_like": e["not_like"].tolist(),
+            "clade_count": e["clade_count"].tolist(), "bin_cov": e["bin_cov"].tolist()}
+    seed, P, n = 112, 31, 120
+    S2 = vb.SynthHaplocart(seed=seed, n_paths=P, n_rows=610, n_nodes=601)
+    alns = S2.reads(n, seed=seed + 1, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    mat, used = ref.soibean_run(orc.Graph(S2.node_sequences(), min_id=1), orc.FlatReads(alns.arrays()), S2.supports(), 0, 7,
+                                vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    with open(os.path.join(HERE, "ref_sibling_golden.json"), "w") as fh:
+        json.dump({"source": "reference readGAM3 lambda (src/readGAM_Euka.h) and analyse_GAM (src/getLCAfromGAM.h) compiled unchanged "
+                             "(oracle/ref_shim/Makefile); quality strings zero-padded",
+                   "euka": euka, "soibean": {"seed": seed, "P": P, "n": n, "matrix": mat.tolist(), "used": used.tolist()}}, fh,
+                  separators=(",", ":"))
+
+
+if __name__ == "__main__":
+    siblings()

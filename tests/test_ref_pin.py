@@ -233,3 +233,104 @@ def test_oracle_reproduces_the_committed_reference_vectors():
             assert total == H.ld_from_pairs([case["total_ll"]])[0]
             assert np.array_equal(conf, np.array(case["confidence_full"]))
             assert len(idx) == len(case["clades"])
+
+
+# ---- siblings: the reference's own euka lambda (readGAM3, src/readGAM_Euka.h:67-577) and soibean analyse_GAM
+#      (src/getLCAfromGAM.h:31-700), compiled unchanged and run over injected alignments ---------------------------------
+def _euka_inputs():
+    S = vb.SynthEuka(seed=11, n_clades=40, genome_len=3000)
+    alns = S.reads(600, seed=12, n_rate=0.01, softclip_rate=0.2, indel_rate=0.01)
+    return S, orc.Graph(S.node_sequences(), min_id=1), orc.FlatReads(alns.arrays()), alns
+
+
+@needs_ref
+@pytest.mark.parametrize("p5,p3", [(vb.DHIGH5P_PROF, vb.DHIGH3P_PROF), ("", ""), (vb.DHIGH5P_PROF, "")])
+def test_euka_lambda_bit_for_bit(p5, p3, capfd):
+    S, og, R, _keep = _euka_inputs()
+    want = orc.euka_run(S.dist, S.bin_off, S.bin_lo, S.bin_hi, og, R, p5, p3)
+    got = ref.euka_run(S.dist, S.bin_off, S.bin_lo, S.bin_hi, og, R, p5, p3)
+    m = want["clade"] >= 0
+    assert m.sum() >= 590 and np.array_equal(want["clade"], got["clade"])
+    assert np.array_equal(want["like"][m], got["like"][m]) and np.array_equal(want["not_like"][m], got["not_like"][m])   # doubles, bit for bit
+    assert np.array_equal(want["clade_count"], got["clade_count"]) and want["clade_count"].sum() > 30
+    assert np.array_equal(want["bin_cov"], got["bin_cov"])
+
+
+@needs_ref
+def test_euka_lambda_symbol_cases_on_the_toy_graph(capfd):
+    nodes, _ = H.toy_graph()
+    og = orc.Graph(nodes)
+    n9, n13 = nodes[9], nodes[13]
+    reads = [
+        H.aln("TTTTTTT" + n9[:2] + "N" + n9[3:7] + "Y" + n9[9:], [(9, 0, False, [(0, 7, "TTTTTTT"), (2, 2, ""), (1, 1, "N"), (4, 4, ""), (1, 1, "Y"), (1, 0, ""), (9, 9, "")])],
+              quality=bytes([10, 20, 30, 40, 41, 35, 2] * 4)[:24], mapq=37),
+        H.aln(H.revcomp(n13), [(13, 0, True, [(32, 32, "")])], quality=bytes([33] * 32), mapq=60),
+        H.aln(n13[:20] + "ACGT" + n13[20:], [(13, 0, False, [(20, 20, ""), (0, 4, "ACGT"), (12, 12, "")])], quality=bytes([25] * 10), mapq=30),
+        H.aln(n13, [(13, 0, False, [(32, 32, "")])], quality=bytes([99, 0, 1, 2, 3] * 7)[:32], mapq=0),   # (a byte >= 100 indexes qscore_vec out of range in the reference)
+    ]
+    dist, boff, blo, bhi = [0.12, 0.07], [0, 2, 3], [1, 10, 12], [9, 11, 40]
+    R = orc.Reads(reads)
+    want = orc.euka_run(dist, boff, blo, bhi, og, R, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    got = ref.euka_run(dist, boff, blo, bhi, og, R, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    assert np.array_equal(want["clade"], got["clade"]) and list(got["clade"]) == [0, 1, 1, 1]
+    assert np.array_equal(want["like"], got["like"]) and np.array_equal(want["not_like"], got["not_like"])
+    assert np.array_equal(want["clade_count"], got["clade_count"]) and np.array_equal(want["bin_cov"], got["bin_cov"])
+
+
+@needs_ref
+@pytest.mark.parametrize("P,p5,p3,penalty", [(31, "", "", 7), (127, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 7), (63, vb.DHIGH5P_PROF, "", 3)])
+def test_soibean_analyse_gam_bit_for_bit(P, p5, p3, penalty, capfd):
+    S = vb.SynthHaplocart(seed=81 + P, n_paths=P, n_rows=610, n_nodes=601)
+    alns = S.reads(200, seed=82 + P, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    g, R, member = orc.Graph(S.node_sequences(), min_id=1), orc.FlatReads(alns.arrays()), S.supports()
+    want, used_w = orc.soibean_run(g, R, member, 0, penalty, p5, p3)
+    got, used = ref.soibean_run(g, R, member, 0, penalty, p5, p3)
+    assert np.array_equal(used_w, used) and used.sum() >= 195
+    assert np.array_equal(want, got)                       # doubles, bit for bit
+
+
+@needs_ref
+def test_soibean_analyse_gam_on_the_toy_reads(capfd):
+    nodes, paths = H.toy_graph()
+    member = np.zeros((max(nodes) + 1, len(paths)), dtype=np.uint8)
+    for p, (_, steps) in enumerate(paths):
+        for nid, _ in steps:
+            member[nid, p] = 1
+    R = orc.Reads(read_gam(os.path.join(H.GOLDEN, "test_reads.gam")))     # match / mismatch / indel / softclip x both strands
+    want, used_w = orc.soibean_run(orc.Graph(nodes), R, member, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    got, used = ref.soibean_run(orc.Graph(nodes), R, member, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    assert used.all() and np.array_equal(used_w, used) and np.array_equal(want, got)
+
+
+@needs_ref
+def test_soibean_base_loglike_equals_compute_base_log_like():
+    """MCMC::computeBaseLogLike (src/MCMC.h:111-296), the per-column HKY term of the soibean MCMC likelihood."""
+    F7 = orc.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
+    n = 0
+    for rb in "ACGT":
+        for gb in "ACGT":
+            for t in (0.0, 1e-3, 0.05, 0.5):
+                for bl in (0.0, 0.01, 0.3):
+                    a = orc.soibean_base_loglike(rb, gb, -0.3, F7, t, bl)
+                    b = ref.soibean_base_loglike(rb, gb, -0.3, F7, t, bl)
+                    assert a == b or (np.isnan(a) and np.isnan(b)), (rb, gb, t, bl, a, b)
+                    n += 1
+    assert n == 192
+
+
+def test_oracle_reproduces_the_committed_sibling_vectors():
+    """Runs everywhere: euka per-read (clade, like, not_like) and a soibean R x P matrix the reference's own code produced."""
+    gold = json.load(open(os.path.join(H.GOLDEN, "ref_sibling_golden.json")))
+    S, og, R, _keep = _euka_inputs()
+    e = gold["euka"]
+    want = orc.euka_run(S.dist, S.bin_off, S.bin_lo, S.bin_hi, og, R, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    assert want["clade"].tolist() == e["clade"]
+    m = want["clade"] >= 0
+    assert np.array_equal(want["like"][m], np.array(e["like"])[m]) and np.array_equal(want["not_like"][m], np.array(e["not_like"])[m])
+    assert want["clade_count"].tolist() == e["clade_count"] and np.array_equal(want["bin_cov"], np.array(e["bin_cov"]))
+    s = gold["soibean"]
+    S2 = vb.SynthHaplocart(seed=s["seed"], n_paths=s["P"], n_rows=610, n_nodes=601)
+    alns = S2.reads(s["n"], seed=s["seed"] + 1, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    mat, used = orc.soibean_run(orc.Graph(S2.node_sequences(), min_id=1), orc.FlatReads(alns.arrays()), S2.supports(), 0, 7,
+                                vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    assert np.array_equal(mat, np.array(s["matrix"])) and used.tolist() == s["used"]
