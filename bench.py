@@ -3,18 +3,26 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
 
-A "step" is one whole sample through the hot path: reset the accumulators, run the read kernel over
-the batch, collapse into the per-path vector (bit-GEMV), (N > 1: all-gather the per-rank vectors over
-NCCL and sum them in rank order), argmax + log-softmax posterior + clade support, and read the result
-back.  `value` times that with the batch already resident in HBM; `e2e` times the same call sequence
-through the host-buffer entry point (pinned host SoA -> H2D -> kernels -> D2H) every step.
+A "step" is one whole sample through the hot path: reset the accumulators, run the read kernel over the batch, collapse
+into the per-path vector (bit-GEMV), (N > 1: exchange the per-rank vectors over NVLink peer memory and sum them in rank
+order), argmax + log-softmax posterior + clade support, and read the result back.
 
-Workloads (SURVEY.md 8d):  N = 1 -> config 2 (10^6 x 100 bp reads, 11825 x 5179 tables);
-N > 1 -> config 3 shape (ancient-damaged fragments, log-normal lengths), R reads per GPU (weak scaling).
-The batch (~0.6 GB) is larger than the 126 MB L2, so every step streams it from HBM.
+  value   the batch already resident in HBM when the timed region starts (device time, CUDA events);
+  e2e     the same sample from what the reference's call site holds -- the FLAT ALIGNMENT FIELDS of vector<AlignmentInfo*>
+          (vgh_alignments, host memory) -- through the reference-facing call vgh_hc_feed (host marshalling into page-locked
+          chunks, H2D, device-side reconstruct_graph_sequence + packing, read kernel) to the posterior on the host, every
+          step.  `e2e_prepacked` keeps the round-1 figure (a batch packed ahead of time in its wire form).
 
-`--impl reference` times the CPU restatement of the reference's own per-path loops (oracle, literal
-mode; the reference itself cannot be compiled here) on all host cores, on a bounded sample per step.
+Workload: config 2 at every N (10^6 x 100 bp reads per GPU, 11825 x 5179 tables): one weak-scaling series.
+The same JSON line carries, as extra blocks, the other BASELINE.json configs where the driver runs them:
+  N > 1: `config3` -- 50 M ancient-damaged reads in total (strong scaling: 50 M / N per GPU), value + e2e;
+  N = 1: `config4` (euka, the reference's own euka_db.clade / .bins tables) and `config5` (soibean, P = 399), each with its
+         own roofline.
+The batch (~0.4 GB) is larger than the 126 MB L2, so every step streams it from HBM.
+
+`--impl reference` times the REFERENCE'S OWN CODE (oracle/_ref/libvgan_ref.so: src/update_likelihood.cpp,
+process_mapping.cpp, get_p_obs_base.cpp compiled unchanged over a header shim) on all host cores, on a bounded sample
+per step; the oracle port stands in only where that library is absent.
 """
 import argparse
 import json
@@ -30,6 +38,7 @@ METRIC = "read x path likelihood evaluations per second"
 UNIT = "evals/s"
 N_PATHS, N_ROWS, N_NODES = 5179, 11825, 11821
 TABLE_SEED = 20260
+CONFIG3_TOTAL_READS = 50_000_000
 
 
 def peaks():
@@ -42,14 +51,12 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def workload(n_gpus, reads, config=2):
-    """Config 2 (BASELINE.json configs[1]) is the bench workload at every N: the same reads-per-GPU, so the per-N values
-    are one weak-scaling series.  --workload 3 selects the config-3 shape (ancient-damaged reads, log-normal lengths)."""
+def workload(reads, config=2):
     if config == 2:
         return dict(name="HaploCart config 2: synthetic %d x 100bp reads per GPU x %d paths" % (reads, N_PATHS), seed=20261,
                     kw=dict(fixed_len=100, sub_rate=0.005, indel_rate=0.0005, damage=False))
-    return dict(name="HaploCart config 3 shape: synthetic ancient-damaged reads (log-normal 30-150bp), %d per GPU x %d "
-                     "paths" % (reads, N_PATHS), seed=20263,
+    return dict(name="HaploCart config 3: synthetic ancient-damaged reads (dhigh5p/dhigh3p profiles, log-normal 30-150bp) x %d "
+                     "paths" % N_PATHS, seed=20263,
                 kw=dict(fixed_len=0, sub_rate=0.005, indel_rate=0.0005, damage=True))
 
 
@@ -104,26 +111,59 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_rate(S, alns, seconds_target, threads=0, hoisted=False):
-    """Time the literal (reference-shaped) CPU restatement on a bounded sample; returns a dict."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code (oracle/_ref) where it was built, the oracle port otherwise
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_inputs(S, alns):
     from oracle import oracle as orc
     node, val = S.pmap()
     T = orc.HcTables(S.supports(), node, val, S.mappab(), min_id=1)
     G = orc.Graph(S.node_sequences(), min_id=1)
     R = orc.FlatReads(alns.arrays())
-    cores = threads if threads > 0 else (os.cpu_count() or 1)
-    # calibrate on a few reads per thread, then size the sample for ~seconds_target of wall clock
+    return T, G, R
+
+
+def _cpu_run(kind, T, G, R, r0, r1, cores):
+    """One pass of the reference's hot loop over reads [r0, r1) on `cores` threads -> (reads used, seconds of the loop)."""
+    from oracle import oracle as orc
+    if kind == "reference":
+        from oracle import ref
+        tm = {}
+        _, _, used = ref.hc_run(T, G, R, r0, r1, n_threads=cores, timing=tm)
+        return used, tm["loop_seconds"]
+    t = time.perf_counter()
+    _, _, used = orc.hc_run(T, G, R, r0=r0, r1=r1, mode=orc.MODE_LITERAL, n_threads=cores)
+    return used, time.perf_counter() - t
+
+
+def cpu_kind():
+    try:
+        from oracle import ref
+        if ref.available():
+            ref.lib()
+            return "reference"
+    except Exception:
+        pass
+    return "port"
+
+
+CPU_WHAT = {"reference": "the reference's own Haplocart::update / process_mapping / get_p_obs_base (oracle/_ref/libvgan_ref.so: "
+                         "/root/reference/src compiled unchanged over a header shim) in the OpenMP read loop of src/HaploCart.cpp:408-421",
+            "port": "literal per-path loops of the oracle port (oracle/vgan_oracle.cpp MODE_LITERAL; oracle/_ref not present)"}
+
+
+def cpu_reference_rate(S, alns, seconds_target, hoisted=False):
+    """Time the reference's CPU path on a bounded sample of the same workload; returns the cpu_baseline dict."""
+    from oracle import oracle as orc
+    kind = cpu_kind()
+    T, G, R = _cpu_inputs(S, alns)
+    cores = os.cpu_count() or 1
     n0 = min(len(alns), 2 * cores)
-    t = time.perf_counter()
-    _, _, used0 = orc.hc_run(T, G, R, r0=0, r1=n0, mode=orc.MODE_LITERAL, n_threads=cores)
-    dt0 = max(time.perf_counter() - t, 1e-6)
-    n = int(min(len(alns), max(n0, n0 * seconds_target / dt0)))
-    t = time.perf_counter()
-    _, argmax, used = orc.hc_run(T, G, R, r0=0, r1=n, mode=orc.MODE_LITERAL, n_threads=cores)
-    dt = time.perf_counter() - t
-    out = {"value": used * N_PATHS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": "first %d reads of the same synthetic set, literal per-path loops (oracle MODE_LITERAL, long double, "
-                     "-O3 -fopenmp), %.1f s wall" % (n, dt),
+    used0, dt0 = _cpu_run(kind, T, G, R, 0, n0, cores)
+    n = int(min(len(alns), max(n0, n0 * seconds_target / max(dt0, 1e-6))))
+    used, dt = _cpu_run(kind, T, G, R, 0, n, cores)
+    out = {"value": used * N_PATHS / dt, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "first %d reads of the same synthetic set, %.1f s: %s (long double, -O3 -fopenmp)" % (n, dt, CPU_WHAT[kind]),
            "reads": used, "seconds": dt}
     if hoisted:
         # the fair optimised-CPU comparator (SURVEY 8d): A_i / B_i once per mapping, then the per-path select-add
@@ -131,51 +171,164 @@ def cpu_reference_rate(S, alns, seconds_target, threads=0, hoisted=False):
         t = time.perf_counter()
         _, _, uh = orc.hc_run(T, G, R, r0=0, r1=nh, mode=orc.MODE_HOISTED, n_threads=cores)
         dth = time.perf_counter() - t
-        out["hoisted"] = {"value": uh * N_PATHS / dth, "reads": uh, "seconds": dth,
-                          "what": "same oracle with A_i / B_i computed once per mapping (MODE_HOISTED)"}
+        out["hoisted"] = {"value": uh * N_PATHS / dth, "reads": uh, "seconds": dth, "kind": "port",
+                          "what": "oracle port with A_i / B_i computed once per mapping (MODE_HOISTED), same threads"}
     return out
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference's own loop nest, all host cores."""
+    """--impl reference: the reference's own CPU implementation of the path, all host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import vgan_b200 as vb
-    from oracle import oracle as orc
-    wl = workload(args.gpus, args.reads, args.workload)
+    kind = cpu_kind()
+    wl = workload(args.reads, 2)
     S = vb.SynthHaplocart(seed=TABLE_SEED, n_paths=N_PATHS, n_rows=N_ROWS, n_nodes=N_NODES)
     cores = os.cpu_count() or 1
-    # bounded sample: sized so that warmup + steps end within a few minutes
     probe_reads = S.reads(4 * cores, seed=wl["seed"], **wl["kw"])
-    probe = cpu_reference_rate(S, probe_reads, seconds_target=2.0)
-    per_read = probe["seconds"] / max(probe["reads"], 1)
-    budget = 150.0 / max(args.steps + args.warmup, 1)
+    T, G, R = _cpu_inputs(S, probe_reads)
+    used, dt = _cpu_run(kind, T, G, R, 0, len(probe_reads), cores)
+    per_read = dt / max(used, 1)
+    budget = 150.0 / max(args.steps + args.warmup, 1)       # the whole run ends within a few minutes
     n = int(max(cores, min(200000, budget / per_read)))
     alns = S.reads(n, seed=wl["seed"], **wl["kw"])
-    node, val = S.pmap()
-    T = orc.HcTables(S.supports(), node, val, S.mappab(), min_id=1)
-    G = orc.Graph(S.node_sequences(), min_id=1)
-    R = orc.FlatReads(alns.arrays())
+    T, G, R = _cpu_inputs(S, alns)
     for _ in range(args.warmup):
-        orc.hc_run(T, G, R, mode=orc.MODE_LITERAL, n_threads=cores)
-    t = time.perf_counter()
-    used = 0
+        _cpu_run(kind, T, G, R, 0, n, cores)
+    used, secs = 0, 0.0
     for _ in range(args.steps):
-        _, _, u = orc.hc_run(T, G, R, mode=orc.MODE_LITERAL, n_threads=cores)
+        u, d = _cpu_run(kind, T, G, R, 0, n, cores)
         used += u
-    dt = time.perf_counter() - t
-    value = used * N_PATHS / dt
+        secs += d
+    value = used * N_PATHS / secs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f80 (long double)", "data": "synthetic",
             "config": {"workload": wl["name"], "sample_reads_per_step": n, "paths": N_PATHS},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d reads per step of the same synthetic workload, literal per-path loops "
-                                       "(oracle MODE_LITERAL; the reference itself cannot be built here)" % n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d reads per step of the same synthetic workload: %s" % (n, CPU_WHAT[kind])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sibling configs (N = 1 only): euka on the reference's own clade / bin tables, soibean at P = 399
+# ---------------------------------------------------------------------------------------------------------------------
+def _event_ms(torch, stream, fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        out = fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def bench_config4(torch, stream, n_reads, peak):
+    """euka (BASELINE.json configs[3]): clades and bins verbatim from the reference's euka_db.clade / euka_db.bins."""
+    import numpy as np
+    import vgan_b200 as vb
+    gold = os.path.join(ROOT, "tests", "golden")
+    S = vb.SynthEuka.from_tables(os.path.join(gold, "euka_db.clade"), os.path.join(gold, "euka_db.bins"), seed=20264)
+    alns = S.reads(n_reads, seed=20265)
+    ek = vb.Euka()
+    ek.set_stream(stream.cuda_stream)
+    ek.load(S.tables(vb.DHIGH5P_PROF, vb.DHIGH3P_PROF))
+    ek.load_graph(S.graph)
+    t0 = time.perf_counter()
+    pb = vb.EukaPackedBatch(S.graph, alns, pinned=True)
+    pack_s = time.perf_counter() - t0
+    cols = int(np.diff(alns.arrays()["seq_off"]).sum())
+    ek.reset()
+    ek.run(pb)               # leaves the batch in HBM
+
+    def resident():          # the kernel again on the resident batch, nothing crosses PCIe
+        ek.reset()
+        return ek.rerun(pb.n_span)
+
+    def from_alignments():
+        ek.reset()
+        return ek.run_raw(vb.RawBatch(alns, pinned=False, euka_rule=True))
+
+    for _ in range(3):
+        resident()
+    ms_dev, _ = _event_ms(torch, stream, resident, 10)
+    k_ms = ek.kernel_ms()
+    for _ in range(2):
+        from_alignments()
+    ms_e2e, res = _event_ms(torch, stream, from_alignments, 3)
+    raw_bytes = vb.RawBatch(alns, pinned=False, euka_rule=True).nbytes
+    # algorithmic bytes (SURVEY 8d): 2 B per aligned column as stored (symbol pair + quality) + 10 B header in, 20 B out per read
+    alg = 2 * cols + 30 * pb.n_reads
+    out = {"workload": "euka config 4: %d synthetic aeDNA reads x 335 clades / 3929 bins taken verbatim from the reference's euka_db.clade "
+                       "/ euka_db.bins (node sequences synthetic, damage dhigh5p / dhigh3p)" % pb.n_reads,
+           "metric": "reads per second (one clade per read: evaluations = reads)", "reads": pb.n_reads, "aligned_columns": cols,
+           "value": pb.n_reads / (ms_dev * 1e-3), "unit": "reads/s", "ms_per_step": ms_dev,
+           "e2e": {"value": pb.n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": raw_bytes,
+                   "d2h_bytes_per_step": 33 * pb.n_reads,
+                   "route": "flat alignment fields -> vgh_euka_raw_build -> vgl_euka_run_raw (H2D, device reconstruction + packing, "
+                            "euka kernel) -> per-read results on the host"},
+           "host_pack_seconds": pack_s, "detected_reads": int(res["pass"].sum()),
+           "roofline": {"bound": "hbm", "kernel": "euka_read_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
+                        "traffic": None}}
+    ek.close()
+    return out
+
+
+def bench_config5(torch, stream, n_reads, peak, P=399):
+    """soibean (BASELINE.json configs[4]): the R x P likelihood matrix that feeds the multi-source MCMC."""
+    import numpy as np
+    import vgan_b200 as vb
+    from vgan_b200.host import pinned_empty
+    Sh = vb.SynthHaplocart(seed=20266, n_paths=P, n_rows=N_ROWS, n_nodes=N_NODES)
+    al = Sh.reads(n_reads, seed=20267, fixed_len=0, sub_rate=0.01, indel_rate=0.001, damage=True)
+    sb = vb.Soibean()
+    sb.set_stream(stream.cuda_stream)
+    sb.load(vb.SoibeanTables(Sh.supports(), 0, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 7))
+    sb.load_graph(Sh.graph)
+    pk = vb.SoibeanPackedBatch(Sh.graph, al, pinned=True)
+    po, pu = pinned_empty((pk.n_span, P), np.float64), pinned_empty((pk.n_span,), np.uint8)
+
+    sb.analyse_into(pk, po, pu)   # leaves the batch in HBM
+
+    def resident():      # the kernels again on the resident batch, the matrix left in HBM for the MCMC kernel: no R x P copy
+        return sb.rerun(pk.n_span)
+
+    def to_host():       # matrix returned into page-locked memory (what convertMapsToVector hands the host MCMC)
+        return sb.analyse_into(pk, po, pu)
+
+    for _ in range(2):
+        resident()
+    ms_dev, _ = _event_ms(torch, stream, resident, 5)
+    k_ms = sb.kernel_ms()
+    to_host()
+    ms_e2e, _ = _event_ms(torch, stream, to_host, 3)
+    # one MCMC proposal scored on the resident batch (SURVEY 8f rank 3)
+    f7 = vb.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
+    rng = np.random.default_rng(5)
+    props = [[(int(rng.integers(P)), int(rng.integers(P)), float(rng.uniform(0.05, 0.95)), float(rng.uniform(0.001, 0.05)), w)
+              for w in (0.6, 0.4)] for _ in range(64)]
+    sb.mcmc_loglike(props, f7, 0.01)
+    t0 = time.perf_counter()
+    sb.mcmc_loglike(props, f7, 0.01)
+    mcmc_ms = (time.perf_counter() - t0) * 1e3 / len(props)
+    alg_out = 8 * P * pk.n_reads
+    out = {"workload": "soibean config 5: %d synthetic damaged reads x %d species-tree paths (PENALTY 7, dhigh profiles)" % (pk.n_reads, P),
+           "reads": pk.n_reads, "paths": P, "value": pk.n_reads * P / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev,
+           "e2e": {"value": pk.n_reads * P / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": pk.nbytes,
+                   "d2h_bytes_per_step": alg_out + pk.n_reads,
+                   "route": "packed host batch -> H2D -> soibean kernels -> R x P matrix into page-locked host memory"},
+           "mcmc_ms_per_proposal_batched_64": mcmc_ms,
+           "roofline": {"bound": "hbm", "kernel": "soibean_path_kernel", "achieved": alg_out / (k_ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg_out / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms,
+                        "algorithmic_bytes_per_launch": alg_out, "traffic": None,
+                        "what": "P * 8 B written per read (SURVEY 8d: the R x P matrix is the dominant stream)"}}
+    sb.close()
+    return out
 
 
 def main():
@@ -183,25 +336,33 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU (config 2)")
     ap.add_argument("--impl", default="vgan_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / 4 / 5 blocks")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU exchange of the P-vector")
-    ap.add_argument("--workload", type=int, default=2, choices=[2, 3], help="SURVEY 8d config whose read shape is generated")
+    ap.add_argument("--workload", type=int, default=2, choices=[2, 3], help="SURVEY 8d config whose read shape the main line uses")
+    ap.add_argument("--config3-tile", type=int, default=1000000, help="config 3: distinct reads generated per GPU (re-scored to reach 50 M / N)")
+    ap.add_argument("--sibling-reads", type=int, default=1000000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    # the host side is sharded too: every rank marshals with its share of the cores
+    host_threads = max(1, (os.cpu_count() or 1) // max(local_world, 1))
+    os.environ["OMP_NUM_THREADS"] = str(host_threads)
+
     import numpy as np
     import torch
     import vgan_b200 as vb
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
@@ -212,26 +373,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
-    wl = workload(n_gpus, args.reads, args.workload)
+    wl = workload(args.reads, args.workload)
     S = vb.SynthHaplocart(seed=TABLE_SEED, n_paths=N_PATHS, n_rows=N_ROWS, n_nodes=N_NODES)
     alns = S.reads(args.reads, seed=wl["seed"] + 1000 * rank, **wl["kw"])
     hc = vb.Haplocart(device=local)
     hc.load(S.tables(), S.tree())
+    hc.load_graph(S.graph)
     # every kernel, copy and collective of a step runs on this stream, and so do the timing events
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     hc.set_stream(stream.cuda_stream)
     t_pack = time.perf_counter()
-    packed = vb.PackedBatch(S.graph, alns, pinned=True)
+    packed = vb.PackedBatch(S.graph, alns, pinned=True, n_threads=host_threads)
     t_pack = time.perf_counter() - t_pack
     dev = hc.upload(packed)
-    # the e2e route ships the batch in its wire form (12- or 16-bit column records + one node id per mapping) and expands it on
-    # the device; graphs with node ids above 65535 would ship the 32-bit batch itself
     try:
         wire = vb.WireBatch(packed, pinned=True)
     except RuntimeError:
         wire = None
-    host_batch = wire if wire is not None else packed
     reads_local = packed.n_reads
     batch_bytes = packed.nbytes
     # algorithmic bytes of the read kernel: 4 per column + 4 per empty mapping + 7 per read + 8 per group
@@ -239,25 +398,35 @@ def main():
     alg_bytes = int(4 * pa["n_cols"].astype(np.int64).sum() + 4 * pa["n_extra"].astype(np.int64).sum() + 7 * reads_local
                     + 8 * (int(packed.batch.n_groups) + 1))
     del pa
+    feeder = vb.Feeder(n_threads=host_threads)
 
     sharded = None
     if world > 1:
         from vgan_b200.dist import ShardedSample
-        # exchange of the per-rank final_vec + fixed-order sum (vgan_b200/dist.py): peer-memory kernels, NCCL as fallback
         sharded = ShardedSample(hc, exchange=args.exchange)
 
-    def step(host_buffers):
+    def finish():
         if sharded is not None:
-            return sharded.run([host_batch] if host_buffers else [dev], device_resident=not host_buffers)
-        hc.reset()
-        if host_buffers:
-            if wire is not None:
-                hc.update_wire(wire)
-            else:
-                hc.update(packed)
-        else:
-            hc.update_device(dev.batch)
+            return sharded.finish(want_ll=False)
         return hc.get_posterior(want_ll=False)
+
+    def step_resident():
+        hc.reset()
+        hc.update_device(dev.batch)
+        return finish()
+
+    def step_e2e():            # from the flat alignment fields, host marshalling inside the step
+        hc.reset()
+        feeder.feed(hc, alns)
+        return finish()
+
+    def step_prepacked():      # round-1 e2e: a batch packed (and turned into its wire form) ahead of time
+        hc.reset()
+        if wire is not None:
+            hc.update_wire(wire)
+        else:
+            hc.update(packed)
+        return finish()
 
     def barrier():
         torch.cuda.synchronize()
@@ -265,14 +434,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(host_buffers, steps):
+    def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k_ms, k_n = 0.0, 0
         barrier()
         l0 = hc.launch_count()
         e0.record(stream)
         for _ in range(steps):
-            res = step(host_buffers)
+            res = fn()
             ms, n = hc.read_kernel_ms()
             k_ms += ms
             k_n += n
@@ -286,57 +455,88 @@ def main():
         return ms_total, k_ms, k_n, hc.launch_count() - l0, res
 
     for _ in range(args.warmup):
-        step(False)
+        step_resident()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, k_ms, k_n, launches, res = timed(False, args.steps)
+    ms_dev, k_ms, k_n, launches, res = timed(step_resident, args.steps)
     for _ in range(3):
-        step(True)
-    e2e_steps = max(3, min(args.steps, 20))
-    ms_e2e, _, _, _, res_e2e = timed(True, e2e_steps)
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 10))
+    st0 = feeder.stats()
+    ms_e2e, _, _, _, res_e2e = timed(step_e2e, e2e_steps)
+    st1 = feeder.stats()
+    for _ in range(3):
+        step_prepacked()
+    ms_pre, _, _, _, res_pre = timed(step_prepacked, e2e_steps)
     clocks = sampler.finish()
+    same_call = res_e2e.get("maxh_index") == res.get("maxh_index") == res_pre.get("maxh_index")
 
-    # the same sample from RAW alignments: H2D of the compact alignment arrays, reconstruction + packing on the device
-    # (SURVEY 8f rank 1), kernels, result -- against the host packer's rate reported in `host_pack`
-    raw_path = None
-    if world == 1:
-        t0 = time.perf_counter()
-        raw = vb.RawBatch(alns, pinned=True)
-        t_raw = time.perf_counter() - t0          # includes cudaHostAlloc of the whole block
-        t_raw_pageable = []
-        for _ in range(2):                        # second pass: the allocator hands back touched pages
-            t0 = time.perf_counter()
-            tmp = vb.RawBatch(alns, pinned=False)
-            t_raw_pageable.append(time.perf_counter() - t0)
-            del tmp
-        hc.load_graph(S.graph)
+    # sharded result == rank-order sum of the ranks' own vectors, identical on every rank (checked on the device-resident step)
+    parity_ok = None
+    if world > 1:
+        final = step_resident_ll = None
+        hc.reset()
+        hc.update_device(dev.batch)
+        mine = torch.zeros(N_PATHS, dtype=torch.float64, device="cuda")
+        hc.paths(mine.data_ptr())
+        torch.cuda.synchronize()
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        want = np.zeros(N_PATHS)
+        for p in parts:
+            want = want + p.cpu().numpy()
+        hc.reset()
+        hc.update_device(dev.batch)
+        got = sharded.finish(want_ll=True)["final_vec"]
+        g = torch.from_numpy(np.ascontiguousarray(got)).cuda()
+        allg = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(allg, g)
+        identical = all(bool(torch.equal(allg[0], x)) for x in allg)
+        parity_ok = bool(identical and np.array_equal(got, want))
 
-        def raw_step():
+    # config 3 (N > 1): 50 M damaged reads in total, 50 M / N per GPU (strong scaling); every GPU holds `tile` distinct reads and
+    # scores them ceil(share / tile) times per step
+    config3 = None
+    if world > 1 and not args.no_extras:
+        wl3 = workload(0, 3)
+        share = CONFIG3_TOTAL_READS // world
+        tile = min(args.config3_tile, share)
+        al3 = S.reads(tile, seed=wl3["seed"] + 1000 * rank, **wl3["kw"])
+        pk3 = vb.PackedBatch(S.graph, al3, pinned=True, n_threads=host_threads)
+        dev3 = hc.upload(pk3)
+        reps = max(1, int(round(share / max(pk3.n_reads, 1))))
+
+        def step3_resident():
             hc.reset()
-            hc.update_raw(raw)
-            return hc.get_posterior(want_ll=False)
+            for _ in range(reps):
+                hc.update_device(dev3.batch)
+            return finish()
 
-        for _ in range(3):
-            res_raw = raw_step()
-        raw_steps = max(3, min(args.steps, 10))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        for _ in range(raw_steps):
-            res_raw = raw_step()
-        e1.record(stream)
-        barrier()
-        ms_raw = e0.elapsed_time(e1) / raw_steps
-        raw_path = {"value": raw.n_reads * N_PATHS / (ms_raw * 1e-3), "unit": UNIT, "ms_per_step": ms_raw, "steps": raw_steps,
-                    "h2d_bytes_per_step": raw.nbytes, "host_build_seconds": t_raw,
-                    "host_build_seconds_pageable": t_raw_pageable,
-                    "same_call_as_packed_route": res_raw.get("maxh_index") == res.get("maxh_index"),
-                    "what": "vgl_hc_accumulate_raw: pinned raw alignments -> H2D -> device reconstruction + packing -> read kernel "
-                            "-> posterior; host_build_seconds is the one-pass copy into the compact raw arrays (no reconstruction) incl. the pinned allocation; _pageable: the same into malloc'ed memory, cold and warm"}
-        del raw
+        def step3_e2e():
+            hc.reset()
+            for _ in range(reps):
+                feeder.feed(hc, al3)
+            return finish()
 
-    # per-sample latency at the size one real sample can reach after duplicate removal (SURVEY 8d scale caveat):
-    # host batch -> H2D -> kernels -> posterior on the host, one sample at a time
+        step3_resident()
+        ms3, k3_ms, k3_n, _, res3 = timed(step3_resident, 3)
+        step3_e2e()
+        ms3e, _, _, _, _ = timed(step3_e2e, 1)
+        t = torch.tensor([pk3.n_reads * reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        tot3 = int(t.item())
+        config3 = {"workload": wl3["name"], "total_reads": tot3, "reads_per_gpu": pk3.n_reads * reps, "scaling": "strong",
+                   "distinct_reads_per_gpu": pk3.n_reads, "passes_per_step": reps,
+                   "value": tot3 * N_PATHS * 3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / 3,
+                   "read_kernel_ms_per_launch": k3_ms / max(k3_n, 1),
+                   "e2e": {"value": tot3 * N_PATHS / (ms3e * 1e-3), "unit": UNIT, "ms_per_step": ms3e,
+                           "route": "vgh_hc_feed per pass (flat alignment fields, host marshalling inside)"},
+                   "mean_columns_per_read": float(pk3.arrays()["n_cols"].astype(np.int64).sum()) / max(pk3.n_reads, 1),
+                   "called_haplogroup": res3.get("predicted_haplotype")}
+        dev3.free()
+        del pk3, al3
+
+    # per-sample latency at the size one real sample can reach after duplicate removal (SURVEY 8d scale caveat)
     latency = None
     if world == 1:
         n_lat = min(20000, len(alns))
@@ -347,21 +547,24 @@ def main():
         for _ in range(20):
             hc.run_sample([small], want_ll=False)
         latency = {"reads": small.n_reads, "ms_per_sample": (time.perf_counter() - t0) / 20 * 1e3,
-                   "what": "reset + accumulate (host batch) + finalize, host wall clock, mean of 20"}
-        # ... and from the alignments themselves, host marshalling included: the host packer route against the raw route
-        def from_alignments(raw_route):
+                   "what": "reset + accumulate (packed host batch) + finalize, host wall clock, mean of 20"}
+
+        def from_alignments(route):
             hc.reset()
-            if raw_route:
+            if route == "feed":
+                feeder.feed(hc, alns, 0, n_lat)
+            elif route == "raw":
                 hc.update_raw(vb.RawBatch(alns, r0=0, r1=n_lat))
             else:
                 hc.update(vb.PackedBatch(S.graph, alns, r0=0, r1=n_lat))
             return hc.get_posterior(want_ll=False)
-        for key, flag in (("ms_per_sample_from_alignments_host_packer", False), ("ms_per_sample_from_alignments_raw_route", True)):
+        for key, route in (("ms_per_sample_from_alignments_host_packer", "pack"), ("ms_per_sample_from_alignments_raw_route", "raw"),
+                           ("ms_per_sample_from_alignments_feeder", "feed")):
             for _ in range(3):
-                from_alignments(flag)
+                from_alignments(route)
             t0 = time.perf_counter()
             for _ in range(10):
-                from_alignments(flag)
+                from_alignments(route)
             latency[key] = (time.perf_counter() - t0) / 10 * 1e3
 
     total_reads = reads_local
@@ -370,21 +573,32 @@ def main():
         dist.all_reduce(t)
         total_reads = int(t.item())
 
+    peak, peak_kind = peaks()
+    extras = {}
+    if world == 1 and not args.no_extras:
+        hc_free = [dev]
+        for name, fn in (("config4", bench_config4), ("config5", bench_config5)):
+            try:
+                extras[name] = fn(torch, stream, args.sibling_reads, peak)
+            except Exception as e:  # a sibling block must not take the headline down
+                extras[name] = {"error": repr(e)}
+
     if rank == 0:
-        peak, peak_kind = peaks()
         value = total_reads * N_PATHS * args.steps / (ms_dev * 1e-3)
         e2e = total_reads * N_PATHS * e2e_steps / (ms_e2e * 1e-3)
+        e2e_pre = total_reads * N_PATHS * e2e_steps / (ms_pre * 1e-3)
         kernel_ms = k_ms / max(k_n, 1)
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
                 if tj.get("reads") == reads_local and tj.get("kernel") == "hc_read_kernel":
-                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             except Exception:
                 pass
+        nsteps = max(e2e_steps, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -393,22 +607,35 @@ def main():
                        "l2": "batch of %.0f MB per step exceeds the 126 MB L2 (no flush needed)" % (batch_bytes / 1e6),
                        "parallelism": "reads sharded over %d GPU(s); one exchange of P doubles per sample (%s)" % (
                            n_gpus, "none" if sharded is None else sharded.exchange),
+                       "host_threads_per_rank": host_threads,
                        "called_haplogroup": res.get("predicted_haplotype")},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_batch.nbytes,
-                    "route": ("vgl_hc_accumulate_wire (wire form, %s columns, expanded on the device)" % ("12-bit" if wire.wire.col8 else "16-bit")) if wire is not None else "vgl_hc_accumulate", "d2h_bytes_per_step": 28 + 8 * hc._max_post,
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
-            "raw_path": raw_path,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // nsteps,
+                    "d2h_bytes_per_step": 28 + 8 * hc._max_post, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "route": "flat alignment fields (vgh_alignments, host) -> vgh_hc_feed: host marshalling into page-locked chunks "
+                             "overlapped with H2D + device reconstruct_graph_sequence + packing + read kernel -> posterior on the host",
+                    "host_marshal_seconds_per_step": (st1["build_seconds"] - st0["build_seconds"]) / nsteps,
+                    "host_wait_seconds_per_step": (st1["wait_seconds"] - st0["wait_seconds"]) / nsteps,
+                    "general_builder_chunks": st1["slow_chunks"] - st0["slow_chunks"],
+                    "same_call_as_resident_and_prepacked": bool(same_call)},
+            "e2e_prepacked": {"value": e2e_pre, "unit": UNIT, "ms_per_step": ms_pre / e2e_steps,
+                              "h2d_bytes_per_step": (wire.nbytes if wire is not None else packed.nbytes),
+                              "route": "batch packed and turned into its wire form AHEAD of the timed region (round-1 e2e)"},
             "latency": latency,
-            "host_pack": {"seconds": t_pack, "reads_per_s": reads_local / t_pack, "threads": os.cpu_count(),
+            "host_pack": {"seconds": t_pack, "reads_per_s": reads_local / t_pack, "threads": host_threads,
                           "what": "vgh_hc_pack (reconstruction + packing, OpenMP) of the step's batch; outside the timed regions"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "hc_read_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "batch_bytes_with_padding": batch_bytes,
                          "kernel_ms": kernel_ms, "bytes_per_read": alg_bytes / max(reads_local, 1),
                          "frac_at_survey_562B_per_read": 562.0 * reads_local / (kernel_ms * 1e-3) / 1e9 / peak},
         }
+        if parity_ok is not None:
+            line["parity_ok"] = parity_ok
+        if config3 is not None:
+            line["config3"] = config3
+        line.update(extras)
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(S, alns, args.cpu_seconds, hoisted=True)
         print(json.dumps(line))

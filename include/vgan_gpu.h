@@ -281,6 +281,10 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* host_wire);
  *   map_node[m]                    Mapping.position.node_id | is_reverse << 31;  map_offset[m] = position.offset
  *   edit_from / edit_to [e]        Edit.from_length / to_length (<= 65535); edit_seq_off[e] .. [e+1] its sequence
  * Only reads with identity >= 1e-10 are listed (src/HaploCart.cpp:411).  All pointers are HOST pointers.      */
+#define VGL_HC_RAW_NARROW_ONLY 1u /* vgl_hc_raw.reserved: only the narrow arrays are present (all six twins, first_offset16
+                                   * form); the batch is at most one device chunk (131072 reads); edit_off and edit_seq_off
+                                   * hold just their two end points {first, last}; map_node / map_offset / edit_from / edit_to
+                                   * are NULL.  What vgh_hc_feed submits.                                                   */
 typedef struct vgl_hc_raw {
     uint32_t n_reads, n_maps, n_edits, reserved;
     const uint32_t* qual_off;     /* [n_reads + 1] */
@@ -446,6 +450,11 @@ int vgl_euka_run(vgl_ctx* ctx, const vgl_euka_batch* host_batch, uint32_t n_out,
  * filled): reconstruct_graph_sequence and the packing run on the device (vgl_hc_set_graph first).               */
 int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
                      double* like, uint8_t* pass);
+/* Score AGAIN the batch the last vgl_euka_run / vgl_euka_run_raw left in HBM (no host -> device traffic): what a caller does
+ * that keeps a sample resident, and what bench.py times as the device-resident figure.  Outputs as vgl_euka_run (each may be NULL). */
+int vgl_euka_rerun(vgl_ctx* ctx, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik, double* like, uint8_t* pass);
+/* Device time (ms, CUDA events on the launching stream) of the last euka read kernel / soibean kernel pair this context ran. */
+int vgl_sibling_kernel_ms(vgl_ctx* ctx, float* ms_out);
 /* Per-clade count (Clade::count) and per-bin coverage (get<3>(chunks[c][j])) accumulated since the reset. */
 int vgl_euka_results(vgl_ctx* ctx, int64_t* clade_count, double* bin_cov);
 /* euka's abundance MCMC (MCMC::run / get_proposal_likelihood, src/MCMC.cpp:1175-1366) re-reads every clade's clade_like vector
@@ -496,6 +505,9 @@ int vgl_soibean_set_tables(vgl_ctx* ctx, const vgl_soibean_tables* tables);
 /* path_ll[r * n_paths + p] = pathMap[pathNames[p]] of read r (r = read_index); used[r] = 1 for reads of the batch. */
 int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* host_batch, uint32_t n_out, double* path_ll, uint8_t* used);
 int vgl_soibean_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, double* path_ll, uint8_t* used);
+/* The same kernels again on the batch the last vgl_soibean_run / _run_raw left in HBM; with path_ll == NULL the R x P matrix stays
+ * on the device (where vgl_soibean_mcmc_loglike reads what it needs), i.e. no device -> host traffic at all.           */
+int vgl_soibean_rerun(vgl_ctx* ctx, uint32_t n_out, double* path_ll, uint8_t* used);
 
 /* ------------------------------------------------------------------------------------------- */
 /* soibean MCMC: log-likelihood of proposals                                                   */

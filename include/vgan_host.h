@@ -33,7 +33,8 @@ enum {
     VGH_ERR_FORMAT = 103,   /* malformed GAM / table text                                          */
     VGH_ERR_BAD_READ = 104, /* an alignment the reference could not process either (it would throw
                                from std::string::substr / vector::at inside a noexcept function)    */
-    VGH_ERR_BAD_NODE = 105
+    VGH_ERR_BAD_NODE = 105,
+    VGH_ERR_DEVICE = 106    /* the likelihood library (include/vgan_gpu.h) reported an error; see vgl_last_error() */
 };
 
 const char* vgh_last_error(void);
@@ -120,6 +121,23 @@ const vgl_hc_raw* vgh_hc_raw_view(const vgh_hc_raw* p);
 int64_t vgh_hc_raw_skipped(const vgh_hc_raw* p);
 void vgh_hc_raw_destroy(vgh_hc_raw* p);
 
+/* ---- feeder: flat alignment fields -> GPU, chunked and overlapped ------------------------------ */
+/* Replaces the `#pragma omp parallel for` of src/HaploCart.cpp:408-421 for a caller that holds the flat alignment fields:
+ * vgh_hc_feed adds reads [r0, r1) to the sample open on `ctx` (between vgl_hc_reset and vgl_hc_finalize).  The reads travel
+ * in chunks of `chunk_reads` (<= 131072): while the device copies, reconstructs (src/vgan_utils.h:6-79) and scores one
+ * chunk, `n_threads` host threads marshal the next into the other of two page-locked blocks the feeder keeps.  Returns
+ * when every chunk has been copied (the kernels run on; errors in the reads surface at vgl_hc_finalize).            */
+typedef struct vgh_hc_feeder vgh_hc_feeder;
+struct vgl_ctx;
+int vgh_hc_feeder_create(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out);
+int vgh_hc_feed(vgh_hc_feeder* f, struct vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1);
+/* One chunk (r1 - r0 <= chunk_reads) marshalled without submitting it, for inspection and tests; *out is NULL when the
+ * chunk does not fit the narrow arrays (vgh_hc_feed then takes vgh_hc_raw_build for it).                            */
+int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out);
+void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* wait_seconds, uint64_t* h2d_bytes, uint64_t* chunks,
+                         uint64_t* slow_chunks);
+void vgh_hc_feeder_destroy(vgh_hc_feeder* f);
+
 /* ---- HaploCart tables ----------------------------------------------------------------------- */
 typedef struct vgh_hc_tables vgh_hc_tables;
 /* Inputs as the reference holds them in memory:
@@ -203,6 +221,10 @@ int vgh_synth_hc_reads(const vgh_synth_hc* s, uint64_t seed, int64_t n_reads, in
 /* euka-shaped workload: clades own consecutive node ranges, 10-15 overlapping bins each. */
 typedef struct vgh_synth_euka vgh_synth_euka;
 int vgh_synth_euka_create(uint64_t seed, int32_t n_clades, int32_t genome_len, vgh_synth_euka** out);
+/* clade table and bins verbatim (share/vgan/euka_dir/euka_db.clade / .bins: dist, snode..enode per
+ * clade, bins as node-id ranges); node sequences synthetic; a read's clade drawn in proportion to its node-range size. */
+int vgh_synth_euka_create_from_tables(uint64_t seed, int32_t n_clades, const double* dist, const int32_t* snode, const int32_t* enode,
+                                      const int32_t* bin_off, const int32_t* bin_lo, const int32_t* bin_hi, vgh_synth_euka** out);
 void vgh_synth_euka_destroy(vgh_synth_euka* s);
 const vgh_graph* vgh_synth_euka_graph(const vgh_synth_euka* s);
 int64_t vgh_synth_euka_graph_seq(const vgh_synth_euka* s, const int64_t** seq_off, const char** seq);

@@ -67,41 +67,46 @@ def reconstruct(graph, reads, r, cap=8192):
     return g[:ng.value].tobytes().decode(), p[:npp.value].tobytes().decode(), s[:ns.value].tolist()
 
 
-def quality_pad(reads, r=None):
+def quality_pad(reads, r0=None, r1=None):
     """Zero bytes to append to a quality string so that the reference's out-of-range quality reads
     (src/update_likelihood.cpp:40-44, quirk Q4) are defined: the window of the last mapping ends below
-    2 * |aligned read| <= 2 * (|sequence| + deleted bases)."""
-    lo, hi = (0, reads.n) if r is None else (r, r + 1)
+    2 * |aligned read|, and |aligned read| <= sum over the read's edits of from_length + to_length."""
+    lo = 0 if r0 is None else int(r0)
+    hi = reads.n if r1 is None else int(r1)
     if hi <= lo:
-        return 1
-    seq_len = int(np.max(reads.seq_off[lo + 1:hi + 1] - reads.seq_off[lo:hi]))
-    m0, m1 = int(reads.map_off[lo]), int(reads.map_off[hi])
-    e0, e1 = int(reads.edit_off[m0]), int(reads.edit_off[m1])
-    dels = int(np.sum(reads.edit_from[e0:e1])) if e1 > e0 else 0
-    return 2 * (seq_len + dels) + 8
+        return 8
+    e_of_read = reads.edit_off[reads.map_off[lo:hi + 1]]
+    span = (reads.edit_from.astype(np.int64) + reads.edit_to.astype(np.int64))
+    csum = np.concatenate([[0], np.cumsum(span[int(e_of_read[0]):int(e_of_read[-1])])])
+    per_read = csum[e_of_read[1:] - e_of_read[0]] - csum[e_of_read[:-1] - e_of_read[0]]
+    return int(2 * (per_read.max() if per_read.size else 0) + 8)
 
 
 def hc_read(tables, graph, reads, r, pad_quality=None):
     """Haplocart::update (src/update_likelihood.cpp:5-53) for one read from the zero vector -> long double[P]."""
     ll = np.zeros(tables.n_paths, dtype=np.longdouble)
-    pad = quality_pad(reads, r) if pad_quality is None else int(pad_quality)
+    pad = quality_pad(reads, r, r + 1) if pad_quality is None else int(pad_quality)
     rc = lib().ref_hc_read(C.byref(tables.c), C.byref(graph.c), C.byref(reads.c), C.c_int64(r), pad, _ptr(ll))
     if rc:
         raise RuntimeError("ref_hc_read failed: %d" % rc)
     return ll
 
 
-def hc_run(tables, graph, reads, r0=0, r1=None, n_threads=1, pad_quality=None):
-    """The read loop of Haplocart::run (src/HaploCart.cpp:408-424) over the reference's update()."""
+def hc_run(tables, graph, reads, r0=0, r1=None, n_threads=1, pad_quality=None, timing=None):
+    """The read loop of Haplocart::run (src/HaploCart.cpp:408-424) over the reference's update().
+    `timing` (a dict) receives "loop_seconds": the OpenMP loop + max_element alone, tables and reads already built."""
     r1 = reads.n if r1 is None else r1
     final = np.zeros(tables.n_paths, dtype=np.longdouble)
     am = C.c_int32()
     used = C.c_int64()
-    pad = quality_pad(reads) if pad_quality is None else int(pad_quality)
+    pad = quality_pad(reads, r0, r1) if pad_quality is None else int(pad_quality)
+    secs = C.c_double(0.0)
     rc = lib().ref_hc_run(C.byref(tables.c), C.byref(graph.c), C.byref(reads.c), C.c_int64(r0), C.c_int64(r1), pad,
-                          int(n_threads), _ptr(final), C.byref(am), C.byref(used))
+                          int(n_threads), _ptr(final), C.byref(am), C.byref(used), C.byref(secs))
     if rc:
         raise RuntimeError("ref_hc_run failed: %d" % rc)
+    if timing is not None:
+        timing["loop_seconds"] = secs.value
     return final, am.value, used.value
 
 

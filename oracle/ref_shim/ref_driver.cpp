@@ -200,7 +200,7 @@ int ref_hc_read(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, 
 // then std::max_element.  `use_background_error_prob` and `is_consensus_fasta` are both set for FASTA input
 // (src/HaploCart.cpp:397-401).  per_read_seconds (optional) receives the wall time spent in update().
 int ref_hc_run(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, int64_t r0, int64_t r1, int pad_quality, int n_threads,
-               long double* final_out, int32_t* argmax_out, int64_t* used_out) {
+               long double* final_out, int32_t* argmax_out, int64_t* used_out, double* loop_seconds) {
     HcState S;
     build_state(T, S);
     const bdsg::ODGI graph = make_graph(g);
@@ -214,6 +214,7 @@ int ref_hc_run(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, i
     const int n_reads = (int)algnvector.size();
     std::vector<long double> log_likelihood_vec((size_t)S.nbpaths, 0), empty_vec((size_t)S.nbpaths, 0), final_vec((size_t)S.nbpaths, 0);
     int64_t used = 0;
+    const double t_loop = omp_get_wtime();
     #pragma omp parallel for num_threads(n_threads) private(log_likelihood_vec) reduction(+:used)
     for (long unsigned int i = 0; i < (long unsigned int)n_reads; ++i) {
         if (algnvector.at(i)->identity < 1e-10) continue;
@@ -225,6 +226,7 @@ int ref_hc_run(const orc_hc_tables* T, const orc_graph* g, const orc_reads* R, i
         used += 1;
     }
     const int maxh_index = (int)(std::max_element(final_vec.begin(), final_vec.end()) - final_vec.begin());
+    if (loop_seconds) *loop_seconds = omp_get_wtime() - t_loop;   // the hot loop + max_element only (tables and reads were built before)
     for (int j = 0; j < S.nbpaths; ++j) final_out[j] = final_vec[(size_t)j];
     *argmax_out = maxh_index;
     *used_out = used;

@@ -134,6 +134,9 @@ GPU_SYMBOLS = {
     "vgl_soibean_set_tables": (C.c_int, [_P, C.POINTER(vgl_soibean_tables)]),
     "vgl_soibean_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P]),
     "vgl_soibean_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    "vgl_soibean_rerun": (C.c_int, [_P, C.c_uint32, _P, _P]),
+    "vgl_euka_rerun": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    "vgl_sibling_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "vgl_soibean_mcmc_loglike": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_uint32, _P, _P]),
     "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
@@ -150,6 +153,12 @@ HOST_SYMBOLS = {
     "vgh_hc_wire_destroy": (None, [_P]),
     "vgh_euka_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vgh_hc_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "vgh_hc_feeder_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P)]),
+    "vgh_hc_feed": (C.c_int, [_P, _P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64]),
+    "vgh_hc_feeder_marshal": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.POINTER(C.POINTER(vgl_hc_raw))]),
+    "vgh_hc_feeder_stats": (None, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_uint64)]),
+    "vgh_hc_feeder_destroy": (None, [_P]),
     "vgh_hc_raw_view": (C.POINTER(vgl_hc_raw), [_P]),
     "vgh_hc_raw_skipped": (C.c_int64, [_P]),
     "vgh_hc_raw_destroy": (None, [_P]),
@@ -188,6 +197,7 @@ HOST_SYMBOLS = {
     "vgh_soibean_tables_destroy": (None, [_P]),
     "vgh_soibean_pack": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
     "vgh_synth_euka_create": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "vgh_synth_euka_create_from_tables": (C.c_int, [C.c_uint64, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "vgh_synth_euka_destroy": (None, [_P]),
     "vgh_synth_euka_graph": (_P, [_P]),
     "vgh_synth_euka_graph_seq": (C.c_int64, [_P, C.POINTER(_P), C.POINTER(_P)]),

@@ -434,6 +434,7 @@ struct vgh_synth_euka {
     std::vector<int32_t> bin_off, bin_lo, bin_hi;
     std::vector<int32_t> node_off;          // coordinate of each node inside its clade's genome
     std::vector<int32_t> clade_len;         // genome length of each clade
+    std::vector<double> clade_cdf;          // empty: clades equally likely; else cumulative weights (config 4: node-range size)
 };
 
 extern "C" {
@@ -508,6 +509,54 @@ int vgh_synth_euka_create(uint64_t seed, int32_t n_clades, int32_t genome_len, v
     *out = S;
     return VGH_OK;
 }
+// the clade table (dist, snode..enode) and the bins are taken verbatim from the reference's
+// share/vgan/euka_dir/euka_db.clade / euka_db.bins; only the node sequences are synthetic (1-4 random bases per node, a
+// clade's genome is the chain of its nodes; ids outside every clade get one base).  A read's clade is drawn in
+// proportion to the clade's node-range size.
+int vgh_synth_euka_create_from_tables(uint64_t seed, int32_t n_clades, const double* dist, const int32_t* snode, const int32_t* enode,
+                                      const int32_t* bin_off, const int32_t* bin_lo, const int32_t* bin_hi, vgh_synth_euka** out) {
+    if (!out || n_clades < 1 || !dist || !snode || !enode || !bin_off || !bin_lo || !bin_hi) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
+    int32_t max_id = 0;
+    for (int c = 0; c < n_clades; ++c) {
+        if (snode[c] < 1 || enode[c] < snode[c]) return vgh_fail(VGH_ERR_INVALID, "clade %d: bad node range", c);
+        max_id = std::max(max_id, enode[c]);
+    }
+    Rng rng(seed);
+    vgh_synth_euka* S = new vgh_synth_euka();
+    S->n_clades = n_clades;
+    S->graph.min_id = 1;
+    S->graph.n_nodes = max_id;
+    std::vector<uint8_t> len((size_t)max_id + 1, 1);
+    std::vector<int32_t> owner((size_t)max_id + 1, -1);
+    for (int c = 0; c < n_clades; ++c)
+        for (int32_t id = snode[c]; id <= enode[c]; ++id) owner[(size_t)id] = c;   // (ranges do not overlap in euka_db.clade)
+    S->graph.off.reserve((size_t)max_id + 1);
+    S->graph.off.push_back(0);
+    S->node_off.assign((size_t)max_id + 1, 0);
+    for (int32_t id = 1; id <= max_id; ++id) {
+        const int l = owner[(size_t)id] >= 0 ? 1 + (int)rng.below(4) : 1;
+        for (int j = 0; j < l; ++j) S->graph.seq.push_back(kBases[rng.below(4)]);
+        S->graph.off.push_back((int64_t)S->graph.seq.size());
+        len[(size_t)id] = (uint8_t)l;
+    }
+    double tot = 0;
+    for (int c = 0; c < n_clades; ++c) {
+        S->dist.push_back(dist[c]);
+        S->snode.push_back(snode[c]);
+        S->enode.push_back(enode[c]);
+        int pos = 0;
+        for (int32_t id = snode[c]; id <= enode[c]; ++id) { S->node_off[(size_t)id] = pos; pos += len[(size_t)id]; }
+        S->clade_len.push_back(pos);
+        tot += (double)(enode[c] - snode[c] + 1);
+        S->clade_cdf.push_back(tot);
+    }
+    for (auto& w : S->clade_cdf) w /= tot;
+    S->bin_off.assign(bin_off, bin_off + n_clades + 1);
+    S->bin_lo.assign(bin_lo, bin_lo + bin_off[n_clades]);
+    S->bin_hi.assign(bin_hi, bin_hi + bin_off[n_clades]);
+    *out = S;
+    return VGH_OK;
+}
 void vgh_synth_euka_destroy(vgh_synth_euka* s) { delete s; }
 const vgh_graph* vgh_synth_euka_graph(const vgh_synth_euka* s) { return &s->graph; }
 int64_t vgh_synth_euka_graph_seq(const vgh_synth_euka* s, const int64_t** seq_off, const char** seq) {
@@ -527,7 +576,11 @@ int vgh_synth_euka_reads(const vgh_synth_euka* S, uint64_t seed, int64_t n_reads
     if (!S || !out || n_reads < 0) return vgh_fail(VGH_ERR_INVALID, "bad synth arguments");
     ReadParams P{fixed_len, 0.03, indel_rate, damage, n_rate, softclip_rate};
     *out = simulate_reads(S->graph, seed, n_reads, P, [&](Rng& rng, int64_t, std::vector<Piece>& walk) {
-        const int c = (int)rng.below((uint64_t)S->n_clades);
+        int c = (int)rng.below((uint64_t)S->n_clades);
+        if (!S->clade_cdf.empty()) {
+            c = (int)(std::lower_bound(S->clade_cdf.begin(), S->clade_cdf.end(), rng.uniform()) - S->clade_cdf.begin());
+            if (c >= S->n_clades) c = S->n_clades - 1;
+        }
         const int glen = S->clade_len[(size_t)c];
         const int L = draw_length(rng, P, glen);
         const int s = (int)rng.below((uint64_t)(glen - L + 1));

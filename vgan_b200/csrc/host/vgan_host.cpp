@@ -17,6 +17,8 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <thread>
+#include <chrono>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -1076,6 +1078,235 @@ void vgh_hc_raw_destroy(vgh_hc_raw* p) {
         else free(p->block);
     }
     delete p;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// feeder: the drop-in for the OpenMP read loop of src/HaploCart.cpp:408-421 when the caller holds the flat
+// alignment fields (what FlatAlignments::assign yields).  Reads go to the GPU in chunks: while the device copies,
+// reconstructs and scores chunk c, the host marshals chunk c + 1 into the other of two page-locked blocks that live
+// as long as the feeder (no allocation, no page faults per sample).  Only the narrow arrays of vgl_hc_raw are
+// written (node ids as 16 bits, one node offset per read, edit counts / lengths / sequence lengths as one byte
+// each); a chunk whose values do not fit, or that holds a read the hot loop skips (identity < 1e-10), goes through
+// vgh_hc_raw_build instead.
+// ------------------------------------------------------------------------------------------------
+struct vgh_hc_feeder {
+    int n_threads = 1;
+    int64_t chunk_reads = 131072;
+    void* block[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    bool pinned[2] = {false, false};
+    vgl_hc_raw view[2];
+    double build_s = 0, wait_s = 0;
+    uint64_t bytes = 0, chunks = 0, slow_chunks = 0, reads = 0;
+};
+
+extern "C" {
+
+int vgh_hc_feeder_create(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out) {
+    if (!out) return fail(VGH_ERR_INVALID, "null output");
+    vgh_hc_feeder* f = new (std::nothrow) vgh_hc_feeder();
+    if (!f) return fail(VGH_ERR_INVALID, "out of host memory");
+#ifdef _OPENMP
+    f->n_threads = n_threads > 0 ? n_threads : omp_get_max_threads();
+#endif
+    if (chunk_reads > 0) f->chunk_reads = std::min<int64_t>(chunk_reads, 131072);  // one device chunk per submission
+    memset(f->view, 0, sizeof(f->view));
+    *out = f;
+    return VGH_OK;
+}
+void vgh_hc_feeder_destroy(vgh_hc_feeder* f) {
+    if (!f) return;
+    for (int k = 0; k < 2; ++k)
+        if (f->block[k]) { if (f->pinned[k]) vgl_host_free(f->block[k]); else free(f->block[k]); }
+    delete f;
+}
+void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* wait_seconds, uint64_t* h2d_bytes, uint64_t* chunks,
+                         uint64_t* slow_chunks) {
+    if (!f) return;
+    if (build_seconds) *build_seconds = f->build_s;
+    if (wait_seconds) *wait_seconds = f->wait_s;
+    if (h2d_bytes) *h2d_bytes = f->bytes;
+    if (chunks) *chunks = f->chunks;
+    if (slow_chunks) *slow_chunks = f->slow_chunks;
+}
+
+// Marshals the reads of [ra, rb) that the hot loop keeps (identity >= 1e-10, src/HaploCart.cpp:411) into block `slot`.
+// Two parallel passes over per-thread ranges of reads: (A) how many mappings / edits / bytes each range keeps (read-level
+// offsets only), (B) the copy itself.  Returns 1 when the chunk needs the general builder instead.
+static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int64_t ra, int64_t rb) {
+    const size_t Rall = (size_t)(rb - ra);
+    int T = std::max(1, f->n_threads);
+    T = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, Rall / 512 + 1));
+    struct Cnt { uint64_t r = 0, m = 0, e = 0, q = 0, s = 0; };
+    std::vector<Cnt> base((size_t)T + 1);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
+        Cnt c;
+        for (size_t k = k0; k < k1; ++k) {
+            const int64_t r = ra + (int64_t)k;
+            if (a->identity[r] < 1e-10) continue;
+            const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
+            const int64_t ea = a->edit_off[ma], eb = a->edit_off[mb];
+            c.r += 1; c.m += (uint64_t)(mb - ma); c.e += (uint64_t)(eb - ea);
+            c.q += (uint64_t)(a->qual_off[r + 1] - a->qual_off[r]);
+            c.s += (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
+        }
+        base[(size_t)t + 1] = c;
+    }
+    for (int t = 0; t < T; ++t) {
+        base[(size_t)t + 1].r += base[(size_t)t].r; base[(size_t)t + 1].m += base[(size_t)t].m; base[(size_t)t + 1].e += base[(size_t)t].e;
+        base[(size_t)t + 1].q += base[(size_t)t].q; base[(size_t)t + 1].s += base[(size_t)t].s;
+    }
+    const size_t R = (size_t)base[(size_t)T].r, nm = (size_t)base[(size_t)T].m, ne = (size_t)base[(size_t)T].e;
+    const size_t nq = (size_t)base[(size_t)T].q, ns = (size_t)base[(size_t)T].s;
+    if (nm >= 0xffffffffull || ne >= 0xffffffffull || nq >= 0xffffffffull || ns >= 0xffffffffull) return 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
+    const size_t o_n16 = take(nm * 2), o_fo16 = take(R * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne);
+    const size_t o_eseq = take(ns), o_ends = take(64);
+    if (o > f->cap[slot]) {
+        if (f->block[slot]) { if (f->pinned[slot]) vgl_host_free(f->block[slot]); else free(f->block[slot]); }
+        f->block[slot] = nullptr;
+        f->cap[slot] = 0;
+        const size_t want = align_up(o + o / 4, 1 << 20);
+        f->pinned[slot] = vgl_host_alloc(&f->block[slot], want) == VGL_OK;
+        if (!f->pinned[slot]) {   // no CUDA device in this process (host-only tests): ordinary memory holds the same bytes
+            f->block[slot] = aligned_alloc(4096, want);
+            if (!f->block[slot]) return fail(VGH_ERR_INVALID, "out of host memory");
+        }
+        f->cap[slot] = want;
+    }
+    uint8_t* blk = (uint8_t*)f->block[slot];
+    uint32_t* qoff = (uint32_t*)(blk + o_qoff); uint32_t* soff = (uint32_t*)(blk + o_soff); uint32_t* moff = (uint32_t*)(blk + o_moff);
+    uint8_t* mq = blk + o_mq; uint8_t* q = blk + o_q;
+    uint16_t* n16 = (uint16_t*)(blk + o_n16); uint16_t* fo16 = (uint16_t*)(blk + o_fo16);
+    uint8_t* ne8 = blk + o_ne8; uint8_t* sl8 = blk + o_sl8; uint8_t* f8 = blk + o_f8; uint8_t* t8 = blk + o_t8; uint8_t* eseq = blk + o_eseq;
+    int bad = 0;
+#pragma omp parallel for schedule(static, 1) num_threads(T) reduction(| : bad)
+    for (int t = 0; t < T; ++t) {
+        const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
+        size_t cr = (size_t)base[(size_t)t].r, cm = (size_t)base[(size_t)t].m, ce = (size_t)base[(size_t)t].e;
+        size_t cq = (size_t)base[(size_t)t].q, cs = (size_t)base[(size_t)t].s;
+        bool good = true;
+        for (size_t k = k0; k < k1 && good; ++k) {
+            const int64_t r = ra + (int64_t)k;
+            if (a->identity[r] < 1e-10) continue;
+            const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
+            good = good && a->mapq[r] >= 0 && a->mapq[r] <= 255 && (mb == ma || (a->map_offset[ma] >= 0 && a->map_offset[ma] <= 65535));
+            qoff[cr] = (uint32_t)cq;
+            moff[cr] = (uint32_t)cm;
+            mq[cr] = (uint8_t)a->mapq[r];
+            fo16[cr] = mb > ma ? (uint16_t)a->map_offset[ma] : (uint16_t)0;
+            const size_t ql = (size_t)(a->qual_off[r + 1] - a->qual_off[r]);
+            memcpy(q + cq, a->qual + a->qual_off[r], ql);
+            cq += ql;
+            uint64_t cap = 0;
+            for (int64_t m = ma; m < mb; ++m) {
+                const int64_t node = a->map_node[m];
+                const int64_t ea = a->edit_off[m], eb = a->edit_off[m + 1];
+                good = good && node >= 0 && node <= 32767 && (m == ma || a->map_offset[m] == 0) && eb - ea <= 255;
+                n16[cm] = (uint16_t)((node & 0x7fff) | (a->map_rev[m] ? 0x8000 : 0));
+                ne8[cm] = (uint8_t)(eb - ea);
+                ++cm;
+                for (int64_t e = ea; e < eb; ++e) {
+                    const int64_t fl = a->edit_from[e], tl = a->edit_to[e], sl = a->edit_seq_off[e + 1] - a->edit_seq_off[e];
+                    good = good && fl >= 0 && fl <= 255 && tl >= 0 && tl <= 255 && sl <= 255;
+                    f8[ce] = (uint8_t)fl;
+                    t8[ce] = (uint8_t)tl;
+                    sl8[ce] = (uint8_t)sl;
+                    ++ce;
+                    cap += (uint64_t)(fl + tl + sl);
+                }
+            }
+            if (mb > ma) {   // a read's edit sequences are contiguous in the source
+                const int64_t sa = a->edit_seq_off[a->edit_off[ma]], sb = a->edit_seq_off[a->edit_off[mb]];
+                memcpy(eseq + cs, a->edit_seq + sa, (size_t)(sb - sa));
+                cs += (size_t)(sb - sa);
+            }
+            soff[cr + 1] = (uint32_t)((cap + 3) & ~(uint64_t)3);  // prefix-summed below
+            ++cr;
+        }
+        bad |= good ? 0 : 1;
+    }
+    if (bad) return 1;
+    soff[0] = 0;
+    uint64_t run = 0;
+    for (size_t k = 0; k < R; ++k) { run += soff[k + 1]; soff[k + 1] = (uint32_t)run; }
+    if (run >= 0xffffffffull) return 1;
+    qoff[R] = (uint32_t)nq; moff[R] = (uint32_t)nm;
+    // the two wide offset arrays are not built: the library only reads their end points for a one-chunk view
+    uint32_t* ends = (uint32_t*)(blk + o_ends);
+    ends[0] = 0; ends[1] = (uint32_t)ne;   // stands in for edit_off[0], edit_off[n_maps]       (see VGL_HC_RAW_NARROW_ONLY)
+    ends[2] = 0; ends[3] = (uint32_t)ns;   // stands in for edit_seq_off[0], edit_seq_off[n_edits]
+    vgl_hc_raw& v = f->view[slot];
+    memset(&v, 0, sizeof(v));
+    v.n_reads = (uint32_t)R; v.n_maps = (uint32_t)nm; v.n_edits = (uint32_t)ne;
+    v.reserved = VGL_HC_RAW_NARROW_ONLY;
+    v.qual_off = qoff; v.qual = q; v.mapq = mq; v.str_off = soff; v.map_off = moff;
+    v.edit_off = ends; v.edit_seq_off = ends + 2;
+    v.edit_seq = eseq;
+    v.map_node16 = n16; v.first_offset16 = fo16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; v.edit_from8 = f8; v.edit_to8 = t8;
+    return 0;
+}
+
+// One chunk marshalled into block 0, for inspection and tests: *out is NULL when the chunk needs the general builder.
+int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+    if (!f || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1 || r1 - r0 > f->chunk_reads) return fail(VGH_ERR_INVALID, "bad arguments");
+    const int how = feeder_fill(f, 0, a, r0, r1);
+    if (how > 1) return how;
+    *out = how == 0 ? &f->view[0] : nullptr;
+    return VGH_OK;
+}
+
+int vgh_hc_feed(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
+    if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+    try {
+        std::thread submit;
+        int submit_rc = VGL_OK;
+        int rc = VGH_OK;
+        int64_t c = 0;
+        for (int64_t ra = r0; ra < r1 && rc == VGH_OK; ra += f->chunk_reads, ++c) {
+            const int64_t rb = std::min(r1, ra + f->chunk_reads);
+            const int slot = (int)(c & 1);
+            const auto t0 = std::chrono::steady_clock::now();
+            const int how = feeder_fill(f, slot, a, ra, rb);   // block `slot` was released when submission c - 2 was joined
+            vgh_hc_raw* general = nullptr;
+            if (how == 1) {
+                ++f->slow_chunks;
+                rc = vgh_hc_raw_build(a, ra, rb, /*pinned=*/0, &general);
+            } else if (how != 0) {
+                rc = how;
+            }
+            const auto t1 = std::chrono::steady_clock::now();
+            f->build_s += std::chrono::duration<double>(t1 - t0).count();
+            if (submit.joinable()) submit.join();
+            f->wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+            if (submit_rc != VGL_OK) { rc = 1000 + submit_rc; }
+            if (rc != VGH_OK) { if (general) vgh_hc_raw_destroy(general); break; }
+            ++f->chunks;
+            f->reads += (uint64_t)(rb - ra);
+            if (general) {   // rare: synchronous, the block is freed right after the copy
+                f->bytes += vgl_hc_raw_bytes(&general->view);
+                submit_rc = vgl_hc_accumulate_raw(ctx, &general->view);
+                vgh_hc_raw_destroy(general);
+                if (submit_rc != VGL_OK) rc = 1000 + submit_rc;
+            } else {
+                f->bytes += vgl_hc_raw_bytes(&f->view[slot]);
+                const vgl_hc_raw* v = &f->view[slot];
+                submit = std::thread([ctx, v, &submit_rc]() { submit_rc = vgl_hc_accumulate_raw(ctx, v); });
+            }
+        }
+        if (submit.joinable()) submit.join();
+        if (rc == VGH_OK && submit_rc != VGL_OK) rc = 1000 + submit_rc;
+        if (rc >= 1000) return fail(VGH_ERR_DEVICE, "likelihood library: %s", vgl_last_error());
+        return rc;
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "feeder: %s", e.what());
+    }
 }
 
 }  // extern "C"

@@ -147,6 +147,7 @@ struct vgl_ctx {
     } slot[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t chunk_groups = 4096;  // 131072 reads per H2D chunk
+    uint32_t raw_seq = 0;          // chunks submitted through vgl_hc_accumulate_raw so far (selects the staging set)
 
     // read-kernel timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -174,6 +175,11 @@ struct vgl_ctx {
     // soibean MCMC: the batch of the last soibean run stays resident (staging area + s_sup / s_uns)
     bool s_last_valid = false;
     vgl::EukaBatchDev s_last{};
+    size_t s_last_nmap = 0;                      // edit records of s_last
+    bool e_last_valid = false;                   // euka: the batch the last vgl_euka_run / _run_raw scored is still in HBM
+    vgl::EukaBatchDev e_last{};
+    cudaEvent_t sib_ev0 = nullptr, sib_ev1 = nullptr;  // around the last euka read kernel / soibean kernel pair
+    bool sib_timed = false;
     DevBuf<vgl_soibean_source> m_src;
     DevBuf<double> m_partials, m_loglike, m_per_read, m_H;
     unsigned char* m_pinned = nullptr;  // proposal in, log-likelihoods + error flag out
@@ -239,6 +245,11 @@ int reserve_result(vgl_ctx* ctx, size_t n_post) {
     return VGL_OK;
 }
 
+int sibling_events(vgl_ctx* ctx) {
+    if (!ctx->sib_ev0) VGL_CUDA(cudaEventCreate(&ctx->sib_ev0));
+    if (!ctx->sib_ev1) VGL_CUDA(cudaEventCreate(&ctx->sib_ev1));
+    return VGL_OK;
+}
 int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik,
                        double* like, uint8_t* pass);
 int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map_rec, uint32_t n_out, double* path_ll, uint8_t* used);
@@ -688,7 +699,8 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
 
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* r) {
     if (!r) return 0;
-    const uint64_t per_read = (uint64_t)(r->n_reads + 1) * 12 + r->n_reads + r->qual_off[r->n_reads] + r->edit_seq_off[r->n_edits];
+    const uint64_t seq_bytes = (r->reserved & VGL_HC_RAW_NARROW_ONLY) ? r->edit_seq_off[1] - r->edit_seq_off[0] : r->edit_seq_off[r->n_edits];
+    const uint64_t per_read = (uint64_t)(r->n_reads + 1) * 12 + r->n_reads + r->qual_off[r->n_reads] + seq_bytes;
     const uint64_t lens = (uint64_t)r->n_edits * (r->edit_from8 ? 2 : 4);  // from_length + to_length per edit
     const uint64_t nodes = (uint64_t)r->n_maps * (r->map_node16 ? 2 : 4);
     if (r->first_offset16 && r->map_n_edits8 && r->edit_slen8)  // one offset per read, edit count 1 per mapping, sequence length 1 per edit
@@ -722,10 +734,12 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
                           vgl::HcBatchDev& d) {
     cudaStream_t s = ctx->stream;
     const size_t n = rb - ra;
+    const bool narrow_only = (raw->reserved & VGL_HC_RAW_NARROW_ONLY) != 0;  // the whole view is this chunk (check_raw)
     const size_t ma = raw->map_off[ra], mb = raw->map_off[rb], nm = mb - ma;
-    const size_t ea = raw->edit_off[ma], eb = raw->edit_off[mb], ne = eb - ea;
+    const size_t ea = narrow_only ? raw->edit_off[0] : raw->edit_off[ma], eb = narrow_only ? raw->edit_off[1] : raw->edit_off[mb], ne = eb - ea;
     const size_t qa = raw->qual_off[ra], nq = raw->qual_off[rb] - qa;
-    const size_t sa = raw->edit_seq_off[ea], nseq = raw->edit_seq_off[eb] - sa;
+    const size_t sa = narrow_only ? raw->edit_seq_off[0] : raw->edit_seq_off[ea];
+    const size_t nseq = (narrow_only ? raw->edit_seq_off[1] : raw->edit_seq_off[eb]) - sa;
     const size_t ca = raw->str_off[ra], ncap = raw->str_off[rb] - ca;
     const size_t G = (n + 31) / 32;
     // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read
@@ -822,9 +836,15 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
 static int check_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
-    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq ||
-        (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))
+    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq)
         return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
+    if (raw->reserved & VGL_HC_RAW_NARROW_ONLY) {
+        if (!raw->map_node16 || !raw->first_offset16 || !raw->map_n_edits8 || !raw->edit_slen8 || !raw->edit_from8 || !raw->edit_to8)
+            return fail(VGL_ERR_INVALID, "a narrow-only raw batch needs all six narrow arrays");
+        if ((size_t)raw->n_reads > (size_t)ctx->chunk_groups * VGL_HC_LANES) return fail(VGL_ERR_INVALID, "a narrow-only raw batch holds at most one chunk");
+    } else if ((raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to))) {
+        return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
+    }
     return VGL_OK;
 }
 
@@ -855,11 +875,11 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     if (int rc = check_raw(ctx, raw)) return rc;
     // Chunks of reads through two staging sets: the H2D copy of a chunk (copy stream) overlaps the reconstruction, packing
     // and read kernel of the chunk before it.
+    // (the staging sets alternate across calls too: a caller that submits chunk-sized batches -- vgh_hc_feed -- gets the same overlap)
     const size_t n = raw->n_reads, step = (size_t)ctx->chunk_groups * VGL_HC_LANES;
-    size_t k = 0;
-    for (size_t ra = 0; ra < n; ra += step, ++k) {
+    for (size_t ra = 0; ra < n; ra += step) {
         const size_t rb = std::min(n, ra + step);
-        vgl_ctx::RawDev& R = ctx->rawdev[k & 1];
+        vgl_ctx::RawDev& R = ctx->rawdev[ctx->raw_seq++ & 1];
         vgl::HcBatchDev d;
         if (int rc = pack_raw_chunk(ctx, raw, ra, rb, R, ctx->copy_stream, d)) return rc;
         if (d.n_groups)
@@ -1209,6 +1229,22 @@ int vgl_euka_run_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, uint32_t n_out, int32_
     return euka_run_on_device(ctx, d, n_out, clade, in_lik, not_lik, like, pass);
 }
 
+int vgl_euka_rerun(vgl_ctx* ctx, uint32_t n_out, int32_t* clade, double* in_lik, double* not_lik, double* like, uint8_t* pass) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_euka || !ctx->e_last_valid) return fail(VGL_ERR_STATE, "vgl_euka_run / vgl_euka_run_raw must come first (its batch is what is scored again)");
+    return euka_run_on_device(ctx, ctx->e_last, n_out, clade, in_lik, not_lik, like, pass);
+}
+
+int vgl_sibling_kernel_ms(vgl_ctx* ctx, float* ms_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ms_out) return fail(VGL_ERR_INVALID, "null output");
+    *ms_out = 0.0f;
+    if (!ctx->sib_timed) return VGL_OK;
+    VGL_CUDA(cudaEventSynchronize(ctx->sib_ev1));
+    VGL_CUDA(cudaEventElapsedTime(ms_out, ctx->sib_ev0, ctx->sib_ev1));
+    return VGL_OK;
+}
+
 int vgl_euka_like_sums(vgl_ctx* ctx, int64_t* like_n, double* like_logsum) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_euka) return fail(VGL_ERR_STATE, "vgl_euka_set_tables must come first");
@@ -1247,6 +1283,7 @@ namespace {
 int stage_symbol_batch(vgl_ctx* ctx, const vgl_euka_batch* b, vgl::EukaBatchDev& d) {
     cudaStream_t s = ctx->stream;
     ctx->s_last_valid = false;  // the staging area is about to be overwritten
+    ctx->e_last_valid = false;
     const size_t G = b->n_groups, nl = G * VGL_HC_LANES;
     const size_t ncol = (size_t)b->n_col_blks * VGL_HC_LANES * VGL_EUKA_COL_BLK, nmap = (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK;
     vgl_ctx::EukaStage& st = ctx->estage;
@@ -1336,6 +1373,13 @@ int vgl_soibean_run(vgl_ctx* ctx, const vgl_soibean_batch* b, uint32_t n_out, do
     return soibean_run_on_device(ctx, d, (size_t)b->n_map_blks * VGL_HC_LANES * VGL_HC_MAP_BLK, n_out, path_ll, used);
 }
 
+int vgl_soibean_rerun(vgl_ctx* ctx, uint32_t n_out, double* path_ll, uint8_t* used) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_soibean || !ctx->s_last_valid) return fail(VGL_ERR_STATE, "vgl_soibean_run / vgl_soibean_run_raw must come first (its batch is what is scored again)");
+    const vgl::EukaBatchDev d = ctx->s_last;
+    return soibean_run_on_device(ctx, d, ctx->s_last_nmap, n_out, path_ll, used);
+}
+
 int vgl_soibean_mcmc_loglike(vgl_ctx* ctx, int32_t n_proposals, int32_t n_sources, const vgl_soibean_source* sources,
                              const double* freqs7, double con, uint32_t n_out, double* per_read, double* loglike) {
     if (int rc = use_device(ctx)) return rc;
@@ -1408,7 +1452,11 @@ int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map
     VGL_CUDA(cudaMemsetAsync(ctx->s_out.p, 0, no * P * 8, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_used.p, 0, no, s));
     VGL_CUDA(cudaMemsetAsync(ctx->s_err.p, 0, sizeof(int), s));
+    if (int rc = sibling_events(ctx)) return rc;
+    VGL_CUDA(cudaEventRecord(ctx->sib_ev0, s));
     VGL_CUDA(vgl::soibean_launch(d, ctx->stab, ctx->s_sup.p, ctx->s_uns.p, ctx->s_mcode.p, n_out, ctx->s_out.p, ctx->s_used.p, ctx->s_err.p, s));
+    VGL_CUDA(cudaEventRecord(ctx->sib_ev1, s));
+    ctx->sib_timed = true;
     ctx->launches += 2;
     int err = 0;
     VGL_CUDA(cudaMemcpyAsync(&err, ctx->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1417,7 +1465,8 @@ int soibean_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, size_t n_map
     VGL_CUDA(cudaStreamSynchronize(s));
     if (err & 2) return fail(VGL_ERR_BAD_NODE, "an edit names a node outside the membership table (the reference would throw from vector::at)");
     if (err & 1) return fail(VGL_ERR_BAD_READ, "an alignment slices past its aligned strings or the damage table (the reference would throw / read out of range)");
-    ctx->s_last = d;  // resident for vgl_soibean_mcmc_loglike
+    ctx->s_last = d;  // resident for vgl_soibean_mcmc_loglike / vgl_soibean_rerun
+    ctx->s_last_nmap = n_map_rec;
     ctx->s_last_valid = true;
     return VGL_OK;
 }
@@ -1442,7 +1491,11 @@ int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out,
     VGL_CUDA(cudaMemsetAsync(ctx->e_pass.p, 0, no, s));
     vgl::EukaOutDev o{n_out, ctx->e_clade.p, ctx->e_in.p, ctx->e_not.p, ctx->e_like.p, ctx->e_pass.p, ctx->e_count.p, ctx->e_bin_cov.p,
                       ctx->e_like_n.p, ctx->e_like_logsum.p};
+    if (int rc = sibling_events(ctx)) return rc;
+    VGL_CUDA(cudaEventRecord(ctx->sib_ev0, s));
     VGL_CUDA(vgl::euka_launch_read_kernel(d, ctx->etab, o, s));
+    VGL_CUDA(cudaEventRecord(ctx->sib_ev1, s));
+    ctx->sib_timed = true;
     ctx->launches += 1;
     if (clade) VGL_CUDA(cudaMemcpyAsync(clade, ctx->e_clade.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, s));
     if (in_lik) VGL_CUDA(cudaMemcpyAsync(in_lik, ctx->e_in.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
@@ -1450,12 +1503,15 @@ int euka_run_on_device(vgl_ctx* ctx, const vgl::EukaBatchDev& d, uint32_t n_out,
     if (like) VGL_CUDA(cudaMemcpyAsync(like, ctx->e_like.p, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
     if (pass) VGL_CUDA(cudaMemcpyAsync(pass, ctx->e_pass.p, (size_t)n_out, cudaMemcpyDeviceToHost, s));
     VGL_CUDA(cudaStreamSynchronize(s));
+    ctx->e_last = d;  // resident for vgl_euka_rerun
+    ctx->e_last_valid = true;
     return VGL_OK;
 }
 
 // euka / soibean: the whole raw batch in one piece -- H2D, reconstruction (mode 1 / 2), group sizes read back, packing.
 int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::EukaBatchDev& d, size_t& n_map_rec) {
     ctx->s_last_valid = false;  // the device-built batch is about to be overwritten
+    ctx->e_last_valid = false;
     if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
     if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq || !raw->seq_len ||
         !raw->read_index || (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))

@@ -72,15 +72,21 @@ class ShardedSample:
         # node); "nccl" = all-gather + vgl_hc_set_paths_from_parts.  Both add the vectors in rank order.
         self.exchange = exchange
         if exchange == "peer":
+            # every rank takes part in every collective whatever happened locally: a rank whose export failed sends None
             try:
                 mine = hc.peer_export(self.world)
-                handles = [None] * self.world
-                dist.all_gather_object(handles, mine, group=group)
-                hc.peer_attach(self.rank, self.world, handles)
-                ok = 1
-            except Exception as e:  # no peer access between these devices: use the collective
+            except Exception as e:  # no exchange buffer on this rank (allocation / IPC failure)
                 self.exchange_error = repr(e)
-                ok = 0
+                mine = None
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            ok = 0
+            if all(h is not None for h in handles):
+                try:
+                    hc.peer_attach(self.rank, self.world, handles)
+                    ok = 1
+                except Exception as e:  # no peer access between these devices: use the collective
+                    self.exchange_error = repr(e)
             t = torch.tensor([ok], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
             if int(t.item()) == 0:
@@ -99,6 +105,14 @@ class ShardedSample:
                     hc.update_wire(b)
                 else:
                     hc.update(b)
+            return self.finish(want_ll=want_ll)
+
+    def finish(self, want_ll=False):
+        """The exchange step + posterior for the sample accumulated on this rank since hc.reset() (every rank calls it)."""
+        import torch
+        import torch.distributed as dist
+        hc = self.hc
+        with torch.cuda.stream(self.stream):
             if self.exchange == "peer":
                 hc.exchange_paths()
             else:

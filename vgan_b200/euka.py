@@ -114,6 +114,29 @@ class Euka:
         out["not_like"] = 1 - out["like"]
         return out
 
+    def set_stream(self, cuda_stream_ptr):
+        check(gpu.vgl_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def rerun(self, n_out=0, want=False):
+        """Score again the batch the last run() / run_raw() left in HBM (no host -> device traffic).  want=True returns the
+        per-read arrays as run() does; otherwise nothing leaves the device (the per-clade sums accumulate as usual)."""
+        if not want:
+            check(gpu.vgl_euka_rerun(self.ctx, int(n_out), None, None, None, None, None))
+            return None
+        out = {"clade": np.full(n_out, -1, dtype=np.int32), "in_lik": np.zeros(n_out), "not_lik": np.zeros(n_out), "like": np.zeros(n_out),
+               "pass": np.zeros(n_out, dtype=np.uint8)}
+        check(gpu.vgl_euka_rerun(self.ctx, int(n_out), out["clade"].ctypes.data_as(C.c_void_p), out["in_lik"].ctypes.data_as(C.c_void_p),
+                                 out["not_lik"].ctypes.data_as(C.c_void_p), out["like"].ctypes.data_as(C.c_void_p),
+                                 out["pass"].ctypes.data_as(C.c_void_p)))
+        out["not_like"] = 1 - out["like"]
+        return out
+
+    def kernel_ms(self):
+        """Device time of the last euka read kernel (CUDA events on its stream)."""
+        ms = C.c_float()
+        check(gpu.vgl_sibling_kernel_ms(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
     def results(self):
         count = np.zeros(self.tables.n_clades, dtype=np.int64)
         cov = np.zeros(max(self.tables.n_bins, 1), dtype=np.float64)
@@ -145,9 +168,42 @@ class Euka:
 class SynthEuka:
     """Synthetic euka-shaped clades / bins / graph."""
 
-    def __init__(self, seed=20264, n_clades=335, genome_len=16000):
-        self.handle = C.c_void_p()
-        check(host.vgh_synth_euka_create(int(seed), int(n_clades), int(genome_len), C.byref(self.handle)))
+    def __init__(self, seed=20264, n_clades=335, genome_len=16000, _handle=None):
+        self.handle = C.c_void_p() if _handle is None else _handle
+        if _handle is None:
+            check(host.vgh_synth_euka_create(int(seed), int(n_clades), int(genome_len), C.byref(self.handle)))
+        self._init_views()
+
+    @classmethod
+    def from_tables(cls, clade_file, bins_file, seed=20264):
+        """clades (dist, snode..enode) and bins verbatim from the reference's `<db>.clade` (6 tokens
+        per line: id name dist noPaths snode enode, src/load.cpp:108-157) and `<db>.bins` (name, then start end entropy
+        triples, src/load.cpp:71-95); only the node sequences are synthetic."""
+        dist, snode, enode, names = [], [], [], []
+        for line in open(clade_file):
+            t = line.split()
+            if len(t) == 6:
+                names.append(t[1]); dist.append(float(t[2])); snode.append(int(t[4])); enode.append(int(t[5]))
+        bin_off, lo, hi = [0], [], []
+        for line in open(bins_file):
+            t = line.split()
+            if not t:
+                continue
+            for j in range(1, len(t) - 2, 3):
+                lo.append(int(float(t[j]))); hi.append(int(float(t[j + 1])))   # stoi("1836.0") == 1836 in the reference
+            bin_off.append(len(lo))
+        if len(bin_off) != len(dist) + 1:
+            raise ValueError("clade and bins files list different numbers of clades")
+        a = lambda x, dt: np.ascontiguousarray(x, dtype=dt)
+        d, s, e, bo, bl, bh = a(dist, np.float64), a(snode, np.int32), a(enode, np.int32), a(bin_off, np.int32), a(lo, np.int32), a(hi, np.int32)
+        h = C.c_void_p()
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        check(host.vgh_synth_euka_create_from_tables(int(seed), len(dist), p(d), p(s), p(e), p(bo), p(bl), p(bh), C.byref(h)))
+        obj = cls(_handle=h)
+        obj.clade_names = names
+        return obj
+
+    def _init_views(self):
         self.n_clades = int(host.vgh_synth_euka_n_clades(self.handle))
         self.graph = Graph(C.c_void_p(host.vgh_synth_euka_graph(self.handle)), owner=self)
         self.dist = _as_array(host.vgh_synth_euka_dist(self.handle), self.n_clades, np.float64)

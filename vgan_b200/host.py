@@ -258,6 +258,42 @@ class RawBatch:
             self.handle = None
 
 
+class Feeder:
+    """vgh_hc_feeder: the drop-in for the OpenMP read loop (src/HaploCart.cpp:408-421) from flat alignment fields -- chunks of
+    reads marshalled by `n_threads` host threads into two page-locked blocks while the GPU works on the chunk before."""
+
+    def __init__(self, n_threads=0, chunk_reads=131072):
+        self.handle = C.c_void_p()
+        check(host.vgh_hc_feeder_create(int(n_threads), int(chunk_reads), C.byref(self.handle)))
+
+    def feed(self, hc, alns, r0=0, r1=None):
+        """Add reads [r0, r1) of `alns` to the sample open on `hc` (between reset and get_posterior)."""
+        r1 = len(alns) if r1 is None else r1
+        check(host.vgh_hc_feed(self.handle, hc.ctx, C.byref(alns.view), int(r0), int(r1)))
+
+    def marshal(self, alns, r0=0, r1=None):
+        """One chunk marshalled into the feeder's first block (inspection / tests): a vgl_hc_raw, or None when the chunk
+        needs the general builder."""
+        r1 = len(alns) if r1 is None else r1
+        out = C.POINTER(_lib.vgl_hc_raw)()
+        check(host.vgh_hc_feeder_marshal(self.handle, C.byref(alns.view), int(r0), int(r1), C.byref(out)))
+        return out.contents if out else None
+
+    def stats(self):
+        b, w = C.c_double(), C.c_double()
+        n, c, sl = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        host.vgh_hc_feeder_stats(self.handle, C.byref(b), C.byref(w), C.byref(n), C.byref(c), C.byref(sl))
+        return {"build_seconds": b.value, "wait_seconds": w.value, "h2d_bytes": n.value, "chunks": c.value, "slow_chunks": sl.value}
+
+    def close(self):
+        if self.handle:
+            host.vgh_hc_feeder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+
 class HcTables:
     """HaploCart tables in the form vgl_hc_set_tables wants, built from the reference's in-memory inputs."""
 

@@ -97,6 +97,26 @@ class Soibean:
         check(gpu.vgl_soibean_run(self.ctx, C.byref(packed.batch), n, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
         return out, used
 
+    def set_stream(self, cuda_stream_ptr):
+        check(gpu.vgl_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def analyse_into(self, packed, out, used):
+        """analyse() into caller-provided (page-locked) arrays [n, P] float64 / [n] uint8."""
+        check(gpu.vgl_soibean_run(self.ctx, C.byref(packed.batch), packed.n_span, out.ctypes.data_as(C.c_void_p), used.ctypes.data_as(C.c_void_p)))
+        return out, used
+
+    def rerun(self, n_out, out=None, used=None):
+        """The kernels again on the batch the last analyse*() left in HBM.  With out=None the R x P matrix stays on the device
+        (where mcmc_loglike reads what it needs): no device -> host traffic."""
+        check(gpu.vgl_soibean_rerun(self.ctx, int(n_out), out.ctypes.data_as(C.c_void_p) if out is not None else None,
+                                    used.ctypes.data_as(C.c_void_p) if used is not None else None))
+
+    def kernel_ms(self):
+        """Device time of the last soibean kernel pair (edit + path kernels; CUDA events on their stream)."""
+        ms = C.c_float()
+        check(gpu.vgl_sibling_kernel_ms(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
     def mcmc_loglike(self, proposals, freqs7, con, n_out=0, per_read=False):
         """Log-likelihood of every proposal over the reads of the last analyse() / analyse_raw() batch.
         proposals: [n_proposals][n_sources] of (child path, parent path, pos_branch, dist, proportion);
