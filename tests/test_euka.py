@@ -167,3 +167,43 @@ def test_oracle_proposal_likelihood_is_counts_and_log_sums():
     like_n = np.bincount(clade[clade >= 0], minlength=C_)
     like_logsum = np.array([np.log(like[clade == c]).sum() for c in range(C_)])
     assert abs(vb.Euka.proposal_loglike(ids, frac, like_n, like_logsum) - got) < 1e-12 * abs(got)
+
+
+@pytest.mark.gpu
+def test_config4_tables_taken_verbatim_from_the_reference(capfd):
+    """335 clades / 3929 bins exactly as share/vgan/euka_dir/euka_db.clade / .bins list them
+    (copied to tests/golden/), synthetic node sequences; packed and raw routes against the oracle, then the resident re-run."""
+    import os
+    S = vb.SynthEuka.from_tables(os.path.join(H.GOLDEN, "euka_db.clade"), os.path.join(H.GOLDEN, "euka_db.bins"))
+    assert S.n_clades == 335 and int(S.bin_off[-1]) == 3929 and S.n_nodes == 6926126
+    alns = S.reads(4000, seed=20265)
+    # (the oracle's graph view of 6.9 M nodes: build it from the flat arrays rather than from a Python list of strings)
+    g = orc.Graph.__new__(orc.Graph)
+    g.min_id, g.n_nodes = 1, S.n_nodes
+    g.seq_off = np.ascontiguousarray(S._off, dtype=np.int64)
+    g.seq = np.concatenate([S._seq, np.zeros(1, dtype=np.uint8)])
+    g.c = orc._Graph(g.n_nodes, g.min_id, orc._ptr(g.seq_off), orc._ptr(g.seq))
+    want = orc.euka_run(S.dist, S.bin_off, S.bin_lo, S.bin_hi, g, orc.FlatReads(alns.arrays()), vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
+    ek = vb.Euka()
+    ek.load(S.tables(vb.DHIGH5P_PROF, vb.DHIGH3P_PROF))
+    ek.load_graph(S.graph)
+    mapped = alns.arrays()["identity"] != 0
+    margin = np.abs(want["in_lik"] - want["not_lik"] - 1.0)
+    for route in ("packed", "raw", "rerun"):
+        ek.reset()
+        if route == "packed":
+            got = ek.run(vb.EukaPackedBatch(S.graph, alns))
+        elif route == "raw":
+            got = ek.run_raw(vb.RawBatch(alns, euka_rule=True))
+        else:
+            got = ek.rerun(len(alns), want=True)
+        assert np.array_equal(got["clade"][mapped], want["clade"][mapped]), route
+        assert H.rel_err(got["in_lik"], want["in_lik"]) < 1e-11 and H.rel_err(got["not_lik"], want["not_lik"]) < 1e-12
+        assert np.allclose(got["like"], want["like"], rtol=1e-9, atol=1e-300)
+        assert np.array_equal(got["pass"][margin > 1e-9], want["pass"][margin > 1e-9])
+        count, cov = ek.results()
+        if np.all(margin > 1e-9):
+            assert np.array_equal(count, want["clade_count"]) and np.allclose(cov, want["bin_cov"], rtol=1e-12)
+        assert ek.kernel_ms() > 0
+    assert len(set(want["clade"][mapped].tolist())) > 200      # reads land in clades in proportion to their node ranges
+    ek.close()

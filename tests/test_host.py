@@ -419,3 +419,14 @@ def test_raw_arrays_ship_one_offset_per_read_when_only_first_mappings_start_insi
     odd = [H.aln("ACGTAC", [(1, 2, False, [(3, 3, "")]), (2, 1, False, [(3, 3, "")])])]
     r2 = vb.RawBatch(vb.Alignments.from_gam_bytes(H.encode_gam(odd))).raw
     assert not r2.first_offset16 and r2.map_offset16
+
+
+def test_crafted_bgzf_sizes_do_not_take_the_process_down():
+    """A BGZF-looking stream whose member trailers claim ~4 GiB each: rejected with an error code, no huge
+    allocation, no exception across the C ABI."""
+    import struct
+    member = (b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 27) +
+              b"\x03\x00" + struct.pack("<II", 0, 0xFFFFFFF0))
+    assert len(member) == 28
+    with pytest.raises(RuntimeError):
+        vb.Alignments.from_gam_bytes(member * 64)

@@ -204,3 +204,20 @@ def test_oracle_mcmc_on_the_toy_graph_fixture():
         _, one = orc.soibean_mcmc_loglike(og, R, member, [(c, c, 0.5, 0.04, 1.0)], F7, 0.01, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
         _, two = orc.soibean_mcmc_loglike(og, R, member, [(c, c, 0.5, 0.04, 0.3), (c, c, 0.5, 0.04, 0.7)], F7, 0.01, 0, 7, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF)
         assert np.allclose(one, two, rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_rerun_on_the_resident_batch_gives_the_same_matrix():
+    S, alns = _inputs(127, 95, 900, fixed_len=0, sub_rate=0.02, indel_rate=0.01, damage=True)
+    sb = vb.Soibean()
+    sb.load(vb.SoibeanTables(S.supports(), 0, vb.DHIGH5P_PROF, vb.DHIGH3P_PROF, 7))
+    pk = vb.SoibeanPackedBatch(S.graph, alns)
+    got, used = sb.analyse(pk)
+    again, used2 = np.full_like(got, 7.0), np.zeros_like(used)
+    sb.rerun(pk.n_span, again, used2)
+    assert np.array_equal(again, got) and np.array_equal(used2, used) and sb.kernel_ms() > 0
+    sb.rerun(pk.n_span)                      # matrix left on the device: the MCMC kernel still scores the same batch
+    f7 = vb.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
+    prop = [[(5, 2, 0.4, 0.01, 1.0)]]
+    assert np.isfinite(sb.mcmc_loglike(prop, f7, 0.01)[0])
+    sb.close()

@@ -187,6 +187,9 @@ bool bgzf_members(const uint8_t* in, size_t n, std::vector<BgzfMember>& ms, size
         m.payload_len = bsize - (12 + xlen) - 8;
         m.crc = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
         m.isize = (uint32_t)tail[4] | ((uint32_t)tail[5] << 8) | ((uint32_t)tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        // BGZF caps a member's uncompressed size at 64 KiB; a trailer that claims more (a crafted file could claim 4 GiB per
+        // 28-byte member) is not BGZF.  The serial inflater then decides what the stream really holds.
+        if (m.isize > 65536u) return false;
         m.out_off = total;
         total += m.isize;
         ms.push_back(m);
@@ -267,7 +270,7 @@ extern "C" {
 
 const char* vgh_last_error(void) { return g_err; }
 
-int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out) {
+static int vgh_graph_create__impl(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out) {
     if (!out || n_nodes < 0 || !seq_off || (!seq && seq_off[n_nodes] > 0)) return fail(VGH_ERR_INVALID, "bad graph arguments");
     vgh_graph* g = new vgh_graph();
     g->min_id = min_id;
@@ -287,7 +290,7 @@ int vgh_graph_view(const vgh_graph* g, int64_t* min_id, int64_t* n_nodes, const 
     return VGH_OK;
 }
 
-int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
+static int vgh_gam_parse__impl(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
     if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
     std::vector<uint8_t> inflated;
     const uint8_t* raw_p = (const uint8_t*)bytes;
@@ -325,7 +328,7 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
     const size_t n_msgs = msgs.size();
     const int n_parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_msgs / 256 + 1));
     std::vector<vgh_gam> parts((size_t)n_parts);
-    bool bad = false;
+    bool bad = false, oom = false;
 #pragma omp parallel for schedule(static, 1) num_threads(n_parts)
     for (int t = 0; t < n_parts; ++t) {
         const size_t lo = n_msgs * (size_t)t / (size_t)n_parts, hi = n_msgs * ((size_t)t + 1) / (size_t)n_parts;
@@ -344,15 +347,21 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
             } catch (const std::bad_alloc&) {
             }
         }
-        for (size_t k = lo; k < hi; ++k) {
-            Cursor item{msgs[k].first, msgs[k].second, true};
-            if (!parse_alignment(item, drop_unmapped, parts[(size_t)t])) {
+        try {   // an exception must not leave the parallel region (std::terminate): a failed allocation becomes an error code
+            for (size_t k = lo; k < hi; ++k) {
+                Cursor item{msgs[k].first, msgs[k].second, true};
+                if (!parse_alignment(item, drop_unmapped, parts[(size_t)t])) {
 #pragma omp atomic write
-                bad = true;
-                break;
+                    bad = true;
+                    break;
+                }
             }
+        } catch (...) {
+#pragma omp atomic write
+            oom = true;
         }
     }
+    if (oom) return fail(VGH_ERR_INVALID, "out of host memory while parsing the GAM stream");
     if (bad) return fail(VGH_ERR_FORMAT, "malformed vg.Alignment message");
     vgh_gam* g = new vgh_gam();
     if (n_parts == 1) {
@@ -427,7 +436,7 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
     return VGH_OK;
 }
 
-int vgh_gam_read_file(const char* path, int drop_unmapped, vgh_gam** out) {
+static int vgh_gam_read_file__impl(const char* path, int drop_unmapped, vgh_gam** out) {
     if (!path || !out) return fail(VGH_ERR_INVALID, "bad arguments");
     FILE* fh = fopen(path, "rb");
     if (!fh) return fail(VGH_ERR_IO, "cannot open %s", path);
@@ -568,7 +577,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
-int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
+static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
                 vgh_hc_packed** out) {
     if (!g || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
 #ifdef _OPENMP
@@ -794,7 +803,7 @@ struct vgh_hc_wire {
 
 extern "C" {
 
-int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, vgh_hc_wire** out) {
+static int vgh_hc_wire_from_packed__impl(const vgh_hc_packed* p, int n_threads, int pinned, vgh_hc_wire** out) {
     if (!p || !out) return fail(VGH_ERR_INVALID, "bad arguments");
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -937,10 +946,10 @@ struct vgh_hc_raw {
 extern "C" {
 
 static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, bool euka_rule, vgh_hc_raw** out);
-int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+static int vgh_hc_raw_build__impl(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
     return raw_build(a, r0, r1, pinned, false, out);
 }
-int vgh_euka_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+static int vgh_euka_raw_build__impl(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
     return raw_build(a, r0, r1, pinned, true, out);
 }
 static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, bool euka_rule, vgh_hc_raw** out) {
@@ -1104,7 +1113,7 @@ struct vgh_hc_feeder {
 
 extern "C" {
 
-int vgh_hc_feeder_create(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out) {
+static int vgh_hc_feeder_create__impl(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out) {
     if (!out) return fail(VGH_ERR_INVALID, "null output");
     vgh_hc_feeder* f = new (std::nothrow) vgh_hc_feeder();
     if (!f) return fail(VGH_ERR_INVALID, "out of host memory");
@@ -1254,7 +1263,7 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
 }
 
 // One chunk marshalled into block 0, for inspection and tests: *out is NULL when the chunk needs the general builder.
-int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+static int vgh_hc_feeder_marshal__impl(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
     if (!f || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1 || r1 - r0 > f->chunk_reads) return fail(VGH_ERR_INVALID, "bad arguments");
     const int how = feeder_fill(f, 0, a, r0, r1);
     if (how > 1) return how;
@@ -1262,7 +1271,7 @@ int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0,
     return VGH_OK;
 }
 
-int vgh_hc_feed(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
+static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
     if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
     try {
         std::thread submit;
@@ -1357,7 +1366,7 @@ double vgh_hc_region_match_prob(int32_t pangenome_base) {
     return std::pow((1 - region_rate_per_generation(pangenome_base)), 8);
 }
 
-int vgh_hc_tables_build(int32_t n_rows, int32_t n_paths, const uint8_t* supports, int64_t n_pmap,
+static int vgh_hc_tables_build__impl(int32_t n_rows, int32_t n_paths, const uint8_t* supports, int64_t n_pmap,
                         const int64_t* pmap_node, const int32_t* pmap_val, int64_t n_mappab, const double* mappab,
                         double background_error_prob, int is_consensus_fasta, vgh_hc_tables** out) {
     if (!out || n_rows <= 0 || n_paths <= 0 || !supports || (n_pmap && (!pmap_node || !pmap_val)) || (n_mappab && !mappab))
@@ -1453,7 +1462,7 @@ Relations parse_relations(const char* text) {
 
 extern "C" {
 
-int vgh_hc_tree_build(int32_t n_paths, const char* path_names_txt, const char* parents_txt, const char* children_txt,
+static int vgh_hc_tree_build__impl(int32_t n_paths, const char* path_names_txt, const char* parents_txt, const char* children_txt,
                       vgh_hc_tree** out) {
     if (!out || n_paths <= 0 || !path_names_txt) return fail(VGH_ERR_INVALID, "bad tree arguments");
     std::vector<std::string> names;
@@ -1530,5 +1539,155 @@ const char* vgh_hc_tree_clade_name(const vgh_hc_tree* t, int32_t clade) {
     return t->clade_names[(size_t)clade].c_str();
 }
 void vgh_hc_tree_destroy(vgh_hc_tree* t) { delete t; }
+
+}  // extern "C"
+
+// No C++ exception crosses the C ABI (allocation failures on crafted inputs included): every entry point that can
+// allocate runs inside a try block and reports an error code instead.
+extern "C" {
+
+int vgh_graph_create(int64_t min_id, int64_t n_nodes, const int64_t* seq_off, const char* seq, vgh_graph** out) {
+    try {
+        return vgh_graph_create__impl(min_id, n_nodes, seq_off, seq, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_graph_create: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_graph_create: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_graph_create: unknown C++ exception");
+    }
+}
+
+int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out) {
+    try {
+        return vgh_gam_parse__impl(bytes, n, drop_unmapped, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_parse: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_parse: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_parse: unknown C++ exception");
+    }
+}
+
+int vgh_gam_read_file(const char* path, int drop_unmapped, vgh_gam** out) {
+    try {
+        return vgh_gam_read_file__impl(path, drop_unmapped, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_read_file: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_read_file: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_read_file: unknown C++ exception");
+    }
+}
+
+int vgh_hc_pack(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned, vgh_hc_packed** out) {
+    try {
+        return vgh_hc_pack__impl(g, a, r0, r1, n_threads, pinned, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_pack: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_pack: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_pack: unknown C++ exception");
+    }
+}
+
+int vgh_hc_wire_from_packed(const vgh_hc_packed* p, int n_threads, int pinned, vgh_hc_wire** out) {
+    try {
+        return vgh_hc_wire_from_packed__impl(p, n_threads, pinned, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_wire_from_packed: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_wire_from_packed: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_wire_from_packed: unknown C++ exception");
+    }
+}
+
+int vgh_hc_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+    try {
+        return vgh_hc_raw_build__impl(a, r0, r1, pinned, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_raw_build: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_raw_build: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_raw_build: unknown C++ exception");
+    }
+}
+
+int vgh_euka_raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned, vgh_hc_raw** out) {
+    try {
+        return vgh_euka_raw_build__impl(a, r0, r1, pinned, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_raw_build: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_raw_build: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_raw_build: unknown C++ exception");
+    }
+}
+
+int vgh_hc_feeder_create(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out) {
+    try {
+        return vgh_hc_feeder_create__impl(n_threads, chunk_reads, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_create: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_create: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_create: unknown C++ exception");
+    }
+}
+
+int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+    try {
+        return vgh_hc_feeder_marshal__impl(f, a, r0, r1, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_marshal: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_marshal: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feeder_marshal: unknown C++ exception");
+    }
+}
+
+int vgh_hc_feed(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
+    try {
+        return vgh_hc_feed__impl(f, ctx, a, r0, r1);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feed: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feed: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_feed: unknown C++ exception");
+    }
+}
+
+int vgh_hc_tables_build(int32_t n_rows, int32_t n_paths, const uint8_t* supports, int64_t n_pmap, const int64_t* pmap_node, const int32_t* pmap_val, int64_t n_mappab, const double* mappab, double background_error_prob, int is_consensus_fasta, vgh_hc_tables** out) {
+    try {
+        return vgh_hc_tables_build__impl(n_rows, n_paths, supports, n_pmap, pmap_node, pmap_val, n_mappab, mappab, background_error_prob, is_consensus_fasta, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tables_build: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tables_build: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tables_build: unknown C++ exception");
+    }
+}
+
+int vgh_hc_tree_build(int32_t n_paths, const char* path_names_txt, const char* parents_txt, const char* children_txt, vgh_hc_tree** out) {
+    try {
+        return vgh_hc_tree_build__impl(n_paths, path_names_txt, parents_txt, children_txt, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tree_build: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tree_build: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_hc_tree_build: unknown C++ exception");
+    }
+}
 
 }  // extern "C"
