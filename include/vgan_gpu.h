@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 1
+#define VGL_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -134,25 +134,29 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
  *   columns from pos_M on belong to no mapping and only their quality bytes count.
  *
  *   column record c of a read (0 <= c < n), 32 bits:
- *       bits 0-7   quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c is past the
- *                  end of the quality string: the reference indexes the quality string by aligned column)
- *       bit 8      MISMATCH: G[c] != the read base process_mapping pairs with it, algnseq[c - pos_i] of the
+ *       bit 0      MISMATCH: G[c] != the read base process_mapping pairs with it, algnseq[c - pos_i] of the
  *                  mapping i that owns column c (src/get_p_obs_base.cpp:15,20)
- *       bit 9      LATCHED: the owning mapping runs in background-error mode: a real quality byte >= 90 lies
+ *       bits 1-2   that read base (A=0 C=1 G=2 T=3)
+ *       bits 3-10  quality byte quality[c] (raw PHRED as in vg.Alignment.quality; 0 when c is past the end of the
+ *                  quality string: the reference indexes the quality string by aligned column), CANONICALISED: every
+ *                  byte the reference treats as "error probability 0.25" -- Q <= 2 in get_p_seq_error and in
+ *                  HaploCart's qscore_vec (src/miscfunc.h:182-186,198-212), and bytes >= 128, negative as signed char --
+ *                  is stored as 0; bytes 3..127 as they are
+ *       bit 11     LATCHED: the owning mapping runs in background-error mode: a real quality byte >= 90 lies
  *                  before the end of its quality window [pos_i, pos_i + n) (src/update_likelihood.cpp:40-44)
- *       bits 10-11 that read base (A=0 C=1 G=2 T=3)
  *       bit 12     VALID: a mapping owns the column and both bases are A/C/G/T (the isValidDNA / 'N'
  *                  filter of src/process_mapping.cpp:62-63)
  *       bit 13     OPEN: last column of its mapping (the kernel walks a read from its last column to its first
  *                  and picks up the node's constants here)
- *       bit 14     CLOSE: some mapping has pos_i == c: the product over the columns walked since the previous
+ *       bit 14     CLOSE: some mapping has pos_i == c: the sum over the columns walked since the previous
  *                  CLOSE and the quality sums from c on are what that mapping needs.  Set also where only
  *                  EMPTY mappings (size 0) start, including c = pos_M when the trailing mappings are empty.
  *       bits 15-31 Mapping.position.node_id of the owning mapping (row of the membership matrix, <=
  *                  VGL_HC_MAX_NODE), VGL_HC_NO_NODE for columns no mapping owns.
  *   The graph base itself is not shipped: get_p_obs_base ignores its base arguments
- *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.  Bits 0-9 index the kernel's table of
- *   per-column factors directly.
+ *   (src/get_p_obs_base.cpp:38-69), only the comparison matters.  Bits 0-11 index the kernel's table of per-column
+ *   factors directly; when no quality exceeds 63 and nothing is latched, bits 0-8 (quality-major: mismatch, base,
+ *   quality) index a table of per-column LOG terms, one table per (mapping quality, node class) pair.
  *
  *   "extra" record, 32 bits, one per EMPTY mapping (size_i == 0 or pos_i == n; it owns no column but still
  *   contributes log(err) over its quality window): bits 0-19 node id, bits 20-31 pos_i (< 4096), in mapping
@@ -171,10 +175,14 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
  * All arrays are host pointers for vgl_hc_accumulate and device pointers for vgl_hc_accumulate_device.
  * Algorithmic bytes per read: 4 n + 7 (+ 4 per empty mapping) plus padding (a few percent when lanes are
  * grouped by shape). */
-#define VGL_HC_COL_QUAL(rec) ((rec) & 0xffu)
-#define VGL_HC_COL_MISMATCH 0x0100u
-#define VGL_HC_COL_LATCHED 0x0200u
-#define VGL_HC_COL_BASE(rec) (((rec) >> 10) & 3u)
+#define VGL_HC_COL_MISMATCH 0x0001u
+#define VGL_HC_COL_BASE_SHIFT 1
+#define VGL_HC_COL_BASE(rec) (((rec) >> VGL_HC_COL_BASE_SHIFT) & 3u)
+#define VGL_HC_COL_QUAL_SHIFT 3
+#define VGL_HC_COL_QUAL(rec) (((rec) >> VGL_HC_COL_QUAL_SHIFT) & 0xffu)
+#define VGL_HC_COL_LATCHED 0x0800u
+/* the byte as stored: 0 for everything whose error probability the reference takes as 0.25 */
+#define VGL_HC_CANON_QUAL(byte) ((((byte) & 0x80u) || ((byte) & 0xffu) <= 2u) ? 0u : ((byte) & 0xffu))
 #define VGL_HC_COL_VALID 0x1000u
 #define VGL_HC_COL_OPEN 0x2000u
 #define VGL_HC_COL_CLOSE 0x4000u
@@ -190,6 +198,16 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
 #define VGL_HC_COL_BLK 4
 #define VGL_HC_MAP_BLK 4
 
+/* What the producer of a batch knows about its value ranges; lets the library take its fastest read kernel (per-column
+ * log terms from shared-memory tables) when no quality exceeds 63 and the tables of the (mapping quality, class) pairs
+ * present fit.  valid == 0: unknown (the general kernel runs).  Filled by vgh_hc_pack / vgh_hc_wire_from_packed /
+ * vgh_hc_raw_build / vgh_hc_feed; copy it along when a batch is moved to the device.                                */
+typedef struct vgl_hc_batch_meta {
+    uint32_t valid;        /* 1: the fields below hold for every read of the batch */
+    uint32_t qual_max;     /* largest CANONICAL quality (bits 3-10 of the column record) */
+    uint32_t mapq_mask[4]; /* bit q set: some read has mapping quality q (0..99) */
+} vgl_hc_batch_meta;
+
 typedef struct vgl_hc_batch {
     uint32_t n_reads;            /* real reads (unused lanes of the last group excluded) */
     uint32_t n_groups;           /* groups of 32 lanes */
@@ -203,6 +221,7 @@ typedef struct vgl_hc_batch {
     const uint16_t* n_close;     /* [n_groups * 32] */
     const uint16_t* n_extra;     /* [n_groups * 32] */
     const uint8_t* mapq;         /* [n_groups * 32] */
+    vgl_hc_batch_meta meta;
 } vgl_hc_batch;
 
 /* Bytes the batch occupies (what crosses PCIe / is read from HBM once per pass).               */
@@ -248,6 +267,7 @@ typedef struct vgl_hc_wire {
     const uint8_t* col8;
     const uint32_t* flag4;
     const uint16_t* n_owned;
+    vgl_hc_batch_meta meta;
 } vgl_hc_wire;
 uint64_t vgl_hc_wire_bytes(const vgl_hc_wire* w);
 
@@ -312,6 +332,7 @@ typedef struct vgl_hc_raw {
     const uint16_t* map_node16;   /* [n_maps] node_id | is_reverse << 15: NULL, or present (every node id <= 32767) */
     const uint16_t* first_offset16; /* [n_reads] offset of the read's FIRST mapping: NULL, or present when every other mapping starts
                                      * at offset 0 of its node (what a graph aligner emits); shipped instead of map_offset16 then */
+    vgl_hc_batch_meta meta;       /* HaploCart only (valid == 0 otherwise): ranges of the quality bytes and mapping qualities */
 } vgl_hc_raw;
 uint64_t vgl_hc_raw_bytes(const vgl_hc_raw* raw);
 
@@ -363,6 +384,8 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
 
 /* Number of kernels this context has launched since creation (bench.py reports it).            */
 uint64_t vgl_launch_count(const vgl_ctx* ctx);
+/* How many read-kernel launches of this context took the log-term kernel (the batch's vgl_hc_batch_meta allowed it). */
+uint64_t vgl_hc_logterm_launches(const vgl_ctx* ctx);
 /* Device time in milliseconds spent in the read kernel since the last vgl_hc_reset (CUDA events
  * on the launching stream); valid after vgl_synchronize / vgl_hc_finalize.                      */
 int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out);

@@ -71,11 +71,12 @@ def test_synthetic_samples_match_oracle(small, kw):
     hc.close()
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
 @pytest.mark.parametrize("fasta", [False, True])
 def test_large_class_tables_take_the_other_kernel_layouts(small, monkeypatch, mode, fasta):
-    """With more (mappability, match probability) classes than shared memory holds per mapping quality, the read kernel
-    keeps the class table itself in shared (mode 1) or global (mode 2) memory; both must agree with the oracle."""
+    """VGL_HC_TABLE_MODE pins the GENERAL read kernel (products of per-column factors, one log per mapping) in one of its three
+    table layouts: per-(mapping quality, class) constants in shared memory (0), the class table itself in shared (1) or
+    global (2) memory -- what runs when a batch cannot take the log-term kernel; all must agree with the oracle."""
     monkeypatch.setenv("VGL_HC_TABLE_MODE", mode)
     alns = small.reads(300, seed=212, sub_rate=0.02, indel_rate=0.005)
     reads = alns
@@ -377,4 +378,81 @@ def test_parts_summed_in_rank_order_equal_the_whole(small):
     assert H.rel_err(both["final_vec"], whole["final_vec"]) < 1e-13
     assert np.allclose(both["confidence_vec"], whole["confidence_vec"], rtol=1e-9)
     check(gpu.vgl_device_free(hc.ctx, parts))
+    hc.close()
+
+
+# ---- the log-term read kernel (per-column log terms from shared-memory tables; the default whenever the batch allows it) ----
+def _capped(reads, cap=63):
+    """The corner-case reads with every quality byte brought into 0..cap (so that nothing latches and the batch qualifies)."""
+    out = []
+    for r in reads:
+        r = dict(r)
+        r["quality"] = bytes((b % (cap + 1)) for b in r["quality"])
+        out.append(r)
+    return out
+
+
+def test_logterm_kernel_is_taken_and_agrees_with_the_general_kernel_and_the_oracle(small, monkeypatch):
+    alns = small.reads(900, seed=221, sub_rate=0.01, indel_rate=0.003, fixed_len=0, damage=True)
+    for bep, fasta in ((1e-4, False), (2e-3, True)):
+        hc = vb.Haplocart()
+        hc.load(small.tables(bep=bep, is_fasta=fasta), small.tree())
+        n0 = hc.logterm_launches()
+        fast = hc.run_sample([vb.PackedBatch(small.graph, alns)])
+        assert hc.logterm_launches() == n0 + 1                      # qualities <= 41, a handful of mapping qualities: it fits
+        final, argmax, _ = _oracle(small, alns, bep=bep, is_fasta=fasta)
+        _check(fast, final, argmax, small)
+        hc.close()
+        monkeypatch.setenv("VGL_HC_TABLE_MODE", "0")
+        hg = vb.Haplocart()
+        hg.load(small.tables(bep=bep, is_fasta=fasta), small.tree())
+        general = hg.run_sample([vb.PackedBatch(small.graph, alns)])
+        assert hg.logterm_launches() == 0
+        monkeypatch.delenv("VGL_HC_TABLE_MODE")
+        assert general["maxh_index"] == fast["maxh_index"] and H.rel_err(fast["final_vec"], general["final_vec"]) < 1e-12
+        hg.close()
+
+
+def test_logterm_kernel_on_the_corner_reads(small):
+    reads = _capped(_edge_reads(small))
+    hc = vb.Haplocart()
+    hc.load(small.tables(bep=2e-3), small.tree())
+    for subset in [[r] for r in reads] + [reads]:
+        alns = vb.Alignments.from_gam_bytes(H.encode_gam(subset))
+        n0 = hc.logterm_launches()
+        res = hc.run_sample([vb.PackedBatch(small.graph, alns)])
+        assert hc.logterm_launches() == n0 + 1
+        final, argmax, used = _oracle(small, alns, bep=2e-3)
+        assert used == len(subset)
+        _check(res, final, argmax, small)
+    # one quality byte of 64 in the batch: the general kernel takes over, same numbers
+    hi = [dict(r) for r in reads]
+    q = bytearray(hi[0]["quality"]); q[0] = 64
+    hi[0]["quality"] = bytes(q)
+    alns = vb.Alignments.from_gam_bytes(H.encode_gam(hi))
+    n0 = hc.logterm_launches()
+    res = hc.run_sample([vb.PackedBatch(small.graph, alns)])
+    assert hc.logterm_launches() == n0
+    final, argmax, _ = _oracle(small, alns, bep=2e-3)
+    _check(res, final, argmax, small)
+    hc.close()
+
+
+def test_logterm_kernel_long_reads_and_every_route(small):
+    alns = small.reads(300, seed=222, fixed_len=700, sub_rate=0.01, indel_rate=0.003)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    final, argmax, _ = _oracle(small, alns)
+    packed = vb.PackedBatch(small.graph, alns)
+    routes = {"packed": lambda: hc.update(packed), "wire": lambda: hc.update_wire(vb.WireBatch(packed)),
+              "raw": lambda: hc.update_raw(vb.RawBatch(alns)), "device": lambda: hc.update_device(hc.upload(packed).batch),
+              "feeder": lambda: vb.Feeder(n_threads=2, chunk_reads=128).feed(hc, alns)}
+    for name, run in routes.items():
+        n0 = hc.logterm_launches()
+        hc.reset()
+        run()
+        res = hc.get_posterior()
+        assert hc.logterm_launches() > n0, name                     # every producer hands the value ranges over
+        _check(res, final, argmax, small)
     hc.close()

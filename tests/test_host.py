@@ -98,18 +98,21 @@ def _repack_with_oracle(og, R, arrays):
         q90 = [c for c in range(len(qual)) if 90 <= int(qual[c]) < 128]
         nodes = arrays["map_node"][arrays["map_off"][r]:arrays["map_off"][r + 1]].tolist()
         # per column: quality byte, owner node, flags
-        qb = [int(qual[c]) if c < len(qual) else 0 for c in range(n)]
+        # canonical quality: every byte whose error probability the reference takes as 0.25 (Q <= 2, or negative as signed
+        # char) is stored as 0; the field sits in bits 3-10 (include/vgan_gpu.h)
+        canon = lambda b: 0 if (b >= 128 or b <= 2) else b
+        qb = [canon(int(qual[c])) << 3 if c < len(qual) else 0 for c in range(n)]
         owner, flags = [NO_NODE] * n, [0] * n
         pos, extras, starts = 0, [], set()
         for i in range(M):
             lg = min(sizes[i], n - pos)
-            latched = 0x0200 if q90 and q90[0] < pos + n else 0   # a byte >= 90 inside the window [pos, pos + n)
+            latched = 0x0800 if q90 and q90[0] < pos + n else 0   # a byte >= 90 inside the window [pos, pos + n)
             for j in range(lg):
                 g, b = gs[pos + j], rs[j]            # the read string is indexed from 0 for every mapping (quirk Q2)
                 owner[pos + j] = nodes[i]
                 flags[pos + j] = latched
                 if g in code and b in code:
-                    flags[pos + j] |= 0x1000 | (code[b] << 10) | (0 if g == b else 0x0100)
+                    flags[pos + j] |= 0x1000 | (code[b] << 1) | (0 if g == b else 0x0001)
             if lg:
                 flags[pos + lg - 1] |= 0x2000        # OPEN on the mapping's last column
             else:
@@ -158,7 +161,8 @@ def test_packer_against_oracle_reconstruction():
     alns = [H.aln("GCTACGATGG", [(9, 0, False, [(10, 10, "")])], quality=bytes([30, 30, 30, 95, 30, 200, 30, 30, 99, 30]))]
     nodes, _ = H.toy_graph()
     one = vb.PackedBatch(vb.Graph.from_sequences(nodes), vb.Alignments.from_gam_bytes(H.encode_gam(alns))).lanes()[0]
-    assert all(c & 0x0200 for c in one["col"]) and one["col"][0] & 0x4000 and one["col"][-1] & 0x2000
+    assert all(c & 0x0800 for c in one["col"]) and one["col"][0] & 0x4000 and one["col"][-1] & 0x2000
+    assert [(c >> 3) & 0xff for c in one["col"]] == [30, 30, 30, 95, 30, 0, 30, 30, 99, 30]    # the negative byte 200 is stored as 0
     # mappings that own no column travel as extra records
     alns = [H.aln("GCTAC", [(9, 0, False, [(0, 0, ""), (5, 5, "")]), (9, 5, False, [(3, 3, "")])])]
     two = vb.PackedBatch(vb.Graph.from_sequences(nodes), vb.Alignments.from_gam_bytes(H.encode_gam(alns))).lanes()[0]
@@ -274,7 +278,7 @@ def test_libraries_export_every_declared_symbol():
         for n in names:
             assert hasattr(lib, n), "%s declared in %s but not exported" % (n, header)
             assert n in table, "%s has no ctypes signature" % n
-    assert _lib.gpu.vgl_abi_version() == 1
+    assert _lib.gpu.vgl_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -351,7 +355,7 @@ def test_wire_form_of_a_packed_batch():
         word = f4[gc[g]:gc[g + 1], l]
         nib = np.array([(int(word[c // 8]) >> (4 * (c % 8))) & 0xF for c in range(byte.size)], dtype=np.uint32)
         c = np.arange(byte.size)
-        rec = (byte & 0x3F) | ((nib & 1) << 8) | ((byte >> 6) << 10) | ((nib & 8) << 9) | ((nib & 2) << 12) | ((nib & 4) << 12) | \
+        rec = ((byte & 0x3F) << 3) | (nib & 1) | ((byte >> 6) << 1) | ((nib & 8) << 9) | ((nib & 2) << 12) | ((nib & 4) << 12) | \
               np.where(c < own[k], 0x8000, 0).astype(np.uint32)
         assert np.array_equal(rec.astype(np.uint16), col[gc[g]:gc[g + 1], l, :].reshape(-1)), k
     narrow_bytes = wb.nbytes

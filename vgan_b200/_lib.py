@@ -26,11 +26,16 @@ class vgl_hc_tables(C.Structure):
                 ("reserved1", C.c_int32)]
 
 
+class vgl_hc_batch_meta(C.Structure):
+    _fields_ = [("valid", C.c_uint32), ("qual_max", C.c_uint32), ("mapq_mask", C.c_uint32 * 4)]
+
+
 class vgl_hc_wire(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_node_blks", C.c_uint64),
                 ("n_map_blks", C.c_uint64), ("grp_col_blk", C.c_void_p), ("grp_node_blk", C.c_void_p), ("grp_map_blk", C.c_void_p),
                 ("col", C.c_void_p), ("node", C.c_void_p), ("map", C.c_void_p), ("n_cols", C.c_void_p), ("n_close", C.c_void_p),
-                ("n_extra", C.c_void_p), ("mapq", C.c_void_p), ("col8", C.c_void_p), ("flag4", C.c_void_p), ("n_owned", C.c_void_p)]
+                ("n_extra", C.c_void_p), ("mapq", C.c_void_p), ("col8", C.c_void_p), ("flag4", C.c_void_p), ("n_owned", C.c_void_p),
+                ("meta", vgl_hc_batch_meta)]
 
 
 class vgl_hc_raw(C.Structure):
@@ -40,18 +45,20 @@ class vgl_hc_raw(C.Structure):
                 ("edit_from", C.c_void_p), ("edit_to", C.c_void_p), ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p),
                 ("seq_len", C.c_void_p), ("read_index", C.c_void_p),
                 ("map_offset16", C.c_void_p), ("map_n_edits8", C.c_void_p), ("edit_slen8", C.c_void_p),
-                ("edit_from8", C.c_void_p), ("edit_to8", C.c_void_p), ("map_node16", C.c_void_p), ("first_offset16", C.c_void_p)]
+                ("edit_from8", C.c_void_p), ("edit_to8", C.c_void_p), ("map_node16", C.c_void_p), ("first_offset16", C.c_void_p),
+                ("meta", vgl_hc_batch_meta)]
 
 
 class vgl_hc_batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_groups", C.c_uint32), ("n_col_blks", C.c_uint64), ("n_map_blks", C.c_uint64),
                 ("grp_col_blk", C.c_void_p), ("grp_map_blk", C.c_void_p), ("col", C.c_void_p), ("map", C.c_void_p),
-                ("n_cols", C.c_void_p), ("n_close", C.c_void_p), ("n_extra", C.c_void_p), ("mapq", C.c_void_p)]
+                ("n_cols", C.c_void_p), ("n_close", C.c_void_p), ("n_extra", C.c_void_p), ("mapq", C.c_void_p),
+                ("meta", vgl_hc_batch_meta)]
 
 
 # column / mapping record fields (include/vgan_gpu.h)
-COL_MISMATCH, COL_LATCHED, COL_VALID, COL_OPEN, COL_CLOSE = 0x0100, 0x0200, 0x1000, 0x2000, 0x4000
-COL_BASE_SHIFT, COL_NODE_SHIFT, NO_NODE = 10, 15, 0x1FFFF
+COL_MISMATCH, COL_LATCHED, COL_VALID, COL_OPEN, COL_CLOSE = 0x0001, 0x0800, 0x1000, 0x2000, 0x4000
+COL_BASE_SHIFT, COL_QUAL_SHIFT, COL_NODE_SHIFT, NO_NODE = 1, 3, 15, 0x1FFFF
 MAP_NODE_BITS = 20
 LANES, COL_BLK, MAP_BLK = 32, 4, 4
 PEER_HANDLE_BYTES = 64
@@ -140,6 +147,7 @@ GPU_SYMBOLS = {
     "vgl_soibean_mcmc_loglike": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_uint32, _P, _P]),
     "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
+    "vgl_hc_logterm_launches": (C.c_uint64, [_P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 

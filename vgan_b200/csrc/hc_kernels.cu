@@ -78,7 +78,7 @@ __device__ __forceinline__ void red_add_f64(double* p, double v) { asm volatile(
 // streaming global loads of the batch: every byte is used exactly once, keep it out of L1
 __device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) { uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
 
-constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_pair);
+constexpr uint32_t kOffFPair = offsetof(HcSmallTables, f_col);
 constexpr uint32_t kOffLogTab = offsetof(HcSmallTables, log_tab);
 constexpr uint32_t kOffBg = offsetof(HcSmallTables, bg);
 constexpr uint32_t kOffPCorrect = offsetof(HcSmallTables, p_correct);
@@ -245,8 +245,8 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
     // closes a mapping, so a branch would be taken by the warp anyway and only add reconvergence overhead.
     auto column = [&](auto rare_tag, int c, uint32_t rec, double f, double bgv, uint32_t cls_raw) {
         constexpr bool kRare = decltype(rare_tag)::value;
-        const uint32_t q = rec & 0xffu;
-        suf += ((int)(int8_t)q > 2) ? q : (1u << 20);
+        const uint32_t q = VGL_HC_COL_QUAL(rec);   // canonical: 0 stands for every quality whose error probability is 0.25
+        suf += q ? q : (1u << 20);
         const uint32_t open = rec & VGL_HC_COL_OPEN;
         // table entry: class id | ALLPATHS bit.  Class VGL_HC_CLASS_NONE: no pangenome_map entry -- the reference would
         // terminate; flag it and use the neutral entry
@@ -328,7 +328,7 @@ __device__ __forceinline__ void hc_process_group(const HcBatchDev& b, const Read
         uint32_t cls[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            f[j] = lds_f64_c(S.f + 8u * (rec[j] & 0x3ffu));
+            f[j] = lds_f64_c(S.f + 8u * (rec[j] & 0xfffu));
             bgv[j] = lds_f64_c(S.bg + 8u * VGL_HC_COL_BASE(rec[j]));
             // the class is needed where a mapping opens only: predicated, so that the other lanes cost no bank conflicts
             uint32_t c32 = 0;  // (a 16-bit load may target a 32-bit register: zero-extended, no pack / unpack around it)
@@ -456,6 +456,221 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
     if (tid == 0) {
         double tot = 0.0;
         for (int w = 0; w < kReadBlock / 32; ++w) tot += s_warp_a[w];
+        red_add_f64(cta_a_total + blockIdx.x % kAccCopies, tot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, log-term mode.  Same batch, same walk (one read per thread, columns from the last to the first), but the
+// per-column work is ONE shared-memory load and two fp64 adds: the term
+//     log((1 - pcm) * bg[base] + pcm * K * (1 - eps(quality, mismatch)))                 src/process_mapping.cpp:59-77
+// of every (mapping quality, node class, quality, mismatch, base) combination comes from tables staged in shared memory
+// (rows of the mapping qualities present in the batch, qualities up to the batch's largest), indexed by bits 0-8 of the
+// column record.  A mapping's A_i is then a plain sum, so a mapping is finalised in line at its CLOSE mark -- no product,
+// no log, no rescaling, no queue: B_i from the integer quality sums, B_i - A_i added to the node vector with a
+// fire-and-forget fp64 reduction.  Needs: no quality above 63 in the batch (so nothing is latched either) and tables
+// that fit (hc_logterm_plan); everything else goes through hc_read_kernel.
+//
+// Quality sums.  The window of a mapping that starts at column c holds the stored qualities of columns c .. n - 1 plus c
+// bytes past the end that count as quality 0.  With nz = the number of columns >= c whose canonical quality
+// is not 0, the entries that cost log 0.25 number (n - c - nz) + c = n - nz, whatever c is:
+//     B_i = (sum of q over columns >= c) * (-ln 10 / 10) + (n - nz) * log 0.25.
+// Records past a read's own columns are zero and change neither sum.
+//
+// Shared memory: [ node table u16[n_rows + 1] | row offset u32[100] | pair tables double[slots][n_class + 1][q_rows * 8] ]
+// node table entry: (byte offset of the class's table inside a row) / 16, bit 15 = every path goes through the node.
+// ------------------------------------------------------------------------------------------
+#ifndef VGL_HC_LT_BLOCK
+#define VGL_HC_LT_BLOCK 768
+#endif
+constexpr int kLtBlock = VGL_HC_LT_BLOCK;
+
+struct LtShared {
+    uint32_t node_tab, tables, row_off;  // shared byte addresses
+    double* acc;
+    int n_rows;
+    uint32_t none_entry;                 // node-table entry of the neutral class (unknown node, no pangenome_map entry)
+    double le0, scale8;                  // log 0.25;  (-ln 10 / 10) / 8
+};
+
+__device__ __forceinline__ uint32_t lds_u32_c(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+__device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtShared& S, uint32_t g, uint32_t gn, const GroupHdr& H,
+                                                 GroupHdr& Hn, uint4& v0, uint4& v1, int lane, double& a_sum, uint32_t& worst_entry,
+                                                 bool& bad_node) {
+    Hn = hc_load_hdr(b, gn, lane);
+    const int ncb = H.ncb;
+    const uint32_t row_base = S.tables + lds_u32_c(S.row_off + 4u * min(H.mapq, 99u));
+    int x = H.n_extra - 1;   // empty mappings (no column of their own): rare, handled on the side
+    bool rare = x >= 0;
+    uint32_t sufq8 = 0;      // 8 * (sum of the canonical qualities of the columns walked so far)
+    uint32_t nz = 0;         // columns walked so far whose canonical quality is not 0
+    double a_m = 0.0;        // sum of the terms of the mapping being walked
+    double a_all = 0.0;      // ... of every valid column of the read: sum_i A_i
+    uint32_t entry = S.none_entry;  // node-table entry of the mapping being walked
+
+    auto extra_rec = [&](int i) -> uint32_t {
+        const uint32_t* gx = b.map + ((size_t)__ldg(b.grp_map_blk + g) * 32 + lane) * VGL_HC_MAP_BLK;
+        return __ldg(gx + (size_t)(i >> 2) * 128 + (i & 3));
+    };
+    auto add_extra = [&](uint32_t xn, double Bx) {
+        if (xn < (uint32_t)S.n_rows && (lds_u16_c(S.node_tab + 2u * xn) & 0x7fffu) != (S.none_entry & 0x7fffu)) red_add_f64(S.acc + xn, Bx);
+        else bad_node = true;
+    };
+    auto quality_sum = [&]() { return fma((double)sufq8, S.scale8, (double)((uint32_t)H.n_cols - nz) * S.le0); };
+
+    auto block = [&](int cb, const uint4& v) {
+        const uint32_t rec[4] = {v.x, v.y, v.z, v.w};
+        // the node-table lookups do not depend on the walk's state: issue the four of them together, each only where a
+        // mapping opens (predicated: the other lanes cost no bank conflicts)
+        uint32_t ent[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t e32 = 0;
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
+                : "+r"(e32)
+                : "r"(S.node_tab + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: neutral
+            ent[j] = e32;
+        }
+        const bool any_rare = __any_sync(kFull, rare);
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            const uint32_t r = rec[j];
+            // OPEN (last column of a mapping): its class's table
+            entry = (r & VGL_HC_COL_OPEN) ? ent[j] : entry;
+            worst_entry = max(worst_entry, entry & 0x7fffu);
+            const uint32_t pair_base = row_base + ((entry & 0x7fffu) << 4);
+            // the column's term; columns that take no part (N, non-ACGT, no owner) add nothing
+            double t = 0.0;
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
+                : "+d"(t)
+                : "r"(pair_base + ((r & 0x1ffu) << 3)), "r"(r & VGL_HC_COL_VALID));
+            a_m += t;
+            a_all += t;
+            const uint32_t q8 = r & (0xffu << VGL_HC_COL_QUAL_SHIFT);
+            sufq8 += q8;
+            nz += q8 ? 1u : 0u;
+            // CLOSE (first column of a mapping): finalise it, unless every path goes through its node (its D[n] is never read)
+            // or nobody owns the column (the CLOSE then only serves empty mappings)
+            static_assert(VGL_HC_CLASS_ALLPATHS == 2 * VGL_HC_COL_CLOSE, "ALLPATHS >> 1 lines up with CLOSE");
+            const uint32_t close = r & VGL_HC_COL_CLOSE;
+            if (any_rare) {
+                if (close && rare) {
+                    const int c = cb * VGL_HC_COL_BLK + j;
+                    const double B = quality_sum();
+                    while (x >= 0) {
+                        const uint32_t xr = extra_rec(x);
+                        const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
+                        if (xp < (uint32_t)c) break;
+                        add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
+                        --x;
+                    }
+                    rare = x >= 0;
+                }
+            }
+            const bool push = (r & ~(entry >> 1) & VGL_HC_COL_CLOSE) != 0u && r < (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT);
+            const double D = quality_sum() - a_m;
+            if (push) {
+                const uint32_t node = VGL_HC_COL_NODE(r);
+                if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, D);
+            }
+            a_m = close ? 0.0 : a_m;
+        }
+    };
+    for (int cb = ncb - 1; cb >= 0; --cb) {
+        const uint4 v = v0;
+        v0 = v1;
+        v1 = hc_fetch(H, cb - 2);
+        block(cb, v);
+    }
+    v0 = hc_fetch(Hn, Hn.ncb - 1);
+    v1 = hc_fetch(Hn, Hn.ncb - 2);
+    a_sum += a_all;
+    while (x >= 0) {  // empty mappings that start past the last column
+        const uint32_t xr = extra_rec(x);
+        add_extra(xr & VGL_HC_MAP_MAX_NODE, (double)(xr >> VGL_HC_MAP_NODE_BITS) * S.le0);
+        --x;
+    }
+}
+
+__global__ void __launch_bounds__(kLtBlock, 1)
+hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double* __restrict__ cta_node_acc, double* __restrict__ cta_a_total,
+                       int* __restrict__ err_flag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ double s_warp_a[kLtBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t node_bytes = (uint32_t)((((size_t)t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
+    const uint32_t pair_bytes = (uint32_t)plan.q_rows * 64u;                       // q_rows * 8 entries of 8 bytes
+    const uint32_t row_bytes = pair_bytes * (uint32_t)(t.n_class + 1);
+    uint16_t* s_node = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(smem_raw + node_bytes);
+    unsigned char* s_tab = smem_raw + node_bytes + 512;
+
+    // staging: the node classes (from the general kernel's image) and one table per (present mapping quality, class),
+    // all as TMA bulk copies on one mbarrier
+    {
+        const uint32_t bar = smem_u32(&s_bar);
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, node_bytes + (uint32_t)plan.n_slots * row_bytes);
+            bulk_g2s(smem_u32(s_node), t.image + t.layout.off_class, node_bytes, bar);
+        }
+        __syncthreads();
+        const int n_pairs = plan.n_slots * (t.n_class + 1);
+        for (int k = tid; k < n_pairs; k += kLtBlock) {
+            const int slot = k / (t.n_class + 1), cls = k - slot * (t.n_class + 1);
+            const double* src = t.logterm + ((size_t)plan.mapq_of_slot[slot] * (size_t)(t.n_class + 1) + (size_t)cls) * kLogTermEntries;
+            bulk_g2s(smem_u32(s_tab) + (uint32_t)slot * row_bytes + (uint32_t)cls * pair_bytes, src, pair_bytes, bar);
+        }
+        if (tid < 100) {
+            uint32_t off = 0;  // a mapping quality that is not in the plan (cannot happen when the batch's mask is right): row 0
+            for (int sidx = 0; sidx < plan.n_slots; ++sidx)
+                if (plan.mapq_of_slot[sidx] == tid) off = (uint32_t)sidx * row_bytes;
+            s_row[tid] = off;
+        }
+        mbar_wait(bar, 0);
+        __syncthreads();
+        // class id -> (byte offset of the class's table inside a row) / 16, ALLPATHS kept in bit 15
+        for (int n = tid; n <= t.n_rows; n += kLtBlock) {
+            const uint32_t e = s_node[n];
+            const uint32_t cls = min(e & VGL_HC_CLASS_MASK, (uint32_t)t.n_class);
+            s_node[n] = (uint16_t)(((cls * pair_bytes) >> 4) | (e & VGL_HC_CLASS_ALLPATHS));
+        }
+        __syncthreads();
+    }
+
+    LtShared S;
+    S.node_tab = smem_u32(s_node);
+    S.row_off = smem_u32(s_row);
+    S.tables = smem_u32(s_tab);
+    S.acc = cta_node_acc + (size_t)(blockIdx.x % kAccCopies) * (size_t)(t.n_words * 32);
+    S.n_rows = t.n_rows;
+    S.none_entry = ((uint32_t)t.n_class * pair_bytes) >> 4;
+    S.le0 = -1.3862943611198906188;               // log(0.25) = log(get_p_seq_error(Q <= 2)), src/miscfunc.h:186
+    S.scale8 = -0.23025850929940456840 / 8.0;     // log(get_p_seq_error(Q)) = Q * (-ln 10 / 10) for Q > 2
+
+    double a_sum = 0.0;
+    bool bad_node = false;
+    uint32_t worst_entry = 0;
+    const uint32_t warps_total = gridDim.x * (kLtBlock / 32);
+    uint32_t g = blockIdx.x * (kLtBlock / 32) + warp;
+    GroupHdr H = hc_load_hdr(b, g, lane), Hn;
+    uint4 v0 = hc_fetch(H, H.ncb - 1), v1 = hc_fetch(H, H.ncb - 2);
+    while (g < b.n_groups) {
+        const uint32_t gn = g + warps_total;
+        lt_process_group(b, S, g, gn, H, Hn, v0, v1, lane, a_sum, worst_entry, bad_node);
+        H = Hn;
+        g = gn;
+    }
+    if (__any_sync(kFull, bad_node || worst_entry == S.none_entry) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
+    a_sum = warp_sum_f64(a_sum);
+    if (lane == 0) s_warp_a[warp] = a_sum;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kLtBlock / 32; ++w) tot += s_warp_a[w];
         red_add_f64(cta_a_total + blockIdx.x % kAccCopies, tot);
     }
 }
@@ -734,6 +949,31 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
     if (cfg.ac_mode == 0) hc_read_kernel<0><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
     else if (cfg.ac_mode == 1) hc_read_kernel<1><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
     else hc_read_kernel<2><<<cfg.grid, cfg.block, cfg.smem, s>>>(batch, tab, cta_node_acc, cta_a_total, err_flag);
+    return cudaGetLastError();
+}
+
+size_t hc_logterm_plan(const HcBatchMeta& meta, int n_rows, int n_class, bool have_tables, int max_smem_optin, HcLogTermLaunch& plan) {
+    if (!have_tables || !meta.valid || meta.qual_max > 63u) return 0;
+    plan.n_slots = 0;
+    plan.q_rows = (int)meta.qual_max + 1;
+    for (int mq = 0; mq < 100; ++mq)
+        if (meta.mapq_mask[mq >> 5] & (1u << (mq & 31))) plan.mapq_of_slot[plan.n_slots++] = (uint8_t)mq;
+    if (plan.n_slots == 0) return 0;
+    const size_t node_bytes = (((size_t)n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    const size_t pair_bytes = (size_t)plan.q_rows * 64;
+    if (((size_t)n_class * pair_bytes >> 4) >= 0x8000u) return 0;   // the node table keeps class offsets in 15 bits
+    const size_t smem = node_bytes + 512 + (size_t)plan.n_slots * (size_t)(n_class + 1) * pair_bytes;
+    if (smem + 1024 > (size_t)max_smem_optin || smem >= (1u << 20)) return 0;  // (one mbarrier counts the staged bytes)
+    return (smem + 127) & ~(size_t)127;
+}
+
+cudaError_t hc_logterm_configure(int max_smem_optin) {
+    return cudaFuncSetAttribute(hc_read_logterm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - 1024);
+}
+
+cudaError_t hc_launch_read_logterm_kernel(int grid, size_t smem, const HcLogTermLaunch& plan, const HcBatchDev& batch, const HcTablesDev& tab,
+                                          double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s) {
+    hc_read_logterm_kernel<<<grid, kLtBlock, smem, s>>>(batch, tab, plan, cta_node_acc, cta_a_total, err_flag);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,22 @@ int vgh_fail(int code, const char* fmt, ...) {
 const char* vgh_error_text() { return g_err; }
 #define fail vgh_fail
 
+// vgl_hc_batch_meta of a set of reads: the largest canonical quality byte and the mapping qualities present.
+namespace {
+struct MetaAcc {
+    uint32_t qmax = 0;
+    uint32_t mask[4] = {0, 0, 0, 0};
+    void quality(const uint8_t* q, size_t n) {
+        uint32_t m = qmax;
+        for (size_t i = 0; i < n; ++i) { const uint32_t c = VGL_HC_CANON_QUAL((uint32_t)q[i]); m = c > m ? c : m; }
+        qmax = m;
+    }
+    void mapq(uint32_t v) { if (v < 128) mask[v >> 5] |= 1u << (v & 31); }
+    void merge(const MetaAcc& o) { qmax = std::max(qmax, o.qmax); for (int k = 0; k < 4; ++k) mask[k] |= o.mask[k]; }
+    void store(vgl_hc_batch_meta& m) const { m.valid = 1; m.qual_max = qmax; for (int k = 0; k < 4; ++k) m.mapq_mask[k] = mask[k]; }
+};
+}  // namespace
+
 namespace {
 
 struct Cursor {
@@ -577,6 +593,24 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
+// Meta of the kept reads `keep` of `a` (one parallel pass over their quality bytes and mapping qualities).
+static void reads_meta(const vgh_alignments* a, const std::vector<int64_t>& keep, vgl_hc_batch_meta& out) {
+    MetaAcc total;
+#pragma omp parallel
+    {
+        MetaAcc mine;
+#pragma omp for schedule(static) nowait
+        for (int64_t k = 0; k < (int64_t)keep.size(); ++k) {
+            const int64_t r = keep[(size_t)k];
+            mine.quality((const uint8_t*)a->qual + a->qual_off[r], (size_t)(a->qual_off[r + 1] - a->qual_off[r]));
+            mine.mapq((uint32_t)a->mapq[r]);
+        }
+#pragma omp critical(vgh_meta)
+        total.merge(mine);
+    }
+    total.store(out);
+}
+
 static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_t r0, int64_t r1, int n_threads, int pinned,
                 vgh_hc_packed** out) {
     if (!g || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
@@ -738,7 +772,7 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
                 size_t first_q90 = (size_t)-1;  // the first REAL quality byte >= 90 latches the background-error mode
                 for (size_t c = 0; c < L; ++c) {
                     const uint8_t qb = (int64_t)c < Lq ? (uint8_t)a->qual[q0 + (int64_t)c] : 0;
-                    col_at(c, l) = (uint32_t)qb | (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT);
+                    col_at(c, l) = (VGL_HC_CANON_QUAL((uint32_t)qb) << VGL_HC_COL_QUAL_SHIFT) | (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT);
                     if ((int64_t)c < Lq && (int)(int8_t)qb >= 90 && first_q90 == (size_t)-1) first_q90 = c;
                 }
                 const int64_t mm = a->map_off[r];
@@ -752,8 +786,8 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
                         const char gb = rc.graph_seq[pos + j], rb = rc.read_seq[j];
                         const int cg = base_code(gb), cb = base_code(rb);
                         uint32_t& rec = col_at(pos + j, l);
-                        rec = (rec & 0xffu) | (node << VGL_HC_COL_NODE_SHIFT) | latched;
-                        if (cg < 4 && cb < 4) rec |= VGL_HC_COL_VALID | ((uint32_t)cb << 10) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
+                        rec = (rec & (0xffu << VGL_HC_COL_QUAL_SHIFT)) | (node << VGL_HC_COL_NODE_SHIFT) | latched;
+                        if (cg < 4 && cb < 4) rec |= VGL_HC_COL_VALID | ((uint32_t)cb << VGL_HC_COL_BASE_SHIFT) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
                     }
                     if (lg) col_at(pos + lg - 1, l) |= VGL_HC_COL_OPEN;
                     else map_at(n_x++, l) = VGL_HC_MAP_REC(node, (uint32_t)pos);
@@ -775,6 +809,7 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
     P->batch.grp_col_blk = grp_col_blk; P->batch.grp_map_blk = grp_map_blk;
     P->batch.col = col; P->batch.map = map;
     P->batch.n_cols = n_cols; P->batch.n_close = n_close; P->batch.n_extra = n_extra; P->batch.mapq = mapq;
+    reads_meta(a, keep, P->batch.meta);
     *out = P;
     return VGH_OK;
 }
@@ -901,9 +936,9 @@ static int vgh_hc_wire_from_packed__impl(const vgh_hc_packed* p, int n_threads, 
                     ++k;
                 }
                 // narrow form of the same record
-                if ((rec & 0xffu) > 63u || (rec & VGL_HC_COL_LATCHED) || ((rec & VGL_HC_COL_VALID) && !own) || (seen_owned && !own)) narrow = false;
+                if (VGL_HC_COL_QUAL(rec) > 63u || (rec & VGL_HC_COL_LATCHED) || ((rec & VGL_HC_COL_VALID) && !own) || (seen_owned && !own)) narrow = false;
                 if (own) { seen_owned = true; ++owned; }
-                gc8[at] = (uint8_t)((rec & 0x3fu) | (VGL_HC_COL_BASE(rec) << 6));
+                gc8[at] = (uint8_t)((VGL_HC_COL_QUAL(rec) & 0x3fu) | (VGL_HC_COL_BASE(rec) << 6));
                 const uint32_t nib = ((rec & VGL_HC_COL_MISMATCH) ? 1u : 0u) | ((rec & VGL_HC_COL_OPEN) ? 2u : 0u) |
                                      ((rec & VGL_HC_COL_CLOSE) ? 4u : 0u) | ((rec & VGL_HC_COL_VALID) ? 8u : 0u);
                 gf4[(size_t)(c / VGL_HC_WIRE_BLK) * VGL_HC_LANES + l] |= nib << (4 * (c % VGL_HC_WIRE_BLK));
@@ -918,6 +953,7 @@ static int vgh_hc_wire_from_packed__impl(const vgh_hc_packed* p, int n_threads, 
     v.n_cols = (const uint16_t*)(base + o_nc); v.n_close = (const uint16_t*)(base + o_ncl); v.n_extra = (const uint16_t*)(base + o_nx);
     v.mapq = base + o_mq;
     if (narrow) { v.col8 = col8; v.flag4 = flag4; v.n_owned = n_owned; }
+    v.meta = b.meta;
     *out = W;
     return VGH_OK;
 }
@@ -1075,6 +1111,7 @@ static int raw_build(const vgh_alignments* a, int64_t r0, int64_t r1, int pinned
     if (narrow && first_only) v.first_offset16 = fo16;  // (narrow: the first offsets fit 16 bits too)
     if (narrow_len) { v.edit_from8 = f8; v.edit_to8 = t8; }
     if (narrow_node) v.map_node16 = n16;
+    if (!euka_rule) reads_meta(a, keep, v.meta);
     *out = P;
     return VGH_OK;
 }
@@ -1195,9 +1232,11 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     uint16_t* n16 = (uint16_t*)(blk + o_n16); uint16_t* fo16 = (uint16_t*)(blk + o_fo16);
     uint8_t* ne8 = blk + o_ne8; uint8_t* sl8 = blk + o_sl8; uint8_t* f8 = blk + o_f8; uint8_t* t8 = blk + o_t8; uint8_t* eseq = blk + o_eseq;
     int bad = 0;
+    std::vector<MetaAcc> metas((size_t)T);
 #pragma omp parallel for schedule(static, 1) num_threads(T) reduction(| : bad)
     for (int t = 0; t < T; ++t) {
         const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
+        MetaAcc& meta = metas[(size_t)t];
         size_t cr = (size_t)base[(size_t)t].r, cm = (size_t)base[(size_t)t].m, ce = (size_t)base[(size_t)t].e;
         size_t cq = (size_t)base[(size_t)t].q, cs = (size_t)base[(size_t)t].s;
         bool good = true;
@@ -1212,6 +1251,8 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
             fo16[cr] = mb > ma ? (uint16_t)a->map_offset[ma] : (uint16_t)0;
             const size_t ql = (size_t)(a->qual_off[r + 1] - a->qual_off[r]);
             memcpy(q + cq, a->qual + a->qual_off[r], ql);
+            meta.quality(q + cq, ql);
+            meta.mapq((uint32_t)a->mapq[r]);
             cq += ql;
             uint64_t cap = 0;
             for (int64_t m = ma; m < mb; ++m) {
@@ -1259,6 +1300,9 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     v.edit_off = ends; v.edit_seq_off = ends + 2;
     v.edit_seq = eseq;
     v.map_node16 = n16; v.first_offset16 = fo16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; v.edit_from8 = f8; v.edit_to8 = t8;
+    MetaAcc all;
+    for (const MetaAcc& m : metas) all.merge(m);
+    all.store(v.meta);
     return 0;
 }
 

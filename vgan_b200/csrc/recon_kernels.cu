@@ -325,7 +325,7 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
         for (int j = 0; j < 4; ++j) {
             const uint32_t c = cb * 4 + j;
             if (c >= L) { rec[j] = 0; continue; }
-            uint32_t v = c < Lq ? raw.qual[q0 + c] : 0u;
+            uint32_t v = c < Lq ? (VGL_HC_CANON_QUAL((uint32_t)raw.qual[q0 + c]) << VGL_HC_COL_QUAL_SHIFT) : 0u;
             while (nxt < M && npos == c) {  // mappings that start at this column (quirk Q1: size slot = the nxt-th edit's size)
                 const uint32_t lg = min((uint32_t)W.sizes[e_first + nxt], L - npos);
                 const uint32_t node = raw.map_node[m0 + nxt] & 0x7fffffffu;
@@ -346,7 +346,7 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
                 const uint8_t gb = gs[c], rb = rs[c - own_pos];
                 const int cg = base_code(gb), cr = base_code(rb);
                 v |= (own_node << VGL_HC_COL_NODE_SHIFT) | latched;
-                if (cg < 4 && cr < 4) v |= VGL_HC_COL_VALID | ((uint32_t)cr << 10) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
+                if (cg < 4 && cr < 4) v |= VGL_HC_COL_VALID | ((uint32_t)cr << VGL_HC_COL_BASE_SHIFT) | (gb == rb ? 0u : VGL_HC_COL_MISMATCH);
                 if (c + 1 == own_end) v |= VGL_HC_COL_OPEN;
             } else {
                 v |= VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT;
@@ -576,8 +576,10 @@ hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const 
             if constexpr (kNarrow) {
                 const uint32_t byte = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
                 const uint32_t nib = (fl >> (4 * j)) & 0xfu;
-                rec = (byte & 0x3fu) | ((nib & 1u) << 8) | ((byte >> 6) << 10) | ((nib & 8u) << 9) | ((nib & 2u) << 12) | ((nib & 4u) << 12) |
-                      (c < n_own ? VGL_HC_WIRE_OWNED : 0u);
+                static_assert(VGL_HC_COL_MISMATCH == 1u && VGL_HC_COL_VALID == 8u << 9 && VGL_HC_COL_OPEN == 2u << 12 && VGL_HC_COL_CLOSE == 4u << 12,
+                              "flag nibble: bit 0 MISMATCH, 1 OPEN, 2 CLOSE, 3 VALID");
+                rec = ((byte & 0x3fu) << VGL_HC_COL_QUAL_SHIFT) | (nib & 1u) | ((byte >> 6) << VGL_HC_COL_BASE_SHIFT) | ((nib & 8u) << 9) |
+                      ((nib & 2u) << 12) | ((nib & 4u) << 12) | (c < n_own ? VGL_HC_WIRE_OWNED : 0u);
             } else {
                 rec = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
             }

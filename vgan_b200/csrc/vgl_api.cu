@@ -73,6 +73,7 @@ struct vgl_ctx {
     int row_words = 0;
     int n_rows_pad = 0;
     DevBuf<double2> d_class_tab;
+    DevBuf<double> d_logterm;   // log-term tables [100][n_class + 1][512] (vgl_internal.h)
     DevBuf<unsigned char> d_image;  // the read kernel's shared-memory image (vgl::HcImageLayout)
     DevBuf<uint32_t> d_node_bits;
     vgl::HcReadLaunch read_cfg{};
@@ -147,6 +148,8 @@ struct vgl_ctx {
     } slot[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t chunk_groups = 4096;  // 131072 reads per H2D chunk
+    bool logterm_off = false;      // VGL_HC_TABLE_MODE pins the general kernel (tests)
+    uint64_t logterm_launches = 0; // read-kernel launches that took the log-term kernel
     uint32_t raw_seq = 0;          // chunks submitted through vgl_hc_accumulate_raw so far (selects the staging set)
 
     // read-kernel timing
@@ -205,7 +208,17 @@ int upload_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     return VGL_OK;
 }
 
-int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
+vgl::HcBatchMeta to_meta(const vgl_hc_batch_meta& m) {
+    vgl::HcBatchMeta r;
+    r.valid = m.valid != 0;
+    if (r.valid) {
+        r.qual_max = m.qual_max;
+        for (int k = 0; k < 4; ++k) r.mapq_mask[k] = m.mapq_mask[k];
+    }
+    return r;
+}
+
+int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b, const vgl::HcBatchMeta& meta) {
     if (b.n_groups == 0) return VGL_OK;
     if (ctx->ev_used == ctx->ev_pool.size()) {
         cudaEvent_t a, c;
@@ -214,9 +227,19 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b) {
         ctx->ev_pool.push_back(std::make_pair(a, c));
     }
     auto& ev = ctx->ev_pool[ctx->ev_used++];
+    // the log-term kernel where the batch allows it (no quality above 63, tables of the pairs present fit), else the general one
+    vgl::HcLogTermLaunch plan;
+    const size_t lt_smem = ctx->logterm_off ? 0 : vgl::hc_logterm_plan(meta, ctx->tab.n_rows, ctx->tab.n_class, ctx->tab.logterm != nullptr,
+                                                                      ctx->max_smem_optin, plan);
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
-    VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total,
-                                        ctx->d_err, ctx->stream));
+    if (lt_smem) {
+        VGL_CUDA(vgl::hc_launch_read_logterm_kernel(ctx->sm_count, lt_smem, plan, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total, ctx->d_err,
+                                                    ctx->stream));
+        ctx->logterm_launches += 1;
+    } else {
+        VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total,
+                                            ctx->d_err, ctx->stream));
+    }
     VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches += 1;
     ctx->ll_valid = false;
@@ -318,7 +341,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release();
+    ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release(); ctx->d_logterm.release();
     ctx->d_cta_node_acc.release();
     ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_tile_done.release();
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
@@ -408,6 +431,7 @@ int vgl_memcpy_d2h(vgl_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
 }
 
 uint64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t vgl_hc_logterm_launches(const vgl_ctx* ctx) { return ctx ? ctx->logterm_launches : 0; }
 
 uint64_t vgl_hc_batch_bytes(const vgl_hc_batch* b) {
     if (!b) return 0;
@@ -472,20 +496,21 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     small.one_minus_bep = 1 - bep;
     small.is_fasta = T->is_consensus_fasta ? 1 : 0;
     small.log_err_scale = -std::log(10.0) / 10.0;
+    // per-column factor 1 - eps, by the low 12 bits of the column record: mismatch | base << 1 | quality << 3 | latched << 11.
+    // The quality field is canonical (0 for Q <= 2 and for bytes that are negative as signed char, i.e. wherever the error
+    // probability is 0.25: qscore_vec[0..2] = 0.25, src/miscfunc.h:198-212; a negative byte would index qscore_vec out of
+    // range in the reference -- defined as 0.25).
+    for (int idx = 0; idx < 4096; ++idx) {
+        const int mm = idx & 1, Q = (idx >> VGL_HC_COL_QUAL_SHIFT) & 0xff, latched = (idx >> 11) & 1;
+        // get_p_no_seq_error_mapping (src/get_p_obs_base.cpp:3-27): eps = qscore[Q] for a match, 1 - qscore[Q] for a mismatch;
+        // the background error probability instead of qscore[Q] once a quality byte >= 90 was seen, and for every base in
+        // consensus-FASTA mode (src/HaploCart.cpp:397-401).  get_p_obs_base: match * (1 - epsilon), src/get_p_obs_base.cpp:67.
+        const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
+        const double eps = (latched || small.is_fasta) ? (mm ? 1 - bep : bep) : (mm ? 1 - qs : qs);
+        small.f_col[idx] = 1 - eps;
+    }
     for (int b = 0; b < 256; ++b) {
         const int Q = (int)(int8_t)(uint8_t)b;  // the reference reads quality bytes as (signed) char
-        // get_p_no_seq_error_mapping (src/get_p_obs_base.cpp:3-27); a negative byte would index qscore_vec
-        // out of range in the reference -- defined here as 0.25.  Bytes >= 90
-        // never reach the table because they latch the background-error mode first.
-        const double qs = (Q >= 0 && Q < 100) ? T->qscore[Q] : 0.25;
-        const double eps_match = qs;
-        const double eps_mis = 1 - qs;
-        // get_p_obs_base: match * (1 - epsilon), src/get_p_obs_base.cpp:67.  In consensus-FASTA mode the
-        // background error probability replaces the quality for every base (src/HaploCart.cpp:397-401).
-        small.f_pair[b] = small.is_fasta ? small.f_match_bep : 1 - eps_match;
-        small.f_pair[256 + b] = small.is_fasta ? small.f_mis_bep : 1 - eps_mis;
-        small.f_pair[512 + b] = small.f_match_bep;  // latched reads: index (record & 0x100) | 0x200
-        small.f_pair[768 + b] = small.f_mis_bep;
         const double perr = (Q > 2) ? std::pow(10, ((-1 * Q) * 0.1)) : 0.25;  // get_p_seq_error, src/miscfunc.h:180-187
         small.log_err[b] = std::log(perr);
         // fast_log table: rc ~ 1 / c_k and -log(rc) for the bucket centre c_k = 1 + (k + 0.5) / 256
@@ -567,6 +592,35 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     ctx->tab.image = ctx->d_image.p;
     ctx->tab.layout = L;
     ctx->tab.node_bits = ctx->d_node_bits.p;
+    // Log-term tables for the fastest read kernel: for every (mapping quality, class) the term of every (quality <= 63,
+    // mismatch, base) combination, computed exactly as the general kernel forms the factor (fma(cc, f, aa * bg)) and then
+    // log() of it.  Built when the class count is small enough for some launch to be able to use them.
+    ctx->tab.logterm = nullptr;
+    ctx->logterm_off = force_mode >= 0;
+    if (n_class + 1 <= 256) {
+        const size_t per_mq = (size_t)(n_class + 1) * vgl::kLogTermEntries;
+        std::vector<double> lt(100 * per_mq);
+        for (int mq = 0; mq < 100; ++mq) {
+            for (int c = 0; c <= n_class; ++c) {
+                double aa = 1.0, cc = 0.0;  // the neutral entry of unknown nodes (they raise VGL_ERR_BAD_NODE anyway)
+                if (c < n_class) {
+                    const double pcm = small.p_correct[mq] * class_tab[(size_t)c].x;
+                    aa = small.is_fasta ? 0.0 : 1.0 - pcm;
+                    cc = (small.is_fasta ? small.one_minus_bep : pcm) * class_tab[(size_t)c].y;
+                }
+                double* row = lt.data() + (size_t)mq * per_mq + (size_t)c * vgl::kLogTermEntries;
+                for (int idx = 0; idx < vgl::kLogTermEntries; ++idx) {
+                    const double f = small.f_col[idx];  // quality <= 63, not latched: the low 9 bits are the whole index
+                    const double bgv = small.bg[(idx >> VGL_HC_COL_BASE_SHIFT) & 3];
+                    row[idx] = std::log(std::fma(cc, f, aa * bgv));
+                }
+            }
+        }
+        if (int rc = ctx->d_logterm.reserve(lt.size())) return rc;
+        VGL_CUDA(cudaMemcpy(ctx->d_logterm.p, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ctx->tab.logterm = ctx->d_logterm.p;
+        VGL_CUDA(vgl::hc_logterm_configure(ctx->max_smem_optin));
+    }
     ctx->row_words = (P + 31) / 32;
     ctx->n_rows_pad = n_words * 32;
     ctx->n_chunks = vgl::hc_path_chunks(n_words);
@@ -634,7 +688,7 @@ int vgl_hc_accumulate_device(vgl_ctx* ctx, const vgl_hc_batch* b) {
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (int rc = check_batch(b)) return rc;
     vgl::HcBatchDev d{b->n_groups, b->grp_col_blk, b->grp_map_blk, b->col, b->map, b->n_cols, b->n_close, b->n_extra, b->mapq};
-    return launch_read(ctx, d);
+    return launch_read(ctx, d, to_meta(b->meta));
 }
 
 int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
@@ -688,7 +742,7 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
         d.n_close = sl.n_close.p;
         d.n_extra = sl.n_extra.p;
         d.mapq = sl.mapq.p;
-        if (int rc = launch_read(ctx, d)) return rc;
+        if (int rc = launch_read(ctx, d, to_meta(b->meta))) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
         sl.used = true;
     }
@@ -883,7 +937,7 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
         vgl::HcBatchDev d;
         if (int rc = pack_raw_chunk(ctx, raw, ra, rb, R, ctx->copy_stream, d)) return rc;
         if (d.n_groups)
-            if (int rc = launch_read(ctx, d)) return rc;
+            if (int rc = launch_read(ctx, d, to_meta(raw->meta))) return rc;
         VGL_CUDA(cudaEventRecord(R.consumed, ctx->stream));
         R.used = true;
     }
@@ -987,7 +1041,7 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
         d.n_close = sl.n_close.p;
         d.n_extra = sl.n_extra.p;
         d.mapq = sl.mapq.p;
-        if (int rc = launch_read(ctx, d)) return rc;
+        if (int rc = launch_read(ctx, d, to_meta(w->meta))) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
         sl.used = true;
     }

@@ -23,8 +23,9 @@ namespace vgl {
 // Indexed by the RAW quality byte (0..255); bytes >= 128 are negative as `signed char`, which is
 // how the reference sees them (src/update_likelihood.cpp:41).
 struct HcSmallTables {
-    double f_pair[1024];   // 1 - eps: [q] graph base == read base (eps = qscore[Q]); [256 + q] mismatch (eps = 1 - qscore[Q]);
-                           // [512] / [768]: the same with the background error probability (latched reads)
+    double f_col[4096];    // 1 - eps, indexed by bits 0-11 of the column record (mismatch | base << 1 | quality << 3 | latched << 11;
+                           // the base bits do not matter): match eps = qscore[Q], mismatch eps = 1 - qscore[Q]; latched (or
+                           // consensus-FASTA mode): the same with the background error probability
     double log_err[256];   // log(get_p_seq_error(Q))           src/process_mapping.cpp:11
     double2 log_tab[256];  // fast_log table: {rc_k ~ 1/c_k, -log(rc_k)}, c_k = 1 + (k + 0.5)/256
     double p_correct[100]; // 1 - p_incorrect_map[mapq]         src/process_mapping.cpp:41
@@ -65,6 +66,7 @@ struct HcTablesDev {
     const unsigned char* image;  // see HcImageLayout
     HcImageLayout layout;
     const uint32_t* node_bits;  // [n_words][n_paths]  bit k of word (w, p) = pathsgo[p] of node 32w+k
+    const double* logterm;      // log-term tables (see kLogTermEntries), or nullptr when there are too many classes
 };
 
 struct HcBatchDev {
@@ -77,6 +79,25 @@ struct HcBatchDev {
     const uint16_t* n_close;
     const uint16_t* n_extra;
     const uint8_t* mapq;
+};
+
+// What the host knows about a batch's value ranges (vgl_hc_batch_meta): decides whether the log-term kernel can run.
+struct HcBatchMeta {
+    bool valid = false;
+    uint32_t qual_max = 255;
+    uint32_t mapq_mask[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfu};
+};
+
+// Log-term tables (the read kernel's fastest mode): for every (mapping quality, node class) pair the per-column term
+//   log((1 - pcm) * bg[base] + pcm * K * (1 - eps(quality, mismatch)))            src/process_mapping.cpp:59-77
+// for quality 0..63, indexed by bits 0-8 of the column record (quality-major).  Global layout:
+//   logterm[(mapq * (n_class + 1) + class) * 512 + (record & 0x1ff)], class n_class = the neutral entry of unknown nodes.
+// A launch stages the rows of the mapping qualities PRESENT in the batch, cut at the batch's largest quality, in shared memory.
+constexpr int kLogTermEntries = 512;
+struct HcLogTermLaunch {
+    int n_slots;             // mapping qualities present
+    int q_rows;              // qualities 0 .. q_rows - 1
+    uint8_t mapq_of_slot[100];
 };
 
 // Read kernel launch geometry (one persistent CTA per SM).
@@ -96,6 +117,14 @@ cudaError_t hc_read_configure(const HcReadLaunch& cfg);
 //   a_total[copy]                 += sum over the copy's mappings of A_i
 cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& batch, const HcTablesDev& tab,
                                   double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
+
+// K1, log-term mode: one table lookup and two fp64 adds per aligned column, mappings finalised in line (no log, no queue).
+// hc_logterm_plan: can this batch run in that mode on this device?  Fills `plan` and returns the dynamic shared memory it
+// needs, or 0 when it cannot (quality above 63, too many (mapping quality, class) pairs for shared memory, no tables).
+size_t hc_logterm_plan(const HcBatchMeta& meta, int n_rows, int n_class, bool have_tables, int max_smem_optin, HcLogTermLaunch& plan);
+cudaError_t hc_logterm_configure(int max_smem_optin);
+cudaError_t hc_launch_read_logterm_kernel(int grid, size_t smem, const HcLogTermLaunch& plan, const HcBatchDev& batch, const HcTablesDev& tab,
+                                          double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
 
 // K2b: sums the copies and runs the bit-GEMV over the node x path membership: chunk_ll[chunk][P].
 int hc_path_chunks(int n_words);

@@ -145,6 +145,10 @@ class Haplocart:
     def synchronize(self):
         check(gpu.vgl_synchronize(self.ctx))
 
+    def logterm_launches(self):
+        """Read-kernel launches so far that took the log-term kernel (the batch's meta allowed it)."""
+        return int(gpu.vgl_hc_logterm_launches(self.ctx))
+
     def launch_count(self):
         return int(gpu.vgl_launch_count(self.ctx))
 
@@ -170,6 +174,7 @@ class DeviceBatch:
         self.batch = _lib.vgl_hc_batch()
         self.batch.n_reads, self.batch.n_groups = b.n_reads, b.n_groups
         self.batch.n_col_blks, self.batch.n_map_blks = b.n_col_blks, b.n_map_blks
+        self.batch.meta = b.meta     # value ranges of the batch: lets the library take the log-term read kernel
         self.ptrs = []
         self.nbytes = 0
         for name, n in sizes.items():

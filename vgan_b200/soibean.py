@@ -40,6 +40,10 @@ class SoibeanPackedBatch:
     def n_reads(self):
         return int(self.batch.n_reads)
 
+    @property
+    def nbytes(self):
+        return int(gpu.vgl_euka_batch_bytes(C.byref(self.batch)))   # (the soibean batch has the euka batch's layout)
+
     def __del__(self):
         if self.handle:
             host.vgh_euka_packed_destroy(self.handle)
