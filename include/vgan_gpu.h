@@ -202,10 +202,19 @@ int vgl_hc_set_tree(vgl_ctx* ctx, int32_t n_clades, const uint32_t* clade_bits, 
  * log terms from shared-memory tables) when no quality exceeds 63 and the tables of the (mapping quality, class) pairs
  * present fit.  valid == 0: unknown (the general kernel runs).  Filled by vgh_hc_pack / vgh_hc_wire_from_packed /
  * vgh_hc_raw_build / vgh_hc_feed; copy it along when a batch is moved to the device.                                */
+#define VGL_HC_MAX_SEGS 16
 typedef struct vgl_hc_batch_meta {
     uint32_t valid;        /* 1: the fields below hold for every read of the batch */
     uint32_t qual_max;     /* largest CANONICAL quality (bits 3-10 of the column record) */
     uint32_t mapq_mask[4]; /* bit q set: some read has mapping quality q (0..99) */
+    /* Segments: the batch's groups are ordered by mapping quality and no group mixes two (a segment's last group is filled up
+     * with unused lanes), so that a CTA of the log-term kernel needs the tables of ONE mapping quality.  n_segs == 0: not so
+     * (more than VGL_HC_MAX_SEGS distinct mapping qualities, or a producer that does not sort); the general kernel runs.
+     *   packed / wire batch : seg_end[k] = group index one past segment k (segment k starts where k - 1 ends)
+     *   raw batch           : seg_end[k] = number of reads with mapping quality seg_mapq[k]; the device sorts and pads */
+    uint32_t n_segs;
+    uint8_t seg_mapq[VGL_HC_MAX_SEGS];
+    uint32_t seg_end[VGL_HC_MAX_SEGS];
 } vgl_hc_batch_meta;
 
 typedef struct vgl_hc_batch {

@@ -142,7 +142,8 @@ def test_packer_against_oracle_reconstruction():
     assert pb.n_reads == len(keep) == len(got) and pb.skipped == len(A) - len(keep)
     # the packer groups reads by shape, so compare as multisets of lanes
     assert sorted(map(_lane_key, got)) == sorted(map(_lane_key, want))
-    shapes = [(d["n_close"], d["n_cols"]) for d in got]
+    # ... within a mapping quality: groups never mix two mapping qualities (segments, vgl_hc_batch_meta)
+    shapes = [(d["mapq"], d["n_close"], d["n_cols"]) for d in got]
     assert shapes == sorted(shapes)
     # mis-slicing (quirk Q1) happened: some read has more edits than mappings, so some columns have no owner
     assert any(d["cov_end"] < d["n_cols"] for d in want)
@@ -150,12 +151,23 @@ def test_packer_against_oracle_reconstruction():
     # padding: rows of a group are as long as its longest lane, unused records are zero
     a = pb.arrays()
     G = int(pb.batch.n_groups)
-    assert G == (pb.n_reads + 31) // 32
+    meta = pb.batch.meta
+    mq = sorted(set(d["mapq"] for d in got))
+    assert meta.valid == 1 and meta.n_segs == len(mq) and list(meta.seg_mapq[:meta.n_segs]) == mq and meta.seg_end[meta.n_segs - 1] == G
+    assert G == sum((sum(1 for d in got if d["mapq"] == q) + 31) // 32 for q in mq)   # every segment's last group is filled up
+    assert meta.qual_max == max((c >> 3) & 0xff for d in got for c in d["col"])
+    lane_mapq = a["mapq"].reshape(G, 32)
+    lane_cols = a["n_cols"].reshape(G, 32)
+    lane_x = a["n_extra"].reshape(G, 32)
+    g0 = 0
+    for k in range(meta.n_segs):
+        g1 = int(meta.seg_end[k])
+        used = (lane_cols[g0:g1] > 0) | (lane_x[g0:g1] > 0)
+        assert np.all(lane_mapq[g0:g1][used] == meta.seg_mapq[k]) and np.all(lane_mapq[g0:g1][~used] == 0)
+        g0 = g1
     for g in range(G):
-        lanes_g = got[g * 32:(g + 1) * 32]
-        assert a["grp_col_blk"][g + 1] - a["grp_col_blk"][g] == (max(d["n_cols"] for d in lanes_g) + 3) // 4
-        assert a["grp_map_blk"][g + 1] - a["grp_map_blk"][g] == (max(len(d["extra"]) for d in lanes_g) + 3) // 4
-    assert a["n_cols"][pb.n_reads:].sum() == 0 and a["n_close"][pb.n_reads:].sum() == 0 and a["n_extra"][pb.n_reads:].sum() == 0
+        assert a["grp_col_blk"][g + 1] - a["grp_col_blk"][g] == (int(lane_cols[g].max()) + 3) // 4
+        assert a["grp_map_blk"][g + 1] - a["grp_map_blk"][g] == (int(lane_x[g].max()) + 3) // 4
     assert pb.nbytes == (G + 1) * 8 + 512 * (int(a["grp_col_blk"][-1]) + int(a["grp_map_blk"][-1])) + 7 * 32 * G
     # a quality byte >= 90 latches the background-error mode of every mapping whose window holds it
     alns = [H.aln("GCTACGATGG", [(9, 0, False, [(10, 10, "")])], quality=bytes([30, 30, 30, 95, 30, 200, 30, 30, 99, 30]))]
@@ -335,7 +347,7 @@ def test_wire_form_of_a_packed_batch():
     assert gc[-1] == w.n_col_blks and gn[-1] == w.n_node_blks
     lanes = pb.lanes()
     for k, d in enumerate(lanes):
-        g, l = divmod(k, 32)
+        g, l = divmod(d["slot"], 32)
         c16 = col[gc[g]:gc[g + 1], l, :].reshape(-1)
         n16 = node[gn[g]:gn[g + 1], l, :].reshape(-1)
         recs = d["col"]
@@ -350,13 +362,13 @@ def test_wire_form_of_a_packed_batch():
     f4 = vb.host._as_array(w.flag4, int(w.n_col_blks) * 32, np.uint32).reshape(-1, 32)
     own = vb.host._as_array(w.n_owned, G * 32, np.uint16)
     for k, d in enumerate(lanes):
-        g, l = divmod(k, 32)
+        g, l = divmod(d["slot"], 32)
         byte = c8[gc[g]:gc[g + 1], l, :].reshape(-1).astype(np.uint32)
         word = f4[gc[g]:gc[g + 1], l]
         nib = np.array([(int(word[c // 8]) >> (4 * (c % 8))) & 0xF for c in range(byte.size)], dtype=np.uint32)
         c = np.arange(byte.size)
         rec = ((byte & 0x3F) << 3) | (nib & 1) | ((byte >> 6) << 1) | ((nib & 8) << 9) | ((nib & 2) << 12) | ((nib & 4) << 12) | \
-              np.where(c < own[k], 0x8000, 0).astype(np.uint32)
+              np.where(c < own[d["slot"]], 0x8000, 0).astype(np.uint32)
         assert np.array_equal(rec.astype(np.uint16), col[gc[g]:gc[g + 1], l, :].reshape(-1)), k
     narrow_bytes = wb.nbytes
     w.col8 = None

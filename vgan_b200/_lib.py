@@ -27,7 +27,8 @@ class vgl_hc_tables(C.Structure):
 
 
 class vgl_hc_batch_meta(C.Structure):
-    _fields_ = [("valid", C.c_uint32), ("qual_max", C.c_uint32), ("mapq_mask", C.c_uint32 * 4)]
+    _fields_ = [("valid", C.c_uint32), ("qual_max", C.c_uint32), ("mapq_mask", C.c_uint32 * 4), ("n_segs", C.c_uint32),
+                ("seg_mapq", C.c_uint8 * 16), ("seg_end", C.c_uint32 * 16)]
 
 
 class vgl_hc_wire(C.Structure):

@@ -477,7 +477,11 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
 //     B_i = (sum of q over columns >= c) * (-ln 10 / 10) + (n - nz) * log 0.25.
 // Records past a read's own columns are zero and change neither sum.
 //
-// Shared memory: [ node table u16[n_rows + 1] | row offset u32[100] | pair tables double[slots][n_class + 1][q_rows * 8] ]
+// Mapping qualities.  The batch's groups come in segments, one mapping quality each (vgl_hc_batch_meta); the CTAs are dealt
+// out to the segments in proportion to their groups and a CTA stages the tables of its segment's mapping quality only --
+// (n_class + 1) x q_rows x 64 bytes, whatever the number of mapping qualities in the batch.
+//
+// Shared memory: [ node table u16[n_rows + 1] | pair tables double[n_class + 1][q_rows * 8] ]
 // node table entry: (byte offset of the class's table inside a row) / 16, bit 15 = every path goes through the node.
 // ------------------------------------------------------------------------------------------
 #ifndef VGL_HC_LT_BLOCK
@@ -486,7 +490,7 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
 constexpr int kLtBlock = VGL_HC_LT_BLOCK;
 
 struct LtShared {
-    uint32_t node_tab, tables, row_off;  // shared byte addresses
+    uint32_t node_tab, tables;           // shared byte addresses
     double* acc;
     int n_rows;
     uint32_t none_entry;                 // node-table entry of the neutral class (unknown node, no pangenome_map entry)
@@ -500,7 +504,7 @@ __device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtSh
                                                  bool& bad_node) {
     Hn = hc_load_hdr(b, gn, lane);
     const int ncb = H.ncb;
-    const uint32_t row_base = S.tables + lds_u32_c(S.row_off + 4u * min(H.mapq, 99u));
+    const uint32_t row_base = S.tables;   // the CTA's segment has one mapping quality: one row of tables
     int x = H.n_extra - 1;   // empty mappings (no column of their own): rare, handled on the side
     bool rare = x >= 0;
     uint32_t sufq8 = 0;      // 8 * (sum of the canonical qualities of the columns walked so far)
@@ -531,6 +535,7 @@ __device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtSh
                 : "+r"(e32)
                 : "r"(S.node_tab + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: neutral
             ent[j] = e32;
+            worst_entry = max(worst_entry, e32 & 0x7fffu);  // (0 where no mapping opens; the neutral class has the largest offset)
         }
         const bool any_rare = __any_sync(kFull, rare);
 #pragma unroll
@@ -538,7 +543,6 @@ __device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtSh
             const uint32_t r = rec[j];
             // OPEN (last column of a mapping): its class's table
             entry = (r & VGL_HC_COL_OPEN) ? ent[j] : entry;
-            worst_entry = max(worst_entry, entry & 0x7fffu);
             const uint32_t pair_base = row_base + ((entry & 0x7fffu) << 4);
             // the column's term; columns that take no part (N, non-ACGT, no owner) add nothing
             double t = 0.0;
@@ -604,8 +608,13 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
     const uint32_t pair_bytes = (uint32_t)plan.q_rows * 64u;                       // q_rows * 8 entries of 8 bytes
     const uint32_t row_bytes = pair_bytes * (uint32_t)(t.n_class + 1);
     uint16_t* s_node = reinterpret_cast<uint16_t*>(smem_raw);
-    uint32_t* s_row = reinterpret_cast<uint32_t*>(smem_raw + node_bytes);
-    unsigned char* s_tab = smem_raw + node_bytes + 512;
+    unsigned char* s_tab = smem_raw + node_bytes;
+    // this CTA's segment: the groups of one mapping quality
+    int seg = 0;
+    while (seg + 1 < plan.n_segs && blockIdx.x >= plan.cta_begin[seg + 1]) ++seg;
+    const uint32_t seg_mapq = plan.seg_mapq[seg];
+    const uint32_t g_begin = plan.seg_begin[seg], g_end = plan.seg_begin[seg + 1];
+    const uint32_t cta_in_seg = blockIdx.x - plan.cta_begin[seg], ctas_of_seg = plan.cta_begin[seg + 1] - plan.cta_begin[seg];
 
     // staging: the node classes (from the general kernel's image) and one table per (present mapping quality, class),
     // all as TMA bulk copies on one mbarrier
@@ -614,21 +623,13 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(bar, node_bytes + (uint32_t)plan.n_slots * row_bytes);
+            mbar_expect_tx(bar, node_bytes + row_bytes);
             bulk_g2s(smem_u32(s_node), t.image + t.layout.off_class, node_bytes, bar);
         }
         __syncthreads();
-        const int n_pairs = plan.n_slots * (t.n_class + 1);
-        for (int k = tid; k < n_pairs; k += kLtBlock) {
-            const int slot = k / (t.n_class + 1), cls = k - slot * (t.n_class + 1);
-            const double* src = t.logterm + ((size_t)plan.mapq_of_slot[slot] * (size_t)(t.n_class + 1) + (size_t)cls) * kLogTermEntries;
-            bulk_g2s(smem_u32(s_tab) + (uint32_t)slot * row_bytes + (uint32_t)cls * pair_bytes, src, pair_bytes, bar);
-        }
-        if (tid < 100) {
-            uint32_t off = 0;  // a mapping quality that is not in the plan (cannot happen when the batch's mask is right): row 0
-            for (int sidx = 0; sidx < plan.n_slots; ++sidx)
-                if (plan.mapq_of_slot[sidx] == tid) off = (uint32_t)sidx * row_bytes;
-            s_row[tid] = off;
+        for (int cls = tid; cls <= t.n_class; cls += kLtBlock) {
+            const double* src = t.logterm + ((size_t)seg_mapq * (size_t)(t.n_class + 1) + (size_t)cls) * kLogTermEntries;
+            bulk_g2s(smem_u32(s_tab) + (uint32_t)cls * pair_bytes, src, pair_bytes, bar);
         }
         mbar_wait(bar, 0);
         __syncthreads();
@@ -643,7 +644,6 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
 
     LtShared S;
     S.node_tab = smem_u32(s_node);
-    S.row_off = smem_u32(s_row);
     S.tables = smem_u32(s_tab);
     S.acc = cta_node_acc + (size_t)(blockIdx.x % kAccCopies) * (size_t)(t.n_words * 32);
     S.n_rows = t.n_rows;
@@ -654,17 +654,21 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
     double a_sum = 0.0;
     bool bad_node = false;
     uint32_t worst_entry = 0;
-    const uint32_t warps_total = gridDim.x * (kLtBlock / 32);
-    uint32_t g = blockIdx.x * (kLtBlock / 32) + warp;
-    GroupHdr H = hc_load_hdr(b, g, lane), Hn;
+    const uint32_t warps_of_seg = ctas_of_seg * (kLtBlock / 32);
+    uint32_t g = g_begin + cta_in_seg * (kLtBlock / 32) + warp;
+    GroupHdr H = hc_load_hdr(b, g < g_end ? g : b.n_groups, lane), Hn;
     uint4 v0 = hc_fetch(H, H.ncb - 1), v1 = hc_fetch(H, H.ncb - 2);
-    while (g < b.n_groups) {
-        const uint32_t gn = g + warps_total;
-        lt_process_group(b, S, g, gn, H, Hn, v0, v1, lane, a_sum, worst_entry, bad_node);
+    bool wrong_mapq = false;
+    while (g < g_end) {
+        const uint32_t gn = g + warps_of_seg;
+        // (a lane with columns whose mapping quality is not the segment's: the producer's segments are wrong)
+        wrong_mapq = wrong_mapq || (H.n_cols != 0 && H.mapq != seg_mapq);
+        lt_process_group(b, S, g, gn < g_end ? gn : b.n_groups, H, Hn, v0, v1, lane, a_sum, worst_entry, bad_node);
         H = Hn;
         g = gn;
     }
     if (__any_sync(kFull, bad_node || worst_entry == S.none_entry) && lane == 0) atomicOr(err_flag, VGL_ERR_BAD_NODE);
+    if (__any_sync(kFull, wrong_mapq) && lane == 0) atomicOr(err_flag, 0x08000000);   // decoded by vgl_hc_finalize
     a_sum = warp_sum_f64(a_sum);
     if (lane == 0) s_warp_a[warp] = a_sum;
     __syncthreads();
@@ -952,18 +956,43 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
     return cudaGetLastError();
 }
 
-size_t hc_logterm_plan(const HcBatchMeta& meta, int n_rows, int n_class, bool have_tables, int max_smem_optin, HcLogTermLaunch& plan) {
-    if (!have_tables || !meta.valid || meta.qual_max > 63u) return 0;
-    plan.n_slots = 0;
+size_t hc_logterm_plan(const HcBatchMeta& meta, uint32_t n_groups, int n_ctas, int n_rows, int n_class, bool have_tables, int max_smem_optin,
+                       HcLogTermLaunch& plan) {
+    if (!have_tables || !meta.valid || meta.qual_max > 63u || meta.n_segs == 0 || n_ctas < (int)meta.n_segs) return 0;
+    if (meta.seg_end[meta.n_segs - 1] != n_groups) return 0;   // the segments must cover the batch
+    plan.n_segs = (int)meta.n_segs;
     plan.q_rows = (int)meta.qual_max + 1;
-    for (int mq = 0; mq < 100; ++mq)
-        if (meta.mapq_mask[mq >> 5] & (1u << (mq & 31))) plan.mapq_of_slot[plan.n_slots++] = (uint8_t)mq;
-    if (plan.n_slots == 0) return 0;
     const size_t node_bytes = (((size_t)n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
     const size_t pair_bytes = (size_t)plan.q_rows * 64;
     if (((size_t)n_class * pair_bytes >> 4) >= 0x8000u) return 0;   // the node table keeps class offsets in 15 bits
-    const size_t smem = node_bytes + 512 + (size_t)plan.n_slots * (size_t)(n_class + 1) * pair_bytes;
+    const size_t smem = node_bytes + (size_t)(n_class + 1) * pair_bytes;
     if (smem + 1024 > (size_t)max_smem_optin || smem >= (1u << 20)) return 0;  // (one mbarrier counts the staged bytes)
+    // CTAs in proportion to the segments' groups (largest remainder), at least one each
+    uint32_t begin = 0;
+    plan.seg_begin[0] = 0;
+    int given = 0;
+    double frac[VGL_HC_MAX_SEGS];
+    int share[VGL_HC_MAX_SEGS];
+    for (int k = 0; k < plan.n_segs; ++k) {
+        if (meta.seg_end[k] < begin || meta.seg_mapq[k] >= 100) return 0;
+        plan.seg_mapq[k] = meta.seg_mapq[k];
+        plan.seg_begin[k + 1] = meta.seg_end[k];
+        const double want = n_groups ? (double)(meta.seg_end[k] - begin) * (double)(n_ctas - plan.n_segs) / (double)n_groups : 0.0;
+        share[k] = 1 + (int)want;
+        frac[k] = want - (double)(int)want;
+        given += share[k];
+        begin = meta.seg_end[k];
+    }
+    while (given < n_ctas) {
+        int best = 0;
+        for (int k = 1; k < plan.n_segs; ++k)
+            if (frac[k] > frac[best]) best = k;
+        share[best] += 1;
+        frac[best] = -1.0;
+        given += 1;
+    }
+    plan.cta_begin[0] = 0;
+    for (int k = 0; k < plan.n_segs; ++k) plan.cta_begin[k + 1] = plan.cta_begin[k] + (uint32_t)share[k];
     return (smem + 127) & ~(size_t)127;
 }
 

@@ -49,7 +49,12 @@ struct MetaAcc {
     }
     void mapq(uint32_t v) { if (v < 128) mask[v >> 5] |= 1u << (v & 31); }
     void merge(const MetaAcc& o) { qmax = std::max(qmax, o.qmax); for (int k = 0; k < 4; ++k) mask[k] |= o.mask[k]; }
-    void store(vgl_hc_batch_meta& m) const { m.valid = 1; m.qual_max = qmax; for (int k = 0; k < 4; ++k) m.mapq_mask[k] = mask[k]; }
+    void store(vgl_hc_batch_meta& m) const {
+        memset(&m, 0, sizeof(m));
+        m.valid = 1;
+        m.qual_max = qmax;
+        for (int k = 0; k < 4; ++k) m.mapq_mask[k] = mask[k];
+    }
 };
 }  // namespace
 
@@ -684,19 +689,49 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
     }
     if (err) return fail(err, "%s", err_msg.c_str());
 
-    // Group reads of similar shape into warps of 32 lanes (the sum over reads is order independent): sort by
-    // (mappings, columns) so that the zero padding up to each group's longest read stays small.
-    std::vector<uint32_t> order(R);
-    for (size_t k = 0; k < R; ++k) order[k] = (uint32_t)k;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        return ((uint64_t)ncloses[x] << 32 | ncols[x]) < ((uint64_t)ncloses[y] << 32 | ncols[y]);
+    // Group reads into warps of 32 lanes (the sum over reads is order independent).  First by mapping quality -- a group
+    // holds reads of ONE mapping quality and every mapping quality's run of groups is a segment of the batch, so that the
+    // log-term read kernel stages the tables of a single mapping quality per CTA (vgl_hc_batch_meta) -- then by shape
+    // (mappings, columns), so that the zero padding up to each group's longest read stays small.  A segment's last group is
+    // filled up with unused lanes.  More than VGL_HC_MAX_SEGS distinct mapping qualities: no segments, shape only.
+    const uint32_t kNoRead = 0xffffffffu;
+    uint32_t mq_count[128];
+    memset(mq_count, 0, sizeof(mq_count));
+    for (size_t k = 0; k < R; ++k) mq_count[(size_t)a->mapq[keep[k]] & 127u] += 1;
+    int n_distinct = 0;
+    for (int q = 0; q < 128; ++q) n_distinct += mq_count[q] ? 1 : 0;
+    const bool segmented = n_distinct >= 1 && n_distinct <= VGL_HC_MAX_SEGS;
+    std::vector<uint32_t> sorted(R);
+    for (size_t k = 0; k < R; ++k) sorted[k] = (uint32_t)k;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t x, uint32_t y) {
+        const uint64_t kx = ((uint64_t)(segmented ? a->mapq[keep[x]] : 0) << 48) | ((uint64_t)ncloses[x] << 24) | ncols[x];
+        const uint64_t ky = ((uint64_t)(segmented ? a->mapq[keep[y]] : 0) << 48) | ((uint64_t)ncloses[y] << 24) | ncols[y];
+        return kx < ky;
     });
-    const size_t n_groups = (R + VGL_HC_LANES - 1) / VGL_HC_LANES;
+    std::vector<uint32_t> order;  // lane -> index into keep, kNoRead for an unused lane
+    vgl_hc_batch_meta seg_meta;
+    memset(&seg_meta, 0, sizeof(seg_meta));
+    if (segmented) {
+        size_t at = 0;
+        for (int q = 0; q < 128; ++q) {
+            if (!mq_count[q]) continue;
+            for (uint32_t i = 0; i < mq_count[q]; ++i) order.push_back(sorted[at++]);
+            while (order.size() % VGL_HC_LANES) order.push_back(kNoRead);
+            seg_meta.seg_mapq[seg_meta.n_segs] = (uint8_t)q;
+            seg_meta.seg_end[seg_meta.n_segs] = (uint32_t)(order.size() / VGL_HC_LANES);
+            seg_meta.n_segs += 1;
+        }
+    } else {
+        order = sorted;
+        while (order.size() % VGL_HC_LANES) order.push_back(kNoRead);
+    }
+    const size_t n_groups = order.size() / VGL_HC_LANES;
     std::vector<uint32_t> g_col(n_groups + 1, 0), g_map(n_groups + 1, 0);
     for (size_t gI = 0; gI < n_groups; ++gI) {
         uint32_t mc = 0, mm = 0;
-        for (size_t l = 0; l < VGL_HC_LANES && gI * VGL_HC_LANES + l < R; ++l) {
+        for (size_t l = 0; l < VGL_HC_LANES; ++l) {
             const uint32_t k = order[gI * VGL_HC_LANES + l];
+            if (k == kNoRead) continue;
             mc = std::max(mc, ncols[k]);
             mm = std::max(mm, nextras[k]);
         }
@@ -763,8 +798,8 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
                 const size_t lane_id = (size_t)gI * VGL_HC_LANES + l;
                 n_cols[lane_id] = n_close[lane_id] = n_extra[lane_id] = 0;
                 mapq[lane_id] = 0;
-                if (lane_id >= R) continue;
                 const uint32_t k = order[lane_id];
+                if (k == kNoRead) continue;
                 const int64_t r = keep[k];
                 if (reconstruct(*g, *a, r, rc)) continue;  // cannot fail: pass 1 succeeded
                 const size_t L = rc.read_seq.size();
@@ -810,6 +845,9 @@ static int vgh_hc_pack__impl(const vgh_graph* g, const vgh_alignments* a, int64_
     P->batch.col = col; P->batch.map = map;
     P->batch.n_cols = n_cols; P->batch.n_close = n_close; P->batch.n_extra = n_extra; P->batch.mapq = mapq;
     reads_meta(a, keep, P->batch.meta);
+    P->batch.meta.n_segs = seg_meta.n_segs;
+    memcpy(P->batch.meta.seg_mapq, seg_meta.seg_mapq, sizeof(seg_meta.seg_mapq));
+    memcpy(P->batch.meta.seg_end, seg_meta.seg_end, sizeof(seg_meta.seg_end));
     *out = P;
     return VGH_OK;
 }

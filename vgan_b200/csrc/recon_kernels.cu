@@ -174,15 +174,19 @@ hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int mode, int*
     W.n_cols[r] = (uint16_t)rlen;
     W.n_close[r] = (uint16_t)n_close;
     W.n_extra[r] = (uint16_t)n_extra;
-    // histogram of column counts: one atomic per distinct value in the warp
-    const uint32_t peers = __match_any_sync(__activemask(), rlen);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + rlen, (uint32_t)__popc(peers));
+    // histogram of (mapping-quality slot, column count): one atomic per distinct value in the warp
+    const uint32_t key = (uint32_t)W.slot_of_mapq[raw.mapq[r] & 127u] * 4096u + rlen;
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + key, (uint32_t)__popc(peers));
 }
 
-// exclusive scan of 4096 counters, one block of 1024 threads (4 per thread)
-__global__ void __launch_bounds__(1024) hc_scan4096(const uint32_t* __restrict__ hist, uint32_t* __restrict__ start) {
+// exclusive scan of a slot's 4096 counters, one block of 1024 threads (4 per thread) per slot; slot s starts at lane lane_base
+__global__ void __launch_bounds__(1024) hc_scan4096(const uint32_t* __restrict__ hist_all, uint32_t* __restrict__ start_all, ReconWorkDev W) {
     __shared__ uint32_t s_warp[32];
     const int t = threadIdx.x;
+    const uint32_t* hist = hist_all + (size_t)blockIdx.x * 4096;
+    uint32_t* start = start_all + (size_t)blockIdx.x * 4096;
+    const uint32_t lane0 = W.lane_base[blockIdx.x];
     const uint32_t a = hist[4 * t], b = hist[4 * t + 1], c = hist[4 * t + 2], d = hist[4 * t + 3];
     const uint32_t mine = a + b + c + d;
     uint32_t v = mine;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(1024) hc_scan4096(const uint32_t* __restrict__
         s_warp[t] = w;
     }
     __syncthreads();
-    const uint32_t base = v - mine + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+    const uint32_t base = lane0 + v - mine + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
     start[4 * t] = base;
     start[4 * t + 1] = base + a;
     start[4 * t + 2] = base + a + b;
@@ -211,11 +215,11 @@ __global__ void __launch_bounds__(1024) hc_scan4096(const uint32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-hc_order_kernel(uint32_t n_reads, const uint16_t* __restrict__ n_cols, const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
-                uint32_t* __restrict__ order) {
+hc_order_kernel(uint32_t n_reads, const uint16_t* __restrict__ n_cols, const uint8_t* __restrict__ mapq, const uint32_t* __restrict__ start,
+                uint32_t* __restrict__ cursor, uint32_t* __restrict__ order, ReconWorkDev W) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    const uint32_t key = n_cols[r];
+    const uint32_t key = (uint32_t)W.slot_of_mapq[mapq[r] & 127u] * 4096u + n_cols[r];
     // one atomic per distinct key in the warp (reads of one batch are mostly equally long: a single hot counter otherwise)
     const uint32_t peers = __match_any_sync(__activemask(), key);
     const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
@@ -231,8 +235,9 @@ hc_groups_kernel(uint32_t n_reads, uint32_t n_groups, const uint32_t* __restrict
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     uint32_t mc = 0, mx = 0;
-    for (uint32_t l = 0; l < 32 && g * 32 + l < n_reads; ++l) {
+    for (uint32_t l = 0; l < 32; ++l) {
         const uint32_t r = order[g * 32 + l];
+        if (r == kReconNoRead) continue;
         mc = max(mc, (uint32_t)n_cols[r]);
         mx = max(mx, (uint32_t)n_extra[r]);
     }
@@ -298,7 +303,7 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     }
     const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0;
     uint4* gc = reinterpret_cast<uint4*>(col) + (size_t)cb0 * 32 + lane;  // block k of this lane: gc[k * 32]
-    if (slot >= raw.n_reads) {  // unused lane of the last group
+    if (W.order[slot] == kReconNoRead) {  // unused lane (the last group of a mapping-quality slot is filled up with them)
         for (uint32_t cb = 0; cb < ncb; ++cb) gc[(size_t)cb * 32] = make_uint4(0, 0, 0, 0);
         o_n_cols[slot] = o_n_close[slot] = o_n_extra[slot] = 0;
         o_mapq[slot] = 0;
@@ -485,7 +490,7 @@ sym_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, int soibean,
     const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0, mb0 = W.grp_mb[g], nmb = W.grp_mb[g + 1] - mb0;
     uint4* gc = reinterpret_cast<uint4*>(col) + (size_t)cb0 * 32 + lane;  // column block k (8 records): gc[k * 32]
     uint4* gm = reinterpret_cast<uint4*>(map) + (size_t)mb0 * 32 + lane;  // mapping block k (4 records): gm[k * 32]
-    const bool live = slot < raw.n_reads && W.n_close[W.order[slot < raw.n_reads ? slot : 0]] != 0xffffu;
+    const bool live = slot < raw.n_reads && W.order[slot] != kReconNoRead && W.n_close[W.order[slot]] != 0xffffu;
     const uint32_t r = live ? W.order[slot] : 0u;
     const uint32_t L = live ? W.n_cols[r] : 0u, n_rec = live ? W.n_extra[r] : 0u;
     const uint32_t m0 = raw.map_off[r], M = raw.map_off[r + 1] - m0;
@@ -615,9 +620,9 @@ cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, cons
     hc_recon_kernel<<<(raw.n_reads + 127) / 128, 128, 0, s>>>(raw, G, W, mode, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    hc_scan4096<<<1, 1024, 0, s>>>(W.hist, W.start);
-    hc_order_kernel<<<(raw.n_reads + 255) / 256, 256, 0, s>>>(raw.n_reads, W.n_cols, W.start, W.cursor, W.order);
-    const uint32_t n_groups = (raw.n_reads + 31) / 32;
+    hc_scan4096<<<W.n_slots, 1024, 0, s>>>(W.hist, W.start, W);
+    hc_order_kernel<<<(raw.n_reads + 255) / 256, 256, 0, s>>>(raw.n_reads, W.n_cols, raw.mapq, W.start, W.cursor, W.order, W);
+    const uint32_t n_groups = W.n_lanes / 32;
     hc_groups_kernel<<<(n_groups + 255) / 256, 256, 0, s>>>(raw.n_reads, n_groups, W.order, W.n_cols, W.n_extra,
                                                             mode == kReconHaplocart ? (uint32_t)VGL_HC_COL_BLK : (uint32_t)VGL_EUKA_COL_BLK, W.grp_cb, W.grp_mb);
     hc_scan_groups<<<1, 1024, 0, s>>>(n_groups, W.grp_cb, W.grp_mb);
@@ -628,7 +633,7 @@ cudaError_t hc_launch_pack(const ReconRawDev& raw, const ReconWorkDev& W, uint32
                            uint32_t* xmap, uint16_t* n_cols, uint16_t* n_close, uint16_t* n_extra, uint8_t* mapq, int* err_flag,
                            cudaStream_t s) {
     if (raw.n_reads == 0) return cudaSuccess;
-    const uint32_t n_groups = (raw.n_reads + 31) / 32;
+    const uint32_t n_groups = W.n_lanes / 32;
     hc_pack_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, s>>>(raw, W, n_groups, col_cap_blks, map_cap_blks, col, xmap, n_cols, n_close,
                                                                n_extra, mapq, err_flag);
     return cudaGetLastError();

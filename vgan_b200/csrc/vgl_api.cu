@@ -213,7 +213,26 @@ vgl::HcBatchMeta to_meta(const vgl_hc_batch_meta& m) {
     r.valid = m.valid != 0;
     if (r.valid) {
         r.qual_max = m.qual_max;
-        for (int k = 0; k < 4; ++k) r.mapq_mask[k] = m.mapq_mask[k];
+        r.n_segs = std::min<uint32_t>(m.n_segs, VGL_HC_MAX_SEGS);
+        for (uint32_t k = 0; k < r.n_segs; ++k) { r.seg_mapq[k] = m.seg_mapq[k]; r.seg_end[k] = m.seg_end[k]; }
+    }
+    return r;
+}
+
+// The segments of groups [g0, g1) of a batch, renumbered from g0 (chunked launches).
+vgl::HcBatchMeta clip_meta(const vgl::HcBatchMeta& m, uint32_t g0, uint32_t g1) {
+    vgl::HcBatchMeta r;
+    r.valid = m.valid;
+    r.qual_max = m.qual_max;
+    uint32_t begin = 0;
+    for (uint32_t k = 0; k < m.n_segs; ++k) {
+        const uint32_t end = m.seg_end[k], lo = std::max(begin, g0), hi = std::min(end, g1);
+        if (hi > lo) {
+            r.seg_mapq[r.n_segs] = m.seg_mapq[k];
+            r.seg_end[r.n_segs] = hi - g0;
+            r.n_segs += 1;
+        }
+        begin = end;
     }
     return r;
 }
@@ -229,8 +248,8 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b, const vgl::HcBatchMeta& 
     auto& ev = ctx->ev_pool[ctx->ev_used++];
     // the log-term kernel where the batch allows it (no quality above 63, tables of the pairs present fit), else the general one
     vgl::HcLogTermLaunch plan;
-    const size_t lt_smem = ctx->logterm_off ? 0 : vgl::hc_logterm_plan(meta, ctx->tab.n_rows, ctx->tab.n_class, ctx->tab.logterm != nullptr,
-                                                                      ctx->max_smem_optin, plan);
+    const size_t lt_smem = ctx->logterm_off ? 0 : vgl::hc_logterm_plan(meta, b.n_groups, ctx->sm_count, ctx->tab.n_rows, ctx->tab.n_class,
+                                                                      ctx->tab.logterm != nullptr, ctx->max_smem_optin, plan);
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
     if (lt_smem) {
         VGL_CUDA(vgl::hc_launch_read_logterm_kernel(ctx->sm_count, lt_smem, plan, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total, ctx->d_err,
@@ -742,7 +761,7 @@ int vgl_hc_accumulate(vgl_ctx* ctx, const vgl_hc_batch* b) {
         d.n_close = sl.n_close.p;
         d.n_extra = sl.n_extra.p;
         d.mapq = sl.mapq.p;
-        if (int rc = launch_read(ctx, d, to_meta(b->meta))) return rc;
+        if (int rc = launch_read(ctx, d, clip_meta(to_meta(b->meta), g0, g1))) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
         sl.used = true;
     }
@@ -785,7 +804,7 @@ int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_
 // ctx->stream; fills the read kernel's batch descriptor.  The slices keep their absolute indices (offsets into the
 // whole batch): the device pointers are shifted back by each slice's first element and only ever dereferenced inside.
 static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t rb, vgl_ctx::RawDev& R, cudaStream_t copy_stream,
-                          vgl::HcBatchDev& d) {
+                          vgl::HcBatchDev& d, vgl::HcBatchMeta* seg_out = nullptr) {
     cudaStream_t s = ctx->stream;
     const size_t n = rb - ra;
     const bool narrow_only = (raw->reserved & VGL_HC_RAW_NARROW_ONLY) != 0;  // the whole view is this chunk (check_raw)
@@ -795,16 +814,49 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     const size_t sa = narrow_only ? raw->edit_seq_off[0] : raw->edit_seq_off[ea];
     const size_t nseq = (narrow_only ? raw->edit_seq_off[1] : raw->edit_seq_off[eb]) - sa;
     const size_t ca = raw->str_off[ra], ncap = raw->str_off[rb] - ca;
-    const size_t G = (n + 31) / 32;
-    // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read
-    const size_t col_cap = ncap / 128 + 1024 + G + 1, map_cap = G + 4096;
+    // Lanes: the reads of one mapping quality take one run of groups (a "slot"; its last group filled up with unused lanes), so
+    // that no group mixes two mapping qualities -- the segments of vgl_hc_batch_meta, which let the log-term read kernel run.
+    // With more than VGL_HC_MAX_SEGS distinct values: one slot, groups by shape only.
+    uint32_t mq_count[128];
+    memset(mq_count, 0, sizeof(mq_count));
+    for (size_t r = ra; r < rb; ++r) mq_count[raw->mapq[r] & 127u] += 1;
+    int n_distinct = 0;
+    for (int q = 0; q < 128; ++q) n_distinct += mq_count[q] ? 1 : 0;
+    const bool segmented = n_distinct >= 1 && n_distinct <= VGL_HC_MAX_SEGS;
+    vgl::HcBatchMeta segs;
+    uint32_t n_slots = 1, lane_base[VGL_HC_MAX_SEGS] = {0};
+    uint8_t slot_of_mapq[128];
+    memset(slot_of_mapq, 0, sizeof(slot_of_mapq));
+    size_t G = (n + 31) / 32;
+    if (segmented) {
+        n_slots = 0;
+        G = 0;
+        for (int q = 0; q < 128; ++q) {
+            if (!mq_count[q]) continue;
+            slot_of_mapq[q] = (uint8_t)n_slots;
+            lane_base[n_slots] = (uint32_t)(G * 32);
+            G += (mq_count[q] + 31) / 32;
+            segs.seg_mapq[n_slots] = (uint8_t)q;
+            segs.seg_end[n_slots] = (uint32_t)G;
+            ++n_slots;
+        }
+        segs.n_segs = n_slots;
+    }
+    if (seg_out) {
+        seg_out->n_segs = segs.n_segs;
+        memcpy(seg_out->seg_mapq, segs.seg_mapq, sizeof(segs.seg_mapq));
+        memcpy(seg_out->seg_end, segs.seg_end, sizeof(segs.seg_end));
+    }
+    // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read (per slot)
+    const size_t col_cap = ncap / 128 + (size_t)n_slots * 1024 + G + 1, map_cap = G + 4096;
     if (col_cap > 0x7fffffffull) return fail(VGL_ERR_INVALID, "batch too large; split it");
     if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
     if (!R.consumed) VGL_CUDA(cudaEventCreateWithFlags(&R.consumed, cudaEventDisableTiming));
     if (R.used) VGL_CUDA(cudaStreamWaitEvent(copy_stream, R.consumed, 0));  // the kernels that last read this staging set
     // growing a buffer frees it: the kernels still reading it must have finished
     if (n + 1 > R.qual_off.cap || nq > R.qual.cap || nm > R.map_node.cap || ne > R.edit_from.cap || nseq > R.edit_seq.cap ||
-        ncap > R.gstr.cap || col_cap * 128 > R.col.cap || map_cap * 128 > R.xmap.cap)
+        ncap > R.gstr.cap || col_cap * 128 > R.col.cap || map_cap * 128 > R.xmap.cap || G * 32 > R.order.cap || G * 32 > R.o_n_cols.cap ||
+        3 * 4096 * (size_t)n_slots > R.hist3.cap || G + 1 > R.grp_cb.cap)
         VGL_CUDA(cudaStreamSynchronize(s));
 #define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
     RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
@@ -812,7 +864,7 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
     RSV(R.off16, nm); RSV(R.fo16, n); RSV(R.n16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
     RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
-    RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
+    RSV(R.hist3, 3 * 4096 * (size_t)n_slots); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
     RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
     RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
 #undef RSV
@@ -871,15 +923,20 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
         VGL_CUDA(vgl::raw_launch_offsets_from_counts(R.sl8.p, (uint32_t)ne, (uint32_t)sa, R.tiles.p, R.edit_seq_off.p, s));
         ctx->launches += 7;
     }
-    VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
+    VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * (size_t)n_slots * sizeof(uint32_t), s));
+    VGL_CUDA(cudaMemsetAsync(R.order.p, 0xff, G * 32 * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
     const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
     // per-read arrays are indexed by the read's position in the chunk; everything they point INTO by absolute index
     const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p - qa, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p - ma,
                               R.map_offset.p - ma, R.edit_off.p - ma, R.edit_from.p - ea, R.edit_to.p - ea, R.edit_seq_off.p - ea,
                               R.edit_seq.p - sa, nullptr, nullptr};
-    const vgl::ReconWorkDev Wd{R.gstr.p - ca, R.rstr.p - ca, R.sizes.p - ea, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
-                               R.hist3.p + 4096, R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    vgl::ReconWorkDev Wd{R.gstr.p - ca, R.rstr.p - ca, R.sizes.p - ea, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
+                         R.hist3.p + 4096 * (size_t)n_slots, R.hist3.p + 8192 * (size_t)n_slots, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    Wd.n_slots = n_slots;
+    Wd.n_lanes = (uint32_t)(G * 32);
+    memcpy(Wd.lane_base, lane_base, sizeof(lane_base));
+    memcpy(Wd.slot_of_mapq, slot_of_mapq, sizeof(slot_of_mapq));
     VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->d_err, s));
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
                                  R.o_mapq.p, ctx->d_err, s));
@@ -907,8 +964,12 @@ int vgl_hc_pack_raw(vgl_ctx* ctx, const vgl_hc_raw* raw, vgl_hc_batch* out) {
     if (!out) return fail(VGL_ERR_INVALID, "null output");
     if (int rc = check_raw(ctx, raw)) return rc;
     vgl::HcBatchDev d;
-    if (int rc = pack_raw_chunk(ctx, raw, 0, raw->n_reads, ctx->rawdev[0], ctx->stream, d)) return rc;
+    vgl::HcBatchMeta meta = to_meta(raw->meta);
+    if (int rc = pack_raw_chunk(ctx, raw, 0, raw->n_reads, ctx->rawdev[0], ctx->stream, d, &meta)) return rc;
     memset(out, 0, sizeof(*out));
+    out->meta = raw->meta;   // value ranges as the producer gave them; the segments are those of the device-built batch
+    out->meta.n_segs = meta.n_segs;
+    for (uint32_t k = 0; k < VGL_HC_MAX_SEGS; ++k) { out->meta.seg_mapq[k] = meta.seg_mapq[k]; out->meta.seg_end[k] = meta.seg_end[k]; }
     out->n_reads = raw->n_reads;
     out->n_groups = d.n_groups;
     out->grp_col_blk = d.grp_col_blk; out->grp_map_blk = d.grp_map_blk; out->col = d.col; out->map = d.map;
@@ -935,9 +996,10 @@ int vgl_hc_accumulate_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
         const size_t rb = std::min(n, ra + step);
         vgl_ctx::RawDev& R = ctx->rawdev[ctx->raw_seq++ & 1];
         vgl::HcBatchDev d;
-        if (int rc = pack_raw_chunk(ctx, raw, ra, rb, R, ctx->copy_stream, d)) return rc;
+        vgl::HcBatchMeta meta = to_meta(raw->meta);   // value ranges from the producer; the segments are this chunk's own
+        if (int rc = pack_raw_chunk(ctx, raw, ra, rb, R, ctx->copy_stream, d, &meta)) return rc;
         if (d.n_groups)
-            if (int rc = launch_read(ctx, d, to_meta(raw->meta))) return rc;
+            if (int rc = launch_read(ctx, d, meta)) return rc;
         VGL_CUDA(cudaEventRecord(R.consumed, ctx->stream));
         R.used = true;
     }
@@ -1041,7 +1103,7 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
         d.n_close = sl.n_close.p;
         d.n_extra = sl.n_extra.p;
         d.mapq = sl.mapq.p;
-        if (int rc = launch_read(ctx, d, to_meta(w->meta))) return rc;
+        if (int rc = launch_read(ctx, d, clip_meta(to_meta(w->meta), g0, g1))) return rc;
         VGL_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
         sl.used = true;
     }
@@ -1150,6 +1212,8 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
         return fail(VGL_ERR_BAD_NODE, "device-side reconstruction: a mapping names a node outside the graph");
     if (err & VGL_ERR_BAD_NODE)
         return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
+    if (err & 0x08000000)
+        return fail(VGL_ERR_INVALID, "a batch's vgl_hc_batch_meta is wrong: a segment holds a read of another mapping quality");
     if (argmax_out) *argmax_out = idx[0];
     if (total_out) *total_out = scalars[0];
     const int n_post = idx[1];
@@ -1583,7 +1647,7 @@ int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::Euka
     RSV(R.read_index, n); RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
     RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
     RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
-    RSV(R.hist3, 3 * 4096); RSV(R.order, n); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1); RSV(R.s_err, 1);
+    RSV(R.hist3, 3 * 4096); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1); RSV(R.s_err, 1);
     RSV(R.s_n_cols, G * 32); RSV(R.s_n_maps, G * 32); RSV(R.s_seq_len, G * 32); RSV(R.s_mapq, G * 32); RSV(R.s_flags, G * 32);
     RSV(R.s_read_index, G * 32);
 #define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, s))
@@ -1598,8 +1662,13 @@ int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::Euka
     const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
     const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p,
                               R.edit_off.p, R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p, R.seq_len.p, R.read_index.p};
-    const vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
-                               R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
+                         R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
+    Wd.n_slots = 1;   // euka / soibean: groups by shape only
+    Wd.n_lanes = (uint32_t)(G * 32);
+    memset(Wd.lane_base, 0, sizeof(Wd.lane_base));
+    memset(Wd.slot_of_mapq, 0, sizeof(Wd.slot_of_mapq));
+    VGL_CUDA(cudaMemsetAsync(R.order.p, 0xff, G * 32 * sizeof(uint32_t), s));
     VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, soibean ? 2 : 1, R.s_err.p, s));
     // the group tables are final: size the record arrays from them
     uint32_t tot[2] = {0, 0};

@@ -85,7 +85,9 @@ struct HcBatchDev {
 struct HcBatchMeta {
     bool valid = false;
     uint32_t qual_max = 255;
-    uint32_t mapq_mask[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfu};
+    uint32_t n_segs = 0;                      // 0: groups are not ordered by mapping quality
+    uint8_t seg_mapq[VGL_HC_MAX_SEGS] = {};   // mapping quality of segment k
+    uint32_t seg_end[VGL_HC_MAX_SEGS] = {};   // group index one past segment k
 };
 
 // Log-term tables (the read kernel's fastest mode): for every (mapping quality, node class) pair the per-column term
@@ -94,10 +96,14 @@ struct HcBatchMeta {
 //   logterm[(mapq * (n_class + 1) + class) * 512 + (record & 0x1ff)], class n_class = the neutral entry of unknown nodes.
 // A launch stages the rows of the mapping qualities PRESENT in the batch, cut at the batch's largest quality, in shared memory.
 constexpr int kLogTermEntries = 512;
+// One launch: every CTA works on ONE segment (= one mapping quality) of the batch and stages that mapping quality's tables;
+// the CTAs are dealt out to the segments in proportion to their groups.
 struct HcLogTermLaunch {
-    int n_slots;             // mapping qualities present
-    int q_rows;              // qualities 0 .. q_rows - 1
-    uint8_t mapq_of_slot[100];
+    int n_segs;
+    int q_rows;                               // qualities 0 .. q_rows - 1
+    uint8_t seg_mapq[VGL_HC_MAX_SEGS];
+    uint32_t seg_begin[VGL_HC_MAX_SEGS + 1];  // groups [seg_begin[k], seg_begin[k + 1])
+    uint32_t cta_begin[VGL_HC_MAX_SEGS + 1];  // CTAs   [cta_begin[k], cta_begin[k + 1]) work on segment k
 };
 
 // Read kernel launch geometry (one persistent CTA per SM).
@@ -121,7 +127,8 @@ cudaError_t hc_launch_read_kernel(const HcReadLaunch& cfg, const HcBatchDev& bat
 // K1, log-term mode: one table lookup and two fp64 adds per aligned column, mappings finalised in line (no log, no queue).
 // hc_logterm_plan: can this batch run in that mode on this device?  Fills `plan` and returns the dynamic shared memory it
 // needs, or 0 when it cannot (quality above 63, too many (mapping quality, class) pairs for shared memory, no tables).
-size_t hc_logterm_plan(const HcBatchMeta& meta, int n_rows, int n_class, bool have_tables, int max_smem_optin, HcLogTermLaunch& plan);
+size_t hc_logterm_plan(const HcBatchMeta& meta, uint32_t n_groups, int n_ctas, int n_rows, int n_class, bool have_tables, int max_smem_optin,
+                       HcLogTermLaunch& plan);
 cudaError_t hc_logterm_configure(int max_smem_optin);
 cudaError_t hc_launch_read_logterm_kernel(int grid, size_t smem, const HcLogTermLaunch& plan, const HcBatchDev& batch, const HcTablesDev& tab,
                                           double* cta_node_acc, double* cta_a_total, int* err_flag, cudaStream_t s);
@@ -185,14 +192,21 @@ struct ReconWorkDev {  // scratch
     uint16_t* n_cols;   // [n_reads] in caller order
     uint16_t* n_close;
     uint16_t* n_extra;  // HaploCart: empty mappings; euka / soibean: mapping / edit records of the read
-    uint32_t* hist;     // [4096] reads per column count
-    uint32_t* start;    // [4096]
-    uint32_t* cursor;   // [4096]
-    uint32_t* order;    // [n_reads] read ids sorted by column count
+    uint32_t* hist;     // [n_slots][4096] reads per (mapping-quality slot, column count)
+    uint32_t* start;    // [n_slots][4096]
+    uint32_t* cursor;   // [n_slots][4096]
+    uint32_t* order;    // [n_lanes] lane -> read id: by slot, then by column count; kReconNoRead for an unused lane
     uint32_t* grp_cb;   // [n_groups + 1] -> the batch's grp_col_blk
     uint32_t* grp_mb;   // [n_groups + 1] -> the batch's grp_map_blk
+    // HaploCart: reads are dealt to slots by mapping quality (a group never mixes two: vgl_hc_batch_meta segments); slot s
+    // owns the lanes from lane_base[s] on, a multiple of 32.  euka / soibean / unsegmented: one slot, lane_base[0] = 0.
+    uint32_t n_slots;
+    uint32_t n_lanes;   // 32 * n_groups
+    uint32_t lane_base[VGL_HC_MAX_SEGS];
+    uint8_t slot_of_mapq[128];
 };
-// hist and cursor must be zero on entry.
+constexpr uint32_t kReconNoRead = 0xffffffffu;
+// hist and cursor must be zero and order all kReconNoRead on entry.
 // The narrow arrays of a vgl_hc_raw, widened on the device: out[i] = base + counts[0] + ... + counts[i-1] for i in [0, n]
 // (tile_scratch: n / 4096 + 1 words); 16-bit offsets to 32 bits.
 cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, uint32_t base, uint32_t* tile_scratch, uint32_t* out,

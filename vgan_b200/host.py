@@ -191,13 +191,13 @@ class PackedBatch:
             m0, m1 = int(a["grp_map_blk"][g]), int(a["grp_map_blk"][g + 1])
             for l in range(_lib.LANES):
                 k = g * _lib.LANES + l
-                if k >= self.n_reads:
-                    break
                 nc, nm = int(a["n_cols"][k]), int(a["n_extra"][k])
+                if nc == 0 and nm == 0:
+                    continue    # an unused lane (the last group of every mapping-quality segment is filled up with them)
                 cols = a["col"][c0:c1, l, :].reshape(-1)
                 maps = a["map"][m0:m1, l, :].reshape(-1)
                 assert not cols[nc:].any() and not maps[nm:].any()  # padding records are zero
-                out.append({"col": cols[:nc].tolist(), "extra": maps[:nm].tolist(), "n_cols": nc,
+                out.append({"slot": k, "col": cols[:nc].tolist(), "extra": maps[:nm].tolist(), "n_cols": nc,
                             "n_close": int(a["n_close"][k]), "mapq": int(a["mapq"][k])})
         return out
 
