@@ -445,8 +445,9 @@ def test_logterm_kernel_long_reads_and_every_route(small):
     hc.load_graph(small.graph)
     final, argmax, _ = _oracle(small, alns)
     packed = vb.PackedBatch(small.graph, alns)
+    resident = hc.upload(packed)     # (stays alive until the kernels that read it have run)
     routes = {"packed": lambda: hc.update(packed), "wire": lambda: hc.update_wire(vb.WireBatch(packed)),
-              "raw": lambda: hc.update_raw(vb.RawBatch(alns)), "device": lambda: hc.update_device(hc.upload(packed).batch),
+              "raw": lambda: hc.update_raw(vb.RawBatch(alns)), "device": lambda: hc.update_device(resident.batch),
               "feeder": lambda: vb.Feeder(n_threads=2, chunk_reads=128).feed(hc, alns)}
     for name, run in routes.items():
         n0 = hc.logterm_launches()

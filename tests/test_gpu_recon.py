@@ -33,13 +33,14 @@ def _device_lanes(hc, b):
             k = g * 32 + l
             cols = col[gcb[g]:gcb[g + 1], l, :].reshape(-1)
             ex = xmap[gmb[g]:gmb[g + 1], l, :].reshape(-1)
-            if k >= n:
-                assert not cols.any() and not ex.any() and n_cols[k] == 0
-                continue
             nc, nx = int(n_cols[k]), int(n_extra[k])
+            if nc == 0 and nx == 0:      # an unused lane: the last group of every mapping-quality segment is filled up with them
+                assert not cols.any() and not ex.any()
+                continue
             assert not cols[nc:].any() and not ex[nx:].any()
             lanes.append((int(n_close[k]), nc, tuple(cols[:nc].tolist()), tuple(ex[:nx].tolist()), int(mapq[k])))
-    return lanes, n_cols[:n]
+    assert len(lanes) == n
+    return lanes, n_cols
 
 
 def _host_lanes(graph, alns):
@@ -64,11 +65,25 @@ def test_device_batch_equals_host_batch(small, kw):
     hc.load(small.tables(), small.tree())
     hc.load_graph(small.graph)
     raw = vb.RawBatch(alns)
-    got, n_cols = _device_lanes(hc, hc.pack_raw(raw))
+    dev = hc.pack_raw(raw)
+    got, n_cols = _device_lanes(hc, dev)
     want, pb = _host_lanes(small.graph, alns)
     assert raw.n_reads == pb.n_reads and raw.skipped == pb.skipped
     assert sorted(got) == sorted(want)
-    assert np.all(np.diff(n_cols.astype(np.int64)) >= 0)      # lanes sorted by column count: groups are evenly long
+    # the device builds the same mapping-quality segments as the host packer; inside one, lanes are sorted by column count
+    # (groups are evenly long) and its last group is filled up with unused lanes
+    m, mh = dev.meta, pb.batch.meta
+    assert m.n_segs == mh.n_segs and list(m.seg_mapq[:m.n_segs]) == list(mh.seg_mapq[:m.n_segs]) and \
+        list(m.seg_end[:m.n_segs]) == list(mh.seg_end[:m.n_segs]) and m.seg_end[m.n_segs - 1] == dev.n_groups
+    mapq = hc.download(dev.mapq, int(dev.n_groups) * 32, np.uint8)
+    g0 = 0
+    for k in range(m.n_segs):
+        g1 = int(m.seg_end[k])
+        nc = n_cols[g0 * 32:g1 * 32].astype(np.int64)
+        used = nc > 0
+        assert np.all(mapq[g0 * 32:g1 * 32][used] == m.seg_mapq[k])
+        assert np.all(np.diff(nc[used]) >= 0) and not used[np.argmin(used):].any() if not used.all() else True
+        g0 = g1
     hc.close()
 
 

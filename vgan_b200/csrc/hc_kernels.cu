@@ -481,8 +481,8 @@ hc_read_kernel(HcBatchDev b, HcTablesDev t, double* __restrict__ cta_node_acc, d
 // out to the segments in proportion to their groups and a CTA stages the tables of its segment's mapping quality only --
 // (n_class + 1) x q_rows x 64 bytes, whatever the number of mapping qualities in the batch.
 //
-// Shared memory: [ node table u16[n_rows + 1] | pair tables double[n_class + 1][q_rows * 8] ]
-// node table entry: (byte offset of the class's table inside a row) / 16, bit 15 = every path goes through the node.
+// Shared memory: [ node table u32[n_rows + 1] | pair tables double[n_class + 1][q_rows * 8] ]
+// node table entry: byte offset of the class's table, bit 31 = every path goes through the node.
 // ------------------------------------------------------------------------------------------
 #ifndef VGL_HC_LT_BLOCK
 #define VGL_HC_LT_BLOCK 768
@@ -496,100 +496,140 @@ struct LtShared {
     uint32_t none_entry;                 // node-table entry of the neutral class (unknown node, no pangenome_map entry)
     double le0, scale8;                  // log 0.25;  (-ln 10 / 10) / 8
 };
+// node table entry (u32): byte offset of the class's table | kLtAllPaths when every path goes through the node
+constexpr uint32_t kLtAllPaths = 0x80000000u;
 
 __device__ __forceinline__ uint32_t lds_u32_c(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// fire-and-forget fp64 add where `on` is non-zero; the address of the other lanes is never dereferenced
+__device__ __forceinline__ void red_add_f64_if(uint32_t on, double* p, double v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(on) : "memory");
+}
+
+// Per-thread state of the walk through one read.
+struct LtWalk {
+    uint32_t sufq8;   // 8 * (sum of the canonical qualities of the columns walked so far)
+    uint32_t nz;      // columns walked so far whose canonical quality is not 0
+    double a_m;       // sum of the terms of the mapping being walked
+    double a_all;     // ... of every valid column of the read: sum_i A_i
+    uint32_t pbase;   // shared byte address of the table of the mapping being walked (its node's class)
+    uint32_t allp;    // its node-table entry (bit 31: every path goes through the node)
+};
+
+// One block of four columns, no lane of the warp with empty mappings pending: straight-line code, nothing but predication.
+__device__ __forceinline__ void lt_block_fast(const LtShared& S, const uint32_t (&rec)[4], const uint32_t (&ent)[4], uint32_t n_cols, LtWalk& w) {
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+        const uint32_t r = rec[j];
+        // OPEN (last column of a mapping): its class's table
+        const bool open = (r & VGL_HC_COL_OPEN) != 0u;
+        w.pbase = open ? S.tables + (ent[j] & ~kLtAllPaths) : w.pbase;
+        w.allp = open ? ent[j] : w.allp;
+        // the column's term; columns that take no part (N, non-ACGT, no owner) add nothing
+        double t = 0.0;
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
+            : "+d"(t)
+            : "r"(w.pbase + ((r & 0x1ffu) << 3)), "r"(r & VGL_HC_COL_VALID));
+        w.a_m += t;
+        w.a_all += t;
+        const uint32_t q8 = r & (0xffu << VGL_HC_COL_QUAL_SHIFT);
+        w.sufq8 += q8;
+        w.nz += q8 ? 1u : 0u;
+        // CLOSE (first column of a mapping): finalise it, unless every path goes through its node (its D[n] is never read);
+        // a CLOSE on a column nobody owns carries the node field VGL_HC_NO_NODE, which is no row of the table
+        const uint32_t node = VGL_HC_COL_NODE(r);
+        const uint32_t close = r & VGL_HC_COL_CLOSE;
+        const uint32_t push = (close != 0u && (w.allp & kLtAllPaths) == 0u && node < (uint32_t)S.n_rows) ? 1u : 0u;
+        const double B = fma((double)w.sufq8, S.scale8, (double)(n_cols - w.nz) * S.le0);
+        red_add_f64_if(push, S.acc + node, B - w.a_m);
+        w.a_m = close ? 0.0 : w.a_m;
+    }
+}
 
 __device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtShared& S, uint32_t g, uint32_t gn, const GroupHdr& H,
                                                  GroupHdr& Hn, uint4& v0, uint4& v1, int lane, double& a_sum, uint32_t& worst_entry,
                                                  bool& bad_node) {
     Hn = hc_load_hdr(b, gn, lane);
     const int ncb = H.ncb;
-    const uint32_t row_base = S.tables;   // the CTA's segment has one mapping quality: one row of tables
     int x = H.n_extra - 1;   // empty mappings (no column of their own): rare, handled on the side
     bool rare = x >= 0;
-    uint32_t sufq8 = 0;      // 8 * (sum of the canonical qualities of the columns walked so far)
-    uint32_t nz = 0;         // columns walked so far whose canonical quality is not 0
-    double a_m = 0.0;        // sum of the terms of the mapping being walked
-    double a_all = 0.0;      // ... of every valid column of the read: sum_i A_i
-    uint32_t entry = S.none_entry;  // node-table entry of the mapping being walked
+    LtWalk w;
+    w.sufq8 = 0; w.nz = 0; w.a_m = 0.0; w.a_all = 0.0;
+    w.pbase = S.tables + S.none_entry;
+    w.allp = S.none_entry;
 
     auto extra_rec = [&](int i) -> uint32_t {
         const uint32_t* gx = b.map + ((size_t)__ldg(b.grp_map_blk + g) * 32 + lane) * VGL_HC_MAP_BLK;
         return __ldg(gx + (size_t)(i >> 2) * 128 + (i & 3));
     };
     auto add_extra = [&](uint32_t xn, double Bx) {
-        if (xn < (uint32_t)S.n_rows && (lds_u16_c(S.node_tab + 2u * xn) & 0x7fffu) != (S.none_entry & 0x7fffu)) red_add_f64(S.acc + xn, Bx);
+        if (xn < (uint32_t)S.n_rows && (lds_u32_c(S.node_tab + 4u * xn) & ~kLtAllPaths) != S.none_entry) red_add_f64(S.acc + xn, Bx);
         else bad_node = true;
     };
-    auto quality_sum = [&]() { return fma((double)sufq8, S.scale8, (double)((uint32_t)H.n_cols - nz) * S.le0); };
-
-    auto block = [&](int cb, const uint4& v) {
+    // the same block with empty mappings pending on some lane: they receive B of the column they start at
+    auto block_slow = [&](int cb, const uint32_t (&rec)[4], const uint32_t (&ent)[4]) {
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {   // (unrolled: a dynamic index would put the records into local memory)
+            const uint32_t r = rec[j];
+            const bool open = (r & VGL_HC_COL_OPEN) != 0u;
+            w.pbase = open ? S.tables + (ent[j] & ~kLtAllPaths) : w.pbase;
+            w.allp = open ? ent[j] : w.allp;
+            double t = 0.0;
+            if (r & VGL_HC_COL_VALID) t = lds_f64_c(w.pbase + ((r & 0x1ffu) << 3));
+            w.a_m += t;
+            w.a_all += t;
+            const uint32_t q8 = r & (0xffu << VGL_HC_COL_QUAL_SHIFT);
+            w.sufq8 += q8;
+            w.nz += q8 ? 1u : 0u;
+            const uint32_t node = VGL_HC_COL_NODE(r);
+            const uint32_t close = r & VGL_HC_COL_CLOSE;
+            const double B = fma((double)w.sufq8, S.scale8, (double)((uint32_t)H.n_cols - w.nz) * S.le0);
+            if (close && rare) {
+                const int c = cb * VGL_HC_COL_BLK + j;
+                while (x >= 0) {
+                    const uint32_t xr = extra_rec(x);
+                    const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
+                    if (xp < (uint32_t)c) break;
+                    add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
+                    --x;
+                }
+                rare = x >= 0;
+            }
+            if (close != 0u && (w.allp & kLtAllPaths) == 0u && node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, B - w.a_m);
+            w.a_m = close ? 0.0 : w.a_m;
+        }
+    };
+    // The node-table lookups do not depend on the walk's state: the four of a block are issued together, each only where a
+    // mapping opens (predicated: the other lanes cost no bank conflicts), and ONE BLOCK AHEAD of their use (the next block's
+    // records are in registers already), so that their latency never shows.
+    auto lookup = [&](const uint4& v, uint32_t (&ent)[4]) {
         const uint32_t rec[4] = {v.x, v.y, v.z, v.w};
-        // the node-table lookups do not depend on the walk's state: issue the four of them together, each only where a
-        // mapping opens (predicated: the other lanes cost no bank conflicts)
-        uint32_t ent[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t e32 = 0;
-            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
+            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
                 : "+r"(e32)
-                : "r"(S.node_tab + 2u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: neutral
+                : "r"(S.node_tab + 4u * min(VGL_HC_COL_NODE(rec[j]), (uint32_t)S.n_rows)), "r"(rec[j] & VGL_HC_COL_OPEN));  // entry n_rows: neutral
             ent[j] = e32;
-            worst_entry = max(worst_entry, e32 & 0x7fffu);  // (0 where no mapping opens; the neutral class has the largest offset)
-        }
-        const bool any_rare = __any_sync(kFull, rare);
-#pragma unroll
-        for (int j = 3; j >= 0; --j) {
-            const uint32_t r = rec[j];
-            // OPEN (last column of a mapping): its class's table
-            entry = (r & VGL_HC_COL_OPEN) ? ent[j] : entry;
-            const uint32_t pair_base = row_base + ((entry & 0x7fffu) << 4);
-            // the column's term; columns that take no part (N, non-ACGT, no owner) add nothing
-            double t = 0.0;
-            asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
-                : "+d"(t)
-                : "r"(pair_base + ((r & 0x1ffu) << 3)), "r"(r & VGL_HC_COL_VALID));
-            a_m += t;
-            a_all += t;
-            const uint32_t q8 = r & (0xffu << VGL_HC_COL_QUAL_SHIFT);
-            sufq8 += q8;
-            nz += q8 ? 1u : 0u;
-            // CLOSE (first column of a mapping): finalise it, unless every path goes through its node (its D[n] is never read)
-            // or nobody owns the column (the CLOSE then only serves empty mappings)
-            static_assert(VGL_HC_CLASS_ALLPATHS == 2 * VGL_HC_COL_CLOSE, "ALLPATHS >> 1 lines up with CLOSE");
-            const uint32_t close = r & VGL_HC_COL_CLOSE;
-            if (any_rare) {
-                if (close && rare) {
-                    const int c = cb * VGL_HC_COL_BLK + j;
-                    const double B = quality_sum();
-                    while (x >= 0) {
-                        const uint32_t xr = extra_rec(x);
-                        const uint32_t xp = xr >> VGL_HC_MAP_NODE_BITS;
-                        if (xp < (uint32_t)c) break;
-                        add_extra(xr & VGL_HC_MAP_MAX_NODE, xp == (uint32_t)c ? B : (double)xp * S.le0);
-                        --x;
-                    }
-                    rare = x >= 0;
-                }
-            }
-            const bool push = (r & ~(entry >> 1) & VGL_HC_COL_CLOSE) != 0u && r < (VGL_HC_NO_NODE << VGL_HC_COL_NODE_SHIFT);
-            const double D = quality_sum() - a_m;
-            if (push) {
-                const uint32_t node = VGL_HC_COL_NODE(r);
-                if (node < (uint32_t)S.n_rows) red_add_f64(S.acc + node, D);
-            }
-            a_m = close ? 0.0 : a_m;
         }
     };
+    uint32_t ent[4], ent_next[4];
+    lookup(v0, ent);
     for (int cb = ncb - 1; cb >= 0; --cb) {
         const uint4 v = v0;
         v0 = v1;
         v1 = hc_fetch(H, cb - 2);
-        block(cb, v);
+        lookup(v0, ent_next);   // (zero records past the first block: no OPEN, no load)
+        const uint32_t rec[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) worst_entry = max(worst_entry, ent[j] & ~kLtAllPaths);  // (0 where no mapping opens; the neutral class has the largest offset)
+        if (__any_sync(kFull, rare)) block_slow(cb, rec, ent);
+        else lt_block_fast(S, rec, ent, (uint32_t)H.n_cols, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ent[j] = ent_next[j];
     }
     v0 = hc_fetch(Hn, Hn.ncb - 1);
     v1 = hc_fetch(Hn, Hn.ncb - 2);
-    a_sum += a_all;
+    a_sum += w.a_all;
     while (x >= 0) {  // empty mappings that start past the last column
         const uint32_t xr = extra_rec(x);
         add_extra(xr & VGL_HC_MAP_MAX_NODE, (double)(xr >> VGL_HC_MAP_NODE_BITS) * S.le0);
@@ -604,11 +644,14 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_warp_a[kLtBlock / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t node_bytes = (uint32_t)((((size_t)t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
+    const uint32_t node_bytes = (uint32_t)((((size_t)t.n_rows + 1) * sizeof(uint32_t) + 15) & ~(size_t)15);
+    const uint32_t cls_bytes = (uint32_t)((((size_t)t.n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
     const uint32_t pair_bytes = (uint32_t)plan.q_rows * 64u;                       // q_rows * 8 entries of 8 bytes
     const uint32_t row_bytes = pair_bytes * (uint32_t)(t.n_class + 1);
-    uint16_t* s_node = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* s_node = reinterpret_cast<uint32_t*>(smem_raw);
     unsigned char* s_tab = smem_raw + node_bytes;
+    // the u16 class ids arrive in the upper half of the node table's space and are widened in place, front to back
+    uint16_t* s_cls = reinterpret_cast<uint16_t*>(smem_raw + node_bytes - cls_bytes);
     // this CTA's segment: the groups of one mapping quality
     int seg = 0;
     while (seg + 1 < plan.n_segs && blockIdx.x >= plan.cta_begin[seg + 1]) ++seg;
@@ -623,8 +666,8 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(bar, node_bytes + row_bytes);
-            bulk_g2s(smem_u32(s_node), t.image + t.layout.off_class, node_bytes, bar);
+            mbar_expect_tx(bar, cls_bytes + row_bytes);
+            bulk_g2s(smem_u32(s_cls), t.image + t.layout.off_class, cls_bytes, bar);
         }
         __syncthreads();
         for (int cls = tid; cls <= t.n_class; cls += kLtBlock) {
@@ -633,13 +676,22 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
         }
         mbar_wait(bar, 0);
         __syncthreads();
-        // class id -> (byte offset of the class's table inside a row) / 16, ALLPATHS kept in bit 15
-        for (int n = tid; n <= t.n_rows; n += kLtBlock) {
-            const uint32_t e = s_node[n];
-            const uint32_t cls = min(e & VGL_HC_CLASS_MASK, (uint32_t)t.n_class);
-            s_node[n] = (uint16_t)(((cls * pair_bytes) >> 4) | (e & VGL_HC_CLASS_ALLPATHS));
+        // class id -> byte offset of the class's table | kLtAllPaths.  In place: entry n (4 bytes at 4n) overwrites class ids
+        // that sit at or before 2n + (node_bytes - cls_bytes) ... so go in rounds of kLtBlock entries, reading a round before
+        // writing it, from the front (a written entry never reaches past the ids still to be read: 4n + 4 <= base + 2n
+        // for every n in the rounds that follow once base >= 2 (n + 2), which holds from the first round on because
+        // base = node_bytes - cls_bytes >= 2 (n_rows + 1) - 16)
+        for (int n0 = 0; n0 <= t.n_rows; n0 += kLtBlock) {
+            const int n = n0 + tid;
+            uint32_t e = 0;
+            if (n <= t.n_rows) e = s_cls[n];
+            __syncthreads();
+            if (n <= t.n_rows) {
+                const uint32_t cls = min(e & VGL_HC_CLASS_MASK, (uint32_t)t.n_class);
+                s_node[n] = cls * pair_bytes | ((e & VGL_HC_CLASS_ALLPATHS) ? kLtAllPaths : 0u);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     LtShared S;
@@ -647,7 +699,7 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
     S.tables = smem_u32(s_tab);
     S.acc = cta_node_acc + (size_t)(blockIdx.x % kAccCopies) * (size_t)(t.n_words * 32);
     S.n_rows = t.n_rows;
-    S.none_entry = ((uint32_t)t.n_class * pair_bytes) >> 4;
+    S.none_entry = (uint32_t)t.n_class * pair_bytes;
     S.le0 = -1.3862943611198906188;               // log(0.25) = log(get_p_seq_error(Q <= 2)), src/miscfunc.h:186
     S.scale8 = -0.23025850929940456840 / 8.0;     // log(get_p_seq_error(Q)) = Q * (-ln 10 / 10) for Q > 2
 
@@ -962,9 +1014,8 @@ size_t hc_logterm_plan(const HcBatchMeta& meta, uint32_t n_groups, int n_ctas, i
     if (meta.seg_end[meta.n_segs - 1] != n_groups) return 0;   // the segments must cover the batch
     plan.n_segs = (int)meta.n_segs;
     plan.q_rows = (int)meta.qual_max + 1;
-    const size_t node_bytes = (((size_t)n_rows + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    const size_t node_bytes = (((size_t)n_rows + 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t pair_bytes = (size_t)plan.q_rows * 64;
-    if (((size_t)n_class * pair_bytes >> 4) >= 0x8000u) return 0;   // the node table keeps class offsets in 15 bits
     const size_t smem = node_bytes + (size_t)(n_class + 1) * pair_bytes;
     if (smem + 1024 > (size_t)max_smem_optin || smem >= (1u << 20)) return 0;  // (one mbarrier counts the staged bytes)
     // CTAs in proportion to the segments' groups (largest remainder), at least one each
