@@ -500,9 +500,12 @@ struct LtShared {
 constexpr uint32_t kLtAllPaths = 0x80000000u;
 
 __device__ __forceinline__ uint32_t lds_u32_c(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-// fire-and-forget fp64 add where `on` is non-zero; the address of the other lanes is never dereferenced
-__device__ __forceinline__ void red_add_f64_if(uint32_t on, double* p, double v) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(on) : "memory");
+// fire-and-forget fp64 add into base[index] where `on` is non-zero (one 64-bit multiply-add forms the address; that of the
+// other lanes is never dereferenced)
+__device__ __forceinline__ void red_add_f64_if(uint32_t on, uint64_t base, uint32_t index, double v) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %3, 0;\n\tmad.wide.u32 a, %1, 8, %0;\n\t@p red.global.add.f64 [a], %2;\n\t}" ::"l"(base),
+                 "r"(index), "d"(v), "r"(on)
+                 : "memory");
 }
 
 // Per-thread state of the walk through one read.
@@ -516,7 +519,8 @@ struct LtWalk {
 };
 
 // One block of four columns, no lane of the warp with empty mappings pending: straight-line code, nothing but predication.
-__device__ __forceinline__ void lt_block_fast(const LtShared& S, const uint32_t (&rec)[4], const uint32_t (&ent)[4], uint32_t n_cols, LtWalk& w) {
+__device__ __forceinline__ void lt_block_fast(const LtShared& S, uint64_t acc, const uint32_t (&rec)[4], const uint32_t (&ent)[4], uint32_t n_cols,
+                                              LtWalk& w) {
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
         const uint32_t r = rec[j];
@@ -536,11 +540,12 @@ __device__ __forceinline__ void lt_block_fast(const LtShared& S, const uint32_t 
         w.nz += q8 ? 1u : 0u;
         // CLOSE (first column of a mapping): finalise it, unless every path goes through its node (its D[n] is never read);
         // a CLOSE on a column nobody owns carries the node field VGL_HC_NO_NODE, which is no row of the table
+        static_assert((kLtAllPaths >> 17) == VGL_HC_COL_CLOSE, "the all-paths bit, shifted, lines up with CLOSE");
         const uint32_t node = VGL_HC_COL_NODE(r);
         const uint32_t close = r & VGL_HC_COL_CLOSE;
-        const uint32_t push = (close != 0u && (w.allp & kLtAllPaths) == 0u && node < (uint32_t)S.n_rows) ? 1u : 0u;
+        const uint32_t push = ((r & ~(w.allp >> 17) & VGL_HC_COL_CLOSE) != 0u && node < (uint32_t)S.n_rows) ? 1u : 0u;
         const double B = fma((double)w.sufq8, S.scale8, (double)(n_cols - w.nz) * S.le0);
-        red_add_f64_if(push, S.acc + node, B - w.a_m);
+        red_add_f64_if(push, acc, node, B - w.a_m);
         w.a_m = close ? 0.0 : w.a_m;
     }
 }
@@ -612,21 +617,31 @@ __device__ __forceinline__ void lt_process_group(const HcBatchDev& b, const LtSh
             ent[j] = e32;
         }
     };
-    uint32_t ent[4], ent_next[4];
-    lookup(v0, ent);
-    for (int cb = ncb - 1; cb >= 0; --cb) {
-        const uint4 v = v0;
-        v0 = v1;
-        v1 = hc_fetch(H, cb - 2);
-        lookup(v0, ent_next);   // (zero records past the first block: no OPEN, no load)
+    const uint64_t acc = (uint64_t)S.acc;
+    auto step = [&](int cb, const uint4& v, const uint32_t (&ent)[4]) {
         const uint32_t rec[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) worst_entry = max(worst_entry, ent[j] & ~kLtAllPaths);  // (0 where no mapping opens; the neutral class has the largest offset)
         if (__any_sync(kFull, rare)) block_slow(cb, rec, ent);
-        else lt_block_fast(S, rec, ent, (uint32_t)H.n_cols, w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ent[j] = ent_next[j];
+        else lt_block_fast(S, acc, rec, ent, (uint32_t)H.n_cols, w);
+    };
+    // two blocks per trip with the two register sets swapping roles (no copies): va / ea = the block being walked, vb / eb the
+    // one after it, whose records are in flight or in registers and whose node-table entries are looked up meanwhile
+    uint4 va = v0, vb = v1;
+    uint32_t ea[4], eb[4];
+    lookup(va, ea);
+    int cb = ncb - 1;
+    for (; cb >= 1; cb -= 2) {
+        const uint4 vc = hc_fetch(H, cb - 2);
+        lookup(vb, eb);
+        step(cb, va, ea);
+        va = hc_fetch(H, cb - 3);
+        lookup(vc, ea);
+        step(cb - 1, vb, eb);
+        vb = va;   // (cb - 3)
+        va = vc;   // (cb - 2)
     }
+    if (cb == 0) step(0, va, ea);
     v0 = hc_fetch(Hn, Hn.ncb - 1);
     v1 = hc_fetch(Hn, Hn.ncb - 2);
     a_sum += w.a_all;
