@@ -567,6 +567,61 @@ def main():
                 from_alignments(route)
             latency[key] = (time.perf_counter() - t0) / 10 * 1e3
 
+        # several samples per pass (vgl_hc_samples_begin / _finalize_samples): 64 samples of <= 2 x 10^4 reads each
+        n_s, per = 64, min(20000, len(alns) // 64)
+        if per >= 1000:
+            small_packed = [vb.PackedBatch(S.graph, alns, r0=k * per, r1=(k + 1) * per, pinned=True) for k in range(n_s)]
+            small_dev = [hc.upload(b) for b in small_packed]
+            small_wire = [vb.WireBatch(b, pinned=True) for b in small_packed] if wire is not None else None
+
+            def one_by_one():
+                out = []
+                for d in small_dev:
+                    hc.reset()
+                    hc.update_device(d.batch)
+                    out.append(hc.get_posterior(want_ll=False)["maxh_index"])
+                return out
+
+            def in_one_pass(route):
+                hc.samples_begin(n_s)
+                for k in range(n_s):
+                    hc.sample_select(k)
+                    if route == "resident":
+                        hc.update_device(small_dev[k].batch)
+                    elif route == "wire":
+                        hc.update_wire(small_wire[k])
+                    else:
+                        feeder.feed(hc, alns, k * per, (k + 1) * per)
+                return [r["maxh_index"] for r in hc.finalize_samples()]
+
+            def clock(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    res = fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / reps, res
+
+            t_one, calls_one = clock(one_by_one, 5)
+            t_res, calls_res = clock(lambda: in_one_pass("resident"), 5)
+            latency["samples"] = {"samples": n_s, "reads_per_sample": per,
+                                  "samples_per_s_one_call_each_resident": n_s / t_one,
+                                  "samples_per_s_one_pass_resident": n_s / t_res,
+                                  "same_calls": calls_one == calls_res,
+                                  "what": "64 samples: reset + accumulate + finalize per sample vs one vgl_hc_samples_begin / "
+                                          "_finalize_samples pass (device-resident batches; host wall clock)"}
+            if small_wire is not None:
+                t_wire, calls_wire = clock(lambda: in_one_pass("wire"), 3)
+                latency["samples"]["samples_per_s_one_pass_wire_from_host"] = n_s / t_wire
+                latency["samples"]["wire_bytes_per_sample"] = small_wire[0].nbytes
+            t_feed, calls_feed = clock(lambda: in_one_pass("feed"), 3)
+            latency["samples"]["samples_per_s_one_pass_from_alignments"] = n_s / t_feed
+            latency["samples"]["same_calls"] = bool(calls_one == calls_res == calls_feed)
+            for d in small_dev:
+                d.free()
+            del small_dev, small_packed, small_wire
+
     total_reads = reads_local
     if world > 1:
         t = torch.tensor([reads_local], dtype=torch.float64, device="cuda")

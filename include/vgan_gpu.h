@@ -391,6 +391,26 @@ int vgl_hc_exchange_paths(vgl_ctx* ctx);
 int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
                     int32_t post_cap, int32_t* n_post_out);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Several samples per pass                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+/* Haplocart::run loops over samples (multifasta / several inputs: src/HaploCart.cpp:303, fill + loop + posterior per sample,
+ * :408-424, :459-462, :480-482), and a real sample is at most ~2 x 10^4 reads after duplicate removal -- microseconds of GPU
+ * work -- so the per-sample fixed costs dominate a one-sample-per-call use.  A pass over S samples:
+ *     vgl_hc_samples_begin(ctx, S);                      zeroes S accumulator sets (instead of vgl_hc_reset)
+ *     for s: vgl_hc_sample_select(ctx, s); any vgl_hc_accumulate* call(s), vgh_hc_feed, ...    (adds into sample s)
+ *     vgl_hc_finalize_samples(ctx, ...);                 ONE collapse over all samples (the node x path bit matrix is read once
+ *                                                        per slice of samples, not once per sample), one posterior kernel with a
+ *                                                        CTA per sample, one copy back, one synchronisation
+ * Results are those of S separate reset / accumulate / finalize sequences, bit for bit (same summation orders).
+ * Outputs (each may be NULL): ll_out[S][P], argmax_out[S], total_out[S], post_out[S][post_cap], n_post_out[S], status_out[S]
+ * (VGL_OK or the error vgl_hc_finalize would have returned for that sample; with status_out == NULL the first such error is the
+ * return value).  Leaves the context in single-sample mode.                                                                    */
+int vgl_hc_samples_begin(vgl_ctx* ctx, int32_t n_samples);
+int vgl_hc_sample_select(vgl_ctx* ctx, int32_t sample);
+int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap,
+                            int32_t* n_post_out, int32_t* status_out);
+
 /* Number of kernels this context has launched since creation (bench.py reports it).            */
 uint64_t vgl_launch_count(const vgl_ctx* ctx);
 /* How many read-kernel launches of this context took the log-term kernel (the batch's vgl_hc_batch_meta allowed it). */

@@ -457,3 +457,62 @@ def test_logterm_kernel_long_reads_and_every_route(small):
         assert hc.logterm_launches() > n0, name                     # every producer hands the value ranges over
         _check(res, final, argmax, small)
     hc.close()
+
+
+# ---- several samples per pass (vgl_hc_samples_begin / _sample_select / _finalize_samples) ------------------------------------
+def test_samples_pass_equals_separate_runs_bit_for_bit(small):
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    samples = [small.reads(n, seed=400 + k, sub_rate=0.01, indel_rate=0.002, origin_path=(17 * k) % small.n_paths)
+               for k, n in enumerate([300, 1, 64, 700, 33, 2, 150, 90, 410])]
+    packed = [vb.PackedBatch(small.graph, a) for a in samples]
+    alone = [hc.run_sample([pb]) for pb in packed]
+    assert len(set(r["maxh_index"] for r in alone)) > 3                      # the samples really differ
+    feeder = vb.Feeder(n_threads=2, chunk_reads=256)
+    hc.samples_begin(len(samples))
+    for k, (a, pb) in enumerate(zip(samples, packed)):
+        hc.sample_select(k)
+        if k % 3 == 0:
+            hc.update(pb)                                                    # packed host batch
+        elif k % 3 == 1:
+            feeder.feed(hc, a)                                               # flat alignment fields, device-side packing
+        else:
+            hc.update(vb.PackedBatch(small.graph, a, r0=0, r1=len(a) // 2))  # two calls into one sample
+            hc.update(vb.PackedBatch(small.graph, a, r0=len(a) // 2, r1=len(a)))
+    got = hc.finalize_samples(want_ll=True)
+    for k, (g, w) in enumerate(zip(got, alone)):
+        assert g["status"] == 0 and g["maxh_index"] == w["maxh_index"], k
+        assert H.rel_err(g["final_vec"], w["final_vec"]) < 1e-13, k
+        assert g["clade_vec"] == w["clade_vec"] and np.allclose(g["confidence_vec"], w["confidence_vec"], rtol=1e-12, atol=1e-300)
+        assert g["total_ll"] == pytest.approx(w["total_ll"], rel=1e-13)
+    final, argmax, _ = _oracle(small, samples[3])
+    _check(got[3], final, argmax, small)
+    # the context is back in single-sample mode
+    again = hc.run_sample([packed[0]])
+    assert again["maxh_index"] == alone[0]["maxh_index"] and H.rel_err(again["final_vec"], alone[0]["final_vec"]) < 1e-13
+    hc.close()
+
+
+def test_samples_pass_reports_a_bad_sample_without_losing_the_others():
+    S = vb.SynthHaplocart(seed=105, n_paths=50, n_rows=312, n_nodes=303)
+    seqs = S.node_sequences()
+    unused = S.n_nodes
+    node, _ = S.pmap()
+    if unused in set(node.tolist()):
+        pytest.skip("no unmapped node in this synthetic graph")
+    s = seqs[unused - 1]
+    bad = vb.Alignments.from_gam_bytes(H.encode_gam([H.aln(s, [(unused, 0, False, [(len(s), len(s), "")])])]))
+    good = S.reads(50, seed=3)
+    hc = vb.Haplocart()
+    hc.load(S.tables(), S.tree())
+    want = hc.run_sample([vb.PackedBatch(S.graph, good)])
+    hc.samples_begin(3)
+    for k, a in enumerate([good, bad, good]):
+        hc.sample_select(k)
+        hc.update(vb.PackedBatch(S.graph, a))
+    got = hc.finalize_samples(want_ll=True)
+    assert [g["status"] for g in got] == [0, 4, 0]                            # VGL_ERR_BAD_NODE for the middle sample only
+    for g in (got[0], got[2]):
+        assert g["maxh_index"] == want["maxh_index"] and H.rel_err(g["final_vec"], want["final_vec"]) < 1e-13
+    hc.close()

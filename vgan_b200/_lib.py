@@ -149,6 +149,9 @@ GPU_SYMBOLS = {
     "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_logterm_launches": (C.c_uint64, [_P]),
+    "vgl_hc_samples_begin": (C.c_int, [_P, C.c_int32]),
+    "vgl_hc_sample_select": (C.c_int, [_P, C.c_int32]),
+    "vgl_hc_finalize_samples": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "vgl_hc_read_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 

@@ -824,6 +824,86 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     }
 }
 
+// K2 for S samples at once (vgl_hc_finalize_samples): the CTA of (path tile, node chunk) fetches its membership words ONCE and
+// walks the samples of its slice (blockIdx.z) with them -- the 7.7 MB bit matrix is read once per slice of samples, not once per
+// sample.  Sample s keeps its node vectors at node_acc + s * acc_stride (layout of the single-sample buffer: [copies][n_words * 32]
+// then the A totals), its chunk partials at chunk_ll + s * chunks * P, its vector at ll + s * P.  Same fixed summation orders as
+// hc_path_kernel, so a sample's result does not depend on which call computed it.
+__global__ void __launch_bounds__(kPathTile)
+hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_acc, size_t acc_stride, double* __restrict__ chunk_ll,
+                       double* __restrict__ ll, unsigned int* __restrict__ tile_done, int n_samples, int samples_per_slice) {
+    __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
+    __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ bool s_last;
+    const int chunk = blockIdx.y;
+    const int w0 = chunk * kWordsPerChunk;
+    const int nw = min(kWordsPerChunk, t.n_words - w0);
+    const int p = blockIdx.x * kPathTile + threadIdx.x;
+    const uint32_t bar = smem_u32(&s_bar);
+    const uint32_t bytes = (uint32_t)nw * 32u * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t words[kWordsPerChunk];
+#pragma unroll
+    for (int k = 0; k < kWordsPerChunk; ++k)
+        words[k] = (k < nw && p < t.n_paths) ? __ldg(t.node_bits + (size_t)(w0 + k) * t.n_paths + p) : 0xffffffffu;
+    __syncthreads();
+    const int s0 = blockIdx.z * samples_per_slice, s1 = min(n_samples, s0 + samples_per_slice);
+    uint32_t phase = 0;
+    for (int sm = s0; sm < s1; ++sm) {
+        const double* acc_s = node_acc + (size_t)sm * acc_stride;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes * kAccCopies);
+            for (int c = 0; c < kAccCopies; ++c)
+                bulk_g2s(smem_u32(&s_c[c][0]), acc_s + (size_t)c * t.n_words * 32 + (size_t)w0 * 32, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        for (int i = threadIdx.x; i < nw * 32; i += kPathTile) {
+            double d = 0.0;
+#pragma unroll
+            for (int c = 0; c < kAccCopies; ++c) d += s_c[c][i];
+            s_d[i] = d;
+        }
+        __syncthreads();
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < kWordsPerChunk; ++k) {
+            const uint32_t unsup = ~words[k];
+            if (k < nw) {
+#pragma unroll
+                for (int bit = 0; bit < 32; ++bit) {
+                    const double d = s_d[k * 32 + bit];
+                    acc += ((unsup >> bit) & 1u) ? d : 0.0;
+                }
+            }
+        }
+        double* chunk_s = chunk_ll + (size_t)sm * gridDim.y * t.n_paths;
+        if (p < t.n_paths) chunk_s[(size_t)chunk * t.n_paths + p] = acc;
+        __threadfence();
+        __syncthreads();   // (also: everybody is done with s_c / s_d before the next sample's copies land)
+        unsigned int* done = tile_done + (size_t)sm * gridDim.x + blockIdx.x;
+        if (threadIdx.x == 0) {
+            s_last = atomicAdd(done, 1u) == gridDim.y - 1;
+            if (s_last) *done = 0;
+        }
+        __syncthreads();
+        if (s_last && p < t.n_paths) {
+            __threadfence();
+            const double* a_total = acc_s + (size_t)kAccCopies * t.n_words * 32;
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < kAccCopies; ++c) a += __ldcg(a_total + c);
+            double sum = 0.0;
+            for (unsigned c = 0; c < gridDim.y; ++c) sum += __ldcg(chunk_s + (size_t)c * t.n_paths + p);
+            ll[(size_t)sm * t.n_paths + p] = a + sum;
+        }
+    }
+}
+
 __global__ void hc_sum_parts_kernel(const double* __restrict__ parts, int n_parts, int n_paths, double* __restrict__ ll) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
@@ -896,7 +976,15 @@ constexpr int kPostBlock = 1024;
 __global__ void __launch_bounds__(kPostBlock)
 hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, const uint32_t* __restrict__ clade_bits,
                     const int32_t* __restrict__ anc_off, const int32_t* __restrict__ anc_clade, double* __restrict__ post,
-                    int post_cap, double* __restrict__ out_scalars, int32_t* __restrict__ out_idx, const int* __restrict__ err_flag) {
+                    int post_cap, double* __restrict__ out_scalars, int32_t* __restrict__ out_idx, const int* __restrict__ err_flag,
+                    size_t ll_stride, size_t result_stride, size_t err_stride) {
+    // one CTA per sample (blockIdx.x): sample s has its vector at ll + s * ll_stride, its result block at + s * result_stride
+    // doubles and its error word at err_flag + s * err_stride ints (all strides 0 for the single-sample call)
+    ll += (size_t)blockIdx.x * ll_stride;
+    post += (size_t)blockIdx.x * result_stride;
+    out_scalars += (size_t)blockIdx.x * result_stride;
+    out_idx += (size_t)blockIdx.x * result_stride * 2;
+    err_flag += (size_t)blockIdx.x * err_stride;
     extern __shared__ __align__(16) double s_e[];  // [n_paths] exp(ll - max)
     __shared__ double s_val[kPostBlock / 32];
     __shared__ int s_idx[kPostBlock / 32];
@@ -1082,6 +1170,16 @@ cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc
 }
 int hc_path_tiles(int n_paths) { return (n_paths + kPathTile - 1) / kPathTile; }
 
+cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* chunk_ll,
+                                          double* ll, unsigned int* tile_done, cudaStream_t s) {
+    // slices of samples along z: enough CTAs to fill the GPU, few enough that the bit matrix is re-read only a handful of times
+    const int slices = n_samples >= 32 ? 4 : n_samples >= 8 ? 2 : 1;
+    const int per_slice = (n_samples + slices - 1) / slices;
+    dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words), (n_samples + per_slice - 1) / per_slice);
+    hc_path_samples_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, acc_stride, chunk_ll, ll, tile_done, n_samples, per_slice);
+    return cudaGetLastError();
+}
+
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s) {
     const int block = 128;
     hc_sum_parts_kernel<<<(n_paths + block - 1) / block, block, 0, s>>>(parts, n_parts, n_paths, ll);
@@ -1098,7 +1196,16 @@ cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, co
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
                                 double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s) {
     hc_posterior_kernel<<<1, kPostBlock, hc_posterior_smem(n_paths), s>>>(ll, n_paths, row_words, clade_bits, anc_off,
-                                                                          anc_clade, post, post_cap, out_scalars, out_idx, err_flag);
+                                                                          anc_clade, post, post_cap, out_scalars, out_idx, err_flag, 0, 0, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_posterior_samples(int n_samples, const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
+                                        const int32_t* anc_off, const int32_t* anc_clade, double* results, int post_cap, size_t result_stride,
+                                        const int* err_flag, size_t err_stride, cudaStream_t s) {
+    hc_posterior_kernel<<<n_samples, kPostBlock, hc_posterior_smem(n_paths), s>>>(
+        ll, n_paths, row_words, clade_bits, anc_off, anc_clade, results + 4, post_cap, results, reinterpret_cast<int32_t*>(results + 2), err_flag,
+        (size_t)n_paths, result_stride, err_stride);
     return cudaGetLastError();
 }
 

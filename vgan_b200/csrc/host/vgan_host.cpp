@@ -1269,6 +1269,9 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     uint8_t* mq = blk + o_mq; uint8_t* q = blk + o_q;
     uint16_t* n16 = (uint16_t*)(blk + o_n16); uint16_t* fo16 = (uint16_t*)(blk + o_fo16);
     uint8_t* ne8 = blk + o_ne8; uint8_t* sl8 = blk + o_sl8; uint8_t* f8 = blk + o_f8; uint8_t* t8 = blk + o_t8; uint8_t* eseq = blk + o_eseq;
+    // Pass B works on RUNS of consecutive kept reads (a chunk is one run unless it holds a read the hot loop skips): inside a
+    // run the mappings, edits, quality bytes and edit sequences are contiguous in the source arrays, so the narrowing copies
+    // are flat loops over whole arrays (the compiler vectorises them) and the range checks OR-accumulate instead of branching.
     int bad = 0;
     std::vector<MetaAcc> metas((size_t)T);
 #pragma omp parallel for schedule(static, 1) num_threads(T) reduction(| : bad)
@@ -1277,48 +1280,91 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
         MetaAcc& meta = metas[(size_t)t];
         size_t cr = (size_t)base[(size_t)t].r, cm = (size_t)base[(size_t)t].m, ce = (size_t)base[(size_t)t].e;
         size_t cq = (size_t)base[(size_t)t].q, cs = (size_t)base[(size_t)t].s;
-        bool good = true;
-        for (size_t k = k0; k < k1 && good; ++k) {
-            const int64_t r = ra + (int64_t)k;
-            if (a->identity[r] < 1e-10) continue;
-            const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
-            good = good && a->mapq[r] >= 0 && a->mapq[r] <= 255 && (mb == ma || (a->map_offset[ma] >= 0 && a->map_offset[ma] <= 65535));
-            qoff[cr] = (uint32_t)cq;
-            moff[cr] = (uint32_t)cm;
-            mq[cr] = (uint8_t)a->mapq[r];
-            fo16[cr] = mb > ma ? (uint16_t)a->map_offset[ma] : (uint16_t)0;
-            const size_t ql = (size_t)(a->qual_off[r + 1] - a->qual_off[r]);
-            memcpy(q + cq, a->qual + a->qual_off[r], ql);
-            meta.quality(q + cq, ql);
-            meta.mapq((uint32_t)a->mapq[r]);
-            cq += ql;
-            uint64_t cap = 0;
-            for (int64_t m = ma; m < mb; ++m) {
-                const int64_t node = a->map_node[m];
-                const int64_t ea = a->edit_off[m], eb = a->edit_off[m + 1];
-                good = good && node >= 0 && node <= 32767 && (m == ma || a->map_offset[m] == 0) && eb - ea <= 255;
-                n16[cm] = (uint16_t)((node & 0x7fff) | (a->map_rev[m] ? 0x8000 : 0));
-                ne8[cm] = (uint8_t)(eb - ea);
-                ++cm;
-                for (int64_t e = ea; e < eb; ++e) {
-                    const int64_t fl = a->edit_from[e], tl = a->edit_to[e], sl = a->edit_seq_off[e + 1] - a->edit_seq_off[e];
-                    good = good && fl >= 0 && fl <= 255 && tl >= 0 && tl <= 255 && sl <= 255;
-                    f8[ce] = (uint8_t)fl;
-                    t8[ce] = (uint8_t)tl;
-                    sl8[ce] = (uint8_t)sl;
-                    ++ce;
-                    cap += (uint64_t)(fl + tl + sl);
+        uint64_t viol = 0;        // any bit set: a value does not fit its narrow field
+        uint64_t nonzero_off = 0, nonzero_first = 0;   // mappings with a non-zero node offset; reads whose FIRST mapping has one
+        int8_t qmax = 0;          // largest quality byte as signed char (bytes >= 128 are negative: canonical 0)
+        size_t k = k0;
+        while (k < k1) {
+            if (a->identity[ra + (int64_t)k] < 1e-10) { ++k; continue; }
+            size_t ke = k + 1;
+            while (ke < k1 && !(a->identity[ra + (int64_t)ke] < 1e-10)) ++ke;
+            const int64_t rs = ra + (int64_t)k, re = ra + (int64_t)ke;   // the run [rs, re)
+            const int64_t M0 = a->map_off[rs], M1 = a->map_off[re], E0 = a->edit_off[M0], E1 = a->edit_off[M1];
+            const int64_t Q0 = a->qual_off[rs], Q1 = a->qual_off[re], S0 = a->edit_seq_off[E0], S1 = a->edit_seq_off[E1];
+            {   // mappings
+                const int64_t* __restrict__ node = a->map_node + M0;
+                const int64_t* __restrict__ offs = a->map_offset + M0;
+                const uint8_t* __restrict__ rev = a->map_rev + M0;
+                const int64_t* __restrict__ eo = a->edit_off + M0;
+                uint16_t* __restrict__ on = n16 + cm;
+                uint8_t* __restrict__ oc = ne8 + cm;
+                const int64_t n = M1 - M0;
+                uint64_t v = 0, nzo = 0;
+                for (int64_t i = 0; i < n; ++i) {
+                    const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);
+                    v |= (nd & ~(uint64_t)0x7fff) | (cnt & ~(uint64_t)0xff);
+                    on[i] = (uint16_t)((nd & 0x7fff) | (rev[i] ? 0x8000u : 0u));
+                    oc[i] = (uint8_t)cnt;
+                    nzo += offs[i] != 0;
                 }
+                viol |= v;
+                nonzero_off += nzo;
             }
-            if (mb > ma) {   // a read's edit sequences are contiguous in the source
-                const int64_t sa = a->edit_seq_off[a->edit_off[ma]], sb = a->edit_seq_off[a->edit_off[mb]];
-                memcpy(eseq + cs, a->edit_seq + sa, (size_t)(sb - sa));
-                cs += (size_t)(sb - sa);
+            {   // edits
+                const int32_t* __restrict__ fr = a->edit_from + E0;
+                const int32_t* __restrict__ to = a->edit_to + E0;
+                const int64_t* __restrict__ so = a->edit_seq_off + E0;
+                uint8_t* __restrict__ of = f8 + ce;
+                uint8_t* __restrict__ ot = t8 + ce;
+                uint8_t* __restrict__ os = sl8 + ce;
+                const int64_t n = E1 - E0;
+                uint64_t v = 0;
+                for (int64_t i = 0; i < n; ++i) {
+                    const uint32_t f_ = (uint32_t)fr[i], t_ = (uint32_t)to[i];
+                    const uint64_t sl = (uint64_t)(so[i + 1] - so[i]);
+                    v |= (uint64_t)((f_ | t_) & ~0xffu) | (sl & ~(uint64_t)0xff);
+                    of[i] = (uint8_t)f_;
+                    ot[i] = (uint8_t)t_;
+                    os[i] = (uint8_t)sl;
+                }
+                viol |= v;
             }
-            soff[cr + 1] = (uint32_t)((cap + 3) & ~(uint64_t)3);  // prefix-summed below
-            ++cr;
+            memcpy(q + cq, a->qual + Q0, (size_t)(Q1 - Q0));
+            memcpy(eseq + cs, a->edit_seq + S0, (size_t)(S1 - S0));
+            {   // largest quality byte of the run, as the reference sees it (signed char)
+                const int8_t* __restrict__ qb = (const int8_t*)a->qual + Q0;
+                int8_t mx = qmax;
+                for (int64_t i = 0; i < Q1 - Q0; ++i) mx = qb[i] > mx ? qb[i] : mx;
+                qmax = mx;
+            }
+            // per read: offsets, mapping quality, first node offset, capacity of its aligned strings
+            for (int64_t r = rs; r < re; ++r) {
+                const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
+                const int64_t ea = a->edit_off[ma], eb = a->edit_off[mb];
+                const uint32_t mqv = (uint32_t)a->mapq[r];
+                viol |= (uint64_t)(mqv & ~0xffu);
+                qoff[cr] = (uint32_t)(cq + (size_t)(a->qual_off[r] - Q0));
+                moff[cr] = (uint32_t)(cm + (size_t)(ma - M0));
+                mq[cr] = (uint8_t)mqv;
+                meta.mapq(mqv);
+                const uint64_t fo = mb > ma ? (uint64_t)a->map_offset[ma] : 0;
+                viol |= fo & ~(uint64_t)0xffff;
+                nonzero_first += fo != 0;
+                fo16[cr] = (uint16_t)fo;
+                uint32_t span = 0;   // sum over the read's edits of from_length + to_length (from the narrowed copies)
+                const uint8_t* __restrict__ pf = f8 + ce + (size_t)(ea - E0);
+                const uint8_t* __restrict__ pt = t8 + ce + (size_t)(ea - E0);
+                for (int64_t i = 0; i < eb - ea; ++i) span += (uint32_t)pf[i] + (uint32_t)pt[i];
+                const uint64_t cap = (uint64_t)span + (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
+                soff[cr + 1] = (uint32_t)((cap + 3) & ~(uint64_t)3);  // prefix-summed below
+                ++cr;
+            }
+            cm += (size_t)(M1 - M0); ce += (size_t)(E1 - E0); cq += (size_t)(Q1 - Q0); cs += (size_t)(S1 - S0);
+            k = ke;
         }
-        bad |= good ? 0 : 1;
+        // only a read's first mapping may start inside its node (first_offset16 form)
+        bad |= (viol != 0 || nonzero_off != nonzero_first) ? 1 : 0;
+        meta.qmax = std::max<uint32_t>(meta.qmax, qmax > 2 ? (uint32_t)qmax : 0u);
     }
     if (bad) return 1;
     soff[0] = 0;

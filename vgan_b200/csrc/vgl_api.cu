@@ -83,6 +83,17 @@ struct vgl_ctx {
     DevBuf<double> d_cta_node_acc, d_chunk_ll, d_ll;
     DevBuf<unsigned int> d_tile_done;  // per path tile: CTAs of the path kernel that have finished
     double* d_a_total = nullptr;
+    // Accumulator set the accumulate entry points add into: the single-sample buffer above, or sample `cur_sample` of the
+    // multi-sample buffer (vgl_hc_samples_begin / vgl_hc_sample_select).  One set = [copies][n_rows_pad] | A totals | error word.
+    double* cur_acc = nullptr;
+    double* cur_a_total = nullptr;
+    int* cur_err = nullptr;
+    DevBuf<double> m_acc, m_chunk_ll, m_ll, m_result;   // [S] sets / [S][chunks][P] / [S][P] / [S][4 + cap]
+    DevBuf<unsigned int> m_tile_done;                   // [S][tiles]
+    double* m_h_result = nullptr;                       // page-locked mirror of m_result
+    size_t m_h_result_cap = 0;
+    int m_samples = 0, cur_sample = -1;
+    size_t acc_set_doubles() const { return (size_t)VGL_HC_ACC_COPIES * (size_t)n_rows_pad + VGL_HC_ACC_COPIES + 1; }
     int* d_err = nullptr;
     int n_chunks = 0;
     bool ll_valid = false;
@@ -252,12 +263,12 @@ int launch_read(vgl_ctx* ctx, const vgl::HcBatchDev& b, const vgl::HcBatchMeta& 
                                                                       ctx->tab.logterm != nullptr, ctx->max_smem_optin, plan);
     VGL_CUDA(cudaEventRecord(ev.first, ctx->stream));
     if (lt_smem) {
-        VGL_CUDA(vgl::hc_launch_read_logterm_kernel(ctx->sm_count, lt_smem, plan, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total, ctx->d_err,
+        VGL_CUDA(vgl::hc_launch_read_logterm_kernel(ctx->sm_count, lt_smem, plan, b, ctx->tab, ctx->cur_acc, ctx->cur_a_total, ctx->cur_err,
                                                     ctx->stream));
         ctx->logterm_launches += 1;
     } else {
-        VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->d_cta_node_acc.p, ctx->d_a_total,
-                                            ctx->d_err, ctx->stream));
+        VGL_CUDA(vgl::hc_launch_read_kernel(ctx->read_cfg, b, ctx->tab, ctx->cur_acc, ctx->cur_a_total,
+                                            ctx->cur_err, ctx->stream));
     }
     VGL_CUDA(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches += 1;
@@ -363,6 +374,8 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release(); ctx->d_logterm.release();
     ctx->d_cta_node_acc.release();
     ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_tile_done.release();
+    ctx->m_acc.release(); ctx->m_chunk_ll.release(); ctx->m_ll.release(); ctx->m_result.release(); ctx->m_tile_done.release();
+    if (ctx->m_h_result) cudaFreeHost(ctx->m_h_result);
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -647,6 +660,8 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     if (int rc = ctx->d_cta_node_acc.reserve((size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad + VGL_HC_ACC_COPIES + 1)) return rc;
     ctx->d_a_total = ctx->d_cta_node_acc.p + (size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad;
     ctx->d_err = reinterpret_cast<int*>(ctx->d_a_total + VGL_HC_ACC_COPIES);
+    ctx->cur_acc = ctx->d_cta_node_acc.p; ctx->cur_a_total = ctx->d_a_total; ctx->cur_err = ctx->d_err;
+    ctx->m_samples = 0; ctx->cur_sample = -1;
     if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
     if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
     if (int rc = ctx->d_tile_done.reserve((size_t)vgl::hc_path_tiles(P))) return rc;
@@ -697,6 +712,8 @@ int vgl_hc_reset(vgl_ctx* ctx) {
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     cudaStream_t s = ctx->stream;
     VGL_CUDA(cudaMemsetAsync(ctx->d_cta_node_acc.p, 0, ((size_t)VGL_HC_ACC_COPIES * ctx->n_rows_pad + VGL_HC_ACC_COPIES + 1) * sizeof(double), s));
+    ctx->cur_acc = ctx->d_cta_node_acc.p; ctx->cur_a_total = ctx->d_a_total; ctx->cur_err = ctx->d_err;   // single-sample mode
+    ctx->m_samples = 0; ctx->cur_sample = -1;
     ctx->ev_used = 0;
     ctx->ll_valid = false;
     return VGL_OK;
@@ -937,9 +954,9 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     Wd.n_lanes = (uint32_t)(G * 32);
     memcpy(Wd.lane_base, lane_base, sizeof(lane_base));
     memcpy(Wd.slot_of_mapq, slot_of_mapq, sizeof(slot_of_mapq));
-    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->d_err, s));
+    VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->cur_err, s));
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
-                                 R.o_mapq.p, ctx->d_err, s));
+                                 R.o_mapq.p, ctx->cur_err, s));
     ctx->launches += 6;
     return VGL_OK;
 }
@@ -1109,6 +1126,96 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
     }
     // The caller may reuse its host buffers as soon as this returns.
     VGL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return VGL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// several samples per pass (src/HaploCart.cpp:303 loops over samples; a real sample is <= ~2 x 10^4 reads after duplicate
+// removal, microseconds of GPU work, so the per-sample fixed costs -- the 7.7 MB bit matrix of K2, K3's launch, the result copy
+// and the host synchronisation -- are paid once per pass instead)
+// -------------------------------------------------------------------------------------------
+int vgl_hc_samples_begin(vgl_ctx* ctx, int32_t n_samples) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (n_samples < 1 || n_samples > 4096) return fail(VGL_ERR_INVALID, "1 <= n_samples <= 4096");
+    cudaStream_t s = ctx->stream;
+    const size_t set = ctx->acc_set_doubles(), P = (size_t)ctx->tab.n_paths, tiles = (size_t)vgl::hc_path_tiles((int)P);
+    const size_t cap = (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1), blk = 4 + cap;
+    if ((size_t)n_samples * set > ctx->m_acc.cap || (size_t)n_samples * P > ctx->m_ll.cap) VGL_CUDA(cudaStreamSynchronize(s));
+    if (int rc = ctx->m_acc.reserve((size_t)n_samples * set)) return rc;
+    if (int rc = ctx->m_chunk_ll.reserve((size_t)n_samples * (size_t)ctx->n_chunks * P)) return rc;
+    if (int rc = ctx->m_ll.reserve((size_t)n_samples * P)) return rc;
+    if (int rc = ctx->m_result.reserve((size_t)n_samples * blk)) return rc;
+    const size_t old_tiles = ctx->m_tile_done.cap;
+    if (int rc = ctx->m_tile_done.reserve((size_t)n_samples * tiles)) return rc;
+    if (ctx->m_tile_done.cap != old_tiles) VGL_CUDA(cudaMemsetAsync(ctx->m_tile_done.p, 0, ctx->m_tile_done.cap * sizeof(unsigned int), s));
+    if ((size_t)n_samples * blk > ctx->m_h_result_cap) {
+        if (ctx->m_h_result) cudaFreeHost(ctx->m_h_result);
+        ctx->m_h_result = nullptr;
+        ctx->m_h_result_cap = 0;
+        VGL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->m_h_result), (size_t)n_samples * blk * sizeof(double)));
+        ctx->m_h_result_cap = (size_t)n_samples * blk;
+    }
+    VGL_CUDA(cudaMemsetAsync(ctx->m_acc.p, 0, (size_t)n_samples * set * sizeof(double), s));
+    ctx->m_samples = n_samples;
+    ctx->ev_used = 0;
+    ctx->ll_valid = false;
+    return vgl_hc_sample_select(ctx, 0);
+}
+
+int vgl_hc_sample_select(vgl_ctx* ctx, int32_t sample) {
+    if (!ctx) return fail(VGL_ERR_INVALID, "null context");
+    if (ctx->m_samples < 1) return fail(VGL_ERR_STATE, "vgl_hc_samples_begin must come first");
+    if (sample < 0 || sample >= ctx->m_samples) return fail(VGL_ERR_INVALID, "sample %d outside [0, %d)", sample, ctx->m_samples);
+    const size_t set = ctx->acc_set_doubles();
+    ctx->cur_acc = ctx->m_acc.p + (size_t)sample * set;
+    ctx->cur_a_total = ctx->cur_acc + (size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad;
+    ctx->cur_err = reinterpret_cast<int*>(ctx->cur_a_total + VGL_HC_ACC_COPIES);
+    ctx->cur_sample = sample;
+    return VGL_OK;
+}
+
+int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap,
+                            int32_t* n_post_out, int32_t* status_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (ctx->m_samples < 1) return fail(VGL_ERR_STATE, "vgl_hc_samples_begin must come first");
+    cudaStream_t s = ctx->stream;
+    const int S = ctx->m_samples, P = ctx->tab.n_paths;
+    const size_t set = ctx->acc_set_doubles();
+    const int cap = ctx->have_tree ? ctx->max_anc + 1 : 1;
+    const size_t blk = 4 + (size_t)cap;
+    VGL_CUDA(vgl::hc_launch_path_samples_kernel(ctx->tab, S, ctx->m_acc.p, set, ctx->m_chunk_ll.p, ctx->m_ll.p, ctx->m_tile_done.p, s));
+    const int* err0 = reinterpret_cast<const int*>(ctx->m_acc.p + (size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad + VGL_HC_ACC_COPIES);
+    VGL_CUDA(vgl::hc_launch_posterior_samples(S, ctx->m_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
+                                              ctx->have_tree ? ctx->d_anc_off.p : nullptr, ctx->have_tree ? ctx->d_anc_clade.p : nullptr,
+                                              ctx->m_result.p, cap, blk, err0, set * 2, s));
+    ctx->launches += 2;
+    VGL_CUDA(cudaMemcpyAsync(ctx->m_h_result, ctx->m_result.p, (size_t)S * blk * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->m_ll.p, (size_t)S * (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    int worst = VGL_OK;
+    for (int k = 0; k < S; ++k) {
+        const double* r = ctx->m_h_result + (size_t)k * blk;
+        const int32_t* idx = reinterpret_cast<const int32_t*>(r + 2);
+        const int err = idx[2];
+        int st = VGL_OK;
+        if (err & 0x30000000) st = (err & 0x20000000) ? VGL_ERR_BAD_READ : VGL_ERR_BAD_NODE;
+        else if (err & VGL_ERR_BAD_NODE) st = VGL_ERR_BAD_NODE;
+        else if (err & 0x08000000) st = VGL_ERR_INVALID;
+        if (status_out) status_out[k] = st;
+        if (st != VGL_OK && worst == VGL_OK) worst = st;
+        if (argmax_out) argmax_out[k] = idx[0];
+        if (total_out) total_out[k] = r[0];
+        const int n_post = idx[1];
+        if (n_post_out) n_post_out[k] = n_post;
+        if (post_out)
+            for (int j = 0; j < std::min(n_post, (int)post_cap); ++j) post_out[(size_t)k * (size_t)post_cap + j] = r[4 + j];
+    }
+    // back to single-sample mode
+    ctx->m_samples = 0;
+    ctx->cur_sample = -1;
+    ctx->cur_acc = ctx->d_cta_node_acc.p; ctx->cur_a_total = ctx->d_a_total; ctx->cur_err = ctx->d_err;
+    if (worst != VGL_OK && !status_out) return fail(worst, "a sample of the pass holds a read the reference could not process (malformed alignment or unknown node)");
     return VGL_OK;
 }
 

@@ -142,6 +142,16 @@ int hc_path_tiles(int n_paths);
 cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
                                   unsigned int* tile_done, cudaStream_t s);
 
+// K2 / K3 over S samples at once (vgl_hc_finalize_samples).  Sample s: node vectors at node_acc + s * acc_stride doubles (single-
+// sample layout), chunk partials chunk_ll[s][chunks][P], vector ll[s][P], counters tile_done[s][tiles] (zero on entry, left zero),
+// result block results + s * result_stride doubles ({total, ll[argmax]}, {argmax, n_post, err}, post[post_cap]), error word
+// err_flag + s * err_stride ints.
+cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* chunk_ll,
+                                          double* ll, unsigned int* tile_done, cudaStream_t s);
+cudaError_t hc_launch_posterior_samples(int n_samples, const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
+                                        const int32_t* anc_off, const int32_t* anc_clade, double* results, int post_cap, size_t result_stride,
+                                        const int* err_flag, size_t err_stride, cudaStream_t s);
+
 // Multi-GPU: ll[p] = sum_k parts[k][p] in k order.
 cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, double* ll, cudaStream_t s);
 

@@ -134,6 +134,36 @@ class Haplocart:
                 res["clade_vec"] = [res["predicted_haplotype"]] + self.tree.clades_of(arg.value)
         return res
 
+    # ---- several samples per pass (the reference loops over samples, src/HaploCart.cpp:303) --------------
+    def samples_begin(self, n_samples):
+        """Start a pass over n_samples samples (instead of reset()); sample 0 is selected."""
+        check(gpu.vgl_hc_samples_begin(self.ctx, int(n_samples)))
+        self._n_samples = int(n_samples)
+
+    def sample_select(self, sample):
+        """The update*() calls / Feeder.feed that follow add into this sample."""
+        check(gpu.vgl_hc_sample_select(self.ctx, int(sample)))
+
+    def finalize_samples(self, want_ll=False):
+        """One collapse + posterior over all samples of the pass, one copy back.  Returns a list of per-sample dicts as
+        get_posterior() gives them (plus "status": 0, or the error code that sample alone would have raised)."""
+        S, P, cap = self._n_samples, self.n_paths, max(self._max_post, 1)
+        ll = np.zeros((S, P), dtype=np.float64) if want_ll else None
+        arg, npost, status = np.zeros(S, dtype=np.int32), np.zeros(S, dtype=np.int32), np.zeros(S, dtype=np.int32)
+        total, post = np.zeros(S), np.zeros((S, cap))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(gpu.vgl_hc_finalize_samples(self.ctx, p(ll) if want_ll else None, p(arg), p(total), p(post), cap, p(npost), p(status)))
+        out = []
+        for k in range(S):
+            res = {"final_vec": ll[k] if want_ll else None, "maxh_index": int(arg[k]), "total_ll": float(total[k]),
+                   "confidence_vec": post[k, :npost[k]].copy(), "status": int(status[k])}
+            if self.path_names is not None and status[k] == 0:
+                res["predicted_haplotype"] = self.path_names[int(arg[k])]
+                if self.tree is not None:
+                    res["clade_vec"] = [res["predicted_haplotype"]] + self.tree.clades_of(int(arg[k]))
+            out.append(res)
+        return out
+
     def run_sample(self, batches, want_ll=True):
         """One sample end to end: reset, update over the packed host batches, posterior."""
         self.reset()
