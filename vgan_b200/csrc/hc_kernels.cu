@@ -750,12 +750,26 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
 // K2b: chunk_ll[chunk][p] = sum over the chunk's nodes n with pathsgo[n][p] == 0 of D[n],
 //      D[n] = sum of the kAccCopies node vectors (fixed order)
 // ------------------------------------------------------------------------------------------
+struct PeerBufs {
+    double* base[VGL_HC_MAX_PEERS];
+};
+// The multi-GPU exchange fused into K2 / K3: world <= 1 switches it off.  Exchange buffer of a rank (vgl_hc_peer_export):
+// parts[2][world][n_pad] doubles, then flags[2][world] u64.  Generation = epoch & 1; a flag counts the path tiles its rank
+// has delivered into that generation since the buffers were created, so the value to wait for is uses * tiles with
+// uses = (epoch + 1) / 2.
+struct PeerFuse {
+    PeerBufs bufs;
+    int rank, world, n_pad;
+    unsigned long long epoch;
+    unsigned long long timeout_ns;
+};
+
 constexpr int kPathTile = 128;       // paths per CTA (one per thread)
 constexpr int kWordsPerChunk = 10;   // 320 nodes per CTA
 
 __global__ void __launch_bounds__(kPathTile)
 hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __restrict__ chunk_ll, const double* __restrict__ a_total,
-               double* __restrict__ ll, unsigned int* __restrict__ tile_done) {
+               double* __restrict__ ll, unsigned int* __restrict__ tile_done, PeerFuse pf) {
     __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -821,6 +835,22 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
         double sum = 0.0;
         for (unsigned c = 0; c < gridDim.y; ++c) sum += __ldcg(chunk_ll + (size_t)c * t.n_paths + p);
         ll[p] = a + sum;
+        // multi-GPU: this tile of the rank's vector goes straight into slot `rank` of EVERY rank's exchange buffer (peer
+        // memory over NVLink) -- the exchange is the epilogue of this kernel, no separate push launch
+        if (pf.world > 1) {
+            const int gen = (int)(pf.epoch & 1ull);
+            for (int q = 0; q < pf.world; ++q) pf.bufs.base[q][((size_t)gen * pf.world + pf.rank) * (size_t)pf.n_pad + p] = a + sum;
+        }
+    }
+    if (pf.world > 1 && s_last) {
+        __threadfence_system();
+        __syncthreads();   // (s_last is uniform across the CTA)
+        if ((int)threadIdx.x < pf.world) {   // one release per peer: "rank has delivered one more tile"
+            const int gen = (int)(pf.epoch & 1ull);
+            unsigned long long* flag = reinterpret_cast<unsigned long long*>(pf.bufs.base[threadIdx.x] + (size_t)2 * pf.world * pf.n_pad) +
+                                       (size_t)gen * pf.world + pf.rank;
+            asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(flag), "l"(1ull) : "memory");
+        }
     }
 }
 
@@ -920,12 +950,8 @@ __global__ void hc_sum_parts_kernel(const double* __restrict__ parts, int n_part
 //   sum : every CTA waits (system-scope acquire) until the `world` flags of the local buffer hold `epoch`, then adds
 //         the slots in rank order.
 // ------------------------------------------------------------------------------------------
-struct PeerBufs {
-    double* base[VGL_HC_MAX_PEERS];
-};
-
 __global__ void __launch_bounds__(256)
-hc_peer_push_kernel(PeerBufs peers, int rank, int world, int n_paths, int n_pad, unsigned long long epoch,
+hc_peer_push_kernel(PeerBufs peers, int rank, int world, int n_paths, int n_pad, unsigned long long epoch, int n_tiles,
                     const double* __restrict__ ll) {
     const int q = blockIdx.x;
     const int gen = (int)(epoch & 1ull);
@@ -935,30 +961,33 @@ hc_peer_push_kernel(PeerBufs peers, int rank, int world, int n_paths, int n_pad,
     if (threadIdx.x == 0) {
         unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[q] + (size_t)2 * world * n_pad) + (size_t)gen * world + rank;
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+        // (the flag counts delivered path tiles, as in the fused exchange: a whole vector is n_tiles of them)
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(flag), "l"((unsigned long long)n_tiles) : "memory");
     }
 }
 
 __global__ void __launch_bounds__(256)
-hc_peer_sum_kernel(const double* __restrict__ local, int world, int n_paths, int n_pad, unsigned long long epoch,
+hc_peer_sum_kernel(const double* __restrict__ local, int world, int n_paths, int n_pad, unsigned long long epoch, int n_tiles,
                    double* __restrict__ ll, int* __restrict__ err_flag) {
     const int gen = (int)(epoch & 1ull);
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(local + (size_t)2 * world * n_pad) + (size_t)gen * world;
+    int gone = 0;
     if ((int)threadIdx.x < world) {
         unsigned long long t0, t1, v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
-            if (v >= epoch) break;
+            if (v >= ((epoch + 1ull) / 2ull) * (unsigned long long)n_tiles) break;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 10000000000ull) {  // 10 s: a peer is gone; report instead of hanging the GPU
+            if (t1 - t0 > 120000000000ull) {  // 120 s: a peer is gone; report instead of hanging the GPU
                 atomicOr(err_flag, 0x40000000);
+                gone = 1;
                 break;
             }
             __nanosleep(200);
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(gone)) return;   // never add up slots that were not delivered
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     const double* parts = local + (size_t)gen * world * (size_t)n_pad;
@@ -974,10 +1003,10 @@ hc_peer_sum_kernel(const double* __restrict__ local, int world, int n_paths, int
 constexpr int kPostBlock = 1024;
 
 __global__ void __launch_bounds__(kPostBlock)
-hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, const uint32_t* __restrict__ clade_bits,
+hc_posterior_kernel(const double* ll, int n_paths, int row_words, const uint32_t* __restrict__ clade_bits,
                     const int32_t* __restrict__ anc_off, const int32_t* __restrict__ anc_clade, double* __restrict__ post,
                     int post_cap, double* __restrict__ out_scalars, int32_t* __restrict__ out_idx, const int* __restrict__ err_flag,
-                    size_t ll_stride, size_t result_stride, size_t err_stride) {
+                    size_t ll_stride, size_t result_stride, size_t err_stride, double* ll_rw, PeerFuse pf, int n_tiles) {
     // one CTA per sample (blockIdx.x): sample s has its vector at ll + s * ll_stride, its result block at + s * result_stride
     // doubles and its error word at err_flag + s * err_stride ints (all strides 0 for the single-sample call)
     ll += (size_t)blockIdx.x * ll_stride;
@@ -991,7 +1020,47 @@ hc_posterior_kernel(const double* __restrict__ ll, int n_paths, int row_words, c
     __shared__ double s_max;
     __shared__ int s_arg;
     __shared__ double s_sum;
+    __shared__ int s_peer_err;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // multi-GPU: the other half of the fused exchange.  Wait until every rank has delivered all its path tiles into the local
+    // buffer's current generation, then ll = the ranks' vectors added IN RANK ORDER (bit-identical on every rank, and exact
+    // ties between identically supported paths survive).
+    if (pf.world > 1) {
+        if (tid == 0) s_peer_err = 0;
+        __syncthreads();
+        const int gen = (int)(pf.epoch & 1ull);
+        const double* local = pf.bufs.base[pf.rank];
+        if (tid < pf.world) {
+            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(local + (size_t)2 * pf.world * pf.n_pad) + (size_t)gen * pf.world + tid;
+            const unsigned long long want = ((pf.epoch + 1ull) / 2ull) * (unsigned long long)n_tiles;
+            unsigned long long t0, t1, v;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+                if (v >= want) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > pf.timeout_ns) {  // a peer is gone: report instead of hanging the GPU, and leave ll alone
+                    s_peer_err = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (s_peer_err) {
+            if (tid == 0) out_idx[2] = 0x40000000;
+            return;
+        }
+        const double* parts = local + (size_t)gen * pf.world * (size_t)pf.n_pad;
+        for (int p = tid; p < n_paths; p += kPostBlock) {
+            double sum = 0.0;
+            for (int k = 0; k < pf.world; ++k) sum += __ldcg(parts + (size_t)k * pf.n_pad + p);  // written by peers: bypass L1
+            ll_rw[p] = sum;
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
 
     // argmax, first max wins (std::max_element, src/HaploCart.cpp:423)
     double best = -CUDART_INF;
@@ -1162,10 +1231,31 @@ cudaError_t hc_launch_read_logterm_kernel(int grid, size_t smem, const HcLogTerm
 
 int hc_path_chunks(int n_words) { return (n_words + kWordsPerChunk - 1) / kWordsPerChunk; }
 
+static PeerFuse no_peers() {
+    PeerFuse pf;
+    memset(&pf, 0, sizeof(pf));
+    return pf;
+}
+static PeerFuse make_fuse(double* const* peer_bufs, int rank, int world, int n_pad, unsigned long long epoch, double timeout_s) {
+    PeerFuse pf = no_peers();
+    for (int k = 0; k < VGL_HC_MAX_PEERS; ++k) pf.bufs.base[k] = k < world ? peer_bufs[k] : nullptr;
+    pf.rank = rank; pf.world = world; pf.n_pad = n_pad; pf.epoch = epoch;
+    pf.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    return pf;
+}
+
 cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
                                   unsigned int* tile_done, cudaStream_t s) {
     dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words));
-    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done);
+    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done, no_peers());
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+                                        unsigned int* tile_done, double* const* peer_bufs, int rank, int world, int n_pad,
+                                        unsigned long long epoch, cudaStream_t s) {
+    dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words));
+    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done, make_fuse(peer_bufs, rank, world, n_pad, epoch, 0));
     return cudaGetLastError();
 }
 int hc_path_tiles(int n_paths) { return (n_paths + kPathTile - 1) / kPathTile; }
@@ -1196,7 +1286,19 @@ cudaError_t hc_launch_posterior(const double* ll, int n_paths, int row_words, co
                                 const int32_t* anc_off, const int32_t* anc_clade, double* post, int post_cap,
                                 double* out_scalars, int32_t* out_idx, const int* err_flag, cudaStream_t s) {
     hc_posterior_kernel<<<1, kPostBlock, hc_posterior_smem(n_paths), s>>>(ll, n_paths, row_words, clade_bits, anc_off,
-                                                                          anc_clade, post, post_cap, out_scalars, out_idx, err_flag, 0, 0, 0);
+                                                                          anc_clade, post, post_cap, out_scalars, out_idx, err_flag, 0, 0, 0,
+                                                                          nullptr, no_peers(), 0);
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_posterior_fused(double* ll, int n_paths, int row_words, const uint32_t* clade_bits, const int32_t* anc_off,
+                                      const int32_t* anc_clade, double* post, int post_cap, double* out_scalars, int32_t* out_idx,
+                                      const int* err_flag, double* const* peer_bufs, int rank, int world, int n_pad,
+                                      unsigned long long epoch, double timeout_s, cudaStream_t s) {
+    hc_posterior_kernel<<<1, kPostBlock, hc_posterior_smem(n_paths), s>>>(ll, n_paths, row_words, clade_bits, anc_off, anc_clade, post, post_cap,
+                                                                          out_scalars, out_idx, err_flag, 0, 0, 0, ll,
+                                                                          make_fuse(peer_bufs, rank, world, n_pad, epoch, timeout_s),
+                                                                          hc_path_tiles(n_paths));
     return cudaGetLastError();
 }
 
@@ -1205,18 +1307,18 @@ cudaError_t hc_launch_posterior_samples(int n_samples, const double* ll, int n_p
                                         const int* err_flag, size_t err_stride, cudaStream_t s) {
     hc_posterior_kernel<<<n_samples, kPostBlock, hc_posterior_smem(n_paths), s>>>(
         ll, n_paths, row_words, clade_bits, anc_off, anc_clade, results + 4, post_cap, results, reinterpret_cast<int32_t*>(results + 2), err_flag,
-        (size_t)n_paths, result_stride, err_stride);
+        (size_t)n_paths, result_stride, err_stride, nullptr, no_peers(), 0);
     return cudaGetLastError();
 }
 
 cudaError_t hc_launch_peer_exchange(double* const* peer_bufs, int rank, int world, int n_paths, int n_pad,
-                                    unsigned long long epoch, double* ll, int* err_flag, cudaStream_t s) {
+                                    unsigned long long epoch, int n_tiles, double* ll, int* err_flag, cudaStream_t s) {
     PeerBufs pb;
     for (int k = 0; k < VGL_HC_MAX_PEERS; ++k) pb.base[k] = k < world ? peer_bufs[k] : nullptr;
-    hc_peer_push_kernel<<<world, 256, 0, s>>>(pb, rank, world, n_paths, n_pad, epoch, ll);
+    hc_peer_push_kernel<<<world, 256, 0, s>>>(pb, rank, world, n_paths, n_pad, epoch, n_tiles, ll);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    hc_peer_sum_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(peer_bufs[rank], world, n_paths, n_pad, epoch, ll, err_flag);
+    hc_peer_sum_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(peer_bufs[rank], world, n_paths, n_pad, epoch, n_tiles, ll, err_flag);
     return cudaGetLastError();
 }
 

@@ -93,7 +93,8 @@ struct vgl_ctx {
     double* m_h_result = nullptr;                       // page-locked mirror of m_result
     size_t m_h_result_cap = 0;
     int m_samples = 0, cur_sample = -1;
-    size_t acc_set_doubles() const { return (size_t)VGL_HC_ACC_COPIES * (size_t)n_rows_pad + VGL_HC_ACC_COPIES + 1; }
+    // (a multiple of 32 doubles: every sample's set starts on a 256-byte boundary, as the bulk copies of the path kernel need)
+    size_t acc_set_doubles() const { return ((size_t)VGL_HC_ACC_COPIES * (size_t)n_rows_pad + VGL_HC_ACC_COPIES + 1 + 31) & ~(size_t)31; }
     int* d_err = nullptr;
     int n_chunks = 0;
     bool ll_valid = false;
@@ -159,6 +160,8 @@ struct vgl_ctx {
     } slot[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t chunk_groups = 4096;  // 131072 reads per H2D chunk
+    bool peer_fused_pending = false;  // vgl_hc_exchange_paths ran K2 with the exchange epilogue: the next posterior kernel completes it
+    double peer_timeout_s = 120.0;    // a peer that never delivers raises VGL_ERR_PEER after this long (VGL_PEER_TIMEOUT_S)
     bool logterm_off = false;      // VGL_HC_TABLE_MODE pins the general kernel (tests)
     uint64_t logterm_launches = 0; // read-kernel launches that took the log-term kernel
     uint32_t raw_seq = 0;          // chunks submitted through vgl_hc_accumulate_raw so far (selects the staging set)
@@ -713,6 +716,7 @@ int vgl_hc_reset(vgl_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     VGL_CUDA(cudaMemsetAsync(ctx->d_cta_node_acc.p, 0, ((size_t)VGL_HC_ACC_COPIES * ctx->n_rows_pad + VGL_HC_ACC_COPIES + 1) * sizeof(double), s));
     ctx->cur_acc = ctx->d_cta_node_acc.p; ctx->cur_a_total = ctx->d_a_total; ctx->cur_err = ctx->d_err;   // single-sample mode
+    ctx->peer_fused_pending = false;
     ctx->m_samples = 0; ctx->cur_sample = -1;
     ctx->ev_used = 0;
     ctx->ll_valid = false;
@@ -1256,6 +1260,8 @@ int vgl_hc_peer_export(vgl_ctx* ctx, int32_t world, unsigned char* handle_out) {
     memcpy(handle_out, &h, sizeof(h));
     ctx->peer_world = world;
     ctx->peer_epoch = 0;
+    ctx->peer_fused_pending = false;
+    if (const char* e = getenv("VGL_PEER_TIMEOUT_S")) { const double v = atof(e); if (v > 0) ctx->peer_timeout_s = v; }
     return VGL_OK;
 }
 
@@ -1278,11 +1284,24 @@ int vgl_hc_peer_attach(vgl_ctx* ctx, int32_t rank, int32_t world, const unsigned
 int vgl_hc_exchange_paths(vgl_ctx* ctx) {
     if (int rc = use_device(ctx)) return rc;
     if (ctx->peer_rank < 0) return fail(VGL_ERR_STATE, "vgl_hc_peer_attach must come first");
-    if (!ctx->ll_valid)
-        if (int rc = vgl_hc_paths(ctx, nullptr)) return rc;
+    if (!ctx->ll_valid) {
+        // the usual case: the collapse has not run yet -- run it with the exchange as its epilogue (every path tile goes to
+        // all peers as soon as its last CTA has it); vgl_hc_finalize's posterior kernel acquires and sums in rank order
+        ctx->peer_epoch += 1;
+        VGL_CUDA(vgl::hc_launch_path_kernel_fused(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, ctx->d_a_total, ctx->d_ll.p,
+                                                  ctx->d_tile_done.p, ctx->peer_bufs, ctx->peer_rank, ctx->peer_world, ctx->peer_pad,
+                                                  ctx->peer_epoch, ctx->stream));
+        ctx->launches += 1;
+        ctx->ll_valid = true;
+        ctx->peer_fused_pending = true;
+        return VGL_OK;
+    }
+    // this rank's vector is already on the device (vgl_hc_paths was called): the two-kernel exchange
     ctx->peer_epoch += 1;
+    const int gen = (int)(ctx->peer_epoch & 1ull);
+    (void)gen;
     VGL_CUDA(vgl::hc_launch_peer_exchange(ctx->peer_bufs, ctx->peer_rank, ctx->peer_world, ctx->tab.n_paths, ctx->peer_pad,
-                                          ctx->peer_epoch, ctx->d_ll.p, ctx->d_err, ctx->stream));
+                                          ctx->peer_epoch, vgl::hc_path_tiles(ctx->tab.n_paths), ctx->d_ll.p, ctx->d_err, ctx->stream));
     ctx->launches += 2;
     return VGL_OK;
 }
@@ -1299,10 +1318,18 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
     double* d_scalars = ctx->d_result.p;
     int32_t* d_idx = reinterpret_cast<int32_t*>(ctx->d_result.p + 2);
     double* d_post = ctx->d_result.p + 4;
-    VGL_CUDA(vgl::hc_launch_posterior(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
-                                      ctx->have_tree ? ctx->d_anc_off.p : nullptr,
-                                      ctx->have_tree ? ctx->d_anc_clade.p : nullptr, d_post, cap, d_scalars, d_idx,
-                                      ctx->d_err, s));
+    if (ctx->peer_fused_pending) {
+        VGL_CUDA(vgl::hc_launch_posterior_fused(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
+                                                ctx->have_tree ? ctx->d_anc_off.p : nullptr, ctx->have_tree ? ctx->d_anc_clade.p : nullptr,
+                                                d_post, cap, d_scalars, d_idx, ctx->d_err, ctx->peer_bufs, ctx->peer_rank, ctx->peer_world,
+                                                ctx->peer_pad, ctx->peer_epoch, ctx->peer_timeout_s, s));
+        ctx->peer_fused_pending = false;
+    } else {
+        VGL_CUDA(vgl::hc_launch_posterior(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
+                                          ctx->have_tree ? ctx->d_anc_off.p : nullptr,
+                                          ctx->have_tree ? ctx->d_anc_clade.p : nullptr, d_post, cap, d_scalars, d_idx,
+                                          ctx->d_err, s));
+    }
     ctx->launches += 1;
     VGL_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, (4 + (size_t)cap) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->d_ll.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -159,7 +159,18 @@ cudaError_t hc_launch_sum_parts(const double* parts, int n_parts, int n_paths, d
 // (layout: parts[2][world][n_pad] doubles, flags[2][world] u64).  Writes this rank's ll into every buffer, waits for
 // all ranks' vectors in the local buffer, leaves their rank-ordered sum in ll.
 cudaError_t hc_launch_peer_exchange(double* const* peer_bufs, int rank, int world, int n_paths, int n_pad,
-                                    unsigned long long epoch, double* ll, int* err_flag, cudaStream_t s);
+                                    unsigned long long epoch, int n_tiles, double* ll, int* err_flag, cudaStream_t s);
+
+// The exchange fused into K2 / K3 (what vgl_hc_exchange_paths + vgl_hc_finalize launch): K2's last CTA of every path tile stores
+// its 128 paths into slot `rank` of every rank's buffer and releases a per-rank tile counter; K3's prologue acquires the
+// world counters of the local buffer and adds the slots in rank order.  No separate exchange kernels.
+cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+                                        unsigned int* tile_done, double* const* peer_bufs, int rank, int world, int n_pad,
+                                        unsigned long long epoch, cudaStream_t s);
+cudaError_t hc_launch_posterior_fused(double* ll, int n_paths, int row_words, const uint32_t* clade_bits, const int32_t* anc_off,
+                                      const int32_t* anc_clade, double* post, int post_cap, double* out_scalars, int32_t* out_idx,
+                                      const int* err_flag, double* const* peer_bufs, int rank, int world, int n_pad,
+                                      unsigned long long epoch, double timeout_s, cudaStream_t s);
 
 // K3: argmax (first max wins), log-sum-exp, posterior of the call and of its listed clades.
 //   out_scalars[0] = total (log-sum-exp), out_scalars[1] = ll[argmax]; out_idx[0] = argmax, out_idx[1] = n_post,
