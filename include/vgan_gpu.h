@@ -411,6 +411,18 @@ int vgl_hc_sample_select(vgl_ctx* ctx, int32_t sample);
 int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap,
                             int32_t* n_post_out, int32_t* status_out);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Duplicate removal                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+/* Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:68-110; update_for_single, :20-39) runs directly in front of the hot
+ * loop (src/HaploCart.cpp:390) as an O(n^2) scan over the position-sorted reads: read j is a duplicate when an EARLIER read i
+ * that is not paired has the same start coordinates.  One hash pass on the device instead (two kernels):
+ *   start_key[r] = node_id << 32 | offset of the read's first mapping (host array; vgh_dedup_keys builds it)
+ *   paired[r]    = Alignment.read_paired (NULL: none).  A paired read marks nothing: update_for_paired indexes
+ *                  mapping()[n_mappings], one past the end (src/rmdup.cpp:48-59), so its result is undefined in the reference.
+ *   is_dup[r]    (host, n_reads bytes) receives 1 for duplicates; *n_kept the number of survivors.               */
+int vgl_dedup(vgl_ctx* ctx, uint32_t n_reads, const uint64_t* start_key, const uint8_t* paired, uint8_t* is_dup, uint64_t* n_kept);
+
 /* Number of kernels this context has launched since creation (bench.py reports it).            */
 uint64_t vgl_launch_count(const vgl_ctx* ctx);
 /* How many read-kernel launches of this context took the log-term kernel (the batch's vgl_hc_batch_meta allowed it). */

@@ -90,6 +90,8 @@ int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char
  * its result is undefined in the reference; here a paired read i marks nothing.
  * is_dup[r] (n_reads bytes) receives 1 for duplicates; returns the number of reads kept via *n_kept.        */
 int vgh_dedup(const vgh_alignments* a, uint8_t* is_dup, int64_t* n_kept);
+/* The start coordinates vgl_dedup (include/vgan_gpu.h) keys on: keys[r] = node_id << 32 | offset of read r's first mapping. */
+int vgh_dedup_keys(const vgh_alignments* a, uint64_t* keys);
 
 /* ---- batch packer --------------------------------------------------------------------------- */
 typedef struct vgh_hc_packed vgh_hc_packed;

@@ -354,3 +354,34 @@ def test_feeder_takes_the_general_builder_where_the_narrow_arrays_do_not_fit(sma
     _check(got, final, argmax, small)
     f.close()
     hc.close()
+
+
+# ---- duplicate removal on the device (src/rmdup.cpp:20-110) ------------------------------------------
+def test_device_dedup_equals_the_reference_scan(small):
+    import os
+    from oracle import ref
+    hc = vb.Haplocart()
+    cases = [small.reads(3000, seed=511), small.reads(40, seed=512),
+             vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "all_the_same.gam")),
+             vb.Alignments.from_gam_file(os.path.join(H.GOLDEN, "J2a1a1a1.gam")),
+             vb.Alignments.from_gam_bytes(b"")]
+    for alns in cases:
+        R = orc.FlatReads(alns.arrays()) if len(alns) else None
+        mask, kept = hc.dedup(alns)
+        if R is None:
+            assert mask.size == 0 and kept == 0
+            continue
+        want = orc.dedup(R)
+        assert np.array_equal(mask, want) and kept == int((~want).sum())
+        host_mask, host_kept = vb.host.dedup(alns)
+        assert np.array_equal(host_mask, want) and host_kept == kept
+        if ref.available() and len(alns) <= 3000:
+            assert np.array_equal(ref.dedup(R), want)          # Dup_Remover::remove_duplicates_internal itself
+    # a paired read marks nothing (the reference's paired branch reads one past the end of the mappings)
+    reads = [H.aln("ACGT", [(5, 1, False, [(4, 4, "")])]) for _ in range(4)]
+    reads[0]["read_paired"] = True
+    alns = vb.Alignments.from_gam_bytes(H.encode_gam(reads))
+    mask, kept = hc.dedup(alns)
+    assert mask.tolist() == [False, False, True, True] and kept == 2
+    assert np.array_equal(mask, vb.host.dedup(alns)[0])
+    hc.close()

@@ -579,6 +579,20 @@ extern "C" int vgh_dedup(const vgh_alignments* a, uint8_t* is_dup, int64_t* n_ke
     return VGH_OK;
 }
 
+extern "C" int vgh_dedup_keys(const vgh_alignments* a, uint64_t* keys) {
+    if (!a || (a->n_reads && !keys)) return fail(VGH_ERR_INVALID, "bad arguments");
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t r = 0; r < a->n_reads; ++r) {
+        if (a->map_off[r + 1] == a->map_off[r]) { bad = 1; keys[r] = 0; continue; }
+        const int64_t node = a->map_node[a->map_off[r]], off = a->map_offset[a->map_off[r]];
+        if (node < 0 || node > 0x7fffffffll || off < 0 || off > 0xffffffffll) bad = 1;
+        keys[r] = ((uint64_t)node << 32) | (uint64_t)(uint32_t)off;
+    }
+    if (bad) return fail(VGH_ERR_BAD_READ, "a read has no mapping (the reference dereferences mapping()[0]) or start coordinates out of range");
+    return VGH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // batch packer
 // ------------------------------------------------------------------------------------------------

@@ -605,6 +605,59 @@ hc_expand_kernel(uint32_t n_groups, const uint32_t* __restrict__ grp_c16, const 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// duplicate removal (reference: Dup_Remover::remove_duplicates_internal, src/rmdup.cpp:20-39,68-110)
+// The reference marks read j when some EARLIER read i that is not paired has the same start coordinates (node id and offset of
+// the first mapping, strand ignored) -- an O(n^2) scan.  Here: an open-addressing table keyed by the coordinates keeps, per
+// key, the smallest index of an unpaired read (atomicMin); read j is a duplicate when that index is below j.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr unsigned long long kDedupEmpty = 0xffffffffffffffffull;
+__device__ __forceinline__ uint32_t dedup_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k;
+}
+__global__ void __launch_bounds__(256)
+dedup_insert_kernel(uint32_t n, const unsigned long long* __restrict__ key, const uint8_t* __restrict__ paired, uint32_t mask,
+                    unsigned long long* __restrict__ tab_key, uint32_t* __restrict__ tab_first) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const unsigned long long k = key[r];
+    uint32_t slot = dedup_hash(k) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(tab_key + slot, kDedupEmpty, k);
+        if (old == kDedupEmpty || old == k) {
+            if (!(paired && paired[r])) atomicMin(tab_first + slot, r);   // a paired read marks nothing (include/vgan_host.h: vgh_dedup)
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+__global__ void __launch_bounds__(256)
+dedup_mark_kernel(uint32_t n, const unsigned long long* __restrict__ key, uint32_t mask, const unsigned long long* __restrict__ tab_key,
+                  const uint32_t* __restrict__ tab_first, uint8_t* __restrict__ is_dup, unsigned int* __restrict__ n_dup) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t dup = 0;
+    if (r < n) {
+        const unsigned long long k = key[r];
+        uint32_t slot = dedup_hash(k) & mask;
+        while (tab_key[slot] != k) slot = (slot + 1) & mask;   // inserted by the first kernel
+        dup = tab_first[slot] < r ? 1u : 0u;
+        is_dup[r] = (uint8_t)dup;
+    }
+    const uint32_t votes = __ballot_sync(0xffffffffu, dup != 0);
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(n_dup, (unsigned int)__popc(votes));
+}
+}  // namespace
+
+cudaError_t dedup_launch(uint32_t n, const unsigned long long* key, const uint8_t* paired, uint32_t table_size, unsigned long long* tab_key,
+                         uint32_t* tab_first, uint8_t* is_dup, unsigned int* n_dup, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    dedup_insert_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, key, paired, table_size - 1, tab_key, tab_first);
+    dedup_mark_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, key, table_size - 1, tab_key, tab_first, is_dup, n_dup);
+    return cudaGetLastError();
+}
+
 cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const uint32_t* grp_n16, const uint16_t* col16,
                              const uint8_t* col8, const uint32_t* flag4, const uint16_t* n_owned, const uint16_t* node16,
                              const uint16_t* n_cols, uint32_t* col32, uint32_t* grp_c32, cudaStream_t s) {

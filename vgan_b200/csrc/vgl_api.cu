@@ -1138,6 +1138,44 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
 // removal, microseconds of GPU work, so the per-sample fixed costs -- the 7.7 MB bit matrix of K2, K3's launch, the result copy
 // and the host synchronisation -- are paid once per pass instead)
 // -------------------------------------------------------------------------------------------
+// -------------------------------------------------------------------------------------------
+// duplicate removal on the device (the O(n^2) scan in front of the hot loop, src/HaploCart.cpp:390, src/rmdup.cpp:20-110)
+// -------------------------------------------------------------------------------------------
+int vgl_dedup(vgl_ctx* ctx, uint32_t n_reads, const uint64_t* start_key, const uint8_t* paired, uint8_t* is_dup, uint64_t* n_kept) {
+    if (int rc = use_device(ctx)) return rc;
+    if (n_reads && (!start_key || !is_dup)) return fail(VGL_ERR_INVALID, "null arrays");
+    if (n_kept) *n_kept = 0;
+    if (n_reads == 0) return VGL_OK;
+    if (n_reads > 0x40000000u) return fail(VGL_ERR_INVALID, "too many reads for one call");
+    cudaStream_t s = ctx->stream;
+    uint32_t size = 1024;
+    while (size < 2u * n_reads) size <<= 1;
+    DevBuf<unsigned long long> d_key, t_key;
+    DevBuf<uint32_t> t_first;
+    DevBuf<uint8_t> d_paired, d_dup;
+    DevBuf<unsigned int> d_n;
+    int rc = VGL_OK;
+    auto done = [&](int code) { d_key.release(); t_key.release(); t_first.release(); d_paired.release(); d_dup.release(); d_n.release(); return code; };
+    if ((rc = d_key.reserve(n_reads)) || (rc = t_key.reserve(size)) || (rc = t_first.reserve(size)) || (rc = d_dup.reserve(n_reads)) ||
+        (rc = d_n.reserve(1)) || (paired && (rc = d_paired.reserve(n_reads))))
+        return done(rc);
+#define DD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(VGL_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    DD(cudaMemcpyAsync(d_key.p, start_key, (size_t)n_reads * 8, cudaMemcpyHostToDevice, s));
+    if (paired) DD(cudaMemcpyAsync(d_paired.p, paired, n_reads, cudaMemcpyHostToDevice, s));
+    DD(cudaMemsetAsync(t_key.p, 0xff, (size_t)size * 8, s));
+    DD(cudaMemsetAsync(t_first.p, 0xff, (size_t)size * 4, s));
+    DD(cudaMemsetAsync(d_n.p, 0, sizeof(unsigned int), s));
+    DD(vgl::dedup_launch(n_reads, d_key.p, paired ? d_paired.p : nullptr, size, t_key.p, t_first.p, d_dup.p, d_n.p, s));
+    ctx->launches += 2;
+    unsigned int n_dup = 0;
+    DD(cudaMemcpyAsync(is_dup, d_dup.p, n_reads, cudaMemcpyDeviceToHost, s));
+    DD(cudaMemcpyAsync(&n_dup, d_n.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    DD(cudaStreamSynchronize(s));
+#undef DD
+    if (n_kept) *n_kept = (uint64_t)n_reads - n_dup;
+    return done(VGL_OK);
+}
+
 int vgl_hc_samples_begin(vgl_ctx* ctx, int32_t n_samples) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");

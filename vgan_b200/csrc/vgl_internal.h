@@ -228,6 +228,10 @@ struct ReconWorkDev {  // scratch
 };
 constexpr uint32_t kReconNoRead = 0xffffffffu;
 // hist and cursor must be zero and order all kReconNoRead on entry.
+// Duplicate removal on the device: table_size a power of two >= 2 n, tab_key all ones and tab_first all ones on entry, *n_dup zero.
+cudaError_t dedup_launch(uint32_t n, const unsigned long long* key, const uint8_t* paired, uint32_t table_size, unsigned long long* tab_key,
+                         uint32_t* tab_first, uint8_t* is_dup, unsigned int* n_dup, cudaStream_t s);
+
 // The narrow arrays of a vgl_hc_raw, widened on the device: out[i] = base + counts[0] + ... + counts[i-1] for i in [0, n]
 // (tile_scratch: n / 4096 + 1 words); 16-bit offsets to 32 bits.
 cudaError_t raw_launch_offsets_from_counts(const uint8_t* counts, uint32_t n, uint32_t base, uint32_t* tile_scratch, uint32_t* out,

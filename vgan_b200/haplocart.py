@@ -175,6 +175,19 @@ class Haplocart:
     def synchronize(self):
         check(gpu.vgl_synchronize(self.ctx))
 
+    def dedup(self, alns):
+        """Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:20-110) on the device: (is_dup mask, reads kept)."""
+        n = len(alns)
+        keys = np.zeros(max(n, 1), dtype=np.uint64)
+        check(_lib.host.vgh_dedup_keys(C.byref(alns.view), keys.ctypes.data_as(C.c_void_p)))
+        paired = alns.arrays().get("paired")
+        pz = np.ascontiguousarray(paired, dtype=np.uint8) if paired is not None and len(paired) == n and n else None
+        mask = np.zeros(max(n, 1), dtype=np.uint8)
+        kept = C.c_uint64()
+        check(gpu.vgl_dedup(self.ctx, n, keys.ctypes.data_as(C.c_void_p), pz.ctypes.data_as(C.c_void_p) if pz is not None else None,
+                            mask.ctypes.data_as(C.c_void_p), C.byref(kept)))
+        return mask[:n].astype(bool), int(kept.value)
+
     def logterm_launches(self):
         """Read-kernel launches so far that took the log-term kernel (the batch's meta allowed it)."""
         return int(gpu.vgl_hc_logterm_launches(self.ctx))
