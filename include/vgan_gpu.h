@@ -412,6 +412,27 @@ int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, d
                             int32_t* n_post_out, int32_t* status_out);
 
 /* ------------------------------------------------------------------------------------------- */
+/* GAM wire decode on the device                                                               */
+/* ------------------------------------------------------------------------------------------- */
+/* readGAM (src/readGAM.h:20-68) hands every vg::Alignment of the stream to a lambda that keeps sequence, path, mapping_quality,
+ * quality, read_paired and identity and drops identity == 0; it is single-threaded protobuf parsing.  Here the host only
+ * inflates the stream and walks its framing (vgh_gam_frame, include/vgan_host.h: offset and length of every serialized
+ * vg.Alignment in the inflated bytes); the messages are parsed ON THE DEVICE, one thread each, straight into the raw-alignment
+ * arrays the reconstruction kernels read, and flow on through reconstruction, packing and the read kernel like
+ * vgl_hc_accumulate_raw.  Reads with identity < 1e-10 are left out, as the hot loop leaves them out (src/HaploCart.cpp:411).
+ * All pointers are HOST pointers; *n_reads_out (optional) receives the number of reads that entered the sample.
+ * A message that does not parse surfaces as VGL_ERR_BAD_READ at vgl_hc_finalize.                                         */
+int vgl_hc_accumulate_gam(vgl_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* msg_off, const uint32_t* msg_len,
+                          uint64_t n_msgs, uint64_t* n_reads_out);
+/* The decoded alignments of at most one chunk of messages (131072), copied back for inspection and tests (every output may be
+ * NULL).  totals6 = {reads kept, mappings, edits, quality bytes, edit-sequence bytes, aligned-string capacity}; arrays as in
+ * vgl_hc_raw (map_node carries is_reverse in bit 31); read_index[r] = index of the message read r came from.            */
+int vgl_gam_decode(vgl_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* msg_off, const uint32_t* msg_len, uint64_t n_msgs,
+                   uint32_t* totals6, uint32_t* qual_off, uint8_t* qual, uint8_t* mapq, uint32_t* map_off, uint32_t* map_node,
+                   uint32_t* map_offset, uint32_t* edit_off, uint16_t* edit_from, uint16_t* edit_to, uint32_t* edit_seq_off,
+                   uint8_t* edit_seq, uint16_t* seq_len, uint32_t* read_index, uint32_t* str_off);
+
+/* ------------------------------------------------------------------------------------------- */
 /* Duplicate removal                                                                           */
 /* ------------------------------------------------------------------------------------------- */
 /* Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:68-110; update_for_single, :20-39) runs directly in front of the hot

@@ -77,6 +77,14 @@ int vgh_gam_parse(const void* bytes, size_t n, int drop_unmapped, vgh_gam** out)
 const vgh_alignments* vgh_gam_view(const vgh_gam* g);
 void vgh_gam_destroy(vgh_gam* g);
 
+/* GAM framing for the DEVICE-side decoder (vgl_hc_accumulate_gam, include/vgan_gpu.h): inflates the stream (BGZF members in
+ * parallel) and walks the group / item framing; the vg.Alignment messages themselves are parsed on the GPU.
+ * vgh_gam_frames_view returns the number of messages and the inflated bytes plus every message's offset and length.     */
+typedef struct vgh_gam_frames vgh_gam_frames;
+int vgh_gam_frame(const void* bytes, size_t n, vgh_gam_frames** out);
+int64_t vgh_gam_frames_view(const vgh_gam_frames* f, const uint8_t** bytes, uint64_t* n_bytes, const uint64_t** msg_off, const uint32_t** msg_len);
+void vgh_gam_frames_destroy(vgh_gam_frames* f);
+
 /* reconstruct_graph_sequence for read r: aligned graph string, aligned read string, one size per
  * EDIT.  Buffers hold `cap` entries.                                                           */
 int vgh_reconstruct(const vgh_graph* g, const vgh_alignments* a, int64_t r, char* graph_seq, char* read_seq,

@@ -385,3 +385,103 @@ def test_device_dedup_equals_the_reference_scan(small):
     assert mask.tolist() == [False, False, True, True] and kept == 2
     assert np.array_equal(mask, vb.host.dedup(alns)[0])
     hc.close()
+
+
+# ---- GAM wire decode on the device (src/readGAM.h:20-68) ----------------------------------------------
+def _expected_flat(alns_d):
+    """The flat arrays the device decoder must produce for a list of alignments decoded by oracle/gam_py.py (the independent
+    Python reader): reads with identity < 1e-10 left out."""
+    kept = [(i, a) for i, a in enumerate(alns_d) if not (a["identity"] < 1e-10)]
+    maps = [m for _, a in kept for m in a["mappings"]]
+    edits = [e for m in maps for e in m["edits"]]
+    cum = lambda xs: np.concatenate([[0], np.cumsum(xs)]).astype(np.uint32)
+    cap = [(sum(e["from_length"] + e["to_length"] + len(e["sequence"]) for m in a["mappings"] for e in m["edits"]) + 3) // 4 * 4 for _, a in kept]
+    return {"n_reads": len(kept), "read_index": np.array([i for i, _ in kept], dtype=np.uint32),
+            "qual_off": cum([len(a["quality"]) for _, a in kept]), "qual": np.frombuffer(b"".join(a["quality"] for _, a in kept), dtype=np.uint8),
+            "mapq": np.array([a["mapping_quality"] for _, a in kept], dtype=np.uint8),
+            "seq_len": np.array([len(a["sequence"]) for _, a in kept], dtype=np.uint16),
+            "map_off": cum([len(a["mappings"]) for _, a in kept]),
+            "map_node": np.array([m["node_id"] | (0x80000000 if m["is_reverse"] else 0) for m in maps], dtype=np.uint32),
+            "map_offset": np.array([m["offset"] for m in maps], dtype=np.uint32),
+            "edit_off": cum([len(m["edits"]) for m in maps]),
+            "edit_from": np.array([e["from_length"] for e in edits], dtype=np.uint16),
+            "edit_to": np.array([e["to_length"] for e in edits], dtype=np.uint16),
+            "edit_seq_off": cum([len(e["sequence"]) for e in edits]),
+            "edit_seq": np.frombuffer(b"".join(e["sequence"] for e in edits), dtype=np.uint8), "str_off": cum(cap)}
+
+
+@pytest.mark.parametrize("name", ["test_reads.gam", "J2a1a1a1.gam", "all_the_same.gam", "all_the_same_reverse.gam", "two_unique.gam"])
+def test_device_gam_decoder_on_the_reference_fixtures(name):
+    import os
+    hc = vb.Haplocart()
+    got = hc.decode_gam(vb.GamFrames(path=os.path.join(H.GOLDEN, name)))
+    want = _expected_flat(H.decoded_fixture(name))
+    assert got["n_reads"] == want["n_reads"] > 0
+    for k, v in want.items():
+        if k != "n_reads":
+            assert np.array_equal(got[k], v), (name, k)
+    hc.close()
+
+
+def test_device_gam_decoder_corner_messages(small):
+    """Hand-encoded streams: unmapped reads (identity 0 and 1e-12) dropped, empty quality, reverse strand, insertions with
+    sequences, an uncompressed stream, several groups, and a truncated message that must raise, not guess."""
+    reads = _edge_reads(small)
+    reads[2]["identity"] = 0.0
+    reads[5]["identity"] = 1e-12
+    data = H.encode_gam(reads, group=4)
+    hc = vb.Haplocart()
+    got = hc.decode_gam(vb.GamFrames(data=data))
+    for r in reads:
+        r.setdefault("read_paired", False)
+    want = _expected_flat(reads)
+    assert got["n_reads"] == len(reads) - 2 and got["read_index"].tolist() == [i for i in range(len(reads)) if i not in (2, 5)]
+    for k, v in want.items():
+        if k != "n_reads":
+            assert np.array_equal(got[k], v), k
+    import gzip
+    same = hc.decode_gam(vb.GamFrames(data=gzip.compress(data)))
+    assert all(np.array_equal(same[k], got[k]) for k in want if k != "n_reads")
+    # a message cut short inside its path: framing still walks (the length prefix is intact), the device parser reports it
+    one = H.encode_gam(reads[:1])
+    msg_start = one.index(reads[0]["sequence"]) - 2
+    broken = bytearray(one)
+    broken[msg_start + 2 + len(reads[0]["sequence"]) + 1] = 0x7f     # the path's length now runs past the end of the message
+    with pytest.raises(_lib.VglError):
+        hc.decode_gam(vb.GamFrames(data=bytes(broken)))
+    hc.close()
+
+
+def test_gam_route_equals_the_host_reader_route(small):
+    alns = small.reads(1500, seed=611, sub_rate=0.01, indel_rate=0.004, fixed_len=0, damage=True)
+    data = H.encode_gam([dict(a, read_paired=False) for a in _alns_to_dicts(alns)], group=100)
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    host = vb.Alignments.from_gam_bytes(data)
+    want = hc.run_sample([vb.PackedBatch(small.graph, host)])
+    n0 = hc.logterm_launches()
+    hc.reset()
+    n = hc.update_gam(vb.GamFrames(data=data))
+    got = hc.get_posterior()
+    assert n == vb.PackedBatch(small.graph, host).n_reads and hc.logterm_launches() == n0 + 1
+    assert got["maxh_index"] == want["maxh_index"] and H.rel_err(got["final_vec"], want["final_vec"]) < 1e-13
+    final, argmax, _ = _oracle(small, host)
+    _check(got, final, argmax, small)
+    hc.close()
+
+
+def _alns_to_dicts(alns):
+    a = alns.arrays()
+    out = []
+    for r in range(len(alns)):
+        maps = []
+        for m in range(int(a["map_off"][r]), int(a["map_off"][r + 1])):
+            eds = [{"from_length": int(a["edit_from"][e]), "to_length": int(a["edit_to"][e]),
+                    "sequence": a["edit_seq"][int(a["edit_seq_off"][e]):int(a["edit_seq_off"][e + 1])].tobytes()}
+                   for e in range(int(a["edit_off"][m]), int(a["edit_off"][m + 1]))]
+            maps.append({"node_id": int(a["map_node"][m]), "offset": int(a["map_offset"][m]), "is_reverse": bool(a["map_rev"][m]), "edits": eds})
+        out.append({"sequence": a["seq"][int(a["seq_off"][r]):int(a["seq_off"][r + 1])].tobytes(),
+                    "quality": a["qual"][int(a["qual_off"][r]):int(a["qual_off"][r + 1])].tobytes(),
+                    "mapping_quality": int(a["mapq"][r]), "identity": float(a["identity"][r]), "mappings": maps})
+    return out

@@ -5,6 +5,6 @@ _lib.py (ctypes), host.py (handles over the host library), haplocart.py (the ref
 interface over the device library).  No CPU fallback exists."""
 from . import _lib  # noqa: F401  (raises if the libraries are not built)
 from .haplocart import DeviceBatch, Haplocart  # noqa: F401
-from .host import Alignments, Feeder, Graph, HcTables, HcTree, PackedBatch, RawBatch, WireBatch, SynthHaplocart, reconstruct  # noqa: F401
+from .host import Alignments, Feeder, GamFrames, Graph, HcTables, HcTree, PackedBatch, RawBatch, WireBatch, SynthHaplocart, reconstruct  # noqa: F401
 from .euka import Euka, EukaPackedBatch, EukaTables, SynthEuka, DHIGH5P_PROF, DHIGH3P_PROF  # noqa: F401
 from .soibean import Soibean, SoibeanPackedBatch, SoibeanTables, soibean_freqs7  # noqa: F401

@@ -149,6 +149,8 @@ GPU_SYMBOLS = {
     "vgl_euka_run_raw": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P]),
     "vgl_launch_count": (C.c_uint64, [_P]),
     "vgl_hc_logterm_launches": (C.c_uint64, [_P]),
+    "vgl_hc_accumulate_gam": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "vgl_gam_decode": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64] + [_P] * 15),
     "vgl_dedup": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "vgl_hc_samples_begin": (C.c_int, [_P, C.c_int32]),
     "vgl_hc_sample_select": (C.c_int, [_P, C.c_int32]),
@@ -166,6 +168,9 @@ HOST_SYMBOLS = {
     "vgh_hc_wire_destroy": (None, [_P]),
     "vgh_euka_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
     "vgh_hc_raw_build": (C.c_int, [C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "vgh_gam_frame": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "vgh_gam_frames_view": (C.c_int64, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(_P), C.POINTER(_P)]),
+    "vgh_gam_frames_destroy": (None, [_P]),
     "vgh_dedup_keys": (C.c_int, [C.POINTER(vgh_alignments), _P]),
     "vgh_hc_feeder_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P)]),
     "vgh_hc_feed": (C.c_int, [_P, _P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64]),

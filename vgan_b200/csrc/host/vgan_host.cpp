@@ -6,6 +6,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -94,6 +95,30 @@ struct Cursor {
         }
     }
 };
+
+// The framing of a GAM stream: groups of "count, then count length-prefixed items"; the first item of a group is the type
+// tag "GAM", the others are serialized vg.Alignment messages.  A first item that does not look like a type tag at all is a
+// message of a legacy (untagged) stream, as libvgio reads it.
+int scan_gam_framing(const uint8_t* raw_p, size_t raw_n, std::vector<std::pair<const uint8_t*, const uint8_t*>>& msgs) {
+    Cursor c{raw_p, raw_p + raw_n, true};
+    while (c.ok && c.p < c.end) {
+        const uint64_t count = c.varint();
+        for (uint64_t k = 0; c.ok && k < count; ++k) {
+            Cursor item = c.sub();
+            if (!c.ok) break;
+            if (k == 0) {
+                const size_t len = (size_t)(item.end - item.p);
+                if (len == 3 && memcmp(item.p, "GAM", 3) == 0) continue;
+                bool tag_like = len > 0 && len <= 25;   // type tags are short identifiers ("VG", "GAM", "MultipathAlignment", ...)
+                for (size_t i = 0; tag_like && i < len; ++i) tag_like = isalnum(item.p[i]) != 0;
+                if (tag_like) return fail(VGH_ERR_FORMAT, "unexpected type tag in GAM stream");
+            }
+            msgs.emplace_back(item.p, item.end);
+        }
+    }
+    if (!c.ok) return fail(VGH_ERR_FORMAT, "truncated GAM stream");
+    return VGH_OK;
+}
 
 // One serialized vg.Alignment (field numbers as on the wire).
 bool parse_alignment(Cursor c, int drop_unmapped, vgh_gam& out) {
@@ -326,22 +351,7 @@ static int vgh_gam_parse__impl(const void* bytes, size_t n, int drop_unmapped, v
     // pieces of their own; the pieces are then appended in order.  readGAM itself (vg::io::for_each, src/readGAM.h:20-68) is
     // single-threaded protobuf parsing.
     std::vector<std::pair<const uint8_t*, const uint8_t*>> msgs;
-    {
-        Cursor c{raw_p, raw_p + raw_n, true};
-        while (c.ok && c.p < c.end) {
-            const uint64_t count = c.varint();  // group: count, then the "GAM" tag, then count-1 messages
-            for (uint64_t k = 0; c.ok && k < count; ++k) {
-                Cursor item = c.sub();
-                if (!c.ok) break;
-                if (k == 0) {
-                    if (item.end - item.p != 3 || memcmp(item.p, "GAM", 3) != 0) return fail(VGH_ERR_FORMAT, "unexpected type tag in GAM stream");
-                    continue;
-                }
-                msgs.emplace_back(item.p, item.end);
-            }
-        }
-        if (!c.ok) return fail(VGH_ERR_FORMAT, "truncated GAM stream");
-    }
+    if (int rc = scan_gam_framing(raw_p, raw_n, msgs)) return rc;
     int n_threads = 1;
 #ifdef _OPENMP
     n_threads = omp_get_max_threads();
@@ -1682,6 +1692,63 @@ const char* vgh_hc_tree_clade_name(const vgh_hc_tree* t, int32_t clade) {
 }
 void vgh_hc_tree_destroy(vgh_hc_tree* t) { delete t; }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// GAM framing for the device-side decoder (vgl_hc_accumulate_gam): inflate + framing scan only; the messages themselves are
+// parsed on the GPU
+// ------------------------------------------------------------------------------------------------
+struct vgh_gam_frames {
+    std::vector<uint8_t> inflated;      // empty when the input was a plain stream and `bytes` points into the caller's buffer
+    const uint8_t* bytes = nullptr;
+    size_t n_bytes = 0;
+    std::vector<uint64_t> msg_off;      // byte offset of every vg.Alignment message
+    std::vector<uint32_t> msg_len;
+};
+extern "C" {
+static int vgh_gam_frame__impl(const void* bytes, size_t n, vgh_gam_frames** out) {
+    if (!out || (!bytes && n)) return fail(VGH_ERR_INVALID, "bad arguments");
+    vgh_gam_frames* F = new vgh_gam_frames();
+    const uint8_t* raw_p = (const uint8_t*)bytes;
+    if (n >= 2 && raw_p[0] == 0x1f && raw_p[1] == 0x8b) {
+        if (int rc = inflate_all(raw_p, n, F->inflated)) { delete F; return rc; }
+    } else {
+        F->inflated.assign(raw_p, raw_p + n);   // the frames own their bytes (the caller's buffer may go away)
+    }
+    F->bytes = F->inflated.data();
+    F->n_bytes = F->inflated.size();
+    std::vector<std::pair<const uint8_t*, const uint8_t*>> msgs;
+    if (int rc = scan_gam_framing(F->bytes, F->n_bytes, msgs)) { delete F; return rc; }
+    F->msg_off.reserve(msgs.size());
+    F->msg_len.reserve(msgs.size());
+    for (const auto& m : msgs) {
+        if ((size_t)(m.second - m.first) > 0x7fffffffu) { delete F; return fail(VGH_ERR_FORMAT, "message too long"); }
+        F->msg_off.push_back((uint64_t)(m.first - F->bytes));
+        F->msg_len.push_back((uint32_t)(m.second - m.first));
+    }
+    *out = F;
+    return VGH_OK;
+}
+int vgh_gam_frame(const void* bytes, size_t n, vgh_gam_frames** out) {
+    try {
+        return vgh_gam_frame__impl(bytes, n, out);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_frame: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_frame: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_gam_frame: unknown C++ exception");
+    }
+}
+int64_t vgh_gam_frames_view(const vgh_gam_frames* f, const uint8_t** bytes, uint64_t* n_bytes, const uint64_t** msg_off, const uint32_t** msg_len) {
+    if (!f) return -1;
+    if (bytes) *bytes = f->bytes;
+    if (n_bytes) *n_bytes = f->n_bytes;
+    if (msg_off) *msg_off = f->msg_off.data();
+    if (msg_len) *msg_len = f->msg_len.data();
+    return (int64_t)f->msg_off.size();
+}
+void vgh_gam_frames_destroy(vgh_gam_frames* f) { delete f; }
 }  // extern "C"
 
 // No C++ exception crosses the C ABI (allocation failures on crafted inputs included): every entry point that can

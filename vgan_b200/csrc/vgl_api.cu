@@ -821,6 +821,38 @@ int vgl_hc_set_graph(vgl_ctx* ctx, int64_t min_id, int64_t n_nodes, const int64_
     return VGL_OK;
 }
 
+// Lanes of a device-built batch: the reads of one mapping quality take one run of groups (a "slot"; its last group filled up with
+// unused lanes), so that no group mixes two mapping qualities -- the segments of vgl_hc_batch_meta, which let the log-term read
+// kernel run.  With more than VGL_HC_MAX_SEGS distinct values: one slot, groups by shape only.
+struct SlotPlan {
+    uint32_t n_slots = 1;
+    uint32_t lane_base[VGL_HC_MAX_SEGS] = {0};
+    uint8_t slot_of_mapq[128] = {0};
+    size_t G = 0;                 // groups of the batch
+    vgl::HcBatchMeta segs;        // n_segs / seg_mapq / seg_end (valid and qual_max are the producer's business)
+};
+static SlotPlan plan_slots(const uint32_t mq_count[128], size_t n) {
+    SlotPlan P;
+    int n_distinct = 0;
+    for (int q = 0; q < 128; ++q) n_distinct += mq_count[q] ? 1 : 0;
+    P.G = (n + 31) / 32;
+    if (n_distinct >= 1 && n_distinct <= VGL_HC_MAX_SEGS) {
+        P.n_slots = 0;
+        P.G = 0;
+        for (int q = 0; q < 128; ++q) {
+            if (!mq_count[q]) continue;
+            P.slot_of_mapq[q] = (uint8_t)P.n_slots;
+            P.lane_base[P.n_slots] = (uint32_t)(P.G * 32);
+            P.G += (mq_count[q] + 31) / 32;
+            P.segs.seg_mapq[P.n_slots] = (uint8_t)q;
+            P.segs.seg_end[P.n_slots] = (uint32_t)P.G;
+            ++P.n_slots;
+        }
+        P.segs.n_segs = P.n_slots;
+    }
+    return P;
+}
+
 // Reads [ra, rb) of `raw`: H2D of their slices on `copy_stream` into staging set `R`, then reconstruction and packing on
 // ctx->stream; fills the read kernel's batch descriptor.  The slices keep their absolute indices (offsets into the
 // whole batch): the device pointers are shifted back by each slice's first element and only ever dereferenced inside.
@@ -835,38 +867,16 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
     const size_t sa = narrow_only ? raw->edit_seq_off[0] : raw->edit_seq_off[ea];
     const size_t nseq = (narrow_only ? raw->edit_seq_off[1] : raw->edit_seq_off[eb]) - sa;
     const size_t ca = raw->str_off[ra], ncap = raw->str_off[rb] - ca;
-    // Lanes: the reads of one mapping quality take one run of groups (a "slot"; its last group filled up with unused lanes), so
-    // that no group mixes two mapping qualities -- the segments of vgl_hc_batch_meta, which let the log-term read kernel run.
-    // With more than VGL_HC_MAX_SEGS distinct values: one slot, groups by shape only.
     uint32_t mq_count[128];
     memset(mq_count, 0, sizeof(mq_count));
     for (size_t r = ra; r < rb; ++r) mq_count[raw->mapq[r] & 127u] += 1;
-    int n_distinct = 0;
-    for (int q = 0; q < 128; ++q) n_distinct += mq_count[q] ? 1 : 0;
-    const bool segmented = n_distinct >= 1 && n_distinct <= VGL_HC_MAX_SEGS;
-    vgl::HcBatchMeta segs;
-    uint32_t n_slots = 1, lane_base[VGL_HC_MAX_SEGS] = {0};
-    uint8_t slot_of_mapq[128];
-    memset(slot_of_mapq, 0, sizeof(slot_of_mapq));
-    size_t G = (n + 31) / 32;
-    if (segmented) {
-        n_slots = 0;
-        G = 0;
-        for (int q = 0; q < 128; ++q) {
-            if (!mq_count[q]) continue;
-            slot_of_mapq[q] = (uint8_t)n_slots;
-            lane_base[n_slots] = (uint32_t)(G * 32);
-            G += (mq_count[q] + 31) / 32;
-            segs.seg_mapq[n_slots] = (uint8_t)q;
-            segs.seg_end[n_slots] = (uint32_t)G;
-            ++n_slots;
-        }
-        segs.n_segs = n_slots;
-    }
+    const SlotPlan plan = plan_slots(mq_count, n);
+    const uint32_t n_slots = plan.n_slots;
+    const size_t G = plan.G;
     if (seg_out) {
-        seg_out->n_segs = segs.n_segs;
-        memcpy(seg_out->seg_mapq, segs.seg_mapq, sizeof(segs.seg_mapq));
-        memcpy(seg_out->seg_end, segs.seg_end, sizeof(segs.seg_end));
+        seg_out->n_segs = plan.segs.n_segs;
+        memcpy(seg_out->seg_mapq, plan.segs.seg_mapq, sizeof(plan.segs.seg_mapq));
+        memcpy(seg_out->seg_end, plan.segs.seg_end, sizeof(plan.segs.seg_end));
     }
     // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read (per slot)
     const size_t col_cap = ncap / 128 + (size_t)n_slots * 1024 + G + 1, map_cap = G + 4096;
@@ -956,8 +966,8 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
                          R.hist3.p + 4096 * (size_t)n_slots, R.hist3.p + 8192 * (size_t)n_slots, R.order.p, R.grp_cb.p, R.grp_mb.p};
     Wd.n_slots = n_slots;
     Wd.n_lanes = (uint32_t)(G * 32);
-    memcpy(Wd.lane_base, lane_base, sizeof(lane_base));
-    memcpy(Wd.slot_of_mapq, slot_of_mapq, sizeof(slot_of_mapq));
+    memcpy(Wd.lane_base, plan.lane_base, sizeof(plan.lane_base));
+    memcpy(Wd.slot_of_mapq, plan.slot_of_mapq, sizeof(plan.slot_of_mapq));
     VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->cur_err, s));
     VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p,
                                  R.o_mapq.p, ctx->cur_err, s));
@@ -1138,6 +1148,153 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* w) {
 // removal, microseconds of GPU work, so the per-sample fixed costs -- the 7.7 MB bit matrix of K2, K3's launch, the result copy
 // and the host synchronisation -- are paid once per pass instead)
 // -------------------------------------------------------------------------------------------
+// -------------------------------------------------------------------------------------------
+// GAM wire decode on the device: framing from the host (vgh_gam_frame), messages parsed on the GPU straight
+// into the raw-alignment arrays, then the same reconstruction + packing + read kernel as the raw route
+// -------------------------------------------------------------------------------------------
+namespace {
+struct GamScratch {
+    DevBuf<uint8_t> bytes, keep;
+    DevBuf<unsigned long long> off;
+    DevBuf<uint32_t> len, counts, small;   // small: totals[6] | mapq_hist[128] | qual_max
+};
+GamScratch g_gam[VGL_HC_MAX_PEERS];   // one per device (a context decodes on its own device)
+
+// Decodes messages [c0, c1) into staging set R; returns the kept reads and their value ranges.
+int gam_decode_chunk(vgl_ctx* ctx, const uint8_t* bytes, const uint64_t* msg_off, const uint32_t* msg_len, size_t c0, size_t c1,
+                     vgl_ctx::RawDev& R, bool want_index, uint32_t totals[6], uint32_t mq_count[128], uint32_t* qual_max) {
+    cudaStream_t s = ctx->stream;
+    GamScratch& S = g_gam[ctx->device % VGL_HC_MAX_PEERS];
+    const size_t n = c1 - c0;
+    const uint64_t b0 = msg_off[c0], b1 = msg_off[c1 - 1] + msg_len[c1 - 1];
+    VGL_CUDA(cudaStreamSynchronize(s));   // the scratch and the staging set are about to be rewritten
+    if (int rc = S.bytes.reserve((size_t)(b1 - b0) + 16)) return rc;
+    if (int rc = S.off.reserve(n)) return rc;
+    if (int rc = S.len.reserve(n)) return rc;
+    if (int rc = S.keep.reserve(n)) return rc;
+    if (int rc = S.counts.reserve(6 * n)) return rc;
+    if (int rc = S.small.reserve(6 + 128 + 1)) return rc;
+    VGL_CUDA(cudaMemcpyAsync(S.bytes.p, bytes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
+    VGL_CUDA(cudaMemcpyAsync(S.off.p, msg_off + c0, n * 8, cudaMemcpyHostToDevice, s));
+    VGL_CUDA(cudaMemcpyAsync(S.len.p, msg_len + c0, n * 4, cudaMemcpyHostToDevice, s));
+    VGL_CUDA(cudaMemsetAsync(S.small.p, 0, (6 + 128 + 1) * sizeof(uint32_t), s));
+    VGL_CUDA(vgl::gam_launch_count(S.bytes.p, reinterpret_cast<const uint64_t*>(S.off.p), S.len.p, (uint32_t)n, b0, S.counts.p, S.keep.p,
+                                   S.small.p + 6, S.small.p + 6 + 128, S.small.p, ctx->cur_err, s));
+    ctx->launches += 2;
+    uint32_t host_small[6 + 128 + 1];
+    VGL_CUDA(cudaMemcpyAsync(host_small, S.small.p, sizeof(host_small), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    memcpy(totals, host_small, 6 * sizeof(uint32_t));
+    memcpy(mq_count, host_small + 6, 128 * sizeof(uint32_t));
+    *qual_max = host_small[6 + 128];
+    const size_t nr = totals[0], nm = totals[1], ne = totals[2], nq = totals[3], nseq = totals[4];
+#define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
+    RSV(R.qual_off, nr + 1); RSV(R.str_off, nr + 1); RSV(R.map_off, nr + 1); RSV(R.mapq, nr); RSV(R.qual, nq);
+    RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
+    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq); RSV(R.seq_len, nr); RSV(R.read_index, nr);
+#undef RSV
+    vgl::GamOutDev o{R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p, R.edit_off.p, R.edit_from.p,
+                     R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p, R.seq_len.p, want_index ? R.read_index.p : nullptr};
+    VGL_CUDA(vgl::gam_launch_fill(S.bytes.p, reinterpret_cast<const uint64_t*>(S.off.p), S.len.p, (uint32_t)n, b0, S.counts.p, S.keep.p,
+                                  S.small.p, o, ctx->cur_err, s));
+    ctx->launches += 1;
+    return VGL_OK;
+}
+}  // namespace
+
+extern "C" int vgl_hc_accumulate_gam(vgl_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* msg_off, const uint32_t* msg_len,
+                                     uint64_t n_msgs, uint64_t* n_reads_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
+    if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
+    if (n_msgs && (!bytes || !msg_off || !msg_len)) return fail(VGL_ERR_INVALID, "null arrays");
+    if (n_reads_out) *n_reads_out = 0;
+    for (uint64_t k = 0; k < n_msgs; ++k)
+        if (msg_off[k] + msg_len[k] > n_bytes || (k && msg_off[k] < msg_off[k - 1])) return fail(VGL_ERR_INVALID, "message %llu lies outside the byte buffer", (unsigned long long)k);
+    cudaStream_t s = ctx->stream;
+    const size_t step = (size_t)ctx->chunk_groups * VGL_HC_LANES;
+    for (size_t c0 = 0; c0 < n_msgs; c0 += step) {
+        const size_t c1 = std::min<size_t>(n_msgs, c0 + step);
+        vgl_ctx::RawDev& R = ctx->rawdev[0];
+        uint32_t totals[6], mq_count[128], qmax = 0;
+        if (int rc = gam_decode_chunk(ctx, bytes, msg_off, msg_len, c0, c1, R, false, totals, mq_count, &qmax)) return rc;
+        const size_t n = totals[0], ne = totals[2], ncap = totals[5];
+        if (n_reads_out) *n_reads_out += n;
+        if (n == 0) continue;
+        const SlotPlan plan = plan_slots(mq_count, n);
+        const size_t G = plan.G, col_cap = ncap / 128 + (size_t)plan.n_slots * 1024 + G + 1, map_cap = G + 4096;
+#define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
+        RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
+        RSV(R.hist3, 3 * 4096 * (size_t)plan.n_slots); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
+        RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
+        RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
+#undef RSV
+        R.col_cap_blks = (uint32_t)col_cap;
+        R.map_cap_blks = (uint32_t)map_cap;
+        VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * (size_t)plan.n_slots * sizeof(uint32_t), s));
+        VGL_CUDA(cudaMemsetAsync(R.order.p, 0xff, G * 32 * sizeof(uint32_t), s));
+        VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
+        const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
+        const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p, R.edit_off.p,
+                                  R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p, nullptr, nullptr};
+        vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p,
+                             R.hist3.p + 4096 * (size_t)plan.n_slots, R.hist3.p + 8192 * (size_t)plan.n_slots, R.order.p, R.grp_cb.p, R.grp_mb.p};
+        Wd.n_slots = plan.n_slots;
+        Wd.n_lanes = (uint32_t)(G * 32);
+        memcpy(Wd.lane_base, plan.lane_base, sizeof(plan.lane_base));
+        memcpy(Wd.slot_of_mapq, plan.slot_of_mapq, sizeof(plan.slot_of_mapq));
+        VGL_CUDA(vgl::hc_launch_recon(Rd, Gd, Wd, 0, ctx->cur_err, s));
+        VGL_CUDA(vgl::hc_launch_pack(Rd, Wd, R.col_cap_blks, R.map_cap_blks, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p,
+                                     ctx->cur_err, s));
+        ctx->launches += 6;
+        vgl::HcBatchDev d{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p};
+        vgl::HcBatchMeta meta = plan.segs;
+        meta.valid = true;
+        meta.qual_max = qmax;
+        if (int rc = launch_read(ctx, d, meta)) return rc;
+        R.used = false;   // (synchronised at the next chunk's start: no event needed)
+    }
+    return VGL_OK;
+}
+
+// The decoded alignments of a (small) GAM, copied back in the flat layout, for tests: every array as the raw route sees it.
+extern "C" int vgl_gam_decode(vgl_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* msg_off, const uint32_t* msg_len, uint64_t n_msgs,
+                              uint32_t* totals6, uint32_t* qual_off, uint8_t* qual, uint8_t* mapq, uint32_t* map_off, uint32_t* map_node,
+                              uint32_t* map_offset, uint32_t* edit_off, uint16_t* edit_from, uint16_t* edit_to, uint32_t* edit_seq_off,
+                              uint8_t* edit_seq, uint16_t* seq_len, uint32_t* read_index, uint32_t* str_off) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!totals6) return fail(VGL_ERR_INVALID, "null totals");
+    memset(totals6, 0, 6 * sizeof(uint32_t));
+    if (n_msgs == 0) return VGL_OK;
+    if (n_msgs > (uint64_t)ctx->chunk_groups * VGL_HC_LANES) return fail(VGL_ERR_INVALID, "vgl_gam_decode takes at most one chunk of messages");
+    for (uint64_t k = 0; k < n_msgs; ++k)
+        if (msg_off[k] + msg_len[k] > n_bytes) return fail(VGL_ERR_INVALID, "message %llu lies outside the byte buffer", (unsigned long long)k);
+    vgl_ctx::RawDev& R = ctx->rawdev[0];
+    uint32_t mq_count[128], qmax = 0;
+    int zero = 0;
+    // (standalone use: errors go to a scratch word of the staging set so that no sample is needed)
+    if (int rc = R.s_err.reserve(1)) return rc;
+    int* saved = ctx->cur_err;
+    ctx->cur_err = R.s_err.p;
+    cudaMemcpy(R.s_err.p, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    const int rc = gam_decode_chunk(ctx, bytes, msg_off, msg_len, 0, (size_t)n_msgs, R, true, totals6, mq_count, &qmax);
+    ctx->cur_err = saved;
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    const size_t n = totals6[0], nm = totals6[1], ne = totals6[2], nq = totals6[3], ns = totals6[4];
+    int err = 0;
+#define D2H(dst, src, bytes_) if ((dst) != nullptr && (size_t)(bytes_) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (bytes_), cudaMemcpyDeviceToHost, s))
+    D2H(qual_off, R.qual_off.p, (n + 1) * 4); D2H(qual, R.qual.p, nq); D2H(mapq, R.mapq.p, n); D2H(map_off, R.map_off.p, (n + 1) * 4);
+    D2H(map_node, R.map_node.p, nm * 4); D2H(map_offset, R.map_offset.p, nm * 4); D2H(edit_off, R.edit_off.p, (nm + 1) * 4);
+    D2H(edit_from, R.edit_from.p, ne * 2); D2H(edit_to, R.edit_to.p, ne * 2); D2H(edit_seq_off, R.edit_seq_off.p, (ne + 1) * 4);
+    D2H(edit_seq, R.edit_seq.p, ns); D2H(seq_len, R.seq_len.p, n * 2); D2H(read_index, R.read_index.p, n * 4); D2H(str_off, R.str_off.p, (n + 1) * 4);
+#undef D2H
+    VGL_CUDA(cudaMemcpyAsync(&err, R.s_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaStreamSynchronize(s));
+    if (err) return fail(VGL_ERR_BAD_READ, "malformed vg.Alignment message (or values that do not fit the raw-alignment arrays)");
+    return VGL_OK;
+}
+
 // -------------------------------------------------------------------------------------------
 // duplicate removal on the device (the O(n^2) scan in front of the hot loop, src/HaploCart.cpp:390, src/rmdup.cpp:20-110)
 // -------------------------------------------------------------------------------------------

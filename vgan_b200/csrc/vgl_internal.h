@@ -228,6 +228,24 @@ struct ReconWorkDev {  // scratch
 };
 constexpr uint32_t kReconNoRead = 0xffffffffu;
 // hist and cursor must be zero and order all kReconNoRead on entry.
+// ---------------------------------------------------------------------------------------------------------
+// GAM wire decode on the device (gam_kernels.cu): serialized vg.Alignment messages -> the raw-alignment arrays of ReconRawDev
+// ---------------------------------------------------------------------------------------------------------
+struct GamOutDev {   // where G2 writes; the layout ReconRawDev reads
+    uint32_t* qual_off; uint8_t* qual; uint8_t* mapq; uint32_t* str_off; uint32_t* map_off; uint32_t* map_node; uint32_t* map_offset;
+    uint32_t* edit_off; uint16_t* edit_from; uint16_t* edit_to; uint32_t* edit_seq_off; uint8_t* edit_seq;
+    uint16_t* seq_len;      // may be nullptr
+    uint32_t* read_index;   // may be nullptr: index of the message in the chunk
+};
+// G1 + scan: counts[6][n] (reads, mappings, edits, quality bytes, edit-sequence bytes, string capacity; turned into exclusive
+// offsets in place), keep[n], mapq_hist[128] and qual_max (zero on entry), totals[6].
+cudaError_t gam_launch_count(const uint8_t* bytes, const uint64_t* msg_off, const uint32_t* msg_len, uint32_t n, uint64_t byte_base,
+                             uint32_t* counts, uint8_t* keep, uint32_t* mapq_hist, uint32_t* qual_max, uint32_t* totals, int* err_flag,
+                             cudaStream_t s);
+cudaError_t gam_launch_fill(const uint8_t* bytes, const uint64_t* msg_off, const uint32_t* msg_len, uint32_t n, uint64_t byte_base,
+                            const uint32_t* offs, const uint8_t* keep, const uint32_t* totals, const GamOutDev& out, int* err_flag,
+                            cudaStream_t s);
+
 // Duplicate removal on the device: table_size a power of two >= 2 n, tab_key all ones and tab_first all ones on entry, *n_dup zero.
 cudaError_t dedup_launch(uint32_t n, const unsigned long long* key, const uint8_t* paired, uint32_t table_size, unsigned long long* tab_key,
                          uint32_t* tab_first, uint8_t* is_dup, unsigned int* n_dup, cudaStream_t s);

@@ -175,6 +175,35 @@ class Haplocart:
     def synchronize(self):
         check(gpu.vgl_synchronize(self.ctx))
 
+    def update_gam(self, frames):
+        """Haplocart::update for every alignment of a GAM stream whose framing the host has walked (host.GamFrames): the messages
+        are parsed on the device.  Returns the number of reads that entered the sample."""
+        n = C.c_uint64()
+        check(gpu.vgl_hc_accumulate_gam(self.ctx, frames.bytes_ptr, frames.n_bytes, frames.off_ptr, frames.len_ptr, frames.n_msgs, C.byref(n)))
+        return int(n.value)
+
+    def decode_gam(self, frames):
+        """The device decoder's output for (at most one chunk of) a GAM stream, as a dict of flat numpy arrays (tests)."""
+        tot = np.zeros(6, dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        cap_m = max(frames.n_bytes, 16)   # generous: every mapping / edit / byte of the output costs at least one input byte
+        n = frames.n_msgs
+        out = {"qual_off": np.zeros(n + 1, np.uint32), "qual": np.zeros(cap_m, np.uint8), "mapq": np.zeros(max(n, 1), np.uint8),
+               "map_off": np.zeros(n + 1, np.uint32), "map_node": np.zeros(cap_m, np.uint32), "map_offset": np.zeros(cap_m, np.uint32),
+               "edit_off": np.zeros(cap_m + 1, np.uint32), "edit_from": np.zeros(cap_m, np.uint16), "edit_to": np.zeros(cap_m, np.uint16),
+               "edit_seq_off": np.zeros(cap_m + 1, np.uint32), "edit_seq": np.zeros(cap_m, np.uint8), "seq_len": np.zeros(max(n, 1), np.uint16),
+               "read_index": np.zeros(max(n, 1), np.uint32), "str_off": np.zeros(n + 1, np.uint32)}
+        check(gpu.vgl_gam_decode(self.ctx, frames.bytes_ptr, frames.n_bytes, frames.off_ptr, frames.len_ptr, n, p(tot), p(out["qual_off"]),
+                                 p(out["qual"]), p(out["mapq"]), p(out["map_off"]), p(out["map_node"]), p(out["map_offset"]),
+                                 p(out["edit_off"]), p(out["edit_from"]), p(out["edit_to"]), p(out["edit_seq_off"]), p(out["edit_seq"]),
+                                 p(out["seq_len"]), p(out["read_index"]), p(out["str_off"])))
+        R, M, E, Q, Sq = (int(x) for x in tot[:5])
+        cut = {"qual_off": R + 1, "qual": Q, "mapq": R, "map_off": R + 1, "map_node": M, "map_offset": M, "edit_off": M + 1, "edit_from": E,
+               "edit_to": E, "edit_seq_off": E + 1, "edit_seq": Sq, "seq_len": R, "read_index": R, "str_off": R + 1}
+        res = {k: v[:cut[k]].copy() for k, v in out.items()}
+        res["n_reads"], res["capacity"] = R, int(tot[5])
+        return res
+
     def dedup(self, alns):
         """Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:20-110) on the device: (is_dup mask, reads kept)."""
         n = len(alns)

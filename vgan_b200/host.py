@@ -258,6 +258,29 @@ class RawBatch:
             self.handle = None
 
 
+class GamFrames:
+    """vgh_gam_frame: a GAM stream inflated and its framing walked -- offset and length of every serialized vg.Alignment --
+    for the device-side decoder (Haplocart.update_gam / decode_gam); the messages are not parsed on the host."""
+
+    def __init__(self, data=None, path=None):
+        if path is not None:
+            with open(path, "rb") as fh:
+                data = fh.read()
+        self._data = bytes(data)
+        self.handle = C.c_void_p()
+        buf = C.create_string_buffer(self._data, len(self._data)) if self._data else None
+        check(host.vgh_gam_frame(C.cast(buf, C.c_void_p) if buf is not None else None, len(self._data), C.byref(self.handle)))
+        b, off, ln = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb = C.c_uint64()
+        self.n_msgs = int(host.vgh_gam_frames_view(self.handle, C.byref(b), C.byref(nb), C.byref(off), C.byref(ln)))
+        self.bytes_ptr, self.n_bytes, self.off_ptr, self.len_ptr = b, int(nb.value), off, ln
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            host.vgh_gam_frames_destroy(self.handle)
+            self.handle = None
+
+
 class Feeder:
     """vgh_hc_feeder: the drop-in for the OpenMP read loop (src/HaploCart.cpp:408-421) from flat alignment fields -- chunks of
     reads marshalled by `n_threads` host threads into two page-locked blocks while the GPU works on the chunk before."""
