@@ -629,6 +629,47 @@ def main():
                 d.free()
             del small_dev, small_packed, small_wire
 
+        # file -> result: a GAM stream of one real-sample size, host reader + feeder against the device decoder; and the
+        # duplicate removal that runs in front of the hot loop (src/HaploCart.cpp:390)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers as TH
+            from test_gpu_recon import _alns_to_dicts
+            n_io = min(20000, len(alns))
+            sub = S.reads(n_io, seed=wl["seed"], **wl["kw"])
+            gam_bytes = TH.encode_gam([dict(a, read_paired=False) for a in _alns_to_dicts(sub)], group=1000)
+
+            def via_host():
+                a = vb.Alignments.from_gam_bytes(gam_bytes)
+                hc.reset()
+                feeder.feed(hc, a)
+                return hc.get_posterior(want_ll=False)["maxh_index"]
+
+            def via_device():
+                hc.reset()
+                hc.update_gam(vb.GamFrames(data=gam_bytes))
+                return hc.get_posterior(want_ll=False)["maxh_index"]
+
+            io = {"reads": len(sub), "gam_bytes": len(gam_bytes)}
+            for key, fn in (("ms_gam_bytes_to_call_host_parser", via_host), ("ms_gam_bytes_to_call_device_decoder", via_device)):
+                fn()
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    call = fn()
+                io[key] = (time.perf_counter() - t0) / 5 * 1e3
+                io[key + "_call"] = int(call)
+            hc.dedup(alns)
+            t0 = time.perf_counter()
+            mask, kept = hc.dedup(alns)
+            io["ms_device_dedup_all_reads"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            hmask, hkept = vb.host.dedup(alns)
+            io["ms_host_dedup_all_reads"] = (time.perf_counter() - t0) * 1e3
+            io["dedup_reads"], io["dedup_kept"], io["dedup_same_mask"] = len(alns), int(kept), bool(np.array_equal(mask, hmask))
+            latency["io"] = io
+        except Exception as e:  # the io block must not take the headline down
+            latency["io"] = {"error": repr(e)}
+
     total_reads = reads_local
     if world > 1:
         t = torch.tensor([reads_local], dtype=torch.float64, device="cuda")
