@@ -19,6 +19,8 @@ int main(int argc, char** argv) {
     const int n_reads = argc > 1 ? atoi(argv[1]) : 200;
     const bool compile_only = argc > 2 && std::string(argv[2]) == "--no-gpu";
     const bool on_device = argc > 2 && std::string(argv[2]) == "--device-reconstruction";  // raw alignments, packed on the GPU
+    const bool streamed = argc > 2 && std::string(argv[2]) == "--streamed";                // the feeder: chunks overlapped with the GPU
+    const bool samples = argc > 2 && std::string(argv[2]) == "--samples";                  // the same sample three times in one pass
     vgh_synth_hc* S = nullptr;
     if (vgh_synth_hc_create(101, 300, 1210, 1201, &S)) return 2;
     vgh_gam* gam = nullptr;
@@ -61,9 +63,29 @@ int main(int argc, char** argv) {
         { std::string all = vgh_synth_hc_names(S); size_t a = 0; for (size_t k = 0; k < all.size(); ++k) if (all[k] == '\n') { names.push_back(all.substr(a, k - a)); a = k + 1; } }
         hc.load_tree(names, vgh_synth_hc_parents(S), vgh_synth_hc_children(S));
         hc.reset();
-        if (on_device) hc.update_on_device(algnvector);
-        else hc.update(algnvector, 4);
-        const vgan_b200::Posterior post = hc.get_posterior(true);
+        // duplicate removal on the device: the same mask as the host pass
+        {
+            const std::vector<uint8_t> dup = hc.duplicates(algnvector);
+            std::vector<uint8_t> host_dup(dup.size());
+            int64_t kept = 0;
+            const vgh_alignments fv = flat.view();
+            vgan_b200::check(vgh_dedup(&fv, host_dup.data(), &kept), "host dedup");
+            if (dup != host_dup) { fprintf(stderr, "device and host duplicate masks differ\n"); return 4; }
+        }
+        vgan_b200::Posterior post;
+        if (samples) {
+            hc.begin_samples(3);
+            for (int k = 0; k < 3; ++k) { hc.select_sample(k); hc.update_streamed(algnvector, 2); }
+            const std::vector<vgan_b200::Posterior> all = hc.finish_samples(true);
+            if (all[0].maxh_index != all[2].maxh_index) { fprintf(stderr, "samples of one pass disagree\n"); return 4; }
+            post = all[1];
+        } else {
+            hc.reset();
+            if (on_device) hc.update_on_device(algnvector);
+            else if (streamed) hc.update_streamed(algnvector, 3);
+            else hc.update(algnvector, 4);
+            post = hc.get_posterior(true);
+        }
         printf("call %d %s total %.17g\n", post.maxh_index, names[post.maxh_index].c_str(), post.total_ll);
         for (size_t k = 0; k < post.confidence_vec.size(); ++k)
             printf("clade %s %.17g\n", k == 0 ? names[post.maxh_index].c_str() : hc.clade_name(post.clade_ids[k - 1]), post.confidence_vec[k]);

@@ -102,6 +102,7 @@ public:
     // CUDA context is created here.
     explicit HaplocartGpu(int device = 0) { check(vgl_create(device, &ctx_), "cannot create the GPU context"); }
     ~HaplocartGpu() {
+        if (feeder_) vgh_hc_feeder_destroy(feeder_);
         if (tree_) vgh_hc_tree_destroy(tree_);
         if (tables_) vgh_hc_tables_destroy(tables_);
         if (graph_) vgh_graph_destroy(graph_);
@@ -182,6 +183,61 @@ public:
         check(rc, "likelihood kernel");
     }
 
+    // Same again, and the route to prefer: the reads travel in chunks, `n_threads` host threads marshal one chunk into
+    // page-locked memory while the GPU copies, reconstructs and scores the chunk before (vgh_hc_feed).  The two blocks live as
+    // long as this object: no allocation per sample.
+    template <typename AlignmentInfoPtrVector>
+    void update_streamed(const AlignmentInfoPtrVector& algnvector, int n_threads = 0) {
+        flat_.assign(algnvector);
+        const vgh_alignments v = flat_.view();
+        if (!feeder_) check(vgh_hc_feeder_create(n_threads, 0, &feeder_), "cannot create the feeder");
+        check(vgh_hc_feed(feeder_, ctx_, &v, 0, v.n_reads), "likelihood kernel");
+    }
+
+    // Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:68-110, called at src/HaploCart.cpp:390) on the device:
+    // is_dup[i] takes the place of the reference's vector<bool>.
+    template <typename AlignmentInfoPtrVector>
+    std::vector<uint8_t> duplicates(const AlignmentInfoPtrVector& algnvector) {
+        flat_.assign(algnvector);
+        const vgh_alignments v = flat_.view();
+        std::vector<uint64_t> keys((size_t)v.n_reads);
+        std::vector<uint8_t> is_dup((size_t)v.n_reads);
+        check(vgh_dedup_keys(&v, keys.data()), "duplicate removal");
+        uint64_t kept = 0;
+        check(vgl_dedup(ctx_, (uint32_t)v.n_reads, keys.data(), v.paired, is_dup.data(), &kept), "duplicate removal");
+        return is_dup;
+    }
+
+    // Several samples per pass (the reference loops over samples, src/HaploCart.cpp:303): begin_samples(S), then for every
+    // sample select_sample(s) + update*(...), then finish_samples() -- one collapse, one posterior kernel, one copy back.
+    void begin_samples(int n_samples) {
+        check(vgl_hc_samples_begin(ctx_, n_samples), "begin_samples");
+        n_samples_ = n_samples;
+    }
+    void select_sample(int s) { check(vgl_hc_sample_select(ctx_, s), "select_sample"); }
+    std::vector<Posterior> finish_samples(bool want_final_vec = false) {
+        const size_t S = (size_t)n_samples_;
+        std::vector<double> ll(want_final_vec ? S * (size_t)n_paths_ : 0), total(S), post(S * (size_t)max_post_);
+        std::vector<int32_t> arg(S), n_post(S);
+        check(vgl_hc_finalize_samples(ctx_, want_final_vec ? ll.data() : nullptr, arg.data(), total.data(), post.data(), max_post_, n_post.data(),
+                                      nullptr),
+              "posterior kernel");
+        std::vector<Posterior> out(S);
+        for (size_t k = 0; k < S; ++k) {
+            Posterior& r = out[k];
+            r.maxh_index = arg[k];
+            r.total_ll = total[k];
+            if (want_final_vec) r.final_vec.assign(ll.begin() + (long)(k * (size_t)n_paths_), ll.begin() + (long)((k + 1) * (size_t)n_paths_));
+            r.confidence_vec.assign(post.begin() + (long)(k * (size_t)max_post_), post.begin() + (long)(k * (size_t)max_post_) + n_post[k]);
+            if (tree_) {
+                const int32_t* off = vgh_hc_tree_anc_off(tree_);
+                const int32_t* cl = vgh_hc_tree_anc_clade(tree_);
+                r.clade_ids.assign(cl + off[arg[k]], cl + off[arg[k] + 1]);
+            }
+        }
+        return out;
+    }
+
     // max_element + Haplocart::get_posterior.
     Posterior get_posterior(bool want_final_vec = false) {
         Posterior r;
@@ -207,8 +263,9 @@ private:
     vgh_graph* graph_ = nullptr;
     vgh_hc_tables* tables_ = nullptr;
     vgh_hc_tree* tree_ = nullptr;
+    vgh_hc_feeder* feeder_ = nullptr;
     FlatAlignments flat_;
-    int32_t n_paths_ = 0, max_post_ = 1;
+    int32_t n_paths_ = 0, max_post_ = 1, n_samples_ = 0;
 };
 
 }  // namespace vgan_b200
