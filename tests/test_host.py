@@ -437,6 +437,39 @@ def test_raw_arrays_ship_one_offset_per_read_when_only_first_mappings_start_insi
     assert not r2.first_offset16 and r2.map_offset16
 
 
+def test_feeder_chunk_holds_the_same_arrays_as_the_general_builder():
+    """vgh_hc_feeder_marshal (the narrowing copies, per-thread ranges, runs between skipped reads) against vgh_hc_raw_build on
+    the same reads, for several thread counts and a chunk that holds reads the hot loop skips (identity < 1e-10)."""
+    S = vb.SynthHaplocart(seed=21, n_paths=33, n_rows=310, n_nodes=301)
+    A = S.reads(3000, seed=31, sub_rate=0.02, indel_rate=0.01, fixed_len=0, damage=True)
+    assert (A.arrays()["identity"] < 1e-10).any()
+    as_arr = vb.host._as_array
+    for r0, r1 in [(0, 3000), (17, 1301), (5, 6)]:
+        general = vb.RawBatch(A, r0, r1)          # keeps the arrays `want` points into alive
+        want = general.raw
+        n, nm, ne = int(want.n_reads), int(want.n_maps), int(want.n_edits)
+        w_eoff = as_arr(want.edit_off, nm + 1, np.uint32)
+        w_soff = as_arr(want.edit_seq_off, ne + 1, np.uint32)
+        for threads in (1, 2, 5):
+            f = vb.Feeder(n_threads=threads, chunk_reads=4096)
+            got = f.marshal(A, r0, r1)
+            assert got is not None and (int(got.n_reads), int(got.n_maps), int(got.n_edits)) == (n, nm, ne)
+            for name, count, dt in [("qual_off", n + 1, np.uint32), ("map_off", n + 1, np.uint32), ("str_off", n + 1, np.uint32),
+                                    ("mapq", n, np.uint8), ("map_node16", nm, np.uint16), ("first_offset16", n, np.uint16),
+                                    ("map_n_edits8", nm, np.uint8), ("edit_slen8", ne, np.uint8), ("edit_from8", ne, np.uint8),
+                                    ("edit_to8", ne, np.uint8)]:
+                assert np.array_equal(as_arr(getattr(got, name), count, dt), as_arr(getattr(want, name), count, dt)), (name, threads)
+            nq = int(as_arr(want.qual_off, n + 1, np.uint32)[-1])
+            assert np.array_equal(as_arr(got.qual, nq, np.uint8), as_arr(want.qual, nq, np.uint8))
+            assert np.array_equal(as_arr(got.edit_seq, int(w_soff[-1]), np.uint8), as_arr(want.edit_seq, int(w_soff[-1]), np.uint8))
+            # the wide offset arrays are not built: their end points stand in for them
+            assert list(as_arr(got.edit_off, 2, np.uint32)) == [0, int(w_eoff[-1])]
+            assert list(as_arr(got.edit_seq_off, 2, np.uint32)) == [0, int(w_soff[-1])]
+            assert got.meta.valid == 1 and got.meta.qual_max == want.meta.qual_max
+            assert list(got.meta.mapq_mask) == list(want.meta.mapq_mask)
+            f.close()
+
+
 def test_crafted_bgzf_sizes_do_not_take_the_process_down():
     """A BGZF-looking stream whose member trailers claim ~4 GiB each: rejected with an error code, no huge
     allocation, no exception across the C ABI."""

@@ -1240,6 +1240,51 @@ void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* 
     if (slow_chunks) *slow_chunks = f->slow_chunks;
 }
 
+// The narrowing copies of the feeder, one flat loop per source array.  Compiled once per vector width the host may have
+// (resolved when the library is loaded): 64-bit -> 16 / 8-bit narrowing is one instruction per vector from AVX-512 on.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define VGH_CLONES __attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default")))
+#else
+#define VGH_CLONES
+#endif
+
+VGH_CLONES static void feeder_narrow_mappings(const int64_t* __restrict__ node, const int64_t* __restrict__ offs, const uint8_t* __restrict__ rev,
+                                              const int64_t* __restrict__ eo, uint16_t* __restrict__ on, uint8_t* __restrict__ oc, int64_t n,
+                                              uint64_t* viol, uint64_t* nonzero_off) {
+    uint64_t v = 0, nzo = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);
+        v |= (nd & ~(uint64_t)0x7fff) | (cnt & ~(uint64_t)0xff);
+        on[i] = (uint16_t)((nd & 0x7fff) | (rev[i] ? 0x8000u : 0u));
+        oc[i] = (uint8_t)cnt;
+        nzo += offs[i] != 0;
+    }
+    *viol |= v;
+    *nonzero_off += nzo;
+}
+
+VGH_CLONES static void feeder_narrow_edits(const int32_t* __restrict__ fr, const int32_t* __restrict__ to, const int64_t* __restrict__ so,
+                                           uint8_t* __restrict__ of, uint8_t* __restrict__ ot, uint8_t* __restrict__ os, int64_t n, uint64_t* viol) {
+    uint64_t v = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t f_ = (uint32_t)fr[i], t_ = (uint32_t)to[i];
+        const uint64_t sl = (uint64_t)(so[i + 1] - so[i]);
+        v |= (uint64_t)((f_ | t_) & ~0xffu) | (sl & ~(uint64_t)0xff);
+        of[i] = (uint8_t)f_;
+        ot[i] = (uint8_t)t_;
+        os[i] = (uint8_t)sl;
+    }
+    *viol |= v;
+}
+
+// largest quality byte as the reference sees it (signed char: bytes >= 128 are negative, canonical 0)
+VGH_CLONES static int8_t feeder_max_quality(const int8_t* __restrict__ qb, int64_t n, int8_t mx) {
+    for (int64_t i = 0; i < n; ++i) mx = qb[i] > mx ? qb[i] : mx;
+    return mx;
+}
+
+static constexpr size_t kFeederRunReads = 128;
+
 // Marshals the reads of [ra, rb) that the hot loop keeps (identity >= 1e-10, src/HaploCart.cpp:411) into block `slot`.
 // Two parallel passes over per-thread ranges of reads: (A) how many mappings / edits / bytes each range keeps (read-level
 // offsets only), (B) the copy itself.  Returns 1 when the chunk needs the general builder instead.
@@ -1253,14 +1298,25 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     for (int t = 0; t < T; ++t) {
         const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
         Cnt c;
-        for (size_t k = k0; k < k1; ++k) {
-            const int64_t r = ra + (int64_t)k;
-            if (a->identity[r] < 1e-10) continue;
-            const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
+        size_t kept = 0;
+        for (size_t k = k0; k < k1; ++k) kept += !(a->identity[ra + (int64_t)k] < 1e-10);
+        if (kept == k1 - k0) {   // the usual case, nothing skipped: the counts are differences of the offsets at the range's ends
+            const int64_t rs = ra + (int64_t)k0, re = ra + (int64_t)k1;
+            const int64_t ma = a->map_off[rs], mb = a->map_off[re];
             const int64_t ea = a->edit_off[ma], eb = a->edit_off[mb];
-            c.r += 1; c.m += (uint64_t)(mb - ma); c.e += (uint64_t)(eb - ea);
-            c.q += (uint64_t)(a->qual_off[r + 1] - a->qual_off[r]);
-            c.s += (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
+            c.r = kept; c.m = (uint64_t)(mb - ma); c.e = (uint64_t)(eb - ea);
+            c.q = (uint64_t)(a->qual_off[re] - a->qual_off[rs]);
+            c.s = (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
+        } else {
+            for (size_t k = k0; k < k1; ++k) {
+                const int64_t r = ra + (int64_t)k;
+                if (a->identity[r] < 1e-10) continue;
+                const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
+                const int64_t ea = a->edit_off[ma], eb = a->edit_off[mb];
+                c.r += 1; c.m += (uint64_t)(mb - ma); c.e += (uint64_t)(eb - ea);
+                c.q += (uint64_t)(a->qual_off[r + 1] - a->qual_off[r]);
+                c.s += (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
+            }
         }
         base[(size_t)t + 1] = c;
     }
@@ -1311,56 +1367,17 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
         while (k < k1) {
             if (a->identity[ra + (int64_t)k] < 1e-10) { ++k; continue; }
             size_t ke = k + 1;
-            while (ke < k1 && !(a->identity[ra + (int64_t)ke] < 1e-10)) ++ke;
+            const size_t kcap = std::min(k1, k + kFeederRunReads);   // short runs: the per-read pass below finds the run's lines still in L2
+            while (ke < kcap && !(a->identity[ra + (int64_t)ke] < 1e-10)) ++ke;
             const int64_t rs = ra + (int64_t)k, re = ra + (int64_t)ke;   // the run [rs, re)
             const int64_t M0 = a->map_off[rs], M1 = a->map_off[re], E0 = a->edit_off[M0], E1 = a->edit_off[M1];
             const int64_t Q0 = a->qual_off[rs], Q1 = a->qual_off[re], S0 = a->edit_seq_off[E0], S1 = a->edit_seq_off[E1];
-            {   // mappings
-                const int64_t* __restrict__ node = a->map_node + M0;
-                const int64_t* __restrict__ offs = a->map_offset + M0;
-                const uint8_t* __restrict__ rev = a->map_rev + M0;
-                const int64_t* __restrict__ eo = a->edit_off + M0;
-                uint16_t* __restrict__ on = n16 + cm;
-                uint8_t* __restrict__ oc = ne8 + cm;
-                const int64_t n = M1 - M0;
-                uint64_t v = 0, nzo = 0;
-                for (int64_t i = 0; i < n; ++i) {
-                    const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);
-                    v |= (nd & ~(uint64_t)0x7fff) | (cnt & ~(uint64_t)0xff);
-                    on[i] = (uint16_t)((nd & 0x7fff) | (rev[i] ? 0x8000u : 0u));
-                    oc[i] = (uint8_t)cnt;
-                    nzo += offs[i] != 0;
-                }
-                viol |= v;
-                nonzero_off += nzo;
-            }
-            {   // edits
-                const int32_t* __restrict__ fr = a->edit_from + E0;
-                const int32_t* __restrict__ to = a->edit_to + E0;
-                const int64_t* __restrict__ so = a->edit_seq_off + E0;
-                uint8_t* __restrict__ of = f8 + ce;
-                uint8_t* __restrict__ ot = t8 + ce;
-                uint8_t* __restrict__ os = sl8 + ce;
-                const int64_t n = E1 - E0;
-                uint64_t v = 0;
-                for (int64_t i = 0; i < n; ++i) {
-                    const uint32_t f_ = (uint32_t)fr[i], t_ = (uint32_t)to[i];
-                    const uint64_t sl = (uint64_t)(so[i + 1] - so[i]);
-                    v |= (uint64_t)((f_ | t_) & ~0xffu) | (sl & ~(uint64_t)0xff);
-                    of[i] = (uint8_t)f_;
-                    ot[i] = (uint8_t)t_;
-                    os[i] = (uint8_t)sl;
-                }
-                viol |= v;
-            }
+            feeder_narrow_mappings(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n16 + cm, ne8 + cm, M1 - M0,
+                                   &viol, &nonzero_off);
+            feeder_narrow_edits(a->edit_from + E0, a->edit_to + E0, a->edit_seq_off + E0, f8 + ce, t8 + ce, sl8 + ce, E1 - E0, &viol);
             memcpy(q + cq, a->qual + Q0, (size_t)(Q1 - Q0));
             memcpy(eseq + cs, a->edit_seq + S0, (size_t)(S1 - S0));
-            {   // largest quality byte of the run, as the reference sees it (signed char)
-                const int8_t* __restrict__ qb = (const int8_t*)a->qual + Q0;
-                int8_t mx = qmax;
-                for (int64_t i = 0; i < Q1 - Q0; ++i) mx = qb[i] > mx ? qb[i] : mx;
-                qmax = mx;
-            }
+            qmax = feeder_max_quality((const int8_t*)a->qual + Q0, Q1 - Q0, qmax);
             // per read: offsets, mapping quality, first node offset, capacity of its aligned strings
             for (int64_t r = rs; r < re; ++r) {
                 const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
