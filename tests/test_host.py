@@ -470,6 +470,26 @@ def test_feeder_chunk_holds_the_same_arrays_as_the_general_builder():
             f.close()
 
 
+def test_batch_format_limits_are_enforced_at_the_limit_itself():
+    """include/vgan_gpu.h: <= 4095 aligned columns per read (VGL_HC_MAP_MAX_POS), node ids <= 131070 (VGL_HC_MAX_NODE, the
+    17-bit node field; 131071 is VGL_HC_NO_NODE).  The value at the limit packs, the next one is refused with a status."""
+    big = "ACGT" * 1024                                     # 4096 bases
+    g = vb.Graph.from_sequences({7: big, 131070: "ACGTACGT", 131071: "ACGTACGT"})
+
+    def pack(a):
+        return vb.PackedBatch(g, vb.Alignments.from_gam_bytes(H.encode_gam([a])))
+
+    at = pack(H.aln(big[:4095], [(7, 0, False, [(4095, 4095, "")])], quality=bytes([30] * 4095)))
+    assert at.n_reads == 1 and int(at.lanes()[0]["n_cols"]) == 4095
+    with pytest.raises(_lib.VglError, match="does not fit the batch records"):
+        pack(H.aln(big, [(7, 0, False, [(4096, 4096, "")])], quality=bytes([30] * 4096)))
+    ok = pack(H.aln("ACGTACGT", [(131070, 0, False, [(8, 8, "")])]))
+    cols = ok.lanes()[0]["col"]
+    assert len(cols) == 8 and all((int(c) >> _lib.COL_NODE_SHIFT) == 131070 for c in cols)
+    with pytest.raises(_lib.VglError, match="does not fit the column record"):
+        pack(H.aln("ACGTACGT", [(131071, 0, False, [(8, 8, "")])]))
+
+
 def test_crafted_bgzf_sizes_do_not_take_the_process_down():
     """A BGZF-looking stream whose member trailers claim ~4 GiB each: rejected with an error code, no huge
     allocation, no exception across the C ABI."""
