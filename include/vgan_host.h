@@ -79,7 +79,8 @@ void vgh_gam_destroy(vgh_gam* g);
 
 /* GAM framing for the DEVICE-side decoder (vgl_hc_accumulate_gam, include/vgan_gpu.h): inflates the stream (BGZF members in
  * parallel) and walks the group / item framing; the vg.Alignment messages themselves are parsed on the GPU.
- * vgh_gam_frames_view returns the number of messages and the inflated bytes plus every message's offset and length.     */
+ * vgh_gam_frames_view returns the number of messages and the inflated bytes plus every message's offset and length.
+ * An UNCOMPRESSED stream is not copied: the view points into `bytes`, which the caller keeps alive as long as the frames.   */
 typedef struct vgh_gam_frames vgh_gam_frames;
 int vgh_gam_frame(const void* bytes, size_t n, vgh_gam_frames** out);
 int64_t vgh_gam_frames_view(const vgh_gam_frames* f, const uint8_t** bytes, uint64_t* n_bytes, const uint64_t** msg_off, const uint32_t** msg_len);

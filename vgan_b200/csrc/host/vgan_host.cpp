@@ -1729,11 +1729,12 @@ static int vgh_gam_frame__impl(const void* bytes, size_t n, vgh_gam_frames** out
     const uint8_t* raw_p = (const uint8_t*)bytes;
     if (n >= 2 && raw_p[0] == 0x1f && raw_p[1] == 0x8b) {
         if (int rc = inflate_all(raw_p, n, F->inflated)) { delete F; return rc; }
+        F->bytes = F->inflated.data();
+        F->n_bytes = F->inflated.size();
     } else {
-        F->inflated.assign(raw_p, raw_p + n);   // the frames own their bytes (the caller's buffer may go away)
+        F->bytes = raw_p;   // an uncompressed stream is walked where it lies (no copy): the caller keeps it alive
+        F->n_bytes = n;
     }
-    F->bytes = F->inflated.data();
-    F->n_bytes = F->inflated.size();
     std::vector<std::pair<const uint8_t*, const uint8_t*>> msgs;
     if (int rc = scan_gam_framing(F->bytes, F->n_bytes, msgs)) { delete F; return rc; }
     F->msg_off.reserve(msgs.size());

@@ -5,7 +5,7 @@
 // them to process_mapping (src/update_likelihood.cpp:33-49); at ~2e6 reads/s on 16 threads it is 60x slower than the
 // read kernel.  These kernels do the same work on the device from the raw alignments (vgl_hc_raw: quality bytes,
 // mappings, edits) and a copy of the node sequences, and leave a vgl_hc_batch in HBM for hc_read_kernel:
-//   R1 hc_recon_kernel   one thread per read: graph string, read string (with the deletion splices), the size slot of
+//   R1 hc_recon_kernel   one WARP per read: graph string, read string (with the deletion splices), the size slot of
 //                        every mapping (quirk Q1), column / CLOSE / empty-mapping counts, histogram of column counts
 //   R2 hc_scan4096       exclusive scan of the histogram                      (counting sort of the reads by columns,
 //   R3 hc_order_kernel   scatter of the read ids into their buckets            so that a group's 32 lanes are equally long)
@@ -36,25 +36,6 @@ __device__ __forceinline__ EditKind classify(uint32_t from, uint32_t to, bool ha
     return kOther;
 }
 
-// Appends bytes to a string in global memory four at a time (the strings start 4-byte aligned): one 32-bit store per four
-// bytes instead of four scattered byte stores.
-struct ByteWriter {
-    uint8_t* base;
-    uint32_t len = 0, word = 0;
-    __device__ __forceinline__ explicit ByteWriter(uint8_t* b) : base(b) {}
-    __device__ __forceinline__ void put(uint8_t c) {
-        word |= (uint32_t)c << (8 * (len & 3));
-        ++len;
-        if ((len & 3) == 0) {
-            *reinterpret_cast<uint32_t*>(base + len - 4) = word;
-            word = 0;
-        }
-    }
-    __device__ __forceinline__ void flush() {  // the tail of a partially filled word
-        for (uint32_t k = len & ~3u; k < len; ++k) base[k] = (uint8_t)(word >> (8 * (k & 3)));
-    }
-};
-
 __device__ __forceinline__ uint8_t complement(uint8_t c) {
     switch (c) {
         case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
@@ -63,121 +44,194 @@ __device__ __forceinline__ uint8_t complement(uint8_t c) {
     }
 }
 
-__global__ void __launch_bounds__(128)
-hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int mode, int* __restrict__ err_flag) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= raw.n_reads) return;
-    const uint32_t m0 = raw.map_off[r], m1 = raw.map_off[r + 1], M = m1 - m0;
-    const uint32_t s0 = raw.str_off[r], cap = raw.str_off[r + 1] - s0;
-    ByteWriter gw(W.gstr + s0), rw(W.rstr + s0);
-    uint32_t e_idx = 0, n_del = 0;
-    int err = 0;
-    for (uint32_t m = m0; m < m1 && !err; ++m) {
-        const uint32_t mn = raw.map_node[m];
-        const uint32_t node = mn & 0x7fffffffu;
-        const bool rev = (mn >> 31) != 0;
-        if (node < G.min_id || node >= G.min_id + G.n_nodes || (mode == kReconHaplocart && node > VGL_HC_MAX_NODE)) { err = kErrBadNodeRaw; break; }
-        const uint32_t na = G.seq_off[node - G.min_id], nlen = G.seq_off[node - G.min_id + 1] - na;
-        uint32_t offset = raw.map_offset[m];
-        uint32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size
-        const uint32_t e1 = raw.edit_off[m + 1];
-        for (uint32_t e = raw.edit_off[m]; e < e1; ++e) {
-            const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
-            const uint32_t q0 = raw.edit_seq_off[e], q1 = raw.edit_seq_off[e + 1];
-            const EditKind kind = classify(from, to, q1 > q0);
-            if (kind == kMatch || kind == kSub || kind == kDel) {
-                if (offset > nlen) { err = kErrBadRead; break; }
-                const uint32_t take = min(from, nlen - offset);  // std::string::substr clips
-                if (gw.len + take > cap || rw.len + max(take, q1 - q0) > cap) { err = kErrBadRead; break; }
+// R1 works a WARP per read: the lanes take the read's mappings 32 at a time, so the mapping / edit arrays are read in
+// consecutive words (one thread per read touched one 32-byte sector per 4-byte field and was bound by L2 sectors: 5 ms per
+// 10^6 reads) and the strings are written in neighbouring bytes.  A CTA of eight warps takes 64 consecutive reads.
+constexpr int kReconWarps = 8, kReconReadsPerCta = 64;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, k);
+        if (lane >= k) v += o;
+    }
+    return v;
+}
+
+// One mapping (src/vgan_utils.h:21-75): what its edits append to the graph string and to the read string.  WRITE = false
+// measures (and stores one size per EDIT, :72); WRITE = true writes the bytes at g_pos / r_pos -- same control flow, so the
+// two passes agree by construction.  Returns an error bit (WRITE = false only).
+template <bool WRITE>
+__device__ __forceinline__ int recon_mapping(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, uint32_t m,
+                                             uint32_t& g_pos, uint32_t& r_pos, uint32_t& n_del, uint8_t* __restrict__ gs, uint8_t* __restrict__ rs) {
+    const uint32_t mn = raw.map_node[m];
+    const uint32_t node = mn & 0x7fffffffu;
+    const bool rev = (mn >> 31) != 0;
+    if (!WRITE && (node < G.min_id || node >= G.min_id + G.n_nodes || (mode == kReconHaplocart && node > VGL_HC_MAX_NODE))) return kErrBadNodeRaw;
+    const uint32_t na = G.seq_off[node - G.min_id], nlen = G.seq_off[node - G.min_id + 1] - na;
+    uint32_t offset = raw.map_offset[m];
+    uint32_t aligned = 0;  // per mapping, NOT per edit: an edit of no recognised kind repeats the previous size
+    const uint32_t e1 = raw.edit_off[m + 1];
+    for (uint32_t e = raw.edit_off[m]; e < e1; ++e) {
+        const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
+        const uint32_t q0 = raw.edit_seq_off[e], q1 = raw.edit_seq_off[e + 1];
+        const EditKind kind = classify(from, to, q1 > q0);
+        if (kind == kMatch || kind == kSub || kind == kDel) {
+            if (!WRITE && offset > nlen) return kErrBadRead;
+            const uint32_t take = min(from, nlen - offset);  // std::string::substr clips
+            if (WRITE) {
                 for (uint32_t k = 0; k < take; ++k) {
                     // base at oriented offset of the node (what get_sequence(get_handle(id, rev))[k] returns)
                     const uint8_t c = rev ? complement(G.seq[na + nlen - 1 - (offset + k)]) : G.seq[na + offset + k];
-                    gw.put(c);
-                    if (kind == kMatch) rw.put(c);
+                    gs[g_pos + k] = c;
+                    if (kind == kMatch) rs[r_pos + k] = c;
                 }
-                aligned = take;
                 if (kind == kSub)
-                    for (uint32_t k = q0; k < q1; ++k) rw.put(raw.edit_seq[k]);
-                n_del += kind == kDel;
-            } else if (kind == kIns) {
-                if (gw.len + to > cap || rw.len + (q1 - q0) > cap) { err = kErrBadRead; break; }
+                    for (uint32_t k = q0; k < q1; ++k) rs[r_pos + (k - q0)] = raw.edit_seq[k];
+            }
+            g_pos += take;
+            r_pos += kind == kMatch ? take : kind == kSub ? q1 - q0 : 0u;
+            aligned = take;
+            n_del += kind == kDel;
+        } else if (kind == kIns) {
+            if (WRITE) {
                 const uint8_t fill = offset == 0 ? 'S' : '-';
-                for (uint32_t k = 0; k < to; ++k) gw.put(fill);
-                for (uint32_t k = q0; k < q1; ++k) rw.put(raw.edit_seq[k]);
-                aligned = to;
+                for (uint32_t k = 0; k < to; ++k) gs[g_pos + k] = fill;
+                for (uint32_t k = q0; k < q1; ++k) rs[r_pos + (k - q0)] = raw.edit_seq[k];
             }
-            offset += from;
-            W.sizes[e] = (uint16_t)min(aligned, 0xffffu);  // one size per EDIT (src/vgan_utils.h:72)
-            ++e_idx;
+            g_pos += to;
+            r_pos += q1 - q0;
+            aligned = to;
         }
+        offset += from;
+        if (!WRITE) W.sizes[e] = (uint16_t)min(aligned, 0xffffu);  // one size per EDIT (src/vgan_utils.h:72)
     }
-    gw.flush();
-    rw.flush();
-    const uint32_t glen = gw.len;
-    uint32_t rlen = rw.len;
-    // deletions: a '-' run spliced into the read string at the running from_length coordinate, in order, each against the
-    // string as it stands (src/vgan_utils.h:67)
-    if (!err && n_del) {
+    return 0;
+}
+
+__global__ void __launch_bounds__(kReconWarps * 32)
+hc_recon_kernel(ReconRawDev raw, ReconGraphDev G, ReconWorkDev W, int mode, int* __restrict__ err_flag) {
+    __shared__ uint32_t s_key[kReconReadsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int it = 0; it < kReconReadsPerCta / kReconWarps; ++it) {
+        const uint32_t slot = (uint32_t)(it * kReconWarps + warp);
+        const uint32_t r = blockIdx.x * kReconReadsPerCta + slot;
+        if (r >= raw.n_reads) {
+            if (lane == 0) s_key[slot] = 0xffffffffu;
+            continue;
+        }
+        const uint32_t m0 = raw.map_off[r], m1 = raw.map_off[r + 1], M = m1 - m0;
+        const uint32_t s0 = raw.str_off[r], cap = raw.str_off[r + 1] - s0;
+        uint8_t* gs = W.gstr + s0;
         uint8_t* rs = W.rstr + s0;
-        uint32_t from_total = 0;
-        for (uint32_t m = m0; m < m1 && !err; ++m) {
-            for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
-                const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
-                const bool has_seq = raw.edit_seq_off[e + 1] > raw.edit_seq_off[e];
-                if (classify(from, to, has_seq) == kDel) {
-                    if (from_total > rlen || rlen + from > cap) { err = kErrBadRead; break; }
-                    for (uint32_t k = rlen; k > from_total; --k) rs[k - 1 + from] = rs[k - 1];
-                    for (uint32_t k = 0; k < from; ++k) rs[from_total + k] = '-';
-                    rlen += from;
+        uint32_t glen = 0, rlen = 0, n_del = 0;
+        int err = 0;
+        for (uint32_t mb = m0; mb < m1 && !err; mb += 32) {
+            const uint32_t m = mb + (uint32_t)lane;
+            uint32_t gl = 0, rl = 0, nd = 0;
+            int e_mine = 0;
+            if (m < m1) e_mine = recon_mapping<false>(raw, G, W, mode, m, gl, rl, nd, nullptr, nullptr);
+            const uint32_t bad = __ballot_sync(0xffffffffu, e_mine != 0);
+            if (bad) {   // the error the serial loop of the reference meets first
+                err = __shfl_sync(0xffffffffu, e_mine, __ffs(bad) - 1);
+                break;
+            }
+            const uint32_t gi = warp_incl_scan(gl, lane), ri = warp_incl_scan(rl, lane);
+            const uint32_t g_chunk = __shfl_sync(0xffffffffu, gi, 31), r_chunk = __shfl_sync(0xffffffffu, ri, 31);
+            if (glen + g_chunk > cap || rlen + r_chunk > cap) { err = kErrBadRead; break; }  // never write past the read's strings
+            if (m < m1) {
+                uint32_t gp = glen + gi - gl, rp = rlen + ri - rl, unused = 0;
+                recon_mapping<true>(raw, G, W, mode, m, gp, rp, unused, gs, rs);
+            }
+            glen += g_chunk;
+            rlen += r_chunk;
+            n_del += __reduce_add_sync(0xffffffffu, nd);
+        }
+        __syncwarp();
+        // deletions: a '-' run spliced into the read string at the running from_length coordinate, in order, each against the
+        // string as it stands (src/vgan_utils.h:67) -- rare, one lane
+        if (!err && n_del) {
+            if (lane == 0) {
+                uint32_t from_total = 0;
+                for (uint32_t m = m0; m < m1 && !err; ++m) {
+                    for (uint32_t e = raw.edit_off[m]; e < raw.edit_off[m + 1]; ++e) {
+                        const uint32_t from = raw.edit_from[e], to = raw.edit_to[e];
+                        const bool has_seq = raw.edit_seq_off[e + 1] > raw.edit_seq_off[e];
+                        if (classify(from, to, has_seq) == kDel) {
+                            if (from_total > rlen || rlen + from > cap) { err = kErrBadRead; break; }
+                            for (uint32_t k = rlen; k > from_total; --k) rs[k - 1 + from] = rs[k - 1];
+                            for (uint32_t k = 0; k < from; ++k) rs[from_total + k] = '-';
+                            rlen += from;
+                        }
+                        from_total += from;
+                    }
                 }
-                from_total += from;
             }
+            rlen = __shfl_sync(0xffffffffu, rlen, 0);
+            err = __shfl_sync(0xffffffffu, err, 0);
+            __syncwarp();
         }
-    }
-    const uint32_t Lq = raw.qual_off[r + 1] - raw.qual_off[r];
-    const uint32_t e_first = M ? raw.edit_off[m0] : 0u;  // the read's edits are e_first .. e_first + e_idx - 1
-    uint32_t n_close = 0, n_extra = 0;
-    if (mode == kReconHaplocart) {
-        if (!err && (glen != rlen || e_idx < M || Lq > rlen || rlen > VGL_HC_MAP_MAX_POS || M > 65535u || raw.mapq[r] >= 100)) err = kErrBadRead;
-        if (!err) {
-            // mapping i starts at pos_i = min(sum of the earlier size slots, n) -- the size slot of mapping i is the size of the
-            // read's i-th EDIT (quirk Q1); CLOSE bits sit at the distinct pos_i < n
-            uint32_t pos = 0, last_close = 0xffffffffu;
-            for (uint32_t i = 0; i < M; ++i) {
-                const uint32_t lg = min((uint32_t)W.sizes[e_first + i], rlen - pos);
-                if (lg == 0) ++n_extra;
-                if (pos < rlen && pos != last_close) { ++n_close; last_close = pos; }
-                pos += lg;
+        const uint32_t Lq = raw.qual_off[r + 1] - raw.qual_off[r];
+        const uint32_t e_first = M ? raw.edit_off[m0] : 0u;  // the read's edits are e_first .. e_first + E - 1
+        const uint32_t E = M ? raw.edit_off[m1] - e_first : 0u;
+        uint32_t n_close = 0, n_extra = 0;
+        if (mode == kReconHaplocart) {
+            if (!err && (glen != rlen || E < M || Lq > rlen || rlen > VGL_HC_MAP_MAX_POS || M > 65535u || raw.mapq[r] >= 100)) err = kErrBadRead;
+            if (!err) {
+                // mapping i starts at pos_i = min(sum of the earlier size slots, n) -- the size slot of mapping i is the size of the
+                // read's i-th EDIT (quirk Q1); CLOSE bits sit at the distinct pos_i < n; a mapping with pos_{i+1} = pos_i owns no column
+                uint32_t carry = 0, carry_lg = 1;
+                for (uint32_t ib = 0; ib < M; ib += 32) {
+                    const uint32_t i = ib + (uint32_t)lane;
+                    const uint32_t sz = i < M ? (uint32_t)W.sizes[e_first + i] : 0u;
+                    const uint32_t incl = warp_incl_scan(sz, lane);
+                    const uint32_t pos = min(carry + incl - sz, rlen), lg = min(carry + incl, rlen) - pos;
+                    uint32_t prev_lg = __shfl_up_sync(0xffffffffu, lg, 1);
+                    if (lane == 0) prev_lg = carry_lg;
+                    n_extra += (uint32_t)__popc(__ballot_sync(0xffffffffu, i < M && lg == 0));
+                    n_close += (uint32_t)__popc(__ballot_sync(0xffffffffu, i < M && pos < rlen && prev_lg > 0));
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                    carry_lg = __shfl_sync(0xffffffffu, lg, 31);
+                }
             }
+        } else {
+            // euka / soibean (vgh_euka_pack / vgh_soibean_pack): fragment length inside the damage table, the damage position
+            // stays inside the read; the "extra" count is the number of mapping (euka) or edit (soibean) records
+            const uint32_t Lseq = mode == kReconSoibean ? glen : (uint32_t)raw.seq_len[r];
+            uint32_t nongap = 0;
+            if (!err)
+                for (uint32_t k = (uint32_t)lane; k < rlen; k += 32) nongap += rs[k] != '-';
+            nongap = __reduce_add_sync(0xffffffffu, nongap);
+            const uint32_t n_rec = mode == kReconSoibean ? E : M;
+            if (!err && (M < 1 || glen != rlen || Lseq < 15u || Lseq > 1000u || glen > 4095u || M > 65535u || n_rec > 65535u || nongap > Lseq)) err = kErrBadRead;
+            if (!err && mode == kReconSoibean) {
+                if (raw.seq_len[r] < 1) err = kErrBadRead;
+                bool far = false;
+                for (uint32_t i = (uint32_t)lane; i < min(M, E); i += 32) far = far || (raw.map_node[m0 + i] & 0x7fffffffu) >= VGL_SOIBEAN_NO_NODE;
+                if (__any_sync(0xffffffffu, far)) err = kErrBadNodeRaw;
+            }
+            n_extra = n_rec;
         }
-    } else {
-        // euka / soibean (vgh_euka_pack / vgh_soibean_pack): fragment length inside the damage table, the damage position
-        // stays inside the read; the "extra" count is the number of mapping (euka) or edit (soibean) records
-        const uint32_t Lseq = mode == kReconSoibean ? glen : (uint32_t)raw.seq_len[r];
-        uint32_t nongap = 0;
-        for (uint32_t k = 0; k < rlen && !err; ++k) nongap += (W.rstr + s0)[k] != '-';
-        const uint32_t n_rec = mode == kReconSoibean ? e_idx : M;
-        if (!err && (M < 1 || glen != rlen || Lseq < 15u || Lseq > 1000u || glen > 4095u || M > 65535u || n_rec > 65535u || nongap > Lseq)) err = kErrBadRead;
-        if (!err && mode == kReconSoibean) {
-            if (raw.seq_len[r] < 1) err = kErrBadRead;
-            for (uint32_t i = 0; i < min(M, e_idx); ++i)
-                if ((raw.map_node[m0 + i] & 0x7fffffffu) >= VGL_SOIBEAN_NO_NODE) err = kErrBadNodeRaw;
+        if (err) {
+            rlen = 0;
+            n_close = 0xffffu;  // marks the read as dead for the packer
+            n_extra = 0;
         }
-        n_extra = n_rec;
+        if (lane == 0) {
+            if (err) atomicOr(err_flag, err);
+            W.n_cols[r] = (uint16_t)rlen;
+            W.n_close[r] = (uint16_t)n_close;
+            W.n_extra[r] = (uint16_t)n_extra;
+            s_key[slot] = (uint32_t)W.slot_of_mapq[raw.mapq[r] & 127u] * 4096u + rlen;
+        }
     }
-    if (err) {
-        atomicOr(err_flag, err);
-        rlen = 0;
-        n_close = 0xffffu;  // marks the read as dead for the packer
-        n_extra = 0;
+    __syncthreads();
+    // histogram of (mapping-quality slot, column count): one atomic per distinct value among 32 reads
+    if (warp < kReconReadsPerCta / 32) {
+        const uint32_t key = s_key[warp * 32 + lane];
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(W.hist + key, (uint32_t)__popc(peers));
     }
-    W.n_cols[r] = (uint16_t)rlen;
-    W.n_close[r] = (uint16_t)n_close;
-    W.n_extra[r] = (uint16_t)n_extra;
-    // histogram of (mapping-quality slot, column count): one atomic per distinct value in the warp
-    const uint32_t key = (uint32_t)W.slot_of_mapq[raw.mapq[r] & 127u] * 4096u + rlen;
-    const uint32_t peers = __match_any_sync(__activemask(), key);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(W.hist + key, (uint32_t)__popc(peers));
 }
 
 // exclusive scan of a slot's 4096 counters, one block of 1024 threads (4 per thread) per slot; slot s starts at lane lane_base
@@ -670,7 +724,7 @@ cudaError_t hc_launch_expand(uint32_t n_groups, const uint32_t* grp_c16, const u
 
 cudaError_t hc_launch_recon(const ReconRawDev& raw, const ReconGraphDev& G, const ReconWorkDev& W, int mode, int* err_flag, cudaStream_t s) {
     if (raw.n_reads == 0) return cudaSuccess;
-    hc_recon_kernel<<<(raw.n_reads + 127) / 128, 128, 0, s>>>(raw, G, W, mode, err_flag);
+    hc_recon_kernel<<<(raw.n_reads + kReconReadsPerCta - 1) / kReconReadsPerCta, kReconWarps * 32, 0, s>>>(raw, G, W, mode, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     hc_scan4096<<<W.n_slots, 1024, 0, s>>>(W.hist, W.start, W);

@@ -209,12 +209,10 @@ class Haplocart:
         n = len(alns)
         keys = np.zeros(max(n, 1), dtype=np.uint64)
         check(_lib.host.vgh_dedup_keys(C.byref(alns.view), keys.ctypes.data_as(C.c_void_p)))
-        paired = alns.arrays().get("paired")
-        pz = np.ascontiguousarray(paired, dtype=np.uint8) if paired is not None and len(paired) == n and n else None
+        pz = alns.view.paired if n else None          # the library's own array (may be NULL: no read is paired)
         mask = np.zeros(max(n, 1), dtype=np.uint8)
         kept = C.c_uint64()
-        check(gpu.vgl_dedup(self.ctx, n, keys.ctypes.data_as(C.c_void_p), pz.ctypes.data_as(C.c_void_p) if pz is not None else None,
-                            mask.ctypes.data_as(C.c_void_p), C.byref(kept)))
+        check(gpu.vgl_dedup(self.ctx, n, keys.ctypes.data_as(C.c_void_p), pz, mask.ctypes.data_as(C.c_void_p), C.byref(kept)))
         return mask[:n].astype(bool), int(kept.value)
 
     def logterm_launches(self):

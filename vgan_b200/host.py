@@ -268,8 +268,8 @@ class GamFrames:
                 data = fh.read()
         self._data = bytes(data)
         self.handle = C.c_void_p()
-        buf = C.create_string_buffer(self._data, len(self._data)) if self._data else None
-        check(host.vgh_gam_frame(C.cast(buf, C.c_void_p) if buf is not None else None, len(self._data), C.byref(self.handle)))
+        src = C.cast(C.c_char_p(self._data), C.c_void_p) if self._data else None     # the bytes object's own buffer, no copy
+        check(host.vgh_gam_frame(src, len(self._data), C.byref(self.handle)))
         b, off, ln = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nb = C.c_uint64()
         self.n_msgs = int(host.vgh_gam_frames_view(self.handle, C.byref(b), C.byref(nb), C.byref(off), C.byref(ln)))
