@@ -249,9 +249,16 @@ def bench_config4(torch, stream, n_reads, peak):
         ek.reset()
         return ek.rerun(pb.n_span)
 
-    def from_alignments():
+    from vgan_b200.host import pinned_empty
+    n_all = len(alns)
+    feeder = vb.Feeder(n_threads=int(os.environ.get("OMP_NUM_THREADS", "0") or 0))
+    outs = {"clade": pinned_empty((n_all,), np.int32), "in_lik": pinned_empty((n_all,), np.float64),
+            "not_lik": pinned_empty((n_all,), np.float64), "like": pinned_empty((n_all,), np.float64),
+            "pass": pinned_empty((n_all,), np.uint8)}
+
+    def from_alignments():   # flat alignment fields -> page-locked chunks -> device reconstruction + kernel -> per-read results
         ek.reset()
-        return ek.run_raw(vb.RawBatch(alns, pinned=False, euka_rule=True))
+        return feeder.feed_euka(ek, alns, out=outs)
 
     for _ in range(3):
         resident()
@@ -259,8 +266,10 @@ def bench_config4(torch, stream, n_reads, peak):
     k_ms = ek.kernel_ms()
     for _ in range(2):
         from_alignments()
+    st0 = feeder.stats()
     ms_e2e, res = _event_ms(torch, stream, from_alignments, 3)
-    raw_bytes = vb.RawBatch(alns, pinned=False, euka_rule=True).nbytes
+    st1 = feeder.stats()
+    raw_bytes = (st1["h2d_bytes"] - st0["h2d_bytes"]) // 3
     # algorithmic bytes: 2 B per aligned column as stored (symbol pair + quality) + 10 B header in, 20 B out per read
     alg = 2 * cols + 30 * pb.n_reads
     out = {"workload": "euka config 4: %d synthetic aeDNA reads x 335 clades / 3929 bins taken verbatim from the reference's euka_db.clade "
@@ -269,8 +278,12 @@ def bench_config4(torch, stream, n_reads, peak):
            "value": pb.n_reads / (ms_dev * 1e-3), "unit": "reads/s", "ms_per_step": ms_dev,
            "e2e": {"value": pb.n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": raw_bytes,
                    "d2h_bytes_per_step": 33 * pb.n_reads,
-                   "route": "flat alignment fields -> vgh_euka_raw_build -> vgl_euka_run_raw (H2D, device reconstruction + packing, "
-                            "euka kernel) -> per-read results on the host"},
+                   "host_marshal_seconds_per_step": (st1["build_seconds"] - st0["build_seconds"]) / 3,
+                   "host_wait_seconds_per_step": (st1["wait_seconds"] - st0["wait_seconds"]) / 3,
+                   "general_builder_chunks": st1["slow_chunks"] - st0["slow_chunks"],
+                   "route": "flat alignment fields -> vgh_euka_feed: host marshalling into page-locked chunks overlapped with "
+                            "vgl_euka_run_raw (H2D, device reconstruction + packing, euka kernel, per-read results into page-locked "
+                            "host memory)"},
            "host_pack_seconds": pack_s, "detected_reads": int(res["pass"].sum()),
            "roofline": {"bound": "hbm", "kernel": "euka_read_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
@@ -307,6 +320,12 @@ def bench_config5(torch, stream, n_reads, peak, P=399):
     k_ms = sb.kernel_ms()
     to_host()
     ms_e2e, _ = _event_ms(torch, stream, to_host, 3)
+    # from the flat alignment fields (vgh_soibean_feed): marshalling, device reconstruction + packing, matrix back, chunk by chunk
+    feeder = vb.Feeder(n_threads=int(os.environ.get("OMP_NUM_THREADS", "0") or 0))
+    assert pk.n_span == len(al)
+    feeder.feed_soibean(sb, al, out=po, used=pu)
+    ms_feed, _ = _event_ms(torch, stream, lambda: feeder.feed_soibean(sb, al, out=po, used=pu), 3)
+    sb.analyse_into(pk, po, pu)   # the whole batch resident again for the MCMC kernel below
     # one MCMC proposal scored on the resident batch
     f7 = vb.soibean_freqs7(0.31, 0.19, 0.2, 0.3)
     rng = np.random.default_rng(5)
@@ -322,6 +341,9 @@ def bench_config5(torch, stream, n_reads, peak, P=399):
            "e2e": {"value": pk.n_reads * P / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": pk.nbytes,
                    "d2h_bytes_per_step": alg_out + pk.n_reads,
                    "route": "packed host batch -> H2D -> soibean kernels -> R x P matrix into page-locked host memory"},
+           "e2e_from_alignments": {"value": pk.n_reads * P / (ms_feed * 1e-3), "unit": UNIT, "ms_per_step": ms_feed,
+                                   "route": "flat alignment fields -> vgh_soibean_feed (marshalling overlapped with H2D, device "
+                                            "reconstruction + packing, kernels, R x P matrix into page-locked host memory)"},
            "mcmc_ms_per_proposal_batched_64": mcmc_ms,
            "roofline": {"bound": "hbm", "kernel": "soibean_path_kernel", "achieved": alg_out / (k_ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg_out / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms,
@@ -345,6 +367,7 @@ def main():
     ap.add_argument("--workload", type=int, default=2, choices=[2, 3], help="SURVEY 8d config whose read shape the main line uses")
     ap.add_argument("--config3-tile", type=int, default=1000000, help="config 3: distinct reads generated per GPU (re-scored to reach 50 M / N)")
     ap.add_argument("--sibling-reads", type=int, default=1000000)
+    ap.add_argument("--feeder-threads", type=int, default=0, help="host threads of the e2e feeder (0: the rank's share of the cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -398,7 +421,7 @@ def main():
     alg_bytes = int(4 * pa["n_cols"].astype(np.int64).sum() + 4 * pa["n_extra"].astype(np.int64).sum() + 7 * reads_local
                     + 8 * (int(packed.batch.n_groups) + 1))
     del pa
-    feeder = vb.Feeder(n_threads=host_threads)
+    feeder = vb.Feeder(n_threads=args.feeder_threads or host_threads)
 
     sharded = None
     if world > 1:
@@ -693,12 +716,16 @@ def main():
         kernel_ms = k_ms / max(k_n, 1)
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
+        # which read kernel the timed steps launched: the log-term kernel when the batch's meta allows it (qualities <= 63,
+        # mapping-quality segments), else the general one
+        read_kernel_name = "hc_read_logterm_kernel" if hc.logterm_launches() > 0 else "hc_read_kernel"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("reads") == reads_local and tj.get("kernel") == "hc_read_kernel":
-                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                ent = tj.get("kernels", {}).get(read_kernel_name)
+                if tj.get("reads") == reads_local and ent:
+                    traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
             except Exception:
                 pass
         nsteps = max(e2e_steps, 1)
@@ -728,7 +755,7 @@ def main():
             "host_pack": {"seconds": t_pack, "reads_per_s": reads_local / t_pack, "threads": host_threads,
                           "what": "vgh_hc_pack (reconstruction + packing, OpenMP) of the step's batch; outside the timed regions"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "hc_read_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": read_kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "batch_bytes_with_padding": batch_bytes,
                          "kernel_ms": kernel_ms, "bytes_per_read": alg_bytes / max(reads_local, 1),

@@ -310,10 +310,11 @@ int vgl_hc_accumulate_wire(vgl_ctx* ctx, const vgl_hc_wire* host_wire);
  *   map_node[m]                    Mapping.position.node_id | is_reverse << 31;  map_offset[m] = position.offset
  *   edit_from / edit_to [e]        Edit.from_length / to_length (<= 65535); edit_seq_off[e] .. [e+1] its sequence
  * Only reads with identity >= 1e-10 are listed (src/HaploCart.cpp:411).  All pointers are HOST pointers.      */
-#define VGL_HC_RAW_NARROW_ONLY 1u /* vgl_hc_raw.reserved: only the narrow arrays are present (all six twins, first_offset16
-                                   * form); the batch is at most one device chunk (131072 reads); edit_off and edit_seq_off
-                                   * hold just their two end points {first, last}; map_node / map_offset / edit_from / edit_to
-                                   * are NULL.  What vgh_hc_feed submits.                                                   */
+#define VGL_HC_RAW_NARROW_ONLY 1u /* vgl_hc_raw.reserved: only the narrow arrays are present (first_offset16 form; node ids in
+                                   * map_node16, or in map_node when one exceeds 32767); the batch is at most one device
+                                   * chunk (131072 reads); edit_off and edit_seq_off hold just their two end points
+                                   * {first, last}; map_offset / edit_from / edit_to are NULL.  What vgh_hc_feed and
+                                   * vgh_euka_feed / vgh_soibean_feed submit.                                                */
 typedef struct vgl_hc_raw {
     uint32_t n_reads, n_maps, n_edits, reserved;
     const uint32_t* qual_off;     /* [n_reads + 1] */

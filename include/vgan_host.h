@@ -145,6 +145,14 @@ int vgh_hc_feed(vgh_hc_feeder* f, struct vgl_ctx* ctx, const vgh_alignments* a, 
 /* One chunk (r1 - r0 <= chunk_reads) marshalled without submitting it, for inspection and tests; *out is NULL when the
  * chunk does not fit the narrow arrays (vgh_hc_feed then takes vgh_hc_raw_build for it).                            */
 int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out);
+/* The same pipeline for the sibling tools (the loops of src/Euka.cpp:534-537 and src/soibean.cpp:558-561): reads [r0, r1) with
+ * identity != 0 (readGAM3's rule) go to vgl_euka_run_raw / vgl_soibean_run_raw chunk by chunk; the per-read outputs are indexed
+ * by the read's position in [r0, r1) (each may be NULL; path_ll is (r1 - r0) x n_paths doubles) and are complete on return.     */
+int vgh_euka_feed(vgh_hc_feeder* f, struct vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t* clade, double* in_lik,
+                  double* not_lik, double* like, uint8_t* pass);
+int vgh_soibean_feed(vgh_hc_feeder* f, struct vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t n_paths, double* path_ll,
+                     uint8_t* used);
+int vgh_euka_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out);
 void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* wait_seconds, uint64_t* h2d_bytes, uint64_t* chunks,
                          uint64_t* slow_chunks);
 void vgh_hc_feeder_destroy(vgh_hc_feeder* f);

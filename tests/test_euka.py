@@ -189,13 +189,20 @@ def test_config4_tables_taken_verbatim_from_the_reference(capfd):
     ek.load_graph(S.graph)
     mapped = alns.arrays()["identity"] != 0
     margin = np.abs(want["in_lik"] - want["not_lik"] - 1.0)
-    for route in ("packed", "raw", "rerun"):
+    feeder = vb.Feeder(n_threads=2, chunk_reads=1024)          # four chunks; node ids up to 6.9 M travel as 32 bits
+    for route in ("packed", "raw", "feeder", "rerun"):
         ek.reset()
         if route == "packed":
             got = ek.run(vb.EukaPackedBatch(S.graph, alns))
         elif route == "raw":
             got = ek.run_raw(vb.RawBatch(alns, euka_rule=True))
-        else:
+        elif route == "feeder":
+            got = feeder.feed_euka(ek, alns)
+            assert feeder.stats()["chunks"] == 4 and feeder.stats()["slow_chunks"] == 0
+        else:                                                      # (the feeder left only its last chunk resident)
+            ek.reset()
+            ek.run_raw(vb.RawBatch(alns, euka_rule=True))
+            ek.reset()
             got = ek.rerun(len(alns), want=True)
         assert np.array_equal(got["clade"][mapped], want["clade"][mapped]), route
         assert H.rel_err(got["in_lik"], want["in_lik"]) < 1e-11 and H.rel_err(got["not_lik"], want["not_lik"]) < 1e-12

@@ -520,7 +520,7 @@ def test_samples_pass_reports_a_bad_sample_without_losing_the_others():
 
 def test_node_table_beyond_the_shared_memory_limit_is_refused_with_a_status():
     """the node -> class table of the read kernel lives in shared memory (2 B per row next to 20 KB of small tables
-    and the queue rings, 227 KB per CTA).  HaploCart's graph has 11 825 rows; 50 000 still load, 120 000 are refused by
+    and the queue rings, 227 KB per CTA).  HaploCart's graph has 11 825 rows; 40 000 still load, 120 000 are refused by
     vgl_hc_set_tables with VGL_ERR_INVALID and a message that names the limit -- nothing is launched."""
     rng = np.random.default_rng(7)
 
@@ -531,7 +531,7 @@ def test_node_table_beyond_the_shared_memory_limit_is_refused_with_a_status():
         return vb.HcTables(sup, node, val, np.full(16569, 0.9))
 
     hc = vb.Haplocart()
-    hc.load(tables(50000))
+    hc.load(tables(40000))
     with pytest.raises(_lib.VglError, match="shared memory"):
         hc.load(tables(120000))
     hc.close()

@@ -490,6 +490,42 @@ def test_batch_format_limits_are_enforced_at_the_limit_itself():
         pack(H.aln("ACGTACGT", [(131071, 0, False, [(8, 8, "")])]))
 
 
+def test_feeder_sibling_form_and_32_bit_node_ids():
+    """The euka / soibean form of the feeder's chunk (identity != 0 kept, |sequence| and the read's position per read) against
+    vgh_euka_raw_build; and node ids above 32767 (euka's graphs), which make the feeder switch to 32-bit node ids once."""
+    S = vb.SynthHaplocart(seed=21, n_paths=33, n_rows=310, n_nodes=301)
+    A = S.reads(2000, seed=37, sub_rate=0.02, indel_rate=0.01, fixed_len=0, damage=True)
+    as_arr = vb.host._as_array
+    f = vb.Feeder(n_threads=3, chunk_reads=4096)
+    general = vb.RawBatch(A, 3, 1900, euka_rule=True)
+    want = general.raw
+    got = f.marshal(A, 3, 1900, sibling=True)
+    n, nm, ne = int(want.n_reads), int(want.n_maps), int(want.n_edits)
+    assert got is not None and (int(got.n_reads), int(got.n_maps), int(got.n_edits)) == (n, nm, ne)
+    for name, count, dt in [("seq_len", n, np.uint16), ("read_index", n, np.uint32), ("map_node16", nm, np.uint16), ("mapq", n, np.uint8),
+                            ("first_offset16", n, np.uint16), ("map_n_edits8", nm, np.uint8), ("edit_slen8", ne, np.uint8),
+                            ("map_off", n + 1, np.uint32), ("str_off", n + 1, np.uint32)]:
+        assert np.array_equal(as_arr(getattr(got, name), count, dt), as_arr(getattr(want, name), count, dt)), name
+    # 32-bit node ids
+    big = {40000: "ACGTACGTACGTACGTACGT", 40001: "TTGCATTGCATTGCATTGCA"}
+    reads = [H.aln(big[40000], [(40000, 0, False, [(20, 20, "")])]),
+             H.aln(big[40001][2:], [(40001, 2, True, [(18, 18, "")])]),
+             H.aln(big[40000] + big[40001], [(40000, 0, False, [(20, 20, "")]), (40001, 0, False, [(20, 20, "")])])]
+    B = vb.Alignments.from_gam_bytes(H.encode_gam(reads))
+    wide_general = vb.RawBatch(B, euka_rule=True)
+    assert not wide_general.raw.map_node16
+    g2 = f.marshal(B, 0, 3, sibling=True)
+    assert g2 is not None and not g2.map_node16 and g2.map_node
+    assert np.array_equal(as_arr(g2.map_node, 4, np.uint32), as_arr(wide_general.raw.map_node, 4, np.uint32))
+    assert list(as_arr(g2.map_node, 4, np.uint32)) == [40000, 40001 | 0x80000000, 40000, 40001]
+    # the switch is sticky: the next chunk with small ids still travels with 32-bit ids, same values
+    g3 = f.marshal(A, 3, 1900, sibling=True)
+    assert g3 is not None and not g3.map_node16
+    w16 = as_arr(want.map_node16, nm, np.uint16).astype(np.uint32)
+    assert np.array_equal(as_arr(g3.map_node, nm, np.uint32), (w16 & 0x7fff) | ((w16 >> 15) << 31))
+    f.close()
+
+
 def test_crafted_bgzf_sizes_do_not_take_the_process_down():
     """A BGZF-looking stream whose member trailers claim ~4 GiB each: rejected with an error code, no huge
     allocation, no exception across the C ABI."""

@@ -61,6 +61,13 @@ def test_path_matrix_matches_oracle(P, p5, p3, penalty):
     top_w = np.sort(want, axis=1)
     clear = (top_w[:, -1] - top_w[:, -2] > 1e-9) & (used_w == 1)
     assert np.array_equal(got.argmax(axis=1)[clear], want.argmax(axis=1)[clear]) and clear.sum() > 0
+    # the feeder route (vgh_soibean_feed): flat alignment fields -> page-locked chunks -> device reconstruction; several chunks
+    sb.load_graph(S.graph)
+    f = vb.Feeder(n_threads=2, chunk_reads=400)
+    fed, fed_used = f.feed_soibean(sb, alns)
+    assert f.stats()["chunks"] == 4 and f.stats()["slow_chunks"] == 0
+    assert np.array_equal(fed_used, used_w) and H.rel_err(fed, want) < 1e-11
+    f.close()
     sb.close()
 
 

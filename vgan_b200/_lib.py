@@ -175,6 +175,9 @@ HOST_SYMBOLS = {
     "vgh_hc_feeder_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(_P)]),
     "vgh_hc_feed": (C.c_int, [_P, _P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64]),
     "vgh_hc_feeder_marshal": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.POINTER(C.POINTER(vgl_hc_raw))]),
+    "vgh_euka_feeder_marshal": (C.c_int, [_P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.POINTER(C.POINTER(vgl_hc_raw))]),
+    "vgh_euka_feed": (C.c_int, [_P, _P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "vgh_soibean_feed": (C.c_int, [_P, _P, C.POINTER(vgh_alignments), C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "vgh_hc_feeder_stats": (None, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64)]),
     "vgh_hc_feeder_destroy": (None, [_P]),

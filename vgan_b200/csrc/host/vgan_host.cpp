@@ -1208,6 +1208,7 @@ struct vgh_hc_feeder {
     vgl_hc_raw view[2];
     double build_s = 0, wait_s = 0;
     uint64_t bytes = 0, chunks = 0, slow_chunks = 0, reads = 0;
+    bool wide_nodes = false;   // a node id above 32767 was seen: node ids travel as 32 bits from then on (euka's graphs)
 };
 
 extern "C" {
@@ -1248,20 +1249,27 @@ void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* 
 #define VGH_CLONES
 #endif
 
-VGH_CLONES static void feeder_narrow_mappings(const int64_t* __restrict__ node, const int64_t* __restrict__ offs, const uint8_t* __restrict__ rev,
-                                              const int64_t* __restrict__ eo, uint16_t* __restrict__ on, uint8_t* __restrict__ oc, int64_t n,
-                                              uint64_t* viol, uint64_t* nonzero_off) {
-    uint64_t v = 0, nzo = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);
-        v |= (nd & ~(uint64_t)0x7fff) | (cnt & ~(uint64_t)0xff);
-        on[i] = (uint16_t)((nd & 0x7fff) | (rev[i] ? 0x8000u : 0u));
-        oc[i] = (uint8_t)cnt;
-        nzo += offs[i] != 0;
+// node ids as 16 bits (HaploCart's graph: ids <= 32767) or 32 bits (euka's graphs); the top bit carries is_reverse
+#define VGH_FEEDER_NARROW_MAPPINGS(NAME, NodeT, ID_MASK, REV_BIT)                                                                          \
+    VGH_CLONES static void NAME(const int64_t* __restrict__ node, const int64_t* __restrict__ offs, const uint8_t* __restrict__ rev,       \
+                                const int64_t* __restrict__ eo, NodeT* __restrict__ on, uint8_t* __restrict__ oc, int64_t n,              \
+                                uint64_t* viol, uint64_t* node_viol, uint64_t* nonzero_off) {                                             \
+        uint64_t v = 0, nv = 0, nzo = 0;                                                                                                   \
+        for (int64_t i = 0; i < n; ++i) {                                                                                                  \
+            const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);                                                    \
+            v |= cnt & ~(uint64_t)0xff;                                                                                                    \
+            nv |= nd & ~(uint64_t)(ID_MASK);                                                                                               \
+            on[i] = (NodeT)((nd & (ID_MASK)) | (rev[i] ? (REV_BIT) : 0ull));                                                               \
+            oc[i] = (uint8_t)cnt;                                                                                                          \
+            nzo += offs[i] != 0;                                                                                                           \
+        }                                                                                                                                  \
+        *viol |= v;                                                                                                                        \
+        *node_viol |= nv;                                                                                                                  \
+        *nonzero_off += nzo;                                                                                                               \
     }
-    *viol |= v;
-    *nonzero_off += nzo;
-}
+VGH_FEEDER_NARROW_MAPPINGS(feeder_narrow_mappings16, uint16_t, 0x7fffull, 0x8000ull)
+VGH_FEEDER_NARROW_MAPPINGS(feeder_narrow_mappings32, uint32_t, 0x7fffffffull, 0x80000000ull)
+#undef VGH_FEEDER_NARROW_MAPPINGS
 
 VGH_CLONES static void feeder_narrow_edits(const int32_t* __restrict__ fr, const int32_t* __restrict__ to, const int64_t* __restrict__ so,
                                            uint8_t* __restrict__ of, uint8_t* __restrict__ ot, uint8_t* __restrict__ os, int64_t n, uint64_t* viol) {
@@ -1288,8 +1296,13 @@ static constexpr size_t kFeederRunReads = 128;
 // Marshals the reads of [ra, rb) that the hot loop keeps (identity >= 1e-10, src/HaploCart.cpp:411) into block `slot`.
 // Two parallel passes over per-thread ranges of reads: (A) how many mappings / edits / bytes each range keeps (read-level
 // offsets only), (B) the copy itself.  Returns 1 when the chunk needs the general builder instead.
-static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int64_t ra, int64_t rb) {
+//   mode 0: HaploCart's rule (identity >= 1e-10 is kept, src/HaploCart.cpp:411) and the batch's value ranges (meta);
+//   mode 1: euka / soibean (identity != 0 is kept, src/readGAM_Euka.h:73) plus |Alignment.sequence| and the read's position in
+//           [ra, rb) per read, which their kernels need (vgl_euka_run_raw / vgl_soibean_run_raw).
+static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int64_t ra, int64_t rb, int mode = 0) {
     const size_t Rall = (size_t)(rb - ra);
+    const auto skipped = [a, mode](int64_t r) { return mode == 0 ? a->identity[r] < 1e-10 : a->identity[r] == 0; };
+    const bool wide = f->wide_nodes;
     int T = std::max(1, f->n_threads);
     T = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, Rall / 512 + 1));
     struct Cnt { uint64_t r = 0, m = 0, e = 0, q = 0, s = 0; };
@@ -1299,7 +1312,7 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
         const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
         Cnt c;
         size_t kept = 0;
-        for (size_t k = k0; k < k1; ++k) kept += !(a->identity[ra + (int64_t)k] < 1e-10);
+        for (size_t k = k0; k < k1; ++k) kept += !skipped(ra + (int64_t)k);
         if (kept == k1 - k0) {   // the usual case, nothing skipped: the counts are differences of the offsets at the range's ends
             const int64_t rs = ra + (int64_t)k0, re = ra + (int64_t)k1;
             const int64_t ma = a->map_off[rs], mb = a->map_off[re];
@@ -1310,7 +1323,7 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
         } else {
             for (size_t k = k0; k < k1; ++k) {
                 const int64_t r = ra + (int64_t)k;
-                if (a->identity[r] < 1e-10) continue;
+                if (skipped(r)) continue;
                 const int64_t ma = a->map_off[r], mb = a->map_off[r + 1];
                 const int64_t ea = a->edit_off[ma], eb = a->edit_off[mb];
                 c.r += 1; c.m += (uint64_t)(mb - ma); c.e += (uint64_t)(eb - ea);
@@ -1330,8 +1343,9 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t o_qoff = take((R + 1) * 4), o_soff = take((R + 1) * 4), o_moff = take((R + 1) * 4), o_mq = take(R), o_q = take(nq);
-    const size_t o_n16 = take(nm * 2), o_fo16 = take(R * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne);
+    const size_t o_n16 = take(nm * (wide ? 4 : 2)), o_fo16 = take(R * 2), o_ne8 = take(nm), o_sl8 = take(ne), o_f8 = take(ne), o_t8 = take(ne);
     const size_t o_eseq = take(ns), o_ends = take(64);
+    const size_t o_slen = take(mode ? R * 2 : 0), o_ridx = take(mode ? R * 4 : 0);
     if (o > f->cap[slot]) {
         if (f->block[slot]) { if (f->pinned[slot]) vgl_host_free(f->block[slot]); else free(f->block[slot]); }
         f->block[slot] = nullptr;
@@ -1347,33 +1361,39 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     uint8_t* blk = (uint8_t*)f->block[slot];
     uint32_t* qoff = (uint32_t*)(blk + o_qoff); uint32_t* soff = (uint32_t*)(blk + o_soff); uint32_t* moff = (uint32_t*)(blk + o_moff);
     uint8_t* mq = blk + o_mq; uint8_t* q = blk + o_q;
-    uint16_t* n16 = (uint16_t*)(blk + o_n16); uint16_t* fo16 = (uint16_t*)(blk + o_fo16);
+    uint16_t* n16 = (uint16_t*)(blk + o_n16); uint32_t* n32 = (uint32_t*)(blk + o_n16); uint16_t* fo16 = (uint16_t*)(blk + o_fo16);
+    uint16_t* slen = (uint16_t*)(blk + o_slen); uint32_t* ridx = (uint32_t*)(blk + o_ridx);
     uint8_t* ne8 = blk + o_ne8; uint8_t* sl8 = blk + o_sl8; uint8_t* f8 = blk + o_f8; uint8_t* t8 = blk + o_t8; uint8_t* eseq = blk + o_eseq;
     // Pass B works on RUNS of consecutive kept reads (a chunk is one run unless it holds a read the hot loop skips): inside a
     // run the mappings, edits, quality bytes and edit sequences are contiguous in the source arrays, so the narrowing copies
     // are flat loops over whole arrays (the compiler vectorises them) and the range checks OR-accumulate instead of branching.
-    int bad = 0;
+    int bad = 0, bad_node = 0;
     std::vector<MetaAcc> metas((size_t)T);
-#pragma omp parallel for schedule(static, 1) num_threads(T) reduction(| : bad)
+#pragma omp parallel for schedule(static, 1) num_threads(T) reduction(| : bad, bad_node)
     for (int t = 0; t < T; ++t) {
         const size_t k0 = Rall * (size_t)t / (size_t)T, k1 = Rall * (size_t)(t + 1) / (size_t)T;
         MetaAcc& meta = metas[(size_t)t];
         size_t cr = (size_t)base[(size_t)t].r, cm = (size_t)base[(size_t)t].m, ce = (size_t)base[(size_t)t].e;
         size_t cq = (size_t)base[(size_t)t].q, cs = (size_t)base[(size_t)t].s;
         uint64_t viol = 0;        // any bit set: a value does not fit its narrow field
+        uint64_t node_viol = 0;   // ... a node id does not fit the node field in use
         uint64_t nonzero_off = 0, nonzero_first = 0;   // mappings with a non-zero node offset; reads whose FIRST mapping has one
         int8_t qmax = 0;          // largest quality byte as signed char (bytes >= 128 are negative: canonical 0)
         size_t k = k0;
         while (k < k1) {
-            if (a->identity[ra + (int64_t)k] < 1e-10) { ++k; continue; }
+            if (skipped(ra + (int64_t)k)) { ++k; continue; }
             size_t ke = k + 1;
             const size_t kcap = std::min(k1, k + kFeederRunReads);   // short runs: the per-read pass below finds the run's lines still in L2
-            while (ke < kcap && !(a->identity[ra + (int64_t)ke] < 1e-10)) ++ke;
+            while (ke < kcap && !skipped(ra + (int64_t)ke)) ++ke;
             const int64_t rs = ra + (int64_t)k, re = ra + (int64_t)ke;   // the run [rs, re)
             const int64_t M0 = a->map_off[rs], M1 = a->map_off[re], E0 = a->edit_off[M0], E1 = a->edit_off[M1];
             const int64_t Q0 = a->qual_off[rs], Q1 = a->qual_off[re], S0 = a->edit_seq_off[E0], S1 = a->edit_seq_off[E1];
-            feeder_narrow_mappings(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n16 + cm, ne8 + cm, M1 - M0,
-                                   &viol, &nonzero_off);
+            if (wide)
+                feeder_narrow_mappings32(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n32 + cm, ne8 + cm, M1 - M0,
+                                         &viol, &node_viol, &nonzero_off);
+            else
+                feeder_narrow_mappings16(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n16 + cm, ne8 + cm, M1 - M0,
+                                         &viol, &node_viol, &nonzero_off);
             feeder_narrow_edits(a->edit_from + E0, a->edit_to + E0, a->edit_seq_off + E0, f8 + ce, t8 + ce, sl8 + ce, E1 - E0, &viol);
             memcpy(q + cq, a->qual + Q0, (size_t)(Q1 - Q0));
             memcpy(eseq + cs, a->edit_seq + S0, (size_t)(S1 - S0));
@@ -1398,6 +1418,10 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
                 for (int64_t i = 0; i < eb - ea; ++i) span += (uint32_t)pf[i] + (uint32_t)pt[i];
                 const uint64_t cap = (uint64_t)span + (uint64_t)(a->edit_seq_off[eb] - a->edit_seq_off[ea]);
                 soff[cr + 1] = (uint32_t)((cap + 3) & ~(uint64_t)3);  // prefix-summed below
+                if (mode) {
+                    slen[cr] = (uint16_t)std::min<int64_t>(a->seq_off[r + 1] - a->seq_off[r], 65535);
+                    ridx[cr] = (uint32_t)(r - ra);
+                }
                 ++cr;
             }
             cm += (size_t)(M1 - M0); ce += (size_t)(E1 - E0); cq += (size_t)(Q1 - Q0); cs += (size_t)(S1 - S0);
@@ -1405,9 +1429,15 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
         }
         // only a read's first mapping may start inside its node (first_offset16 form)
         bad |= (viol != 0 || nonzero_off != nonzero_first) ? 1 : 0;
+        bad_node |= node_viol != 0 ? 1 : 0;
         meta.qmax = std::max<uint32_t>(meta.qmax, qmax > 2 ? (uint32_t)qmax : 0u);
     }
     if (bad) return 1;
+    if (bad_node) {   // a node id above the field in use: 32-bit node ids from now on (once per feeder), or the general builder
+        if (wide) return 1;
+        f->wide_nodes = true;
+        return feeder_fill(f, slot, a, ra, rb, mode);
+    }
     soff[0] = 0;
     uint64_t run = 0;
     for (size_t k = 0; k < R; ++k) { run += soff[k + 1]; soff[k + 1] = (uint32_t)run; }
@@ -1424,24 +1454,43 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     v.qual_off = qoff; v.qual = q; v.mapq = mq; v.str_off = soff; v.map_off = moff;
     v.edit_off = ends; v.edit_seq_off = ends + 2;
     v.edit_seq = eseq;
-    v.map_node16 = n16; v.first_offset16 = fo16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; v.edit_from8 = f8; v.edit_to8 = t8;
-    MetaAcc all;
-    for (const MetaAcc& m : metas) all.merge(m);
-    all.store(v.meta);
+    if (wide) v.map_node = n32; else v.map_node16 = n16;
+    v.first_offset16 = fo16; v.map_n_edits8 = ne8; v.edit_slen8 = sl8; v.edit_from8 = f8; v.edit_to8 = t8;
+    if (mode) {
+        v.seq_len = slen; v.read_index = ridx;
+    } else {
+        MetaAcc all;
+        for (const MetaAcc& m : metas) all.merge(m);
+        all.store(v.meta);
+    }
     return 0;
 }
 
 // One chunk marshalled into block 0, for inspection and tests: *out is NULL when the chunk needs the general builder.
-static int vgh_hc_feeder_marshal__impl(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+static int feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, int mode, const vgl_hc_raw** out) {
     if (!f || !a || !out || r0 < 0 || r1 > a->n_reads || r0 > r1 || r1 - r0 > f->chunk_reads) return fail(VGH_ERR_INVALID, "bad arguments");
-    const int how = feeder_fill(f, 0, a, r0, r1);
+    const int how = feeder_fill(f, 0, a, r0, r1, mode);
     if (how > 1) return how;
     *out = how == 0 ? &f->view[0] : nullptr;
     return VGH_OK;
 }
+static int vgh_hc_feeder_marshal__impl(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+    return feeder_marshal(f, a, r0, r1, 0, out);
+}
+int vgh_euka_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, const vgl_hc_raw** out) {
+    try {
+        return feeder_marshal(f, a, r0, r1, 1, out);
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_feeder_marshal: %s", e.what());
+    }
+}
 
-static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
-    if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+}  // extern "C" (the pipeline below is a template)
+
+// The pipeline shared by the three tools: chunk c + 1 is marshalled while a second thread submits chunk c (its H2D copies,
+// kernels and -- for the sibling tools -- the copy of its per-read results back).  submit(view, ra, rb) returns a vgl status.
+template <typename Submit>
+static int feeder_run(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int64_t r1, int mode, Submit submit_chunk) {
     try {
         std::thread submit;
         int submit_rc = VGL_OK;
@@ -1451,11 +1500,11 @@ static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignment
             const int64_t rb = std::min(r1, ra + f->chunk_reads);
             const int slot = (int)(c & 1);
             const auto t0 = std::chrono::steady_clock::now();
-            const int how = feeder_fill(f, slot, a, ra, rb);   // block `slot` was released when submission c - 2 was joined
+            const int how = feeder_fill(f, slot, a, ra, rb, mode);   // block `slot` was released when submission c - 2 was joined
             vgh_hc_raw* general = nullptr;
             if (how == 1) {
                 ++f->slow_chunks;
-                rc = vgh_hc_raw_build(a, ra, rb, /*pinned=*/0, &general);
+                rc = raw_build(a, ra, rb, /*pinned=*/0, /*euka_rule=*/mode != 0, &general);
             } else if (how != 0) {
                 rc = how;
             }
@@ -1469,13 +1518,13 @@ static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignment
             f->reads += (uint64_t)(rb - ra);
             if (general) {   // rare: synchronous, the block is freed right after the copy
                 f->bytes += vgl_hc_raw_bytes(&general->view);
-                submit_rc = vgl_hc_accumulate_raw(ctx, &general->view);
+                submit_rc = submit_chunk(&general->view, ra, rb);
                 vgh_hc_raw_destroy(general);
                 if (submit_rc != VGL_OK) rc = 1000 + submit_rc;
             } else {
                 f->bytes += vgl_hc_raw_bytes(&f->view[slot]);
                 const vgl_hc_raw* v = &f->view[slot];
-                submit = std::thread([ctx, v, &submit_rc]() { submit_rc = vgl_hc_accumulate_raw(ctx, v); });
+                submit = std::thread([v, ra, rb, &submit_rc, &submit_chunk]() { submit_rc = submit_chunk(v, ra, rb); });
             }
         }
         if (submit.joinable()) submit.join();
@@ -1485,6 +1534,32 @@ static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignment
     } catch (const std::exception& e) {
         return fail(VGH_ERR_INVALID, "feeder: %s", e.what());
     }
+}
+
+extern "C" {
+
+static int vgh_hc_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1) {
+    if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+    return feeder_run(f, a, r0, r1, 0, [ctx](const vgl_hc_raw* v, int64_t, int64_t) { return vgl_hc_accumulate_raw(ctx, v); });
+}
+
+static int vgh_euka_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t* clade,
+                               double* in_lik, double* not_lik, double* like, uint8_t* pass) {
+    if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1) return fail(VGH_ERR_INVALID, "bad arguments");
+    return feeder_run(f, a, r0, r1, 1, [=](const vgl_hc_raw* v, int64_t ra, int64_t rb) {
+        const int64_t at = ra - r0;   // read_index counts from the chunk's first read
+        return vgl_euka_run_raw(ctx, v, (uint32_t)(rb - ra), clade ? clade + at : nullptr, in_lik ? in_lik + at : nullptr,
+                                not_lik ? not_lik + at : nullptr, like ? like + at : nullptr, pass ? pass + at : nullptr);
+    });
+}
+
+static int vgh_soibean_feed__impl(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t n_paths,
+                                  double* path_ll, uint8_t* used) {
+    if (!f || !ctx || !a || r0 < 0 || r1 > a->n_reads || r0 > r1 || n_paths < 1) return fail(VGH_ERR_INVALID, "bad arguments");
+    return feeder_run(f, a, r0, r1, 1, [=](const vgl_hc_raw* v, int64_t ra, int64_t rb) {
+        const int64_t at = ra - r0;
+        return vgl_soibean_run_raw(ctx, v, (uint32_t)(rb - ra), path_ll ? path_ll + at * (int64_t)n_paths : nullptr, used ? used + at : nullptr);
+    });
 }
 
 }  // extern "C"
@@ -1878,6 +1953,32 @@ int vgh_hc_feeder_marshal(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0,
         return fail(VGH_ERR_INVALID, "vgh_hc_feeder_marshal: %s", e.what());
     } catch (...) {
         return fail(VGH_ERR_INVALID, "vgh_hc_feeder_marshal: unknown C++ exception");
+    }
+}
+
+int vgh_euka_feed(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t* clade, double* in_lik,
+                  double* not_lik, double* like, uint8_t* pass) {
+    try {
+        return vgh_euka_feed__impl(f, ctx, a, r0, r1, clade, in_lik, not_lik, like, pass);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_feed: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_feed: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_euka_feed: unknown C++ exception");
+    }
+}
+
+int vgh_soibean_feed(vgh_hc_feeder* f, vgl_ctx* ctx, const vgh_alignments* a, int64_t r0, int64_t r1, int32_t n_paths, double* path_ll,
+                     uint8_t* used) {
+    try {
+        return vgh_soibean_feed__impl(f, ctx, a, r0, r1, n_paths, path_ll, used);
+    } catch (const std::bad_alloc&) {
+        return fail(VGH_ERR_INVALID, "vgh_soibean_feed: out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VGH_ERR_INVALID, "vgh_soibean_feed: %s", e.what());
+    } catch (...) {
+        return fail(VGH_ERR_INVALID, "vgh_soibean_feed: unknown C++ exception");
     }
 }
 

@@ -853,56 +853,47 @@ static SlotPlan plan_slots(const uint32_t mq_count[128], size_t n) {
     return P;
 }
 
-// Reads [ra, rb) of `raw`: H2D of their slices on `copy_stream` into staging set `R`, then reconstruction and packing on
-// ctx->stream; fills the read kernel's batch descriptor.  The slices keep their absolute indices (offsets into the
-// whole batch): the device pointers are shifted back by each slice's first element and only ever dereferenced inside.
-static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t rb, vgl_ctx::RawDev& R, cudaStream_t copy_stream,
-                          vgl::HcBatchDev& d, vgl::HcBatchMeta* seg_out = nullptr) {
-    cudaStream_t s = ctx->stream;
-    const size_t n = rb - ra;
-    const bool narrow_only = (raw->reserved & VGL_HC_RAW_NARROW_ONLY) != 0;  // the whole view is this chunk (check_raw)
-    const size_t ma = raw->map_off[ra], mb = raw->map_off[rb], nm = mb - ma;
-    const size_t ea = narrow_only ? raw->edit_off[0] : raw->edit_off[ma], eb = narrow_only ? raw->edit_off[1] : raw->edit_off[mb], ne = eb - ea;
-    const size_t qa = raw->qual_off[ra], nq = raw->qual_off[rb] - qa;
-    const size_t sa = narrow_only ? raw->edit_seq_off[0] : raw->edit_seq_off[ea];
-    const size_t nseq = (narrow_only ? raw->edit_seq_off[1] : raw->edit_seq_off[eb]) - sa;
-    const size_t ca = raw->str_off[ra], ncap = raw->str_off[rb] - ca;
-    uint32_t mq_count[128];
-    memset(mq_count, 0, sizeof(mq_count));
-    for (size_t r = ra; r < rb; ++r) mq_count[raw->mapq[r] & 127u] += 1;
-    const SlotPlan plan = plan_slots(mq_count, n);
-    const uint32_t n_slots = plan.n_slots;
-    const size_t G = plan.G;
-    if (seg_out) {
-        seg_out->n_segs = plan.segs.n_segs;
-        memcpy(seg_out->seg_mapq, plan.segs.seg_mapq, sizeof(plan.segs.seg_mapq));
-        memcpy(seg_out->seg_end, plan.segs.seg_end, sizeof(plan.segs.seg_end));
-    }
-    // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read (per slot)
-    const size_t col_cap = ncap / 128 + (size_t)n_slots * 1024 + G + 1, map_cap = G + 4096;
-    if (col_cap > 0x7fffffffull) return fail(VGL_ERR_INVALID, "batch too large; split it");
-    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
-    if (!R.consumed) VGL_CUDA(cudaEventCreateWithFlags(&R.consumed, cudaEventDisableTiming));
-    if (R.used) VGL_CUDA(cudaStreamWaitEvent(copy_stream, R.consumed, 0));  // the kernels that last read this staging set
-    // growing a buffer frees it: the kernels still reading it must have finished
-    if (n + 1 > R.qual_off.cap || nq > R.qual.cap || nm > R.map_node.cap || ne > R.edit_from.cap || nseq > R.edit_seq.cap ||
-        ncap > R.gstr.cap || col_cap * 128 > R.col.cap || map_cap * 128 > R.xmap.cap || G * 32 > R.order.cap || G * 32 > R.o_n_cols.cap ||
-        3 * 4096 * (size_t)n_slots > R.hist3.cap || G + 1 > R.grp_cb.cap)
-        VGL_CUDA(cudaStreamSynchronize(s));
+// Where reads [ra, rb) of a raw batch sit in its arrays (a narrow-only view is one chunk: its two wide offset arrays are
+// stand-ins that hold only their end points, VGL_HC_RAW_NARROW_ONLY).
+struct RawSpan {
+    size_t n, ma, nm, ea, ne, qa, nq, sa, nseq, ca, ncap;
+};
+static RawSpan raw_span(const vgl_hc_raw* raw, size_t ra, size_t rb) {
+    const bool narrow_only = (raw->reserved & VGL_HC_RAW_NARROW_ONLY) != 0;
+    RawSpan sp;
+    sp.n = rb - ra;
+    sp.ma = raw->map_off[ra];
+    sp.nm = raw->map_off[rb] - sp.ma;
+    sp.ea = narrow_only ? raw->edit_off[0] : raw->edit_off[sp.ma];
+    sp.ne = (narrow_only ? raw->edit_off[1] : raw->edit_off[sp.ma + sp.nm]) - sp.ea;
+    sp.qa = raw->qual_off[ra];
+    sp.nq = raw->qual_off[rb] - sp.qa;
+    sp.sa = narrow_only ? raw->edit_seq_off[0] : raw->edit_seq_off[sp.ea];
+    sp.nseq = (narrow_only ? raw->edit_seq_off[1] : raw->edit_seq_off[sp.ea + sp.ne]) - sp.sa;
+    sp.ca = raw->str_off[ra];
+    sp.ncap = raw->str_off[rb] - sp.ca;
+    return sp;
+}
+
+// Device buffers for the input arrays of one span (wide and narrow forms).
+static int reserve_raw_inputs(vgl_ctx::RawDev& R, const RawSpan& sp) {
+    const size_t n = sp.n, nm = sp.nm, ne = sp.ne;
 #define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
-    RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq);
+    RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, sp.nq);
     RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
-    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
+    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, sp.nseq);
     RSV(R.off16, nm); RSV(R.fo16, n); RSV(R.n16, nm); RSV(R.ne8, nm); RSV(R.sl8, ne); RSV(R.f8, ne); RSV(R.t8, ne); RSV(R.tiles, std::max(nm, ne) / 4096 + 2);
-    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
-    RSV(R.hist3, 3 * 4096 * (size_t)n_slots); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
-    RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
-    RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
 #undef RSV
-    R.col_cap_blks = (uint32_t)col_cap;
-    R.map_cap_blks = (uint32_t)map_cap;
-    d = vgl::HcBatchDev{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p};
-    if (n == 0) return VGL_OK;
+    return VGL_OK;
+}
+
+// H2D of the span's input arrays on `copy_stream` (event R.copied), then on ctx->stream the widening of whatever travelled
+// in narrow form: 16-bit node ids, one node offset per read, counts and lengths as bytes -> the 32-bit values and offsets the
+// reconstruction kernel reads.  The slices keep their absolute indices.
+static int stage_raw_inputs(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, const RawSpan& sp, vgl_ctx::RawDev& R, cudaStream_t copy_stream) {
+    cudaStream_t s = ctx->stream;
+    const size_t n = sp.n, ma = sp.ma, nm = sp.nm, ea = sp.ea, ne = sp.ne, qa = sp.qa, nq = sp.nq, sa = sp.sa, nseq = sp.nseq;
+    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
 #define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, copy_stream))
     H2D(R.qual_off.p, raw->qual_off + ra, (n + 1) * 4); H2D(R.str_off.p, raw->str_off + ra, (n + 1) * 4);
     H2D(R.map_off.p, raw->map_off + ra, (n + 1) * 4); H2D(R.mapq.p, raw->mapq + ra, n); H2D(R.qual.p, raw->qual + qa, nq);
@@ -954,6 +945,51 @@ static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t
         VGL_CUDA(vgl::raw_launch_offsets_from_counts(R.sl8.p, (uint32_t)ne, (uint32_t)sa, R.tiles.p, R.edit_seq_off.p, s));
         ctx->launches += 7;
     }
+    return VGL_OK;
+}
+
+// Reads [ra, rb) of `raw`: H2D of their slices on `copy_stream` into staging set `R`, then reconstruction and packing on
+// ctx->stream; fills the read kernel's batch descriptor.  The slices keep their absolute indices (offsets into the
+// whole batch): the device pointers are shifted back by each slice's first element and only ever dereferenced inside.
+static int pack_raw_chunk(vgl_ctx* ctx, const vgl_hc_raw* raw, size_t ra, size_t rb, vgl_ctx::RawDev& R, cudaStream_t copy_stream,
+                          vgl::HcBatchDev& d, vgl::HcBatchMeta* seg_out = nullptr) {
+    cudaStream_t s = ctx->stream;
+    const RawSpan sp = raw_span(raw, ra, rb);
+    const size_t n = sp.n, ma = sp.ma, nm = sp.nm, ea = sp.ea, ne = sp.ne, qa = sp.qa, nq = sp.nq, sa = sp.sa, nseq = sp.nseq, ca = sp.ca, ncap = sp.ncap;
+    uint32_t mq_count[128];
+    memset(mq_count, 0, sizeof(mq_count));
+    for (size_t r = ra; r < rb; ++r) mq_count[raw->mapq[r] & 127u] += 1;
+    const SlotPlan plan = plan_slots(mq_count, n);
+    const uint32_t n_slots = plan.n_slots;
+    const size_t G = plan.G;
+    if (seg_out) {
+        seg_out->n_segs = plan.segs.n_segs;
+        memcpy(seg_out->seg_mapq, plan.segs.seg_mapq, sizeof(plan.segs.seg_mapq));
+        memcpy(seg_out->seg_end, plan.segs.seg_end, sizeof(plan.segs.seg_end));
+    }
+    // sorted groups: sum over groups of the longest lane <= (sum of all lanes) / 32 + the longest read (per slot)
+    const size_t col_cap = ncap / 128 + (size_t)n_slots * 1024 + G + 1, map_cap = G + 4096;
+    if (col_cap > 0x7fffffffull) return fail(VGL_ERR_INVALID, "batch too large; split it");
+    if (!R.copied) VGL_CUDA(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
+    if (!R.consumed) VGL_CUDA(cudaEventCreateWithFlags(&R.consumed, cudaEventDisableTiming));
+    if (R.used) VGL_CUDA(cudaStreamWaitEvent(copy_stream, R.consumed, 0));  // the kernels that last read this staging set
+    // growing a buffer frees it: the kernels still reading it must have finished
+    if (n + 1 > R.qual_off.cap || nq > R.qual.cap || nm > R.map_node.cap || ne > R.edit_from.cap || nseq > R.edit_seq.cap ||
+        ncap > R.gstr.cap || col_cap * 128 > R.col.cap || map_cap * 128 > R.xmap.cap || G * 32 > R.order.cap || G * 32 > R.o_n_cols.cap ||
+        3 * 4096 * (size_t)n_slots > R.hist3.cap || G + 1 > R.grp_cb.cap)
+        VGL_CUDA(cudaStreamSynchronize(s));
+    if (int rc = reserve_raw_inputs(R, sp)) return rc;
+#define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
+    RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
+    RSV(R.hist3, 3 * 4096 * (size_t)n_slots); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1);
+    RSV(R.col, col_cap * 128); RSV(R.xmap, map_cap * 128);
+    RSV(R.o_n_cols, G * 32); RSV(R.o_n_close, G * 32); RSV(R.o_n_extra, G * 32); RSV(R.o_mapq, G * 32);
+#undef RSV
+    R.col_cap_blks = (uint32_t)col_cap;
+    R.map_cap_blks = (uint32_t)map_cap;
+    d = vgl::HcBatchDev{(uint32_t)G, R.grp_cb.p, R.grp_mb.p, R.col.p, R.xmap.p, R.o_n_cols.p, R.o_n_close.p, R.o_n_extra.p, R.o_mapq.p};
+    if (n == 0) return VGL_OK;
+    if (int rc = stage_raw_inputs(ctx, raw, ra, sp, R, copy_stream)) return rc;
     VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * (size_t)n_slots * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.order.p, 0xff, G * 32 * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.xmap.p, 0, map_cap * 512, s));
@@ -981,8 +1017,8 @@ static int check_raw(vgl_ctx* ctx, const vgl_hc_raw* raw) {
     if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq)
         return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
     if (raw->reserved & VGL_HC_RAW_NARROW_ONLY) {
-        if (!raw->map_node16 || !raw->first_offset16 || !raw->map_n_edits8 || !raw->edit_slen8 || !raw->edit_from8 || !raw->edit_to8)
-            return fail(VGL_ERR_INVALID, "a narrow-only raw batch needs all six narrow arrays");
+        if (!(raw->map_node16 || raw->map_node) || !raw->first_offset16 || !raw->map_n_edits8 || !raw->edit_slen8 || !raw->edit_from8 || !raw->edit_to8)
+            return fail(VGL_ERR_INVALID, "a narrow-only raw batch needs the narrow arrays (node ids as 16 or 32 bits)");
         if ((size_t)raw->n_reads > (size_t)ctx->chunk_groups * VGL_HC_LANES) return fail(VGL_ERR_INVALID, "a narrow-only raw batch holds at most one chunk");
     } else if ((raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to))) {
         return fail(VGL_ERR_INVALID, "raw alignment arrays missing");
@@ -1960,38 +1996,41 @@ int pack_raw_symbols(vgl_ctx* ctx, const vgl_hc_raw* raw, int soibean, vgl::Euka
     ctx->s_last_valid = false;  // the device-built batch is about to be overwritten
     ctx->e_last_valid = false;
     if (!ctx->have_graph) return fail(VGL_ERR_STATE, "vgl_hc_set_graph must come first");
-    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq || !raw->seq_len ||
-        !raw->read_index || (raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to)))
+    if (!raw || !raw->qual_off || !raw->str_off || !raw->map_off || !raw->edit_off || !raw->edit_seq_off || !raw->mapq || !raw->seq_len || !raw->read_index)
         return fail(VGL_ERR_INVALID, "raw alignment arrays missing (euka / soibean need seq_len and read_index: vgh_euka_raw_build)");
+    if (raw->reserved & VGL_HC_RAW_NARROW_ONLY) {
+        if (!(raw->map_node16 || raw->map_node) || !raw->first_offset16 || !raw->map_n_edits8 || !raw->edit_slen8 || !raw->edit_from8 || !raw->edit_to8)
+            return fail(VGL_ERR_INVALID, "a narrow-only raw batch needs the narrow arrays (node ids as 16 or 32 bits)");
+    } else if ((raw->n_maps && (!raw->map_node || !raw->map_offset)) || (raw->n_edits && (!raw->edit_from || !raw->edit_to))) {
+        return fail(VGL_ERR_INVALID, "raw alignment arrays missing (euka / soibean need seq_len and read_index: vgh_euka_raw_build)");
+    }
     vgl_ctx::RawDev& R = ctx->rawdev[0];
     cudaStream_t s = ctx->stream;
     VGL_CUDA(cudaStreamSynchronize(s));  // single staging area
-    const size_t n = raw->n_reads, nm = raw->n_maps, ne = raw->n_edits;
-    const size_t nq = raw->qual_off[n], nseq = raw->edit_seq_off[ne], ncap = raw->str_off[n], G = (n + 31) / 32;
+    const RawSpan sp = raw_span(raw, 0, raw->n_reads);
+    const size_t n = sp.n, ne = sp.ne, ncap = sp.ncap, G = (n + 31) / 32;
     d = vgl::EukaBatchDev{};
     n_map_rec = 0;
     if (n == 0) return VGL_OK;
+    if (int rc = reserve_raw_inputs(R, sp)) return rc;
 #define RSV(buf, cnt) if (int rc = (buf).reserve(std::max<size_t>((cnt), 1))) return rc
-    RSV(R.qual_off, n + 1); RSV(R.str_off, n + 1); RSV(R.map_off, n + 1); RSV(R.mapq, n); RSV(R.qual, nq); RSV(R.seq_len, n);
-    RSV(R.read_index, n); RSV(R.map_node, nm); RSV(R.map_offset, nm); RSV(R.edit_off, nm + 1); RSV(R.edit_from, ne); RSV(R.edit_to, ne);
-    RSV(R.edit_seq_off, ne + 1); RSV(R.edit_seq, nseq);
+    RSV(R.seq_len, n); RSV(R.read_index, n);
     RSV(R.gstr, ncap); RSV(R.rstr, ncap); RSV(R.sizes, ne); RSV(R.n_cols, n); RSV(R.n_close, n); RSV(R.n_extra, n);
     RSV(R.hist3, 3 * 4096); RSV(R.order, G * 32); RSV(R.grp_cb, G + 1); RSV(R.grp_mb, G + 1); RSV(R.s_err, 1);
     RSV(R.s_n_cols, G * 32); RSV(R.s_n_maps, G * 32); RSV(R.s_seq_len, G * 32); RSV(R.s_mapq, G * 32); RSV(R.s_flags, G * 32);
     RSV(R.s_read_index, G * 32);
-#define H2D(dst, src, bytes) if ((size_t)(bytes) != 0) VGL_CUDA(cudaMemcpyAsync((dst), (src), (size_t)(bytes), cudaMemcpyHostToDevice, s))
-    H2D(R.qual_off.p, raw->qual_off, (n + 1) * 4); H2D(R.str_off.p, raw->str_off, (n + 1) * 4); H2D(R.map_off.p, raw->map_off, (n + 1) * 4);
-    H2D(R.mapq.p, raw->mapq, n); H2D(R.qual.p, raw->qual, nq); H2D(R.seq_len.p, raw->seq_len, n * 2); H2D(R.read_index.p, raw->read_index, n * 4);
-    H2D(R.map_node.p, raw->map_node, nm * 4); H2D(R.map_offset.p, raw->map_offset, nm * 4); H2D(R.edit_off.p, raw->edit_off, (nm + 1) * 4);
-    H2D(R.edit_from.p, raw->edit_from, ne * 2); H2D(R.edit_to.p, raw->edit_to, ne * 2); H2D(R.edit_seq_off.p, raw->edit_seq_off, (ne + 1) * 4);
-    H2D(R.edit_seq.p, raw->edit_seq, nseq);
-#undef H2D
+    // the input arrays (wide, or narrow and widened on the device like HaploCart's raw route), then the two per-read arrays
+    if (int rc = stage_raw_inputs(ctx, raw, 0, sp, R, s)) return rc;
+    VGL_CUDA(cudaMemcpyAsync(R.seq_len.p, raw->seq_len, n * 2, cudaMemcpyHostToDevice, s));
+    VGL_CUDA(cudaMemcpyAsync(R.read_index.p, raw->read_index, n * 4, cudaMemcpyHostToDevice, s));
     VGL_CUDA(cudaMemsetAsync(R.hist3.p, 0, 3 * 4096 * sizeof(uint32_t), s));
     VGL_CUDA(cudaMemsetAsync(R.s_err.p, 0, sizeof(int), s));
     const vgl::ReconGraphDev Gd{ctx->g_min_id, ctx->g_n_nodes, ctx->g_seq_off.p, ctx->g_seq.p};
-    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p, R.map_offset.p,
-                              R.edit_off.p, R.edit_from.p, R.edit_to.p, R.edit_seq_off.p, R.edit_seq.p, R.seq_len.p, R.read_index.p};
-    vgl::ReconWorkDev Wd{R.gstr.p, R.rstr.p, R.sizes.p, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
+    // per-read arrays are indexed by the read's position; everything they point INTO by absolute index (as pack_raw_chunk)
+    const vgl::ReconRawDev Rd{(uint32_t)n, R.qual_off.p, R.qual.p - sp.qa, R.mapq.p, R.str_off.p, R.map_off.p, R.map_node.p - sp.ma,
+                              R.map_offset.p - sp.ma, R.edit_off.p - sp.ma, R.edit_from.p - sp.ea, R.edit_to.p - sp.ea, R.edit_seq_off.p - sp.ea,
+                              R.edit_seq.p - sp.sa, R.seq_len.p, R.read_index.p};
+    vgl::ReconWorkDev Wd{R.gstr.p - sp.ca, R.rstr.p - sp.ca, R.sizes.p - sp.ea, R.n_cols.p, R.n_close.p, R.n_extra.p, R.hist3.p, R.hist3.p + 4096,
                          R.hist3.p + 8192, R.order.p, R.grp_cb.p, R.grp_mb.p};
     Wd.n_slots = 1;   // euka / soibean: groups by shape only
     Wd.n_lanes = (uint32_t)(G * 32);

@@ -294,12 +294,36 @@ class Feeder:
         r1 = len(alns) if r1 is None else r1
         check(host.vgh_hc_feed(self.handle, hc.ctx, C.byref(alns.view), int(r0), int(r1)))
 
-    def marshal(self, alns, r0=0, r1=None):
+    def feed_euka(self, ek, alns, r0=0, r1=None, out=None):
+        """The reads of [r0, r1) through vgl_euka_run_raw chunk by chunk (vgh_euka_feed): the per-read results of Euka.run, indexed
+        by the read's position in [r0, r1).  `out` may hold caller-provided (page-locked) arrays under the same keys."""
+        r1 = len(alns) if r1 is None else r1
+        n = int(r1 - r0)
+        if out is None:
+            out = {"clade": np.full(n, -1, dtype=np.int32), "in_lik": np.zeros(n), "not_lik": np.zeros(n), "like": np.zeros(n),
+                   "pass": np.zeros(n, dtype=np.uint8)}
+        p = lambda k: out[k].ctypes.data_as(C.c_void_p) if out.get(k) is not None else None
+        check(host.vgh_euka_feed(self.handle, ek.ctx, C.byref(alns.view), int(r0), int(r1), p("clade"), p("in_lik"), p("not_lik"),
+                                 p("like"), p("pass")))
+        return out
+
+    def feed_soibean(self, sb, alns, r0=0, r1=None, out=None, used=None):
+        """The reads of [r0, r1) through vgl_soibean_run_raw chunk by chunk (vgh_soibean_feed): (matrix [n, P], used [n])."""
+        r1 = len(alns) if r1 is None else r1
+        n, P = int(r1 - r0), int(sb.tables.n_paths)
+        out = np.zeros((n, P), dtype=np.float64) if out is None else out
+        used = np.zeros(n, dtype=np.uint8) if used is None else used
+        check(host.vgh_soibean_feed(self.handle, sb.ctx, C.byref(alns.view), int(r0), int(r1), P, out.ctypes.data_as(C.c_void_p),
+                                    used.ctypes.data_as(C.c_void_p)))
+        return out, used
+
+    def marshal(self, alns, r0=0, r1=None, sibling=False):
         """One chunk marshalled into the feeder's first block (inspection / tests): a vgl_hc_raw, or None when the chunk
-        needs the general builder."""
+        needs the general builder.  sibling=True: the euka / soibean form (identity != 0 kept; seq_len and read_index filled)."""
         r1 = len(alns) if r1 is None else r1
         out = C.POINTER(_lib.vgl_hc_raw)()
-        check(host.vgh_hc_feeder_marshal(self.handle, C.byref(alns.view), int(r0), int(r1), C.byref(out)))
+        fn = host.vgh_euka_feeder_marshal if sibling else host.vgh_hc_feeder_marshal
+        check(fn(self.handle, C.byref(alns.view), int(r0), int(r1), C.byref(out)))
         return out.contents if out else None
 
     def stats(self):
