@@ -251,7 +251,7 @@ def bench_config4(torch, stream, n_reads, peak):
 
     from vgan_b200.host import pinned_empty
     n_all = len(alns)
-    feeder = vb.Feeder(n_threads=int(os.environ.get("OMP_NUM_THREADS", "0") or 0))
+    feeder = vb.Feeder(n_threads=0)      # auto: three quarters of OMP_NUM_THREADS
     outs = {"clade": pinned_empty((n_all,), np.int32), "in_lik": pinned_empty((n_all,), np.float64),
             "not_lik": pinned_empty((n_all,), np.float64), "like": pinned_empty((n_all,), np.float64),
             "pass": pinned_empty((n_all,), np.uint8)}
@@ -321,7 +321,7 @@ def bench_config5(torch, stream, n_reads, peak, P=399):
     to_host()
     ms_e2e, _ = _event_ms(torch, stream, to_host, 3)
     # from the flat alignment fields (vgh_soibean_feed): marshalling, device reconstruction + packing, matrix back, chunk by chunk
-    feeder = vb.Feeder(n_threads=int(os.environ.get("OMP_NUM_THREADS", "0") or 0))
+    feeder = vb.Feeder(n_threads=0)
     assert pk.n_span == len(al)
     feeder.feed_soibean(sb, al, out=po, used=pu)
     ms_feed, _ = _event_ms(torch, stream, lambda: feeder.feed_soibean(sb, al, out=po, used=pu), 3)
@@ -421,7 +421,8 @@ def main():
     alg_bytes = int(4 * pa["n_cols"].astype(np.int64).sum() + 4 * pa["n_extra"].astype(np.int64).sum() + 7 * reads_local
                     + 8 * (int(packed.batch.n_groups) + 1))
     del pa
-    feeder = vb.Feeder(n_threads=args.feeder_threads or host_threads)
+    feeder_threads = args.feeder_threads or max(1, host_threads * 3 // 4)   # the submitting thread and the driver need cores too
+    feeder = vb.Feeder(n_threads=feeder_threads)
 
     sharded = None
     if world > 1:
@@ -744,6 +745,7 @@ def main():
                     "d2h_bytes_per_step": 28 + 8 * hc._max_post, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "route": "flat alignment fields (vgh_alignments, host) -> vgh_hc_feed: host marshalling into page-locked chunks "
                              "overlapped with H2D + device reconstruct_graph_sequence + packing + read kernel -> posterior on the host",
+                    "host_marshal_threads": feeder_threads,
                     "host_marshal_seconds_per_step": (st1["build_seconds"] - st0["build_seconds"]) / nsteps,
                     "host_wait_seconds_per_step": (st1["wait_seconds"] - st0["wait_seconds"]) / nsteps,
                     "general_builder_chunks": st1["slow_chunks"] - st0["slow_chunks"],

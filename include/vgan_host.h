@@ -137,7 +137,8 @@ void vgh_hc_raw_destroy(vgh_hc_raw* p);
  * vgh_hc_feed adds reads [r0, r1) to the sample open on `ctx` (between vgl_hc_reset and vgl_hc_finalize).  The reads travel
  * in chunks of `chunk_reads` (<= 131072): while the device copies, reconstructs (src/vgan_utils.h:6-79) and scores one
  * chunk, `n_threads` host threads marshal the next into the other of two page-locked blocks the feeder keeps.  Returns
- * when every chunk has been copied (the kernels run on; errors in the reads surface at vgl_hc_finalize).            */
+ * when every chunk has been copied (the kernels run on; errors in the reads surface at vgl_hc_finalize).
+ * n_threads = 0: three quarters of the OpenMP threads (the submitting thread and the driver's threads need cores too). */
 typedef struct vgh_hc_feeder vgh_hc_feeder;
 struct vgl_ctx;
 int vgh_hc_feeder_create(int n_threads, int64_t chunk_reads, vgh_hc_feeder** out);

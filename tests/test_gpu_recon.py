@@ -325,6 +325,32 @@ def test_feeder_route_equals_the_packed_route_and_the_oracle(small, chunk):
     hc.close()
 
 
+def test_a_chunk_with_more_empty_mappings_than_the_device_batch_reserves_says_so(small):
+    """The device-built batch reserves groups + 4096 blocks of extra records (one per mapping that owns no column).  A read with
+    20 000 empty mappings packs on the host and is scored; on the raw route the sample fails at finalize with a status that names
+    the way out -- not with "malformed alignment"."""
+    seqs = small.node_sequences()
+    node, _ = small.pmap()
+    a = sorted(set(node.tolist()))[20]
+    sa = seqs[a - 1]
+    many = [(a, 0, False, [(len(sa), len(sa), "")])] + [(a, 0, False, [(0, 0, "")])] * 20000
+    reads = [H.aln(sa, many, quality=bytes([30] * len(sa)))]
+    alns = vb.Alignments.from_gam_bytes(H.encode_gam(reads))
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    hc.load_graph(small.graph)
+    packed = vb.PackedBatch(small.graph, alns)
+    assert len(packed.lanes()[0]["extra"]) == 20000
+    want = hc.run_sample([packed])
+    final, argmax, _ = _oracle(small, alns)
+    _check(want, final, argmax, small)
+    hc.reset()
+    hc.update_raw(vb.RawBatch(alns))
+    with pytest.raises(_lib.VglError, match="empty mappings"):
+        hc.get_posterior()
+    hc.close()
+
+
 def test_feeder_takes_the_general_builder_where_the_narrow_arrays_do_not_fit(small):
     """An edit longer than 255 bases (here a 300-base deletion) does not fit the one-byte lengths: that chunk goes through
     vgh_hc_raw_build, the others stay on the fast path; the corner-case reads ride along."""

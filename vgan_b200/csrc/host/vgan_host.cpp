@@ -1218,7 +1218,9 @@ static int vgh_hc_feeder_create__impl(int n_threads, int64_t chunk_reads, vgh_hc
     vgh_hc_feeder* f = new (std::nothrow) vgh_hc_feeder();
     if (!f) return fail(VGH_ERR_INVALID, "out of host memory");
 #ifdef _OPENMP
-    f->n_threads = n_threads > 0 ? n_threads : omp_get_max_threads();
+    // auto: three quarters of the OpenMP threads -- the submitting thread and the driver's own threads need cores too (measured:
+    // 16 marshalling threads on 16 cores 28.5 ms per 10^6 reads, 12 threads 23.7 ms)
+    f->n_threads = n_threads > 0 ? n_threads : std::max(1, omp_get_max_threads() * 3 / 4);
 #endif
     if (chunk_reads > 0) f->chunk_reads = std::min<int64_t>(chunk_reads, 131072);  // one device chunk per submission
     memset(f->view, 0, sizeof(f->view));

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kErrBadRead = 0x20000000;   // bits of the context's error word
 constexpr int kErrBadNodeRaw = 0x10000000;
+constexpr int kErrBatchCapacity = 0x04000000;   // the device-built batch has no room left (vgl_hc_finalize names the way out)
 constexpr int kReconHaplocart = 0, kReconSoibean = 2;  // (1 = euka)
 
 enum EditKind { kMatch, kSub, kIns, kDel, kOther };
@@ -351,8 +352,8 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t g = slot >> 5, lane = slot & 31;
     if (g >= n_groups) return;
-    if (W.grp_cb[n_groups] > col_cap_blks || W.grp_mb[n_groups] > map_cap_blks) {  // cannot happen for sorted groups; never write past the buffers
-        if (slot == 0) atomicOr(err_flag, kErrBadRead);
+    if (W.grp_cb[n_groups] > col_cap_blks || W.grp_mb[n_groups] > map_cap_blks) {  // columns: cannot happen for sorted groups; extra records: a chunk with very many empty mappings.  Never write past the buffers
+        if (slot == 0) atomicOr(err_flag, kErrBatchCapacity);
         return;
     }
     const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0;
