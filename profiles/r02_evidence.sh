@@ -10,7 +10,7 @@ if [ "${2:-tests}" = "tests" ]; then
   cat gpurun_out/${TAG}_pytest.txt
   timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/${TAG}_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?" >> gpurun_out/${TAG}_sanitizer_memcheck.txt
   timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/${TAG}_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?" >> gpurun_out/${TAG}_sanitizer_racecheck.txt
-  tail -3 gpurun_out/${TAG}_sanitizer_memcheck.txt gpurun_out/${TAG}_sanitizer_racecheck.txt
+  tail -n 3 gpurun_out/${TAG}_sanitizer_memcheck.txt; tail -n 3 gpurun_out/${TAG}_sanitizer_racecheck.txt
 fi
 timeout 1200 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.log
 tail -c 400 gpurun_out/bench_${TAG}.log
@@ -38,7 +38,8 @@ if [ "${3:-ncu}" = "ncu" ]; then
   # one full capture per kernel (a launch after the warm-up of its route)
   for K in hc_read_logterm_kernel hc_path_kernel hc_path_samples_kernel hc_posterior_kernel hc_recon_kernel hc_pack_kernel hc_expand_kernel \
            euka_read_kernel soibean_edit_kernel soibean_path_kernel soibean_mcmc_kernel gam_count_kernel gam_fill_kernel dedup_insert_kernel; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:${K} -s 2 -c 1 -f -o gpurun_out/${TAG}_${K} \
+    SKIP=2; case $K in soibean_mcmc_kernel|dedup_insert_kernel) SKIP=1;; esac   # (kernels the bench launches only twice)
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:${K} -s $SKIP -c 1 -f -o gpurun_out/${TAG}_${K} \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sibling-reads 200000 > gpurun_out/${TAG}_ncu_${K}.log 2>&1
     python profiles/ncu_summary.py gpurun_out/${TAG}_${K}.ncu-rep > gpurun_out/${TAG}_${K}.txt 2>&1
     echo "== ${K}"; head -3 gpurun_out/${TAG}_${K}.txt
