@@ -1498,8 +1498,11 @@ static int feeder_run(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int
         int submit_rc = VGL_OK;
         int rc = VGH_OK;
         int64_t c = 0;
-        for (int64_t ra = r0; ra < r1 && rc == VGH_OK; ra += f->chunk_reads, ++c) {
-            const int64_t rb = std::min(r1, ra + f->chunk_reads);
+        // a sample smaller than one chunk still travels in up to four pieces (>= 4096 reads each), so that its marshalling
+        // overlaps its own copies and kernels
+        const int64_t step = std::min<int64_t>(f->chunk_reads, std::max<int64_t>(4096, (r1 - r0 + 3) / 4));
+        for (int64_t ra = r0; ra < r1 && rc == VGH_OK; ra += step, ++c) {
+            const int64_t rb = std::min(r1, ra + step);
             const int slot = (int)(c & 1);
             const auto t0 = std::chrono::steady_clock::now();
             const int how = feeder_fill(f, slot, a, ra, rb, mode);   // block `slot` was released when submission c - 2 was joined

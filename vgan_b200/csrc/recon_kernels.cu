@@ -354,6 +354,8 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     if (g >= n_groups) return;
     if (W.grp_cb[n_groups] > col_cap_blks || W.grp_mb[n_groups] > map_cap_blks) {  // columns: cannot happen for sorted groups; extra records: a chunk with very many empty mappings.  Never write past the buffers
         if (slot == 0) atomicOr(err_flag, kErrBatchCapacity);
+        o_n_cols[slot] = o_n_close[slot] = o_n_extra[slot] = 0;   // the read kernel still runs over the chunk: no lane may point
+        o_mapq[slot] = 0;                                          // past the extra records that were never written
         return;
     }
     const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0;

@@ -1434,9 +1434,10 @@ int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, d
         const int32_t* idx = reinterpret_cast<const int32_t*>(r + 2);
         const int err = idx[2];
         int st = VGL_OK;
-        if (err & 0x30000000) st = (err & 0x20000000) ? VGL_ERR_BAD_READ : VGL_ERR_BAD_NODE;
+        if (err & 0x04000000) st = VGL_ERR_INVALID;   // (device-built batch out of room: nothing else the flags say counts)
+        else if (err & 0x30000000) st = (err & 0x20000000) ? VGL_ERR_BAD_READ : VGL_ERR_BAD_NODE;
         else if (err & VGL_ERR_BAD_NODE) st = VGL_ERR_BAD_NODE;
-        else if (err & 0x0c000000) st = VGL_ERR_INVALID;
+        else if (err & 0x08000000) st = VGL_ERR_INVALID;
         if (status_out) status_out[k] = st;
         if (st != VGL_OK && worst == VGL_OK) worst = st;
         if (argmax_out) argmax_out[k] = idx[0];
@@ -1571,6 +1572,10 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
     const int err = idx[2];
     if (err & 0x40000000)
         return fail(VGL_ERR_PEER, "multi-GPU exchange: a peer rank did not deliver its vector in time (VGL_PEER_TIMEOUT_S, default 120 s)");
+    // (first: the chunk's batch was never written, so whatever the read kernel made of it means nothing)
+    if (err & 0x04000000)
+        return fail(VGL_ERR_INVALID, "device-side packing: a chunk holds more empty mappings than the device-built batch reserves "
+                                     "(groups + 4096 blocks of extra records); pack this sample on the host (vgh_hc_pack + vgl_hc_accumulate)");
     if (err & 0x20000000)
         return fail(VGL_ERR_BAD_READ, "device-side reconstruction rejected a read (malformed alignment: lengths, offsets, mapping quality or edit sizes out of range)");
     if (err & 0x10000000)
@@ -1579,9 +1584,6 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
         return fail(VGL_ERR_BAD_NODE, "a mapping names a node without a pangenome_map entry (the reference would terminate in map::at)");
     if (err & 0x08000000)
         return fail(VGL_ERR_INVALID, "a batch's vgl_hc_batch_meta is wrong: a segment holds a read of another mapping quality");
-    if (err & 0x04000000)
-        return fail(VGL_ERR_INVALID, "device-side packing: a chunk holds more empty mappings than the device-built batch reserves "
-                                     "(groups + 4096 blocks of extra records); pack this sample on the host (vgh_hc_pack + vgl_hc_accumulate)");
     if (argmax_out) *argmax_out = idx[0];
     if (total_out) *total_out = scalars[0];
     const int n_post = idx[1];
