@@ -1188,7 +1188,10 @@ size_t hc_logterm_plan(const HcBatchMeta& meta, uint32_t n_groups, int n_ctas, i
     plan.q_rows = (int)meta.qual_max + 1;
     const size_t node_bytes = (((size_t)n_rows + 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t pair_bytes = (size_t)plan.q_rows * 64;
-    const size_t smem = node_bytes + (size_t)(n_class + 1) * pair_bytes;
+    // + slack behind the last table: a record whose quality exceeds the meta's qual_max (a wrong meta, or a chunk whose packing
+    // was abandoned) indexes up to 512 entries into a table of q_rows * 8 -- garbage in, but never past the shared-memory window
+    const size_t slack = (size_t)(64 - plan.q_rows) * 64;
+    const size_t smem = node_bytes + (size_t)(n_class + 1) * pair_bytes + slack;
     if (smem + 1024 > (size_t)max_smem_optin || smem >= (1u << 20)) return 0;  // (one mbarrier counts the staged bytes)
     // CTAs in proportion to the segments' groups (largest remainder), at least one each
     uint32_t begin = 0;

@@ -354,8 +354,13 @@ hc_pack_kernel(ReconRawDev raw, ReconWorkDev W, uint32_t n_groups, uint32_t col_
     if (g >= n_groups) return;
     if (W.grp_cb[n_groups] > col_cap_blks || W.grp_mb[n_groups] > map_cap_blks) {  // columns: cannot happen for sorted groups; extra records: a chunk with very many empty mappings.  Never write past the buffers
         if (slot == 0) atomicOr(err_flag, kErrBatchCapacity);
-        o_n_cols[slot] = o_n_close[slot] = o_n_extra[slot] = 0;   // the read kernel still runs over the chunk: no lane may point
-        o_mapq[slot] = 0;                                          // past the extra records that were never written
+        // the read kernel still runs over the chunk: every lane empty (no extra record is ever fetched), its column blocks zero
+        o_n_cols[slot] = o_n_close[slot] = o_n_extra[slot] = 0;
+        o_mapq[slot] = 0;
+        if (W.grp_cb[n_groups] <= col_cap_blks) {
+            uint4* z = reinterpret_cast<uint4*>(col) + (size_t)W.grp_cb[g] * 32 + lane;
+            for (uint32_t cb = 0; cb < W.grp_cb[g + 1] - W.grp_cb[g]; ++cb) z[(size_t)cb * 32] = make_uint4(0, 0, 0, 0);
+        }
         return;
     }
     const uint32_t cb0 = W.grp_cb[g], ncb = W.grp_cb[g + 1] - cb0;
