@@ -61,6 +61,11 @@ struct DevBuf {
 struct vgl_ctx {
     int device = 0;
     int sm_count = 0;
+    // duplicate removal (vgl_dedup): keys, hash table, mask -- kept between calls (allocation costs more than the two kernels)
+    DevBuf<unsigned long long> dd_key, dd_tab_key;
+    DevBuf<uint32_t> dd_tab_first;
+    DevBuf<uint8_t> dd_paired, dd_dup;
+    DevBuf<unsigned int> dd_n;
     int max_smem_optin = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -374,6 +379,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->dd_key.release(); ctx->dd_tab_key.release(); ctx->dd_tab_first.release(); ctx->dd_paired.release(); ctx->dd_dup.release(); ctx->dd_n.release();
     ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release(); ctx->d_logterm.release();
     ctx->d_cta_node_acc.release();
     ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_tile_done.release();
@@ -1343,12 +1349,13 @@ int vgl_dedup(vgl_ctx* ctx, uint32_t n_reads, const uint64_t* start_key, const u
     cudaStream_t s = ctx->stream;
     uint32_t size = 1024;
     while (size < 2u * n_reads) size <<= 1;
-    DevBuf<unsigned long long> d_key, t_key;
-    DevBuf<uint32_t> t_first;
-    DevBuf<uint8_t> d_paired, d_dup;
-    DevBuf<unsigned int> d_n;
+    DevBuf<unsigned long long>&d_key = ctx->dd_key, &t_key = ctx->dd_tab_key;
+    DevBuf<uint32_t>& t_first = ctx->dd_tab_first;
+    DevBuf<uint8_t>&d_paired = ctx->dd_paired, &d_dup = ctx->dd_dup;
+    DevBuf<unsigned int>& d_n = ctx->dd_n;
     int rc = VGL_OK;
-    auto done = [&](int code) { d_key.release(); t_key.release(); t_first.release(); d_paired.release(); d_dup.release(); d_n.release(); return code; };
+    auto done = [&](int code) { return code; };
+    if (n_reads > d_key.cap || size > t_key.cap) VGL_CUDA(cudaStreamSynchronize(s));   // growing a buffer frees it
     if ((rc = d_key.reserve(n_reads)) || (rc = t_key.reserve(size)) || (rc = t_first.reserve(size)) || (rc = d_dup.reserve(n_reads)) ||
         (rc = d_n.reserve(1)) || (paired && (rc = d_paired.reserve(n_reads))))
         return done(rc);
