@@ -172,6 +172,34 @@ def dedup(reads, paired=None):
     return out[:reads.n].astype(bool)
 
 
+def facade_flatten(reads, paired=None):
+    """The PRODUCT's vgan_b200::FlatAlignments::assign (vgan_b200/csrc/host/vgan_haplocart.hpp) instantiated with the reference's
+    own AlignmentInfo (src/AlignmentInfo.h; objects filled as the readGAM lambda fills them, src/readGAM.h:41-46): the flat arrays
+    it yields, as a dict keyed like oracle.FlatReads / host.Alignments.arrays()."""
+    L = lib()
+    pr = None if paired is None else np.ascontiguousarray(paired, dtype=np.uint8)
+    cnt = np.zeros(5, dtype=np.int64)
+    nulls = [None] * 16
+    rc = L.ref_facade_flatten(C.byref(reads.c), None if pr is None else _ptr(pr), _ptr(cnt), *nulls)
+    if rc:
+        raise RuntimeError("ref_facade_flatten failed: %d" % rc)
+    n, nm, ne, nseq, neseq = (int(x) for x in cnt)
+    out = {"seq_off": np.zeros(n + 1, np.int64), "seq": np.zeros(max(nseq, 1), np.uint8), "qual_off": np.zeros(n + 1, np.int64),
+           "qual": np.zeros(max(int(reads.qual_off[reads.n]), 1), np.uint8), "mapq": np.zeros(max(n, 1), np.int32),
+           "identity": np.zeros(max(n, 1), np.float64), "paired": np.zeros(max(n, 1), np.uint8), "map_off": np.zeros(n + 1, np.int64),
+           "map_node": np.zeros(max(nm, 1), np.int64), "map_offset": np.zeros(max(nm, 1), np.int64), "map_rev": np.zeros(max(nm, 1), np.uint8),
+           "edit_off": np.zeros(nm + 1, np.int64), "edit_from": np.zeros(max(ne, 1), np.int32), "edit_to": np.zeros(max(ne, 1), np.int32),
+           "edit_seq_off": np.zeros(ne + 1, np.int64), "edit_seq": np.zeros(max(neseq, 1), np.uint8)}
+    order = ["seq_off", "seq", "qual_off", "qual", "mapq", "identity", "paired", "map_off", "map_node", "map_offset", "map_rev", "edit_off",
+             "edit_from", "edit_to", "edit_seq_off", "edit_seq"]
+    rc = L.ref_facade_flatten(C.byref(reads.c), None if pr is None else _ptr(pr), _ptr(cnt), *[_ptr(out[k]) for k in order])
+    if rc:
+        raise RuntimeError("ref_facade_flatten failed: %d" % rc)
+    cut = {"seq": nseq, "qual": int(out["qual_off"][-1]), "mapq": n, "identity": n, "paired": n, "map_node": nm, "map_offset": nm,
+           "map_rev": nm, "edit_from": ne, "edit_to": ne, "edit_seq": neseq}
+    return {k: (v[:cut[k]] if k in cut else v) for k, v in out.items()}
+
+
 class Damage:
     """Damage::initDeamProbabilities (src/damage.cpp:41-323) on two .prof files ('' = no damage)."""
 

@@ -23,6 +23,7 @@
 #include "damage.h"
 #include "Euka.h"          // pulls in readGAM_Euka.h (the readGAM3 lambda) and MCMC.h (computeBaseLogLike)
 #include "soibean.h"       // pulls in getLCAfromGAM.h (analyse_GAM)
+#include "vgan_haplocart.hpp"   // the PRODUCT's C++ facade: its FlatAlignments::assign is compiled here against the reference's AlignmentInfo
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -353,6 +354,35 @@ double ref_hc_background_freq(char b) { Haplocart hc; return hc.get_background_f
 // get_p_obs_base with epsilon = 0 is the per-region match probability pow(1 - 30 mu, 8)
 double ref_hc_region_match_prob(int pangenome_base) { Haplocart hc; return (double)hc.get_p_obs_base(pangenome_base, 'A', 'A', 0.0, 8); }
 long double ref_hc_p_obs_base(int pangenome_base, char mapping_base, char graph_base, double epsilon) { Haplocart hc; return hc.get_p_obs_base(pangenome_base, mapping_base, graph_base, epsilon, 8); }
+
+// ---- the product's facade against the reference's own AlignmentInfo ----
+// vgan_b200::FlatAlignments::assign (vgan_b200/csrc/host/vgan_haplocart.hpp) is a template over "vector of AlignmentInfo*"; here it
+// is instantiated with the REFERENCE'S class (src/AlignmentInfo.h, filled as the readGAM lambda fills it, src/readGAM.h:41-46) and
+// its flat arrays are handed back so that a test can hold them against what went in.  Sizes first (all outputs may be NULL).
+int ref_facade_flatten(const orc_reads* R, const uint8_t* paired, int64_t* counts5, int64_t* seq_off, char* seq, int64_t* qual_off, char* qual,
+                       int32_t* mapq, double* identity, uint8_t* is_paired, int64_t* map_off, int64_t* map_node, int64_t* map_offset,
+                       uint8_t* map_rev, int64_t* edit_off, int32_t* edit_from, int32_t* edit_to, int64_t* edit_seq_off, char* edit_seq) {
+    std::vector<AlignmentInfo*> v;
+    for (int64_t r = 0; r < R->n_reads; ++r) v.emplace_back(make_info(make_alignment(R, r), paired && paired[r]));
+    vgan_b200::FlatAlignments F;
+    F.assign(v);
+    for (auto* ai : v) delete ai;
+    const vgh_alignments a = F.view();
+    if (counts5) {
+        counts5[0] = a.n_reads; counts5[1] = (int64_t)F.map_node.size(); counts5[2] = (int64_t)F.edit_from.size();
+        counts5[3] = (int64_t)F.seq.size(); counts5[4] = (int64_t)F.edit_seq.size();
+    }
+    if (!seq_off) return 0;
+    const size_t n = (size_t)a.n_reads, nm = F.map_node.size(), ne = F.edit_from.size();
+    memcpy(seq_off, a.seq_off, (n + 1) * 8); memcpy(seq, a.seq, F.seq.size());
+    memcpy(qual_off, a.qual_off, (n + 1) * 8); memcpy(qual, a.qual, F.qual.size());
+    memcpy(mapq, a.mapq, n * 4); memcpy(identity, a.identity, n * 8); memcpy(is_paired, a.paired, n);
+    memcpy(map_off, a.map_off, (n + 1) * 8); memcpy(map_node, a.map_node, nm * 8); memcpy(map_offset, a.map_offset, nm * 8);
+    memcpy(map_rev, a.map_rev, nm);
+    memcpy(edit_off, a.edit_off, (nm + 1) * 8); memcpy(edit_from, a.edit_from, ne * 4); memcpy(edit_to, a.edit_to, ne * 4);
+    memcpy(edit_seq_off, a.edit_seq_off, (ne + 1) * 8); memcpy(edit_seq, a.edit_seq, F.edit_seq.size());
+    return 0;
+}
 
 // ---- Dup_Remover::remove_duplicates_internal (src/rmdup.cpp:68-110), the reference's own ----
 // The paired branch indexes mapping()[n_mappings] (src/rmdup.cpp:50,55), one past the end: undefined in the

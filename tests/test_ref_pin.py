@@ -201,6 +201,31 @@ def test_dedup_equals_dup_remover(small):
 
 
 @needs_ref
+def test_product_facade_flattens_the_references_own_alignment_objects(small):
+    """The drop-in boundary compiled against the reference's class: vgan_b200::FlatAlignments::assign (the product's C++ facade,
+    vgan_b200/csrc/host/vgan_haplocart.hpp) instantiated with vector<AlignmentInfo*> -- the reference's own src/AlignmentInfo.h,
+    objects filled as the readGAM lambda fills them (src/readGAM.h:41-46) -- yields exactly the flat fields that went in: synthetic
+    reads with indels and damage, both strands, and the reference's GAM fixtures."""
+    import os
+    import vgan_b200 as vb
+    cases = [small.reads(400, seed=223, sub_rate=0.02, indel_rate=0.01, fixed_len=0, damage=True).arrays()]
+    for name in ("test_reads.gam", "J2a1a1a1.gam", "all_the_same_reverse.gam"):
+        path = os.path.join(H.GOLDEN, name)
+        if os.path.exists(path):
+            cases.append(vb.Alignments.from_gam_file(path).arrays())
+    for a in cases:
+        R = orc.FlatReads(a)
+        paired = (np.arange(R.n) % 3 == 0).astype(np.uint8)
+        got = ref.facade_flatten(R, paired)
+        for key in ("seq_off", "seq", "qual_off", "qual", "mapq", "identity", "map_off", "map_node", "map_offset", "map_rev", "edit_off",
+                    "edit_from", "edit_to", "edit_seq_off", "edit_seq"):
+            want = np.asarray(a[key])
+            assert np.array_equal(np.asarray(got[key]).astype(want.dtype), want), key
+        assert np.array_equal(got["paired"], paired)
+        assert (a["map_rev"] != 0).any() or len(cases) > 1
+
+
+@needs_ref
 @pytest.mark.parametrize("profiles", [("dhigh5p.prof", "dhigh3p.prof"), ("none.prof", "none.prof"), ("dhigh5p.prof", "")])
 def test_damage_matrices_equal_init_deam_probabilities(profiles):
     """The product's collapsed (k5 x k3) damage table and the oracle's, against Damage::initDeamProbabilities."""
