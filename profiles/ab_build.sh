@@ -8,7 +8,8 @@ out=../../build_ab/$name
 mkdir -p $out
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC "$@" -c -o $out/hc_kernels.o hc_kernels.cu
-/usr/local/cuda/bin/nvcc $ARCH -shared -o $out/libvgan_gpu.so vgl_api.o $out/hc_kernels.o euka_kernels.o recon_kernels.o gam_kernels.o -cudart static
+/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC "$@" -c -o $out/vgl_api.o vgl_api.cu   # (shares the sizing macros)
+/usr/local/cuda/bin/nvcc $ARCH -shared -o $out/libvgan_gpu.so $out/vgl_api.o $out/hc_kernels.o euka_kernels.o recon_kernels.o gam_kernels.o -cudart static
 g++ -O3 -std=c++17 -fPIC -fopenmp -shared -o $out/libvgan_host.so host/vgan_host.cpp host/synth.cpp host/euka_host.cpp -L$out -lvgan_gpu -lz -Wl,-rpath,'$ORIGIN'
-rm -f $out/hc_kernels.o
+rm -f $out/hc_kernels.o $out/vgl_api.o
 echo built $out

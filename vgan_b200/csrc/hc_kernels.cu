@@ -747,8 +747,31 @@ hc_read_logterm_kernel(HcBatchDev b, HcTablesDev t, HcLogTermLaunch plan, double
 }
 
 // ------------------------------------------------------------------------------------------
-// K2b: chunk_ll[chunk][p] = sum over the chunk's nodes n with pathsgo[n][p] == 0 of D[n],
-//      D[n] = sum of the kAccCopies node vectors (fixed order)
+// K2a: D[n] = sum of the kAccCopies node vectors the read kernel's CTAs added into, in copy order (the same order whichever
+//      CTA added what), and the sum of the A totals -- once per sample, so that the 41 path tiles of K2b stage 2.5 KB each
+//      instead of every copy of their node slice.  node_sum of a sample: [n_words * 32] doubles, then the A total.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hc_collapse_kernel(const double* __restrict__ node_acc, size_t acc_stride, int n_pad, double* __restrict__ node_sum, size_t sum_stride) {
+    const double* acc = node_acc + (size_t)blockIdx.y * acc_stride;
+    double* out = node_sum + (size_t)blockIdx.y * sum_stride;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < n_pad) {
+        double d = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < kAccCopies; ++c) d += __ldcg(acc + (size_t)c * n_pad + n);
+        out[n] = d;
+    }
+    if (n == 0) {
+        const double* a_total = acc + (size_t)kAccCopies * n_pad;
+        double a = 0.0;
+        for (int c = 0; c < kAccCopies; ++c) a += __ldcg(a_total + c);
+        out[n_pad] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: chunk_ll[chunk][p] = sum over the chunk's nodes n with pathsgo[n][p] == 0 of D[n]
 // ------------------------------------------------------------------------------------------
 struct PeerBufs {
     double* base[VGL_HC_MAX_PEERS];
@@ -768,9 +791,8 @@ constexpr int kPathTile = 128;       // paths per CTA (one per thread)
 constexpr int kWordsPerChunk = 10;   // 320 nodes per CTA
 
 __global__ void __launch_bounds__(kPathTile)
-hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __restrict__ chunk_ll, const double* __restrict__ a_total,
+hc_path_kernel(HcTablesDev t, const double* __restrict__ node_sum, double* __restrict__ chunk_ll,
                double* __restrict__ ll, unsigned int* __restrict__ tile_done, PeerFuse pf) {
-    __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
     __shared__ __align__(8) unsigned long long s_bar;
     const int chunk = blockIdx.y;
@@ -778,7 +800,7 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     const int nw = min(kWordsPerChunk, t.n_words - w0);
     const int p = blockIdx.x * kPathTile + threadIdx.x;
 
-    // Stage this chunk of every copy of the node vector with TMA bulk copies (cp.async.bulk -> UBLKCP).
+    // Stage this chunk of the node vector with a TMA bulk copy (cp.async.bulk -> UBLKCP).
     const uint32_t bar = smem_u32(&s_bar);
     const uint32_t bytes = (uint32_t)nw * 32u * 8u;
     if (threadIdx.x == 0) {
@@ -787,23 +809,15 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, bytes * kAccCopies);
-        for (int c = 0; c < kAccCopies; ++c)
-            bulk_g2s(smem_u32(&s_c[c][0]), node_acc + (size_t)c * t.n_words * 32 + (size_t)w0 * 32, bytes, bar);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(&s_d[0]), node_sum + (size_t)w0 * 32, bytes, bar);
     }
-    // Issue the membership loads while the bulk copies are in flight.
+    // Issue the membership loads while the bulk copy is in flight.
     uint32_t words[kWordsPerChunk];
 #pragma unroll
     for (int k = 0; k < kWordsPerChunk; ++k)
         words[k] = (k < nw && p < t.n_paths) ? __ldg(t.node_bits + (size_t)(w0 + k) * t.n_paths + p) : 0xffffffffu;
     mbar_wait(bar, 0);
-    for (int i = threadIdx.x; i < nw * 32; i += kPathTile) {
-        double d = 0.0;
-#pragma unroll
-        for (int c = 0; c < kAccCopies; ++c) d += s_c[c][i];
-        s_d[i] = d;
-    }
-    __syncthreads();
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < kWordsPerChunk; ++k) {
@@ -829,9 +843,7 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
     __syncthreads();
     if (s_last && p < t.n_paths) {
         __threadfence();
-        double a = 0.0;
-#pragma unroll
-        for (int c = 0; c < kAccCopies; ++c) a += a_total[c];
+        const double a = __ldcg(node_sum + (size_t)t.n_words * 32);   // sum of the A totals (K2a)
         double sum = 0.0;
         for (unsigned c = 0; c < gridDim.y; ++c) sum += __ldcg(chunk_ll + (size_t)c * t.n_paths + p);
         ll[p] = a + sum;
@@ -860,9 +872,8 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_acc, double* __res
 // then the A totals), its chunk partials at chunk_ll + s * chunks * P, its vector at ll + s * P.  Same fixed summation orders as
 // hc_path_kernel, so a sample's result does not depend on which call computed it.
 __global__ void __launch_bounds__(kPathTile)
-hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_acc, size_t acc_stride, double* __restrict__ chunk_ll,
+hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_sum, size_t sum_stride, double* __restrict__ chunk_ll,
                        double* __restrict__ ll, unsigned int* __restrict__ tile_done, int n_samples, int samples_per_slice) {
-    __shared__ __align__(16) double s_c[kAccCopies][kWordsPerChunk * 32];
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ bool s_last;
@@ -884,21 +895,13 @@ hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_acc, size_
     const int s0 = blockIdx.z * samples_per_slice, s1 = min(n_samples, s0 + samples_per_slice);
     uint32_t phase = 0;
     for (int sm = s0; sm < s1; ++sm) {
-        const double* acc_s = node_acc + (size_t)sm * acc_stride;
+        const double* sum_s = node_sum + (size_t)sm * sum_stride;
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, bytes * kAccCopies);
-            for (int c = 0; c < kAccCopies; ++c)
-                bulk_g2s(smem_u32(&s_c[c][0]), acc_s + (size_t)c * t.n_words * 32 + (size_t)w0 * 32, bytes, bar);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(&s_d[0]), sum_s + (size_t)w0 * 32, bytes, bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
-        for (int i = threadIdx.x; i < nw * 32; i += kPathTile) {
-            double d = 0.0;
-#pragma unroll
-            for (int c = 0; c < kAccCopies; ++c) d += s_c[c][i];
-            s_d[i] = d;
-        }
-        __syncthreads();
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < kWordsPerChunk; ++k) {
@@ -914,7 +917,7 @@ hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_acc, size_
         double* chunk_s = chunk_ll + (size_t)sm * gridDim.y * t.n_paths;
         if (p < t.n_paths) chunk_s[(size_t)chunk * t.n_paths + p] = acc;
         __threadfence();
-        __syncthreads();   // (also: everybody is done with s_c / s_d before the next sample's copies land)
+        __syncthreads();   // (also: everybody is done with s_d before the next sample's copy lands)
         unsigned int* done = tile_done + (size_t)sm * gridDim.x + blockIdx.x;
         if (threadIdx.x == 0) {
             s_last = atomicAdd(done, 1u) == gridDim.y - 1;
@@ -923,10 +926,7 @@ hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_acc, size_
         __syncthreads();
         if (s_last && p < t.n_paths) {
             __threadfence();
-            const double* a_total = acc_s + (size_t)kAccCopies * t.n_words * 32;
-            double a = 0.0;
-#pragma unroll
-            for (int c = 0; c < kAccCopies; ++c) a += __ldcg(a_total + c);
+            const double a = __ldcg(sum_s + (size_t)t.n_words * 32);
             double sum = 0.0;
             for (unsigned c = 0; c < gridDim.y; ++c) sum += __ldcg(chunk_s + (size_t)c * t.n_paths + p);
             ll[(size_t)sm * t.n_paths + p] = a + sum;
@@ -1247,29 +1247,41 @@ static PeerFuse make_fuse(double* const* peer_bufs, int rank, int world, int n_p
     return pf;
 }
 
-cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+static cudaError_t launch_collapse(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* node_sum,
+                                   size_t sum_stride, cudaStream_t s) {
+    const int n_pad = tab.n_words * 32;
+    hc_collapse_kernel<<<dim3((n_pad + 255) / 256, n_samples), 256, 0, s>>>(node_acc, acc_stride, n_pad, node_sum, sum_stride);
+    return cudaGetLastError();
+}
+size_t hc_node_sum_doubles(int n_words) { return (((size_t)n_words * 32 + 1) + 31) & ~(size_t)31; }   // per sample: D[n], then the A total
+
+cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* node_sum, double* chunk_ll, double* ll,
                                   unsigned int* tile_done, cudaStream_t s) {
+    if (cudaError_t e = launch_collapse(tab, 1, node_acc, 0, node_sum, 0, s)) return e;
     dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words));
-    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done, no_peers());
+    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_sum, chunk_ll, ll, tile_done, no_peers());
     return cudaGetLastError();
 }
 
-cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* node_sum, double* chunk_ll, double* ll,
                                         unsigned int* tile_done, double* const* peer_bufs, int rank, int world, int n_pad,
                                         unsigned long long epoch, cudaStream_t s) {
+    if (cudaError_t e = launch_collapse(tab, 1, node_acc, 0, node_sum, 0, s)) return e;
     dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words));
-    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, chunk_ll, a_total, ll, tile_done, make_fuse(peer_bufs, rank, world, n_pad, epoch, 0));
+    hc_path_kernel<<<grid, kPathTile, 0, s>>>(tab, node_sum, chunk_ll, ll, tile_done, make_fuse(peer_bufs, rank, world, n_pad, epoch, 0));
     return cudaGetLastError();
 }
 int hc_path_tiles(int n_paths) { return (n_paths + kPathTile - 1) / kPathTile; }
 
-cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* chunk_ll,
-                                          double* ll, unsigned int* tile_done, cudaStream_t s) {
+cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* node_sum,
+                                          double* chunk_ll, double* ll, unsigned int* tile_done, cudaStream_t s) {
+    const size_t sum_stride = hc_node_sum_doubles(tab.n_words);
+    if (cudaError_t e = launch_collapse(tab, n_samples, node_acc, acc_stride, node_sum, sum_stride, s)) return e;
     // slices of samples along z: enough CTAs to fill the GPU, few enough that the bit matrix is re-read only a handful of times
     const int slices = n_samples >= 32 ? 4 : n_samples >= 8 ? 2 : 1;
     const int per_slice = (n_samples + slices - 1) / slices;
     dim3 grid((tab.n_paths + kPathTile - 1) / kPathTile, hc_path_chunks(tab.n_words), (n_samples + per_slice - 1) / per_slice);
-    hc_path_samples_kernel<<<grid, kPathTile, 0, s>>>(tab, node_acc, acc_stride, chunk_ll, ll, tile_done, n_samples, per_slice);
+    hc_path_samples_kernel<<<grid, kPathTile, 0, s>>>(tab, node_sum, sum_stride, chunk_ll, ll, tile_done, n_samples, per_slice);
     return cudaGetLastError();
 }
 

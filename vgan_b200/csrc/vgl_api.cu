@@ -85,7 +85,7 @@ struct vgl_ctx {
 
     // accumulators
     // one allocation, one memset per sample: node vectors [copies][n_rows_pad] | A totals [copies] | error flag
-    DevBuf<double> d_cta_node_acc, d_chunk_ll, d_ll;
+    DevBuf<double> d_cta_node_acc, d_node_sum, d_chunk_ll, d_ll;   // d_node_sum: the copies collapsed (K2a), hc_node_sum_doubles()
     DevBuf<unsigned int> d_tile_done;  // per path tile: CTAs of the path kernel that have finished
     double* d_a_total = nullptr;
     // Accumulator set the accumulate entry points add into: the single-sample buffer above, or sample `cur_sample` of the
@@ -93,7 +93,7 @@ struct vgl_ctx {
     double* cur_acc = nullptr;
     double* cur_a_total = nullptr;
     int* cur_err = nullptr;
-    DevBuf<double> m_acc, m_chunk_ll, m_ll, m_result;   // [S] sets / [S][chunks][P] / [S][P] / [S][4 + cap]
+    DevBuf<double> m_acc, m_node_sum, m_chunk_ll, m_ll, m_result;   // [S] sets / [S] collapsed vectors / [S][chunks][P] / [S][P] / [S][4 + cap]
     DevBuf<unsigned int> m_tile_done;                   // [S][tiles]
     double* m_h_result = nullptr;                       // page-locked mirror of m_result
     size_t m_h_result_cap = 0;
@@ -382,6 +382,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->dd_key.release(); ctx->dd_tab_key.release(); ctx->dd_tab_first.release(); ctx->dd_paired.release(); ctx->dd_dup.release(); ctx->dd_n.release();
     ctx->d_class_tab.release(); ctx->d_image.release(); ctx->d_node_bits.release(); ctx->d_logterm.release();
     ctx->d_cta_node_acc.release();
+    ctx->d_node_sum.release(); ctx->m_node_sum.release();
     ctx->d_chunk_ll.release(); ctx->d_ll.release(); ctx->d_tile_done.release();
     ctx->m_acc.release(); ctx->m_chunk_ll.release(); ctx->m_ll.release(); ctx->m_result.release(); ctx->m_tile_done.release();
     if (ctx->m_h_result) cudaFreeHost(ctx->m_h_result);
@@ -671,6 +672,7 @@ int vgl_hc_set_tables(vgl_ctx* ctx, const vgl_hc_tables* T) {
     ctx->d_err = reinterpret_cast<int*>(ctx->d_a_total + VGL_HC_ACC_COPIES);
     ctx->cur_acc = ctx->d_cta_node_acc.p; ctx->cur_a_total = ctx->d_a_total; ctx->cur_err = ctx->d_err;
     ctx->m_samples = 0; ctx->cur_sample = -1;
+    if (int rc = ctx->d_node_sum.reserve(vgl::hc_node_sum_doubles(ctx->tab.n_words))) return rc;
     if (int rc = ctx->d_chunk_ll.reserve((size_t)ctx->n_chunks * (size_t)P)) return rc;
     if (int rc = ctx->d_ll.reserve((size_t)P)) return rc;
     if (int rc = ctx->d_tile_done.reserve((size_t)vgl::hc_path_tiles(P))) return rc;
@@ -1385,6 +1387,7 @@ int vgl_hc_samples_begin(vgl_ctx* ctx, int32_t n_samples) {
     const size_t cap = (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1), blk = 4 + cap;
     if ((size_t)n_samples * set > ctx->m_acc.cap || (size_t)n_samples * P > ctx->m_ll.cap) VGL_CUDA(cudaStreamSynchronize(s));
     if (int rc = ctx->m_acc.reserve((size_t)n_samples * set)) return rc;
+    if (int rc = ctx->m_node_sum.reserve((size_t)n_samples * vgl::hc_node_sum_doubles(ctx->tab.n_words))) return rc;
     if (int rc = ctx->m_chunk_ll.reserve((size_t)n_samples * (size_t)ctx->n_chunks * P)) return rc;
     if (int rc = ctx->m_ll.reserve((size_t)n_samples * P)) return rc;
     if (int rc = ctx->m_result.reserve((size_t)n_samples * blk)) return rc;
@@ -1426,12 +1429,12 @@ int vgl_hc_finalize_samples(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, d
     const size_t set = ctx->acc_set_doubles();
     const int cap = ctx->have_tree ? ctx->max_anc + 1 : 1;
     const size_t blk = 4 + (size_t)cap;
-    VGL_CUDA(vgl::hc_launch_path_samples_kernel(ctx->tab, S, ctx->m_acc.p, set, ctx->m_chunk_ll.p, ctx->m_ll.p, ctx->m_tile_done.p, s));
+    VGL_CUDA(vgl::hc_launch_path_samples_kernel(ctx->tab, S, ctx->m_acc.p, set, ctx->m_node_sum.p, ctx->m_chunk_ll.p, ctx->m_ll.p, ctx->m_tile_done.p, s));
     const int* err0 = reinterpret_cast<const int*>(ctx->m_acc.p + (size_t)VGL_HC_ACC_COPIES * (size_t)ctx->n_rows_pad + VGL_HC_ACC_COPIES);
     VGL_CUDA(vgl::hc_launch_posterior_samples(S, ctx->m_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
                                               ctx->have_tree ? ctx->d_anc_off.p : nullptr, ctx->have_tree ? ctx->d_anc_clade.p : nullptr,
                                               ctx->m_result.p, cap, blk, err0, set * 2, s));
-    ctx->launches += 2;
+    ctx->launches += 3;
     VGL_CUDA(cudaMemcpyAsync(ctx->m_h_result, ctx->m_result.p, (size_t)S * blk * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->m_ll.p, (size_t)S * (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
     VGL_CUDA(cudaStreamSynchronize(s));
@@ -1466,8 +1469,8 @@ int vgl_hc_paths(vgl_ctx* ctx, double* ll_dev) {
     if (int rc = use_device(ctx)) return rc;
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     cudaStream_t s = ctx->stream;
-    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, ctx->d_a_total, ctx->d_ll.p, ctx->d_tile_done.p, s));
-    ctx->launches += 1;
+    VGL_CUDA(vgl::hc_launch_path_kernel(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_node_sum.p, ctx->d_chunk_ll.p, ctx->d_ll.p, ctx->d_tile_done.p, s));
+    ctx->launches += 2;
     ctx->ll_valid = true;
     if (ll_dev) VGL_CUDA(cudaMemcpyAsync(ll_dev, ctx->d_ll.p, (size_t)ctx->tab.n_paths * sizeof(double), cudaMemcpyDeviceToDevice, s));
     return VGL_OK;
@@ -1527,10 +1530,10 @@ int vgl_hc_exchange_paths(vgl_ctx* ctx) {
         // the usual case: the collapse has not run yet -- run it with the exchange as its epilogue (every path tile goes to
         // all peers as soon as its last CTA has it); vgl_hc_finalize's posterior kernel acquires and sums in rank order
         ctx->peer_epoch += 1;
-        VGL_CUDA(vgl::hc_launch_path_kernel_fused(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_chunk_ll.p, ctx->d_a_total, ctx->d_ll.p,
+        VGL_CUDA(vgl::hc_launch_path_kernel_fused(ctx->tab, ctx->d_cta_node_acc.p, ctx->d_node_sum.p, ctx->d_chunk_ll.p, ctx->d_ll.p,
                                                   ctx->d_tile_done.p, ctx->peer_bufs, ctx->peer_rank, ctx->peer_world, ctx->peer_pad,
                                                   ctx->peer_epoch, ctx->stream));
-        ctx->launches += 1;
+        ctx->launches += 2;
         ctx->ll_valid = true;
         ctx->peer_fused_pending = true;
         return VGL_OK;

@@ -7,7 +7,7 @@
 #include "../../include/vgan_gpu.h"
 
 #ifndef VGL_HC_ACC_COPIES
-#define VGL_HC_ACC_COPIES 16
+#define VGL_HC_ACC_COPIES 32
 #endif
 
 #define VGL_HC_MAX_PEERS 16
@@ -139,15 +139,18 @@ int hc_path_tiles(int n_paths);
 // K2b + K2c: chunk_ll[chunk][P], then (by the last CTA of every path tile) ll[p] = sum_copies a_total[copy] + sum_chunks
 // chunk_ll[chunk][p] in a fixed order that is the same for every p.  tile_done: hc_path_tiles(P) counters, zero on entry
 // (the kernel leaves them zero).
-cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+// (K2a first: the copies of the node vector -- and of the A total, which follow them in node_acc -- collapse into node_sum,
+// hc_node_sum_doubles(n_words) doubles per sample)
+size_t hc_node_sum_doubles(int n_words);
+cudaError_t hc_launch_path_kernel(const HcTablesDev& tab, const double* node_acc, double* node_sum, double* chunk_ll, double* ll,
                                   unsigned int* tile_done, cudaStream_t s);
 
 // K2 / K3 over S samples at once (vgl_hc_finalize_samples).  Sample s: node vectors at node_acc + s * acc_stride doubles (single-
 // sample layout), chunk partials chunk_ll[s][chunks][P], vector ll[s][P], counters tile_done[s][tiles] (zero on entry, left zero),
 // result block results + s * result_stride doubles ({total, ll[argmax]}, {argmax, n_post, err}, post[post_cap]), error word
 // err_flag + s * err_stride ints.
-cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* chunk_ll,
-                                          double* ll, unsigned int* tile_done, cudaStream_t s);
+cudaError_t hc_launch_path_samples_kernel(const HcTablesDev& tab, int n_samples, const double* node_acc, size_t acc_stride, double* node_sum,
+                                          double* chunk_ll, double* ll, unsigned int* tile_done, cudaStream_t s);
 cudaError_t hc_launch_posterior_samples(int n_samples, const double* ll, int n_paths, int row_words, const uint32_t* clade_bits,
                                         const int32_t* anc_off, const int32_t* anc_clade, double* results, int post_cap, size_t result_stride,
                                         const int* err_flag, size_t err_stride, cudaStream_t s);
@@ -164,7 +167,7 @@ cudaError_t hc_launch_peer_exchange(double* const* peer_bufs, int rank, int worl
 // The exchange fused into K2 / K3 (what vgl_hc_exchange_paths + vgl_hc_finalize launch): K2's last CTA of every path tile stores
 // its 128 paths into slot `rank` of every rank's buffer and releases a per-rank tile counter; K3's prologue acquires the
 // world counters of the local buffer and adds the slots in rank order.  No separate exchange kernels.
-cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* chunk_ll, const double* a_total, double* ll,
+cudaError_t hc_launch_path_kernel_fused(const HcTablesDev& tab, const double* node_acc, double* node_sum, double* chunk_ll, double* ll,
                                         unsigned int* tile_done, double* const* peer_bufs, int rank, int world, int n_pad,
                                         unsigned long long epoch, cudaStream_t s);
 cudaError_t hc_launch_posterior_fused(double* ll, int n_paths, int row_words, const uint32_t* clade_bits, const int32_t* anc_off,
