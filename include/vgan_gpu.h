@@ -391,6 +391,13 @@ int vgl_hc_exchange_paths(vgl_ctx* ctx);
  * If no tree was set only post_out[0] is produced.                                             */
 int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
                     int32_t post_cap, int32_t* n_post_out);
+/* The same in two halves, for a caller that loops over samples (src/HaploCart.cpp:303) and wants the GPU busy across them:
+ * _begin enqueues the collapse, the posterior kernel and the copy of the result block into one of two page-locked slots and
+ * returns at once -- the next sample's vgl_hc_reset / accumulate calls may follow immediately, on the same stream --; _end waits
+ * for that slot alone and hands the result out (outputs as vgl_hc_finalize without ll_out).  At most two results in flight.  */
+int vgl_hc_finalize_begin(vgl_ctx* ctx, int32_t* ticket_out);
+int vgl_hc_finalize_end(vgl_ctx* ctx, int32_t ticket, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap,
+                        int32_t* n_post_out);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Several samples per pass                                                                    */

@@ -535,3 +535,39 @@ def test_node_table_beyond_the_shared_memory_limit_is_refused_with_a_status():
     with pytest.raises(_lib.VglError, match="shared memory"):
         hc.load(tables(120000))
     hc.close()
+
+
+def test_posterior_begin_end_keeps_two_samples_in_flight(small):
+    """vgl_hc_finalize_begin / _end: a sample's posterior is enqueued, the next sample is accumulated behind it on the same stream,
+    and each result comes back from its own slot -- the same calls, vectors and posteriors as one get_posterior() per sample."""
+    hc = vb.Haplocart()
+    hc.load(small.tables(), small.tree())
+    batches = [vb.PackedBatch(small.graph, small.reads(300 + 40 * k, seed=700 + k, sub_rate=0.01, indel_rate=0.002, origin_path=3 + 11 * k))
+               for k in range(5)]
+    want = [hc.run_sample([b]) for b in batches]
+    got, pending = [], None
+    for b in batches:
+        hc.reset()
+        hc.update(b)
+        t = hc.posterior_begin()
+        if pending is not None:
+            got.append(hc.posterior_end(pending))
+        pending = t
+    got.append(hc.posterior_end(pending))
+    assert len({w["maxh_index"] for w in want}) > 1
+    for g, w in zip(got, want):
+        assert g["maxh_index"] == w["maxh_index"] and g["clade_vec"] == w["clade_vec"]
+        assert np.allclose(g["confidence_vec"], w["confidence_vec"], rtol=1e-9, atol=1e-300)
+        assert abs(g["total_ll"] - w["total_ll"]) <= 1e-12 * abs(w["total_ll"])
+    # a third result cannot be begun while two are in flight; a ticket is good once
+    hc.reset(); hc.update(batches[0]); t0 = hc.posterior_begin()
+    hc.reset(); hc.update(batches[1]); t1 = hc.posterior_begin()
+    hc.reset(); hc.update(batches[2])
+    with pytest.raises(_lib.VglError, match="in flight"):
+        hc.posterior_begin()
+    assert hc.posterior_end(t0)["maxh_index"] == want[0]["maxh_index"]
+    assert hc.posterior_end(t1)["maxh_index"] == want[1]["maxh_index"]
+    with pytest.raises(_lib.VglError, match="no result pending"):
+        hc.posterior_end(t1)
+    assert hc.get_posterior(want_ll=False)["maxh_index"] == want[2]["maxh_index"]
+    hc.close()

@@ -132,6 +132,8 @@ GPU_SYMBOLS = {
     "vgl_hc_exchange_paths": (C.c_int, [_P]),
     "vgl_hc_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, C.c_int32,
                                   C.POINTER(C.c_int32)]),
+    "vgl_hc_finalize_begin": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "vgl_hc_finalize_end": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, C.c_int32, C.POINTER(C.c_int32)]),
     "vgl_euka_set_tables": (C.c_int, [_P, C.POINTER(vgl_euka_tables)]),
     "vgl_euka_reset": (C.c_int, [_P]),
     "vgl_euka_run": (C.c_int, [_P, C.POINTER(vgl_euka_batch), C.c_uint32, _P, _P, _P, _P, _P]),

@@ -238,6 +238,28 @@ public:
         return out;
     }
 
+    // get_posterior in two halves, for a loop over samples that keeps the GPU busy: begin_posterior() enqueues the kernels and the
+    // copy of the result and returns a ticket; the next sample's reset() / update*() may follow at once; end_posterior(ticket)
+    // waits for that result alone.  At most two in flight.
+    int begin_posterior() {
+        int32_t t = -1;
+        check(vgl_hc_finalize_begin(ctx_, &t), "begin_posterior");
+        return t;
+    }
+    Posterior end_posterior(int ticket) {
+        Posterior p;
+        std::vector<double> post((size_t)max_post_ > 0 ? (size_t)max_post_ : 1);
+        int32_t n_post = 0;
+        check(vgl_hc_finalize_end(ctx_, ticket, &p.maxh_index, &p.total_ll, post.data(), (int32_t)post.size(), &n_post), "end_posterior");
+        p.confidence_vec.assign(post.begin(), post.begin() + n_post);
+        if (tree_) {
+            const int32_t* off = vgh_hc_tree_anc_off(tree_);
+            const int32_t* cl = vgh_hc_tree_anc_clade(tree_);
+            p.clade_ids.assign(cl + off[p.maxh_index], cl + off[p.maxh_index + 1]);
+        }
+        return p;
+    }
+
     // max_element + Haplocart::get_posterior.
     Posterior get_posterior(bool want_final_vec = false) {
         Posterior r;

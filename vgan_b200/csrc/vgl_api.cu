@@ -147,9 +147,15 @@ struct vgl_ctx {
     unsigned long long peer_epoch = 0;
 
     // one block {double total, max; int32 argmax, n_post, err, pad; double post[]} and its pinned host mirror
+    // result blocks {total, ll[argmax]}, {argmax, n_post, err}, post[cap]: TWO of them (device + page-locked mirror + event), so that
+    // a sample's posterior kernel and copy can be in flight while the next sample is already being accumulated
+    // (vgl_hc_finalize_begin / _end); slot k starts at k * (4 + h_result_cap) doubles
     DevBuf<double> d_result;
     double* h_result = nullptr;
     size_t h_result_cap = 0;
+    cudaEvent_t res_ev[2] = {nullptr, nullptr};
+    uint32_t res_seq = 0;
+    bool res_pending[2] = {false, false};
 
     // staging for host batches: two slots so that the H2D copy of chunk k+1 overlaps the read kernel on chunk k
     struct Slot {
@@ -296,12 +302,16 @@ void peer_detach(vgl_ctx* ctx) {
 }
 
 int reserve_result(vgl_ctx* ctx, size_t n_post) {
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->res_ev[k]) VGL_CUDA(cudaEventCreateWithFlags(&ctx->res_ev[k], cudaEventDisableTiming));
     if (n_post <= ctx->h_result_cap) return VGL_OK;
-    if (int rc = ctx->d_result.reserve(4 + n_post)) return rc;
+    VGL_CUDA(cudaStreamSynchronize(ctx->stream));   // (a result in flight still points into the old blocks)
+    ctx->res_pending[0] = ctx->res_pending[1] = false;
+    if (int rc = ctx->d_result.reserve(2 * (4 + n_post))) return rc;
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     ctx->h_result = nullptr;
     ctx->h_result_cap = 0;
-    VGL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_result), (4 + n_post) * sizeof(double)));
+    VGL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_result), 2 * (4 + n_post) * sizeof(double)));
     ctx->h_result_cap = n_post;
     return VGL_OK;
 }
@@ -389,6 +399,7 @@ void vgl_destroy(vgl_ctx* ctx) {
     ctx->d_clade_bits.release(); ctx->d_anc_off.release(); ctx->d_anc_clade.release();
     ctx->d_result.release();
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    for (auto& ev : ctx->res_ev) if (ev) cudaEventDestroy(ev);
     peer_detach(ctx);
     ctx->g_seq_off.release(); ctx->g_seq.release();
     for (vgl_ctx::RawDev& R : ctx->rawdev) {
@@ -1548,18 +1559,21 @@ int vgl_hc_exchange_paths(vgl_ctx* ctx) {
     return VGL_OK;
 }
 
-int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
-                    int32_t post_cap, int32_t* n_post_out) {
-    if (int rc = use_device(ctx)) return rc;
+}  // extern "C"
+
+namespace {
+// The posterior kernel and the copy of its result block into slot `slot`, enqueued; the slot's event marks the copy.
+int finalize_enqueue(vgl_ctx* ctx, int slot) {
     if (!ctx->have_tables) return fail(VGL_ERR_STATE, "vgl_hc_set_tables must come first");
     if (!ctx->ll_valid)
         if (int rc = vgl_hc_paths(ctx, nullptr)) return rc;
     cudaStream_t s = ctx->stream;
     const int P = ctx->tab.n_paths;
     const int cap = (int)std::min<size_t>(ctx->h_result_cap, (size_t)(ctx->have_tree ? ctx->max_anc + 1 : 1));
-    double* d_scalars = ctx->d_result.p;
-    int32_t* d_idx = reinterpret_cast<int32_t*>(ctx->d_result.p + 2);
-    double* d_post = ctx->d_result.p + 4;
+    const size_t at = (size_t)slot * (4 + ctx->h_result_cap);
+    double* d_scalars = ctx->d_result.p + at;
+    int32_t* d_idx = reinterpret_cast<int32_t*>(d_scalars + 2);
+    double* d_post = d_scalars + 4;
     if (ctx->peer_fused_pending) {
         VGL_CUDA(vgl::hc_launch_posterior_fused(ctx->d_ll.p, P, ctx->row_words, ctx->have_tree ? ctx->d_clade_bits.p : nullptr,
                                                 ctx->have_tree ? ctx->d_anc_off.p : nullptr, ctx->have_tree ? ctx->d_anc_clade.p : nullptr,
@@ -1573,12 +1587,20 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
                                           ctx->d_err, s));
     }
     ctx->launches += 1;
-    VGL_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, (4 + (size_t)cap) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (ll_out) VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->d_ll.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, s));
-    VGL_CUDA(cudaStreamSynchronize(s));
-    const double* scalars = ctx->h_result;
-    const int32_t* idx = reinterpret_cast<const int32_t*>(ctx->h_result + 2);
-    const double* post = ctx->h_result + 4;
+    VGL_CUDA(cudaMemcpyAsync(ctx->h_result + at, d_scalars, (4 + (size_t)cap) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    VGL_CUDA(cudaEventRecord(ctx->res_ev[slot], s));
+    ctx->res_pending[slot] = true;
+    return VGL_OK;
+}
+
+// Waits for slot `slot` and decodes it.
+int finalize_collect(vgl_ctx* ctx, int slot, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap, int32_t* n_post_out) {
+    if (!ctx->res_pending[slot]) return fail(VGL_ERR_STATE, "no result pending in this slot (vgl_hc_finalize_begin comes first)");
+    VGL_CUDA(cudaEventSynchronize(ctx->res_ev[slot]));
+    ctx->res_pending[slot] = false;
+    const double* scalars = ctx->h_result + (size_t)slot * (4 + ctx->h_result_cap);
+    const int32_t* idx = reinterpret_cast<const int32_t*>(scalars + 2);
+    const double* post = scalars + 4;
     const int err = idx[2];
     if (err & 0x40000000)
         return fail(VGL_ERR_PEER, "multi-GPU exchange: a peer rank did not deliver its vector in time (VGL_PEER_TIMEOUT_S, default 120 s)");
@@ -1603,6 +1625,40 @@ int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* t
         for (int k = 0; k < n_post; ++k) post_out[k] = post[k];
     }
     return VGL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vgl_hc_finalize(vgl_ctx* ctx, double* ll_out, int32_t* argmax_out, double* total_out, double* post_out,
+                    int32_t post_cap, int32_t* n_post_out) {
+    if (int rc = use_device(ctx)) return rc;
+    const int slot = (int)(ctx->res_seq++ & 1u);
+    if (ctx->res_pending[slot]) return fail(VGL_ERR_STATE, "two results are in flight already (vgl_hc_finalize_end first)");
+    if (int rc = finalize_enqueue(ctx, slot)) return rc;
+    if (ll_out) {
+        VGL_CUDA(cudaMemcpyAsync(ll_out, ctx->d_ll.p, (size_t)ctx->tab.n_paths * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VGL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return finalize_collect(ctx, slot, argmax_out, total_out, post_out, post_cap, n_post_out);
+}
+
+int vgl_hc_finalize_begin(vgl_ctx* ctx, int32_t* ticket_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (!ticket_out) return fail(VGL_ERR_INVALID, "null ticket");
+    const int slot = (int)(ctx->res_seq & 1u);
+    if (ctx->res_pending[slot]) return fail(VGL_ERR_STATE, "two results are in flight already (vgl_hc_finalize_end first)");
+    if (int rc = finalize_enqueue(ctx, slot)) return rc;
+    ctx->res_seq += 1;
+    *ticket_out = slot;
+    return VGL_OK;
+}
+
+int vgl_hc_finalize_end(vgl_ctx* ctx, int32_t ticket, int32_t* argmax_out, double* total_out, double* post_out, int32_t post_cap,
+                        int32_t* n_post_out) {
+    if (int rc = use_device(ctx)) return rc;
+    if (ticket < 0 || ticket > 1) return fail(VGL_ERR_INVALID, "bad ticket");
+    return finalize_collect(ctx, ticket, argmax_out, total_out, post_out, post_cap, n_post_out);
 }
 
 int vgl_hc_read_kernel_ms(vgl_ctx* ctx, float* ms_out, int32_t* launches_out) {

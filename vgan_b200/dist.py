@@ -107,6 +107,15 @@ class ShardedSample:
                     hc.update(b)
             return self.finish(want_ll=want_ll)
 
+    def finish_begin(self):
+        """The exchange step + posterior, enqueued (Haplocart.posterior_begin): returns a ticket for Haplocart.posterior_end."""
+        import torch
+        with torch.cuda.stream(self.stream):
+            if self.exchange != "peer":
+                raise RuntimeError("finish_begin needs the peer exchange (the NCCL fallback synchronises per sample)")
+            self.hc.exchange_paths()
+            return self.hc.posterior_begin()
+
     def finish(self, want_ll=False):
         """The exchange step + posterior for the sample accumulated on this rank since hc.reset() (every rank calls it)."""
         import torch

@@ -134,6 +134,26 @@ class Haplocart:
                 res["clade_vec"] = [res["predicted_haplotype"]] + self.tree.clades_of(arg.value)
         return res
 
+    def posterior_begin(self):
+        """First half of get_posterior(): enqueue the collapse, the posterior kernel and the copy of the result; returns a ticket.
+        The next sample's reset() / update*() may follow at once (at most two results in flight)."""
+        t = C.c_int32()
+        check(gpu.vgl_hc_finalize_begin(self.ctx, C.byref(t)))
+        return int(t.value)
+
+    def posterior_end(self, ticket):
+        """Second half: wait for that result alone and return it (as get_posterior(want_ll=False))."""
+        arg, npost, total = C.c_int32(), C.c_int32(), C.c_double()
+        post = np.zeros(max(self._max_post, 1), dtype=np.float64)
+        check(gpu.vgl_hc_finalize_end(self.ctx, int(ticket), C.byref(arg), C.byref(total), post.ctypes.data_as(C.c_void_p), post.size,
+                                      C.byref(npost)))
+        res = {"final_vec": None, "maxh_index": arg.value, "total_ll": total.value, "confidence_vec": post[:npost.value].copy()}
+        if self.path_names is not None:
+            res["predicted_haplotype"] = self.path_names[arg.value]
+            if self.tree is not None:
+                res["clade_vec"] = [res["predicted_haplotype"]] + self.tree.clades_of(arg.value)
+        return res
+
     # ---- several samples per pass (the reference loops over samples, src/HaploCart.cpp:303) --------------
     def samples_begin(self, n_samples):
         """Start a pass over n_samples samples (instead of reset()); sample 0 is selected."""
