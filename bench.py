@@ -486,7 +486,8 @@ def main():
     # later -- every step's result still reaches the host inside the timed region; the GPU does not idle while it does.
     pipelined = sharded is None or sharded.exchange == "peer"
 
-    def timed_pipelined(steps):
+    def timed_pipelined(steps, accumulate=None):
+        accumulate = accumulate or (lambda: hc.update_device(dev.batch))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         l0 = hc.launch_count()
@@ -494,7 +495,7 @@ def main():
         pending, out = None, None
         for _ in range(steps):
             hc.reset()
-            hc.update_device(dev.batch)
+            accumulate()
             ticket = sharded.finish_begin() if sharded is not None else hc.posterior_begin()
             if pending is not None:
                 out = hc.posterior_end(pending)
@@ -524,7 +525,10 @@ def main():
         step_e2e()
     e2e_steps = max(3, min(args.steps, 10))
     st0 = feeder.stats()
-    ms_e2e, _, _, _, res_e2e = timed(step_e2e, e2e_steps)
+    if pipelined:   # (as the device-resident loop: the host marshals step s + 1 while the GPU finishes step s and its result comes back)
+        ms_e2e, _, res_e2e = timed_pipelined(e2e_steps, lambda: feeder.feed(hc, alns))
+    else:
+        ms_e2e, _, _, _, res_e2e = timed(step_e2e, e2e_steps)
     st1 = feeder.stats()
     for _ in range(3):
         step_prepacked()
@@ -783,7 +787,8 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // nsteps,
                     "d2h_bytes_per_step": 28 + 8 * hc._max_post, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "route": "flat alignment fields (vgh_alignments, host) -> vgh_hc_feed: host marshalling into page-locked chunks "
-                             "overlapped with H2D + device reconstruct_graph_sequence + packing + read kernel -> posterior on the host",
+                             "overlapped with H2D + device reconstruct_graph_sequence + packing + read kernel -> posterior on the host"
+                             + (" (two samples in flight: step s + 1 is marshalled while step s's last chunk and posterior finish)" if pipelined else ""),
                     "host_marshal_threads": feeder_threads,
                     "host_marshal_seconds_per_step": (st1["build_seconds"] - st0["build_seconds"]) / nsteps,
                     "host_wait_seconds_per_step": (st1["wait_seconds"] - st0["wait_seconds"]) / nsteps,
