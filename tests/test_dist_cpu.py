@@ -100,6 +100,35 @@ def test_two_rank_mcmc_proposal_sum(tmp_path):
     assert np.allclose(r0, want, rtol=1e-13, atol=0)
 
 
+def _euka_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vgan_b200 import dist as vd
+    rng = np.random.default_rng(100 + rank)               # this rank's per-clade sums (the device's, in production)
+    count = rng.integers(0, 50, 7)
+    cov = rng.random(19)
+    like_n = rng.integers(0, 50, 7)
+    like_ls = -rng.random(7) * 30
+    np.save(os.path.join(out_dir, "euka_in%d.npy" % rank), np.concatenate([count, cov, like_n, like_ls]))
+    tot = vd.sum_euka_results(count, cov, like_n, like_ls)
+    np.save(os.path.join(out_dir, "euka_out%d.npy" % rank), np.concatenate([np.ravel(t).astype(np.float64) for t in tot]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_euka_sums(tmp_path):
+    """euka over sharded reads: per-clade counts all-reduced, coverage and log sums added in rank order."""
+    world = 2
+    mp.spawn(_euka_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ins = [np.load(tmp_path / ("euka_in%d.npy" % r)) for r in range(world)]
+    outs = [np.load(tmp_path / ("euka_out%d.npy" % r)) for r in range(world)]
+    assert np.array_equal(outs[0], outs[1])
+    want = ins[0].copy()
+    want += ins[1]
+    assert np.array_equal(outs[0], want)                      # rank-order sum (two ranks: one addition per entry)
+
+
 def test_shard_range_partitions():
     from vgan_b200 import dist as vd
     for n in (0, 1, 7, 64, 1000003):

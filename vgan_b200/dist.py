@@ -51,6 +51,32 @@ def sum_proposal_loglikes(local_loglike, group=None, device=None):
     return sum_in_rank_order(parts.cpu().numpy())
 
 
+def sum_euka_results(clade_count, bin_cov, like_n=None, like_logsum=None, group=None, device=None):
+    """euka on sharded reads: the per-read outputs stay with the rank that scored the reads; what the detection
+    filter and the abundance MCMC need are per-clade sums -- read counts (`Clade::count`), bin coverage, and the two sums behind
+    `get_proposal_likelihood` (number of scored reads and sum of log(clade_like) per clade: `Euka.like_sums`).  Integer counts
+    are all-reduced; the floating-point vectors are all-gathered and added in rank order, so every rank holds bit-identical
+    totals.  Returns numpy arrays (clade_count, bin_cov[, like_n, like_logsum])."""
+    import torch
+    import torch.distributed as dist
+
+    def dev(a, dtype):
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=dtype))
+        return t.to(device) if device is not None else t
+
+    ints = [dev(clade_count, np.int64)] + ([dev(like_n, np.int64)] if like_n is not None else [])
+    for t in ints:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    floats = [dev(np.ravel(bin_cov), np.float64)] + ([dev(like_logsum, np.float64)] if like_logsum is not None else [])
+    sums = [sum_in_rank_order(gather_paths(t, group).cpu().numpy()) if t.numel() else np.zeros(0) for t in floats]
+    out = [ints[0].cpu().numpy(), sums[0].reshape(np.shape(bin_cov))]
+    if like_n is not None:
+        out.append(ints[1].cpu().numpy())
+    if like_logsum is not None:
+        out.append(sums[1])
+    return tuple(out)
+
+
 class ShardedSample:
     """One sample spread over the ranks of a process group.  Each rank owns a `Haplocart` on its own GPU."""
 
