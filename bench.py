@@ -518,9 +518,9 @@ def main():
     ms_sync, k_ms, k_n, launches, res = timed(step_resident, args.steps)
     if pipelined:
         ms_dev, launches, res_p = timed_pipelined(args.steps)
-        assert res_p["maxh_index"] == res["maxh_index"]
+        pipelined_same_call = bool(res_p["maxh_index"] == res["maxh_index"])
     else:
-        ms_dev = ms_sync
+        ms_dev, pipelined_same_call = ms_sync, None
     for _ in range(3):
         step_e2e()
     e2e_steps = max(3, min(args.steps, 10))
@@ -778,7 +778,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "reads_per_gpu": reads_local, "paths": N_PATHS, "rows": N_ROWS,
                        "l2": "batch of %.0f MB per step exceeds the 126 MB L2 (no flush needed)" % (batch_bytes / 1e6),
-                       "steps_in_flight": 2 if pipelined else 1,
+                       "steps_in_flight": 2 if pipelined else 1, "same_call_as_one_result_at_a_time": pipelined_same_call,
                        "parallelism": "reads sharded over %d GPU(s); one exchange of P doubles per sample (%s)" % (
                            n_gpus, "none" if sharded is None else sharded.exchange),
                        "host_threads_per_rank": host_threads,
