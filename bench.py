@@ -654,6 +654,18 @@ def main():
                     out.append(hc.get_posterior(want_ll=False)["maxh_index"])
                 return out
 
+            def two_in_flight():
+                out, pending = [], None
+                for d in small_dev:
+                    hc.reset()
+                    hc.update_device(d.batch)
+                    t = hc.posterior_begin()
+                    if pending is not None:
+                        out.append(hc.posterior_end(pending)["maxh_index"])
+                    pending = t
+                out.append(hc.posterior_end(pending)["maxh_index"])
+                return out
+
             def in_one_pass(route):
                 hc.samples_begin(n_s)
                 for k in range(n_s):
@@ -676,11 +688,13 @@ def main():
                 return (time.perf_counter() - t0) / reps, res
 
             t_one, calls_one = clock(one_by_one, 5)
+            t_two, calls_two = clock(two_in_flight, 5)
             t_res, calls_res = clock(lambda: in_one_pass("resident"), 5)
             latency["samples"] = {"samples": n_s, "reads_per_sample": per,
                                   "samples_per_s_one_call_each_resident": n_s / t_one,
+                                  "samples_per_s_two_in_flight_resident": n_s / t_two,
                                   "samples_per_s_one_pass_resident": n_s / t_res,
-                                  "same_calls": calls_one == calls_res,
+                                  "same_calls": calls_one == calls_res == calls_two,
                                   "what": "64 samples: reset + accumulate + finalize per sample vs one vgl_hc_samples_begin / "
                                           "_finalize_samples pass (device-resident batches; host wall clock)"}
             if small_wire is not None:
@@ -689,7 +703,7 @@ def main():
                 latency["samples"]["wire_bytes_per_sample"] = small_wire[0].nbytes
             t_feed, calls_feed = clock(lambda: in_one_pass("feed"), 3)
             latency["samples"]["samples_per_s_one_pass_from_alignments"] = n_s / t_feed
-            latency["samples"]["same_calls"] = bool(calls_one == calls_res == calls_feed)
+            latency["samples"]["same_calls"] = bool(calls_one == calls_res == calls_feed == calls_two)
             for d in small_dev:
                 d.free()
             del small_dev, small_packed, small_wire
