@@ -36,7 +36,7 @@ if [ "${3:-ncu}" = "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sibling-reads 200000 > gpurun_out/${TAG}_ncu_list.log 2>&1
   # one full capture per kernel (a launch after the warm-up of its route)
-  for K in hc_read_logterm_kernel hc_path_kernel hc_path_samples_kernel hc_posterior_kernel hc_recon_kernel hc_pack_kernel hc_expand_kernel \
+  for K in hc_read_logterm_kernel hc_collapse_kernel hc_path_kernel hc_path_samples_kernel hc_posterior_kernel hc_recon_kernel hc_pack_kernel hc_expand_kernel \
            euka_read_kernel soibean_edit_kernel soibean_path_kernel soibean_mcmc_kernel gam_count_kernel gam_fill_kernel dedup_insert_kernel; do
     SKIP=2; case $K in soibean_mcmc_kernel|dedup_insert_kernel) SKIP=1;; esac   # (kernels the bench launches only twice)
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:${K} -s $SKIP -c 1 -f -o gpurun_out/${TAG}_${K} \
@@ -51,5 +51,5 @@ if [ "${3:-ncu}" = "ncu" ]; then
   head -3 gpurun_out/${TAG}_hc_read_kernel_general.txt
   python profiles/ncu_summary.py gpurun_out/${TAG}_hc_read_logterm_kernel.ncu-rep 998978 > gpurun_out/${TAG}_hc_read_logterm_kernel.txt 2>&1
   rm -f gpurun_out/${TAG}_hc_path_samples_kernel.ncu-rep gpurun_out/${TAG}_gam_*.ncu-rep gpurun_out/${TAG}_dedup_*.ncu-rep gpurun_out/${TAG}_soibean_*.ncu-rep \
-        gpurun_out/${TAG}_hc_expand_kernel.ncu-rep gpurun_out/${TAG}_hc_pack_kernel.ncu-rep gpurun_out/${TAG}_hc_posterior_kernel.ncu-rep   # (size limit of the return channel; summaries kept)
+        gpurun_out/${TAG}_hc_expand_kernel.ncu-rep gpurun_out/${TAG}_hc_pack_kernel.ncu-rep gpurun_out/${TAG}_hc_posterior_kernel.ncu-rep gpurun_out/${TAG}_hc_collapse_kernel.ncu-rep   # (size limit of the return channel; summaries kept)
 fi
