@@ -66,12 +66,7 @@ typedef struct vgh_alignments {
     const int32_t* edit_to;
     const int64_t* edit_seq_off; /* [n_edits + 1] into edit_seq                           */
     const char* edit_seq;
-    uint32_t flags;          /* VGH_ALN_*: invariants the producer verified while it built the arrays (0: none claimed) */
 } vgh_alignments;
-/* Only a read's FIRST mapping has a non-zero position.offset -- true of every alignment path vg emits (a path enters the nodes
- * after the first at their start).  The GAM reader, the synthetic generator and FlatAlignments::assign check it as they write
- * map_offset; with the flag set the feeder does not read the array again (17 % of the bytes it touches per read).            */
-#define VGH_ALN_INNER_OFFSETS_ZERO 1u
 
 /* GAM reader: gzip/BGZF or plain stream of framed vg.Alignment messages.  Like the reference's
  * readGAM it drops alignments whose identity is exactly 0 when drop_unmapped != 0

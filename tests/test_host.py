@@ -444,18 +444,6 @@ def test_feeder_chunk_holds_the_same_arrays_as_the_general_builder():
     A = S.reads(3000, seed=31, sub_rate=0.02, indel_rate=0.01, fixed_len=0, damage=True)
     assert (A.arrays()["identity"] < 1e-10).any()
     as_arr = vb.host._as_array
-    # the generator vouches that only first mappings start inside a node (VGH_ALN_INNER_OFFSETS_ZERO): the feeder then skips its own
-    # pass over map_offset; with the flag cleared it checks for itself -- same arrays either way
-    assert A.view.flags & 1
-    f0 = vb.Feeder(n_threads=2, chunk_reads=4096)             # (a marshalled chunk lives in its feeder's block)
-    vouched = f0.marshal(A, 0, 3000)
-    first_vouched = as_arr(vouched.first_offset16, int(vouched.n_reads), np.uint16).copy()
-    nodes_vouched = as_arr(vouched.map_node16, int(vouched.n_maps), np.uint16).copy()
-    A.view.flags = 0
-    checked = f0.marshal(A, 0, 3000)
-    assert checked is not None and np.array_equal(as_arr(checked.first_offset16, int(checked.n_reads), np.uint16), first_vouched)
-    assert np.array_equal(as_arr(checked.map_node16, int(checked.n_maps), np.uint16), nodes_vouched)
-    f0.close()
     for r0, r1 in [(0, 3000), (17, 1301), (5, 6)]:
         general = vb.RawBatch(A, r0, r1)          # keeps the arrays `want` points into alive
         want = general.raw

@@ -95,7 +95,7 @@ class vgh_alignments(C.Structure):
                 ("qual", C.c_void_p), ("mapq", C.c_void_p), ("identity", C.c_void_p), ("paired", C.c_void_p),
                 ("map_off", C.c_void_p), ("map_node", C.c_void_p), ("map_offset", C.c_void_p), ("map_rev", C.c_void_p),
                 ("edit_off", C.c_void_p), ("edit_from", C.c_void_p), ("edit_to", C.c_void_p),
-                ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p), ("flags", C.c_uint32)]
+                ("edit_seq_off", C.c_void_p), ("edit_seq", C.c_void_p)]
 
 
 # every symbol include/vgan_gpu.h declares: name -> (restype, argtypes)

@@ -56,13 +56,6 @@ struct vgh_gam {
         view.map_rev = map_rev.data();
         view.edit_off = edit_off.data(); view.edit_from = edit_from.data(); view.edit_to = edit_to.data();
         view.edit_seq_off = edit_seq_off.data(); view.edit_seq = edit_seq.data();
-        // invariants worth a flag (vgan_host.h): one parallel pass here, where the arrays are made, instead of one per feed
-        bool inner_zero = true;
-        const int64_t n = view.n_reads;
-#pragma omp parallel for schedule(static) reduction(&& : inner_zero)
-        for (int64_t r = 0; r < n; ++r)
-            for (int64_t m = map_off[(size_t)r] + 1; m < map_off[(size_t)r + 1]; ++m) inner_zero = inner_zero && map_offset[(size_t)m] == 0;
-        view.flags = inner_zero ? VGH_ALN_INNER_OFFSETS_ZERO : 0u;
     }
 };
 

@@ -47,13 +47,11 @@ struct FlatAlignments {
     std::vector<double> identity;
     std::vector<uint8_t> paired, map_rev;
     std::vector<int64_t> map_node, map_offset;
-    bool inner_offsets_zero = true;   // only a read's first mapping starts inside its node (VGH_ALN_INNER_OFFSETS_ZERO)
 
     template <typename AlignmentInfoPtrVector>
     void assign(const AlignmentInfoPtrVector& algnvector) {
         *this = FlatAlignments();
         for (const auto* ai : algnvector) {
-            bool first = true;
             seq += ai->seq;
             seq_off.push_back((int64_t)seq.size());
             qual += ai->quality_scores;
@@ -64,8 +62,6 @@ struct FlatAlignments {
             for (const auto& m : ai->path.mapping()) {
                 map_node.push_back((int64_t)m.position().node_id());
                 map_offset.push_back((int64_t)m.position().offset());
-                inner_offsets_zero = inner_offsets_zero && (first || m.position().offset() == 0);
-                first = false;
                 map_rev.push_back(m.position().is_reverse() ? 1 : 0);
                 for (const auto& e : m.edit()) {
                     edit_from.push_back((int32_t)e.from_length());
@@ -88,7 +84,6 @@ struct FlatAlignments {
         v.map_off = map_off.data(); v.map_node = map_node.data(); v.map_offset = map_offset.data(); v.map_rev = map_rev.data();
         v.edit_off = edit_off.data(); v.edit_from = edit_from.data(); v.edit_to = edit_to.data();
         v.edit_seq_off = edit_seq_off.data(); v.edit_seq = edit_seq.data();
-        v.flags = inner_offsets_zero ? VGH_ALN_INNER_OFFSETS_ZERO : 0u;
         return v;
     }
 };

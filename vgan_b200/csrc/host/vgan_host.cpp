@@ -1272,24 +1272,6 @@ void vgh_hc_feeder_stats(const vgh_hc_feeder* f, double* build_seconds, double* 
 VGH_FEEDER_NARROW_MAPPINGS(feeder_narrow_mappings16, uint16_t, 0x7fffull, 0x8000ull)
 VGH_FEEDER_NARROW_MAPPINGS(feeder_narrow_mappings32, uint32_t, 0x7fffffffull, 0x80000000ull)
 #undef VGH_FEEDER_NARROW_MAPPINGS
-// the same without the pass over map_offset, for alignments whose producer vouches for VGH_ALN_INNER_OFFSETS_ZERO
-#define VGH_FEEDER_NARROW_MAPPINGS_NO_OFFS(NAME, NodeT, ID_MASK, REV_BIT)                                                                  \
-    VGH_CLONES static void NAME(const int64_t* __restrict__ node, const uint8_t* __restrict__ rev, const int64_t* __restrict__ eo,         \
-                                NodeT* __restrict__ on, uint8_t* __restrict__ oc, int64_t n, uint64_t* viol, uint64_t* node_viol) {        \
-        uint64_t v = 0, nv = 0;                                                                                                            \
-        for (int64_t i = 0; i < n; ++i) {                                                                                                  \
-            const uint64_t nd = (uint64_t)node[i], cnt = (uint64_t)(eo[i + 1] - eo[i]);                                                    \
-            v |= cnt & ~(uint64_t)0xff;                                                                                                    \
-            nv |= nd & ~(uint64_t)(ID_MASK);                                                                                               \
-            on[i] = (NodeT)((nd & (ID_MASK)) | (rev[i] ? (REV_BIT) : 0ull));                                                               \
-            oc[i] = (uint8_t)cnt;                                                                                                          \
-        }                                                                                                                                  \
-        *viol |= v;                                                                                                                        \
-        *node_viol |= nv;                                                                                                                  \
-    }
-VGH_FEEDER_NARROW_MAPPINGS_NO_OFFS(feeder_narrow_mappings16_no_offs, uint16_t, 0x7fffull, 0x8000ull)
-VGH_FEEDER_NARROW_MAPPINGS_NO_OFFS(feeder_narrow_mappings32_no_offs, uint32_t, 0x7fffffffull, 0x80000000ull)
-#undef VGH_FEEDER_NARROW_MAPPINGS_NO_OFFS
 
 VGH_CLONES static void feeder_narrow_edits(const int32_t* __restrict__ fr, const int32_t* __restrict__ to, const int64_t* __restrict__ so,
                                            uint8_t* __restrict__ of, uint8_t* __restrict__ ot, uint8_t* __restrict__ os, int64_t n, uint64_t* viol) {
@@ -1323,7 +1305,6 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
     const size_t Rall = (size_t)(rb - ra);
     const auto skipped = [a, mode](int64_t r) { return mode == 0 ? a->identity[r] < 1e-10 : a->identity[r] == 0; };
     const bool wide = f->wide_nodes;
-    const bool offsets_vouched = (a->flags & VGH_ALN_INNER_OFFSETS_ZERO) != 0;   // the producer checked: map_offset is read per read only
     int T = std::max(1, f->n_threads);
     T = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, Rall / 512 + 1));
     struct Cnt { uint64_t r = 0, m = 0, e = 0, q = 0, s = 0; };
@@ -1409,16 +1390,12 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
             const int64_t rs = ra + (int64_t)k, re = ra + (int64_t)ke;   // the run [rs, re)
             const int64_t M0 = a->map_off[rs], M1 = a->map_off[re], E0 = a->edit_off[M0], E1 = a->edit_off[M1];
             const int64_t Q0 = a->qual_off[rs], Q1 = a->qual_off[re], S0 = a->edit_seq_off[E0], S1 = a->edit_seq_off[E1];
-            if (offsets_vouched) {
-                if (wide) feeder_narrow_mappings32_no_offs(a->map_node + M0, a->map_rev + M0, a->edit_off + M0, n32 + cm, ne8 + cm, M1 - M0, &viol, &node_viol);
-                else feeder_narrow_mappings16_no_offs(a->map_node + M0, a->map_rev + M0, a->edit_off + M0, n16 + cm, ne8 + cm, M1 - M0, &viol, &node_viol);
-            } else if (wide) {
+            if (wide)
                 feeder_narrow_mappings32(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n32 + cm, ne8 + cm, M1 - M0,
                                          &viol, &node_viol, &nonzero_off);
-            } else {
+            else
                 feeder_narrow_mappings16(a->map_node + M0, a->map_offset + M0, a->map_rev + M0, a->edit_off + M0, n16 + cm, ne8 + cm, M1 - M0,
                                          &viol, &node_viol, &nonzero_off);
-            }
             feeder_narrow_edits(a->edit_from + E0, a->edit_to + E0, a->edit_seq_off + E0, f8 + ce, t8 + ce, sl8 + ce, E1 - E0, &viol);
             memcpy(q + cq, a->qual + Q0, (size_t)(Q1 - Q0));
             memcpy(eseq + cs, a->edit_seq + S0, (size_t)(S1 - S0));
@@ -1453,7 +1430,7 @@ static int feeder_fill(vgh_hc_feeder* f, int slot, const vgh_alignments* a, int6
             k = ke;
         }
         // only a read's first mapping may start inside its node (first_offset16 form)
-        bad |= (viol != 0 || (!offsets_vouched && nonzero_off != nonzero_first)) ? 1 : 0;
+        bad |= (viol != 0 || nonzero_off != nonzero_first) ? 1 : 0;
         bad_node |= node_viol != 0 ? 1 : 0;
         meta.qmax = std::max<uint32_t>(meta.qmax, qmax > 2 ? (uint32_t)qmax : 0u);
     }
