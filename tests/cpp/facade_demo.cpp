@@ -21,6 +21,7 @@ int main(int argc, char** argv) {
     const bool on_device = argc > 2 && std::string(argv[2]) == "--device-reconstruction";  // raw alignments, packed on the GPU
     const bool streamed = argc > 2 && std::string(argv[2]) == "--streamed";                // the feeder: chunks overlapped with the GPU
     const bool samples = argc > 2 && std::string(argv[2]) == "--samples";                  // the same sample three times in one pass
+    const bool in_flight = argc > 2 && std::string(argv[2]) == "--in-flight";              // two samples in flight (begin / end_posterior)
     vgh_synth_hc* S = nullptr;
     if (vgh_synth_hc_create(101, 300, 1210, 1201, &S)) return 2;
     vgh_gam* gam = nullptr;
@@ -79,6 +80,23 @@ int main(int argc, char** argv) {
             const std::vector<vgan_b200::Posterior> all = hc.finish_samples(true);
             if (all[0].maxh_index != all[2].maxh_index) { fprintf(stderr, "samples of one pass disagree\n"); return 4; }
             post = all[1];
+        } else if (in_flight) {
+            // sample after sample with the posterior of one still in flight while the next is accumulated
+            hc.reset();
+            hc.update_streamed(algnvector, 2);
+            const int t0 = hc.begin_posterior();
+            hc.reset();
+            hc.update_streamed(algnvector, 2);
+            const int t1 = hc.begin_posterior();
+            const vgan_b200::Posterior first = hc.end_posterior(t0), second = hc.end_posterior(t1);
+            if (first.maxh_index != second.maxh_index || first.confidence_vec.size() != second.confidence_vec.size()) {
+                fprintf(stderr, "samples in flight disagree\n");
+                return 4;
+            }
+            hc.reset();
+            hc.update_streamed(algnvector, 2);
+            post = hc.get_posterior(true);
+            if (post.maxh_index != first.maxh_index) { fprintf(stderr, "in-flight and synchronous results disagree\n"); return 4; }
         } else {
             hc.reset();
             if (on_device) hc.update_on_device(algnvector);

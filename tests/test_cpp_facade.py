@@ -31,7 +31,7 @@ def test_facade_compiles_and_flattens_alignment_objects():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("route", [[], ["--device-reconstruction"], ["--streamed"], ["--samples"]])
+@pytest.mark.parametrize("route", [[], ["--device-reconstruction"], ["--streamed"], ["--samples"], ["--in-flight"]])
 def test_facade_end_to_end_matches_oracle(route):
     out = subprocess.check_output([_build(), "200"] + route).decode().splitlines()
     S = vb.SynthHaplocart(seed=101, n_paths=300, n_rows=1210, n_nodes=1201)
