@@ -790,10 +790,37 @@ struct PeerFuse {
 constexpr int kPathTile = 128;       // paths per CTA (one per thread)
 constexpr int kWordsPerChunk = 10;   // 320 nodes per CTA
 
+// The masked sum over a chunk's nodes goes four nodes at a time: s_t[g][m] holds the sum of D[4g + b] over the bits b of m (added in the
+// order b = 0..3), so a path costs one 8-byte lookup and one add per nibble of its membership word instead of two selects and an add per
+// bit.  A row is 128 bytes: the lanes of a warp read different entries of the same row without bank conflicts.  The table is the same
+// for every path, so identically supported paths still get bit-identical sums.
+__device__ __forceinline__ void path_build_nibble_table(const double* __restrict__ s_d, double (*s_t)[16], int nw) {
+    for (int e = threadIdx.x; e < nw * 8 * 16; e += kPathTile) {
+        const int g = e >> 4, m = e & 15;
+        double v = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v += ((m >> b) & 1) ? s_d[4 * g + b] : 0.0;
+        s_t[g][m] = v;
+    }
+}
+__device__ __forceinline__ double path_masked_sum(const double (*s_t)[16], const uint32_t (&words)[kWordsPerChunk], int nw) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kWordsPerChunk; ++k) {
+        const uint32_t unsup = ~words[k];
+        if (k < nw) {
+#pragma unroll
+            for (int nib = 0; nib < 8; ++nib) acc += s_t[k * 8 + nib][(unsup >> (4 * nib)) & 15u];
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(kPathTile)
 hc_path_kernel(HcTablesDev t, const double* __restrict__ node_sum, double* __restrict__ chunk_ll,
                double* __restrict__ ll, unsigned int* __restrict__ tile_done, PeerFuse pf) {
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
+    __shared__ __align__(128) double s_t[kWordsPerChunk * 8][16];
     __shared__ __align__(8) unsigned long long s_bar;
     const int chunk = blockIdx.y;
     const int w0 = chunk * kWordsPerChunk;
@@ -818,18 +845,9 @@ hc_path_kernel(HcTablesDev t, const double* __restrict__ node_sum, double* __res
     for (int k = 0; k < kWordsPerChunk; ++k)
         words[k] = (k < nw && p < t.n_paths) ? __ldg(t.node_bits + (size_t)(w0 + k) * t.n_paths + p) : 0xffffffffu;
     mbar_wait(bar, 0);
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < kWordsPerChunk; ++k) {
-        const uint32_t unsup = ~words[k];
-        if (k < nw) {
-#pragma unroll
-            for (int bit = 0; bit < 32; ++bit) {
-                const double d = s_d[k * 32 + bit];
-                acc += ((unsup >> bit) & 1u) ? d : 0.0;
-            }
-        }
-    }
+    path_build_nibble_table(s_d, s_t, nw);
+    __syncthreads();
+    const double acc = path_masked_sum(s_t, words, nw);
     if (p < t.n_paths) chunk_ll[(size_t)chunk * t.n_paths + p] = acc;
     // K2c, run by whichever CTA of this path tile finishes last: ll[p] = sum of the A totals + sum over chunks, both in a
     // fixed order that is the same for every p (who does the sum changes from run to run, the sum does not)
@@ -875,6 +893,7 @@ __global__ void __launch_bounds__(kPathTile)
 hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_sum, size_t sum_stride, double* __restrict__ chunk_ll,
                        double* __restrict__ ll, unsigned int* __restrict__ tile_done, int n_samples, int samples_per_slice) {
     __shared__ __align__(16) double s_d[kWordsPerChunk * 32];
+    __shared__ __align__(128) double s_t[kWordsPerChunk * 8][16];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ bool s_last;
     const int chunk = blockIdx.y;
@@ -902,22 +921,13 @@ hc_path_samples_kernel(HcTablesDev t, const double* __restrict__ node_sum, size_
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < kWordsPerChunk; ++k) {
-            const uint32_t unsup = ~words[k];
-            if (k < nw) {
-#pragma unroll
-                for (int bit = 0; bit < 32; ++bit) {
-                    const double d = s_d[k * 32 + bit];
-                    acc += ((unsup >> bit) & 1u) ? d : 0.0;
-                }
-            }
-        }
+        path_build_nibble_table(s_d, s_t, nw);
+        __syncthreads();
+        const double acc = path_masked_sum(s_t, words, nw);
         double* chunk_s = chunk_ll + (size_t)sm * gridDim.y * t.n_paths;
         if (p < t.n_paths) chunk_s[(size_t)chunk * t.n_paths + p] = acc;
         __threadfence();
-        __syncthreads();   // (also: everybody is done with s_d before the next sample's copy lands)
+        __syncthreads();   // (also: everybody is done with s_d / s_t before the next sample's copy lands)
         unsigned int* done = tile_done + (size_t)sm * gridDim.x + blockIdx.x;
         if (threadIdx.x == 0) {
             s_last = atomicAdd(done, 1u) == gridDim.y - 1;
